@@ -1,0 +1,107 @@
+/* muse_b200.h - C ABI of libmuse_b200.so: the B200 (sm_100a) hot path of huggingface/open-muse.
+ *
+ * The reference (pure PyTorch, no FFI of its own) reaches the device through torch ops; each
+ * entry point below replaces the torch call(s) cited next to it (paths relative to the reference
+ * repo).  All functions:
+ *   - take raw device pointers + sizes + a cudaStream_t (passed as void*), never torch types;
+ *   - enqueue work on that stream and return immediately (asynchronous, like the torch ops);
+ *   - allocate nothing: scratch and outputs are caller-provided;
+ *   - return 0 (MUSE_OK) or a non-zero status; muse_last_error() gives the message (thread-local).
+ * Dtype codes: 0 = float32, 1 = bfloat16.  "bf16" pointers are 16-bit bfloat16 arrays.
+ */
+#ifndef MUSE_B200_H_
+#define MUSE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUSE_OK 0
+#define MUSE_ERR_INVALID 1
+#define MUSE_ERR_CUDA 2
+#define MUSE_ERR_UNSUPPORTED 3
+
+#define MUSE_B200_ABI_VERSION 1
+
+/* library / device plumbing */
+int muse_abi_version(void);
+const char* muse_last_error(void);
+int muse_set_device(int device);            /* cudaSetDevice for this library's runtime instance */
+int muse_device_info(int* sm_major, int* sm_minor, int* num_sms);
+
+/* GEMM epilogues */
+#define MUSE_EPI_BF16 0        /* C bf16 = acc                                   */
+#define MUSE_EPI_F32 1         /* C fp32 = acc                                   */
+#define MUSE_EPI_ATOMIC_F32 2  /* C fp32 += acc (split-K; weight gradients)      */
+#define MUSE_EPI_RESADD_F32 3  /* C fp32 = res fp32 + bf16(acc) (residual add)   */
+#define MUSE_GEMM_TCGEN05 0
+#define MUSE_GEMM_MMA_SYNC 1   /* legacy tensor-core cross-check kernel, not the product path */
+
+/* C[M,N] = opA(A) * opB(B)^T, bf16 inputs, fp32 accumulation.
+ *   a_mn == 0: A is row-major [M,K] (pitch lda); a_mn == 1: A is row-major [K,M].
+ *   b_mn == 0: B is row-major [N,K] (pitch ldb); b_mn == 1: B is row-major [K,N].
+ * Replaces every nn.Linear forward (muse/modeling_transformer.py:198-200,218,789-798,980,984) and,
+ * through the a_mn/b_mn views, their autograd dgrad / wgrad matmuls. */
+int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
+                   int ldc, int a_mn, int b_mn, int epilogue, int backend, void* stream);
+
+/* fp32 -> bf16 weight packing: table_dev is a device array of n_entries
+ * {const float* src; bf16* dst; int64 numel; int64 first_block} with 1024 elements per block.
+ * Replaces autocast's per-Linear weight casts (torch.autocast, training/train_maskgit_imagenet.py:152). */
+int muse_pack_bf16(const void* table_dev, int n_entries, long long total_blocks, void* stream);
+int muse_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+
+/* Embed.forward (muse/modeling_transformer.py:942-957): out[b,s,:] = word[ids[b,s],:] + pos[s,:] (fp32). */
+int muse_embed_fwd(const long long* ids, const float* word, const float* pos, float* out, int B, int S, int H,
+                   int vocab, void* stream);
+/* its backward: dword[ids] += dx (atomic), dpos[s] += sum_b dx[b,s]. dword/dpos must be initialised. */
+int muse_embed_bwd(const long long* ids, const float* dx, float* dword, float* dpos, int B, int S, int H, int vocab,
+                   void* stream);
+
+/* LayerNorm (weight only, :124-137) / RMSNorm (:79-100) over the last dim of [rows,H].
+ *   y = (res ? res : 0) + norm(act ? gelu(x) : x) * w ; mean/rstd [rows] are saved for backward.
+ *   act = 1 fuses the exact-erf GELU of MlmLayer (:980-983); rms = 1 selects RMSNorm. */
+int muse_norm_fwd(const void* x, int x_dtype, const float* w, const float* res, void* y, int y_dtype, float* mean,
+                  float* rstd, int rows, int H, float eps, int act, int rms, void* stream);
+/* dx = norm_bwd(dy) (* gelu'(x) if act) (+ dres if given); dw[H] += sum_rows dy * xhat (atomic). */
+int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
+                  const float* rstd, const float* dres, void* dx, int dx_dtype, float* dw, int rows, int H, int act,
+                  int rms, void* stream);
+
+/* GLU of FeedForward (:789-792): ab bf16 [rows, 2I] = [wi_0(x) | wi_1(x)], out bf16 [rows, I] = gelu(a) * b. */
+int muse_glu_fwd(const void* ab, void* out, long long rows, int I, void* stream);
+int muse_glu_bwd(const void* ab, const void* dout, void* dab, long long rows, int I, void* stream);
+
+/* Attention.attention (:221-241) fused: O = softmax(Q K^T * scale) V per (batch, head), head_dim 64.
+ * Q/K/V/O are bf16 with row strides (elements) q_rs/k_rs/v_rs/o_rs, head h at column offset h*64,
+ * batch b at row offset b*Sq (Q,O) or b*Skv (K,V).  lse fp32 [B,nh,Sq] is saved for backward. */
+int muse_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv,
+                  int head_dim, int q_rs, int k_rs, int v_rs, int o_rs, float scale, void* stream);
+/* dvec: fp32 scratch [B,nh,Sq]. */
+int muse_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                  float* dvec, void* dq, void* dk, void* dv, int B, int nh, int Sq, int Skv, int head_dim, int q_rs,
+                  int k_rs, int v_rs, int o_rs, int do_rs, int dq_rs, int dk_rs, int dv_rs, float scale,
+                  void* stream);
+
+/* F.cross_entropy(logits.view(-1,V), labels.view(-1), ignore_index=-100, label_smoothing) (:1276-1280).
+ * logits bf16 [rows, ld] (ld >= V, multiple of 8). lse/row_loss: fp32 [rows] scratch (lse kept for bwd).
+ * loss_out[0] = mean loss, loss_out[1] = number of non-ignored rows. */
+int muse_ce_fwd(const void* logits, const long long* labels, float* lse, float* row_loss, float* loss_out, int rows,
+                int V, int ld, float label_smoothing, void* stream);
+/* dlogits bf16 [rows, ld] = dloss[0]/N * (softmax - (1-ls) onehot - ls/V); zero for ignored rows / pad cols. */
+int muse_ce_bwd(const void* logits, const long long* labels, const float* lse, const float* dloss,
+                const float* loss_out, void* dlogits, int rows, int V, int ld, float label_smoothing, void* stream);
+
+/* VectorQuantizer.get_code (muse/modeling_maskgit_vqgan.py:303-316,342-348): ids[r] = argmin_c
+ * fl(fl(|z_r|^2 + |e_c|^2) - 2 z_r.e_c), first minimum. z fp32 [n,D] (NHWC-flattened), codebook fp32
+ * [ncodes,D], enorm_ws fp32 [ncodes] scratch, dmin (optional) fp32 [n]. Bit-exact vs oracle/vq_oracle.c. */
+int muse_vq_argmin(const float* z, const float* codebook, float* enorm_ws, long long* ids, float* dmin, int n,
+                   int ncodes, int D, void* stream);
+/* VectorQuantizer.get_codebook_entry (:318-324): out fp32 [B, D, P] (NCHW) = codebook[ids[B,P]]. */
+int muse_vq_lookup_nchw(const long long* ids, const float* codebook, float* out, int B, int P, int D, int ncodes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSE_B200_H_ */

@@ -1,0 +1,470 @@
+// Fused multi-head attention, forward and backward, head_dim = 64, no mask, no dropout.
+// Replaces the reference's materialised path (muse/modeling_transformer.py:221-241):
+//   transpose+contiguous x3 -> baddbmm(zeros, q, k^T, alpha=1/sqrt(hd)) -> softmax -> matmul(P, V)
+//   -> transpose+contiguous,
+// i.e. three [B*nh, S, S] tensors and five layout copies per layer, with a flash-style kernel that
+// keeps scores on-chip (online softmax, fp32 statistics) and reads Q/K/V straight out of the fused
+// [tokens, 3H] QKV projection (strided per head) and writes [tokens, H] context directly.
+// Used for self-attention (kv_len = S = 257/256/1024) and cross-attention (kv_len = 77, :886-899).
+//
+// Round-1 implementation uses mma.sync.m16n8k16 bf16 tensor-core tiles (attention core is ~5.7 % of
+// the step FLOPs at the base config); the tcgen05/TMEM version is the planned upgrade.
+#include "common.cuh"
+
+namespace muse {
+namespace {
+
+constexpr int D = 64;     // head dim
+constexpr int BQ = 64;    // rows per CTA (4 warps x 16)
+constexpr int BKV = 64;   // kv rows per inner step
+constexpr int LDS = 72;   // padded smem row stride (elements) = 144 B: conflict-free ldmatrix
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+// Cooperative load of a [64 x 64] bf16 tile (rows row0.., row pitch rs elements) into padded smem;
+// rows >= nrows are zero-filled.  128 threads.
+__device__ __forceinline__ void load_tile(bf16* s, const bf16* g, int row0, int nrows, long long rs) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = threadIdx.x + i * 128;  // 512 16-byte chunks
+    const int r = idx >> 3, c = (idx & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row0 + r < nrows) v = *reinterpret_cast<const uint4*>(g + static_cast<long long>(row0 + r) * rs + c);
+    *reinterpret_cast<uint4*>(s + r * LDS + c) = v;
+  }
+}
+
+// A fragments (16 rows x 64 k) of this warp's rows from a smem tile: a[ks][0..3]
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const bf16* s, int warp_row0, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const bf16* p = s + (warp_row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8;
+    ldsm_x4(a[ks], p);
+  }
+}
+
+// C[16 x 64] = A(frags, 16 x 64k) * T^T where T is a smem tile [64 n][64 k] (row = n, contiguous k).
+__device__ __forceinline__ void gemm_a_tT(float (&c)[8][4], const uint32_t (&a)[4][4], const bf16* t, int lane) {
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+    for (int kp = 0; kp < 2; ++kp) {  // pairs of k-steps
+      uint32_t b[4];
+      ldsm_x4(b, t + (nb * 8 + (lane & 7)) * LDS + kp * 32 + (lane >> 3) * 8);
+      mma16816(c[nb], a[kp * 2], b[0], b[1]);
+      mma16816(c[nb], a[kp * 2 + 1], b[2], b[3]);
+    }
+  }
+}
+
+// C[16 x 64] += A(frags, 16 x 64k) * T where T is a smem tile [64 k][64 n] (row = k, contiguous n).
+__device__ __forceinline__ void gemm_a_t(float (&c)[8][4], const uint32_t (&a)[4][4], const bf16* t, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {  // pairs of n-blocks
+      uint32_t b[4];
+      ldsm_x4_t(b, t + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8);
+      mma16816(c[np * 2], a[ks], b[0], b[1]);
+      mma16816(c[np * 2 + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+
+// fp32 C fragments [16 x 64] -> bf16 A fragments (16 x 64k)
+__device__ __forceinline__ void c_to_a(uint32_t (&a)[4][4], const float (&c)[8][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    a[ks][0] = pack_bf16(c[2 * ks][0], c[2 * ks][1]);
+    a[ks][1] = pack_bf16(c[2 * ks][2], c[2 * ks][3]);
+    a[ks][2] = pack_bf16(c[2 * ks + 1][0], c[2 * ks + 1][1]);
+    a[ks][3] = pack_bf16(c[2 * ks + 1][2], c[2 * ks + 1][3]);
+  }
+}
+
+struct AttnPtrs {
+  const bf16* q; const bf16* k; const bf16* v;
+  long long q_bs, k_bs, v_bs;  // batch strides (elements)
+  int q_rs, k_rs, v_rs;        // row strides (elements)
+};
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(AttnPtrs P, bf16* __restrict__ O, long long o_bs, int o_rs, float* __restrict__ LSE, int Sq, int Skv,
+                int nh, float scale) {
+  __shared__ __align__(16) bf16 sQ[BQ * LDS];
+  __shared__ __align__(16) bf16 sK[BKV * LDS];
+  __shared__ __align__(16) bf16 sV[BKV * LDS];
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const bf16* qg = P.q + b * P.q_bs + h * D;
+  const bf16* kg = P.k + b * P.k_bs + h * D;
+  const bf16* vg = P.v + b * P.v_bs + h * D;
+
+  load_tile(sQ, qg, q0, Sq, P.q_rs);
+  __syncthreads();
+  uint32_t qf[4][4];
+  load_a_frags(qf, sQ, warp * 16, lane);
+
+  const float sl2 = scale * kLog2e;
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+
+  for (int kv0 = 0; kv0 < Skv; kv0 += BKV) {
+    __syncthreads();
+    load_tile(sK, kg, kv0, Skv, P.k_rs);
+    load_tile(sV, vg, kv0, Skv, P.v_rs);
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    gemm_a_tT(s, qf, sK, lane);
+    float mx[2] = {m[0], m[1]};
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = kv0 + nb * 8 + 2 * t + (j & 1);
+        const float v = (col < Skv) ? s[nb][j] * sl2 : -INFINITY;
+        s[nb][j] = v;
+        mx[j >> 1] = fmaxf(mx[j >> 1], v);
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float corr[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      corr[r] = exp2f(m[r] - mx[r]);  // m = -inf on the first chunk -> 0
+      m[r] = mx[r];
+    }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p = exp2f(s[nb][j] - m[j >> 1]);
+        s[nb][j] = p;
+        rs[j >> 1] += p;
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l[r] = l[r] * corr[r] + rs[r];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[nb][j] *= corr[j >> 1];
+    uint32_t pf[4][4];
+    c_to_a(pf, s);
+    gemm_a_t(o, pf, sV, lane);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  const float inv[2] = {1.f / l[0], 1.f / l[1]};
+  // stage the output tile through this warp's rows of sQ (already consumed into registers)
+  __syncwarp();
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    *reinterpret_cast<uint32_t*>(sQ + (warp * 16 + g) * LDS + nb * 8 + 2 * t) = pack_bf16(o[nb][0] * inv[0], o[nb][1] * inv[0]);
+    *reinterpret_cast<uint32_t*>(sQ + (warp * 16 + g + 8) * LDS + nb * 8 + 2 * t) = pack_bf16(o[nb][2] * inv[1], o[nb][3] * inv[1]);
+  }
+  __syncwarp();
+  bf16* og = O + b * o_bs + h * D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = lane + i * 32;  // 16 rows x 8 chunks
+    const int r = warp * 16 + (idx >> 3), c = (idx & 7) * 8;
+    if (q0 + r < Sq)
+      *reinterpret_cast<uint4*>(og + static_cast<long long>(q0 + r) * o_rs + c) = *reinterpret_cast<const uint4*>(sQ + r * LDS + c);
+  }
+  if (t == 0) {
+    const int r0 = q0 + warp * 16 + g;
+    float* lse = LSE + (static_cast<long long>(b) * nh + h) * Sq;
+    if (r0 < Sq) lse[r0] = (m[0] + log2f(l[0])) * kLn2;
+    if (r0 + 8 < Sq) lse[r0 + 8] = (m[1] + log2f(l[1])) * kLn2;
+  }
+}
+
+// ------------------------------------------------------------------ backward: D = rowsum(dO * O)
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, long long o_bs, int o_rs, long long do_bs,
+                     int do_rs, float* __restrict__ Dout, int B, int Sq, int nh) {
+  const long long idx = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) >> 3;  // (b, h, s)
+  const int sub = threadIdx.x & 7;
+  const long long total = static_cast<long long>(B) * nh * Sq;
+  float acc = 0.f;
+  if (idx < total) {
+    const int s = static_cast<int>(idx % Sq);
+    const int h = static_cast<int>((idx / Sq) % nh);
+    const int b = static_cast<int>(idx / (static_cast<long long>(Sq) * nh));
+    float a[8], d[8];
+    load8(O + b * o_bs + static_cast<long long>(s) * o_rs + h * D + sub * 8, a);
+    load8(dO + b * do_bs + static_cast<long long>(s) * do_rs + h * D + sub * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += a[j] * d[j];
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (idx < total && sub == 0) Dout[idx] = acc;
+}
+
+// ------------------------------------------------------------------ backward: dK, dV (CTA owns 64 kv rows)
+__global__ void __launch_bounds__(128)
+attn_bwd_dkdv_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, int do_rs, const float* __restrict__ LSE,
+                     const float* __restrict__ Dv, bf16* __restrict__ dK, long long dk_bs, int dk_rs,
+                     bf16* __restrict__ dV, long long dv_bs, int dv_rs, int Sq, int Skv, int nh, float scale) {
+  __shared__ __align__(16) bf16 sA[BKV * LDS];  // K_j then Q_i
+  __shared__ __align__(16) bf16 sB[BKV * LDS];  // V_j then dO_i
+  __shared__ float sL[BQ], sD[BQ];
+  const int kv0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const bf16* qg = P.q + b * P.q_bs + h * D;
+  const bf16* kg = P.k + b * P.k_bs + h * D;
+  const bf16* vg = P.v + b * P.v_bs + h * D;
+  const bf16* dog = dO + b * do_bs + h * D;
+  const float* lse = LSE + (static_cast<long long>(b) * nh + h) * Sq;
+  const float* dv_ = Dv + (static_cast<long long>(b) * nh + h) * Sq;
+
+  load_tile(sA, kg, kv0, Skv, P.k_rs);
+  load_tile(sB, vg, kv0, Skv, P.v_rs);
+  __syncthreads();
+  uint32_t kf[4][4], vf[4][4];
+  load_a_frags(kf, sA, warp * 16, lane);
+  load_a_frags(vf, sB, warp * 16, lane);
+
+  const float sl2 = scale * kLog2e;
+  float dk[8][4], dvv[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dk[i][j] = 0.f; dvv[i][j] = 0.f; }
+  const int kvr0 = kv0 + warp * 16 + g;  // this thread's kv rows: kvr0, kvr0 + 8
+
+  for (int q0 = 0; q0 < Sq; q0 += BQ) {
+    __syncthreads();
+    load_tile(sA, qg, q0, Sq, P.q_rs);
+    load_tile(sB, dog, q0, Sq, do_rs);
+    if (threadIdx.x < BQ) {
+      const int r = q0 + threadIdx.x;
+      sL[threadIdx.x] = (r < Sq) ? lse[r] * kLog2e : 0.f;
+      sD[threadIdx.x] = (r < Sq) ? dv_[r] : 0.f;
+    }
+    __syncthreads();
+    // S^T = K_j Q_i^T  (rows: kv, cols: q)
+    float st[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st[i][j] = 0.f;
+    gemm_a_tT(st, kf, sA, lane);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int qc = nb * 8 + 2 * t + (j & 1);
+        const int kr = kvr0 + (j >> 1) * 8;
+        const bool ok = (q0 + qc < Sq) && (kr < Skv);
+        st[nb][j] = ok ? exp2f(st[nb][j] * sl2 - sL[qc]) : 0.f;
+      }
+    uint32_t pf[4][4];
+    c_to_a(pf, st);
+    gemm_a_t(dvv, pf, sB, lane);  // dV += P^T dO
+    // dP^T = V_j dO_i^T
+    float dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dp[i][j] = 0.f;
+    gemm_a_tT(dp, vf, sB, lane);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int qc = nb * 8 + 2 * t + (j & 1);
+        dp[nb][j] = st[nb][j] * (dp[nb][j] - sD[qc]) * scale;
+      }
+    c_to_a(pf, dp);
+    gemm_a_t(dk, pf, sA, lane);  // dK += dS^T Q
+  }
+  // write dK, dV (bf16) through smem for 16B stores
+  __syncthreads();
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    *reinterpret_cast<uint32_t*>(sA + (warp * 16 + g) * LDS + nb * 8 + 2 * t) = pack_bf16(dk[nb][0], dk[nb][1]);
+    *reinterpret_cast<uint32_t*>(sA + (warp * 16 + g + 8) * LDS + nb * 8 + 2 * t) = pack_bf16(dk[nb][2], dk[nb][3]);
+    *reinterpret_cast<uint32_t*>(sB + (warp * 16 + g) * LDS + nb * 8 + 2 * t) = pack_bf16(dvv[nb][0], dvv[nb][1]);
+    *reinterpret_cast<uint32_t*>(sB + (warp * 16 + g + 8) * LDS + nb * 8 + 2 * t) = pack_bf16(dvv[nb][2], dvv[nb][3]);
+  }
+  __syncwarp();
+  bf16* dkg = dK + b * dk_bs + h * D;
+  bf16* dvg = dV + b * dv_bs + h * D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = lane + i * 32;
+    const int r = warp * 16 + (idx >> 3), c = (idx & 7) * 8;
+    if (kv0 + r < Skv) {
+      *reinterpret_cast<uint4*>(dkg + static_cast<long long>(kv0 + r) * dk_rs + c) = *reinterpret_cast<const uint4*>(sA + r * LDS + c);
+      *reinterpret_cast<uint4*>(dvg + static_cast<long long>(kv0 + r) * dv_rs + c) = *reinterpret_cast<const uint4*>(sB + r * LDS + c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward: dQ (CTA owns 64 q rows)
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, int do_rs, const float* __restrict__ LSE,
+                   const float* __restrict__ Dv, bf16* __restrict__ dQ, long long dq_bs, int dq_rs, int Sq, int Skv,
+                   int nh, float scale) {
+  __shared__ __align__(16) bf16 sA[BKV * LDS];  // Q_i then K_j
+  __shared__ __align__(16) bf16 sB[BKV * LDS];  // dO_i then V_j
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const bf16* qg = P.q + b * P.q_bs + h * D;
+  const bf16* kg = P.k + b * P.k_bs + h * D;
+  const bf16* vg = P.v + b * P.v_bs + h * D;
+  const bf16* dog = dO + b * do_bs + h * D;
+  const float* lse = LSE + (static_cast<long long>(b) * nh + h) * Sq;
+  const float* dv_ = Dv + (static_cast<long long>(b) * nh + h) * Sq;
+
+  load_tile(sA, qg, q0, Sq, P.q_rs);
+  load_tile(sB, dog, q0, Sq, do_rs);
+  __syncthreads();
+  uint32_t qf[4][4], dof[4][4];
+  load_a_frags(qf, sA, warp * 16, lane);
+  load_a_frags(dof, sB, warp * 16, lane);
+  const int r0 = q0 + warp * 16 + g;
+  float l2[2], dd[2];
+  l2[0] = (r0 < Sq) ? lse[r0] * kLog2e : 0.f;
+  l2[1] = (r0 + 8 < Sq) ? lse[r0 + 8] * kLog2e : 0.f;
+  dd[0] = (r0 < Sq) ? dv_[r0] : 0.f;
+  dd[1] = (r0 + 8 < Sq) ? dv_[r0 + 8] : 0.f;
+  const float sl2 = scale * kLog2e;
+  float dq[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+
+  for (int kv0 = 0; kv0 < Skv; kv0 += BKV) {
+    __syncthreads();
+    load_tile(sA, kg, kv0, Skv, P.k_rs);
+    load_tile(sB, vg, kv0, Skv, P.v_rs);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; dp[i][j] = 0.f; }
+    gemm_a_tT(s, qf, sA, lane);    // S = Q K^T
+    gemm_a_tT(dp, dof, sB, lane);  // dP = dO V^T
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = kv0 + nb * 8 + 2 * t + (j & 1);
+        const int rr = r0 + (j >> 1) * 8;
+        const bool ok = (col < Skv) && (rr < Sq);
+        const float p = ok ? exp2f(s[nb][j] * sl2 - l2[j >> 1]) : 0.f;
+        s[nb][j] = p * (dp[nb][j] - dd[j >> 1]) * scale;
+      }
+    uint32_t dsf[4][4];
+    c_to_a(dsf, s);
+    gemm_a_t(dq, dsf, sA, lane);  // dQ += dS K
+  }
+  __syncthreads();
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    *reinterpret_cast<uint32_t*>(sA + (warp * 16 + g) * LDS + nb * 8 + 2 * t) = pack_bf16(dq[nb][0], dq[nb][1]);
+    *reinterpret_cast<uint32_t*>(sA + (warp * 16 + g + 8) * LDS + nb * 8 + 2 * t) = pack_bf16(dq[nb][2], dq[nb][3]);
+  }
+  __syncwarp();
+  bf16* dqg = dQ + b * dq_bs + h * D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = lane + i * 32;
+    const int r = warp * 16 + (idx >> 3), c = (idx & 7) * 8;
+    if (q0 + r < Sq)
+      *reinterpret_cast<uint4*>(dqg + static_cast<long long>(q0 + r) * dq_rs + c) = *reinterpret_cast<const uint4*>(sA + r * LDS + c);
+  }
+}
+
+int check_strides(const char* who, int hd, int a, int b, int c) {
+  if (hd != D) { set_last_error("%s: head_dim=%d unsupported (only 64)", who, hd); return MUSE_ERR_UNSUPPORTED; }
+  if ((a | b | c) % 8 != 0) { set_last_error("%s: row strides must be multiples of 8 elements", who); return MUSE_ERR_INVALID; }
+  return MUSE_OK;
+}
+
+}  // namespace
+
+int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv, int hd,
+             int q_rs, int k_rs, int v_rs, int o_rs, float scale, cudaStream_t s) {
+  if (B <= 0 || Sq <= 0 || Skv <= 0) return MUSE_OK;
+  int rc = check_strides("attn_fwd", hd, q_rs | o_rs, k_rs, v_rs);
+  if (rc) return rc;
+  AttnPtrs P;
+  P.q = reinterpret_cast<const bf16*>(q); P.k = reinterpret_cast<const bf16*>(k); P.v = reinterpret_cast<const bf16*>(v);
+  P.q_rs = q_rs; P.k_rs = k_rs; P.v_rs = v_rs;
+  P.q_bs = static_cast<long long>(Sq) * q_rs; P.k_bs = static_cast<long long>(Skv) * k_rs; P.v_bs = static_cast<long long>(Skv) * v_rs;
+  dim3 grid(ceil_div(Sq, BQ), nh, B);
+  attn_fwd_kernel<<<grid, 128, 0, s>>>(P, reinterpret_cast<bf16*>(o), static_cast<long long>(Sq) * o_rs, o_rs, lse, Sq, Skv, nh, scale);
+  return check_launch("attn_fwd");
+}
+
+int attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+             float* dvec, void* dq, void* dk, void* dv, int B, int nh, int Sq, int Skv, int hd, int q_rs, int k_rs,
+             int v_rs, int o_rs, int do_rs, int dq_rs, int dk_rs, int dv_rs, float scale, cudaStream_t s) {
+  if (B <= 0 || Sq <= 0 || Skv <= 0) return MUSE_OK;
+  int rc = check_strides("attn_bwd", hd, q_rs | o_rs | do_rs | dq_rs, k_rs | dk_rs, v_rs | dv_rs);
+  if (rc) return rc;
+  AttnPtrs P;
+  P.q = reinterpret_cast<const bf16*>(q); P.k = reinterpret_cast<const bf16*>(k); P.v = reinterpret_cast<const bf16*>(v);
+  P.q_rs = q_rs; P.k_rs = k_rs; P.v_rs = v_rs;
+  P.q_bs = static_cast<long long>(Sq) * q_rs; P.k_bs = static_cast<long long>(Skv) * k_rs; P.v_bs = static_cast<long long>(Skv) * v_rs;
+  const long long total = static_cast<long long>(B) * nh * Sq;
+  attn_bwd_prep_kernel<<<static_cast<unsigned>(ceil_div_ll(total * 8, 256)), 256, 0, s>>>(
+      reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * o_rs, o_rs,
+      static_cast<long long>(Sq) * do_rs, do_rs, dvec, B, Sq, nh);
+  rc = check_launch("attn_bwd_prep");
+  if (rc) return rc;
+  attn_bwd_dkdv_kernel<<<dim3(ceil_div(Skv, BKV), nh, B), 128, 0, s>>>(
+      P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
+      reinterpret_cast<bf16*>(dk), static_cast<long long>(Skv) * dk_rs, dk_rs, reinterpret_cast<bf16*>(dv),
+      static_cast<long long>(Skv) * dv_rs, dv_rs, Sq, Skv, nh, scale);
+  rc = check_launch("attn_bwd_dkdv");
+  if (rc) return rc;
+  attn_bwd_dq_kernel<<<dim3(ceil_div(Sq, BQ), nh, B), 128, 0, s>>>(
+      P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
+      reinterpret_cast<bf16*>(dq), static_cast<long long>(Sq) * dq_rs, dq_rs, Sq, Skv, nh, scale);
+  return check_launch("attn_bwd_dq");
+}
+
+}  // namespace muse

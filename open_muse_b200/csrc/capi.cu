@@ -1,0 +1,135 @@
+// extern "C" boundary of libmuse_b200.so (declared in include/muse_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/muse_b200.h"
+#include "common.cuh"
+
+namespace muse {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+    return MUSE_ERR_CUDA;
+  }
+  return MUSE_OK;
+}
+
+// kernels (defined in the other translation units)
+int gemm_tcgen05(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int gemm_mma(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int pack_bf16(const void*, int, long long, cudaStream_t);
+int cast_bf16(const float*, void*, long long, cudaStream_t);
+int embed_fwd(const long long*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
+int embed_bwd(const long long*, const float*, float*, float*, int, int, int, int, cudaStream_t);
+int norm_fwd(const void*, int, const float*, const float*, void*, int, float*, float*, int, int, float, int, int, cudaStream_t);
+int norm_bwd(const void*, int, const void*, int, const float*, const float*, const float*, const float*, void*, int, float*, int, int, int, int, cudaStream_t);
+int glu_fwd(const void*, void*, long long, int, cudaStream_t);
+int glu_bwd(const void*, const void*, void*, long long, int, cudaStream_t);
+int attn_fwd(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
+int attn_bwd(const void*, const void*, const void*, const void*, const void*, const float*, float*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
+int ce_fwd(const void*, const long long*, float*, float*, float*, int, int, int, float, cudaStream_t);
+int ce_bwd(const void*, const long long*, const float*, const float*, const float*, void*, int, int, int, float, cudaStream_t);
+int vq_argmin(const float*, const float*, float*, long long*, float*, int, int, int, cudaStream_t);
+int vq_lookup_nchw(const long long*, const float*, float*, int, int, int, int, cudaStream_t);
+
+}  // namespace muse
+
+using namespace muse;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int muse_abi_version(void) { return MUSE_B200_ABI_VERSION; }
+const char* muse_last_error(void) { return g_err; }
+
+int muse_set_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { set_last_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); return MUSE_ERR_CUDA; }
+  return MUSE_OK;
+}
+
+int muse_device_info(int* sm_major, int* sm_minor, int* num_sms) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_last_error("cudaGetDevice: %s", cudaGetErrorString(e)); return MUSE_ERR_CUDA; }
+  cudaDeviceGetAttribute(sm_major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(sm_minor, cudaDevAttrComputeCapabilityMinor, dev);
+  cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, dev);
+  return MUSE_OK;
+}
+
+int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
+                   int ldc, int a_mn, int b_mn, int epilogue, int backend, void* stream) {
+  if (epilogue == MUSE_EPI_RESADD_F32 && res == nullptr) { set_last_error("gemm: RESADD epilogue needs res"); return MUSE_ERR_INVALID; }
+  if (backend == MUSE_GEMM_MMA_SYNC) return gemm_mma(A, B, C, res, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, ST(stream));
+  return gemm_tcgen05(A, B, C, res, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, ST(stream));
+}
+
+int muse_pack_bf16(const void* table_dev, int n_entries, long long total_blocks, void* stream) {
+  return pack_bf16(table_dev, n_entries, total_blocks, ST(stream));
+}
+int muse_cast_bf16(const float* src, void* dst, long long n, void* stream) { return cast_bf16(src, dst, n, ST(stream)); }
+
+int muse_embed_fwd(const long long* ids, const float* word, const float* pos, float* out, int B, int S, int H, int vocab, void* stream) {
+  return embed_fwd(ids, word, pos, out, B, S, H, vocab, ST(stream));
+}
+int muse_embed_bwd(const long long* ids, const float* dx, float* dword, float* dpos, int B, int S, int H, int vocab, void* stream) {
+  return embed_bwd(ids, dx, dword, dpos, B, S, H, vocab, ST(stream));
+}
+
+int muse_norm_fwd(const void* x, int x_dtype, const float* w, const float* res, void* y, int y_dtype, float* mean,
+                  float* rstd, int rows, int H, float eps, int act, int rms, void* stream) {
+  return norm_fwd(x, x_dtype, w, res, y, y_dtype, mean, rstd, rows, H, eps, act, rms, ST(stream));
+}
+int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
+                  const float* rstd, const float* dres, void* dx, int dx_dtype, float* dw, int rows, int H, int act,
+                  int rms, void* stream) {
+  return norm_bwd(dy, dy_dtype, x, x_dtype, w, mean, rstd, dres, dx, dx_dtype, dw, rows, H, act, rms, ST(stream));
+}
+
+int muse_glu_fwd(const void* ab, void* out, long long rows, int I, void* stream) { return glu_fwd(ab, out, rows, I, ST(stream)); }
+int muse_glu_bwd(const void* ab, const void* dout, void* dab, long long rows, int I, void* stream) {
+  return glu_bwd(ab, dout, dab, rows, I, ST(stream));
+}
+
+int muse_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv,
+                  int head_dim, int q_rs, int k_rs, int v_rs, int o_rs, float scale, void* stream) {
+  return attn_fwd(q, k, v, o, lse, B, nh, Sq, Skv, head_dim, q_rs, k_rs, v_rs, o_rs, scale, ST(stream));
+}
+int muse_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                  float* dvec, void* dq, void* dk, void* dv, int B, int nh, int Sq, int Skv, int head_dim, int q_rs,
+                  int k_rs, int v_rs, int o_rs, int do_rs, int dq_rs, int dk_rs, int dv_rs, float scale,
+                  void* stream) {
+  return attn_bwd(q, k, v, o, d_o, lse, dvec, dq, dk, dv, B, nh, Sq, Skv, head_dim, q_rs, k_rs, v_rs, o_rs, do_rs,
+                  dq_rs, dk_rs, dv_rs, scale, ST(stream));
+}
+
+int muse_ce_fwd(const void* logits, const long long* labels, float* lse, float* row_loss, float* loss_out, int rows,
+                int V, int ld, float label_smoothing, void* stream) {
+  return ce_fwd(logits, labels, lse, row_loss, loss_out, rows, V, ld, label_smoothing, ST(stream));
+}
+int muse_ce_bwd(const void* logits, const long long* labels, const float* lse, const float* dloss,
+                const float* loss_out, void* dlogits, int rows, int V, int ld, float label_smoothing, void* stream) {
+  return ce_bwd(logits, labels, lse, dloss, loss_out, dlogits, rows, V, ld, label_smoothing, ST(stream));
+}
+
+int muse_vq_argmin(const float* z, const float* codebook, float* enorm_ws, long long* ids, float* dmin, int n,
+                   int ncodes, int D, void* stream) {
+  return vq_argmin(z, codebook, enorm_ws, ids, dmin, n, ncodes, D, ST(stream));
+}
+int muse_vq_lookup_nchw(const long long* ids, const float* codebook, float* out, int B, int P, int D, int ncodes, void* stream) {
+  return vq_lookup_nchw(ids, codebook, out, B, P, D, ncodes, ST(stream));
+}
+
+}  // extern "C"

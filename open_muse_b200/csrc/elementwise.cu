@@ -1,0 +1,185 @@
+// HBM-bound elementwise / gather kernels of the transformer step:
+//   * multi-tensor fp32 -> bf16 weight packing (one launch for all Linear weights of a model)
+//   * token + position embedding gather (muse/modeling_transformer.py:942-957) and its backward
+//   * GLU: gelu(a) * b (muse/modeling_transformer.py:789-792) forward / backward
+//   * plain fp32 -> bf16 cast (gradient of the residual stream entering a dgrad GEMM)
+#include "common.cuh"
+
+namespace muse {
+namespace {
+
+// ---------------------------------------------------------------- multi-tensor pack
+// table[i] = {src fp32 ptr, dst bf16 ptr, numel(multiple of 4), first 1024-element block index}
+struct PackEntry {
+  const float* src;
+  bf16* dst;
+  long long numel;
+  long long first_block;
+};
+
+__global__ void __launch_bounds__(256) pack_bf16_kernel(const PackEntry* __restrict__ table, int n_entries) {
+  const long long blk = blockIdx.x;
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {  // last entry with first_block <= blk
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].first_block <= blk) lo = mid; else hi = mid - 1;
+  }
+  const PackEntry e = table[lo];
+  const long long i = ((blk - e.first_block) * 256 + threadIdx.x) * 4;
+  if (i < e.numel) {
+    const float4 v = *reinterpret_cast<const float4*>(e.src + i);
+    uint2 u;
+    u.x = pack_bf16(v.x, v.y);
+    u.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(e.dst + i) = u;
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n8) {
+    float v[8];
+    load8(src + i * 8, v);
+    store8(dst + i * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------- embedding
+__global__ void __launch_bounds__(128)
+embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
+                 float* __restrict__ out, int tokens, int S, int H, int vocab) {
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (t >= tokens) return;
+  const int lane = threadIdx.x & 31;
+  long long id = ids[t];
+  if (id < 0 || id >= vocab) id = 0;  // torch raises on OOB ids; host validates, device stays in-bounds
+  const float* wr = word + id * H;
+  const float* pr = pos + static_cast<size_t>(t % S) * H;
+  float* o = out + static_cast<size_t>(t) * H;
+  for (int c = lane * 4; c < H; c += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(wr + c);
+    const float4 b = *reinterpret_cast<const float4*>(pr + c);
+    *reinterpret_cast<float4*>(o + c) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+// dword[ids[t]] += dx[t] (atomics; the mask token row is hot) ; one warp per token
+__global__ void __launch_bounds__(128)
+embed_bwd_word_kernel(const long long* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ dword,
+                      int tokens, int H, int vocab) {
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (t >= tokens) return;
+  const int lane = threadIdx.x & 31;
+  long long id = ids[t];
+  if (id < 0 || id >= vocab) return;
+  const float* g = dx + static_cast<size_t>(t) * H;
+  float* d = dword + id * H;
+  for (int c = lane * 4; c < H; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(g + c);
+    atomicAdd(reinterpret_cast<float4*>(d + c), v);
+  }
+}
+
+// dpos[s] += sum_b dx[b, s]; block (s, column chunk of 128 floats), threads stride over batch
+__global__ void __launch_bounds__(128)
+embed_bwd_pos_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B, int S, int H) {
+  const int s = blockIdx.x;
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= H) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc += dx[(static_cast<size_t>(b) * S + s) * H + c];
+  dpos[static_cast<size_t>(s) * H + c] += acc;
+}
+
+// ---------------------------------------------------------------- GLU
+// ab: [rows, 2*I] bf16 (a = cols [0,I), b = cols [I,2I)); out [rows, I] bf16.
+// Rounding points follow the reference under bf16 autocast: gelu(a) is rounded to bf16 before the product.
+__global__ void __launch_bounds__(256)
+glu_fwd_kernel(const bf16* __restrict__ ab, bf16* __restrict__ out, long long rows, int I) {
+  const int chunks = I / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= rows * chunks) return;
+  const long long r = idx / chunks;
+  const int c = static_cast<int>(idx % chunks) * 8;
+  float a[8], b[8], o[8];
+  load8(ab + r * 2 * I + c, a);
+  load8(ab + r * 2 * I + I + c, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = bf16_round(gelu_f(a[j])) * b[j];
+  store8(out + r * I + c, o);
+}
+
+__global__ void __launch_bounds__(256)
+glu_bwd_kernel(const bf16* __restrict__ ab, const bf16* __restrict__ dout, bf16* __restrict__ dab, long long rows, int I) {
+  const int chunks = I / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= rows * chunks) return;
+  const long long r = idx / chunks;
+  const int c = static_cast<int>(idx % chunks) * 8;
+  float a[8], b[8], d[8], da[8], db[8];
+  load8(ab + r * 2 * I + c, a);
+  load8(ab + r * 2 * I + I + c, b);
+  load8(dout + r * I + c, d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    da[j] = d[j] * b[j] * gelu_grad_f(a[j]);
+    db[j] = d[j] * bf16_round(gelu_f(a[j]));
+  }
+  store8(dab + r * 2 * I + c, da);
+  store8(dab + r * 2 * I + I + c, db);
+}
+
+}  // namespace
+
+int pack_bf16(const void* table_dev, int n_entries, long long total_blocks, cudaStream_t s) {
+  if (n_entries <= 0 || total_blocks <= 0) return MUSE_OK;
+  pack_bf16_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, s>>>(reinterpret_cast<const PackEntry*>(table_dev), n_entries);
+  return check_launch("pack_bf16");
+}
+
+int cast_bf16(const float* src, void* dst, long long n, cudaStream_t s) {
+  if (n <= 0) return MUSE_OK;
+  if (n % 8 != 0) { set_last_error("cast_bf16: n=%lld must be a multiple of 8", n); return MUSE_ERR_INVALID; }
+  const long long n8 = n / 8;
+  cast_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(n8, 256)), 256, 0, s>>>(src, reinterpret_cast<bf16*>(dst), n8);
+  return check_launch("cast_bf16");
+}
+
+int embed_fwd(const long long* ids, const float* word, const float* pos, float* out, int B, int S, int H, int vocab,
+              cudaStream_t s) {
+  if (H % 4 != 0) { set_last_error("embed_fwd: H must be a multiple of 4"); return MUSE_ERR_INVALID; }
+  const int tokens = B * S;
+  if (tokens <= 0) return MUSE_OK;
+  embed_fwd_kernel<<<ceil_div(tokens, 4), 128, 0, s>>>(ids, word, pos, out, tokens, S, H, vocab);
+  return check_launch("embed_fwd");
+}
+
+int embed_bwd(const long long* ids, const float* dx, float* dword, float* dpos, int B, int S, int H, int vocab,
+              cudaStream_t s) {
+  if (H % 4 != 0) { set_last_error("embed_bwd: H must be a multiple of 4"); return MUSE_ERR_INVALID; }
+  const int tokens = B * S;
+  if (tokens <= 0) return MUSE_OK;
+  embed_bwd_word_kernel<<<ceil_div(tokens, 4), 128, 0, s>>>(ids, dx, dword, tokens, H, vocab);
+  int rc = check_launch("embed_bwd_word");
+  if (rc) return rc;
+  embed_bwd_pos_kernel<<<dim3(S, ceil_div(H, 128)), 128, 0, s>>>(dx, dpos, B, S, H);
+  return check_launch("embed_bwd_pos");
+}
+
+int glu_fwd(const void* ab, void* out, long long rows, int I, cudaStream_t s) {
+  if (I % 8 != 0) { set_last_error("glu_fwd: I must be a multiple of 8"); return MUSE_ERR_INVALID; }
+  const long long n = rows * (I / 8);
+  if (n <= 0) return MUSE_OK;
+  glu_fwd_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(reinterpret_cast<const bf16*>(ab), reinterpret_cast<bf16*>(out), rows, I);
+  return check_launch("glu_fwd");
+}
+
+int glu_bwd(const void* ab, const void* dout, void* dab, long long rows, int I, cudaStream_t s) {
+  if (I % 8 != 0) { set_last_error("glu_bwd: I must be a multiple of 8"); return MUSE_ERR_INVALID; }
+  const long long n = rows * (I / 8);
+  if (n <= 0) return MUSE_OK;
+  glu_bwd_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(reinterpret_cast<const bf16*>(ab), reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dab), rows, I);
+  return check_launch("glu_bwd");
+}
+
+}  // namespace muse

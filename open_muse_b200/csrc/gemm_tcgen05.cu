@@ -1,0 +1,408 @@
+// bf16 GEMM on the 5th-gen tensor cores: C[M,N] = A[M,K] * B[N,K]^T, fp32 accumulation in TMEM.
+//
+// This is the kernel every nn.Linear of the reference's transformer maps to
+// (muse/modeling_transformer.py:198-200,218 q/k/v/out; :789-798 wi_0/wi_1/wo; :980,984 mlm head)
+// and, with transposed operand views, their dgrad / wgrad in backward.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0  : TMA producer  - cp.async.bulk.tensor 2D tiles (128B swizzle) into a smem ring
+//   warp 1  : MMA issuer    - one elected thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
+//   warp 2  : TMEM allocator
+//   warps 4-7: epilogue     - tcgen05.ld accumulators -> registers -> global (bf16 / fp32 / atomic / +residual)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+//
+// Operand "major-ness": an operand is K-major when the reduction dim is contiguous in memory
+// (activations X[T,K], weights W[N,K] in forward) and MN-major when the M/N dim is contiguous
+// (W[N,K] used as the B operand of dgrad; dY[T,N] and X[T,K] as operands of wgrad, where the
+// reduction runs over T). Both are fed straight from their row-major tensors through TMA; the
+// smem (matrix) descriptors tell the tensor core which layout it is looking at, so no transposes
+// are materialised anywhere in the training step.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace muse {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+
+enum Epi { EPI_BF16 = 0, EPI_F32 = 1, EPI_ATOMIC_F32 = 2, EPI_RESADD_F32 = 3 };
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
+};
+
+struct GemmParams {
+  void* C;
+  const float* res;
+  int M, N, K;
+  int ldc;
+  int num_m, num_n, num_kb, kb_per_split, splits;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using C_ = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::kStages * C_::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C_::kStages;
+  uint64_t* tmem_full = bars + 2 * C_::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C_::kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_holder, C_::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int tiles_mn = p.num_m * p.num_n;
+  const int total_tiles = tiles_mn * p.splits;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_idx = tile % p.num_n;
+        const int m_idx = (tile / p.num_n) % p.num_m;
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int m0 = m_idx * BM, n0 = n_idx * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], C_::kStageBytes);
+          uint8_t* sa = smem + stage * C_::kStageBytes;
+          uint8_t* sb = sa + C_::kABytes;
+          if (!A_MN) {
+            ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              ptx::tma_load_2d(sa + i * (BK * 128), &tmA, &full_bar[stage], m0 + i * 64, kb * BK);
+          }
+          if (!B_MN) {
+            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              ptx::tma_load_2d(sb + i * (BK * 128), &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
+          }
+          if (++stage == C_::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // ------------------------------------------------------------ MMA issuer (single thread)
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * C_::kStageBytes);
+          const uint32_t b_addr = a_addr + C_::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major  : 8-row groups 1024 B apart (SBO); a 16-element K step is +32 B inside the row.
+            // MN-major : 64-element MN chunks BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
+            //            a 16-row K step is +2048 B.
+            const uint64_t adesc = A_MN ? ptx::make_smem_desc_sw128(a_addr + k * 2048, BK * 128, 1024)
+                                        : ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(b_addr + k * 2048, BK * 128, 1024)
+                                        : ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs have read it
+          if (++stage == C_::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------------------- epilogue (128 threads = 128 TMEM lanes)
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_idx = tile % p.num_n;
+      const int m_idx = (tile / p.num_n) % p.num_m;
+      const int row = m_idx * BM + ew * 32 + lane;
+      const int n0 = n_idx * BN;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                                 static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + c, r);
+        ptx::tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (row < p.M && col0 < p.N) {
+          const bool full = (col0 + 32 <= p.N);
+          const size_t off = static_cast<size_t>(row) * p.ldc + col0;
+          if (EPI == EPI_BF16) {
+            bf16* dst = reinterpret_cast<bf16*>(p.C) + off;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                u.x = pack_bf16(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1]));
+                u.y = pack_bf16(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                u.z = pack_bf16(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+                u.w = pack_bf16(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+                *reinterpret_cast<uint4*>(dst + j) = u;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+            }
+          } else if (EPI == EPI_F32) {
+            float* dst = reinterpret_cast<float*>(p.C) + off;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) =
+                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]);
+            }
+          } else if (EPI == EPI_ATOMIC_F32) {
+            float* dst = reinterpret_cast<float*>(p.C) + off;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                atomicAdd(reinterpret_cast<float4*>(dst + j),
+                          make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(dst + j, __uint_as_float(r[j]));
+            }
+          } else {  // EPI_RESADD_F32: out = residual + bf16(acc)  (Linear output is bf16 under autocast)
+            float* dst = reinterpret_cast<float*>(p.C) + off;
+            const float* rs = p.res + off;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(rs + j);
+                *reinterpret_cast<float4*>(dst + j) =
+                    make_float4(q.x + bf16_round(__uint_as_float(r[j])),
+                                q.y + bf16_round(__uint_as_float(r[j + 1])),
+                                q.z + bf16_round(__uint_as_float(r[j + 2])),
+                                q.w + bf16_round(__uint_as_float(r[j + 3])));
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) dst[j] = rs[j] + bf16_round(__uint_as_float(r[j]));
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C_::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+    set_last_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// 2D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch `ld` elements.
+int make_tmap(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_inner,
+              int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MUSE_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) {
+    set_last_error("gemm: operand base must be 16B aligned and leading dim a multiple of 8 elements");
+    return MUSE_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld ld=%lld)", (int)r, inner,
+                   outer, ld);
+    return MUSE_ERR_CUDA;
+  }
+  return MUSE_OK;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(gemm smem=%d): %s", Cfg<BN>::kSmemBytes, cudaGetErrorString(e));
+      return MUSE_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int total = p.num_m * p.num_n * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, 256, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, p);
+  return check_launch("gemm_tcgen05");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BF16: return launch<BN, A_MN, B_MN, EPI_BF16>(ta, tb, p, s);
+    case EPI_F32: return launch<BN, A_MN, B_MN, EPI_F32>(ta, tb, p, s);
+    case EPI_ATOMIC_F32: return launch<BN, A_MN, B_MN, EPI_ATOMIC_F32>(ta, tb, p, s);
+    case EPI_RESADD_F32: return launch<BN, A_MN, B_MN, EPI_RESADD_F32>(ta, tb, p, s);
+  }
+  set_last_error("gemm: unknown epilogue %d", epi);
+  return MUSE_ERR_INVALID;
+}
+
+template <int BN>
+int launch_major(int a_mn, int b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                 cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch_epi<BN, false, false>(epi, ta, tb, p, s);
+  if (!a_mn && b_mn) return launch_epi<BN, false, true>(epi, ta, tb, p, s);
+  if (a_mn && b_mn) return launch_epi<BN, true, true>(epi, ta, tb, p, s);
+  return launch_epi<BN, true, false>(epi, ta, tb, p, s);
+}
+
+}  // namespace
+
+// C[M,N] (ldc) = op(A) * op(B)^T with op selected by a_mn / b_mn:
+//   a_mn == 0: A points at a row-major [M, K] matrix (pitch lda);  a_mn == 1: at a row-major [K, M] matrix.
+//   b_mn == 0: B points at a row-major [N, K] matrix (pitch ldb);  b_mn == 1: at a row-major [K, N] matrix.
+int gemm_tcgen05(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
+                 int ldc, int a_mn, int b_mn, int epi, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return MUSE_OK;
+  if (epi == EPI_BF16 ? (ldc % 8 != 0) : (ldc % 4 != 0)) {
+    set_last_error("gemm: ldc=%d must be a multiple of %d", ldc, epi == EPI_BF16 ? 8 : 4);
+    return MUSE_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(C) & 15) != 0) {
+    set_last_error("gemm: C must be 16B aligned");
+    return MUSE_ERR_INVALID;
+  }
+  const int BN = (N >= 256) ? 256 : 128;
+  CUtensorMap ta, tb;
+  int rc;
+  rc = a_mn ? make_tmap(&ta, A, M, K, lda, 64, BK) : make_tmap(&ta, A, K, M, lda, BK, BM);
+  if (rc) return rc;
+  rc = b_mn ? make_tmap(&tb, B, N, K, ldb, 64, BK) : make_tmap(&tb, B, K, N, ldb, BK, BN);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.C = C;
+  p.res = res;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+  p.num_m = ceil_div(M, BM);
+  p.num_n = ceil_div(N, BN);
+  p.num_kb = ceil_div(K, BK);
+  p.splits = 1;
+  p.kb_per_split = p.num_kb;
+  if (epi == EPI_ATOMIC_F32) {
+    // split-K so that a weight-gradient GEMM (few output tiles, very long K = tokens) fills the 148 SMs.
+    const int tiles = p.num_m * p.num_n;
+    int want = num_sms() / tiles;
+    if (want < 1) want = 1;
+    if (want > p.num_kb) want = p.num_kb;
+    p.kb_per_split = ceil_div(p.num_kb, want);
+    p.splits = ceil_div(p.num_kb, p.kb_per_split);
+  }
+  if (BN == 256) return launch_major<256>(a_mn, b_mn, epi, ta, tb, p, stream);
+  return launch_major<128>(a_mn, b_mn, epi, ta, tb, p, stream);
+}
+
+}  // namespace muse

@@ -1,0 +1,729 @@
+"""``MaskGitTransformer`` with the reference's Python surface and a hand-written sm_100a hot path.
+
+Boundary (reference: muse/modeling_transformer.py:1083-1456): same constructor arguments, ``config``
+keys, parameter names / shapes / construction order (so ``torch.manual_seed(s); Model(**cfg)`` gives
+the reference's initial weights and ``pytorch_model.bin`` files are interchangeable), same
+``forward`` / ``generate2`` signatures and return values.
+
+Underneath, nothing is torch-eager: the module tree only *holds* the fp32 master parameters.
+``forward`` runs three kinds of ``torch.autograd.Function`` -- embedding, one per transformer layer
+(so DDP's gradient buckets fire layer by layer during backward), and head+loss -- whose bodies are
+sequences of libmuse_b200 kernels (tcgen05 GEMMs, fused attention, fused norm/GELU/residual, masked
+cross-entropy).  Compute precision is the reference's bf16-autocast recipe: bf16 GEMM operands with
+fp32 accumulation, fp32 residual stream, fp32 norm / softmax / loss statistics.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .modeling_utils import ConfigMixin, ModelMixin, register_to_config
+from .sampling import cosine_schedule, mask_by_random_topk
+
+
+# --------------------------------------------------------------------------------------------
+# Parameter containers (names/shapes/order == reference modules; they carry no compute)
+# --------------------------------------------------------------------------------------------
+class LayerNorm(nn.Module):
+    """Weight-only LayerNorm parameters (reference :124-137)."""
+
+    def __init__(self, dim, eps=1e-5, use_bias=False, elementwise_affine=True):
+        super().__init__()
+        self.dim, self.eps = dim, eps
+        self.weight = nn.Parameter(torch.ones(dim)) if elementwise_affine else None
+        self.bias = nn.Parameter(torch.zeros(dim)) if (elementwise_affine and use_bias) else None
+
+
+class RMSNorm(nn.Module):
+    """RMSNorm parameters (reference :79-100)."""
+
+    def __init__(self, normalized_shape, eps=1e-6, elementwise_affine=True):
+        super().__init__()
+        self.elementwise_affine = elementwise_affine
+        if elementwise_affine:
+            self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.variance_epsilon = eps
+
+
+def _norm(norm_type, dim, eps, use_bias=False):
+    return LayerNorm(dim, eps=eps, use_bias=use_bias) if norm_type == "layernorm" else RMSNorm(dim, eps=eps)
+
+
+class Attention(nn.Module):
+    def __init__(self, hidden_size, num_heads, encoder_hidden_size=None, attention_dropout=0.0, use_bias=False):
+        super().__init__()
+        self.hidden_size, self.num_heads = hidden_size, num_heads
+        self.head_dim = hidden_size // num_heads
+        self.attention_dropout = attention_dropout
+        if self.head_dim * num_heads != hidden_size:
+            raise ValueError(
+                f"embed_dim must be divisible by num_heads (got `embed_dim`: {hidden_size} and `num_heads`: {num_heads})."
+            )
+        kv_in = hidden_size if encoder_hidden_size is None else encoder_hidden_size
+        self.query = nn.Linear(hidden_size, hidden_size, bias=use_bias)
+        self.key = nn.Linear(kv_in, hidden_size, bias=use_bias)
+        self.value = nn.Linear(kv_in, hidden_size, bias=use_bias)
+        self.out = nn.Linear(hidden_size, hidden_size, bias=use_bias)
+        self.dropout = nn.Dropout(attention_dropout)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, hidden_size, intermediate_size, hidden_dropout, norm_type, eps, use_normformer, use_bias):
+        super().__init__()
+        self.use_normformer = use_normformer
+        self.pre_mlp_layer_norm = LayerNorm(hidden_size, eps=eps, use_bias=use_bias)  # always LayerNorm (:767)
+        self.wi_0 = nn.Linear(hidden_size, intermediate_size, bias=use_bias)
+        self.wi_1 = nn.Linear(hidden_size, intermediate_size, bias=use_bias)
+        if use_normformer:
+            self.mid_mlp_layer_norm = _norm(norm_type, intermediate_size, eps, use_bias)
+        self.wo = nn.Linear(intermediate_size, hidden_size, bias=use_bias)
+        self.dropout = nn.Dropout(hidden_dropout)
+
+
+class TransformerLayer(nn.Module):
+    def __init__(self, hidden_size, intermediate_size, num_attention_heads, encoder_hidden_size, add_cross_attention,
+                 hidden_dropout, attention_dropout, norm_type, eps, use_normformer, use_bias):
+        super().__init__()
+        self.use_normformer = use_normformer
+        self.attn_layer_norm = _norm(norm_type, hidden_size, eps, use_bias)
+        self.attention = Attention(hidden_size, num_attention_heads, attention_dropout=attention_dropout, use_bias=use_bias)
+        if use_normformer:
+            self.post_attn_layer_norm = _norm(norm_type, hidden_size, eps, use_bias)
+        self.ffn = FeedForward(hidden_size, intermediate_size, hidden_dropout, norm_type, eps, use_normformer, use_bias)
+        if add_cross_attention:
+            self.crossattn_layer_norm = _norm(norm_type, hidden_size, eps, use_bias)
+            self.crossattention = Attention(hidden_size, num_attention_heads, encoder_hidden_size, attention_dropout, use_bias)
+            if use_normformer:
+                self.post_crossattn_layer_norm = _norm(norm_type, hidden_size, eps, use_bias)
+
+
+class Embed(nn.Module):
+    def __init__(self, vocab_size, embedding_size, hidden_dropout, max_position_embeddings):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(vocab_size, embedding_size)
+        self.position_embeddings = nn.Embedding(max_position_embeddings, embedding_size)
+        self.dropout = nn.Dropout(hidden_dropout)
+
+
+class MlmLayer(nn.Module):
+    def __init__(self, hidden_size, vocab_size, norm_type, eps, use_mlm_layernorm, use_bias):
+        super().__init__()
+        self.use_mlm_layernorm = use_mlm_layernorm
+        self.mlm_dense = nn.Linear(hidden_size, hidden_size, bias=use_bias)
+        if use_mlm_layernorm:
+            self.mlm_ln = _norm(norm_type, hidden_size, eps, use_bias)
+        self.to_logits = nn.Linear(hidden_size, vocab_size, bias=use_bias)
+
+
+# --------------------------------------------------------------------------------------------
+# bf16 operand cache: every Linear weight packed (fused per GEMM) in ONE kernel launch per update
+# --------------------------------------------------------------------------------------------
+class _PackedWeights:
+    """Fused bf16 copies of the Linear weights: [q;k;v] -> [3H,H], [wi_0;wi_1] -> [2I,H], padded
+    to_logits -> [Vpad,H] ...  Re-packed (one ``muse_pack_bf16`` launch) whenever a parameter's
+    version counter or storage changes, i.e. once per optimizer step and never during ``generate2``."""
+
+    def __init__(self, model: "MaskGitTransformer"):
+        self.model = model
+        self.key = None
+        self.layers = []
+        self.head = {}
+
+    def _plan(self):
+        m = self.model
+        groups = []  # (name, [params], rows_padded)
+        for i, layer in enumerate(m.transformer_layers):
+            a, f = layer.attention, layer.ffn
+            groups.append((i, "qkv", [a.query.weight, a.key.weight, a.value.weight], None))
+            groups.append((i, "ao", [a.out.weight], None))
+            groups.append((i, "wi", [f.wi_0.weight, f.wi_1.weight], None))
+            groups.append((i, "wo", [f.wo.weight], None))
+            if m.config.add_cross_attention:
+                c = layer.crossattention
+                groups.append((i, "cq", [c.query.weight], None))
+                groups.append((i, "ckv", [c.key.weight, c.value.weight], None))
+                groups.append((i, "co", [c.out.weight], None))
+        if m.config.use_mlm_layer:
+            groups.append((-1, "dense", [m.mlm_layer.mlm_dense.weight], None))
+            groups.append((-1, "logits", [m.mlm_layer.to_logits.weight], m.padded_output_size))
+        else:
+            groups.append((-1, "logits", [m.to_logits.weight], m.padded_output_size))
+        return groups
+
+    def refresh(self):
+        m = self.model
+        params = [p for _, _, ps, _ in self._plan() for p in ps]
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in params)
+        if key == self.key:
+            return self
+        dev = params[0].device
+        groups = self._plan()
+        layout_key = tuple(p.data_ptr() for p in params)
+        if getattr(self, "layout_key", None) != layout_key:
+            total = 0
+            offs = []
+            for _, _, ps, rows_pad in groups:
+                cols = ps[0].shape[1]
+                rows = sum(p.shape[0] for p in ps)
+                rows_alloc = rows_pad if rows_pad is not None else rows
+                offs.append((total, rows_alloc, cols))
+                total += ((rows_alloc * cols + 127) // 128) * 128  # keep every group 256B aligned
+            self.flat = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+            self.layers = [dict() for _ in m.transformer_layers]
+            self.head = {}
+            entries = []
+            block = 0
+            self.slow = []  # non-fp32 parameters are copied by torch (inference-only convenience)
+            for (li, name, ps, _), (off, rows_alloc, cols) in zip(groups, offs):
+                view = self.flat[off: off + rows_alloc * cols].view(rows_alloc, cols)
+                (self.head if li < 0 else self.layers[li])[name] = view
+                r = 0
+                for p in ps:
+                    dst = view[r: r + p.shape[0]]
+                    if p.dtype == torch.float32 and p.numel() % 4 == 0:
+                        entries.append((p.data_ptr(), dst.data_ptr(), p.numel(), block))
+                        block += (p.numel() + 1023) // 1024
+                    else:
+                        self.slow.append((p, dst))
+                    r += p.shape[0]
+            self.n_entries, self.n_blocks = len(entries), block
+            self.table = torch.tensor(entries, dtype=torch.int64).to(dev) if entries else None
+            self.layout_key = layout_key
+        if self.table is not None:
+            ops.pack_bf16(self.table, self.n_entries, self.n_blocks)
+        for p, dst in self.slow:
+            dst.copy_(p.detach())
+        self.key = key
+        return self
+
+
+# --------------------------------------------------------------------------------------------
+# autograd Functions (bodies are libmuse_b200 kernel sequences)
+# --------------------------------------------------------------------------------------------
+def _f32(p):
+    return p if p.dtype == torch.float32 else p.float()
+
+
+class _EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, word, pos):
+        ctx.save_for_backward(ids)
+        ctx.shapes = (word.shape, pos.shape)
+        return ops.embed_fwd(ids, _f32(word), _f32(pos))
+
+    @staticmethod
+    def backward(ctx, dx):
+        (ids,) = ctx.saved_tensors
+        wshape, pshape = ctx.shapes
+        dword = torch.zeros(wshape, dtype=torch.float32, device=dx.device)
+        dpos = torch.zeros(pshape, dtype=torch.float32, device=dx.device)
+        ops.embed_bwd(ids, dx.contiguous(), dword, dpos)
+        return None, dword, dpos
+
+
+class _LayerSpec:
+    """Static description of one transformer layer handed to the layer Function."""
+
+    def __init__(self, B, S, H, I, nh, eps, rms, normformer, cross, Skv, E, w):
+        self.B, self.S, self.H, self.I, self.nh = B, S, H, I, nh
+        self.eps, self.rms, self.normformer, self.cross = eps, rms, normformer, cross
+        self.Skv, self.E = Skv, E
+        self.w = w  # dict of packed bf16 weights for this layer
+        self.scale = 1.0 / math.sqrt(H // nh)
+
+
+class _LayerFn(torch.autograd.Function):
+    """One pre-LN (normformer) transformer layer: reference TransformerLayer.forward (:875-904)."""
+
+    @staticmethod
+    def forward(ctx, x, enc, spec, *params):
+        s = spec
+        grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        it = iter(params)
+        w_attn_ln, _, _, _, _ = next(it), next(it), next(it), next(it), next(it)
+        w_post = next(it) if s.normformer else None
+        w_pre, _, _ = next(it), next(it), next(it)
+        w_mid = next(it) if s.normformer else None
+        next(it)
+        if s.cross:
+            w_cln = next(it)
+            next(it), next(it), next(it), next(it)
+            w_cpost = next(it) if s.normformer else None
+        H, I, B, S, nh = s.H, s.I, s.B, s.S, s.nh
+        sv = {}
+        # ---- self attention
+        h1, st1 = ops.norm_fwd(x, _f32(w_attn_ln), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
+        qkv = ops.linear_fwd(h1, s.w["qkv"])
+        ctxt, lse = ops.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, nh, S, S, s.scale)
+        if s.normformer:
+            ao = ops.linear_fwd(ctxt, s.w["ao"])
+            x2, st2 = ops.norm_fwd(ao, _f32(w_post), s.eps, torch.float32, res=x, rms=s.rms, save_stats=grad)
+        else:
+            ao, st2 = None, None
+            x2 = ops.linear_fwd(ctxt, s.w["ao"], res=x)
+        if grad:
+            sv.update(x=x, h1=h1, st1=st1, qkv=qkv, ctxt=ctxt, lse=lse, ao=ao, st2=st2, x2=x2)
+        # ---- cross attention (text conditioning, :886-899)
+        if s.cross:
+            hc, stc = ops.norm_fwd(x2, _f32(w_cln), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
+            qc = ops.linear_fwd(hc, s.w["cq"])
+            kvc = ops.linear_fwd(enc, s.w["ckv"])
+            cctx, clse = ops.attn_fwd(qc, kvc[:, :H], kvc[:, H:], B, nh, S, s.Skv, s.scale)
+            if s.normformer:
+                cao = ops.linear_fwd(cctx, s.w["co"])
+                x2b, stcp = ops.norm_fwd(cao, _f32(w_cpost), s.eps, torch.float32, res=x2, rms=s.rms, save_stats=grad)
+            else:
+                cao, stcp = None, None
+                x2b = ops.linear_fwd(cctx, s.w["co"], res=x2)
+            if grad:
+                sv.update(hc=hc, stc=stc, qc=qc, kvc=kvc, cctx=cctx, clse=clse, cao=cao, stcp=stcp, enc=enc)
+            x2 = x2b
+            if grad:
+                sv["x2b"] = x2b
+        # ---- GLU feed-forward (:785-799)
+        h2, st3 = ops.norm_fwd(x2, _f32(w_pre), s.eps, torch.bfloat16, rms=0, save_stats=grad)
+        ab = ops.linear_fwd(h2, s.w["wi"])
+        gl = ops.glu_fwd(ab)
+        if s.normformer:
+            ml, st4 = ops.norm_fwd(gl, _f32(w_mid), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
+        else:
+            ml, st4 = gl, None
+        x3 = ops.linear_fwd(ml, s.w["wo"], res=x2)
+        if grad:
+            sv.update(h2=h2, st3=st3, ab=ab, gl=gl, ml=ml, st4=st4)
+            ctx.sv, ctx.spec, ctx.params = sv, s, params
+        return x3
+
+    @staticmethod
+    def backward(ctx, dx3):
+        s, sv, params = ctx.spec, ctx.sv, ctx.params
+        H, I, B, S, nh = s.H, s.I, s.B, s.S, s.nh
+        dev = dx3.device
+        dx3 = dx3.contiguous()
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        it = iter(params)
+        w_attn_ln = next(it); next(it); next(it); next(it); next(it)
+        w_post = next(it) if s.normformer else None
+        w_pre = next(it); next(it); next(it)
+        w_mid = next(it) if s.normformer else None
+        next(it)
+        if s.cross:
+            w_cln = next(it); next(it); next(it); next(it); next(it)
+            w_cpost = next(it) if s.normformer else None
+        # ---- FFN
+        g_wo = z(H, I)
+        dy = ops.cast_bf16(dx3)
+        ops.linear_wgrad(dy, sv["ml"], g_wo)
+        d_ml = ops.linear_dgrad(dy, s.w["wo"])
+        if s.normformer:
+            g_mid = z(I)
+            d_gl = ops.norm_bwd(d_ml, sv["gl"], _f32(w_mid), sv["st4"], torch.bfloat16, dw=g_mid, rms=s.rms)
+        else:
+            g_mid, d_gl = None, d_ml
+        d_ab = ops.glu_bwd(sv["ab"], d_gl)
+        g_wi = z(2 * I, H)
+        ops.linear_wgrad(d_ab, sv["h2"], g_wi)
+        d_h2 = ops.linear_dgrad(d_ab, s.w["wi"])
+        g_pre = z(H)
+        x_mid = sv["x2b"] if s.cross else sv["x2"]
+        dx2 = ops.norm_bwd(d_h2, x_mid, _f32(w_pre), sv["st3"], torch.float32, dw=g_pre, dres=dx3, rms=0)
+        # ---- cross attention
+        cross_grads = []
+        if s.cross:
+            if s.normformer:
+                g_cpost = z(H)
+                d_cao = ops.norm_bwd(dx2, sv["cao"], _f32(w_cpost), sv["stcp"], torch.bfloat16, dw=g_cpost, rms=s.rms)
+            else:
+                g_cpost, d_cao = None, ops.cast_bf16(dx2)
+            g_co = z(H, H)
+            ops.linear_wgrad(d_cao, sv["cctx"], g_co)
+            d_cctx = ops.linear_dgrad(d_cao, s.w["co"])
+            d_qc = torch.empty_like(sv["qc"])
+            d_kvc = torch.empty_like(sv["kvc"])
+            kvc = sv["kvc"]
+            ops.attn_bwd(sv["qc"], kvc[:, :H], kvc[:, H:], sv["cctx"], d_cctx, sv["clse"], d_qc, d_kvc[:, :H],
+                         d_kvc[:, H:], B, nh, S, s.Skv, s.scale)
+            g_ckv = z(2 * H, s.E)
+            ops.linear_wgrad(d_kvc, sv["enc"], g_ckv)
+            g_cq = z(H, H)
+            ops.linear_wgrad(d_qc, sv["hc"], g_cq)
+            d_hc = ops.linear_dgrad(d_qc, s.w["cq"])
+            g_cln = z(H)
+            dx2 = ops.norm_bwd(d_hc, sv["x2"], _f32(w_cln), sv["stc"], torch.float32, dw=g_cln, dres=dx2, rms=s.rms)
+            cross_grads = [g_cln, g_cq, g_ckv[:H], g_ckv[H:], g_co] + ([g_cpost] if s.normformer else [])
+        # ---- self attention
+        if s.normformer:
+            g_post = z(H)
+            d_ao = ops.norm_bwd(dx2, sv["ao"], _f32(w_post), sv["st2"], torch.bfloat16, dw=g_post, rms=s.rms)
+        else:
+            g_post, d_ao = None, ops.cast_bf16(dx2)
+        g_ao = z(H, H)
+        ops.linear_wgrad(d_ao, sv["ctxt"], g_ao)
+        d_ctx = ops.linear_dgrad(d_ao, s.w["ao"])
+        qkv = sv["qkv"]
+        d_qkv = torch.empty_like(qkv)
+        ops.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["ctxt"], d_ctx, sv["lse"], d_qkv[:, :H],
+                     d_qkv[:, H:2 * H], d_qkv[:, 2 * H:], B, nh, S, S, s.scale)
+        g_qkv = z(3 * H, H)
+        ops.linear_wgrad(d_qkv, sv["h1"], g_qkv)
+        d_h1 = ops.linear_dgrad(d_qkv, s.w["qkv"])
+        g_attn_ln = z(H)
+        dx1 = ops.norm_bwd(d_h1, sv["x"], _f32(w_attn_ln), sv["st1"], torch.float32, dw=g_attn_ln, dres=dx2, rms=s.rms)
+        grads = [g_attn_ln, g_qkv[:H], g_qkv[H:2 * H], g_qkv[2 * H:], g_ao]
+        if s.normformer:
+            grads.append(g_post)
+        grads += [g_pre, g_wi[:I], g_wi[I:]]
+        if s.normformer:
+            grads.append(g_mid)
+        grads.append(g_wo)
+        grads += cross_grads
+        ctx.sv = None
+        return (dx1, None, None, *grads)
+
+
+class _HeadSpec:
+    def __init__(self, T, H, V, Vpad, eps, rms, use_enc_ln, use_mlm, w, label_smoothing):
+        self.T, self.H, self.V, self.Vpad, self.eps, self.rms = T, H, V, Vpad, eps, rms
+        self.use_enc_ln, self.use_mlm, self.w, self.ls = use_enc_ln, use_mlm, w, label_smoothing
+
+
+class _HeadFn(torch.autograd.Function):
+    """encoder_layer_norm -> MlmLayer (dense, GELU, LN, to_logits) -> masked CE (:1268-1280)."""
+
+    @staticmethod
+    def forward(ctx, x, labels, spec, *params):
+        s = spec
+        grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        it = iter(params)
+        w_enc = next(it) if s.use_enc_ln else None
+        if s.use_mlm:
+            next(it)
+            w_mlm_ln = next(it)
+        sv = {}
+        if s.use_enc_ln:
+            hN, st0 = ops.norm_fwd(x, _f32(w_enc), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
+        else:
+            hN, st0 = ops.cast_bf16(x), None
+        if s.use_mlm:
+            d = ops.linear_fwd(hN, s.w["dense"])
+            e, st1 = ops.norm_fwd(d, _f32(w_mlm_ln), s.eps, torch.bfloat16, act=1, rms=s.rms, save_stats=grad)
+        else:
+            d, e, st1 = None, hN, None
+        logits = torch.empty(s.T, s.Vpad, dtype=torch.bfloat16, device=x.device)
+        ops.gemm(e, s.w["logits"], logits, s.T, s.Vpad, s.H, s.H, s.H, s.Vpad)
+        loss = None
+        if labels is not None:
+            loss_out, ws = ops.ce_fwd(logits, labels, s.V, s.ls)
+            loss = loss_out[0]
+            sv.update(loss_out=loss_out, ws=ws, labels=labels)
+        if grad:
+            sv.update(x=x, hN=hN, st0=st0, d=d, e=e, st1=st1, logits=logits)
+            ctx.sv, ctx.spec, ctx.params = sv, s, params
+        out_logits = logits[:, : s.V]
+        if loss is None:
+            return out_logits
+        return out_logits, loss
+
+    @staticmethod
+    def backward(ctx, d_logits, d_loss=None):
+        s, sv, params = ctx.spec, ctx.sv, ctx.params
+        dev = sv["x"].device
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        it = iter(params)
+        w_enc = next(it) if s.use_enc_ln else None
+        if s.use_mlm:
+            next(it)
+            w_mlm_ln = next(it)
+        dl = None
+        if d_loss is not None and "labels" in sv:
+            dl = ops.ce_bwd(sv["logits"], sv["labels"], sv["ws"], d_loss.to(torch.float32).reshape(1).contiguous(),
+                            sv["loss_out"], s.V, s.ls)
+        if d_logits is not None:  # gradient arriving through the returned logits (rare: custom losses)
+            extra = torch.zeros(s.T, s.Vpad, dtype=torch.bfloat16, device=dev)
+            extra[:, : s.V] = d_logits.to(torch.bfloat16)
+            dl = extra if dl is None else dl + extra
+        if dl is None:
+            raise RuntimeError("MaskGitTransformer head: backward called without any gradient")
+        g_logits = z(s.Vpad, s.H)
+        ops.linear_wgrad(dl, sv["e"], g_logits)
+        d_e = ops.linear_dgrad(dl, s.w["logits"])
+        grads = []
+        if s.use_mlm:
+            g_mlm_ln = z(s.H)
+            d_d = ops.norm_bwd(d_e, sv["d"], _f32(w_mlm_ln), sv["st1"], torch.bfloat16, dw=g_mlm_ln, act=1, rms=s.rms)
+            g_dense = z(s.H, s.H)
+            ops.linear_wgrad(d_d, sv["hN"], g_dense)
+            d_hN = ops.linear_dgrad(d_d, s.w["dense"])
+            grads = [g_dense, g_mlm_ln]
+        else:
+            d_hN = d_e
+        if s.use_enc_ln:
+            g_enc = z(s.H)
+            dx = ops.norm_bwd(d_hN, sv["x"], _f32(w_enc), sv["st0"], torch.float32, dw=g_enc, rms=s.rms)
+            grads = [g_enc] + grads
+        else:
+            dx = d_hN.float()
+        grads.append(g_logits[: s.V])
+        ctx.sv = None
+        return (dx, None, None, *grads)
+
+
+# --------------------------------------------------------------------------------------------
+# The model
+# --------------------------------------------------------------------------------------------
+class MaskGitTransformer(ModelMixin, ConfigMixin):
+    _supports_gradient_checkpointing = True
+
+    @register_to_config
+    def __init__(
+        self,
+        vocab_size,  # codebook_size + 1 (mask token) [+ num_classes for class-conditional models]
+        hidden_size=768,
+        embedding_size=None,
+        num_hidden_layers=12,
+        num_attention_heads=12,
+        intermediate_size=3072,
+        hidden_dropout=0.1,
+        attention_dropout=0.1,
+        max_position_embeddings=256,
+        add_cross_attention=False,
+        encoder_hidden_size=1024,
+        project_encoder_hidden_states=False,
+        initializer_range=0.02,
+        norm_type="layernorm",
+        layer_norm_eps=1e-5,
+        use_normformer=True,
+        use_encoder_layernorm=True,
+        use_mlm_layer=True,
+        use_mlm_layernorm=True,
+        use_bias=False,
+        codebook_size=1024,
+        num_vq_tokens=256,
+        num_classes=None,
+        use_codebook_size_for_output=False,
+        use_conv_in_out=False,
+        patch_size=1,
+        **kwargs,
+    ):
+        super().__init__()
+        if use_bias:
+            raise NotImplementedError("open_muse_b200: use_bias=True is not supported (no reference config enables it)")
+        if use_conv_in_out:
+            raise NotImplementedError("open_muse_b200: use_conv_in_out=True (ConvEmbed/ConvMlmLayer) is not supported yet")
+        if project_encoder_hidden_states:
+            raise NotImplementedError("open_muse_b200: project_encoder_hidden_states=True is not supported yet")
+        if (embedding_size or hidden_size) != hidden_size:
+            raise NotImplementedError("open_muse_b200: embedding_size != hidden_size is not supported")
+        if use_mlm_layer and not use_mlm_layernorm:
+            raise NotImplementedError("open_muse_b200: use_mlm_layer without use_mlm_layernorm is not supported yet")
+        if hidden_size % num_attention_heads or hidden_size // num_attention_heads != 64:
+            if hidden_size % num_attention_heads:
+                raise ValueError(
+                    f"embed_dim must be divisible by num_heads (got `embed_dim`: {hidden_size} and `num_heads`:"
+                    f" {num_attention_heads})."
+                )
+            raise NotImplementedError("open_muse_b200: only head_dim == 64 is supported (every reference config uses 64)")
+        self.vocab_size = vocab_size
+        self.hidden_size = hidden_size
+        self.num_hidden_layers = num_hidden_layers
+        self.num_attention_heads = num_attention_heads
+        self.intermediate_size = intermediate_size
+        self.hidden_dropout = hidden_dropout
+        self.attention_dropout = attention_dropout
+        self.max_position_embeddings = max_position_embeddings
+        self.initializer_range = initializer_range
+        self.embedding_size = embedding_size or hidden_size
+        self.register_to_config(mask_token_id=vocab_size - 1)
+
+        # construction order == reference (:1130-1197) so seeded initialisation is identical
+        self.embed = Embed(vocab_size, hidden_size, hidden_dropout, max_position_embeddings)
+        self.transformer_layers = nn.ModuleList(
+            [
+                TransformerLayer(hidden_size, intermediate_size, num_attention_heads, encoder_hidden_size,
+                                 add_cross_attention, hidden_dropout, attention_dropout, norm_type, layer_norm_eps,
+                                 use_normformer, use_bias)
+                for _ in range(num_hidden_layers)
+            ]
+        )
+        if use_encoder_layernorm:
+            self.encoder_layer_norm = _norm(norm_type, hidden_size, layer_norm_eps, use_bias)
+        self.output_size = codebook_size if use_codebook_size_for_output else vocab_size
+        self.padded_output_size = ((self.output_size + 63) // 64) * 64  # TMA-friendly logits pitch
+        if use_mlm_layer:
+            self.mlm_layer = MlmLayer(hidden_size, self.output_size, norm_type, layer_norm_eps, use_mlm_layernorm, use_bias)
+        else:
+            self.to_logits = nn.Linear(hidden_size, self.output_size, bias=use_bias)
+        self.gradient_checkpointing = False
+        self.apply(self._init_weights)
+        self._packed = _PackedWeights(self)
+
+    def _init_weights(self, module):
+        # truncated normal for Linear / Embedding, ones for norm weights (reference :1201-1219)
+        if isinstance(module, nn.Linear):
+            nn.init.trunc_normal_(module.weight, std=self.config.initializer_range)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            nn.init.trunc_normal_(module.weight, std=self.config.initializer_range)
+        elif isinstance(module, (nn.LayerNorm, RMSNorm)):
+            if getattr(module, "weight", None) is not None:
+                module.weight.data.fill_(1.0)
+
+    def _set_gradient_checkpointing(self, module, value=False):
+        self.gradient_checkpointing = True  # (reference quirk Q6: ``value`` is ignored)
+
+    # ------------------------------------------------------------------ parameter lists (Function order)
+    def _layer_params(self, layer):
+        c = self.config
+        a, f = layer.attention, layer.ffn
+        ps = [layer.attn_layer_norm.weight, a.query.weight, a.key.weight, a.value.weight, a.out.weight]
+        if c.use_normformer:
+            ps.append(layer.post_attn_layer_norm.weight)
+        ps += [f.pre_mlp_layer_norm.weight, f.wi_0.weight, f.wi_1.weight]
+        if c.use_normformer:
+            ps.append(f.mid_mlp_layer_norm.weight)
+        ps.append(f.wo.weight)
+        if c.add_cross_attention:
+            x = layer.crossattention
+            ps += [layer.crossattn_layer_norm.weight, x.query.weight, x.key.weight, x.value.weight, x.out.weight]
+            if c.use_normformer:
+                ps.append(layer.post_crossattn_layer_norm.weight)
+        return ps
+
+    def _head_params(self):
+        c = self.config
+        ps = [self.encoder_layer_norm.weight] if c.use_encoder_layernorm else []
+        if c.use_mlm_layer:
+            ps += [self.mlm_layer.mlm_dense.weight, self.mlm_layer.mlm_ln.weight, self.mlm_layer.to_logits.weight]
+        else:
+            ps.append(self.to_logits.weight)
+        return ps
+
+    # ------------------------------------------------------------------ forward
+    def forward(
+        self,
+        input_ids,
+        encoder_hidden_states=None,
+        encoder_attention_mask=None,
+        labels=None,
+        label_smoothing=0.0,
+        cond_dropout_prob=0.0,
+        **kwargs,  # cond_embeds / loss_weight / micro_conds from train_muse.py:742-750 are accepted and ignored
+    ):
+        c = self.config
+        if c.add_cross_attention and encoder_hidden_states is None:
+            raise ValueError("If `add_cross_attention` is True, `encoder_hidden_states` should be provided.")
+        if encoder_attention_mask is not None:
+            raise TypeError("encoder_attention_mask is not supported (it raises in the reference too: quirk Q2)")
+        if self.training and (self.hidden_dropout > 0.0 or self.attention_dropout > 0.0):
+            raise NotImplementedError(
+                "open_muse_b200: dropout > 0 in training mode is not implemented (all reference configs use 0.0); "
+                "construct the model with hidden_dropout=0.0, attention_dropout=0.0"
+            )
+        if not input_ids.is_cuda:
+            raise RuntimeError("open_muse_b200.MaskGitTransformer runs on CUDA (sm_100a) only; move inputs to the GPU")
+        B, S = input_ids.shape
+        if S > self.max_position_embeddings:
+            raise IndexError(f"sequence length {S} exceeds max_position_embeddings {self.max_position_embeddings}")
+        H = self.hidden_size
+        packed = self._packed.refresh()
+        ids = input_ids.contiguous().to(torch.int64)
+        x = _EmbedFn.apply(ids, self.embed.word_embeddings.weight, self.embed.position_embeddings.weight)
+
+        enc = None
+        Skv = E = 0
+        if c.add_cross_attention and encoder_hidden_states is not None:
+            if encoder_hidden_states.requires_grad:
+                raise NotImplementedError("gradients w.r.t. encoder_hidden_states are not implemented")
+            ehs = encoder_hidden_states
+            if self.training and cond_dropout_prob > 0.0:  # classifier-free-guidance dropout (:1244-1247)
+                keep = torch.zeros((ehs.shape[0], 1, 1), device=ehs.device).float().uniform_(0, 1) < (1.0 - cond_dropout_prob)
+                ehs = ehs * keep
+            Skv, E = ehs.shape[1], ehs.shape[2]
+            enc = ehs.reshape(B * Skv, E).to(torch.bfloat16).contiguous()
+        rms = 0 if c.norm_type == "layernorm" else 1
+        for i, layer in enumerate(self.transformer_layers):
+            spec = _LayerSpec(B, S, H, self.intermediate_size, self.num_attention_heads, c.layer_norm_eps, rms,
+                              c.use_normformer, enc is not None, Skv, E, packed.layers[i])
+            x = _LayerFn.apply(x, enc, spec, *self._layer_params(layer))
+
+        flat_labels = labels.reshape(-1).contiguous().to(torch.int64) if labels is not None else None
+        hspec = _HeadSpec(B * S, H, self.output_size, self.padded_output_size, c.layer_norm_eps, rms,
+                          c.use_encoder_layernorm, c.use_mlm_layer, packed.head, label_smoothing)
+        out = _HeadFn.apply(x, flat_labels, hspec, *self._head_params())
+        if labels is not None:
+            logits, loss = out
+        else:
+            logits, loss = out, None
+        logits = logits.view(B, S, self.output_size) if logits.is_contiguous() else logits.unflatten(0, (B, S))
+        if not torch.is_autocast_enabled("cuda"):
+            logits = logits.float()  # the reference returns fp32 logits outside autocast
+        if labels is not None:
+            return logits, loss
+        return logits
+
+    # ------------------------------------------------------------------ generation
+    def generate(self, *args, **kwargs):
+        raise AttributeError(
+            "MaskGitTransformer.generate is broken in the reference at this commit (quirk Q1: `None.scatter`); "
+            "use generate2, which is what PipelineMuse calls"
+        )
+
+    @torch.no_grad()
+    def generate2(
+        self,
+        input_ids: torch.LongTensor = None,
+        class_ids: torch.LongTensor = None,
+        encoder_hidden_states: torch.FloatTensor = None,
+        negative_embeds: torch.FloatTensor = None,
+        temperature=1.0,
+        timesteps=18,
+        guidance_scale=0,
+        noise_schedule=cosine_schedule,
+        generator: torch.Generator = None,
+        **kwargs,
+    ):
+        """MaskGIT iterative parallel decoding, same semantics as the reference (:1363-1456)."""
+        c = self.config
+        mask_id, seq_len, n_codes = c.mask_token_id, c.num_vq_tokens, c.codebook_size
+        batch = len(class_ids) if class_ids is not None else encoder_hidden_states.shape[0]
+        if class_ids is not None:
+            class_ids += n_codes  # in place on the caller's tensor, like the reference (quirk Q3)
+        if input_ids is None:
+            input_ids = torch.full((batch, seq_len), mask_id, dtype=torch.long, device=self.device)
+        use_cfg = encoder_hidden_states is not None and guidance_scale > 0
+        if use_cfg:
+            uncond = torch.zeros_like(encoder_hidden_states) if negative_embeds is None else negative_embeds
+            cfg_states = torch.cat([encoder_hidden_states, uncond])
+        sampled_ids = input_ids
+        for step in range(timesteps):
+            model_in = input_ids if class_ids is None else torch.cat([class_ids[:, None], input_ids], dim=1)
+            if use_cfg:
+                both = self(torch.cat([model_in] * 2), encoder_hidden_states=cfg_states)
+                cond, unc = both.chunk(2)
+                cond, unc = cond[..., :n_codes], unc[..., :n_codes]
+                logits = unc + guidance_scale * (cond - unc)
+            else:
+                logits = self(model_in, encoder_hidden_states=encoder_hidden_states)[..., :n_codes]
+            if class_ids is not None:
+                logits = logits[:, 1:]
+            probs = logits.softmax(dim=-1)
+            draws = torch.multinomial(probs.reshape(-1, probs.size(-1)), 1, generator=generator)[:, 0]
+            sampled_ids = draws.view(*probs.shape[:-1])
+            unknown = input_ids == mask_id
+            sampled_ids = torch.where(unknown, sampled_ids, input_ids)
+            ratio = 1.0 * (step + 1) / timesteps
+            mask_ratio = noise_schedule(torch.tensor(ratio))
+            sel = probs.gather(-1, sampled_ids.long()[..., None]).squeeze(-1)
+            sel = torch.where(unknown, sel, torch.finfo(sel.dtype).max)
+            mask_len = (seq_len * mask_ratio).floor().unsqueeze(0).to(logits.device)
+            mask_len = torch.max(torch.tensor([1], device=logits.device),
+                                 torch.min(unknown.sum(dim=-1, keepdim=True) - 1, mask_len))
+            temperature = temperature * (1.0 - ratio)  # compounds across steps (quirk Q4)
+            masking = mask_by_random_topk(mask_len, sel, temperature, generator=generator)
+            input_ids = torch.where(masking, mask_id, sampled_ids)
+        return sampled_ids

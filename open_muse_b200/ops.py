@@ -1,0 +1,218 @@
+"""Thin tensor-level wrappers over the C ABI (pointers, sizes, current CUDA stream).
+
+PyTorch here is plumbing only: device memory (``torch.empty``), streams, autograd bookkeeping.
+Every function launches hand-written sm_100a kernels from libmuse_b200.so and raises if the
+library is missing or the tensors are not CUDA tensors -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+EPI_BF16, EPI_F32, EPI_ATOMIC_F32, EPI_RESADD_F32 = 0, 1, 2, 3
+
+_state = {"device": None, "launches": 0}
+
+
+def gemm_backend() -> int:
+    return 1 if os.environ.get("MUSE_B200_GEMM", "tcgen05") == "mma" else 0
+
+
+def launches() -> int:
+    """Number of libmuse_b200 kernel-launching calls made so far (bench.py's gpu_launches)."""
+    return _state["launches"]
+
+
+def _prep(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.MuseB200Error("open_muse_b200 ops need CUDA tensors (no CPU fallback)")
+    dev = t.device.index
+    if _state["device"] != dev:
+        _lib.check(_lib.load().muse_set_device(dev), "muse_set_device")
+        _state["device"] = dev
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _call(name, *args):
+    _state["launches"] += 1
+    _lib.check(getattr(_lib.load(), name)(*args), name)
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm(a, b, c, M, N, K, lda, ldb, ldc, a_mn=0, b_mn=0, epi=EPI_BF16, res=None):
+    st = _prep(c)
+    _call("muse_gemm_bf16", _p(a), _p(b), _p(c), _p(res), M, N, K, lda, ldb, ldc, a_mn, b_mn, epi, gemm_backend(), st)
+    return c
+
+
+def linear_fwd(x, w, out_dtype=torch.bfloat16, res=None, n_valid=None):
+    """y[T,N] = x[T,K] @ w[N,K]^T.  res (fp32 [T,N]) selects the fused residual epilogue."""
+    T, K = x.shape
+    N = w.shape[0] if n_valid is None else n_valid
+    if res is not None:
+        y = torch.empty(T, N, dtype=torch.float32, device=x.device)
+        return gemm(x, w, y, T, N, K, x.stride(0), w.stride(0), N, 0, 0, EPI_RESADD_F32, res)
+    y = torch.empty(T, N, dtype=out_dtype, device=x.device)
+    return gemm(x, w, y, T, N, K, x.stride(0), w.stride(0), N, 0, 0, EPI_BF16 if out_dtype == torch.bfloat16 else EPI_F32)
+
+
+def linear_dgrad(dy, w):
+    """dx[T,K] = dy[T,N] @ w[N,K]  (w consumed as an MN-major B operand; no transpose copy)."""
+    T, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty(T, K, dtype=torch.bfloat16, device=dy.device)
+    return gemm(dy, w, dx, T, K, N, dy.stride(0), w.stride(0), K, 0, 1, EPI_BF16)
+
+
+def linear_wgrad(dy, x, dw):
+    """dw[N,K] += dy[T,N]^T @ x[T,K]  (both operands MN-major, split-K over tokens, fp32 atomics)."""
+    T, N = dy.shape
+    K = x.shape[1]
+    return gemm(dy, x, dw, N, K, T, dy.stride(0), x.stride(0), dw.stride(0), 1, 1, EPI_ATOMIC_F32)
+
+
+# ------------------------------------------------------------------------------------------ packing
+def pack_bf16(table_dev, n_entries, total_blocks):
+    st = _prep(table_dev)
+    _call("muse_pack_bf16", _p(table_dev), n_entries, total_blocks, st)
+
+
+def cast_bf16(src):
+    st = _prep(src)
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    _call("muse_cast_bf16", _p(src), _p(dst), src.numel(), st)
+    return dst
+
+
+# ------------------------------------------------------------------------------------------ embedding
+def embed_fwd(ids, word, pos):
+    st = _prep(word)
+    B, S = ids.shape
+    H = word.shape[1]
+    out = torch.empty(B * S, H, dtype=torch.float32, device=word.device)
+    _call("muse_embed_fwd", _p(ids), _p(word), _p(pos), _p(out), B, S, H, word.shape[0], st)
+    return out
+
+
+def embed_bwd(ids, dx, dword, dpos):
+    st = _prep(dx)
+    B, S = ids.shape
+    _call("muse_embed_bwd", _p(ids), _p(dx), _p(dword), _p(dpos), B, S, dword.shape[1], dword.shape[0], st)
+
+
+# ------------------------------------------------------------------------------------------ norms
+def norm_fwd(x, w, eps, out_dtype, res=None, act=0, rms=0, save_stats=True):
+    st = _prep(x)
+    rows, H = x.shape
+    y = torch.empty(rows, H, dtype=out_dtype, device=x.device)
+    if save_stats:
+        stats = torch.empty(2, rows, dtype=torch.float32, device=x.device)
+        mean, rstd = stats[0], stats[1]
+    else:
+        stats = mean = rstd = None
+    _call("muse_norm_fwd", _p(x), _dt(x), _p(w), _p(res), _p(y), _dt(y), _p(mean), _p(rstd), rows, H, float(eps),
+          act, rms, st)
+    return y, stats
+
+
+def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0):
+    st = _prep(x)
+    rows, H = x.shape
+    dx = torch.empty(rows, H, dtype=dx_dtype, device=x.device)
+    _call("muse_norm_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(w), _p(stats[0]), _p(stats[1]), _p(dres), _p(dx),
+          _dt(dx), _p(dw), rows, H, act, rms, st)
+    return dx
+
+
+# ------------------------------------------------------------------------------------------ GLU
+def glu_fwd(ab):
+    st = _prep(ab)
+    rows, two_i = ab.shape
+    out = torch.empty(rows, two_i // 2, dtype=torch.bfloat16, device=ab.device)
+    _call("muse_glu_fwd", _p(ab), _p(out), rows, two_i // 2, st)
+    return out
+
+
+def glu_bwd(ab, dout):
+    st = _prep(ab)
+    rows, two_i = ab.shape
+    dab = torch.empty_like(ab)
+    _call("muse_glu_bwd", _p(ab), _p(dout), _p(dab), rows, two_i // 2, st)
+    return dab
+
+
+# ------------------------------------------------------------------------------------------ attention
+def attn_fwd(q, k, v, B, nh, Sq, Skv, scale):
+    """q: [B*Sq, *] view with head h at columns h*64; k, v: [B*Skv, *] views. Returns ctx [B*Sq, nh*64], lse."""
+    st = _prep(q)
+    hd = 64
+    o = torch.empty(B * Sq, nh * hd, dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty(B, nh, Sq, dtype=torch.float32, device=q.device)
+    _call("muse_attn_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, nh, Sq, Skv, hd, q.stride(0), k.stride(0),
+          v.stride(0), o.stride(0), float(scale), st)
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, scale):
+    st = _prep(q)
+    dvec = torch.empty(B, nh, Sq, dtype=torch.float32, device=q.device)
+    _call("muse_attn_bwd", _p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _p(dvec), _p(dq), _p(dk), _p(dv), B, nh, Sq,
+          Skv, 64, q.stride(0), k.stride(0), v.stride(0), o.stride(0), do.stride(0), dq.stride(0), dk.stride(0),
+          dv.stride(0), float(scale), st)
+
+
+# ------------------------------------------------------------------------------------------ loss
+def ce_fwd(logits_padded, labels, V, label_smoothing):
+    st = _prep(logits_padded)
+    rows, ld = logits_padded.shape
+    ws = torch.empty(2, rows, dtype=torch.float32, device=logits_padded.device)  # lse, row_loss
+    out = torch.empty(2, dtype=torch.float32, device=logits_padded.device)
+    _call("muse_ce_fwd", _p(logits_padded), _p(labels), _p(ws[0]), _p(ws[1]), _p(out), rows, V, ld,
+          float(label_smoothing), st)
+    return out, ws
+
+
+def ce_bwd(logits_padded, labels, ws, dloss, loss_out, V, label_smoothing):
+    st = _prep(logits_padded)
+    rows, ld = logits_padded.shape
+    dl = torch.empty_like(logits_padded)
+    _call("muse_ce_bwd", _p(logits_padded), _p(labels), _p(ws[0]), _p(dloss), _p(loss_out), _p(dl), rows, V, ld,
+          float(label_smoothing), st)
+    return dl
+
+
+# ------------------------------------------------------------------------------------------ VQ
+def vq_argmin(z_flat, codebook, return_dmin=False):
+    st = _prep(z_flat)
+    n, D = z_flat.shape
+    ncodes = codebook.shape[0]
+    ids = torch.empty(n, dtype=torch.int64, device=z_flat.device)
+    ws = torch.empty(ncodes, dtype=torch.float32, device=z_flat.device)
+    dmin = torch.empty(n, dtype=torch.float32, device=z_flat.device) if return_dmin else None
+    _call("muse_vq_argmin", _p(z_flat), _p(codebook), _p(ws), _p(ids), _p(dmin), n, ncodes, D, st)
+    return (ids, dmin) if return_dmin else ids
+
+
+def vq_lookup_nchw(ids, codebook):
+    st = _prep(codebook)
+    B, P = ids.shape
+    D = codebook.shape[1]
+    out = torch.empty(B, D, P, dtype=torch.float32, device=codebook.device)
+    _call("muse_vq_lookup_nchw", _p(ids), _p(codebook), _p(out), B, P, D, codebook.shape[0], st)
+    return out

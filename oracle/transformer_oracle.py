@@ -1,0 +1,181 @@
+"""ORACLE (test infrastructure, never shipped or measured as the product): a plain fp32, CPU-runnable,
+functional restatement of the reference's MaskGitTransformer forward / loss / generate2.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  It is pinned against the fixtures in tests/golden/ that were produced by running the
+unmodified reference itself (tests/golden/make_golden.py; the reference holds no golden vectors of
+its own).
+
+Each function cites the reference lines it restates (paths relative to huggingface/open-muse @ 64e1afe).
+Parameters are taken from a flat ``state_dict`` (reference names), gradients come from torch autograd
+over these plain ops -- the checker may use autograd; the product implements backward by hand in CUDA.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+def _norm(x, w, eps, norm_type):
+    """muse/modeling_transformer.py:124-137 (LayerNorm, weight only) and :79-100 (RMSNorm)."""
+    if norm_type == "layernorm":
+        return F.layer_norm(x, (x.shape[-1],), w, None, eps)
+    var = x.float().pow(2).mean(-1, keepdim=True)
+    return x * torch.rsqrt(var + eps) * w
+
+
+def _attention(x, ctx, p, prefix, nh):
+    """Attention.forward + .attention, muse/modeling_transformer.py:190-241 (no mask, no dropout)."""
+    B, Sq, H = x.shape
+    Skv = ctx.shape[1]
+    hd = H // nh
+    q = (x @ p[prefix + "query.weight"].t()).view(B, Sq, nh, hd).transpose(1, 2)
+    k = (ctx @ p[prefix + "key.weight"].t()).view(B, Skv, nh, hd).transpose(1, 2)
+    v = (ctx @ p[prefix + "value.weight"].t()).view(B, Skv, nh, hd).transpose(1, 2)
+    scores = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(hd))
+    probs = scores.softmax(dim=-1)
+    out = (probs @ v).transpose(1, 2).reshape(B, Sq, H)
+    return out @ p[prefix + "out.weight"].t()
+
+
+def _layer(x, enc, p, pre, cfg):
+    """TransformerLayer.forward (:875-904) + FeedForward.forward (:785-799)."""
+    eps, nt, nf, nh = cfg["layer_norm_eps"], cfg["norm_type"], cfg["use_normformer"], cfg["num_attention_heads"]
+    h = _norm(x, p[pre + "attn_layer_norm.weight"], eps, nt)
+    a = _attention(h, h, p, pre + "attention.", nh)
+    if nf:
+        a = _norm(a, p[pre + "post_attn_layer_norm.weight"], eps, nt)
+    x = x + a
+    if enc is not None:
+        h = _norm(x, p[pre + "crossattn_layer_norm.weight"], eps, nt)
+        a = _attention(h, enc, p, pre + "crossattention.", nh)
+        if nf:
+            a = _norm(a, p[pre + "post_crossattn_layer_norm.weight"], eps, nt)
+        x = x + a
+    h = _norm(x, p[pre + "ffn.pre_mlp_layer_norm.weight"], eps, "layernorm")  # always LayerNorm (:767)
+    g = F.gelu(h @ p[pre + "ffn.wi_0.weight"].t()) * (h @ p[pre + "ffn.wi_1.weight"].t())
+    if nf:
+        g = _norm(g, p[pre + "ffn.mid_mlp_layer_norm.weight"], eps, nt)
+    return x + g @ p[pre + "ffn.wo.weight"].t()
+
+
+DEFAULTS = dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                max_position_embeddings=256, add_cross_attention=False, norm_type="layernorm", layer_norm_eps=1e-5,
+                use_normformer=True, use_encoder_layernorm=True, use_mlm_layer=True, use_mlm_layernorm=True,
+                codebook_size=1024, num_vq_tokens=256, use_codebook_size_for_output=False)
+
+
+def full_config(cfg: dict) -> dict:
+    c = dict(DEFAULTS)
+    c.update(cfg)
+    c["mask_token_id"] = c["vocab_size"] - 1
+    c["output_size"] = c["codebook_size"] if c["use_codebook_size_for_output"] else c["vocab_size"]
+    return c
+
+
+def forward(p: Dict[str, torch.Tensor], cfg: dict, input_ids, encoder_hidden_states=None, labels=None,
+            label_smoothing: float = 0.0):
+    """MaskGitTransformer.forward, muse/modeling_transformer.py:1224-1281.  Returns logits or (logits, loss)."""
+    c = full_config(cfg)
+    S = input_ids.shape[-1]
+    # Embed.forward :942-957
+    x = F.embedding(input_ids, p["embed.word_embeddings.weight"]) + p["embed.position_embeddings.weight"][:S][None]
+    enc = encoder_hidden_states if c["add_cross_attention"] else None
+    for i in range(c["num_hidden_layers"]):
+        x = _layer(x, enc, p, f"transformer_layers.{i}.", c)
+    if c["use_encoder_layernorm"]:
+        x = _norm(x, p["encoder_layer_norm.weight"], c["layer_norm_eps"], c["norm_type"])
+    if c["use_mlm_layer"]:  # MlmLayer.forward :979-985
+        x = F.gelu(x @ p["mlm_layer.mlm_dense.weight"].t())
+        if c["use_mlm_layernorm"]:
+            x = _norm(x, p["mlm_layer.mlm_ln.weight"], c["layer_norm_eps"], c["norm_type"])
+        logits = x @ p["mlm_layer.to_logits.weight"].t()
+    else:
+        logits = x @ p["to_logits.weight"].t()
+    if labels is None:
+        return logits
+    loss = F.cross_entropy(logits.view(-1, c["output_size"]), labels.view(-1), ignore_index=-100,
+                           label_smoothing=label_smoothing)  # :1276-1280
+    return logits, loss
+
+
+def forward_backward(p, cfg, input_ids, labels, encoder_hidden_states=None, label_smoothing=0.0):
+    """Loss + gradients w.r.t. every parameter (autograd over the restated ops)."""
+    q = {k: v.detach().clone().float().requires_grad_(True) for k, v in p.items()}
+    logits, loss = forward(q, cfg, input_ids, encoder_hidden_states, labels, label_smoothing)
+    loss.backward()
+    return logits.detach(), loss.detach(), {k: v.grad for k, v in q.items()}
+
+
+def cosine_schedule(t):
+    """muse/sampling.py:38-39"""
+    return torch.cos(t * math.pi * 0.5)
+
+
+def generate2(p, cfg, class_ids, timesteps, temperature=1.0, generator=None, trace=None):
+    """MaskGitTransformer.generate2 (class-conditional, no CFG), muse/modeling_transformer.py:1363-1456 with
+    mask_by_random_topk / gumbel_noise / log from muse/sampling.py:9-35.  Consumes ``generator`` exactly like the
+    reference: one torch.multinomial and one uniform_ per step."""
+    c = full_config(cfg)
+    mask_id, L, K = c["mask_token_id"], c["num_vq_tokens"], c["codebook_size"]
+    cls = class_ids + K
+    B = cls.shape[0]
+    input_ids = torch.full((B, L), mask_id, dtype=torch.long)
+    sampled = input_ids
+    for step in range(timesteps):
+        logits = forward(p, cfg, torch.cat([cls[:, None], input_ids], dim=1))[..., :K][:, 1:]
+        probs = logits.softmax(dim=-1)
+        sampled = torch.multinomial(probs.reshape(-1, K), 1, generator=generator)[:, 0].view(B, L)
+        unknown = input_ids == mask_id
+        sampled = torch.where(unknown, sampled, input_ids)
+        ratio = 1.0 * (step + 1) / timesteps
+        mask_ratio = cosine_schedule(torch.tensor(ratio))
+        sel = probs.gather(-1, sampled[..., None]).squeeze(-1)
+        sel = torch.where(unknown, sel, torch.finfo(sel.dtype).max)
+        mask_len = (L * mask_ratio).floor().unsqueeze(0)
+        mask_len = torch.max(torch.tensor([1]), torch.min(unknown.sum(dim=-1, keepdim=True) - 1, mask_len))
+        temperature = temperature * (1.0 - ratio)
+        u = torch.zeros_like(sel).uniform_(0, 1, generator=generator)
+        gumbel = -torch.log((-torch.log(u.clamp(min=1e-20))).clamp(min=1e-20))
+        conf = torch.log(sel.clamp(min=1e-20)) + temperature * gumbel
+        cut = conf.sort(dim=-1).values.gather(1, mask_len.long())
+        masking = conf < cut
+        if trace is not None:
+            trace.append(dict(logits=logits, probs=probs, sampled=sampled.clone(), unknown=unknown, u=u, conf=conf,
+                              mask_len=mask_len.clone(), temperature=temperature, masking=masking))
+        input_ids = torch.where(masking, mask_id, sampled)
+    return sampled
+
+
+def sample_step(probs, input_ids, mask_id, q_exp, u, mask_len, temperature):
+    """One generate2 step with PRE-DRAWN noise (what the fused CUDA kernel implements):
+    ``q_exp`` ~ Exp(1) [B,L,K] (torch.multinomial(p,1) == argmax(p / q), ATen's multinomial recipe),
+    ``u`` ~ U(0,1) [B,L].  Returns (sampled_ids, next_input_ids)."""
+    sampled = (probs / q_exp).argmax(dim=-1)
+    unknown = input_ids == mask_id
+    sampled = torch.where(unknown, sampled, input_ids)
+    sel = probs.gather(-1, sampled[..., None]).squeeze(-1)
+    sel = torch.where(unknown, sel, torch.finfo(sel.dtype).max)
+    gumbel = -torch.log((-torch.log(u.clamp(min=1e-20))).clamp(min=1e-20))
+    conf = torch.log(sel.clamp(min=1e-20)) + temperature * gumbel
+    cut = conf.sort(dim=-1).values.gather(1, mask_len.long())
+    masking = conf < cut
+    return sampled, torch.where(masking, mask_id, sampled)
+
+
+def mask_tokens(tokens, class_ids, timesteps, rand, codebook_size, mask_id, min_masking_rate=0.0):
+    """Training-time masking recipe, training/train_maskgit_imagenet.py:375-393, with the two random draws
+    (``timesteps`` = rand(B), ``rand`` = rand(B,S)) passed in."""
+    B, S = tokens.shape
+    mask_prob = cosine_schedule(timesteps).clip(min_masking_rate)
+    n_mask = (S * mask_prob).round().clamp(min=1)
+    perm = rand.argsort(dim=-1)
+    mask = perm < n_mask.unsqueeze(-1)  # quirk Q7: compares the argsort *indices*
+    input_ids = torch.where(mask, mask_id, tokens)
+    labels = torch.where(mask, tokens, -100)
+    input_ids = torch.cat([(class_ids + codebook_size).unsqueeze(-1), input_ids], dim=-1)
+    labels = torch.cat([torch.full((B, 1), -100, dtype=labels.dtype), labels], dim=-1)
+    return input_ids, labels

@@ -1,0 +1,185 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures in this directory by running the UNMODIFIED reference
+(huggingface/open-muse @ 64e1afe, mounted at /root/reference) on CPU in fp32.
+
+The reference has no tests, goldens or known-answer vectors of its own, so
+these outputs of the reference itself are what pins oracle/ (and, through the oracle, the CUDA path).
+Run from the repo root, in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+`accelerate` is not installed; the reference imports two symbols from it that are only used by
+`from_pretrained(low_cpu_mem_usage=True)`, so a two-symbol in-memory stub is registered.
+"""
+import contextlib
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("MUSE_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    import transformers  # noqa: F401  (must be imported before the accelerate stub is registered)
+
+    if "accelerate" not in sys.modules:
+        acc = types.ModuleType("accelerate")
+        acc.init_empty_weights = contextlib.nullcontext
+        accu = types.ModuleType("accelerate.utils")
+        accu.set_module_tensor_to_device = lambda *a, **k: None
+        acc.utils = accu
+        acc.__spec__ = None
+        sys.modules["accelerate"] = acc
+        sys.modules["accelerate.utils"] = accu
+    sys.path.insert(0, REF)
+    import muse  # the reference package
+
+    assert os.path.realpath(muse.__file__).startswith(os.path.realpath(REF)), muse.__file__
+    return muse
+
+
+MICRO = dict(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_attention_heads=1, intermediate_size=128,
+             hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=17, codebook_size=64,
+             num_vq_tokens=16, num_classes=7, layer_norm_eps=1e-6)
+MICRO_T2I = dict(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_attention_heads=1, intermediate_size=128,
+                 hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=16, codebook_size=64,
+                 num_vq_tokens=16, add_cross_attention=True, encoder_hidden_size=32, norm_type="rmsnorm",
+                 use_normformer=False, layer_norm_eps=1e-6, use_codebook_size_for_output=True)
+TINY = dict(vocab_size=2025, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
+            hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=257, codebook_size=1024,
+            num_vq_tokens=256, num_classes=1000)
+MICRO_VQ = dict(resolution=32, num_channels=3, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=1,
+                z_channels=16, num_embeddings=64, quantized_embed_dim=16)
+
+
+def masked_batch(gen, B, S, codebook, n_classes, mask_id):
+    """The masking recipe of training/train_maskgit_imagenet.py:375-393 (class-conditional)."""
+    tokens = torch.randint(0, codebook, (B, S), generator=gen)
+    class_ids = torch.randint(0, n_classes, (B,), generator=gen)
+    timesteps = torch.rand(B, generator=gen)
+    mask_prob = torch.cos(timesteps * math.pi * 0.5).clip(0.0)
+    n_mask = (S * mask_prob).round().clamp(min=1)
+    rand = torch.rand(B, S, generator=gen)
+    perm = rand.argsort(dim=-1)
+    mask = perm < n_mask.unsqueeze(-1)
+    input_ids = torch.where(mask, mask_id, tokens)
+    labels = torch.where(mask, tokens, -100)
+    input_ids = torch.cat([(class_ids + codebook).unsqueeze(-1), input_ids], dim=-1)
+    labels = torch.cat([torch.full((B, 1), -100), labels], dim=-1)
+    return dict(tokens=tokens, class_ids=class_ids, timesteps=timesteps, rand=rand, input_ids=input_ids, labels=labels)
+
+
+def grads_of(model):
+    return {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+
+
+def main():
+    muse = import_reference()
+    torch.set_num_threads(4)
+    out = {}
+
+    # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
+    torch.manual_seed(0)
+    m = muse.MaskGitTransformer(**MICRO)
+    m.train()
+    g = torch.Generator().manual_seed(1)
+    batch = masked_batch(g, 3, 16, 64, 7, m.config.mask_token_id)
+    logits, loss = m(batch["input_ids"], labels=batch["labels"], label_smoothing=0.1)
+    loss.backward()
+    torch.save(dict(config=MICRO, state_dict={k: v.clone() for k, v in m.state_dict().items()}, batch=batch,
+                    label_smoothing=0.1, logits=logits.detach(), loss=loss.detach(), grads=grads_of(m)),
+               os.path.join(HERE, "micro_transformer.pt"))
+    print("micro transformer: loss", float(loss))
+
+    # ---- (1b) generate2 trace on the micro model (final ids; the generator stream is torch's own)
+    m.eval()
+    for steps in (4, 7):
+        cls = torch.tensor([1, 5, 0, 3])
+        gen = torch.Generator().manual_seed(7)
+        ids = m.generate2(class_ids=cls.clone(), timesteps=steps, temperature=1.0, generator=gen)
+        out[f"micro_generate2_steps{steps}"] = ids.clone()
+    torch.save(dict(class_ids=torch.tensor([1, 5, 0, 3]), seed=7, temperature=1.0,
+                    ids={k: v for k, v in out.items() if k.startswith("micro_generate2")}),
+               os.path.join(HERE, "micro_generate2.pt"))
+
+    # ---- (2) micro text-conditional variant: cross-attention + rmsnorm + no normformer
+    torch.manual_seed(2)
+    mt = muse.MaskGitTransformer(**MICRO_T2I)
+    mt.train()
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, 64, (2, 16), generator=g)
+    enc = torch.randn(2, 5, 32, generator=g)
+    mask = torch.rand(2, 16, generator=g) < 0.5
+    inp = torch.where(mask, mt.config.mask_token_id, ids)
+    lab = torch.where(mask, ids, -100)
+    logits, loss = mt(inp, encoder_hidden_states=enc, labels=lab)
+    loss.backward()
+    torch.save(dict(config=MICRO_T2I, state_dict={k: v.clone() for k, v in mt.state_dict().items()},
+                    input_ids=inp, labels=lab, encoder_hidden_states=enc, logits=logits.detach(), loss=loss.detach(),
+                    grads=grads_of(mt)), os.path.join(HERE, "micro_t2i_transformer.pt"))
+    print("micro t2i transformer: loss", float(loss))
+
+    # ---- (3) BASELINE config 1 (tiny, seed-constructed: no weights stored)
+    torch.manual_seed(0)
+    t = muse.MaskGitTransformer(**TINY)
+    t.train()
+    g = torch.Generator().manual_seed(1)
+    batch = masked_batch(g, 2, 256, 1024, 1000, t.config.mask_token_id)
+    logits, loss = t(batch["input_ids"], labels=batch["labels"])
+    loss.backward()
+    gr = grads_of(t)
+    torch.save(dict(config=TINY, seed=0, batch=batch, loss=loss.detach(),
+                    logits_slice=logits.detach()[:, ::16, ::25].clone(), logits_mean=logits.mean().detach(),
+                    logits_std=logits.std().detach(),
+                    param_norms={k: v.norm().clone() for k, v in t.state_dict().items()},
+                    grad_norms={k: v.norm() for k, v in gr.items()},
+                    grad_heads={k: v.flatten()[:8].clone() for k, v in gr.items()}),
+               os.path.join(HERE, "tiny_transformer.pt"))
+    print("tiny transformer (config 1): loss", float(loss))
+
+    # ---- (4) vector quantiser: distances/ids on a margin-screened batch (small codebook)
+    torch.manual_seed(4)
+    vq = muse.modeling_maskgit_vqgan.VectorQuantizer(128, 64, 0.25)
+    z = torch.randn(2, 64, 8, 8)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(torch.randn(128, 64) * z.std())
+        zq, ids, _ = vq(z)
+        d = vq.compute_distances(z.permute(0, 2, 3, 1).contiguous())
+        top2 = d.topk(2, dim=1, largest=False).values
+        margin = (top2[:, 1] - top2[:, 0])
+        code = vq.get_code(z)
+        entry = vq.get_codebook_entry(ids)
+    assert torch.equal(code, ids)
+    print("vq: min top-2 margin", float(margin.min()), "relative", float((margin / top2[:, 0].abs()).min()))
+    torch.save(dict(z=z, codebook=vq.embedding.weight.detach().clone(), ids=ids, z_q=zq, dmin=top2[:, 0].clone(),
+                    margin=margin, entry=entry.clone()), os.path.join(HERE, "vq_quantizer.pt"))
+
+    # ---- (5) micro MaskGitVQGAN: encode / decode_code round trip
+    torch.manual_seed(5)
+    v = muse.MaskGitVQGAN(**MICRO_VQ)
+    v.eval()
+    img = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        zenc = v.encoder(img)
+        v.quantize.embedding.weight.copy_(torch.randn(64, 16, generator=torch.Generator().manual_seed(8)) * zenc.std())
+        zq, ids = v.encode(img)
+        rec = v.decode_code(ids)
+        d = v.quantize.compute_distances(zenc.permute(0, 2, 3, 1).contiguous())
+        top2 = d.topk(2, dim=1, largest=False).values
+    print("micro vqgan: min top-2 margin", float((top2[:, 1] - top2[:, 0]).min()))
+    torch.save(dict(config=MICRO_VQ, state_dict={k: x.clone() for k, x in v.state_dict().items()}, image=img,
+                    z=zenc, ids=ids, z_q=zq, recon=rec, margin=(top2[:, 1] - top2[:, 0])),
+               os.path.join(HERE, "micro_vqgan.pt"))
+
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

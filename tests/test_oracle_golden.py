@@ -1,0 +1,130 @@
+"""CPU: the oracle (oracle/*.py, oracle/vq_oracle.c) against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  This is what "pins" the oracle; the -m gpu tests then compare CUDA to it."""
+import numpy as np
+import torch
+
+from oracle import transformer_oracle as T
+from oracle import vq_oracle as VQ
+from oracle import vqgan_oracle as G
+
+
+def _close(a, b, rtol, atol):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+def test_micro_transformer_forward_backward(golden):
+    g = golden("micro_transformer.pt")
+    logits, loss, grads = T.forward_backward(g["state_dict"], g["config"], g["batch"]["input_ids"], g["batch"]["labels"],
+                                             label_smoothing=g["label_smoothing"])
+    _close(logits, g["logits"], 1e-5, 1e-6)
+    _close(loss, g["loss"], 1e-6, 0)
+    assert set(grads) == set(g["grads"])
+    for k, v in g["grads"].items():
+        _close(grads[k], v, 1e-4, 1e-7)
+
+
+def test_micro_t2i_transformer_forward_backward(golden):
+    g = golden("micro_t2i_transformer.pt")
+    logits, loss, grads = T.forward_backward(g["state_dict"], g["config"], g["input_ids"], g["labels"],
+                                             encoder_hidden_states=g["encoder_hidden_states"])
+    assert logits.shape[-1] == 64  # use_codebook_size_for_output
+    _close(logits, g["logits"], 1e-5, 1e-6)
+    _close(loss, g["loss"], 1e-6, 0)
+    for k, v in g["grads"].items():
+        _close(grads[k], v, 1e-4, 1e-7)
+
+
+def test_masking_recipe(golden):
+    b = golden("micro_transformer.pt")["batch"]
+    inp, lab = T.mask_tokens(b["tokens"], b["class_ids"], b["timesteps"], b["rand"], 64, 71)
+    assert torch.equal(inp, b["input_ids"]) and torch.equal(lab, b["labels"])
+    b = golden("tiny_transformer.pt")["batch"]
+    inp, lab = T.mask_tokens(b["tokens"], b["class_ids"], b["timesteps"], b["rand"], 1024, 2024)
+    assert torch.equal(inp, b["input_ids"]) and torch.equal(lab, b["labels"])
+
+
+def test_micro_generate2_matches_reference_stream(golden):
+    g = golden("micro_generate2.pt")
+    p = golden("micro_transformer.pt")
+    for steps in (4, 7):
+        gen = torch.Generator().manual_seed(g["seed"])
+        with torch.no_grad():
+            ids = T.generate2(p["state_dict"], p["config"], g["class_ids"].clone(), steps, g["temperature"], gen)
+        assert torch.equal(ids, g["ids"][f"micro_generate2_steps{steps}"])
+
+
+def test_sample_step_equals_generator_path(golden):
+    """The pre-drawn-noise formulation the CUDA kernel implements == the torch.multinomial formulation."""
+    p = golden("micro_transformer.pt")
+    trace = []
+    gen = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        T.generate2(p["state_dict"], p["config"], torch.tensor([2, 4]), 3, 1.0, gen, trace=trace)
+    gen = torch.Generator().manual_seed(11)
+    ids = torch.full((2, 16), 71, dtype=torch.long)
+    for st in trace:
+        probs = st["probs"]
+        # ATen multinomial(n=1): q ~ Exp(1) drawn with the generator over probs.shape, result argmax(p / q)
+        q = torch.empty_like(probs.reshape(-1, 64)).exponential_(1, generator=gen).view_as(probs)
+        u = torch.zeros(2, 16).uniform_(0, 1, generator=gen)
+        sampled, nxt = T.sample_step(probs, ids, 71, q, u, st["mask_len"], st["temperature"])
+        assert torch.equal(sampled, st["sampled"])
+        assert torch.equal(nxt == 71, st["masking"])
+        ids = nxt
+
+
+def test_tiny_config1_seeded(golden):
+    """BASELINE config 1: our facade's seeded init == the reference's, and oracle(loss, logits, grads) == reference."""
+    from open_muse_b200.modeling_transformer import MaskGitTransformer
+
+    g = golden("tiny_transformer.pt")
+    torch.manual_seed(g["seed"])
+    m = MaskGitTransformer(**g["config"])
+    sd = m.state_dict()
+    for k, n in g["param_norms"].items():
+        _close(sd[k].norm(), n, 1e-6, 0)
+    logits, loss, grads = T.forward_backward(sd, g["config"], g["batch"]["input_ids"], g["batch"]["labels"])
+    _close(loss, g["loss"], 1e-6, 0)
+    _close(logits[:, ::16, ::25], g["logits_slice"], 1e-4, 1e-6)
+    for k, n in g["grad_norms"].items():
+        _close(grads[k].norm(), n, 1e-4, 1e-8)
+        _close(grads[k].flatten()[:8], g["grad_heads"][k], 1e-3, 1e-8)
+
+
+def test_vq_oracle_c_matches_reference_ids(golden):
+    g = golden("vq_quantizer.pt")
+    z = VQ.nchw_to_rows(g["z"].numpy())
+    ids, dmin = VQ.argmin(z, g["codebook"].numpy())
+    assert np.array_equal(ids.reshape(2, -1), g["ids"].numpy())
+    np.testing.assert_allclose(dmin, g["dmin"].numpy(), rtol=1e-5, atol=1e-4)
+    # numpy restatement of the reference formula agrees as well
+    d = VQ.distances_numpy(z, g["codebook"].numpy())
+    assert np.array_equal(d.argmin(axis=1).reshape(2, -1), g["ids"].numpy())
+    np.testing.assert_array_equal(VQ.codebook_entry_nchw(g["ids"].numpy(), g["codebook"].numpy()), g["entry"].numpy())
+
+
+def test_vq_oracle_tie_break_and_edges():
+    cb = np.zeros((5, 16), dtype=np.float32)
+    cb[1] = 1.0
+    cb[3] = 1.0  # duplicate of row 1: the lower index must win
+    z = np.ones((3, 16), dtype=np.float32)
+    ids, _ = VQ.argmin(z, cb)
+    assert ids.tolist() == [1, 1, 1]
+    ids, _ = VQ.argmin(np.zeros((0, 16), dtype=np.float32), cb)
+    assert ids.shape == (0,)
+
+
+def test_micro_vqgan(golden):
+    g = golden("micro_vqgan.pt")
+    p, cfg = g["state_dict"], g["config"]
+    with torch.no_grad():
+        z = G.encoder(p, cfg, g["image"])
+        _close(z, g["z"], 1e-5, 1e-6)
+        zq, ids = G.quantize(p, g["z"])
+        assert torch.equal(ids, g["ids"])
+        _close(zq, g["z_q"], 0, 0)
+        rec = G.decode_code(p, cfg, g["ids"])
+        _close(rec, g["recon"], 1e-5, 1e-6)
+    ids_c, _ = VQ.argmin(VQ.nchw_to_rows(g["z"].numpy()), p["quantize.embedding.weight"].numpy())
+    ok = g["margin"].numpy() > 1e-4  # margin screen: fp32 re-association cannot flip these
+    assert np.array_equal(ids_c[ok], g["ids"].numpy().reshape(-1)[ok])
