@@ -49,15 +49,40 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+_KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 3, "muse_embed_bwd": 2, "muse_vq_argmin": 2}
+_prof = {"on": False, "events": []}
+
+
 def _call(name, *args):
-    _state["launches"] += 1
+    _state["launches"] += _KERNELS_PER_CALL.get(name, 1)
     _lib.check(getattr(_lib.load(), name)(*args), name)
+
+
+def profile_gemms(enable: bool):
+    """bench.py hook: while enabled every GEMM launch is bracketed by CUDA events on its stream.
+    Disabling returns (total_ms, total_flops, n_launches)."""
+    if enable:
+        _prof["on"], _prof["events"] = True, []
+        return None
+    _prof["on"] = False
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b, _ in _prof["events"])
+    fl = sum(f for _, _, f in _prof["events"])
+    n = len(_prof["events"])
+    _prof["events"] = []
+    return ms, fl, n
 
 
 # ------------------------------------------------------------------------------------------ GEMM
 def gemm(a, b, c, M, N, K, lda, ldb, ldc, a_mn=0, b_mn=0, epi=EPI_BF16, res=None):
     st = _prep(c)
+    if _prof["on"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _call("muse_gemm_bf16", _p(a), _p(b), _p(c), _p(res), M, N, K, lda, ldb, ldc, a_mn, b_mn, epi, gemm_backend(), st)
+    if _prof["on"]:
+        e1.record()
+        _prof["events"].append((e0, e1, 2.0 * M * N * K))
     return c
 
 

@@ -1,0 +1,66 @@
+"""CPU: the C-ABI library loads and exports every symbol include/muse_b200.h declares; host-side logic
+(config registration, checkpoint format, argument checking) without any GPU compute."""
+import json
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from open_muse_b200 import _lib, build
+
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "muse_b200.h")).read()
+    declared = set(re.findall(r"\b(muse_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.muse_abi_version() == _lib.ABI_VERSION
+
+
+def test_ops_refuse_cpu_tensors():
+    from open_muse_b200 import _lib, ops
+
+    with pytest.raises(_lib.MuseB200Error):
+        ops.glu_fwd(torch.zeros(4, 16, dtype=torch.bfloat16))
+
+
+def test_config_registration_and_checkpoint_format(tmp_path):
+    from open_muse_b200.modeling_transformer import MaskGitTransformer
+
+    m = MaskGitTransformer(vocab_size=72, hidden_size=64, num_hidden_layers=1, num_attention_heads=1,
+                           intermediate_size=128, max_position_embeddings=17, codebook_size=64, num_vq_tokens=16,
+                           num_classes=7, some_unknown_uvit_key=3)
+    assert m.config.mask_token_id == 71 and m.config["hidden_size"] == 64 and m.hidden_size == 64
+    assert "some_unknown_uvit_key" not in m.config  # swallowed by **kwargs like the reference
+    assert m.output_size == 72 and m.gradient_checkpointing is False
+    m.save_pretrained(tmp_path)
+    cfg = json.load(open(tmp_path / "config.json"))
+    assert cfg["_class_name"] == "MaskGitTransformer" and cfg["_version"] == "0.0.1" and cfg["mask_token_id"] == 71
+    assert list(cfg) == sorted(cfg)
+    sd = torch.load(tmp_path / "pytorch_model.bin")
+    assert set(sd) == set(m.state_dict())
+    m2 = MaskGitTransformer.from_pretrained(str(tmp_path))
+    assert not m2.training
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k])
+    assert m2.num_parameters() == sum(p.numel() for p in m.parameters())
+
+
+def test_argument_errors():
+    from open_muse_b200.modeling_transformer import MaskGitTransformer
+
+    with pytest.raises(ValueError):
+        MaskGitTransformer(vocab_size=10, hidden_size=100, num_attention_heads=3)
+    m = MaskGitTransformer(vocab_size=72, hidden_size=64, num_hidden_layers=1, num_attention_heads=1,
+                           intermediate_size=128, add_cross_attention=True, encoder_hidden_size=32)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 4, dtype=torch.long))
+    with pytest.raises(AttributeError):
+        m.generate()

@@ -1,0 +1,218 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes).
+Checkers are plain fp32 torch math on the same seeded inputs (floating-point kernels) and the C oracle
+(bit-exact integer output of the VQ search)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from open_muse_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+GEMM_SHAPES = [
+    (128, 128, 64), (128, 256, 128), (256, 512, 512), (304, 200, 136), (1028, 1536, 512), (64, 72, 64),
+    (514, 2048, 512), (2056, 512, 2048),
+]
+
+
+@pytest.mark.parametrize("backend", ["tcgen05", "mma"])
+@pytest.mark.parametrize("majors", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_bf16_out(monkeypatch, backend, majors, shape):
+    monkeypatch.setenv("MUSE_B200_GEMM", backend)
+    M, N, K = shape
+    a_mn, b_mn = majors
+    A = _rand((K, M) if a_mn else (M, K), 1)
+    B = _rand((K, N) if b_mn else (N, K), 2)
+    ref = (A.float().t() if a_mn else A.float()) @ (B.float() if b_mn else B.float().t())
+    ldc = ((N + 7) // 8) * 8
+    C = torch.full((M, ldc), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, B, C, M, N, K, A.stride(0), B.stride(0), ldc, a_mn, b_mn, ops.EPI_BF16)
+    torch.cuda.synchronize()
+    assert _rel(C[:, :N], ref) < 6e-3  # bf16 output rounding (2^-9 relative per element)
+    if ldc > N:
+        assert bool((C[:, N:] == 7.0).all())  # pad columns untouched
+
+
+@pytest.mark.parametrize("backend", ["tcgen05", "mma"])
+def test_gemm_epilogues(monkeypatch, backend):
+    monkeypatch.setenv("MUSE_B200_GEMM", backend)
+    M, N, K = 384, 320, 192
+    A, B = _rand((M, K), 3), _rand((N, K), 4)
+    ref = A.float() @ B.float().t()
+    C = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ops.gemm(A, B, C, M, N, K, K, K, N, 0, 0, ops.EPI_F32)
+    assert _rel(C, ref) < 1e-5
+    res = torch.randn(M, N, device=DEV)
+    C2 = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ops.gemm(A, B, C2, M, N, K, K, K, N, 0, 0, ops.EPI_RESADD_F32, res=res)
+    assert _rel(C2, res + ref.to(torch.bfloat16).float()) < 1e-5
+    # split-K atomic accumulate (wgrad shape: short M,N, long K, both operands MN-major)
+    T, No, Ki = 4112, 192, 128
+    dY, X = _rand((T, No), 5), _rand((T, Ki), 6)
+    dW = torch.ones(No, Ki, dtype=torch.float32, device=DEV)
+    ops.linear_wgrad(dY, X, dW)
+    assert _rel(dW, 1.0 + dY.float().t() @ X.float()) < 1e-4
+
+
+@pytest.mark.parametrize("H", [128, 512, 2048, 1000])
+@pytest.mark.parametrize("rms", [0, 1])
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)])
+def test_norm_fwd_bwd(H, rms, xdt, ydt):
+    rows, eps = 77, 1e-6
+    x = _rand((rows, H), 1, dtype=xdt)
+    w = (1 + 0.1 * torch.randn(H, generator=torch.Generator().manual_seed(2))).to(DEV)
+    res = torch.randn(rows, H, device=DEV) if ydt == torch.float32 else None
+    for act in (0, 1):
+        y, stats = ops.norm_fwd(x, w, eps, ydt, res=res, act=act, rms=rms)
+        xr = x.float().clone().requires_grad_(True)
+        wr = w.clone().requires_grad_(True)
+        a = torch.nn.functional.gelu(xr) if act else xr
+        if rms:
+            n = a * torch.rsqrt(a.pow(2).mean(-1, keepdim=True) + eps) * wr
+        else:
+            n = torch.nn.functional.layer_norm(a, (H,), wr, None, eps)
+        yr = n + (res if res is not None else 0)
+        tol = 5e-3 if ydt == torch.bfloat16 else 1e-5
+        assert _rel(y, yr) < tol
+        dy = _rand((rows, H), 3, dtype=torch.bfloat16 if ydt == torch.bfloat16 else torch.float32)
+        dres = torch.randn(rows, H, device=DEV)
+        dw = torch.zeros(H, device=DEV)
+        dx = ops.norm_bwd(dy, x, w, stats, torch.float32, dw=dw, dres=dres, act=act, rms=rms)
+        yr.backward(dy.float())
+        assert _rel(dx, xr.grad + dres) < 1e-4
+        assert _rel(dw, wr.grad) < 1e-4
+
+
+def test_embed_fwd_bwd():
+    B, S, H, V = 5, 17, 128, 72
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, V, (B, S), generator=g).to(DEV)
+    ids[:, 3] = V - 1  # hot row
+    word, pos = torch.randn(V, H, generator=g).to(DEV), torch.randn(S + 3, H, generator=g).to(DEV)
+    out = ops.embed_fwd(ids, word, pos)
+    ref = word[ids] + pos[:S][None]
+    assert torch.equal(out.view(B, S, H), ref)
+    dx = torch.randn(B * S, H, device=DEV)
+    dword, dpos = torch.zeros_like(word), torch.zeros_like(pos)
+    ops.embed_bwd(ids, dx, dword, dpos)
+    rw = torch.zeros_like(word).index_add_(0, ids.view(-1), dx)
+    assert _rel(dword, rw) < 1e-6
+    assert _rel(dpos[:S], dx.view(B, S, H).sum(0)) < 1e-6 and bool((dpos[S:] == 0).all())
+
+
+def test_glu_fwd_bwd():
+    rows, I = 33, 256
+    ab = _rand((rows, 2 * I), 1)
+    out = ops.glu_fwd(ab)
+    a = ab[:, :I].float().clone().requires_grad_(True)
+    b = ab[:, I:].float().clone().requires_grad_(True)
+    ref = torch.nn.functional.gelu(a) * b
+    assert _rel(out, ref) < 6e-3
+    d = _rand((rows, I), 2)
+    dab = ops.glu_bwd(ab, d)
+    ref.backward(d.float())
+    assert _rel(dab[:, :I], a.grad) < 8e-3 and _rel(dab[:, I:], b.grad) < 8e-3
+
+
+@pytest.mark.parametrize("V,ld,ls", [(2025, 2048, 0.0), (2025, 2048, 0.1), (64, 64, 0.0), (8192, 8192, 0.1)])
+def test_cross_entropy(V, ld, ls):
+    rows = 203
+    g = torch.Generator().manual_seed(0)
+    logits = torch.zeros(rows, ld, dtype=torch.bfloat16, device=DEV)
+    logits[:, :V] = (torch.randn(rows, V, generator=g) * 2).to(torch.bfloat16).to(DEV)
+    labels = torch.randint(0, V, (rows,), generator=g)
+    labels[torch.rand(rows, generator=g) < 0.4] = -100
+    labels = labels.to(DEV)
+    out, ws = ops.ce_fwd(logits, labels, V, ls)
+    lr = logits[:, :V].float().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr, labels, ignore_index=-100, label_smoothing=ls)
+    assert abs(float(out[0]) - float(ref)) < 2e-5 * max(1.0, abs(float(ref)))
+    assert int(out[1]) == int((labels != -100).sum())
+    dloss = torch.tensor([0.5], device=DEV)
+    dl = ops.ce_bwd(logits, labels, ws, dloss, out, V, ls)
+    ref.backward(torch.tensor(0.5, device=DEV))
+    assert _rel(dl[:, :V], lr.grad) < 6e-3
+    assert bool((dl[:, V:] == 0).all())
+    assert bool((dl[labels == -100] == 0).all())
+
+
+def _attn_ref(q, k, v, scale):
+    s = (q @ k.transpose(-1, -2)) * scale
+    return s.softmax(-1) @ v
+
+
+@pytest.mark.parametrize("B,nh,Sq,Skv", [(2, 2, 257, 257), (1, 1, 64, 64), (3, 2, 16, 77), (2, 8, 256, 256), (1, 2, 130, 5)])
+def test_attention_fwd_bwd(B, nh, Sq, Skv):
+    H = nh * 64
+    cross = Sq != Skv
+    scale = 1.0 / math.sqrt(64)
+    if cross:
+        qb = _rand((B * Sq, H), 1)
+        kvb = _rand((B * Skv, 2 * H), 2)
+        q, k, v = qb, kvb[:, :H], kvb[:, H:]
+    else:
+        qkv = _rand((B * Sq, 3 * H), 1)
+        q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    o, lse = ops.attn_fwd(q, k, v, B, nh, Sq, Skv, scale)
+    qr = q.float().reshape(B, Sq, nh, 64).transpose(1, 2).clone().requires_grad_(True)
+    kr = k.float().reshape(B, Skv, nh, 64).transpose(1, 2).clone().requires_grad_(True)
+    vr = v.float().reshape(B, Skv, nh, 64).transpose(1, 2).clone().requires_grad_(True)
+    ref = _attn_ref(qr, kr, vr, scale)
+    assert _rel(o.view(B, Sq, nh, 64).transpose(1, 2), ref) < 8e-3
+    lse_ref = torch.logsumexp((qr @ kr.transpose(-1, -2)) * scale, dim=-1)
+    assert _rel(lse, lse_ref) < 1e-4
+    do = _rand((B * Sq, H), 3)
+    dq = torch.empty_like(q.contiguous()) if cross else None
+    if cross:
+        dkv = torch.empty_like(kvb)
+        ops.attn_bwd(q, k, v, o, do, lse, dq, dkv[:, :H], dkv[:, H:], B, nh, Sq, Skv, scale)
+        dk, dv = dkv[:, :H], dkv[:, H:]
+    else:
+        dqkv = torch.empty_like(qkv)
+        ops.attn_bwd(q, k, v, o, do, lse, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, nh, Sq, Skv, scale)
+        dq, dk, dv = dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:]
+    ref.backward(do.float().view(B, Sq, nh, 64).transpose(1, 2))
+    assert _rel(dq.reshape(B, Sq, nh, 64).transpose(1, 2), qr.grad) < 1.5e-2
+    assert _rel(dk.reshape(B, Skv, nh, 64).transpose(1, 2), kr.grad) < 1.5e-2
+    assert _rel(dv.reshape(B, Skv, nh, 64).transpose(1, 2), vr.grad) < 1.5e-2
+
+
+@pytest.mark.parametrize("n,ncodes,D", [(512, 1024, 256), (300, 128, 64), (1, 64, 16), (4096, 1024, 256)])
+def test_vq_argmin_bit_exact_vs_c_oracle(n, ncodes, D):
+    from oracle import vq_oracle as VQ
+
+    g = torch.Generator().manual_seed(n)
+    z = torch.randn(n, D, generator=g)
+    cb = torch.randn(ncodes, D, generator=g) * 0.7
+    cb[ncodes // 2] = cb[3]  # exact duplicate code: lowest index must win
+    ids, dmin = ops.vq_argmin(z.to(DEV), cb.to(DEV), return_dmin=True)
+    ids_o, dmin_o = VQ.argmin(z.numpy(), cb.numpy())
+    assert np.array_equal(ids.cpu().numpy(), ids_o)
+    assert np.array_equal(dmin.cpu().numpy().view(np.uint32), dmin_o.view(np.uint32))  # distances bit-identical too
+
+
+def test_vq_golden_ids(golden):
+    from oracle import vq_oracle as VQ
+
+    g = golden("vq_quantizer.pt")
+    z = torch.from_numpy(VQ.nchw_to_rows(g["z"].numpy())).to(DEV)
+    ids = ops.vq_argmin(z, g["codebook"].to(DEV))
+    assert torch.equal(ids.cpu().view(2, -1), g["ids"])
+    entry = ops.vq_lookup_nchw(g["ids"].to(DEV), g["codebook"].to(DEV))
+    assert torch.equal(entry.cpu().view_as(g["entry"]), g["entry"])
