@@ -101,6 +101,30 @@ int muse_vq_argmin(const float* z, const float* codebook, float* enorm_ws, long 
 int muse_vq_lookup_nchw(const long long* ids, const float* codebook, float* out, int B, int P, int D, int ncodes,
                         void* stream);
 
+/* One generate2 decoding step fused into one kernel (muse/modeling_transformer.py:1424-1454 + muse/sampling.py:9-35):
+ * categorical sample (argmax softmax/q_exp == torch.multinomial(p,1) given the same Exp(1) draws), confidence
+ * = log p_sel + temperature * gumbel(u), per-row (k+1)-th smallest cut-off, re-mask.  logits bf16 with
+ * row_stride / batch_stride in elements (first K columns used); logits_unc (nullable) + guidance fuse CFG (:1410-1414).
+ * input_ids/sampled/next_ids int64 [B,L]; q_exp fp32 [B,L,K]; u fp32 [B,L]; conf_out (nullable) fp32 [B,L]. */
+int muse_sample_step(const void* logits, const void* logits_unc, long long row_stride, long long batch_stride,
+                     float guidance, const long long* input_ids, const float* q_exp, const float* u,
+                     long long* sampled, long long* next_ids, float* conf_out, int B, int L, int K,
+                     long long mask_id, int mask_len, float temperature, void* stream);
+
+/* MaskGitVQGAN encoder/decoder blocks, fp32 NHWC (muse/modeling_maskgit_vqgan.py).
+ * conv2d: Conv2dSame (:33-45) stride 1, ksize 1|3, x [B,Hi,Wi,Cin] (Hi=H/2 if upsample2x: nearest x2 of :146 folded
+ * into the gather), wk [ksize*ksize*Cin, Cout] packed (tap-major, then input channel), optional bias [Cout] and
+ * residual [B,H,W,Cout] (ResnetBlock :82-85) -> y [B,H,W,Cout]. */
+int muse_conv2d_nhwc(const float* x, const float* wk, const float* bias, const float* res, float* y, int B, int H,
+                     int W, int Cin, int Cout, int ksize, int upsample2x, void* stream);
+/* nn.GroupNorm(groups, C, eps) + F.silu (:61-79); scratch: moments_ws double [B*C*2], scale_shift_ws float [B*C*2]. */
+int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, double* moments_ws,
+                             float* scale_shift_ws, int B, int HW, int C, int groups, float eps, void* stream);
+/* F.avg_pool2d(2,2) (:112): x [B,2Ho,2Wo,C] -> y [B,Ho,Wo,C]. */
+int muse_avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, void* stream);
+/* [B, rows, cols] -> [B, cols, rows] (NCHW <-> NHWC at the model boundary). */
+int muse_transpose_batched(const float* in, float* out, int B, int rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,11 @@ int ce_fwd(const void*, const long long*, float*, float*, float*, int, int, int,
 int ce_bwd(const void*, const long long*, const float*, const float*, const float*, void*, int, int, int, float, cudaStream_t);
 int vq_argmin(const float*, const float*, float*, long long*, float*, int, int, int, cudaStream_t);
 int vq_lookup_nchw(const long long*, const float*, float*, int, int, int, int, cudaStream_t);
+int sample_step(const void*, const void*, long long, long long, float, const long long*, const float*, const float*, long long*, long long*, float*, int, int, int, long long, int, float, cudaStream_t);
+int conv2d_nhwc(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int groupnorm_silu_nhwc(const float*, const float*, const float*, float*, double*, float*, int, int, int, int, float, cudaStream_t);
+int avgpool2_nhwc(const float*, float*, int, int, int, int, cudaStream_t);
+int transpose_batched(const float*, float*, int, int, int, cudaStream_t);
 
 }  // namespace muse
 
@@ -130,6 +135,28 @@ int muse_vq_argmin(const float* z, const float* codebook, float* enorm_ws, long 
 }
 int muse_vq_lookup_nchw(const long long* ids, const float* codebook, float* out, int B, int P, int D, int ncodes, void* stream) {
   return vq_lookup_nchw(ids, codebook, out, B, P, D, ncodes, ST(stream));
+}
+
+int muse_sample_step(const void* logits, const void* logits_unc, long long row_stride, long long batch_stride,
+                     float guidance, const long long* input_ids, const float* q_exp, const float* u,
+                     long long* sampled, long long* next_ids, float* conf_out, int B, int L, int K,
+                     long long mask_id, int mask_len, float temperature, void* stream) {
+  return sample_step(logits, logits_unc, row_stride, batch_stride, guidance, input_ids, q_exp, u, sampled, next_ids,
+                     conf_out, B, L, K, mask_id, mask_len, temperature, ST(stream));
+}
+int muse_conv2d_nhwc(const float* x, const float* wk, const float* bias, const float* res, float* y, int B, int H,
+                     int W, int Cin, int Cout, int ksize, int upsample2x, void* stream) {
+  return conv2d_nhwc(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x, ST(stream));
+}
+int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, double* moments_ws,
+                             float* scale_shift_ws, int B, int HW, int C, int groups, float eps, void* stream) {
+  return groupnorm_silu_nhwc(x, gamma, beta, y, moments_ws, scale_shift_ws, B, HW, C, groups, eps, ST(stream));
+}
+int muse_avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, void* stream) {
+  return avgpool2_nhwc(x, y, B, Ho, Wo, C, ST(stream));
+}
+int muse_transpose_batched(const float* in, float* out, int B, int rows, int cols, void* stream) {
+  return transpose_batched(in, out, B, rows, cols, ST(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,302 @@
+// MaskGitVQGAN encoder / decoder building blocks in fp32, NHWC (muse/modeling_maskgit_vqgan.py):
+//   * conv2d 'same' stride-1, k = 3 or 1 (Conv2dSame :33-45) as an implicit GEMM:
+//       M = B*H*W output pixels, N = C_out, K = k*k*C_in  (weights pre-packed to [K, C_out])
+//     with fused bias, fused residual add (ResnetBlock :82-85) and the nearest x2 upsample of
+//     UpsamplingBlock (:146) folded into the input gather (index >> 1) so the 4x larger tensor is never written.
+//   * GroupNorm(32, eps=1e-6) + SiLU (:61-79): one statistics pass (fp64 atomics for the 2 moments) + one apply pass.
+//   * avg_pool2d(2,2) (:112), NCHW <-> NHWC layout changes at the model boundary.
+// fp32 SIMT on purpose: token ids must agree with the fp32 reference; each output is one ascending-K
+// fma chain (taps row-major, then input channel), so results do not depend on tiling.
+// The tensor-core upgrade (3x bf16-split tcgen05 implicit GEMM with TMA im2col) is planned, see DESIGN.md.
+#include "common.cuh"
+
+namespace muse {
+namespace {
+
+constexpr int KT = 8;  // k per smem stage
+
+template <int TM, int TN, bool VEC>
+__global__ void __launch_bounds__(256)
+conv2d_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias,
+                   const float* __restrict__ res, float* __restrict__ y, int B, int H, int W, int Cin, int Cout,
+                   int ksize, int up) {
+  constexpr int BM = 16 * TM, BN = 16 * TN;
+  __shared__ __align__(16) float sA[KT][BM];
+  __shared__ __align__(16) float sB[KT][BN];
+  const long long M = static_cast<long long>(B) * H * W;
+  const int K = ksize * ksize * Cin;
+  const long long m0 = static_cast<long long>(blockIdx.x) * BM;
+  const int n0 = blockIdx.y * BN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int Hi = up ? H / 2 : H, Wi = up ? W / 2 : W;
+  const int pad = ksize / 2;
+
+  // A-loader role: BM rows x 8 k per stage. VEC: one float4 per (row, half); scalar: BM*8/256 elements.
+  constexpr int A_PER_THREAD = BM * KT / 256;  // 4 for BM=128
+  int a_row[A_PER_THREAD], a_k[A_PER_THREAD];
+  int ab[A_PER_THREAD], ay[A_PER_THREAD], ax[A_PER_THREAD];
+  bool a_ok[A_PER_THREAD];
+  if (VEC) {
+    const int r = threadIdx.x / 2;  // requires BM == 128
+    a_row[0] = r; a_k[0] = (threadIdx.x & 1) * 4;
+  } else {
+#pragma unroll
+    for (int i = 0; i < A_PER_THREAD; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      a_row[i] = idx / KT; a_k[i] = idx % KT;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < (VEC ? 1 : A_PER_THREAD); ++i) {
+    const long long m = m0 + a_row[i];
+    a_ok[i] = m < M;
+    const long long mm = a_ok[i] ? m : 0;
+    ax[i] = static_cast<int>(mm % W);
+    ay[i] = static_cast<int>((mm / W) % H);
+    ab[i] = static_cast<int>(mm / (static_cast<long long>(W) * H));
+  }
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += KT) {
+    __syncthreads();
+    if (VEC) {
+      const int k = k0 + a_k[0];
+      const int tap = k / Cin, ci = k % Cin;
+      const int iy = ay[0] + tap / ksize - pad, ix = ax[0] + tap % ksize - pad;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_ok[0] && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const int sy = up ? (iy >> 1) : iy, sx = up ? (ix >> 1) : ix;
+        v = *reinterpret_cast<const float4*>(x + ((static_cast<long long>(ab[0]) * Hi + sy) * Wi + sx) * Cin + ci);
+      }
+      sA[a_k[0] + 0][a_row[0]] = v.x; sA[a_k[0] + 1][a_row[0]] = v.y;
+      sA[a_k[0] + 2][a_row[0]] = v.z; sA[a_k[0] + 3][a_row[0]] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < A_PER_THREAD; ++i) {
+        const int k = k0 + a_k[i];
+        float v = 0.f;
+        if (k < K && a_ok[i]) {
+          const int tap = k / Cin, ci = k % Cin;
+          const int iy = ay[i] + tap / ksize - pad, ix = ax[i] + tap % ksize - pad;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            const int sy = up ? (iy >> 1) : iy, sx = up ? (ix >> 1) : ix;
+            v = x[((static_cast<long long>(ab[i]) * Hi + sy) * Wi + sx) * Cin + ci];
+          }
+        }
+        sA[a_k[i]][a_row[i]] = v;
+      }
+    }
+    // B tile: [KT][BN] from wk[k][n]
+    for (int idx = threadIdx.x; idx < KT * BN; idx += 256) {
+      const int kk = idx / BN, nn = idx % BN;
+      const int k = k0 + kk, n = n0 + nn;
+      sB[kk][nn] = (k < K && n < Cout) ? wk[static_cast<long long>(k) * Cout + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = sA[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = sB[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const long long m = m0 + ty * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n < Cout) {
+        float v = acc[i][j];
+        if (bias) v += bias[n];
+        if (res) v += res[m * Cout + n];
+        y[m * Cout + n] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- GroupNorm + SiLU (NHWC)
+// pass 1: per-(image, channel) moments {sum, sumsq} in fp64 (atomics across pixel chunks)
+// pass 2: fold channels into groups -> per-(image, channel) scale = rstd*gamma, shift = beta - mean*scale
+// pass 3: y = silu(x * scale + shift)
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x, double* __restrict__ moments, int HW, int C, int rows_per_block) {
+  extern __shared__ float s_part[];  // [C][2]
+  const int b = blockIdx.y;
+  const int c4 = C / 4;
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) s_part[i] = 0.f;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  const float* base = x + static_cast<long long>(b) * HW * C;
+  const int q = threadIdx.x % c4;          // fixed channel quad per thread (256 % c4 == 0)
+  const int rstep = blockDim.x / c4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = r0 + threadIdx.x / c4; r < r1; r += rstep) {
+    const float4 v = *reinterpret_cast<const float4*>(base + static_cast<long long>(r) * C + q * 4);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    atomicAdd(&s_part[(q * 4 + j) * 2], s[j]);
+    atomicAdd(&s_part[(q * 4 + j) * 2 + 1], ss[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
+    atomicAdd(&moments[static_cast<long long>(b) * C * 2 + i], static_cast<double>(s_part[i]));
+}
+
+__global__ void gn_finalize_kernel(const double* __restrict__ moments, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale_shift, int HW, int C,
+                                   int groups, float eps) {
+  const int b = blockIdx.x;
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    double sum = 0.0, sq = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+      sum += moments[(static_cast<long long>(b) * C + g * cpg + k) * 2];
+      sq += moments[(static_cast<long long>(b) * C + g * cpg + k) * 2 + 1];
+    }
+    const double n = static_cast<double>(HW) * cpg;
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = rstd * gamma[c];
+    scale_shift[(static_cast<long long>(b) * C + c) * 2] = sc;
+    scale_shift[(static_cast<long long>(b) * C + c) * 2 + 1] = beta[c] - static_cast<float>(mean) * sc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift, float* __restrict__ y,
+                     long long total4, int HW, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = C / 4;
+  const int q = static_cast<int>(i % c4);
+  const int b = static_cast<int>(i / (static_cast<long long>(c4) * HW));
+  const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+  const float4 s0 = *reinterpret_cast<const float4*>(scale_shift + (static_cast<long long>(b) * C + q * 4) * 2);
+  const float4 s1 = *reinterpret_cast<const float4*>(scale_shift + (static_cast<long long>(b) * C + q * 4) * 2 + 4);
+  float o[4] = {fmaf(v.x, s0.x, s0.y), fmaf(v.y, s0.z, s0.w), fmaf(v.z, s1.x, s1.y), fmaf(v.w, s1.z, s1.w)};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = o[j] / (1.f + expf(-o[j]));
+  *reinterpret_cast<float4*>(y + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// ---------------------------------------------------------------- pooling / layout
+__global__ void __launch_bounds__(256)
+avgpool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int Ho, int Wo, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const int c4 = C / 4;
+  const long long total = static_cast<long long>(B) * Ho * Wo * c4;
+  if (i >= total) return;
+  const int q = static_cast<int>(i % c4);
+  const int ox = static_cast<int>((i / c4) % Wo);
+  const int oy = static_cast<int>((i / (static_cast<long long>(c4) * Wo)) % Ho);
+  const int b = static_cast<int>(i / (static_cast<long long>(c4) * Wo * Ho));
+  const int Wi = Wo * 2;
+  const float* p = x + ((static_cast<long long>(b) * Ho * 2 + oy * 2) * Wi + ox * 2) * C + q * 4;
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 bb = *reinterpret_cast<const float4*>(p + C);
+  const float4 c = *reinterpret_cast<const float4*>(p + static_cast<long long>(Wi) * C);
+  const float4 d = *reinterpret_cast<const float4*>(p + static_cast<long long>(Wi) * C + C);
+  // same association as ATen's avg_pool2d accumulation: ((a + b) + c) + d, then / 4
+  *reinterpret_cast<float4*>(y + i * 4) = make_float4(((a.x + bb.x) + c.x + d.x) * 0.25f, ((a.y + bb.y) + c.y + d.y) * 0.25f,
+                                                      ((a.z + bb.z) + c.z + d.z) * 0.25f, ((a.w + bb.w) + c.w + d.w) * 0.25f);
+}
+
+// out[b, p, c] = in[b, c, p] (to_nhwc) or the inverse; 32x32 smem transpose tiles
+__global__ void __launch_bounds__(256)
+transpose_cp_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const float* ip = in + static_cast<long long>(b) * rows * cols;
+  float* op = out + static_cast<long long>(b) * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    if (r < rows && c < cols) t[j][tx] = ip[static_cast<long long>(r) * cols + c];
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < rows && c < cols) op[static_cast<long long>(c) * rows + r] = t[tx][j];
+  }
+}
+
+}  // namespace
+
+int conv2d_nhwc(const float* x, const float* wk, const float* bias, const float* res, float* y, int B, int H, int W,
+                int Cin, int Cout, int ksize, int upsample2x, cudaStream_t s) {
+  if (ksize != 1 && ksize != 3) { set_last_error("conv2d: kernel size %d unsupported (1 or 3)", ksize); return MUSE_ERR_UNSUPPORTED; }
+  if (upsample2x && ((H | W) & 1)) { set_last_error("conv2d: upsample2x needs even output dims"); return MUSE_ERR_INVALID; }
+  const long long M = static_cast<long long>(B) * H * W;
+  if (M <= 0) return MUSE_OK;
+  const bool vec = (Cin % 8 == 0);
+  if (Cout > 16) {
+    dim3 grid(static_cast<unsigned>(ceil_div_ll(M, 128)), ceil_div(Cout, 128));
+    if (vec) conv2d_nhwc_kernel<8, 8, true><<<grid, 256, 0, s>>>(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
+    else conv2d_nhwc_kernel<8, 8, false><<<grid, 256, 0, s>>>(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
+  } else {
+    dim3 grid(static_cast<unsigned>(ceil_div_ll(M, 128)), 1);
+    if (vec) conv2d_nhwc_kernel<8, 1, true><<<grid, 256, 0, s>>>(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
+    else conv2d_nhwc_kernel<8, 1, false><<<grid, 256, 0, s>>>(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
+  }
+  return check_launch("conv2d_nhwc");
+}
+
+int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, double* moments_ws,
+                        float* scale_shift_ws, int B, int HW, int C, int groups, float eps, cudaStream_t s) {
+  if (C % groups != 0 || C % 4 != 0 || C > 1024 || 256 % (C / 4) != 0) {
+    set_last_error("groupnorm: C=%d groups=%d unsupported (C must divide into groups, C/4 must divide 256)", C, groups);
+    return MUSE_ERR_UNSUPPORTED;
+  }
+  if (B <= 0 || HW <= 0) return MUSE_OK;
+  cudaError_t e = cudaMemsetAsync(moments_ws, 0, sizeof(double) * 2 * B * C, s);
+  if (e != cudaSuccess) { set_last_error("groupnorm memset: %s", cudaGetErrorString(e)); return MUSE_ERR_CUDA; }
+  const int rows_per_block = (256 / (C / 4)) * 16;
+  gn_stats_kernel<<<dim3(ceil_div(HW, rows_per_block), B), 256, C * 2 * sizeof(float), s>>>(x, moments_ws, HW, C, rows_per_block);
+  int rc = check_launch("gn_stats");
+  if (rc) return rc;
+  gn_finalize_kernel<<<B, 256, 0, s>>>(moments_ws, gamma, beta, scale_shift_ws, HW, C, groups, eps);
+  rc = check_launch("gn_finalize");
+  if (rc) return rc;
+  const long long total4 = static_cast<long long>(B) * HW * (C / 4);
+  gn_apply_silu_kernel<<<static_cast<unsigned>(ceil_div_ll(total4, 256)), 256, 0, s>>>(x, scale_shift_ws, y, total4, HW, C);
+  return check_launch("gn_apply_silu");
+}
+
+int avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, cudaStream_t s) {
+  if (C % 4 != 0) { set_last_error("avgpool: C must be a multiple of 4"); return MUSE_ERR_UNSUPPORTED; }
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C / 4);
+  if (total <= 0) return MUSE_OK;
+  avgpool2_nhwc_kernel<<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, s>>>(x, y, B, Ho, Wo, C);
+  return check_launch("avgpool2_nhwc");
+}
+
+// in: [B, rows, cols] -> out: [B, cols, rows]
+int transpose_batched(const float* in, float* out, int B, int rows, int cols, cudaStream_t s) {
+  if (B <= 0 || rows <= 0 || cols <= 0) return MUSE_OK;
+  transpose_cp_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32), B), 256, 0, s>>>(in, out, rows, cols);
+  return check_launch("transpose_batched");
+}
+
+}  // namespace muse

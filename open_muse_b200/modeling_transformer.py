@@ -242,7 +242,7 @@ class _LayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, enc, spec, *params):
         s = spec
-        grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        grad = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward)
         it = iter(params)
         w_attn_ln, _, _, _, _ = next(it), next(it), next(it), next(it), next(it)
         w_post = next(it) if s.normformer else None
@@ -397,7 +397,7 @@ class _HeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, labels, spec, *params):
         s = spec
-        grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        grad = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward)
         it = iter(params)
         w_enc = next(it) if s.use_enc_ln else None
         if s.use_mlm:
@@ -612,6 +612,7 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
         labels=None,
         label_smoothing=0.0,
         cond_dropout_prob=0.0,
+        _raw_bf16=False,
         **kwargs,  # cond_embeds / loss_weight / micro_conds from train_muse.py:742-750 are accepted and ignored
     ):
         c = self.config
@@ -660,6 +661,8 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
         else:
             logits, loss = out, None
         logits = logits.view(B, S, self.output_size) if logits.is_contiguous() else logits.unflatten(0, (B, S))
+        if _raw_bf16:
+            return logits, loss
         if not torch.is_autocast_enabled("cuda"):
             logits = logits.float()  # the reference returns fp32 logits outside autocast
         if labels is not None:
@@ -700,30 +703,23 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
             uncond = torch.zeros_like(encoder_hidden_states) if negative_embeds is None else negative_embeds
             cfg_states = torch.cat([encoder_hidden_states, uncond])
         sampled_ids = input_ids
+        input_ids = input_ids.contiguous()
         for step in range(timesteps):
             model_in = input_ids if class_ids is None else torch.cat([class_ids[:, None], input_ids], dim=1)
             if use_cfg:
-                both = self(torch.cat([model_in] * 2), encoder_hidden_states=cfg_states)
-                cond, unc = both.chunk(2)
-                cond, unc = cond[..., :n_codes], unc[..., :n_codes]
-                logits = unc + guidance_scale * (cond - unc)
+                both, _ = self(torch.cat([model_in] * 2), encoder_hidden_states=cfg_states, _raw_bf16=True)
+                logits, logits_unc = both[:batch], both[batch:]
             else:
-                logits = self(model_in, encoder_hidden_states=encoder_hidden_states)[..., :n_codes]
-            if class_ids is not None:
-                logits = logits[:, 1:]
-            probs = logits.softmax(dim=-1)
-            draws = torch.multinomial(probs.reshape(-1, probs.size(-1)), 1, generator=generator)[:, 0]
-            sampled_ids = draws.view(*probs.shape[:-1])
-            unknown = input_ids == mask_id
-            sampled_ids = torch.where(unknown, sampled_ids, input_ids)
+                logits, _ = self(model_in, encoder_hidden_states=encoder_hidden_states, _raw_bf16=True)
+                logits_unc = None
+            # the generator is consumed exactly like the reference: multinomial(n=1) draws Exp(1) noise of the
+            # probabilities' shape (ATen), mask_by_random_topk draws one uniform per token (sampling.py:13-15)
+            q_exp = torch.empty(batch * seq_len, n_codes, dtype=torch.float32, device=logits.device).exponential_(1, generator=generator)
+            u = torch.zeros(batch, seq_len, dtype=torch.float32, device=logits.device).uniform_(0, 1, generator=generator)
             ratio = 1.0 * (step + 1) / timesteps
-            mask_ratio = noise_schedule(torch.tensor(ratio))
-            sel = probs.gather(-1, sampled_ids.long()[..., None]).squeeze(-1)
-            sel = torch.where(unknown, sel, torch.finfo(sel.dtype).max)
-            mask_len = (seq_len * mask_ratio).floor().unsqueeze(0).to(logits.device)
-            mask_len = torch.max(torch.tensor([1], device=logits.device),
-                                 torch.min(unknown.sum(dim=-1, keepdim=True) - 1, mask_len))
+            mask_len = int((seq_len * noise_schedule(torch.tensor(ratio))).floor())
             temperature = temperature * (1.0 - ratio)  # compounds across steps (quirk Q4)
-            masking = mask_by_random_topk(mask_len, sel, temperature, generator=generator)
-            input_ids = torch.where(masking, mask_id, sampled_ids)
+            sampled_ids, input_ids = ops.sample_step(
+                logits, input_ids, q_exp, u, n_codes, mask_id, mask_len, temperature, logits_unc=logits_unc,
+                guidance=guidance_scale, skip_first_token=class_ids is not None)
         return sampled_ids

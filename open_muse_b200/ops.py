@@ -49,7 +49,8 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-_KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 3, "muse_embed_bwd": 2, "muse_vq_argmin": 2}
+_KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 3, "muse_embed_bwd": 2, "muse_vq_argmin": 2,
+                     "muse_groupnorm_silu_nhwc": 3}
 _prof = {"on": False, "events": []}
 
 
@@ -241,3 +242,83 @@ def vq_lookup_nchw(ids, codebook):
     out = torch.empty(B, D, P, dtype=torch.float32, device=codebook.device)
     _call("muse_vq_lookup_nchw", _p(ids), _p(codebook), _p(out), B, P, D, codebook.shape[0], st)
     return out
+
+
+# ------------------------------------------------------------------------------------------ generate2 step
+def sample_step(logits, input_ids, q_exp, u, K, mask_id, mask_len, temperature, logits_unc=None, guidance=0.0,
+                skip_first_token=False, return_conf=False):
+    """logits: bf16 [B, S, ld] view (S = L (+1 with a class token, skipped when skip_first_token)); see csrc/sample.cu."""
+    st = _prep(logits)
+    B, L = input_ids.shape
+    off = 1 if skip_first_token else 0
+    lg = logits[:, off:]
+    lu = logits_unc[:, off:] if logits_unc is not None else None
+    sampled = torch.empty(B, L, dtype=torch.int64, device=logits.device)
+    nxt = torch.empty(B, L, dtype=torch.int64, device=logits.device)
+    conf = torch.empty(B, L, dtype=torch.float32, device=logits.device) if return_conf else None
+    _call("muse_sample_step", _p(lg), _p(lu), lg.stride(1), lg.stride(0), float(guidance), _p(input_ids), _p(q_exp),
+          _p(u), _p(sampled), _p(nxt), _p(conf), B, L, K, int(mask_id), int(mask_len), float(temperature), st)
+    return (sampled, nxt, conf) if return_conf else (sampled, nxt)
+
+
+# ------------------------------------------------------------------------------------------ VQGAN blocks (fp32 NHWC)
+_wk_cache = {}
+
+
+def _packed_conv_weight(w):
+    """[Cout, Cin, kh, kw] -> [kh*kw*Cin, Cout] (tap-major, then input channel); cached per weight version."""
+    key = (w.data_ptr(), w._version, w.device)
+    hit = _wk_cache.get(id(w))
+    if hit is None or hit[0] != key:
+        wk = w.detach().float().permute(2, 3, 1, 0).reshape(-1, w.shape[0]).contiguous()
+        _wk_cache[id(w)] = (key, wk)
+        return wk
+    return hit[1]
+
+
+def conv2d(x, w, bias=None, residual=None, upsample2x=False):
+    """x fp32 NHWC [B,Hi,Wi,Cin]; w the nn.Conv2d weight [Cout,Cin,k,k]; returns NHWC [B,H,W,Cout]."""
+    st = _prep(x)
+    B, Hi, Wi, Cin = x.shape
+    H, W = (Hi * 2, Wi * 2) if upsample2x else (Hi, Wi)
+    Cout, k = w.shape[0], w.shape[2]
+    y = torch.empty(B, H, W, Cout, dtype=torch.float32, device=x.device)
+    b = None if bias is None else bias.detach().float()
+    _call("muse_conv2d_nhwc", _p(x), _p(_packed_conv_weight(w)), _p(b), _p(residual), _p(y), B, H, W, Cin, Cout, k,
+          1 if upsample2x else 0, st)
+    return y
+
+
+def groupnorm_silu(x, gamma, beta, groups, eps):
+    st = _prep(x)
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    ws = torch.empty(B * C * 2, dtype=torch.float64, device=x.device)
+    ss = torch.empty(B * C * 2, dtype=torch.float32, device=x.device)
+    _call("muse_groupnorm_silu_nhwc", _p(x), _p(gamma.detach().float()), _p(beta.detach().float()), _p(y), _p(ws),
+          _p(ss), B, H * W, C, groups, float(eps), st)
+    return y
+
+
+def avg_pool2x2(x):
+    st = _prep(x)
+    B, H, W, C = x.shape
+    y = torch.empty(B, H // 2, W // 2, C, dtype=torch.float32, device=x.device)
+    _call("muse_avgpool2_nhwc", _p(x), _p(y), B, H // 2, W // 2, C, st)
+    return y
+
+
+def to_nhwc(x_nchw):
+    st = _prep(x_nchw)
+    B, C, H, W = x_nchw.shape
+    y = torch.empty(B, H, W, C, dtype=torch.float32, device=x_nchw.device)
+    _call("muse_transpose_batched", _p(x_nchw), _p(y), B, C, H * W, st)
+    return y
+
+
+def to_nchw(x_nhwc):
+    st = _prep(x_nhwc)
+    B, H, W, C = x_nhwc.shape
+    y = torch.empty(B, C, H, W, dtype=torch.float32, device=x_nhwc.device)
+    _call("muse_transpose_batched", _p(x_nhwc), _p(y), B, H * W, C, st)
+    return y

@@ -1,0 +1,157 @@
+"""GPU parity: fused generate2 step kernel vs the oracle's sample_step on identical pre-drawn noise (token ids and
+mask positions bit-exact on margin-screened tokens), and the MaskGitVQGAN path vs reference goldens."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from open_muse_b200 import ops  # noqa: E402
+from oracle import transformer_oracle as T  # noqa: E402
+from oracle import vq_oracle as VQ  # noqa: E402
+from oracle import vqgan_oracle as G  # noqa: E402
+
+DEV = "cuda"
+
+
+def _step_inputs(B, L, K, ld, seed, known_frac):
+    g = torch.Generator().manual_seed(seed)
+    logits = (torch.randn(B, L + 1, ld, generator=g) * 2.0).to(torch.bfloat16)
+    ids = torch.full((B, L), K + 7, dtype=torch.long)  # mask id
+    known = torch.rand(B, L, generator=g) < known_frac
+    ids[known] = torch.randint(0, K, (int(known.sum()),), generator=g)
+    q = torch.empty(B * L, K).exponential_(1, generator=g).view(B, L, K)
+    u = torch.zeros(B, L).uniform_(0, 1, generator=g)
+    return logits, ids, q, u
+
+
+@pytest.mark.parametrize("B,L,K,ld,known_frac,mask_len,temp", [
+    (4, 16, 64, 72, 0.0, 9, 1.0), (3, 16, 64, 72, 0.5, 3, 0.4), (64, 256, 1024, 2048, 0.3, 100, 0.7),
+    (2, 256, 1024, 2048, 0.99, 200, 0.0), (2, 1024, 1024, 1032, 0.0, 1000, 2.0)])
+def test_sample_step_vs_oracle(B, L, K, ld, known_frac, mask_len, temp):
+    logits, ids, q, u = _step_inputs(B, L, K, ld, B * L + K, known_frac)
+    mask_id = K + 7
+    sampled, nxt, conf = ops.sample_step(logits.to(DEV), ids.to(DEV), q.to(DEV).contiguous(), u.to(DEV), K, mask_id,
+                                         mask_len, temp, skip_first_token=True, return_conf=True)
+    probs = logits[:, 1:, :K].float().softmax(-1)
+    unknown = ids == mask_id
+    ml = torch.max(torch.tensor([1]), torch.min(unknown.sum(-1, keepdim=True) - 1, torch.tensor([[mask_len]])))
+    o_sampled, o_next = T.sample_step(probs, ids, mask_id, q, u, ml, temp)
+    # margin screen 1: categorical draw = argmax(p/q); skip tokens whose top-2 scores are within 1e-5 relative
+    sc = (probs / q).topk(2, dim=-1).values
+    safe = (sc[..., 0] - sc[..., 1]) > 1e-5 * sc[..., 0]
+    assert float(safe.float().mean()) > 0.999
+    assert torch.equal(sampled.cpu()[safe], o_sampled[safe])
+    assert torch.equal(sampled.cpu()[~unknown], ids[~unknown])  # known tokens are never overwritten
+    # margin screen 2: re-mask decision conf < cut; skip rows with a sampling mismatch or a near-tie at the cut
+    row_ok = (sampled.cpu() == o_sampled).all(-1)
+    c = conf.cpu()
+    cut = c.sort(-1).values.gather(1, ml)
+    near = ((c - cut).abs() < 1e-4).any(-1)
+    rows = row_ok & ~near
+    assert int(rows.sum()) >= max(1, int(0.9 * B))
+    assert torch.equal(nxt.cpu()[rows], o_next[rows])
+    # size-independent property: exactly k tokens are re-masked per row (no ties at the cut)
+    assert torch.equal((nxt.cpu()[rows] == mask_id).sum(-1), ml[rows, 0])
+
+
+def test_sample_step_cfg_matches_manual_mix():
+    B, L, K, ld = 2, 16, 64, 72
+    logits, ids, q, u = _step_inputs(B, L, K, ld, 5, 0.2)
+    unc = (logits.float() * 0.5 + 0.1).to(torch.bfloat16)
+    g = 3.0
+    mixed = (unc.float() + g * (logits.float() - unc.float()))
+    s1, n1 = ops.sample_step(logits.to(DEV), ids.to(DEV), q.to(DEV), u.to(DEV), K, K + 7, 5, 0.5,
+                             logits_unc=unc.to(DEV), guidance=g, skip_first_token=True)
+    probs = mixed[:, 1:, :K].softmax(-1)
+    ml = torch.full((B, 1), 5)
+    o_s, o_n = T.sample_step(probs, ids, K + 7, q, u, ml, 0.5)
+    assert float((s1.cpu() == o_s).float().mean()) > 0.97
+
+
+def test_generate2_full_size_properties():
+    """BASELINE config 5 shape (base model, B=64, 256 tokens, 12 steps): ids in range, deterministic per seed."""
+    from open_muse_b200.modeling_transformer import MaskGitTransformer
+
+    cfg = dict(vocab_size=2025, max_position_embeddings=257, hidden_size=512, num_hidden_layers=8,
+               num_attention_heads=8, intermediate_size=2048, codebook_size=1024, num_vq_tokens=256, num_classes=1000,
+               hidden_dropout=0.0, attention_dropout=0.0)
+    torch.manual_seed(0)
+    m = MaskGitTransformer(**cfg).to(DEV).eval()
+    outs = []
+    for _ in range(2):
+        cls = torch.randint(0, 1000, (64,), generator=torch.Generator().manual_seed(6)).to(DEV)
+        gen = torch.Generator(device=DEV).manual_seed(7)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ids = m.generate2(class_ids=cls, timesteps=12, generator=gen)
+        assert ids.shape == (64, 256) and int(ids.min()) >= 0 and int(ids.max()) < 1024
+        outs.append(ids)
+    assert torch.equal(outs[0], outs[1])
+
+
+# ----------------------------------------------------------------------------------------- VQGAN blocks
+def test_conv_gn_pool_blocks_vs_torch():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 64, 12, 10, generator=g)
+    for cout, k, up, bias in [(128, 3, False, False), (64, 1, False, True), (3, 3, False, True), (96, 3, True, True)]:
+        w = torch.randn(cout, 64, k, k, generator=g) * 0.05
+        b = torch.randn(cout, generator=g) if bias else None
+        xin = torch.nn.functional.interpolate(x, scale_factor=2.0, mode="nearest") if up else x
+        ref = G.conv_same(xin, w, b)
+        res = torch.randn(ref.shape, generator=g)
+        y = ops.conv2d(ops.to_nhwc(x.to(DEV)), w.to(DEV), bias=None if b is None else b.to(DEV),
+                       residual=ops.to_nhwc(res.to(DEV)), upsample2x=up)
+        torch.testing.assert_close(ops.to_nchw(y).cpu(), ref + res, rtol=1e-4, atol=1e-5)
+    x3 = torch.rand(2, 3, 16, 16, generator=g)
+    w3 = torch.randn(32, 3, 3, 3, generator=g) * 0.2
+    torch.testing.assert_close(ops.to_nchw(ops.conv2d(ops.to_nhwc(x3.to(DEV)), w3.to(DEV))).cpu(), G.conv_same(x3, w3),
+                               rtol=1e-4, atol=1e-5)
+    ga, be = torch.randn(64, generator=g), torch.randn(64, generator=g)
+    gn = ops.groupnorm_silu(ops.to_nhwc(x.to(DEV)), ga.to(DEV), be.to(DEV), 32, 1e-6)
+    torch.testing.assert_close(ops.to_nchw(gn).cpu(), G.gn_silu(x, ga, be), rtol=1e-4, atol=1e-5)
+    pooled = ops.avg_pool2x2(ops.to_nhwc(x.to(DEV)))
+    torch.testing.assert_close(ops.to_nchw(pooled).cpu(), torch.nn.functional.avg_pool2d(x, 2, 2), rtol=1e-6, atol=1e-6)
+
+
+def test_micro_vqgan_vs_reference(golden):
+    from open_muse_b200.modeling_maskgit_vqgan import MaskGitVQGAN
+
+    g = golden("micro_vqgan.pt")
+    m = MaskGitVQGAN(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.to(DEV).eval()
+    img = g["image"].to(DEV)
+    z_q, ids = m.encode(img)
+    ok = (g["margin"] > 1e-4).view(ids.shape)  # margin screen (fp32 re-association cannot flip these)
+    assert float(ok.float().mean()) > 0.95
+    assert torch.equal(ids.cpu()[ok], g["ids"][ok])
+    assert torch.equal(m.get_code(img).cpu(), ids.cpu())
+    rec = m.decode_code(g["ids"].to(DEV))
+    torch.testing.assert_close(rec.cpu(), g["recon"], rtol=1e-3, atol=1e-4)
+    zq_ref = m.quantize.get_codebook_entry(g["ids"].to(DEV))
+    assert torch.equal(zq_ref.cpu(), g["z_q"])
+    out = m(img)
+    assert out[0].shape == g["recon"].shape and len(out) == 3
+
+
+def test_vqgan_f16_256_roundtrip_properties():
+    """BASELINE config 3 architecture (f16, 256 px) on a small batch: decode_code(ids) depends only on ids,
+    encode is deterministic, ids match the oracle's search on the encoder output bit-for-bit."""
+    from open_muse_b200.modeling_maskgit_vqgan import MaskGitVQGAN
+
+    torch.manual_seed(5)
+    m = MaskGitVQGAN().to(DEV).eval()
+    img = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(5)).to(DEV)
+    z = ops.to_nchw(m.encoder.run(ops.to_nhwc(img)))
+    with torch.no_grad():
+        m.quantize.embedding.weight.copy_(torch.randn(1024, 256, device=DEV) * z.std())
+    z_q, ids = m.encode(img)
+    z_q2, ids2 = m.encode(img)
+    assert torch.equal(ids, ids2) and ids.shape == (2, 256) and z_q.shape == (2, 256, 16, 16)
+    ids_o, _ = VQ.argmin(VQ.nchw_to_rows(z.cpu().numpy()), m.quantize.embedding.weight.detach().cpu().numpy())
+    assert np.array_equal(ids.cpu().numpy().reshape(-1), ids_o)
+    rec = m.decode_code(ids)
+    assert rec.shape == (2, 3, 256, 256) and bool(torch.isfinite(rec).all())
+    assert torch.equal(rec, m.decode(z_q))
