@@ -117,8 +117,10 @@ int muse_sample_step(const void* logits, const void* logits_unc, long long row_s
  * residual [B,H,W,Cout] (ResnetBlock :82-85) -> y [B,H,W,Cout]. */
 int muse_conv2d_nhwc(const float* x, const float* wk, const float* bias, const float* res, float* y, int B, int H,
                      int W, int Cin, int Cout, int ksize, int upsample2x, void* stream);
-/* nn.GroupNorm(groups, C, eps) + F.silu (:61-79); scratch: moments_ws double [B*C*2], scale_shift_ws float [B*C*2]. */
-int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, double* moments_ws,
+/* nn.GroupNorm(groups, C, eps) + F.silu (:61-79), deterministic (no atomics). Scratch: partials_ws float
+ * [muse_groupnorm_workspace_floats(B,HW,C)] (-1 if the shape is unsupported), scale_shift_ws float [B*C*2]. */
+long long muse_groupnorm_workspace_floats(int B, int HW, int C);
+int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, float* partials_ws,
                              float* scale_shift_ws, int B, int HW, int C, int groups, float eps, void* stream);
 /* F.avg_pool2d(2,2) (:112): x [B,2Ho,2Wo,C] -> y [B,Ho,Wo,C]. */
 int muse_avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, void* stream);

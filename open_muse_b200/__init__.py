@@ -1,0 +1,11 @@
+"""open_muse_b200 -- the B200 (sm_100a) hot path of huggingface/open-muse behind the reference's Python surface.
+
+    from open_muse_b200 import MaskGitTransformer, MaskGitVQGAN
+
+See DESIGN.md (scope, kernels, parity) and INTEGRATION.md (how the reference binds it).
+"""
+__version__ = "0.1.0"
+
+from .modeling_maskgit_vqgan import MaskGitVQGAN  # noqa: F401
+from .modeling_transformer import MaskGitTransformer  # noqa: F401
+from .sampling import get_mask_chedule  # noqa: F401

@@ -39,6 +39,7 @@ SIGNATURES = {
     "muse_vq_lookup_nchw": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_sample_step": (c_int, [_P, _P, _L, _L, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _F, _P]),
     "muse_conv2d_nhwc": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "muse_groupnorm_workspace_floats": (c_longlong, [_I, _I, _I]),
     "muse_groupnorm_silu_nhwc": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "muse_avgpool2_nhwc": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "muse_transpose_batched": (c_int, [_P, _P, _I, _I, _I, _P]),

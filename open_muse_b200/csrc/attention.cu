@@ -212,30 +212,6 @@ attn_fwd_kernel(AttnPtrs P, bf16* __restrict__ O, long long o_bs, int o_rs, floa
   }
 }
 
-// ------------------------------------------------------------------ backward: D = rowsum(dO * O)
-__global__ void __launch_bounds__(256)
-attn_bwd_prep_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, long long o_bs, int o_rs, long long do_bs,
-                     int do_rs, float* __restrict__ Dout, int B, int Sq, int nh) {
-  const long long idx = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) >> 3;  // (b, h, s)
-  const int sub = threadIdx.x & 7;
-  const long long total = static_cast<long long>(B) * nh * Sq;
-  float acc = 0.f;
-  if (idx < total) {
-    const int s = static_cast<int>(idx % Sq);
-    const int h = static_cast<int>((idx / Sq) % nh);
-    const int b = static_cast<int>(idx / (static_cast<long long>(Sq) * nh));
-    float a[8], d[8];
-    load8(O + b * o_bs + static_cast<long long>(s) * o_rs + h * D + sub * 8, a);
-    load8(dO + b * do_bs + static_cast<long long>(s) * do_rs + h * D + sub * 8, d);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc += a[j] * d[j];
-  }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (idx < total && sub == 0) Dout[idx] = acc;
-}
-
 // ------------------------------------------------------------------ backward: dK, dV (CTA owns 64 kv rows)
 __global__ void __launch_bounds__(128)
 attn_bwd_dkdv_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, int do_rs, const float* __restrict__ LSE,
@@ -341,7 +317,7 @@ attn_bwd_dkdv_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, i
 // ------------------------------------------------------------------ backward: dQ (CTA owns 64 q rows)
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, int do_rs, const float* __restrict__ LSE,
-                   const float* __restrict__ Dv, bf16* __restrict__ dQ, long long dq_bs, int dq_rs, int Sq, int Skv,
+                   float* __restrict__ Dv, bf16* __restrict__ dQ, long long dq_bs, int dq_rs, int Sq, int Skv,
                    int nh, float scale) {
   __shared__ __align__(16) bf16 sA[BKV * LDS];  // Q_i then K_j
   __shared__ __align__(16) bf16 sB[BKV * LDS];  // dO_i then V_j
@@ -353,7 +329,7 @@ attn_bwd_dq_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, int
   const bf16* vg = P.v + b * P.v_bs + h * D;
   const bf16* dog = dO + b * do_bs + h * D;
   const float* lse = LSE + (static_cast<long long>(b) * nh + h) * Sq;
-  const float* dv_ = Dv + (static_cast<long long>(b) * nh + h) * Sq;
+  float* dv_ = Dv + (static_cast<long long>(b) * nh + h) * Sq;
 
   load_tile(sA, qg, q0, Sq, P.q_rs);
   load_tile(sB, dog, q0, Sq, do_rs);
@@ -362,12 +338,45 @@ attn_bwd_dq_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, int
   load_a_frags(qf, sA, warp * 16, lane);
   load_a_frags(dof, sB, warp * 16, lane);
   const int r0 = q0 + warp * 16 + g;
-  float l2[2], dd[2];
+  float l2[2], dd[2] = {0.f, 0.f};
   l2[0] = (r0 < Sq) ? lse[r0] * kLog2e : 0.f;
   l2[1] = (r0 + 8 < Sq) ? lse[r0 + 8] * kLog2e : 0.f;
-  dd[0] = (r0 < Sq) ? dv_[r0] : 0.f;
-  dd[1] = (r0 + 8 < Sq) ? dv_[r0 + 8] : 0.f;
   const float sl2 = scale * kLog2e;
+  // pass 1: D_i = sum_j P_ij * dP_ij from the SAME fp32 P and dP that pass 2 uses, so sum_j dS_ij == 0 up to fp32
+  // rounding (softmax backward as the reference's fp32 autograd computes it).  rowsum(dO * O) with the bf16-rounded O
+  // leaves a systematic P_ij * eps_i term that swamps the (tiny) true dQ/dK when attention is near-uniform.
+  for (int kv0 = 0; kv0 < Skv; kv0 += BKV) {
+    __syncthreads();
+    load_tile(sA, kg, kv0, Skv, P.k_rs);
+    load_tile(sB, vg, kv0, Skv, P.v_rs);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; dp[i][j] = 0.f; }
+    gemm_a_tT(s, qf, sA, lane);
+    gemm_a_tT(dp, dof, sB, lane);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = kv0 + nb * 8 + 2 * t + (j & 1);
+        const int rr = r0 + (j >> 1) * 8;
+        const bool ok = (col < Skv) && (rr < Sq);
+        const float p = ok ? exp2f(s[nb][j] * sl2 - l2[j >> 1]) : 0.f;
+        dd[j >> 1] += p * dp[nb][j];
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    dd[r] += __shfl_xor_sync(0xffffffffu, dd[r], 1);
+    dd[r] += __shfl_xor_sync(0xffffffffu, dd[r], 2);
+  }
+  if (t == 0) {
+    if (r0 < Sq) dv_[r0] = dd[0];
+    if (r0 + 8 < Sq) dv_[r0 + 8] = dd[1];
+  }
   float dq[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -449,22 +458,17 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   P.q = reinterpret_cast<const bf16*>(q); P.k = reinterpret_cast<const bf16*>(k); P.v = reinterpret_cast<const bf16*>(v);
   P.q_rs = q_rs; P.k_rs = k_rs; P.v_rs = v_rs;
   P.q_bs = static_cast<long long>(Sq) * q_rs; P.k_bs = static_cast<long long>(Skv) * k_rs; P.v_bs = static_cast<long long>(Skv) * v_rs;
-  const long long total = static_cast<long long>(B) * nh * Sq;
-  attn_bwd_prep_kernel<<<static_cast<unsigned>(ceil_div_ll(total * 8, 256)), 256, 0, s>>>(
-      reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * o_rs, o_rs,
-      static_cast<long long>(Sq) * do_rs, do_rs, dvec, B, Sq, nh);
-  rc = check_launch("attn_bwd_prep");
+  (void)o; (void)o_rs;  // D is recomputed from (P, dP) inside the dQ kernel; O is not needed by backward
+  attn_bwd_dq_kernel<<<dim3(ceil_div(Sq, BQ), nh, B), 128, 0, s>>>(
+      P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
+      reinterpret_cast<bf16*>(dq), static_cast<long long>(Sq) * dq_rs, dq_rs, Sq, Skv, nh, scale);
+  rc = check_launch("attn_bwd_dq");
   if (rc) return rc;
   attn_bwd_dkdv_kernel<<<dim3(ceil_div(Skv, BKV), nh, B), 128, 0, s>>>(
       P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
       reinterpret_cast<bf16*>(dk), static_cast<long long>(Skv) * dk_rs, dk_rs, reinterpret_cast<bf16*>(dv),
       static_cast<long long>(Skv) * dv_rs, dv_rs, Sq, Skv, nh, scale);
-  rc = check_launch("attn_bwd_dkdv");
-  if (rc) return rc;
-  attn_bwd_dq_kernel<<<dim3(ceil_div(Sq, BQ), nh, B), 128, 0, s>>>(
-      P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
-      reinterpret_cast<bf16*>(dq), static_cast<long long>(Sq) * dq_rs, dq_rs, Sq, Skv, nh, scale);
-  return check_launch("attn_bwd_dq");
+  return check_launch("attn_bwd_dkdv");
 }
 
 }  // namespace muse

@@ -44,7 +44,8 @@ int vq_argmin(const float*, const float*, float*, long long*, float*, int, int, 
 int vq_lookup_nchw(const long long*, const float*, float*, int, int, int, int, cudaStream_t);
 int sample_step(const void*, const void*, long long, long long, float, const long long*, const float*, const float*, long long*, long long*, float*, int, int, int, long long, int, float, cudaStream_t);
 int conv2d_nhwc(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
-int groupnorm_silu_nhwc(const float*, const float*, const float*, float*, double*, float*, int, int, int, int, float, cudaStream_t);
+int groupnorm_silu_nhwc(const float*, const float*, const float*, float*, float*, float*, int, int, int, int, float, cudaStream_t);
+long long gn_workspace_floats(int, int, int);
 int avgpool2_nhwc(const float*, float*, int, int, int, int, cudaStream_t);
 int transpose_batched(const float*, float*, int, int, int, cudaStream_t);
 
@@ -148,9 +149,10 @@ int muse_conv2d_nhwc(const float* x, const float* wk, const float* bias, const f
                      int W, int Cin, int Cout, int ksize, int upsample2x, void* stream) {
   return conv2d_nhwc(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x, ST(stream));
 }
-int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, double* moments_ws,
+long long muse_groupnorm_workspace_floats(int B, int HW, int C) { return gn_workspace_floats(B, HW, C); }
+int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, float* partials_ws,
                              float* scale_shift_ws, int B, int HW, int C, int groups, float eps, void* stream) {
-  return groupnorm_silu_nhwc(x, gamma, beta, y, moments_ws, scale_shift_ws, B, HW, C, groups, eps, ST(stream));
+  return groupnorm_silu_nhwc(x, gamma, beta, y, partials_ws, scale_shift_ws, B, HW, C, groups, eps, ST(stream));
 }
 int muse_avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, void* stream) {
   return avgpool2_nhwc(x, y, B, Ho, Wo, C, ST(stream));

@@ -3,7 +3,8 @@
 //       M = B*H*W output pixels, N = C_out, K = k*k*C_in  (weights pre-packed to [K, C_out])
 //     with fused bias, fused residual add (ResnetBlock :82-85) and the nearest x2 upsample of
 //     UpsamplingBlock (:146) folded into the input gather (index >> 1) so the 4x larger tensor is never written.
-//   * GroupNorm(32, eps=1e-6) + SiLU (:61-79): one statistics pass (fp64 atomics for the 2 moments) + one apply pass.
+//   * GroupNorm(32, eps=1e-6) + SiLU (:61-79): deterministic statistics pass (per-block partials, fp64 final sum)
+//     + one apply pass.
 //   * avg_pool2d(2,2) (:112), NCHW <-> NHWC layout changes at the model boundary.
 // fp32 SIMT on purpose: token ids must agree with the fp32 reference; each output is one ascending-K
 // fma chain (taps row-major, then input channel), so results do not depend on tiling.
@@ -133,44 +134,52 @@ conv2d_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ wk, co
 // pass 2: fold channels into groups -> per-(image, channel) scale = rstd*gamma, shift = beta - mean*scale
 // pass 3: y = silu(x * scale + shift)
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const float* __restrict__ x, double* __restrict__ moments, int HW, int C, int rows_per_block) {
-  extern __shared__ float s_part[];  // [C][2]
+gn_stats_kernel(const float* __restrict__ x, float* __restrict__ partials, int HW, int C, int rows_per_block) {
+  // deterministic: fixed thread->data mapping, fixed-order in-block reduction, per-block partials (no atomics)
+  extern __shared__ float s_part[];  // [rstep][C][2]
   const int b = blockIdx.y;
   const int c4 = C / 4;
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) s_part[i] = 0.f;
-  __syncthreads();
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(HW, r0 + rows_per_block);
   const float* base = x + static_cast<long long>(b) * HW * C;
   const int q = threadIdx.x % c4;          // fixed channel quad per thread (256 % c4 == 0)
+  const int lane_r = threadIdx.x / c4;
   const int rstep = blockDim.x / c4;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int r = r0 + threadIdx.x / c4; r < r1; r += rstep) {
+  for (int r = r0 + lane_r; r < r1; r += rstep) {
     const float4 v = *reinterpret_cast<const float4*>(base + static_cast<long long>(r) * C + q * 4);
     s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
     ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    atomicAdd(&s_part[(q * 4 + j) * 2], s[j]);
-    atomicAdd(&s_part[(q * 4 + j) * 2 + 1], ss[j]);
+    s_part[(lane_r * C + q * 4 + j) * 2] = s[j];
+    s_part[(lane_r * C + q * 4 + j) * 2 + 1] = ss[j];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x)
-    atomicAdd(&moments[static_cast<long long>(b) * C * 2 + i], static_cast<double>(s_part[i]));
+  float* out = partials + (static_cast<long long>(blockIdx.x) * gridDim.y + b) * C * 2;
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < rstep; ++k) acc += s_part[k * C * 2 + i];
+    out[i] = acc;
+  }
 }
 
-__global__ void gn_finalize_kernel(const double* __restrict__ moments, const float* __restrict__ gamma,
+__global__ void gn_finalize_kernel(const float* __restrict__ partials, int nblocks, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ scale_shift, int HW, int C,
                                    int groups, float eps) {
   const int b = blockIdx.x;
+  const int B = gridDim.x;
   const int cpg = C / groups;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     double sum = 0.0, sq = 0.0;
-    for (int k = 0; k < cpg; ++k) {
-      sum += moments[(static_cast<long long>(b) * C + g * cpg + k) * 2];
-      sq += moments[(static_cast<long long>(b) * C + g * cpg + k) * 2 + 1];
+    for (int blk = 0; blk < nblocks; ++blk) {
+      const float* p = partials + (static_cast<long long>(blk) * B + b) * C * 2;
+      for (int k = 0; k < cpg; ++k) {
+        sum += static_cast<double>(p[(g * cpg + k) * 2]);
+        sq += static_cast<double>(p[(g * cpg + k) * 2 + 1]);
+      }
     }
     const double n = static_cast<double>(HW) * cpg;
     const double mean = sum / n;
@@ -263,20 +272,28 @@ int conv2d_nhwc(const float* x, const float* wk, const float* bias, const float*
   return check_launch("conv2d_nhwc");
 }
 
-int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, double* moments_ws,
+// workspace: partials float [nblocks*B*C*2] with nblocks = ceil(HW / rows_per_block) (see gn_workspace_floats)
+static int gn_rows_per_block(int C) { return (256 / (C / 4)) * 64; }
+
+long long gn_workspace_floats(int B, int HW, int C) {
+  if (C % 4 != 0 || C > 1024 || 256 % (C / 4) != 0) return -1;
+  return static_cast<long long>(ceil_div(HW, gn_rows_per_block(C))) * B * C * 2;
+}
+
+int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, float* partials_ws,
                         float* scale_shift_ws, int B, int HW, int C, int groups, float eps, cudaStream_t s) {
   if (C % groups != 0 || C % 4 != 0 || C > 1024 || 256 % (C / 4) != 0) {
     set_last_error("groupnorm: C=%d groups=%d unsupported (C must divide into groups, C/4 must divide 256)", C, groups);
     return MUSE_ERR_UNSUPPORTED;
   }
   if (B <= 0 || HW <= 0) return MUSE_OK;
-  cudaError_t e = cudaMemsetAsync(moments_ws, 0, sizeof(double) * 2 * B * C, s);
-  if (e != cudaSuccess) { set_last_error("groupnorm memset: %s", cudaGetErrorString(e)); return MUSE_ERR_CUDA; }
-  const int rows_per_block = (256 / (C / 4)) * 16;
-  gn_stats_kernel<<<dim3(ceil_div(HW, rows_per_block), B), 256, C * 2 * sizeof(float), s>>>(x, moments_ws, HW, C, rows_per_block);
+  const int rows_per_block = gn_rows_per_block(C);
+  const int nblocks = ceil_div(HW, rows_per_block);
+  const int rstep = 256 / (C / 4);
+  gn_stats_kernel<<<dim3(nblocks, B), 256, rstep * C * 2 * sizeof(float), s>>>(x, partials_ws, HW, C, rows_per_block);
   int rc = check_launch("gn_stats");
   if (rc) return rc;
-  gn_finalize_kernel<<<B, 256, 0, s>>>(moments_ws, gamma, beta, scale_shift_ws, HW, C, groups, eps);
+  gn_finalize_kernel<<<B, 256, 0, s>>>(partials_ws, nblocks, gamma, beta, scale_shift_ws, HW, C, groups, eps);
   rc = check_launch("gn_finalize");
   if (rc) return rc;
   const long long total4 = static_cast<long long>(B) * HW * (C / 4);

@@ -49,7 +49,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-_KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 3, "muse_embed_bwd": 2, "muse_vq_argmin": 2,
+_KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_vq_argmin": 2,
                      "muse_groupnorm_silu_nhwc": 3}
 _prof = {"on": False, "events": []}
 
@@ -293,7 +293,10 @@ def groupnorm_silu(x, gamma, beta, groups, eps):
     st = _prep(x)
     B, H, W, C = x.shape
     y = torch.empty_like(x)
-    ws = torch.empty(B * C * 2, dtype=torch.float64, device=x.device)
+    n_ws = _lib.load().muse_groupnorm_workspace_floats(B, H * W, C)
+    if n_ws < 0:
+        raise _lib.MuseB200Error(f"groupnorm: unsupported channel count {C}")
+    ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
     ss = torch.empty(B * C * 2, dtype=torch.float32, device=x.device)
     _call("muse_groupnorm_silu_nhwc", _p(x), _p(gamma.detach().float()), _p(beta.detach().float()), _p(y), _p(ws),
           _p(ss), B, H * W, C, groups, float(eps), st)

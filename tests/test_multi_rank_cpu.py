@@ -1,0 +1,80 @@
+"""CPU, world_size 2 (gloo): the N>1 recipe of the hot path.  The path shards by batch with ONE exchange per step --
+the DDP gradient all-reduce (mean).  The reference's loss is a per-rank mean over that rank's masked tokens and DDP
+averages the per-rank gradients equally; bench.py uses torch DDP the same way.  These tests pin that
+recipe with the oracle as the per-rank model, and the launch contract of `bench.py --impl reference` under torchrun."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = dict(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_attention_heads=1, intermediate_size=128,
+           max_position_embeddings=17, codebook_size=64, num_vq_tokens=16, num_classes=7, layer_norm_eps=1e-6)
+
+
+class OracleModule(torch.nn.Module):
+    def __init__(self, state_dict):
+        super().__init__()
+        self.names = list(state_dict)
+        self.params = torch.nn.ParameterList([torch.nn.Parameter(v.clone()) for v in state_dict.values()])
+
+    def forward(self, input_ids, labels):
+        from oracle import transformer_oracle as T
+
+        return T.forward(dict(zip(self.names, self.params)), CFG, input_ids, labels=labels)[1]
+
+
+def _worker(rank, world, port, sd, batches, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    model = torch.nn.parallel.DistributedDataParallel(OracleModule(sd))
+    inp, lab = batches[rank]
+    loss = model(inp, lab)
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in zip(model.module.names, model.module.params)}
+    if rank == 0:
+        torch.save(dict(grads=grads, loss=loss.detach()), out)
+    dist.destroy_process_group()
+
+
+def test_ddp_mean_of_per_rank_means(tmp_path, golden):
+    from oracle import transformer_oracle as T
+
+    g = golden("micro_transformer.pt")
+    sd = g["state_dict"]
+    gen = torch.Generator().manual_seed(0)
+    batches = []
+    for r in range(2):
+        tokens = torch.randint(0, 64, (2 + r, 16), generator=gen)
+        cls = torch.randint(0, 7, (2 + r,), generator=gen)
+        batches.append(T.mask_tokens(tokens, cls, torch.rand(2 + r, generator=gen), torch.rand(2 + r, 16, generator=gen), 64, 71))
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, 29500 + os.getpid() % 2000, sd, batches, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    per_rank = [T.forward_backward(sd, CFG, b[0], b[1])[2] for b in batches]
+    for k in sd:
+        expect = 0.5 * (per_rank[0][k] + per_rank[1][k])  # equal-weight mean of per-rank (mean-loss) gradients
+        torch.testing.assert_close(got["grads"][k], expect, rtol=1e-5, atol=1e-7)
+    # and this is NOT the gradient of the global masked-token mean when ranks hold different numbers of masked tokens
+    n0, n1 = [(b[1] != -100).sum().item() for b in batches]
+    assert n0 != n1
+
+
+def test_reference_arm_prints_only_on_rank0():
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(29700 + os.getpid() % 200), os.path.join(ROOT, "bench.py"), "--impl",
+           "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "images/s"

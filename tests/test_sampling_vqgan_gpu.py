@@ -49,7 +49,7 @@ def test_sample_step_vs_oracle(B, L, K, ld, known_frac, mask_len, temp):
     row_ok = (sampled.cpu() == o_sampled).all(-1)
     c = conf.cpu()
     cut = c.sort(-1).values.gather(1, ml)
-    near = ((c - cut).abs() < 1e-4).any(-1)
+    near = ((c - cut).abs() < 1e-4).sum(-1) > 1  # another confidence within 1e-4 of the cut value itself
     rows = row_ok & ~near
     assert int(rows.sum()) >= max(1, int(0.9 * B))
     assert torch.equal(nxt.cpu()[rows], o_next[rows])
