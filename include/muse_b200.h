@@ -59,11 +59,14 @@ int muse_embed_bwd(const long long* ids, const float* dx, float* dword, float* d
                    void* stream);
 
 /* LayerNorm (weight only, :124-137) / RMSNorm (:79-100) over the last dim of [rows,H].
- *   y = (res ? res : 0) + norm(act ? gelu(x) : x) * w ; mean/rstd [rows] are saved for backward.
- *   act = 1 fuses the exact-erf GELU of MlmLayer (:980-983); rms = 1 selects RMSNorm. */
+ *   y = (res ? res : 0) + norm(v) * w ; mean/rstd [rows] are saved for backward.  v = x (act 0), gelu(x) (act 1: the
+ *   exact-erf GELU of MlmLayer :980-983) or, with act 2, x is [rows, 2H] = [a | b] and v = bf16(gelu(a)) * b: the
+ *   FeedForward GLU product (:789-792) feeding mid_mlp_layer_norm (:795-796) without materialising it.
+ *   rms = 1 selects RMSNorm. */
 int muse_norm_fwd(const void* x, int x_dtype, const float* w, const float* res, void* y, int y_dtype, float* mean,
                   float* rstd, int rows, int H, float eps, int act, int rms, void* stream);
-/* dx = norm_bwd(dy) (* gelu'(x) if act) (+ dres if given); dw[H] += sum_rows dy * xhat (atomic). */
+/* dx = norm_bwd(dy) (* gelu'(x) if act 1) (+ dres if given); dw[H] += sum_rows dy * xhat (atomic).
+ * act 2: dx is [rows, 2H] = d[a | b] (LayerNorm backward and GLU backward in one pass; v is recomputed from x). */
 int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
                   const float* rstd, const float* dres, void* dx, int dx_dtype, float* dw, int rows, int H, int act,
                   int rms, void* stream);

@@ -287,14 +287,13 @@ class _LayerFn(torch.autograd.Function):
         # ---- GLU feed-forward (:785-799)
         h2, st3 = ops.norm_fwd(x2, _f32(w_pre), s.eps, torch.bfloat16, rms=0, save_stats=grad)
         ab = ops.linear_fwd(h2, s.w["wi"])
-        gl = ops.glu_fwd(ab)
-        if s.normformer:
-            ml, st4 = ops.norm_fwd(gl, _f32(w_mid), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
+        if s.normformer:  # GLU product + mid_mlp_layer_norm in one pass; gelu(a)*b is never written to HBM
+            ml, st4 = ops.norm_fwd(ab, _f32(w_mid), s.eps, torch.bfloat16, act=2, rms=s.rms, save_stats=grad)
         else:
-            ml, st4 = gl, None
+            ml, st4 = ops.glu_fwd(ab), None
         x3 = ops.linear_fwd(ml, s.w["wo"], res=x2)
         if grad:
-            sv.update(h2=h2, st3=st3, ab=ab, gl=gl, ml=ml, st4=st4)
+            sv.update(h2=h2, st3=st3, ab=ab, ml=ml, st4=st4)
             ctx.sv, ctx.spec, ctx.params = sv, s, params
         return x3
 
@@ -319,12 +318,12 @@ class _LayerFn(torch.autograd.Function):
         dy = ops.cast_bf16(dx3)
         ops.linear_wgrad(dy, sv["ml"], g_wo)
         d_ml = ops.linear_dgrad(dy, s.w["wo"])
-        if s.normformer:
+        if s.normformer:  # LN backward + GLU backward fused: reads d_ml and [a|b], writes d[a|b]
             g_mid = z(I)
-            d_gl = ops.norm_bwd(d_ml, sv["gl"], _f32(w_mid), sv["st4"], torch.bfloat16, dw=g_mid, rms=s.rms)
+            d_ab = ops.norm_bwd(d_ml, sv["ab"], _f32(w_mid), sv["st4"], torch.bfloat16, dw=g_mid, act=2, rms=s.rms)
         else:
-            g_mid, d_gl = None, d_ml
-        d_ab = ops.glu_bwd(sv["ab"], d_gl)
+            g_mid = None
+            d_ab = ops.glu_bwd(sv["ab"], d_ml)
         g_wi = z(2 * I, H)
         ops.linear_wgrad(d_ab, sv["h2"], g_wi)
         d_h2 = ops.linear_dgrad(d_ab, s.w["wi"])
@@ -416,6 +415,7 @@ class _HeadFn(torch.autograd.Function):
         logits = torch.empty(s.T, s.Vpad, dtype=torch.bfloat16, device=x.device)
         ops.gemm(e, s.w["logits"], logits, s.T, s.Vpad, s.H, s.H, s.H, s.Vpad)
         loss = None
+        ctx.set_materialize_grads(False)  # an unused logits output must not cost a zero-filled [T,V] gradient
         if labels is not None:
             loss_out, ws = ops.ce_fwd(logits, labels, s.V, s.ls)
             loss = loss_out[0]

@@ -144,8 +144,10 @@ def embed_bwd(ids, dx, dword, dpos):
 
 # ------------------------------------------------------------------------------------------ norms
 def norm_fwd(x, w, eps, out_dtype, res=None, act=0, rms=0, save_stats=True):
+    """act: 0 none, 1 GELU(x) first, 2 GLU (x is [rows, 2H] = [a | b], the normalised value is gelu(a) * b)."""
     st = _prep(x)
-    rows, H = x.shape
+    rows = x.shape[0]
+    H = x.shape[1] // 2 if act == 2 else x.shape[1]
     y = torch.empty(rows, H, dtype=out_dtype, device=x.device)
     if save_stats:
         stats = torch.empty(2, rows, dtype=torch.float32, device=x.device)
@@ -159,8 +161,9 @@ def norm_fwd(x, w, eps, out_dtype, res=None, act=0, rms=0, save_stats=True):
 
 def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0):
     st = _prep(x)
-    rows, H = x.shape
-    dx = torch.empty(rows, H, dtype=dx_dtype, device=x.device)
+    rows = x.shape[0]
+    H = x.shape[1] // 2 if act == 2 else x.shape[1]
+    dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
     _call("muse_norm_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(w), _p(stats[0]), _p(stats[1]), _p(dres), _p(dx),
           _dt(dx), _p(dw), rows, H, act, rms, st)
     return dx
@@ -266,14 +269,19 @@ _wk_cache = {}
 
 
 def _packed_conv_weight(w):
-    """[Cout, Cin, kh, kw] -> [kh*kw*Cin, Cout] (tap-major, then input channel); cached per weight version."""
-    key = (w.data_ptr(), w._version, w.device)
+    """[Cout, Cin, kh, kw] -> [kh*kw*Cin, Cout] (tap-major, then input channel); cached per live weight tensor
+    (weakref identity + storage pointer + version counter, so a recycled id() or an in-place update never hits)."""
+    import weakref
+
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
     hit = _wk_cache.get(id(w))
-    if hit is None or hit[0] != key:
-        wk = w.detach().float().permute(2, 3, 1, 0).reshape(-1, w.shape[0]).contiguous()
-        _wk_cache[id(w)] = (key, wk)
-        return wk
-    return hit[1]
+    if hit is not None and hit[0]() is w and hit[1] == key:
+        return hit[2]
+    wk = w.detach().float().permute(2, 3, 1, 0).reshape(-1, w.shape[0]).contiguous()
+    if len(_wk_cache) > 4096:
+        _wk_cache.clear()
+    _wk_cache[id(w)] = (weakref.ref(w), key, wk)
+    return wk
 
 
 def conv2d(x, w, bias=None, residual=None, upsample2x=False):

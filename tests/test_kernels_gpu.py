@@ -216,3 +216,25 @@ def test_vq_golden_ids(golden):
     assert torch.equal(ids.cpu().view(2, -1), g["ids"])
     entry = ops.vq_lookup_nchw(g["ids"].to(DEV), g["codebook"].to(DEV))
     assert torch.equal(entry.cpu().view_as(g["entry"]), g["entry"])
+
+
+@pytest.mark.parametrize("I,rms", [(2048, 0), (128, 0), (512, 1), (4096, 0)])
+def test_norm_glu_fused_fwd_bwd(I, rms):
+    """act=2: LN(gelu(a) * b) straight from the [a | b] GEMM output; backward emits d[a | b]."""
+    rows, eps = 67, 1e-6
+    ab = _rand((rows, 2 * I), 1)
+    w = (1 + 0.1 * torch.randn(I, generator=torch.Generator().manual_seed(2))).to(DEV)
+    y, stats = ops.norm_fwd(ab, w, eps, torch.bfloat16, act=2, rms=rms)
+    a = ab[:, :I].float().clone().requires_grad_(True)
+    b = ab[:, I:].float().clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    v = torch.nn.functional.gelu(a) * b
+    n = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps) * wr if rms else torch.nn.functional.layer_norm(v, (I,), wr, None, eps)
+    assert y.shape == (rows, I) and _rel(y, n) < 8e-3
+    dy = _rand((rows, I), 3)
+    dw = torch.zeros(I, device=DEV)
+    dab = ops.norm_bwd(dy, ab, w, stats, torch.bfloat16, dw=dw, act=2, rms=rms)
+    n.backward(dy.float())
+    assert dab.shape == ab.shape
+    assert _rel(dab[:, :I], a.grad) < 1.2e-2 and _rel(dab[:, I:], b.grad) < 1.2e-2
+    assert _rel(dw, wr.grad) < 1e-2
