@@ -45,14 +45,32 @@ __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
 
-// Exact (erf) GELU, as F.gelu default (reference: muse/modeling_transformer.py:789,981).
+// Exact (erf-based) GELU, as F.gelu default (reference: muse/modeling_transformer.py:789,981), value and
+// derivative from ONE exponential: erf through Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32 ulp level for
+// the CDF), whose exp(-z^2) with z = x/sqrt(2) is also the Gaussian pdf factor exp(-x^2/2) of the derivative.
+// The elementwise GLU / GELU passes are otherwise limited by libdevice erff (~3 calls per element in backward).
+__device__ __forceinline__ void gelu_eval(float x, float& val, float& grad) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-z * z);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  val = x * cdf;
+  grad = fmaf(x * 0.39894228040143267794f, e, cdf);
+}
 __device__ __forceinline__ float gelu_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float v, g;
+  gelu_eval(x, v, g);
+  return v;
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float v, g;
+  gelu_eval(x, v, g);
+  return g;
 }
 
 // 8 consecutive elements starting at p (16B for bf16, 32B for fp32) -> 8 floats.

@@ -122,8 +122,10 @@ glu_bwd_kernel(const bf16* __restrict__ ab, const bf16* __restrict__ dout, bf16*
   load8(dout + r * I + c, d);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    da[j] = d[j] * b[j] * gelu_grad_f(a[j]);
-    db[j] = d[j] * bf16_round(gelu_f(a[j]));
+    float gv, gg;
+    gelu_eval(a[j], gv, gg);
+    da[j] = d[j] * b[j] * gg;
+    db[j] = d[j] * bf16_round(gv);
   }
   store8(dab + r * 2 * I + c, da);
   store8(dab + r * 2 * I + I + c, db);

@@ -17,6 +17,166 @@ namespace {
 
 constexpr int ACT_NONE = 0, ACT_GELU = 1, ACT_GLU = 2;
 
+// ---- warp-per-row kernels (H <= 1024, no GLU): the whole row lives in registers, no block barriers
+constexpr int kWarpsPerBlock = 4;
+
+template <typename TX, typename TY, int CH>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+norm_fwd_warp_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ res,
+                TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
+                float eps, int act, int rms) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TX* xr = x + static_cast<size_t>(row) * H;
+  float v[CH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < H) {
+      load8(xr + col, v[c]);
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[c][j] = gelu_f(v[c][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[c][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
+    }
+  }
+  const float inv_h = 1.0f / static_cast<float>(H);
+  float mean = rms ? 0.f : warp_sum(sum) * inv_h;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < H) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[c][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float var = warp_sum(sq) * inv_h;
+  const float rstd = rsqrtf(var + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  TY* yr = y + static_cast<size_t>(row) * H;
+  const float* rr = res ? res + static_cast<size_t>(row) * H : nullptr;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < H) {
+      float o[8], wv[8];
+      if (w) load8(w + col, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * (w ? wv[j] : 1.f);
+      if (rr) {
+        float r8[8];
+        load8(rr + col, r8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r8[j];
+      }
+      store8(yr + col, o);
+    }
+  }
+}
+
+template <typename TDY, typename TX, typename TDX, int CH>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ w,
+                const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw, int rows, int H,
+                int act, int rms) {
+  extern __shared__ float s_dw[];  // [H]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  if (dw) {
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s_dw[i] = 0.f;
+    __syncthreads();
+  }
+  float dw_acc[CH][8];
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dw_acc[c][j] = 0.f;
+  const float inv_h = 1.0f / static_cast<float>(H);
+
+  for (int row = blockIdx.x * kWarpsPerBlock + warp; row < rows; row += gridDim.x * kWarpsPerBlock) {
+    const TX* xr = x + static_cast<size_t>(row) * H;
+    const TDY* dyr = dy + static_cast<size_t>(row) * H;
+    const float mean = rms ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    float xh[CH][8], g[CH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < H) {
+        float xv[8], dv[8], wv[8];
+        load8(xr + col, xv);
+        load8(dyr + col, dv);
+        if (w) load8(w + col, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = act ? gelu_f(xv[j]) : xv[j];
+          xh[c][j] = (a - mean) * rstd;
+          dw_acc[c][j] += dv[j] * xh[c][j];
+          g[c][j] = dv[j] * (w ? wv[j] : 1.f);
+          s1 += g[c][j];
+          s2 += g[c][j] * xh[c][j];
+        }
+      }
+    }
+    s1 = rms ? 0.f : warp_sum(s1) * inv_h;
+    s2 = warp_sum(s2) * inv_h;
+    TDX* dxr = dx + static_cast<size_t>(row) * H;
+    const float* drr = dres ? dres + static_cast<size_t>(row) * H : nullptr;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < H) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] - s1 - xh[c][j] * s2);
+        if (act) {
+          float xv[8];
+          load8(xr + col, xv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] *= gelu_grad_f(xv[j]);
+        }
+        if (drr) {
+          float r8[8];
+          load8(drr + col, r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r8[j];
+        }
+        store8(dxr + col, o);
+      }
+    }
+  }
+  if (dw) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < H) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&s_dw[col + j], dw_acc[c][j]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(&dw[i], s_dw[i]);
+  }
+}
+
+
+// ---- CTA-per-row(-group) kernels (H > 1024 or GLU mode)
 struct RowMap {
   int tpr;        // threads per row (power of two, >= 8)
   int rpb;        // rows per block
@@ -58,26 +218,37 @@ __device__ __forceinline__ void row_sum(float (&v)[NV], int tpr, float* s_red, i
   }
 }
 
+// v = value to normalise; gv8 = bf16(gelu(a)) and ga8 = gelu'(a) (GLU / GELU modes), b8 = the linear GLU half
 template <typename TX>
-__device__ __forceinline__ void load_value(const TX* xr, int col, int H, int act, float (&v)[8], float (&a8)[8],
-                                           float (&b8)[8]) {
+__device__ __forceinline__ void load_value(const TX* xr, int col, int H, int act, float (&v)[8], float (&gv8)[8],
+                                           float (&ga8)[8], float (&b8)[8]) {
   if (act == ACT_GLU) {
+    float a8[8];
     load8(xr + col, a8);
     load8(xr + H + col, b8);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = bf16_round(bf16_round(gelu_f(a8[j])) * b8[j]);
+    for (int j = 0; j < 8; ++j) {
+      float gv;
+      gelu_eval(a8[j], gv, ga8[j]);
+      gv8[j] = bf16_round(gv);
+      v[j] = bf16_round(gv8[j] * b8[j]);
+    }
   } else {
     load8(xr + col, v);
     if (act == ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a8[j] = v[j]; v[j] = gelu_f(v[j]); }
+      for (int j = 0; j < 8; ++j) {
+        float gv;
+        gelu_eval(v[j], gv, ga8[j]);
+        v[j] = gv;
+      }
     }
   }
 }
 
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(512)
-norm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ res,
+norm_fwd_block_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ res,
                 TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
                 float eps, int act, int rms, int tpr) {
   __shared__ float s_red[16 * 16 * 2];
@@ -87,10 +258,10 @@ norm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const flo
   const int col = tir * 8;
   const bool active = (row < rows) && (col < H);
   const int xs = (act == ACT_GLU) ? 2 * H : H;
-  float v[8], a8[8], b8[8];
+  float v[8], gv8[8], ga8[8], b8[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  if (active) load_value(x + static_cast<size_t>(row) * xs, col, H, act, v, a8, b8);
+  if (active) load_value(x + static_cast<size_t>(row) * xs, col, H, act, v, gv8, ga8, b8);
   const float inv_h = 1.0f / static_cast<float>(H);
   float s[1] = {0.f};
 #pragma unroll
@@ -128,7 +299,7 @@ norm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const flo
 
 template <typename TDY, typename TX, typename TDX>
 __global__ void __launch_bounds__(512)
-norm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ w,
+norm_bwd_block_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                 const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw, int rows, int H,
                 int act, int rms, int tpr) {
@@ -152,11 +323,11 @@ norm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const floa
   for (int batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
     const int row = batch * rpb + rib;
     const bool active = (row < rows) && col_ok;
-    float v[8], a8[8], b8[8], dv[8], xh[8], g[8];
+    float v[8], gv8[8], ga8[8], b8[8], dv[8], xh[8], g[8];
     float s[2] = {0.f, 0.f};
     float mean = 0.f, rstd = 0.f;
     if (active) {
-      load_value(x + static_cast<size_t>(row) * xs, col, H, act, v, a8, b8);
+      load_value(x + static_cast<size_t>(row) * xs, col, H, act, v, gv8, ga8, b8);
       load8(dy + static_cast<size_t>(row) * H + col, dv);
       mean = rms ? 0.f : mean_in[row];
       rstd = rstd_in[row];
@@ -180,15 +351,15 @@ norm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const floa
         float da[8], db[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          da[j] = o[j] * b8[j] * gelu_grad_f(a8[j]);
-          db[j] = o[j] * bf16_round(gelu_f(a8[j]));
+          da[j] = o[j] * b8[j] * ga8[j];
+          db[j] = o[j] * gv8[j];
         }
         store8(dx + static_cast<size_t>(row) * xs + col, da);
         store8(dx + static_cast<size_t>(row) * xs + H + col, db);
       } else {
         if (act == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] *= gelu_grad_f(a8[j]);
+          for (int j = 0; j < 8; ++j) o[j] *= ga8[j];
         }
         if (dres) {
           float r8[8];
@@ -220,8 +391,21 @@ norm_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const floa
 template <typename TX, typename TY>
 int fwd_dispatch(const void* x, const float* w, const float* res, void* y, float* mean, float* rstd, int rows, int H,
                  float eps, int act, int rms, cudaStream_t s) {
+  if (H <= 1024 && act != ACT_GLU) {
+    const int grid = ceil_div(rows, kWarpsPerBlock);
+    const int ch = ceil_div(H, 256);
+#define MUSE_NF(CH)                                                                                                \
+  norm_fwd_warp_kernel<TX, TY, CH><<<grid, kWarpsPerBlock * 32, 0, s>>>(reinterpret_cast<const TX*>(x), w, res,    \
+                                                                         reinterpret_cast<TY*>(y), mean, rstd, rows, \
+                                                                         H, eps, act, rms)
+    if (ch <= 1) MUSE_NF(1);
+    else if (ch <= 2) MUSE_NF(2);
+    else MUSE_NF(4);
+#undef MUSE_NF
+    return check_launch("norm_fwd");
+  }
   const RowMap m = row_map(H);
-  norm_fwd_kernel<TX, TY><<<ceil_div(rows, m.rpb), m.threads, 0, s>>>(
+  norm_fwd_block_kernel<TX, TY><<<ceil_div(rows, m.rpb), m.threads, 0, s>>>(
       reinterpret_cast<const TX*>(x), w, res, reinterpret_cast<TY*>(y), mean, rstd, rows, H, eps, act, rms, m.tpr);
   return check_launch("norm_fwd");
 }
@@ -229,12 +413,27 @@ int fwd_dispatch(const void* x, const float* w, const float* res, void* y, float
 template <typename TDY, typename TX, typename TDX>
 int bwd_dispatch(const void* dy, const void* x, const float* w, const float* mean, const float* rstd,
                  const float* dres, void* dx, float* dw, int rows, int H, int act, int rms, cudaStream_t s) {
+  if (H <= 1024 && act != ACT_GLU) {
+    int grid = ceil_div(rows, kWarpsPerBlock);
+    if (grid > 148 * 8) grid = 148 * 8;
+    const int ch = ceil_div(H, 256);
+    const size_t smem = dw ? H * sizeof(float) : 0;
+#define MUSE_NB(CH)                                                                                          \
+  norm_bwd_warp_kernel<TDY, TX, TDX, CH><<<grid, kWarpsPerBlock * 32, smem, s>>>(                            \
+      reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd, dres,                 \
+      reinterpret_cast<TDX*>(dx), dw, rows, H, act, rms)
+    if (ch <= 1) MUSE_NB(1);
+    else if (ch <= 2) MUSE_NB(2);
+    else MUSE_NB(4);
+#undef MUSE_NB
+    return check_launch("norm_bwd");
+  }
   const RowMap m = row_map(H);
   int grid = ceil_div(rows, m.rpb);
   const int cap = 148 * (m.threads > 256 ? 2 : 6);
   if (grid > cap) grid = cap;
   const size_t smem = (dw && m.rpb > 1) ? H * sizeof(float) : 0;
-  norm_bwd_kernel<TDY, TX, TDX><<<grid, m.threads, smem, s>>>(
+  norm_bwd_block_kernel<TDY, TX, TDX><<<grid, m.threads, smem, s>>>(
       reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd, dres,
       reinterpret_cast<TDX*>(dx), dw, rows, H, act, rms, m.tpr);
   return check_launch("norm_bwd");
