@@ -1,8 +1,7 @@
 // Row normalisation (LayerNorm without bias / RMSNorm), forward and backward, HBM-bound.
 // Reference: muse/modeling_transformer.py:124-137 (LayerNorm -> F.layer_norm, weight only),
-// :79-100 (RMSNorm).  Each thread owns exactly one 8-element chunk of a row (16 B of bf16 / 32 B of fp32), a row is
-// spread over H/8 threads (8..512), several rows share a CTA when rows are short; every element is read from HBM once
-// and written once, row statistics are reduced with shuffles (+ one smem hop when a row spans several warps).
+// :79-100 (RMSNorm).  One warp owns one row (16-byte vector loads, shuffle reductions, no block barriers); every
+// element is read from HBM once and written once.
 // Fusions folded in (they are separate ATen launches in the reference):
 //   * act=1  : exact GELU applied to the input first (mlm_dense -> gelu -> mlm_ln, :980-983)
 //   * act=2  : GLU: the input is [rows, 2H] = [a | b] and the normalised value is bf16(gelu(a)) * b, i.e. the
@@ -176,47 +175,10 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
 }
 
 
-// ---- CTA-per-row(-group) kernels (H > 1024 or GLU mode)
-struct RowMap {
-  int tpr;        // threads per row (power of two, >= 8)
-  int rpb;        // rows per block
-  int threads;    // block size
-};
-
-RowMap row_map(int H) {
-  int chunks = ceil_div(H, 8);
-  int tpr = 8;
-  while (tpr < chunks) tpr <<= 1;
-  RowMap m;
-  m.tpr = tpr;
-  m.threads = tpr > 256 ? tpr : 256;
-  m.rpb = m.threads / tpr;
-  return m;
-}
-
-// Sum `v` over the tpr threads of a row. s_red: [rows_per_block][16] scratch; all threads of the block must call.
-template <int NV>
-__device__ __forceinline__ void row_sum(float (&v)[NV], int tpr, float* s_red, int row_in_block, int tid_in_row) {
-  const int w = tpr < 32 ? tpr : 32;
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-    for (int o = w >> 1; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-  if (tpr > 32) {
-    const int nw = tpr >> 5, wi = tid_in_row >> 5;
-    __syncthreads();  // previous use of s_red finished
-    if ((tid_in_row & 31) == 0) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) s_red[(row_in_block * 16 + wi) * NV + i] = v[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float a = 0.f;
-      for (int k = 0; k < nw; ++k) a += s_red[(row_in_block * 16 + k) * NV + i];
-      v[i] = a;
-    }
-  }
-}
+// ---- wide rows (H > 1024) and GLU mode: warp-per-row STREAMING kernels.  Nothing row-sized lives in registers:
+// pass 1 streams the row for the statistics, pass 2 streams it again (L1/L2 hits) to produce the output.  Few
+// registers -> many resident warps -> enough bytes in flight to approach HBM bandwidth without any block barrier.
+// (A CTA-per-row variant with barriers measured 2-3x below the HBM roofline: two resident rows per SM.)
 
 // v = value to normalise; gv8 = bf16(gelu(a)) and ga8 = gelu'(a) (GLU / GELU modes), b8 = the linear GLU half
 template <typename TX>
@@ -246,145 +208,136 @@ __device__ __forceinline__ void load_value(const TX* xr, int col, int H, int act
   }
 }
 
+constexpr int kWideWarps = 8;
+
 template <typename TX, typename TY>
-__global__ void __launch_bounds__(512)
-norm_fwd_block_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ res,
-                TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
-                float eps, int act, int rms, int tpr) {
-  __shared__ float s_red[16 * 16 * 2];
-  const int rpb = blockDim.x / tpr;
-  const int rib = threadIdx.x / tpr, tir = threadIdx.x % tpr;
-  const int row = blockIdx.x * rpb + rib;
-  const int col = tir * 8;
-  const bool active = (row < rows) && (col < H);
+__global__ void __launch_bounds__(kWideWarps * 32)
+norm_fwd_wide_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ res,
+                     TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
+                     float eps, int act, int rms) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWideWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int xs = (act == ACT_GLU) ? 2 * H : H;
-  float v[8], gv8[8], ga8[8], b8[8];
+  const TX* xr = x + static_cast<size_t>(row) * xs;
+  float gv8[8], ga8[8], b8[8];
+  // pass 1: shifted single-pass moments (shift = first element of the row kills the cancellation in E[v^2]-E[v]^2)
+  float shift;
+  {
+    float v0[8];
+    if (lane == 0) load_value(xr, 0, H, act, v0, gv8, ga8, b8);
+    shift = rms ? 0.f : __shfl_sync(0xffffffffu, v0[0], 0);
+  }
+  float s = 0.f, ss = 0.f;
+  for (int col = lane * 8; col < H; col += 256) {
+    float v[8];
+    load_value(xr, col, H, act, v, gv8, ga8, b8);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  if (active) load_value(x + static_cast<size_t>(row) * xs, col, H, act, v, gv8, ga8, b8);
+    for (int j = 0; j < 8; ++j) { const float d = v[j] - shift; s += d; ss += d * d; }
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
   const float inv_h = 1.0f / static_cast<float>(H);
-  float s[1] = {0.f};
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[0] += v[j];
-  float mean = 0.f;
-  if (!rms) {
-    row_sum<1>(s, tpr, s_red, rib, tir);
-    mean = s[0] * inv_h;
+  const float dm = rms ? 0.f : s * inv_h;          // mean - shift
+  const float mean = shift + dm;
+  const float var = fmaxf(ss * inv_h - dm * dm, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
   }
-  float q[1] = {0.f};
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q[0] += d * d; }
-  }
-  row_sum<1>(q, tpr, s_red, rib, tir);
-  const float rstd = rsqrtf(q[0] * inv_h + eps);
-  if (active) {
-    if (tir == 0) {
-      if (mean_out) mean_out[row] = mean;
-      if (rstd_out) rstd_out[row] = rstd;
-    }
-    float o[8], wv[8];
+  TY* yr = y + static_cast<size_t>(row) * H;
+  const float* rr = res ? res + static_cast<size_t>(row) * H : nullptr;
+  for (int col = lane * 8; col < H; col += 256) {
+    float v[8], o[8], wv[8];
+    load_value(xr, col, H, act, v, gv8, ga8, b8);
     if (w) load8(w + col, wv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd * (w ? wv[j] : 1.f);
-    if (res) {
+    if (rr) {
       float r8[8];
-      load8(res + static_cast<size_t>(row) * H + col, r8);
+      load8(rr + col, r8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] += r8[j];
     }
-    store8(y + static_cast<size_t>(row) * H + col, o);
+    store8(yr + col, o);
   }
 }
 
 template <typename TDY, typename TX, typename TDX>
-__global__ void __launch_bounds__(512)
-norm_bwd_block_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ w,
-                const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw, int rows, int H,
-                int act, int rms, int tpr) {
-  __shared__ float s_red[16 * 16 * 2];
-  extern __shared__ float s_dw[];  // [H] (only when several rows share the block)
-  const int rpb = blockDim.x / tpr;
-  const int rib = threadIdx.x / tpr, tir = threadIdx.x % tpr;
-  const int col = tir * 8;
-  const bool col_ok = col < H;
+__global__ void __launch_bounds__(kWideWarps * 32)
+norm_bwd_wide_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ w,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                     const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw, int rows, int H,
+                     int act, int rms) {
+  extern __shared__ float s_dw[];  // [H]: per-CTA weight-gradient accumulator (shared-memory atomics)
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  if (dw) {
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s_dw[i] = 0.f;
+    __syncthreads();
+  }
   const int xs = (act == ACT_GLU) ? 2 * H : H;
   const float inv_h = 1.0f / static_cast<float>(H);
-  float wv[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) wv[j] = 1.f;
-  if (w && col_ok) load8(w + col, wv);
-  float dw_acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) dw_acc[j] = 0.f;
-
-  const int nbatches = ceil_div(rows, rpb);
-  for (int batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
-    const int row = batch * rpb + rib;
-    const bool active = (row < rows) && col_ok;
-    float v[8], gv8[8], ga8[8], b8[8], dv[8], xh[8], g[8];
-    float s[2] = {0.f, 0.f};
-    float mean = 0.f, rstd = 0.f;
-    if (active) {
-      load_value(x + static_cast<size_t>(row) * xs, col, H, act, v, gv8, ga8, b8);
-      load8(dy + static_cast<size_t>(row) * H + col, dv);
-      mean = rms ? 0.f : mean_in[row];
-      rstd = rstd_in[row];
+  for (int row = blockIdx.x * kWideWarps + warp; row < rows; row += gridDim.x * kWideWarps) {
+    const TX* xr = x + static_cast<size_t>(row) * xs;
+    const TDY* dyr = dy + static_cast<size_t>(row) * H;
+    const float mean = rms ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int col = lane * 8; col < H; col += 256) {
+      float v[8], gv8[8], ga8[8], b8[8], dv[8], wv[8];
+      load_value(xr, col, H, act, v, gv8, ga8, b8);
+      load8(dyr + col, dv);
+      if (w) load8(w + col, wv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        xh[j] = (v[j] - mean) * rstd;
-        dw_acc[j] += dv[j] * xh[j];
-        g[j] = dv[j] * wv[j];
-        s[0] += g[j];
-        s[1] += g[j] * xh[j];
+        const float xh = (v[j] - mean) * rstd;
+        const float g = dv[j] * (w ? wv[j] : 1.f);
+        s1 += g;
+        s2 += g * xh;
+        if (dw) atomicAdd(&s_dw[col + j], dv[j] * xh);
       }
     }
-    row_sum<2>(s, tpr, s_red, rib, tir);
-    const float s1 = rms ? 0.f : s[0] * inv_h;
-    const float s2 = s[1] * inv_h;
-    if (active) {
-      float o[8];
+    s1 = rms ? 0.f : warp_sum(s1) * inv_h;
+    s2 = warp_sum(s2) * inv_h;
+    TDX* dxr = dx + static_cast<size_t>(row) * xs;
+    const float* drr = dres ? dres + static_cast<size_t>(row) * H : nullptr;
+    for (int col = lane * 8; col < H; col += 256) {
+      float v[8], gv8[8], ga8[8], b8[8], dv[8], wv[8], o[8];
+      load_value(xr, col, H, act, v, gv8, ga8, b8);
+      load8(dyr + col, dv);
+      if (w) load8(w + col, wv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] - s1 - xh[j] * s2);
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (v[j] - mean) * rstd;
+        const float g = dv[j] * (w ? wv[j] : 1.f);
+        o[j] = rstd * (g - s1 - xh * s2);
+      }
       if (act == ACT_GLU) {
         float da[8], db[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          da[j] = o[j] * b8[j] * ga8[j];
-          db[j] = o[j] * gv8[j];
-        }
-        store8(dx + static_cast<size_t>(row) * xs + col, da);
-        store8(dx + static_cast<size_t>(row) * xs + H + col, db);
+        for (int j = 0; j < 8; ++j) { da[j] = o[j] * b8[j] * ga8[j]; db[j] = o[j] * gv8[j]; }
+        store8(dxr + col, da);
+        store8(dxr + H + col, db);
       } else {
         if (act == ACT_GELU) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] *= ga8[j];
         }
-        if (dres) {
+        if (drr) {
           float r8[8];
-          load8(dres + static_cast<size_t>(row) * H + col, r8);
+          load8(drr + col, r8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += r8[j];
         }
-        store8(dx + static_cast<size_t>(row) * H + col, o);
+        store8(dxr + col, o);
       }
     }
   }
   if (dw) {
-    if (rpb > 1) {
-      for (int i = threadIdx.x; i < H; i += blockDim.x) s_dw[i] = 0.f;
-      __syncthreads();
-      if (col_ok) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&s_dw[col + j], dw_acc[j]);
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(&dw[i], s_dw[i]);
-    } else if (col_ok) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&dw[col + j], dw_acc[j]);
-    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(&dw[i], s_dw[i]);
   }
 }
 
@@ -404,9 +357,8 @@ int fwd_dispatch(const void* x, const float* w, const float* res, void* y, float
 #undef MUSE_NF
     return check_launch("norm_fwd");
   }
-  const RowMap m = row_map(H);
-  norm_fwd_block_kernel<TX, TY><<<ceil_div(rows, m.rpb), m.threads, 0, s>>>(
-      reinterpret_cast<const TX*>(x), w, res, reinterpret_cast<TY*>(y), mean, rstd, rows, H, eps, act, rms, m.tpr);
+  norm_fwd_wide_kernel<TX, TY><<<ceil_div(rows, kWideWarps), kWideWarps * 32, 0, s>>>(
+      reinterpret_cast<const TX*>(x), w, res, reinterpret_cast<TY*>(y), mean, rstd, rows, H, eps, act, rms);
   return check_launch("norm_fwd");
 }
 
@@ -428,14 +380,11 @@ int bwd_dispatch(const void* dy, const void* x, const float* w, const float* mea
 #undef MUSE_NB
     return check_launch("norm_bwd");
   }
-  const RowMap m = row_map(H);
-  int grid = ceil_div(rows, m.rpb);
-  const int cap = 148 * (m.threads > 256 ? 2 : 6);
-  if (grid > cap) grid = cap;
-  const size_t smem = (dw && m.rpb > 1) ? H * sizeof(float) : 0;
-  norm_bwd_block_kernel<TDY, TX, TDX><<<grid, m.threads, smem, s>>>(
+  int grid = ceil_div(rows, kWideWarps);
+  if (grid > 148 * 8) grid = 148 * 8;
+  norm_bwd_wide_kernel<TDY, TX, TDX><<<grid, kWideWarps * 32, dw ? H * sizeof(float) : 0, s>>>(
       reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd, dres,
-      reinterpret_cast<TDX*>(dx), dw, rows, H, act, rms, m.tpr);
+      reinterpret_cast<TDX*>(dx), dw, rows, H, act, rms);
   return check_launch("norm_bwd");
 }
 
