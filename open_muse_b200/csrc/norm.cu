@@ -341,6 +341,181 @@ norm_bwd_wide_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
   }
 }
 
+// ---- GLU + LayerNorm/RMSNorm fused (act = 2), the FeedForward middle of every normformer layer ([T, 2I] -> [T, I]).
+// These two passes are compute-heavy for an "elementwise" op (erf, exp, rcp per element), so the GELU is evaluated
+// exactly ONCE per element: forward keeps v = bf16(bf16(gelu(a)) * b) packed as bf16 pairs in registers between the
+// statistics and the normalise pass (v is bf16-exact, so packing loses nothing); backward keeps bf16(gelu(a)) and
+// gelu'(a) packed and re-reads b / dy from L2 for the second pass.  Weight gradients accumulate in a PRIVATE
+// per-warp shared-memory row (plain vector read-modify-write; shared-memory float atomics cost ~64 cycles per warp
+// instruction and made the first version of this kernel 4x slower than its HBM roofline).
+constexpr int kGluWarps = 8;
+
+template <int CH>
+__global__ void __launch_bounds__(kGluWarps * 32)
+glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf16* __restrict__ y,
+                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H, float eps, int rms) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kGluWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bf16* xr = ab + static_cast<size_t>(row) * 2 * H;
+  uint32_t vp[CH][4];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < H) {
+      float a8[8], b8[8], v[8];
+      load8(xr + col, a8);
+      load8(xr + H + col, b8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gv, gg;
+        gelu_eval(a8[j], gv, gg);
+        v[j] = bf16_round(bf16_round(gv) * b8[j]);
+        sum += v[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) vp[c][j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) vp[c][j] = 0u;
+    }
+  }
+  const float inv_h = 1.0f / static_cast<float>(H);
+  const float mean = rms ? 0.f : warp_sum(sum) * inv_h;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if ((c * 32 + lane) * 8 < H) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 p = unpack_bf16(vp[c][j]);
+        sq += (p.x - mean) * (p.x - mean) + (p.y - mean) * (p.y - mean);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * inv_h + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  bf16* yr = y + static_cast<size_t>(row) * H;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < H) {
+      float o[8], wv[8];
+      if (w) load8(w + col, wv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 p = unpack_bf16(vp[c][j]);
+        o[2 * j] = (p.x - mean) * rstd * (w ? wv[2 * j] : 1.f);
+        o[2 * j + 1] = (p.y - mean) * rstd * (w ? wv[2 * j + 1] : 1.f);
+      }
+      store8(yr + col, o);
+    }
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kGluWarps * 32)
+glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, const float* __restrict__ w,
+                    const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dab,
+                    float* __restrict__ dw, int rows, int H, int rms) {
+  extern __shared__ __align__(16) float s_dw[];  // [kGluWarps][H] private rows
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float* my_dw = s_dw + static_cast<size_t>(warp) * H;
+  if (dw) {
+    for (int i = lane * 4; i < H; i += 128) *reinterpret_cast<float4*>(my_dw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+  }
+  const float inv_h = 1.0f / static_cast<float>(H);
+  for (int row = blockIdx.x * kGluWarps + warp; row < rows; row += gridDim.x * kGluWarps) {
+    const bf16* xr = ab + static_cast<size_t>(row) * 2 * H;
+    const bf16* dyr = dy + static_cast<size_t>(row) * H;
+    const float mean = rms ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    uint32_t gvp[CH][4], gap[CH][4];  // bf16(gelu(a)), gelu'(a) packed
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < H) {
+        float a8[8], b8[8], dv[8], wv[8], gv[8], gg[8], pr[8];
+        load8(xr + col, a8);
+        load8(xr + H + col, b8);
+        load8(dyr + col, dv);
+        if (w) load8(w + col, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          gelu_eval(a8[j], gv[j], gg[j]);
+          gv[j] = bf16_round(gv[j]);
+          const float v = bf16_round(gv[j] * b8[j]);
+          const float xh = (v - mean) * rstd;
+          const float g = dv[j] * (w ? wv[j] : 1.f);
+          s1 += g;
+          s2 += g * xh;
+          pr[j] = dv[j] * xh;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          gvp[c][j] = pack_bf16(gv[2 * j], gv[2 * j + 1]);
+          gap[c][j] = pack_bf16(gg[2 * j], gg[2 * j + 1]);
+        }
+        if (dw) {
+          float4 d0 = *reinterpret_cast<float4*>(my_dw + col);
+          float4 d1 = *reinterpret_cast<float4*>(my_dw + col + 4);
+          d0.x += pr[0]; d0.y += pr[1]; d0.z += pr[2]; d0.w += pr[3];
+          d1.x += pr[4]; d1.y += pr[5]; d1.z += pr[6]; d1.w += pr[7];
+          *reinterpret_cast<float4*>(my_dw + col) = d0;
+          *reinterpret_cast<float4*>(my_dw + col + 4) = d1;
+        }
+      }
+    }
+    s1 = rms ? 0.f : warp_sum(s1) * inv_h;
+    s2 = warp_sum(s2) * inv_h;
+    bf16* dr = dab + static_cast<size_t>(row) * 2 * H;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < H) {
+        float b8[8], dv[8], wv[8], da[8], db[8];
+        load8(xr + H + col, b8);
+        load8(dyr + col, dv);
+        if (w) load8(w + col, wv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 gv = unpack_bf16(gvp[c][j]);
+          const float2 gg = unpack_bf16(gap[c][j]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int e = 2 * j + h;
+            const float gve = h ? gv.y : gv.x, gge = h ? gg.y : gg.x;
+            const float v = bf16_round(gve * b8[e]);
+            const float xh = (v - mean) * rstd;
+            const float g = dv[e] * (w ? wv[e] : 1.f);
+            const float o = rstd * (g - s1 - xh * s2);
+            da[e] = o * b8[e] * gge;
+            db[e] = o * gve;
+          }
+        }
+        store8(dr + col, da);
+        store8(dr + H + col, db);
+      }
+    }
+  }
+  if (dw) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kGluWarps; ++k) acc += s_dw[static_cast<size_t>(k) * H + i];
+      atomicAdd(&dw[i], acc);
+    }
+  }
+}
+
 template <typename TX, typename TY>
 int fwd_dispatch(const void* x, const float* w, const float* res, void* y, float* mean, float* rstd, int rows, int H,
                  float eps, int act, int rms, cudaStream_t s) {
@@ -406,6 +581,14 @@ int norm_fwd(const void* x, int x_dt, const float* w, const float* res, void* y,
   if (rows <= 0) return MUSE_OK;
   int rc = check_args("norm_fwd", H, act, res);
   if (rc) return rc;
+  if (act == ACT_GLU && x_dt == 1 && y_dt == 1 && H <= 4096) {
+    const int grid = ceil_div(rows, kGluWarps);
+    const int ch = ceil_div(H, 256);
+#define MUSE_GF(CH) glu_norm_fwd_kernel<CH><<<grid, kGluWarps * 32, 0, s>>>(reinterpret_cast<const bf16*>(x), w, reinterpret_cast<bf16*>(y), mean, rstd, rows, H, eps, rms)
+    if (ch <= 1) MUSE_GF(1); else if (ch <= 2) MUSE_GF(2); else if (ch <= 4) MUSE_GF(4); else if (ch <= 8) MUSE_GF(8); else MUSE_GF(16);
+#undef MUSE_GF
+    return check_launch("glu_norm_fwd");
+  }
   if (x_dt == 0 && y_dt == 1) return fwd_dispatch<float, bf16>(x, w, res, y, mean, rstd, rows, H, eps, act, rms, s);
   if (x_dt == 1 && y_dt == 1) return fwd_dispatch<bf16, bf16>(x, w, res, y, mean, rstd, rows, H, eps, act, rms, s);
   if (x_dt == 1 && y_dt == 0) return fwd_dispatch<bf16, float>(x, w, res, y, mean, rstd, rows, H, eps, act, rms, s);
@@ -419,6 +602,21 @@ int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w,
   if (rows <= 0) return MUSE_OK;
   int rc = check_args("norm_bwd", H, act, dres);
   if (rc) return rc;
+  if (act == ACT_GLU && dy_dt == 1 && x_dt == 1 && dx_dt == 1 && H <= 4096) {
+    int grid = ceil_div(rows, kGluWarps);
+    if (grid > 148 * 4) grid = 148 * 4;
+    const int ch = ceil_div(H, 256);
+    const size_t smem = dw ? static_cast<size_t>(kGluWarps) * H * sizeof(float) : 0;
+#define MUSE_GB(CH)                                                                                               \
+  do {                                                                                                            \
+    static bool attr = false;                                                                                     \
+    if (!attr) { cudaFuncSetAttribute(glu_norm_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 4096 * 4); attr = true; } \
+    glu_norm_bwd_kernel<CH><<<grid, kGluWarps * 32, smem, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw, rows, H, rms); \
+  } while (0)
+    if (ch <= 1) MUSE_GB(1); else if (ch <= 2) MUSE_GB(2); else if (ch <= 4) MUSE_GB(4); else if (ch <= 8) MUSE_GB(8); else MUSE_GB(16);
+#undef MUSE_GB
+    return check_launch("glu_norm_bwd");
+  }
   const int key = dy_dt * 4 + x_dt * 2 + dx_dt;
   switch (key) {
     case 0: return bwd_dispatch<float, float, float>(dy, x, w, mean, rstd, dres, dx, dw, rows, H, act, rms, s);
