@@ -350,8 +350,15 @@ norm_bwd_wide_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
 // instruction and made the first version of this kernel 4x slower than its HBM roofline).
 constexpr int kGluWarps = 8;
 
+__device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {  // bf16 * bf16 -> bf16 (rn), two lanes
+  __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// forward: v = bf16(bf16(gelu(a)) * b) is produced directly as packed bf16 pairs (cvt.rn.bf16x2 + HMUL2.BF16) and
+// stays in registers between the statistics and the normalise pass.
 template <int CH>
-__global__ void __launch_bounds__(kGluWarps * 32)
+__global__ void __launch_bounds__(kGluWarps * 32, (CH <= 8) ? 3 : 1)
 glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf16* __restrict__ y,
                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H, float eps, int rms) {
   const int lane = threadIdx.x & 31;
@@ -364,18 +371,19 @@ glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf
   for (int c = 0; c < CH; ++c) {
     const int col = (c * 32 + lane) * 8;
     if (col < H) {
-      float a8[8], b8[8], v[8];
-      load8(xr + col, a8);
-      load8(xr + H + col, b8);
+      const uint4 au = *reinterpret_cast<const uint4*>(xr + col);
+      const uint4 bu = *reinterpret_cast<const uint4*>(xr + H + col);
+      const uint32_t aw[4] = {au.x, au.y, au.z, au.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float gv, gg;
-        gelu_eval(a8[j], gv, gg);
-        v[j] = bf16_round(bf16_round(gv) * b8[j]);
-        sum += v[j];
+      for (int j = 0; j < 4; ++j) {
+        const float2 a2 = unpack_bf16(aw[j]);
+        float g0, g1, d0, d1;
+        gelu_eval(a2.x, g0, d0);
+        gelu_eval(a2.y, g1, d1);
+        vp[c][j] = bf16x2_mul(pack_bf16(g0, g1), bw[j]);
+        const float2 v2 = unpack_bf16(vp[c][j]);
+        sum += v2.x + v2.y;
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) vp[c][j] = pack_bf16(v[2 * j], v[2 * j + 1]);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) vp[c][j] = 0u;
@@ -390,7 +398,9 @@ glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 p = unpack_bf16(vp[c][j]);
-        sq += (p.x - mean) * (p.x - mean) + (p.y - mean) * (p.y - mean);
+        const float dx = p.x - mean, dy_ = p.y - mean;
+        sq = fmaf(dx, dx, sq);
+        sq = fmaf(dy_, dy_, sq);
       }
     }
   }
@@ -404,21 +414,24 @@ glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf
   for (int c = 0; c < CH; ++c) {
     const int col = (c * 32 + lane) * 8;
     if (col < H) {
-      float o[8], wv[8];
+      float wv[8];
       if (w) load8(w + col, wv);
+      uint4 ou;
+      uint32_t* op = reinterpret_cast<uint32_t*>(&ou);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 p = unpack_bf16(vp[c][j]);
-        o[2 * j] = (p.x - mean) * rstd * (w ? wv[2 * j] : 1.f);
-        o[2 * j + 1] = (p.y - mean) * rstd * (w ? wv[2 * j + 1] : 1.f);
+        const float r0 = w ? rstd * wv[2 * j] : rstd, r1 = w ? rstd * wv[2 * j + 1] : rstd;
+        op[j] = pack_bf16((p.x - mean) * r0, (p.y - mean) * r1);
       }
-      store8(yr + col, o);
+      *reinterpret_cast<uint4*>(yr + col) = ou;
     }
   }
 }
 
-template <int CH>
-__global__ void __launch_bounds__(kGluWarps * 32)
+// backward: two streaming passes over the row with the GELU recomputed in the second one (nothing row-sized in
+// registers -> 3 CTAs/SM); weight gradients go to a private per-warp shared-memory row.
+__global__ void __launch_bounds__(kGluWarps * 32, 3)
 glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, const float* __restrict__ w,
                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dab,
                     float* __restrict__ dw, int rows, int H, int rms) {
@@ -436,73 +449,71 @@ glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, co
     const bf16* dyr = dy + static_cast<size_t>(row) * H;
     const float mean = rms ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
-    uint32_t gvp[CH][4], gap[CH][4];  // bf16(gelu(a)), gelu'(a) packed
     float s1 = 0.f, s2 = 0.f;
+    for (int col = lane * 8; col < H; col += 256) {
+      const uint4 au = *reinterpret_cast<const uint4*>(xr + col);
+      const uint4 bu = *reinterpret_cast<const uint4*>(xr + H + col);
+      const uint4 du = *reinterpret_cast<const uint4*>(dyr + col);
+      const uint32_t aw[4] = {au.x, au.y, au.z, au.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w}, dd[4] = {du.x, du.y, du.z, du.w};
+      float wv[8], pr[8];
+      if (w) load8(w + col, wv);
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int col = (c * 32 + lane) * 8;
-      if (col < H) {
-        float a8[8], b8[8], dv[8], wv[8], gv[8], gg[8], pr[8];
-        load8(xr + col, a8);
-        load8(xr + H + col, b8);
-        load8(dyr + col, dv);
-        if (w) load8(w + col, wv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          gelu_eval(a8[j], gv[j], gg[j]);
-          gv[j] = bf16_round(gv[j]);
-          const float v = bf16_round(gv[j] * b8[j]);
-          const float xh = (v - mean) * rstd;
-          const float g = dv[j] * (w ? wv[j] : 1.f);
-          s1 += g;
-          s2 += g * xh;
-          pr[j] = dv[j] * xh;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          gvp[c][j] = pack_bf16(gv[2 * j], gv[2 * j + 1]);
-          gap[c][j] = pack_bf16(gg[2 * j], gg[2 * j + 1]);
-        }
-        if (dw) {
-          float4 d0 = *reinterpret_cast<float4*>(my_dw + col);
-          float4 d1 = *reinterpret_cast<float4*>(my_dw + col + 4);
-          d0.x += pr[0]; d0.y += pr[1]; d0.z += pr[2]; d0.w += pr[3];
-          d1.x += pr[4]; d1.y += pr[5]; d1.z += pr[6]; d1.w += pr[7];
-          *reinterpret_cast<float4*>(my_dw + col) = d0;
-          *reinterpret_cast<float4*>(my_dw + col + 4) = d1;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 a2 = unpack_bf16(aw[j]);
+        float g0, g1, t0, t1;
+        gelu_eval(a2.x, g0, t0);
+        gelu_eval(a2.y, g1, t1);
+        const float2 v2 = unpack_bf16(bf16x2_mul(pack_bf16(g0, g1), bw[j]));
+        const float2 d2 = unpack_bf16(dd[j]);
+        const float xh0 = (v2.x - mean) * rstd, xh1 = (v2.y - mean) * rstd;
+        const float q0 = w ? d2.x * wv[2 * j] : d2.x, q1 = w ? d2.y * wv[2 * j + 1] : d2.y;
+        s1 += q0 + q1;
+        s2 = fmaf(q0, xh0, s2);
+        s2 = fmaf(q1, xh1, s2);
+        pr[2 * j] = d2.x * xh0;
+        pr[2 * j + 1] = d2.y * xh1;
+      }
+      if (dw) {
+        float4 e0 = *reinterpret_cast<float4*>(my_dw + col);
+        float4 e1 = *reinterpret_cast<float4*>(my_dw + col + 4);
+        e0.x += pr[0]; e0.y += pr[1]; e0.z += pr[2]; e0.w += pr[3];
+        e1.x += pr[4]; e1.y += pr[5]; e1.z += pr[6]; e1.w += pr[7];
+        *reinterpret_cast<float4*>(my_dw + col) = e0;
+        *reinterpret_cast<float4*>(my_dw + col + 4) = e1;
       }
     }
     s1 = rms ? 0.f : warp_sum(s1) * inv_h;
     s2 = warp_sum(s2) * inv_h;
     bf16* dr = dab + static_cast<size_t>(row) * 2 * H;
+    for (int col = lane * 8; col < H; col += 256) {
+      const uint4 au = *reinterpret_cast<const uint4*>(xr + col);
+      const uint4 bu = *reinterpret_cast<const uint4*>(xr + H + col);
+      const uint4 du = *reinterpret_cast<const uint4*>(dyr + col);
+      const uint32_t aw[4] = {au.x, au.y, au.z, au.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w}, dd[4] = {du.x, du.y, du.z, du.w};
+      float wv[8];
+      if (w) load8(w + col, wv);
+      uint4 oa, ob;
+      uint32_t* pa = reinterpret_cast<uint32_t*>(&oa);
+      uint32_t* pb = reinterpret_cast<uint32_t*>(&ob);
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int col = (c * 32 + lane) * 8;
-      if (col < H) {
-        float b8[8], dv[8], wv[8], da[8], db[8];
-        load8(xr + H + col, b8);
-        load8(dyr + col, dv);
-        if (w) load8(w + col, wv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 gv = unpack_bf16(gvp[c][j]);
-          const float2 gg = unpack_bf16(gap[c][j]);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int e = 2 * j + h;
-            const float gve = h ? gv.y : gv.x, gge = h ? gg.y : gg.x;
-            const float v = bf16_round(gve * b8[e]);
-            const float xh = (v - mean) * rstd;
-            const float g = dv[e] * (w ? wv[e] : 1.f);
-            const float o = rstd * (g - s1 - xh * s2);
-            da[e] = o * b8[e] * gge;
-            db[e] = o * gve;
-          }
-        }
-        store8(dr + col, da);
-        store8(dr + H + col, db);
+      for (int j = 0; j < 4; ++j) {
+        const float2 a2 = unpack_bf16(aw[j]);
+        float g0, g1, t0, t1;
+        gelu_eval(a2.x, g0, t0);
+        gelu_eval(a2.y, g1, t1);
+        const uint32_t gp = pack_bf16(g0, g1);
+        const float2 gr = unpack_bf16(gp);  // bf16(gelu(a))
+        const float2 v2 = unpack_bf16(bf16x2_mul(gp, bw[j]));
+        const float2 b2 = unpack_bf16(bw[j]);
+        const float2 d2 = unpack_bf16(dd[j]);
+        const float xh0 = (v2.x - mean) * rstd, xh1 = (v2.y - mean) * rstd;
+        const float q0 = w ? d2.x * wv[2 * j] : d2.x, q1 = w ? d2.y * wv[2 * j + 1] : d2.y;
+        const float o0 = rstd * (q0 - s1 - xh0 * s2), o1 = rstd * (q1 - s1 - xh1 * s2);
+        pa[j] = pack_bf16(o0 * b2.x * t0, o1 * b2.y * t1);
+        pb[j] = pack_bf16(o0 * gr.x, o1 * gr.y);
       }
+      *reinterpret_cast<uint4*>(dr + col) = oa;
+      *reinterpret_cast<uint4*>(dr + H + col) = ob;
     }
   }
   if (dw) {
@@ -604,17 +615,15 @@ int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w,
   if (rc) return rc;
   if (act == ACT_GLU && dy_dt == 1 && x_dt == 1 && dx_dt == 1 && H <= 4096) {
     int grid = ceil_div(rows, kGluWarps);
-    if (grid > 148 * 4) grid = 148 * 4;
-    const int ch = ceil_div(H, 256);
+    if (grid > 148 * 3) grid = 148 * 3;
     const size_t smem = dw ? static_cast<size_t>(kGluWarps) * H * sizeof(float) : 0;
-#define MUSE_GB(CH)                                                                                               \
-  do {                                                                                                            \
-    static bool attr = false;                                                                                     \
-    if (!attr) { cudaFuncSetAttribute(glu_norm_bwd_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 4096 * 4); attr = true; } \
-    glu_norm_bwd_kernel<CH><<<grid, kGluWarps * 32, smem, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw, rows, H, rms); \
-  } while (0)
-    if (ch <= 1) MUSE_GB(1); else if (ch <= 2) MUSE_GB(2); else if (ch <= 4) MUSE_GB(4); else if (ch <= 8) MUSE_GB(8); else MUSE_GB(16);
-#undef MUSE_GB
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(glu_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 4096 * 4);
+      attr = true;
+    }
+    glu_norm_bwd_kernel<<<grid, kGluWarps * 32, smem, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w,
+                                                           mean, rstd, reinterpret_cast<bf16*>(dx), dw, rows, H, rms);
     return check_launch("glu_norm_bwd");
   }
   const int key = dy_dt * 4 + x_dt * 2 + dx_dt;
