@@ -9,6 +9,9 @@
 //
 // Round-1 implementation uses mma.sync.m16n8k16 bf16 tensor-core tiles (attention core is ~5.7 % of
 // the step FLOPs at the base config); the tcgen05/TMEM version is the planned upgrade.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace muse {
@@ -132,11 +135,11 @@ struct AttnPtrs {
 // ------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(AttnPtrs P, bf16* __restrict__ O, long long o_bs, int o_rs, float* __restrict__ LSE, int Sq, int Skv,
-                int nh, float scale) {
+                int nh, float scale, int blk0) {
   __shared__ __align__(16) bf16 sQ[BQ * LDS];
   __shared__ __align__(16) bf16 sK[2][BKV * LDS];
   __shared__ __align__(16) bf16 sV[2][BKV * LDS];
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = (blockIdx.x + blk0) * BQ, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const bf16* qg = P.q + b * P.q_bs + h * D;
@@ -257,11 +260,11 @@ attn_fwd_kernel(AttnPtrs P, bf16* __restrict__ O, long long o_bs, int o_rs, floa
 __global__ void __launch_bounds__(128)
 attn_bwd_dkdv_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, int do_rs, const float* __restrict__ LSE,
                      const float* __restrict__ Dv, bf16* __restrict__ dK, long long dk_bs, int dk_rs,
-                     bf16* __restrict__ dV, long long dv_bs, int dv_rs, int Sq, int Skv, int nh, float scale) {
+                     bf16* __restrict__ dV, long long dv_bs, int dv_rs, int Sq, int Skv, int nh, float scale, int blk0) {
   __shared__ __align__(16) bf16 sA[2][BKV * LDS];  // K_j (buffer 1) then Q_i chunks (alternating)
   __shared__ __align__(16) bf16 sB[2][BKV * LDS];  // V_j (buffer 1) then dO_i chunks
   __shared__ float sL[2][BQ], sD[2][BQ];
-  const int kv0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+  const int kv0 = (blockIdx.x + blk0) * BKV, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const bf16* qg = P.q + b * P.q_bs + h * D;
@@ -390,10 +393,10 @@ attn_bwd_dkdv_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, i
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(AttnPtrs P, const bf16* __restrict__ dO, long long do_bs, int do_rs, const float* __restrict__ LSE,
                    float* __restrict__ Dv, bf16* __restrict__ dQ, long long dq_bs, int dq_rs, int Sq, int Skv,
-                   int nh, float scale) {
+                   int nh, float scale, int blk0) {
   __shared__ __align__(16) bf16 sA[2][BKV * LDS];  // Q_i (buffer 1) then K_j chunks
   __shared__ __align__(16) bf16 sB[2][BKV * LDS];  // dO_i (buffer 1) then V_j chunks
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = (blockIdx.x + blk0) * BQ, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const bf16* qg = P.q + b * P.q_bs + h * D;
@@ -519,17 +522,43 @@ int check_strides(const char* who, int hd, int a, int b, int c) {
 
 }  // namespace
 
+// tcgen05 kernels (attention_tc.cu)
+int attn_fwd_tc(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, float,
+                cudaStream_t, int*);
+int attn_bwd_dq_tc(const void*, const void*, const void*, const void*, const float*, float*, void*, int, int, int, int,
+                   int, int, int, int, int, float, cudaStream_t, int*);
+int attn_bwd_dkdv_tc(const void*, const void*, const void*, const void*, const float*, const float*, void*, void*, int,
+                     int, int, int, int, int, int, int, int, int, float, cudaStream_t, int*);
+
+static bool use_tc_attention() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MUSE_B200_ATTN");
+    v = (e && strcmp(e, "legacy") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Full 128-row tiles of the owned dimension run on the tcgen05 kernels; the ragged remainder (and everything when
+// MUSE_B200_ATTN=legacy) runs on the mma.sync kernels above.
 int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv, int hd,
              int q_rs, int k_rs, int v_rs, int o_rs, float scale, cudaStream_t s) {
   if (B <= 0 || Sq <= 0 || Skv <= 0) return MUSE_OK;
   int rc = check_strides("attn_fwd", hd, q_rs | o_rs, k_rs, v_rs);
   if (rc) return rc;
+  int done = 0;
+  if (use_tc_attention()) {
+    rc = attn_fwd_tc(q, k, v, o, lse, B, nh, Sq, Skv, q_rs, k_rs, v_rs, o_rs, scale, s, &done);
+    if (rc) return rc;
+  }
+  if (done >= Sq) return MUSE_OK;
   AttnPtrs P;
   P.q = reinterpret_cast<const bf16*>(q); P.k = reinterpret_cast<const bf16*>(k); P.v = reinterpret_cast<const bf16*>(v);
   P.q_rs = q_rs; P.k_rs = k_rs; P.v_rs = v_rs;
   P.q_bs = static_cast<long long>(Sq) * q_rs; P.k_bs = static_cast<long long>(Skv) * k_rs; P.v_bs = static_cast<long long>(Skv) * v_rs;
-  dim3 grid(ceil_div(Sq, BQ), nh, B);
-  attn_fwd_kernel<<<grid, 128, 0, s>>>(P, reinterpret_cast<bf16*>(o), static_cast<long long>(Sq) * o_rs, o_rs, lse, Sq, Skv, nh, scale);
+  const int blk0 = done / BQ;
+  dim3 grid(ceil_div(Sq, BQ) - blk0, nh, B);
+  attn_fwd_kernel<<<grid, 128, 0, s>>>(P, reinterpret_cast<bf16*>(o), static_cast<long long>(Sq) * o_rs, o_rs, lse, Sq, Skv, nh, scale, blk0);
   return check_launch("attn_fwd");
 }
 
@@ -539,21 +568,40 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   if (B <= 0 || Sq <= 0 || Skv <= 0) return MUSE_OK;
   int rc = check_strides("attn_bwd", hd, q_rs | o_rs | do_rs | dq_rs, k_rs | dk_rs, v_rs | dv_rs);
   if (rc) return rc;
+  (void)o; (void)o_rs;  // D is recomputed from (P, dP) inside the dQ kernels; O is not needed by backward
   AttnPtrs P;
   P.q = reinterpret_cast<const bf16*>(q); P.k = reinterpret_cast<const bf16*>(k); P.v = reinterpret_cast<const bf16*>(v);
   P.q_rs = q_rs; P.k_rs = k_rs; P.v_rs = v_rs;
   P.q_bs = static_cast<long long>(Sq) * q_rs; P.k_bs = static_cast<long long>(Skv) * k_rs; P.v_bs = static_cast<long long>(Skv) * v_rs;
-  (void)o; (void)o_rs;  // D is recomputed from (P, dP) inside the dQ kernel; O is not needed by backward
-  attn_bwd_dq_kernel<<<dim3(ceil_div(Sq, BQ), nh, B), 128, 0, s>>>(
-      P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
-      reinterpret_cast<bf16*>(dq), static_cast<long long>(Sq) * dq_rs, dq_rs, Sq, Skv, nh, scale);
-  rc = check_launch("attn_bwd_dq");
-  if (rc) return rc;
-  attn_bwd_dkdv_kernel<<<dim3(ceil_div(Skv, BKV), nh, B), 128, 0, s>>>(
-      P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
-      reinterpret_cast<bf16*>(dk), static_cast<long long>(Skv) * dk_rs, dk_rs, reinterpret_cast<bf16*>(dv),
-      static_cast<long long>(Skv) * dv_rs, dv_rs, Sq, Skv, nh, scale);
-  return check_launch("attn_bwd_dkdv");
+  const bool tc = use_tc_attention();
+  int done_q = 0, done_kv = 0;
+  if (tc) {
+    rc = attn_bwd_dq_tc(q, k, v, d_o, lse, dvec, dq, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dq_rs, scale, s, &done_q);
+    if (rc) return rc;
+  }
+  if (done_q < Sq) {
+    const int blk0 = done_q / BQ;
+    attn_bwd_dq_kernel<<<dim3(ceil_div(Sq, BQ) - blk0, nh, B), 128, 0, s>>>(
+        P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
+        reinterpret_cast<bf16*>(dq), static_cast<long long>(Sq) * dq_rs, dq_rs, Sq, Skv, nh, scale, blk0);
+    rc = check_launch("attn_bwd_dq");
+    if (rc) return rc;
+  }
+  if (tc) {
+    rc = attn_bwd_dkdv_tc(q, k, v, d_o, lse, dvec, dk, dv, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dk_rs, dv_rs, scale,
+                          s, &done_kv);
+    if (rc) return rc;
+  }
+  if (done_kv < Skv) {
+    const int blk0 = done_kv / BKV;
+    attn_bwd_dkdv_kernel<<<dim3(ceil_div(Skv, BKV) - blk0, nh, B), 128, 0, s>>>(
+        P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
+        reinterpret_cast<bf16*>(dk), static_cast<long long>(Skv) * dk_rs, dk_rs, reinterpret_cast<bf16*>(dv),
+        static_cast<long long>(Skv) * dv_rs, dv_rs, Sq, Skv, nh, scale, blk0);
+    rc = check_launch("attn_bwd_dkdv");
+    if (rc) return rc;
+  }
+  return MUSE_OK;
 }
 
 }  // namespace muse

@@ -1,0 +1,655 @@
+// tcgen05 / TMEM / TMA attention for head_dim 64 (sm_100a): forward, dQ and dK/dV kernels.
+// Replaces the reference's materialised attention (muse/modeling_transformer.py:221-241) and its autograd backward.
+//
+// One CTA = one (batch, head) x one 128-row tile of the "owned" sequence dimension; its 128 threads each own one
+// TMEM lane (= one row).  Thread 0 also drives TMA and issues the MMAs; the CTA is internally sequential
+// (load -> score MMA -> row-wise softmax math -> accumulate MMA) and the SM overlaps TWO co-resident CTAs
+// (each <= 256 TMEM columns and <= ~112 KB smem), so tensor core, TMA and the softmax lanes of different CTAs overlap.
+//
+//   forward  : owned = q rows.   S = Q K_j^T -> online softmax (fp32) -> P (bf16, smem) -> O += P V_j      (TMEM: S 128 + O 64)
+//   dQ       : owned = q rows.   S, dP = dO V_j^T -> sweep 1: D = sum P*dP ; sweep 2: dS -> dQ += dS K_j  (TMEM: 64+64+64)
+//   dK/dV    : owned = kv rows.  S^T = K Q_i^T, dP^T = V dO_i^T -> P^T, dS^T -> dV += P^T dO_i, dK += dS^T Q_i
+//                                                                                       (TMEM: 64+64+64+64)
+// Operands are read straight from the strided [tokens, 3H] QKV projection through 3-D TMA tensor maps
+// {64 head columns, S rows, B} (rows past the end of a sequence are zero-filled by the TMA unit), with the same
+// 128-byte-swizzled tiles serving as K-major or MN-major MMA operands depending on the product.
+// Rows of the owned dimension beyond the last full 128-row tile (the class token makes S = 257) are delegated to the
+// legacy mma.sync kernels in attention.cu; the looped dimension handles ragged tails by shrinking the MMA N/K to a
+// multiple of 16.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace muse {
+
+int make_tmap3(CUtensorMap* map, const void* base, long long cols, long long rows, long long batches,
+               long long row_pitch_elems, int box_rows);  // gemm_tcgen05.cu
+
+namespace {
+
+constexpr int HD = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+// 16-column TMEM load (used for ragged 16-wide tails)
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Operand descriptors for [rows x 64] bf16 tiles laid out by TMA with the 128-byte swizzle (rows of 128 B).
+//  K-major view : row = M/N index, the 64 columns are K.  k-step ks (16 K) -> +32 B.
+//  MN-major view: row = K index, the 64 columns are M/N.  k-step ks (16 rows) -> +2048 B.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int ks) {
+  return ptx::make_smem_desc_sw128(tile_addr + ks * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int ks) {
+  return ptx::make_smem_desc_sw128(tile_addr + ks * 2048, 8192, 1024);
+}
+
+// Store 8 consecutive bf16 (one 16-byte chunk) of row r, columns [k0, k0+8) of a [128 x K] K-major SW128 operand
+// made of 64-column atoms (16 KB each).
+__device__ __forceinline__ void st_operand_chunk(uint8_t* base, int r, int k0, uint4 v) {
+  const int atom = k0 >> 6, c8 = (k0 & 63) >> 3;
+  *reinterpret_cast<uint4*>(base + atom * 16384 + r * 128 + ((c8 ^ (r & 7)) << 4)) = v;
+}
+
+struct TcParams {
+  int Sq, Skv, nh;
+  float scale;
+  // outputs / side inputs (plain global pointers; rows addressed as b*S + s)
+  bf16* out0;  long long out0_rs;   // fwd: O ; dq: dQ ; dkdv: dK
+  bf16* out1;  long long out1_rs;   // dkdv: dV
+  float* lse;                        // [B, nh, Sq]
+  float* dvec;                       // [B, nh, Sq]
+};
+
+// ------------------------------------------------------------------------------------------------ forward
+constexpr int FWD_BN = 128;
+constexpr int FWD_SMEM = 16384 /*Q*/ + 16384 /*K*/ + 16384 /*V*/ + 32768 /*P*/ + 1024 /*align*/ + 64;
+
+__global__ void __launch_bounds__(128)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 32768;
+  uint8_t* sP = smem + 49152;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
+  uint64_t* bar_kv = bars;      // TMA landed
+  uint64_t* bar_s = bars + 1;   // score MMA done
+  uint64_t* bar_o = bars + 2;   // accumulate MMA done
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  if (tid == 0) {
+    ptx::mbar_init(bar_kv, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t t_s = tmem + (static_cast<uint32_t>(warp * 32) << 16);        // S: columns [0,128)
+  const uint32_t t_o = t_s + 128;                                               // O: columns [128,192)
+  const int ntiles = ceil_div(p.Skv, FWD_BN);
+
+  if (tid == 0) {
+    ptx::mbar_expect_tx(bar_kv, 16384 * 3);
+    tma_load_3d(sQ, &tmQ, bar_kv, h * HD, q0, b);
+    tma_load_3d(sK, &tmK, bar_kv, h * HD, 0, b);
+    tma_load_3d(sV, &tmV, bar_kv, h * HD, 0, b);
+  }
+  const float sl2 = p.scale * kLog2e;
+  float m = -INFINITY, l = 0.f;
+
+  for (int j = 0; j < ntiles; ++j) {
+    const uint32_t par = j & 1;
+    const int nvalid = min(FWD_BN, p.Skv - j * FWD_BN);
+    const int n16 = (nvalid + 15) & ~15;
+    if (tid == 0) {
+      ptx::mbar_wait(bar_kv, par);
+      ptx::tc_fence_after();
+      const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc, ks > 0);
+      ptx::umma_commit(bar_s);
+    }
+    ptx::mbar_wait(bar_s, par);
+    ptx::tc_fence_after();
+    // pass 1: row maximum of the scaled scores
+    float mx = m;
+    for (int c = 0; c < n16; c += 32) {
+      uint32_t r[32];
+      if (n16 - c >= 32) {
+        ptx::tmem_ld_32x32b_x32(t_s + c, r);
+      } else {
+        uint32_t r16[16];
+        tmem_ld_32x32b_x16(t_s + c, r16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0xff800000u; }
+      }
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]) * sl2);
+    }
+    const float alpha = exp2f(m - mx);  // 0 on the first tile (m = -inf)
+    m = mx;
+    // pass 2: P = exp2(s - m) -> bf16 operand in smem; row sum
+    float ladd = 0.f;
+    for (int c = 0; c < n16; c += 32) {
+      uint32_t r[32];
+      if (n16 - c >= 32) {
+        ptx::tmem_ld_32x32b_x32(t_s + c, r);
+      } else {
+        uint32_t r16[16];
+        tmem_ld_32x32b_x16(t_s + c, r16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
+      }
+      ptx::tmem_ld_wait();
+      float pv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e = (c + i < nvalid) ? exp2f(__uint_as_float(r[i]) * sl2 - m) : 0.f;
+        pv[i] = e;
+        ladd += e;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (c + i < n16) {
+          uint4 u;
+          u.x = pack_bf16(pv[i], pv[i + 1]); u.y = pack_bf16(pv[i + 2], pv[i + 3]);
+          u.z = pack_bf16(pv[i + 4], pv[i + 5]); u.w = pack_bf16(pv[i + 6], pv[i + 7]);
+          st_operand_chunk(sP, tid, c + i, u);
+        }
+      }
+    }
+    l = l * alpha + ladd;
+    // rescale the running output (the previous accumulate MMA finished: bar_o was waited at the end of iteration j-1)
+    if (j > 0) {
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_o + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+        tmem_st_32x32b_x32(t_o + c, r);
+      }
+      tmem_st_wait();
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
+      const int ksteps = n16 >> 4;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t a = ptx::make_smem_desc_sw128(ptx::smem_u32(sP) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+        ptx::umma_f16(tmem + 128, a, desc_mnmajor(ptx::smem_u32(sV), ks), idesc, (j > 0 || ks > 0) ? 1u : 0u);
+      }
+      ptx::umma_commit(bar_o);
+    }
+    ptx::mbar_wait(bar_o, par);
+    ptx::tc_fence_after();
+    if (tid == 0 && j + 1 < ntiles) {
+      ptx::mbar_expect_tx(bar_kv, 16384 * 2);
+      tma_load_3d(sK, &tmK, bar_kv, h * HD, (j + 1) * FWD_BN, b);
+      tma_load_3d(sV, &tmV, bar_kv, h * HD, (j + 1) * FWD_BN, b);
+    }
+  }
+  // epilogue: O / l -> bf16 rows, LSE
+  const int row = q0 + tid;
+  const float inv = 1.f / l;
+  bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD;
+#pragma unroll
+  for (int c = 0; c < HD; c += 32) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(t_o + c, r);
+    ptx::tmem_ld_wait();
+    if (row < p.Sq) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+        u.y = pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+        u.z = pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+        u.w = pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + c + i) = u;
+      }
+    }
+  }
+  if (row < p.Sq) p.lse[(static_cast<long long>(b) * p.nh + h) * p.Sq + row] = (m + log2f(l)) * kLn2;
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dQ
+// TMEM columns: S [0,64)  dP [64,128)  dQ [128,192).  smem: Q 16K | dO 16K | K_j 8K | V_j 8K | dS 16K
+constexpr int BWD_BN = 64;
+constexpr int DQ_SMEM = 16384 * 2 + 8192 * 2 + 16384 + 1024 + 64;
+
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                      const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + 16384;
+  uint8_t* sK = smem + 32768;
+  uint8_t* sV = smem + 40960;
+  uint8_t* sdS = smem + 49152;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536);
+  uint64_t* bar_kv = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_o = bars + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  if (tid == 0) {
+    ptx::mbar_init(bar_kv, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const int ntiles = ceil_div(p.Skv, BWD_BN);
+  const int nsteps = 2 * ntiles;
+  const int row = q0 + tid;
+  const long long stat_idx = (static_cast<long long>(b) * p.nh + h) * p.Sq + row;
+  const float lse2 = (row < p.Sq) ? p.lse[stat_idx] * kLog2e : 0.f;
+  const float sl2 = p.scale * kLog2e;
+
+  if (tid == 0) {
+    ptx::mbar_expect_tx(bar_kv, 16384 * 2 + 8192 * 2);
+    tma_load_3d(sQ, &tmQ, bar_kv, h * HD, q0, b);
+    tma_load_3d(sdO, &tmdO, bar_kv, h * HD, q0, b);
+    tma_load_3d(sK, &tmK, bar_kv, h * HD, 0, b);
+    tma_load_3d(sV, &tmV, bar_kv, h * HD, 0, b);
+  }
+  float dsum = 0.f;
+  uint32_t par_o = 0;
+  for (int st = 0; st < nsteps; ++st) {
+    const int j = st % ntiles;
+    const bool sweep2 = st >= ntiles;
+    const uint32_t par = st & 1;
+    const int nvalid = min(BWD_BN, p.Skv - j * BWD_BN);
+    const int n16 = (nvalid + 15) & ~15;
+    if (tid == 0) {
+      ptx::mbar_wait(bar_kv, par);
+      ptx::tc_fence_after();
+      const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)  // S = Q K_j^T
+        ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc, ks > 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)  // dP = dO V_j^T
+        ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sdO), ks), desc_kmajor(ptx::smem_u32(sV), ks), idesc, ks > 0);
+      ptx::umma_commit(bar_s);
+    }
+    ptx::mbar_wait(bar_s, par);
+    ptx::tc_fence_after();
+    for (int c = 0; c < n16; c += 16) {
+      uint32_t s16[16], d16[16];
+      tmem_ld_32x32b_x16(t_row + c, s16);
+      tmem_ld_32x32b_x16(t_row + 64 + c, d16);
+      ptx::tmem_ld_wait();
+      if (!sweep2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s16[i]) * sl2 - lse2) : 0.f;
+          dsum = fmaf(pr, __uint_as_float(d16[i]), dsum);
+        }
+      } else {
+        float ds[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s16[i]) * sl2 - lse2) : 0.f;
+          ds[i] = pr * (__uint_as_float(d16[i]) - dsum) * p.scale;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          uint4 u;
+          u.x = pack_bf16(ds[i], ds[i + 1]); u.y = pack_bf16(ds[i + 2], ds[i + 3]);
+          u.z = pack_bf16(ds[i + 4], ds[i + 5]); u.w = pack_bf16(ds[i + 6], ds[i + 7]);
+          st_operand_chunk(sdS, tid, c + i, u);
+        }
+      }
+    }
+    if (st == ntiles - 1 && row < p.Sq) p.dvec[stat_idx] = dsum;  // D for the dK/dV kernels
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (sweep2) {
+      if (tid == 0) {
+        ptx::tc_fence_after();
+        const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
+        const int ksteps = n16 >> 4;
+        for (int ks = 0; ks < ksteps; ++ks)  // dQ += dS K_j   (K_j consumed as an MN-major operand)
+          ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(sdS), ks), desc_mnmajor(ptx::smem_u32(sK), ks), idesc,
+                        (st > ntiles || ks > 0) ? 1u : 0u);
+        ptx::umma_commit(bar_o);
+      }
+      ptx::mbar_wait(bar_o, par_o);
+      par_o ^= 1;
+      ptx::tc_fence_after();
+    }
+    if (tid == 0 && st + 1 < nsteps) {
+      const int jn = (st + 1) % ntiles;
+      ptx::mbar_expect_tx(bar_kv, 8192 * 2);
+      tma_load_3d(sK, &tmK, bar_kv, h * HD, jn * BWD_BN, b);
+      tma_load_3d(sV, &tmV, bar_kv, h * HD, jn * BWD_BN, b);
+    }
+  }
+  bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD;
+#pragma unroll
+  for (int c = 0; c < HD; c += 32) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(t_row + 128 + c, r);
+    ptx::tmem_ld_wait();
+    if (row < p.Sq) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+        u.y = pack_bf16(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        u.z = pack_bf16(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+        u.w = pack_bf16(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+        *reinterpret_cast<uint4*>(orow + c + i) = u;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dK, dV
+// TMEM columns: S^T [0,64)  dP^T [64,128)  dK [128,192)  dV [192,256).
+// smem: K_j 16K | V_j 16K | Q_i 8K | dO_i 8K | P^T 16K | dS^T 16K | lse/D 512 B
+constexpr int DKDV_SMEM = 16384 * 2 + 8192 * 2 + 16384 * 2 + 512 + 1024 + 64;
+
+__global__ void __launch_bounds__(128)
+attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                        const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                        const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + 16384;
+  uint8_t* sQ = smem + 32768;
+  uint8_t* sdO = smem + 40960;
+  uint8_t* sPT = smem + 49152;
+  uint8_t* sdST = smem + 65536;
+  float* sL = reinterpret_cast<float*>(smem + 81920);
+  float* sD = sL + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920 + 512);
+  uint64_t* bar_ld = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_o = bars + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  if (tid == 0) {
+    ptx::mbar_init(bar_ld, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const int ntiles = ceil_div(p.Sq, BWD_BN);
+  const int kvrow = kv0 + tid;
+  const bool kv_ok = kvrow < p.Skv;
+  const float sl2 = p.scale * kLog2e;
+  const long long stat_base = (static_cast<long long>(b) * p.nh + h) * p.Sq;
+
+  if (tid == 0) {
+    ptx::mbar_expect_tx(bar_ld, 16384 * 2 + 8192 * 2);
+    tma_load_3d(sK, &tmK, bar_ld, h * HD, kv0, b);
+    tma_load_3d(sV, &tmV, bar_ld, h * HD, kv0, b);
+    tma_load_3d(sQ, &tmQ, bar_ld, h * HD, 0, b);
+    tma_load_3d(sdO, &tmdO, bar_ld, h * HD, 0, b);
+  }
+  for (int i = 0; i < ntiles; ++i) {
+    const uint32_t par = i & 1;
+    const int q0 = i * BWD_BN;
+    const int nvalid = min(BWD_BN, p.Sq - q0);
+    const int n16 = (nvalid + 15) & ~15;
+    if (tid < BWD_BN) {
+      const int r = q0 + tid;
+      sL[tid] = (r < p.Sq) ? p.lse[stat_base + r] * kLog2e : 0.f;
+      sD[tid] = (r < p.Sq) ? p.dvec[stat_base + r] : 0.f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      ptx::mbar_wait(bar_ld, par);
+      ptx::tc_fence_after();
+      const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)  // S^T = K_j Q_i^T
+        ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sK), ks), desc_kmajor(ptx::smem_u32(sQ), ks), idesc, ks > 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)  // dP^T = V_j dO_i^T
+        ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sV), ks), desc_kmajor(ptx::smem_u32(sdO), ks), idesc, ks > 0);
+      ptx::umma_commit(bar_s);
+    }
+    ptx::mbar_wait(bar_s, par);
+    ptx::tc_fence_after();
+    for (int c = 0; c < n16; c += 16) {
+      uint32_t s16[16], d16[16];
+      tmem_ld_32x32b_x16(t_row + c, s16);
+      tmem_ld_32x32b_x16(t_row + 64 + c, d16);
+      ptx::tmem_ld_wait();
+      float pt[16], ds[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const bool ok = kv_ok && (c + k < nvalid);
+        const float pr = ok ? exp2f(__uint_as_float(s16[k]) * sl2 - sL[c + k]) : 0.f;
+        pt[k] = pr;
+        ds[k] = pr * (__uint_as_float(d16[k]) - sD[c + k]) * p.scale;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k += 8) {
+        uint4 u, v;
+        u.x = pack_bf16(pt[k], pt[k + 1]); u.y = pack_bf16(pt[k + 2], pt[k + 3]);
+        u.z = pack_bf16(pt[k + 4], pt[k + 5]); u.w = pack_bf16(pt[k + 6], pt[k + 7]);
+        v.x = pack_bf16(ds[k], ds[k + 1]); v.y = pack_bf16(ds[k + 2], ds[k + 3]);
+        v.z = pack_bf16(ds[k + 4], ds[k + 5]); v.w = pack_bf16(ds[k + 6], ds[k + 7]);
+        st_operand_chunk(sPT, tid, c + k, u);
+        st_operand_chunk(sdST, tid, c + k, v);
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
+      const int ksteps = n16 >> 4;
+      for (int ks = 0; ks < ksteps; ++ks)  // dV += P^T dO_i
+        ptx::umma_f16(tmem + 192, desc_kmajor(ptx::smem_u32(sPT), ks), desc_mnmajor(ptx::smem_u32(sdO), ks), idesc,
+                      (i > 0 || ks > 0) ? 1u : 0u);
+      for (int ks = 0; ks < ksteps; ++ks)  // dK += dS^T Q_i
+        ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(sdST), ks), desc_mnmajor(ptx::smem_u32(sQ), ks), idesc,
+                      (i > 0 || ks > 0) ? 1u : 0u);
+      ptx::umma_commit(bar_o);
+    }
+    ptx::mbar_wait(bar_o, par);
+    ptx::tc_fence_after();
+    if (tid == 0 && i + 1 < ntiles) {
+      ptx::mbar_expect_tx(bar_ld, 8192 * 2);
+      tma_load_3d(sQ, &tmQ, bar_ld, h * HD, (i + 1) * BWD_BN, b);
+      tma_load_3d(sdO, &tmdO, bar_ld, h * HD, (i + 1) * BWD_BN, b);
+    }
+  }
+  bf16* krow = p.out0 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out0_rs + h * HD;
+  bf16* vrow = p.out1 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out1_rs + h * HD;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(t_row + 128 + half * 64 + c, r);
+      ptx::tmem_ld_wait();
+      if (kv_ok) {
+        bf16* dst = (half == 0 ? krow : vrow) + c;
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
+          u.y = pack_bf16(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
+          u.z = pack_bf16(__uint_as_float(r[k + 4]), __uint_as_float(r[k + 5]));
+          u.w = pack_bf16(__uint_as_float(r[k + 6]), __uint_as_float(r[k + 7]));
+          *reinterpret_cast<uint4*>(dst + k) = u;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+template <typename K>
+int set_smem(K kern, int bytes, bool* done) {
+  if (*done) return MUSE_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(attention smem=%d): %s", bytes, cudaGetErrorString(e)); return MUSE_ERR_CUDA; }
+  *done = true;
+  return MUSE_OK;
+}
+
+}  // namespace
+
+// Full 128-row q tiles of the forward pass. Returns the number of q rows covered (a multiple of 128).
+int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv,
+                int q_rs, int k_rs, int v_rs, int o_rs, float scale, cudaStream_t s, int* rows_done) {
+  *rows_done = 0;
+  const int ntile = Sq / 128;
+  if (ntile == 0) return MUSE_OK;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap3(&tq, q, nh * HD, Sq, B, q_rs, 128))) return rc;
+  if ((rc = make_tmap3(&tk, k, nh * HD, Skv, B, k_rs, FWD_BN))) return rc;
+  if ((rc = make_tmap3(&tv, v, nh * HD, Skv, B, v_rs, FWD_BN))) return rc;
+  static bool attr = false;
+  if ((rc = set_smem(attn_fwd_tc_kernel, FWD_SMEM, &attr))) return rc;
+  TcParams p{};
+  p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
+  p.out0 = reinterpret_cast<bf16*>(o); p.out0_rs = o_rs; p.lse = lse;
+  attn_fwd_tc_kernel<<<dim3(ntile, nh, B), 128, FWD_SMEM, s>>>(tq, tk, tv, p);
+  *rows_done = ntile * 128;
+  return check_launch("attn_fwd_tc");
+}
+
+int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o, const float* lse, float* dvec,
+                   void* dq, int B, int nh, int Sq, int Skv, int q_rs, int k_rs, int v_rs, int do_rs, int dq_rs,
+                   float scale, cudaStream_t s, int* rows_done) {
+  *rows_done = 0;
+  const int ntile = Sq / 128;
+  if (ntile == 0) return MUSE_OK;
+  CUtensorMap tq, tdo, tk, tv;
+  int rc;
+  if ((rc = make_tmap3(&tq, q, nh * HD, Sq, B, q_rs, 128))) return rc;
+  if ((rc = make_tmap3(&tdo, d_o, nh * HD, Sq, B, do_rs, 128))) return rc;
+  if ((rc = make_tmap3(&tk, k, nh * HD, Skv, B, k_rs, BWD_BN))) return rc;
+  if ((rc = make_tmap3(&tv, v, nh * HD, Skv, B, v_rs, BWD_BN))) return rc;
+  static bool attr = false;
+  if ((rc = set_smem(attn_bwd_dq_tc_kernel, DQ_SMEM, &attr))) return rc;
+  TcParams p{};
+  p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
+  p.out0 = reinterpret_cast<bf16*>(dq); p.out0_rs = dq_rs; p.lse = const_cast<float*>(lse); p.dvec = dvec;
+  attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 128, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
+  *rows_done = ntile * 128;
+  return check_launch("attn_bwd_dq_tc");
+}
+
+int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_o, const float* lse,
+                     const float* dvec, void* dk, void* dv, int B, int nh, int Sq, int Skv, int q_rs, int k_rs,
+                     int v_rs, int do_rs, int dk_rs, int dv_rs, float scale, cudaStream_t s, int* rows_done) {
+  *rows_done = 0;
+  const int ntile = Skv / 128;
+  if (ntile == 0) return MUSE_OK;
+  CUtensorMap tq, tdo, tk, tv;
+  int rc;
+  if ((rc = make_tmap3(&tk, k, nh * HD, Skv, B, k_rs, 128))) return rc;
+  if ((rc = make_tmap3(&tv, v, nh * HD, Skv, B, v_rs, 128))) return rc;
+  if ((rc = make_tmap3(&tq, q, nh * HD, Sq, B, q_rs, BWD_BN))) return rc;
+  if ((rc = make_tmap3(&tdo, d_o, nh * HD, Sq, B, do_rs, BWD_BN))) return rc;
+  static bool attr = false;
+  if ((rc = set_smem(attn_bwd_dkdv_tc_kernel, DKDV_SMEM, &attr))) return rc;
+  TcParams p{};
+  p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
+  p.out0 = reinterpret_cast<bf16*>(dk); p.out0_rs = dk_rs; p.out1 = reinterpret_cast<bf16*>(dv); p.out1_rs = dv_rs;
+  p.lse = const_cast<float*>(lse); p.dvec = const_cast<float*>(dvec);
+  attn_bwd_dkdv_tc_kernel<<<dim3(ntile, nh, B), 128, DKDV_SMEM, s>>>(tk, tv, tq, tdo, p);
+  *rows_done = ntile * 128;
+  return check_launch("attn_bwd_dkdv_tc");
+}
+
+}  // namespace muse

@@ -309,6 +309,36 @@ int make_tmap(CUtensorMap* map, const void* base, long long inner, long long out
   return MUSE_OK;
 }
 
+}  // namespace
+
+// 3-D bf16 tensor map {cols, rows, batches} over a [batches*rows, pitch] row-major buffer: box {64 cols, box_rows, 1},
+// 128-byte swizzle.  Rows past `rows` inside a batch are out of bounds -> zero-filled by the TMA unit.
+int make_tmap3(CUtensorMap* map, const void* base, long long cols, long long rows, long long batches,
+               long long row_pitch_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MUSE_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_pitch_elems * 2) % 16 != 0) {
+    set_last_error("attention: operand base must be 16B aligned and the row stride a multiple of 8 elements");
+    return MUSE_ERR_INVALID;
+  }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batches)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_pitch_elems) * 2,
+                           static_cast<cuuint64_t>(rows) * static_cast<cuuint64_t>(row_pitch_elems) * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(3D) failed with CUresult %d (cols=%lld rows=%lld batches=%lld pitch=%lld)",
+                   (int)r, cols, rows, batches, row_pitch_elems);
+    return MUSE_ERR_CUDA;
+  }
+  return MUSE_OK;
+}
+
+namespace {
+
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
