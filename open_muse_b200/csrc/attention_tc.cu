@@ -89,27 +89,28 @@ struct TcParams {
 
 // ------------------------------------------------------------------------------------------------ forward
 constexpr int FWD_BN = 128;
-constexpr int FWD_SMEM = 16384 /*Q*/ + 16384 /*K*/ + 16384 /*V*/ + 32768 /*P*/ + 1024 /*align*/ + 64;
+constexpr int FWD_SMEM = 16384 /*Q*/ + 2 * (16384 /*K*/ + 16384 /*V*/) + 32768 /*P*/ + 64;  // 2 CTAs/SM: <= 113 KB each
 
 __global__ void __launch_bounds__(128)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzled tiles need 1024 B alignment
+  uint8_t* smem = smem_raw;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;
-  uint8_t* sV = smem + 32768;
-  uint8_t* sP = smem + 49152;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
-  uint64_t* bar_kv = bars;      // TMA landed
-  uint64_t* bar_s = bars + 1;   // score MMA done
-  uint64_t* bar_o = bars + 2;   // accumulate MMA done
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+  uint8_t* sKV = smem + 16384;  // 2 stages x {K 16 KB, V 16 KB}
+  uint8_t* sP = smem + 16384 + 65536;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 65536 + 32768);
+  uint64_t* bar_kv = bars;      // [2] TMA landed (per stage)
+  uint64_t* bar_s = bars + 2;   // score MMA done
+  uint64_t* bar_o = bars + 3;   // accumulate MMA done
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (tid == 0) {
-    ptx::mbar_init(bar_kv, 1);
+    ptx::mbar_init(&bar_kv[0], 1);
+    ptx::mbar_init(&bar_kv[1], 1);
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_o, 1);
     ptx::fence_barrier_init();
@@ -127,10 +128,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int ntiles = ceil_div(p.Skv, FWD_BN);
 
   if (tid == 0) {
-    ptx::mbar_expect_tx(bar_kv, 16384 * 3);
-    tma_load_3d(sQ, &tmQ, bar_kv, h * HD, q0, b);
-    tma_load_3d(sK, &tmK, bar_kv, h * HD, 0, b);
-    tma_load_3d(sV, &tmV, bar_kv, h * HD, 0, b);
+    ptx::mbar_expect_tx(&bar_kv[0], 16384 * 3);
+    tma_load_3d(sQ, &tmQ, &bar_kv[0], h * HD, q0, b);
+    tma_load_3d(sKV, &tmK, &bar_kv[0], h * HD, 0, b);
+    tma_load_3d(sKV + 16384, &tmV, &bar_kv[0], h * HD, 0, b);
   }
   const float sl2 = p.scale * kLog2e;
   float m = -INFINITY, l = 0.f;
@@ -139,8 +140,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t par = j & 1;
     const int nvalid = min(FWD_BN, p.Skv - j * FWD_BN);
     const int n16 = (nvalid + 15) & ~15;
+    uint8_t* sK = sKV + (j & 1) * 32768;
+    uint8_t* sV = sK + 16384;
     if (tid == 0) {
-      ptx::mbar_wait(bar_kv, par);
+      if (j + 1 < ntiles) {  // prefetch the next K/V tile into the other stage (its last readers finished at bar_o of j-1)
+        uint8_t* nK = sKV + ((j + 1) & 1) * 32768;
+        ptx::mbar_expect_tx(&bar_kv[(j + 1) & 1], 16384 * 2);
+        tma_load_3d(nK, &tmK, &bar_kv[(j + 1) & 1], h * HD, (j + 1) * FWD_BN, b);
+        tma_load_3d(nK + 16384, &tmV, &bar_kv[(j + 1) & 1], h * HD, (j + 1) * FWD_BN, b);
+      }
+      ptx::mbar_wait(&bar_kv[j & 1], (j >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
 #pragma unroll
@@ -228,11 +237,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     ptx::mbar_wait(bar_o, par);
     ptx::tc_fence_after();
-    if (tid == 0 && j + 1 < ntiles) {
-      ptx::mbar_expect_tx(bar_kv, 16384 * 2);
-      tma_load_3d(sK, &tmK, bar_kv, h * HD, (j + 1) * FWD_BN, b);
-      tma_load_3d(sV, &tmV, bar_kv, h * HD, (j + 1) * FWD_BN, b);
-    }
   }
   // epilogue: O / l -> bf16 rows, LSE
   const int row = q0 + tid;
@@ -267,29 +271,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ------------------------------------------------------------------------------------------------ backward: dQ
 // TMEM columns: S [0,64)  dP [64,128)  dQ [128,192).  smem: Q 16K | dO 16K | K_j 8K | V_j 8K | dS 16K
 constexpr int BWD_BN = 64;
-constexpr int DQ_SMEM = 16384 * 2 + 8192 * 2 + 16384 + 1024 + 64;
+constexpr int DQ_SMEM = 16384 * 2 + 2 * (8192 * 2) + 16384 + 64;
 
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzled tiles need 1024 B alignment
+  uint8_t* smem = smem_raw;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + 16384;
-  uint8_t* sK = smem + 32768;
-  uint8_t* sV = smem + 40960;
-  uint8_t* sdS = smem + 49152;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536);
-  uint64_t* bar_kv = bars;
-  uint64_t* bar_s = bars + 1;
-  uint64_t* bar_o = bars + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+  uint8_t* sKV = smem + 32768;   // 2 stages x {K 8 KB, V 8 KB}
+  uint8_t* sdS = smem + 65536;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
+  uint64_t* bar_kv = bars;       // [2]
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_o = bars + 3;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (tid == 0) {
-    ptx::mbar_init(bar_kv, 1);
+    ptx::mbar_init(&bar_kv[0], 1);
+    ptx::mbar_init(&bar_kv[1], 1);
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_o, 1);
     ptx::fence_barrier_init();
@@ -311,11 +316,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const float sl2 = p.scale * kLog2e;
 
   if (tid == 0) {
-    ptx::mbar_expect_tx(bar_kv, 16384 * 2 + 8192 * 2);
-    tma_load_3d(sQ, &tmQ, bar_kv, h * HD, q0, b);
-    tma_load_3d(sdO, &tmdO, bar_kv, h * HD, q0, b);
-    tma_load_3d(sK, &tmK, bar_kv, h * HD, 0, b);
-    tma_load_3d(sV, &tmV, bar_kv, h * HD, 0, b);
+    ptx::mbar_expect_tx(&bar_kv[0], 16384 * 2 + 8192 * 2);
+    tma_load_3d(sQ, &tmQ, &bar_kv[0], h * HD, q0, b);
+    tma_load_3d(sdO, &tmdO, &bar_kv[0], h * HD, q0, b);
+    tma_load_3d(sKV, &tmK, &bar_kv[0], h * HD, 0, b);
+    tma_load_3d(sKV + 8192, &tmV, &bar_kv[0], h * HD, 0, b);
   }
   float dsum = 0.f;
   uint32_t par_o = 0;
@@ -325,8 +330,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t par = st & 1;
     const int nvalid = min(BWD_BN, p.Skv - j * BWD_BN);
     const int n16 = (nvalid + 15) & ~15;
+    uint8_t* sK = sKV + (st & 1) * 16384;
+    uint8_t* sV = sK + 8192;
     if (tid == 0) {
-      ptx::mbar_wait(bar_kv, par);
+      if (st + 1 < nsteps) {  // prefetch the next K/V tile into the other stage
+        const int jn = (st + 1) % ntiles;
+        uint8_t* nK = sKV + ((st + 1) & 1) * 16384;
+        ptx::mbar_expect_tx(&bar_kv[(st + 1) & 1], 8192 * 2);
+        tma_load_3d(nK, &tmK, &bar_kv[(st + 1) & 1], h * HD, jn * BWD_BN, b);
+        tma_load_3d(nK + 8192, &tmV, &bar_kv[(st + 1) & 1], h * HD, jn * BWD_BN, b);
+      }
+      ptx::mbar_wait(&bar_kv[st & 1], (st >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
 #pragma unroll
@@ -384,12 +398,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       par_o ^= 1;
       ptx::tc_fence_after();
     }
-    if (tid == 0 && st + 1 < nsteps) {
-      const int jn = (st + 1) % ntiles;
-      ptx::mbar_expect_tx(bar_kv, 8192 * 2);
-      tma_load_3d(sK, &tmK, bar_kv, h * HD, jn * BWD_BN, b);
-      tma_load_3d(sV, &tmV, bar_kv, h * HD, jn * BWD_BN, b);
-    }
   }
   bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD;
 #pragma unroll
@@ -420,32 +428,33 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 // TMEM columns: S^T [0,64)  dP^T [64,128)  dK [128,192)  dV [192,256).
 // smem: K_j 16K | V_j 16K | Q_i 8K | dO_i 8K | P^T 16K | dS^T 16K | lse/D 512 B
-constexpr int DKDV_SMEM = 16384 * 2 + 8192 * 2 + 16384 * 2 + 512 + 1024 + 64;
+constexpr int DKDV_SMEM = 16384 * 2 + 2 * (8192 * 2) + 16384 * 2 + 512 + 64;
 
 __global__ void __launch_bounds__(128)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                         const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzled tiles need 1024 B alignment
+  uint8_t* smem = smem_raw;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sK = smem;
   uint8_t* sV = smem + 16384;
-  uint8_t* sQ = smem + 32768;
-  uint8_t* sdO = smem + 40960;
-  uint8_t* sPT = smem + 49152;
-  uint8_t* sdST = smem + 65536;
-  float* sL = reinterpret_cast<float*>(smem + 81920);
+  uint8_t* sQO = smem + 32768;   // 2 stages x {Q_i 8 KB, dO_i 8 KB}
+  uint8_t* sPT = smem + 65536;
+  uint8_t* sdST = smem + 81920;
+  float* sL = reinterpret_cast<float*>(smem + 98304);
   float* sD = sL + 64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920 + 512);
-  uint64_t* bar_ld = bars;
-  uint64_t* bar_s = bars + 1;
-  uint64_t* bar_o = bars + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 98304 + 512);
+  uint64_t* bar_ld = bars;       // [2]
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_o = bars + 3;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (tid == 0) {
-    ptx::mbar_init(bar_ld, 1);
+    ptx::mbar_init(&bar_ld[0], 1);
+    ptx::mbar_init(&bar_ld[1], 1);
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_o, 1);
     ptx::fence_barrier_init();
@@ -466,17 +475,19 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   const long long stat_base = (static_cast<long long>(b) * p.nh + h) * p.Sq;
 
   if (tid == 0) {
-    ptx::mbar_expect_tx(bar_ld, 16384 * 2 + 8192 * 2);
-    tma_load_3d(sK, &tmK, bar_ld, h * HD, kv0, b);
-    tma_load_3d(sV, &tmV, bar_ld, h * HD, kv0, b);
-    tma_load_3d(sQ, &tmQ, bar_ld, h * HD, 0, b);
-    tma_load_3d(sdO, &tmdO, bar_ld, h * HD, 0, b);
+    ptx::mbar_expect_tx(&bar_ld[0], 16384 * 2 + 8192 * 2);
+    tma_load_3d(sK, &tmK, &bar_ld[0], h * HD, kv0, b);
+    tma_load_3d(sV, &tmV, &bar_ld[0], h * HD, kv0, b);
+    tma_load_3d(sQO, &tmQ, &bar_ld[0], h * HD, 0, b);
+    tma_load_3d(sQO + 8192, &tmdO, &bar_ld[0], h * HD, 0, b);
   }
   for (int i = 0; i < ntiles; ++i) {
     const uint32_t par = i & 1;
     const int q0 = i * BWD_BN;
     const int nvalid = min(BWD_BN, p.Sq - q0);
     const int n16 = (nvalid + 15) & ~15;
+    uint8_t* sQ = sQO + (i & 1) * 16384;
+    uint8_t* sdO = sQ + 8192;
     if (tid < BWD_BN) {
       const int r = q0 + tid;
       sL[tid] = (r < p.Sq) ? p.lse[stat_base + r] * kLog2e : 0.f;
@@ -484,7 +495,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     }
     __syncthreads();
     if (tid == 0) {
-      ptx::mbar_wait(bar_ld, par);
+      if (i + 1 < ntiles) {  // prefetch the next Q/dO tile into the other stage
+        uint8_t* nQ = sQO + ((i + 1) & 1) * 16384;
+        ptx::mbar_expect_tx(&bar_ld[(i + 1) & 1], 8192 * 2);
+        tma_load_3d(nQ, &tmQ, &bar_ld[(i + 1) & 1], h * HD, (i + 1) * BWD_BN, b);
+        tma_load_3d(nQ + 8192, &tmdO, &bar_ld[(i + 1) & 1], h * HD, (i + 1) * BWD_BN, b);
+      }
+      ptx::mbar_wait(&bar_ld[i & 1], (i >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
 #pragma unroll
@@ -538,11 +555,6 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     }
     ptx::mbar_wait(bar_o, par);
     ptx::tc_fence_after();
-    if (tid == 0 && i + 1 < ntiles) {
-      ptx::mbar_expect_tx(bar_ld, 8192 * 2);
-      tma_load_3d(sQ, &tmQ, bar_ld, h * HD, (i + 1) * BWD_BN, b);
-      tma_load_3d(sdO, &tmdO, bar_ld, h * HD, (i + 1) * BWD_BN, b);
-    }
   }
   bf16* krow = p.out0 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out0_rs + h * HD;
   bf16* vrow = p.out1 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out1_rs + h * HD;
