@@ -88,8 +88,10 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------------------------------------ forward
-constexpr int FWD_BN = 128;
-constexpr int FWD_SMEM = 16384 /*Q*/ + 2 * (16384 /*K*/ + 16384 /*V*/) + 32768 /*P*/ + 64;  // 2 CTAs/SM: <= 113 KB each
+// TMEM columns: S [0,64)  O [64,128) -> 128 columns per CTA; smem 48 KB -> FOUR co-resident CTAs per SM overlap each
+// other's TMA / MMA / softmax latencies (a 128-wide score tile with 2 CTAs/SM measured slower than the mma.sync kernel).
+constexpr int FWD_BN = 64;
+constexpr int FWD_SMEM = 16384 /*Q*/ + 8192 /*K*/ + 8192 /*V*/ + 16384 /*P*/ + 64;
 
 __global__ void __launch_bounds__(128)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -98,40 +100,40 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* smem = smem_raw;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + 16384;  // 2 stages x {K 16 KB, V 16 KB}
-  uint8_t* sP = smem + 16384 + 65536;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384 + 65536 + 32768);
-  uint64_t* bar_kv = bars;      // [2] TMA landed (per stage)
-  uint64_t* bar_s = bars + 2;   // score MMA done
-  uint64_t* bar_o = bars + 3;   // accumulate MMA done
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 24576;
+  uint8_t* sP = smem + 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint64_t* bar_kv = bars;      // TMA landed
+  uint64_t* bar_s = bars + 1;   // score MMA done
+  uint64_t* bar_o = bars + 2;   // accumulate MMA done
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (tid == 0) {
-    ptx::mbar_init(&bar_kv[0], 1);
-    ptx::mbar_init(&bar_kv[1], 1);
+    ptx::mbar_init(bar_kv, 1);
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_o, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(tmem_holder, 256);
+    ptx::tmem_alloc(tmem_holder, 128);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
-  const uint32_t t_s = tmem + (static_cast<uint32_t>(warp * 32) << 16);        // S: columns [0,128)
-  const uint32_t t_o = t_s + 128;                                               // O: columns [128,192)
+  const uint32_t t_s = tmem + (static_cast<uint32_t>(warp * 32) << 16);        // S: columns [0,64)
+  const uint32_t t_o = t_s + 64;                                                // O: columns [64,128)
   const int ntiles = ceil_div(p.Skv, FWD_BN);
 
   if (tid == 0) {
-    ptx::mbar_expect_tx(&bar_kv[0], 16384 * 3);
-    tma_load_3d(sQ, &tmQ, &bar_kv[0], h * HD, q0, b);
-    tma_load_3d(sKV, &tmK, &bar_kv[0], h * HD, 0, b);
-    tma_load_3d(sKV + 16384, &tmV, &bar_kv[0], h * HD, 0, b);
+    ptx::mbar_expect_tx(bar_kv, 16384 + 8192 * 2);
+    tma_load_3d(sQ, &tmQ, bar_kv, h * HD, q0, b);
+    tma_load_3d(sK, &tmK, bar_kv, h * HD, 0, b);
+    tma_load_3d(sV, &tmV, bar_kv, h * HD, 0, b);
   }
   const float sl2 = p.scale * kLog2e;
   float m = -INFINITY, l = 0.f;
@@ -140,16 +142,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t par = j & 1;
     const int nvalid = min(FWD_BN, p.Skv - j * FWD_BN);
     const int n16 = (nvalid + 15) & ~15;
-    uint8_t* sK = sKV + (j & 1) * 32768;
-    uint8_t* sV = sK + 16384;
     if (tid == 0) {
-      if (j + 1 < ntiles) {  // prefetch the next K/V tile into the other stage (its last readers finished at bar_o of j-1)
-        uint8_t* nK = sKV + ((j + 1) & 1) * 32768;
-        ptx::mbar_expect_tx(&bar_kv[(j + 1) & 1], 16384 * 2);
-        tma_load_3d(nK, &tmK, &bar_kv[(j + 1) & 1], h * HD, (j + 1) * FWD_BN, b);
-        tma_load_3d(nK + 16384, &tmV, &bar_kv[(j + 1) & 1], h * HD, (j + 1) * FWD_BN, b);
-      }
-      ptx::mbar_wait(&bar_kv[j & 1], (j >> 1) & 1);
+      ptx::mbar_wait(bar_kv, par);
       ptx::tc_fence_after();
       const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
 #pragma unroll
@@ -159,56 +153,42 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     ptx::mbar_wait(bar_s, par);
     ptx::tc_fence_after();
-    // pass 1: row maximum of the scaled scores
-    float mx = m;
-    for (int c = 0; c < n16; c += 32) {
-      uint32_t r[32];
-      if (n16 - c >= 32) {
-        ptx::tmem_ld_32x32b_x32(t_s + c, r);
-      } else {
+    // the whole score row (<= 64 columns) fits in registers: one TMEM read, max, exp2, pack
+    float sc[64];
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) {
+      if (c < n16) {
         uint32_t r16[16];
         tmem_ld_32x32b_x16(t_s + c, r16);
+        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0xff800000u; }
+        for (int i = 0; i < 16; ++i) sc[c + i] = (c + i < nvalid) ? __uint_as_float(r16[i]) * sl2 : -INFINITY;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sc[c + i] = -INFINITY;
       }
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c + i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]) * sl2);
     }
+    float mx = m;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) mx = fmaxf(mx, sc[i]);
     const float alpha = exp2f(m - mx);  // 0 on the first tile (m = -inf)
     m = mx;
-    // pass 2: P = exp2(s - m) -> bf16 operand in smem; row sum
     float ladd = 0.f;
-    for (int c = 0; c < n16; c += 32) {
-      uint32_t r[32];
-      if (n16 - c >= 32) {
-        ptx::tmem_ld_32x32b_x32(t_s + c, r);
-      } else {
-        uint32_t r16[16];
-        tmem_ld_32x32b_x16(t_s + c, r16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { r[i] = r16[i]; r[16 + i] = 0u; }
-      }
-      ptx::tmem_ld_wait();
-      float pv[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = (c + i < nvalid) ? exp2f(__uint_as_float(r[i]) * sl2 - m) : 0.f;
-        pv[i] = e;
-        ladd += e;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (c + i < n16) {
-          uint4 u;
-          u.x = pack_bf16(pv[i], pv[i + 1]); u.y = pack_bf16(pv[i + 2], pv[i + 3]);
-          u.z = pack_bf16(pv[i + 4], pv[i + 5]); u.w = pack_bf16(pv[i + 6], pv[i + 7]);
-          st_operand_chunk(sP, tid, c + i, u);
-        }
-      }
+    for (int i = 0; i < 64; ++i) {
+      sc[i] = exp2f(sc[i] - m);
+      ladd += sc[i];
     }
     l = l * alpha + ladd;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+      if (i < n16) {
+        uint4 u;
+        u.x = pack_bf16(sc[i], sc[i + 1]); u.y = pack_bf16(sc[i + 2], sc[i + 3]);
+        u.z = pack_bf16(sc[i + 4], sc[i + 5]); u.w = pack_bf16(sc[i + 6], sc[i + 7]);
+        st_operand_chunk(sP, tid, i, u);
+      }
+    }
     // rescale the running output (the previous accumulate MMA finished: bar_o was waited at the end of iteration j-1)
     if (j > 0) {
 #pragma unroll
@@ -229,14 +209,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::tc_fence_after();
       const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
       const int ksteps = n16 >> 4;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t a = ptx::make_smem_desc_sw128(ptx::smem_u32(sP) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-        ptx::umma_f16(tmem + 128, a, desc_mnmajor(ptx::smem_u32(sV), ks), idesc, (j > 0 || ks > 0) ? 1u : 0u);
-      }
+      for (int ks = 0; ks < ksteps; ++ks)
+        ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sP), ks), desc_mnmajor(ptx::smem_u32(sV), ks), idesc,
+                      (j > 0 || ks > 0) ? 1u : 0u);
       ptx::umma_commit(bar_o);
     }
     ptx::mbar_wait(bar_o, par);
     ptx::tc_fence_after();
+    if (tid == 0 && j + 1 < ntiles) {
+      ptx::mbar_expect_tx(bar_kv, 8192 * 2);
+      tma_load_3d(sK, &tmK, bar_kv, h * HD, (j + 1) * FWD_BN, b);
+      tma_load_3d(sV, &tmV, bar_kv, h * HD, (j + 1) * FWD_BN, b);
+    }
   }
   // epilogue: O / l -> bf16 rows, LSE
   const int row = q0 + tid;
@@ -264,33 +248,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   if (warp == 0) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, 256);
+    ptx::tmem_dealloc(tmem, 128);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dQ
-// TMEM columns: S [0,64)  dP [64,128)  dQ [128,192).  smem: Q 16K | dO 16K | K_j 8K | V_j 8K | dS 16K
+// 256 threads: warps w and w+4 share TMEM lanes (rows) 32*(w%4).. and split the 64 score columns in two halves, which
+// doubles the exp2/FMA lanes per CTA (TMEM limits these kernels to two CTAs per SM).
+// TMEM columns: S [0,64)  dP [64,128)  dQ [128,192).  smem: Q 16K | dO 16K | 2 x {K_j 8K, V_j 8K} | dS 16K
 constexpr int BWD_BN = 64;
-constexpr int DQ_SMEM = 16384 * 2 + 2 * (8192 * 2) + 16384 + 64;
+constexpr int DQ_SMEM = 16384 * 2 + 2 * (8192 * 2) + 16384 + 1024 + 64;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const TcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzled tiles need 1024 B alignment
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + 16384;
   uint8_t* sKV = smem + 32768;   // 2 stages x {K 8 KB, V 8 KB}
   uint8_t* sdS = smem + 65536;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
+  float* sDp = reinterpret_cast<float*>(smem + 81920);  // [2][128] partial D of the two column halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920 + 1024);
   uint64_t* bar_kv = bars;       // [2]
   uint64_t* bar_s = bars + 2;
   uint64_t* bar_o = bars + 3;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;                 // column half handled by this thread
+  const int r = (warp & 3) * 32 + lane;       // row (TMEM lane) handled by this thread
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (tid == 0) {
     ptx::mbar_init(&bar_kv[0], 1);
@@ -307,10 +296,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const int ntiles = ceil_div(p.Skv, BWD_BN);
   const int nsteps = 2 * ntiles;
-  const int row = q0 + tid;
+  const int row = q0 + r;
   const long long stat_idx = (static_cast<long long>(b) * p.nh + h) * p.Sq + row;
   const float lse2 = (row < p.Sq) ? p.lse[stat_idx] * kLog2e : 0.f;
   const float sl2 = p.scale * kLog2e;
@@ -353,37 +342,45 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     ptx::mbar_wait(bar_s, par);
     ptx::tc_fence_after();
-    for (int c = 0; c < n16; c += 16) {
-      uint32_t s16[16], d16[16];
-      tmem_ld_32x32b_x16(t_row + c, s16);
-      tmem_ld_32x32b_x16(t_row + 64 + c, d16);
-      ptx::tmem_ld_wait();
-      if (!sweep2) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s16[i]) * sl2 - lse2) : 0.f;
-          dsum = fmaf(pr, __uint_as_float(d16[i]), dsum);
-        }
-      } else {
-        float ds[16];
+    for (int cc = 0; cc < 32; cc += 16) {
+      const int c = half * 32 + cc;
+      if (c < n16) {
+        uint32_t s16[16], d16[16];
+        tmem_ld_32x32b_x16(t_row + c, s16);
+        tmem_ld_32x32b_x16(t_row + 64 + c, d16);
+        ptx::tmem_ld_wait();
+        if (!sweep2) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s16[i]) * sl2 - lse2) : 0.f;
-          ds[i] = pr * (__uint_as_float(d16[i]) - dsum) * p.scale;
-        }
+          for (int i = 0; i < 16; ++i) {
+            const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s16[i]) * sl2 - lse2) : 0.f;
+            dsum = fmaf(pr, __uint_as_float(d16[i]), dsum);
+          }
+        } else {
+          float ds[16];
 #pragma unroll
-        for (int i = 0; i < 16; i += 8) {
-          uint4 u;
-          u.x = pack_bf16(ds[i], ds[i + 1]); u.y = pack_bf16(ds[i + 2], ds[i + 3]);
-          u.z = pack_bf16(ds[i + 4], ds[i + 5]); u.w = pack_bf16(ds[i + 6], ds[i + 7]);
-          st_operand_chunk(sdS, tid, c + i, u);
+          for (int i = 0; i < 16; ++i) {
+            const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s16[i]) * sl2 - lse2) : 0.f;
+            ds[i] = pr * (__uint_as_float(d16[i]) - dsum) * p.scale;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 8) {
+            uint4 u;
+            u.x = pack_bf16(ds[i], ds[i + 1]); u.y = pack_bf16(ds[i + 2], ds[i + 3]);
+            u.z = pack_bf16(ds[i + 4], ds[i + 5]); u.w = pack_bf16(ds[i + 6], ds[i + 7]);
+            st_operand_chunk(sdS, r, c + i, u);
+          }
         }
       }
     }
-    if (st == ntiles - 1 && row < p.Sq) p.dvec[stat_idx] = dsum;  // D for the dK/dV kernels
+    if (st == ntiles - 1) sDp[half * 128 + r] = dsum;  // partial D of this column half
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
     __syncthreads();
+    if (st == ntiles - 1) {  // D = sum over both halves, identical in both threads of the row
+      dsum = sDp[r] + sDp[128 + r];
+      if (half == 0 && row < p.Sq) p.dvec[stat_idx] = dsum;  // for the dK/dV kernels
+    }
     if (sweep2) {
       if (tid == 0) {
         ptx::tc_fence_after();
@@ -399,21 +396,20 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::tc_fence_after();
     }
   }
-  bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD;
-#pragma unroll
-  for (int c = 0; c < HD; c += 32) {
-    uint32_t r[32];
-    ptx::tmem_ld_32x32b_x32(t_row + 128 + c, r);
+  {
+    bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD + half * 32;
+    uint32_t rr[32];
+    ptx::tmem_ld_32x32b_x32(t_row + 128 + half * 32, rr);
     ptx::tmem_ld_wait();
     if (row < p.Sq) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 u;
-        u.x = pack_bf16(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-        u.y = pack_bf16(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-        u.z = pack_bf16(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
-        u.w = pack_bf16(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
-        *reinterpret_cast<uint4*>(orow + c + i) = u;
+        u.x = pack_bf16(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1]));
+        u.y = pack_bf16(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
+        u.z = pack_bf16(__uint_as_float(rr[i + 4]), __uint_as_float(rr[i + 5]));
+        u.w = pack_bf16(__uint_as_float(rr[i + 6]), __uint_as_float(rr[i + 7]));
+        *reinterpret_cast<uint4*>(orow + i) = u;
       }
     }
   }
@@ -426,15 +422,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
-// TMEM columns: S^T [0,64)  dP^T [64,128)  dK [128,192)  dV [192,256).
-// smem: K_j 16K | V_j 16K | Q_i 8K | dO_i 8K | P^T 16K | dS^T 16K | lse/D 512 B
+// TMEM columns: S^T [0,64)  dP^T [64,128)  dK [128,192)  dV [192,256).  256 threads, column halves as in the dQ kernel.
+// smem: K_j 16K | V_j 16K | 2 x {Q_i 8K, dO_i 8K} | P^T 16K | dS^T 16K | lse/D 512 B
 constexpr int DKDV_SMEM = 16384 * 2 + 2 * (8192 * 2) + 16384 * 2 + 512 + 64;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                         const TcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzled tiles need 1024 B alignment
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sK = smem;
@@ -450,7 +446,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   uint64_t* bar_o = bars + 3;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
+  const int r = (warp & 3) * 32 + lane;
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (tid == 0) {
     ptx::mbar_init(&bar_ld[0], 1);
@@ -467,9 +465,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const int ntiles = ceil_div(p.Sq, BWD_BN);
-  const int kvrow = kv0 + tid;
+  const int kvrow = kv0 + r;
   const bool kv_ok = kvrow < p.Skv;
   const float sl2 = p.scale * kLog2e;
   const long long stat_base = (static_cast<long long>(b) * p.nh + h) * p.Sq;
@@ -489,9 +487,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     uint8_t* sQ = sQO + (i & 1) * 16384;
     uint8_t* sdO = sQ + 8192;
     if (tid < BWD_BN) {
-      const int r = q0 + tid;
-      sL[tid] = (r < p.Sq) ? p.lse[stat_base + r] * kLog2e : 0.f;
-      sD[tid] = (r < p.Sq) ? p.dvec[stat_base + r] : 0.f;
+      const int qr = q0 + tid;
+      sL[tid] = (qr < p.Sq) ? p.lse[stat_base + qr] * kLog2e : 0.f;
+      sD[tid] = (qr < p.Sq) ? p.dvec[stat_base + qr] : 0.f;
     }
     __syncthreads();
     if (tid == 0) {
@@ -514,28 +512,32 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     }
     ptx::mbar_wait(bar_s, par);
     ptx::tc_fence_after();
-    for (int c = 0; c < n16; c += 16) {
-      uint32_t s16[16], d16[16];
-      tmem_ld_32x32b_x16(t_row + c, s16);
-      tmem_ld_32x32b_x16(t_row + 64 + c, d16);
-      ptx::tmem_ld_wait();
-      float pt[16], ds[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const bool ok = kv_ok && (c + k < nvalid);
-        const float pr = ok ? exp2f(__uint_as_float(s16[k]) * sl2 - sL[c + k]) : 0.f;
-        pt[k] = pr;
-        ds[k] = pr * (__uint_as_float(d16[k]) - sD[c + k]) * p.scale;
-      }
+    for (int cc = 0; cc < 32; cc += 16) {
+      const int c = half * 32 + cc;
+      if (c < n16) {
+        uint32_t s16[16], d16[16];
+        tmem_ld_32x32b_x16(t_row + c, s16);
+        tmem_ld_32x32b_x16(t_row + 64 + c, d16);
+        ptx::tmem_ld_wait();
+        float pt[16], ds[16];
 #pragma unroll
-      for (int k = 0; k < 16; k += 8) {
-        uint4 u, v;
-        u.x = pack_bf16(pt[k], pt[k + 1]); u.y = pack_bf16(pt[k + 2], pt[k + 3]);
-        u.z = pack_bf16(pt[k + 4], pt[k + 5]); u.w = pack_bf16(pt[k + 6], pt[k + 7]);
-        v.x = pack_bf16(ds[k], ds[k + 1]); v.y = pack_bf16(ds[k + 2], ds[k + 3]);
-        v.z = pack_bf16(ds[k + 4], ds[k + 5]); v.w = pack_bf16(ds[k + 6], ds[k + 7]);
-        st_operand_chunk(sPT, tid, c + k, u);
-        st_operand_chunk(sdST, tid, c + k, v);
+        for (int k = 0; k < 16; ++k) {
+          const bool ok = kv_ok && (c + k < nvalid);
+          const float pr = ok ? exp2f(__uint_as_float(s16[k]) * sl2 - sL[c + k]) : 0.f;
+          pt[k] = pr;
+          ds[k] = pr * (__uint_as_float(d16[k]) - sD[c + k]) * p.scale;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k += 8) {
+          uint4 u, v;
+          u.x = pack_bf16(pt[k], pt[k + 1]); u.y = pack_bf16(pt[k + 2], pt[k + 3]);
+          u.z = pack_bf16(pt[k + 4], pt[k + 5]); u.w = pack_bf16(pt[k + 6], pt[k + 7]);
+          v.x = pack_bf16(ds[k], ds[k + 1]); v.y = pack_bf16(ds[k + 2], ds[k + 3]);
+          v.z = pack_bf16(ds[k + 4], ds[k + 5]); v.w = pack_bf16(ds[k + 6], ds[k + 7]);
+          st_operand_chunk(sPT, r, c + k, u);
+          st_operand_chunk(sdST, r, c + k, v);
+        }
       }
     }
     ptx::fence_proxy_async();
@@ -556,26 +558,23 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     ptx::mbar_wait(bar_o, par);
     ptx::tc_fence_after();
   }
-  bf16* krow = p.out0 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out0_rs + h * HD;
-  bf16* vrow = p.out1 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out1_rs + h * HD;
+  bf16* krow = p.out0 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out0_rs + h * HD + half * 32;
+  bf16* vrow = p.out1 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out1_rs + h * HD + half * 32;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
+  for (int which = 0; which < 2; ++which) {
+    uint32_t rr[32];
+    ptx::tmem_ld_32x32b_x32(t_row + 128 + which * 64 + half * 32, rr);
+    ptx::tmem_ld_wait();
+    if (kv_ok) {
+      bf16* dst = which == 0 ? krow : vrow;
 #pragma unroll
-    for (int c = 0; c < HD; c += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(t_row + 128 + half * 64 + c, r);
-      ptx::tmem_ld_wait();
-      if (kv_ok) {
-        bf16* dst = (half == 0 ? krow : vrow) + c;
-#pragma unroll
-        for (int k = 0; k < 32; k += 8) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
-          u.y = pack_bf16(__uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
-          u.z = pack_bf16(__uint_as_float(r[k + 4]), __uint_as_float(r[k + 5]));
-          u.w = pack_bf16(__uint_as_float(r[k + 6]), __uint_as_float(r[k + 7]));
-          *reinterpret_cast<uint4*>(dst + k) = u;
-        }
+      for (int k = 0; k < 32; k += 8) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(rr[k]), __uint_as_float(rr[k + 1]));
+        u.y = pack_bf16(__uint_as_float(rr[k + 2]), __uint_as_float(rr[k + 3]));
+        u.z = pack_bf16(__uint_as_float(rr[k + 4]), __uint_as_float(rr[k + 5]));
+        u.w = pack_bf16(__uint_as_float(rr[k + 6]), __uint_as_float(rr[k + 7]));
+        *reinterpret_cast<uint4*>(dst + k) = u;
       }
     }
   }
@@ -590,6 +589,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
 template <typename K>
 int set_smem(K kern, int bytes, bool* done) {
   if (*done) return MUSE_OK;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);  // all of L1/smem as shared memory
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(attention smem=%d): %s", bytes, cudaGetErrorString(e)); return MUSE_ERR_CUDA; }
   *done = true;
@@ -636,7 +636,7 @@ int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o,
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dq); p.out0_rs = dq_rs; p.lse = const_cast<float*>(lse); p.dvec = dvec;
-  attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 128, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
+  attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 256, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
   *rows_done = ntile * 128;
   return check_launch("attn_bwd_dq_tc");
 }
@@ -659,7 +659,7 @@ int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dk); p.out0_rs = dk_rs; p.out1 = reinterpret_cast<bf16*>(dv); p.out1_rs = dv_rs;
   p.lse = const_cast<float*>(lse); p.dvec = const_cast<float*>(dvec);
-  attn_bwd_dkdv_tc_kernel<<<dim3(ntile, nh, B), 128, DKDV_SMEM, s>>>(tk, tv, tq, tdo, p);
+  attn_bwd_dkdv_tc_kernel<<<dim3(ntile, nh, B), 256, DKDV_SMEM, s>>>(tk, tv, tq, tdo, p);
   *rows_done = ntile * 128;
   return check_launch("attn_bwd_dkdv_tc");
 }
