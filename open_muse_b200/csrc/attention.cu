@@ -530,6 +530,15 @@ int attn_bwd_dq_tc(const void*, const void*, const void*, const void*, const flo
 int attn_bwd_dkdv_tc(const void*, const void*, const void*, const void*, const float*, const float*, void*, void*, int,
                      int, int, int, int, int, int, int, int, int, float, cudaStream_t, int*);
 
+// CUDA-core kernels for a few ragged rows (attention_rows.cu)
+bool attn_rows_ok(int nrows);
+int attn_fwd_rows(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, float,
+                  int, int, cudaStream_t);
+int attn_bwd_dq_rows(const void*, const void*, const void*, const void*, const float*, float*, void*, int, int, int,
+                     int, int, int, int, int, int, float, int, int, cudaStream_t);
+int attn_bwd_dkdv_rows(const void*, const void*, const void*, const void*, const float*, const float*, void*, void*,
+                       int, int, int, int, int, int, int, int, int, int, float, int, int, cudaStream_t);
+
 static bool use_tc_attention() {
   static int v = -1;
   if (v < 0) {
@@ -552,6 +561,8 @@ int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, i
     if (rc) return rc;
   }
   if (done >= Sq) return MUSE_OK;
+  if (done > 0 && attn_rows_ok(Sq - done))
+    return attn_fwd_rows(q, k, v, o, lse, B, nh, Sq, Skv, q_rs, k_rs, v_rs, o_rs, scale, done, Sq - done, s);
   AttnPtrs P;
   P.q = reinterpret_cast<const bf16*>(q); P.k = reinterpret_cast<const bf16*>(k); P.v = reinterpret_cast<const bf16*>(v);
   P.q_rs = q_rs; P.k_rs = k_rs; P.v_rs = v_rs;
@@ -579,7 +590,11 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
     rc = attn_bwd_dq_tc(q, k, v, d_o, lse, dvec, dq, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dq_rs, scale, s, &done_q);
     if (rc) return rc;
   }
-  if (done_q < Sq) {
+  if (done_q > 0 && attn_rows_ok(Sq - done_q)) {
+    rc = attn_bwd_dq_rows(q, k, v, d_o, lse, dvec, dq, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dq_rs, scale, done_q,
+                          Sq - done_q, s);
+    if (rc) return rc;
+  } else if (done_q < Sq) {
     const int blk0 = done_q / BQ;
     attn_bwd_dq_kernel<<<dim3(ceil_div(Sq, BQ) - blk0, nh, B), 128, 0, s>>>(
         P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
@@ -592,7 +607,11 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
                           s, &done_kv);
     if (rc) return rc;
   }
-  if (done_kv < Skv) {
+  if (done_kv > 0 && attn_rows_ok(Skv - done_kv)) {
+    rc = attn_bwd_dkdv_rows(q, k, v, d_o, lse, dvec, dk, dv, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dk_rs, dv_rs,
+                            scale, done_kv, Skv - done_kv, s);
+    if (rc) return rc;
+  } else if (done_kv < Skv) {
     const int blk0 = done_kv / BKV;
     attn_bwd_dkdv_kernel<<<dim3(ceil_div(Skv, BKV) - blk0, nh, B), 128, 0, s>>>(
         P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
