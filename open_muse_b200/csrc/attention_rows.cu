@@ -1,8 +1,10 @@
-// Attention for a handful of ragged rows (CUDA cores, one warp per (batch, head, row)).
+// Attention for a handful of ragged rows (CUDA cores, one 128-thread CTA per (batch, head, row)).
 // MaskGIT sequences are 256 image tokens + 1 class token (S = 257, muse/modeling_transformer.py:1407): the tcgen05
 // kernels own 128-row tiles, which leaves exactly ONE query row / key row per (batch, head).  Running those through a
-// 64-row tensor-core tile costs as much as a third of the whole backward; a warp per row needs ~70 KFLOP and is ~20x
-// cheaper.  Used when (S mod 128) <= kMaxRows, otherwise the mma.sync kernels take the remainder.
+// 64-row tensor-core tile cost a third of the whole attention backward; one small CTA per row is ~10x cheaper.
+// Phase 1: each thread owns rows of the looped dimension (row-wise 128-byte reads, dot products against the fixed
+// row held in shared memory); phase 2: each thread owns one output column (column-wise, coalesced reads).
+// Used when (S mod 128) <= kMaxRows, otherwise the mma.sync kernels take the remainder.
 #include "common.cuh"
 
 namespace muse {
@@ -12,16 +14,7 @@ constexpr int HD = 64;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-__device__ __forceinline__ void load_row64(const bf16* p, float (&v)[64]) {
-#pragma unroll
-  for (int c = 0; c < 64; c += 8) {
-    float t[8];
-    load8(p + c, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[c + j] = t[j];
-  }
-}
-__device__ __forceinline__ float dot_row64(const bf16* p, const float (&q)[64]) {
+__device__ __forceinline__ float dot_row64(const bf16* p, const float* q) {
   float acc = 0.f;
 #pragma unroll
   for (int c = 0; c < 64; c += 8) {
@@ -32,24 +25,33 @@ __device__ __forceinline__ float dot_row64(const bf16* p, const float (&q)[64]) 
   }
   return acc;
 }
-__device__ __forceinline__ void axpy_row64(float a, const bf16* p, float (&acc)[64]) {
-#pragma unroll
-  for (int c = 0; c < 64; c += 8) {
-    float t[8];
-    load8(p + c, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[c + j] = fmaf(a, t[j], acc[c + j]);
-  }
+
+// block-wide reductions over 128 threads (4 warps)
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
 }
-// warp-reduce 64 accumulators; lane l ends up holding elements 2l, 2l+1 -> written as one bf16x2
-__device__ __forceinline__ void reduce_store_row64(float (&acc)[64], bf16* dst, int lane, float mul) {
-  float mine0 = 0.f, mine1 = 0.f;
-#pragma unroll
-  for (int d = 0; d < 64; ++d) {
-    const float s = warp_sum(acc[d]);
-    if ((d >> 1) == lane) { if (d & 1) mine1 = s; else mine0 = s; }
-  }
-  *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pack_bf16(mine0 * mul, mine1 * mul);
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+}
+
+// out[d] = sum_j wgt[j] * M[j][d] over j in [0, n): thread = (d = tid & 63, half = tid >> 6), halves combined in smem
+__device__ __forceinline__ void weighted_colsum(const float* wgt, const bf16* M, long long rs, int n, float* part,
+                                                bf16* dst, float mul) {
+  const int d = threadIdx.x & 63, half = threadIdx.x >> 6;
+  float acc = 0.f;
+  for (int j = half; j < n; j += 2) acc = fmaf(wgt[j], __bfloat162float(M[static_cast<long long>(j) * rs + d]), acc);
+  __syncthreads();
+  if (half == 1) part[d] = acc;
+  __syncthreads();
+  if (half == 0) dst[d] = __float2bfloat16_rn((acc + part[d]) * mul);
 }
 
 struct RowArgs {
@@ -59,97 +61,93 @@ struct RowArgs {
   float scale;
 };
 
-// forward for query rows [row0, row0 + nrows)
+// forward for query rows [row0, row0 + nrows): grid = (nrows, nh, B)
 __global__ void __launch_bounds__(128)
 attn_fwd_rows_kernel(RowArgs a, bf16* __restrict__ O, long long o_rs, float* __restrict__ LSE) {
-  const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (w >= a.B * a.nh * a.nrows) return;
-  const int qi = a.row0 + w % a.nrows, h = (w / a.nrows) % a.nh, b = w / (a.nrows * a.nh);
-  float q[64];
-  load_row64(a.q + (static_cast<long long>(b) * a.Sq + qi) * a.q_rs + h * HD, q);
+  extern __shared__ float sm[];  // [Skv] scores -> probabilities
+  __shared__ float fixed[64], part[64], red[4];
+  const int qi = a.row0 + blockIdx.x, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+  if (tid < 64) fixed[tid] = __bfloat162float(a.q[(static_cast<long long>(b) * a.Sq + qi) * a.q_rs + h * HD + tid]);
+  __syncthreads();
+  const bf16* kb = a.k + static_cast<long long>(b) * a.Skv * a.k_rs + h * HD;
+  const bf16* vb = a.v + static_cast<long long>(b) * a.Skv * a.v_rs + h * HD;
   const float sl2 = a.scale * kLog2e;
-  float m = -INFINITY;
-  for (int j = lane; j < a.Skv; j += 32)
-    m = fmaxf(m, dot_row64(a.k + (static_cast<long long>(b) * a.Skv + j) * a.k_rs + h * HD, q) * sl2);
-  m = warp_max(m);
-  float l = 0.f, o[64];
-#pragma unroll
-  for (int d = 0; d < 64; ++d) o[d] = 0.f;
-  for (int j = lane; j < a.Skv; j += 32) {
-    const float s = dot_row64(a.k + (static_cast<long long>(b) * a.Skv + j) * a.k_rs + h * HD, q) * sl2;
-    const float p = bf16_round(exp2f(s - m));  // P is rounded to bf16 before the PV product, like the tensor-core path
-    l += exp2f(s - m);
-    axpy_row64(p, a.v + (static_cast<long long>(b) * a.Skv + j) * a.v_rs + h * HD, o);
+  float mx = -INFINITY;
+  for (int j = tid; j < a.Skv; j += 128) {
+    const float s = dot_row64(kb + static_cast<long long>(j) * a.k_rs, fixed) * sl2;
+    sm[j] = s;
+    mx = fmaxf(mx, s);
   }
-  l = warp_sum(l);
-  reduce_store_row64(o, O + (static_cast<long long>(b) * a.Sq + qi) * o_rs + h * HD, lane, 1.f / l);
-  if (lane == 0) LSE[(static_cast<long long>(b) * a.nh + h) * a.Sq + qi] = (m + log2f(l)) * kLn2;
+  mx = block_max(mx, red);
+  float l = 0.f;
+  for (int j = tid; j < a.Skv; j += 128) {
+    const float p = exp2f(sm[j] - mx);
+    l += p;
+    sm[j] = bf16_round(p);  // P is rounded to bf16 before the PV product, like the tensor-core path
+  }
+  l = block_sum(l, red);
+  weighted_colsum(sm, vb, a.v_rs, a.Skv, part, O + (static_cast<long long>(b) * a.Sq + qi) * o_rs + h * HD, 1.f / l);
+  if (tid == 0) LSE[(static_cast<long long>(b) * a.nh + h) * a.Sq + qi] = (mx + log2f(l)) * kLn2;
 }
 
 // dQ (+ D) for query rows [row0, row0 + nrows)
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_rows_kernel(RowArgs a, const float* __restrict__ LSE, float* __restrict__ Dv, bf16* __restrict__ dQ,
                         long long dq_rs) {
-  const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (w >= a.B * a.nh * a.nrows) return;
-  const int qi = a.row0 + w % a.nrows, h = (w / a.nrows) % a.nh, b = w / (a.nrows * a.nh);
+  extern __shared__ float sm[];  // [2][Skv]: p, dp -> ds
+  __shared__ float fq[64], fg[64], part[64], red[4];
+  const int qi = a.row0 + blockIdx.x, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
   const long long sidx = (static_cast<long long>(b) * a.nh + h) * a.Sq + qi;
-  float q[64], g[64];
-  load_row64(a.q + (static_cast<long long>(b) * a.Sq + qi) * a.q_rs + h * HD, q);
-  load_row64(a.d_o + (static_cast<long long>(b) * a.Sq + qi) * a.do_rs + h * HD, g);
+  if (tid < 64) {
+    fq[tid] = __bfloat162float(a.q[(static_cast<long long>(b) * a.Sq + qi) * a.q_rs + h * HD + tid]);
+    fg[tid] = __bfloat162float(a.d_o[(static_cast<long long>(b) * a.Sq + qi) * a.do_rs + h * HD + tid]);
+  }
+  __syncthreads();
+  const bf16* kb = a.k + static_cast<long long>(b) * a.Skv * a.k_rs + h * HD;
+  const bf16* vb = a.v + static_cast<long long>(b) * a.Skv * a.v_rs + h * HD;
   const float sl2 = a.scale * kLog2e, lse2 = LSE[sidx] * kLog2e;
+  float* sp = sm;
+  float* sdp = sm + a.Skv;
   float dsum = 0.f;
-  for (int j = lane; j < a.Skv; j += 32) {
-    const float p = exp2f(dot_row64(a.k + (static_cast<long long>(b) * a.Skv + j) * a.k_rs + h * HD, q) * sl2 - lse2);
-    dsum = fmaf(p, dot_row64(a.v + (static_cast<long long>(b) * a.Skv + j) * a.v_rs + h * HD, g), dsum);
+  for (int j = tid; j < a.Skv; j += 128) {
+    const float p = exp2f(dot_row64(kb + static_cast<long long>(j) * a.k_rs, fq) * sl2 - lse2);
+    const float dp = dot_row64(vb + static_cast<long long>(j) * a.v_rs, fg);
+    sp[j] = p;
+    sdp[j] = dp;
+    dsum = fmaf(p, dp, dsum);
   }
-  dsum = warp_sum(dsum);
-  if (lane == 0) Dv[sidx] = dsum;
-  float acc[64];
-#pragma unroll
-  for (int d = 0; d < 64; ++d) acc[d] = 0.f;
-  for (int j = lane; j < a.Skv; j += 32) {
-    const bf16* kr = a.k + (static_cast<long long>(b) * a.Skv + j) * a.k_rs + h * HD;
-    const float p = exp2f(dot_row64(kr, q) * sl2 - lse2);
-    const float dp = dot_row64(a.v + (static_cast<long long>(b) * a.Skv + j) * a.v_rs + h * HD, g);
-    axpy_row64(bf16_round(p * (dp - dsum) * a.scale), kr, acc);
-  }
-  reduce_store_row64(acc, dQ + (static_cast<long long>(b) * a.Sq + qi) * dq_rs + h * HD, lane, 1.f);
+  dsum = block_sum(dsum, red);
+  if (tid == 0) Dv[sidx] = dsum;
+  for (int j = tid; j < a.Skv; j += 128) sp[j] = bf16_round(sp[j] * (sdp[j] - dsum) * a.scale);
+  weighted_colsum(sp, kb, a.k_rs, a.Skv, part, dQ + (static_cast<long long>(b) * a.Sq + qi) * dq_rs + h * HD, 1.f);
 }
 
 // dK, dV for key rows [row0, row0 + nrows)
 __global__ void __launch_bounds__(128)
 attn_bwd_dkdv_rows_kernel(RowArgs a, const float* __restrict__ LSE, const float* __restrict__ Dv,
                           bf16* __restrict__ dK, long long dk_rs, bf16* __restrict__ dV, long long dv_rs) {
-  const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (w >= a.B * a.nh * a.nrows) return;
-  const int kj = a.row0 + w % a.nrows, h = (w / a.nrows) % a.nh, b = w / (a.nrows * a.nh);
+  extern __shared__ float sm[];  // [2][Sq]: ds, p
+  __shared__ float fk[64], fv[64], part[64];
+  const int kj = a.row0 + blockIdx.x, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
   const long long sbase = (static_cast<long long>(b) * a.nh + h) * a.Sq;
-  float kk[64], vv[64];
-  load_row64(a.k + (static_cast<long long>(b) * a.Skv + kj) * a.k_rs + h * HD, kk);
-  load_row64(a.v + (static_cast<long long>(b) * a.Skv + kj) * a.v_rs + h * HD, vv);
+  if (tid < 64) {
+    fk[tid] = __bfloat162float(a.k[(static_cast<long long>(b) * a.Skv + kj) * a.k_rs + h * HD + tid]);
+    fv[tid] = __bfloat162float(a.v[(static_cast<long long>(b) * a.Skv + kj) * a.v_rs + h * HD + tid]);
+  }
+  __syncthreads();
+  const bf16* qb = a.q + static_cast<long long>(b) * a.Sq * a.q_rs + h * HD;
+  const bf16* gb = a.d_o + static_cast<long long>(b) * a.Sq * a.do_rs + h * HD;
   const float sl2 = a.scale * kLog2e;
-  float ak[64];
-#pragma unroll
-  for (int d = 0; d < 64; ++d) ak[d] = 0.f;
-  // dK first, dV in a second sweep (keeps the accumulator count at 64 registers)
-  for (int i = lane; i < a.Sq; i += 32) {
-    const bf16* qr = a.q + (static_cast<long long>(b) * a.Sq + i) * a.q_rs + h * HD;
-    const bf16* gr = a.d_o + (static_cast<long long>(b) * a.Sq + i) * a.do_rs + h * HD;
-    const float p = exp2f(dot_row64(qr, kk) * sl2 - LSE[sbase + i] * kLog2e);
-    const float dp = dot_row64(gr, vv);
-    axpy_row64(bf16_round(p * (dp - Dv[sbase + i]) * a.scale), qr, ak);
+  float* sds = sm;
+  float* spp = sm + a.Sq;
+  for (int i = tid; i < a.Sq; i += 128) {
+    const float p = exp2f(dot_row64(qb + static_cast<long long>(i) * a.q_rs, fk) * sl2 - LSE[sbase + i] * kLog2e);
+    const float dp = dot_row64(gb + static_cast<long long>(i) * a.do_rs, fv);
+    sds[i] = bf16_round(p * (dp - Dv[sbase + i]) * a.scale);
+    spp[i] = bf16_round(p);
   }
-  reduce_store_row64(ak, dK + (static_cast<long long>(b) * a.Skv + kj) * dk_rs + h * HD, lane, 1.f);
-#pragma unroll
-  for (int d = 0; d < 64; ++d) ak[d] = 0.f;
-  for (int i = lane; i < a.Sq; i += 32) {
-    const bf16* qr = a.q + (static_cast<long long>(b) * a.Sq + i) * a.q_rs + h * HD;
-    const bf16* gr = a.d_o + (static_cast<long long>(b) * a.Sq + i) * a.do_rs + h * HD;
-    const float p = exp2f(dot_row64(qr, kk) * sl2 - LSE[sbase + i] * kLog2e);
-    axpy_row64(bf16_round(p), gr, ak);
-  }
-  reduce_store_row64(ak, dV + (static_cast<long long>(b) * a.Skv + kj) * dv_rs + h * HD, lane, 1.f);
+  weighted_colsum(sds, qb, a.q_rs, a.Sq, part, dK + (static_cast<long long>(b) * a.Skv + kj) * dk_rs + h * HD, 1.f);
+  weighted_colsum(spp, gb, a.do_rs, a.Sq, part, dV + (static_cast<long long>(b) * a.Skv + kj) * dv_rs + h * HD, 1.f);
 }
 
 }  // namespace
@@ -169,25 +167,28 @@ static RowArgs make_args(const void* q, const void* k, const void* v, const void
 
 int attn_fwd_rows(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv,
                   int q_rs, int k_rs, int v_rs, int o_rs, float scale, int row0, int nrows, cudaStream_t s) {
+  if (Skv > 8192) { set_last_error("attn rows: Skv too long"); return MUSE_ERR_UNSUPPORTED; }
   RowArgs a = make_args(q, k, v, nullptr, B, nh, Sq, Skv, q_rs, k_rs, v_rs, 0, scale, row0, nrows);
-  attn_fwd_rows_kernel<<<ceil_div(B * nh * nrows, 4), 128, 0, s>>>(a, reinterpret_cast<bf16*>(o), o_rs, lse);
+  attn_fwd_rows_kernel<<<dim3(nrows, nh, B), 128, Skv * sizeof(float), s>>>(a, reinterpret_cast<bf16*>(o), o_rs, lse);
   return check_launch("attn_fwd_rows");
 }
 
 int attn_bwd_dq_rows(const void* q, const void* k, const void* v, const void* d_o, const float* lse, float* dvec,
                      void* dq, int B, int nh, int Sq, int Skv, int q_rs, int k_rs, int v_rs, int do_rs, int dq_rs,
                      float scale, int row0, int nrows, cudaStream_t s) {
+  if (Skv > 4096) { set_last_error("attn rows: Skv too long"); return MUSE_ERR_UNSUPPORTED; }
   RowArgs a = make_args(q, k, v, d_o, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, scale, row0, nrows);
-  attn_bwd_dq_rows_kernel<<<ceil_div(B * nh * nrows, 4), 128, 0, s>>>(a, lse, dvec, reinterpret_cast<bf16*>(dq), dq_rs);
+  attn_bwd_dq_rows_kernel<<<dim3(nrows, nh, B), 128, 2 * Skv * sizeof(float), s>>>(a, lse, dvec, reinterpret_cast<bf16*>(dq), dq_rs);
   return check_launch("attn_bwd_dq_rows");
 }
 
 int attn_bwd_dkdv_rows(const void* q, const void* k, const void* v, const void* d_o, const float* lse,
                        const float* dvec, void* dk, void* dv, int B, int nh, int Sq, int Skv, int q_rs, int k_rs,
                        int v_rs, int do_rs, int dk_rs, int dv_rs, float scale, int row0, int nrows, cudaStream_t s) {
+  if (Sq > 4096) { set_last_error("attn rows: Sq too long"); return MUSE_ERR_UNSUPPORTED; }
   RowArgs a = make_args(q, k, v, d_o, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, scale, row0, nrows);
-  attn_bwd_dkdv_rows_kernel<<<ceil_div(B * nh * nrows, 4), 128, 0, s>>>(a, lse, dvec, reinterpret_cast<bf16*>(dk), dk_rs,
-                                                                        reinterpret_cast<bf16*>(dv), dv_rs);
+  attn_bwd_dkdv_rows_kernel<<<dim3(nrows, nh, B), 128, 2 * Sq * sizeof(float), s>>>(
+      a, lse, dvec, reinterpret_cast<bf16*>(dk), dk_rs, reinterpret_cast<bf16*>(dv), dv_rs);
   return check_launch("attn_bwd_dkdv_rows");
 }
 
