@@ -42,16 +42,32 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
 }
 
-// out[d] = sum_j wgt[j] * M[j][d] over j in [0, n): thread = (d = tid & 63, half = tid >> 6), halves combined in smem
+// out[d] = sum_j wgt[j] * M[j][d] over j in [0, n).  thread = (8-column group dg = tid & 7, row group jg = tid >> 3):
+// 16-byte loads, 16 row groups in flight, partial sums combined through shared memory (part: [16][64] floats).
 __device__ __forceinline__ void weighted_colsum(const float* wgt, const bf16* M, long long rs, int n, float* part,
                                                 bf16* dst, float mul) {
-  const int d = threadIdx.x & 63, half = threadIdx.x >> 6;
-  float acc = 0.f;
-  for (int j = half; j < n; j += 2) acc = fmaf(wgt[j], __bfloat162float(M[static_cast<long long>(j) * rs + d]), acc);
+  const int dg = threadIdx.x & 7, jg = threadIdx.x >> 3;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 4
+  for (int j = jg; j < n; j += 16) {
+    float t[8];
+    load8(M + static_cast<long long>(j) * rs + dg * 8, t);
+    const float w = wgt[j];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, t[k], acc[k]);
+  }
   __syncthreads();
-  if (half == 1) part[d] = acc;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[jg * 64 + dg * 8 + k] = acc[k];
   __syncthreads();
-  if (half == 0) dst[d] = __float2bfloat16_rn((acc + part[d]) * mul);
+  if (threadIdx.x < 64) {
+    float sum = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) sum += part[g * 64 + threadIdx.x];
+    dst[threadIdx.x] = __float2bfloat16_rn(sum * mul);
+  }
 }
 
 struct RowArgs {
@@ -65,7 +81,7 @@ struct RowArgs {
 __global__ void __launch_bounds__(128)
 attn_fwd_rows_kernel(RowArgs a, bf16* __restrict__ O, long long o_rs, float* __restrict__ LSE) {
   extern __shared__ float sm[];  // [Skv] scores -> probabilities
-  __shared__ float fixed[64], part[64], red[4];
+  __shared__ float fixed[64], part[16 * 64], red[4];
   const int qi = a.row0 + blockIdx.x, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
   if (tid < 64) fixed[tid] = __bfloat162float(a.q[(static_cast<long long>(b) * a.Sq + qi) * a.q_rs + h * HD + tid]);
   __syncthreads();
@@ -95,7 +111,7 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dq_rows_kernel(RowArgs a, const float* __restrict__ LSE, float* __restrict__ Dv, bf16* __restrict__ dQ,
                         long long dq_rs) {
   extern __shared__ float sm[];  // [2][Skv]: p, dp -> ds
-  __shared__ float fq[64], fg[64], part[64], red[4];
+  __shared__ float fq[64], fg[64], part[16 * 64], red[4];
   const int qi = a.row0 + blockIdx.x, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
   const long long sidx = (static_cast<long long>(b) * a.nh + h) * a.Sq + qi;
   if (tid < 64) {
@@ -127,7 +143,7 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dkdv_rows_kernel(RowArgs a, const float* __restrict__ LSE, const float* __restrict__ Dv,
                           bf16* __restrict__ dK, long long dk_rs, bf16* __restrict__ dV, long long dv_rs) {
   extern __shared__ float sm[];  // [2][Sq]: ds, p
-  __shared__ float fk[64], fv[64], part[64];
+  __shared__ float fk[64], fv[64], part[16 * 64];
   const int kj = a.row0 + blockIdx.x, h = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
   const long long sbase = (static_cast<long long>(b) * a.nh + h) * a.Sq;
   if (tid < 64) {
