@@ -26,13 +26,6 @@ __device__ __forceinline__ float dot_row64(const bf16* p, const float* q) {
   return acc;
 }
 
-// warp-cooperative dot product of one 64-element bf16 row with a vector whose elements (2*lane, 2*lane+1) this lane
-// holds in (f0, f1): one coalesced 128-byte read per row, 5 shuffles.
-__device__ __forceinline__ float warp_row_dot(const bf16* row, int lane, float f0, float f1) {
-  const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(row + 2 * lane));
-  return warp_sum(fmaf(x.x, f0, x.y * f1));
-}
-
 // block-wide reductions over 128 threads (4 warps)
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -85,7 +78,7 @@ struct RowArgs {
 };
 
 // forward for query rows [row0, row0 + nrows): grid = (nrows, nh, B)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attn_fwd_rows_kernel(RowArgs a, bf16* __restrict__ O, long long o_rs, float* __restrict__ LSE) {
   extern __shared__ float sm[];  // [Skv] scores -> probabilities
   __shared__ float fixed[64], part[16 * 64], red[4];
@@ -95,16 +88,12 @@ attn_fwd_rows_kernel(RowArgs a, bf16* __restrict__ O, long long o_rs, float* __r
   const bf16* kb = a.k + static_cast<long long>(b) * a.Skv * a.k_rs + h * HD;
   const bf16* vb = a.v + static_cast<long long>(b) * a.Skv * a.v_rs + h * HD;
   const float sl2 = a.scale * kLog2e;
-  const int warp = tid >> 5, lane = tid & 31;
-  const float q0 = fixed[2 * lane], q1 = fixed[2 * lane + 1];
   float mx = -INFINITY;
-#pragma unroll 8
-  for (int j = warp; j < a.Skv; j += 4) {
-    const float s = warp_row_dot(kb + static_cast<long long>(j) * a.k_rs, lane, q0, q1) * sl2;
-    if (lane == 0) sm[j] = s;
+  for (int j = tid; j < a.Skv; j += 128) {
+    const float s = dot_row64(kb + static_cast<long long>(j) * a.k_rs, fixed) * sl2;
+    sm[j] = s;
     mx = fmaxf(mx, s);
   }
-  __syncthreads();
   mx = block_max(mx, red);
   float l = 0.f;
   for (int j = tid; j < a.Skv; j += 128) {
@@ -118,7 +107,7 @@ attn_fwd_rows_kernel(RowArgs a, bf16* __restrict__ O, long long o_rs, float* __r
 }
 
 // dQ (+ D) for query rows [row0, row0 + nrows)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attn_bwd_dq_rows_kernel(RowArgs a, const float* __restrict__ LSE, float* __restrict__ Dv, bf16* __restrict__ dQ,
                         long long dq_rs) {
   extern __shared__ float sm[];  // [2][Skv]: p, dp -> ds
@@ -135,16 +124,14 @@ attn_bwd_dq_rows_kernel(RowArgs a, const float* __restrict__ LSE, float* __restr
   const float sl2 = a.scale * kLog2e, lse2 = LSE[sidx] * kLog2e;
   float* sp = sm;
   float* sdp = sm + a.Skv;
-  const int warp = tid >> 5, lane = tid & 31;
-  const float q0 = fq[2 * lane], q1 = fq[2 * lane + 1], g0 = fg[2 * lane], g1 = fg[2 * lane + 1];
   float dsum = 0.f;
-#pragma unroll 4
-  for (int j = warp; j < a.Skv; j += 4) {
-    const float p = exp2f(warp_row_dot(kb + static_cast<long long>(j) * a.k_rs, lane, q0, q1) * sl2 - lse2);
-    const float dp = warp_row_dot(vb + static_cast<long long>(j) * a.v_rs, lane, g0, g1);
-    if (lane == 0) { sp[j] = p; sdp[j] = dp; dsum = fmaf(p, dp, dsum); }
+  for (int j = tid; j < a.Skv; j += 128) {
+    const float p = exp2f(dot_row64(kb + static_cast<long long>(j) * a.k_rs, fq) * sl2 - lse2);
+    const float dp = dot_row64(vb + static_cast<long long>(j) * a.v_rs, fg);
+    sp[j] = p;
+    sdp[j] = dp;
+    dsum = fmaf(p, dp, dsum);
   }
-  __syncthreads();
   dsum = block_sum(dsum, red);
   if (tid == 0) Dv[sidx] = dsum;
   for (int j = tid; j < a.Skv; j += 128) sp[j] = bf16_round(sp[j] * (sdp[j] - dsum) * a.scale);
@@ -152,7 +139,7 @@ attn_bwd_dq_rows_kernel(RowArgs a, const float* __restrict__ LSE, float* __restr
 }
 
 // dK, dV for key rows [row0, row0 + nrows)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attn_bwd_dkdv_rows_kernel(RowArgs a, const float* __restrict__ LSE, const float* __restrict__ Dv,
                           bf16* __restrict__ dK, long long dk_rs, bf16* __restrict__ dV, long long dv_rs) {
   extern __shared__ float sm[];  // [2][Sq]: ds, p
@@ -169,19 +156,12 @@ attn_bwd_dkdv_rows_kernel(RowArgs a, const float* __restrict__ LSE, const float*
   const float sl2 = a.scale * kLog2e;
   float* sds = sm;
   float* spp = sm + a.Sq;
-  const int warp = tid >> 5, lane = tid & 31;
-  const float k0 = fk[2 * lane], k1 = fk[2 * lane + 1], v0 = fv[2 * lane], v1 = fv[2 * lane + 1];
-#pragma unroll 4
-  for (int i = warp; i < a.Sq; i += 4) {
-    const float sdot = warp_row_dot(qb + static_cast<long long>(i) * a.q_rs, lane, k0, k1);
-    const float dp = warp_row_dot(gb + static_cast<long long>(i) * a.do_rs, lane, v0, v1);
-    if (lane == 0) {
-      const float p = exp2f(sdot * sl2 - LSE[sbase + i] * kLog2e);
-      sds[i] = bf16_round(p * (dp - Dv[sbase + i]) * a.scale);
-      spp[i] = bf16_round(p);
-    }
+  for (int i = tid; i < a.Sq; i += 128) {
+    const float p = exp2f(dot_row64(qb + static_cast<long long>(i) * a.q_rs, fk) * sl2 - LSE[sbase + i] * kLog2e);
+    const float dp = dot_row64(gb + static_cast<long long>(i) * a.do_rs, fv);
+    sds[i] = bf16_round(p * (dp - Dv[sbase + i]) * a.scale);
+    spp[i] = bf16_round(p);
   }
-  __syncthreads();
   weighted_colsum(sds, qb, a.q_rs, a.Sq, part, dK + (static_cast<long long>(b) * a.Skv + kj) * dk_rs + h * HD, 1.f);
   weighted_colsum(spp, gb, a.do_rs, a.Sq, part, dV + (static_cast<long long>(b) * a.Skv + kj) * dv_rs + h * HD, 1.f);
 }
