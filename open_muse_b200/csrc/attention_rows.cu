@@ -47,6 +47,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 __device__ __forceinline__ void weighted_colsum(const float* wgt, const bf16* M, long long rs, int n, float* part,
                                                 bf16* dst, float mul) {
   const int dg = threadIdx.x & 7, jg = threadIdx.x >> 3;
+  __syncthreads();  // wgt[] was just written by other threads of the CTA
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
