@@ -37,7 +37,9 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes;
+  static constexpr int kStagingRowBytes = 144;                       // 128 B of payload + 16 B pad: conflict-free
+  static constexpr int kStagingBytes = 4 * 32 * kStagingRowBytes;    // one [32 rows x 128 B] slab per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + kBarBytes;
 };
 
 struct GemmParams {
@@ -56,7 +58,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::kStages * C_::kStageBytes);
+  uint8_t* staging = smem + C_::kStages * C_::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C_::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C_::kStages;
   uint64_t* tmem_full = bars + 2 * C_::kStages;
@@ -175,80 +178,91 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_idx = tile % p.num_n;
       const int m_idx = (tile / p.num_n) % p.num_m;
-      const int row = m_idx * BM + ew * 32 + lane;
       const int n0 = n_idx * BN;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                                  static_cast<uint32_t>(acc * BN);
+      // Accumulator rows live one-per-thread in TMEM; storing them straight to global would make every warp store
+      // touch 32 different rows (half-filled 32 B sectors, ~1.7 TB/s measured).  Each warp therefore transposes its
+      // [32 rows x 128 B] slab through a padded shared-memory staging buffer so that 8 consecutive lanes write one full
+      // 128-byte row segment.
+      uint8_t* stg = staging + ew * (32 * C_::kStagingRowBytes);
+      constexpr int kColsPerSlab = (EPI == EPI_BF16) ? 64 : 32;
+      constexpr int kElemsPerChunk = (EPI == EPI_BF16) ? 8 : 4;  // elements in a 16-byte chunk
+      const int row_base = m_idx * BM + ew * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + c, r);
-        ptx::tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (row < p.M && col0 < p.N) {
-          const bool full = (col0 + 32 <= p.N);
-          const size_t off = static_cast<size_t>(row) * p.ldc + col0;
-          if (EPI == EPI_BF16) {
-            bf16* dst = reinterpret_cast<bf16*>(p.C) + off;
-            if (full) {
+      for (int c = 0; c < BN; c += kColsPerSlab) {
+        if (n0 + c >= p.N) break;  // warp-uniform
+        uint4* my_row = reinterpret_cast<uint4*>(stg + lane * C_::kStagingRowBytes);
+        if (EPI == EPI_BF16) {
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + c, r0);
+          ptx::tmem_ld_32x32b_x32(lane_addr + c + 32, r1);
+          ptx::tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack_bf16(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1]));
-                u.y = pack_bf16(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                u.z = pack_bf16(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
-                u.w = pack_bf16(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
-                *reinterpret_cast<uint4*>(dst + j) = u;
+          for (int q = 0; q < 4; ++q) {
+            uint4 u, v;
+            u.x = pack_bf16(__uint_as_float(r0[8 * q + 0]), __uint_as_float(r0[8 * q + 1]));
+            u.y = pack_bf16(__uint_as_float(r0[8 * q + 2]), __uint_as_float(r0[8 * q + 3]));
+            u.z = pack_bf16(__uint_as_float(r0[8 * q + 4]), __uint_as_float(r0[8 * q + 5]));
+            u.w = pack_bf16(__uint_as_float(r0[8 * q + 6]), __uint_as_float(r0[8 * q + 7]));
+            v.x = pack_bf16(__uint_as_float(r1[8 * q + 0]), __uint_as_float(r1[8 * q + 1]));
+            v.y = pack_bf16(__uint_as_float(r1[8 * q + 2]), __uint_as_float(r1[8 * q + 3]));
+            v.z = pack_bf16(__uint_as_float(r1[8 * q + 4]), __uint_as_float(r1[8 * q + 5]));
+            v.w = pack_bf16(__uint_as_float(r1[8 * q + 6]), __uint_as_float(r1[8 * q + 7]));
+            my_row[q] = u;
+            my_row[4 + q] = v;
+          }
+        } else {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + c, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) my_row[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = (lane >> 3) + 4 * it, ch = lane & 7;
+          const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * C_::kStagingRowBytes + ch * 16);
+          const int grow = row_base + rr;
+          const int gcol = n0 + c + ch * kElemsPerChunk;
+          if (grow < p.M && gcol < p.N) {
+            const size_t off = static_cast<size_t>(grow) * p.ldc + gcol;
+            const bool full = gcol + kElemsPerChunk <= p.N;
+            if (EPI == EPI_BF16) {
+              bf16* dst = reinterpret_cast<bf16*>(p.C) + off;
+              if (full) {
+                *reinterpret_cast<uint4*>(dst) = v;
+              } else {
+                const bf16* e = reinterpret_cast<const bf16*>(&v);
+                for (int k = 0; k < 8; ++k)
+                  if (gcol + k < p.N) dst[k] = e[k];
               }
             } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
-            }
-          } else if (EPI == EPI_F32) {
-            float* dst = reinterpret_cast<float*>(p.C) + off;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + j) =
-                    make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) dst[j] = __uint_as_float(r[j]);
-            }
-          } else if (EPI == EPI_ATOMIC_F32) {
-            float* dst = reinterpret_cast<float*>(p.C) + off;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                atomicAdd(reinterpret_cast<float4*>(dst + j),
-                          make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) atomicAdd(dst + j, __uint_as_float(r[j]));
-            }
-          } else {  // EPI_RESADD_F32: out = residual + bf16(acc)  (Linear output is bf16 under autocast)
-            float* dst = reinterpret_cast<float*>(p.C) + off;
-            const float* rs = p.res + off;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 q = *reinterpret_cast<const float4*>(rs + j);
-                *reinterpret_cast<float4*>(dst + j) =
-                    make_float4(q.x + bf16_round(__uint_as_float(r[j])),
-                                q.y + bf16_round(__uint_as_float(r[j + 1])),
-                                q.z + bf16_round(__uint_as_float(r[j + 2])),
-                                q.w + bf16_round(__uint_as_float(r[j + 3])));
+              const float f[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+              float* dst = reinterpret_cast<float*>(p.C) + off;
+              if (EPI == EPI_F32) {
+                if (full) *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+                else for (int k = 0; k < 4; ++k) if (gcol + k < p.N) dst[k] = f[k];
+              } else if (EPI == EPI_ATOMIC_F32) {
+                if (full) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(f[0], f[1], f[2], f[3]));
+                else for (int k = 0; k < 4; ++k) if (gcol + k < p.N) atomicAdd(dst + k, f[k]);
+              } else {  // EPI_RESADD_F32: out = residual + bf16(acc)  (Linear output is bf16 under autocast)
+                const float* rs = p.res + off;
+                if (full) {
+                  const float4 q4 = *reinterpret_cast<const float4*>(rs);
+                  *reinterpret_cast<float4*>(dst) = make_float4(q4.x + bf16_round(f[0]), q4.y + bf16_round(f[1]),
+                                                                q4.z + bf16_round(f[2]), q4.w + bf16_round(f[3]));
+                } else {
+                  for (int k = 0; k < 4; ++k) if (gcol + k < p.N) dst[k] = rs[k] + bf16_round(f[k]);
+                }
               }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) dst[j] = rs[j] + bf16_round(__uint_as_float(r[j]));
             }
           }
         }
+        __syncwarp();
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
