@@ -179,6 +179,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n_idx = tile % p.num_n;
       const int m_idx = (tile / p.num_n) % p.num_m;
       const int n0 = n_idx * BN;
+      // residual epilogue: the residual slab is fetched in the coalesced (row = lane/8 + 4*it, chunk = lane%8) pattern
+      // one slab ahead, starting before the accumulator is even ready, so its HBM latency hides under the mainloop.
+      float4 res_next[8];
+      auto fetch_res = [&](int c, float4 (&dst)[8]) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = m_idx * BM + ew * 32 + (lane >> 3) + 4 * it;
+          const int gcol = n0 + c + (lane & 7) * 4;
+          dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < BN && grow < p.M && gcol + 4 <= p.N)
+            dst[it] = *reinterpret_cast<const float4*>(p.res + static_cast<size_t>(grow) * p.ldc + gcol);
+        }
+      };
+      if (EPI == EPI_RESADD_F32) fetch_res(0, res_next);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
@@ -194,6 +208,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int c = 0; c < BN; c += kColsPerSlab) {
         if (n0 + c >= p.N) break;  // warp-uniform
+        float4 res_cur[8];
+        if (EPI == EPI_RESADD_F32) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) res_cur[it] = res_next[it];
+          fetch_res(c + kColsPerSlab, res_next);
+        }
         uint4* my_row = reinterpret_cast<uint4*>(stg + lane * C_::kStagingRowBytes);
         if (EPI == EPI_BF16) {
           uint32_t r0[32], r1[32];
@@ -252,7 +272,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               } else {  // EPI_RESADD_F32: out = residual + bf16(acc)  (Linear output is bf16 under autocast)
                 const float* rs = p.res + off;
                 if (full) {
-                  const float4 q4 = *reinterpret_cast<const float4*>(rs);
+                  const float4 q4 = res_cur[it];
                   *reinterpret_cast<float4*>(dst) = make_float4(q4.x + bf16_round(f[0]), q4.y + bf16_round(f[1]),
                                                                 q4.z + bf16_round(f[2]), q4.w + bf16_round(f[3]));
                 } else {
