@@ -100,6 +100,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def gemm_traffic_from_profile():
+    """Average DRAM bytes per tcgen05-GEMM launch from the committed `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_gemm.txt")
+    if not os.path.exists(path):
+        return None
+    tot, n = 0.0, 0
+    for line in open(path):
+        if "gemm_tcgen05_kernel" not in line:
+            continue
+        try:
+            rd = float(line.split("dram_read=")[1].split("MB")[0])
+            wr = float(line.split("dram_write=")[1].split("MB")[0])
+            tot += (rd + wr) * 1e6
+            n += 1
+        except Exception:
+            pass
+    return tot / n if n else None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -261,7 +280,8 @@ def main():
     if gemm_n:
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all Linear fwd/dgrad/wgrad GEMMs of the step)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": gemm_traffic_from_profile(), "algorithmic_flops_per_launch": gemm_flops / gemm_n,
                 "peak_source": peak_src, "launches_per_step": gemm_n // 2,
                 "gemm_share_of_step": (gemm_ms / 2) / ms_dev}
 

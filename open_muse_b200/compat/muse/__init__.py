@@ -1,0 +1,7 @@
+"""Drop-in ``muse`` package: put ``open_muse_b200/compat`` on PYTHONPATH and the reference's
+``from muse import MaskGitTransformer, MaskGitVQGAN, PipelineMuse`` / ``from muse.sampling import cosine_schedule``
+(training/train_maskgit_imagenet.py:30-33) resolve to the B200 implementations."""
+__version__ = "0.0.1"
+
+from open_muse_b200 import MaskGitTransformer, MaskGitVQGAN, PipelineMuse, get_mask_chedule  # noqa: F401
+from open_muse_b200 import sampling  # noqa: F401

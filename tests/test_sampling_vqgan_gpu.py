@@ -155,3 +155,21 @@ def test_vqgan_f16_256_roundtrip_properties():
     rec = m.decode_code(ids)
     assert rec.shape == (2, 3, 256, 256) and bool(torch.isfinite(rec).all())
     assert torch.equal(rec, m.decode(z_q))
+
+
+def test_pipeline_class_conditional_end_to_end():
+    from open_muse_b200 import MaskGitTransformer, MaskGitVQGAN, PipelineMuse
+
+    torch.manual_seed(0)
+    vae = MaskGitVQGAN(resolution=32, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=1, z_channels=16,
+                       num_embeddings=64, quantized_embed_dim=16)
+    tr = MaskGitTransformer(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_attention_heads=1,
+                            intermediate_size=128, max_position_embeddings=257, codebook_size=64, num_vq_tokens=256,
+                            num_classes=7, hidden_dropout=0.0, attention_dropout=0.0)
+    pipe = PipelineMuse(vae=vae, transformer=tr, is_class_conditioned=True).to(DEV)
+    a = pipe(class_ids=[1, 5], timesteps=4, num_images_per_prompt=2, generator=torch.Generator(device=DEV).manual_seed(3))
+    b = pipe(class_ids=[1, 5], timesteps=4, num_images_per_prompt=2, generator=torch.Generator(device=DEV).manual_seed(3))
+    assert len(a) == 4 and a[0].size == (32, 32) and a[0].mode == "RGB"
+    assert all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(a, b))
+    pt = pipe(class_ids=3, timesteps=2, output_type="pt")
+    assert pt.shape == (1, 3, 32, 32)
