@@ -253,11 +253,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dQ
-// 256 threads: warps w and w+4 share TMEM lanes (rows) 32*(w%4).. and split the 64 score columns in two halves, which
-// doubles the exp2/FMA lanes per CTA (TMEM limits these kernels to two CTAs per SM).
-// TMEM columns: S [0,64)  dP [64,128)  dQ [128,192).  smem: Q 16K | dO 16K | 2 x {K_j 8K, V_j 8K} | dS 16K
+// 256 threads: warps w and w+4 share TMEM lanes (rows) 32*(w%4).. and split the 64 score columns in two halves.
+// Software pipeline inside the CTA: as soon as every thread has pulled its S / dP columns out of TMEM into registers
+// (barrier A), thread 0 issues the score MMAs of the NEXT step, so the tensor core works while the exp2 / FMA math of
+// the current step runs; the dQ MMA of a step is never waited for by the step that issued it (dS is double-buffered,
+// K/V tiles sit in a 3-stage TMA ring with prefetch distance 2).
+// TMEM columns: S [0,64)  dP [64,128)  dQ [128,192).
+// smem: Q 16K | dO 16K | 3 x {K_j 8K, V_j 8K} | 2 x dS 16K (the partial-D exchange buffer aliases dS[0])
 constexpr int BWD_BN = 64;
-constexpr int DQ_SMEM = 16384 * 2 + 2 * (8192 * 2) + 16384 + 1024 + 64;
+constexpr int DQ_SMEM = 16384 * 2 + 3 * 16384 + 2 * 16384 + 64;
 
 __global__ void __launch_bounds__(256)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
@@ -268,24 +272,24 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + 16384;
-  uint8_t* sKV = smem + 32768;   // 2 stages x {K 8 KB, V 8 KB}
-  uint8_t* sdS = smem + 65536;
-  float* sDp = reinterpret_cast<float*>(smem + 81920);  // [2][128] partial D of the two column halves
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920 + 1024);
-  uint64_t* bar_kv = bars;       // [2]
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_o = bars + 3;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
+  uint8_t* sKV = smem + 32768;             // 3 stages x {K 8 KB, V 8 KB}
+  uint8_t* sdS = smem + 32768 + 49152;     // 2 buffers x 16 KB
+  float* sDp = reinterpret_cast<float*>(sdS);  // [2][128] partial D (only used between the two sweeps)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768 + 49152 + 32768);
+  uint64_t* bar_kv = bars;       // [3]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_o = bars + 4;    // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;                 // column half handled by this thread
   const int r = (warp & 3) * 32 + lane;       // row (TMEM lane) handled by this thread
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (tid == 0) {
-    ptx::mbar_init(&bar_kv[0], 1);
-    ptx::mbar_init(&bar_kv[1], 1);
+    for (int i = 0; i < 3; ++i) ptx::mbar_init(&bar_kv[i], 1);
     ptx::mbar_init(bar_s, 1);
-    ptx::mbar_init(bar_o, 1);
+    ptx::mbar_init(&bar_o[0], 1);
+    ptx::mbar_init(&bar_o[1], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
@@ -304,97 +308,127 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const float lse2 = (row < p.Sq) ? p.lse[stat_idx] * kLog2e : 0.f;
   const float sl2 = p.scale * kLog2e;
 
+  auto n16_of = [&](int step) { return (min(BWD_BN, p.Skv - (step % ntiles) * BWD_BN) + 15) & ~15; };
+  auto issue_scores = [&](int step) {  // thread 0: S = Q K^T and dP = dO V^T of `step` into TMEM [0,128)
+    uint8_t* sK = sKV + (step % 3) * 16384;
+    const uint32_t idesc = ptx::make_idesc_bf16(128, n16_of(step), 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sdO), ks), desc_kmajor(ptx::smem_u32(sK + 8192), ks), idesc, ks > 0);
+    ptx::umma_commit(bar_s);
+  };
+  auto load_kv = [&](int step) {       // thread 0: TMA of the K/V tile of `step` into its ring stage
+    uint8_t* sK = sKV + (step % 3) * 16384;
+    const int jn = step % ntiles;
+    tma_load_3d(sK, &tmK, &bar_kv[step % 3], h * HD, jn * BWD_BN, b);
+    tma_load_3d(sK + 8192, &tmV, &bar_kv[step % 3], h * HD, jn * BWD_BN, b);
+  };
+
   if (tid == 0) {
     ptx::mbar_expect_tx(&bar_kv[0], 16384 * 2 + 8192 * 2);
     tma_load_3d(sQ, &tmQ, &bar_kv[0], h * HD, q0, b);
     tma_load_3d(sdO, &tmdO, &bar_kv[0], h * HD, q0, b);
-    tma_load_3d(sKV, &tmK, &bar_kv[0], h * HD, 0, b);
-    tma_load_3d(sKV + 8192, &tmV, &bar_kv[0], h * HD, 0, b);
+    load_kv(0);
+    if (nsteps > 1) {
+      ptx::mbar_expect_tx(&bar_kv[1], 8192 * 2);
+      load_kv(1);
+    }
+    ptx::mbar_wait(&bar_kv[0], 0);
+    ptx::tc_fence_after();
+    issue_scores(0);
   }
   float dsum = 0.f;
-  uint32_t par_o = 0;
   for (int st = 0; st < nsteps; ++st) {
     const int j = st % ntiles;
     const bool sweep2 = st >= ntiles;
-    const uint32_t par = st & 1;
+    const int u = st - ntiles;  // index among the sweep-2 steps
     const int nvalid = min(BWD_BN, p.Skv - j * BWD_BN);
     const int n16 = (nvalid + 15) & ~15;
-    uint8_t* sK = sKV + (st & 1) * 16384;
-    uint8_t* sV = sK + 8192;
-    if (tid == 0) {
-      if (st + 1 < nsteps) {  // prefetch the next K/V tile into the other stage
-        const int jn = (st + 1) % ntiles;
-        uint8_t* nK = sKV + ((st + 1) & 1) * 16384;
-        ptx::mbar_expect_tx(&bar_kv[(st + 1) & 1], 8192 * 2);
-        tma_load_3d(nK, &tmK, &bar_kv[(st + 1) & 1], h * HD, jn * BWD_BN, b);
-        tma_load_3d(nK + 8192, &tmV, &bar_kv[(st + 1) & 1], h * HD, jn * BWD_BN, b);
-      }
-      ptx::mbar_wait(&bar_kv[st & 1], (st >> 1) & 1);
-      ptx::tc_fence_after();
-      const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)  // S = Q K_j^T
-        ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc, ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)  // dP = dO V_j^T
-        ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sdO), ks), desc_kmajor(ptx::smem_u32(sV), ks), idesc, ks > 0);
-      ptx::umma_commit(bar_s);
-    }
-    ptx::mbar_wait(bar_s, par);
+    ptx::mbar_wait(bar_s, st & 1);
     ptx::tc_fence_after();
+    uint32_t s_reg[32], d_reg[32];
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
       if (c < n16) {
-        uint32_t s16[16], d16[16];
-        tmem_ld_32x32b_x16(t_row + c, s16);
-        tmem_ld_32x32b_x16(t_row + 64 + c, d16);
-        ptx::tmem_ld_wait();
+        uint32_t a16[16], b16[16];
+        tmem_ld_32x32b_x16(t_row + c, a16);
+        tmem_ld_32x32b_x16(t_row + 64 + c, b16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { s_reg[cc + i] = a16[i]; d_reg[cc + i] = b16[i]; }
+      }
+    }
+    ptx::tmem_ld_wait();
+    ptx::tc_fence_before();
+    __syncthreads();  // (A) every thread holds its scores in registers: TMEM [0,128) may be overwritten
+    if (tid == 0 && st + 1 < nsteps) {
+      if (st + 2 < nsteps) {
+        // ring stage (st+2)%3 was last read by the dQ MMA of step st-1
+        if (st - 1 >= ntiles) ptx::mbar_wait(&bar_o[(u - 1) & 1], ((u - 1) >> 1) & 1);
+        ptx::mbar_expect_tx(&bar_kv[(st + 2) % 3], 8192 * 2);
+        load_kv(st + 2);
+      }
+      ptx::mbar_wait(&bar_kv[(st + 1) % 3], ((st + 1) / 3) & 1);
+      ptx::tc_fence_after();
+      issue_scores(st + 1);
+    }
+    uint8_t* dS = sdS + (u & 1) * 16384;
+    if (sweep2 && u >= 2) ptx::mbar_wait(&bar_o[u & 1], ((u >> 1) - 1) & 1);  // dQ MMA of step st-2 read this buffer
+#pragma unroll
+    for (int cc = 0; cc < 32; cc += 16) {
+      const int c = half * 32 + cc;
+      if (c < n16) {
         if (!sweep2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s16[i]) * sl2 - lse2) : 0.f;
-            dsum = fmaf(pr, __uint_as_float(d16[i]), dsum);
+            const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s_reg[cc + i]) * sl2 - lse2) : 0.f;
+            dsum = fmaf(pr, __uint_as_float(d_reg[cc + i]), dsum);
           }
         } else {
           float ds[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s16[i]) * sl2 - lse2) : 0.f;
-            ds[i] = pr * (__uint_as_float(d16[i]) - dsum) * p.scale;
+            const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s_reg[cc + i]) * sl2 - lse2) : 0.f;
+            ds[i] = pr * (__uint_as_float(d_reg[cc + i]) - dsum) * p.scale;
           }
 #pragma unroll
           for (int i = 0; i < 16; i += 8) {
-            uint4 u;
-            u.x = pack_bf16(ds[i], ds[i + 1]); u.y = pack_bf16(ds[i + 2], ds[i + 3]);
-            u.z = pack_bf16(ds[i + 4], ds[i + 5]); u.w = pack_bf16(ds[i + 6], ds[i + 7]);
-            st_operand_chunk(sdS, r, c + i, u);
+            uint4 v;
+            v.x = pack_bf16(ds[i], ds[i + 1]); v.y = pack_bf16(ds[i + 2], ds[i + 3]);
+            v.z = pack_bf16(ds[i + 4], ds[i + 5]); v.w = pack_bf16(ds[i + 6], ds[i + 7]);
+            st_operand_chunk(dS, r, c + i, v);
           }
         }
       }
     }
     if (st == ntiles - 1) sDp[half * 128 + r] = dsum;  // partial D of this column half
     ptx::fence_proxy_async();
-    ptx::tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // (B)
     if (st == ntiles - 1) {  // D = sum over both halves, identical in both threads of the row
       dsum = sDp[r] + sDp[128 + r];
       if (half == 0 && row < p.Sq) p.dvec[stat_idx] = dsum;  // for the dK/dV kernels
+      __syncthreads();       // sDp aliases dS[0]: everyone has read it before sweep 2 writes dS
     }
-    if (sweep2) {
-      if (tid == 0) {
-        ptx::tc_fence_after();
-        const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
-        const int ksteps = n16 >> 4;
-        for (int ks = 0; ks < ksteps; ++ks)  // dQ += dS K_j   (K_j consumed as an MN-major operand)
-          ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(sdS), ks), desc_mnmajor(ptx::smem_u32(sK), ks), idesc,
-                        (st > ntiles || ks > 0) ? 1u : 0u);
-        ptx::umma_commit(bar_o);
-      }
-      ptx::mbar_wait(bar_o, par_o);
-      par_o ^= 1;
-      ptx::tc_fence_after();
+    if (sweep2 && tid == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
+      uint8_t* sK = sKV + (st % 3) * 16384;
+      const int ksteps = n16 >> 4;
+      for (int ks = 0; ks < ksteps; ++ks)  // dQ += dS K_j   (K_j consumed as an MN-major operand)
+        ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(dS), ks), desc_mnmajor(ptx::smem_u32(sK), ks), idesc,
+                      (u > 0 || ks > 0) ? 1u : 0u);
+      ptx::umma_commit(&bar_o[u & 1]);
     }
+  }
+  // all dQ MMAs must have landed: last use of each completion barrier
+  {
+    const int U = ntiles;
+    const int ua = U - 1;
+    ptx::mbar_wait(&bar_o[ua & 1], (ua >> 1) & 1);
+    if (U >= 2) { const int ub = U - 2; ptx::mbar_wait(&bar_o[ub & 1], (ub >> 1) & 1); }
+    ptx::tc_fence_after();
   }
   {
     bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD + half * 32;
@@ -404,12 +438,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (row < p.Sq) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1]));
-        u.y = pack_bf16(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
-        u.z = pack_bf16(__uint_as_float(rr[i + 4]), __uint_as_float(rr[i + 5]));
-        u.w = pack_bf16(__uint_as_float(rr[i + 6]), __uint_as_float(rr[i + 7]));
-        *reinterpret_cast<uint4*>(orow + i) = u;
+        uint4 v;
+        v.x = pack_bf16(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1]));
+        v.y = pack_bf16(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
+        v.z = pack_bf16(__uint_as_float(rr[i + 4]), __uint_as_float(rr[i + 5]));
+        v.w = pack_bf16(__uint_as_float(rr[i + 6]), __uint_as_float(rr[i + 7]));
+        *reinterpret_cast<uint4*>(orow + i) = v;
       }
     }
   }
@@ -422,9 +456,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
-// TMEM columns: S^T [0,64)  dP^T [64,128)  dK [128,192)  dV [192,256).  256 threads, column halves as in the dQ kernel.
-// smem: K_j 16K | V_j 16K | 2 x {Q_i 8K, dO_i 8K} | P^T 16K | dS^T 16K | lse/D 512 B
-constexpr int DKDV_SMEM = 16384 * 2 + 2 * (8192 * 2) + 16384 * 2 + 512 + 64;
+// Same software pipeline as the dQ kernel, looping over 64-row q tiles.
+// TMEM columns: S^T [0,64)  dP^T [64,128)  dK [128,192)  dV [192,256).
+// smem: K_j 16K | V_j 16K | 3 x {Q_i 8K, dO_i 8K} | P^T 16K | dS^T 16K | lse/D 512 B
+constexpr int DKDV_SMEM = 16384 * 2 + 3 * 16384 + 16384 * 2 + 512 + 64;
 
 __global__ void __launch_bounds__(256)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -435,24 +470,23 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sK = smem;
   uint8_t* sV = smem + 16384;
-  uint8_t* sQO = smem + 32768;   // 2 stages x {Q_i 8 KB, dO_i 8 KB}
-  uint8_t* sPT = smem + 65536;
-  uint8_t* sdST = smem + 81920;
-  float* sL = reinterpret_cast<float*>(smem + 98304);
+  uint8_t* sQO = smem + 32768;             // 3 stages x {Q_i 8 KB, dO_i 8 KB}
+  uint8_t* sPT = smem + 32768 + 49152;
+  uint8_t* sdST = sPT + 16384;
+  float* sL = reinterpret_cast<float*>(sdST + 16384);
   float* sD = sL + 64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 98304 + 512);
-  uint64_t* bar_ld = bars;       // [2]
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_o = bars + 3;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdST + 16384 + 512);
+  uint64_t* bar_ld = bars;       // [3]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;
   const int r = (warp & 3) * 32 + lane;
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (tid == 0) {
-    ptx::mbar_init(&bar_ld[0], 1);
-    ptx::mbar_init(&bar_ld[1], 1);
+    for (int i = 0; i < 3; ++i) ptx::mbar_init(&bar_ld[i], 1);
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_o, 1);
     ptx::fence_barrier_init();
@@ -472,92 +506,115 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   const float sl2 = p.scale * kLog2e;
   const long long stat_base = (static_cast<long long>(b) * p.nh + h) * p.Sq;
 
+  auto n16_of = [&](int i) { return (min(BWD_BN, p.Sq - i * BWD_BN) + 15) & ~15; };
+  auto issue_scores = [&](int i) {  // thread 0: S^T = K Q_i^T, dP^T = V dO_i^T
+    uint8_t* sQ = sQO + (i % 3) * 16384;
+    const uint32_t idesc = ptx::make_idesc_bf16(128, n16_of(i), 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sK), ks), desc_kmajor(ptx::smem_u32(sQ), ks), idesc, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sV), ks), desc_kmajor(ptx::smem_u32(sQ + 8192), ks), idesc, ks > 0);
+    ptx::umma_commit(bar_s);
+  };
+  auto load_q = [&](int i) {
+    uint8_t* sQ = sQO + (i % 3) * 16384;
+    tma_load_3d(sQ, &tmQ, &bar_ld[i % 3], h * HD, i * BWD_BN, b);
+    tma_load_3d(sQ + 8192, &tmdO, &bar_ld[i % 3], h * HD, i * BWD_BN, b);
+  };
+
   if (tid == 0) {
     ptx::mbar_expect_tx(&bar_ld[0], 16384 * 2 + 8192 * 2);
     tma_load_3d(sK, &tmK, &bar_ld[0], h * HD, kv0, b);
     tma_load_3d(sV, &tmV, &bar_ld[0], h * HD, kv0, b);
-    tma_load_3d(sQO, &tmQ, &bar_ld[0], h * HD, 0, b);
-    tma_load_3d(sQO + 8192, &tmdO, &bar_ld[0], h * HD, 0, b);
+    load_q(0);
+    if (ntiles > 1) {
+      ptx::mbar_expect_tx(&bar_ld[1], 8192 * 2);
+      load_q(1);
+    }
+    ptx::mbar_wait(&bar_ld[0], 0);
+    ptx::tc_fence_after();
+    issue_scores(0);
   }
   for (int i = 0; i < ntiles; ++i) {
-    const uint32_t par = i & 1;
     const int q0 = i * BWD_BN;
     const int nvalid = min(BWD_BN, p.Sq - q0);
     const int n16 = (nvalid + 15) & ~15;
-    uint8_t* sQ = sQO + (i & 1) * 16384;
-    uint8_t* sdO = sQ + 8192;
-    if (tid < BWD_BN) {
+    if (tid < BWD_BN) {  // (previous readers of sL/sD passed barrier (B) of step i-1)
       const int qr = q0 + tid;
       sL[tid] = (qr < p.Sq) ? p.lse[stat_base + qr] * kLog2e : 0.f;
       sD[tid] = (qr < p.Sq) ? p.dvec[stat_base + qr] : 0.f;
     }
-    __syncthreads();
-    if (tid == 0) {
-      if (i + 1 < ntiles) {  // prefetch the next Q/dO tile into the other stage
-        uint8_t* nQ = sQO + ((i + 1) & 1) * 16384;
-        ptx::mbar_expect_tx(&bar_ld[(i + 1) & 1], 8192 * 2);
-        tma_load_3d(nQ, &tmQ, &bar_ld[(i + 1) & 1], h * HD, (i + 1) * BWD_BN, b);
-        tma_load_3d(nQ + 8192, &tmdO, &bar_ld[(i + 1) & 1], h * HD, (i + 1) * BWD_BN, b);
-      }
-      ptx::mbar_wait(&bar_ld[i & 1], (i >> 1) & 1);
-      ptx::tc_fence_after();
-      const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)  // S^T = K_j Q_i^T
-        ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sK), ks), desc_kmajor(ptx::smem_u32(sQ), ks), idesc, ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)  // dP^T = V_j dO_i^T
-        ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sV), ks), desc_kmajor(ptx::smem_u32(sdO), ks), idesc, ks > 0);
-      ptx::umma_commit(bar_s);
-    }
-    ptx::mbar_wait(bar_s, par);
+    ptx::mbar_wait(bar_s, i & 1);
     ptx::tc_fence_after();
+    uint32_t s_reg[32], d_reg[32];
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
       if (c < n16) {
-        uint32_t s16[16], d16[16];
-        tmem_ld_32x32b_x16(t_row + c, s16);
-        tmem_ld_32x32b_x16(t_row + 64 + c, d16);
-        ptx::tmem_ld_wait();
+        uint32_t a16[16], b16[16];
+        tmem_ld_32x32b_x16(t_row + c, a16);
+        tmem_ld_32x32b_x16(t_row + 64 + c, b16);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { s_reg[cc + k] = a16[k]; d_reg[cc + k] = b16[k]; }
+      }
+    }
+    ptx::tmem_ld_wait();
+    ptx::tc_fence_before();
+    __syncthreads();  // (A) scores are in registers, sL/sD are visible
+    if (tid == 0 && i + 1 < ntiles) {
+      if (i + 2 < ntiles) {
+        if (i >= 1) ptx::mbar_wait(bar_o, (i - 1) & 1);  // stage (i+2)%3 was last read by the dV/dK MMAs of step i-1
+        ptx::mbar_expect_tx(&bar_ld[(i + 2) % 3], 8192 * 2);
+        load_q(i + 2);
+      }
+      ptx::mbar_wait(&bar_ld[(i + 1) % 3], ((i + 1) / 3) & 1);
+      ptx::tc_fence_after();
+      issue_scores(i + 1);
+    }
+    if (i >= 1) ptx::mbar_wait(bar_o, (i - 1) & 1);  // P^T / dS^T buffers were read by the MMAs of step i-1
+#pragma unroll
+    for (int cc = 0; cc < 32; cc += 16) {
+      const int c = half * 32 + cc;
+      if (c < n16) {
         float pt[16], ds[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           const bool ok = kv_ok && (c + k < nvalid);
-          const float pr = ok ? exp2f(__uint_as_float(s16[k]) * sl2 - sL[c + k]) : 0.f;
+          const float pr = ok ? exp2f(__uint_as_float(s_reg[cc + k]) * sl2 - sL[c + k]) : 0.f;
           pt[k] = pr;
-          ds[k] = pr * (__uint_as_float(d16[k]) - sD[c + k]) * p.scale;
+          ds[k] = pr * (__uint_as_float(d_reg[cc + k]) - sD[c + k]) * p.scale;
         }
 #pragma unroll
         for (int k = 0; k < 16; k += 8) {
-          uint4 u, v;
-          u.x = pack_bf16(pt[k], pt[k + 1]); u.y = pack_bf16(pt[k + 2], pt[k + 3]);
-          u.z = pack_bf16(pt[k + 4], pt[k + 5]); u.w = pack_bf16(pt[k + 6], pt[k + 7]);
-          v.x = pack_bf16(ds[k], ds[k + 1]); v.y = pack_bf16(ds[k + 2], ds[k + 3]);
-          v.z = pack_bf16(ds[k + 4], ds[k + 5]); v.w = pack_bf16(ds[k + 6], ds[k + 7]);
-          st_operand_chunk(sPT, r, c + k, u);
-          st_operand_chunk(sdST, r, c + k, v);
+          uint4 x, y;
+          x.x = pack_bf16(pt[k], pt[k + 1]); x.y = pack_bf16(pt[k + 2], pt[k + 3]);
+          x.z = pack_bf16(pt[k + 4], pt[k + 5]); x.w = pack_bf16(pt[k + 6], pt[k + 7]);
+          y.x = pack_bf16(ds[k], ds[k + 1]); y.y = pack_bf16(ds[k + 2], ds[k + 3]);
+          y.z = pack_bf16(ds[k + 4], ds[k + 5]); y.w = pack_bf16(ds[k + 6], ds[k + 7]);
+          st_operand_chunk(sPT, r, c + k, x);
+          st_operand_chunk(sdST, r, c + k, y);
         }
       }
     }
     ptx::fence_proxy_async();
-    ptx::tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // (B)
     if (tid == 0) {
-      ptx::tc_fence_after();
+      uint8_t* sQ = sQO + (i % 3) * 16384;
       const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
       const int ksteps = n16 >> 4;
       for (int ks = 0; ks < ksteps; ++ks)  // dV += P^T dO_i
-        ptx::umma_f16(tmem + 192, desc_kmajor(ptx::smem_u32(sPT), ks), desc_mnmajor(ptx::smem_u32(sdO), ks), idesc,
+        ptx::umma_f16(tmem + 192, desc_kmajor(ptx::smem_u32(sPT), ks), desc_mnmajor(ptx::smem_u32(sQ + 8192), ks), idesc,
                       (i > 0 || ks > 0) ? 1u : 0u);
       for (int ks = 0; ks < ksteps; ++ks)  // dK += dS^T Q_i
         ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(sdST), ks), desc_mnmajor(ptx::smem_u32(sQ), ks), idesc,
                       (i > 0 || ks > 0) ? 1u : 0u);
       ptx::umma_commit(bar_o);
     }
-    ptx::mbar_wait(bar_o, par);
-    ptx::tc_fence_after();
   }
+  ptx::mbar_wait(bar_o, (ntiles - 1) & 1);
+  ptx::tc_fence_after();
   bf16* krow = p.out0 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out0_rs + h * HD + half * 32;
   bf16* vrow = p.out1 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out1_rs + h * HD + half * 32;
 #pragma unroll
@@ -569,12 +626,12 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       bf16* dst = which == 0 ? krow : vrow;
 #pragma unroll
       for (int k = 0; k < 32; k += 8) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(rr[k]), __uint_as_float(rr[k + 1]));
-        u.y = pack_bf16(__uint_as_float(rr[k + 2]), __uint_as_float(rr[k + 3]));
-        u.z = pack_bf16(__uint_as_float(rr[k + 4]), __uint_as_float(rr[k + 5]));
-        u.w = pack_bf16(__uint_as_float(rr[k + 6]), __uint_as_float(rr[k + 7]));
-        *reinterpret_cast<uint4*>(dst + k) = u;
+        uint4 v;
+        v.x = pack_bf16(__uint_as_float(rr[k]), __uint_as_float(rr[k + 1]));
+        v.y = pack_bf16(__uint_as_float(rr[k + 2]), __uint_as_float(rr[k + 3]));
+        v.z = pack_bf16(__uint_as_float(rr[k + 4]), __uint_as_float(rr[k + 5]));
+        v.w = pack_bf16(__uint_as_float(rr[k + 6]), __uint_as_float(rr[k + 7]));
+        *reinterpret_cast<uint4*>(dst + k) = v;
       }
     }
   }
