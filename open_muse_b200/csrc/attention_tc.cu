@@ -60,6 +60,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+// exp2 on the SFU without the denormal/range fix-ups of exp2f (inputs here are <= 0 or bounded scores)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Operand descriptors for [rows x 64] bf16 tiles laid out by TMA with the 128-byte swizzle (rows of 128 B).
 //  K-major view : row = M/N index, the 64 columns are K.  k-step ks (16 K) -> +32 B.
 //  MN-major view: row = K index, the 64 columns are M/N.  k-step ks (16 rows) -> +2048 B.
@@ -153,7 +160,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     ptx::mbar_wait(bar_s, par);
     ptx::tc_fence_after();
-    // the whole score row (<= 64 columns) fits in registers: one TMEM read, max, exp2, pack
+    // the whole score row (<= 64 columns) fits in registers: one TMEM read, max, exp2, pack.  The instruction count
+    // per score element is what bounds this kernel (issue slots, not the tensor core), so the ragged-tail masking is
+    // kept out of the full-tile path and the softmax scale is folded into one FFMA per element.
     float sc[64];
 #pragma unroll
     for (int c = 0; c < 64; c += 16) {
@@ -162,24 +171,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_32x32b_x16(t_s + c, r16);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) sc[c + i] = (c + i < nvalid) ? __uint_as_float(r16[i]) * sl2 : -INFINITY;
+        for (int i = 0; i < 16; ++i) sc[c + i] = __uint_as_float(r16[i]);
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) sc[c + i] = -INFINITY;
       }
     }
-    float mx = m;
+    if (nvalid < FWD_BN) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) mx = fmaxf(mx, sc[i]);
-    const float alpha = exp2f(m - mx);  // 0 on the first tile (m = -inf)
+      for (int i = 0; i < 64; ++i) sc[i] = (i < nvalid) ? sc[i] : -INFINITY;
+    }
+    float raw = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) raw = fmaxf(raw, sc[i]);
+    const float mx = fmaxf(m, raw * sl2);
+    const float alpha = ex2(m - mx);  // 0 on the first tile (m = -inf)
     m = mx;
     float ladd = 0.f;
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
-      sc[i] = exp2f(sc[i] - m);
+      sc[i] = ex2(fmaf(sc[i], sl2, -m));
       ladd += sc[i];
     }
-    l = l * alpha + ladd;
+    l = fmaf(l, alpha, ladd);
 #pragma unroll
     for (int i = 0; i < 64; i += 8) {
       if (i < n16) {
@@ -377,28 +391,29 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     uint8_t* dS = sdS + (u & 1) * 16384;
     if (sweep2 && u >= 2) ptx::mbar_wait(&bar_o[u & 1], ((u >> 1) - 1) & 1);  // dQ MMA of step st-2 read this buffer
+    const float neg_d_scaled = -dsum * p.scale;
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
       if (c < n16) {
+        float pr[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pr[i] = ex2(fmaf(__uint_as_float(s_reg[cc + i]), sl2, -lse2));
+        if (nvalid < BWD_BN) {  // ragged last tile only
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pr[i] = (c + i < nvalid) ? pr[i] : 0.f;
+        }
         if (!sweep2) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s_reg[cc + i]) * sl2 - lse2) : 0.f;
-            dsum = fmaf(pr, __uint_as_float(d_reg[cc + i]), dsum);
-          }
+          for (int i = 0; i < 16; ++i) dsum = fmaf(pr[i], __uint_as_float(d_reg[cc + i]), dsum);
         } else {
-          float ds[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float pr = (c + i < nvalid) ? exp2f(__uint_as_float(s_reg[cc + i]) * sl2 - lse2) : 0.f;
-            ds[i] = pr * (__uint_as_float(d_reg[cc + i]) - dsum) * p.scale;
-          }
+          for (int i = 0; i < 16; ++i) pr[i] *= fmaf(__uint_as_float(d_reg[cc + i]), p.scale, neg_d_scaled);
 #pragma unroll
           for (int i = 0; i < 16; i += 8) {
             uint4 v;
-            v.x = pack_bf16(ds[i], ds[i + 1]); v.y = pack_bf16(ds[i + 2], ds[i + 3]);
-            v.z = pack_bf16(ds[i + 4], ds[i + 5]); v.w = pack_bf16(ds[i + 6], ds[i + 7]);
+            v.x = pack_bf16(pr[i], pr[i + 1]); v.y = pack_bf16(pr[i + 2], pr[i + 3]);
+            v.z = pack_bf16(pr[i + 4], pr[i + 5]); v.w = pack_bf16(pr[i + 6], pr[i + 7]);
             st_operand_chunk(dS, r, c + i, v);
           }
         }
@@ -544,7 +559,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     if (tid < BWD_BN) {  // (previous readers of sL/sD passed barrier (B) of step i-1)
       const int qr = q0 + tid;
       sL[tid] = (qr < p.Sq) ? p.lse[stat_base + qr] * kLog2e : 0.f;
-      sD[tid] = (qr < p.Sq) ? p.dvec[stat_base + qr] : 0.f;
+      sD[tid] = (qr < p.Sq) ? p.dvec[stat_base + qr] * p.scale : 0.f;  // pre-scaled: dS = P (dP*scale - D*scale)
     }
     ptx::mbar_wait(bar_s, i & 1);
     ptx::tc_fence_after();
@@ -578,14 +593,22 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
       if (c < n16) {
-        float pt[16], ds[16];
+        float pt[16], ds[16], lq[16], dq_[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const bool ok = kv_ok && (c + k < nvalid);
-          const float pr = ok ? exp2f(__uint_as_float(s_reg[cc + k]) * sl2 - sL[c + k]) : 0.f;
-          pt[k] = pr;
-          ds[k] = pr * (__uint_as_float(d_reg[cc + k]) - sD[c + k]) * p.scale;
+        for (int k = 0; k < 16; k += 4) {  // per-column lse / D: 16-byte broadcast reads
+          const float4 a = *reinterpret_cast<const float4*>(sL + c + k);
+          const float4 e = *reinterpret_cast<const float4*>(sD + c + k);
+          lq[k] = a.x; lq[k + 1] = a.y; lq[k + 2] = a.z; lq[k + 3] = a.w;
+          dq_[k] = e.x; dq_[k + 1] = e.y; dq_[k + 2] = e.z; dq_[k + 3] = e.w;
         }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pt[k] = ex2(fmaf(__uint_as_float(s_reg[cc + k]), sl2, -lq[k]));
+        if (nvalid < BWD_BN || !kv_ok) {  // ragged q tile / kv rows past the end of the sequence
+#pragma unroll
+          for (int k = 0; k < 16; ++k) pt[k] = (kv_ok && c + k < nvalid) ? pt[k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) ds[k] = pt[k] * fmaf(__uint_as_float(d_reg[cc + k]), p.scale, -dq_[k]);
 #pragma unroll
         for (int k = 0; k < 16; k += 8) {
           uint4 x, y;
