@@ -67,6 +67,9 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// named barrier over the 256 math threads (barrier 0 stays __syncthreads for the whole CTA)
+__device__ __forceinline__ void math_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
 // Operand descriptors for [rows x 64] bf16 tiles laid out by TMA with the 128-byte swizzle (rows of 128 B).
 //  K-major view : row = M/N index, the 64 columns are K.  k-step ks (16 K) -> +32 B.
 //  MN-major view: row = K index, the 64 columns are M/N.  k-step ks (16 rows) -> +2048 B.
@@ -277,7 +280,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int BWD_BN = 64;
 constexpr int DQ_SMEM = 16384 * 2 + 3 * 16384 + 2 * 16384 + 64;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(288, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const TcParams p) {
@@ -290,10 +293,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint8_t* sdS = smem + 32768 + 49152;     // 2 buffers x 16 KB
   float* sDp = reinterpret_cast<float*>(sdS);  // [2][128] partial D (only used between the two sweeps)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768 + 49152 + 32768);
-  uint64_t* bar_kv = bars;       // [3]
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_o = bars + 4;    // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_kv = bars;       // [3] TMA landed
+  uint64_t* bar_s = bars + 3;    //     score MMAs done
+  uint64_t* bar_o = bars + 4;    // [2] dQ MMA done
+  uint64_t* bar_free = bars + 6; //     all math threads pulled their scores out of TMEM (count 256)
+  uint64_t* bar_ds = bars + 7;   // [2] dS operand written (count 256)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;                 // column half handled by this thread
@@ -304,6 +309,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(&bar_o[0], 1);
     ptx::mbar_init(&bar_o[1], 1);
+    ptx::mbar_init(bar_free, 256);
+    ptx::mbar_init(&bar_ds[0], 256);
+    ptx::mbar_init(&bar_ds[1], 256);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
@@ -341,19 +349,50 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tma_load_3d(sK + 8192, &tmV, &bar_kv[step % 3], h * HD, jn * BWD_BN, b);
   };
 
-  if (tid == 0) {
-    ptx::mbar_expect_tx(&bar_kv[0], 16384 * 2 + 8192 * 2);
-    tma_load_3d(sQ, &tmQ, &bar_kv[0], h * HD, q0, b);
-    tma_load_3d(sdO, &tmdO, &bar_kv[0], h * HD, q0, b);
-    load_kv(0);
-    if (nsteps > 1) {
-      ptx::mbar_expect_tx(&bar_kv[1], 8192 * 2);
-      load_kv(1);
+  // ---- warp 8: control thread (TMA + MMA issue), never touches the softmax math -----------------------------------
+  if (warp == 8) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(&bar_kv[0], 16384 * 2 + 8192 * 2);
+      tma_load_3d(sQ, &tmQ, &bar_kv[0], h * HD, q0, b);
+      tma_load_3d(sdO, &tmdO, &bar_kv[0], h * HD, q0, b);
+      load_kv(0);
+      if (nsteps > 1) {
+        ptx::mbar_expect_tx(&bar_kv[1], 8192 * 2);
+        load_kv(1);
+      }
+      ptx::mbar_wait(&bar_kv[0], 0);
+      ptx::tc_fence_after();
+      issue_scores(0);
+      for (int st = 0; st < nsteps; ++st) {
+        const int u = st - ntiles;
+        ptx::mbar_wait(bar_free, st & 1);  // scores of step st are in registers: TMEM [0,128) may be overwritten
+        ptx::tc_fence_after();
+        if (st + 1 < nsteps) {
+          if (st + 2 < nsteps) {
+            // ring stage (st+2)%3 was last read by the dQ MMA of step st-1
+            if (st - 1 >= ntiles) ptx::mbar_wait(&bar_o[(u - 1) & 1], ((u - 1) >> 1) & 1);
+            ptx::mbar_expect_tx(&bar_kv[(st + 2) % 3], 8192 * 2);
+            load_kv(st + 2);
+          }
+          ptx::mbar_wait(&bar_kv[(st + 1) % 3], ((st + 1) / 3) & 1);
+          ptx::tc_fence_after();
+          issue_scores(st + 1);
+        }
+        if (u >= 0) {
+          ptx::mbar_wait(&bar_ds[u & 1], (u >> 1) & 1);  // dS of this step is in shared memory
+          const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
+          uint8_t* sK = sKV + (st % 3) * 16384;
+          uint8_t* dS = sdS + (u & 1) * 16384;
+          const int ksteps = n16_of(st) >> 4;
+          for (int ks = 0; ks < ksteps; ++ks)  // dQ += dS K_j   (K_j consumed as an MN-major operand)
+            ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(dS), ks), desc_mnmajor(ptx::smem_u32(sK), ks), idesc,
+                          (u > 0 || ks > 0) ? 1u : 0u);
+          ptx::umma_commit(&bar_o[u & 1]);
+        }
+      }
     }
-    ptx::mbar_wait(&bar_kv[0], 0);
-    ptx::tc_fence_after();
-    issue_scores(0);
-  }
+  } else {
+  // ---- warps 0-7: math threads ------------------------------------------------------------------------------------
   float dsum = 0.f;
   for (int st = 0; st < nsteps; ++st) {
     const int j = st % ntiles;
@@ -377,18 +416,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     ptx::tmem_ld_wait();
     ptx::tc_fence_before();
-    __syncthreads();  // (A) every thread holds its scores in registers: TMEM [0,128) may be overwritten
-    if (tid == 0 && st + 1 < nsteps) {
-      if (st + 2 < nsteps) {
-        // ring stage (st+2)%3 was last read by the dQ MMA of step st-1
-        if (st - 1 >= ntiles) ptx::mbar_wait(&bar_o[(u - 1) & 1], ((u - 1) >> 1) & 1);
-        ptx::mbar_expect_tx(&bar_kv[(st + 2) % 3], 8192 * 2);
-        load_kv(st + 2);
-      }
-      ptx::mbar_wait(&bar_kv[(st + 1) % 3], ((st + 1) / 3) & 1);
-      ptx::tc_fence_after();
-      issue_scores(st + 1);
-    }
+    ptx::mbar_arrive(bar_free);  // (A) this thread holds its scores in registers
     uint8_t* dS = sdS + (u & 1) * 16384;
     if (sweep2 && u >= 2) ptx::mbar_wait(&bar_o[u & 1], ((u >> 1) - 1) & 1);  // dQ MMA of step st-2 read this buffer
     const float neg_d_scaled = -dsum * p.scale;
@@ -396,56 +424,51 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
       if (c < n16) {
-        float pr[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pr[i] = ex2(fmaf(__uint_as_float(s_reg[cc + i]), sl2, -lse2));
-        if (nvalid < BWD_BN) {  // ragged last tile only
+        for (int i8 = 0; i8 < 16; i8 += 8) {
+          float pr[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pr[i] = (c + i < nvalid) ? pr[i] : 0.f;
-        }
-        if (!sweep2) {
+          for (int i = 0; i < 8; ++i) pr[i] = ex2(fmaf(__uint_as_float(s_reg[cc + i8 + i]), sl2, -lse2));
+          if (nvalid < BWD_BN) {  // ragged last tile only
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dsum = fmaf(pr[i], __uint_as_float(d_reg[cc + i]), dsum);
-        } else {
+            for (int i = 0; i < 8; ++i) pr[i] = (c + i8 + i < nvalid) ? pr[i] : 0.f;
+          }
+          if (!sweep2) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pr[i] *= fmaf(__uint_as_float(d_reg[cc + i]), p.scale, neg_d_scaled);
+            for (int i = 0; i < 8; ++i) dsum = fmaf(pr[i], __uint_as_float(d_reg[cc + i8 + i]), dsum);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; i += 8) {
+            for (int i = 0; i < 8; ++i) pr[i] *= fmaf(__uint_as_float(d_reg[cc + i8 + i]), p.scale, neg_d_scaled);
             uint4 v;
-            v.x = pack_bf16(pr[i], pr[i + 1]); v.y = pack_bf16(pr[i + 2], pr[i + 3]);
-            v.z = pack_bf16(pr[i + 4], pr[i + 5]); v.w = pack_bf16(pr[i + 6], pr[i + 7]);
-            st_operand_chunk(dS, r, c + i, v);
+            v.x = pack_bf16(pr[0], pr[1]); v.y = pack_bf16(pr[2], pr[3]);
+            v.z = pack_bf16(pr[4], pr[5]); v.w = pack_bf16(pr[6], pr[7]);
+            st_operand_chunk(dS, r, c + i8, v);
           }
         }
       }
     }
-    if (st == ntiles - 1) sDp[half * 128 + r] = dsum;  // partial D of this column half
-    ptx::fence_proxy_async();
-    __syncthreads();  // (B)
-    if (st == ntiles - 1) {  // D = sum over both halves, identical in both threads of the row
+    if (sweep2) {
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&bar_ds[u & 1]);  // (B) this thread's part of dS is visible to the tensor core
+    }
+    if (st == ntiles - 1) {  // D = sum over both column halves, identical in both threads of the row
+      sDp[half * 128 + r] = dsum;
+      math_sync();
       dsum = sDp[r] + sDp[128 + r];
       if (half == 0 && row < p.Sq) p.dvec[stat_idx] = dsum;  // for the dK/dV kernels
-      __syncthreads();       // sDp aliases dS[0]: everyone has read it before sweep 2 writes dS
-    }
-    if (sweep2 && tid == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
-      uint8_t* sK = sKV + (st % 3) * 16384;
-      const int ksteps = n16 >> 4;
-      for (int ks = 0; ks < ksteps; ++ks)  // dQ += dS K_j   (K_j consumed as an MN-major operand)
-        ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(dS), ks), desc_mnmajor(ptx::smem_u32(sK), ks), idesc,
-                      (u > 0 || ks > 0) ? 1u : 0u);
-      ptx::umma_commit(&bar_o[u & 1]);
+      math_sync();  // sDp aliases dS[0]: everyone has read it before sweep 2 writes dS
     }
   }
+  }  // math threads
   // all dQ MMAs must have landed: last use of each completion barrier
-  {
+  if (warp < 8) {
     const int U = ntiles;
     const int ua = U - 1;
     ptx::mbar_wait(&bar_o[ua & 1], (ua >> 1) & 1);
     if (U >= 2) { const int ub = U - 2; ptx::mbar_wait(&bar_o[ub & 1], (ub >> 1) & 1); }
     ptx::tc_fence_after();
   }
-  {
+  if (warp < 8) {
     bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD + half * 32;
     uint32_t rr[32];
     ptx::tmem_ld_32x32b_x32(t_row + 128 + half * 32, rr);
@@ -474,9 +497,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // Same software pipeline as the dQ kernel, looping over 64-row q tiles.
 // TMEM columns: S^T [0,64)  dP^T [64,128)  dK [128,192)  dV [192,256).
 // smem: K_j 16K | V_j 16K | 3 x {Q_i 8K, dO_i 8K} | P^T 16K | dS^T 16K | lse/D 512 B
-constexpr int DKDV_SMEM = 16384 * 2 + 3 * 16384 + 16384 * 2 + 512 + 64;
+constexpr int DKDV_SMEM = 16384 * 2 + 3 * 16384 + 16384 * 2 + 512 + 128;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(288, 2)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                         const TcParams p) {
@@ -488,13 +511,14 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   uint8_t* sQO = smem + 32768;             // 3 stages x {Q_i 8 KB, dO_i 8 KB}
   uint8_t* sPT = smem + 32768 + 49152;
   uint8_t* sdST = sPT + 16384;
-  float* sL = reinterpret_cast<float*>(sdST + 16384);
-  float* sD = sL + 64;
+  float* sLD = reinterpret_cast<float*>(sdST + 16384);  // [lse 64 | D 64] of the current q tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdST + 16384 + 512);
-  uint64_t* bar_ld = bars;       // [3]
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_ld = bars;       // [3] TMA landed
+  uint64_t* bar_s = bars + 3;    //     score MMAs done
+  uint64_t* bar_o = bars + 4;    //     dV / dK MMAs done
+  uint64_t* bar_free = bars + 5; //     scores pulled out of TMEM by all math threads (count 256)
+  uint64_t* bar_ps = bars + 6;   //     P^T / dS^T operands written (count 256)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;
@@ -504,6 +528,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     for (int i = 0; i < 3; ++i) ptx::mbar_init(&bar_ld[i], 1);
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_o, 1);
+    ptx::mbar_init(bar_free, 256);
+    ptx::mbar_init(bar_ps, 256);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
@@ -539,24 +565,55 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     tma_load_3d(sQ + 8192, &tmdO, &bar_ld[i % 3], h * HD, i * BWD_BN, b);
   };
 
-  if (tid == 0) {
-    ptx::mbar_expect_tx(&bar_ld[0], 16384 * 2 + 8192 * 2);
-    tma_load_3d(sK, &tmK, &bar_ld[0], h * HD, kv0, b);
-    tma_load_3d(sV, &tmV, &bar_ld[0], h * HD, kv0, b);
-    load_q(0);
-    if (ntiles > 1) {
-      ptx::mbar_expect_tx(&bar_ld[1], 8192 * 2);
-      load_q(1);
+  // ---- warp 8: control thread (TMA + MMA issue) --------------------------------------------------------------------
+  if (warp == 8) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(&bar_ld[0], 16384 * 2 + 8192 * 2);
+      tma_load_3d(sK, &tmK, &bar_ld[0], h * HD, kv0, b);
+      tma_load_3d(sV, &tmV, &bar_ld[0], h * HD, kv0, b);
+      load_q(0);
+      if (ntiles > 1) {
+        ptx::mbar_expect_tx(&bar_ld[1], 8192 * 2);
+        load_q(1);
+      }
+      ptx::mbar_wait(&bar_ld[0], 0);
+      ptx::tc_fence_after();
+      issue_scores(0);
+      for (int i = 0; i < ntiles; ++i) {
+        ptx::mbar_wait(bar_free, i & 1);
+        ptx::tc_fence_after();
+        if (i + 1 < ntiles) {
+          if (i + 2 < ntiles) {
+            if (i >= 1) ptx::mbar_wait(bar_o, (i - 1) & 1);  // stage (i+2)%3 was last read by the dV/dK MMAs of step i-1
+            ptx::mbar_expect_tx(&bar_ld[(i + 2) % 3], 8192 * 2);
+            load_q(i + 2);
+          }
+          ptx::mbar_wait(&bar_ld[(i + 1) % 3], ((i + 1) / 3) & 1);
+          ptx::tc_fence_after();
+          issue_scores(i + 1);
+        }
+        ptx::mbar_wait(bar_ps, i & 1);  // P^T and dS^T of this step are in shared memory
+        uint8_t* sQ = sQO + (i % 3) * 16384;
+        const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
+        const int ksteps = n16_of(i) >> 4;
+        for (int ks = 0; ks < ksteps; ++ks)  // dV += P^T dO_i
+          ptx::umma_f16(tmem + 192, desc_kmajor(ptx::smem_u32(sPT), ks), desc_mnmajor(ptx::smem_u32(sQ + 8192), ks), idesc,
+                        (i > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < ksteps; ++ks)  // dK += dS^T Q_i
+          ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(sdST), ks), desc_mnmajor(ptx::smem_u32(sQ), ks), idesc,
+                        (i > 0 || ks > 0) ? 1u : 0u);
+        ptx::umma_commit(bar_o);
+      }
     }
-    ptx::mbar_wait(&bar_ld[0], 0);
-    ptx::tc_fence_after();
-    issue_scores(0);
-  }
+  } else {
+  // ---- warps 0-7: math threads ------------------------------------------------------------------------------------
   for (int i = 0; i < ntiles; ++i) {
     const int q0 = i * BWD_BN;
     const int nvalid = min(BWD_BN, p.Sq - q0);
     const int n16 = (nvalid + 15) & ~15;
-    if (tid < BWD_BN) {  // (previous readers of sL/sD passed barrier (B) of step i-1)
+    float* sL = sLD;  // (the trailing math_sync of the previous step fenced its readers)
+    float* sD = sL + 64;
+    if (tid < BWD_BN) {
       const int qr = q0 + tid;
       sL[tid] = (qr < p.Sq) ? p.lse[stat_base + qr] * kLog2e : 0.f;
       sD[tid] = (qr < p.Sq) ? p.dvec[stat_base + qr] * p.scale : 0.f;  // pre-scaled: dS = P (dP*scale - D*scale)
@@ -577,64 +634,44 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     }
     ptx::tmem_ld_wait();
     ptx::tc_fence_before();
-    __syncthreads();  // (A) scores are in registers, sL/sD are visible
-    if (tid == 0 && i + 1 < ntiles) {
-      if (i + 2 < ntiles) {
-        if (i >= 1) ptx::mbar_wait(bar_o, (i - 1) & 1);  // stage (i+2)%3 was last read by the dV/dK MMAs of step i-1
-        ptx::mbar_expect_tx(&bar_ld[(i + 2) % 3], 8192 * 2);
-        load_q(i + 2);
-      }
-      ptx::mbar_wait(&bar_ld[(i + 1) % 3], ((i + 1) / 3) & 1);
-      ptx::tc_fence_after();
-      issue_scores(i + 1);
-    }
+    ptx::mbar_arrive(bar_free);  // (A) scores are in registers
+    math_sync();                 // sL / sD of this step are visible to all math threads
     if (i >= 1) ptx::mbar_wait(bar_o, (i - 1) & 1);  // P^T / dS^T buffers were read by the MMAs of step i-1
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
       if (c < n16) {
-        float pt[16], ds[16], lq[16], dq_[16];
 #pragma unroll
-        for (int k = 0; k < 16; k += 4) {  // per-column lse / D: 16-byte broadcast reads
-          const float4 a = *reinterpret_cast<const float4*>(sL + c + k);
-          const float4 e = *reinterpret_cast<const float4*>(sD + c + k);
-          lq[k] = a.x; lq[k + 1] = a.y; lq[k + 2] = a.z; lq[k + 3] = a.w;
-          dq_[k] = e.x; dq_[k + 1] = e.y; dq_[k + 2] = e.z; dq_[k + 3] = e.w;
-        }
+        for (int k8 = 0; k8 < 16; k8 += 8) {
+          float pt[8], ds[8], lq[8], dq_[8];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) pt[k] = ex2(fmaf(__uint_as_float(s_reg[cc + k]), sl2, -lq[k]));
-        if (nvalid < BWD_BN || !kv_ok) {  // ragged q tile / kv rows past the end of the sequence
+          for (int k = 0; k < 8; k += 4) {  // per-column lse / D: 16-byte broadcast reads
+            const float4 a = *reinterpret_cast<const float4*>(sL + c + k8 + k);
+            const float4 e = *reinterpret_cast<const float4*>(sD + c + k8 + k);
+            lq[k] = a.x; lq[k + 1] = a.y; lq[k + 2] = a.z; lq[k + 3] = a.w;
+            dq_[k] = e.x; dq_[k + 1] = e.y; dq_[k + 2] = e.z; dq_[k + 3] = e.w;
+          }
 #pragma unroll
-          for (int k = 0; k < 16; ++k) pt[k] = (kv_ok && c + k < nvalid) ? pt[k] : 0.f;
-        }
+          for (int k = 0; k < 8; ++k) pt[k] = ex2(fmaf(__uint_as_float(s_reg[cc + k8 + k]), sl2, -lq[k]));
+          if (nvalid < BWD_BN || !kv_ok) {  // ragged q tile / kv rows past the end of the sequence
 #pragma unroll
-        for (int k = 0; k < 16; ++k) ds[k] = pt[k] * fmaf(__uint_as_float(d_reg[cc + k]), p.scale, -dq_[k]);
+            for (int k = 0; k < 8; ++k) pt[k] = (kv_ok && c + k8 + k < nvalid) ? pt[k] : 0.f;
+          }
 #pragma unroll
-        for (int k = 0; k < 16; k += 8) {
+          for (int k = 0; k < 8; ++k) ds[k] = pt[k] * fmaf(__uint_as_float(d_reg[cc + k8 + k]), p.scale, -dq_[k]);
           uint4 x, y;
-          x.x = pack_bf16(pt[k], pt[k + 1]); x.y = pack_bf16(pt[k + 2], pt[k + 3]);
-          x.z = pack_bf16(pt[k + 4], pt[k + 5]); x.w = pack_bf16(pt[k + 6], pt[k + 7]);
-          y.x = pack_bf16(ds[k], ds[k + 1]); y.y = pack_bf16(ds[k + 2], ds[k + 3]);
-          y.z = pack_bf16(ds[k + 4], ds[k + 5]); y.w = pack_bf16(ds[k + 6], ds[k + 7]);
-          st_operand_chunk(sPT, r, c + k, x);
-          st_operand_chunk(sdST, r, c + k, y);
+          x.x = pack_bf16(pt[0], pt[1]); x.y = pack_bf16(pt[2], pt[3]);
+          x.z = pack_bf16(pt[4], pt[5]); x.w = pack_bf16(pt[6], pt[7]);
+          y.x = pack_bf16(ds[0], ds[1]); y.y = pack_bf16(ds[2], ds[3]);
+          y.z = pack_bf16(ds[4], ds[5]); y.w = pack_bf16(ds[6], ds[7]);
+          st_operand_chunk(sPT, r, c + k8, x);
+          st_operand_chunk(sdST, r, c + k8, y);
         }
       }
     }
     ptx::fence_proxy_async();
-    __syncthreads();  // (B)
-    if (tid == 0) {
-      uint8_t* sQ = sQO + (i % 3) * 16384;
-      const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
-      const int ksteps = n16 >> 4;
-      for (int ks = 0; ks < ksteps; ++ks)  // dV += P^T dO_i
-        ptx::umma_f16(tmem + 192, desc_kmajor(ptx::smem_u32(sPT), ks), desc_mnmajor(ptx::smem_u32(sQ + 8192), ks), idesc,
-                      (i > 0 || ks > 0) ? 1u : 0u);
-      for (int ks = 0; ks < ksteps; ++ks)  // dK += dS^T Q_i
-        ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(sdST), ks), desc_mnmajor(ptx::smem_u32(sQ), ks), idesc,
-                      (i > 0 || ks > 0) ? 1u : 0u);
-      ptx::umma_commit(bar_o);
-    }
+    ptx::mbar_arrive(bar_ps);  // (B) this thread's part of P^T / dS^T is visible to the tensor core
+    math_sync();               // all reads of sL / sD are done before the next step overwrites them
   }
   ptx::mbar_wait(bar_o, (ntiles - 1) & 1);
   ptx::tc_fence_after();
@@ -658,6 +695,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       }
     }
   }
+  }  // math threads
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -716,7 +754,7 @@ int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o,
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dq); p.out0_rs = dq_rs; p.lse = const_cast<float*>(lse); p.dvec = dvec;
-  attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 256, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
+  attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 288, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
   *rows_done = ntile * 128;
   return check_launch("attn_bwd_dq_tc");
 }
@@ -739,7 +777,7 @@ int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dk); p.out0_rs = dk_rs; p.out1 = reinterpret_cast<bf16*>(dv); p.out1_rs = dv_rs;
   p.lse = const_cast<float*>(lse); p.dvec = const_cast<float*>(dvec);
-  attn_bwd_dkdv_tc_kernel<<<dim3(ntile, nh, B), 256, DKDV_SMEM, s>>>(tk, tv, tq, tdo, p);
+  attn_bwd_dkdv_tc_kernel<<<dim3(ntile, nh, B), 288, DKDV_SMEM, s>>>(tk, tv, tq, tdo, p);
   *rows_done = ntile * 128;
   return check_launch("attn_bwd_dkdv_tc");
 }
