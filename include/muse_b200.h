@@ -100,6 +100,11 @@ int muse_ce_bwd(const void* logits, const long long* labels, const float* lse, c
  * [ncodes,D], enorm_ws fp32 [ncodes] scratch, dmin (optional) fp32 [n]. Bit-exact vs oracle/vq_oracle.c. */
 int muse_vq_argmin(const float* z, const float* codebook, float* enorm_ws, long long* ids, float* dmin, int n,
                    int ncodes, int D, void* stream);
+/* VectorQuantizer.get_soft_code (muse/modeling_maskgit_vqgan.py:327-340): soft fp32 [n,ncodes] = softmax_c(-d[r,c]/temp)
+ * with d exactly as muse_vq_argmin; ids = argmin d (expo_noise NULL, stochastic=False) or multinomial(soft,1) realised
+ * as argmax_c soft/q with q = expo_noise fp32 [n,ncodes] ~ Exp(1) drawn by the caller (stochastic=True). */
+int muse_vq_soft_code(const float* z, const float* codebook, float* enorm_ws, float* soft, long long* ids,
+                      const float* expo_noise, float temp, int n, int ncodes, int D, void* stream);
 /* VectorQuantizer.get_codebook_entry (:318-324): out fp32 [B, D, P] (NCHW) = codebook[ids[B,P]]. */
 int muse_vq_lookup_nchw(const long long* ids, const float* codebook, float* out, int B, int P, int D, int ncodes,
                         void* stream);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "muse_ce_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "muse_ce_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "muse_vq_argmin": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "muse_vq_soft_code": (c_int, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _P]),
     "muse_vq_lookup_nchw": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_sample_step": (c_int, [_P, _P, _L, _L, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _F, _P]),
     "muse_conv2d_nhwc": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -3,5 +3,11 @@
 (training/train_maskgit_imagenet.py:30-33) resolve to the B200 implementations."""
 __version__ = "0.0.1"
 
-from open_muse_b200 import MaskGitTransformer, MaskGitVQGAN, PipelineMuse, get_mask_chedule  # noqa: F401
+from open_muse_b200 import (  # noqa: F401
+    MaskGitTransformer,
+    MaskGitVQGAN,
+    PipelineMuse,
+    PipelineMuseInpainting,
+    get_mask_chedule,
+)
 from open_muse_b200 import sampling  # noqa: F401

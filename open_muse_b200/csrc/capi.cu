@@ -42,6 +42,7 @@ int ce_fwd(const void*, const long long*, float*, float*, float*, int, int, int,
 int ce_bwd(const void*, const long long*, const float*, const float*, const float*, void*, int, int, int, float, cudaStream_t);
 int vq_argmin(const float*, const float*, float*, long long*, float*, int, int, int, cudaStream_t);
 int vq_lookup_nchw(const long long*, const float*, float*, int, int, int, int, cudaStream_t);
+int vq_soft_code(const float*, const float*, float*, float*, long long*, const float*, float, int, int, int, cudaStream_t);
 int sample_step(const void*, const void*, long long, long long, float, const long long*, const float*, const float*, long long*, long long*, float*, int, int, int, long long, int, float, cudaStream_t);
 int conv2d_nhwc(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int groupnorm_silu_nhwc(const float*, const float*, const float*, float*, float*, float*, int, int, int, int, float, cudaStream_t);
@@ -133,6 +134,10 @@ int muse_ce_bwd(const void* logits, const long long* labels, const float* lse, c
 int muse_vq_argmin(const float* z, const float* codebook, float* enorm_ws, long long* ids, float* dmin, int n,
                    int ncodes, int D, void* stream) {
   return vq_argmin(z, codebook, enorm_ws, ids, dmin, n, ncodes, D, ST(stream));
+}
+int muse_vq_soft_code(const float* z, const float* codebook, float* enorm_ws, float* soft, long long* ids,
+                       const float* expo_noise, float temp, int n, int ncodes, int D, void* stream) {
+  return vq_soft_code(z, codebook, enorm_ws, soft, ids, expo_noise, temp, n, ncodes, D, ST(stream));
 }
 int muse_vq_lookup_nchw(const long long* ids, const float* codebook, float* out, int B, int P, int D, int ncodes, void* stream) {
   return vq_lookup_nchw(ids, codebook, out, B, P, D, ncodes, ST(stream));

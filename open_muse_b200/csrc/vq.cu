@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ x
 
 __global__ void __launch_bounds__(256)
 vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb, const float* __restrict__ enorm,
-                 long long* __restrict__ ids, float* __restrict__ dmin_out, int n, int ncodes, int D) {
+                 long long* __restrict__ ids, float* __restrict__ dmin_out, float* __restrict__ dist_out, int n,
+                 int ncodes, int D) {
   __shared__ __align__(16) float sZ[TKK][TR];
   __shared__ __align__(16) float sE[TKK][TC];
   __shared__ float sZn[TR];
@@ -94,6 +95,8 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb, cons
         if (code < ncodes) {
           const float d = fmaf(-2.0f, acc[i][j], zn + enorm[code]);
           if (d < bestv[i]) { bestv[i] = d; besti[i] = code; }  // strict: lowest index wins ties
+          if (dist_out != nullptr && row0 + ty * 8 + i < n)
+            dist_out[static_cast<size_t>(row0 + ty * 8 + i) * ncodes + code] = d;
         }
       }
     }
@@ -115,6 +118,45 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb, cons
       ids[r] = bi;
       if (dmin_out) dmin_out[r] = bv;
     }
+  }
+}
+
+// VectorQuantizer.get_soft_code (muse/modeling_maskgit_vqgan.py:327-340): soft = softmax(-d / temp) over the codebook,
+// in place over the distance matrix written by vq_argmin_kernel; optional stochastic code = multinomial(soft, 1),
+// realised as argmax_c soft[c] / q[c] with q ~ Exp(1) pre-drawn by the caller (the construction torch.multinomial
+// itself uses for one sample). One warp per row.
+__global__ void __launch_bounds__(256)
+vq_soft_kernel(float* __restrict__ dist, const float* __restrict__ expo, long long* __restrict__ ids, float temp, int n,
+               int ncodes) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const int lane = threadIdx.x & 31;
+  float* row = dist + static_cast<size_t>(r) * ncodes;
+  float m = -INFINITY;
+  for (int c = lane; c < ncodes; c += 32) m = fmaxf(m, -row[c] / temp);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int c = lane; c < ncodes; c += 32) sum += expf(-row[c] / temp - m);
+  sum = warp_sum(sum);
+  float bestv = -INFINITY;
+  int besti = 0x7fffffff;
+  const float* q = expo ? expo + static_cast<size_t>(r) * ncodes : nullptr;
+  for (int c = lane; c < ncodes; c += 32) {
+    const float p = expf(-row[c] / temp - m) / sum;
+    row[c] = p;
+    if (q) {
+      const float v = p / q[c];
+      if (v > bestv) { bestv = v; besti = c; }
+    }
+  }
+  if (q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ov > bestv || (ov == bestv && oi < besti)) { bestv = ov; besti = oi; }
+    }
+    if (lane == 0) ids[r] = besti;
   }
 }
 
@@ -142,8 +184,23 @@ int vq_argmin(const float* z, const float* codebook, float* enorm_ws, long long*
   sqnorm_kernel<<<ceil_div(ncodes, 256), 256, 0, s>>>(codebook, enorm_ws, ncodes, D);
   int rc = check_launch("vq_sqnorm");
   if (rc) return rc;
-  vq_argmin_kernel<<<ceil_div(n, TR), 256, 0, s>>>(z, codebook, enorm_ws, ids, dmin, n, ncodes, D);
+  vq_argmin_kernel<<<ceil_div(n, TR), 256, 0, s>>>(z, codebook, enorm_ws, ids, dmin, nullptr, n, ncodes, D);
   return check_launch("vq_argmin");
+}
+
+int vq_soft_code(const float* z, const float* codebook, float* enorm_ws, float* soft, long long* ids, const float* expo,
+                 float temp, int n, int ncodes, int D, cudaStream_t s) {
+  if (n <= 0) return MUSE_OK;
+  if (D % TKK != 0) { set_last_error("vq_soft_code: D=%d must be a multiple of %d", D, TKK); return MUSE_ERR_UNSUPPORTED; }
+  if (!(temp > 0.f)) { set_last_error("vq_soft_code: temp must be > 0"); return MUSE_ERR_INVALID; }
+  sqnorm_kernel<<<ceil_div(ncodes, 256), 256, 0, s>>>(codebook, enorm_ws, ncodes, D);
+  int rc = check_launch("vq_sqnorm");
+  if (rc) return rc;
+  vq_argmin_kernel<<<ceil_div(n, TR), 256, 0, s>>>(z, codebook, enorm_ws, ids, nullptr, soft, n, ncodes, D);
+  rc = check_launch("vq_argmin(dist)");
+  if (rc) return rc;
+  vq_soft_kernel<<<ceil_div(n, 8), 256, 0, s>>>(soft, expo, ids, temp, n, ncodes);
+  return check_launch("vq_soft");
 }
 
 int vq_lookup_nchw(const long long* ids, const float* codebook, float* out, int B, int P, int D, int ncodes,

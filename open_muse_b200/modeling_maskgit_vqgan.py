@@ -178,8 +178,19 @@ class VectorQuantizer(nn.Module):
             loss = torch.mean((z_q - ops.to_nchw(z_nhwc)) ** 2) * (1.0 + self.commitment_cost)
         return z_q, ids, loss
 
+    def get_soft_code_nhwc(self, z_nhwc, temp=1.0, stochastic=False, generator=None):
+        """soft targets of train_maskgit_imagenet.py:101-117,364-367 (reference :327-340). stochastic=True draws the
+        Exp(1) noise of torch.multinomial(soft, 1) with torch and takes argmax soft/q in the kernel."""
+        b = z_nhwc.shape[0]
+        z = z_nhwc.reshape(-1, self.embedding_dim)
+        q = None
+        if stochastic:
+            q = torch.empty(z.shape[0], self.num_embeddings, dtype=torch.float32, device=z.device).exponential_(generator=generator)
+        soft, ids = ops.vq_soft_code(z, self.embedding.weight.float(), temp, q)
+        return soft.view(b, -1, self.num_embeddings), ids.view(b, -1)
+
     def get_soft_code(self, z_nchw, temp=1.0, stochastic=False):
-        raise NotImplementedError("get_soft_code (soft targets, train_maskgit_imagenet.py:101-117) is a 'next' row in DESIGN.md")
+        return self.get_soft_code_nhwc(ops.to_nhwc(z_nchw.float().contiguous()), temp, stochastic)
 
 
 class MaskGitVQGAN(ModelMixin, ConfigMixin):
@@ -225,8 +236,9 @@ class MaskGitVQGAN(ModelMixin, ConfigMixin):
     def decode_code(self, codebook_indices):
         return self.decode(self.quantize.get_codebook_entry(codebook_indices))
 
+    @torch.no_grad()
     def get_soft_code(self, pixel_values, temp=1.0, stochastic=False):
-        return self.quantize.get_soft_code(None, temp, stochastic)
+        return self.quantize.get_soft_code_nhwc(self._encode_nhwc(pixel_values), temp, stochastic)
 
     @torch.no_grad()
     def get_code(self, pixel_values):

@@ -49,7 +49,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-_KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_vq_argmin": 2,
+_KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
                      "muse_groupnorm_silu_nhwc": 3}
 _prof = {"on": False, "events": []}
 
@@ -236,6 +236,19 @@ def vq_argmin(z_flat, codebook, return_dmin=False):
     dmin = torch.empty(n, dtype=torch.float32, device=z_flat.device) if return_dmin else None
     _call("muse_vq_argmin", _p(z_flat), _p(codebook), _p(ws), _p(ids), _p(dmin), n, ncodes, D, st)
     return (ids, dmin) if return_dmin else ids
+
+
+def vq_soft_code(z_flat, codebook, temp=1.0, expo_noise=None):
+    """softmax(-d/temp) over the codebook + ids (argmin, or argmax soft/q when Exp(1) noise q is given)."""
+    st = _prep(z_flat)
+    n, D = z_flat.shape
+    ncodes = codebook.shape[0]
+    soft = torch.empty(n, ncodes, dtype=torch.float32, device=z_flat.device)
+    ids = torch.empty(n, dtype=torch.int64, device=z_flat.device)
+    ws = torch.empty(ncodes, dtype=torch.float32, device=z_flat.device)
+    _call("muse_vq_soft_code", _p(z_flat), _p(codebook), _p(ws), _p(soft), _p(ids), _p(expo_noise), float(temp), n,
+          ncodes, D, st)
+    return soft, ids
 
 
 def vq_lookup_nchw(ids, codebook):

@@ -159,3 +159,85 @@ class PipelineMuse:
             tokenizer = AutoTokenizer.from_pretrained(full)
         return cls(vae=vae, transformer=transformer, is_class_conditioned=is_class_conditioned,
                    text_encoder=text_encoder, tokenizer=tokenizer)
+
+
+class PipelineMuseInpainting(PipelineMuse):
+    """Masked-region regeneration (muse/pipeline_muse.py:372-512): tokenise the image, overwrite the masked token
+    positions with the mask id and let ``generate2`` fill them in; known tokens are kept by the fused decode step."""
+
+    @staticmethod
+    def _to_pixel_values(image, image_size):
+        """Resize(shorter side, bilinear) -> CenterCrop -> ToTensor of the reference (:404-410), without torchvision."""
+        if isinstance(image, torch.Tensor):
+            return image if image.dim() == 4 else image.unsqueeze(0)
+        from PIL import Image
+
+        w, h = image.size
+        if w <= h:
+            nw, nh = image_size, int(image_size * h / w)
+        else:
+            nw, nh = int(image_size * w / h), image_size
+        image = image.convert("RGB").resize((nw, nh), Image.BILINEAR)
+        left, top = int(round((nw - image_size) / 2.0)), int(round((nh - image_size) / 2.0))
+        image = image.crop((left, top, left + image_size, top + image_size))
+        x = torch.from_numpy(np.asarray(image, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255.0)
+        return x.unsqueeze(0)
+
+    @torch.no_grad()
+    def __call__(
+        self,
+        image,
+        mask: torch.BoolTensor,
+        text: Optional[Union[str, List[str]]] = None,
+        negative_text: Optional[Union[str, List[str]]] = None,
+        class_ids: torch.LongTensor = None,
+        timesteps: int = 8,
+        guidance_scale: float = 8.0,
+        guidance_schedule=None,
+        temperature: float = 1.0,
+        topk_filter_thres: float = 0.9,
+        num_images_per_prompt: int = 1,
+        use_maskgit_generate: bool = True,
+        generator: Optional[torch.Generator] = None,
+        use_fp16: bool = False,
+        image_size: int = 256,
+        orig_size=(256, 256),
+        crop_coords=(0, 0),
+        aesthetic_score=6.0,
+        prompt_embeds: Optional[torch.Tensor] = None,
+        negative_prompt_embeds: Optional[torch.Tensor] = None,
+        output_type: str = "pil",
+    ):
+        assert use_maskgit_generate
+        if text is None and class_ids is None and prompt_embeds is None:
+            raise ValueError("Either text or class_ids must be provided.")
+        if text is not None and class_ids is not None:
+            raise ValueError("Only one of text or class_ids may be provided.")
+        pixel_values = self._to_pixel_values(image, image_size).to(self.device)
+        _, image_tokens = self.vae.encode(pixel_values)
+        image_tokens[mask.to(image_tokens.device).reshape(1, -1).expand_as(image_tokens)] = self.transformer.config.mask_token_id
+        image_tokens = image_tokens.repeat(num_images_per_prompt, 1)
+        kwargs = {}
+        if class_ids is not None:
+            if isinstance(class_ids, int):
+                class_ids = [class_ids]
+            ids = torch.as_tensor(class_ids, device=self.device, dtype=torch.long)
+            kwargs["class_ids"] = ids.repeat_interleave(num_images_per_prompt, dim=0)
+        else:
+            if prompt_embeds is None:
+                text = [text] if isinstance(text, str) else text
+                prompt_embeds = self._encode_text(text)
+                if negative_text is not None and negative_prompt_embeds is None:
+                    neg = [negative_text] if isinstance(negative_text, str) else negative_text
+                    negative_prompt_embeds = self._encode_text(neg)
+            kwargs["encoder_hidden_states"] = prompt_embeds.to(self.device).repeat_interleave(num_images_per_prompt, dim=0)
+            if negative_prompt_embeds is not None:
+                kwargs["negative_embeds"] = negative_prompt_embeds.to(self.device).repeat_interleave(num_images_per_prompt, dim=0)
+            kwargs["guidance_scale"] = guidance_scale
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            tokens = self.transformer.generate2(input_ids=image_tokens, timesteps=timesteps, temperature=temperature,
+                                                generator=generator, **kwargs)
+        images = self.vae.decode_code(tokens)
+        if output_type == "pt":
+            return images
+        return [self.to_pil_image(img) for img in images]

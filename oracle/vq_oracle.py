@@ -63,3 +63,18 @@ def codebook_entry_nchw(ids: np.ndarray, codebook: np.ndarray) -> np.ndarray:
     b, t = ids.shape
     s = int(round(t ** 0.5))
     return np.transpose(codebook[ids].reshape(b, s, s, -1), (0, 3, 1, 2))
+
+
+def soft_code(z: np.ndarray, codebook: np.ndarray, temp: float = 1.0, expo_noise: np.ndarray | None = None):
+    """get_soft_code (:327-340): soft = softmax(-d / temp) over the codebook; code = argmin d (stochastic=False) or
+    multinomial(soft, 1) restated as argmax soft / q for q ~ Exp(1) (what torch.multinomial computes for one draw)."""
+    d = distances_numpy(z, codebook)
+    x = -d / np.float32(temp)
+    x = x - x.max(axis=1, keepdims=True)
+    e = np.exp(x, dtype=np.float32)
+    soft = e / e.sum(axis=1, keepdims=True, dtype=np.float32)
+    if expo_noise is None:
+        ids, _ = argmin(z, codebook)
+    else:
+        ids = np.argmax(soft / expo_noise.astype(np.float32), axis=1).astype(np.int64)
+    return soft, ids

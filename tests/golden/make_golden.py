@@ -159,6 +159,16 @@ def main():
     torch.save(dict(z=z, codebook=vq.embedding.weight.detach().clone(), ids=ids, z_q=zq, dmin=top2[:, 0].clone(),
                     margin=margin, entry=entry.clone()), os.path.join(HERE, "vq_quantizer.pt"))
 
+    # ---- (4b) soft codes (get_soft_code, :327-340): deterministic and stochastic (multinomial through torch's RNG)
+    with torch.no_grad():
+        soft, code = vq.get_soft_code(z, temp=0.5, stochastic=False)
+        torch.manual_seed(9)
+        soft_s, code_s = vq.get_soft_code(z, temp=2.0, stochastic=True)
+    assert torch.equal(code, ids)
+    torch.save(dict(z=z, codebook=vq.embedding.weight.detach().clone(), temp=0.5, soft=soft.clone(), code=code.clone(),
+                    temp_s=2.0, seed_s=9, soft_s=soft_s.clone(), code_s=code_s.clone()),
+               os.path.join(HERE, "vq_soft_code.pt"))
+
     # ---- (5) micro MaskGitVQGAN: encode / decode_code round trip
     torch.manual_seed(5)
     v = muse.MaskGitVQGAN(**MICRO_VQ)

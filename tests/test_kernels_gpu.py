@@ -218,6 +218,32 @@ def test_vq_golden_ids(golden):
     assert torch.equal(entry.cpu().view_as(g["entry"]), g["entry"])
 
 
+def test_vq_soft_code_vs_reference_fixture_and_oracle(golden):
+    """get_soft_code (:327-340): soft within fp32 tolerance, deterministic ids exact, stochastic ids exact through
+    torch's RNG stream (Exp(1) draws reproduced on the CPU generator)."""
+    from oracle import vq_oracle as VQ
+
+    g = golden("vq_soft_code.pt")
+    z = torch.from_numpy(VQ.nchw_to_rows(g["z"].numpy())).to(DEV)
+    cb = g["codebook"].to(DEV)
+    soft, ids = ops.vq_soft_code(z, cb, g["temp"])
+    assert torch.equal(ids.cpu().view(2, -1), g["code"])
+    torch.testing.assert_close(soft.cpu().view_as(g["soft"]), g["soft"], rtol=2e-4, atol=1e-9)
+    torch.testing.assert_close(soft.sum(1).cpu(), torch.ones(soft.shape[0]), rtol=1e-5, atol=1e-5)
+    torch.manual_seed(g["seed_s"])
+    q = torch.empty(z.shape[0], cb.shape[0]).exponential_()
+    soft_s, ids_s = ops.vq_soft_code(z, cb, g["temp_s"], q.to(DEV))
+    assert torch.equal(ids_s.cpu().view(2, -1), g["code_s"])
+    torch.testing.assert_close(soft_s.cpu().view_as(g["soft_s"]), g["soft_s"], rtol=2e-4, atol=1e-9)
+    # full-size shape (1024 codes x 256 dims, ragged row count) against the oracle
+    gen = torch.Generator().manual_seed(11)
+    z2, cb2 = torch.randn(700, 256, generator=gen), torch.randn(1024, 256, generator=gen) * 0.7
+    soft2, ids2 = ops.vq_soft_code(z2.to(DEV), cb2.to(DEV), 100.0)
+    soft_o, ids_o = VQ.soft_code(z2.numpy(), cb2.numpy(), 100.0)
+    assert np.array_equal(ids2.cpu().numpy(), ids_o)
+    np.testing.assert_allclose(soft2.cpu().numpy(), soft_o, rtol=1e-3, atol=1e-8)
+
+
 @pytest.mark.parametrize("I,rms", [(2048, 0), (128, 0), (512, 1), (4096, 0)])
 def test_norm_glu_fused_fwd_bwd(I, rms):
     """act=2: LN(gelu(a) * b) straight from the [a | b] GEMM output; backward emits d[a | b]."""

@@ -103,6 +103,20 @@ def test_vq_oracle_c_matches_reference_ids(golden):
     np.testing.assert_array_equal(VQ.codebook_entry_nchw(g["ids"].numpy(), g["codebook"].numpy()), g["entry"].numpy())
 
 
+def test_vq_oracle_soft_code_matches_reference(golden):
+    g = golden("vq_soft_code.pt")
+    z, cb = VQ.nchw_to_rows(g["z"].numpy()), g["codebook"].numpy()
+    soft, code = VQ.soft_code(z, cb, g["temp"])
+    np.testing.assert_allclose(soft.reshape(2, 64, -1), g["soft"].numpy(), rtol=2e-4, atol=1e-9)
+    assert np.array_equal(code.reshape(2, -1), g["code"].numpy())
+    # stochastic=True: torch.multinomial(soft, 1) == argmax soft / q with q the Exp(1) draws of the same RNG stream
+    torch.manual_seed(g["seed_s"])
+    q = torch.empty(z.shape[0], cb.shape[0]).exponential_().numpy()
+    soft_s, code_s = VQ.soft_code(z, cb, g["temp_s"], q)
+    np.testing.assert_allclose(soft_s.reshape(2, 64, -1), g["soft_s"].numpy(), rtol=2e-4, atol=1e-9)
+    assert np.array_equal(code_s.reshape(2, -1), g["code_s"].numpy())
+
+
 def test_vq_oracle_tie_break_and_edges():
     cb = np.zeros((5, 16), dtype=np.float32)
     cb[1] = 1.0

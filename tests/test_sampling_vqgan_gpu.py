@@ -173,3 +173,35 @@ def test_pipeline_class_conditional_end_to_end():
     assert all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(a, b))
     pt = pipe(class_ids=3, timesteps=2, output_type="pt")
     assert pt.shape == (1, 3, 32, 32)
+
+
+def test_pipeline_inpainting_keeps_known_tokens():
+    from open_muse_b200 import MaskGitTransformer, MaskGitVQGAN, PipelineMuseInpainting
+
+    torch.manual_seed(0)
+    vae = MaskGitVQGAN(resolution=32, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=1, z_channels=16,
+                       num_embeddings=64, quantized_embed_dim=16)
+    tr = MaskGitTransformer(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_attention_heads=1,
+                            intermediate_size=128, max_position_embeddings=257, codebook_size=64, num_vq_tokens=256,
+                            num_classes=7, hidden_dropout=0.0, attention_dropout=0.0)
+    pipe = PipelineMuseInpainting(vae=vae, transformer=tr, is_class_conditioned=True).to(DEV)
+    image = torch.rand(1, 3, 32, 32, generator=torch.Generator().manual_seed(5))
+    mask = torch.zeros(256, dtype=torch.bool)
+    mask[64:192] = True
+    seen = {}
+    decode = vae.decode_code
+    vae.decode_code = lambda ids: (seen.__setitem__("ids", ids.clone()), decode(ids))[1]
+    out = pipe(image, mask, class_ids=[2], timesteps=4, num_images_per_prompt=3,
+               generator=torch.Generator(device=DEV).manual_seed(1))
+    assert len(out) == 3 and out[0].size == (32, 32)
+    orig = vae.get_code(image.to(DEV))
+    got = seen["ids"]
+    assert got.shape == (3, 256) and int(got.max()) < 64 and int(got.min()) >= 0  # no mask ids left
+    assert torch.equal(got[:, ~mask], orig[:, ~mask].expand(3, -1))  # unmasked tokens are never resampled
+    # PIL input path: resize + centre crop + ToTensor
+    from PIL import Image
+
+    pil = Image.fromarray((np.random.RandomState(0).rand(40, 48, 3) * 255).astype(np.uint8))
+    assert PipelineMuseInpainting._to_pixel_values(pil, 32).shape == (1, 3, 32, 32)
+    out = pipe(pil, mask, class_ids=2, timesteps=2, image_size=32, output_type="pt")
+    assert out.shape == (1, 3, 32, 32)
