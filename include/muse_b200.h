@@ -126,10 +126,27 @@ int muse_sample_step(const void* logits, const void* logits_unc, long long row_s
 int muse_conv2d_nhwc(const float* x, const float* wk, const float* bias, const float* res, float* y, int B, int H,
                      int W, int Cin, int Cout, int ksize, int upsample2x, void* stream);
 /* nn.GroupNorm(groups, C, eps) + F.silu (:61-79), deterministic (no atomics). Scratch: partials_ws float
- * [muse_groupnorm_workspace_floats(B,HW,C)] (-1 if the shape is unsupported), scale_shift_ws float [B*C*2]. */
+ * [muse_groupnorm_workspace_floats(B,HW,C)] (-1 if the shape is unsupported), scale_shift_ws float [B*C*2].
+ * Output either y (fp32) or the pair y_hi / y_lo (bf16 planes with y = hi + lo, the operand form of
+ * muse_conv2d_nhwc_tc); the unused form is NULL. */
 long long muse_groupnorm_workspace_floats(int B, int HW, int C);
-int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, float* partials_ws,
-                             float* scale_shift_ws, int B, int HW, int C, int groups, float eps, void* stream);
+int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, void* y_hi, void* y_lo,
+                             float* partials_ws, float* scale_shift_ws, int B, int HW, int C, int groups, float eps,
+                             void* stream);
+/* Conv2dSame (:33-45) on the tcgen05 tensor cores with fp32-level accuracy (3 bf16 products hi*hi + lo*hi + hi*lo,
+ * fp32 accumulation): x_hi/x_lo bf16 [B,H,W,Cin], w_hi/w_lo bf16 [Cout, ksize*ksize*Cin] (tap-major, then input
+ * channel), optional bias [Cout] and residual [B,H,W,Cout] -> y fp32 [B,H,W,Cout].
+ * muse_conv2d_tc_supported says whether the geometry is handled (Cin % 64 == 0, W a multiple or a divisor of 128 ...);
+ * other shapes use muse_conv2d_nhwc. */
+int muse_conv2d_tc_supported(int H, int W, int Cin, int Cout, int ksize);
+int muse_conv2d_nhwc_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                        const float* res, float* y, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
+/* fp32 [B,H/(1+up),W/(1+up),C] -> bf16 planes hi = bf16(x), lo = bf16(x - hi), [B,H,W,C]; upsample2x folds the nearest
+ * x2 of UpsamplingBlock (:146) into the gather. */
+int muse_split_bf16_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int C, int upsample2x, void* stream);
+/* Stem convolutions with ksize*ksize*Cin <= 64 (3 -> 128 conv_in): im2col of the taps into 64-wide bf16 hi/lo rows
+ * [B,H,W,64] (tap-major, zero padded), consumed by muse_conv2d_nhwc_tc as a 1x1 convolution with Cin = 64. */
+int muse_im2col_split_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int Cin, int ksize, void* stream);
 /* F.avg_pool2d(2,2) (:112): x [B,2Ho,2Wo,C] -> y [B,Ho,Wo,C]. */
 int muse_avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, void* stream);
 /* [B, rows, cols] -> [B, cols, rows] (NCHW <-> NHWC at the model boundary). */

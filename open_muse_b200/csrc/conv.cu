@@ -8,7 +8,8 @@
 //   * avg_pool2d(2,2) (:112), NCHW <-> NHWC layout changes at the model boundary.
 // fp32 SIMT on purpose: token ids must agree with the fp32 reference; each output is one ascending-K
 // fma chain (taps row-major, then input channel), so results do not depend on tiling.
-// The tensor-core upgrade (3x bf16-split tcgen05 implicit GEMM with TMA im2col) is planned, see DESIGN.md.
+// This is the general-shape kernel (3-channel stem / head, odd geometries); the heavy layers run on the tensor cores
+// with the same fp32-level accuracy in conv_tc.cu.
 #include "common.cuh"
 
 namespace muse {
@@ -192,9 +193,11 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partials, int nbloc
   }
 }
 
+// SPLIT: instead of fp32 y, emit the bf16 hi/lo planes (y = hi + lo) the tensor-core convolution consumes (conv_tc.cu)
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift, float* __restrict__ y,
-                     long long total4, int HW, int C) {
+                     bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, long long total4, int HW, int C) {
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total4) return;
   const int c4 = C / 4;
@@ -206,7 +209,18 @@ gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scal
   float o[4] = {fmaf(v.x, s0.x, s0.y), fmaf(v.y, s0.z, s0.w), fmaf(v.z, s1.x, s1.y), fmaf(v.w, s1.z, s1.w)};
 #pragma unroll
   for (int j = 0; j < 4; ++j) o[j] = o[j] / (1.f + expf(-o[j]));
-  *reinterpret_cast<float4*>(y + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  if (SPLIT) {
+    float h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = bf16_round(o[j]);
+    uint2 uh, ul;
+    uh.x = pack_bf16(h[0], h[1]); uh.y = pack_bf16(h[2], h[3]);
+    ul.x = pack_bf16(o[0] - h[0], o[1] - h[1]); ul.y = pack_bf16(o[2] - h[2], o[3] - h[3]);
+    *reinterpret_cast<uint2*>(y_hi + i * 4) = uh;
+    *reinterpret_cast<uint2*>(y_lo + i * 4) = ul;
+  } else {
+    *reinterpret_cast<float4*>(y + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 // ---------------------------------------------------------------- pooling / layout
@@ -280,8 +294,14 @@ long long gn_workspace_floats(int B, int HW, int C) {
   return static_cast<long long>(ceil_div(HW, gn_rows_per_block(C))) * B * C * 2;
 }
 
-int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, float* partials_ws,
-                        float* scale_shift_ws, int B, int HW, int C, int groups, float eps, cudaStream_t s) {
+// y (fp32) or y_hi / y_lo (bf16 split planes) receive the result: exactly one of the two forms must be given.
+int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, void* y_hi, void* y_lo,
+                        float* partials_ws, float* scale_shift_ws, int B, int HW, int C, int groups, float eps,
+                        cudaStream_t s) {
+  if ((y != nullptr) == (y_hi != nullptr) || (y_hi != nullptr) != (y_lo != nullptr)) {
+    set_last_error("groupnorm: give either y (fp32) or both y_hi and y_lo (bf16 split)");
+    return MUSE_ERR_INVALID;
+  }
   if (C % groups != 0 || C % 4 != 0 || C > 1024 || 256 % (C / 4) != 0) {
     set_last_error("groupnorm: C=%d groups=%d unsupported (C must divide into groups, C/4 must divide 256)", C, groups);
     return MUSE_ERR_UNSUPPORTED;
@@ -297,7 +317,12 @@ int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, f
   rc = check_launch("gn_finalize");
   if (rc) return rc;
   const long long total4 = static_cast<long long>(B) * HW * (C / 4);
-  gn_apply_silu_kernel<<<static_cast<unsigned>(ceil_div_ll(total4, 256)), 256, 0, s>>>(x, scale_shift_ws, y, total4, HW, C);
+  const unsigned blocks = static_cast<unsigned>(ceil_div_ll(total4, 256));
+  if (y != nullptr)
+    gn_apply_silu_kernel<false><<<blocks, 256, 0, s>>>(x, scale_shift_ws, y, nullptr, nullptr, total4, HW, C);
+  else
+    gn_apply_silu_kernel<true><<<blocks, 256, 0, s>>>(x, scale_shift_ws, nullptr, reinterpret_cast<bf16*>(y_hi),
+                                                      reinterpret_cast<bf16*>(y_lo), total4, HW, C);
   return check_launch("gn_apply_silu");
 }
 

@@ -1,0 +1,426 @@
+// MaskGitVQGAN convolutions on the 5th-gen tensor cores (muse/modeling_maskgit_vqgan.py:33-45 Conv2dSame, stride 1,
+// k = 3 or 1) as an implicit GEMM with fp32-faithful accuracy:
+//
+//     y[m, co] = bias[co] + res[m, co] + sum_{tap, ci} x[pixel(m) + tap, ci] * w[co, tap, ci]
+//
+//   M = B*H*W output pixels (128 per tile), N = C_out (128 or 256 per tile), K = k*k*C_in.
+//
+// * No im2col buffer: activations stay NHWC and the A tile of one (tap, 64-channel chunk) is ONE 4-D TMA box
+//   {64 ch, tile_w, tile_h, 1 image} fetched at pixel offset (kw - pad, kh - pad); coordinates outside the image are
+//   zero-filled by the TMA unit, which is exactly the 'same' padding.  The box lands in shared memory as 128 rows x 128 B
+//   (128-byte swizzle) = a K-major tcgen05 operand, rows ordered like the output pixels of the tile.
+// * fp32 accuracy from bf16 tensor cores: every fp32 operand is carried as two bf16 planes  v = hi + lo
+//   (hi = bf16(v), lo = bf16(v - hi), representation error 2^-18 |v|) and the product is accumulated as
+//   hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (the dropped lo*lo term is ~2^-18 relative).  The token ids of the
+//   quantiser downstream need this: a single bf16/TF32 pass perturbs z by ~1e-3 and flips near-tie codes.
+//   The planes are produced by the preceding GroupNorm+SiLU kernel (same bytes as one fp32 tensor) or by
+//   split_bf16_nhwc (which also folds the nearest x2 upsample of UpsamplingBlock :146 into its gather).
+// * Same persistent warp-specialised pipeline as gemm_tcgen05.cu: warp 0 TMA producer, warp 1 MMA issuer
+//   (tcgen05.mma 128 x BN x 16, kind::f16), warp 2 TMEM allocator, warps 4-7 epilogue with double-buffered TMEM
+//   accumulators; epilogue adds bias / residual and writes fp32 NHWC rows through a padded smem staging slab.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace muse {
+
+int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                 const unsigned long long* strides_bytes, const unsigned* box);
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;  // a multiple of 1024 for BN in {16, 128, 256}
+  static constexpr int kTmemCols = 2 * BN;               // 32 (the minimum allocation) for BN = 16
+  static constexpr int kBarBytes = 256;
+  static constexpr int kStagingRowBytes = 144;
+  static constexpr int kStagingBytes = 4 * 32 * kStagingRowBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + kBarBytes;
+};
+
+struct ConvParams {
+  float* y;
+  const float* bias;
+  const float* res;
+  int N;  // C_out
+  int H, W, Cin, ksize;
+  int tile_w, tile_h, tiles_x, tiles_per_img;
+  int num_m, num_n, cchunks, num_kb;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+          "r"(ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const ConvParams p) {
+  using C_ = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* staging = smem + C_::kStages * C_::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C_::kStagingBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C_::kStages;
+  uint64_t* tmem_full = bars + 2 * C_::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmAh);
+    ptx::prefetch_tmap(&tmAl);
+    ptx::prefetch_tmap(&tmBh);
+    ptx::prefetch_tmap(&tmBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C_::kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_holder, C_::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const int total_tiles = p.num_m * p.num_n;
+  const int pad = p.ksize / 2;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_idx = tile % p.num_n;
+        const int m_idx = tile / p.num_n;
+        const int img = m_idx / p.tiles_per_img;
+        const int t = m_idx % p.tiles_per_img;
+        const int y0 = (t / p.tiles_x) * p.tile_h, x0 = (t % p.tiles_x) * p.tile_w;
+        const int n0 = n_idx * BN;
+        int pass = 0, cc = 0, tap = 0;  // kb = (tap * cchunks + cc) * 3 + pass
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], C_::kStageBytes);
+          uint8_t* sa = smem + stage * C_::kStageBytes;
+          uint8_t* sb = sa + C_::kABytes;
+          // passes: 0 = hi*hi, 1 = lo(A)*hi(B), 2 = hi(A)*lo(B)
+          const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+          tma_load_4d(sa, pass == 1 ? &tmAl : &tmAh, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
+          ptx::tma_load_2d(sb, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, n0);
+          if (++stage == C_::kStages) { stage = 0; phase ^= 1; }
+          if (++pass == 3) {
+            pass = 0;
+            if (++cc == p.cchunks) { cc = 0; ++tap; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * C_::kStageBytes);
+          const uint32_t b_addr = a_addr + C_::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            ptx::umma_f16(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == C_::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------------------- epilogue: y = acc + bias (+ res), fp32 NHWC
+    const int ew = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint8_t* stg = staging + ew * (32 * C_::kStagingRowBytes);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_idx = tile % p.num_n;
+      const int m_idx = tile / p.num_n;
+      const int img = m_idx / p.tiles_per_img;
+      const int t = m_idx % p.tiles_per_img;
+      const int y0 = (t / p.tiles_x) * p.tile_h, x0 = (t % p.tiles_x) * p.tile_w;
+      const long long row_base = (static_cast<long long>(img) * p.H + y0) * p.W + x0 + ew * 32;  // tile pixels are contiguous
+      const int n0 = n_idx * BN;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      if (BN == 16) {
+        // narrow head (C_out <= 16, e.g. the 3-channel pixel output): one row per thread, rows of N floats are
+        // contiguous across the warp, so registers go straight to global
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(lane_addr, r);
+        ptx::tmem_ld_wait();
+        const size_t off = static_cast<size_t>(row_base + lane) * p.N;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j < p.N) {
+            float v = __uint_as_float(r[j]);
+            if (p.bias != nullptr) v += p.bias[j];
+            if (p.res != nullptr) v += p.res[off + j];
+            p.y[off + j] = v;
+          }
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < (BN == 16 ? 0 : BN); c += 32) {
+        if (n0 + c >= p.N) break;
+        uint4* my_row = reinterpret_cast<uint4*>(stg + lane * C_::kStagingRowBytes);
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) my_row[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        __syncwarp();
+        const int ch = lane & 7;
+        const int gcol = n0 + c + ch * 4;
+        const bool col_ok = gcol < p.N;  // N % 4 == 0
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && col_ok) b4 = *reinterpret_cast<const float4*>(p.bias + gcol);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = (lane >> 3) + 4 * it;
+          const float4 v = *reinterpret_cast<const float4*>(stg + rr * C_::kStagingRowBytes + ch * 16);
+          if (col_ok) {
+            const size_t off = static_cast<size_t>(row_base + rr) * p.N + gcol;
+            float4 o = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
+            if (p.res != nullptr) {
+              const float4 q4 = *reinterpret_cast<const float4*>(p.res + off);
+              o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
+            }
+            *reinterpret_cast<float4*>(p.y + off) = o;
+          }
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C_::kTmemCols);
+  }
+}
+
+// v = hi + lo with hi = bf16(v), lo = bf16(v - hi); optional nearest x2 upsample folded into the gather.
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long long total8, int H, int W,
+                  int C, int up) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= total8) return;
+  long long src = i;
+  if (up) {
+    const int c8 = C / 8;
+    const int q = static_cast<int>(i % c8);
+    const long long pix = i / c8;
+    const int ox = static_cast<int>(pix % W);
+    const int oy = static_cast<int>((pix / W) % H);
+    const long long b = pix / (static_cast<long long>(W) * H);
+    src = ((b * (H / 2) + (oy >> 1)) * (W / 2) + (ox >> 1)) * c8 + q;
+  }
+  float v[8], h[8], l[8];
+  load8(x + src * 8, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    h[j] = bf16_round(v[j]);
+    l[j] = v[j] - h[j];
+  }
+  store8(hi + i * 8, h);
+  store8(lo + i * 8, l);
+}
+
+// Small-C_in stem (3 -> 128 at full resolution): im2col of the k*k*C_in <= 64 taps into 64-wide bf16 hi/lo rows, so the
+// stem runs as a 1x1 tensor-core convolution with C_in = 64 (zero columns past k*k*C_in).  8 threads per pixel.
+__global__ void __launch_bounds__(256)
+im2col_split_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long long pixels, int H, int W,
+                    int Cin, int ksize) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= pixels * 8) return;
+  const long long pix = i >> 3;
+  const int chunk = static_cast<int>(i & 7);
+  const int ox = static_cast<int>(pix % W);
+  const int oy = static_cast<int>((pix / W) % H);
+  const long long b = pix / (static_cast<long long>(W) * H);
+  const int pad = ksize / 2, K = ksize * ksize * Cin;
+  float h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = chunk * 8 + j;
+    float v = 0.f;
+    if (k < K) {
+      const int tap = k / Cin, ci = k % Cin;
+      const int iy = oy + tap / ksize - pad, ix = ox + tap % ksize - pad;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[((b * H + iy) * W + ix) * Cin + ci];
+    }
+    h[j] = bf16_round(v);
+    l[j] = v - h[j];
+  }
+  store8(hi + i * 8, h);
+  store8(lo + i * 8, l);
+}
+
+int g_sms = 0;
+int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                const ConvParams& p, cudaStream_t s) {
+  auto kern = conv_tc_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) { set_last_error("cudaFuncSetAttribute(conv_tc): %s", cudaGetErrorString(e)); return MUSE_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int total = p.num_m * p.num_n;
+  const int grid = total < sm_count() ? total : sm_count();
+  kern<<<grid, 256, Cfg<BN>::kSmemBytes, s>>>(ah, al, bh, bl, p);
+  return check_launch("conv_tc");
+}
+
+}  // namespace
+
+// 1 if conv2d_tc handles the shape (otherwise the caller uses the fp32 SIMT kernel of conv.cu).
+int conv2d_tc_supported(int H, int W, int Cin, int Cout, int ksize) {
+  if (ksize != 1 && ksize != 3) return 0;
+  if (Cin % 64 != 0 || Cout < 1 || (Cout > 16 && Cout % 4 != 0)) return 0;
+  if (W >= 128) return W % 128 == 0;
+  if (W < 8 || 128 % W != 0) return 0;
+  return H % (128 / W) == 0;
+}
+
+// x_hi/x_lo: bf16 [B,H,W,Cin]; w_hi/w_lo: bf16 [Cout, k*k*Cin] (tap-major, then input channel); y fp32 [B,H,W,Cout].
+int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, const float* res,
+              float* y, int B, int H, int W, int Cin, int Cout, int ksize, cudaStream_t s) {
+  if (B <= 0) return MUSE_OK;
+  if (!conv2d_tc_supported(H, W, Cin, Cout, ksize)) {
+    set_last_error("conv2d_tc: unsupported shape H=%d W=%d Cin=%d Cout=%d k=%d", H, W, Cin, Cout, ksize);
+    return MUSE_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(y) & 15) || (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) ||
+      (res && (reinterpret_cast<uintptr_t>(res) & 15))) {
+    set_last_error("conv2d_tc: y / bias / res must be 16B aligned");
+    return MUSE_ERR_INVALID;
+  }
+  ConvParams p;
+  p.y = y; p.bias = bias; p.res = res;
+  p.N = Cout; p.H = H; p.W = W; p.Cin = Cin; p.ksize = ksize;
+  p.tile_w = W >= 128 ? 128 : W;
+  p.tile_h = 128 / p.tile_w;
+  p.tiles_x = W / p.tile_w;
+  p.tiles_per_img = p.tiles_x * (H / p.tile_h);
+  p.num_m = B * p.tiles_per_img;
+  const int BN = Cout >= 256 ? 256 : (Cout > 16 ? 128 : 16);
+  p.num_n = ceil_div(Cout, BN);
+  p.cchunks = Cin / BK;
+  p.num_kb = ksize * ksize * p.cchunks * 3;
+
+  CUtensorMap ah, al, bh, bl;
+  const unsigned long long adims[4] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
+  const unsigned long long astr[3] = {(unsigned long long)Cin * 2, (unsigned long long)W * Cin * 2, (unsigned long long)H * W * Cin * 2};
+  const unsigned abox[4] = {64, (unsigned)p.tile_w, (unsigned)p.tile_h, 1};
+  int rc;
+  if ((rc = make_tmap_nd(&ah, x_hi, 4, adims, astr, abox))) return rc;
+  if ((rc = make_tmap_nd(&al, x_lo, 4, adims, astr, abox))) return rc;
+  const unsigned long long K = static_cast<unsigned long long>(ksize) * ksize * Cin;
+  const unsigned long long bdims[2] = {K, (unsigned long long)Cout};
+  const unsigned long long bstr[1] = {K * 2};
+  const unsigned bbox[2] = {64, (unsigned)BN};
+  if ((rc = make_tmap_nd(&bh, w_hi, 2, bdims, bstr, bbox))) return rc;
+  if ((rc = make_tmap_nd(&bl, w_lo, 2, bdims, bstr, bbox))) return rc;
+  if (BN == 256) return launch_conv<256>(ah, al, bh, bl, p, s);
+  if (BN == 128) return launch_conv<128>(ah, al, bh, bl, p, s);
+  return launch_conv<16>(ah, al, bh, bl, p, s);
+}
+
+// x fp32 [B,H,W,Cin] with k*k*Cin <= 64 -> hi, lo bf16 [B,H,W,64]: row = the k*k*Cin taps of the pixel (tap-major), zero padded
+int im2col_split_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int Cin, int ksize, cudaStream_t s) {
+  if (ksize * ksize * Cin > 64 || (ksize != 1 && ksize != 3)) {
+    set_last_error("im2col_split: k*k*Cin = %d must be <= 64", ksize * ksize * Cin);
+    return MUSE_ERR_UNSUPPORTED;
+  }
+  const long long pixels = static_cast<long long>(B) * H * W;
+  if (pixels <= 0) return MUSE_OK;
+  im2col_split_kernel<<<static_cast<unsigned>(ceil_div_ll(pixels * 8, 256)), 256, 0, s>>>(
+      x, reinterpret_cast<bf16*>(hi), reinterpret_cast<bf16*>(lo), pixels, H, W, Cin, ksize);
+  return check_launch("im2col_split");
+}
+
+// x fp32 [B, H/(1+up), W/(1+up), C] -> hi, lo bf16 [B,H,W,C]
+int split_bf16_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int C, int upsample2x, cudaStream_t s) {
+  if (C % 8 != 0) { set_last_error("split_bf16: C must be a multiple of 8"); return MUSE_ERR_UNSUPPORTED; }
+  if (upsample2x && ((H | W) & 1)) { set_last_error("split_bf16: upsample2x needs even output dims"); return MUSE_ERR_INVALID; }
+  const long long total8 = static_cast<long long>(B) * H * W * (C / 8);
+  if (total8 <= 0) return MUSE_OK;
+  split_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s>>>(x, reinterpret_cast<bf16*>(hi),
+                                                                                    reinterpret_cast<bf16*>(lo), total8, H, W, C, upsample2x);
+  return check_launch("split_bf16");
+}
+
+}  // namespace muse

@@ -371,6 +371,27 @@ int make_tmap3(CUtensorMap* map, const void* base, long long cols, long long row
   return MUSE_OK;
 }
 
+// Generic bf16 tensor map (rank <= 5), 128-byte swizzle, zero fill out of bounds.  dims[0] is the contiguous dimension;
+// strides_bytes[i] is the byte stride of dims[i + 1].
+int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                 const unsigned long long* strides_bytes, const unsigned* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MUSE_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) { set_last_error("tensor map: base must be 16B aligned"); return MUSE_ERR_INVALID; }
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    st[i] = strides_bytes[i];
+    if (st[i] % 16 != 0) { set_last_error("tensor map: stride %d (%llu B) must be a multiple of 16 B", i, strides_bytes[i]); return MUSE_ERR_INVALID; }
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, st, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(rank %d) failed with CUresult %d", rank, (int)r); return MUSE_ERR_CUDA; }
+  return MUSE_OK;
+}
+
 namespace {
 
 int g_num_sms = 0;

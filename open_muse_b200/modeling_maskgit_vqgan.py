@@ -7,9 +7,11 @@ Same constructor / config keys / parameter names (``encoder.down.{l}.block.{b}.c
 Hot-path status:
   * tokenise search (``VectorQuantizer``: distances + arg-min, :303-316,342-348) and detokenise lookup
     (``get_codebook_entry``, :318-324) run in libmuse_b200 kernels with a bit-exact contract (csrc/vq.cu).
-  * the convolutional encoder / decoder (GroupNorm+SiLU+3x3 conv stacks) run in libmuse_b200's fp32
-    implicit-GEMM convolution and fused GroupNorm+SiLU kernels (csrc/conv.cu); fp32 because token ids must match
-    the fp32 reference (bf16/TF32 products flip ~2 % of ids).
+  * the convolutional encoder / decoder (GroupNorm+SiLU+3x3 conv stacks) run as tcgen05 implicit-GEMM convolutions
+    with fp32-level accuracy (operands carried as bf16 hi/lo planes, three products, fp32 accumulation:
+    csrc/conv_tc.cu) fed by a fused GroupNorm+SiLU(+split) kernel; the 3-channel stem/head and odd geometries use the
+    fp32 SIMT kernel (csrc/conv.cu).  fp32-faithful because token ids must match the fp32 reference (single-pass
+    bf16/TF32 products flip ~2 % of ids).
 The tokenizer is frozen in both training scripts (train_maskgit_imagenet.py:220-226), so only forward exists.
 """
 from __future__ import annotations
@@ -43,13 +45,13 @@ class ResnetBlock(nn.Module):
             self.nin_shortcut = Conv2dSame(self.out_channels_, self.out_channels_, kernel_size=1, bias=False)
 
     def run(self, x):
-        h = ops.conv2d(ops.groupnorm_silu(x, self.norm1.weight, self.norm1.bias, 32, 1e-6), self.conv1.weight)
-        h2 = ops.groupnorm_silu(h, self.norm2.weight, self.norm2.bias, 32, 1e-6)
+        h = ops.conv2d(x, self.conv1.weight, gn=(self.norm1.weight, self.norm1.bias, 32, 1e-6))
+        gn2 = (self.norm2.weight, self.norm2.bias, 32, 1e-6)
         if self.in_channels != self.out_channels_:
-            h = ops.conv2d(h2, self.conv2.weight)
+            h = ops.conv2d(h, self.conv2.weight, gn=gn2)
             # quirk Q8 (:82-85): shortcut of the post-conv2 activation, block input dropped
             return ops.conv2d(h, self.nin_shortcut.weight, residual=h)
-        return ops.conv2d(h2, self.conv2.weight, residual=x)
+        return ops.conv2d(h, self.conv2.weight, residual=x, gn=gn2)
 
 
 class DownsamplingBlock(nn.Module):
@@ -113,8 +115,8 @@ class Encoder(nn.Module):
             h = blk.run(h)
         for blk in self.mid:
             h = blk.run(h)
-        h = ops.groupnorm_silu(h, self.norm_out.weight, self.norm_out.bias, 32, 1e-6)
-        return ops.conv2d(h, self.conv_out.weight, bias=self.conv_out.bias)
+        return ops.conv2d(h, self.conv_out.weight, bias=self.conv_out.bias,
+                          gn=(self.norm_out.weight, self.norm_out.bias, 32, 1e-6))
 
 
 class Decoder(nn.Module):
@@ -138,8 +140,8 @@ class Decoder(nn.Module):
             h = blk.run(h)
         for blk in reversed(self.up):
             h = blk.run(h)
-        h = ops.groupnorm_silu(h, self.norm_out.weight, self.norm_out.bias, 32, 1e-6)
-        return ops.conv2d(h, self.conv_out.weight, bias=self.conv_out.bias)
+        return ops.conv2d(h, self.conv_out.weight, bias=self.conv_out.bias,
+                          gn=(self.norm_out.weight, self.norm_out.bias, 32, 1e-6))
 
 
 class VectorQuantizer(nn.Module):

@@ -297,14 +297,97 @@ def _packed_conv_weight(w):
     return wk
 
 
-def conv2d(x, w, bias=None, residual=None, upsample2x=False):
-    """x fp32 NHWC [B,Hi,Wi,Cin]; w the nn.Conv2d weight [Cout,Cin,k,k]; returns NHWC [B,H,W,Cout]."""
+def _packed_conv_weight_split(w):
+    """[Cout, Cin, kh, kw] -> bf16 planes (hi, lo) of [Cout, kh*kw*Cin] (tap-major, then input channel), w = hi + lo."""
+    import weakref
+
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+    hit = _wk_cache.get(("split", id(w)))
+    if hit is not None and hit[0]() is w and hit[1] == key:
+        return hit[2]
+    wk = w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+    hi = wk.to(torch.bfloat16)
+    lo = (wk - hi.float()).to(torch.bfloat16)
+    if len(_wk_cache) > 4096:
+        _wk_cache.clear()
+    _wk_cache[("split", id(w))] = (weakref.ref(w), key, (hi, lo))
+    return hi, lo
+
+
+def conv_uses_tensor_cores(H, W, Cin, Cout, k):
+    """Route of conv2d(): tcgen05 bf16x3 implicit GEMM unless the geometry is unsupported or MUSE_B200_CONV=simt.
+    Stems with k*k*Cin <= 64 go through an im2col to 64 columns and run as a 1x1 convolution."""
+    import os
+
+    if os.environ.get("MUSE_B200_CONV", "tc") == "simt":
+        return False
+    if Cin % 64 != 0 and k * k * Cin <= 64:
+        return bool(_lib.load().muse_conv2d_tc_supported(H, W, 64, Cout, 1))
+    return bool(_lib.load().muse_conv2d_tc_supported(H, W, Cin, Cout, k))
+
+
+def _packed_conv_weight_split_stem(w):
+    """Stem weight [Cout, Cin, k, k] with k*k*Cin <= 64 -> bf16 (hi, lo) of [Cout, 64], columns tap-major, zero padded."""
+    import weakref
+
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+    hit = _wk_cache.get(("stem", id(w)))
+    if hit is not None and hit[0]() is w and hit[1] == key:
+        return hit[2]
+    wk = torch.zeros(w.shape[0], 64, dtype=torch.float32, device=w.device)
+    flat = w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+    wk[:, : flat.shape[1]] = flat
+    hi = wk.to(torch.bfloat16)
+    lo = (wk - hi.float()).to(torch.bfloat16)
+    _wk_cache[("stem", id(w))] = (weakref.ref(w), key, (hi, lo))
+    return hi, lo
+
+
+def _gn_scratch(x):
+    B, H, W, C = x.shape
+    n_ws = _lib.load().muse_groupnorm_workspace_floats(B, H * W, C)
+    if n_ws < 0:
+        raise _lib.MuseB200Error(f"groupnorm: unsupported channel count {C}")
+    return (torch.empty(n_ws, dtype=torch.float32, device=x.device),
+            torch.empty(B * C * 2, dtype=torch.float32, device=x.device))
+
+
+def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
+    """Conv2dSame on fp32 NHWC x [B,Hi,Wi,Cin] with the nn.Conv2d weight w [Cout,Cin,k,k] -> fp32 NHWC [B,H,W,Cout].
+
+    gn = (gamma, beta, groups, eps) applies GroupNorm+SiLU to x first (the ResnetBlock pattern); upsample2x applies the
+    nearest x2 upsample first.  Heavy layers run on the tensor cores (csrc/conv_tc.cu) with operands carried as bf16
+    hi/lo planes; the GroupNorm kernel emits the planes directly."""
     st = _prep(x)
     B, Hi, Wi, Cin = x.shape
     H, W = (Hi * 2, Wi * 2) if upsample2x else (Hi, Wi)
     Cout, k = w.shape[0], w.shape[2]
     y = torch.empty(B, H, W, Cout, dtype=torch.float32, device=x.device)
     b = None if bias is None else bias.detach().float()
+    if conv_uses_tensor_cores(H, W, Cin, Cout, k) and Cin % 64 != 0:
+        assert gn is None and not upsample2x
+        hi = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi)
+        _call("muse_im2col_split_nhwc", _p(x), _p(hi), _p(lo), B, H, W, Cin, k, st)
+        w_hi, w_lo = _packed_conv_weight_split_stem(w)
+        _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), B, H, W, 64, Cout, 1, st)
+        return y
+    if conv_uses_tensor_cores(H, W, Cin, Cout, k):
+        hi = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi)
+        if gn is not None:
+            assert not upsample2x
+            ws, ss = _gn_scratch(x)
+            _call("muse_groupnorm_silu_nhwc", _p(x), _p(gn[0].detach().float()), _p(gn[1].detach().float()), None, _p(hi),
+                  _p(lo), _p(ws), _p(ss), B, H * W, Cin, int(gn[2]), float(gn[3]), st)
+        else:
+            _call("muse_split_bf16_nhwc", _p(x), _p(hi), _p(lo), B, H, W, Cin, 1 if upsample2x else 0, st)
+        w_hi, w_lo = _packed_conv_weight_split(w)
+        _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), B, H, W, Cin, Cout, k,
+              st)
+        return y
+    if gn is not None:
+        x = groupnorm_silu(x, *gn)
     _call("muse_conv2d_nhwc", _p(x), _p(_packed_conv_weight(w)), _p(b), _p(residual), _p(y), B, H, W, Cin, Cout, k,
           1 if upsample2x else 0, st)
     return y
@@ -314,13 +397,9 @@ def groupnorm_silu(x, gamma, beta, groups, eps):
     st = _prep(x)
     B, H, W, C = x.shape
     y = torch.empty_like(x)
-    n_ws = _lib.load().muse_groupnorm_workspace_floats(B, H * W, C)
-    if n_ws < 0:
-        raise _lib.MuseB200Error(f"groupnorm: unsupported channel count {C}")
-    ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
-    ss = torch.empty(B * C * 2, dtype=torch.float32, device=x.device)
-    _call("muse_groupnorm_silu_nhwc", _p(x), _p(gamma.detach().float()), _p(beta.detach().float()), _p(y), _p(ws),
-          _p(ss), B, H * W, C, groups, float(eps), st)
+    ws, ss = _gn_scratch(x)
+    _call("muse_groupnorm_silu_nhwc", _p(x), _p(gamma.detach().float()), _p(beta.detach().float()), _p(y), None, None,
+          _p(ws), _p(ss), B, H * W, C, groups, float(eps), st)
     return y
 
 

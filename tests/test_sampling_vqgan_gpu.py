@@ -115,6 +115,47 @@ def test_conv_gn_pool_blocks_vs_torch():
     torch.testing.assert_close(ops.to_nchw(pooled).cpu(), torch.nn.functional.avg_pool2d(x, 2, 2), rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout,k,bias,res,up,gn", [
+    (2, 16, 16, 128, 128, 3, False, True, False, True),    # ResnetBlock conv2 at the 16x16 level (8-row tiles)
+    (1, 32, 32, 64, 256, 3, True, False, False, False),    # 4-row tiles, BN = 256
+    (3, 16, 16, 128, 256, 1, False, True, False, False),   # nin_shortcut 1x1
+    (1, 3, 128, 64, 64, 3, True, False, False, False),     # one image row per tile, C_out below the N tile
+    (1, 2, 256, 64, 512, 3, False, False, False, True),    # two tiles per image row, two N tiles
+    (2, 32, 32, 128, 128, 3, True, False, True, False),    # UpsamplingBlock: nearest x2 folded into the split
+    (2, 4, 128, 128, 3, 3, True, False, False, True),      # decoder conv_out: 3 output channels (16-wide N tile)
+    (2, 32, 32, 3, 128, 3, False, False, False, False),    # encoder conv_in: 27 taps through the im2col stem
+    (1, 8, 128, 64, 7, 1, True, True, False, False),       # odd narrow head with bias + residual
+    (2, 16, 8, 128, 48, 3, True, True, False, True),       # narrow image: one 16-row tile per image, C_out = 48
+])
+def test_conv_tensor_core_path_vs_fp64(B, H, W, cin, cout, k, bias, res, up, gn):
+    """bf16x3 tcgen05 implicit GEMM (csrc/conv_tc.cu) against an fp64 convolution: fp32-level accuracy is the contract
+    (a single bf16 pass would sit at ~4e-3)."""
+    if not ops.conv_uses_tensor_cores(H, W, cin, cout, k):
+        pytest.skip("geometry routed to the SIMT kernel")
+    g = torch.Generator().manual_seed(B * 1000 + W)
+    hi, wi = (H // 2, W // 2) if up else (H, W)
+    x = torch.randn(B, cin, hi, wi, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g) if bias else None
+    r = torch.randn(B, cout, H, W, generator=g) if res else None
+    ga, be = (torch.randn(cin, generator=g), torch.randn(cin, generator=g)) if gn else (None, None)
+    xin = x.double()
+    if gn:
+        xin = torch.nn.functional.silu(torch.nn.functional.group_norm(xin, 32, ga.double(), be.double(), 1e-6))
+    if up:
+        xin = torch.nn.functional.interpolate(xin, scale_factor=2.0, mode="nearest")
+    ref = torch.nn.functional.conv2d(xin, w.double(), None if b is None else b.double(), padding=k // 2)
+    if res:
+        ref = ref + r.double()
+    y = ops.conv2d(ops.to_nhwc(x.to(DEV)), w.to(DEV), bias=None if b is None else b.to(DEV),
+                   residual=None if r is None else ops.to_nhwc(r.to(DEV)), upsample2x=up,
+                   gn=(ga.to(DEV), be.to(DEV), 32, 1e-6) if gn else None)
+    y = ops.to_nchw(y).cpu().double()
+    rel = float((y - ref).norm() / ref.norm())
+    assert rel < 2e-5, rel
+    assert float((y - ref).abs().max()) < 2e-4 * float(ref.abs().max())
+
+
 def test_micro_vqgan_vs_reference(golden):
     from open_muse_b200.modeling_maskgit_vqgan import MaskGitVQGAN
 
@@ -155,6 +196,36 @@ def test_vqgan_f16_256_roundtrip_properties():
     rec = m.decode_code(ids)
     assert rec.shape == (2, 3, 256, 256) and bool(torch.isfinite(rec).all())
     assert torch.equal(rec, m.decode(z_q))
+
+
+def test_vqgan_f16_256_tensor_core_route_matches_fp32_simt_route(monkeypatch):
+    """The tcgen05 bf16x3 convolutions must be interchangeable with the fp32 SIMT kernels: encoder output and decoded
+    pixels agree to fp32-level tolerance and the token ids are identical wherever the arg-min margin is not tiny."""
+    from open_muse_b200.modeling_maskgit_vqgan import MaskGitVQGAN
+
+    torch.manual_seed(7)
+    m = MaskGitVQGAN().to(DEV).eval()
+    img = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(8)).to(DEV)
+    outs = {}
+    for route in ("simt", "tc"):
+        monkeypatch.setenv("MUSE_B200_CONV", route)
+        assert ops.conv_uses_tensor_cores(16, 16, 512, 512, 3) == (route == "tc")
+        z = m.encoder.run(ops.to_nhwc(img))
+        if route == "simt":
+            with torch.no_grad():
+                m.quantize.embedding.weight.copy_(torch.randn(1024, 256, device=DEV) * z.std())
+        ids, dmin = ops.vq_argmin(z.reshape(-1, 256), m.quantize.embedding.weight.float(), return_dmin=True)
+        outs[route] = (z, ids, m.decode_code(ids.view(2, -1)) if route == "tc" else None)
+    z_s, ids_s, _ = outs["simt"]
+    z_t, ids_t, rec_t = outs["tc"]
+    assert float((z_t - z_s).norm() / z_s.norm()) < 1e-4  # measured 3e-5 over the 28 encoder convolutions
+    d = torch.cdist(z_s.reshape(-1, 256), m.quantize.embedding.weight.float()) ** 2
+    top2 = d.topk(2, dim=1, largest=False).values
+    safe = (top2[:, 1] - top2[:, 0]) > 1e-3 * top2[:, 0].abs()
+    assert int(safe.sum()) > 400 and torch.equal(ids_s[safe], ids_t[safe])
+    monkeypatch.setenv("MUSE_B200_CONV", "simt")
+    rec_s = m.decode_code(ids_t.view(2, -1))
+    assert float((rec_t - rec_s).norm() / rec_s.norm()) < 1.5e-4  # measured 6.6e-5 over the 32 decoder convolutions
 
 
 def test_pipeline_class_conditional_end_to_end():
