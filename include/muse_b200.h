@@ -128,19 +128,23 @@ int muse_conv2d_nhwc(const float* x, const float* wk, const float* bias, const f
 /* nn.GroupNorm(groups, C, eps) + F.silu (:61-79), deterministic (no atomics). Scratch: partials_ws float
  * [muse_groupnorm_workspace_floats(B,HW,C)] (-1 if the shape is unsupported), scale_shift_ws float [B*C*2].
  * Output either y (fp32) or the pair y_hi / y_lo (bf16 planes with y = hi + lo, the operand form of
- * muse_conv2d_nhwc_tc); the unused form is NULL. */
+ * muse_conv2d_nhwc_tc); the unused form is NULL.  precomputed_tiles > 0: partials_ws already holds the {sum, sumsq}
+ * per [image][tile][C] written by muse_conv2d_nhwc_tc(stats=...) for x and the statistics pass is skipped. */
 long long muse_groupnorm_workspace_floats(int B, int HW, int C);
 int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, void* y_hi, void* y_lo,
                              float* partials_ws, float* scale_shift_ws, int B, int HW, int C, int groups, float eps,
-                             void* stream);
+                             int precomputed_tiles, void* stream);
 /* Conv2dSame (:33-45) on the tcgen05 tensor cores with fp32-level accuracy (3 bf16 products hi*hi + lo*hi + hi*lo,
  * fp32 accumulation): x_hi/x_lo bf16 [B,H,W,Cin], w_hi/w_lo bf16 [Cout, ksize*ksize*Cin] (tap-major, then input
  * channel), optional bias [Cout] and residual [B,H,W,Cout] -> y fp32 [B,H,W,Cout].
  * muse_conv2d_tc_supported says whether the geometry is handled (Cin % 64 == 0, W a multiple or a divisor of 128 ...);
- * other shapes use muse_conv2d_nhwc. */
+ * other shapes use muse_conv2d_nhwc.  stats (nullable, Cout > 16): fp32 [B][tiles][Cout][2] receives {sum, sumsq} of y
+ * per pixel tile, tiles = muse_conv2d_tc_tiles_per_image(...) -- the GroupNorm statistics of the next layer for free. */
 int muse_conv2d_tc_supported(int H, int W, int Cin, int Cout, int ksize);
+int muse_conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize);
 int muse_conv2d_nhwc_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
-                        const float* res, float* y, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
+                        const float* res, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize,
+                        void* stream);
 /* fp32 [B,H/(1+up),W/(1+up),C] -> bf16 planes hi = bf16(x), lo = bf16(x - hi), [B,H,W,C]; upsample2x folds the nearest
  * x2 of UpsamplingBlock (:146) into the gather. */
 int muse_split_bf16_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int C, int upsample2x, void* stream);

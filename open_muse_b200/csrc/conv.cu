@@ -158,7 +158,7 @@ gn_stats_kernel(const float* __restrict__ x, float* __restrict__ partials, int H
     s_part[(lane_r * C + q * 4 + j) * 2 + 1] = ss[j];
   }
   __syncthreads();
-  float* out = partials + (static_cast<long long>(blockIdx.x) * gridDim.y + b) * C * 2;
+  float* out = partials + (static_cast<long long>(b) * gridDim.x + blockIdx.x) * C * 2;  // [image][block][C][2]
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
     float acc = 0.f;
     for (int k = 0; k < rstep; ++k) acc += s_part[k * C * 2 + i];
@@ -166,27 +166,37 @@ gn_stats_kernel(const float* __restrict__ x, float* __restrict__ partials, int H
   }
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ partials, int nblocks, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ scale_shift, int HW, int C,
-                                   int groups, float eps) {
-  const int b = blockIdx.x;
-  const int B = gridDim.x;
+// one warp per (image, group): fp64 sum of the per-block partials [image][block][C][2] in a fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float* __restrict__ partials, int nblocks, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ scale_shift, int B, int HW, int C, int groups,
+                   float eps) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= B * groups) return;
+  const int lane = threadIdx.x & 31;
+  const int b = w / groups, g = w % groups;
   const int cpg = C / groups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    double sum = 0.0, sq = 0.0;
-    for (int blk = 0; blk < nblocks; ++blk) {
-      const float* p = partials + (static_cast<long long>(blk) * B + b) * C * 2;
-      for (int k = 0; k < cpg; ++k) {
-        sum += static_cast<double>(p[(g * cpg + k) * 2]);
-        sq += static_cast<double>(p[(g * cpg + k) * 2 + 1]);
-      }
-    }
-    const double n = static_cast<double>(HW) * cpg;
-    const double mean = sum / n;
-    double var = sq / n - mean * mean;
-    if (var < 0) var = 0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float* base = partials + static_cast<long long>(b) * nblocks * C * 2;
+  double sum = 0.0, sq = 0.0;
+  const int items = nblocks * cpg;
+  for (int i = lane; i < items; i += 32) {
+    const int blk = i / cpg, k = i % cpg;
+    const float2 v = *reinterpret_cast<const float2*>(base + (static_cast<long long>(blk) * C + g * cpg + k) * 2);
+    sum += static_cast<double>(v.x);
+    sq += static_cast<double>(v.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  const double n = static_cast<double>(HW) * cpg;
+  const double mean = sum / n;
+  double var = sq / n - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  for (int k = lane; k < cpg; k += 32) {
+    const int c = g * cpg + k;
     const float sc = rstd * gamma[c];
     scale_shift[(static_cast<long long>(b) * C + c) * 2] = sc;
     scale_shift[(static_cast<long long>(b) * C + c) * 2 + 1] = beta[c] - static_cast<float>(mean) * sc;
@@ -297,7 +307,7 @@ long long gn_workspace_floats(int B, int HW, int C) {
 // y (fp32) or y_hi / y_lo (bf16 split planes) receive the result: exactly one of the two forms must be given.
 int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, void* y_hi, void* y_lo,
                         float* partials_ws, float* scale_shift_ws, int B, int HW, int C, int groups, float eps,
-                        cudaStream_t s) {
+                        int precomputed_tiles, cudaStream_t s) {
   if ((y != nullptr) == (y_hi != nullptr) || (y_hi != nullptr) != (y_lo != nullptr)) {
     set_last_error("groupnorm: give either y (fp32) or both y_hi and y_lo (bf16 split)");
     return MUSE_ERR_INVALID;
@@ -307,13 +317,20 @@ int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, f
     return MUSE_ERR_UNSUPPORTED;
   }
   if (B <= 0 || HW <= 0) return MUSE_OK;
-  const int rows_per_block = gn_rows_per_block(C);
-  const int nblocks = ceil_div(HW, rows_per_block);
-  const int rstep = 256 / (C / 4);
-  gn_stats_kernel<<<dim3(nblocks, B), 256, rstep * C * 2 * sizeof(float), s>>>(x, partials_ws, HW, C, rows_per_block);
-  int rc = check_launch("gn_stats");
-  if (rc) return rc;
-  gn_finalize_kernel<<<B, 256, 0, s>>>(partials_ws, nblocks, gamma, beta, scale_shift_ws, HW, C, groups, eps);
+  // precomputed_tiles > 0: partials_ws already holds {sum, sumsq} per [image][tile][C], written by the epilogue of the
+  // tensor-core convolution that produced x (conv_tc.cu), and the statistics pass over x is skipped.
+  int nblocks = precomputed_tiles;
+  int rc;
+  if (precomputed_tiles <= 0) {
+    const int rows_per_block = gn_rows_per_block(C);
+    nblocks = ceil_div(HW, rows_per_block);
+    const int rstep = 256 / (C / 4);
+    gn_stats_kernel<<<dim3(nblocks, B), 256, rstep * C * 2 * sizeof(float), s>>>(x, partials_ws, HW, C, rows_per_block);
+    rc = check_launch("gn_stats");
+    if (rc) return rc;
+  }
+  gn_finalize_kernel<<<ceil_div(B * groups, 8), 256, 0, s>>>(partials_ws, nblocks, gamma, beta, scale_shift_ws, B, HW, C,
+                                                             groups, eps);
   rc = check_launch("gn_finalize");
   if (rc) return rc;
   const long long total4 = static_cast<long long>(B) * HW * (C / 4);

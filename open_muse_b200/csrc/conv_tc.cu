@@ -41,13 +41,15 @@ struct Cfg {
   static constexpr int kBarBytes = 256;
   static constexpr int kStagingRowBytes = 144;
   static constexpr int kStagingBytes = 4 * 32 * kStagingRowBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 + kBarBytes;
+  static constexpr int kStatBytes = 4 * BN * 2 * 4;  // per-epilogue-warp {sum, sumsq} of every tile column
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kStatBytes + 1024 + kBarBytes;
 };
 
 struct ConvParams {
   float* y;
   const float* bias;
   const float* res;
+  float* stats;  // nullable: per [pixel tile][C_out] {sum, sumsq} of y, the GroupNorm statistics of the next layer
   int N;  // C_out
   int H, W, Cin, ksize;
   int tile_w, tile_h, tiles_x, tiles_per_img;
@@ -73,7 +75,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-template <int BN>
+// SWAP (used for C_out == 128, the full-resolution layers): the roles of the operands are exchanged so that the MMA
+// is 128 (output channels, A = weights) x 256 (pixels, B = activations) instead of 128 pixels x 128 channels.  A 128-wide
+// N reads 128 B/clk of operands from shared memory per MMA -- the shared-memory bandwidth limit -- while N = 256 needs
+// 96 B/clk (measured: 0.99 vs 1.34 PFLOP/s).  The accumulator then holds one output channel per TMEM lane and one pixel per
+// column; a warp store of one column is 32 consecutive channels = one full 128-byte segment of the NHWC output.
+template <int BN, bool SWAP>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const ConvParams p) {
@@ -81,7 +88,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* staging = smem + C_::kStages * C_::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C_::kStagingBytes);
+  float* stat_smem = reinterpret_cast<float*>(staging + C_::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C_::kStagingBytes + C_::kStatBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C_::kStages;
   uint64_t* tmem_full = bars + 2 * C_::kStages;
@@ -139,8 +147,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           uint8_t* sb = sa + C_::kABytes;
           // passes: 0 = hi*hi, 1 = lo(A)*hi(B), 2 = hi(A)*lo(B)
           const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
-          tma_load_4d(sa, pass == 1 ? &tmAl : &tmAh, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
-          ptx::tma_load_2d(sb, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, n0);
+          if (!SWAP) {
+            tma_load_4d(sa, pass == 1 ? &tmAl : &tmAh, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
+            ptx::tma_load_2d(sb, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, n0);
+          } else {  // A = 128 weight rows, B = 256 pixels
+            ptx::tma_load_2d(sa, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, n_idx * 128);
+            tma_load_4d(sb, pass == 1 ? &tmAl : &tmAh, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
+          }
           if (++stage == C_::kStages) { stage = 0; phase ^= 1; }
           if (++pass == 3) {
             pass = 0;
@@ -192,12 +205,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const int img = m_idx / p.tiles_per_img;
       const int t = m_idx % p.tiles_per_img;
       const int y0 = (t / p.tiles_x) * p.tile_h, x0 = (t % p.tiles_x) * p.tile_w;
-      const long long row_base = (static_cast<long long>(img) * p.H + y0) * p.W + x0 + ew * 32;  // tile pixels are contiguous
+      const long long row_base = (static_cast<long long>(img) * p.H + y0) * p.W + x0 + (SWAP ? 0 : ew * 32);  // tile pixels are contiguous
       const int n0 = n_idx * BN;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      if (BN == 16) {
+      if (SWAP) {
+        const int ch = n_idx * 128 + ew * 32 + lane;  // this thread's output channel
+        const float bch = (p.bias != nullptr) ? p.bias[ch] : 0.f;
+        float st_s = 0.f, st_q = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + c, r);
+          float rs[32];
+          if (p.res != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rs[j] = p.res[static_cast<size_t>(row_base + c + j) * p.N + ch];
+          }
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]) + bch;
+            if (p.res != nullptr) v += rs[j];
+            p.y[static_cast<size_t>(row_base + c + j) * p.N + ch] = v;
+            st_s += v;
+            st_q = fmaf(v, v, st_q);
+          }
+        }
+        if (p.stats != nullptr)
+          *reinterpret_cast<float2*>(p.stats + (static_cast<size_t>(m_idx) * p.N + ch) * 2) = make_float2(st_s, st_q);
+      } else if (BN == 16) {
         // narrow head (C_out <= 16, e.g. the 3-channel pixel output): one row per thread, rows of N floats are
         // contiguous across the warp, so registers go straight to global
         uint32_t r[16];
@@ -215,7 +253,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
       }
 #pragma unroll 1
-      for (int c = 0; c < (BN == 16 ? 0 : BN); c += 32) {
+      for (int c = 0; c < ((BN == 16 || SWAP) ? 0 : BN); c += 32) {
         if (n0 + c >= p.N) break;
         uint4* my_row = reinterpret_cast<uint4*>(stg + lane * C_::kStagingRowBytes);
         uint32_t r[32];
@@ -229,6 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const bool col_ok = gcol < p.N;  // N % 4 == 0
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias != nullptr && col_ok) b4 = *reinterpret_cast<const float4*>(p.bias + gcol);
+        float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = (lane >> 3) + 4 * it;
@@ -241,9 +280,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
             }
             *reinterpret_cast<float4*>(p.y + off) = o;
+            st_s[0] += o.x; st_s[1] += o.y; st_s[2] += o.z; st_s[3] += o.w;
+            st_q[0] = fmaf(o.x, o.x, st_q[0]); st_q[1] = fmaf(o.y, o.y, st_q[1]);
+            st_q[2] = fmaf(o.z, o.z, st_q[2]); st_q[3] = fmaf(o.w, o.w, st_q[3]);
+          }
+        }
+        if (p.stats != nullptr) {  // fold the 4 row groups of the warp (lane >> 3), lanes 0-7 publish 4 channels each
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            st_s[k] += __shfl_xor_sync(0xffffffffu, st_s[k], 8);
+            st_s[k] += __shfl_xor_sync(0xffffffffu, st_s[k], 16);
+            st_q[k] += __shfl_xor_sync(0xffffffffu, st_q[k], 8);
+            st_q[k] += __shfl_xor_sync(0xffffffffu, st_q[k], 16);
+          }
+          if (lane < 8) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<float2*>(stat_smem + ((ew * BN) + c + lane * 4 + k) * 2) = make_float2(st_s[k], st_q[k]);
           }
         }
         __syncwarp();
+      }
+      if (!SWAP && BN != 16 && p.stats != nullptr) {
+        ptx::tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        for (int col = threadIdx.x - 128; col < BN; col += 128) {
+          if (n0 + col < p.N) {
+            float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int wq = 0; wq < 4; ++wq) {
+              const float2 v = *reinterpret_cast<const float2*>(stat_smem + ((wq * BN) + col) * 2);
+              a.x += v.x; a.y += v.y;
+            }
+            *reinterpret_cast<float2*>(p.stats + (static_cast<size_t>(m_idx) * p.N + n0 + col) * 2) = a;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
@@ -328,10 +400,10 @@ int sm_count() {
   return g_sms;
 }
 
-template <int BN>
+template <int BN, bool SWAP = false>
 int launch_conv(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                 const ConvParams& p, cudaStream_t s) {
-  auto kern = conv_tc_kernel<BN>;
+  auto kern = conv_tc_kernel<BN, SWAP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
@@ -356,8 +428,18 @@ int conv2d_tc_supported(int H, int W, int Cin, int Cout, int ksize) {
 }
 
 // x_hi/x_lo: bf16 [B,H,W,Cin]; w_hi/w_lo: bf16 [Cout, k*k*Cin] (tap-major, then input channel); y fp32 [B,H,W,Cout].
+static bool use_swap(int H, int W, int Cout) {
+  return Cout == 128 && (W >= 256 ? W % 256 == 0 : (256 % W == 0 && H % (256 / W) == 0));
+}
+
+// Pixel tiles per image of conv2d_tc for this shape (= the leading extent of its stats output), 0 if unsupported.
+int conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize) {
+  if (!conv2d_tc_supported(H, W, Cin, Cout, ksize)) return 0;
+  return H * W / (use_swap(H, W, Cout) ? 256 : 128);
+}
+
 int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, const float* res,
-              float* y, int B, int H, int W, int Cin, int Cout, int ksize, cudaStream_t s) {
+              float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize, cudaStream_t s) {
   if (B <= 0) return MUSE_OK;
   if (!conv2d_tc_supported(H, W, Cin, Cout, ksize)) {
     set_last_error("conv2d_tc: unsupported shape H=%d W=%d Cin=%d Cout=%d k=%d", H, W, Cin, Cout, ksize);
@@ -369,15 +451,18 @@ int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
     return MUSE_ERR_INVALID;
   }
   ConvParams p;
-  p.y = y; p.bias = bias; p.res = res;
+  p.y = y; p.bias = bias; p.res = res; p.stats = (Cout > 16) ? stats : nullptr;
   p.N = Cout; p.H = H; p.W = W; p.Cin = Cin; p.ksize = ksize;
-  p.tile_w = W >= 128 ? 128 : W;
-  p.tile_h = 128 / p.tile_w;
+  // C_out == 128: swapped operands, 256-pixel tiles (needs the image to tile into 256-pixel boxes)
+  const bool swap = use_swap(H, W, Cout);
+  const int tile_px = swap ? 256 : 128;
+  p.tile_w = W >= tile_px ? tile_px : W;
+  p.tile_h = tile_px / p.tile_w;
   p.tiles_x = W / p.tile_w;
   p.tiles_per_img = p.tiles_x * (H / p.tile_h);
   p.num_m = B * p.tiles_per_img;
-  const int BN = Cout >= 256 ? 256 : (Cout > 16 ? 128 : 16);
-  p.num_n = ceil_div(Cout, BN);
+  const int BN = (swap || Cout >= 256) ? 256 : (Cout > 16 ? 128 : 16);
+  p.num_n = swap ? 1 : ceil_div(Cout, BN);
   p.cchunks = Cin / BK;
   p.num_kb = ksize * ksize * p.cchunks * 3;
 
@@ -391,9 +476,10 @@ int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
   const unsigned long long K = static_cast<unsigned long long>(ksize) * ksize * Cin;
   const unsigned long long bdims[2] = {K, (unsigned long long)Cout};
   const unsigned long long bstr[1] = {K * 2};
-  const unsigned bbox[2] = {64, (unsigned)BN};
+  const unsigned bbox[2] = {64, swap ? 128u : (unsigned)BN};
   if ((rc = make_tmap_nd(&bh, w_hi, 2, bdims, bstr, bbox))) return rc;
   if ((rc = make_tmap_nd(&bl, w_lo, 2, bdims, bstr, bbox))) return rc;
+  if (swap) return launch_conv<256, true>(ah, al, bh, bl, p, s);
   if (BN == 256) return launch_conv<256>(ah, al, bh, bl, p, s);
   if (BN == 128) return launch_conv<128>(ah, al, bh, bl, p, s);
   return launch_conv<16>(ah, al, bh, bl, p, s);

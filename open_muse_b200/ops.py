@@ -352,6 +352,17 @@ def _gn_scratch(x):
             torch.empty(B * C * 2, dtype=torch.float32, device=x.device))
 
 
+def _conv_stats_buffer(y, H, W, Cin, Cout, k):
+    """The tensor-core convolution's epilogue leaves per-tile {sum, sumsq} of its output: they ride along on the output
+    tensor (``y._gn_stats``) so that a following conv2d(gn=...) skips the GroupNorm statistics pass over y."""
+    if Cout <= 16 or Cout % 32 != 0:
+        return None, 0
+    tiles = _lib.load().muse_conv2d_tc_tiles_per_image(H, W, Cin, Cout, k)
+    stats = torch.empty(y.shape[0], tiles, Cout, 2, dtype=torch.float32, device=y.device)
+    y._gn_stats = (stats, tiles)
+    return stats, tiles
+
+
 def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
     """Conv2dSame on fp32 NHWC x [B,Hi,Wi,Cin] with the nn.Conv2d weight w [Cout,Cin,k,k] -> fp32 NHWC [B,H,W,Cout].
 
@@ -370,21 +381,29 @@ def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
         lo = torch.empty_like(hi)
         _call("muse_im2col_split_nhwc", _p(x), _p(hi), _p(lo), B, H, W, Cin, k, st)
         w_hi, w_lo = _packed_conv_weight_split_stem(w)
-        _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), B, H, W, 64, Cout, 1, st)
+        stats, tiles = _conv_stats_buffer(y, H, W, 64, Cout, 1)
+        _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), _p(stats), B, H, W, 64,
+              Cout, 1, st)
         return y
     if conv_uses_tensor_cores(H, W, Cin, Cout, k):
         hi = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device=x.device)
         lo = torch.empty_like(hi)
         if gn is not None:
             assert not upsample2x
-            ws, ss = _gn_scratch(x)
+            pre = getattr(x, "_gn_stats", None)  # {sum, sumsq} tiles left by the convolution that produced x
+            if pre is not None:
+                ws, tiles = pre
+                ss = torch.empty(B * Cin * 2, dtype=torch.float32, device=x.device)
+            else:
+                (ws, ss), tiles = _gn_scratch(x), 0
             _call("muse_groupnorm_silu_nhwc", _p(x), _p(gn[0].detach().float()), _p(gn[1].detach().float()), None, _p(hi),
-                  _p(lo), _p(ws), _p(ss), B, H * W, Cin, int(gn[2]), float(gn[3]), st)
+                  _p(lo), _p(ws), _p(ss), B, H * W, Cin, int(gn[2]), float(gn[3]), tiles, st)
         else:
             _call("muse_split_bf16_nhwc", _p(x), _p(hi), _p(lo), B, H, W, Cin, 1 if upsample2x else 0, st)
         w_hi, w_lo = _packed_conv_weight_split(w)
-        _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), B, H, W, Cin, Cout, k,
-              st)
+        stats, tiles = _conv_stats_buffer(y, H, W, Cin, Cout, k)
+        _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), _p(stats), B, H, W, Cin,
+              Cout, k, st)
         return y
     if gn is not None:
         x = groupnorm_silu(x, *gn)
@@ -399,7 +418,7 @@ def groupnorm_silu(x, gamma, beta, groups, eps):
     y = torch.empty_like(x)
     ws, ss = _gn_scratch(x)
     _call("muse_groupnorm_silu_nhwc", _p(x), _p(gamma.detach().float()), _p(beta.detach().float()), _p(y), None, None,
-          _p(ws), _p(ss), B, H * W, C, groups, float(eps), st)
+          _p(ws), _p(ss), B, H * W, C, groups, float(eps), 0, st)
     return y
 
 

@@ -122,6 +122,8 @@ def test_conv_gn_pool_blocks_vs_torch():
     (1, 3, 128, 64, 64, 3, True, False, False, False),     # one image row per tile, C_out below the N tile
     (1, 2, 256, 64, 512, 3, False, False, False, True),    # two tiles per image row, two N tiles
     (2, 32, 32, 128, 128, 3, True, False, True, False),    # UpsamplingBlock: nearest x2 folded into the split
+    (1, 2, 256, 64, 128, 3, True, True, False, False),     # C_out = 128: swapped operands, one 256-pixel row per tile
+    (1, 3, 128, 64, 128, 3, True, True, False, False),     # C_out = 128 but odd height: unswapped 128-wide N tile
     (2, 4, 128, 128, 3, 3, True, False, False, True),      # decoder conv_out: 3 output channels (16-wide N tile)
     (2, 32, 32, 3, 128, 3, False, False, False, False),    # encoder conv_in: 27 taps through the im2col stem
     (1, 8, 128, 64, 7, 1, True, True, False, False),       # odd narrow head with bias + residual
@@ -154,6 +156,25 @@ def test_conv_tensor_core_path_vs_fp64(B, H, W, cin, cout, k, bias, res, up, gn)
     rel = float((y - ref).norm() / ref.norm())
     assert rel < 2e-5, rel
     assert float((y - ref).abs().max()) < 2e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("c_mid,H,W", [(128, 16, 16), (256, 16, 16), (128, 2, 256), (64, 8, 32)])
+def test_conv_epilogue_groupnorm_statistics_feed_next_layer(c_mid, H, W):
+    """conv -> GroupNorm+SiLU -> conv where the GroupNorm statistics come from the first convolution's epilogue
+    (swapped and unswapped tiles) instead of a pass over its output."""
+    g = torch.Generator().manual_seed(c_mid + W)
+    x = torch.randn(2, 64, H, W, generator=g)
+    w1 = torch.randn(c_mid, 64, 3, 3, generator=g) / 24.0
+    b1 = torch.randn(c_mid, generator=g)
+    w2 = torch.randn(64, c_mid, 3, 3, generator=g) / math.sqrt(9 * c_mid)
+    ga, be = torch.randn(c_mid, generator=g), torch.randn(c_mid, generator=g)
+    y1 = ops.conv2d(ops.to_nhwc(x.to(DEV)), w1.to(DEV), bias=b1.to(DEV))
+    assert getattr(y1, "_gn_stats", None) is not None
+    y2 = ops.to_nchw(ops.conv2d(y1, w2.to(DEV), gn=(ga.to(DEV), be.to(DEV), 32, 1e-6))).cpu().double()
+    r1 = torch.nn.functional.conv2d(x.double(), w1.double(), b1.double(), padding=1)
+    r1 = torch.nn.functional.silu(torch.nn.functional.group_norm(r1, 32, ga.double(), be.double(), 1e-6))
+    r2 = torch.nn.functional.conv2d(r1, w2.double(), None, padding=1)
+    assert float((y2 - r2).norm() / r2.norm()) < 3e-5
 
 
 def test_micro_vqgan_vs_reference(golden):
