@@ -127,21 +127,24 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md: ~1.4 PF sustained, 6.65 TB/s)"
 
 
-def cpu_reference_step_fn(batch):
-    """The reference algorithm (oracle port, fp32 torch eager on CPU): fwd + bwd + AdamW on `batch` samples."""
+def cpu_reference_step_fn(batch, device="cpu"):
+    """The reference algorithm (oracle port, torch eager): fwd + bwd + AdamW on `batch` samples.  fp32 on the host CPU
+    (the reference arm); with device="cuda" the same eager op sequence under bf16 autocast on the GPU -- what the
+    reference's own PyTorch modules would run on this B200 (`--impl reference --ref-device cuda`, informational)."""
     from oracle import transformer_oracle as T
     from open_muse_b200.modeling_transformer import MaskGitTransformer
 
     torch.manual_seed(0)
-    params = {k: v.clone().requires_grad_(True) for k, v in MaskGitTransformer(**BASE_CFG).state_dict().items()}
-    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.01)
-    g = torch.Generator().manual_seed(1)
+    params = {k: v.clone().to(device).requires_grad_(True) for k, v in MaskGitTransformer(**BASE_CFG).state_dict().items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.01, fused=(device != "cpu"))
+    g = torch.Generator(device=device).manual_seed(1)
 
     def step():
-        tokens = torch.randint(0, 1024, (batch, 256), generator=g)
-        cls = torch.randint(0, 1000, (batch,), generator=g)
+        tokens = torch.randint(0, 1024, (batch, 256), generator=g, device=device)
+        cls = torch.randint(0, 1000, (batch,), generator=g, device=device)
         inp, lab = mask_batch(tokens, cls, 2024, 1024, gen=g)
-        _, loss = T.forward(params, BASE_CFG, inp, labels=lab)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(device != "cpu")):
+            _, loss = T.forward(params, BASE_CFG, inp, labels=lab)
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
@@ -165,21 +168,26 @@ def run_reference(args):
         return
     cores = cpu_threads()
     torch.set_num_threads(cores)
-    batch = CPU_SAMPLE_BATCH
-    step = cpu_reference_step_fn(batch)
+    on_gpu = args.ref_device == "cuda"
+    batch = args.batch if on_gpu else CPU_SAMPLE_BATCH
+    step = cpu_reference_step_fn(batch, args.ref_device)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
+    if on_gpu:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        step()  # returns float(loss): synchronises every step
     dt = (time.perf_counter() - t0) / args.steps
     value = batch / dt
-    sample = f"{args.steps} steps x batch {batch} of the base-256 train step (fwd+bwd+AdamW), fp32 torch eager"
+    sample = f"{args.steps} steps x batch {batch} of the base-256 train step (fwd+bwd+AdamW), " + (
+        "bf16-autocast torch eager on cuda:0 (informational)" if on_gpu else "fp32 torch eager")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MaskGitTransformer base (8x512, seq 257, vocab 2025) class-cond train step, CPU sample batch {batch}",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if on_gpu else "f32", "data": "synthetic",
+        "ref_device": args.ref_device,
+        "config": {"workload": f"MaskGitTransformer base (8x512, seq 257, vocab 2025) class-cond train step, {args.ref_device} sample batch {batch}",
                    "global_batch": batch, "seq_len": 257},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -194,6 +202,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-step", action="store_true", help="skip the extra 'train step incl. VQ encode' measurement")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu (the reference arm) or cuda (same eager ops under bf16 autocast, informational)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -285,6 +296,33 @@ def main():
                 "peak_source": peak_src, "launches_per_step": gemm_n // 2,
                 "gemm_share_of_step": (gemm_ms / 2) / ms_dev}
 
+    # ---- BASELINE config 2 (ii): the same train step fed from pixels, i.e. including the frozen MaskGitVQGAN tokeniser
+    # (train_maskgit_imagenet.py:357-369: fp32, no autocast) in front of the transformer step.  N=1 only, informational.
+    full = None
+    if world == 1 and not args.no_full_step:
+        from open_muse_b200 import MaskGitVQGAN
+
+        torch.manual_seed(1)
+        vq = MaskGitVQGAN().to(dev).eval()
+        pix = torch.rand(B, 3, 256, 256, device=dev)
+        chunk = 64
+
+        def tokenise():
+            return torch.cat([vq.get_code(pix[j:j + chunk]) for j in range(0, B, chunk)])
+
+        def full_step(i):
+            return step(tokenise(), dev_cls[i % n_buf])
+
+        full_step(0)
+        ms_full = timed(full_step, 3)
+        ms_enc = timed(lambda i: tokenise(), 3)
+        full = {"value": B / (ms_full * 1e-3), "unit": "images/s", "ms_per_step": ms_full, "vq_encode_ms": ms_enc,
+                "vq_encode_images_per_s": B / (ms_enc * 1e-3),
+                "note": "pixels resident in HBM -> MaskGitVQGAN f16-256 get_code (fp32-faithful bf16x3 tcgen05 convs) -> "
+                        "masking -> train step; random-init tokeniser"}
+        del vq, pix
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = cpu_threads()
@@ -315,7 +353,7 @@ def main():
                     "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4},
             "gpu_launches": launches,
             "tflops_per_gpu_model": 3 * FWD_GFLOP_PER_IMG * B / ms_dev,
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "full_step_incl_vq_encode": full,
         }
         print(json.dumps(out))
     if world > 1:

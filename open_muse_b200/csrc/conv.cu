@@ -233,6 +233,32 @@ gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scal
   }
 }
 
+// 8 channels per thread variant of the SPLIT apply (two 16-byte loads in flight, 16-byte stores per plane)
+__global__ void __launch_bounds__(256)
+gn_apply_silu_split8_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift, bf16* __restrict__ y_hi,
+                            bf16* __restrict__ y_lo, long long total8, int HW, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = C / 8;
+  const int q = static_cast<int>(i % c8);
+  const int b = static_cast<int>(i / (static_cast<long long>(c8) * HW));
+  float v[8];
+  load8(x + i * 8, v);
+  const float4* ssp = reinterpret_cast<const float4*>(scale_shift + (static_cast<long long>(b) * C + q * 8) * 2);
+  float h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 s2 = ssp[j];  // {scale, shift} of channels 2j, 2j+1
+    float o0 = fmaf(v[2 * j], s2.x, s2.y), o1 = fmaf(v[2 * j + 1], s2.z, s2.w);
+    o0 = o0 / (1.f + expf(-o0));
+    o1 = o1 / (1.f + expf(-o1));
+    h[2 * j] = bf16_round(o0); h[2 * j + 1] = bf16_round(o1);
+    l[2 * j] = o0 - h[2 * j]; l[2 * j + 1] = o1 - h[2 * j + 1];
+  }
+  store8(y_hi + i * 8, h);
+  store8(y_lo + i * 8, l);
+}
+
 // ---------------------------------------------------------------- pooling / layout
 __global__ void __launch_bounds__(256)
 avgpool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int Ho, int Wo, int C) {
@@ -337,6 +363,9 @@ int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, f
   const unsigned blocks = static_cast<unsigned>(ceil_div_ll(total4, 256));
   if (y != nullptr)
     gn_apply_silu_kernel<false><<<blocks, 256, 0, s>>>(x, scale_shift_ws, y, nullptr, nullptr, total4, HW, C);
+  else if (C % 8 == 0)
+    gn_apply_silu_split8_kernel<<<static_cast<unsigned>(ceil_div_ll(total4 / 2, 256)), 256, 0, s>>>(
+        x, scale_shift_ws, reinterpret_cast<bf16*>(y_hi), reinterpret_cast<bf16*>(y_lo), total4 / 2, HW, C);
   else
     gn_apply_silu_kernel<true><<<blocks, 256, 0, s>>>(x, scale_shift_ws, nullptr, reinterpret_cast<bf16*>(y_hi),
                                                       reinterpret_cast<bf16*>(y_lo), total4, HW, C);
