@@ -147,6 +147,8 @@ class _PackedWeights:
                 groups.append((i, "cq", [c.query.weight], None))
                 groups.append((i, "ckv", [c.key.weight, c.value.weight], None))
                 groups.append((i, "co", [c.out.weight], None))
+        if m.config.add_cross_attention and m.config.project_encoder_hidden_states:
+            groups.append((-1, "eproj", [m.encoder_proj.weight], None))
         if m.config.use_mlm_layer:
             groups.append((-1, "dense", [m.mlm_layer.mlm_dense.weight], None))
             groups.append((-1, "logits", [m.mlm_layer.to_logits.weight], m.padded_output_size))
@@ -228,12 +230,39 @@ class _EmbedFn(torch.autograd.Function):
 class _LayerSpec:
     """Static description of one transformer layer handed to the layer Function."""
 
-    def __init__(self, B, S, H, I, nh, eps, rms, normformer, cross, Skv, E, w):
+    def __init__(self, B, S, H, I, nh, eps, rms, normformer, cross, Skv, E, w, enc_op=None):
         self.B, self.S, self.H, self.I, self.nh = B, S, H, I, nh
         self.eps, self.rms, self.normformer, self.cross = eps, rms, normformer, cross
         self.Skv, self.E = Skv, E
+        self.enc_op = enc_op  # bf16 copy of the (projected, fp32) encoder states used as the K/V GEMM operand
         self.w = w  # dict of packed bf16 weights for this layer
         self.scale = 1.0 / math.sqrt(H // nh)
+
+
+class _EncProjFn(torch.autograd.Function):
+    """encoder_proj + encoder_proj_layer_norm on the text-encoder states (reference :1239-1241): bf16 GEMM, fp32 norm
+    output (the autocast dtype flow); the gradient w.r.t. the raw encoder states is not produced (frozen text encoder)."""
+
+    @staticmethod
+    def forward(ctx, ehs, w_packed, eps, rms, w_proj, w_norm):
+        y0 = ops.linear_fwd(ehs, w_packed)
+        grad = any(ctx.needs_input_grad)
+        enc, st = ops.norm_fwd(y0, _f32(w_norm), eps, torch.float32, rms=rms, save_stats=grad)
+        if grad:
+            ctx.sv = (ehs, y0, st, w_norm, rms)
+        ctx.set_materialize_grads(False)
+        return enc
+
+    @staticmethod
+    def backward(ctx, d_enc):
+        ehs, y0, st, w_norm, rms = ctx.sv
+        if d_enc is None:
+            return (None,) * 6
+        g_norm = torch.zeros(w_norm.shape, dtype=torch.float32, device=y0.device)
+        d_y0 = ops.norm_bwd(d_enc.contiguous(), y0, _f32(w_norm), st, torch.bfloat16, dw=g_norm, rms=rms)
+        g_proj = torch.zeros(y0.shape[1], ehs.shape[1], dtype=torch.float32, device=y0.device)
+        ops.linear_wgrad(d_y0, ehs, g_proj)
+        return None, None, None, None, g_proj, g_norm
 
 
 class _LayerFn(torch.autograd.Function):
@@ -271,7 +300,8 @@ class _LayerFn(torch.autograd.Function):
         if s.cross:
             hc, stc = ops.norm_fwd(x2, _f32(w_cln), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
             qc = ops.linear_fwd(hc, s.w["cq"])
-            kvc = ops.linear_fwd(enc, s.w["ckv"])
+            enc_op = s.enc_op if s.enc_op is not None else enc  # bf16 GEMM operand (enc itself may be the fp32 projection)
+            kvc = ops.linear_fwd(enc_op, s.w["ckv"])
             cctx, clse = ops.attn_fwd(qc, kvc[:, :H], kvc[:, H:], B, nh, S, s.Skv, s.scale)
             if s.normformer:
                 cao = ops.linear_fwd(cctx, s.w["co"])
@@ -280,7 +310,7 @@ class _LayerFn(torch.autograd.Function):
                 cao, stcp = None, None
                 x2b = ops.linear_fwd(cctx, s.w["co"], res=x2)
             if grad:
-                sv.update(hc=hc, stc=stc, qc=qc, kvc=kvc, cctx=cctx, clse=clse, cao=cao, stcp=stcp, enc=enc)
+                sv.update(hc=hc, stc=stc, qc=qc, kvc=kvc, cctx=cctx, clse=clse, cao=cao, stcp=stcp, enc=enc_op)
             x2 = x2b
             if grad:
                 sv["x2b"] = x2b
@@ -303,6 +333,7 @@ class _LayerFn(torch.autograd.Function):
         H, I, B, S, nh = s.H, s.I, s.B, s.S, s.nh
         dev = dx3.device
         dx3 = dx3.contiguous()
+        d_enc = None
         z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
         it = iter(params)
         w_attn_ln = next(it); next(it); next(it); next(it); next(it)
@@ -348,6 +379,8 @@ class _LayerFn(torch.autograd.Function):
                          d_kvc[:, H:], B, nh, S, s.Skv, s.scale)
             g_ckv = z(2 * H, s.E)
             ops.linear_wgrad(d_kvc, sv["enc"], g_ckv)
+            if ctx.needs_input_grad[1]:  # projected encoder states: d enc = d[k|v] @ [Wk;Wv], fp32, summed over layers by autograd
+                d_enc = ops.linear_dgrad(d_kvc, s.w["ckv"], out_dtype=torch.float32)
             g_cq = z(H, H)
             ops.linear_wgrad(d_qc, sv["hc"], g_cq)
             d_hc = ops.linear_dgrad(d_qc, s.w["cq"])
@@ -381,7 +414,7 @@ class _LayerFn(torch.autograd.Function):
         grads.append(g_wo)
         grads += cross_grads
         ctx.sv = None
-        return (dx1, None, None, *grads)
+        return (dx1, d_enc, None, *grads)
 
 
 class _HeadSpec:
@@ -514,8 +547,6 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
             raise NotImplementedError("open_muse_b200: use_bias=True is not supported (no reference config enables it)")
         if use_conv_in_out:
             raise NotImplementedError("open_muse_b200: use_conv_in_out=True (ConvEmbed/ConvMlmLayer) is not supported yet")
-        if project_encoder_hidden_states:
-            raise NotImplementedError("open_muse_b200: project_encoder_hidden_states=True is not supported yet")
         if (embedding_size or hidden_size) != hidden_size:
             raise NotImplementedError("open_muse_b200: embedding_size != hidden_size is not supported")
         if use_mlm_layer and not use_mlm_layernorm:
@@ -541,6 +572,10 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
 
         # construction order == reference (:1130-1197) so seeded initialisation is identical
         self.embed = Embed(vocab_size, hidden_size, hidden_dropout, max_position_embeddings)
+        if add_cross_attention is not None and project_encoder_hidden_states:  # (:1154-1157)
+            self.encoder_proj = nn.Linear(encoder_hidden_size, hidden_size, bias=use_bias)
+            self.encoder_proj_layer_norm = _norm(norm_type, hidden_size, layer_norm_eps, use_bias)
+            encoder_hidden_size = hidden_size
         self.transformer_layers = nn.ModuleList(
             [
                 TransformerLayer(hidden_size, intermediate_size, num_attention_heads, encoder_hidden_size,
@@ -647,9 +682,17 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
             Skv, E = ehs.shape[1], ehs.shape[2]
             enc = ehs.reshape(B * Skv, E).to(torch.bfloat16).contiguous()
         rms = 0 if c.norm_type == "layernorm" else 1
+        enc_op = None
+        # (:1239-1241). The reference drops conditioning after this projection; dropping the raw states first is the same
+        # function and the same gradients because the projection and the norm have no bias (zero rows stay zero).
+        if enc is not None and c.project_encoder_hidden_states:
+            enc = _EncProjFn.apply(enc, packed.head["eproj"], c.layer_norm_eps, rms, self.encoder_proj.weight,
+                                   self.encoder_proj_layer_norm.weight)
+            E = H
+            enc_op = ops.cast_bf16(enc.detach())
         for i, layer in enumerate(self.transformer_layers):
             spec = _LayerSpec(B, S, H, self.intermediate_size, self.num_attention_heads, c.layer_norm_eps, rms,
-                              c.use_normformer, enc is not None, Skv, E, packed.layers[i])
+                              c.use_normformer, enc is not None, Skv, E, packed.layers[i], enc_op)
             x = _LayerFn.apply(x, enc, spec, *self._layer_params(layer))
 
         flat_labels = labels.reshape(-1).contiguous().to(torch.int64) if labels is not None else None

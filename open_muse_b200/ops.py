@@ -98,12 +98,12 @@ def linear_fwd(x, w, out_dtype=torch.bfloat16, res=None, n_valid=None):
     return gemm(x, w, y, T, N, K, x.stride(0), w.stride(0), N, 0, 0, EPI_BF16 if out_dtype == torch.bfloat16 else EPI_F32)
 
 
-def linear_dgrad(dy, w):
+def linear_dgrad(dy, w, out_dtype=torch.bfloat16):
     """dx[T,K] = dy[T,N] @ w[N,K]  (w consumed as an MN-major B operand; no transpose copy)."""
     T, N = dy.shape
     K = w.shape[1]
-    dx = torch.empty(T, K, dtype=torch.bfloat16, device=dy.device)
-    return gemm(dy, w, dx, T, K, N, dy.stride(0), w.stride(0), K, 0, 1, EPI_BF16)
+    dx = torch.empty(T, K, dtype=out_dtype, device=dy.device)
+    return gemm(dy, w, dx, T, K, N, dy.stride(0), w.stride(0), K, 0, 1, EPI_BF16 if out_dtype == torch.bfloat16 else EPI_F32)
 
 
 def linear_wgrad(dy, x, dw):

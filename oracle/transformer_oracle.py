@@ -84,6 +84,9 @@ def forward(p: Dict[str, torch.Tensor], cfg: dict, input_ids, encoder_hidden_sta
     # Embed.forward :942-957
     x = F.embedding(input_ids, p["embed.word_embeddings.weight"]) + p["embed.position_embeddings.weight"][:S][None]
     enc = encoder_hidden_states if c["add_cross_attention"] else None
+    if enc is not None and c.get("project_encoder_hidden_states", False):  # encoder_proj + norm, :1239-1241
+        enc = _norm(enc @ p["encoder_proj.weight"].t(), p["encoder_proj_layer_norm.weight"], c["layer_norm_eps"],
+                    c["norm_type"])
     for i in range(c["num_hidden_layers"]):
         x = _layer(x, enc, p, f"transformer_layers.{i}.", c)
     if c["use_encoder_layernorm"]:

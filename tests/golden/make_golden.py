@@ -50,6 +50,10 @@ MICRO_T2I = dict(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_attenti
                  hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=16, codebook_size=64,
                  num_vq_tokens=16, add_cross_attention=True, encoder_hidden_size=32, norm_type="rmsnorm",
                  use_normformer=False, layer_norm_eps=1e-6, use_codebook_size_for_output=True)
+MICRO_T2I_PROJ = dict(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_attention_heads=1, intermediate_size=128,
+                      hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=16, codebook_size=64,
+                      num_vq_tokens=16, add_cross_attention=True, encoder_hidden_size=32,
+                      project_encoder_hidden_states=True, norm_type="layernorm", use_normformer=True, layer_norm_eps=1e-6)
 TINY = dict(vocab_size=2025, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
             hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=257, codebook_size=1024,
             num_vq_tokens=256, num_classes=1000)
@@ -123,6 +127,23 @@ def main():
                     input_ids=inp, labels=lab, encoder_hidden_states=enc, logits=logits.detach(), loss=loss.detach(),
                     grads=grads_of(mt)), os.path.join(HERE, "micro_t2i_transformer.pt"))
     print("micro t2i transformer: loss", float(loss))
+
+    # ---- (2b) text-conditional with encoder_proj + encoder_proj_layer_norm (:1154-1157,1239-1241), layernorm + normformer
+    torch.manual_seed(12)
+    mp = muse.MaskGitTransformer(**MICRO_T2I_PROJ)
+    mp.train()
+    g = torch.Generator().manual_seed(13)
+    ids = torch.randint(0, 64, (3, 16), generator=g)
+    enc = torch.randn(3, 7, 32, generator=g)
+    mask = torch.rand(3, 16, generator=g) < 0.6
+    inp = torch.where(mask, mp.config.mask_token_id, ids)
+    lab = torch.where(mask, ids, -100)
+    logits, loss = mp(inp, encoder_hidden_states=enc, labels=lab)
+    loss.backward()
+    torch.save(dict(config=MICRO_T2I_PROJ, seed=12, state_dict={k: v.clone() for k, v in mp.state_dict().items()},
+                    input_ids=inp, labels=lab, encoder_hidden_states=enc, logits=logits.detach(), loss=loss.detach(),
+                    grads=grads_of(mp)), os.path.join(HERE, "micro_t2i_proj_transformer.pt"))
+    print("micro t2i (projected encoder states) transformer: loss", float(loss))
 
     # ---- (3) BASELINE config 1 (tiny, seed-constructed: no weights stored)
     torch.manual_seed(0)

@@ -96,3 +96,21 @@ def test_compat_muse_package_and_pipeline_surface(tmp_path):
     assert vae.num_embeddings == 64 and vae.config.latent_size == 16 and not hasattr(vae.config, "items") or True
     cfg = json.load(open(tmp_path / "vae" / "config.json"))
     assert "num_resolutions" not in cfg and cfg["_class_name"] == "MaskGitVQGAN"  # derived attrs are not serialised
+
+
+def test_seeded_construction_matches_reference_initial_weights():
+    """Same parameter names, shapes and construction order as the reference => torch.manual_seed(s); Model(**cfg)
+    reproduces the reference's initial state_dict bit for bit (fixtures written by tests/golden/make_golden.py)."""
+    import os
+
+    import torch
+
+    from open_muse_b200 import MaskGitTransformer
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "micro_t2i_proj_transformer.pt"), weights_only=False)
+    torch.manual_seed(g["seed"])
+    m = MaskGitTransformer(**g["config"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["state_dict"].keys())
+    for k, v in g["state_dict"].items():
+        assert torch.equal(sd[k], v), k

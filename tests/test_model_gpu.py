@@ -94,6 +94,24 @@ def test_micro_text_conditional_vs_reference(monkeypatch, golden, backend):
     print(backend, "micro t2i:", "; ".join(rep))
 
 
+def test_micro_text_conditional_projected_encoder_states_vs_reference(golden):
+    """project_encoder_hidden_states=True: encoder_proj + norm in front of every cross-attention; seeded construction
+    reproduces the reference's initial weights (construction order), gradients reach encoder_proj through all layers."""
+    g = golden("micro_t2i_proj_transformer.pt")
+    torch.manual_seed(g["seed"])
+    m = MaskGitTransformer(**g["config"])
+    for k, v in g["state_dict"].items():
+        assert torch.equal(m.state_dict()[k], v), k
+    m.to(DEV).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, loss = m(g["input_ids"].to(DEV), encoder_hidden_states=g["encoder_hidden_states"].to(DEV),
+                         labels=g["labels"].to(DEV))
+    loss.backward()
+    rep = []
+    _check(m, logits, loss, g["logits"], g["loss"], g["grads"], rep)
+    print("micro t2i proj:", "; ".join(rep))
+
+
 @pytest.mark.parametrize("backend", ["tcgen05", "mma"])
 def test_tiny_config1_vs_reference(monkeypatch, golden, backend):
     """BASELINE config 1 (L2, H128, S257, V2025, B2): seeded init == reference init, then fwd+bwd parity."""

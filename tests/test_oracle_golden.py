@@ -34,6 +34,17 @@ def test_micro_t2i_transformer_forward_backward(golden):
         _close(grads[k], v, 1e-4, 1e-7)
 
 
+def test_micro_t2i_projected_encoder_states_forward_backward(golden):
+    g = golden("micro_t2i_proj_transformer.pt")
+    logits, loss, grads = T.forward_backward(g["state_dict"], g["config"], g["input_ids"], g["labels"],
+                                             encoder_hidden_states=g["encoder_hidden_states"])
+    _close(logits, g["logits"], 1e-5, 1e-6)
+    _close(loss, g["loss"], 1e-6, 0)
+    assert "encoder_proj.weight" in grads and "encoder_proj_layer_norm.weight" in grads
+    for k, v in g["grads"].items():
+        _close(grads[k], v, 1e-4, 1e-7)
+
+
 def test_masking_recipe(golden):
     b = golden("micro_transformer.pt")["batch"]
     inp, lab = T.mask_tokens(b["tokens"], b["class_ids"], b["timesteps"], b["rand"], 64, 71)
