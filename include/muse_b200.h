@@ -139,12 +139,16 @@ int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* be
  * channel), optional bias [Cout] and residual [B,H,W,Cout] -> y fp32 [B,H,W,Cout].
  * muse_conv2d_tc_supported says whether the geometry is handled (Cin % 64 == 0, W a multiple or a divisor of 128 ...);
  * other shapes use muse_conv2d_nhwc.  stats (nullable, Cout > 16): fp32 [B][tiles][Cout][2] receives {sum, sumsq} of y
- * per pixel tile, tiles = muse_conv2d_tc_tiles_per_image(...) -- the GroupNorm statistics of the next layer for free. */
+ * per pixel tile, tiles = muse_conv2d_tc_tiles_per_image(...) -- the GroupNorm statistics of the next layer for free.
+ * upsample2x (UpsamplingBlock :141-149, ksize 3): H, W are the output dims, x_hi/x_lo the LOW-resolution input
+ * [B,H/2,W/2,Cin] and w_hi/w_lo the four 2x2 parity matrices stacked as [4*Cout, 4*Cin] (row = parity*Cout + co with
+ * parity = 2*(y&1) + (x&1); column = (a*2+b)*Cin + ci for window offset (a,b); entries are sums of the 3x3 taps that
+ * land on the same low-resolution pixel); tiles_per_image returns 0 when the upsample form is unsupported. */
 int muse_conv2d_tc_supported(int H, int W, int Cin, int Cout, int ksize);
-int muse_conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize);
+int muse_conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize, int upsample2x);
 int muse_conv2d_nhwc_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
                         const float* res, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize,
-                        void* stream);
+                        int upsample2x, void* stream);
 /* fp32 [B,H/(1+up),W/(1+up),C] -> bf16 planes hi = bf16(x), lo = bf16(x - hi), [B,H,W,C]; upsample2x folds the nearest
  * x2 of UpsamplingBlock (:146) into the gather. */
 int muse_split_bf16_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int C, int upsample2x, void* stream);

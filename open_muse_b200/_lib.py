@@ -42,9 +42,9 @@ SIGNATURES = {
     "muse_conv2d_nhwc": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "muse_groupnorm_workspace_floats": (c_longlong, [_I, _I, _I]),
     "muse_groupnorm_silu_nhwc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
-    "muse_conv2d_tc_tiles_per_image": (c_int, [_I, _I, _I, _I, _I]),
+    "muse_conv2d_tc_tiles_per_image": (c_int, [_I, _I, _I, _I, _I, _I]),
     "muse_conv2d_tc_supported": (c_int, [_I, _I, _I, _I, _I]),
-    "muse_conv2d_nhwc_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "muse_conv2d_nhwc_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "muse_im2col_split_nhwc": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "muse_split_bf16_nhwc": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "muse_avgpool2_nhwc": (c_int, [_P, _P, _I, _I, _I, _I, _P]),

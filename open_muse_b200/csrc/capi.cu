@@ -46,9 +46,9 @@ int vq_soft_code(const float*, const float*, float*, float*, long long*, const f
 int sample_step(const void*, const void*, long long, long long, float, const long long*, const float*, const float*, long long*, long long*, float*, int, int, int, long long, int, float, cudaStream_t);
 int conv2d_nhwc(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int groupnorm_silu_nhwc(const float*, const float*, const float*, float*, void*, void*, float*, float*, int, int, int, int, float, int, cudaStream_t);
-int conv2d_tc_tiles_per_image(int, int, int, int, int);
+int conv2d_tc_tiles_per_image(int, int, int, int, int, int);
 int conv2d_tc_supported(int, int, int, int, int);
-int conv2d_tc(const void*, const void*, const void*, const void*, const float*, const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
+int conv2d_tc(const void*, const void*, const void*, const void*, const float*, const float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int split_bf16_nhwc(const float*, void*, void*, int, int, int, int, int, cudaStream_t);
 int im2col_split_nhwc(const float*, void*, void*, int, int, int, int, int, cudaStream_t);
 long long gn_workspace_floats(int, int, int);
@@ -166,14 +166,14 @@ int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* be
   return groupnorm_silu_nhwc(x, gamma, beta, y, y_hi, y_lo, partials_ws, scale_shift_ws, B, HW, C, groups, eps,
                              precomputed_tiles, ST(stream));
 }
-int muse_conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize) {
-  return conv2d_tc_tiles_per_image(H, W, Cin, Cout, ksize);
+int muse_conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize, int upsample2x) {
+  return conv2d_tc_tiles_per_image(H, W, Cin, Cout, ksize, upsample2x);
 }
 int muse_conv2d_tc_supported(int H, int W, int Cin, int Cout, int ksize) { return conv2d_tc_supported(H, W, Cin, Cout, ksize); }
 int muse_conv2d_nhwc_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
                         const float* res, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize,
-                        void* stream) {
-  return conv2d_tc(x_hi, x_lo, w_hi, w_lo, bias, res, y, stats, B, H, W, Cin, Cout, ksize, ST(stream));
+                        int upsample2x, void* stream) {
+  return conv2d_tc(x_hi, x_lo, w_hi, w_lo, bias, res, y, stats, B, H, W, Cin, Cout, ksize, upsample2x, ST(stream));
 }
 int muse_split_bf16_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int C, int upsample2x, void* stream) {
   return split_bf16_nhwc(x, hi, lo, B, H, W, C, upsample2x, ST(stream));

@@ -15,6 +15,10 @@
 //   quantiser downstream need this: a single bf16/TF32 pass perturbs z by ~1e-3 and flips near-tie codes.
 //   The planes are produced by the preceding GroupNorm+SiLU kernel (same bytes as one fp32 tensor) or by
 //   split_bf16_nhwc (which also folds the nearest x2 upsample of UpsamplingBlock :146 into its gather).
+// * UpsamplingBlock (nearest x2 then 3x3 conv, :141-149) never materialises the upsampled tensor and skips its redundant
+//   arithmetic: output pixel (2y+py, 2x+px) only sees a 2x2 window of the low-resolution input, so each of the four
+//   parities (py, px) is a 2x2 convolution with pre-summed weights (K = 4*C_in instead of 9*C_in, 2.25x fewer FLOPs)
+//   whose tile rows scatter to every other output pixel.
 // * Same persistent warp-specialised pipeline as gemm_tcgen05.cu: warp 0 TMA producer, warp 1 MMA issuer
 //   (tcgen05.mma 128 x BN x 16, kind::f16), warp 2 TMEM allocator, warps 4-7 epilogue with double-buffered TMEM
 //   accumulators; epilogue adds bias / residual and writes fp32 NHWC rows through a padded smem staging slab.
@@ -53,6 +57,7 @@ struct ConvParams {
   int N;  // C_out
   int H, W, Cin, ksize;
   int tile_w, tile_h, tiles_x, tiles_per_img;
+  int up, tile_w_log2;  // up: nearest x2 upsample folded in as four 2x2 parity convolutions on the H x W (input) grid
   int num_m, num_n, cchunks, num_kb;
 };
 
@@ -124,7 +129,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const int total_tiles = p.num_m * p.num_n;
+  const int tiles_mn = p.num_m * p.num_n;
+  const int total_tiles = tiles_mn * (p.up ? 4 : 1);
   const int pad = p.ksize / 2;
 
   if (warp == 0) {
@@ -133,12 +139,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_idx = tile % p.num_n;
-        const int m_idx = tile / p.num_n;
+        const int parity = tile / tiles_mn, tl = tile % tiles_mn;
+        const int n_idx = tl % p.num_n;
+        const int m_idx = tl / p.num_n;
         const int img = m_idx / p.tiles_per_img;
         const int t = m_idx % p.tiles_per_img;
         const int y0 = (t / p.tiles_x) * p.tile_h, x0 = (t % p.tiles_x) * p.tile_w;
         const int n0 = n_idx * BN;
+        const int wrow0 = parity * p.N;  // up: the four parity weight matrices are stacked along the rows
         int pass = 0, cc = 0, tap = 0;  // kb = (tap * cchunks + cc) * 3 + pass
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -146,12 +154,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           uint8_t* sa = smem + stage * C_::kStageBytes;
           uint8_t* sb = sa + C_::kABytes;
           // passes: 0 = hi*hi, 1 = lo(A)*hi(B), 2 = hi(A)*lo(B)
-          const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+          const int dy = p.up ? (tap >> 1) + (parity >> 1) - 1 : tap / p.ksize - pad;
+          const int dx = p.up ? (tap & 1) + (parity & 1) - 1 : tap % p.ksize - pad;
           if (!SWAP) {
             tma_load_4d(sa, pass == 1 ? &tmAl : &tmAh, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
-            ptx::tma_load_2d(sb, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, n0);
+            ptx::tma_load_2d(sb, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, wrow0 + n0);
           } else {  // A = 128 weight rows, B = 256 pixels
-            ptx::tma_load_2d(sa, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, n_idx * 128);
+            ptx::tma_load_2d(sa, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, wrow0 + n_idx * 128);
             tma_load_4d(sb, pass == 1 ? &tmAl : &tmAh, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
           }
           if (++stage == C_::kStages) { stage = 0; phase ^= 1; }
@@ -200,48 +209,100 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     uint32_t acc_phase = 0;
     uint8_t* stg = staging + ew * (32 * C_::kStagingRowBytes);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_idx = tile % p.num_n;
-      const int m_idx = tile / p.num_n;
+      const int parity = tile / tiles_mn, tl = tile % tiles_mn;
+      const int n_idx = tl % p.num_n;
+      const int m_idx = tl / p.num_n;
       const int img = m_idx / p.tiles_per_img;
       const int t = m_idx % p.tiles_per_img;
       const int y0 = (t / p.tiles_x) * p.tile_h, x0 = (t % p.tiles_x) * p.tile_w;
-      const long long row_base = (static_cast<long long>(img) * p.H + y0) * p.W + x0 + (SWAP ? 0 : ew * 32);  // tile pixels are contiguous
+      const long long row_base0 = (static_cast<long long>(img) * p.H + y0) * p.W + x0;  // tile pixels are contiguous
+      // output row (pixel index) of tile-local pixel tr; up: parity (py, px) scatters to every other pixel of the 2H x 2W grid
+      auto out_row = [&](int tr) -> long long {
+        if (!p.up) return row_base0 + tr;
+        const int ty = tr >> p.tile_w_log2, tx = tr & (p.tile_w - 1);
+        return (static_cast<long long>(img) * (2 * p.H) + 2 * (y0 + ty) + (parity >> 1)) * (2 * p.W) + 2 * (x0 + tx) + (parity & 1);
+      };
+      const size_t stat_row = p.up ? (static_cast<size_t>(img) * 4 + parity) * p.tiles_per_img + t : static_cast<size_t>(m_idx);
       const int n0 = n_idx * BN;
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
-      ptx::tc_fence_after();
+      // (each branch waits for the accumulator only after issuing its first residual fetch)
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
       if (SWAP) {
-        const int ch = n_idx * 128 + ew * 32 + lane;  // this thread's output channel
-        const float bch = (p.bias != nullptr) ? p.bias[ch] : 0.f;
-        float st_s = 0.f, st_q = 0.f;
+        // thread = output channel (TMEM lane), columns = the tile's 256 pixels.  Each 32-pixel slab is transposed through
+        // the warp's staging buffer ([pixel][32 channels], padded rows) so that the global stores are 16 bytes per lane and
+        // 8 lanes cover the 128-byte channel segment of one pixel (4x fewer store instructions than storing columns).
+        const int chq = lane & 7;                          // 4-channel chunk handled in the store phase
+        const int gch = n_idx * 128 + ew * 32 + chq * 4;   // first of its 4 output channels
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) b4 = *reinterpret_cast<const float4*>(p.bias + gch);
+        float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+        // the residual slab is fetched one slab ahead (first one before the accumulator is even ready)
+        float4 res_next[8];
+        auto fetch_res = [&](int c, float4 (&dst)[8]) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < BN)
+              dst[it] = *reinterpret_cast<const float4*>(p.res + static_cast<size_t>(out_row(c + (lane >> 3) + 4 * it)) * p.N + gch);
+          }
+        };
+        if (p.res != nullptr) fetch_res(0, res_next);
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(lane_addr + c, r);
-          float rs[32];
+          float4 res_cur[8];
           if (p.res != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rs[j] = p.res[static_cast<size_t>(row_base + c + j) * p.N + ch];
+            for (int it = 0; it < 8; ++it) res_cur[it] = res_next[it];
+            fetch_res(c + 32, res_next);
           }
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + c, r);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]) + bch;
-            if (p.res != nullptr) v += rs[j];
-            p.y[static_cast<size_t>(row_base + c + j) * p.N + ch] = v;
-            st_s += v;
-            st_q = fmaf(v, v, st_q);
+          for (int jj = 0; jj < 32; ++jj)
+            *reinterpret_cast<uint32_t*>(stg + jj * C_::kStagingRowBytes + lane * 4) = r[jj];
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = (lane >> 3) + 4 * it;  // pixel c + rr of the tile
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * C_::kStagingRowBytes + chq * 16);
+            const size_t off = static_cast<size_t>(out_row(c + rr)) * p.N + gch;
+            float4 o = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
+            if (p.res != nullptr) {
+              const float4 q4 = res_cur[it];
+              o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
+            }
+            *reinterpret_cast<float4*>(p.y + off) = o;
+            st_s[0] += o.x; st_s[1] += o.y; st_s[2] += o.z; st_s[3] += o.w;
+            st_q[0] = fmaf(o.x, o.x, st_q[0]); st_q[1] = fmaf(o.y, o.y, st_q[1]);
+            st_q[2] = fmaf(o.z, o.z, st_q[2]); st_q[3] = fmaf(o.w, o.w, st_q[3]);
+          }
+          __syncwarp();
+        }
+        if (p.stats != nullptr) {  // this warp owns its 32 channels: fold the 4 row groups, lanes 0-7 publish
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            st_s[k] += __shfl_xor_sync(0xffffffffu, st_s[k], 8);
+            st_s[k] += __shfl_xor_sync(0xffffffffu, st_s[k], 16);
+            st_q[k] += __shfl_xor_sync(0xffffffffu, st_q[k], 8);
+            st_q[k] += __shfl_xor_sync(0xffffffffu, st_q[k], 16);
+          }
+          if (lane < 8) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<float2*>(p.stats + (stat_row * p.N + gch + k) * 2) = make_float2(st_s[k], st_q[k]);
           }
         }
-        if (p.stats != nullptr)
-          *reinterpret_cast<float2*>(p.stats + (static_cast<size_t>(m_idx) * p.N + ch) * 2) = make_float2(st_s, st_q);
       } else if (BN == 16) {
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
         // narrow head (C_out <= 16, e.g. the 3-channel pixel output): one row per thread, rows of N floats are
         // contiguous across the warp, so registers go straight to global
         uint32_t r[16];
         tmem_ld_32x32b_x16(lane_addr, r);
         ptx::tmem_ld_wait();
-        const size_t off = static_cast<size_t>(row_base + lane) * p.N;
+        const size_t off = static_cast<size_t>(out_row(ew * 32 + lane)) * p.N;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (j < p.N) {
@@ -252,9 +313,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           }
         }
       }
+      float4 nres_next[8];
+      auto nfetch_res = [&](int c, float4 (&dst)[8]) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int gcol = n0 + c + (lane & 7) * 4;
+          dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < BN && gcol < p.N)
+            dst[it] = *reinterpret_cast<const float4*>(p.res + static_cast<size_t>(out_row(ew * 32 + (lane >> 3) + 4 * it)) * p.N + gcol);
+        }
+      };
+      if (!SWAP && BN != 16) {
+        if (p.res != nullptr) nfetch_res(0, nres_next);
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
+      }
 #pragma unroll 1
       for (int c = 0; c < ((BN == 16 || SWAP) ? 0 : BN); c += 32) {
         if (n0 + c >= p.N) break;
+        float4 nres_cur[8];
+        if (p.res != nullptr) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) nres_cur[it] = nres_next[it];
+          nfetch_res(c + 32, nres_next);
+        }
         uint4* my_row = reinterpret_cast<uint4*>(stg + lane * C_::kStagingRowBytes);
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(lane_addr + c, r);
@@ -273,10 +355,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const int rr = (lane >> 3) + 4 * it;
           const float4 v = *reinterpret_cast<const float4*>(stg + rr * C_::kStagingRowBytes + ch * 16);
           if (col_ok) {
-            const size_t off = static_cast<size_t>(row_base + rr) * p.N + gcol;
+            const size_t off = static_cast<size_t>(out_row(ew * 32 + rr)) * p.N + gcol;
             float4 o = make_float4(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
             if (p.res != nullptr) {
-              const float4 q4 = *reinterpret_cast<const float4*>(p.res + off);
+              const float4 q4 = nres_cur[it];
               o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
             }
             *reinterpret_cast<float4*>(p.y + off) = o;
@@ -312,7 +394,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
               const float2 v = *reinterpret_cast<const float2*>(stat_smem + ((wq * BN) + col) * 2);
               a.x += v.x; a.y += v.y;
             }
-            *reinterpret_cast<float2*>(p.stats + (static_cast<size_t>(m_idx) * p.N + n0 + col) * 2) = a;
+            *reinterpret_cast<float2*>(p.stats + (stat_row * p.N + n0 + col) * 2) = a;
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -433,14 +515,28 @@ static bool use_swap(int H, int W, int Cout) {
 }
 
 // Pixel tiles per image of conv2d_tc for this shape (= the leading extent of its stats output), 0 if unsupported.
-int conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize) {
+// H, W are the OUTPUT dims; with upsample2x the tiling runs on the H/2 x W/2 input grid, four parities each.
+int conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize, int upsample2x) {
+  if (upsample2x) {
+    if ((H | W) & 1 || ksize != 3 || Cout <= 16) return 0;
+    H /= 2; W /= 2;
+  }
   if (!conv2d_tc_supported(H, W, Cin, Cout, ksize)) return 0;
-  return H * W / (use_swap(H, W, Cout) ? 256 : 128);
+  return (upsample2x ? 4 : 1) * (H * W / (use_swap(H, W, Cout) ? 256 : 128));
 }
 
+// upsample2x: x planes are the LOW-resolution input [B,H/2,W/2,Cin] and w planes the four stacked parity matrices
+// [4*Cout, 4*Cin] (ops.py packs them); y / res / stats are at the output resolution [B,H,W,Cout].
 int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, const float* res,
-              float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize, cudaStream_t s) {
+              float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize, int upsample2x, cudaStream_t s) {
   if (B <= 0) return MUSE_OK;
+  if (upsample2x) {
+    if (conv2d_tc_tiles_per_image(H, W, Cin, Cout, ksize, 1) == 0) {
+      set_last_error("conv2d_tc: unsupported upsample shape H=%d W=%d Cin=%d Cout=%d k=%d", H, W, Cin, Cout, ksize);
+      return MUSE_ERR_UNSUPPORTED;
+    }
+    H /= 2; W /= 2;  // the tiling / TMA grid is the input grid
+  }
   if (!conv2d_tc_supported(H, W, Cin, Cout, ksize)) {
     set_last_error("conv2d_tc: unsupported shape H=%d W=%d Cin=%d Cout=%d k=%d", H, W, Cin, Cout, ksize);
     return MUSE_ERR_UNSUPPORTED;
@@ -461,10 +557,15 @@ int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
   p.tiles_x = W / p.tile_w;
   p.tiles_per_img = p.tiles_x * (H / p.tile_h);
   p.num_m = B * p.tiles_per_img;
+  p.up = upsample2x ? 1 : 0;
+  p.tile_w_log2 = 0;
+  while ((1 << p.tile_w_log2) < p.tile_w) ++p.tile_w_log2;
+  if (p.up && (1 << p.tile_w_log2) != p.tile_w) { set_last_error("conv2d_tc: upsample needs a power-of-two tile width"); return MUSE_ERR_UNSUPPORTED; }
   const int BN = (swap || Cout >= 256) ? 256 : (Cout > 16 ? 128 : 16);
   p.num_n = swap ? 1 : ceil_div(Cout, BN);
   p.cchunks = Cin / BK;
-  p.num_kb = ksize * ksize * p.cchunks * 3;
+  const int taps = p.up ? 4 : ksize * ksize;
+  p.num_kb = taps * p.cchunks * 3;
 
   CUtensorMap ah, al, bh, bl;
   const unsigned long long adims[4] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};
@@ -473,8 +574,8 @@ int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
   int rc;
   if ((rc = make_tmap_nd(&ah, x_hi, 4, adims, astr, abox))) return rc;
   if ((rc = make_tmap_nd(&al, x_lo, 4, adims, astr, abox))) return rc;
-  const unsigned long long K = static_cast<unsigned long long>(ksize) * ksize * Cin;
-  const unsigned long long bdims[2] = {K, (unsigned long long)Cout};
+  const unsigned long long K = static_cast<unsigned long long>(taps) * Cin;
+  const unsigned long long bdims[2] = {K, (unsigned long long)Cout * (p.up ? 4 : 1)};
   const unsigned long long bstr[1] = {K * 2};
   const unsigned bbox[2] = {64, swap ? 128u : (unsigned)BN};
   if ((rc = make_tmap_nd(&bh, w_hi, 2, bdims, bstr, bbox))) return rc;

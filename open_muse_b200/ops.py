@@ -352,12 +352,45 @@ def _gn_scratch(x):
             torch.empty(B * C * 2, dtype=torch.float32, device=x.device))
 
 
-def _conv_stats_buffer(y, H, W, Cin, Cout, k):
+def _packed_conv_weight_upsample(w):
+    """3x3 weight of an UpsamplingBlock conv -> bf16 (hi, lo) of the four stacked 2x2 parity matrices [4*Cout, 4*Cin].
+
+    Output pixel (2y+py, 2x+px) of conv3x3(nearest_x2(v)) reads only v[y+a+py-1, x+b+px-1] for a, b in {0, 1}; the 3x3
+    taps that land on the same low-resolution pixel are summed (fp32): rows R(0,0)={0}, R(0,1)={1,2}, R(1,0)={0,1},
+    R(1,1)={2} (same for columns)."""
+    import weakref
+
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+    hit = _wk_cache.get(("up", id(w)))
+    if hit is not None and hit[0]() is w and hit[1] == key:
+        return hit[2]
+    wf = w.detach().float()  # [Cout, Cin, 3, 3]
+    sets = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}
+    mats = []
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for a in (0, 1):
+                for b in (0, 1):
+                    acc = 0
+                    for kh in sets[(py, a)]:
+                        for kw in sets[(px, b)]:
+                            acc = acc + wf[:, :, kh, kw]
+                    taps.append(acc)  # [Cout, Cin]
+            mats.append(torch.stack(taps, dim=1).reshape(wf.shape[0], -1))  # [Cout, 4*Cin], column = (a*2+b)*Cin + ci
+    wk = torch.cat(mats, dim=0).contiguous()  # [4*Cout, 4*Cin], row = parity*Cout + co
+    hi = wk.to(torch.bfloat16)
+    lo = (wk - hi.float()).to(torch.bfloat16)
+    _wk_cache[("up", id(w))] = (weakref.ref(w), key, (hi, lo))
+    return hi, lo
+
+
+def _conv_stats_buffer(y, H, W, Cin, Cout, k, up=0):
     """The tensor-core convolution's epilogue leaves per-tile {sum, sumsq} of its output: they ride along on the output
     tensor (``y._gn_stats``) so that a following conv2d(gn=...) skips the GroupNorm statistics pass over y."""
     if Cout <= 16 or Cout % 32 != 0:
         return None, 0
-    tiles = _lib.load().muse_conv2d_tc_tiles_per_image(H, W, Cin, Cout, k)
+    tiles = _lib.load().muse_conv2d_tc_tiles_per_image(H, W, Cin, Cout, k, up)
     stats = torch.empty(y.shape[0], tiles, Cout, 2, dtype=torch.float32, device=y.device)
     y._gn_stats = (stats, tiles)
     return stats, tiles
@@ -383,7 +416,18 @@ def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
         w_hi, w_lo = _packed_conv_weight_split_stem(w)
         stats, tiles = _conv_stats_buffer(y, H, W, 64, Cout, 1)
         _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), _p(stats), B, H, W, 64,
-              Cout, 1, st)
+              Cout, 1, 0, st)
+        return y
+    if upsample2x and gn is None and conv_uses_tensor_cores(H, W, Cin, Cout, k) and \
+            _lib.load().muse_conv2d_tc_tiles_per_image(H, W, Cin, Cout, k, 1) > 0:
+        # nearest x2 + 3x3 conv as four 2x2 parity convolutions on the low-resolution planes (2.25x fewer FLOPs)
+        hi = torch.empty(B, Hi, Wi, Cin, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi)
+        _call("muse_split_bf16_nhwc", _p(x), _p(hi), _p(lo), B, Hi, Wi, Cin, 0, st)
+        w_hi, w_lo = _packed_conv_weight_upsample(w)
+        stats, tiles = _conv_stats_buffer(y, H, W, Cin, Cout, k, 1)
+        _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), _p(stats), B, H, W, Cin,
+              Cout, k, 1, st)
         return y
     if conv_uses_tensor_cores(H, W, Cin, Cout, k):
         hi = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device=x.device)
@@ -403,7 +447,7 @@ def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
         w_hi, w_lo = _packed_conv_weight_split(w)
         stats, tiles = _conv_stats_buffer(y, H, W, Cin, Cout, k)
         _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), _p(stats), B, H, W, Cin,
-              Cout, k, st)
+              Cout, k, 0, st)
         return y
     if gn is not None:
         x = groupnorm_silu(x, *gn)

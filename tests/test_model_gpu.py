@@ -108,7 +108,10 @@ def test_micro_text_conditional_projected_encoder_states_vs_reference(golden):
                          labels=g["labels"].to(DEV))
     loss.backward()
     rep = []
-    _check(m, logits, loss, g["logits"], g["loss"], g["grads"], rep)
+    cal = _bf16_recipe_grad_errors(g, input_ids=g["input_ids"], labels=g["labels"],
+                                   encoder_hidden_states=g["encoder_hidden_states"])
+    _check(m, logits, loss, g["logits"], g["loss"], g["grads"], rep, recipe_err=cal)
+    assert float(m.encoder_proj.weight.grad.abs().max()) > 0
     print("micro t2i proj:", "; ".join(rep))
 
 

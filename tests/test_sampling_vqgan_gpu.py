@@ -121,7 +121,9 @@ def test_conv_gn_pool_blocks_vs_torch():
     (3, 16, 16, 128, 256, 1, False, True, False, False),   # nin_shortcut 1x1
     (1, 3, 128, 64, 64, 3, True, False, False, False),     # one image row per tile, C_out below the N tile
     (1, 2, 256, 64, 512, 3, False, False, False, True),    # two tiles per image row, two N tiles
-    (2, 32, 32, 128, 128, 3, True, False, True, False),    # UpsamplingBlock: nearest x2 folded into the split
+    (2, 32, 32, 128, 128, 3, True, False, True, False),    # UpsamplingBlock as four 2x2 parity convs (swapped tiles)
+    (1, 32, 64, 64, 256, 3, True, True, True, False),      # UpsamplingBlock, unswapped 256-wide N tile, residual
+    (1, 64, 16, 64, 512, 3, False, False, True, False),    # UpsamplingBlock, narrow low-res grid (8 wide), two N tiles
     (1, 2, 256, 64, 128, 3, True, True, False, False),     # C_out = 128: swapped operands, one 256-pixel row per tile
     (1, 3, 128, 64, 128, 3, True, True, False, False),     # C_out = 128 but odd height: unswapped 128-wide N tile
     (2, 4, 128, 128, 3, 3, True, False, False, True),      # decoder conv_out: 3 output channels (16-wide N tile)
