@@ -66,10 +66,12 @@ int muse_embed_bwd(const long long* ids, const float* dx, float* dword, float* d
 int muse_norm_fwd(const void* x, int x_dtype, const float* w, const float* res, void* y, int y_dtype, float* mean,
                   float* rstd, int rows, int H, float eps, int act, int rms, void* stream);
 /* dx = norm_bwd(dy) (* gelu'(x) if act 1) (+ dres if given); dw[H] += sum_rows dy * xhat (atomic).
- * act 2: dx is [rows, 2H] = d[a | b] (LayerNorm backward and GLU backward in one pass; v is recomputed from x). */
+ * act 2: dx is [rows, 2H] = d[a | b] (LayerNorm backward and GLU backward in one pass; v is recomputed from x).
+ * y_fwd (nullable, act 2 with bf16 tensors only): the forward output bf16 [rows, H]; when given, the row reductions of
+ * the first pass come from (dy, y_fwd) alone instead of re-evaluating the GELU over [a | b]. */
 int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
-                  const float* rstd, const float* dres, void* dx, int dx_dtype, float* dw, int rows, int H, int act,
-                  int rms, void* stream);
+                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, float* dw, int rows,
+                  int H, int act, int rms, void* stream);
 
 /* GLU of FeedForward (:789-792): ab bf16 [rows, 2I] = [wi_0(x) | wi_1(x)], out bf16 [rows, I] = gelu(a) * b. */
 int muse_glu_fwd(const void* ab, void* out, long long rows, int I, void* stream);

@@ -28,7 +28,7 @@ SIGNATURES = {
     "muse_embed_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_embed_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_norm_fwd": (c_int, [_P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P]),
-    "muse_norm_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "muse_norm_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "muse_glu_fwd": (c_int, [_P, _P, _L, _I, _P]),
     "muse_glu_bwd": (c_int, [_P, _P, _P, _L, _I, _P]),
     "muse_attn_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),

@@ -33,7 +33,7 @@ int cast_bf16(const float*, void*, long long, cudaStream_t);
 int embed_fwd(const long long*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
 int embed_bwd(const long long*, const float*, float*, float*, int, int, int, int, cudaStream_t);
 int norm_fwd(const void*, int, const float*, const float*, void*, int, float*, float*, int, int, float, int, int, cudaStream_t);
-int norm_bwd(const void*, int, const void*, int, const float*, const float*, const float*, const float*, void*, int, float*, int, int, int, int, cudaStream_t);
+int norm_bwd(const void*, int, const void*, int, const float*, const float*, const float*, const float*, const void*, void*, int, float*, int, int, int, int, cudaStream_t);
 int glu_fwd(const void*, void*, long long, int, cudaStream_t);
 int glu_bwd(const void*, const void*, void*, long long, int, cudaStream_t);
 int attn_fwd(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
@@ -105,9 +105,9 @@ int muse_norm_fwd(const void* x, int x_dtype, const float* w, const float* res, 
   return norm_fwd(x, x_dtype, w, res, y, y_dtype, mean, rstd, rows, H, eps, act, rms, ST(stream));
 }
 int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
-                  const float* rstd, const float* dres, void* dx, int dx_dtype, float* dw, int rows, int H, int act,
-                  int rms, void* stream) {
-  return norm_bwd(dy, dy_dtype, x, x_dtype, w, mean, rstd, dres, dx, dx_dtype, dw, rows, H, act, rms, ST(stream));
+                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, float* dw, int rows,
+                  int H, int act, int rms, void* stream) {
+  return norm_bwd(dy, dy_dtype, x, x_dtype, w, mean, rstd, dres, y_fwd, dx, dx_dtype, dw, rows, H, act, rms, ST(stream));
 }
 
 int muse_glu_fwd(const void* ab, void* out, long long rows, int I, void* stream) { return glu_fwd(ab, out, rows, I, ST(stream)); }

@@ -431,10 +431,14 @@ glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf
 
 // backward: two streaming passes over the row with the GELU recomputed in the second one (nothing row-sized in
 // registers -> 3 CTAs/SM); weight gradients go to a private per-warp shared-memory row.
+// HAVE_Y: the saved forward output y = bf16(xhat * w) is available, so the first pass gets its two row reductions from
+// (dy, y) alone -- s1 = mean(dy * w), s2 = mean(dy * w * xhat) = mean(dy * y) -- without reading [a | b] or evaluating the
+// GELU, and the weight-gradient accumulation moves into the second pass.
+template <bool HAVE_Y>
 __global__ void __launch_bounds__(kGluWarps * 32, 3)
 glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, const float* __restrict__ w,
                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dab,
-                    float* __restrict__ dw, int rows, int H, int rms) {
+                    float* __restrict__ dw, const bf16* __restrict__ yf, int rows, int H, int rms) {
   extern __shared__ __align__(16) float s_dw[];  // [kGluWarps][H] private rows
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -450,7 +454,21 @@ glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, co
     const float mean = rms ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
     float s1 = 0.f, s2 = 0.f;
-    for (int col = lane * 8; col < H; col += 256) {
+    if (HAVE_Y) {
+      const bf16* yr = yf + static_cast<size_t>(row) * H;
+      for (int col = lane * 8; col < H; col += 256) {
+        float d[8], yv[8], wv[8];
+        load8(dyr + col, d);
+        load8(yr + col, yv);
+        if (w) load8(w + col, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1 += w ? d[j] * wv[j] : d[j];
+          s2 = fmaf(d[j], yv[j], s2);
+        }
+      }
+    }
+    for (int col = lane * 8; !HAVE_Y && col < H; col += 256) {
       const uint4 au = *reinterpret_cast<const uint4*>(xr + col);
       const uint4 bu = *reinterpret_cast<const uint4*>(xr + H + col);
       const uint4 du = *reinterpret_cast<const uint4*>(dyr + col);
@@ -493,6 +511,7 @@ glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, co
       float wv[8];
       if (w) load8(w + col, wv);
       uint4 oa, ob;
+      float pr2[8];
       uint32_t* pa = reinterpret_cast<uint32_t*>(&oa);
       uint32_t* pb = reinterpret_cast<uint32_t*>(&ob);
 #pragma unroll
@@ -511,6 +530,16 @@ glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, co
         const float o0 = rstd * (q0 - s1 - xh0 * s2), o1 = rstd * (q1 - s1 - xh1 * s2);
         pa[j] = pack_bf16(o0 * b2.x * t0, o1 * b2.y * t1);
         pb[j] = pack_bf16(o0 * gr.x, o1 * gr.y);
+        pr2[2 * j] = d2.x * xh0;
+        pr2[2 * j + 1] = d2.y * xh1;
+      }
+      if (HAVE_Y && dw) {
+        float4 e0 = *reinterpret_cast<float4*>(my_dw + col);
+        float4 e1 = *reinterpret_cast<float4*>(my_dw + col + 4);
+        e0.x += pr2[0]; e0.y += pr2[1]; e0.z += pr2[2]; e0.w += pr2[3];
+        e1.x += pr2[4]; e1.y += pr2[5]; e1.z += pr2[6]; e1.w += pr2[7];
+        *reinterpret_cast<float4*>(my_dw + col) = e0;
+        *reinterpret_cast<float4*>(my_dw + col + 4) = e1;
       }
       *reinterpret_cast<uint4*>(dr + col) = oa;
       *reinterpret_cast<uint4*>(dr + H + col) = ob;
@@ -609,7 +638,8 @@ int norm_fwd(const void* x, int x_dt, const float* w, const float* res, void* y,
 }
 
 int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w, const float* mean, const float* rstd,
-             const float* dres, void* dx, int dx_dt, float* dw, int rows, int H, int act, int rms, cudaStream_t s) {
+             const float* dres, const void* y_fwd, void* dx, int dx_dt, float* dw, int rows, int H, int act, int rms,
+             cudaStream_t s) {
   if (rows <= 0) return MUSE_OK;
   int rc = check_args("norm_bwd", H, act, dres);
   if (rc) return rc;
@@ -619,11 +649,18 @@ int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w,
     const size_t smem = dw ? static_cast<size_t>(kGluWarps) * H * sizeof(float) : 0;
     static bool attr = false;
     if (!attr) {
-      cudaFuncSetAttribute(glu_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 4096 * 4);
+      cudaFuncSetAttribute(glu_norm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 4096 * 4);
+      cudaFuncSetAttribute(glu_norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 4096 * 4);
       attr = true;
     }
-    glu_norm_bwd_kernel<<<grid, kGluWarps * 32, smem, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w,
-                                                           mean, rstd, reinterpret_cast<bf16*>(dx), dw, rows, H, rms);
+    if (y_fwd != nullptr)
+      glu_norm_bwd_kernel<true><<<grid, kGluWarps * 32, smem, s>>>(
+          reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw,
+          reinterpret_cast<const bf16*>(y_fwd), rows, H, rms);
+    else
+      glu_norm_bwd_kernel<false><<<grid, kGluWarps * 32, smem, s>>>(
+          reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw,
+          nullptr, rows, H, rms);
     return check_launch("glu_norm_bwd");
   }
   const int key = dy_dt * 4 + x_dt * 2 + dx_dt;

@@ -351,7 +351,8 @@ class _LayerFn(torch.autograd.Function):
         d_ml = ops.linear_dgrad(dy, s.w["wo"])
         if s.normformer:  # LN backward + GLU backward fused: reads d_ml and [a|b], writes d[a|b]
             g_mid = z(I)
-            d_ab = ops.norm_bwd(d_ml, sv["ab"], _f32(w_mid), sv["st4"], torch.bfloat16, dw=g_mid, act=2, rms=s.rms)
+            d_ab = ops.norm_bwd(d_ml, sv["ab"], _f32(w_mid), sv["st4"], torch.bfloat16, dw=g_mid, act=2, rms=s.rms,
+                                y_fwd=sv["ml"])
         else:
             g_mid = None
             d_ab = ops.glu_bwd(sv["ab"], d_ml)

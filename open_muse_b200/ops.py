@@ -159,12 +159,15 @@ def norm_fwd(x, w, eps, out_dtype, res=None, act=0, rms=0, save_stats=True):
     return y, stats
 
 
-def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0):
+def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None):
+    """y_fwd: the saved forward output (act=2, bf16 only) -- lets the kernel skip one GELU pass over [a | b]."""
     st = _prep(x)
     rows = x.shape[0]
     H = x.shape[1] // 2 if act == 2 else x.shape[1]
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
-    _call("muse_norm_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(w), _p(stats[0]), _p(stats[1]), _p(dres), _p(dx),
+    if y_fwd is not None and not (act == 2 and y_fwd.dtype == torch.bfloat16 and y_fwd.is_contiguous()):
+        y_fwd = None
+    _call("muse_norm_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(w), _p(stats[0]), _p(stats[1]), _p(dres), _p(y_fwd), _p(dx),
           _dt(dx), _p(dw), rows, H, act, rms, st)
     return dx
 

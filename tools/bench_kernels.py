@@ -57,6 +57,7 @@ if want("glu"):
     y, st = ops.norm_fwd(ab, w, 1e-6, torch.bfloat16, act=2)
     report("glu+LN fwd (fused)", timeit(lambda: ops.norm_fwd(ab, w, 1e-6, torch.bfloat16, act=2)), 12 * u)
     report("glu+LN bwd (fused)", timeit(lambda: ops.norm_bwd(dy, ab, w, st, torch.bfloat16, dw=dw, act=2)), 20 * u)
+    report("glu+LN bwd (fused, saved y)", timeit(lambda: ops.norm_bwd(dy, ab, w, st, torch.bfloat16, dw=dw, act=2, y_fwd=y)), 24 * u)
     report("glu fwd (plain)", timeit(lambda: ops.glu_fwd(ab)), 12 * u)
     report("glu bwd (plain)", timeit(lambda: ops.glu_bwd(ab, dy)), 20 * u)
     gl = ops.glu_fwd(ab)
