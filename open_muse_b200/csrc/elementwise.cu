@@ -63,10 +63,65 @@ embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ wo
   }
 }
 
-// dword[ids[t]] += dx[t] (atomics; the mask token row is hot) ; one warp per token
-__global__ void __launch_bounds__(128)
+// dword[ids[t]] += dx[t].  Roughly half of the tokens of a training batch are the mask token (id = vocab - 1 in every
+// reference config, modeling_transformer.py:1128), so plain atomics serialise T/2 adds on one row.  Each warp therefore
+// keeps the hot row's contribution of its 8 tokens in registers, the CTA folds its 8 warps in shared memory, and one
+// atomic per column and CTA reaches global memory; all other ids (spread over ~1000 rows) use vector atomics directly.
+constexpr int kEmbTokPerWarp = 8;
+template <int CH>  // CH float4 chunks per lane: H = CH * 128
+__global__ void __launch_bounds__(256)
 embed_bwd_word_kernel(const long long* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ dword,
-                      int tokens, int H, int vocab) {
+                      int tokens, int H, int vocab, int hot_id) {
+  __shared__ float s_hot[CH * 128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < CH * 128; i += 256) s_hot[i] = 0.f;
+  __syncthreads();
+  float4 acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool any_hot = false;
+  const int t0 = (blockIdx.x * 8 + warp) * kEmbTokPerWarp;
+  for (int k = 0; k < kEmbTokPerWarp; ++k) {
+    const int t = t0 + k;
+    if (t >= tokens) break;
+    const long long id = ids[t];
+    if (id < 0 || id >= vocab) continue;
+    const float* g = dx + static_cast<size_t>(t) * H;
+    if (id == hot_id) {
+      any_hot = true;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(g + c * 128 + lane * 4);
+        acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+      }
+    } else {
+      float* d = dword + id * H;
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        atomicAdd(reinterpret_cast<float4*>(d + c * 128 + lane * 4), *reinterpret_cast<const float4*>(g + c * 128 + lane * 4));
+    }
+  }
+  if (any_hot) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float* h = s_hot + c * 128 + lane * 4;
+      atomicAdd(h + 0, acc[c].x); atomicAdd(h + 1, acc[c].y); atomicAdd(h + 2, acc[c].z); atomicAdd(h + 3, acc[c].w);
+    }
+  }
+  __syncthreads();
+  if (hot_id >= 0 && hot_id < vocab) {
+    float* d = dword + static_cast<size_t>(hot_id) * H;
+    for (int i = threadIdx.x; i < CH * 128; i += 256) {
+      const float v = s_hot[i];
+      if (v != 0.f) atomicAdd(d + i, v);
+    }
+  }
+}
+
+// generic H (any multiple of 4): one warp per token, vector atomics
+__global__ void __launch_bounds__(128)
+embed_bwd_word_generic_kernel(const long long* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ dword,
+                              int tokens, int H, int vocab) {
   const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (t >= tokens) return;
   const int lane = threadIdx.x & 31;
@@ -161,7 +216,13 @@ int embed_bwd(const long long* ids, const float* dx, float* dword, float* dpos, 
   if (H % 4 != 0) { set_last_error("embed_bwd: H must be a multiple of 4"); return MUSE_ERR_INVALID; }
   const int tokens = B * S;
   if (tokens <= 0) return MUSE_OK;
-  embed_bwd_word_kernel<<<ceil_div(tokens, 4), 128, 0, s>>>(ids, dx, dword, tokens, H, vocab);
+  const int hot = vocab - 1;  // the reference's mask_token_id
+  const int grid = ceil_div(tokens, 8 * kEmbTokPerWarp);
+  if (H == 512) embed_bwd_word_kernel<4><<<grid, 256, 0, s>>>(ids, dx, dword, tokens, H, vocab, hot);
+  else if (H == 768) embed_bwd_word_kernel<6><<<grid, 256, 0, s>>>(ids, dx, dword, tokens, H, vocab, hot);
+  else if (H == 1024) embed_bwd_word_kernel<8><<<grid, 256, 0, s>>>(ids, dx, dword, tokens, H, vocab, hot);
+  else if (H == 128) embed_bwd_word_kernel<1><<<grid, 256, 0, s>>>(ids, dx, dword, tokens, H, vocab, hot);
+  else embed_bwd_word_generic_kernel<<<ceil_div(tokens, 4), 128, 0, s>>>(ids, dx, dword, tokens, H, vocab);
   int rc = check_launch("embed_bwd_word");
   if (rc) return rc;
   embed_bwd_pos_kernel<<<dim3(S, ceil_div(H, 128)), 128, 0, s>>>(dx, dpos, B, S, H);

@@ -112,8 +112,9 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
     const TDY* dyr = dy + static_cast<size_t>(row) * H;
     const float mean = rms ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
-    float xh[CH][8], g[CH][8];
+    float xh[CH][8], g[CH][8], rs[CH][8];
     float s1 = 0.f, s2 = 0.f;
+    const float* drr = dres ? dres + static_cast<size_t>(row) * H : nullptr;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int col = (c * 32 + lane) * 8;
@@ -121,6 +122,7 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
         float xv[8], dv[8], wv[8];
         load8(xr + col, xv);
         load8(dyr + col, dv);
+        if (drr) load8(drr + col, rs[c]);  // residual-gradient row fetched with the first wave of loads, not after the reductions
         if (w) load8(w + col, wv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -136,7 +138,6 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
     s1 = rms ? 0.f : warp_sum(s1) * inv_h;
     s2 = warp_sum(s2) * inv_h;
     TDX* dxr = dx + static_cast<size_t>(row) * H;
-    const float* drr = dres ? dres + static_cast<size_t>(row) * H : nullptr;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int col = (c * 32 + lane) * 8;
@@ -151,10 +152,8 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
           for (int j = 0; j < 8; ++j) o[j] *= gelu_grad_f(xv[j]);
         }
         if (drr) {
-          float r8[8];
-          load8(drr + col, r8);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r8[j];
+          for (int j = 0; j < 8; ++j) o[j] += rs[c][j];
         }
         store8(dxr + col, o);
       }

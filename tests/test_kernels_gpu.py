@@ -99,11 +99,12 @@ def test_norm_fwd_bwd(H, rms, xdt, ydt):
         assert _rel(dw, wr.grad) < 1e-4
 
 
-def test_embed_fwd_bwd():
-    B, S, H, V = 5, 17, 128, 72
+@pytest.mark.parametrize("B,S,H,V", [(5, 17, 128, 72), (7, 257, 512, 2025), (3, 33, 96, 50), (2, 256, 1024, 8256)])
+def test_embed_fwd_bwd(B, S, H, V):
     g = torch.Generator().manual_seed(0)
     ids = torch.randint(0, V, (B, S), generator=g).to(DEV)
-    ids[:, 3] = V - 1  # hot row
+    ids[:, 3] = V - 1  # hot row (mask token): accumulated per CTA before touching global memory
+    ids[torch.rand(B, S, generator=g).to(DEV) < 0.5] = V - 1
     word, pos = torch.randn(V, H, generator=g).to(DEV), torch.randn(S + 3, H, generator=g).to(DEV)
     out = ops.embed_fwd(ids, word, pos)
     ref = word[ids] + pos[:S][None]
@@ -112,7 +113,7 @@ def test_embed_fwd_bwd():
     dword, dpos = torch.zeros_like(word), torch.zeros_like(pos)
     ops.embed_bwd(ids, dx, dword, dpos)
     rw = torch.zeros_like(word).index_add_(0, ids.view(-1), dx)
-    assert _rel(dword, rw) < 1e-6
+    assert _rel(dword, rw) < 2e-6 and _rel(dword[V - 1], rw[V - 1]) < 2e-6
     assert _rel(dpos[:S], dx.view(B, S, H).sum(0)) < 1e-6 and bool((dpos[S:] == 0).all())
 
 

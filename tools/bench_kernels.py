@@ -77,6 +77,10 @@ if want("norm"):
     report("LN bwd bf16 dy, fp32 x, +dres", timeit(lambda: ops.norm_bwd(xb, x, w, st, torch.float32, dw=dw, dres=dres)), 7 * u)
     report("LN bwd fp32 dy, bf16 x -> bf16", timeit(lambda: ops.norm_bwd(x, xb, w, st, torch.bfloat16, dw=dw)), 4 * u)
     report("cast fp32->bf16", timeit(lambda: ops.cast_bf16(x)), 3 * u)
+    ids_e = torch.randint(0, 1024, (256, 257), device=dev)
+    ids_e[torch.rand(256, 257, device=dev) < 0.5] = 2024
+    dword, dpos = torch.zeros(2025, H, device=dev), torch.zeros(257, H, device=dev)
+    report("embed bwd (half of the tokens = mask id)", timeit(lambda: ops.embed_bwd(ids_e, x, dword, dpos)), 2 * u)
 if want("attn"):
     qkv = bf(T, 3 * H)
     scale = 0.125
