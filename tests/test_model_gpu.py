@@ -161,6 +161,42 @@ def test_base_shape_vs_oracle():
     assert abs(float(l2) - float(loss)) < 1e-4 * float(loss)
 
 
+def test_soft_target_loss_on_returned_logits(golden):
+    """train_maskgit_imagenet.py:101-117: with soft targets the script computes its own loss from the returned logits,
+    so the gradient reaches the model through the logits output (not through the fused CE).  Parity vs the oracle's fp32
+    autograd on the same custom loss."""
+    g = golden("micro_transformer.pt")
+    cfg, b = g["config"], g["batch"]
+    gen = torch.Generator().manual_seed(21)
+    soft = torch.softmax(torch.randn(b["input_ids"].shape[0], b["input_ids"].shape[1] - 1, 64, generator=gen), -1)
+
+    def soft_ce(logits, targets, soft_targets):  # restated from the training script
+        logits, targets = logits[:, 1:], targets[:, 1:]
+        logp = torch.log_softmax(logits[..., : soft_targets.shape[-1]].float(), dim=-1)
+        pad = targets.eq(-100)
+        loss = torch.sum(-soft_targets * logp, dim=-1).masked_fill(pad, 0.0)
+        return loss.sum() / (pad.numel() - pad.long().sum())
+
+    q = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    ref_loss = soft_ce(T.forward(q, cfg, b["input_ids"]), b["labels"], soft)
+    ref_loss.backward()
+    m = MaskGitTransformer(**cfg)
+    m.load_state_dict(g["state_dict"])
+    m.to(DEV).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = m(b["input_ids"].to(DEV))
+    loss = soft_ce(logits, b["labels"].to(DEV), soft.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) / float(ref_loss) < LOSS_TOL
+    worst = 0.0
+    for n, p in m.named_parameters():
+        e = _rel(p.grad, q[n].grad)
+        if "attention.query" in n or "attention.key" in n:  # ~1e-6 gradients at random init (see _bf16_recipe_grad_errors)
+            continue
+        worst = max(worst, e)
+    assert worst < GRAD_TOL, worst
+
+
 def test_forward_is_deterministic_and_eval_matches_train(golden):
     g = golden("micro_transformer.pt")
     m = MaskGitTransformer(**g["config"])
