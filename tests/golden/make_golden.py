@@ -54,6 +54,10 @@ MICRO_T2I_PROJ = dict(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_at
                       hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=16, codebook_size=64,
                       num_vq_tokens=16, add_cross_attention=True, encoder_hidden_size=32,
                       project_encoder_hidden_states=True, norm_type="layernorm", use_normformer=True, layer_norm_eps=1e-6)
+MICRO_V2 = dict(hidden_size=128, num_attention_heads=2, in_channels=64, block_out_channels=(64,), block_num_heads=1,
+                num_res_blocks=1, num_hidden_layers=2, intermediate_size=128, vocab_size=72, codebook_size=64,
+                encoder_hidden_size=32, cond_embed_dim=16, micro_cond_encode_dim=8, micro_cond_embed_dim=40,
+                norm_type="rmsnorm")
 TINY = dict(vocab_size=2025, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
             hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=257, codebook_size=1024,
             num_vq_tokens=256, num_classes=1000)
@@ -206,6 +210,43 @@ def main():
     torch.save(dict(config=MICRO_VQ, state_dict={k: x.clone() for k, x in v.state_dict().items()}, image=img,
                     z=zenc, ids=ids, z_q=zq, recon=rec, margin=(top2[:, 1] - top2[:, 0])),
                os.path.join(HERE, "micro_vqgan.pt"))
+
+    # ---- (6) MaskGiTUViT_v2 (modeling_transformer_v2.py): micro config; the zero-initialised tensors (adaLN mappers, GRN
+    # gamma/beta, mlm conv1) are re-drawn so that every branch contributes to the fixture
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+
+    torch.manual_seed(30)
+    v2 = MaskGiTUViT_v2(**MICRO_V2)
+    init_sig = {k: (float(x.double().sum()), float(x.double().norm())) for k, x in v2.state_dict().items()}
+    g = torch.Generator().manual_seed(31)
+    with torch.no_grad():
+        for k, x in v2.state_dict().items():
+            if "adaLN_modulation.mapper" in k or k.endswith("gamma") or k.endswith("beta") or k == "mlm_layer.conv1.weight":
+                x.copy_(torch.randn(x.shape, generator=g) * 0.05)
+            elif k.endswith("norm.weight"):
+                x.copy_(1.0 + 0.1 * torch.randn(x.shape, generator=g))
+    v2.train()
+    ids = torch.randint(0, 64, (3, 16), generator=g)
+    mask = torch.rand(3, 16, generator=g) < 0.6
+    inp = torch.where(mask, 71, ids)
+    lab = torch.where(mask, ids, -100)
+    enc = torch.randn(3, 5, 32, generator=g)
+    ce = torch.randn(3, 16, generator=g)
+    mc = torch.tensor([[256.0, 256.0, 0.0, 0.0, 6.0], [512.0, 384.0, 10.0, 20.0, 5.5], [128.0, 256.0, 3.0, 0.0, 7.25]])
+    logits, loss = v2(inp, enc, ce, mc, labels=lab, label_smoothing=0.1)
+    lw = torch.rand(3, 16, generator=g)
+    _, loss_w = v2(inp, enc, ce, mc, labels=lab, loss_weight=lw)
+    v2.eval()
+    empty_e, empty_c = torch.randn(1, 5, 32, generator=g), torch.randn(1, 16, generator=g)
+    with torch.no_grad():
+        gen_ids = v2.generate2(enc, ce, mc[:1], empty_e, empty_c, temperature=(2.0, 0.0), timesteps=4,
+                               guidance_scale=3.0, seq_len=16, generator=torch.Generator().manual_seed(32))
+    torch.save(dict(config=MICRO_V2, seed=30, init_signature=init_sig, empty_embeds=empty_e, empty_cond_embeds=empty_c,
+                    state_dict={k: x.clone() for k, x in v2.state_dict().items()}, input_ids=inp, labels=lab,
+                    encoder_hidden_states=enc, cond_embeds=ce, micro_conds=mc, logits=logits.detach(), loss=loss.detach(),
+                    loss_weight=lw, loss_weighted=loss_w.detach(), gen_seed=32, gen_ids=gen_ids.clone()),
+               os.path.join(HERE, "micro_uvit_v2.pt"))
+    print("micro uvit v2: loss", float(loss), "weighted", float(loss_w), "logits std", float(logits.std()))
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

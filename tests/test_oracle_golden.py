@@ -45,6 +45,27 @@ def test_micro_t2i_projected_encoder_states_forward_backward(golden):
         _close(grads[k], v, 1e-4, 1e-7)
 
 
+def test_micro_uvit_v2_forward_loss_and_generate2(golden):
+    """MaskGiTUViT_v2 restatement (oracle/transformer_v2_oracle.py) against the unmodified reference: logits, both loss
+    forms, and the CFG generate2 id trace through the same torch generator."""
+    from oracle import transformer_v2_oracle as V2
+
+    g = golden("micro_uvit_v2.pt")
+    p, cfg = g["state_dict"], g["config"]
+    with torch.no_grad():
+        logits, loss = V2.forward(p, cfg, g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"],
+                                  labels=g["labels"], label_smoothing=0.1)
+        _close(logits, g["logits"], 1e-4, 2e-5)
+        _close(loss, g["loss"], 1e-5, 0)
+        _, loss_w = V2.forward(p, cfg, g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"],
+                               labels=g["labels"], loss_weight=g["loss_weight"])
+        _close(loss_w, g["loss_weighted"], 1e-5, 0)
+        ids = V2.generate2(p, cfg, g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"][:1], g["empty_embeds"],
+                           g["empty_cond_embeds"], timesteps=4, temperature=(2.0, 0.0), guidance_scale=3.0,
+                           generator=torch.Generator().manual_seed(g["gen_seed"]), seq_len=16)
+    assert torch.equal(ids, g["gen_ids"])
+
+
 def test_masking_recipe(golden):
     b = golden("micro_transformer.pt")["batch"]
     inp, lab = T.mask_tokens(b["tokens"], b["class_ids"], b["timesteps"], b["rand"], 64, 71)
