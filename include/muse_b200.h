@@ -97,6 +97,29 @@ int muse_ce_fwd(const void* logits, const long long* labels, float* lse, float* 
 int muse_ce_bwd(const void* logits, const long long* labels, const float* lse, const float* dloss,
                 const float* loss_out, void* dlogits, int rows, int V, int ld, float label_smoothing, void* stream);
 
+/* ---- MaskGiTUViT_v2 forward (muse/modeling_transformer_v2.py); dtype codes as muse_norm_fwd (0 = fp32, 1 = bf16) ----
+ * Prenorm-residual norm (unfused_rms_norm / unfused_layer_norm, :673-738) fused with the adaLN modulation that follows it
+ * in TransformerLayer / GLUFeedForward (:757-792, :926-951, AdaLNModulation :1025-1037):
+ *   r_out = a + r (r NULL: r_out = a; r_out NULL: not stored);  y = norm(r_out) * w  [* (1 + scale_b) + shift_b].
+ * scale_shift (nullable) fp32: scale of sample b at [b*ss_stride, +H), shift at [b*ss_stride + H, +H); a row belongs to
+ * sample row / rows_per_sample.  H <= 1024, H % 8 == 0. */
+int muse_add_norm_mod_fwd(const void* a, int a_dtype, const float* r, const float* w, const float* scale_shift,
+                          long long ss_stride, int rows_per_sample, float* r_out, void* y, int y_dtype, int rows, int H,
+                          float eps, int rms, void* stream);
+/* ResBlock head (:604-612): depthwise 3x3 'same' conv (groups = C, no bias; output rounded to bf16 like the autocast conv)
+ * + Norm2D over channels.  x fp32 [B,h,w,C] token-major, wk fp32 [9, C] (tap-major), norm_w fp32 [C] or NULL -> y bf16. */
+int muse_dwconv3x3_norm_fwd(const float* x, const float* wk, const float* norm_w, void* y, int B, int h, int w, int C,
+                            float eps, int rms, void* stream);
+/* nn.GELU + GlobalResponseNorm (:741-751) on x bf16 [B, HW, C]: g = gelu(x), Gx = ||g||_2 over the HW tokens,
+ * Nx = Gx / (mean_c Gx + 1e-6), out = gamma * (g * Nx) + beta + g (bf16).  stat_ws: fp32 [B, C] scratch. */
+int muse_grn_fwd(const void* x, const float* gamma, const float* beta, void* out, float* stat_ws, int B, int HW, int C,
+                 void* stream);
+/* AdaLNModulation at the end of a ResBlock (:617): x fp32 [B*rows_per_sample, C] *= (1 + scale_b), += shift_b, in place. */
+int muse_adaln_apply(float* x, const float* scale_shift, long long ss_stride, int B, int rows_per_sample, int C,
+                     void* stream);
+/* F.silu feeding the adaLN / kv mappers (:812, :1031): y bf16 = silu(x), n % 8 == 0. */
+int muse_silu_bf16(const void* x, int x_dtype, void* y, long long n, void* stream);
+
 /* VectorQuantizer.get_code (muse/modeling_maskgit_vqgan.py:303-316,342-348): ids[r] = argmin_c
  * fl(fl(|z_r|^2 + |e_c|^2) - 2 z_r.e_c), first minimum. z fp32 [n,D] (NHWC-flattened), codebook fp32
  * [ncodes,D], enorm_ws fp32 [ncodes] scratch, dmin (optional) fp32 [n]. Bit-exact vs oracle/vq_oracle.c. */

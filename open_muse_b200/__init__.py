@@ -8,5 +8,6 @@ __version__ = "0.1.0"
 
 from .modeling_maskgit_vqgan import MaskGitVQGAN  # noqa: F401
 from .modeling_transformer import MaskGitTransformer  # noqa: F401
+from .modeling_transformer_v2 import MaskGiTUViT_v2  # noqa: F401
 from .pipeline_muse import PipelineMuse, PipelineMuseInpainting  # noqa: F401
 from .sampling import get_mask_chedule  # noqa: F401

@@ -5,9 +5,10 @@ __version__ = "0.0.1"
 
 from open_muse_b200 import (  # noqa: F401
     MaskGitTransformer,
+    MaskGiTUViT_v2,
     MaskGitVQGAN,
     PipelineMuse,
     PipelineMuseInpainting,
     get_mask_chedule,
 )
-from open_muse_b200 import sampling  # noqa: F401
+from open_muse_b200 import modeling_transformer_v2, sampling  # noqa: F401

@@ -42,6 +42,11 @@ int ce_fwd(const void*, const long long*, float*, float*, float*, int, int, int,
 int ce_bwd(const void*, const long long*, const float*, const float*, const float*, void*, int, int, int, float, cudaStream_t);
 int vq_argmin(const float*, const float*, float*, long long*, float*, int, int, int, cudaStream_t);
 int vq_lookup_nchw(const long long*, const float*, float*, int, int, int, int, cudaStream_t);
+int add_norm_mod_fwd(const void*, int, const float*, const float*, const float*, long long, int, float*, void*, int, int, int, float, int, cudaStream_t);
+int dwconv3x3_norm_fwd(const float*, const float*, const float*, void*, int, int, int, int, float, int, cudaStream_t);
+int grn_fwd(const void*, const float*, const float*, void*, float*, int, int, int, cudaStream_t);
+int adaln_apply(float*, const float*, long long, int, int, int, cudaStream_t);
+int silu_bf16(const void*, int, void*, long long, cudaStream_t);
 int vq_soft_code(const float*, const float*, float*, float*, long long*, const float*, float, int, int, int, cudaStream_t);
 int sample_step(const void*, const void*, long long, long long, float, const long long*, const float*, const float*, long long*, long long*, float*, int, int, int, long long, int, float, cudaStream_t);
 int conv2d_nhwc(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
@@ -139,6 +144,27 @@ int muse_ce_bwd(const void* logits, const long long* labels, const float* lse, c
 int muse_vq_argmin(const float* z, const float* codebook, float* enorm_ws, long long* ids, float* dmin, int n,
                    int ncodes, int D, void* stream) {
   return vq_argmin(z, codebook, enorm_ws, ids, dmin, n, ncodes, D, ST(stream));
+}
+int muse_add_norm_mod_fwd(const void* a, int a_dtype, const float* r, const float* w, const float* scale_shift,
+                          long long ss_stride, int rows_per_sample, float* r_out, void* y, int y_dtype, int rows, int H,
+                          float eps, int rms, void* stream) {
+  return add_norm_mod_fwd(a, a_dtype, r, w, scale_shift, ss_stride, rows_per_sample, r_out, y, y_dtype, rows, H, eps, rms,
+                          ST(stream));
+}
+int muse_dwconv3x3_norm_fwd(const float* x, const float* wk, const float* norm_w, void* y, int B, int h, int w, int C,
+                            float eps, int rms, void* stream) {
+  return dwconv3x3_norm_fwd(x, wk, norm_w, y, B, h, w, C, eps, rms, ST(stream));
+}
+int muse_grn_fwd(const void* x, const float* gamma, const float* beta, void* out, float* stat_ws, int B, int HW, int C,
+                 void* stream) {
+  return grn_fwd(x, gamma, beta, out, stat_ws, B, HW, C, ST(stream));
+}
+int muse_adaln_apply(float* x, const float* scale_shift, long long ss_stride, int B, int rows_per_sample, int C,
+                     void* stream) {
+  return adaln_apply(x, scale_shift, ss_stride, B, rows_per_sample, C, ST(stream));
+}
+int muse_silu_bf16(const void* x, int x_dtype, void* y, long long n, void* stream) {
+  return silu_bf16(x, x_dtype, y, n, ST(stream));
 }
 int muse_vq_soft_code(const float* z, const float* codebook, float* enorm_ws, float* soft, long long* ids,
                        const float* expo_noise, float temp, int n, int ncodes, int D, void* stream) {

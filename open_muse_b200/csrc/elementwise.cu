@@ -54,11 +54,11 @@ embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ wo
   long long id = ids[t];
   if (id < 0 || id >= vocab) id = 0;  // torch raises on OOB ids; host validates, device stays in-bounds
   const float* wr = word + id * H;
-  const float* pr = pos + static_cast<size_t>(t % S) * H;
+  const float* pr = pos ? pos + static_cast<size_t>(t % S) * H : nullptr;  // pos == null: plain gather (ConvEmbed of v2)
   float* o = out + static_cast<size_t>(t) * H;
   for (int c = lane * 4; c < H; c += 128) {
     const float4 a = *reinterpret_cast<const float4*>(wr + c);
-    const float4 b = *reinterpret_cast<const float4*>(pr + c);
+    const float4 b = pr ? *reinterpret_cast<const float4*>(pr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(o + c) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
   }
 }

@@ -50,7 +50,7 @@ def _p(t):
 
 
 _KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
-                     "muse_groupnorm_silu_nhwc": 3}
+                     "muse_groupnorm_silu_nhwc": 3, "muse_grn_fwd": 3}
 _prof = {"on": False, "events": []}
 
 
@@ -227,6 +227,51 @@ def ce_bwd(logits_padded, labels, ws, dloss, loss_out, V, label_smoothing):
     _call("muse_ce_bwd", _p(logits_padded), _p(labels), _p(ws[0]), _p(dloss), _p(loss_out), _p(dl), rows, V, ld,
           float(label_smoothing), st)
     return dl
+
+
+# ------------------------------------------------------------------------------------------ U-ViT v2 forward ops
+def add_norm_mod(a, w, eps, rms, out_dtype=torch.bfloat16, residual=None, mod=None, rows_per_sample=1, want_residual=True):
+    """(r', y): r' = a + residual (fp32), y = norm(r') * w [* (1 + scale_b) + shift_b].  mod: fp32 [B, 2H] view (scale |
+    shift per sample, row pitch mod.stride(0)) of the batched adaLN mapper output."""
+    st = _prep(a)
+    rows, H = a.shape
+    y = torch.empty(rows, H, dtype=out_dtype, device=a.device)
+    r_out = torch.empty(rows, H, dtype=torch.float32, device=a.device) if want_residual else None
+    _call("muse_add_norm_mod_fwd", _p(a), _dt(a), _p(residual), _p(w), _p(mod), 0 if mod is None else mod.stride(0),
+          int(rows_per_sample), _p(r_out), _p(y), _dt(y), rows, H, float(eps), int(rms), st)
+    return r_out, y
+
+
+def dwconv3x3_norm(x, wk, norm_w, B, hh, ww, eps, rms):
+    """x fp32 [B*hh*ww, C] token-major, wk fp32 [9, C] -> bf16 [B*hh*ww, C] = Norm2D(depthwise3x3(x))."""
+    st = _prep(x)
+    C = x.shape[1]
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _call("muse_dwconv3x3_norm_fwd", _p(x), _p(wk), _p(norm_w), _p(y), B, hh, ww, C, float(eps), int(rms), st)
+    return y
+
+
+def grn(x, gamma, beta, B, HW):
+    """bf16 [B*HW, C] -> bf16: GELU + GlobalResponseNorm."""
+    st = _prep(x)
+    C = x.shape[1]
+    out = torch.empty_like(x)
+    ws = torch.empty(B, C, dtype=torch.float32, device=x.device)
+    _call("muse_grn_fwd", _p(x), _p(gamma), _p(beta), _p(out), _p(ws), B, HW, C, st)
+    return out
+
+
+def adaln_apply_(x, mod, B, rows_per_sample):
+    st = _prep(x)
+    _call("muse_adaln_apply", _p(x), _p(mod), mod.stride(0), B, int(rows_per_sample), x.shape[1], st)
+    return x
+
+
+def silu_bf16(x):
+    st = _prep(x)
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _call("muse_silu_bf16", _p(x), _dt(x), _p(y), x.numel(), st)
+    return y
 
 
 # ------------------------------------------------------------------------------------------ VQ

@@ -114,3 +114,27 @@ def test_seeded_construction_matches_reference_initial_weights():
     assert list(sd.keys()) == list(g["state_dict"].keys())
     for k, v in g["state_dict"].items():
         assert torch.equal(sd[k], v), k
+
+
+def test_uvit_v2_seeded_construction_matches_reference():
+    """MaskGiTUViT_v2: parameter names / order and every initial tensor (trunc-normal, xavier, tied mlm conv2, zeroed adaLN
+    mappers and mlm conv1) equal the reference's under the same seed; training-mode forward refuses to run."""
+    import os
+
+    import pytest
+    import torch
+
+    from open_muse_b200 import MaskGiTUViT_v2
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "micro_uvit_v2.pt"), weights_only=False)
+    torch.manual_seed(g["seed"])
+    m = MaskGiTUViT_v2(**g["config"], some_unknown_legacy_key=3)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["state_dict"].keys())
+    for k, (s, n) in g["init_signature"].items():
+        assert abs(float(sd[k].double().sum()) - s) <= 1e-9 * max(1.0, abs(s)), k
+        assert abs(float(sd[k].double().norm()) - n) <= 1e-9 * max(1.0, n), k
+    assert m.config.mask_token_id == 71 and m.output_size == 64 and "some_unknown_legacy_key" not in m.config
+    m.train()
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        m(g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"])

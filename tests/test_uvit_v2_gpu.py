@@ -1,0 +1,164 @@
+"""GPU parity of the MaskGiTUViT_v2 inference path: new kernels vs fp32 torch math, the assembled model vs the reference
+fixture (micro) and vs the pinned oracle at U-ViT-sized widths, CFG generate2 properties."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from open_muse_b200 import MaskGiTUViT_v2, ops  # noqa: E402
+from oracle import transformer_v2_oracle as V2  # noqa: E402
+
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+@pytest.mark.parametrize("H,rms,with_res,with_mod,a_bf16", [(1024, 1, True, True, True), (768, 0, True, False, True),
+                                                           (64, 1, False, True, False), (128, 0, True, True, False)])
+def test_add_norm_mod_vs_torch(H, rms, with_res, with_mod, a_bf16):
+    g = torch.Generator().manual_seed(H)
+    B, S = 3, 20
+    a = torch.randn(B * S, H, generator=g)
+    a = a.to(torch.bfloat16) if a_bf16 else a
+    r = torch.randn(B * S, H, generator=g) if with_res else None
+    w = 1 + 0.1 * torch.randn(H, generator=g)
+    mod_all = torch.randn(B, 4 * H + 64, generator=g) * 0.3
+    mod = mod_all[:, 64:64 + 2 * H] if with_mod else None
+    x = a.float() + (r if with_res else 0)
+    if rms:
+        y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    else:
+        y = torch.nn.functional.layer_norm(x, (H,), w, None, 1e-6)
+    if with_mod:
+        y = (y.view(B, S, H) * (1 + mod[:, None, :H]) + mod[:, None, H:]).view(B * S, H)
+    mod_dev = mod_all.to(DEV)[:, 64:64 + 2 * H] if with_mod else None
+    r_out, yk = ops.add_norm_mod(a.to(DEV), w.to(DEV), 1e-6, rms, residual=None if r is None else r.to(DEV), mod=mod_dev,
+                                 rows_per_sample=S)
+    assert torch.allclose(r_out.cpu(), x, atol=1e-6) and _rel(yk, y) < 5e-3
+    _, yf = ops.add_norm_mod(a.to(DEV), w.to(DEV), 1e-6, rms, out_dtype=torch.float32, residual=None if r is None else r.to(DEV),
+                             mod=mod_dev, rows_per_sample=S, want_residual=False)
+    assert _rel(yf, y) < 1e-5
+
+
+@pytest.mark.parametrize("C,hw,rms", [(768, 16, 1), (64, 4, 0), (1024, 8, 1)])
+def test_dwconv_norm_grn_adaln_silu_vs_torch(C, hw, rms):
+    g = torch.Generator().manual_seed(C)
+    B = 2
+    x = torch.randn(B, hw, hw, C, generator=g)
+    wd = torch.randn(C, 1, 3, 3, generator=g) * 0.3
+    nw = 1 + 0.1 * torch.randn(C, generator=g)
+    conv = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), wd, None, padding=1, groups=C).permute(0, 2, 3, 1)
+    conv = conv.to(torch.bfloat16).float()
+    ref = conv * torch.rsqrt(conv.pow(2).mean(-1, keepdim=True) + 1e-6) * nw if rms else \
+        torch.nn.functional.layer_norm(conv, (C,), nw, None, 1e-6)
+    y = ops.dwconv3x3_norm(x.view(-1, C).to(DEV), wd.view(C, 9).t().contiguous().to(DEV), nw.to(DEV), B, hw, hw, 1e-6, rms)
+    assert _rel(y, ref.view(-1, C)) < 6e-3
+    # GELU + GRN
+    z = (torch.randn(B, hw, hw, C, generator=g) * 1.5).to(torch.bfloat16)
+    gamma, beta = torch.randn(C, generator=g) * 0.2, torch.randn(C, generator=g) * 0.2
+    gg = torch.nn.functional.gelu(z.float()).to(torch.bfloat16).float()
+    gx = torch.norm(gg, p=2, dim=(1, 2), keepdim=True)
+    nx = gx / (gx.mean(dim=-1, keepdim=True) + 1e-6)
+    ref = gamma * (gg * nx) + beta + gg
+    out = ops.grn(z.view(-1, C).to(DEV), gamma.to(DEV), beta.to(DEV), B, hw * hw)
+    assert _rel(out, ref.view(-1, C)) < 6e-3
+    # in-place adaLN and SiLU
+    mod = torch.randn(B, 2 * C + 32, generator=g)
+    h = torch.randn(B * hw * hw, C, generator=g)
+    ref = (h.view(B, -1, C) * (1 + mod[:, None, 32:32 + C]) + mod[:, None, 32 + C:32 + 2 * C]).view(-1, C)
+    hk = ops.adaln_apply_(h.to(DEV).clone(), mod.to(DEV)[:, 32:32 + 2 * C], B, hw * hw)
+    assert _rel(hk, ref) < 1e-6
+    s = ops.silu_bf16(h.to(DEV))
+    assert _rel(s, torch.nn.functional.silu(h)) < 5e-3
+
+
+def _stage_report(m, ref_stages):
+    rep = []
+    for k, v in m._debug_stages.items():
+        if k in ref_stages:
+            rep.append(f"{k}={_rel(v, ref_stages[k]):.2e}")
+    return " ".join(rep)
+
+
+def test_micro_uvit_v2_vs_reference_fixture(golden):
+    g = golden("micro_uvit_v2.pt")
+    m = MaskGiTUViT_v2(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.to(DEV).eval()
+    st = {}
+    with torch.no_grad():
+        V2.forward(g["state_dict"], g["config"], g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"],
+                   g["micro_conds"], stages=st)
+    m._debug_stages = {}
+    args = [g[k].to(DEV) for k in ("input_ids", "encoder_hidden_states", "cond_embeds", "micro_conds")]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, loss = m(*args, labels=g["labels"].to(DEV), label_smoothing=0.1)
+    print("stages:", _stage_report(m, st))
+    m._debug_stages = None
+    assert logits.dtype == torch.bfloat16 and logits.shape == g["logits"].shape
+    assert _rel(logits, g["logits"]) < 2e-2, _rel(logits, g["logits"])
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 2e-3
+    _, loss_w = m(*args, labels=g["labels"].to(DEV), loss_weight=g["loss_weight"].to(DEV))
+    assert abs(float(loss_w) - float(g["loss_weighted"])) / float(g["loss_weighted"]) < 2e-3
+    out = m(*args)
+    assert out.dtype == torch.float32 and _rel(out, g["logits"]) < 2e-2
+
+
+def test_uvit_v2_default_widths_vs_oracle():
+    """U-ViT widths of the cc12m configs (hidden 1024 / 16 heads, blocks 768 / 12 heads, kv_mapper, 256 tokens, 77 text
+    states) with a shortened stack, random re-draw of the zero-initialised tensors; fp32 oracle on the CPU."""
+    cfg = dict(num_hidden_layers=2, num_res_blocks=1, vocab_size=1032, codebook_size=1024, intermediate_size=2816)
+    torch.manual_seed(0)
+    m = MaskGiTUViT_v2(**cfg)
+    gen = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for k, x in m.state_dict().items():
+            if "adaLN_modulation.mapper" in k or k.endswith("gamma") or k.endswith("beta") or k == "mlm_layer.conv1.weight":
+                x.copy_(torch.randn(x.shape, generator=gen) * 0.03)
+    B = 2
+    ids = torch.randint(0, 1024, (B, 256), generator=gen)
+    ids[torch.rand(B, 256, generator=gen) < 0.5] = 1031
+    enc = torch.randn(B, 77, 768, generator=gen)
+    ce = torch.randn(B, 768, generator=gen)
+    mc = torch.tensor([[256.0, 256.0, 0.0, 0.0, 6.0], [512.0, 512.0, 32.0, 16.0, 5.0]])
+    st = {}
+    with torch.no_grad():
+        ref = V2.forward({k: v.float() for k, v in m.state_dict().items()}, cfg, ids, enc, ce, mc, stages=st)
+    m.to(DEV).eval()
+    m._debug_stages = {}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = m(ids.to(DEV), enc.to(DEV), ce.to(DEV), mc.to(DEV))
+    print("stages:", _stage_report(m, st))
+    assert _rel(logits, ref) < 2e-2, _rel(logits, ref)
+    agree = float((logits.float().cpu().argmax(-1) == ref.argmax(-1)).float().mean())
+    assert agree > 0.9, agree
+
+
+def test_uvit_v2_generate2_cfg_properties(golden):
+    g = golden("micro_uvit_v2.pt")
+    m = MaskGiTUViT_v2(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.to(DEV).eval()
+    kw = dict(encoder_hidden_states=g["encoder_hidden_states"].to(DEV), cond_embeds=g["cond_embeds"].to(DEV),
+              micro_conds=g["micro_conds"][:1].to(DEV), empty_embeds=g["empty_embeds"].to(DEV),
+              empty_cond_embeds=g["empty_cond_embeds"].to(DEV), temperature=(2.0, 0.0), timesteps=4, seq_len=16)
+    a = m.generate2(**kw, guidance_scale=3.0, generator=torch.Generator(device=DEV).manual_seed(5))
+    b = m.generate2(**kw, guidance_scale=3.0, generator=torch.Generator(device=DEV).manual_seed(5))
+    assert a.shape == (3, 16) and a.dtype == torch.int64 and torch.equal(a, b)
+    assert int(a.min()) >= 0 and int(a.max()) < 64  # no mask tokens left, codebook range
+    ids, inter = m.generate2(**kw, guidance_scale=3.0, guidance_schedule="linear", return_intermediate=True,
+                             generator=torch.Generator(device=DEV).manual_seed(5))
+    assert len(inter) == 4 and torch.equal(inter[-1], ids)
+    # partially given tokens are kept
+    start = torch.full((3, 16), 71, dtype=torch.long, device=DEV)
+    start[:, :5] = torch.arange(5, device=DEV)
+    c = m.generate2(**kw, guidance_scale=2.0, input_ids=start, generator=torch.Generator(device=DEV).manual_seed(6))
+    assert torch.equal(c[:, :5], start[:, :5]) and int(c.max()) < 64
