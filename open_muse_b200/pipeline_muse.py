@@ -17,6 +17,7 @@ import torch
 
 from .modeling_maskgit_vqgan import MaskGitVQGAN
 from .modeling_transformer import MaskGitTransformer
+from .modeling_transformer_v2 import MaskGiTUViT_v2
 from .sampling import get_mask_chedule
 
 
@@ -69,14 +70,22 @@ class PipelineMuse:
         use_fp16: bool = False,
         return_intermediate: bool = False,
         output_type: str = "pil",
+        orig_size=(256, 256),
+        crop_coords=(0, 0),
+        aesthetic_score=6.0,
         **unused,
     ):
         if text is None and class_ids is None and prompt_embeds is None:
             raise ValueError("Either text or class_ids must be provided.")
         if text is not None and class_ids is not None:
             raise ValueError("Only one of text or class_ids may be provided.")
+        if getattr(self.transformer.config, "add_micro_cond_embeds", False):  # MaskGiTUViT_v2 conditioning (:121-214)
+            return self._call_uvit_v2(prompt_embeds, pooled_embeds, negative_prompt_embeds, negative_pooled_embeds, timesteps,
+                                      noise_schedule, guidance_scale, guidance_schedule, temperature,
+                                      num_images_per_prompt, generator, return_intermediate, output_type, orig_size,
+                                      crop_coords, aesthetic_score)
         if return_intermediate:
-            raise NotImplementedError("return_intermediate is a MaskGiTUViT_v2.generate2 feature (not built, see DESIGN.md)")
+            raise NotImplementedError("return_intermediate is a MaskGiTUViT_v2.generate2 feature")
         if isinstance(temperature, (tuple, list)):
             temperature = float(temperature[0])  # v1 generate2 takes a scalar that it anneals itself (quirk Q4)
         kwargs = {}
@@ -105,6 +114,44 @@ class PipelineMuse:
         if output_type == "pt":
             return images
         return [self.to_pil_image(img) for img in images]
+
+    def _call_uvit_v2(self, prompt_embeds, pooled_embeds, negative_prompt_embeds, negative_pooled_embeds, timesteps,
+                      noise_schedule, guidance_scale, guidance_schedule, temperature, num_images_per_prompt, generator,
+                      return_intermediate, output_type, orig_size, crop_coords, aesthetic_score):
+        """Text-to-image with ``MaskGiTUViT_v2``: penultimate-layer text states + pooled embedding + micro-conditioning
+        (reference pipeline_muse.py:121-233).  The text encoder is third-party and out of scope, so the embeddings (and the
+        negative / empty ones needed for guidance) are passed in precomputed."""
+        if prompt_embeds is None or pooled_embeds is None:
+            raise ValueError("MaskGiTUViT_v2 needs prompt_embeds (text states) and pooled_embeds; run the text encoder "
+                             "outside or attach one and encode before calling")
+        if guidance_scale > 0 and (negative_prompt_embeds is None or negative_pooled_embeds is None):
+            raise ValueError("classifier-free guidance needs negative_prompt_embeds and negative_pooled_embeds (the encoded "
+                             "empty prompt)")
+        n = num_images_per_prompt
+        rep = lambda t: None if t is None else t.to(self.device).repeat_interleave(n, dim=0)
+        states, pooled = rep(prompt_embeds), rep(pooled_embeds)
+        micro = torch.tensor([list(orig_size) + list(crop_coords) + [aesthetic_score]], device=self.device,
+                             dtype=torch.float32)
+        if isinstance(temperature, list):
+            temperature = tuple(temperature)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = self.transformer.generate2(
+                encoder_hidden_states=states, cond_embeds=pooled, micro_conds=micro, empty_embeds=None,
+                empty_cond_embeds=None, negative_embeds=rep(negative_prompt_embeds),
+                negative_cond_embeds=rep(negative_pooled_embeds), temperature=temperature, timesteps=timesteps,
+                guidance_scale=guidance_scale, guidance_schedule=guidance_schedule,
+                noise_schedule=get_mask_chedule(noise_schedule), generator=generator,
+                return_intermediate=return_intermediate)
+        tokens, intermediate = out if return_intermediate else (out, None)
+        images = self.vae.decode_code(tokens)
+        if output_type != "pt":
+            images = [self.to_pil_image(img) for img in images]
+        if return_intermediate:
+            inter = [self.vae.decode_code(t) for t in intermediate]
+            if output_type != "pt":
+                inter = [[self.to_pil_image(img) for img in batch] for batch in inter]
+            return images, inter
+        return images
 
     def to_pil_image(self, image: torch.Tensor):
         """[0,1] -> uint8 with the reference's clamp / truncation recipe (pipeline_muse.py:245-252, quirk Q10)."""
@@ -145,9 +192,12 @@ class PipelineMuse:
         if transformer is None:
             path, folder = sub(transformer_path, "transformer")
             name = class_name(path, folder)
-            if name not in (None, "MaskGitTransformer"):
-                raise NotImplementedError(f"transformer class {name} is not built yet (see DESIGN.md: MaskGiTUViT_v2 is next)")
-            transformer = MaskGitTransformer.from_pretrained(path, subfolder=folder)
+            if name in ("MaskGiTUViT", "MaskGiTUViT_v2"):  # (reference :317-318)
+                transformer = MaskGiTUViT_v2.from_pretrained(path, subfolder=folder)
+            elif name in (None, "MaskGitTransformer"):
+                transformer = MaskGitTransformer.from_pretrained(path, subfolder=folder)
+            else:
+                raise ValueError(f"Unknown Transformer class: {name}")
         tokenizer = None
         if not is_class_conditioned and text_encoder is None:
             path, folder = sub(text_encoder_path, "text_encoder")

@@ -162,3 +162,29 @@ def test_uvit_v2_generate2_cfg_properties(golden):
     start[:, :5] = torch.arange(5, device=DEV)
     c = m.generate2(**kw, guidance_scale=2.0, input_ids=start, generator=torch.Generator(device=DEV).manual_seed(6))
     assert torch.equal(c[:, :5], start[:, :5]) and int(c.max()) < 64
+
+
+def test_pipeline_with_uvit_v2_and_checkpoint_roundtrip(tmp_path, golden):
+    """PipelineMuse(text-conditioned U-ViT + MaskGitVQGAN detokeniser) from precomputed text embeddings, and the
+    <dir>/{vae,transformer} layout through save_pretrained / from_pretrained (class name dispatch)."""
+    from open_muse_b200 import MaskGitVQGAN, PipelineMuse
+
+    g = golden("micro_uvit_v2.pt")
+    tr = MaskGiTUViT_v2(**g["config"])
+    tr.load_state_dict(g["state_dict"])
+    torch.manual_seed(0)
+    vae = MaskGitVQGAN(resolution=8, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=1, z_channels=16,
+                       num_embeddings=64, quantized_embed_dim=16)
+    pipe = PipelineMuse(vae=vae, transformer=tr, is_class_conditioned=False).to(DEV)
+    kw = dict(prompt_embeds=g["encoder_hidden_states"][:2], pooled_embeds=g["cond_embeds"][:2],
+              negative_prompt_embeds=g["empty_embeds"].expand(2, -1, -1), negative_pooled_embeds=g["empty_cond_embeds"].expand(2, -1),
+              timesteps=3, guidance_scale=2.0, num_images_per_prompt=2, output_type="pt")
+    a = pipe(**kw, generator=torch.Generator(device=DEV).manual_seed(1))
+    assert a.shape == (4, 3, 32, 32) and bool(torch.isfinite(a).all())  # 256 tokens = 16x16 latent, f = 2
+    pipe.save_pretrained(tmp_path)
+    assert sorted(os.listdir(tmp_path)) == ["transformer", "vae"]
+    pipe2 = PipelineMuse.from_pretrained(str(tmp_path), is_class_conditioned=True).to(DEV)
+    pipe2.is_class_conditioned = False
+    assert isinstance(pipe2.transformer, MaskGiTUViT_v2)
+    b = pipe2(**kw, generator=torch.Generator(device=DEV).manual_seed(1))
+    assert torch.equal(a, b)

@@ -57,3 +57,29 @@ if "vqgan" in which:
                       "decode_images_per_s": B / (ms_dec * 1e-3), "encode_ms": ms_enc, "decode_ms": ms_dec,
                       "encode_tflops": 128.76 * B / ms_enc, "decode_tflops": 186.55 * B / ms_dec,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
+if "uvit" in which:
+    # MaskGiTUViT_v2 at the reference defaults (603 M params: 22 x 1024 + 768-wide U blocks), the model benchmark/muse_perf.py
+    # times: 12-step CFG generate2 for 256 px (256 tokens), text states 77 x 768, batch 1 and 8 (doubled by guidance).
+    from open_muse_b200 import MaskGiTUViT_v2
+
+    torch.manual_seed(0)
+    u = MaskGiTUViT_v2().to(dev).eval()
+    n_params = sum(p.numel() for p in u.parameters())
+    for bs in (1, 8):
+        g = torch.Generator(device=dev).manual_seed(3)
+        enc = torch.randn(bs, 77, 768, device=dev)
+        pooled = torch.randn(bs, 768, device=dev)
+        micro = torch.tensor([[256.0, 256.0, 0.0, 0.0, 6.0]], device=dev)
+        e_enc, e_pool = torch.randn(1, 77, 768, device=dev), torch.randn(1, 768, device=dev)
+
+        def run_uvit():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return u.generate2(enc, pooled, micro, e_enc, e_pool, timesteps=12, guidance_scale=8.0, temperature=(2.0, 0.0),
+                                   generator=g)
+
+        l0 = ops.launches()
+        ms = timed(run_uvit, 3, warm=2)
+        print(json.dumps({"metric": f"MaskGiTUViT_v2 generate2 latency (defaults, {n_params / 1e6:.0f} M params, bs {bs}, 12 steps, "
+                                    "256 tokens, CFG)", "value": ms, "unit": "ms", "images_per_s": bs / (ms * 1e-3),
+                          "ms_per_step": ms / 12, "launches_per_call": (ops.launches() - l0) // 5}), flush=True)
+    del u
