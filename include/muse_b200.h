@@ -108,17 +108,39 @@ int muse_add_norm_mod_fwd(const void* a, int a_dtype, const float* r, const floa
                           float eps, int rms, void* stream);
 /* ResBlock head (:604-612): depthwise 3x3 'same' conv (groups = C, no bias; output rounded to bf16 like the autocast conv)
  * + Norm2D over channels.  x fp32 [B,h,w,C] token-major, wk fp32 [9, C] (tap-major), norm_w fp32 [C] or NULL -> y bf16. */
-int muse_dwconv3x3_norm_fwd(const float* x, const float* wk, const float* norm_w, void* y, int B, int h, int w, int C,
-                            float eps, int rms, void* stream);
+int muse_dwconv3x3_norm_fwd(const float* x, const float* wk, const float* norm_w, void* y, void* conv_out, int B, int h,
+                            int w, int C, float eps, int rms, void* stream);  /* conv_out (nullable) bf16: saved for bwd */
 /* nn.GELU + GlobalResponseNorm (:741-751) on x bf16 [B, HW, C]: g = gelu(x), Gx = ||g||_2 over the HW tokens,
- * Nx = Gx / (mean_c Gx + 1e-6), out = gamma * (g * Nx) + beta + g (bf16).  stat_ws: fp32 [B, C] scratch. */
-int muse_grn_fwd(const void* x, const float* gamma, const float* beta, void* out, float* stat_ws, int B, int HW, int C,
-                 void* stream);
+ * Nx = Gx / (mean_c Gx + 1e-6), out = gamma * (g * Nx) + beta + g (bf16).  sumsq_ws (Gx^2) and nx_ws: fp32 [B, C],
+ * left filled for muse_grn_bwd. */
+int muse_grn_fwd(const void* x, const float* gamma, const float* beta, void* out, float* sumsq_ws, float* nx_ws, int B,
+                 int HW, int C, void* stream);
 /* AdaLNModulation at the end of a ResBlock (:617): x fp32 [B*rows_per_sample, C] *= (1 + scale_b), += shift_b, in place. */
 int muse_adaln_apply(float* x, const float* scale_shift, long long ss_stride, int B, int rows_per_sample, int C,
                      void* stream);
 /* F.silu feeding the adaLN / kv mappers (:812, :1031): y bf16 = silu(x), n % 8 == 0. */
 int muse_silu_bf16(const void* x, int x_dtype, void* y, long long n, void* stream);
+/* Backward of the five ops above (training of MaskGiTUViT_v2).  Reductions accumulate (+=) into zero-initialised buffers.
+ * add_norm_mod: dy = grad of y, dr_out = grad of the prenorm-residual output (nullable), x = the saved r_out;
+ *   g = norm_bwd(dy * (1 + scale)) + dr_out is written to da (grad of a) and dr (grad of r, nullable); dw[H] +=,
+ *   dscale_shift[b] += (sum_rows dy * n | sum_rows dy) with the layout of scale_shift. */
+int muse_add_norm_mod_bwd(const void* dy, int dy_dtype, const float* dr_out, const float* x, const float* w,
+                          const float* scale_shift, long long ss_stride, int rows_per_sample, void* da, int da_dtype,
+                          float* dr, float* dw, float* dscale_shift, int rows, int H, float eps, int rms, void* stream);
+/* dy bf16 = grad of the normalised output, conv = conv_out saved by the forward, x = the forward input; dc_ws fp32
+ * [B*h*w, C] scratch; dx fp32 = dres (nullable) + transposed depthwise conv of d_conv; dwk [9,C], dnorm_w [C] +=. */
+int muse_dwconv3x3_norm_bwd(const void* dy, const void* conv, const float* x, const float* wk, const float* norm_w,
+                            const float* dres, float* dc_ws, float* dx, float* dwk, float* dnorm_w, int B, int h, int w,
+                            int C, float eps, int rms, void* stream);
+/* x = forward input (bf16), dout bf16, nx / sumsq from the forward, s1_ws fp32 [B,C] scratch -> dx bf16; dgamma, dbeta +=. */
+int muse_grn_bwd(const void* x, const void* dout, const float* nx, const float* sumsq, const float* gamma, float* s1_ws,
+                 void* dx, float* dgamma, float* dbeta, int B, int HW, int C, void* stream);
+/* y = x * (1 + scale_b) + shift_b: dx = dy * (1 + scale_b); dscale_shift[b] += (sum dy * x | sum dy). */
+int muse_adaln_bwd(const float* dy, const float* x, const float* scale_shift, long long ss_stride, float* dx,
+                   float* dscale_shift, int B, int rows_per_sample, int C, void* stream);
+/* dx (+)= dy * silu'(x); dy bf16, x / dx dtype codes (bf16/bf16, bf16/fp32, fp32/fp32). */
+int muse_silu_bwd(const void* dy, const void* x, int x_dtype, void* dx, int dx_dtype, long long n, int accumulate,
+                  void* stream);
 
 /* VectorQuantizer.get_code (muse/modeling_maskgit_vqgan.py:303-316,342-348): ids[r] = argmin_c
  * fl(fl(|z_r|^2 + |e_c|^2) - 2 z_r.e_c), first minimum. z fp32 [n,D] (NHWC-flattened), codebook fp32

@@ -36,8 +36,13 @@ SIGNATURES = {
     "muse_ce_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "muse_ce_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "muse_add_norm_mod_fwd": (c_int, [_P, _I, _P, _P, _P, _L, _I, _P, _P, _I, _I, _I, _F, _I, _P]),
-    "muse_dwconv3x3_norm_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
-    "muse_grn_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "muse_dwconv3x3_norm_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "muse_grn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "muse_add_norm_mod_bwd": (c_int, [_P, _I, _P, _P, _P, _P, _L, _I, _P, _I, _P, _P, _P, _I, _I, _F, _I, _P]),
+    "muse_dwconv3x3_norm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "muse_grn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "muse_adaln_bwd": (c_int, [_P, _P, _P, _L, _P, _P, _I, _I, _I, _P]),
+    "muse_silu_bwd": (c_int, [_P, _P, _I, _P, _I, _L, _I, _P]),
     "muse_adaln_apply": (c_int, [_P, _P, _L, _I, _I, _I, _P]),
     "muse_silu_bf16": (c_int, [_P, _I, _P, _L, _P]),
     "muse_vq_argmin": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),

@@ -43,8 +43,13 @@ int ce_bwd(const void*, const long long*, const float*, const float*, const floa
 int vq_argmin(const float*, const float*, float*, long long*, float*, int, int, int, cudaStream_t);
 int vq_lookup_nchw(const long long*, const float*, float*, int, int, int, int, cudaStream_t);
 int add_norm_mod_fwd(const void*, int, const float*, const float*, const float*, long long, int, float*, void*, int, int, int, float, int, cudaStream_t);
-int dwconv3x3_norm_fwd(const float*, const float*, const float*, void*, int, int, int, int, float, int, cudaStream_t);
-int grn_fwd(const void*, const float*, const float*, void*, float*, int, int, int, cudaStream_t);
+int dwconv3x3_norm_fwd(const float*, const float*, const float*, void*, void*, int, int, int, int, float, int, cudaStream_t);
+int grn_fwd(const void*, const float*, const float*, void*, float*, float*, int, int, int, cudaStream_t);
+int add_norm_mod_bwd(const void*, int, const float*, const float*, const float*, const float*, long long, int, void*, int, float*, float*, float*, int, int, float, int, cudaStream_t);
+int dwconv3x3_norm_bwd(const void*, const void*, const float*, const float*, const float*, const float*, float*, float*, float*, float*, int, int, int, int, float, int, cudaStream_t);
+int grn_bwd(const void*, const void*, const float*, const float*, const float*, float*, void*, float*, float*, int, int, int, cudaStream_t);
+int adaln_bwd(const float*, const float*, const float*, long long, float*, float*, int, int, int, cudaStream_t);
+int silu_bwd(const void*, const void*, int, void*, int, long long, int, cudaStream_t);
 int adaln_apply(float*, const float*, long long, int, int, int, cudaStream_t);
 int silu_bf16(const void*, int, void*, long long, cudaStream_t);
 int vq_soft_code(const float*, const float*, float*, float*, long long*, const float*, float, int, int, int, cudaStream_t);
@@ -151,13 +156,36 @@ int muse_add_norm_mod_fwd(const void* a, int a_dtype, const float* r, const floa
   return add_norm_mod_fwd(a, a_dtype, r, w, scale_shift, ss_stride, rows_per_sample, r_out, y, y_dtype, rows, H, eps, rms,
                           ST(stream));
 }
-int muse_dwconv3x3_norm_fwd(const float* x, const float* wk, const float* norm_w, void* y, int B, int h, int w, int C,
-                            float eps, int rms, void* stream) {
-  return dwconv3x3_norm_fwd(x, wk, norm_w, y, B, h, w, C, eps, rms, ST(stream));
+int muse_dwconv3x3_norm_fwd(const float* x, const float* wk, const float* norm_w, void* y, void* conv_out, int B, int h,
+                            int w, int C, float eps, int rms, void* stream) {
+  return dwconv3x3_norm_fwd(x, wk, norm_w, y, conv_out, B, h, w, C, eps, rms, ST(stream));
 }
-int muse_grn_fwd(const void* x, const float* gamma, const float* beta, void* out, float* stat_ws, int B, int HW, int C,
-                 void* stream) {
-  return grn_fwd(x, gamma, beta, out, stat_ws, B, HW, C, ST(stream));
+int muse_grn_fwd(const void* x, const float* gamma, const float* beta, void* out, float* sumsq_ws, float* nx_ws, int B,
+                 int HW, int C, void* stream) {
+  return grn_fwd(x, gamma, beta, out, sumsq_ws, nx_ws, B, HW, C, ST(stream));
+}
+int muse_add_norm_mod_bwd(const void* dy, int dy_dtype, const float* dr_out, const float* x, const float* w,
+                          const float* scale_shift, long long ss_stride, int rows_per_sample, void* da, int da_dtype,
+                          float* dr, float* dw, float* dscale_shift, int rows, int H, float eps, int rms, void* stream) {
+  return add_norm_mod_bwd(dy, dy_dtype, dr_out, x, w, scale_shift, ss_stride, rows_per_sample, da, da_dtype, dr, dw,
+                          dscale_shift, rows, H, eps, rms, ST(stream));
+}
+int muse_dwconv3x3_norm_bwd(const void* dy, const void* conv, const float* x, const float* wk, const float* norm_w,
+                            const float* dres, float* dc_ws, float* dx, float* dwk, float* dnorm_w, int B, int h, int w,
+                            int C, float eps, int rms, void* stream) {
+  return dwconv3x3_norm_bwd(dy, conv, x, wk, norm_w, dres, dc_ws, dx, dwk, dnorm_w, B, h, w, C, eps, rms, ST(stream));
+}
+int muse_grn_bwd(const void* x, const void* dout, const float* nx, const float* sumsq, const float* gamma, float* s1_ws,
+                 void* dx, float* dgamma, float* dbeta, int B, int HW, int C, void* stream) {
+  return grn_bwd(x, dout, nx, sumsq, gamma, s1_ws, dx, dgamma, dbeta, B, HW, C, ST(stream));
+}
+int muse_adaln_bwd(const float* dy, const float* x, const float* scale_shift, long long ss_stride, float* dx,
+                   float* dscale_shift, int B, int rows_per_sample, int C, void* stream) {
+  return adaln_bwd(dy, x, scale_shift, ss_stride, dx, dscale_shift, B, rows_per_sample, C, ST(stream));
+}
+int muse_silu_bwd(const void* dy, const void* x, int x_dtype, void* dx, int dx_dtype, long long n, int accumulate,
+                  void* stream) {
+  return silu_bwd(dy, x, x_dtype, dx, dx_dtype, n, accumulate, ST(stream));
 }
 int muse_adaln_apply(float* x, const float* scale_shift, long long ss_stride, int B, int rows_per_sample, int C,
                      void* stream) {

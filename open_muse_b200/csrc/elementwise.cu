@@ -225,6 +225,7 @@ int embed_bwd(const long long* ids, const float* dx, float* dword, float* dpos, 
   else embed_bwd_word_generic_kernel<<<ceil_div(tokens, 4), 128, 0, s>>>(ids, dx, dword, tokens, H, vocab);
   int rc = check_launch("embed_bwd_word");
   if (rc) return rc;
+  if (dpos == nullptr) return MUSE_OK;  // no position table (ConvEmbed of MaskGiTUViT_v2)
   embed_bwd_pos_kernel<<<dim3(S, ceil_div(H, 128)), 128, 0, s>>>(dx, dpos, B, S, H);
   return check_launch("embed_bwd_pos");
 }

@@ -91,7 +91,7 @@ add_norm_mod_kernel(const TA* __restrict__ a, const float* __restrict__ r, const
 template <int CH>
 __global__ void __launch_bounds__(kWarps * 32)
 dwconv3x3_norm_kernel(const float* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ nw,
-                      bf16* __restrict__ y, int B, int hh, int ww, int C, float eps, int rms) {
+                      bf16* __restrict__ y, bf16* __restrict__ conv_out, int B, int hh, int ww, int C, float eps, int rms) {
   const int lane = threadIdx.x & 31;
   const long long pix = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
   if (pix >= static_cast<long long>(B) * hh * ww) return;
@@ -122,6 +122,7 @@ dwconv3x3_norm_kernel(const float* __restrict__ x, const float* __restrict__ wk,
         v[c][j] = bf16_round(v[c][j]);  // the conv output is a bf16 tensor under autocast
         sum += v[c][j];
       }
+      if (conv_out != nullptr) store8(conv_out + pix * C + col, v[c]);  // saved for the backward pass
     }
   }
   const float inv_c = 1.0f / static_cast<float>(C);
@@ -170,11 +171,12 @@ grn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ sumsq, int HW, 
   sumsq[static_cast<size_t>(b) * C + c + 1] = s1;
 }
 
-// GRN pass 2 (one CTA per image): nx[c] = sqrt(sumsq[c]) / (mean_c sqrt(sumsq) + 1e-6), in place
+// GRN pass 2 (one CTA per image): nx[c] = sqrt(sumsq[c]) / (mean_c sqrt(sumsq) + 1e-6)
 __global__ void __launch_bounds__(256)
-grn_finalize_kernel(float* __restrict__ stat, int C) {
+grn_finalize_kernel(const float* __restrict__ stat, float* __restrict__ nx_out, int C) {
   __shared__ float s_part[8];
-  float* p = stat + static_cast<size_t>(blockIdx.x) * C;
+  const float* p = stat + static_cast<size_t>(blockIdx.x) * C;
+  float* o = nx_out + static_cast<size_t>(blockIdx.x) * C;
   float acc = 0.f;
   for (int c = threadIdx.x; c < C; c += 256) acc += sqrtf(p[c]);
   acc = warp_sum(acc);
@@ -184,7 +186,7 @@ grn_finalize_kernel(float* __restrict__ stat, int C) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) tot += s_part[i];
   const float denom = tot / static_cast<float>(C) + 1e-6f;
-  for (int c = threadIdx.x; c < C; c += 256) p[c] = sqrtf(p[c]) / denom;
+  for (int c = threadIdx.x; c < C; c += 256) o[c] = sqrtf(p[c]) / denom;
 }
 
 // GRN pass 3: out = gamma * (g * nx) + beta + g, g = bf16(gelu(x)); 8 channels per thread
@@ -269,34 +271,35 @@ int add_norm_mod_fwd(const void* a, int a_dt, const float* r, const float* w, co
   return MUSE_ERR_INVALID;
 }
 
-int dwconv3x3_norm_fwd(const float* x, const float* wk, const float* nw, void* y, int B, int hh, int ww, int C, float eps,
-                       int rms, cudaStream_t s) {
+int dwconv3x3_norm_fwd(const float* x, const float* wk, const float* nw, void* y, void* conv_out, int B, int hh, int ww,
+                       int C, float eps, int rms, cudaStream_t s) {
   const long long pixels = static_cast<long long>(B) * hh * ww;
   if (pixels <= 0) return MUSE_OK;
   if (C % 8 != 0 || C > 1024) { set_last_error("dwconv3x3_norm: C=%d must be a multiple of 8 and <= 1024", C); return MUSE_ERR_UNSUPPORTED; }
   const unsigned grid = static_cast<unsigned>(ceil_div_ll(pixels, kWarps));
   bf16* yp = reinterpret_cast<bf16*>(y);
-  if (C <= 256) dwconv3x3_norm_kernel<1><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, B, hh, ww, C, eps, rms);
-  else if (C <= 512) dwconv3x3_norm_kernel<2><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, B, hh, ww, C, eps, rms);
-  else if (C <= 768) dwconv3x3_norm_kernel<3><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, B, hh, ww, C, eps, rms);
-  else dwconv3x3_norm_kernel<4><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, B, hh, ww, C, eps, rms);
+  bf16* cp = reinterpret_cast<bf16*>(conv_out);
+  if (C <= 256) dwconv3x3_norm_kernel<1><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
+  else if (C <= 512) dwconv3x3_norm_kernel<2><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
+  else if (C <= 768) dwconv3x3_norm_kernel<3><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
+  else dwconv3x3_norm_kernel<4><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
   return check_launch("dwconv3x3_norm");
 }
 
-// x bf16 [B, HW, C] -> out bf16 [B, HW, C]; stat_ws fp32 [B, C] scratch
-int grn_fwd(const void* x, const float* gamma, const float* beta, void* out, float* stat_ws, int B, int HW, int C,
-            cudaStream_t s) {
+// x bf16 [B, HW, C] -> out bf16 [B, HW, C]; sumsq_ws / nx_ws fp32 [B, C] (kept by the caller for the backward pass)
+int grn_fwd(const void* x, const float* gamma, const float* beta, void* out, float* stat_ws, float* nx_ws, int B, int HW,
+            int C, cudaStream_t s) {
   if (B <= 0 || HW <= 0) return MUSE_OK;
   if (C % 8 != 0) { set_last_error("grn: C must be a multiple of 8"); return MUSE_ERR_UNSUPPORTED; }
   const bf16* xp = reinterpret_cast<const bf16*>(x);
   grn_stats_kernel<<<dim3(ceil_div(C, 256), B), 128, 0, s>>>(xp, stat_ws, HW, C);
   int rc = check_launch("grn_stats");
   if (rc) return rc;
-  grn_finalize_kernel<<<B, 256, 0, s>>>(stat_ws, C);
+  grn_finalize_kernel<<<B, 256, 0, s>>>(stat_ws, nx_ws, C);
   rc = check_launch("grn_finalize");
   if (rc) return rc;
   const long long total8 = static_cast<long long>(B) * HW * (C / 8);
-  grn_apply_kernel<<<static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s>>>(xp, stat_ws, gamma, beta,
+  grn_apply_kernel<<<static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s>>>(xp, nx_ws, gamma, beta,
                                                                                    reinterpret_cast<bf16*>(out), total8, HW, C);
   return check_launch("grn_apply");
 }

@@ -5,10 +5,10 @@ MaskGiTUViT_v2(**cfg)`` reproduces the reference's initial weights, including th
 ``forward(input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels=, label_smoothing=, loss_weight=)`` and the
 classifier-free-guidance ``generate2`` (:330-479).
 
-Round-1 status: the INFERENCE path runs on libmuse_b200 (tcgen05 GEMMs, tcgen05 attention, fused prenorm-residual norm +
-adaLN modulation, depthwise-conv + Norm2D, GELU + GlobalResponseNorm, fused decode step); the backward pass of the new
-blocks is not built yet, so ``forward`` in training mode raises instead of silently returning gradient-free outputs
-(DESIGN.md section 7).  The modules below are parameter containers; the arithmetic lives in ``_forward_tokens``.
+Everything runs on libmuse_b200: tcgen05 GEMMs for every Linear / 1x1 conv, tcgen05 attention, fused prenorm-residual
+norm + adaLN modulation, depthwise-conv + Norm2D, GELU + GlobalResponseNorm, the fused decode step; training goes through
+one autograd Function for the whole network (``uvit_v2_train.py``: forward with saved activations + hand-written backward).
+The modules below are parameter containers; the inference arithmetic lives in ``_forward_tokens``.
 Activations are token-major ``[B*h*w, C]`` throughout -- the NCHW <-> NHWC permutes of the reference disappear.
 """
 from __future__ import annotations
@@ -406,12 +406,22 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
 
     def forward(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels=None, label_smoothing=0.0,
                 loss_weight=None, _raw_bf16=False):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError(
-                "open_muse_b200.MaskGiTUViT_v2: only the inference path is built (call .eval() / torch.no_grad()); the "
-                "backward pass of the U-ViT blocks is the next item in DESIGN.md section 7")
         c = self.config
         B, S = input_ids.shape
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training: one autograd Function for the whole network (uvit_v2_train.py)
+            if loss_weight is not None:
+                raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: loss_weight is supported in evaluation only")
+            if self.training and (c.hidden_dropout > 0.0 or c.attention_dropout > 0.0):
+                raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: dropout > 0 in training mode is not implemented")
+            from .uvit_v2_train import UViTTrainFn
+
+            padded, loss = UViTTrainFn.apply(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels,
+                                             label_smoothing, *self.parameters())
+            logits = padded.view(B, S, -1)[:, :, : c.codebook_size]
+            if not (_raw_bf16 or torch.is_autocast_enabled()):
+                logits = logits.float()
+            return logits if labels is None else (logits, loss)
         with torch.no_grad():
             padded = self._forward_tokens(input_ids, encoder_hidden_states, cond_embeds, micro_conds)
             V = c.codebook_size

@@ -50,7 +50,8 @@ def _p(t):
 
 
 _KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
-                     "muse_groupnorm_silu_nhwc": 3, "muse_grn_fwd": 3}
+                     "muse_groupnorm_silu_nhwc": 3, "muse_grn_fwd": 3, "muse_grn_bwd": 3,
+                     "muse_dwconv3x3_norm_bwd": 2}
 _prof = {"on": False, "events": []}
 
 
@@ -104,6 +105,13 @@ def linear_dgrad(dy, w, out_dtype=torch.bfloat16):
     K = w.shape[1]
     dx = torch.empty(T, K, dtype=out_dtype, device=dy.device)
     return gemm(dy, w, dx, T, K, N, dy.stride(0), w.stride(0), K, 0, 1, EPI_BF16 if out_dtype == torch.bfloat16 else EPI_F32)
+
+
+def linear_dgrad_acc(dy, w, acc):
+    """acc[T,K] (fp32) += dy[T,N] @ w[N,K]: gradients of a tensor consumed by many GEMMs (text states of U-ViT)."""
+    T, N = dy.shape
+    K = w.shape[1]
+    return gemm(dy, w, acc, T, K, N, dy.stride(0), w.stride(0), acc.stride(0), 0, 1, EPI_ATOMIC_F32)
 
 
 def linear_wgrad(dy, x, dw):
@@ -242,23 +250,80 @@ def add_norm_mod(a, w, eps, rms, out_dtype=torch.bfloat16, residual=None, mod=No
     return r_out, y
 
 
-def dwconv3x3_norm(x, wk, norm_w, B, hh, ww, eps, rms):
-    """x fp32 [B*hh*ww, C] token-major, wk fp32 [9, C] -> bf16 [B*hh*ww, C] = Norm2D(depthwise3x3(x))."""
+def dwconv3x3_norm(x, wk, norm_w, B, hh, ww, eps, rms, save_conv=False):
+    """x fp32 [B*hh*ww, C] token-major, wk fp32 [9, C] -> bf16 [B*hh*ww, C] = Norm2D(depthwise3x3(x)).
+    save_conv: also return the bf16 conv output (needed by dwconv3x3_norm_bwd)."""
     st = _prep(x)
     C = x.shape[1]
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _call("muse_dwconv3x3_norm_fwd", _p(x), _p(wk), _p(norm_w), _p(y), B, hh, ww, C, float(eps), int(rms), st)
-    return y
+    conv = torch.empty_like(y) if save_conv else None
+    _call("muse_dwconv3x3_norm_fwd", _p(x), _p(wk), _p(norm_w), _p(y), _p(conv), B, hh, ww, C, float(eps), int(rms), st)
+    return (y, conv) if save_conv else y
 
 
-def grn(x, gamma, beta, B, HW):
-    """bf16 [B*HW, C] -> bf16: GELU + GlobalResponseNorm."""
+def grn(x, gamma, beta, B, HW, save_stats=False):
+    """bf16 [B*HW, C] -> bf16: GELU + GlobalResponseNorm.  save_stats: also return (sumsq, nx) for grn_bwd."""
     st = _prep(x)
     C = x.shape[1]
     out = torch.empty_like(x)
+    ws = torch.empty(2, B, C, dtype=torch.float32, device=x.device)
+    _call("muse_grn_fwd", _p(x), _p(gamma), _p(beta), _p(out), _p(ws[0]), _p(ws[1]), B, HW, C, st)
+    return (out, ws) if save_stats else out
+
+
+def add_norm_mod_bwd(dy, dr_out, x_saved, w, eps, rms, da_dtype, mod=None, rows_per_sample=1, dw=None, dmod=None,
+                     want_dr=True):
+    """Backward of add_norm_mod: returns (da, dr); dw [H] and dmod (view with the layout of mod) are accumulated."""
+    st = _prep(x_saved)
+    rows, H = x_saved.shape
+    da = torch.empty(rows, H, dtype=da_dtype, device=x_saved.device)
+    dr = torch.empty(rows, H, dtype=torch.float32, device=x_saved.device) if want_dr else None
+    _call("muse_add_norm_mod_bwd", _p(dy), _dt(dy), _p(dr_out), _p(x_saved), _p(w), _p(mod),
+          0 if mod is None else mod.stride(0), int(rows_per_sample), _p(da), _dt(da), _p(dr), _p(dw), _p(dmod), rows, H,
+          float(eps), int(rms), st)
+    return da, dr
+
+
+def dwconv3x3_norm_bwd(dy, conv, x, wk, norm_w, dres, dwk, dnw, B, hh, ww, eps, rms):
+    st = _prep(x)
+    C = x.shape[1]
+    ws = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    _call("muse_dwconv3x3_norm_bwd", _p(dy), _p(conv), _p(x), _p(wk), _p(norm_w), _p(dres), _p(ws), _p(dx), _p(dwk), _p(dnw),
+          B, hh, ww, C, float(eps), int(rms), st)
+    return dx
+
+
+def grn_bwd(x, dout, stats, gamma, dgamma, dbeta, B, HW):
+    st = _prep(x)
+    C = x.shape[1]
+    dx = torch.empty_like(x)
     ws = torch.empty(B, C, dtype=torch.float32, device=x.device)
-    _call("muse_grn_fwd", _p(x), _p(gamma), _p(beta), _p(out), _p(ws), B, HW, C, st)
+    _call("muse_grn_bwd", _p(x), _p(dout), _p(stats[1]), _p(stats[0]), _p(gamma), _p(ws), _p(dx), _p(dgamma), _p(dbeta), B, HW,
+          C, st)
+    return dx
+
+
+def adaln_bwd(dy, x, mod, dmod, B, rows_per_sample):
+    st = _prep(x)
+    dx = torch.empty_like(x)
+    _call("muse_adaln_bwd", _p(dy), _p(x), _p(mod), mod.stride(0), _p(dx), _p(dmod), B, int(rows_per_sample), x.shape[1], st)
+    return dx
+
+
+def silu_bwd(dy, x, out=None, out_dtype=None):
+    """dx = dy * silu'(x); out given: accumulate into it."""
+    st = _prep(x)
+    acc = out is not None
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    _call("muse_silu_bwd", _p(dy), _p(x), _dt(x), _p(out), _dt(out), x.numel(), 1 if acc else 0, st)
     return out
+
+
+def adaln_apply(x, mod, B, rows_per_sample):
+    """out-of-place variant (training keeps the pre-modulation tensor for the backward pass)."""
+    return adaln_apply_(x.clone(), mod, B, rows_per_sample)
 
 
 def adaln_apply_(x, mod, B, rows_per_sample):

@@ -1,0 +1,382 @@
+"""Training step (forward with saved activations + hand-written backward) of ``MaskGiTUViT_v2`` on libmuse_b200.
+
+One ``torch.autograd.Function`` covers the whole network: its forward is the inference path of
+``modeling_transformer_v2.py`` with the activations each backward kernel needs kept alive, its backward walks the blocks in
+reverse and returns the gradient of every parameter (reference names, fp32).  All arithmetic is in the C-ABI kernels: tcgen05
+GEMMs for every Linear / 1x1 conv (dgrad with an MN-major weight operand, split-K wgrad), tcgen05 attention backward, and
+the U-ViT kernels of csrc/uvit_bwd.cu.  Things that are single tensors consumed by many blocks get ONE accumulator:
+the text states (fp32, atomic-accumulating dgrad) and the stacked adaLN mapper output ``mod_all`` (each op adds into its own
+column slice), so no gradient is summed with eager ops.
+
+Because all parameter gradients appear when this one Function returns, DDP's bucket all-reduces do not overlap the
+backward pass of this model yet (the v1 model uses one Function per layer for that reason) -- see DESIGN.md.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _z(like, dtype=F32):
+    return torch.zeros(like.shape, dtype=dtype, device=like.device)
+
+
+def _lin_bwd(dy, x, w, g, dx_dtype=BF16, need_dx=True):
+    """y = x @ w^T: g (fp32, same shape as w) += dy^T x ; returns dx = dy @ w."""
+    ops.linear_wgrad(dy, x, g)
+    return ops.linear_dgrad(dy, w, out_dtype=dx_dtype) if need_dx else None
+
+
+class _G(dict):
+    """fp32 gradient buffers mirroring the packed-weight dict W (created on first use)."""
+
+    def __init__(self, W):
+        super().__init__()
+        self.W = W
+
+    def of(self, key):
+        if key not in self:
+            self[key] = _z(self.W[key])
+        return self[key]
+
+
+def _sub(G, W, key, idx=None):
+    """gradient dict for a nested block of W (W[key] is a dict, or a list of dicts when idx is given)."""
+    holder = G.setdefault(key, {} if idx is None else {})
+    if idx is None:
+        if not isinstance(holder, _G):
+            holder = G[key] = _G(W[key])
+        return holder
+    if idx not in holder:
+        holder[idx] = _G(W[key][idx])
+    return holder[idx]
+
+
+# ------------------------------------------------------------------------------------------------ attention helper
+def _attn_fwd(y, ctx_in, a, B, S, Skv, fused):
+    Hc = a["o"].shape[0]
+    if fused:
+        qkv = ops.linear_fwd(y, a["qkv"])
+        q, k, v = qkv[:, :Hc], qkv[:, Hc:2 * Hc], qkv[:, 2 * Hc:]
+        saved = qkv
+    else:
+        q = ops.linear_fwd(y, a["q"])
+        kv = ops.linear_fwd(ctx_in, a["kv"])
+        k, v = kv[:, :Hc], kv[:, Hc:]
+        saved = (q, kv)
+    o, lse = ops.attn_fwd(q, k, v, B, a["nh"], S, Skv, 0.125)
+    return o, (saved, o, lse)
+
+
+def _attn_bwd(do, y, ctx_in, a, ga, st, B, S, Skv, fused, d_ctx_acc=None):
+    """returns dy (bf16); the context gradient is accumulated into d_ctx_acc (fp32) for cross attention."""
+    saved, o, lse = st
+    Hc = a["o"].shape[0]
+    if fused:
+        qkv = saved
+        dqkv = torch.empty_like(qkv)
+        ops.attn_bwd(qkv[:, :Hc], qkv[:, Hc:2 * Hc], qkv[:, 2 * Hc:], o, do, lse, dqkv[:, :Hc], dqkv[:, Hc:2 * Hc],
+                     dqkv[:, 2 * Hc:], B, a["nh"], S, Skv, 0.125)
+        return _lin_bwd(dqkv, y, a["qkv"], ga.of("qkv"))
+    q, kv = saved
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    ops.attn_bwd(q, kv[:, :Hc], kv[:, Hc:], o, do, lse, dq, dkv[:, :Hc], dkv[:, Hc:], B, a["nh"], S, Skv, 0.125)
+    ops.linear_wgrad(dkv, ctx_in, ga.of("kv"))
+    ops.linear_dgrad_acc(dkv, a["kv"], d_ctx_acc)
+    return _lin_bwd(dq, y, a["q"], ga.of("q"))
+
+
+# ------------------------------------------------------------------------------------------------ blocks
+def _res_block_fwd(h, w, mod_all, B, hw, eps, rms):
+    d, conv = ops.dwconv3x3_norm(h, w["dw"], w["dw_norm"], B, hw, hw, eps, rms, save_conv=True)
+    g1 = ops.linear_fwd(d, w["cw0"])
+    g2, stats = ops.grn(g1, w["gamma"], w["beta"], B, hw * hw, save_stats=True)
+    h2 = ops.linear_fwd(g2, w["cw4"], res=h)
+    o, n = w["mod"]
+    h3 = ops.adaln_apply(h2, mod_all[:, o:o + n], B, hw * hw)
+    return h3, (h, d, conv, g1, g2, stats, h2)
+
+
+def _res_block_bwd(dh3, st, w, g, mod_all, d_mod_all, B, hw, eps, rms):
+    h, d, conv, g1, g2, stats, h2 = st
+    o, n = w["mod"]
+    dh2 = ops.adaln_bwd(dh3, h2, mod_all[:, o:o + n], d_mod_all[:, o:o + n], B, hw * hw)
+    dg2 = _lin_bwd(ops.cast_bf16(dh2), g2, w["cw4"], g.of("cw4"))
+    dg1 = ops.grn_bwd(g1, dg2, stats, w["gamma"], g.of("gamma"), g.of("beta"), B, hw * hw)
+    dd = _lin_bwd(dg1, d, w["cw0"], g.of("cw0"))
+    return ops.dwconv3x3_norm_bwd(dd, conv, h, w["dw"], w["dw_norm"], dh2, g.of("dw"), g.of("dw_norm"), B, hw, hw, eps, rms)
+
+
+def _attn_block_fwd(h, enc, w, B, S, Skv, eps, rms):
+    se = encb = None
+    if w["kvm"] is not None:
+        se = ops.silu_bf16(enc)
+        encb = ops.linear_fwd(se, w["kvm"])
+    ctx_in = enc if encb is None else encb
+    _, y1 = ops.add_norm_mod(h, w["ln1"], eps, rms, want_residual=False)
+    c1, s1 = _attn_fwd(y1, ctx_in, w["a1"], B, S, Skv, False)
+    a1o = ops.linear_fwd(c1, w["a1"]["o"])
+    r2, y2 = ops.add_norm_mod(a1o, w["ln2"], eps, rms, residual=h)
+    c2, s2 = _attn_fwd(y2, ctx_in, w["a2"], B, S, Skv, False)
+    out = ops.linear_fwd(c2, w["a2"]["o"], res=r2)
+    return out, (h, se, ctx_in, y1, c1, s1, r2, y2, c2, s2)
+
+
+def _attn_block_bwd(dout, st, w, g, enc, d_enc, B, S, Skv, eps, rms):
+    h, se, ctx_in, y1, c1, s1, r2, y2, c2, s2 = st
+    g1, g2 = _sub(g, w, "a1"), _sub(g, w, "a2")
+    d_ctx = d_enc if se is None else _z(ctx_in)  # fp32 accumulator of the (mapped) text states of this block
+    dc2 = _lin_bwd(ops.cast_bf16(dout), c2, w["a2"]["o"], g2.of("o"))
+    dy2 = _attn_bwd(dc2, y2, ctx_in, w["a2"], g2, s2, B, S, Skv, False, d_ctx)
+    da1o, dh_res = ops.add_norm_mod_bwd(dy2, dout, r2, w["ln2"], eps, rms, BF16, dw=g.of("ln2"))
+    dc1 = _lin_bwd(da1o, c1, w["a1"]["o"], g1.of("o"))
+    dy1 = _attn_bwd(dc1, y1, ctx_in, w["a1"], g1, s1, B, S, Skv, False, d_ctx)
+    dh, _ = ops.add_norm_mod_bwd(dy1, dh_res, h, w["ln1"], eps, rms, F32, dw=g.of("ln1"), want_dr=False)
+    if se is not None:  # kv_mapper(silu(enc))
+        d_se = _lin_bwd(ops.cast_bf16(d_ctx), se, w["kvm"], g.of("kvm"))
+        ops.silu_bwd(d_se, enc, out=d_enc)
+    return dh
+
+
+def _layer_fwd(x, r, enc, w, mod_all, B, S, Skv, H, eps, rms):
+    m = lambda k: mod_all[:, w[k][0]:w[k][0] + w[k][1]]
+    r1, y1 = ops.add_norm_mod(x, w["ln1"], eps, rms, residual=r, mod=m("mod1"), rows_per_sample=S)
+    c, s_sa = _attn_fwd(y1, None, w["sa"], B, S, S, True)
+    a = ops.linear_fwd(c, w["sa"]["o"])
+    r2, y2 = ops.add_norm_mod(a, w["ln2"], eps, rms, residual=r1, mod=m("mod2"), rows_per_sample=S)
+    cc, s_ca = _attn_fwd(y2, enc, w["ca"], B, S, Skv, False)
+    co = ops.linear_fwd(cc, w["ca"]["o"])
+    r3, y3 = ops.add_norm_mod(co, w["ln3"], eps, 0, residual=r2, mod=m("mod3"), rows_per_sample=S)
+    ab = ops.linear_fwd(y3, w["wi"])
+    gl = ops.glu_fwd(ab)
+    f = ops.linear_fwd(gl, w["wo"])
+    return f, r3, (r is not None, r1, y1, c, s_sa, r2, y2, cc, s_ca, r3, y3, ab, gl)
+
+
+def _layer_bwd(df, dr3, st, w, g, enc, d_enc, mod_all, d_mod_all, B, S, Skv, eps, rms):
+    had_r, r1, y1, c, s_sa, r2, y2, cc, s_ca, r3, y3, ab, gl = st
+    m = lambda t, k: t[:, w[k][0]:w[k][0] + w[k][1]]
+    gsa, gca = _sub(g, w, "sa"), _sub(g, w, "ca")
+    dgl = _lin_bwd(df, gl, w["wo"], g.of("wo"))
+    dy3 = _lin_bwd(ops.glu_bwd(ab, dgl), y3, w["wi"], g.of("wi"))
+    dco, dr2 = ops.add_norm_mod_bwd(dy3, dr3, r3, w["ln3"], eps, 0, BF16, mod=m(mod_all, "mod3"), rows_per_sample=S,
+                                    dw=g.of("ln3"), dmod=m(d_mod_all, "mod3"))
+    dcc = _lin_bwd(dco, cc, w["ca"]["o"], gca.of("o"))
+    dy2 = _attn_bwd(dcc, y2, enc, w["ca"], gca, s_ca, B, S, Skv, False, d_enc)
+    da, dr1 = ops.add_norm_mod_bwd(dy2, dr2, r2, w["ln2"], eps, rms, BF16, mod=m(mod_all, "mod2"), rows_per_sample=S,
+                                   dw=g.of("ln2"), dmod=m(d_mod_all, "mod2"))
+    dc = _lin_bwd(da, c, w["sa"]["o"], gsa.of("o"))
+    dy1 = _attn_bwd(dc, y1, None, w["sa"], gsa, s_sa, B, S, S, True)
+    dx, dr = ops.add_norm_mod_bwd(dy1, dr1, r1, w["ln1"], eps, rms, BF16, mod=m(mod_all, "mod1"), rows_per_sample=S,
+                                  dw=g.of("ln1"), dmod=m(d_mod_all, "mod1"), want_dr=had_r)
+    return dx, dr
+
+
+# ------------------------------------------------------------------------------------------------ whole network
+def forward(model, W, input_ids, encoder_hidden_states, cond_embeds, micro_conds):
+    """Inference-identical forward that also returns the saved state for ``backward``."""
+    from .modeling_transformer_v2 import sinusoidal_encode
+
+    c = model.config
+    B, S = input_ids.shape
+    hw = int(S ** 0.5)
+    rms, eps, H = (0 if c.norm_type == "layernorm" else 1), c.layer_norm_eps, c.hidden_size
+    Skv = encoder_hidden_states.shape[1]
+    ehs = encoder_hidden_states.reshape(B * Skv, -1).to(BF16).contiguous()
+    r_enc, enc = ops.add_norm_mod(ops.linear_fwd(ehs, W["encoder_proj"]), W["enc_norm"], eps, rms)
+    mc = sinusoidal_encode(micro_conds.flatten(), c.micro_cond_encode_dim).reshape(B, -1)
+    cond_in = torch.cat([cond_embeds.float(), mc], dim=1).to(BF16).contiguous()
+    c1 = ops.linear_fwd(cond_in, W["cond0"])
+    c1s = ops.silu_bf16(c1)
+    cond = ops.linear_fwd(c1s, W["cond2"])
+    sc = ops.silu_bf16(cond)
+    mod_all = ops.linear_fwd(sc, W["mappers"], out_dtype=F32)
+    ids = input_ids.contiguous().to(torch.int64)
+    e = ops.embed_fwd(ids, W["emb"], None)
+    _, en = ops.add_norm_mod(e, W["emb_norm"], eps, rms, want_residual=False)
+    h = ops.linear_fwd(en, W["emb_conv"], out_dtype=F32)
+    blocks = {"down": [], "up": []}
+    for w in W["down"]:
+        h, s_r = _res_block_fwd(h, w, mod_all, B, hw, eps, rms)
+        h, s_a = _attn_block_fwd(h, enc, w, B, S, Skv, eps, rms)
+        blocks["down"].append((s_r, s_a))
+    h_down = h
+    _, y_pth = ops.add_norm_mod(h, W["pth_norm"], eps, rms, want_residual=False)
+    x, r, layers = ops.linear_fwd(y_pth, W["pth"]), None, []
+    for w in W["layers"]:
+        x, r, s_l = _layer_fwd(x, r, enc, w, mod_all, B, S, Skv, H, eps, rms)
+        layers.append(s_l)
+    r_f, y_f = ops.add_norm_mod(x, W["pfh_norm"], eps, rms, residual=r)
+    h = ops.linear_fwd(y_f, W["pfh"], out_dtype=F32)
+    for w in W["up"]:
+        h, s_r = _res_block_fwd(h, w, mod_all, B, hw, eps, rms)
+        h, s_a = _attn_block_fwd(h, enc, w, B, S, Skv, eps, rms)
+        blocks["up"].append((s_r, s_a))
+    hb = ops.cast_bf16(h)
+    y1 = ops.linear_fwd(hb, W["mlm1"])
+    r_m, y2 = ops.add_norm_mod(y1, W["mlm_norm"], eps, rms)
+    logits = ops.linear_fwd(y2, W["mlm2"])
+    saved = dict(B=B, S=S, hw=hw, Skv=Skv, ehs=ehs, r_enc=r_enc, enc=enc, cond_in=cond_in, c1=c1, c1s=c1s, cond=cond, sc=sc,
+                 mod_all=mod_all, ids=ids, e=e, en=en, blocks=blocks, h_down=h_down, y_pth=y_pth, layers=layers, r_f=r_f,
+                 y_f=y_f, hb=hb, y1=y1, r_m=r_m, y2=y2)
+    return logits, saved
+
+
+def backward(model, W, saved, d_logits):
+    """d_logits: bf16 [B*S, vpad].  Returns the nested fp32 gradient dict G mirroring W."""
+    c = model.config
+    s = saved
+    B, S, hw, Skv = s["B"], s["S"], s["hw"], s["Skv"]
+    rms, eps = (0 if c.norm_type == "layernorm" else 1), c.layer_norm_eps
+    enc, mod_all = s["enc"], s["mod_all"]
+    G = _G(W)
+    d_enc = _z(enc)          # fp32 accumulator: the text states feed every cross attention
+    d_mod = _z(mod_all)      # every adaLN op adds into its own column slice
+    # ConvMlmLayer
+    dy2 = _lin_bwd(d_logits, s["y2"], W["mlm2"], G.of("mlm2"))
+    dy1, _ = ops.add_norm_mod_bwd(dy2, None, s["r_m"], W["mlm_norm"], eps, rms, BF16, dw=G.of("mlm_norm"), want_dr=False)
+    dh = _lin_bwd(dy1, s["hb"], W["mlm1"], G.of("mlm1"), dx_dtype=F32)
+    for i in reversed(range(len(W["up"]))):
+        w, g = W["up"][i], _sub(G, W, "up", i)
+        s_r, s_a = s["blocks"]["up"][i]
+        dh = _attn_block_bwd(dh, s_a, w, g, enc, d_enc, B, S, Skv, eps, rms)
+        dh = _res_block_bwd(dh, s_r, w, g, mod_all, d_mod, B, hw, eps, rms)
+    dy_f = _lin_bwd(ops.cast_bf16(dh), s["y_f"], W["pfh"], G.of("pfh"))
+    dx, dr = ops.add_norm_mod_bwd(dy_f, None, s["r_f"], W["pfh_norm"], eps, rms, BF16, dw=G.of("pfh_norm"))
+    for i in reversed(range(len(W["layers"]))):
+        dx, dr = _layer_bwd(dx, dr, s["layers"][i], W["layers"][i], _sub(G, W, "layers", i), enc, d_enc, mod_all, d_mod, B, S,
+                            Skv, eps, rms)
+    dy_pth = _lin_bwd(dx, s["y_pth"], W["pth"], G.of("pth"))
+    dh, _ = ops.add_norm_mod_bwd(dy_pth, None, s["h_down"], W["pth_norm"], eps, rms, F32, dw=G.of("pth_norm"), want_dr=False)
+    for i in reversed(range(len(W["down"]))):
+        w, g = W["down"][i], _sub(G, W, "down", i)
+        s_r, s_a = s["blocks"]["down"][i]
+        dh = _attn_block_bwd(dh, s_a, w, g, enc, d_enc, B, S, Skv, eps, rms)
+        dh = _res_block_bwd(dh, s_r, w, g, mod_all, d_mod, B, hw, eps, rms)
+    # ConvEmbed
+    d_en = _lin_bwd(ops.cast_bf16(dh), s["en"], W["emb_conv"], G.of("emb_conv"))
+    d_e, _ = ops.add_norm_mod_bwd(d_en, None, s["e"], W["emb_norm"], eps, rms, F32, dw=G.of("emb_norm"), want_dr=False)
+    ops.embed_bwd(s["ids"], d_e, G.of("emb"), None)
+    # conditioning: stacked adaLN mappers <- SiLU <- cond_embed MLP
+    d_sc = _lin_bwd(ops.cast_bf16(d_mod), s["sc"], W["mappers"], G.of("mappers"))
+    d_cond = ops.silu_bwd(d_sc, s["cond"])
+    d_c1s = _lin_bwd(d_cond, s["c1s"], W["cond2"], G.of("cond2"))
+    d_c1 = ops.silu_bwd(d_c1s, s["c1"])
+    _lin_bwd(d_c1, s["cond_in"], W["cond0"], G.of("cond0"), need_dx=False)
+    # text states: encoder_proj + norm
+    d_y0, _ = ops.add_norm_mod_bwd(d_enc, None, s["r_enc"], W["enc_norm"], eps, rms, BF16, dw=G.of("enc_norm"), want_dr=False)
+    _lin_bwd(d_y0, s["ehs"], W["encoder_proj"], G.of("encoder_proj"), need_dx=False)
+    return G
+
+
+def param_grads(model, G):
+    """Maps the packed gradient buffers back onto the parameters (reference names), in ``model.parameters()`` order."""
+    c = model.config
+    out = {}
+
+    def put(p, g):
+        if p is not None:
+            out[p] = g.reshape(p.shape)
+
+    def rows(g, *ps):
+        o = 0
+        for p in ps:
+            put(p, g[o:o + p.shape[0]])
+            o += p.shape[0]
+
+    def attn(a, g, fused):
+        if fused:
+            rows(g["qkv"], a.query.weight, a.key.weight, a.value.weight)
+        else:
+            put(a.query.weight, g["q"])
+            rows(g["kv"], a.key.weight, a.value.weight)
+        put(a.out.weight, g["o"])
+
+    mappers = []
+
+    def block(blk, gl):
+        for i, (rb, ab) in enumerate(zip(blk.res_blocks, blk.attention_blocks)):
+            g = gl[i]
+            put(rb.depthwise.weight, g["dw"].t().contiguous())
+            put(rb.norm.norm.weight, g["dw_norm"])
+            put(rb.channelwise[0].weight, g["cw0"])
+            put(rb.channelwise[2].gamma, g["gamma"])
+            put(rb.channelwise[2].beta, g["beta"])
+            put(rb.channelwise[4].weight, g["cw4"])
+            mappers.append(rb.adaLN_modulation.mapper.weight)
+            if ab.kv_mapper is not None:
+                put(ab.kv_mapper.weight, g["kvm"])
+            put(ab.attn_layer_norm.weight, g["ln1"])
+            attn(ab.attention, g["a1"], False)
+            put(ab.crossattn_layer_norm.weight, g["ln2"])
+            attn(ab.crossattention, g["a2"], False)
+
+    put(model.encoder_proj.weight, G["encoder_proj"])
+    put(model.encoder_proj_layer_norm.weight, G["enc_norm"])
+    put(model.cond_embed[0].weight, G["cond0"])
+    put(model.cond_embed[2].weight, G["cond2"])
+    put(model.embed.embeddings.weight, G["emb"])
+    put(model.embed.layer_norm.weight, G["emb_norm"])
+    put(model.embed.conv.weight, G["emb_conv"])
+    put(model.project_to_hidden_norm.weight, G["pth_norm"])
+    put(model.project_to_hidden.weight, G["pth"])
+    put(model.project_from_hidden_norm.weight, G["pfh_norm"])
+    put(model.project_from_hidden.weight, G["pfh"])
+    put(model.mlm_layer.conv1.weight, G["mlm1"])
+    put(model.mlm_layer.layer_norm.norm.weight, G["mlm_norm"])
+    put(model.mlm_layer.conv2.weight, G["mlm2"][: c.codebook_size])
+    block(model.down_blocks[0], G["down"])  # mapper order must match _weights(): down, layers, up
+    for i, l in enumerate(model.transformer_layers):
+        g = G["layers"][i]
+        put(l.attn_layer_norm.weight, g["ln1"])
+        mappers.append(l.self_attn_adaLN_modulation.mapper.weight)
+        attn(l.attention, g["sa"], True)
+        put(l.crossattn_layer_norm.weight, g["ln2"])
+        attn(l.crossattention, g["ca"], False)
+        mappers.append(l.cross_attn_adaLN_modulation.mapper.weight)
+        put(l.ffn.pre_mlp_layer_norm.weight, g["ln3"])
+        mappers.append(l.ffn.adaLN_modulation.mapper.weight)
+        rows(g["wi"], l.ffn.wi_0.weight, l.ffn.wi_1.weight)
+        put(l.ffn.wo.weight, g["wo"])
+    block(model.up_blocks[0], G["up"])
+    rows(G["mappers"], *mappers)
+    return [out.get(p) for p in model.parameters()]
+
+
+class UViTTrainFn(torch.autograd.Function):
+    """(logits_padded, loss) = f(params...): the whole MaskGiTUViT_v2 training forward; backward returns every gradient."""
+
+    @staticmethod
+    def forward(ctx, model, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels, label_smoothing, *params):
+        W = model._weights()
+        logits, saved = forward(model, W, input_ids, encoder_hidden_states, cond_embeds, micro_conds)
+        V = model.config.codebook_size
+        ctx.model, ctx.W, ctx.saved, ctx.V, ctx.ls = model, W, saved, V, label_smoothing
+        ctx.set_materialize_grads(False)
+        if labels is None:
+            ctx.ce = None
+            return logits, None
+        labels = labels.reshape(-1).contiguous().to(torch.int64)
+        out, ws = ops.ce_fwd(logits, labels, V, label_smoothing)
+        ctx.ce = (labels, ws, out)
+        ctx.logits = logits
+        return logits, out[0]
+
+    @staticmethod
+    def backward(ctx, d_logits, d_loss):
+        dl = None
+        if d_loss is not None and ctx.ce is not None:
+            labels, ws, out = ctx.ce
+            dl = ops.ce_bwd(ctx.logits, labels, ws, d_loss.to(F32).reshape(1).contiguous(), out, ctx.V, ctx.ls)
+        if d_logits is not None:
+            extra = d_logits.to(BF16).contiguous()
+            dl = extra if dl is None else dl + extra
+        if dl is None:
+            raise RuntimeError("MaskGiTUViT_v2: backward called without any gradient")
+        G = backward(ctx.model, ctx.W, ctx.saved, dl)
+        grads = param_grads(ctx.model, G)
+        ctx.saved = None
+        return (None,) * 7 + tuple(grads)

@@ -188,3 +188,113 @@ def test_pipeline_with_uvit_v2_and_checkpoint_roundtrip(tmp_path, golden):
     assert isinstance(pipe2.transformer, MaskGiTUViT_v2)
     b = pipe2(**kw, generator=torch.Generator(device=DEV).manual_seed(1))
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("C,hw,rms", [(768, 16, 1), (64, 4, 0)])
+def test_uvit_backward_kernels_vs_autograd(C, hw, rms):
+    """add_norm_mod / dwconv+norm / GELU+GRN / adaLN / SiLU backward kernels against torch autograd of the fp32 math."""
+    g = torch.Generator().manual_seed(C + hw)
+    B, S = 2, hw * hw
+    T = B * S
+    dev = lambda t: t.to(DEV)
+    # ---- add_norm_mod
+    a = torch.randn(T, C, generator=g).requires_grad_(True)
+    r = torch.randn(T, C, generator=g).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).requires_grad_(True)
+    mod = (torch.randn(B, 2 * C, generator=g) * 0.3).requires_grad_(True)
+    x = a + r
+    n = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w if rms else torch.nn.functional.layer_norm(x, (C,), w, None, 1e-6)
+    y = (n.view(B, S, C) * (1 + mod[:, None, :C]) + mod[:, None, C:]).view(T, C)
+    dy, dro = torch.randn(T, C, generator=g), torch.randn(T, C, generator=g)
+    (y * dy).sum().backward(retain_graph=True)
+    (x * dro).sum().backward()
+    mod_d, dmod, dw = dev(mod.detach()), torch.zeros(B, 2 * C, device=DEV), torch.zeros(C, device=DEV)
+    da, dr = ops.add_norm_mod_bwd(dev(dy), dev(dro), dev(x.detach()), dev(w.detach()), 1e-6, rms, torch.float32, mod=mod_d,
+                                  rows_per_sample=S, dw=dw, dmod=dmod)
+    assert _rel(da, a.grad) < 1e-4 and _rel(dr, r.grad) < 1e-4 and _rel(dw, w.grad) < 1e-4 and _rel(dmod, mod.grad) < 1e-4
+    # ---- depthwise conv + norm
+    xin = torch.randn(B, hw, hw, C, generator=g).requires_grad_(True)
+    wd = (torch.randn(C, 1, 3, 3, generator=g) * 0.3).requires_grad_(True)
+    nw = (1 + 0.1 * torch.randn(C, generator=g)).requires_grad_(True)
+    conv = torch.nn.functional.conv2d(xin.permute(0, 3, 1, 2), wd, None, padding=1, groups=C).permute(0, 2, 3, 1)
+    out = conv * torch.rsqrt(conv.pow(2).mean(-1, keepdim=True) + 1e-6) * nw if rms else torch.nn.functional.layer_norm(conv, (C,), nw, None, 1e-6)
+    dyc = torch.randn(B, hw, hw, C, generator=g).to(torch.bfloat16)
+    (out * dyc.float()).sum().backward()
+    wk = dev(wd.detach().view(C, 9).t().contiguous())
+    yk, convk = ops.dwconv3x3_norm(dev(xin.detach().view(T, C)), wk, dev(nw.detach()), B, hw, hw, 1e-6, rms, save_conv=True)
+    dwk, dnw = torch.zeros(9, C, device=DEV), torch.zeros(C, device=DEV)
+    dres = torch.randn(T, C, generator=g)
+    dx = ops.dwconv3x3_norm_bwd(dev(dyc.view(T, C)), convk, dev(xin.detach().view(T, C)), wk, dev(nw.detach()), dev(dres), dwk,
+                                dnw, B, hw, hw, 1e-6, rms)
+    assert _rel(dx.cpu() - dres, xin.grad.view(T, C)) < 1e-2
+    assert _rel(dwk.t().reshape(C, 1, 3, 3), wd.grad) < 1e-2 and _rel(dnw, nw.grad) < 1e-2
+    # ---- GELU + GRN
+    z = (torch.randn(B, hw, hw, C, generator=g) * 1.5).to(torch.bfloat16)
+    zf = z.float().requires_grad_(True)
+    gamma = (torch.randn(C, generator=g) * 0.2).requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.2).requires_grad_(True)
+    gg = torch.nn.functional.gelu(zf)
+    gx = torch.norm(gg, p=2, dim=(1, 2), keepdim=True)
+    og = gamma * (gg * (gx / (gx.mean(dim=-1, keepdim=True) + 1e-6))) + beta + gg
+    dog = torch.randn(B, hw, hw, C, generator=g).to(torch.bfloat16)
+    (og * dog.float()).sum().backward()
+    _, stats = ops.grn(dev(z.view(T, C)), dev(gamma.detach()), dev(beta.detach()), B, S, save_stats=True)
+    dgam, dbet = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dz = ops.grn_bwd(dev(z.view(T, C)), dev(dog.view(T, C)), stats, dev(gamma.detach()), dgam, dbet, B, S)
+    assert _rel(dz, zf.grad.view(T, C)) < 1.5e-2 and _rel(dgam, gamma.grad) < 1e-2 and _rel(dbet, beta.grad) < 1e-2
+    # ---- adaLN apply and SiLU
+    h = torch.randn(T, C, generator=g).requires_grad_(True)
+    m2 = (torch.randn(B, 2 * C, generator=g) * 0.5).requires_grad_(True)
+    o2 = (h.view(B, S, C) * (1 + m2[:, None, :C]) + m2[:, None, C:]).view(T, C)
+    do2 = torch.randn(T, C, generator=g)
+    (o2 * do2).sum().backward()
+    dm2 = torch.zeros(B, 2 * C, device=DEV)
+    dh = ops.adaln_bwd(dev(do2), dev(h.detach()), dev(m2.detach()), dm2, B, S)
+    assert _rel(dh, h.grad) < 1e-5 and _rel(dm2, m2.grad) < 1e-4
+    sx = torch.randn(T, C, generator=g).requires_grad_(True)
+    dsy = torch.randn(T, C, generator=g).to(torch.bfloat16)
+    (torch.nn.functional.silu(sx) * dsy.float()).sum().backward()
+    acc = torch.ones(T, C, device=DEV)
+    ops.silu_bwd(dev(dsy), dev(sx.detach()), out=acc)
+    assert _rel(acc.cpu() - 1, sx.grad) < 1e-4
+    assert _rel(ops.silu_bwd(dev(dsy), dev(sx.detach().to(torch.bfloat16))), sx.grad) < 1.5e-2
+
+
+def test_micro_uvit_v2_training_gradients_vs_oracle(golden):
+    """One training forward/backward of MaskGiTUViT_v2 (hand-written backward through every block) against the oracle's fp32
+    autograd on the reference fixture weights; then a few optimizer steps must reduce the loss."""
+    g = golden("micro_uvit_v2.pt")
+    q = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    _, ref_loss = V2.forward(q, g["config"], g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"],
+                             labels=g["labels"], label_smoothing=0.1)
+    ref_loss.backward()
+    m = MaskGiTUViT_v2(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.to(DEV).train()
+    args = [g[k].to(DEV) for k in ("input_ids", "encoder_hidden_states", "cond_embeds", "micro_conds")]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, loss = m(*args, labels=g["labels"].to(DEV), label_smoothing=0.1)
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) / float(ref_loss) < 2e-3
+    errs = {}
+    for n, p in m.named_parameters():
+        assert p.grad is not None, n
+        errs[n] = _rel(p.grad, q[n].grad)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:8]
+    print("worst grad rel-L2:", ", ".join(f"{k}={v:.2e}" for k, v in worst))
+    bad = {k: v for k, v in errs.items() if v > 8e-2 and not (".query." in k or ".key." in k)}
+    assert not bad, bad
+    cos = {n: float(torch.nn.functional.cosine_similarity(p.grad.float().cpu().flatten(), q[n].grad.flatten(), dim=0))
+           for n, p in m.named_parameters()}
+    assert min(cos.values()) > 0.95, sorted(cos.items(), key=lambda kv: kv[1])[:5]
+    opt = torch.optim.AdamW(m.parameters(), lr=2e-3)
+    opt.zero_grad(set_to_none=True)
+    losses = []
+    for _ in range(6):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            _, l = m(*args, labels=g["labels"].to(DEV))
+        l.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(float(l))
+    assert losses[-1] < losses[0] - 0.05, losses
