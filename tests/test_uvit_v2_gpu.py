@@ -298,3 +298,36 @@ def test_micro_uvit_v2_training_gradients_vs_oracle(golden):
         opt.zero_grad(set_to_none=True)
         losses.append(float(l))
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+def test_uvit_v2_default_widths_training_gradients_vs_oracle():
+    """Training backward at the U-ViT widths (hidden 1024 / 16 heads, blocks 768 / 12 heads + kv_mapper, 256 tokens, 77 text
+    states): exercises the tcgen05 attention backward, the 4-chunk norm kernels and the wide GRN against fp32 autograd."""
+    cfg = dict(num_hidden_layers=2, num_res_blocks=1, vocab_size=1032, codebook_size=1024, intermediate_size=2816)
+    torch.manual_seed(0)
+    m = MaskGiTUViT_v2(**cfg)
+    gen = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for k, x in m.state_dict().items():
+            if "adaLN_modulation.mapper" in k or k.endswith("gamma") or k.endswith("beta") or k == "mlm_layer.conv1.weight":
+                x.copy_(torch.randn(x.shape, generator=gen) * 0.03)
+    B = 2
+    ids = torch.randint(0, 1024, (B, 256), generator=gen)
+    mask = torch.rand(B, 256, generator=gen) < 0.5
+    inp, lab = torch.where(mask, 1031, ids), torch.where(mask, ids, -100)
+    enc = torch.randn(B, 77, 768, generator=gen)
+    ce = torch.randn(B, 768, generator=gen)
+    mc = torch.tensor([[256.0, 256.0, 0.0, 0.0, 6.0], [512.0, 512.0, 32.0, 16.0, 5.0]])
+    q = {k: v.detach().clone().float().requires_grad_(True) for k, v in m.state_dict().items()}
+    _, ref_loss = V2.forward(q, cfg, inp, enc, ce, mc, labels=lab)
+    ref_loss.backward()
+    m.to(DEV).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        _, loss = m(inp.to(DEV), enc.to(DEV), ce.to(DEV), mc.to(DEV), labels=lab.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) / float(ref_loss) < 2e-3
+    errs = {n: _rel(p.grad, q[n].grad) for n, p in m.named_parameters()}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    print("worst grad rel-L2:", ", ".join(f"{k}={v:.2e}" for k, v in worst))
+    bad = {k: v for k, v in errs.items() if v > 8e-2 and not (".query." in k or ".key." in k)}
+    assert not bad, bad

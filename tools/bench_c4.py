@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--model", default="v1", choices=["v1", "uvit"],
+                    help="v1: MaskGitTransformer with the cc12m dims (BASELINE config 4); uvit: MaskGiTUViT_v2 at the reference "
+                         "defaults (what configs/cc12m_uvit_clip.yaml's architecture: 'uvit' instantiates)")
     args = ap.parse_args()
     import torch.distributed as dist
 
@@ -40,7 +43,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    model = MaskGitTransformer(**CFG).to(dev).train()
+    if args.model == "uvit":
+        from open_muse_b200 import MaskGiTUViT_v2
+
+        model = MaskGiTUViT_v2().to(dev).train()
+        with torch.no_grad():  # leave the zero-init regime so that every branch carries signal
+            for k, x in model.state_dict().items():
+                if "adaLN_modulation.mapper" in k or k.endswith("gamma") or k.endswith("beta") or k == "mlm_layer.conv1.weight":
+                    x.normal_(0, 0.02)
+    else:
+        model = MaskGitTransformer(**CFG).to(dev).train()
     n_params = sum(p.numel() for p in model.parameters())
     net = model
     if world > 1:
@@ -49,6 +61,8 @@ def main():
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     B, mask_id = args.batch, CFG["vocab_size"] - 1
     enc = torch.randn(B, 77, 768, device=dev, generator=g)
+    pooled = torch.randn(B, 768, device=dev, generator=g)
+    micro = torch.tensor([[256.0, 256.0, 0.0, 0.0, 6.0]], device=dev).repeat(B, 1)
 
     def step(i):
         ids = torch.randint(0, 8192, (B, 256), device=dev, generator=g)
@@ -59,7 +73,10 @@ def main():
         inp = torch.where(mask, mask_id, ids)
         lab = torch.where(mask, ids, -100)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            _, loss = net(inp, encoder_hidden_states=enc, labels=lab)
+            if args.model == "uvit":
+                _, loss = net(inp, enc, pooled, micro, labels=lab)
+            else:
+                _, loss = net(inp, encoder_hidden_states=enc, labels=lab)
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
@@ -86,10 +103,11 @@ def main():
     ms = float(ms) / args.steps
     if rank == 0:
         print(json.dumps({
-            "metric": "samples/sec text2image MaskGitTransformer train step (cc12m dims, config 4)",
+            "metric": "samples/sec text2image train step: " + ("MaskGiTUViT_v2 (reference defaults)" if args.model == "uvit"
+                                                                 else "MaskGitTransformer (cc12m dims, config 4)"),
             "value": B * world / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "ms_per_step": ms, "steps": args.steps,
             "per_gpu_batch": B, "params_m": n_params / 1e6, "loss": float(loss),
-            "tflops_per_gpu_model": TRAIN_GFLOP_PER_SAMPLE * B / ms, "gpu_launches_per_step": (ops.launches() - l0) // args.steps,
+            "tflops_per_gpu_model": (TRAIN_GFLOP_PER_SAMPLE if args.model == "v1" else 3 * 266.0) * B / ms, "gpu_launches_per_step": (ops.launches() - l0) // args.steps,
             "grad_allreduce_gb": n_params * 4 / 1e9, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
     if world > 1:
         dist.destroy_process_group()
