@@ -231,6 +231,7 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
                 nn.init.constant_(m.mapper.weight, 0)
         self._cache_key, self._cache = None, None
         self._debug_stages = None  # tests set this to a dict to receive the block-boundary activations
+        self._graph = None         # CUDA graph of one decode-step forward (generate2), keyed by shapes and weight versions
 
     def _init_weights(self, module):
         if isinstance(module, (nn.Linear, nn.Conv2d)):
@@ -438,12 +439,37 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
                 loss = out[0]
             return logits, loss
 
+    # ------------------------------------------------------------------------------------------- CUDA graph of one forward
+    def _graphed_forward(self, model_in, enc, cond, micro):
+        """Replays a captured CUDA graph of ``_forward_tokens`` (≈420 kernel launches per decode step, which at small batch
+        are bound by launch latency, not by the GPU).  Captured once per (shapes, weight versions); inputs are copied into
+        the graph's static buffers.  Returns the static logits buffer, valid until the next replay."""
+        self._weights()  # make sure the operand cache is built outside the capture
+        key = (tuple(model_in.shape), tuple(enc.shape), tuple(cond.shape), enc.dtype, cond.dtype, model_in.device, self._cache_key)
+        st = self._graph
+        if st is None or st["key"] != key:
+            bufs = [t.clone() for t in (model_in, enc, cond, micro)]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up off the capture: lazy attribute / cache initialisation
+                self._forward_tokens(*bufs)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_tokens(*bufs)
+            st = self._graph = dict(key=key, graph=graph, bufs=bufs, out=out)
+        for dst, src in zip(st["bufs"], (model_in, enc, cond, micro)):
+            dst.copy_(src)
+        st["graph"].replay()
+        return st["out"]
+
     # ------------------------------------------------------------------------------------------- generate2
     @torch.no_grad()
     def generate2(self, encoder_hidden_states, cond_embeds, micro_conds, empty_embeds, empty_cond_embeds, input_ids=None,
                   negative_embeds=None, negative_cond_embeds=None, temperature=1.0, timesteps=18, guidance_scale=0,
                   guidance_schedule=None, noise_schedule=cosine_schedule, generator=None, return_intermediate=False,
-                  seq_len=None, use_tqdm=None, topk_filter_thres=None, noise_type=None, predict_all_tokens=None):
+                  seq_len=None, use_tqdm=None, topk_filter_thres=None, noise_type=None, predict_all_tokens=None,
+                  use_cuda_graph=None):
         """MaskGIT parallel decoding with classifier-free guidance, semantics of the reference (:330-479); per step one
         doubled-batch forward and ONE fused kernel (guidance mix, categorical sample, confidence, k-th cut, re-mask)."""
         c = self.config
@@ -475,9 +501,16 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
         intermediate = []
         sampled = input_ids
         input_ids = input_ids.contiguous()
+        if use_cuda_graph is None:
+            import os
+
+            use_cuda_graph = os.environ.get("MUSE_B200_CUDA_GRAPH", "1") != "0" and self._debug_stages is None
         for step in range(timesteps):
             model_in = torch.cat([input_ids] * 2) if use_cfg else input_ids
-            padded = self._forward_tokens(model_in, encoder_hidden_states, cond_embeds, micro_conds)
+            if use_cuda_graph:
+                padded = self._graphed_forward(model_in, encoder_hidden_states, cond_embeds, micro_conds)
+            else:
+                padded = self._forward_tokens(model_in, encoder_hidden_states, cond_embeds, micro_conds)
             lg = padded.view(model_in.shape[0], seq_len, -1)
             logits, logits_unc = (lg[:B], lg[B:]) if use_cfg else (lg, None)
             # generator consumed like the reference: multinomial(n=1) draws Exp(1) noise of the probabilities' shape,

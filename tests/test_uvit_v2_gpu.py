@@ -157,6 +157,9 @@ def test_uvit_v2_generate2_cfg_properties(golden):
     ids, inter = m.generate2(**kw, guidance_scale=3.0, guidance_schedule="linear", return_intermediate=True,
                              generator=torch.Generator(device=DEV).manual_seed(5))
     assert len(inter) == 4 and torch.equal(inter[-1], ids)
+    # the CUDA-graph replay of the step forward is bit-identical to launching the kernels one by one
+    e = m.generate2(**kw, guidance_scale=3.0, use_cuda_graph=False, generator=torch.Generator(device=DEV).manual_seed(5))
+    assert torch.equal(a, e) and m._graph is not None
     # partially given tokens are kept
     start = torch.full((3, 16), 71, dtype=torch.long, device=DEV)
     start[:, :5] = torch.arange(5, device=DEV)
