@@ -95,7 +95,9 @@ int muse_ce_fwd(const void* logits, const long long* labels, float* lse, float* 
                 int V, int ld, float label_smoothing, void* stream);
 /* dlogits bf16 [rows, ld] = dloss[0]/N * (softmax - (1-ls) onehot - ls/V); zero for ignored rows / pad cols. */
 int muse_ce_bwd(const void* logits, const long long* labels, const float* lse, const float* dloss,
-                const float* loss_out, void* dlogits, int rows, int V, int ld, float label_smoothing, void* stream);
+                const float* loss_out, const float* row_scale, void* dlogits, int rows, int V, int ld,
+                float label_smoothing, void* stream);  /* row_scale (nullable) fp32 [rows]: per-row weight w_r / sum w
+                                                          replacing the 1 / #valid of the mean (loss_weight of v2 :305-317) */
 
 /* ---- MaskGiTUViT_v2 forward (muse/modeling_transformer_v2.py); dtype codes as muse_norm_fwd (0 = fp32, 1 = bf16) ----
  * Prenorm-residual norm (unfused_rms_norm / unfused_layer_norm, :673-738) fused with the adaLN modulation that follows it

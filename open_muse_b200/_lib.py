@@ -34,7 +34,7 @@ SIGNATURES = {
     "muse_attn_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
     "muse_attn_bwd": (c_int, [_P] * 10 + [_I] * 13 + [_F, _P]),
     "muse_ce_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
-    "muse_ce_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "muse_ce_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "muse_add_norm_mod_fwd": (c_int, [_P, _I, _P, _P, _P, _L, _I, _P, _P, _I, _I, _I, _F, _I, _P]),
     "muse_dwconv3x3_norm_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "muse_grn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),

@@ -39,7 +39,7 @@ int glu_bwd(const void*, const void*, void*, long long, int, cudaStream_t);
 int attn_fwd(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
 int attn_bwd(const void*, const void*, const void*, const void*, const void*, const float*, float*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
 int ce_fwd(const void*, const long long*, float*, float*, float*, int, int, int, float, cudaStream_t);
-int ce_bwd(const void*, const long long*, const float*, const float*, const float*, void*, int, int, int, float, cudaStream_t);
+int ce_bwd(const void*, const long long*, const float*, const float*, const float*, const float*, void*, int, int, int, float, cudaStream_t);
 int vq_argmin(const float*, const float*, float*, long long*, float*, int, int, int, cudaStream_t);
 int vq_lookup_nchw(const long long*, const float*, float*, int, int, int, int, cudaStream_t);
 int add_norm_mod_fwd(const void*, int, const float*, const float*, const float*, long long, int, float*, void*, int, int, int, float, int, cudaStream_t);
@@ -142,8 +142,9 @@ int muse_ce_fwd(const void* logits, const long long* labels, float* lse, float* 
   return ce_fwd(logits, labels, lse, row_loss, loss_out, rows, V, ld, label_smoothing, ST(stream));
 }
 int muse_ce_bwd(const void* logits, const long long* labels, const float* lse, const float* dloss,
-                const float* loss_out, void* dlogits, int rows, int V, int ld, float label_smoothing, void* stream) {
-  return ce_bwd(logits, labels, lse, dloss, loss_out, dlogits, rows, V, ld, label_smoothing, ST(stream));
+                const float* loss_out, const float* row_scale, void* dlogits, int rows, int V, int ld,
+                float label_smoothing, void* stream) {
+  return ce_bwd(logits, labels, lse, dloss, loss_out, row_scale, dlogits, rows, V, ld, label_smoothing, ST(stream));
 }
 
 int muse_vq_argmin(const float* z, const float* codebook, float* enorm_ws, long long* ids, float* dmin, int n,

@@ -96,8 +96,8 @@ ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict
 
 __global__ void __launch_bounds__(128)
 ce_bwd_kernel(const bf16* __restrict__ logits, const long long* __restrict__ labels, const float* __restrict__ lse_in,
-              const float* __restrict__ dloss, const float* __restrict__ loss_cnt, bf16* __restrict__ dlogits, int rows,
-              int V, int ld, float ls) {
+              const float* __restrict__ dloss, const float* __restrict__ loss_cnt, const float* __restrict__ row_scale,
+              bf16* __restrict__ dlogits, int rows, int V, int ld, float ls) {
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -109,7 +109,9 @@ ce_bwd_kernel(const bf16* __restrict__ logits, const long long* __restrict__ lab
     for (int c = lane * 8; c < ld; c += 256) *reinterpret_cast<uint4*>(d + c) = make_uint4(0, 0, 0, 0);
     return;
   }
-  const float scale = dloss[0] / loss_cnt[1];
+  // mean over the valid rows, or (row_scale given) a caller-defined per-row weight w_r / sum w (loss_weight of
+  // MaskGiTUViT_v2.forward, modeling_transformer_v2.py:305-317)
+  const float scale = row_scale ? dloss[0] * row_scale[row] : dloss[0] / loss_cnt[1];
   const float lse = lse_in[row];
   const float smooth = ls / static_cast<float>(V);
   for (int c = lane * 8; c < ld; c += 256) {
@@ -140,10 +142,10 @@ int ce_fwd(const void* logits, const long long* labels, float* lse, float* row_l
 }
 
 int ce_bwd(const void* logits, const long long* labels, const float* lse, const float* dloss, const float* loss_cnt,
-           void* dlogits, int rows, int V, int ld, float ls, cudaStream_t s) {
+           const float* row_scale, void* dlogits, int rows, int V, int ld, float ls, cudaStream_t s) {
   if (rows <= 0) return MUSE_OK;
   if (ld % 8 != 0 || ld < V) { set_last_error("ce_bwd: ld=%d must be a multiple of 8 and >= V=%d", ld, V); return MUSE_ERR_INVALID; }
-  ce_bwd_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(reinterpret_cast<const bf16*>(logits), labels, lse, dloss, loss_cnt, reinterpret_cast<bf16*>(dlogits), rows, V, ld, ls);
+  ce_bwd_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(reinterpret_cast<const bf16*>(logits), labels, lse, dloss, loss_cnt, row_scale, reinterpret_cast<bf16*>(dlogits), rows, V, ld, ls);
   return check_launch("ce_bwd");
 }
 

@@ -411,14 +411,12 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
         B, S = input_ids.shape
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training: one autograd Function for the whole network (uvit_v2_train.py)
-            if loss_weight is not None:
-                raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: loss_weight is supported in evaluation only")
             if self.training and (c.hidden_dropout > 0.0 or c.attention_dropout > 0.0):
                 raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: dropout > 0 in training mode is not implemented")
             from .uvit_v2_train import UViTTrainFn
 
             padded, loss = UViTTrainFn.apply(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels,
-                                             label_smoothing, *self.parameters())
+                                             label_smoothing, loss_weight, *self.parameters())
             logits = padded.view(B, S, -1)[:, :, : c.codebook_size]
             if not (_raw_bf16 or torch.is_autocast_enabled()):
                 logits = logits.float()

@@ -228,12 +228,12 @@ def ce_fwd(logits_padded, labels, V, label_smoothing):
     return out, ws
 
 
-def ce_bwd(logits_padded, labels, ws, dloss, loss_out, V, label_smoothing):
+def ce_bwd(logits_padded, labels, ws, dloss, loss_out, V, label_smoothing, row_scale=None):
     st = _prep(logits_padded)
     rows, ld = logits_padded.shape
     dl = torch.empty_like(logits_padded)
-    _call("muse_ce_bwd", _p(logits_padded), _p(labels), _p(ws[0]), _p(dloss), _p(loss_out), _p(dl), rows, V, ld,
-          float(label_smoothing), st)
+    _call("muse_ce_bwd", _p(logits_padded), _p(labels), _p(ws[0]), _p(dloss), _p(loss_out), _p(row_scale), _p(dl), rows, V,
+          ld, float(label_smoothing), st)
     return dl
 
 

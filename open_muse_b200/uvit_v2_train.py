@@ -350,7 +350,8 @@ class UViTTrainFn(torch.autograd.Function):
     """(logits_padded, loss) = f(params...): the whole MaskGiTUViT_v2 training forward; backward returns every gradient."""
 
     @staticmethod
-    def forward(ctx, model, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels, label_smoothing, *params):
+    def forward(ctx, model, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels, label_smoothing,
+                loss_weight, *params):
         W = model._weights()
         logits, saved = forward(model, W, input_ids, encoder_hidden_states, cond_embeds, micro_conds)
         V = model.config.codebook_size
@@ -361,16 +362,22 @@ class UViTTrainFn(torch.autograd.Function):
             return logits, None
         labels = labels.reshape(-1).contiguous().to(torch.int64)
         out, ws = ops.ce_fwd(logits, labels, V, label_smoothing)
-        ctx.ce = (labels, ws, out)
+        row_scale, loss = None, out[0]
+        if loss_weight is not None:  # (sum_r w_r loss_r) / sum_r w_r on the unreduced loss (:305-317)
+            lw = loss_weight.reshape(-1).float()
+            row_scale = (lw / lw.sum()).contiguous()
+            loss = (ws[1] * row_scale).sum()
+        ctx.ce = (labels, ws, out, row_scale)
         ctx.logits = logits
-        return logits, out[0]
+        return logits, loss
 
     @staticmethod
     def backward(ctx, d_logits, d_loss):
         dl = None
         if d_loss is not None and ctx.ce is not None:
-            labels, ws, out = ctx.ce
-            dl = ops.ce_bwd(ctx.logits, labels, ws, d_loss.to(F32).reshape(1).contiguous(), out, ctx.V, ctx.ls)
+            labels, ws, out, row_scale = ctx.ce
+            dl = ops.ce_bwd(ctx.logits, labels, ws, d_loss.to(F32).reshape(1).contiguous(), out, ctx.V, ctx.ls,
+                            row_scale=row_scale)
         if d_logits is not None:
             extra = d_logits.to(BF16).contiguous()
             dl = extra if dl is None else dl + extra
@@ -379,4 +386,4 @@ class UViTTrainFn(torch.autograd.Function):
         G = backward(ctx.model, ctx.W, ctx.saved, dl)
         grads = param_grads(ctx.model, G)
         ctx.saved = None
-        return (None,) * 7 + tuple(grads)
+        return (None,) * 8 + tuple(grads)

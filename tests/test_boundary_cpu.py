@@ -138,3 +138,28 @@ def test_uvit_v2_seeded_construction_matches_reference():
     m.eval()
     with pytest.raises(RuntimeError), torch.no_grad():
         m(g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"])
+
+
+def test_uvit_v2_checkpoint_roundtrip(tmp_path):
+    import json
+    import os
+
+    import torch
+
+    from open_muse_b200 import MaskGiTUViT_v2
+
+    cfg = dict(hidden_size=128, num_attention_heads=2, in_channels=64, block_out_channels=(64,), block_num_heads=(1,),
+               num_res_blocks=1, num_hidden_layers=1, intermediate_size=128, vocab_size=72, codebook_size=64,
+               encoder_hidden_size=32, cond_embed_dim=16, micro_cond_encode_dim=8, micro_cond_embed_dim=40)
+    torch.manual_seed(3)
+    m = MaskGiTUViT_v2(**cfg)
+    m.save_pretrained(tmp_path)
+    conf = json.load(open(os.path.join(tmp_path, "config.json")))
+    assert conf["_class_name"] == "MaskGiTUViT_v2" and conf["mask_token_id"] == 71 and conf["block_num_heads"] == 1
+    assert conf["block_out_channels"] == [64]
+    m2 = MaskGiTUViT_v2.from_pretrained(tmp_path)
+    assert not m2.training
+    for (k, a), (k2, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k == k2 and torch.equal(a, b)
+    with __import__("pytest").raises(NotImplementedError):
+        MaskGiTUViT_v2(**dict(cfg, use_bias=True))

@@ -334,3 +334,23 @@ def test_uvit_v2_default_widths_training_gradients_vs_oracle():
     print("worst grad rel-L2:", ", ".join(f"{k}={v:.2e}" for k, v in worst))
     bad = {k: v for k, v in errs.items() if v > 8e-2 and not (".query." in k or ".key." in k)}
     assert not bad, bad
+
+
+def test_micro_uvit_v2_loss_weight_training(golden):
+    """per-token loss_weight (train_muse.py:216-224 -> modeling_transformer_v2.py:305-317) in training mode: weighted loss
+    value vs the reference fixture, gradients vs the oracle's autograd."""
+    g = golden("micro_uvit_v2.pt")
+    q = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    _, ref = V2.forward(q, g["config"], g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"],
+                        labels=g["labels"], loss_weight=g["loss_weight"])
+    ref.backward()
+    m = MaskGiTUViT_v2(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.to(DEV).train()
+    args = [g[k].to(DEV) for k in ("input_ids", "encoder_hidden_states", "cond_embeds", "micro_conds")]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        _, loss = m(*args, labels=g["labels"].to(DEV), loss_weight=g["loss_weight"].to(DEV))
+    loss.backward()
+    assert abs(float(loss) - float(g["loss_weighted"])) / float(g["loss_weighted"]) < 2e-3
+    for n in ("mlm_layer.conv2.weight", "transformer_layers.1.ffn.wo.weight", "embed.embeddings.weight", "encoder_proj.weight"):
+        assert _rel(dict(m.named_parameters())[n].grad, q[n].grad) < 5e-2, n
