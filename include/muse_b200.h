@@ -169,7 +169,8 @@ int muse_sample_step(const void* logits, const void* logits_unc, long long row_s
                      long long mask_id, int mask_len, float temperature, void* stream);
 
 /* MaskGitVQGAN encoder/decoder blocks, fp32 NHWC (muse/modeling_maskgit_vqgan.py).
- * conv2d: Conv2dSame (:33-45) stride 1, ksize 1|3, x [B,Hi,Wi,Cin] (Hi=H/2 if upsample2x: nearest x2 of :146 folded
+ * conv2d: Conv2dSame (:33-45) stride 1, ksize 1|3, x [B,Hi,Wi,Cin] (upsample2x = 2: stride 2, pad (0,1,0,1), Hi = 2H;
+ * Hi=H/2 if upsample2x == 1: nearest x2 of :146 folded
  * into the gather), wk [ksize*ksize*Cin, Cout] packed (tap-major, then input channel), optional bias [Cout] and
  * residual [B,H,W,Cout] (ResnetBlock :82-85) -> y [B,H,W,Cout]. */
 int muse_conv2d_nhwc(const float* x, const float* wk, const float* bias, const float* res, float* y, int B, int H,
@@ -182,7 +183,8 @@ int muse_conv2d_nhwc(const float* x, const float* wk, const float* bias, const f
 long long muse_groupnorm_workspace_floats(int B, int HW, int C);
 int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, void* y_hi, void* y_lo,
                              float* partials_ws, float* scale_shift_ws, int B, int HW, int C, int groups, float eps,
-                             int precomputed_tiles, void* stream);
+                             int precomputed_tiles, int apply_silu, void* stream);  /* apply_silu 0: plain GroupNorm
+                             (AttnBlock.norm of the taming VQGAN, modeling_taming_vqgan.py:137-150) */
 /* Conv2dSame (:33-45) on the tcgen05 tensor cores with fp32-level accuracy (3 bf16 products hi*hi + lo*hi + hi*lo,
  * fp32 accumulation): x_hi/x_lo bf16 [B,H,W,Cin], w_hi/w_lo bf16 [Cout, ksize*ksize*Cin] (tap-major, then input
  * channel), optional bias [Cout] and residual [B,H,W,Cout] -> y fp32 [B,H,W,Cout].
@@ -197,7 +199,18 @@ int muse_conv2d_tc_supported(int H, int W, int Cin, int Cout, int ksize);
 int muse_conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize, int upsample2x);
 int muse_conv2d_nhwc_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
                         const float* res, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize,
-                        int upsample2x, void* stream);
+                        int mode, void* stream);
+/* mode & 3: 0 plain, 1 upsample2x (above), 2 = ksize 2 with taps at offsets (0,0),(0,1),(1,0),(1,1) and zeros beyond the
+ * right / bottom edge: the stride-2 3x3 convolution with pad (0,1,0,1) of the taming Downsample
+ * (modeling_taming_vqgan.py:47-62) after muse_split_s2d_bf16_nhwc, weights [Cout, 4 taps * 4 Cin].  mode & 4: per-image
+ * weights [B][Cout][K] -- the attention products of AttnBlock (:160-170) run as 1x1 convolutions whose weights are the
+ * image's own keys / values.  */
+/* space-to-depth + split: x fp32 [B,2Ho,2Wo,C] -> bf16 planes [B,Ho,Wo,4C], channel = (row parity*2 + col parity)*C + c. */
+int muse_split_s2d_bf16_nhwc(const float* x, void* hi, void* lo, int B, int Ho, int Wo, int C, void* stream);
+/* softmax(scale * x) over rows of n fp32 values (AttnBlock attention weights :162-163), written as bf16 hi/lo planes, or
+ * as plain fp32 when out_f32 is given (hi / lo then unused). */
+int muse_softmax_split_rows(const float* x, void* hi, void* lo, float* out_f32, long long rows, int n, float scale,
+                            void* stream);
 /* fp32 [B,H/(1+up),W/(1+up),C] -> bf16 planes hi = bf16(x), lo = bf16(x - hi), [B,H,W,C]; upsample2x folds the nearest
  * x2 of UpsamplingBlock (:146) into the gather. */
 int muse_split_bf16_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int C, int upsample2x, void* stream);

@@ -51,7 +51,9 @@ SIGNATURES = {
     "muse_sample_step": (c_int, [_P, _P, _L, _L, _F, _P, _P, _P, _P, _P, _P, _I, _I, _I, _L, _I, _F, _P]),
     "muse_conv2d_nhwc": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "muse_groupnorm_workspace_floats": (c_longlong, [_I, _I, _I]),
-    "muse_groupnorm_silu_nhwc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "muse_groupnorm_silu_nhwc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
+    "muse_split_s2d_bf16_nhwc": (c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "muse_softmax_split_rows": (c_int, [_P, _P, _P, _P, _L, _I, _F, _P]),
     "muse_conv2d_tc_tiles_per_image": (c_int, [_I, _I, _I, _I, _I, _I]),
     "muse_conv2d_tc_supported": (c_int, [_I, _I, _I, _I, _I]),
     "muse_conv2d_nhwc_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -9,6 +9,7 @@ from open_muse_b200 import (  # noqa: F401
     MaskGitVQGAN,
     PipelineMuse,
     PipelineMuseInpainting,
+    VQGANModel,
     get_mask_chedule,
 )
 from open_muse_b200 import modeling_transformer_v2, sampling  # noqa: F401

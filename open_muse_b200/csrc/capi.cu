@@ -55,7 +55,9 @@ int silu_bf16(const void*, int, void*, long long, cudaStream_t);
 int vq_soft_code(const float*, const float*, float*, float*, long long*, const float*, float, int, int, int, cudaStream_t);
 int sample_step(const void*, const void*, long long, long long, float, const long long*, const float*, const float*, long long*, long long*, float*, int, int, int, long long, int, float, cudaStream_t);
 int conv2d_nhwc(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
-int groupnorm_silu_nhwc(const float*, const float*, const float*, float*, void*, void*, float*, float*, int, int, int, int, float, int, cudaStream_t);
+int groupnorm_silu_nhwc(const float*, const float*, const float*, float*, void*, void*, float*, float*, int, int, int, int, float, int, int, cudaStream_t);
+int split_s2d_bf16_nhwc(const float*, void*, void*, int, int, int, int, cudaStream_t);
+int softmax_split_rows(const float*, void*, void*, float*, long long, int, float, cudaStream_t);
 int conv2d_tc_tiles_per_image(int, int, int, int, int, int);
 int conv2d_tc_supported(int, int, int, int, int);
 int conv2d_tc(const void*, const void*, const void*, const void*, const float*, const float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
@@ -217,9 +219,16 @@ int muse_conv2d_nhwc(const float* x, const float* wk, const float* bias, const f
 long long muse_groupnorm_workspace_floats(int B, int HW, int C) { return gn_workspace_floats(B, HW, C); }
 int muse_groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, void* y_hi, void* y_lo,
                              float* partials_ws, float* scale_shift_ws, int B, int HW, int C, int groups, float eps,
-                             int precomputed_tiles, void* stream) {
+                             int precomputed_tiles, int apply_silu, void* stream) {
   return groupnorm_silu_nhwc(x, gamma, beta, y, y_hi, y_lo, partials_ws, scale_shift_ws, B, HW, C, groups, eps,
-                             precomputed_tiles, ST(stream));
+                             precomputed_tiles, apply_silu, ST(stream));
+}
+int muse_split_s2d_bf16_nhwc(const float* x, void* hi, void* lo, int B, int Ho, int Wo, int C, void* stream) {
+  return split_s2d_bf16_nhwc(x, hi, lo, B, Ho, Wo, C, ST(stream));
+}
+int muse_softmax_split_rows(const float* x, void* hi, void* lo, float* out_f32, long long rows, int n, float scale,
+                            void* stream) {
+  return softmax_split_rows(x, hi, lo, out_f32, rows, n, scale, ST(stream));
 }
 int muse_conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize, int upsample2x) {
   return conv2d_tc_tiles_per_image(H, W, Cin, Cout, ksize, upsample2x);
@@ -227,8 +236,8 @@ int muse_conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize, i
 int muse_conv2d_tc_supported(int H, int W, int Cin, int Cout, int ksize) { return conv2d_tc_supported(H, W, Cin, Cout, ksize); }
 int muse_conv2d_nhwc_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
                         const float* res, float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize,
-                        int upsample2x, void* stream) {
-  return conv2d_tc(x_hi, x_lo, w_hi, w_lo, bias, res, y, stats, B, H, W, Cin, Cout, ksize, upsample2x, ST(stream));
+                        int mode, void* stream) {
+  return conv2d_tc(x_hi, x_lo, w_hi, w_lo, bias, res, y, stats, B, H, W, Cin, Cout, ksize, mode, ST(stream));
 }
 int muse_split_bf16_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int C, int upsample2x, void* stream) {
   return split_bf16_nhwc(x, hi, lo, B, H, W, C, upsample2x, ST(stream));

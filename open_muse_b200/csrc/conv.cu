@@ -30,8 +30,11 @@ conv2d_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ wk, co
   const long long m0 = static_cast<long long>(blockIdx.x) * BM;
   const int n0 = blockIdx.y * BN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int Hi = up ? H / 2 : H, Wi = up ? W / 2 : W;
-  const int pad = ksize / 2;
+  // up: 0 plain 'same'; 1 nearest x2 upsample folded into the gather; 2 stride 2 with pad (0,1,0,1) (taming Downsample)
+  const int s2 = (up == 2);
+  const int Hi = up == 1 ? H / 2 : (s2 ? 2 * H : H), Wi = up == 1 ? W / 2 : (s2 ? 2 * W : W);
+  const int pad = s2 ? 0 : ksize / 2;
+  const int st = s2 ? 2 : 1;
 
   // A-loader role: BM rows x 8 k per stage. VEC: one float4 per (row, half); scalar: BM*8/256 elements.
   constexpr int A_PER_THREAD = BM * KT / 256;  // 4 for BM=128
@@ -69,10 +72,11 @@ conv2d_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ wk, co
     if (VEC) {
       const int k = k0 + a_k[0];
       const int tap = k / Cin, ci = k % Cin;
-      const int iy = ay[0] + tap / ksize - pad, ix = ax[0] + tap % ksize - pad;
+      const int iy = ay[0] * st + tap / ksize - pad, ix = ax[0] * st + tap % ksize - pad;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a_ok[0] && iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        const int sy = up ? (iy >> 1) : iy, sx = up ? (ix >> 1) : ix;
+      const int Hb = s2 ? Hi : H, Wb = s2 ? Wi : W;  // bounds of the (virtual) input grid the taps index
+      if (a_ok[0] && iy >= 0 && iy < Hb && ix >= 0 && ix < Wb) {
+        const int sy = up == 1 ? (iy >> 1) : iy, sx = up == 1 ? (ix >> 1) : ix;
         v = *reinterpret_cast<const float4*>(x + ((static_cast<long long>(ab[0]) * Hi + sy) * Wi + sx) * Cin + ci);
       }
       sA[a_k[0] + 0][a_row[0]] = v.x; sA[a_k[0] + 1][a_row[0]] = v.y;
@@ -84,9 +88,10 @@ conv2d_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ wk, co
         float v = 0.f;
         if (k < K && a_ok[i]) {
           const int tap = k / Cin, ci = k % Cin;
-          const int iy = ay[i] + tap / ksize - pad, ix = ax[i] + tap % ksize - pad;
-          if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-            const int sy = up ? (iy >> 1) : iy, sx = up ? (ix >> 1) : ix;
+          const int iy = ay[i] * st + tap / ksize - pad, ix = ax[i] * st + tap % ksize - pad;
+          const int Hb = s2 ? Hi : H, Wb = s2 ? Wi : W;
+          if (iy >= 0 && iy < Hb && ix >= 0 && ix < Wb) {
+            const int sy = up == 1 ? (iy >> 1) : iy, sx = up == 1 ? (ix >> 1) : ix;
             v = x[((static_cast<long long>(ab[i]) * Hi + sy) * Wi + sx) * Cin + ci];
           }
         }
@@ -207,7 +212,7 @@ gn_finalize_kernel(const float* __restrict__ partials, int nblocks, const float*
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift, float* __restrict__ y,
-                     bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, long long total4, int HW, int C) {
+                     bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, long long total4, int HW, int C, int silu) {
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total4) return;
   const int c4 = C / 4;
@@ -218,7 +223,7 @@ gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scal
   const float4 s1 = *reinterpret_cast<const float4*>(scale_shift + (static_cast<long long>(b) * C + q * 4) * 2 + 4);
   float o[4] = {fmaf(v.x, s0.x, s0.y), fmaf(v.y, s0.z, s0.w), fmaf(v.z, s1.x, s1.y), fmaf(v.w, s1.z, s1.w)};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) o[j] = o[j] / (1.f + expf(-o[j]));
+  for (int j = 0; j < 4; ++j) o[j] = silu ? o[j] / (1.f + expf(-o[j])) : o[j];
   if (SPLIT) {
     float h[4];
 #pragma unroll
@@ -236,7 +241,7 @@ gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scal
 // 8 channels per thread variant of the SPLIT apply (two 16-byte loads in flight, 16-byte stores per plane)
 __global__ void __launch_bounds__(256)
 gn_apply_silu_split8_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift, bf16* __restrict__ y_hi,
-                            bf16* __restrict__ y_lo, long long total8, int HW, int C) {
+                            bf16* __restrict__ y_lo, long long total8, int HW, int C, int silu) {
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total8) return;
   const int c8 = C / 8;
@@ -250,8 +255,10 @@ gn_apply_silu_split8_kernel(const float* __restrict__ x, const float* __restrict
   for (int j = 0; j < 4; ++j) {
     const float4 s2 = ssp[j];  // {scale, shift} of channels 2j, 2j+1
     float o0 = fmaf(v[2 * j], s2.x, s2.y), o1 = fmaf(v[2 * j + 1], s2.z, s2.w);
-    o0 = o0 / (1.f + expf(-o0));
-    o1 = o1 / (1.f + expf(-o1));
+    if (silu) {
+      o0 = o0 / (1.f + expf(-o0));
+      o1 = o1 / (1.f + expf(-o1));
+    }
     h[2 * j] = bf16_round(o0); h[2 * j + 1] = bf16_round(o1);
     l[2 * j] = o0 - h[2 * j]; l[2 * j + 1] = o1 - h[2 * j + 1];
   }
@@ -306,7 +313,8 @@ transpose_cp_kernel(const float* __restrict__ in, float* __restrict__ out, int r
 int conv2d_nhwc(const float* x, const float* wk, const float* bias, const float* res, float* y, int B, int H, int W,
                 int Cin, int Cout, int ksize, int upsample2x, cudaStream_t s) {
   if (ksize != 1 && ksize != 3) { set_last_error("conv2d: kernel size %d unsupported (1 or 3)", ksize); return MUSE_ERR_UNSUPPORTED; }
-  if (upsample2x && ((H | W) & 1)) { set_last_error("conv2d: upsample2x needs even output dims"); return MUSE_ERR_INVALID; }
+  if (upsample2x == 1 && ((H | W) & 1)) { set_last_error("conv2d: upsample2x needs even output dims"); return MUSE_ERR_INVALID; }
+  if (upsample2x == 2 && ksize != 3) { set_last_error("conv2d: the stride-2 mode is the 3x3 taming Downsample"); return MUSE_ERR_INVALID; }
   const long long M = static_cast<long long>(B) * H * W;
   if (M <= 0) return MUSE_OK;
   const bool vec = (Cin % 8 == 0);
@@ -333,7 +341,7 @@ long long gn_workspace_floats(int B, int HW, int C) {
 // y (fp32) or y_hi / y_lo (bf16 split planes) receive the result: exactly one of the two forms must be given.
 int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, void* y_hi, void* y_lo,
                         float* partials_ws, float* scale_shift_ws, int B, int HW, int C, int groups, float eps,
-                        int precomputed_tiles, cudaStream_t s) {
+                        int precomputed_tiles, int apply_silu, cudaStream_t s) {
   if ((y != nullptr) == (y_hi != nullptr) || (y_hi != nullptr) != (y_lo != nullptr)) {
     set_last_error("groupnorm: give either y (fp32) or both y_hi and y_lo (bf16 split)");
     return MUSE_ERR_INVALID;
@@ -362,13 +370,13 @@ int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, f
   const long long total4 = static_cast<long long>(B) * HW * (C / 4);
   const unsigned blocks = static_cast<unsigned>(ceil_div_ll(total4, 256));
   if (y != nullptr)
-    gn_apply_silu_kernel<false><<<blocks, 256, 0, s>>>(x, scale_shift_ws, y, nullptr, nullptr, total4, HW, C);
+    gn_apply_silu_kernel<false><<<blocks, 256, 0, s>>>(x, scale_shift_ws, y, nullptr, nullptr, total4, HW, C, apply_silu);
   else if (C % 8 == 0)
     gn_apply_silu_split8_kernel<<<static_cast<unsigned>(ceil_div_ll(total4 / 2, 256)), 256, 0, s>>>(
-        x, scale_shift_ws, reinterpret_cast<bf16*>(y_hi), reinterpret_cast<bf16*>(y_lo), total4 / 2, HW, C);
+        x, scale_shift_ws, reinterpret_cast<bf16*>(y_hi), reinterpret_cast<bf16*>(y_lo), total4 / 2, HW, C, apply_silu);
   else
     gn_apply_silu_kernel<true><<<blocks, 256, 0, s>>>(x, scale_shift_ws, nullptr, reinterpret_cast<bf16*>(y_hi),
-                                                      reinterpret_cast<bf16*>(y_lo), total4, HW, C);
+                                                      reinterpret_cast<bf16*>(y_lo), total4, HW, C, apply_silu);
   return check_launch("gn_apply_silu");
 }
 

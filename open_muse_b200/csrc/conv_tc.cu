@@ -58,6 +58,8 @@ struct ConvParams {
   int H, W, Cin, ksize;
   int tile_w, tile_h, tiles_x, tiles_per_img;
   int up, tile_w_log2;  // up: nearest x2 upsample folded in as four 2x2 parity convolutions on the H x W (input) grid
+  int fwd2x2;           // taps are the 2x2 window at offsets (0..1, 0..1): the stride-2 3x3 conv after space-to-depth
+  int wbatch;           // weights are per image: [B][C_out][K] (attention scores / values as 1x1 convolutions)
   int num_m, num_n, cchunks, num_kb;
 };
 
@@ -67,6 +69,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
           "r"(ptx::smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
+          "r"(ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 
@@ -154,13 +164,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           uint8_t* sa = smem + stage * C_::kStageBytes;
           uint8_t* sb = sa + C_::kABytes;
           // passes: 0 = hi*hi, 1 = lo(A)*hi(B), 2 = hi(A)*lo(B)
-          const int dy = p.up ? (tap >> 1) + (parity >> 1) - 1 : tap / p.ksize - pad;
-          const int dx = p.up ? (tap & 1) + (parity & 1) - 1 : tap % p.ksize - pad;
+          const int dy = p.up ? (tap >> 1) + (parity >> 1) - 1 : (p.fwd2x2 ? (tap >> 1) : tap / p.ksize - pad);
+          const int dx = p.up ? (tap & 1) + (parity & 1) - 1 : (p.fwd2x2 ? (tap & 1) : tap % p.ksize - pad);
+          const int wb = p.wbatch ? img : 0;
           if (!SWAP) {
             tma_load_4d(sa, pass == 1 ? &tmAl : &tmAh, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
-            ptx::tma_load_2d(sb, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, wrow0 + n0);
+            tma_load_3d(sb, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, wrow0 + n0, wb);
           } else {  // A = 128 weight rows, B = 256 pixels
-            ptx::tma_load_2d(sa, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, wrow0 + n_idx * 128);
+            tma_load_3d(sa, pass == 2 ? &tmBl : &tmBh, &full_bar[stage], tap * p.Cin + cc * BK, wrow0 + n_idx * 128, wb);
             tma_load_4d(sb, pass == 1 ? &tmAl : &tmAh, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
           }
           if (++stage == C_::kStages) { stage = 0; phase ^= 1; }
@@ -471,6 +482,54 @@ im2col_split_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __
   store8(lo + i * 8, l);
 }
 
+// space-to-depth + hi/lo split: x fp32 [B,H,W,C] -> planes bf16 [B,H/2,W/2,4C], channel = (row parity * 2 + col parity) * C + c
+__global__ void __launch_bounds__(256)
+split_s2d_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long long total8, int Ho, int Wo,
+                 int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = C / 8;
+  const int q = static_cast<int>(i % c8);
+  const int par = static_cast<int>((i / c8) % 4);
+  const long long pix = i / (static_cast<long long>(c8) * 4);
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const long long b = pix / (static_cast<long long>(Wo) * Ho);
+  const long long src = ((b * (2 * Ho) + 2 * oy + (par >> 1)) * (2 * Wo) + 2 * ox + (par & 1)) * C + q * 8;
+  float v[8], h[8], l[8];
+  load8(x + src, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    h[j] = bf16_round(v[j]);
+    l[j] = v[j] - h[j];
+  }
+  store8(hi + i * 8, h);
+  store8(lo + i * 8, l);
+}
+
+// softmax(scale * x) over rows of n fp32 values (one warp per row), emitted as bf16 hi/lo planes
+__global__ void __launch_bounds__(256)
+softmax_split_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, float* __restrict__ out,
+                     long long rows, int n, float scale) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * n;
+  float m = -INFINITY;
+  for (int c = lane; c < n; c += 32) m = fmaxf(m, xr[c] * scale);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int c = lane; c < n; c += 32) sum += expf(xr[c] * scale - m);
+  sum = warp_sum(sum);
+  for (int c = lane; c < n; c += 32) {
+    const float pv = expf(xr[c] * scale - m) / sum;
+    if (out) { out[row * n + c] = pv; continue; }
+    const float h = bf16_round(pv);
+    hi[row * n + c] = __float2bfloat16_rn(h);
+    lo[row * n + c] = __float2bfloat16_rn(pv - h);
+  }
+}
+
 int g_sms = 0;
 int sm_count() {
   if (g_sms == 0) {
@@ -502,7 +561,7 @@ int launch_conv(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap&
 
 // 1 if conv2d_tc handles the shape (otherwise the caller uses the fp32 SIMT kernel of conv.cu).
 int conv2d_tc_supported(int H, int W, int Cin, int Cout, int ksize) {
-  if (ksize != 1 && ksize != 3) return 0;
+  if (ksize != 1 && ksize != 3 && ksize != 2) return 0;  // 2: the 2x2 forward-offset window (mode 2 of conv2d_tc)
   if (Cin % 64 != 0 || Cout < 1 || (Cout > 16 && Cout % 4 != 0)) return 0;
   if (W >= 128) return W % 128 == 0;
   if (W < 8 || 128 % W != 0) return 0;
@@ -525,11 +584,17 @@ int conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize, int up
   return (upsample2x ? 4 : 1) * (H * W / (use_swap(H, W, Cout) ? 256 : 128));
 }
 
-// upsample2x: x planes are the LOW-resolution input [B,H/2,W/2,Cin] and w planes the four stacked parity matrices
-// [4*Cout, 4*Cin] (ops.py packs them); y / res / stats are at the output resolution [B,H,W,Cout].
+// mode & 3 == 1 (upsample2x): x planes are the LOW-resolution input [B,H/2,W/2,Cin] and w planes the four stacked parity
+//   matrices [4*Cout, 4*Cin] (ops.py packs them); y / res / stats are at the output resolution [B,H,W,Cout].
+// mode & 3 == 2: ksize 2, taps at offsets (0,0),(0,1),(1,0),(1,1), zero beyond the right / bottom edge -- a stride-2 3x3
+//   convolution with pad (0,1,0,1) (taming Downsample) after a space-to-depth of its input (w: [Cout, 4 * Cin]).
+// mode & 4: per-image weights, w planes are [B][Cout][K].
 int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, const float* res,
-              float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize, int upsample2x, cudaStream_t s) {
+              float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize, int mode, cudaStream_t s) {
   if (B <= 0) return MUSE_OK;
+  const int upsample2x = (mode & 3) == 1;
+  const int fwd2x2 = (mode & 3) == 2;
+  if (fwd2x2 != (ksize == 2)) { set_last_error("conv2d_tc: ksize 2 and mode 2 go together"); return MUSE_ERR_INVALID; }
   if (upsample2x) {
     if (conv2d_tc_tiles_per_image(H, W, Cin, Cout, ksize, 1) == 0) {
       set_last_error("conv2d_tc: unsupported upsample shape H=%d W=%d Cin=%d Cout=%d k=%d", H, W, Cin, Cout, ksize);
@@ -558,13 +623,15 @@ int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
   p.tiles_per_img = p.tiles_x * (H / p.tile_h);
   p.num_m = B * p.tiles_per_img;
   p.up = upsample2x ? 1 : 0;
+  p.fwd2x2 = fwd2x2;
+  p.wbatch = (mode & 4) ? 1 : 0;
   p.tile_w_log2 = 0;
   while ((1 << p.tile_w_log2) < p.tile_w) ++p.tile_w_log2;
   if (p.up && (1 << p.tile_w_log2) != p.tile_w) { set_last_error("conv2d_tc: upsample needs a power-of-two tile width"); return MUSE_ERR_UNSUPPORTED; }
   const int BN = (swap || Cout >= 256) ? 256 : (Cout > 16 ? 128 : 16);
   p.num_n = swap ? 1 : ceil_div(Cout, BN);
   p.cchunks = Cin / BK;
-  const int taps = p.up ? 4 : ksize * ksize;
+  const int taps = (p.up || p.fwd2x2) ? 4 : ksize * ksize;
   p.num_kb = taps * p.cchunks * 3;
 
   CUtensorMap ah, al, bh, bl;
@@ -575,11 +642,12 @@ int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
   if ((rc = make_tmap_nd(&ah, x_hi, 4, adims, astr, abox))) return rc;
   if ((rc = make_tmap_nd(&al, x_lo, 4, adims, astr, abox))) return rc;
   const unsigned long long K = static_cast<unsigned long long>(taps) * Cin;
-  const unsigned long long bdims[2] = {K, (unsigned long long)Cout * (p.up ? 4 : 1)};
-  const unsigned long long bstr[1] = {K * 2};
-  const unsigned bbox[2] = {64, swap ? 128u : (unsigned)BN};
-  if ((rc = make_tmap_nd(&bh, w_hi, 2, bdims, bstr, bbox))) return rc;
-  if ((rc = make_tmap_nd(&bl, w_lo, 2, bdims, bstr, bbox))) return rc;
+  const unsigned long long wrows = (unsigned long long)Cout * (p.up ? 4 : 1);
+  const unsigned long long bdims[3] = {K, wrows, (unsigned long long)(p.wbatch ? B : 1)};
+  const unsigned long long bstr[2] = {K * 2, K * 2 * wrows};
+  const unsigned bbox[3] = {64, swap ? 128u : (unsigned)BN, 1};
+  if ((rc = make_tmap_nd(&bh, w_hi, 3, bdims, bstr, bbox))) return rc;
+  if ((rc = make_tmap_nd(&bl, w_lo, 3, bdims, bstr, bbox))) return rc;
   if (swap) return launch_conv<256, true>(ah, al, bh, bl, p, s);
   if (BN == 256) return launch_conv<256>(ah, al, bh, bl, p, s);
   if (BN == 128) return launch_conv<128>(ah, al, bh, bl, p, s);
@@ -597,6 +665,25 @@ int im2col_split_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, i
   im2col_split_kernel<<<static_cast<unsigned>(ceil_div_ll(pixels * 8, 256)), 256, 0, s>>>(
       x, reinterpret_cast<bf16*>(hi), reinterpret_cast<bf16*>(lo), pixels, H, W, Cin, ksize);
   return check_launch("im2col_split");
+}
+
+// x fp32 [B,2Ho,2Wo,C] -> hi, lo bf16 [B,Ho,Wo,4C]
+int split_s2d_bf16_nhwc(const float* x, void* hi, void* lo, int B, int Ho, int Wo, int C, cudaStream_t s) {
+  if (C % 8 != 0) { set_last_error("split_s2d: C must be a multiple of 8"); return MUSE_ERR_UNSUPPORTED; }
+  const long long total8 = static_cast<long long>(B) * Ho * Wo * 4 * (C / 8);
+  if (total8 <= 0) return MUSE_OK;
+  split_s2d_kernel<<<static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s>>>(x, reinterpret_cast<bf16*>(hi),
+                                                                                   reinterpret_cast<bf16*>(lo), total8, Ho, Wo, C);
+  return check_launch("split_s2d");
+}
+
+// out_f32 given: plain fp32 softmax (hi / lo unused); else the bf16 hi/lo planes
+int softmax_split_rows(const float* x, void* hi, void* lo, float* out_f32, long long rows, int n, float scale, cudaStream_t s) {
+  if (rows <= 0 || n <= 0) return MUSE_OK;
+  if (out_f32 == x) { set_last_error("softmax: in-place output is not supported"); return MUSE_ERR_INVALID; }
+  softmax_split_kernel<<<static_cast<unsigned>(ceil_div_ll(rows, 8)), 256, 0, s>>>(x, reinterpret_cast<bf16*>(hi),
+                                                                                   reinterpret_cast<bf16*>(lo), out_f32, rows, n, scale);
+  return check_launch("softmax_split");
 }
 
 // x fp32 [B, H/(1+up), W/(1+up), C] -> hi, lo bf16 [B,H,W,C]

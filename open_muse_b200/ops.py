@@ -554,7 +554,7 @@ def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
             else:
                 (ws, ss), tiles = _gn_scratch(x), 0
             _call("muse_groupnorm_silu_nhwc", _p(x), _p(gn[0].detach().float()), _p(gn[1].detach().float()), None, _p(hi),
-                  _p(lo), _p(ws), _p(ss), B, H * W, Cin, int(gn[2]), float(gn[3]), tiles, st)
+                  _p(lo), _p(ws), _p(ss), B, H * W, Cin, int(gn[2]), float(gn[3]), tiles, int(gn[4]) if len(gn) > 4 else 1, st)
         else:
             _call("muse_split_bf16_nhwc", _p(x), _p(hi), _p(lo), B, H, W, Cin, 1 if upsample2x else 0, st)
         w_hi, w_lo = _packed_conv_weight_split(w)
@@ -569,14 +569,114 @@ def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
     return y
 
 
-def groupnorm_silu(x, gamma, beta, groups, eps):
+def groupnorm_silu(x, gamma, beta, groups, eps, silu=1):
+    """GroupNorm (+ SiLU unless silu=0), fp32 NHWC in and out."""
     st = _prep(x)
     B, H, W, C = x.shape
     y = torch.empty_like(x)
     ws, ss = _gn_scratch(x)
     _call("muse_groupnorm_silu_nhwc", _p(x), _p(gamma.detach().float()), _p(beta.detach().float()), _p(y), None, None,
-          _p(ws), _p(ss), B, H * W, C, groups, float(eps), 0, st)
+          _p(ws), _p(ss), B, H * W, C, groups, float(eps), 0, int(silu), st)
     return y
+
+
+def _packed_conv_weight_down(w):
+    """3x3 stride-2 weight (pad (0,1,0,1)) -> bf16 (hi, lo) [Cout, 4 taps * 4 * Cin] for the space-to-depth form:
+    tap (a, b) in {0,1}^2 and plane (p, q) hold w[:, :, 2a + p, 2b + q] (zero where 2a + p or 2b + q exceeds 2)."""
+    import weakref
+
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+    hit = _wk_cache.get(("down", id(w)))
+    if hit is not None and hit[0]() is w and hit[1] == key:
+        return hit[2]
+    wf = w.detach().float()
+    Cout, Cin = wf.shape[0], wf.shape[1]
+    wk = torch.zeros(Cout, 2, 2, 2, 2, Cin, dtype=torch.float32, device=w.device)  # [co, a, b, p, q, ci]
+    for a in (0, 1):
+        for b in (0, 1):
+            for p_ in (0, 1):
+                for q in (0, 1):
+                    kh, kw = 2 * a + p_, 2 * b + q
+                    if kh <= 2 and kw <= 2:
+                        wk[:, a, b, p_, q] = wf[:, :, kh, kw]
+    wk = wk.reshape(Cout, -1).contiguous()
+    hi = wk.to(torch.bfloat16)
+    lo = (wk - hi.float()).to(torch.bfloat16)
+    _wk_cache[("down", id(w))] = (weakref.ref(w), key, (hi, lo))
+    return hi, lo
+
+
+def conv2d_down(x, w, bias=None):
+    """taming Downsample (modeling_taming_vqgan.py:47-62): F.pad(x, (0,1,0,1)) then 3x3 conv with stride 2.
+    x fp32 NHWC [B, 2H, 2W, Cin] -> fp32 [B, H, W, Cout].  Tensor-core route: space-to-depth + hi/lo split, then a
+    stride-1 2x2 convolution over 4*Cin channels; other geometries use the fp32 SIMT kernel's stride-2 mode."""
+    st = _prep(x)
+    B, Hi, Wi, Cin = x.shape
+    H, W = Hi // 2, Wi // 2
+    Cout = w.shape[0]
+    y = torch.empty(B, H, W, Cout, dtype=torch.float32, device=x.device)
+    b = None if bias is None else bias.detach().float()
+    import os
+
+    if os.environ.get("MUSE_B200_CONV", "tc") != "simt" and (4 * Cin) % 64 == 0 and \
+            _lib.load().muse_conv2d_tc_supported(H, W, 4 * Cin, Cout, 2):
+        hi = torch.empty(B, H, W, 4 * Cin, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi)
+        _call("muse_split_s2d_bf16_nhwc", _p(x), _p(hi), _p(lo), B, H, W, Cin, st)
+        w_hi, w_lo = _packed_conv_weight_down(w)
+        stats, tiles = _conv_stats_buffer(y, H, W, 4 * Cin, Cout, 2)
+        _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), None, _p(y), _p(stats), B, H, W, 4 * Cin, Cout,
+              2, 2, st)
+        return y
+    _call("muse_conv2d_nhwc", _p(x), _p(_packed_conv_weight(w)), _p(b), None, _p(y), B, H, W, Cin, Cout, 3, 2, st)
+    return y
+
+
+def attention_single_head(q, k, v, B, hh, ww):
+    """softmax(q k^T / sqrt(C)) v per image with ONE head of width C (AttnBlock of the taming VQGAN, :148-174), fp32-faithful:
+    q, k, v fp32 [B*hh*ww, C] -> fp32 [B*hh*ww, C].  Both products run as 1x1 tensor-core convolutions whose weights are
+    the image's own keys / values (per-image weight mode of muse_conv2d_nhwc_tc); small geometries loop over the images
+    with the SIMT kernel."""
+    import os
+
+    st = _prep(q)
+    HW, C = hh * ww, q.shape[1]
+    lib = _lib.load()
+    scale = float(C) ** -0.5
+    out = torch.empty(B * HW, C, dtype=torch.float32, device=q.device)
+    scores = torch.empty(B * HW, HW, dtype=torch.float32, device=q.device)
+    vt = torch.empty(B, C, HW, dtype=torch.float32, device=q.device)
+    _call("muse_transpose_batched", _p(v), _p(vt), B, HW, C, st)
+    tc = os.environ.get("MUSE_B200_CONV", "tc") != "simt" and lib.muse_conv2d_tc_supported(hh, ww, C, HW, 1) and \
+        lib.muse_conv2d_tc_supported(hh, ww, HW, C, 1) and HW % 64 == 0 and C % 64 == 0
+
+    def planes(t):
+        hi = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+        lo = torch.empty_like(hi)
+        _call("muse_split_bf16_nhwc", _p(t), _p(hi), _p(lo), 1, 1, t.numel() // t.shape[-1], t.shape[-1], 0, st)
+        return hi, lo
+
+    if tc:
+        qh, ql = planes(q)
+        kh, kl = planes(k)        # per-image weights [B][HW keys][C]
+        _call("muse_conv2d_nhwc_tc", _p(qh), _p(ql), _p(kh), _p(kl), None, None, _p(scores), None, B, hh, ww, C, HW, 1, 4, st)
+        ph = torch.empty(B * HW, HW, dtype=torch.bfloat16, device=q.device)
+        pl = torch.empty_like(ph)
+        _call("muse_softmax_split_rows", _p(scores), _p(ph), _p(pl), None, B * HW, HW, scale, st)
+        vh, vl = planes(vt)       # per-image weights [B][C][HW keys]
+        _call("muse_conv2d_nhwc_tc", _p(ph), _p(pl), _p(vh), _p(vl), None, None, _p(out), None, B, hh, ww, HW, C, 1, 4, st)
+        return out
+    kt = torch.empty(B, C, HW, dtype=torch.float32, device=q.device)
+    _call("muse_transpose_batched", _p(k), _p(kt), B, HW, C, st)
+    probs = torch.empty_like(scores)
+    for b in range(B):  # SIMT weights are [K, Cout]: k_b^T for the scores, v_b for the output
+        qb, sb = q[b * HW:(b + 1) * HW], scores[b * HW:(b + 1) * HW]
+        _call("muse_conv2d_nhwc", _p(qb), _p(kt[b]), None, None, _p(sb), 1, hh, ww, C, HW, 1, 0, st)
+    _call("muse_softmax_split_rows", _p(scores), None, None, _p(probs), B * HW, HW, scale, st)
+    for b in range(B):
+        pb, ob = probs[b * HW:(b + 1) * HW], out[b * HW:(b + 1) * HW]
+        _call("muse_conv2d_nhwc", _p(pb), _p(v[b * HW:(b + 1) * HW]), None, None, _p(ob), 1, hh, ww, HW, C, 1, 0, st)
+    return out
 
 
 def avg_pool2x2(x):

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from .modeling_maskgit_vqgan import MaskGitVQGAN
+from .modeling_taming_vqgan import VQGANModel
 from .modeling_transformer import MaskGitTransformer
 from .modeling_transformer_v2 import MaskGiTUViT_v2
 from .sampling import get_mask_chedule
@@ -186,9 +187,12 @@ class PipelineMuse:
         if vae is None:
             path, folder = sub(vae_path, "vae")
             name = class_name(path, folder)
-            if name not in (None, "MaskGitVQGAN"):
-                raise NotImplementedError(f"tokenizer class {name} is out of scope (only MaskGitVQGAN is built, see DESIGN.md)")
-            vae = MaskGitVQGAN.from_pretrained(path, subfolder=folder)
+            if name == "VQGANModel":  # (reference :327-328)
+                vae = VQGANModel.from_pretrained(path, subfolder=folder)
+            elif name in (None, "MaskGitVQGAN"):
+                vae = MaskGitVQGAN.from_pretrained(path, subfolder=folder)
+            else:
+                raise NotImplementedError(f"tokenizer class {name} is out of scope (MaskGitVQGAN and VQGANModel are built)")
         if transformer is None:
             path, folder = sub(transformer_path, "transformer")
             name = class_name(path, folder)

@@ -248,6 +248,29 @@ def main():
                os.path.join(HERE, "micro_uvit_v2.pt"))
     print("micro uvit v2: loss", float(loss), "weighted", float(loss_w), "logits std", float(logits.std()))
 
+    # ---- (7) taming VQGANModel (modeling_taming_vqgan.py), micro config with attention at the last level and in the mid block
+    from muse.modeling_taming_vqgan import VQGANModel
+
+    TAMING = dict(resolution=32, num_channels=3, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=2,
+                  attn_resolutions=(16,), z_channels=16, num_embeddings=64, quantized_embed_dim=16)
+    torch.manual_seed(40)
+    tv = VQGANModel(**TAMING)
+    tv.eval()
+    init_sig = {k: (float(x.double().sum()), float(x.double().norm())) for k, x in tv.state_dict().items()}
+    img = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(41))
+    with torch.no_grad():
+        z = tv.quant_conv(tv.encoder(img))
+        tv.quantize.embedding.weight.copy_(torch.randn(64, 16, generator=torch.Generator().manual_seed(42)) * z.std())
+        zq, ids = tv.encode(img)
+        rec = tv.decode_code(ids)
+        d = tv.quantize.compute_distances(z.permute(0, 2, 3, 1).contiguous())
+        top2 = d.topk(2, dim=1, largest=False).values
+    print("micro taming vqgan: min top-2 margin", float((top2[:, 1] - top2[:, 0]).min()), "attn blocks",
+          sum(1 for k in tv.state_dict() if k.endswith("proj_out.weight")))
+    torch.save(dict(config=TAMING, seed=40, init_signature=init_sig,
+                    state_dict={k: x.clone() for k, x in tv.state_dict().items()}, image=img, z=z, ids=ids, z_q=zq,
+                    recon=rec, margin=(top2[:, 1] - top2[:, 0])), os.path.join(HERE, "micro_taming_vqgan.pt"))
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

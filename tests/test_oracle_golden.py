@@ -66,6 +66,19 @@ def test_micro_uvit_v2_forward_loss_and_generate2(golden):
     assert torch.equal(ids, g["gen_ids"])
 
 
+def test_micro_taming_vqgan(golden):
+    """taming VQGANModel restatement (strided Downsample with (0,1,0,1) padding, AttnBlocks, input-side shortcuts)."""
+    from oracle import taming_vqgan_oracle as TG
+
+    g = golden("micro_taming_vqgan.pt")
+    with torch.no_grad():
+        z, zq, ids = TG.encode(g["state_dict"], g["config"], g["image"])
+        _close(z, g["z"], 1e-5, 1e-6)
+        assert torch.equal(ids, g["ids"])
+        _close(zq, g["z_q"], 0, 0)
+        _close(TG.decoder(g["state_dict"], g["config"], g["z_q"]), g["recon"], 1e-5, 1e-5)
+
+
 def test_masking_recipe(golden):
     b = golden("micro_transformer.pt")["batch"]
     inp, lab = T.mask_tokens(b["tokens"], b["class_ids"], b["timesteps"], b["rand"], 64, 71)
