@@ -83,3 +83,17 @@ if "uvit" in which:
                                     "256 tokens, CFG)", "value": ms, "unit": "ms", "images_per_s": bs / (ms * 1e-3),
                           "ms_per_step": ms / 12, "launches_per_call": (ops.launches() - l0) // 5}), flush=True)
     del u
+if "taming" in which:
+    # the taming VQGANModel at the geometry of the text-to-image configs (f16, 256 px, 8192 codes, attention at 16x16)
+    from open_muse_b200 import VQGANModel
+
+    torch.manual_seed(0)
+    t = VQGANModel(num_embeddings=8192).to(dev).eval()
+    B = int(os.environ.get("VQ_BATCH", "64"))
+    img = torch.rand(B, 3, 256, 256, device=dev)
+    ids = t.get_code(img)
+    ms_enc = timed(lambda: t.get_code(img), 2, warm=1)
+    ms_dec = timed(lambda: t.decode_code(ids), 2, warm=1)
+    print(json.dumps({"metric": f"taming VQGANModel f16-256 encode / decode_code (fp32-faithful, B={B})",
+                      "encode_images_per_s": B / (ms_enc * 1e-3), "decode_images_per_s": B / (ms_dec * 1e-3),
+                      "encode_ms": ms_enc, "decode_ms": ms_dec, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
