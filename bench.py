@@ -203,6 +203,8 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-step", action="store_true", help="skip the extra 'train step incl. VQ encode' measurement")
+    ap.add_argument("--no-cuda-graph", action="store_true",
+                    help="launch the kernels of each step one by one instead of replaying the captured step (N=1 default: graph)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu (the reference arm) or cuda (same eager ops under bf16 autocast, informational)")
     args = ap.parse_args()
@@ -228,8 +230,10 @@ def main():
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
-    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    use_graph = world == 1 and not args.no_cuda_graph
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True, capturable=use_graph)
+    gen = None if use_graph else torch.Generator(device=dev).manual_seed(100 + rank)  # graph capture: default generator
+    torch.cuda.manual_seed(100 + rank)
     n_buf = 4
     host_tok = [torch.randint(0, 1024, (B, 256), generator=torch.Generator().manual_seed(1000 * rank + i)).pin_memory() for i in range(n_buf)]
     host_cls = [torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(2000 * rank + i)).pin_memory() for i in range(n_buf)]
@@ -265,20 +269,31 @@ def main():
 
     for i in range(warmup):
         step(dev_tok[i % n_buf], dev_cls[i % n_buf])
+    torch.cuda.synchronize()
+    l_eager = ops.launches()
+    step(dev_tok[0], dev_cls[0])
+    launches_per_step = ops.launches() - l_eager  # kernels of this package per step (a replayed graph launches the same)
+    run = step
+    if use_graph:  # the whole step (masking, fwd, loss, bwd, AdamW) captured once, replayed per step
+        from open_muse_b200.graphs import GraphedStep
+
+        run = GraphedStep(step, (dev_tok[0], dev_cls[0]), warmup=2)
+        for i in range(2):
+            run(dev_tok[i % n_buf], dev_cls[i % n_buf])
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ops.launches()
-    ms_dev = timed(lambda i: step(dev_tok[i % n_buf], dev_cls[i % n_buf]), args.steps)
-    launches = (ops.launches() - l0)
+    ms_dev = timed(lambda i: run(dev_tok[i % n_buf], dev_cls[i % n_buf]), args.steps)
+    launches = launches_per_step * args.steps
 
     def e2e_step(i):
         tok = host_tok[i % n_buf].to(dev, non_blocking=True)
         cls = host_cls[i % n_buf].to(dev, non_blocking=True)
-        return float(step(tok, cls))  # .item(): device->host read of the loss
+        return float(run(tok, cls))  # .item(): device->host read of the loss
 
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    model._packed.key = None  # graph replays update the parameters without bumping their version counters: re-pack for eager use
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM), measured live with CUDA events around every launch
     peak_tf, peak_hbm, peak_src = measured_peaks()
@@ -348,7 +363,8 @@ def main():
                        "global_batch": gb, "per_gpu_batch": B, "seq_len": 257,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "no explicit flush: per-step working set (~15 GB activations + 0.5 GB weights/grads/optimizer) >> 126 MB L2",
-                       "gemm_backend": os.environ.get("MUSE_B200_GEMM", "tcgen05")},
+                       "gemm_backend": os.environ.get("MUSE_B200_GEMM", "tcgen05"),
+                       "cuda_graph": bool(use_graph)},
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4},
             "gpu_launches": launches,
