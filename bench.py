@@ -277,9 +277,14 @@ def main():
     if use_graph:  # the whole step (masking, fwd, loss, bwd, AdamW) captured once, replayed per step
         from open_muse_b200.graphs import GraphedStep
 
-        run = GraphedStep(step, (dev_tok[0], dev_cls[0]), warmup=2)
-        for i in range(2):
-            run(dev_tok[i % n_buf], dev_cls[i % n_buf])
+        try:
+            run = GraphedStep(step, (dev_tok[0], dev_cls[0]), warmup=2)
+            for i in range(2):
+                run(dev_tok[i % n_buf], dev_cls[i % n_buf])
+        except Exception as e:  # same kernels launched one by one (reported in config.cuda_graph)
+            print(f"bench: CUDA graph capture failed ({type(e).__name__}: {e}); timing the eager launch path", file=sys.stderr)
+            torch.cuda.synchronize()
+            run, use_graph = step, False
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
