@@ -413,10 +413,16 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
             # training: one autograd Function for the whole network (uvit_v2_train.py)
             if self.training and (c.hidden_dropout > 0.0 or c.attention_dropout > 0.0):
                 raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: dropout > 0 in training mode is not implemented")
-            from .uvit_v2_train import UViTTrainFn
+            import os
 
-            padded, loss = UViTTrainFn.apply(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels,
-                                             label_smoothing, loss_weight, *self.parameters())
+            from . import uvit_v2_train as T
+
+            if os.environ.get("MUSE_B200_UVIT_TRAIN", "blocks") == "mono":  # one Function for the network (cross-check)
+                padded, loss = T.UViTTrainFn.apply(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels,
+                                                   label_smoothing, loss_weight, *self.parameters())
+            else:  # one Function per block: parameter gradients appear during backward (DDP overlap)
+                padded, loss = T.train_forward(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels,
+                                               label_smoothing, loss_weight)
             logits = padded.view(B, S, -1)[:, :, : c.codebook_size]
             if not (_raw_bf16 or torch.is_autocast_enabled()):
                 logits = logits.float()

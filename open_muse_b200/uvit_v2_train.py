@@ -38,6 +38,8 @@ class _G(dict):
         self.W = W
 
     def of(self, key):
+        if self.W[key] is None:  # e.g. a norm without elementwise affine
+            return None
         if key not in self:
             self[key] = _z(self.W[key])
         return self[key]
@@ -278,7 +280,7 @@ def param_grads(model, G):
     out = {}
 
     def put(p, g):
-        if p is not None:
+        if p is not None and g is not None:
             out[p] = g.reshape(p.shape)
 
     def rows(g, *ps):
@@ -301,7 +303,7 @@ def param_grads(model, G):
         for i, (rb, ab) in enumerate(zip(blk.res_blocks, blk.attention_blocks)):
             g = gl[i]
             put(rb.depthwise.weight, g["dw"].t().contiguous())
-            put(rb.norm.norm.weight, g["dw_norm"])
+            put(rb.norm.norm.weight, g.get("dw_norm"))
             put(rb.channelwise[0].weight, g["cw0"])
             put(rb.channelwise[2].gamma, g["gamma"])
             put(rb.channelwise[2].beta, g["beta"])
@@ -309,35 +311,35 @@ def param_grads(model, G):
             mappers.append(rb.adaLN_modulation.mapper.weight)
             if ab.kv_mapper is not None:
                 put(ab.kv_mapper.weight, g["kvm"])
-            put(ab.attn_layer_norm.weight, g["ln1"])
+            put(ab.attn_layer_norm.weight, g.get("ln1"))
             attn(ab.attention, g["a1"], False)
-            put(ab.crossattn_layer_norm.weight, g["ln2"])
+            put(ab.crossattn_layer_norm.weight, g.get("ln2"))
             attn(ab.crossattention, g["a2"], False)
 
     put(model.encoder_proj.weight, G["encoder_proj"])
-    put(model.encoder_proj_layer_norm.weight, G["enc_norm"])
+    put(model.encoder_proj_layer_norm.weight, G.get("enc_norm"))
     put(model.cond_embed[0].weight, G["cond0"])
     put(model.cond_embed[2].weight, G["cond2"])
     put(model.embed.embeddings.weight, G["emb"])
-    put(model.embed.layer_norm.weight, G["emb_norm"])
+    put(model.embed.layer_norm.weight, G.get("emb_norm"))
     put(model.embed.conv.weight, G["emb_conv"])
-    put(model.project_to_hidden_norm.weight, G["pth_norm"])
+    put(model.project_to_hidden_norm.weight, G.get("pth_norm"))
     put(model.project_to_hidden.weight, G["pth"])
-    put(model.project_from_hidden_norm.weight, G["pfh_norm"])
+    put(model.project_from_hidden_norm.weight, G.get("pfh_norm"))
     put(model.project_from_hidden.weight, G["pfh"])
     put(model.mlm_layer.conv1.weight, G["mlm1"])
-    put(model.mlm_layer.layer_norm.norm.weight, G["mlm_norm"])
+    put(model.mlm_layer.layer_norm.norm.weight, G.get("mlm_norm"))
     put(model.mlm_layer.conv2.weight, G["mlm2"][: c.codebook_size])
     block(model.down_blocks[0], G["down"])  # mapper order must match _weights(): down, layers, up
     for i, l in enumerate(model.transformer_layers):
         g = G["layers"][i]
-        put(l.attn_layer_norm.weight, g["ln1"])
+        put(l.attn_layer_norm.weight, g.get("ln1"))
         mappers.append(l.self_attn_adaLN_modulation.mapper.weight)
         attn(l.attention, g["sa"], True)
-        put(l.crossattn_layer_norm.weight, g["ln2"])
+        put(l.crossattn_layer_norm.weight, g.get("ln2"))
         attn(l.crossattention, g["ca"], False)
         mappers.append(l.cross_attn_adaLN_modulation.mapper.weight)
-        put(l.ffn.pre_mlp_layer_norm.weight, g["ln3"])
+        put(l.ffn.pre_mlp_layer_norm.weight, g.get("ln3"))
         mappers.append(l.ffn.adaLN_modulation.mapper.weight)
         rows(g["wi"], l.ffn.wi_0.weight, l.ffn.wi_1.weight)
         put(l.ffn.wo.weight, g["wo"])
@@ -387,3 +389,296 @@ class UViTTrainFn(torch.autograd.Function):
         grads = param_grads(ctx.model, G)
         ctx.saved = None
         return (None,) * 8 + tuple(grads)
+
+
+# =================================================================================================================
+# Per-block autograd Functions: the same forward / backward helpers as above, cut at the block boundaries so that the
+# gradients of a block's parameters exist as soon as its backward has run and DDP's bucket all-reduces overlap the rest
+# of the backward pass (the whole-network Function above releases everything at the very end).  Tensors consumed by
+# every block enter each Function as fp32 inputs -- the normalised text states ``enc32`` and the SiLU'd conditioning
+# vector ``sc32`` -- and autograd sums their per-block gradients; each block computes its own adaLN (scale | shift) rows
+# from ``sc`` with its slice of the stacked mapper matrix.
+class _Shared:
+    """per-forward constants and bf16 operand copies shared by the block Functions"""
+
+    def __init__(self, model, W, B, S, Skv):
+        c = model.config
+        self.W, self.B, self.S, self.Skv, self.hw = W, B, S, Skv, int(S ** 0.5)
+        self.rms, self.eps, self.H = (0 if c.norm_type == "layernorm" else 1), c.layer_norm_eps, c.hidden_size
+        self.enc = self.sc = None  # bf16 GEMM operands of enc32 / sc32
+
+
+def _present(params):
+    return [p for p in params if p is not None]
+
+
+def _align(params, grads):
+    """gradients of the non-None parameters, in order"""
+    return [g.reshape(p.shape) for p, g in zip(params, grads) if p is not None]
+
+
+def _local_mods(sh, w, keys):
+    """this block's rows of the stacked mapper matrix and its W entry re-based onto the block-local (scale | shift) tensor"""
+    base = w[keys[0]][0]
+    total = sum(w[k][1] for k in keys)
+    wl = dict(w)
+    for k in keys:
+        wl[k] = (w[k][0] - base, w[k][1])
+    return wl, sh.W["mappers"][base:base + total]
+
+
+def _mapper_bwd(sh, d_mod, w_map):
+    g_map = _z(w_map)
+    d_sc32 = _lin_bwd(ops.cast_bf16(d_mod), sh.sc, w_map, g_map, dx_dtype=F32)
+    return g_map, d_sc32
+
+
+def _attn_params(a):
+    return [a.query.weight, a.key.weight, a.value.weight, a.out.weight]
+
+
+def _attn_grads(g, a, fused):
+    n = a.query.weight.shape[0]
+    if fused:
+        q, k, v = g["qkv"][:n], g["qkv"][n:2 * n], g["qkv"][2 * n:]
+    else:
+        q, k, v = g["q"], g["kv"][:n], g["kv"][n:]
+    return [q, k, v, g["o"]]
+
+
+class CondFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh, cond_in, w0, w2):
+        W = sh.W
+        c1 = ops.linear_fwd(cond_in, W["cond0"])
+        c1s = ops.silu_bf16(c1)
+        cond = ops.linear_fwd(c1s, W["cond2"])
+        sh.sc = ops.silu_bf16(cond)
+        ctx.sh, ctx.sv = sh, (cond_in, c1, c1s, cond)
+        ctx.set_materialize_grads(False)
+        return sh.sc.float()
+
+    @staticmethod
+    def backward(ctx, d_sc32):
+        W, (cond_in, c1, c1s, cond) = ctx.sh.W, ctx.sv
+        g0, g2 = _z(W["cond0"]), _z(W["cond2"])
+        d_cond = ops.silu_bwd(ops.cast_bf16(d_sc32.contiguous()), cond)
+        d_c1 = ops.silu_bwd(_lin_bwd(d_cond, c1s, W["cond2"], g2), c1)
+        _lin_bwd(d_c1, cond_in, W["cond0"], g0, need_dx=False)
+        return None, None, g0, g2
+
+
+class EncFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh, ehs, w_proj, w_norm):
+        W = sh.W
+        r_enc, sh.enc = ops.add_norm_mod(ops.linear_fwd(ehs, W["encoder_proj"]), W["enc_norm"], sh.eps, sh.rms)
+        ctx.sh, ctx.sv, ctx.has_norm = sh, (ehs, r_enc), w_norm is not None
+        ctx.set_materialize_grads(False)
+        return sh.enc.float()
+
+    @staticmethod
+    def backward(ctx, d_enc32):
+        sh, (ehs, r_enc) = ctx.sh, ctx.sv
+        W = sh.W
+        g_p = _z(W["encoder_proj"])
+        g_n = _z(W["enc_norm"]) if ctx.has_norm else None
+        d_y0, _ = ops.add_norm_mod_bwd(d_enc32.contiguous(), None, r_enc, W["enc_norm"], sh.eps, sh.rms, BF16, dw=g_n, want_dr=False)
+        _lin_bwd(d_y0, ehs, W["encoder_proj"], g_p, need_dx=False)
+        return None, None, g_p, g_n
+
+
+class EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh, ids, w_emb, w_norm, w_conv):
+        W = sh.W
+        e = ops.embed_fwd(ids, W["emb"], None)
+        _, en = ops.add_norm_mod(e, W["emb_norm"], sh.eps, sh.rms, want_residual=False)
+        ctx.sh, ctx.sv, ctx.has_norm, ctx.conv_shape = sh, (ids, e, en), w_norm is not None, w_conv.shape
+        ctx.set_materialize_grads(False)
+        return ops.linear_fwd(en, W["emb_conv"], out_dtype=F32)
+
+    @staticmethod
+    def backward(ctx, dh):
+        sh, (ids, e, en) = ctx.sh, ctx.sv
+        W = sh.W
+        g_c, g_e = _z(W["emb_conv"]), _z(W["emb"])
+        g_n = _z(W["emb_norm"]) if ctx.has_norm else None
+        d_en = _lin_bwd(ops.cast_bf16(dh.contiguous()), en, W["emb_conv"], g_c)
+        d_e, _ = ops.add_norm_mod_bwd(d_en, None, e, W["emb_norm"], sh.eps, sh.rms, F32, dw=g_n, want_dr=False)
+        ops.embed_bwd(ids, d_e, g_e, None)
+        return None, None, g_e, g_n, g_c.reshape(ctx.conv_shape)
+
+
+def block_params(rb, ab):
+    return [rb.depthwise.weight, rb.norm.norm.weight, rb.channelwise[0].weight, rb.channelwise[2].gamma, rb.channelwise[2].beta,
+            rb.channelwise[4].weight, rb.adaLN_modulation.mapper.weight, None if ab.kv_mapper is None else ab.kv_mapper.weight,
+            ab.attn_layer_norm.weight] + _attn_params(ab.attention) + [ab.crossattn_layer_norm.weight] + _attn_params(ab.crossattention)
+
+
+class UBlockFn(torch.autograd.Function):
+    """ResBlock + AttentionBlock2D pair of the down / up stage"""
+
+    @staticmethod
+    def forward(ctx, sh, model, which, idx, h, enc32, sc32, *params):
+        w = sh.W[which][idx]
+        wl, w_map = _local_mods(sh, w, ["mod"])
+        mod = ops.linear_fwd(sh.sc, w_map, out_dtype=F32)
+        h, s_r = _res_block_fwd(h, wl, mod, sh.B, sh.hw, sh.eps, sh.rms)
+        h, s_a = _attn_block_fwd(h, sh.enc, wl, sh.B, sh.S, sh.Skv, sh.eps, sh.rms)
+        ctx.sh, ctx.sv, ctx.key = sh, (wl, w_map, mod, s_r, s_a), (model, which, idx)
+        ctx.set_materialize_grads(False)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        sh, (wl, w_map, mod, s_r, s_a), (model, which, idx) = ctx.sh, ctx.sv, ctx.key
+        stage = model.down_blocks[0] if which == "down" else model.up_blocks[0]
+        rb, ab = stage.res_blocks[idx], stage.attention_blocks[idx]
+        g, d_enc, d_mod = _G(wl), _z(sh.enc), _z(mod)
+        dh = _attn_block_bwd(dh.contiguous(), s_a, wl, g, sh.enc, d_enc, sh.B, sh.S, sh.Skv, sh.eps, sh.rms)
+        dh = _res_block_bwd(dh, s_r, wl, g, mod, d_mod, sh.B, sh.hw, sh.eps, sh.rms)
+        g_map, d_sc32 = _mapper_bwd(sh, d_mod, w_map)
+        params = block_params(rb, ab)
+        grads = [g["dw"].t().contiguous(), g.get("dw_norm"), g["cw0"], g["gamma"], g["beta"], g["cw4"], g_map, g.get("kvm"),
+                 g.get("ln1")] + _attn_grads(g["a1"], ab.attention, False) + [g.get("ln2")] + _attn_grads(g["a2"], ab.crossattention, False)
+        return (None, None, None, None, dh, d_enc, d_sc32, *_align(params, grads))
+
+
+def layer_params(l):
+    return [l.attn_layer_norm.weight, l.self_attn_adaLN_modulation.mapper.weight] + _attn_params(l.attention) + \
+        [l.crossattn_layer_norm.weight] + _attn_params(l.crossattention) + \
+        [l.cross_attn_adaLN_modulation.mapper.weight, l.ffn.pre_mlp_layer_norm.weight, l.ffn.adaLN_modulation.mapper.weight,
+         l.ffn.wi_0.weight, l.ffn.wi_1.weight, l.ffn.wo.weight]
+
+
+class ULayerFn(torch.autograd.Function):
+    """one TransformerLayer carrying (hidden, residual)"""
+
+    @staticmethod
+    def forward(ctx, sh, model, idx, x, r, enc32, sc32, *params):
+        w = sh.W["layers"][idx]
+        wl, w_map = _local_mods(sh, w, ["mod1", "mod2", "mod3"])
+        mod = ops.linear_fwd(sh.sc, w_map, out_dtype=F32)
+        f, r3, s_l = _layer_fwd(x, r, sh.enc, wl, mod, sh.B, sh.S, sh.Skv, sh.H, sh.eps, sh.rms)
+        ctx.sh, ctx.sv, ctx.key = sh, (wl, w_map, mod, s_l), (model, idx)
+        ctx.set_materialize_grads(False)
+        return f, r3
+
+    @staticmethod
+    def backward(ctx, df, dr3):
+        sh, (wl, w_map, mod, s_l), (model, idx) = ctx.sh, ctx.sv, ctx.key
+        l = model.transformer_layers[idx]
+        g, d_enc, d_mod = _G(wl), _z(sh.enc), _z(mod)
+        if df is None:
+            df = torch.zeros(s_l[1].shape, dtype=BF16, device=s_l[1].device)
+        dx, dr = _layer_bwd(df.contiguous(), None if dr3 is None else dr3.contiguous(), s_l, wl, g, sh.enc, d_enc, mod, d_mod,
+                            sh.B, sh.S, sh.Skv, sh.eps, sh.rms)
+        g_map, d_sc32 = _mapper_bwd(sh, d_mod, w_map)
+        H2 = 2 * sh.H
+        I = l.ffn.wi_0.weight.shape[0]
+        params = layer_params(l)
+        grads = [g.get("ln1"), g_map[:H2]] + _attn_grads(g["sa"], l.attention, True) + [g.get("ln2")] + \
+            _attn_grads(g["ca"], l.crossattention, False) + [g_map[H2:2 * H2], g.get("ln3"), g_map[2 * H2:], g["wi"][:I], g["wi"][I:],
+                                                             g["wo"]]
+        return (None, None, None, dx, dr, d_enc, d_sc32, *_align(params, grads))
+
+
+class ProjFn(torch.autograd.Function):
+    """project_to_hidden (norm + Linear, residual=None) and project_from_hidden ((x + residual) -> norm + Linear)"""
+
+    @staticmethod
+    def forward(ctx, sh, key, x, r, w_norm, w_lin):
+        W = sh.W
+        r_out, y = ops.add_norm_mod(x, W[key + "_norm"], sh.eps, sh.rms, residual=r)
+        ctx.sh, ctx.sv, ctx.key, ctx.has_norm = sh, (r_out, y, x.dtype, r is not None), key, w_norm is not None
+        ctx.set_materialize_grads(False)
+        return ops.linear_fwd(y, W[key], out_dtype=BF16 if key == "pth" else F32)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        sh, (r_out, y, x_dtype, had_r), key = ctx.sh, ctx.sv, ctx.key
+        W = sh.W
+        g_l = _z(W[key])
+        g_n = _z(W[key + "_norm"]) if ctx.has_norm else None
+        d = d_out.contiguous()
+        dy = _lin_bwd(d if d.dtype == BF16 else ops.cast_bf16(d), y, W[key], g_l)
+        dx, dr = ops.add_norm_mod_bwd(dy, None, r_out, W[key + "_norm"], sh.eps, sh.rms, x_dtype, dw=g_n, want_dr=had_r)
+        return None, None, dx, dr, g_n, g_l
+
+
+class TailFn(torch.autograd.Function):
+    """ConvMlmLayer + cross-entropy"""
+
+    @staticmethod
+    def forward(ctx, sh, V, h, labels, label_smoothing, loss_weight, w1, w_norm, w2):
+        W = sh.W
+        hb = ops.cast_bf16(h)
+        y1 = ops.linear_fwd(hb, W["mlm1"])
+        r_m, y2 = ops.add_norm_mod(y1, W["mlm_norm"], sh.eps, sh.rms)
+        logits = ops.linear_fwd(y2, W["mlm2"])
+        ctx.sh, ctx.sv, ctx.V, ctx.ls = sh, (hb, r_m, y2, logits), V, label_smoothing
+        ctx.has_norm, ctx.shapes = w_norm is not None, (w1.shape, w2.shape)
+        ctx.set_materialize_grads(False)
+        if labels is None:
+            ctx.ce = None
+            return logits, None
+        labels = labels.reshape(-1).contiguous().to(torch.int64)
+        out, ws = ops.ce_fwd(logits, labels, V, label_smoothing)
+        row_scale, loss = None, out[0]
+        if loss_weight is not None:
+            lw = loss_weight.reshape(-1).float()
+            row_scale = (lw / lw.sum()).contiguous()
+            loss = (ws[1] * row_scale).sum()
+        ctx.ce = (labels, ws, out, row_scale)
+        return logits, loss
+
+    @staticmethod
+    def backward(ctx, d_logits, d_loss):
+        sh, (hb, r_m, y2, logits) = ctx.sh, ctx.sv
+        W = sh.W
+        dl = None
+        if d_loss is not None and ctx.ce is not None:
+            labels, ws, out, row_scale = ctx.ce
+            dl = ops.ce_bwd(logits, labels, ws, d_loss.to(F32).reshape(1).contiguous(), out, ctx.V, ctx.ls, row_scale=row_scale)
+        if d_logits is not None:
+            extra = d_logits.to(BF16).contiguous()
+            dl = extra if dl is None else dl + extra
+        if dl is None:
+            raise RuntimeError("MaskGiTUViT_v2: backward called without any gradient")
+        g1, g2 = _z(W["mlm1"]), _z(W["mlm2"])
+        g_n = _z(W["mlm_norm"]) if ctx.has_norm else None
+        dy2 = _lin_bwd(dl, y2, W["mlm2"], g2)
+        dy1, _ = ops.add_norm_mod_bwd(dy2, None, r_m, W["mlm_norm"], sh.eps, sh.rms, BF16, dw=g_n, want_dr=False)
+        dh = _lin_bwd(dy1, hb, W["mlm1"], g1, dx_dtype=F32)
+        return None, None, dh, None, None, None, g1.reshape(ctx.shapes[0]), g_n, g2[: ctx.V].reshape(ctx.shapes[1])
+
+
+def train_forward(model, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels, label_smoothing, loss_weight):
+    """(logits_padded, loss) through the per-block Functions."""
+    from .modeling_transformer_v2 import sinusoidal_encode
+
+    c = model.config
+    W = model._weights()
+    B, S = input_ids.shape
+    Skv = encoder_hidden_states.shape[1]
+    sh = _Shared(model, W, B, S, Skv)
+    ehs = encoder_hidden_states.reshape(B * Skv, -1).to(BF16).contiguous()
+    mc = sinusoidal_encode(micro_conds.flatten(), c.micro_cond_encode_dim).reshape(B, -1)
+    cond_in = torch.cat([cond_embeds.float(), mc], dim=1).to(BF16).contiguous()
+    sc32 = CondFn.apply(sh, cond_in, model.cond_embed[0].weight, model.cond_embed[2].weight)
+    enc32 = EncFn.apply(sh, ehs, model.encoder_proj.weight, model.encoder_proj_layer_norm.weight)
+    h = EmbedFn.apply(sh, input_ids.contiguous().to(torch.int64), model.embed.embeddings.weight, model.embed.layer_norm.weight,
+                      model.embed.conv.weight)
+    down, up = model.down_blocks[0], model.up_blocks[0]
+    for i, (rb, ab) in enumerate(zip(down.res_blocks, down.attention_blocks)):
+        h = UBlockFn.apply(sh, model, "down", i, h, enc32, sc32, *_present(block_params(rb, ab)))
+    x = ProjFn.apply(sh, "pth", h, None, model.project_to_hidden_norm.weight, model.project_to_hidden.weight)
+    r = None
+    for i, l in enumerate(model.transformer_layers):
+        x, r = ULayerFn.apply(sh, model, i, x, r, enc32, sc32, *_present(layer_params(l)))
+    h = ProjFn.apply(sh, "pfh", x, r, model.project_from_hidden_norm.weight, model.project_from_hidden.weight)
+    for i, (rb, ab) in enumerate(zip(up.res_blocks, up.attention_blocks)):
+        h = UBlockFn.apply(sh, model, "up", i, h, enc32, sc32, *_present(block_params(rb, ab)))
+    return TailFn.apply(sh, c.codebook_size, h, labels, label_smoothing, loss_weight, model.mlm_layer.conv1.weight,
+                        model.mlm_layer.layer_norm.norm.weight, model.mlm_layer.conv2.weight)

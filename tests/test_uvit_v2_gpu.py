@@ -354,3 +354,25 @@ def test_micro_uvit_v2_loss_weight_training(golden):
     assert abs(float(loss) - float(g["loss_weighted"])) / float(g["loss_weighted"]) < 2e-3
     for n in ("mlm_layer.conv2.weight", "transformer_layers.1.ffn.wo.weight", "embed.embeddings.weight", "encoder_proj.weight"):
         assert _rel(dict(m.named_parameters())[n].grad, q[n].grad) < 5e-2, n
+
+
+def test_uvit_v2_block_functions_match_whole_network_function(golden, monkeypatch):
+    """The per-block autograd Functions (default: gradients appear during backward, DDP overlap) and the single
+    whole-network Function (MUSE_B200_UVIT_TRAIN=mono) run the same kernels: loss identical, gradients equal up to the
+    summation order of the shared accumulators."""
+    g = golden("micro_uvit_v2.pt")
+    args = [g[k].to(DEV) for k in ("input_ids", "encoder_hidden_states", "cond_embeds", "micro_conds")]
+    grads, losses = {}, {}
+    for mode in ("blocks", "mono"):
+        monkeypatch.setenv("MUSE_B200_UVIT_TRAIN", mode)
+        m = MaskGiTUViT_v2(**g["config"])
+        m.load_state_dict(g["state_dict"])
+        m.to(DEV).train()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            _, loss = m(*args, labels=g["labels"].to(DEV), label_smoothing=0.1)
+        loss.backward()
+        losses[mode] = float(loss)
+        grads[mode] = {n: p.grad.clone() for n, p in m.named_parameters()}
+    assert losses["blocks"] == losses["mono"]
+    worst = max(_rel(grads["blocks"][n], grads["mono"][n]) for n in grads["mono"])
+    assert worst < 2e-2, worst
