@@ -370,7 +370,7 @@ class UViTTrainFn(torch.autograd.Function):
             row_scale = (lw / lw.sum()).contiguous()
             loss = (ws[1] * row_scale).sum()
         ctx.ce = (labels, ws, out, row_scale)
-        ctx.logits = logits
+        ctx.save_for_backward(logits)  # an OUTPUT of this Function: as a plain ctx attribute it would form a reference cycle
         return logits, loss
 
     @staticmethod
@@ -378,7 +378,7 @@ class UViTTrainFn(torch.autograd.Function):
         dl = None
         if d_loss is not None and ctx.ce is not None:
             labels, ws, out, row_scale = ctx.ce
-            dl = ops.ce_bwd(ctx.logits, labels, ws, d_loss.to(F32).reshape(1).contiguous(), out, ctx.V, ctx.ls,
+            dl = ops.ce_bwd(ctx.saved_tensors[0], labels, ws, d_loss.to(F32).reshape(1).contiguous(), out, ctx.V, ctx.ls,
                             row_scale=row_scale)
         if d_logits is not None:
             extra = d_logits.to(BF16).contiguous()
@@ -561,6 +561,10 @@ class ULayerFn(torch.autograd.Function):
         wl, w_map = _local_mods(sh, w, ["mod1", "mod2", "mod3"])
         mod = ops.linear_fwd(sh.sc, w_map, out_dtype=F32)
         f, r3, s_l = _layer_fwd(x, r, sh.enc, wl, mod, sh.B, sh.S, sh.Skv, sh.H, sh.eps, sh.rms)
+        s_l = list(s_l)
+        assert s_l[9] is r3
+        s_l[9] = None  # r3 is an OUTPUT of this Function: held through save_for_backward, a ctx attribute would be a cycle
+        ctx.save_for_backward(r3)
         ctx.sh, ctx.sv, ctx.key = sh, (wl, w_map, mod, s_l), (model, idx)
         ctx.set_materialize_grads(False)
         return f, r3
@@ -568,6 +572,8 @@ class ULayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, df, dr3):
         sh, (wl, w_map, mod, s_l), (model, idx) = ctx.sh, ctx.sv, ctx.key
+        s_l = list(s_l)
+        s_l[9] = ctx.saved_tensors[0]
         l = model.transformer_layers[idx]
         g, d_enc, d_mod = _G(wl), _z(sh.enc), _z(mod)
         if df is None:
@@ -617,7 +623,8 @@ class TailFn(torch.autograd.Function):
         y1 = ops.linear_fwd(hb, W["mlm1"])
         r_m, y2 = ops.add_norm_mod(y1, W["mlm_norm"], sh.eps, sh.rms)
         logits = ops.linear_fwd(y2, W["mlm2"])
-        ctx.sh, ctx.sv, ctx.V, ctx.ls = sh, (hb, r_m, y2, logits), V, label_smoothing
+        ctx.sh, ctx.sv, ctx.V, ctx.ls = sh, (hb, r_m, y2), V, label_smoothing
+        ctx.save_for_backward(logits)  # output of this Function (see ULayerFn)
         ctx.has_norm, ctx.shapes = w_norm is not None, (w1.shape, w2.shape)
         ctx.set_materialize_grads(False)
         if labels is None:
@@ -635,7 +642,8 @@ class TailFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_logits, d_loss):
-        sh, (hb, r_m, y2, logits) = ctx.sh, ctx.sv
+        sh, (hb, r_m, y2) = ctx.sh, ctx.sv
+        logits = ctx.saved_tensors[0]
         W = sh.W
         dl = None
         if d_loss is not None and ctx.ce is not None:
