@@ -465,6 +465,7 @@ class CondFn(torch.autograd.Function):
         d_cond = ops.silu_bwd(ops.cast_bf16(d_sc32.contiguous()), cond)
         d_c1 = ops.silu_bwd(_lin_bwd(d_cond, c1s, W["cond2"], g2), c1)
         _lin_bwd(d_c1, cond_in, W["cond0"], g0, need_dx=False)
+        ctx.sv = None  # release the block's activations now, not when the graph dies
         return None, None, g0, g2
 
 
@@ -485,6 +486,7 @@ class EncFn(torch.autograd.Function):
         g_n = _z(W["enc_norm"]) if ctx.has_norm else None
         d_y0, _ = ops.add_norm_mod_bwd(d_enc32.contiguous(), None, r_enc, W["enc_norm"], sh.eps, sh.rms, BF16, dw=g_n, want_dr=False)
         _lin_bwd(d_y0, ehs, W["encoder_proj"], g_p, need_dx=False)
+        ctx.sv = None  # release the block's activations now, not when the graph dies
         return None, None, g_p, g_n
 
 
@@ -507,6 +509,7 @@ class EmbedFn(torch.autograd.Function):
         d_en = _lin_bwd(ops.cast_bf16(dh.contiguous()), en, W["emb_conv"], g_c)
         d_e, _ = ops.add_norm_mod_bwd(d_en, None, e, W["emb_norm"], sh.eps, sh.rms, F32, dw=g_n, want_dr=False)
         ops.embed_bwd(ids, d_e, g_e, None)
+        ctx.sv = None  # release the block's activations now, not when the graph dies
         return None, None, g_e, g_n, g_c.reshape(ctx.conv_shape)
 
 
@@ -542,6 +545,7 @@ class UBlockFn(torch.autograd.Function):
         params = block_params(rb, ab)
         grads = [g["dw"].t().contiguous(), g.get("dw_norm"), g["cw0"], g["gamma"], g["beta"], g["cw4"], g_map, g.get("kvm"),
                  g.get("ln1")] + _attn_grads(g["a1"], ab.attention, False) + [g.get("ln2")] + _attn_grads(g["a2"], ab.crossattention, False)
+        ctx.sv = None  # release the block's activations now, not when the graph dies
         return (None, None, None, None, dh, d_enc, d_sc32, *_align(params, grads))
 
 
@@ -587,6 +591,7 @@ class ULayerFn(torch.autograd.Function):
         grads = [g.get("ln1"), g_map[:H2]] + _attn_grads(g["sa"], l.attention, True) + [g.get("ln2")] + \
             _attn_grads(g["ca"], l.crossattention, False) + [g_map[H2:2 * H2], g.get("ln3"), g_map[2 * H2:], g["wi"][:I], g["wi"][I:],
                                                              g["wo"]]
+        ctx.sv = None  # release the block's activations now, not when the graph dies
         return (None, None, None, dx, dr, d_enc, d_sc32, *_align(params, grads))
 
 
@@ -610,6 +615,7 @@ class ProjFn(torch.autograd.Function):
         d = d_out.contiguous()
         dy = _lin_bwd(d if d.dtype == BF16 else ops.cast_bf16(d), y, W[key], g_l)
         dx, dr = ops.add_norm_mod_bwd(dy, None, r_out, W[key + "_norm"], sh.eps, sh.rms, x_dtype, dw=g_n, want_dr=had_r)
+        ctx.sv = None  # release the block's activations now, not when the graph dies
         return None, None, dx, dr, g_n, g_l
 
 
@@ -659,6 +665,7 @@ class TailFn(torch.autograd.Function):
         dy2 = _lin_bwd(dl, y2, W["mlm2"], g2)
         dy1, _ = ops.add_norm_mod_bwd(dy2, None, r_m, W["mlm_norm"], sh.eps, sh.rms, BF16, dw=g_n, want_dr=False)
         dh = _lin_bwd(dy1, hb, W["mlm1"], g1, dx_dtype=F32)
+        ctx.sv = None  # release the block's activations now, not when the graph dies
         return None, None, dh, None, None, None, g1.reshape(ctx.shapes[0]), g_n, g2[: ctx.V].reshape(ctx.shapes[1])
 
 
