@@ -417,11 +417,10 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
 
             from . import uvit_v2_train as T
 
-            if os.environ.get("MUSE_B200_UVIT_TRAIN", "mono") != "blocks":  # one Function for the whole network (default)
+            if os.environ.get("MUSE_B200_UVIT_TRAIN", "blocks") == "mono":  # one Function for the whole network (cross-check)
                 padded, loss = T.UViTTrainFn.apply(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels,
                                                    label_smoothing, loss_weight, *self.parameters())
-            else:  # opt-in: one Function per block so that parameter gradients appear during backward (DDP overlap);
-                   # numerically validated, but its memory behaviour at the 604 M scale is not yet
+            else:  # default: one Function per block, so parameter gradients appear during backward (DDP overlap)
                 padded, loss = T.train_forward(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels,
                                                label_smoothing, loss_weight)
             logits = padded.view(B, S, -1)[:, :, : c.codebook_size]

@@ -357,9 +357,9 @@ def test_micro_uvit_v2_loss_weight_training(golden):
 
 
 def test_uvit_v2_block_functions_match_whole_network_function(golden, monkeypatch):
-    """The per-block autograd Functions (MUSE_B200_UVIT_TRAIN=blocks: gradients appear during backward, DDP overlap) and
-    the single whole-network Function (default) run the same kernels: loss identical, gradients equal up to the summation
-    order of the shared accumulators."""
+    """The per-block autograd Functions (default: gradients appear during backward, DDP overlap) and the single
+    whole-network Function (MUSE_B200_UVIT_TRAIN=mono) run the same kernels: loss identical, gradients equal up to the
+    summation order of the shared accumulators."""
     g = golden("micro_uvit_v2.pt")
     args = [g[k].to(DEV) for k in ("input_ids", "encoder_hidden_states", "cond_embeds", "micro_conds")]
     grads, losses = {}, {}
