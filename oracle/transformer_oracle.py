@@ -118,18 +118,33 @@ def cosine_schedule(t):
     return torch.cos(t * math.pi * 0.5)
 
 
-def generate2(p, cfg, class_ids, timesteps, temperature=1.0, generator=None, trace=None):
-    """MaskGitTransformer.generate2 (class-conditional, no CFG), muse/modeling_transformer.py:1363-1456 with
-    mask_by_random_topk / gumbel_noise / log from muse/sampling.py:9-35.  Consumes ``generator`` exactly like the
-    reference: one torch.multinomial and one uniform_ per step."""
+def generate2(p, cfg, class_ids, timesteps, temperature=1.0, generator=None, trace=None, encoder_hidden_states=None,
+              negative_embeds=None, guidance_scale=0.0, input_ids=None):
+    """MaskGitTransformer.generate2, muse/modeling_transformer.py:1363-1456 with mask_by_random_topk / gumbel_noise / log
+    from muse/sampling.py:9-35: class-conditional (class token prepended, :1404-1407,1420-1423) or text-conditional with
+    classifier-free guidance (:1395-1414: doubled batch, zeros or ``negative_embeds`` as the unconditional states,
+    ``uncond + g * (cond - uncond)``).  Consumes ``generator`` exactly like the reference: one torch.multinomial and one
+    uniform_ per step."""
     c = full_config(cfg)
     mask_id, L, K = c["mask_token_id"], c["num_vq_tokens"], c["codebook_size"]
-    cls = class_ids + K
-    B = cls.shape[0]
-    input_ids = torch.full((B, L), mask_id, dtype=torch.long)
+    cls = None if class_ids is None else class_ids + K
+    B = cls.shape[0] if cls is not None else encoder_hidden_states.shape[0]
+    if input_ids is None:
+        input_ids = torch.full((B, L), mask_id, dtype=torch.long)
+    use_cfg = encoder_hidden_states is not None and guidance_scale > 0
+    if use_cfg:
+        uncond = torch.zeros_like(encoder_hidden_states) if negative_embeds is None else negative_embeds
+        cond_states = torch.cat([encoder_hidden_states, uncond])
     sampled = input_ids
     for step in range(timesteps):
-        logits = forward(p, cfg, torch.cat([cls[:, None], input_ids], dim=1))[..., :K][:, 1:]
+        model_in = input_ids if cls is None else torch.cat([cls[:, None], input_ids], dim=1)
+        if use_cfg:
+            cl, ul = forward(p, cfg, torch.cat([model_in] * 2), encoder_hidden_states=cond_states).chunk(2)
+            logits = ul[..., :K] + guidance_scale * (cl[..., :K] - ul[..., :K])
+        else:
+            logits = forward(p, cfg, model_in, encoder_hidden_states=encoder_hidden_states)[..., :K]
+        if cls is not None:
+            logits = logits[:, 1:]
         probs = logits.softmax(dim=-1)
         sampled = torch.multinomial(probs.reshape(-1, K), 1, generator=generator)[:, 0].view(B, L)
         unknown = input_ids == mask_id

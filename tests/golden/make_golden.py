@@ -131,6 +131,19 @@ def main():
                     input_ids=inp, labels=lab, encoder_hidden_states=enc, logits=logits.detach(), loss=loss.detach(),
                     grads=grads_of(mt)), os.path.join(HERE, "micro_t2i_transformer.pt"))
     print("micro t2i transformer: loss", float(loss))
+    # generate2 with classifier-free guidance (zeros as the unconditional states, then explicit negative embeds) and a
+    # partially given start sequence
+    mt.eval()
+    neg = torch.randn(2, 5, 32, generator=g)
+    start = torch.full((2, 16), mt.config.mask_token_id, dtype=torch.long)
+    start[:, :3] = torch.tensor([[4, 9, 1], [60, 2, 33]])
+    with torch.no_grad():
+        cfg_ids = mt.generate2(encoder_hidden_states=enc, timesteps=4, guidance_scale=3.0, generator=torch.Generator().manual_seed(5))
+        neg_ids = mt.generate2(input_ids=start.clone(), encoder_hidden_states=enc, negative_embeds=neg, timesteps=3,
+                               guidance_scale=1.5, temperature=0.7, generator=torch.Generator().manual_seed(6))
+    mt.train()
+    torch.save(dict(encoder_hidden_states=enc, negative_embeds=neg, start=start, cfg_ids=cfg_ids, neg_ids=neg_ids),
+               os.path.join(HERE, "micro_t2i_generate2.pt"))
 
     # ---- (2b) text-conditional with encoder_proj + encoder_proj_layer_norm (:1154-1157,1239-1241), layernorm + normformer
     torch.manual_seed(12)

@@ -98,6 +98,20 @@ def test_micro_generate2_matches_reference_stream(golden):
         assert torch.equal(ids, g["ids"][f"micro_generate2_steps{steps}"])
 
 
+def test_micro_t2i_generate2_classifier_free_guidance(golden):
+    """generate2 on the text-conditional micro model: guidance with zero / explicit negative states, given start tokens."""
+    w = golden("micro_t2i_transformer.pt")
+    g = golden("micro_t2i_generate2.pt")
+    with torch.no_grad():
+        ids = T.generate2(w["state_dict"], w["config"], None, 4, 1.0, torch.Generator().manual_seed(5),
+                          encoder_hidden_states=g["encoder_hidden_states"], guidance_scale=3.0)
+        assert torch.equal(ids, g["cfg_ids"])
+        ids = T.generate2(w["state_dict"], w["config"], None, 3, 0.7, torch.Generator().manual_seed(6),
+                          encoder_hidden_states=g["encoder_hidden_states"], negative_embeds=g["negative_embeds"],
+                          guidance_scale=1.5, input_ids=g["start"].clone())
+        assert torch.equal(ids, g["neg_ids"]) and torch.equal(ids[:, :3], g["start"][:, :3])
+
+
 def test_sample_step_equals_generator_path(golden):
     """The pre-drawn-noise formulation the CUDA kernel implements == the torch.multinomial formulation."""
     p = golden("micro_transformer.pt")
