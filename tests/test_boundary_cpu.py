@@ -64,6 +64,15 @@ def test_argument_errors():
         m(torch.zeros(1, 4, dtype=torch.long))
     with pytest.raises(AttributeError):
         m.generate()
+    with pytest.raises(TypeError):  # quirk Q2: the attention-mask path raises upstream as well
+        m(torch.zeros(1, 4, dtype=torch.long), encoder_hidden_states=torch.zeros(1, 3, 32),
+          encoder_attention_mask=torch.ones(1, 3, dtype=torch.bool))
+    from open_muse_b200 import MaskGiTUViT_v2
+
+    with pytest.raises(ValueError):  # quirk Q14: 1024 is not divisible by the default 12 block heads
+        MaskGiTUViT_v2(hidden_size=1024, block_out_channels=(1024,), num_hidden_layers=1, num_res_blocks=1)
+    with pytest.raises(NotImplementedError):
+        MaskGiTUViT_v2(num_hidden_layers=1, num_res_blocks=1, force_down_up_sample=True)
 
 
 def test_compat_muse_package_and_pipeline_surface(tmp_path):
