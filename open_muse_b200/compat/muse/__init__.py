@@ -4,6 +4,8 @@
 __version__ = "0.0.1"
 
 from open_muse_b200 import (  # noqa: F401
+    EMAModel,
+    MaskGiTUViT,
     MaskGitTransformer,
     MaskGiTUViT_v2,
     MaskGitVQGAN,

@@ -284,6 +284,23 @@ def main():
                     state_dict={k: x.clone() for k, x in tv.state_dict().items()}, image=img, z=z, ids=ids, z_q=zq,
                     recon=rec, margin=(top2[:, 1] - top2[:, 0])), os.path.join(HERE, "micro_taming_vqgan.pt"))
 
+    # ---- (8) EMAModel (modeling_ema.py): shadow parameters after a scripted sequence of updates, both decay schedules
+    ema_out = {}
+    for warm in (False, True):
+        gq = torch.Generator().manual_seed(50)
+        ps = [torch.nn.Parameter(torch.randn(5, 7, generator=gq)), torch.nn.Parameter(torch.randn(11, generator=gq)),
+              torch.nn.Parameter(torch.randn(3, 2, generator=gq), requires_grad=False)]
+        ema = muse.EMAModel(ps, decay=0.999, update_after_step=2, update_every=2, use_ema_warmup=warm, inv_gamma=2.0, power=0.75)
+        decays = []
+        for _ in range(40):
+            with torch.no_grad():
+                for q in ps:
+                    q.add_(torch.randn(q.shape, generator=gq) * 0.1)
+            ema.step(ps)
+            decays.append(ema.cur_decay_value)
+        ema_out[warm] = dict(shadow=[s.clone() for s in ema.shadow_params], decays=decays, step=ema.optimization_step)
+    torch.save(dict(seed=50, runs=ema_out), os.path.join(HERE, "ema_model.pt"))
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
