@@ -21,7 +21,7 @@ extern "C" {
 #define MUSE_ERR_CUDA 2
 #define MUSE_ERR_UNSUPPORTED 3
 
-#define MUSE_B200_ABI_VERSION 1
+#define MUSE_B200_ABI_VERSION 2
 
 /* library / device plumbing */
 int muse_abi_version(void);
@@ -34,6 +34,7 @@ int muse_device_info(int* sm_major, int* sm_minor, int* num_sms);
 #define MUSE_EPI_F32 1         /* C fp32 = acc                                   */
 #define MUSE_EPI_ATOMIC_F32 2  /* C fp32 += acc (split-K; weight gradients)      */
 #define MUSE_EPI_RESADD_F32 3  /* C fp32 = res fp32 + bf16(acc) (residual add)   */
+#define MUSE_EPI_SPLITK_F32 4  /* C fp32 = acc, deterministic split-K (muse_gemm_bf16_splitk only) */
 #define MUSE_GEMM_TCGEN05 0
 #define MUSE_GEMM_MMA_SYNC 1   /* legacy tensor-core cross-check kernel, not the product path */
 
@@ -45,6 +46,16 @@ int muse_device_info(int* sm_major, int* sm_minor, int* num_sms);
 int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
                    int ldc, int a_mn, int b_mn, int epilogue, int backend, void* stream);
 
+/* Weight-gradient GEMM with a run-to-run reproducible result: C fp32 [M,N] = opA(A) * opB(B)^T split over K (= tokens) so
+ * that the few output tiles fill the SMs; every split stores its partial tile into `ws`, the CTA finishing a tile last
+ * sums the partials in split order and stores C (no zero fill of C needed, no atomics on C).  `counters` is an int array of
+ * at least *n_counters entries that is zero before the first call; the kernel leaves it zero.  One (ws, counters) pair per
+ * stream.  Replaces the autograd weight-gradient matmuls of every nn.Linear (muse/modeling_transformer.py:198-200,218,
+ * 789-798,980,984), which the reference's bf16 step computes reproducibly. */
+long long muse_gemm_splitk_workspace_bytes(int M, int N, int K, int* n_counters);
+int muse_gemm_bf16_splitk(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                          int a_mn, int b_mn, void* ws, long long ws_bytes, int* counters, void* stream);
+
 /* fp32 -> bf16 weight packing: table_dev is a device array of n_entries
  * {const float* src; bf16* dst; int64 numel; int64 first_block} with 1024 elements per block.
  * Replaces autocast's per-Linear weight casts (torch.autocast, training/train_maskgit_imagenet.py:152). */
@@ -54,9 +65,17 @@ int muse_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 /* Embed.forward (muse/modeling_transformer.py:942-957): out[b,s,:] = word[ids[b,s],:] + pos[s,:] (fp32). */
 int muse_embed_fwd(const long long* ids, const float* word, const float* pos, float* out, int B, int S, int H,
                    int vocab, void* stream);
-/* its backward: dword[ids] += dx (atomic), dpos[s] += sum_b dx[b,s]. dword/dpos must be initialised. */
+/* its backward: dword[ids] += dx (atomic: dword must be initialised, order-dependent), dpos[s] = sum_b dx[b,s] (stored). */
 int muse_embed_bwd(const long long* ids, const float* dx, float* dword, float* dpos, int B, int S, int H, int vocab,
                    void* stream);
+
+/* Reproducible variant (the reference's index_add backward is deterministic on its bf16 CPU path): `order` = stable
+ * argsort of the flattened ids, `bounds[v]` = first sorted position holding id v (vocab + 1 entries, bounds[vocab] = B*S).
+ * dword[v] (all vocab rows, STORED) = sum of dx[t] over ids[t] == v in ascending t; dpos as above.  ws:
+ * muse_embed_bwd_sorted_workspace_bytes(B*S, H, vocab) bytes, 16-byte aligned. */
+long long muse_embed_bwd_sorted_workspace_bytes(int tokens, int H, int vocab);
+int muse_embed_bwd_sorted(const long long* order, const long long* bounds, const float* dx, float* dword, float* dpos,
+                          void* ws, int B, int S, int H, int vocab, void* stream);
 
 /* LayerNorm (weight only, :124-137) / RMSNorm (:79-100) over the last dim of [rows,H].
  *   y = (res ? res : 0) + norm(v) * w ; mean/rstd [rows] are saved for backward.  v = x (act 0), gelu(x) (act 1: the
@@ -65,13 +84,16 @@ int muse_embed_bwd(const long long* ids, const float* dx, float* dword, float* d
  *   rms = 1 selects RMSNorm. */
 int muse_norm_fwd(const void* x, int x_dtype, const float* w, const float* res, void* y, int y_dtype, float* mean,
                   float* rstd, int rows, int H, float eps, int act, int rms, void* stream);
-/* dx = norm_bwd(dy) (* gelu'(x) if act 1) (+ dres if given); dw[H] += sum_rows dy * xhat (atomic).
+/* dx = norm_bwd(dy) (* gelu'(x) if act 1) (+ dres if given).  Weight gradient dw[H] = sum_rows dy * xhat (nullable):
+ *   dw_ws given (muse_norm_bwd_workspace_floats(rows, H, act) floats): dw is STORED, reduced in a fixed order -> run-to-run
+ *   bit-identical, no zero fill needed; dw_ws null: dw += ... with atomics (caller zero-fills; order-dependent).
  * act 2: dx is [rows, 2H] = d[a | b] (LayerNorm backward and GLU backward in one pass; v is recomputed from x).
  * y_fwd (nullable, act 2 with bf16 tensors only): the forward output bf16 [rows, H]; when given, the row reductions of
  * the first pass come from (dy, y_fwd) alone instead of re-evaluating the GELU over [a | b]. */
 int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
-                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, float* dw, int rows,
-                  int H, int act, int rms, void* stream);
+                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, float* dw,
+                  float* dw_ws, int rows, int H, int act, int rms, void* stream);
+long long muse_norm_bwd_workspace_floats(int rows, int H, int act);
 
 /* GLU of FeedForward (:789-792): ab bf16 [rows, 2I] = [wi_0(x) | wi_1(x)], out bf16 [rows, I] = gelu(a) * b. */
 int muse_glu_fwd(const void* ab, void* out, long long rows, int I, void* stream);

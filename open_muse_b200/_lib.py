@@ -23,12 +23,17 @@ SIGNATURES = {
     "muse_set_device": (c_int, [_I]),
     "muse_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "muse_gemm_bf16": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "muse_gemm_splitk_workspace_bytes": (c_longlong, [_I, _I, _I, POINTER(c_int)]),
+    "muse_gemm_bf16_splitk": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P]),
     "muse_pack_bf16": (c_int, [_P, _I, _L, _P]),
     "muse_cast_bf16": (c_int, [_P, _P, _L, _P]),
     "muse_embed_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_embed_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "muse_embed_bwd_sorted_workspace_bytes": (c_longlong, [_I, _I, _I]),
+    "muse_embed_bwd_sorted": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_norm_fwd": (c_int, [_P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P]),
-    "muse_norm_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "muse_norm_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "muse_norm_bwd_workspace_floats": (c_longlong, [_I, _I, _I]),
     "muse_glu_fwd": (c_int, [_P, _P, _L, _I, _P]),
     "muse_glu_bwd": (c_int, [_P, _P, _P, _L, _I, _P]),
     "muse_attn_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
@@ -63,7 +68,7 @@ SIGNATURES = {
     "muse_transpose_batched": (c_int, [_P, _P, _I, _I, _I, _P]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class MuseB200Error(RuntimeError):

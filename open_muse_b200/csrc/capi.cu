@@ -26,14 +26,18 @@ int check_launch(const char* what) {
 }
 
 // kernels (defined in the other translation units)
-int gemm_tcgen05(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int gemm_tcgen05(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t, void*, long long, int*);
+long long gemm_splitk_workspace_bytes(int, int, int, int*);
 int gemm_mma(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int pack_bf16(const void*, int, long long, cudaStream_t);
 int cast_bf16(const float*, void*, long long, cudaStream_t);
 int embed_fwd(const long long*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
 int embed_bwd(const long long*, const float*, float*, float*, int, int, int, int, cudaStream_t);
+int embed_bwd_sorted(const long long*, const long long*, const float*, float*, float*, void*, int, int, int, int, cudaStream_t);
+long long embed_bwd_sorted_workspace_bytes(int, int, int);
 int norm_fwd(const void*, int, const float*, const float*, void*, int, float*, float*, int, int, float, int, int, cudaStream_t);
-int norm_bwd(const void*, int, const void*, int, const float*, const float*, const float*, const float*, const void*, void*, int, float*, int, int, int, int, cudaStream_t);
+int norm_bwd(const void*, int, const void*, int, const float*, const float*, const float*, const float*, const void*, void*, int, float*, float*, int, int, int, int, cudaStream_t);
+long long norm_bwd_workspace_floats(int, int, int);
 int glu_fwd(const void*, void*, long long, int, cudaStream_t);
 int glu_bwd(const void*, const void*, void*, long long, int, cudaStream_t);
 int attn_fwd(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
@@ -97,7 +101,17 @@ int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int 
                    int ldc, int a_mn, int b_mn, int epilogue, int backend, void* stream) {
   if (epilogue == MUSE_EPI_RESADD_F32 && res == nullptr) { set_last_error("gemm: RESADD epilogue needs res"); return MUSE_ERR_INVALID; }
   if (backend == MUSE_GEMM_MMA_SYNC) return gemm_mma(A, B, C, res, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, ST(stream));
-  return gemm_tcgen05(A, B, C, res, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, ST(stream));
+  if (epilogue == MUSE_EPI_SPLITK_F32) { set_last_error("gemm: the deterministic split-K epilogue goes through muse_gemm_bf16_splitk"); return MUSE_ERR_INVALID; }
+  return gemm_tcgen05(A, B, C, res, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, ST(stream), nullptr, 0, nullptr);
+}
+
+long long muse_gemm_splitk_workspace_bytes(int M, int N, int K, int* n_counters) {
+  return gemm_splitk_workspace_bytes(M, N, K, n_counters);
+}
+int muse_gemm_bf16_splitk(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                          int a_mn, int b_mn, void* ws, long long ws_bytes, int* counters, void* stream) {
+  return gemm_tcgen05(A, B, C, nullptr, M, N, K, lda, ldb, ldc, a_mn, b_mn, MUSE_EPI_SPLITK_F32, ST(stream), ws, ws_bytes,
+                      counters);
 }
 
 int muse_pack_bf16(const void* table_dev, int n_entries, long long total_blocks, void* stream) {
@@ -112,15 +126,22 @@ int muse_embed_bwd(const long long* ids, const float* dx, float* dword, float* d
   return embed_bwd(ids, dx, dword, dpos, B, S, H, vocab, ST(stream));
 }
 
+long long muse_embed_bwd_sorted_workspace_bytes(int tokens, int H, int vocab) { return embed_bwd_sorted_workspace_bytes(tokens, H, vocab); }
+int muse_embed_bwd_sorted(const long long* order, const long long* bounds, const float* dx, float* dword, float* dpos,
+                          void* ws, int B, int S, int H, int vocab, void* stream) {
+  return embed_bwd_sorted(order, bounds, dx, dword, dpos, ws, B, S, H, vocab, ST(stream));
+}
+
 int muse_norm_fwd(const void* x, int x_dtype, const float* w, const float* res, void* y, int y_dtype, float* mean,
                   float* rstd, int rows, int H, float eps, int act, int rms, void* stream) {
   return norm_fwd(x, x_dtype, w, res, y, y_dtype, mean, rstd, rows, H, eps, act, rms, ST(stream));
 }
 int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
-                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, float* dw, int rows,
-                  int H, int act, int rms, void* stream) {
-  return norm_bwd(dy, dy_dtype, x, x_dtype, w, mean, rstd, dres, y_fwd, dx, dx_dtype, dw, rows, H, act, rms, ST(stream));
+                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, float* dw,
+                  float* dw_ws, int rows, int H, int act, int rms, void* stream) {
+  return norm_bwd(dy, dy_dtype, x, x_dtype, w, mean, rstd, dres, y_fwd, dx, dx_dtype, dw, dw_ws, rows, H, act, rms, ST(stream));
 }
+long long muse_norm_bwd_workspace_floats(int rows, int H, int act) { return norm_bwd_workspace_floats(rows, H, act); }
 
 int muse_glu_fwd(const void* ab, void* out, long long rows, int I, void* stream) { return glu_fwd(ab, out, rows, I, ST(stream)); }
 int muse_glu_bwd(const void* ab, const void* dout, void* dab, long long rows, int I, void* stream) {

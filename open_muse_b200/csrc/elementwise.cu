@@ -143,7 +143,103 @@ embed_bwd_pos_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int
   if (c >= H) return;
   float acc = 0.f;
   for (int b = 0; b < B; ++b) acc += dx[(static_cast<size_t>(b) * S + s) * H + c];
-  dpos[static_cast<size_t>(s) * H + c] += acc;
+  dpos[static_cast<size_t>(s) * H + c] = acc;  // fixed summation order, plain store: reproducible, no zero fill
+}
+
+// ---------------------------------------------------------------- reproducible word-embedding gradient
+// dword[v] = sum of dx[t] over the tokens t with ids[t] == v, summed in ascending t whatever the launch order:
+// the host passes the stable sort permutation of the ids (`order`) and the segment bounds (`bounds[v]` = first sorted
+// position of id v); segments are cut into chunks of kSegChunk tokens, every chunk is summed by one CTA (four thread
+// groups take a quarter each, rows in order, then the quarters are added in order), single-chunk segments are stored
+// straight to dword[v], longer ones go through per-chunk partial rows that a second kernel adds in chunk order.
+constexpr int kSegChunk = 256;
+
+__global__ void __launch_bounds__(1024)
+embed_seg_plan_kernel(const long long* __restrict__ bounds, int* __restrict__ chunk_off, int vocab) {
+  __shared__ int s_part[1024];
+  const int per = ceil_div(vocab, 1024);
+  const int v0 = threadIdx.x * per;
+  int sum = 0;
+  for (int v = v0; v < min(vocab, v0 + per); ++v)
+    sum += static_cast<int>((bounds[v + 1] - bounds[v] + kSegChunk - 1) / kSegChunk);
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < 1024; ++i) { const int t = s_part[i]; s_part[i] = run; run += t; }
+    chunk_off[vocab] = run;
+  }
+  __syncthreads();
+  int run = s_part[threadIdx.x];
+  for (int v = v0; v < min(vocab, v0 + per); ++v) {
+    chunk_off[v] = run;
+    run += static_cast<int>((bounds[v + 1] - bounds[v] + kSegChunk - 1) / kSegChunk);
+  }
+}
+
+// ordered sum of `n` rows of H floats: row(i) gives the row pointer; 4 groups x ncol threads, result valid in group 0
+template <typename RowFn>
+__device__ __forceinline__ void ordered_rows_sum(RowFn row, int n, int H, float* s_q, float* out_row) {
+  const int ncol = blockDim.x >> 2;
+  const int grp = threadIdx.x / ncol, tx = threadIdx.x % ncol;
+  const int per = (n + 3) >> 2;
+  const int i0 = grp * per, i1 = min(n, i0 + per);
+  for (int c = tx * 4; c < H; c += ncol * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int i = i0; i < i1; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(row(i) + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(s_q + static_cast<size_t>(grp) * H + c) = acc;
+  }
+  __syncthreads();
+  if (grp == 0) {
+    for (int c = tx * 4; c < H; c += ncol * 4) {
+      float4 a = *reinterpret_cast<const float4*>(s_q + c);
+#pragma unroll
+      for (int g = 1; g < 4; ++g) {
+        const float4 b = *reinterpret_cast<const float4*>(s_q + static_cast<size_t>(g) * H + c);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      *reinterpret_cast<float4*>(out_row + c) = a;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void embed_seg_chunk_kernel(const long long* __restrict__ order, const long long* __restrict__ bounds,
+                                       const int* __restrict__ chunk_off, const float* __restrict__ dx,
+                                       float* __restrict__ dword, float* __restrict__ ws, int H, int vocab) {
+  extern __shared__ __align__(16) float s_q[];  // [4][H]
+  const int g = blockIdx.x;
+  if (g >= chunk_off[vocab]) return;
+  int lo = 0, hi = vocab - 1;
+  while (lo < hi) {  // last v with chunk_off[v] <= g (empty segments share their successor's offset and lose the tie)
+    const int mid = (lo + hi + 1) >> 1;
+    if (chunk_off[mid] <= g) lo = mid; else hi = mid - 1;
+  }
+  const int v = lo;
+  const int j = g - chunk_off[v];
+  const long long p0 = bounds[v] + static_cast<long long>(j) * kSegChunk;
+  const int n = static_cast<int>(min(static_cast<long long>(kSegChunk), bounds[v + 1] - p0));
+  const bool single = (chunk_off[v + 1] - chunk_off[v]) == 1;
+  float* out = single ? dword + static_cast<size_t>(v) * H : ws + static_cast<size_t>(g) * H;
+  ordered_rows_sum([&](int i) { return dx + static_cast<size_t>(order[p0 + i]) * H; }, n, H, s_q, out);
+}
+
+__global__ void embed_seg_final_kernel(const int* __restrict__ chunk_off, const float* __restrict__ ws,
+                                       float* __restrict__ dword, int H, int vocab) {
+  extern __shared__ __align__(16) float s_q[];
+  const int v = blockIdx.x;
+  const int c0 = chunk_off[v], nc = chunk_off[v + 1] - c0;
+  if (nc == 1) return;  // stored by the chunk kernel
+  float* out = dword + static_cast<size_t>(v) * H;
+  if (nc == 0) {
+    for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) *reinterpret_cast<float4*>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  ordered_rows_sum([&](int i) { return ws + static_cast<size_t>(c0 + i) * H; }, nc, H, s_q, out);
 }
 
 // ---------------------------------------------------------------- GLU
@@ -226,6 +322,33 @@ int embed_bwd(const long long* ids, const float* dx, float* dword, float* dpos, 
   int rc = check_launch("embed_bwd_word");
   if (rc) return rc;
   if (dpos == nullptr) return MUSE_OK;  // no position table (ConvEmbed of MaskGiTUViT_v2)
+  embed_bwd_pos_kernel<<<dim3(S, ceil_div(H, 128)), 128, 0, s>>>(dx, dpos, B, S, H);
+  return check_launch("embed_bwd_pos");
+}
+
+// workspace: (tokens / kSegChunk + vocab) partial rows of H floats, then vocab + 1 ints of chunk offsets
+long long embed_bwd_sorted_workspace_bytes(int tokens, int H, int vocab) {
+  return (static_cast<long long>(tokens) / kSegChunk + vocab) * H * 4 + (static_cast<long long>(vocab) + 1) * 4;
+}
+
+int embed_bwd_sorted(const long long* order, const long long* bounds, const float* dx, float* dword, float* dpos,
+                     void* ws, int B, int S, int H, int vocab, cudaStream_t s) {
+  if (H % 4 != 0) { set_last_error("embed_bwd_sorted: H must be a multiple of 4"); return MUSE_ERR_INVALID; }
+  const int tokens = B * S;
+  if (tokens <= 0 || vocab <= 0) return MUSE_OK;
+  const int max_chunks = tokens / kSegChunk + vocab;
+  float* partial = reinterpret_cast<float*>(ws);
+  int* chunk_off = reinterpret_cast<int*>(partial + static_cast<size_t>(max_chunks) * H);
+  int ncol = H / 4;
+  if (ncol > 256) ncol = 256;
+  const size_t smem = static_cast<size_t>(4) * H * sizeof(float);
+  if (smem > 48 * 1024) { set_last_error("embed_bwd_sorted: H=%d too wide", H); return MUSE_ERR_UNSUPPORTED; }
+  embed_seg_plan_kernel<<<1, 1024, 0, s>>>(bounds, chunk_off, vocab);
+  embed_seg_chunk_kernel<<<max_chunks, 4 * ncol, smem, s>>>(order, bounds, chunk_off, dx, dword, partial, H, vocab);
+  embed_seg_final_kernel<<<vocab, 4 * ncol, smem, s>>>(chunk_off, partial, dword, H, vocab);
+  int rc = check_launch("embed_bwd_sorted");
+  if (rc) return rc;
+  if (dpos == nullptr) return MUSE_OK;
   embed_bwd_pos_kernel<<<dim3(S, ceil_div(H, 128)), 128, 0, s>>>(dx, dpos, B, S, H);
   return check_launch("embed_bwd_pos");
 }

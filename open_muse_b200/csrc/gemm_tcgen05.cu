@@ -27,7 +27,10 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 
-enum Epi { EPI_BF16 = 0, EPI_F32 = 1, EPI_ATOMIC_F32 = 2, EPI_RESADD_F32 = 3 };
+// EPI_SPLITK_F32: deterministic split-K.  Every split stores its fp32 partial tile into a workspace; the CTA that
+// finishes a tile last (ticket counter) sums the partials in split order and STORES the result, so the output needs no
+// zero fill and is bit-identical from run to run (the atomic variant is order-dependent).
+enum Epi { EPI_BF16 = 0, EPI_F32 = 1, EPI_ATOMIC_F32 = 2, EPI_RESADD_F32 = 3, EPI_SPLITK_F32 = 4 };
 
 template <int BN>
 struct Cfg {
@@ -48,6 +51,8 @@ struct GemmParams {
   int M, N, K;
   int ldc;
   int num_m, num_n, num_kb, kb_per_split, splits;
+  float* ws;      // EPI_SPLITK_F32: [splits][num_m * num_n][BM * BN] fp32 partial tiles
+  int* counters;  // EPI_SPLITK_F32: [num_m * num_n] tickets, zero on entry, zero again on exit
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -65,6 +70,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full = bars + 2 * C_::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  int* ticket_sh = reinterpret_cast<int*>(tmem_holder) + 2;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,6 +211,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr int kColsPerSlab = (EPI == EPI_BF16) ? 64 : 32;
       constexpr int kElemsPerChunk = (EPI == EPI_BF16) ? 8 : 4;  // elements in a 16-byte chunk
       const int row_base = m_idx * BM + ew * 32;
+      const bool partial = (EPI == EPI_SPLITK_F32) && p.splits > 1;
+      const int tile_mn = tile % tiles_mn;
+      float* ws_tile = nullptr;
+      if (EPI == EPI_SPLITK_F32 && partial)
+        ws_tile = p.ws + (static_cast<size_t>(tile / tiles_mn) * tiles_mn + tile_mn) * (BM * BN);
 #pragma unroll 1
       for (int c = 0; c < BN; c += kColsPerSlab) {
         if (n0 + c >= p.N) break;  // warp-uniform
@@ -248,7 +259,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * C_::kStagingRowBytes + ch * 16);
           const int grow = row_base + rr;
           const int gcol = n0 + c + ch * kElemsPerChunk;
-          if (grow < p.M && gcol < p.N) {
+          if (EPI == EPI_SPLITK_F32 && partial) {
+            *reinterpret_cast<uint4*>(ws_tile + static_cast<size_t>(ew * 32 + rr) * BN + c + ch * 4) = v;
+          } else if (grow < p.M && gcol < p.N) {
             const size_t off = static_cast<size_t>(grow) * p.ldc + gcol;
             const bool full = gcol + kElemsPerChunk <= p.N;
             if (EPI == EPI_BF16) {
@@ -263,7 +276,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             } else {
               const float f[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
               float* dst = reinterpret_cast<float*>(p.C) + off;
-              if (EPI == EPI_F32) {
+              if (EPI == EPI_F32 || EPI == EPI_SPLITK_F32) {
                 if (full) *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
                 else for (int k = 0; k < 4; ++k) if (gcol + k < p.N) dst[k] = f[k];
               } else if (EPI == EPI_ATOMIC_F32) {
@@ -288,6 +301,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if (EPI == EPI_SPLITK_F32 && partial) {
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) *ticket_sh = atomicAdd(&p.counters[tile_mn], 1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool last = (*ticket_sh == p.splits - 1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone has read the ticket before the next tile rewrites it
+        if (last) {
+          __threadfence();
+          if (threadIdx.x == 128) p.counters[tile_mn] = 0;
+          const float* ws0 = p.ws + static_cast<size_t>(tile_mn) * (BM * BN);
+          const size_t split_stride = static_cast<size_t>(tiles_mn) * (BM * BN);
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 32) {
+            if (n0 + c >= p.N) break;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = (lane >> 3) + 4 * it, ch = lane & 7;
+              const int grow = row_base + rr, gcol = n0 + c + ch * 4;
+              if (grow < p.M && gcol < p.N) {
+                const float* src = ws0 + static_cast<size_t>(ew * 32 + rr) * BN + c + ch * 4;
+                float4 a = __ldcg(reinterpret_cast<const float4*>(src));
+                for (int sp = 1; sp < p.splits; ++sp) {
+                  const float4 b = __ldcg(reinterpret_cast<const float4*>(src + sp * split_stride));
+                  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                }
+                float* dst = reinterpret_cast<float*>(p.C) + static_cast<size_t>(grow) * p.ldc + gcol;
+                if (gcol + 4 <= p.N) *reinterpret_cast<float4*>(dst) = a;
+                else { const float f[4] = {a.x, a.y, a.z, a.w}; for (int k = 0; k < 4; ++k) if (gcol + k < p.N) dst[k] = f[k]; }
+              }
+            }
+          }
+        }
+      }
     }
   }
 
@@ -430,6 +477,7 @@ int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
     case EPI_F32: return launch<BN, A_MN, B_MN, EPI_F32>(ta, tb, p, s);
     case EPI_ATOMIC_F32: return launch<BN, A_MN, B_MN, EPI_ATOMIC_F32>(ta, tb, p, s);
     case EPI_RESADD_F32: return launch<BN, A_MN, B_MN, EPI_RESADD_F32>(ta, tb, p, s);
+    case EPI_SPLITK_F32: return launch<BN, A_MN, B_MN, EPI_SPLITK_F32>(ta, tb, p, s);
   }
   set_last_error("gemm: unknown epilogue %d", epi);
   return MUSE_ERR_INVALID;
@@ -449,8 +497,31 @@ int launch_major(int a_mn, int b_mn, int epi, const CUtensorMap& ta, const CUten
 // C[M,N] (ldc) = op(A) * op(B)^T with op selected by a_mn / b_mn:
 //   a_mn == 0: A points at a row-major [M, K] matrix (pitch lda);  a_mn == 1: at a row-major [K, M] matrix.
 //   b_mn == 0: B points at a row-major [N, K] matrix (pitch ldb);  b_mn == 1: at a row-major [K, N] matrix.
+// Split plan shared by the launcher and the workspace query: how many K splits a weight-gradient GEMM (few output tiles,
+// very long K = tokens) needs to fill the SMs.
+static void split_plan(int M, int N, int K, int* num_m, int* num_n, int* num_kb, int* kb_per_split, int* splits, int* bn) {
+  *bn = (N >= 256) ? 256 : 128;
+  *num_m = ceil_div(M, BM);
+  *num_n = ceil_div(N, *bn);
+  *num_kb = ceil_div(K, BK);
+  const int tiles = *num_m * *num_n;
+  int want = num_sms() / tiles;
+  if (want < 1) want = 1;
+  if (want > *num_kb) want = *num_kb;
+  *kb_per_split = ceil_div(*num_kb, want);
+  *splits = ceil_div(*num_kb, *kb_per_split);
+}
+
+long long gemm_splitk_workspace_bytes(int M, int N, int K, int* n_counters) {
+  int num_m, num_n, num_kb, kbs, splits, bn;
+  split_plan(M, N, K, &num_m, &num_n, &num_kb, &kbs, &splits, &bn);
+  if (n_counters) *n_counters = num_m * num_n;
+  if (splits <= 1) return 0;
+  return static_cast<long long>(splits) * num_m * num_n * BM * bn * 4;
+}
+
 int gemm_tcgen05(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
-                 int ldc, int a_mn, int b_mn, int epi, cudaStream_t stream) {
+                 int ldc, int a_mn, int b_mn, int epi, cudaStream_t stream, void* ws, long long ws_bytes, int* counters) {
   if (M <= 0 || N <= 0 || K <= 0) return MUSE_OK;
   if (epi == EPI_BF16 ? (ldc % 8 != 0) : (ldc % 4 != 0)) {
     set_last_error("gemm: ldc=%d must be a multiple of %d", ldc, epi == EPI_BF16 ? 8 : 4);
@@ -477,14 +548,19 @@ int gemm_tcgen05(const void* A, const void* B, void* C, const float* res, int M,
   p.num_kb = ceil_div(K, BK);
   p.splits = 1;
   p.kb_per_split = p.num_kb;
-  if (epi == EPI_ATOMIC_F32) {
-    // split-K so that a weight-gradient GEMM (few output tiles, very long K = tokens) fills the 148 SMs.
-    const int tiles = p.num_m * p.num_n;
-    int want = num_sms() / tiles;
-    if (want < 1) want = 1;
-    if (want > p.num_kb) want = p.num_kb;
-    p.kb_per_split = ceil_div(p.num_kb, want);
-    p.splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.ws = reinterpret_cast<float*>(ws);
+  p.counters = counters;
+  if (epi == EPI_ATOMIC_F32 || epi == EPI_SPLITK_F32) {
+    int num_m, num_n, num_kb, bn;
+    split_plan(M, N, K, &num_m, &num_n, &num_kb, &p.kb_per_split, &p.splits, &bn);
+    if (epi == EPI_SPLITK_F32 && p.splits > 1) {
+      const long long need = static_cast<long long>(p.splits) * p.num_m * p.num_n * BM * BN * 4;
+      if (ws == nullptr || counters == nullptr || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) {
+        set_last_error("gemm: deterministic split-K needs a 16B-aligned workspace of %lld bytes (got %lld) and a counter array",
+                       need, ws_bytes);
+        return MUSE_ERR_INVALID;
+      }
+    }
   }
   if (BN == 256) return launch_major<256>(a_mn, b_mn, epi, ta, tb, p, stream);
   return launch_major<128>(a_mn, b_mn, epi, ta, tb, p, stream);

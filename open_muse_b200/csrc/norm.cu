@@ -87,19 +87,53 @@ norm_fwd_warp_kernel(const TX* __restrict__ x, const float* __restrict__ w, cons
   }
 }
 
+// Weight gradients (dw[H] = sum over rows of dy * xhat) are reduced in a FIXED order so that the result is bit-identical
+// from run to run: every warp owns a static set of rows (grid-stride) and keeps its partial in registers / a private
+// shared-memory row, the CTA sums its warps in warp order, and
+//   * dw_ws != nullptr: the CTA stores its partial row to dw_ws[blockIdx.x][H]; colsum_ordered_kernel then sums the CTA
+//     rows in index order and STORES dw (no zero fill needed);
+//   * dw_ws == nullptr: the CTA adds its partial to dw with atomics (accumulating, order-dependent; legacy callers).
+constexpr int kBwdWarps = 8;
+
+__device__ __forceinline__ void flush_cta_dw(const float* s_dw, int nwarps, int H, float* dw, float* dw_ws) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < nwarps; ++k) acc += s_dw[static_cast<size_t>(k) * H + i];
+    if (dw_ws) dw_ws[static_cast<size_t>(blockIdx.x) * H + i] = acc;
+    else atomicAdd(&dw[i], acc);
+  }
+}
+
+// dw[i] = sum_g ws[g][i] in ascending g (32 x 32 threads: thread (ty, tx) sums rows ty, ty+32, ... of column tx).
+__global__ void __launch_bounds__(1024) colsum_ordered_kernel(const float* __restrict__ ws, float* __restrict__ dw, int G, int H) {
+  __shared__ float s[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (col < H) {
+#pragma unroll 8
+    for (int g = ty; g < G; g += 32) acc += ws[static_cast<size_t>(g) * H + col];
+  }
+  s[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += s[k][tx];
+    dw[col] = t;
+  }
+}
+
 template <typename TDY, typename TX, typename TDX, int CH>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kBwdWarps * 32)
 norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw, int rows, int H,
-                int act, int rms) {
-  extern __shared__ float s_dw[];  // [H]
+                const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw,
+                float* __restrict__ dw_ws, int rows, int H, int act, int rms) {
+  extern __shared__ float s_dw[];  // [kBwdWarps][H] private rows
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  if (dw) {
-    for (int i = threadIdx.x; i < H; i += blockDim.x) s_dw[i] = 0.f;
-    __syncthreads();
-  }
   float dw_acc[CH][8];
 #pragma unroll
   for (int c = 0; c < CH; ++c)
@@ -107,7 +141,7 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
     for (int j = 0; j < 8; ++j) dw_acc[c][j] = 0.f;
   const float inv_h = 1.0f / static_cast<float>(H);
 
-  for (int row = blockIdx.x * kWarpsPerBlock + warp; row < rows; row += gridDim.x * kWarpsPerBlock) {
+  for (int row = blockIdx.x * kBwdWarps + warp; row < rows; row += gridDim.x * kBwdWarps) {
     const TX* xr = x + static_cast<size_t>(row) * H;
     const TDY* dyr = dy + static_cast<size_t>(row) * H;
     const float mean = rms ? 0.f : mean_in[row];
@@ -160,16 +194,13 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
     }
   }
   if (dw) {
+    float* my_dw = s_dw + static_cast<size_t>(warp) * H;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int col = (c * 32 + lane) * 8;
-      if (col < H) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&s_dw[col + j], dw_acc[c][j]);
-      }
+      if (col < H) store8(my_dw + col, dw_acc[c]);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(&dw[i], s_dw[i]);
+    flush_cta_dw(s_dw, kBwdWarps, H, dw, dw_ws);
   }
 }
 
@@ -267,14 +298,15 @@ template <typename TDY, typename TX, typename TDX>
 __global__ void __launch_bounds__(kWideWarps * 32)
 norm_bwd_wide_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                     const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw, int rows, int H,
-                     int act, int rms) {
-  extern __shared__ float s_dw[];  // [H]: per-CTA weight-gradient accumulator (shared-memory atomics)
+                     const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw,
+                     float* __restrict__ dw_ws, int rows, int H, int act, int rms) {
+  extern __shared__ __align__(16) float s_dw[];  // [kWideWarps][H] private per-warp weight-gradient rows
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  float* my_dw = s_dw + static_cast<size_t>(warp) * H;
   if (dw) {
-    for (int i = threadIdx.x; i < H; i += blockDim.x) s_dw[i] = 0.f;
-    __syncthreads();
+    for (int i = lane * 4; i < H; i += 128) *reinterpret_cast<float4*>(my_dw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
   }
   const int xs = (act == ACT_GLU) ? 2 * H : H;
   const float inv_h = 1.0f / static_cast<float>(H);
@@ -285,7 +317,7 @@ norm_bwd_wide_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
     const float rstd = rstd_in[row];
     float s1 = 0.f, s2 = 0.f;
     for (int col = lane * 8; col < H; col += 256) {
-      float v[8], gv8[8], ga8[8], b8[8], dv[8], wv[8];
+      float v[8], gv8[8], ga8[8], b8[8], dv[8], wv[8], pr[8];
       load_value(xr, col, H, act, v, gv8, ga8, b8);
       load8(dyr + col, dv);
       if (w) load8(w + col, wv);
@@ -295,7 +327,14 @@ norm_bwd_wide_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
         const float g = dv[j] * (w ? wv[j] : 1.f);
         s1 += g;
         s2 += g * xh;
-        if (dw) atomicAdd(&s_dw[col + j], dv[j] * xh);
+        pr[j] = dv[j] * xh;
+      }
+      if (dw) {
+        float e[8];
+        load8(my_dw + col, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] += pr[j];
+        store8(my_dw + col, e);
       }
     }
     s1 = rms ? 0.f : warp_sum(s1) * inv_h;
@@ -334,10 +373,7 @@ norm_bwd_wide_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
       }
     }
   }
-  if (dw) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(&dw[i], s_dw[i]);
-  }
+  if (dw) flush_cta_dw(s_dw, kWideWarps, H, dw, dw_ws);
 }
 
 // ---- GLU + LayerNorm/RMSNorm fused (act = 2), the FeedForward middle of every normformer layer ([T, 2I] -> [T, I]).
@@ -437,7 +473,8 @@ template <bool HAVE_Y>
 __global__ void __launch_bounds__(kGluWarps * 32, 3)
 glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, const float* __restrict__ w,
                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dab,
-                    float* __restrict__ dw, const bf16* __restrict__ yf, int rows, int H, int rms) {
+                    float* __restrict__ dw, float* __restrict__ dw_ws, const bf16* __restrict__ yf, int rows, int H,
+                    int rms) {
   extern __shared__ __align__(16) float s_dw[];  // [kGluWarps][H] private rows
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -544,15 +581,7 @@ glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, co
       *reinterpret_cast<uint4*>(dr + H + col) = ob;
     }
   }
-  if (dw) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < H; i += blockDim.x) {
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < kGluWarps; ++k) acc += s_dw[static_cast<size_t>(k) * H + i];
-      atomicAdd(&dw[i], acc);
-    }
-  }
+  if (dw) flush_cta_dw(s_dw, kGluWarps, H, dw, dw_ws);
 }
 
 template <typename TX, typename TY>
@@ -576,30 +605,48 @@ int fwd_dispatch(const void* x, const float* w, const float* res, void* y, float
   return check_launch("norm_fwd");
 }
 
+int bwd_grid(int rows, int H, int act) {
+  if (act == ACT_GLU) { const int g = ceil_div(rows, kGluWarps); return g > 148 * 3 ? 148 * 3 : g; }
+  if (H <= 1024) { const int g = ceil_div(rows, kBwdWarps); return g > 148 * 4 ? 148 * 4 : g; }
+  const int g = ceil_div(rows, kWideWarps);
+  return g > 148 * 4 ? 148 * 4 : g;
+}
+
+int reduce_dw(const float* dw_ws, float* dw, int grid, int H, cudaStream_t s) {
+  colsum_ordered_kernel<<<ceil_div(H, 32), 1024, 0, s>>>(dw_ws, dw, grid, H);
+  return check_launch("norm_bwd colsum");
+}
+
 template <typename TDY, typename TX, typename TDX>
 int bwd_dispatch(const void* dy, const void* x, const float* w, const float* mean, const float* rstd,
-                 const float* dres, void* dx, float* dw, int rows, int H, int act, int rms, cudaStream_t s) {
+                 const float* dres, void* dx, float* dw, float* dw_ws, int rows, int H, int act, int rms,
+                 cudaStream_t s) {
+  const int grid = bwd_grid(rows, H, act);
   if (H <= 1024 && act != ACT_GLU) {
-    int grid = ceil_div(rows, kWarpsPerBlock);
-    if (grid > 148 * 8) grid = 148 * 8;
     const int ch = ceil_div(H, 256);
-    const size_t smem = dw ? H * sizeof(float) : 0;
+    const size_t smem = dw ? static_cast<size_t>(kBwdWarps) * H * sizeof(float) : 0;
 #define MUSE_NB(CH)                                                                                          \
-  norm_bwd_warp_kernel<TDY, TX, TDX, CH><<<grid, kWarpsPerBlock * 32, smem, s>>>(                            \
+  norm_bwd_warp_kernel<TDY, TX, TDX, CH><<<grid, kBwdWarps * 32, smem, s>>>(                                 \
       reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd, dres,                 \
-      reinterpret_cast<TDX*>(dx), dw, rows, H, act, rms)
+      reinterpret_cast<TDX*>(dx), dw, dw_ws, rows, H, act, rms)
     if (ch <= 1) MUSE_NB(1);
     else if (ch <= 2) MUSE_NB(2);
     else MUSE_NB(4);
 #undef MUSE_NB
-    return check_launch("norm_bwd");
+  } else {
+    const size_t smem = dw ? static_cast<size_t>(kWideWarps) * H * sizeof(float) : 0;
+    auto kern = norm_bwd_wide_kernel<TDY, TX, TDX>;
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideWarps * 4096 * 4);
+      attr = true;
+    }
+    kern<<<grid, kWideWarps * 32, smem, s>>>(reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd,
+                                             dres, reinterpret_cast<TDX*>(dx), dw, dw_ws, rows, H, act, rms);
   }
-  int grid = ceil_div(rows, kWideWarps);
-  if (grid > 148 * 8) grid = 148 * 8;
-  norm_bwd_wide_kernel<TDY, TX, TDX><<<grid, kWideWarps * 32, dw ? H * sizeof(float) : 0, s>>>(
-      reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd, dres,
-      reinterpret_cast<TDX*>(dx), dw, rows, H, act, rms);
-  return check_launch("norm_bwd");
+  int rc = check_launch("norm_bwd");
+  if (rc || !dw || !dw_ws) return rc;
+  return reduce_dw(dw_ws, dw, grid, H, s);
 }
 
 int check_args(const char* who, int H, int act, const void* res_or_dres) {
@@ -636,15 +683,20 @@ int norm_fwd(const void* x, int x_dt, const float* w, const float* res, void* y,
   return MUSE_ERR_INVALID;
 }
 
+// floats of workspace a deterministic (dw_ws != nullptr) backward needs: one partial row of H per CTA
+long long norm_bwd_workspace_floats(int rows, int H, int act) {
+  if (rows <= 0) return 0;
+  return static_cast<long long>(bwd_grid(rows, H, act)) * H;
+}
+
 int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w, const float* mean, const float* rstd,
-             const float* dres, const void* y_fwd, void* dx, int dx_dt, float* dw, int rows, int H, int act, int rms,
-             cudaStream_t s) {
+             const float* dres, const void* y_fwd, void* dx, int dx_dt, float* dw, float* dw_ws, int rows, int H, int act,
+             int rms, cudaStream_t s) {
   if (rows <= 0) return MUSE_OK;
   int rc = check_args("norm_bwd", H, act, dres);
   if (rc) return rc;
   if (act == ACT_GLU && dy_dt == 1 && x_dt == 1 && dx_dt == 1 && H <= 4096) {
-    int grid = ceil_div(rows, kGluWarps);
-    if (grid > 148 * 3) grid = 148 * 3;
+    const int grid = bwd_grid(rows, H, act);
     const size_t smem = dw ? static_cast<size_t>(kGluWarps) * H * sizeof(float) : 0;
     static bool attr = false;
     if (!attr) {
@@ -655,23 +707,25 @@ int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w,
     if (y_fwd != nullptr)
       glu_norm_bwd_kernel<true><<<grid, kGluWarps * 32, smem, s>>>(
           reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw,
-          reinterpret_cast<const bf16*>(y_fwd), rows, H, rms);
+          dw_ws, reinterpret_cast<const bf16*>(y_fwd), rows, H, rms);
     else
       glu_norm_bwd_kernel<false><<<grid, kGluWarps * 32, smem, s>>>(
           reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw,
-          nullptr, rows, H, rms);
-    return check_launch("glu_norm_bwd");
+          dw_ws, nullptr, rows, H, rms);
+    rc = check_launch("glu_norm_bwd");
+    if (rc || !dw || !dw_ws) return rc;
+    return reduce_dw(dw_ws, dw, grid, H, s);
   }
   const int key = dy_dt * 4 + x_dt * 2 + dx_dt;
   switch (key) {
-    case 0: return bwd_dispatch<float, float, float>(dy, x, w, mean, rstd, dres, dx, dw, rows, H, act, rms, s);
-    case 1: return bwd_dispatch<float, float, bf16>(dy, x, w, mean, rstd, dres, dx, dw, rows, H, act, rms, s);
-    case 2: return bwd_dispatch<float, bf16, float>(dy, x, w, mean, rstd, dres, dx, dw, rows, H, act, rms, s);
-    case 3: return bwd_dispatch<float, bf16, bf16>(dy, x, w, mean, rstd, dres, dx, dw, rows, H, act, rms, s);
-    case 4: return bwd_dispatch<bf16, float, float>(dy, x, w, mean, rstd, dres, dx, dw, rows, H, act, rms, s);
-    case 5: return bwd_dispatch<bf16, float, bf16>(dy, x, w, mean, rstd, dres, dx, dw, rows, H, act, rms, s);
-    case 6: return bwd_dispatch<bf16, bf16, float>(dy, x, w, mean, rstd, dres, dx, dw, rows, H, act, rms, s);
-    case 7: return bwd_dispatch<bf16, bf16, bf16>(dy, x, w, mean, rstd, dres, dx, dw, rows, H, act, rms, s);
+    case 0: return bwd_dispatch<float, float, float>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
+    case 1: return bwd_dispatch<float, float, bf16>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
+    case 2: return bwd_dispatch<float, bf16, float>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
+    case 3: return bwd_dispatch<float, bf16, bf16>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
+    case 4: return bwd_dispatch<bf16, float, float>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
+    case 5: return bwd_dispatch<bf16, float, bf16>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
+    case 6: return bwd_dispatch<bf16, bf16, float>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
+    case 7: return bwd_dispatch<bf16, bf16, bf16>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
   }
   set_last_error("norm_bwd: bad dtype codes");
   return MUSE_ERR_INVALID;

@@ -221,9 +221,7 @@ class _EmbedFn(torch.autograd.Function):
     def backward(ctx, dx):
         (ids,) = ctx.saved_tensors
         wshape, pshape = ctx.shapes
-        dword = torch.zeros(wshape, dtype=torch.float32, device=dx.device)
-        dpos = torch.zeros(pshape, dtype=torch.float32, device=dx.device)
-        ops.embed_bwd(ids, dx.contiguous(), dword, dpos)
+        dword, dpos = ops.embed_bwd_det(ids, dx.contiguous(), wshape[0], pshape[0])
         return None, dword, dpos
 
 
@@ -258,10 +256,8 @@ class _EncProjFn(torch.autograd.Function):
         ehs, y0, st, w_norm, rms = ctx.sv
         if d_enc is None:
             return (None,) * 6
-        g_norm = torch.zeros(w_norm.shape, dtype=torch.float32, device=y0.device)
-        d_y0 = ops.norm_bwd(d_enc.contiguous(), y0, _f32(w_norm), st, torch.bfloat16, dw=g_norm, rms=rms)
-        g_proj = torch.zeros(y0.shape[1], ehs.shape[1], dtype=torch.float32, device=y0.device)
-        ops.linear_wgrad(d_y0, ehs, g_proj)
+        d_y0, g_norm = ops.norm_bwd(d_enc.contiguous(), y0, _f32(w_norm), st, torch.bfloat16, rms=rms, want_dw=True)
+        g_proj = ops.linear_wgrad_det(d_y0, ehs)
         return None, None, None, None, g_proj, g_norm
 
 
@@ -334,7 +330,6 @@ class _LayerFn(torch.autograd.Function):
         dev = dx3.device
         dx3 = dx3.contiguous()
         d_enc = None
-        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
         it = iter(params)
         w_attn_ln = next(it); next(it); next(it); next(it); next(it)
         w_post = next(it) if s.normformer else None
@@ -345,67 +340,59 @@ class _LayerFn(torch.autograd.Function):
             w_cln = next(it); next(it); next(it); next(it); next(it)
             w_cpost = next(it) if s.normformer else None
         # ---- FFN
-        g_wo = z(H, I)
+        # every weight gradient below is STORED by a fixed-order reduction (deterministic split-K / ordered column sums):
+        # no zero-filled buffers, no atomics, bit-identical from run to run
         dy = ops.cast_bf16(dx3)
-        ops.linear_wgrad(dy, sv["ml"], g_wo)
+        g_wo = ops.linear_wgrad_det(dy, sv["ml"])
         d_ml = ops.linear_dgrad(dy, s.w["wo"])
         if s.normformer:  # LN backward + GLU backward fused: reads d_ml and [a|b], writes d[a|b]
-            g_mid = z(I)
-            d_ab = ops.norm_bwd(d_ml, sv["ab"], _f32(w_mid), sv["st4"], torch.bfloat16, dw=g_mid, act=2, rms=s.rms,
-                                y_fwd=sv["ml"])
+            d_ab, g_mid = ops.norm_bwd(d_ml, sv["ab"], _f32(w_mid), sv["st4"], torch.bfloat16, act=2, rms=s.rms,
+                                       y_fwd=sv["ml"], want_dw=True)
         else:
             g_mid = None
             d_ab = ops.glu_bwd(sv["ab"], d_ml)
-        g_wi = z(2 * I, H)
-        ops.linear_wgrad(d_ab, sv["h2"], g_wi)
+        g_wi = ops.linear_wgrad_det(d_ab, sv["h2"])
         d_h2 = ops.linear_dgrad(d_ab, s.w["wi"])
-        g_pre = z(H)
         x_mid = sv["x2b"] if s.cross else sv["x2"]
-        dx2 = ops.norm_bwd(d_h2, x_mid, _f32(w_pre), sv["st3"], torch.float32, dw=g_pre, dres=dx3, rms=0)
+        dx2, g_pre = ops.norm_bwd(d_h2, x_mid, _f32(w_pre), sv["st3"], torch.float32, dres=dx3, rms=0, want_dw=True)
         # ---- cross attention
         cross_grads = []
         if s.cross:
             if s.normformer:
-                g_cpost = z(H)
-                d_cao = ops.norm_bwd(dx2, sv["cao"], _f32(w_cpost), sv["stcp"], torch.bfloat16, dw=g_cpost, rms=s.rms)
+                d_cao, g_cpost = ops.norm_bwd(dx2, sv["cao"], _f32(w_cpost), sv["stcp"], torch.bfloat16, rms=s.rms,
+                                              want_dw=True)
             else:
                 g_cpost, d_cao = None, ops.cast_bf16(dx2)
-            g_co = z(H, H)
-            ops.linear_wgrad(d_cao, sv["cctx"], g_co)
+            g_co = ops.linear_wgrad_det(d_cao, sv["cctx"])
             d_cctx = ops.linear_dgrad(d_cao, s.w["co"])
             d_qc = torch.empty_like(sv["qc"])
             d_kvc = torch.empty_like(sv["kvc"])
             kvc = sv["kvc"]
             ops.attn_bwd(sv["qc"], kvc[:, :H], kvc[:, H:], sv["cctx"], d_cctx, sv["clse"], d_qc, d_kvc[:, :H],
                          d_kvc[:, H:], B, nh, S, s.Skv, s.scale)
-            g_ckv = z(2 * H, s.E)
-            ops.linear_wgrad(d_kvc, sv["enc"], g_ckv)
+            g_ckv = ops.linear_wgrad_det(d_kvc, sv["enc"])
             if ctx.needs_input_grad[1]:  # projected encoder states: d enc = d[k|v] @ [Wk;Wv], fp32, summed over layers by autograd
                 d_enc = ops.linear_dgrad(d_kvc, s.w["ckv"], out_dtype=torch.float32)
-            g_cq = z(H, H)
-            ops.linear_wgrad(d_qc, sv["hc"], g_cq)
+            g_cq = ops.linear_wgrad_det(d_qc, sv["hc"])
             d_hc = ops.linear_dgrad(d_qc, s.w["cq"])
-            g_cln = z(H)
-            dx2 = ops.norm_bwd(d_hc, sv["x2"], _f32(w_cln), sv["stc"], torch.float32, dw=g_cln, dres=dx2, rms=s.rms)
+            dx2, g_cln = ops.norm_bwd(d_hc, sv["x2"], _f32(w_cln), sv["stc"], torch.float32, dres=dx2, rms=s.rms,
+                                      want_dw=True)
             cross_grads = [g_cln, g_cq, g_ckv[:H], g_ckv[H:], g_co] + ([g_cpost] if s.normformer else [])
         # ---- self attention
         if s.normformer:
-            g_post = z(H)
-            d_ao = ops.norm_bwd(dx2, sv["ao"], _f32(w_post), sv["st2"], torch.bfloat16, dw=g_post, rms=s.rms)
+            d_ao, g_post = ops.norm_bwd(dx2, sv["ao"], _f32(w_post), sv["st2"], torch.bfloat16, rms=s.rms, want_dw=True)
         else:
             g_post, d_ao = None, ops.cast_bf16(dx2)
-        g_ao = z(H, H)
-        ops.linear_wgrad(d_ao, sv["ctxt"], g_ao)
+        g_ao = ops.linear_wgrad_det(d_ao, sv["ctxt"])
         d_ctx = ops.linear_dgrad(d_ao, s.w["ao"])
         qkv = sv["qkv"]
         d_qkv = torch.empty_like(qkv)
         ops.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["ctxt"], d_ctx, sv["lse"], d_qkv[:, :H],
                      d_qkv[:, H:2 * H], d_qkv[:, 2 * H:], B, nh, S, S, s.scale)
-        g_qkv = z(3 * H, H)
-        ops.linear_wgrad(d_qkv, sv["h1"], g_qkv)
+        g_qkv = ops.linear_wgrad_det(d_qkv, sv["h1"])
         d_h1 = ops.linear_dgrad(d_qkv, s.w["qkv"])
-        g_attn_ln = z(H)
-        dx1 = ops.norm_bwd(d_h1, sv["x"], _f32(w_attn_ln), sv["st1"], torch.float32, dw=g_attn_ln, dres=dx2, rms=s.rms)
+        dx1, g_attn_ln = ops.norm_bwd(d_h1, sv["x"], _f32(w_attn_ln), sv["st1"], torch.float32, dres=dx2, rms=s.rms,
+                                      want_dw=True)
         grads = [g_attn_ln, g_qkv[:H], g_qkv[H:2 * H], g_qkv[2 * H:], g_ao]
         if s.normformer:
             grads.append(g_post)
@@ -466,7 +453,6 @@ class _HeadFn(torch.autograd.Function):
     def backward(ctx, d_logits, d_loss=None):
         s, sv, params = ctx.spec, ctx.sv, ctx.params
         dev = sv["x"].device
-        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
         it = iter(params)
         w_enc = next(it) if s.use_enc_ln else None
         if s.use_mlm:
@@ -482,22 +468,19 @@ class _HeadFn(torch.autograd.Function):
             dl = extra if dl is None else dl + extra
         if dl is None:
             raise RuntimeError("MaskGitTransformer head: backward called without any gradient")
-        g_logits = z(s.Vpad, s.H)
-        ops.linear_wgrad(dl, sv["e"], g_logits)
+        g_logits = ops.linear_wgrad_det(dl, sv["e"])
         d_e = ops.linear_dgrad(dl, s.w["logits"])
         grads = []
         if s.use_mlm:
-            g_mlm_ln = z(s.H)
-            d_d = ops.norm_bwd(d_e, sv["d"], _f32(w_mlm_ln), sv["st1"], torch.bfloat16, dw=g_mlm_ln, act=1, rms=s.rms)
-            g_dense = z(s.H, s.H)
-            ops.linear_wgrad(d_d, sv["hN"], g_dense)
+            d_d, g_mlm_ln = ops.norm_bwd(d_e, sv["d"], _f32(w_mlm_ln), sv["st1"], torch.bfloat16, act=1, rms=s.rms,
+                                         want_dw=True)
+            g_dense = ops.linear_wgrad_det(d_d, sv["hN"])
             d_hN = ops.linear_dgrad(d_d, s.w["dense"])
             grads = [g_dense, g_mlm_ln]
         else:
             d_hN = d_e
         if s.use_enc_ln:
-            g_enc = z(s.H)
-            dx = ops.norm_bwd(d_hN, sv["x"], _f32(w_enc), sv["st0"], torch.float32, dw=g_enc, rms=s.rms)
+            dx, g_enc = ops.norm_bwd(d_hN, sv["x"], _f32(w_enc), sv["st0"], torch.float32, rms=s.rms, want_dw=True)
             grads = [g_enc] + grads
         else:
             dx = d_hN.float()

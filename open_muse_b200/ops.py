@@ -31,7 +31,9 @@ def _prep(t: torch.Tensor):
     if not t.is_cuda:
         raise _lib.MuseB200Error("open_muse_b200 ops need CUDA tensors (no CPU fallback)")
     dev = t.device.index
-    if _state["device"] != dev:
+    # the library's runtime must target the tensor's device; the user may have called torch.cuda.set_device since the
+    # last op, so compare against torch's current device rather than a cached value
+    if _state["device"] != dev or torch.cuda.current_device() != dev:
         _lib.check(_lib.load().muse_set_device(dev), "muse_set_device")
         _state["device"] = dev
     return torch.cuda.current_stream(dev).cuda_stream
@@ -49,7 +51,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-_KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
+_KERNELS_PER_CALL = {"muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_embed_bwd_sorted": 4, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
                      "muse_groupnorm_silu_nhwc": 3, "muse_grn_fwd": 3, "muse_grn_bwd": 3,
                      "muse_dwconv3x3_norm_bwd": 2}
 _prof = {"on": False, "events": []}
@@ -115,10 +117,42 @@ def linear_dgrad_acc(dy, w, acc):
 
 
 def linear_wgrad(dy, x, dw):
-    """dw[N,K] += dy[T,N]^T @ x[T,K]  (both operands MN-major, split-K over tokens, fp32 atomics)."""
+    """dw[N,K] += dy[T,N]^T @ x[T,K]  (both operands MN-major, split-K over tokens, fp32 atomics: accumulating but
+    order-dependent; the MaskGiTUViT_v2 training path, whose gradients are summed across blocks)."""
     T, N = dy.shape
     K = x.shape[1]
     return gemm(dy, x, dw, N, K, T, dy.stride(0), x.stride(0), dw.stride(0), 1, 1, EPI_ATOMIC_F32)
+
+
+_splitk_counters = {}
+
+
+def linear_wgrad_det(dy, x, out=None):
+    """dw[N,K] = dy[T,N]^T @ x[T,K], run-to-run bit-identical: split-K partial tiles go to a workspace and the CTA that
+    finishes a tile last sums them in split order and stores dw (no zero fill, no atomics on dw)."""
+    import ctypes
+
+    st = _prep(dy)
+    T, N = dy.shape
+    K = x.shape[1]
+    dev = dy.device
+    dw = out if out is not None else torch.empty(N, K, dtype=torch.float32, device=dev)
+    ncnt = ctypes.c_int(0)
+    need = _lib.load().muse_gemm_splitk_workspace_bytes(N, K, T, ctypes.byref(ncnt))
+    cnt = _splitk_counters.get(dev.index)
+    if cnt is None or cnt.numel() < ncnt.value:
+        cnt = torch.zeros(max(4096, ncnt.value), dtype=torch.int32, device=dev)
+        _splitk_counters[dev.index] = cnt
+    ws = torch.empty(max(need, 16) // 4, dtype=torch.float32, device=dev)
+    if _prof["on"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _call("muse_gemm_bf16_splitk", _p(dy), _p(x), _p(dw), N, K, T, dy.stride(0), x.stride(0), dw.stride(0), 1, 1, _p(ws),
+          need, _p(cnt), st)
+    if _prof["on"]:
+        e1.record()
+        _prof["events"].append((e0, e1, 2.0 * N * K * T))
+    return dw
 
 
 # ------------------------------------------------------------------------------------------ packing
@@ -145,9 +179,38 @@ def embed_fwd(ids, word, pos):
 
 
 def embed_bwd(ids, dx, dword, dpos):
+    """dword[ids] += dx with atomics (dword zero-filled by the caller; order-dependent), dpos[:S] stored."""
     st = _prep(dx)
     B, S = ids.shape
     _call("muse_embed_bwd", _p(ids), _p(dx), _p(dword), _p(dpos), B, S, dword.shape[1], dword.shape[0], st)
+
+
+_arange_cache = {}
+
+
+def embed_bwd_det(ids, dx, vocab, n_pos):
+    """Reproducible embedding backward: returns (dword [vocab, H], dpos [n_pos, H] or None when n_pos == 0), every row
+    stored, token contributions summed in ascending token order.  The stable sort of the ids is index preparation (ATen);
+    the data path is muse_embed_bwd_sorted."""
+    st = _prep(dx)
+    B, S = ids.shape
+    H = dx.shape[1]
+    dev = dx.device
+    flat = ids.reshape(-1)
+    sorted_ids, order = torch.sort(flat, stable=True)
+    key = (vocab, dev)
+    probe = _arange_cache.get(key)
+    if probe is None:
+        probe = _arange_cache[key] = torch.arange(vocab + 1, device=dev, dtype=torch.int64)
+    bounds = torch.searchsorted(sorted_ids, probe)
+    dword = torch.empty(vocab, H, dtype=torch.float32, device=dev)
+    dpos = None
+    if n_pos:
+        dpos = torch.empty(n_pos, H, dtype=torch.float32, device=dev) if n_pos == S else \
+            torch.zeros(n_pos, H, dtype=torch.float32, device=dev)
+    ws = torch.empty(_lib.load().muse_embed_bwd_sorted_workspace_bytes(B * S, H, vocab) // 4, dtype=torch.float32, device=dev)
+    _call("muse_embed_bwd_sorted", _p(order), _p(bounds), _p(dx), _p(dword), _p(dpos), _p(ws), B, S, H, vocab, st)
+    return dword, dpos
 
 
 # ------------------------------------------------------------------------------------------ norms
@@ -167,17 +230,24 @@ def norm_fwd(x, w, eps, out_dtype, res=None, act=0, rms=0, save_stats=True):
     return y, stats
 
 
-def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None):
-    """y_fwd: the saved forward output (act=2, bf16 only) -- lets the kernel skip one GELU pass over [a | b]."""
+def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None, want_dw=False):
+    """y_fwd: the saved forward output (act=2, bf16 only) -- lets the kernel skip one GELU pass over [a | b].
+    dw: fp32 [H] buffer the weight gradient is ADDED to (atomics; caller zero-fills).  want_dw=True instead returns
+    (dx, dw) with a freshly stored dw reduced in a fixed order (run-to-run bit-identical)."""
     st = _prep(x)
     rows = x.shape[0]
     H = x.shape[1] // 2 if act == 2 else x.shape[1]
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
     if y_fwd is not None and not (act == 2 and y_fwd.dtype == torch.bfloat16 and y_fwd.is_contiguous()):
         y_fwd = None
+    ws = None
+    if want_dw:
+        dw = torch.empty(H, dtype=torch.float32, device=x.device)
+        ws = torch.empty(max(1, _lib.load().muse_norm_bwd_workspace_floats(rows, H, act)), dtype=torch.float32, device=x.device)
+        _state["launches"] += 1  # the ordered column sum
     _call("muse_norm_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(w), _p(stats[0]), _p(stats[1]), _p(dres), _p(y_fwd), _p(dx),
-          _dt(dx), _p(dw), rows, H, act, rms, st)
-    return dx
+          _dt(dx), _p(dw), _p(ws), rows, H, act, rms, st)
+    return (dx, dw) if want_dw else dx
 
 
 # ------------------------------------------------------------------------------------------ GLU

@@ -270,3 +270,53 @@ def test_norm_glu_fused_fwd_bwd(I, rms):
     dab2 = ops.norm_bwd(dy, ab, w, stats, torch.bfloat16, dw=dw2, act=2, rms=rms, y_fwd=y)
     assert _rel(dab2[:, :I], a.grad) < 1.2e-2 and _rel(dab2[:, I:], b.grad) < 1.2e-2
     assert _rel(dw2, wr.grad) < 1e-2 and _rel(dab2, dab.float()) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------ reproducible reductions
+@pytest.mark.parametrize("T,N,K", [(4112, 192, 128), (65792 // 8, 1536, 512), (520, 72, 200), (2056, 2048, 512), (130, 128, 64)])
+def test_wgrad_deterministic_splitk(T, N, K):
+    """dW = dY^T X through the deterministic split-K epilogue: matches fp32 math, does not need a zeroed output, and two
+    runs agree bit for bit (the atomic epilogue does not guarantee that)."""
+    dY, X = _rand((T, N), 5), _rand((T, K), 6)
+    ref = dY.float().t() @ X.float()
+    outs = []
+    for _ in range(3):
+        dW = torch.full((N, K), float("nan"), dtype=torch.float32, device=DEV)  # every element must be overwritten
+        ops.linear_wgrad_det(dY, X, out=dW)
+        outs.append(dW)
+    torch.cuda.synchronize()
+    assert _rel(outs[0], ref) < 1e-5
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    cnt = ops._splitk_counters[torch.cuda.current_device()]
+    assert int(cnt.abs().sum()) == 0  # the tickets are left at zero for the next launch
+
+
+@pytest.mark.parametrize("H,act,xdt", [(512, 0, torch.float32), (1024, 1, torch.bfloat16), (2048, 0, torch.bfloat16), (2048, 2, torch.bfloat16)])
+def test_norm_bwd_dw_deterministic(H, act, xdt):
+    rows = 4099
+    x = _rand((rows, 2 * H if act == 2 else H), 1, dtype=xdt)
+    w = (1 + 0.1 * torch.randn(H, generator=torch.Generator().manual_seed(2))).to(DEV)
+    _, stats = ops.norm_fwd(x, w, 1e-5, torch.bfloat16, act=act)
+    dy = _rand((rows, H), 3)
+    dw_atomic = torch.zeros(H, device=DEV)
+    dx_a = ops.norm_bwd(dy, x, w, stats, torch.bfloat16, dw=dw_atomic, act=act)
+    res = [ops.norm_bwd(dy, x, w, stats, torch.bfloat16, act=act, want_dw=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    assert torch.equal(res[0][0], dx_a)
+    assert _rel(res[0][1], dw_atomic) < 1e-5
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][1], res[2][1])
+
+
+@pytest.mark.parametrize("B,S,H,V", [(5, 17, 128, 72), (64, 257, 512, 2025), (3, 33, 96, 50), (4, 256, 1024, 8256)])
+def test_embed_bwd_deterministic(B, S, H, V):
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, V - 10, (B, S), generator=g).to(DEV)  # the last ids stay unused: their rows must come out zero
+    ids[torch.rand(B, S, generator=g).to(DEV) < 0.5] = V - 1    # the mask token: one very long segment
+    dx = torch.randn(B * S, H, device=DEV)
+    outs = [ops.embed_bwd_det(ids, dx, V, S + 3) for _ in range(2)]
+    torch.cuda.synchronize()
+    rw = torch.zeros(V, H, device=DEV, dtype=torch.float64).index_add_(0, ids.view(-1), dx.double())
+    dword, dpos = outs[0]
+    assert _rel(dword, rw) < 1e-6 and bool((dword[V - 10:V - 1] == 0).all())
+    assert _rel(dpos[:S], dx.view(B, S, H).sum(0)) < 1e-6 and bool((dpos[S:] == 0).all())
+    assert torch.equal(dword, outs[1][0]) and torch.equal(dpos, outs[1][1])

@@ -2,9 +2,15 @@
 unmodified reference stored in tests/golden/ (fp32 CPU) and against the fp32 oracle on larger seeded inputs.
 
 Tolerances (bf16 GEMM operands, fp32 accumulation / statistics, as the reference's own bf16-autocast mode):
-  logits: relative L2 error <= 2e-2 vs the fp32 reference (the reference's own bf16 path sits at 1.2e-2)
+  logits: relative L2 error <= 1e-2 (north_star).  Against the fp32 reference fixtures for the 1-2 layer models; for the
+          8-layer base-256 and the cc12m-width models, where the reference's OWN bf16-autocast forward is 1.2e-2 away from
+          its fp32 forward, the 1e-2 is asserted against the reference recipe executed in the same precision
+          mode on the same GPU (oracle ops under torch.autocast(cuda, bf16)), and the distance to fp32 must not exceed
+          the reference's own bf16 distance by more than 10 %.
   loss  : relative error <= 2e-3
-  grads : relative L2 error <= 6e-2 per parameter (and cosine similarity >= 0.998)
+  grads : relative L2 error <= 6e-2 per parameter (and cosine similarity >= 0.998); a parameter may exceed it only where
+          the reference recipe's own bf16 gradients are within 1.5x as noisy (query/key weights of deeper layers at random
+          init) -- those parameters are listed in the test output and their number is bounded.
 """
 import os
 
@@ -17,7 +23,7 @@ from open_muse_b200.modeling_transformer import MaskGitTransformer  # noqa: E402
 from oracle import transformer_oracle as T  # noqa: E402
 
 DEV = "cuda"
-LOGIT_TOL, LOSS_TOL, GRAD_TOL = 2e-2, 2e-3, 6e-2
+LOGIT_TOL, LOSS_TOL, GRAD_TOL = 1e-2, 2e-3, 6e-2
 
 
 def _rel(a, b):
@@ -36,14 +42,26 @@ def _bf16_recipe_grad_errors(g, **fwd_kwargs):
     return {k: _rel(q[k].grad, g["grads"][k]) for k in q}
 
 
-def _check(model, logits, loss, ref_logits, ref_loss, ref_grads, report, recipe_err=None):
+def _same_mode_reference(sd, cfg, input_ids, labels, **kw):
+    """The reference recipe in the SAME precision mode on the SAME device: oracle ops (= the reference's torch calls)
+    under torch.autocast(cuda, bf16), i.e. what the unmodified reference computes on this GPU.  Checker only."""
+    q = {k: v.detach().clone().float().to(DEV).requires_grad_(True) for k, v in sd.items()}
+    kw = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in kw.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, loss = T.forward(q, cfg, input_ids.to(DEV), labels=labels.to(DEV), **kw)
+    loss.backward()
+    return logits.detach().float().cpu(), loss.detach().float().cpu(), {k: v.grad.cpu() for k, v in q.items()}
+
+
+def _check(model, logits, loss, ref_logits, ref_loss, ref_grads, report, recipe_err=None, logit_tol=LOGIT_TOL,
+           max_hatch=0):
     r = _rel(logits, ref_logits)
     report.append(f"logits rel-L2 {r:.3e}")
-    assert r < LOGIT_TOL
+    assert r < logit_tol
     lr = abs(float(loss) - float(ref_loss)) / abs(float(ref_loss))
     report.append(f"loss rel {lr:.3e}")
     assert lr < LOSS_TOL
-    worst = 0.0
+    worst, hatch = 0.0, []
     for n, p in model.named_parameters():
         assert p.grad is not None, n
         g, rg = p.grad.float().cpu(), ref_grads[n].float()
@@ -52,10 +70,14 @@ def _check(model, logits, loss, ref_logits, ref_loss, ref_grads, report, recipe_
         floor = 1.5 * recipe_err[n] if recipe_err is not None else 0.0
         if e >= GRAD_TOL:
             assert e < floor, (n, e, cos, floor)  # only allowed where the reference's own bf16 mode is as noisy
+            assert "attention.query" in n or "attention.key" in n, (n, e)  # ... which is the ~1e-6 q/k gradients only
+            hatch.append(f"{n}={e:.2e} (reference bf16 recipe {recipe_err[n]:.2e})")
         else:
             assert cos > 0.998, (n, e, cos)
             worst = max(worst, e)
     report.append(f"worst grad rel-L2 {worst:.3e}")
+    report.append(f"{len(hatch)} parameter(s) above {GRAD_TOL:g} within 1.5x of the reference's own bf16 noise: {hatch}")
+    assert len(hatch) <= max_hatch, hatch
 
 
 @pytest.mark.parametrize("backend", ["tcgen05", "mma"])
@@ -73,7 +95,7 @@ def test_micro_class_conditional_vs_reference(monkeypatch, golden, backend):
     rep = []
     cal = _bf16_recipe_grad_errors(g, input_ids=g["batch"]["input_ids"], labels=g["batch"]["labels"],
                                    label_smoothing=g["label_smoothing"])
-    _check(m, logits, loss, g["logits"], g["loss"], g["grads"], rep, recipe_err=cal)
+    _check(m, logits, loss, g["logits"], g["loss"], g["grads"], rep, recipe_err=cal, max_hatch=2)
     print(backend, "micro:", "; ".join(rep))
 
 
@@ -110,7 +132,7 @@ def test_micro_text_conditional_projected_encoder_states_vs_reference(golden):
     rep = []
     cal = _bf16_recipe_grad_errors(g, input_ids=g["input_ids"], labels=g["labels"],
                                    encoder_hidden_states=g["encoder_hidden_states"])
-    _check(m, logits, loss, g["logits"], g["loss"], g["grads"], rep, recipe_err=cal)
+    _check(m, logits, loss, g["logits"], g["loss"], g["grads"], rep, recipe_err=cal, max_hatch=4)
     assert float(m.encoder_proj.weight.grad.abs().max()) > 0
     print("micro t2i proj:", "; ".join(rep))
 
@@ -148,17 +170,89 @@ def test_base_shape_vs_oracle():
     cls = torch.randint(0, 1000, (B,), generator=g)
     inp, lab = T.mask_tokens(tokens, cls, torch.rand(B, generator=g), torch.rand(B, 256, generator=g), 1024, 2024)
     ref_logits, ref_loss, ref_grads = T.forward_backward(sd, cfg, inp, lab)
+    same_logits, same_loss, _ = _same_mode_reference(sd, cfg, inp, lab)
     m.to(DEV).train()
     with torch.autocast("cuda", dtype=torch.bfloat16):
         logits, loss = m(inp.to(DEV), labels=lab.to(DEV))
     loss.backward()
     rep = []
-    _check(m, logits, loss, ref_logits, ref_loss, ref_grads, rep)
+    r_same, r_ref_own = _rel(logits, same_logits), _rel(same_logits, ref_logits)
+    rep.append(f"logits vs reference recipe in bf16 autocast on this GPU {r_same:.3e} (that recipe vs fp32: {r_ref_own:.3e})")
+    assert r_same < LOGIT_TOL
+    assert abs(float(loss) - float(same_loss)) / float(same_loss) < LOSS_TOL
+    # against fp32: no further from it than the reference's own bf16 mode (+10 %)
+    _check(m, logits, loss, ref_logits, ref_loss, ref_grads, rep, logit_tol=max(LOGIT_TOL, 1.1 * r_ref_own))
     print("base-256 B=4:", "; ".join(rep))
     # linearity-style property at the loss level: two identical half-batches give the same loss as one
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         _, l2 = m(torch.cat([inp, inp]).to(DEV), labels=torch.cat([lab, lab]).to(DEV))
     assert abs(float(l2) - float(loss)) < 1e-4 * float(loss)
+
+
+def test_cc12m_width_text_conditional_vs_oracle():
+    """BASELINE config 4 at its own widths (configs/cc12m_uvit_clip.yaml:29-54: H 1024, 16 heads, I 4096, vocab 8256 with
+    codebook-sized output 8192, cross-attention to 77 x 768 CLIP states, RMSNorm, no normformer, eps 1e-6), two layers,
+    batch 2: logits, loss and every gradient against the fp32 oracle, and logits against the reference recipe in bf16
+    autocast on this GPU."""
+    cfg = dict(vocab_size=8256, max_position_embeddings=256, hidden_size=1024, num_hidden_layers=2,
+               num_attention_heads=16, intermediate_size=4096, codebook_size=8192, num_vq_tokens=256,
+               add_cross_attention=True, encoder_hidden_size=768, norm_type="rmsnorm", layer_norm_eps=1e-6,
+               use_normformer=False, use_codebook_size_for_output=True, hidden_dropout=0.0, attention_dropout=0.0)
+    torch.manual_seed(0)
+    m = MaskGitTransformer(**cfg)
+    assert m.output_size == 8192 and m.config.mask_token_id == 8255
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(11)
+    B = 2
+    tokens = torch.randint(0, 8192, (B, 256), generator=g)
+    mask = torch.rand(B, 256, generator=g) < 0.6
+    inp = torch.where(mask, 8255, tokens)
+    lab = torch.where(mask, tokens, -100)
+    ehs = torch.randn(B, 77, 768, generator=g)
+    ref_logits, ref_loss, ref_grads = T.forward_backward(sd, cfg, inp, lab, encoder_hidden_states=ehs)
+    same_logits, same_loss, same_grads = _same_mode_reference(sd, cfg, inp, lab, encoder_hidden_states=ehs)
+    cal = {k: _rel(same_grads[k], ref_grads[k]) for k in ref_grads}  # the reference recipe's own bf16 gradient noise
+    m.to(DEV).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, loss = m(inp.to(DEV), encoder_hidden_states=ehs.to(DEV), labels=lab.to(DEV))
+    assert logits.shape == (B, 256, 8192)
+    loss.backward()
+    rep = []
+    r_same, r_ref_own = _rel(logits, same_logits), _rel(same_logits, ref_logits)
+    rep.append(f"logits vs reference recipe in bf16 autocast on this GPU {r_same:.3e} (that recipe vs fp32: {r_ref_own:.3e})")
+    assert r_same < LOGIT_TOL
+    _check(m, logits, loss, ref_logits, ref_loss, ref_grads, rep, recipe_err=cal, logit_tol=max(LOGIT_TOL, 1.1 * r_ref_own),
+           max_hatch=8)
+    print("cc12m widths L=2 B=2:", "; ".join(rep))
+
+
+def test_train_step_gradients_are_bit_reproducible():
+    """The reference's bf16 step is run-to-run bit-identical.  Two identical forward+backward passes of the
+    base-256 architecture must give bit-identical logits, loss and gradients for EVERY parameter: weight gradients come
+    from fixed-order reductions (deterministic split-K GEMM, ordered column sums, sorted embedding backward), no atomics."""
+    cfg = dict(vocab_size=2025, max_position_embeddings=257, hidden_size=512, num_hidden_layers=3,
+               num_attention_heads=8, intermediate_size=2048, codebook_size=1024, num_vq_tokens=256, num_classes=1000,
+               hidden_dropout=0.0, attention_dropout=0.0)
+    torch.manual_seed(0)
+    m = MaskGitTransformer(**cfg).to(DEV).train()
+    g = torch.Generator().manual_seed(5)
+    B = 24
+    tokens = torch.randint(0, 1024, (B, 256), generator=g)
+    cls = torch.randint(0, 1000, (B,), generator=g)
+    inp, lab = T.mask_tokens(tokens, cls, torch.rand(B, generator=g), torch.rand(B, 256, generator=g), 1024, 2024)
+    inp, lab = inp.to(DEV), lab.to(DEV)
+    runs = []
+    for _ in range(3):
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits, loss = m(inp, labels=lab)
+        loss.backward()
+        torch.cuda.synchronize()
+        runs.append((logits.clone(), loss.clone(), {n: p.grad.clone() for n, p in m.named_parameters()}))
+    for other in runs[1:]:
+        assert torch.equal(runs[0][0], other[0]) and torch.equal(runs[0][1], other[1])
+        for n, gr in runs[0][2].items():
+            assert torch.equal(gr, other[2][n]), n
 
 
 def test_soft_target_loss_on_returned_logits(golden):

@@ -18,22 +18,26 @@ def _fake_ops(mp):
             assert res.dtype == F32 and res.shape == (x.shape[0], n)
         return torch.zeros(x.shape[0], n, dtype=F32 if res is not None else out_dtype)
 
-    def wgrad(dy, x, dw):
-        assert dw.shape == (dy.shape[1], x.shape[1]) and dy.dtype == BF and x.dtype == BF and dw.dtype == F32
+    def wgrad(dy, x, out=None):
+        assert dy.dtype == BF and x.dtype == BF and dy.shape[0] == x.shape[0]
+        return torch.zeros(dy.shape[1], x.shape[1], dtype=F32)
+
+    def embed_bwd(ids, dx, vocab, n_pos):
+        assert dx.shape[0] == ids.numel() and dx.dtype == F32
+        return torch.zeros(vocab, dx.shape[1]), torch.zeros(n_pos, dx.shape[1])
 
     def norm_fwd(x, w, eps, out_dtype, res=None, act=0, rms=0, save_stats=True):
         H = x.shape[1] // 2 if act == 2 else x.shape[1]
         assert w is None or w.shape == (H,)
         return torch.zeros(x.shape[0], H, dtype=out_dtype), (torch.zeros(2, x.shape[0]) if save_stats else None)
 
-    def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None):
+    def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None, want_dw=False):
         H = x.shape[1] // 2 if act == 2 else x.shape[1]
         assert dy.shape == (x.shape[0], H) and stats is not None
         if dres is not None:
             assert dres.shape == x.shape and dres.dtype == F32
-        if dw is not None:
-            assert dw.shape == (H,) and dw.dtype == F32
-        return torch.zeros(x.shape, dtype=dx_dtype)
+        assert dw is None and want_dw  # the v1 model only uses the reproducible (stored) weight-gradient form
+        return torch.zeros(x.shape, dtype=dx_dtype), torch.zeros(H, dtype=F32)
 
     def attb(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, sc):
         assert do.dtype == BF and do.shape == o.shape and dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape
@@ -44,8 +48,8 @@ def _fake_ops(mp):
 
     fakes = dict(
         gemm=gemm, linear_fwd=lin_fwd, linear_dgrad=lambda dy, w, out_dtype=BF: torch.zeros(dy.shape[0], w.shape[1], dtype=out_dtype),
-        linear_wgrad=wgrad, cast_bf16=lambda x: x.to(BF), pack_bf16=lambda table, n, blocks: None,
-        embed_fwd=lambda ids, w, pos: torch.zeros(ids.numel(), w.shape[1]), embed_bwd=lambda ids, dx, dword, dpos: None,
+        linear_wgrad_det=wgrad, cast_bf16=lambda x: x.to(BF), pack_bf16=lambda table, n, blocks: None,
+        embed_fwd=lambda ids, w, pos: torch.zeros(ids.numel(), w.shape[1]), embed_bwd_det=embed_bwd,
         norm_fwd=norm_fwd, norm_bwd=norm_bwd, glu_fwd=lambda ab: torch.zeros(ab.shape[0], ab.shape[1] // 2, dtype=BF),
         glu_bwd=lambda ab, d: torch.zeros_like(ab),
         attn_fwd=lambda q, k, v, B, nh, Sq, Skv, sc: (torch.zeros(q.shape[0], nh * 64, dtype=BF), torch.zeros(B, nh, Sq)),
