@@ -76,9 +76,13 @@ class EMAModel:
             if not p.requires_grad:
                 s.copy_(p)
 
+    @torch.no_grad()
     def copy_to(self, parameters: Iterable[torch.nn.Parameter]) -> None:
+        # p.copy_ (not p.data.copy_): the in-place write must bump the parameter's version counter, which is what the
+        # models' packed bf16 operand caches key on -- validation with EMA weights (training/train_muse.py:857-908:
+        # store / copy_to / validate / restore) would otherwise run every GEMM with the stale non-EMA operands.
         for s, p in zip(self.shadow_params, list(parameters)):
-            p.data.copy_(s.to(p.device).data)
+            p.copy_(s.to(p.device))
 
     def to(self, device=None, dtype=None) -> None:
         self.shadow_params = [p.to(device=device, dtype=dtype) if p.is_floating_point() else p.to(device=device)
@@ -95,8 +99,9 @@ class EMAModel:
     def restore(self, parameters: Iterable[torch.nn.Parameter]) -> None:
         if self.temp_stored_params is None:
             raise RuntimeError("This ExponentialMovingAverage has no `store()`ed weights to `restore()`")
-        for c, p in zip(self.temp_stored_params, parameters):
-            p.data.copy_(c.data)
+        with torch.no_grad():
+            for c, p in zip(self.temp_stored_params, parameters):
+                p.copy_(c)  # bumps the version counter (see copy_to)
         self.temp_stored_params = None
 
     def load_state_dict(self, state_dict: dict) -> None:

@@ -24,6 +24,10 @@ from . import ops
 from .modeling_utils import ConfigMixin, ModelMixin, register_to_config
 from .sampling import cosine_schedule, mask_by_random_topk
 
+import os as _os
+
+_CHECK_IDS = _os.environ.get("MUSE_B200_CHECK_IDS", "0") == "1"
+
 
 # --------------------------------------------------------------------------------------------
 # Parameter containers (names/shapes/order == reference modules; they carry no compute)
@@ -406,9 +410,12 @@ class _LayerFn(torch.autograd.Function):
 
 
 class _HeadSpec:
-    def __init__(self, T, H, V, Vpad, eps, rms, use_enc_ln, use_mlm, w, label_smoothing):
+    def __init__(self, T, H, V, Vpad, eps, rms, use_enc_ln, use_mlm, w, label_smoothing, n_cols=None):
         self.T, self.H, self.V, self.Vpad, self.eps, self.rms = T, H, V, Vpad, eps, rms
         self.use_enc_ln, self.use_mlm, self.w, self.ls = use_enc_ln, use_mlm, w, label_smoothing
+        # inference only: compute just the first n_cols logit columns (generate2 reads the codebook_size columns of a
+        # vocab_size-wide head, reference :1417 -- the other half of that GEMM would be thrown away)
+        self.n_cols = n_cols
 
 
 class _HeadFn(torch.autograd.Function):
@@ -433,6 +440,13 @@ class _HeadFn(torch.autograd.Function):
             e, st1 = ops.norm_fwd(d, _f32(w_mlm_ln), s.eps, torch.bfloat16, act=1, rms=s.rms, save_stats=grad)
         else:
             d, e, st1 = None, hN, None
+        if s.n_cols is not None:
+            if grad or labels is not None:
+                raise RuntimeError("column-restricted logits are an inference-only path")
+            ncol = ((s.n_cols + 7) // 8) * 8
+            logits = torch.empty(s.T, ncol, dtype=torch.bfloat16, device=x.device)
+            ops.gemm(e, s.w["logits"], logits, s.T, ncol, s.H, s.H, s.H, ncol)
+            return logits[:, : s.n_cols]
         logits = torch.empty(s.T, s.Vpad, dtype=torch.bfloat16, device=x.device)
         ops.gemm(e, s.w["logits"], logits, s.T, s.Vpad, s.H, s.H, s.H, s.Vpad)
         loss = None
@@ -632,6 +646,7 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
         label_smoothing=0.0,
         cond_dropout_prob=0.0,
         _raw_bf16=False,
+        _logit_cols=None,
         **kwargs,  # cond_embeds / loss_weight / micro_conds from train_muse.py:742-750 are accepted and ignored
     ):
         c = self.config
@@ -647,6 +662,15 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
         if not input_ids.is_cuda:
             raise RuntimeError("open_muse_b200.MaskGitTransformer runs on CUDA (sm_100a) only; move inputs to the GPU")
         B, S = input_ids.shape
+        if _CHECK_IDS:  # debug switch (MUSE_B200_CHECK_IDS=1): torch raises a device assert on out-of-range ids / labels,
+            # the kernels clamp silently -- this host-side check (one sync) catches class-offset / vocab mix-ups
+            lo, hi = int(input_ids.min()), int(input_ids.max())
+            if lo < 0 or hi >= self.vocab_size:
+                raise IndexError(f"input_ids out of range [0, {self.vocab_size}): min {lo}, max {hi}")
+            if labels is not None:
+                bad = (labels != -100) & ((labels < 0) | (labels >= self.output_size))
+                if bool(bad.any()):
+                    raise IndexError(f"labels out of range [0, {self.output_size}) (other than -100)")
         if S > self.max_position_embeddings:
             raise IndexError(f"sequence length {S} exceeds max_position_embeddings {self.max_position_embeddings}")
         H = self.hidden_size
@@ -680,14 +704,16 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
             x = _LayerFn.apply(x, enc, spec, *self._layer_params(layer))
 
         flat_labels = labels.reshape(-1).contiguous().to(torch.int64) if labels is not None else None
+        if _logit_cols is not None and (_logit_cols >= self.output_size or labels is not None or torch.is_grad_enabled()):
+            _logit_cols = None
         hspec = _HeadSpec(B * S, H, self.output_size, self.padded_output_size, c.layer_norm_eps, rms,
-                          c.use_encoder_layernorm, c.use_mlm_layer, packed.head, label_smoothing)
+                          c.use_encoder_layernorm, c.use_mlm_layer, packed.head, label_smoothing, n_cols=_logit_cols)
         out = _HeadFn.apply(x, flat_labels, hspec, *self._head_params())
         if labels is not None:
             logits, loss = out
         else:
             logits, loss = out, None
-        logits = logits.view(B, S, self.output_size) if logits.is_contiguous() else logits.unflatten(0, (B, S))
+        logits = logits.unflatten(0, (B, S))
         if _raw_bf16:
             return logits, loss
         if not torch.is_autocast_enabled("cuda"):
@@ -715,9 +741,17 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
         guidance_scale=0,
         noise_schedule=cosine_schedule,
         generator: torch.Generator = None,
+        _noise=None,
+        _trace=None,
         **kwargs,
     ):
-        """MaskGIT iterative parallel decoding, same semantics as the reference (:1363-1456)."""
+        """MaskGIT iterative parallel decoding, same semantics as the reference (:1363-1456).
+
+        The whole loop -- ``timesteps`` x (forward, Exp(1) / uniform draws from the torch generator, fused sample /
+        confidence / re-mask kernel) -- is captured once per (shape, schedule) into ONE CUDA graph and replayed: a call
+        costs a handful of host launches instead of ~80 per step.  ``use_cuda_graph=False`` (or the private test hooks
+        ``_noise`` = per-step (q_exp, u) tensors, ``_trace`` = list collecting per-step state) run the same kernels launched
+        one by one."""
         c = self.config
         mask_id, seq_len, n_codes = c.mask_token_id, c.num_vq_tokens, c.codebook_size
         batch = len(class_ids) if class_ids is not None else encoder_hidden_states.shape[0]
@@ -725,28 +759,91 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
             class_ids += n_codes  # in place on the caller's tensor, like the reference (quirk Q3)
         if input_ids is None:
             input_ids = torch.full((batch, seq_len), mask_id, dtype=torch.long, device=self.device)
+        input_ids = input_ids.contiguous()
+        use_graph = kwargs.pop("use_cuda_graph", None)
+        if use_graph is None:
+            use_graph = _os.environ.get("MUSE_B200_GENERATE_GRAPH", "1") != "0"
+        use_graph = bool(use_graph) and _noise is None and _trace is None and input_ids.is_cuda
+        args = (input_ids, class_ids, encoder_hidden_states, negative_embeds)
+        sched = (float(temperature), int(timesteps), float(guidance_scale), noise_schedule)
+        if not use_graph:
+            return self._generate2_loop(*args, *sched, generator, _noise, _trace)
+        return self._generate2_graphed(args, sched, generator)
+
+    def _generate2_loop(self, input_ids, class_ids, encoder_hidden_states, negative_embeds, temperature, timesteps,
+                        guidance_scale, noise_schedule, generator, noise=None, trace=None):
+        c = self.config
+        mask_id, n_codes = c.mask_token_id, c.codebook_size
+        batch, seq_len = input_ids.shape  # every shape below follows the ids (inpainting may pass its own length)
         use_cfg = encoder_hidden_states is not None and guidance_scale > 0
         if use_cfg:
             uncond = torch.zeros_like(encoder_hidden_states) if negative_embeds is None else negative_embeds
             cfg_states = torch.cat([encoder_hidden_states, uncond])
         sampled_ids = input_ids
-        input_ids = input_ids.contiguous()
         for step in range(timesteps):
             model_in = input_ids if class_ids is None else torch.cat([class_ids[:, None], input_ids], dim=1)
             if use_cfg:
-                both, _ = self(torch.cat([model_in] * 2), encoder_hidden_states=cfg_states, _raw_bf16=True)
+                both, _ = self(torch.cat([model_in] * 2), encoder_hidden_states=cfg_states, _raw_bf16=True, _logit_cols=n_codes)
                 logits, logits_unc = both[:batch], both[batch:]
             else:
-                logits, _ = self(model_in, encoder_hidden_states=encoder_hidden_states, _raw_bf16=True)
+                logits, _ = self(model_in, encoder_hidden_states=encoder_hidden_states, _raw_bf16=True, _logit_cols=n_codes)
                 logits_unc = None
             # the generator is consumed exactly like the reference: multinomial(n=1) draws Exp(1) noise of the
             # probabilities' shape (ATen), mask_by_random_topk draws one uniform per token (sampling.py:13-15)
-            q_exp = torch.empty(batch * seq_len, n_codes, dtype=torch.float32, device=logits.device).exponential_(1, generator=generator)
-            u = torch.zeros(batch, seq_len, dtype=torch.float32, device=logits.device).uniform_(0, 1, generator=generator)
+            if noise is not None:
+                q_exp, u = noise[step]
+            else:
+                q_exp = torch.empty(batch * seq_len, n_codes, dtype=torch.float32, device=logits.device).exponential_(1, generator=generator)
+                u = torch.zeros(batch, seq_len, dtype=torch.float32, device=logits.device).uniform_(0, 1, generator=generator)
             ratio = 1.0 * (step + 1) / timesteps
             mask_len = int((seq_len * noise_schedule(torch.tensor(ratio))).floor())
             temperature = temperature * (1.0 - ratio)  # compounds across steps (quirk Q4)
+            prev = input_ids
             sampled_ids, input_ids = ops.sample_step(
                 logits, input_ids, q_exp, u, n_codes, mask_id, mask_len, temperature, logits_unc=logits_unc,
                 guidance=guidance_scale, skip_first_token=class_ids is not None)
+            if trace is not None:
+                off = 1 if class_ids is not None else 0
+                trace.append(dict(step=step, input_ids=prev.clone(), logits=logits[:, off:, :n_codes].clone(),
+                                  logits_unc=None if logits_unc is None else logits_unc[:, off:, :n_codes].clone(),
+                                  sampled=sampled_ids.clone(), next_ids=input_ids.clone(), mask_len=mask_len,
+                                  temperature=temperature))
         return sampled_ids
+
+    def _generate2_graphed(self, args, sched, generator):
+        """Replay (capturing on first use) the whole decode loop as one CUDA graph.  Static input buffers; the torch
+        generator is registered with the graph, so replays consume its stream exactly like the launched-one-by-one path."""
+        packed = self._packed.refresh()  # outside the graph: replays must see the current weights in the same buffers
+        key = (tuple((tuple(a.shape), a.dtype, a.device) if a is not None else None for a in args), sched,
+               None if generator is None else id(generator), getattr(packed, "layout_key", None),
+               torch.is_autocast_enabled("cuda"))
+        cache = self.__dict__.setdefault("_gen_graphs", {})
+        entry = cache.get(key)
+        if entry is None:
+            static = [None if a is None else a.clone() for a in args]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            dev = args[0].device
+            state = torch.cuda.get_rng_state(dev) if generator is None else generator.get_state()
+            with torch.cuda.stream(side):  # lazy initialisation (kernel attributes, allocator) off the capture
+                self._generate2_loop(*static, *sched, generator)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            if generator is not None:  # the warm-up run must not advance the caller's random stream
+                generator.set_state(state)
+            else:
+                torch.cuda.set_rng_state(state, dev)
+            graph = torch.cuda.CUDAGraph()
+            if generator is not None:
+                graph.register_generator_state(generator)
+            with torch.cuda.graph(graph):
+                out = self._generate2_loop(*static, *sched, generator)
+            if len(cache) >= 8:
+                cache.pop(next(iter(cache)))
+            entry = cache[key] = (graph, static, out, generator)
+        graph, static, out, _ = entry
+        for dst, src in zip(static, args):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return out.clone()

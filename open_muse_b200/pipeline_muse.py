@@ -69,13 +69,20 @@ class PipelineMuse:
         use_maskgit_generate: bool = True,
         generator: Optional[torch.Generator] = None,
         use_fp16: bool = False,
-        return_intermediate: bool = False,
-        output_type: str = "pil",
-        orig_size=(256, 256),
+        noise_type="mask",  # accepted like the reference; only "mask" is implemented
+        predict_all_tokens=False,
+        orig_size=(512, 512),
         crop_coords=(0, 0),
         aesthetic_score=6.0,
+        return_intermediate: bool = False,
+        use_tqdm=True,
+        transformer_seq_len=None,
+        clip_skip: int = None,
+        output_type: str = "pil",  # extension: "pt" returns the decoded tensor instead of PIL images
         **unused,
     ):
+        if noise_type != "mask" or predict_all_tokens:
+            raise NotImplementedError("open_muse_b200.PipelineMuse: only noise_type='mask' without predict_all_tokens")
         if text is None and class_ids is None and prompt_embeds is None:
             raise ValueError("Either text or class_ids must be provided.")
         if text is not None and class_ids is not None:
@@ -84,7 +91,7 @@ class PipelineMuse:
             return self._call_uvit_v2(prompt_embeds, pooled_embeds, negative_prompt_embeds, negative_pooled_embeds, timesteps,
                                       noise_schedule, guidance_scale, guidance_schedule, temperature,
                                       num_images_per_prompt, generator, return_intermediate, output_type, orig_size,
-                                      crop_coords, aesthetic_score)
+                                      crop_coords, aesthetic_score, transformer_seq_len)
         if return_intermediate:
             raise NotImplementedError("return_intermediate is a MaskGiTUViT_v2.generate2 feature")
         if isinstance(temperature, (tuple, list)):
@@ -118,7 +125,7 @@ class PipelineMuse:
 
     def _call_uvit_v2(self, prompt_embeds, pooled_embeds, negative_prompt_embeds, negative_pooled_embeds, timesteps,
                       noise_schedule, guidance_scale, guidance_schedule, temperature, num_images_per_prompt, generator,
-                      return_intermediate, output_type, orig_size, crop_coords, aesthetic_score):
+                      return_intermediate, output_type, orig_size, crop_coords, aesthetic_score, seq_len=None):
         """Text-to-image with ``MaskGiTUViT_v2``: penultimate-layer text states + pooled embedding + micro-conditioning
         (reference pipeline_muse.py:121-233).  The text encoder is third-party and out of scope, so the embeddings (and the
         negative / empty ones needed for guidance) are passed in precomputed."""
@@ -142,7 +149,7 @@ class PipelineMuse:
                 negative_cond_embeds=rep(negative_pooled_embeds), temperature=temperature, timesteps=timesteps,
                 guidance_scale=guidance_scale, guidance_schedule=guidance_schedule,
                 noise_schedule=get_mask_chedule(noise_schedule), generator=generator,
-                return_intermediate=return_intermediate)
+                return_intermediate=return_intermediate, seq_len=seq_len)
         tokens, intermediate = out if return_intermediate else (out, None)
         images = self.vae.decode_code(tokens)
         if output_type != "pt":

@@ -197,3 +197,44 @@ def mask_tokens(tokens, class_ids, timesteps, rand, codebook_size, mask_id, min_
     input_ids = torch.cat([(class_ids + codebook_size).unsqueeze(-1), input_ids], dim=-1)
     labels = torch.cat([torch.full((B, 1), -100, dtype=labels.dtype), labels], dim=-1)
     return input_ids, labels
+
+
+def generate2_scalars(cfg, timesteps, temperature=1.0, seq_len=None):
+    """The host-side scalars of the reference loop (:1443-1451, sampling.py:38-39), per step: (mask_len before the
+    per-row clamp, temperature AFTER the compounding update of quirk Q4 -- the value the step's gumbel term uses)."""
+    c = full_config(cfg)
+    L = c["num_vq_tokens"] if seq_len is None else seq_len
+    out = []
+    for step in range(timesteps):
+        ratio = 1.0 * (step + 1) / timesteps
+        mask_len = (L * cosine_schedule(torch.tensor(ratio))).floor()
+        temperature = temperature * (1.0 - ratio)
+        out.append((mask_len, temperature))
+    return out
+
+
+def generate2_step_teacher_forced(p, cfg, model_input_ids, input_ids, step, timesteps, scalars, q_exp, u, logits=None,
+                                  encoder_hidden_states=None):
+    """ONE iteration of the reference loop (:1397-1454) from a GIVEN state, with pre-drawn noise: forward (or the given
+    ``logits`` [B, L, K]) -> softmax -> categorical draw as argmax(p / q_exp) (ATen's multinomial(n=1) recipe, proven
+    equal to the generator path in tests/test_oracle_golden.py) -> keep known tokens -> confidence -> cut -> re-mask.
+    Returns a dict with the sampled ids, the next input ids and the quantities a margin screen needs."""
+    c = full_config(cfg)
+    mask_id, K = c["mask_token_id"], c["codebook_size"]
+    L = input_ids.shape[1]
+    if logits is None:
+        full = forward(p, cfg, model_input_ids, encoder_hidden_states=encoder_hidden_states)[..., :K]
+        logits = full[:, model_input_ids.shape[1] - L:]
+    probs = logits.float().softmax(dim=-1)
+    mask_len, temperature = scalars[step]
+    unknown = input_ids == mask_id
+    ml = torch.max(torch.ones(1, dtype=torch.float32, device=probs.device),
+                   torch.min(unknown.sum(dim=-1, keepdim=True) - 1, mask_len.to(probs.device)))
+    sampled, nxt = sample_step(probs, input_ids, mask_id, q_exp, u, ml, temperature)
+    score = (probs / q_exp).topk(2, dim=-1).values
+    sel = probs.gather(-1, sampled[..., None]).squeeze(-1)
+    sel = torch.where(unknown, sel, torch.finfo(sel.dtype).max)
+    gumbel = -torch.log((-torch.log(u.clamp(min=1e-20))).clamp(min=1e-20))
+    conf = torch.log(sel.clamp(min=1e-20)) + temperature * gumbel
+    cut = conf.sort(dim=-1).values.gather(1, ml.long())
+    return dict(sampled=sampled, next_ids=nxt, probs=probs, top2=score, conf=conf, cut=cut, mask_len=ml, unknown=unknown)

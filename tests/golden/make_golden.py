@@ -86,10 +86,85 @@ def grads_of(model):
     return {n: p.grad.detach().clone() for n, p in model.named_parameters()}
 
 
+def make_f16_256(muse):
+    """(9) BASELINE config 3 at its own size: MaskGitVQGAN f16-256 (class defaults, modeling_maskgit_vqgan.py:353-367),
+    default init from a seed (no weights stored: construction order == RNG order, checked through per-tensor signatures),
+    codebook re-drawn N(0, std(z)) so that the arg-min is not degenerate, two rand images.  Stores the encoder
+    output, the token ids with their top-2 distance margins, the quantised latents and the reconstruction."""
+    torch.manual_seed(60)
+    v = muse.MaskGitVQGAN()
+    v.eval()
+    init_sig = {k: (float(x.double().sum()), float(x.double().norm())) for k, x in v.state_dict().items()}
+    img = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(61))
+    with torch.no_grad():
+        z = v.encoder(img)
+        cb = torch.randn(1024, 256, generator=torch.Generator().manual_seed(62)) * z.std()
+        v.quantize.embedding.weight.copy_(cb)
+        zq, ids = v.encode(img)
+        rec = v.decode_code(ids)
+        d = v.quantize.compute_distances(z.permute(0, 2, 3, 1).contiguous())
+        top2 = d.topk(2, dim=1, largest=False).values
+    margin = top2[:, 1] - top2[:, 0]
+    rel = margin / top2[:, 0].abs()
+    print("f16-256 vqgan: z std", float(z.std()), "min top-2 margin", float(margin.min()), "relative", float(rel.min()),
+          "rows with relative margin < 1e-4:", int((rel < 1e-4).sum()), "of", rel.numel(), "distinct ids", ids.unique().numel())
+    torch.save(dict(seed=60, image_seed=61, codebook_seed=62, init_signature=init_sig, codebook=cb.clone(), z=z.clone(),
+                    ids=ids.clone(), z_q=zq.clone(), recon=rec.clone(), dmin=top2[:, 0].clone(), margin=margin.clone()),
+               os.path.join(HERE, "f16_256_vqgan.pt"))
+
+
+def make_signatures(muse):
+    """(10) the public call signatures of the boundary (parameter names, order and defaults), as JSON."""
+    import inspect
+    import json
+
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+    from muse.modeling_taming_vqgan import VQGANModel
+
+    def sig(fn):
+        out = []
+        for name, p in inspect.signature(fn).parameters.items():
+            d = p.default
+            if d is inspect.Parameter.empty:
+                d = "<required>"
+            elif callable(d):
+                d = f"<callable {getattr(d, '__name__', type(d).__name__)}>"
+            elif isinstance(d, tuple):
+                d = list(d)
+            out.append([name, str(p.kind), d])
+        return out
+
+    table = {
+        "MaskGitTransformer.__init__": sig(muse.MaskGitTransformer.__init__),
+        "MaskGitTransformer.forward": sig(muse.MaskGitTransformer.forward),
+        "MaskGitTransformer.generate2": sig(muse.MaskGitTransformer.generate2),
+        "MaskGiTUViT_v2.forward": sig(MaskGiTUViT_v2.forward),
+        "MaskGiTUViT_v2.generate2": sig(MaskGiTUViT_v2.generate2),
+        "MaskGitVQGAN.__init__": sig(muse.MaskGitVQGAN.__init__),
+        "MaskGitVQGAN.encode": sig(muse.MaskGitVQGAN.encode),
+        "MaskGitVQGAN.get_soft_code": sig(muse.MaskGitVQGAN.get_soft_code),
+        "VQGANModel.__init__": sig(VQGANModel.__init__),
+        "PipelineMuse.__init__": sig(muse.PipelineMuse.__init__),
+        "PipelineMuse.__call__": sig(muse.PipelineMuse.__call__),
+        "PipelineMuseInpainting.__call__": sig(muse.PipelineMuseInpainting.__call__),
+        "EMAModel.__init__": sig(muse.EMAModel.__init__),
+    }
+    with open(os.path.join(HERE, "signatures.json"), "w") as f:
+        json.dump(table, f, indent=1, sort_keys=True)
+    print("signatures:", ", ".join(f"{k} ({len(v)})" for k, v in table.items()))
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
     out = {}
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv[1:] if a.startswith("--only=")]
+    if only:  # regenerate a subset: --only=f16,signatures
+        if "f16" in only[0]:
+            make_f16_256(muse)
+        if "signatures" in only[0]:
+            make_signatures(muse)
+        return
 
     # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
     torch.manual_seed(0)
@@ -300,6 +375,9 @@ def main():
             decays.append(ema.cur_decay_value)
         ema_out[warm] = dict(shadow=[s.clone() for s in ema.shadow_params], decays=decays, step=ema.optimization_step)
     torch.save(dict(seed=50, runs=ema_out), os.path.join(HERE, "ema_model.pt"))
+
+    make_f16_256(muse)
+    make_signatures(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

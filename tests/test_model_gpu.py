@@ -342,3 +342,33 @@ def test_generate2_runs_and_is_seed_deterministic(golden):
         assert torch.equal(cls.cpu(), torch.tensor([1, 5, 0, 3]) + 64)  # in-place shift, quirk Q3
         outs.append(ids)
     assert torch.equal(outs[0], outs[1])
+
+
+def test_ema_copy_to_refreshes_the_packed_operands(golden):
+    """training/train_muse.py:857-908 validates with EMA weights: ema.store / ema.copy_to / forward / ema.restore.  The
+    forward after copy_to must use the EMA weights in every GEMM (the packed bf16 operand cache follows the parameters'
+    version counters), and the forward after restore must reproduce the original output."""
+    from open_muse_b200 import EMAModel
+
+    g = golden("micro_transformer.pt")
+    m = MaskGitTransformer(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.to(DEV).eval()
+    ids = g["batch"]["input_ids"].to(DEV)
+    ema = EMAModel(m.parameters(), decay=0.5)
+    with torch.no_grad():
+        base = m(ids).clone()
+        gen = torch.Generator(device=DEV).manual_seed(3)
+        for sp in ema.shadow_params:  # make the EMA weights differ from the live ones
+            sp.add_(torch.randn(sp.shape, device=sp.device, generator=gen) * 0.02)
+        ema.store(m.parameters())
+        ema.copy_to(m.parameters())
+        with_ema = m(ids).clone()
+        fresh = MaskGitTransformer(**g["config"]).to(DEV).eval()
+        fresh.load_state_dict({k: p.detach().clone() for k, p in m.state_dict().items()})
+        expect = fresh(ids)
+        ema.restore(m.parameters())
+        back = m(ids)
+    assert not torch.equal(with_ema, base)
+    assert torch.equal(with_ema, expect)
+    assert torch.equal(back, base)

@@ -201,3 +201,83 @@ def test_micro_vqgan(golden):
     ids_c, _ = VQ.argmin(VQ.nchw_to_rows(g["z"].numpy()), p["quantize.embedding.weight"].numpy())
     ok = g["margin"].numpy() > 1e-4  # margin screen: fp32 re-association cannot flip these
     assert np.array_equal(ids_c[ok], g["ids"].numpy().reshape(-1)[ok])
+
+
+F16_CFG = dict(resolution=256, num_channels=3, hidden_channels=128, channel_mult=(1, 1, 2, 2, 4), num_res_blocks=2,
+               z_channels=256, num_embeddings=1024, quantized_embed_dim=256)
+
+
+def _f16_state_dict(g):
+    """The f16-256 fixture stores no weights: seeded construction reproduces the reference's default init (construction
+    order == RNG order), which the stored per-tensor signatures verify."""
+    from open_muse_b200.modeling_maskgit_vqgan import MaskGitVQGAN
+
+    torch.manual_seed(g["seed"])
+    m = MaskGitVQGAN()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    assert set(sd) == set(g["init_signature"])
+    for k, (s, n) in g["init_signature"].items():
+        assert abs(float(sd[k].double().sum()) - s) <= 1e-9 * max(1.0, abs(s)), k
+        assert abs(float(sd[k].double().norm()) - n) <= 1e-9 * max(1.0, n), k
+    sd["quantize.embedding.weight"] = g["codebook"].clone()
+    return sd
+
+
+def test_f16_256_vqgan_oracle_at_full_architecture(golden):
+    """BASELINE config 3 at its own size: the oracle's encoder / quantiser / decoder against the outputs of the unmodified
+    reference MaskGitVQGAN f16-256 (class defaults) on the committed two-image batch."""
+    g = golden("f16_256_vqgan.pt")
+    p = _f16_state_dict(g)
+    img = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(g["image_seed"]))
+    with torch.no_grad():
+        z = G.encoder(p, F16_CFG, img)
+        _close(z, g["z"], 1e-4, 1e-5)
+        zq, ids = G.quantize(p, g["z"])
+        assert torch.equal(ids, g["ids"])
+        _close(zq, g["z_q"], 0, 0)
+        rec = G.decode_code(p, F16_CFG, g["ids"])
+        _close(rec, g["recon"], 1e-3, 1e-4)  # 32 fp32 convolutions: oneDNN re-association differs with the thread count
+    ids_c, dmin = VQ.argmin(VQ.nchw_to_rows(g["z"].numpy()), p["quantize.embedding.weight"].numpy())
+    ok = (g["margin"] > 1e-4 * g["dmin"].abs()).numpy()  # margin screen: fp32 re-association cannot flip these
+    assert ok.mean() > 0.98
+    assert np.array_equal(ids_c[ok], g["ids"].numpy().reshape(-1)[ok])
+
+
+def test_public_signatures_match_reference():
+    """Parameter names, order and defaults of the boundary's public calls against the reference's
+    (tests/golden/signatures.json, written by make_golden.py from the imported reference)."""
+    import inspect
+    import json
+    import os
+
+    import open_muse_b200 as ours
+    from open_muse_b200.modeling_taming_vqgan import VQGANModel
+    from open_muse_b200.modeling_transformer_v2 import MaskGiTUViT_v2
+
+    table = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "signatures.json")))
+    objs = {"MaskGitTransformer": ours.MaskGitTransformer, "MaskGiTUViT_v2": MaskGiTUViT_v2, "MaskGitVQGAN": ours.MaskGitVQGAN,
+            "VQGANModel": VQGANModel, "PipelineMuse": ours.PipelineMuse, "PipelineMuseInpainting": ours.PipelineMuseInpainting,
+            "EMAModel": ours.EMAModel}
+    private_ok = lambda n: n.startswith("_")  # our private test hooks (e.g. _raw_bf16) are keyword-only extras
+    for key, ref in table.items():
+        cls, meth = key.split(".")
+        params = inspect.signature(getattr(objs[cls], meth)).parameters
+        ours_named = {n: p for n, p in params.items() if p.kind not in (p.VAR_KEYWORD, p.VAR_POSITIONAL) and not private_ok(n)}
+        ref_named = [r for r in ref if "VAR_" not in r[1]]
+        has_kwargs = any(p.kind == p.VAR_KEYWORD for p in params.values())
+        for name, kind, default in ref_named:
+            if name not in ours_named:
+                assert has_kwargs, f"{key}: reference parameter {name!r} is neither named nor swallowed by **kwargs"
+                continue
+            d = ours_named[name].default
+            if default == "<required>":
+                assert d is inspect.Parameter.empty, (key, name)
+            elif isinstance(default, str) and default.startswith("<callable"):
+                assert callable(d), (key, name)
+            else:
+                d = list(d) if isinstance(d, tuple) else d
+                assert d == default, f"{key}: default of {name!r} is {d!r}, reference has {default!r}"
+        # positional order of the shared leading parameters
+        ref_order = [r[0] for r in ref_named if r[0] in ours_named]
+        ours_order = [n for n in ours_named if n in set(ref_order)]
+        assert ours_order == ref_order, (key, ours_order, ref_order)
