@@ -127,10 +127,45 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md: ~1.4 PF sustained, 6.65 TB/s)"
 
 
+def reference_kind():
+    """"reference": the UNMODIFIED reference modules (oracle/_ref snapshot made by __graft_entry__.build() from
+    /root/reference; git-ignored, travels with the repo) are what gets timed; "port": the oracle restatement."""
+    from oracle import ref_snapshot
+
+    return "reference" if ref_snapshot.available() else "port"
+
+
+def reference_module_step_fn(batch, device="cpu"):
+    """fwd + bwd + AdamW of the unmodified reference ``muse.MaskGitTransformer`` (torch eager; fp32 on the CPU, bf16
+    autocast on cuda), the loop body of training/train_maskgit_imagenet.py:403-452 on pre-tokenised synthetic batches."""
+    from oracle import ref_snapshot
+
+    muse = ref_snapshot.import_reference()
+    torch.manual_seed(0)
+    model = muse.MaskGitTransformer(**BASE_CFG).to(device).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=(device != "cpu"))
+    g = torch.Generator(device=device).manual_seed(1)
+
+    def step():
+        tokens = torch.randint(0, 1024, (batch, 256), generator=g, device=device)
+        cls = torch.randint(0, 1000, (batch,), generator=g, device=device)
+        inp, lab = mask_batch(tokens, cls, 2024, 1024, gen=g)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(device != "cpu")):
+            _, loss = model(inp, labels=lab)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return float(loss)
+
+    return step
+
+
 def cpu_reference_step_fn(batch, device="cpu"):
-    """The reference algorithm (oracle port, torch eager): fwd + bwd + AdamW on `batch` samples.  fp32 on the host CPU
-    (the reference arm); with device="cuda" the same eager op sequence under bf16 autocast on the GPU -- what the
-    reference's own PyTorch modules would run on this B200 (`--impl reference --ref-device cuda`, informational)."""
+    """The reference arm's step: the unmodified reference modules when the oracle/_ref snapshot is present, else the
+    oracle port (same torch op sequence, fp32 eager): fwd + bwd + AdamW on `batch` samples.  With device="cuda" the same
+    eager ops run under bf16 autocast on the GPU -- what the reference executes on this B200 (the real bar)."""
+    if reference_kind() == "reference":
+        return reference_module_step_fn(batch, device)
     from oracle import transformer_oracle as T
     from open_muse_b200.modeling_transformer import MaskGitTransformer
 
@@ -181,7 +216,8 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     value = batch / dt
     sample = f"{args.steps} steps x batch {batch} of the base-256 train step (fwd+bwd+AdamW), " + (
-        "bf16-autocast torch eager on cuda:0 (informational)" if on_gpu else "fp32 torch eager")
+        "bf16-autocast torch eager on cuda:0 (informational)" if on_gpu else "fp32 torch eager") + (
+        "; unmodified reference modules (oracle/_ref)" if reference_kind() == "reference" else "; oracle port of the reference ops")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -189,9 +225,181 @@ def run_reference(args):
         "ref_device": args.ref_device,
         "config": {"workload": f"MaskGitTransformer base (8x512, seq 257, vocab 2025) class-cond train step, {args.ref_device} sample batch {batch}",
                    "global_batch": batch, "seq_len": 257},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": reference_kind(), "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def _timeit(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def kernel_rooflines(dev, peak_tf, peak_hbm):
+    """Every named kernel of the hot path timed alone at its BASELINE-config shape (CUDA events on the launching stream,
+    inputs >> L2 or freshly produced), with its ALGORITHMIC bytes / FLOPs against the measured
+    peaks.  The ncu --set full captures of the same launches are committed under profiles/ (r02_ncu_kernels.txt)."""
+    from open_muse_b200 import ops
+
+    B, S, H, I, nh = 256, 257, 512, 2048, 8
+    T = B * S
+    out = []
+    FP32_SIMT_TF = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FMA lanes at the max SM clock
+
+    def add(name, ms, nbytes=None, flops=None, bound=None, peak=None):
+        if nbytes is not None:
+            ach, pk, unit, bound = nbytes / (ms * 1e-3) / 1e9, peak_hbm, "GB/s", bound or "hbm"
+            out.append({"kernel": name, "bound": bound, "algorithmic_bytes": nbytes, "us": ms * 1e3, "achieved": ach,
+                        "peak": pk, "unit": unit, "frac": ach / pk})
+        else:
+            pk = peak or peak_tf
+            ach = flops / (ms * 1e-3) / 1e12
+            out.append({"kernel": name, "bound": bound or "tensor", "algorithmic_flops": flops, "us": ms * 1e3,
+                        "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk})
+
+    bf = lambda *sh: torch.randn(*sh, device=dev).to(torch.bfloat16)
+    # ---- norms / GLU / casts (HBM)
+    x = torch.randn(T, H, device=dev)
+    xb = bf(T, H)
+    w = torch.ones(H, device=dev)
+    dres = torch.randn(T, H, device=dev)
+    _, st = ops.norm_fwd(x, w, 1e-6, torch.bfloat16)
+    add("norm_fwd_warp_kernel fp32->bf16 [T,512]", _timeit(lambda: ops.norm_fwd(x, w, 1e-6, torch.bfloat16)), T * H * 6)
+    add("norm_fwd_warp_kernel bf16->fp32 +residual", _timeit(lambda: ops.norm_fwd(xb, w, 1e-6, torch.float32, res=x)), T * H * 10)
+    add("norm_bwd_warp_kernel bf16 dy, fp32 x, +dres (+ordered dw)",
+        _timeit(lambda: ops.norm_bwd(xb, x, w, st, torch.float32, dres=dres, want_dw=True)), T * H * 14)
+    add("norm_bwd_warp_kernel fp32 dy, bf16 x -> bf16 (+ordered dw)",
+        _timeit(lambda: ops.norm_bwd(x, xb, w, st, torch.bfloat16, want_dw=True)), T * H * 8)
+    add("cast_bf16_kernel", _timeit(lambda: ops.cast_bf16(x)), T * H * 6)
+    ab, wI, dyI = bf(T, 2 * I), torch.ones(I, device=dev), bf(T, I)
+    y, st4 = ops.norm_fwd(ab, wI, 1e-6, torch.bfloat16, act=2)
+    add("glu_norm_fwd_kernel [T,2x2048]->[T,2048]", _timeit(lambda: ops.norm_fwd(ab, wI, 1e-6, torch.bfloat16, act=2)), T * I * 6)
+    add("glu_norm_bwd_kernel (saved y, +ordered dw)",
+        _timeit(lambda: ops.norm_bwd(dyI, ab, wI, st4, torch.bfloat16, act=2, y_fwd=y, want_dw=True)), T * I * 12)
+    del ab, dyI, y
+    # ---- embedding / loss
+    ids = torch.randint(0, 1024, (B, S), device=dev)
+    ids[torch.rand(B, S, device=dev) < 0.5] = 2024
+    word, pos = torch.randn(2025, H, device=dev), torch.randn(S, H, device=dev)
+    add("embed_fwd_kernel", _timeit(lambda: ops.embed_fwd(ids, word, pos)), T * H * 4 + T * 8)
+    add("embed_bwd (sorted segments: plan + chunk + final + pos)", _timeit(lambda: ops.embed_bwd_det(ids, x, 2025, S)), 2 * T * H * 4)
+    logits = bf(T, 2048)
+    lab = torch.randint(0, 1024, (T,), device=dev)
+    lab[torch.rand(T, device=dev) < 0.5] = -100
+    lo, ws = ops.ce_fwd(logits, lab, 2025, 0.0)
+    one = torch.ones(1, device=dev)
+    add("ce_fwd_kernel (+ce_reduce) [T,2025]", _timeit(lambda: ops.ce_fwd(logits, lab, 2025, 0.0)), T * 2048 * 2)
+    add("ce_bwd_kernel", _timeit(lambda: ops.ce_bwd(logits, lab, ws, one, lo, 2025, 0.0)), T * 2048 * 4)
+    del logits
+    # ---- attention (tensor)
+    qkv = bf(T, 3 * H)
+    o, lse = ops.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, nh, S, S, 0.125)
+    do, dqkv = bf(T, H), torch.empty(T, 3 * H, dtype=torch.bfloat16, device=dev)
+    fl = 4.0 * S * S * 64 * B * nh
+    add("attn_fwd_tc_kernel (S=257: 3 balanced tiles)", _timeit(lambda: ops.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, nh, S, S, 0.125)), flops=fl)
+    add("attn_bwd_dq_tc_kernel + attn_bwd_dkdv_tc_kernel",
+        _timeit(lambda: ops.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, do, lse, dqkv[:, :H], dqkv[:, H:2 * H],
+                                     dqkv[:, 2 * H:], B, nh, S, S, 0.125)), flops=2.5 * fl)
+    del qkv, dqkv
+    # ---- GEMMs by role (tensor)
+    for name, N, K in [("qkv", 3 * H, H), ("attn out (+residual)", H, H), ("wi", 2 * I, H), ("wo (+residual)", H, I), ("logits", 2048, H)]:
+        wt, xin, dyy = bf(N, K), bf(T, K), bf(T, N)
+        res = torch.randn(T, N, device=dev) if "residual" in name else None
+        f = 2.0 * T * N * K
+        add(f"gemm_tcgen05_kernel fwd {name} [T,{K}]x[{N},{K}]", _timeit(lambda: ops.linear_fwd(xin, wt, res=res)), flops=f)
+        add(f"gemm_tcgen05_kernel dgrad {name}", _timeit(lambda: ops.linear_dgrad(dyy, wt)), flops=f)
+        add(f"gemm_tcgen05_kernel wgrad {name} (deterministic split-K)", _timeit(lambda: ops.linear_wgrad_det(dyy, xin)), flops=f)
+        del wt, xin, dyy, res
+    # ---- tokenizer search and the decode-step kernel
+    n = 128 * 256
+    z, cb = torch.randn(n, 256, device=dev), torch.randn(1024, 256, device=dev)
+    add("vq_argmin_kernel (config 3: 32768 rows x 1024 codes x 256)", _timeit(lambda: ops.vq_argmin(z, cb)),
+        flops=2.0 * n * 1024 * 256, bound="fp32-simt", peak=FP32_SIMT_TF)
+    Bg, L, K = 64, 256, 1024
+    lg = bf(Bg, L + 1, K)
+    cur = torch.full((Bg, L), 2024, dtype=torch.long, device=dev)
+    q = torch.empty(Bg * L, K, device=dev).exponential_(1)
+    u = torch.rand(Bg, L, device=dev)
+    add("sample_step_kernel (config 5: 64 x 256 x 1024)",
+        _timeit(lambda: ops.sample_step(lg, cur, q, u, K, 2024, 100, 0.5, skip_first_token=True)), Bg * L * K * 6)
+    # ---- one full-resolution tokenizer convolution + its GroupNorm producer stage
+    xc = torch.randn(8, 256, 256, 128, device=dev)
+    wc = torch.randn(128, 128, 3, 3, device=dev) * 0.03
+    ga, be = torch.ones(128, device=dev), torch.zeros(128, device=dev)
+    ms = _timeit(lambda: ops.conv2d(xc, wc, gn=(ga, be, 32, 1e-6)), n=5, warm=2)
+    add("groupnorm+SiLU+split -> conv_tc_kernel 3x3 128->128 @256x256 (bf16x3, B=8)", ms, flops=3 * 2.0 * 8 * 256 * 256 * 128 * 128 * 9)
+    return out
+
+
+def secondary_metrics(dev, base_model, peak_tf, peak_hbm):
+    """The rest of BASELINE.json's metric and configs on the same box: decode steps/sec (config 5), the tokenizer round
+    trip (config 3), the reference recipe in torch eager on this same GPU (the real bar), per-kernel rooflines."""
+    from open_muse_b200 import MaskGitVQGAN, ops
+
+    out = {}
+    # ---- config 5: generate2, base model, B=64, 256 tokens, 12 steps (the whole loop replayed as one CUDA graph)
+    base_model.eval()
+    gen = torch.Generator(device=dev).manual_seed(7)
+    cls0 = torch.randint(0, 1000, (64,), device=dev)
+
+    def dec(graph):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return base_model.generate2(class_ids=cls0.clone(), timesteps=12, generator=gen, use_cuda_graph=graph)
+
+    ms_g = _timeit(lambda: dec(True), n=5, warm=2)
+    l0 = ops.launches()
+    ms_e = _timeit(lambda: dec(False), n=3, warm=1)
+    out["decode_steps_per_s"] = {"value": 12 / (ms_g * 1e-3), "unit": "steps/s", "ms_per_step": ms_g / 12, "ms_per_call": ms_g,
+                                 "images_per_s": 64 / (ms_g * 1e-3), "host_launches_per_call": 5,
+                                 "config": "generate2, base-256 model, B=64, 256 tokens, 12 steps, temperature 1.0; whole loop "
+                                           "replayed as one CUDA graph (+4 input copies)",
+                                 "launched_one_by_one": {"steps_per_s": 12 / (ms_e * 1e-3), "ms_per_call": ms_e,
+                                                         "kernels_per_call": (ops.launches() - l0) // 4}}
+    base_model.train()
+    # ---- config 3: MaskGitVQGAN f16-256 encode -> ids -> decode_code, B=128 (chunks of 64)
+    torch.manual_seed(1)
+    vq = MaskGitVQGAN().to(dev).eval()
+    pix = torch.rand(128, 3, 256, 256, device=dev)
+    ids = torch.cat([vq.get_code(pix[j:j + 64]) for j in range(0, 128, 64)])
+    ms_enc = _timeit(lambda: [vq.get_code(pix[j:j + 64]) for j in range(0, 128, 64)], n=2, warm=1)
+    ms_dec = _timeit(lambda: [vq.decode_code(ids[j:j + 64]) for j in range(0, 128, 64)], n=2, warm=1)
+    out["vqgan_roundtrip"] = {"value": 128 / ((ms_enc + ms_dec) * 1e-3), "unit": "images/s", "batch": 128, "encode_ms": ms_enc,
+                              "decode_ms": ms_dec, "encode_images_per_s": 128 / (ms_enc * 1e-3),
+                              "decode_images_per_s": 128 / (ms_dec * 1e-3),
+                              "model_tflops": (128.76 + 186.55) * 128 / (ms_enc + ms_dec),
+                              "config": "MaskGitVQGAN f16-256 (class defaults) encode -> ids -> decode_code, fp32-faithful bf16x3 "
+                                        "tcgen05 convolutions, bit-exact arg-min"}
+    del vq, pix
+    torch.cuda.empty_cache()
+    # ---- the reference recipe in torch eager on this GPU (bf16 autocast): what the unmodified reference runs here
+    try:
+        rstep = cpu_reference_step_fn(PER_GPU_BATCH, "cuda")
+        for _ in range(2):
+            rstep()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            rstep()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        out["torch_eager_same_gpu"] = {"value": PER_GPU_BATCH / dt, "unit": "images/s", "ms_per_step": dt * 1e3,
+                                       "kind": reference_kind(),
+                                       "config": "the reference train step (fwd + bwd + AdamW, bf16 autocast, cuBLAS/ATen kernels) "
+                                                 f"at batch {PER_GPU_BATCH} on this B200"}
+        del rstep
+    except Exception as e:  # informational leg: never sinks the bench line
+        out["torch_eager_same_gpu"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    out["roofline_kernels"] = kernel_rooflines(dev, peak_tf, peak_hbm)
+    return out
 
 
 def main():
@@ -203,6 +411,8 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-step", action="store_true", help="skip the extra 'train step incl. VQ encode' measurement")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip decode steps/s, the tokenizer round trip, torch-eager-on-this-GPU and the per-kernel rooflines")
     ap.add_argument("--no-cuda-graph", action="store_true",
                     help="launch the kernels of each step one by one instead of replaying the captured step (N=1 default: graph)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -343,6 +553,10 @@ def main():
         del vq, pix
         torch.cuda.empty_cache()
 
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = secondary_metrics(dev, model, peak_tf, peak_hbm)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = cpu_threads()
@@ -354,8 +568,9 @@ def main():
         while n < 2 or (time.perf_counter() - t0 < 15 and n < 12):
             cstep(); n += 1
         cdt = (time.perf_counter() - t0) / n
-        cpu = {"value": CPU_SAMPLE_BATCH / cdt, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"{n} steps x batch {CPU_SAMPLE_BATCH} of the same train step, oracle fp32 torch eager on {cores} host threads"}
+        cpu = {"value": CPU_SAMPLE_BATCH / cdt, "unit": "images/s", "cores": cores, "kind": reference_kind(),
+               "sample": f"{n} steps x batch {CPU_SAMPLE_BATCH} of the same train step, fp32 torch eager on {cores} host threads, "
+                         + ("unmodified reference modules (oracle/_ref)" if reference_kind() == "reference" else "oracle port")}
 
     if rank == 0:
         gb = B * world
@@ -368,7 +583,6 @@ def main():
                        "global_batch": gb, "per_gpu_batch": B, "seq_len": 257,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "no explicit flush: per-step working set (~15 GB activations + 0.5 GB weights/grads/optimizer) >> 126 MB L2",
-                       "gemm_backend": os.environ.get("MUSE_B200_GEMM", "tcgen05"),
                        "cuda_graph": bool(use_graph)},
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4},
@@ -376,6 +590,8 @@ def main():
             "tflops_per_gpu_model": 3 * FWD_GFLOP_PER_IMG * B / ms_dev,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "full_step_incl_vq_encode": full,
         }
+        if secondary:
+            out.update(secondary)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

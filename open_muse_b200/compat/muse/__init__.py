@@ -15,3 +15,26 @@ from open_muse_b200 import (  # noqa: F401
     get_mask_chedule,
 )
 from open_muse_b200 import modeling_transformer_v2, sampling  # noqa: F401
+from . import logging, lr_schedulers  # noqa: F401,E402
+
+
+class _OutOfScopeTokenizer:
+    """MOVQ / PaellaVQModel are other tokenizers the training scripts import by name (training/train_muse.py:49-58,
+    train_maskgit_imagenet.py:38); they are outside this package's hot path and fail loudly if a
+    config actually selects them."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError(f"open_muse_b200: {type(self).__name__} is not part of the B200 hot path; use "
+                                  "MaskGitVQGAN (model.vq_model.type: maskgit_vqgan) or VQGANModel (taming)")
+
+    @classmethod
+    def from_pretrained(cls, *a, **k):
+        return cls()
+
+
+class MOVQ(_OutOfScopeTokenizer):
+    pass
+
+
+class PaellaVQModel(_OutOfScopeTokenizer):
+    pass

@@ -13,8 +13,11 @@
 // Operands are read straight from the strided [tokens, 3H] QKV projection through 3-D TMA tensor maps
 // {64 head columns, S rows, B} (rows past the end of a sequence are zero-filled by the TMA unit), with the same
 // 128-byte-swizzled tiles serving as K-major or MN-major MMA operands depending on the product.
-// Rows of the owned dimension beyond the last full 128-row tile (the class token makes S = 257) are delegated to the
-// legacy mma.sync kernels in attention.cu; the looped dimension handles ragged tails by shrinking the MMA N/K to a
+// The owned dimension is cut into ceil(S / 128) tiles of EQUAL height R = ceil(S / tiles) (S = 257 with the class token ->
+// three tiles of 86 rows; S = 256 -> two of 128; the 77 text states of cross-attention -> one of 77): a tile starts at row
+// i * R, its CTA still loads a 128-row box (rows past R belong to the next tile or are zero-filled past the sequence), the
+// MMAs run on all 128 lanes, but only rows < R are kept, and warps whose 32 lanes all lie past R skip the softmax math.
+// No row is ever handed to another kernel.  The looped dimension handles ragged tails by shrinking the MMA N/K to a
 // multiple of 16.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -89,6 +92,7 @@ __device__ __forceinline__ void st_operand_chunk(uint8_t* base, int r, int k0, u
 
 struct TcParams {
   int Sq, Skv, nh;
+  int tile_rows;  // R: owned rows per CTA (<= 128)
   float scale;
   // outputs / side inputs (plain global pointers; rows addressed as b*S + s)
   bf16* out0;  long long out0_rs;   // fwd: O ; dq: dQ ; dkdv: dK
@@ -101,7 +105,7 @@ struct TcParams {
 // TMEM columns: S [0,64)  O [64,128) -> 128 columns per CTA; smem 48 KB -> FOUR co-resident CTAs per SM overlap each
 // other's TMA / MMA / softmax latencies (a 128-wide score tile with 2 CTAs/SM measured slower than the mma.sync kernel).
 constexpr int FWD_BN = 64;
-constexpr int FWD_SMEM = 16384 /*Q*/ + 8192 /*K*/ + 8192 /*V*/ + 16384 /*P*/ + 64;
+constexpr int FWD_SMEM = 16384 /*Q*/ + 8192 /*K*/ + 8192 /*V*/ + 16384 /*P*/ + 64;  // 5 mbarriers + the TMEM holder
 
 __global__ void __launch_bounds__(128)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -114,17 +118,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sV = smem + 24576;
   uint8_t* sP = smem + 32768;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152);
-  uint64_t* bar_kv = bars;      // TMA landed
+  uint64_t* bar_kv = bars;      // Q (first use) + K tile landed
   uint64_t* bar_s = bars + 1;   // score MMA done
   uint64_t* bar_o = bars + 2;   // accumulate MMA done
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bar_v = bars + 3;   // V tile landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * p.tile_rows, h = blockIdx.y, b = blockIdx.z;
+  const int rows_here = min(p.tile_rows, p.Sq - q0);
+  const bool warp_active = warp * 32 < rows_here;  // warps whose rows all belong to the next tile skip the softmax math
   if (tid == 0) {
     ptx::mbar_init(bar_kv, 1);
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_o, 1);
+    ptx::mbar_init(bar_v, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
@@ -140,10 +148,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int ntiles = ceil_div(p.Skv, FWD_BN);
 
   if (tid == 0) {
-    ptx::mbar_expect_tx(bar_kv, 16384 + 8192 * 2);
+    ptx::mbar_expect_tx(bar_kv, 16384 + 8192);
     tma_load_3d(sQ, &tmQ, bar_kv, h * HD, q0, b);
     tma_load_3d(sK, &tmK, bar_kv, h * HD, 0, b);
-    tma_load_3d(sV, &tmV, bar_kv, h * HD, 0, b);
+    ptx::mbar_expect_tx(bar_v, 8192);
+    tma_load_3d(sV, &tmV, bar_v, h * HD, 0, b);
   }
   const float sl2 = p.scale * kLog2e;
   float m = -INFINITY, l = 0.f;
@@ -163,6 +172,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     ptx::mbar_wait(bar_s, par);
     ptx::tc_fence_after();
+    if (tid == 0 && j + 1 < ntiles) {  // the score MMA has consumed K_j: fetch K_{j+1} under the softmax math
+      ptx::mbar_expect_tx(bar_kv, 8192);
+      tma_load_3d(sK, &tmK, bar_kv, h * HD, (j + 1) * FWD_BN, b);
+    }
+    if (warp_active) {
     // the whole score row (<= 64 columns) fits in registers: one TMEM read, max, exp2, pack.  The instruction count
     // per score element is what bounds this kernel (issue slots, not the tensor core), so the ragged-tail masking is
     // kept out of the full-tile path and the softmax scale is folded into one FFMA per element.
@@ -219,10 +233,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       tmem_st_wait();
     }
+    }  // warp_active
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
     __syncthreads();
     if (tid == 0) {
+      ptx::mbar_wait(bar_v, par);
       ptx::tc_fence_after();
       const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
       const int ksteps = n16 >> 4;
@@ -233,14 +249,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     ptx::mbar_wait(bar_o, par);
     ptx::tc_fence_after();
-    if (tid == 0 && j + 1 < ntiles) {
-      ptx::mbar_expect_tx(bar_kv, 8192 * 2);
-      tma_load_3d(sK, &tmK, bar_kv, h * HD, (j + 1) * FWD_BN, b);
-      tma_load_3d(sV, &tmV, bar_kv, h * HD, (j + 1) * FWD_BN, b);
+    if (tid == 0 && j + 1 < ntiles) {  // the accumulate MMA has consumed V_j
+      ptx::mbar_expect_tx(bar_v, 8192);
+      tma_load_3d(sV, &tmV, bar_v, h * HD, (j + 1) * FWD_BN, b);
     }
   }
   // epilogue: O / l -> bf16 rows, LSE
   const int row = q0 + tid;
+  const bool row_ok = tid < rows_here;
   const float inv = 1.f / l;
   bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD;
 #pragma unroll
@@ -248,7 +264,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t r[32];
     ptx::tmem_ld_32x32b_x32(t_o + c, r);
     ptx::tmem_ld_wait();
-    if (row < p.Sq) {
+    if (row_ok) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 u;
@@ -260,7 +276,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   }
-  if (row < p.Sq) p.lse[(static_cast<long long>(b) * p.nh + h) * p.Sq + row] = (m + log2f(l)) * kLn2;
+  if (row_ok) p.lse[(static_cast<long long>(b) * p.nh + h) * p.Sq + row] = (m + log2f(l)) * kLn2;
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -303,7 +319,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;                 // column half handled by this thread
   const int r = (warp & 3) * 32 + lane;       // row (TMEM lane) handled by this thread
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * p.tile_rows, h = blockIdx.y, b = blockIdx.z;
+  const int rows_here = min(p.tile_rows, p.Sq - q0);
+  const bool warp_active = (warp & 3) * 32 < rows_here;  // other warps keep the barrier protocol but skip the math
+  const bool row_ok = r < rows_here;
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) ptx::mbar_init(&bar_kv[i], 1);
     ptx::mbar_init(bar_s, 1);
@@ -327,7 +346,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int nsteps = 2 * ntiles;
   const int row = q0 + r;
   const long long stat_idx = (static_cast<long long>(b) * p.nh + h) * p.Sq + row;
-  const float lse2 = (row < p.Sq) ? p.lse[stat_idx] * kLog2e : 0.f;
+  const float lse2 = row_ok ? p.lse[stat_idx] * kLog2e : 0.f;
   const float sl2 = p.scale * kLog2e;
 
   auto n16_of = [&](int step) { return (min(BWD_BN, p.Skv - (step % ntiles) * BWD_BN) + 15) & ~15; };
@@ -403,6 +422,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ptx::mbar_wait(bar_s, st & 1);
     ptx::tc_fence_after();
     uint32_t s_reg[32], d_reg[32];
+    if (warp_active) {
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
@@ -415,6 +435,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
     ptx::tmem_ld_wait();
+    }
     ptx::tc_fence_before();
     ptx::mbar_arrive(bar_free);  // (A) this thread holds its scores in registers
     uint8_t* dS = sdS + (u & 1) * 16384;
@@ -423,7 +444,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
-      if (c < n16) {
+      if (warp_active && c < n16) {
 #pragma unroll
         for (int i8 = 0; i8 < 16; i8 += 8) {
           float pr[8];
@@ -455,7 +476,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       sDp[half * 128 + r] = dsum;
       math_sync();
       dsum = sDp[r] + sDp[128 + r];
-      if (half == 0 && row < p.Sq) p.dvec[stat_idx] = dsum;  // for the dK/dV kernels
+      if (half == 0 && row_ok) p.dvec[stat_idx] = dsum;  // for the dK/dV kernels
       math_sync();  // sDp aliases dS[0]: everyone has read it before sweep 2 writes dS
     }
   }
@@ -473,7 +494,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint32_t rr[32];
     ptx::tmem_ld_32x32b_x32(t_row + 128 + half * 32, rr);
     ptx::tmem_ld_wait();
-    if (row < p.Sq) {
+    if (row_ok) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 v;
@@ -523,7 +544,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;
   const int r = (warp & 3) * 32 + lane;
-  const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int kv0 = blockIdx.x * p.tile_rows, h = blockIdx.y, b = blockIdx.z;
+  const int rows_here = min(p.tile_rows, p.Skv - kv0);
+  const bool warp_active = (warp & 3) * 32 < rows_here;
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) ptx::mbar_init(&bar_ld[i], 1);
     ptx::mbar_init(bar_s, 1);
@@ -543,7 +566,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const int ntiles = ceil_div(p.Sq, BWD_BN);
   const int kvrow = kv0 + r;
-  const bool kv_ok = kvrow < p.Skv;
+  const bool kv_ok = r < rows_here;  // rows past the tile's share belong to the next CTA (or lie past the sequence)
   const float sl2 = p.scale * kLog2e;
   const long long stat_base = (static_cast<long long>(b) * p.nh + h) * p.Sq;
 
@@ -621,6 +644,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     ptx::mbar_wait(bar_s, i & 1);
     ptx::tc_fence_after();
     uint32_t s_reg[32], d_reg[32];
+    if (warp_active) {
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
@@ -633,6 +657,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
       }
     }
     ptx::tmem_ld_wait();
+    }
     ptx::tc_fence_before();
     ptx::mbar_arrive(bar_free);  // (A) scores are in registers
     math_sync();                 // sL / sD of this step are visible to all math threads
@@ -640,7 +665,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
-      if (c < n16) {
+      if (warp_active && c < n16) {
 #pragma unroll
         for (int k8 = 0; k8 < 16; k8 += 8) {
           float pt[8], ds[8], lq[8], dq_[8];
@@ -716,12 +741,18 @@ int set_smem(K kern, int bytes, bool* done) {
 
 }  // namespace
 
-// Full 128-row q tiles of the forward pass. Returns the number of q rows covered (a multiple of 128).
+// Balanced tiling of an owned dimension of S rows: ceil(S / 128) tiles of R = ceil(S / tiles) rows each.
+static inline void balanced_tiles(int S, int* ntile, int* rows) {
+  *ntile = ceil_div(S, 128);
+  *rows = ceil_div(S, *ntile);
+}
+
+// Forward pass over all q rows (rows_done = Sq on return).
 int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv,
                 int q_rs, int k_rs, int v_rs, int o_rs, float scale, cudaStream_t s, int* rows_done) {
   *rows_done = 0;
-  const int ntile = Sq / 128;
-  if (ntile == 0) return MUSE_OK;
+  int ntile, tile_rows;
+  balanced_tiles(Sq, &ntile, &tile_rows);
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_tmap3(&tq, q, nh * HD, Sq, B, q_rs, 128))) return rc;
@@ -730,10 +761,10 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
   static bool attr = false;
   if ((rc = set_smem(attn_fwd_tc_kernel, FWD_SMEM, &attr))) return rc;
   TcParams p{};
-  p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
+  p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale; p.tile_rows = tile_rows;
   p.out0 = reinterpret_cast<bf16*>(o); p.out0_rs = o_rs; p.lse = lse;
   attn_fwd_tc_kernel<<<dim3(ntile, nh, B), 128, FWD_SMEM, s>>>(tq, tk, tv, p);
-  *rows_done = ntile * 128;
+  *rows_done = Sq;
   return check_launch("attn_fwd_tc");
 }
 
@@ -741,8 +772,8 @@ int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o,
                    void* dq, int B, int nh, int Sq, int Skv, int q_rs, int k_rs, int v_rs, int do_rs, int dq_rs,
                    float scale, cudaStream_t s, int* rows_done) {
   *rows_done = 0;
-  const int ntile = Sq / 128;
-  if (ntile == 0) return MUSE_OK;
+  int ntile, tile_rows;
+  balanced_tiles(Sq, &ntile, &tile_rows);
   CUtensorMap tq, tdo, tk, tv;
   int rc;
   if ((rc = make_tmap3(&tq, q, nh * HD, Sq, B, q_rs, 128))) return rc;
@@ -754,8 +785,9 @@ int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o,
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dq); p.out0_rs = dq_rs; p.lse = const_cast<float*>(lse); p.dvec = dvec;
+  p.tile_rows = tile_rows;
   attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 288, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
-  *rows_done = ntile * 128;
+  *rows_done = Sq;
   return check_launch("attn_bwd_dq_tc");
 }
 
@@ -763,8 +795,8 @@ int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_
                      const float* dvec, void* dk, void* dv, int B, int nh, int Sq, int Skv, int q_rs, int k_rs,
                      int v_rs, int do_rs, int dk_rs, int dv_rs, float scale, cudaStream_t s, int* rows_done) {
   *rows_done = 0;
-  const int ntile = Skv / 128;
-  if (ntile == 0) return MUSE_OK;
+  int ntile, tile_rows;
+  balanced_tiles(Skv, &ntile, &tile_rows);
   CUtensorMap tq, tdo, tk, tv;
   int rc;
   if ((rc = make_tmap3(&tk, k, nh * HD, Skv, B, k_rs, 128))) return rc;
@@ -777,8 +809,9 @@ int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dk); p.out0_rs = dk_rs; p.out1 = reinterpret_cast<bf16*>(dv); p.out1_rs = dv_rs;
   p.lse = const_cast<float*>(lse); p.dvec = const_cast<float*>(dvec);
+  p.tile_rows = tile_rows;
   attn_bwd_dkdv_tc_kernel<<<dim3(ntile, nh, B), 288, DKDV_SMEM, s>>>(tk, tv, tq, tdo, p);
-  *rows_done = ntile * 128;
+  *rows_done = Skv;
   return check_launch("attn_bwd_dkdv_tc");
 }
 

@@ -1,0 +1,94 @@
+"""CPU: the UNMODIFIED reference script training/train_maskgit_imagenet.py runs for two optimizer steps against the drop-in
+``muse`` package, with the C-ABI kernels replaced by shape/dtype-checking stand-ins (the numerics are the GPU twin's job,
+tests/test_train_script_gpu.py).  What this pins is the host-side surface the script relies on: constructor kwargs from
+the yaml, ``config.mask_token_id``, ``requires_grad_``, ``enable_xformers_memory_efficient_attention``, the forward
+keywords, ``parameters()`` into AdamW, the prepare / accumulate / backward / clip / step / zero_grad loop, validation in
+eval mode, ``save_pretrained(save_function=, state_dict=)`` checkpoints and the final export."""
+import json
+import os
+
+import pytest
+import torch
+
+from tests.train_script_harness import find_script, make_config, run_script
+from tests.test_v1_plumbing_cpu import _fake_ops
+
+SCRIPT = find_script()
+pytestmark = pytest.mark.skipif(SCRIPT is None, reason="reference training script not available")
+
+
+def _fake_tokenizer(mp):
+    import open_muse_b200.modeling_maskgit_vqgan as V
+
+    def encode(self, pixel_values, return_loss=False):
+        g = torch.Generator().manual_seed(int(pixel_values.sum() * 1000) % 100000)
+        ids = torch.randint(0, self.num_embeddings, (pixel_values.shape[0], 256), generator=g)
+        return None, ids
+
+    def soft(self, pixel_values, temp=1.0, stochastic=False):
+        _, ids = encode(self, pixel_values)
+        return torch.softmax(torch.randn(ids.shape[0], 256, self.num_embeddings), -1), ids
+
+    mp.setattr(V.MaskGitVQGAN, "encode", encode)
+    mp.setattr(V.MaskGitVQGAN, "get_soft_code", soft)
+
+
+@pytest.mark.parametrize("soft_targets", [False, True])
+def test_reference_training_script_runs_unchanged(monkeypatch, tmp_path, soft_targets):
+    _fake_ops(monkeypatch)
+    _fake_tokenizer(monkeypatch)
+    monkeypatch.setenv("ACCELERATE_USE_CPU", "1")
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    cfg, out = make_config(str(tmp_path), steps=2, batch=3, mixed_precision="no", soft_targets=soft_targets, save_every=2)
+    acc = run_script(SCRIPT, cfg)
+    steps_logged = [s for v, s in acc.logged if "step_loss" in v]
+    assert steps_logged == [1, 2]
+    assert any("eval_loss" in v for v, _ in acc.logged)            # validate_model at the end of training
+    assert any(k.startswith("grad_norm/") for v, _ in acc.logged for k in v)
+    # final export + the step-2 checkpoint written through save_pretrained(save_function=accelerator.save, state_dict=...)
+    assert sorted(os.listdir(out))[:2] == ["checkpoint-2", "config.json"] or "pytorch_model.bin" in os.listdir(out)
+    assert os.path.exists(os.path.join(out, "pytorch_model.bin")) and os.path.exists(os.path.join(out, "config.yaml"))
+    ck = os.path.join(out, "checkpoint-2")
+    assert json.load(open(os.path.join(ck, "metadata.json"))) == {"global_step": 2}
+    assert os.path.exists(os.path.join(ck, "unwrapped_model", "pytorch_model.bin"))
+    cfg_json = json.load(open(os.path.join(out, "config.json")))
+    assert cfg_json["_class_name"] == "MaskGitTransformer" and cfg_json["mask_token_id"] == 74
+
+
+def test_lr_schedulers_match_reference():
+    """compat muse.lr_schedulers.get_scheduler against the reference's, every schedule name, 12 steps."""
+    import importlib.util
+    import sys
+
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(SCRIPT)), "muse")
+    if not os.path.exists(os.path.join(ref_dir, "lr_schedulers.py")):
+        pytest.skip("reference muse/ not available")
+    import types
+
+    pkg = types.ModuleType("_ref_muse")
+    pkg.__path__ = [ref_dir]
+    sys.modules["_ref_muse"] = pkg
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_muse.logging", os.path.join(ref_dir, "logging.py"))
+        lg = importlib.util.module_from_spec(spec); sys.modules["_ref_muse.logging"] = lg; spec.loader.exec_module(lg)
+        spec = importlib.util.spec_from_file_location("_ref_muse.lr_schedulers", os.path.join(ref_dir, "lr_schedulers.py"))
+        ref = importlib.util.module_from_spec(spec); sys.modules["_ref_muse.lr_schedulers"] = ref; spec.loader.exec_module(ref)
+    finally:
+        pass
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "open_muse_b200", "compat"))
+    try:
+        from muse.lr_schedulers import NAMES, get_scheduler
+    finally:
+        sys.path.pop(0)
+    for name in NAMES:
+        lrs = []
+        for impl in (ref.get_scheduler, get_scheduler):
+            opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.5)
+            sch = impl(name, optimizer=opt, num_warmup_steps=3, num_training_steps=10)
+            seq = []
+            for _ in range(12):
+                opt.step(); sch.step(); seq.append(sch.get_last_lr()[0])
+            lrs.append(seq)
+        assert lrs[0] == pytest.approx(lrs[1], rel=1e-12, abs=1e-15), name
+    for k in [k for k in sys.modules if k.startswith("_ref_muse")]:
+        del sys.modules[k]

@@ -1,0 +1,92 @@
+"""Runs the UNMODIFIED reference training script (training/train_maskgit_imagenet.py) against the drop-in ``muse`` package
+(open_muse_b200/compat) for a couple of optimizer steps -- the "scripts run unchanged" half of the boundary (north_star,
+SURVEY.md 8c).  Third-party packages the image lacks come from tests/shims; the script itself is executed with runpy from
+where it lies: /root/reference/training in the build container, oracle/_ref/training (the git-ignored snapshot taken by
+__graft_entry__.build()) on the GPU box.  Test infrastructure only."""
+import os
+import runpy
+import sys
+
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIMS = os.path.join(ROOT, "tests", "shims")
+COMPAT = os.path.join(ROOT, "open_muse_b200", "compat")
+
+MICRO_VQ = dict(resolution=32, num_channels=3, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=1,
+                z_channels=16, num_embeddings=64, quantized_embed_dim=16)
+
+
+def find_script(name="train_maskgit_imagenet.py"):
+    for base in (os.environ.get("MUSE_REFERENCE", "/root/reference"), os.path.join(ROOT, "oracle", "_ref")):
+        p = os.path.join(base, "training", name)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def make_config(tmp, steps, batch, mixed_precision, soft_targets=False, save_every=1000):
+    from open_muse_b200 import MaskGitVQGAN
+
+    torch.manual_seed(3)
+    vq_dir = os.path.join(tmp, "vq")
+    MaskGitVQGAN(**MICRO_VQ).save_pretrained(vq_dir)
+    out = os.path.join(tmp, "run")
+    cfg = {
+        "wandb": {"entity": None},
+        "experiment": {"project": "muse", "name": "shim-run", "output_dir": out, "max_train_examples": batch * 64,
+                       "max_eval_examples": batch * 2, "save_every": save_every, "eval_every": 1000,
+                       "generate_every": 1000,  # quirk Q11: generate_images crashes upstream; keep it beyond max_train_steps
+                       "log_every": 1, "log_grad_norm_every": 1, "resume_from_checkpoint": False, "resume_lr_scheduler": True},
+        "model": {"vq_model": {"type": "maskgit_vqgan", "pretrained": vq_dir},
+                  "transformer": {"vocab_size": 64 + 10 + 1, "max_position_embeddings": 257, "hidden_size": 64,
+                                  "num_hidden_layers": 2, "num_attention_heads": 1, "intermediate_size": 128,
+                                  "codebook_size": 64, "num_vq_tokens": 256, "num_classes": 10, "initializer_range": 0.02,
+                                  "norm_type": "layernorm", "layer_norm_eps": 1e-6, "use_normformer": True,
+                                  "use_encoder_layernorm": True, "use_mlm_layer": True, "use_mlm_layernorm": True,
+                                  "use_bias": False, "hidden_dropout": 0.0, "attention_dropout": 0.0},
+                  "gradient_checkpointing": True, "enable_xformers_memory_efficient_attention": True},
+        "dataset": {"params": {"train_shards_path_or_url": "synthetic", "eval_shards_path_or_url": "synthetic",
+                               "batch_size": batch, "shuffle_buffer_size": 10, "num_workers": 0, "resolution": 32,
+                               "pin_memory": False, "persistent_workers": False},
+                    "preprocessing": {"resolution": 32, "center_crop": True, "random_flip": False}},
+        "optimizer": {"name": "adamw", "params": {"learning_rate": 1.0e-3, "scale_lr": False, "beta1": 0.9, "beta2": 0.999,
+                                                  "weight_decay": 0.01, "epsilon": 1.0e-8}},
+        "lr_scheduler": {"scheduler": "constant_with_warmup", "params": {"learning_rate": 1.0e-3, "warmup_steps": 1}},
+        "training": {"gradient_accumulation_steps": 1, "batch_size": batch, "mixed_precision": mixed_precision,
+                     "enable_tf32": True, "use_ema": False, "seed": 42, "max_train_steps": steps, "overfit_one_batch": False,
+                     "min_masking_rate": 0.0, "label_smoothing": 0.1, "max_grad_norm": 1.0,
+                     "use_soft_code_target": soft_targets, "use_stochastic_code": False, "soft_code_temp": 1.0},
+    }
+    path = os.path.join(tmp, "config.yaml")
+    with open(path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    return path, out
+
+
+def run_script(script, config_path, extra_cli=()):
+    """Execute the script as __main__ with the shims and the drop-in package importable; returns the shim Accelerator the
+    script created (its .logged list holds every accelerator.log call)."""
+    saved_path, saved_argv = list(sys.path), list(sys.argv)
+    saved_mods = {k: sys.modules.get(k) for k in ("muse", "accelerate", "omegaconf", "wandb", "data", "optimizer")}
+    for k in list(sys.modules):
+        if k == "muse" or k.startswith("muse.") or k in ("accelerate", "omegaconf", "wandb", "data", "optimizer") or \
+                k.startswith("accelerate."):
+            del sys.modules[k]
+    sys.path[:0] = [SHIMS, COMPAT, os.path.dirname(script)]  # shims shadow the script directory's own data.py
+    sys.argv = [script, f"config={config_path}", *extra_cli]
+    try:
+        import accelerate
+
+        runpy.run_path(script, run_name="__main__")
+        return accelerate.Accelerator.last
+    finally:
+        sys.path[:], sys.argv[:] = saved_path, saved_argv
+        for k in list(sys.modules):
+            if k == "muse" or k.startswith("muse.") or k in ("accelerate", "omegaconf", "wandb", "data", "optimizer") or \
+                    k.startswith("accelerate."):
+                del sys.modules[k]
+        for k, v in saved_mods.items():
+            if v is not None:
+                sys.modules[k] = v
