@@ -232,7 +232,7 @@ gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scal
     uh.x = pack_bf16(h[0], h[1]); uh.y = pack_bf16(h[2], h[3]);
     ul.x = pack_bf16(o[0] - h[0], o[1] - h[1]); ul.y = pack_bf16(o[2] - h[2], o[3] - h[3]);
     *reinterpret_cast<uint2*>(y_hi + i * 4) = uh;
-    *reinterpret_cast<uint2*>(y_lo + i * 4) = ul;
+    if (y_lo) *reinterpret_cast<uint2*>(y_lo + i * 4) = ul;
   } else {
     *reinterpret_cast<float4*>(y + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }
@@ -263,7 +263,7 @@ gn_apply_silu_split8_kernel(const float* __restrict__ x, const float* __restrict
     l[2 * j] = o0 - h[2 * j]; l[2 * j + 1] = o1 - h[2 * j + 1];
   }
   store8(y_hi + i * 8, h);
-  store8(y_lo + i * 8, l);
+  if (y_lo) store8(y_lo + i * 8, l);  // single-pass bf16 tokenizer mode needs the hi plane only
 }
 
 // ---------------------------------------------------------------- pooling / layout
@@ -342,8 +342,8 @@ long long gn_workspace_floats(int B, int HW, int C) {
 int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, float* y, void* y_hi, void* y_lo,
                         float* partials_ws, float* scale_shift_ws, int B, int HW, int C, int groups, float eps,
                         int precomputed_tiles, int apply_silu, cudaStream_t s) {
-  if ((y != nullptr) == (y_hi != nullptr) || (y_hi != nullptr) != (y_lo != nullptr)) {
-    set_last_error("groupnorm: give either y (fp32) or both y_hi and y_lo (bf16 split)");
+  if ((y != nullptr) == (y_hi != nullptr) || (y_hi == nullptr && y_lo != nullptr)) {
+    set_last_error("groupnorm: give either y (fp32) or y_hi (+ y_lo unless the single-pass bf16 mode is used)");
     return MUSE_ERR_INVALID;
   }
   if (C % groups != 0 || C % 4 != 0 || C > 1024 || 256 % (C / 4) != 0) {

@@ -61,6 +61,7 @@ struct ConvParams {
   int fwd2x2;           // taps are the 2x2 window at offsets (0..1, 0..1): the stride-2 3x3 conv after space-to-depth
   int wbatch;           // weights are per image: [B][C_out][K] (attention scores / values as 1x1 convolutions)
   int num_m, num_n, cchunks, num_kb;
+  int passes;           // 3: bf16x3 (hi*hi + lo*hi + hi*lo, fp32-faithful); 1: hi*hi only (plain bf16 operands, fast mode)
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -157,7 +158,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int y0 = (t / p.tiles_x) * p.tile_h, x0 = (t % p.tiles_x) * p.tile_w;
         const int n0 = n_idx * BN;
         const int wrow0 = parity * p.N;  // up: the four parity weight matrices are stacked along the rows
-        int pass = 0, cc = 0, tap = 0;  // kb = (tap * cchunks + cc) * 3 + pass
+        int pass = 0, cc = 0, tap = 0;  // kb = (tap * cchunks + cc) * passes + pass
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full_bar[stage], C_::kStageBytes);
@@ -175,7 +176,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             tma_load_4d(sb, pass == 1 ? &tmAl : &tmAh, &full_bar[stage], cc * BK, x0 + dx, y0 + dy, img);
           }
           if (++stage == C_::kStages) { stage = 0; phase ^= 1; }
-          if (++pass == 3) {
+          if (++pass == p.passes) {
             pass = 0;
             if (++cc == p.cchunks) { cc = 0; ++tap; }
           }
@@ -449,7 +450,7 @@ split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __re
     l[j] = v[j] - h[j];
   }
   store8(hi + i * 8, h);
-  store8(lo + i * 8, l);
+  if (lo) store8(lo + i * 8, l);
 }
 
 // Small-C_in stem (3 -> 128 at full resolution): im2col of the k*k*C_in <= 64 taps into 64-wide bf16 hi/lo rows, so the
@@ -479,7 +480,7 @@ im2col_split_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __
     l[j] = v - h[j];
   }
   store8(hi + i * 8, h);
-  store8(lo + i * 8, l);
+  if (lo) store8(lo + i * 8, l);
 }
 
 // space-to-depth + hi/lo split: x fp32 [B,H,W,C] -> planes bf16 [B,H/2,W/2,4C], channel = (row parity * 2 + col parity) * C + c
@@ -504,7 +505,7 @@ split_s2d_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __res
     l[j] = v[j] - h[j];
   }
   store8(hi + i * 8, h);
-  store8(lo + i * 8, l);
+  if (lo) store8(lo + i * 8, l);
 }
 
 // softmax(scale * x) over rows of n fp32 values (one warp per row), emitted as bf16 hi/lo planes
@@ -589,6 +590,8 @@ int conv2d_tc_tiles_per_image(int H, int W, int Cin, int Cout, int ksize, int up
 // mode & 3 == 2: ksize 2, taps at offsets (0,0),(0,1),(1,0),(1,1), zero beyond the right / bottom edge -- a stride-2 3x3
 //   convolution with pad (0,1,0,1) (taming Downsample) after a space-to-depth of its input (w: [Cout, 4 * Cin]).
 // mode & 4: per-image weights, w planes are [B][Cout][K].
+// mode & 8: single-pass bf16 (fast tokenizer mode): only the hi planes are multiplied (x_lo / w_lo may be null): one tensor-core
+//   product per fp32 product instead of three, bf16-operand accuracy (~4e-3 per layer instead of ~2e-5).
 int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, const float* res,
               float* y, float* stats, int B, int H, int W, int Cin, int Cout, int ksize, int mode, cudaStream_t s) {
   if (B <= 0) return MUSE_OK;
@@ -632,7 +635,9 @@ int conv2d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* 
   p.num_n = swap ? 1 : ceil_div(Cout, BN);
   p.cchunks = Cin / BK;
   const int taps = (p.up || p.fwd2x2) ? 4 : ksize * ksize;
-  p.num_kb = taps * p.cchunks * 3;
+  p.passes = (mode & 8) ? 1 : 3;
+  p.num_kb = taps * p.cchunks * p.passes;
+  if (p.passes == 1) { x_lo = x_hi; w_lo = w_hi; }  // the lo maps are never dereferenced; keep the encodes valid
 
   CUtensorMap ah, al, bh, bl;
   const unsigned long long adims[4] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B};

@@ -276,12 +276,22 @@ class VQGANModel(ModelMixin, ConfigMixin):
         self.quantize = VectorQuantizer(self.config.num_embeddings, self.config.quantized_embed_dim, self.config.commitment_cost)
         self.quant_conv = nn.Conv2d(self.config.z_channels, self.config.quantized_embed_dim, kernel_size=1)
         self.post_quant_conv = nn.Conv2d(self.config.quantized_embed_dim, self.config.z_channels, kernel_size=1)
+        self.conv_precision = "bf16x3"
+
+    def set_conv_precision(self, mode: str):
+        """See MaskGitVQGAN.set_conv_precision: "bf16x3" (fp32-faithful, default) or "bf16" (single pass; the AttnBlock
+        attention products stay fp32-faithful)."""
+        with ops.conv_precision(mode):
+            pass
+        self.conv_precision = mode
+        return self
 
     def _encode_nhwc(self, pixel_values):
         if not pixel_values.is_cuda:
             raise RuntimeError("open_muse_b200.VQGANModel runs on CUDA (sm_100a) only; move inputs to the GPU")
-        h = self.encoder.run(ops.to_nhwc(pixel_values.float().contiguous()))
-        return ops.conv2d(h, self.quant_conv.weight, bias=self.quant_conv.bias)
+        with ops.conv_precision(self.conv_precision):
+            h = self.encoder.run(ops.to_nhwc(pixel_values.float().contiguous()))
+            return ops.conv2d(h, self.quant_conv.weight, bias=self.quant_conv.bias)
 
     def _quantize_nhwc(self, z_nhwc, return_loss):
         ids = self.quantize.get_code_nhwc(z_nhwc)
@@ -298,9 +308,10 @@ class VQGANModel(ModelMixin, ConfigMixin):
 
     @torch.no_grad()
     def decode(self, quantized_states):
-        z = ops.to_nhwc(quantized_states.float().contiguous())
-        h = ops.conv2d(z, self.post_quant_conv.weight, bias=self.post_quant_conv.bias)
-        return ops.to_nchw(self.decoder.run(h))
+        with ops.conv_precision(self.conv_precision):
+            z = ops.to_nhwc(quantized_states.float().contiguous())
+            h = ops.conv2d(z, self.post_quant_conv.weight, bias=self.post_quant_conv.bias)
+            return ops.to_nchw(self.decoder.run(h))
 
     @torch.no_grad()
     def decode_code(self, codebook_indices):

@@ -463,6 +463,56 @@ def sample_step(logits, input_ids, q_exp, u, K, mask_id, mask_len, temperature, 
 # ------------------------------------------------------------------------------------------ VQGAN blocks (fp32 NHWC)
 _wk_cache = {}
 
+# Tensor-core convolution precision: "bf16x3" (default) carries every fp32 operand as bf16 hi + lo planes and accumulates
+# hi*hi + lo*hi + hi*lo in fp32 -- fp32-faithful, what the bit-exact token-id contract needs.  "bf16" multiplies the hi
+# planes only: one product instead of three and no lo planes written, at bf16-operand accuracy (the reference itself runs
+# its tokenizer convolutions in TF32 on the GPU: cudnn.allow_tf32 defaults to True and training/train_maskgit_imagenet.py:
+# 146-149 also enables it for matmuls, quirk Q19).  Token ids from the fast mode agree with the exact ones except near
+# ties; bench.py reports the agreement rate.
+_conv_state = {"single": False, "route": None}
+
+
+class conv_precision:
+    """``with ops.conv_precision("bf16"): ...`` -- scoped selection of the tokenizer convolution mode."""
+
+    def __init__(self, mode):
+        if mode not in ("bf16x3", "bf16"):
+            raise ValueError("conv precision must be 'bf16x3' (fp32-faithful) or 'bf16' (single pass)")
+        self.single = mode == "bf16"
+
+    def __enter__(self):
+        self.prev = _conv_state["single"]
+        _conv_state["single"] = self.single
+
+    def __exit__(self, *exc):
+        _conv_state["single"] = self.prev
+        return False
+
+
+class conv_route:
+    """Test hook: ``with ops.conv_route("simt")`` forces the fp32 FMA convolution kernels (the route geometries without a TMA
+    tiling take anyway) so that tests can compare the tensor-core route against them.  Not a product switch."""
+
+    def __init__(self, route):
+        assert route in (None, "simt")
+        self.route = route
+
+    def __enter__(self):
+        self.prev = _conv_state["route"]
+        _conv_state["route"] = self.route
+
+    def __exit__(self, *exc):
+        _conv_state["route"] = self.prev
+        return False
+
+
+def _lo_like(hi):
+    return None if _conv_state["single"] else torch.empty_like(hi)
+
+
+def _tc_mode(mode):
+    return mode | 8 if _conv_state["single"] else mode
+
 
 def _packed_conv_weight(w):
     """[Cout, Cin, kh, kw] -> [kh*kw*Cin, Cout] (tap-major, then input channel); cached per live weight tensor
@@ -500,9 +550,7 @@ def _packed_conv_weight_split(w):
 def conv_uses_tensor_cores(H, W, Cin, Cout, k):
     """Route of conv2d(): tcgen05 bf16x3 implicit GEMM unless the geometry is unsupported or MUSE_B200_CONV=simt.
     Stems with k*k*Cin <= 64 go through an im2col to 64 columns and run as a 1x1 convolution."""
-    import os
-
-    if os.environ.get("MUSE_B200_CONV", "tc") == "simt":
+    if _conv_state["route"] == "simt":  # private test hook (ops.conv_route): cross-check against the fp32 FMA kernels
         return False
     if Cin % 64 != 0 and k * k * Cin <= 64:
         return bool(_lib.load().muse_conv2d_tc_supported(H, W, 64, Cout, 1))
@@ -594,27 +642,27 @@ def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
     if conv_uses_tensor_cores(H, W, Cin, Cout, k) and Cin % 64 != 0:
         assert gn is None and not upsample2x
         hi = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=x.device)
-        lo = torch.empty_like(hi)
+        lo = _lo_like(hi)
         _call("muse_im2col_split_nhwc", _p(x), _p(hi), _p(lo), B, H, W, Cin, k, st)
         w_hi, w_lo = _packed_conv_weight_split_stem(w)
         stats, tiles = _conv_stats_buffer(y, H, W, 64, Cout, 1)
         _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), _p(stats), B, H, W, 64,
-              Cout, 1, 0, st)
+              Cout, 1, _tc_mode(0), st)
         return y
     if upsample2x and gn is None and conv_uses_tensor_cores(H, W, Cin, Cout, k) and \
             _lib.load().muse_conv2d_tc_tiles_per_image(H, W, Cin, Cout, k, 1) > 0:
         # nearest x2 + 3x3 conv as four 2x2 parity convolutions on the low-resolution planes (2.25x fewer FLOPs)
         hi = torch.empty(B, Hi, Wi, Cin, dtype=torch.bfloat16, device=x.device)
-        lo = torch.empty_like(hi)
+        lo = _lo_like(hi)
         _call("muse_split_bf16_nhwc", _p(x), _p(hi), _p(lo), B, Hi, Wi, Cin, 0, st)
         w_hi, w_lo = _packed_conv_weight_upsample(w)
         stats, tiles = _conv_stats_buffer(y, H, W, Cin, Cout, k, 1)
         _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), _p(stats), B, H, W, Cin,
-              Cout, k, 1, st)
+              Cout, k, _tc_mode(1), st)
         return y
     if conv_uses_tensor_cores(H, W, Cin, Cout, k):
         hi = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device=x.device)
-        lo = torch.empty_like(hi)
+        lo = _lo_like(hi)
         if gn is not None:
             assert not upsample2x
             pre = getattr(x, "_gn_stats", None)  # {sum, sumsq} tiles left by the convolution that produced x
@@ -630,7 +678,7 @@ def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
         w_hi, w_lo = _packed_conv_weight_split(w)
         stats, tiles = _conv_stats_buffer(y, H, W, Cin, Cout, k)
         _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), _p(residual), _p(y), _p(stats), B, H, W, Cin,
-              Cout, k, 0, st)
+              Cout, k, _tc_mode(0), st)
         return y
     if gn is not None:
         x = groupnorm_silu(x, *gn)
@@ -686,17 +734,15 @@ def conv2d_down(x, w, bias=None):
     Cout = w.shape[0]
     y = torch.empty(B, H, W, Cout, dtype=torch.float32, device=x.device)
     b = None if bias is None else bias.detach().float()
-    import os
-
-    if os.environ.get("MUSE_B200_CONV", "tc") != "simt" and (4 * Cin) % 64 == 0 and \
+    if _conv_state["route"] != "simt" and (4 * Cin) % 64 == 0 and \
             _lib.load().muse_conv2d_tc_supported(H, W, 4 * Cin, Cout, 2):
         hi = torch.empty(B, H, W, 4 * Cin, dtype=torch.bfloat16, device=x.device)
-        lo = torch.empty_like(hi)
+        lo = _lo_like(hi)
         _call("muse_split_s2d_bf16_nhwc", _p(x), _p(hi), _p(lo), B, H, W, Cin, st)
         w_hi, w_lo = _packed_conv_weight_down(w)
         stats, tiles = _conv_stats_buffer(y, H, W, 4 * Cin, Cout, 2)
         _call("muse_conv2d_nhwc_tc", _p(hi), _p(lo), _p(w_hi), _p(w_lo), _p(b), None, _p(y), _p(stats), B, H, W, 4 * Cin, Cout,
-              2, 2, st)
+              2, _tc_mode(2), st)
         return y
     _call("muse_conv2d_nhwc", _p(x), _p(_packed_conv_weight(w)), _p(b), None, _p(y), B, H, W, Cin, Cout, 3, 2, st)
     return y
@@ -717,7 +763,7 @@ def attention_single_head(q, k, v, B, hh, ww):
     scores = torch.empty(B * HW, HW, dtype=torch.float32, device=q.device)
     vt = torch.empty(B, C, HW, dtype=torch.float32, device=q.device)
     _call("muse_transpose_batched", _p(v), _p(vt), B, HW, C, st)
-    tc = os.environ.get("MUSE_B200_CONV", "tc") != "simt" and lib.muse_conv2d_tc_supported(hh, ww, C, HW, 1) and \
+    tc = _conv_state["route"] != "simt" and lib.muse_conv2d_tc_supported(hh, ww, C, HW, 1) and \
         lib.muse_conv2d_tc_supported(hh, ww, HW, C, 1) and HW % 64 == 0 and C % 64 == 0
 
     def planes(t):

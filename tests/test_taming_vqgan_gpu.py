@@ -31,8 +31,8 @@ def test_downsample_conv_vs_fp64(B, H, W, cin, cout, monkeypatch):
     b = torch.randn(cout, generator=g)
     ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x.double(), (0, 1, 0, 1)), w.double(), b.double(), stride=2)
     for route in ("tc", "simt"):
-        monkeypatch.setenv("MUSE_B200_CONV", route)
-        y = ops.to_nchw(ops.conv2d_down(ops.to_nhwc(x.to(DEV)), w.to(DEV), b.to(DEV)))
+        with ops.conv_route(None if route == "tc" else "simt"):
+            y = ops.to_nchw(ops.conv2d_down(ops.to_nhwc(x.to(DEV)), w.to(DEV), b.to(DEV)))
         assert y.shape == ref.shape and _rel(y, ref) < 2e-5, (route, _rel(y, ref))
 
 
@@ -44,8 +44,8 @@ def test_single_head_attention_and_plain_groupnorm(B, hw, C, monkeypatch):
     w = torch.softmax(torch.bmm(q.double(), k.double().transpose(1, 2)) * C ** -0.5, dim=2)
     ref = torch.bmm(w, v.double())
     for route in ("tc", "simt"):
-        monkeypatch.setenv("MUSE_B200_CONV", route)
-        o = ops.attention_single_head(q.view(-1, C).to(DEV), k.view(-1, C).to(DEV), v.view(-1, C).to(DEV), B, hw, hw)
+        with ops.conv_route(None if route == "tc" else "simt"):
+            o = ops.attention_single_head(q.view(-1, C).to(DEV), k.view(-1, C).to(DEV), v.view(-1, C).to(DEV), B, hw, hw)
         assert _rel(o.view(B, HW, C), ref) < 3e-5, (route, _rel(o.view(B, HW, C), ref))
     x = torch.randn(B, C, hw, hw, generator=g)
     ga, be = torch.randn(C, generator=g), torch.randn(C, generator=g)
@@ -82,13 +82,12 @@ def test_taming_f16_tensor_core_route_matches_fp32_simt_route(monkeypatch):
     img = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(4)).to(DEV)
     outs = {}
     for route in ("simt", "tc"):
-        monkeypatch.setenv("MUSE_B200_CONV", route)
-        outs[route] = m._encode_nhwc(img)
+        with ops.conv_route(None if route == "tc" else "simt"):
+            outs[route] = m._encode_nhwc(img)
     z_s, z_t = outs["simt"], outs["tc"]
     assert z_t.shape == (2, 16, 16, 256) and _rel(z_t, z_s) < 1e-4, _rel(z_t, z_s)
     ids = torch.randint(0, 8192, (2, 256), generator=torch.Generator().manual_seed(5)).to(DEV)
-    monkeypatch.setenv("MUSE_B200_CONV", "tc")
     rec_t = m.decode_code(ids)
-    monkeypatch.setenv("MUSE_B200_CONV", "simt")
-    rec_s = m.decode_code(ids)
+    with ops.conv_route("simt"):
+        rec_s = m.decode_code(ids)
     assert rec_t.shape == (2, 3, 256, 256) and _rel(rec_t, rec_s) < 2e-4, _rel(rec_t, rec_s)
