@@ -62,6 +62,18 @@ int muse_gemm_bf16_splitk(const void* A, const void* B, float* C, int M, int N, 
 int muse_pack_bf16(const void* table_dev, int n_entries, long long total_blocks, void* stream);
 int muse_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 
+/* One pass over all parameters: AdamW (training/train_maskgit_imagenet.py:242-261,438 -- torch.optim.AdamW / apex FusedAdam,
+ * decoupled weight decay, bias-corrected) + EMAModel.step of the UPDATED weights (muse/modeling_ema.py:89-126, same decay
+ * schedule incl. warm-up / update_after_step / update_every) + the bf16 copy into the packed GEMM operand cache.
+ * table_dev: device array of n_entries {float* p; const float* g; float* m; float* v; float* ema (nullable);
+ * bf16* packed (nullable); int64 numel (multiple of 4); int64 first_block} with 1024 elements per block.
+ * step_dev (int64, steps taken so far) is incremented on the device and scal_dev (8 floats) receives the per-step scalars, so
+ * the call is CUDA-graph capturable; lr_dev (nullable device float) overrides lr_host. */
+int muse_adamw_ema_step(const void* table_dev, int n_entries, long long total_blocks, float* scal_dev, long long* step_dev,
+                        const float* lr_dev, float lr_host, float beta1, float beta2, float eps, float weight_decay,
+                        int ema_enabled, float ema_decay, float ema_min_decay, int ema_update_after_step,
+                        int ema_update_every, int ema_use_warmup, float ema_inv_gamma, float ema_power, void* stream);
+
 /* Embed.forward (muse/modeling_transformer.py:942-957): out[b,s,:] = word[ids[b,s],:] + pos[s,:] (fp32). */
 int muse_embed_fwd(const long long* ids, const float* word, const float* pos, float* out, int B, int S, int H,
                    int vocab, void* stream);

@@ -15,3 +15,5 @@ from .modeling_transformer_v2 import MaskGiTUViT_v2  # noqa: F401
 MaskGiTUViT = MaskGiTUViT_v2  # the reference's alias (muse/modeling_transformer.py:41)
 from .pipeline_muse import PipelineMuse, PipelineMuseInpainting  # noqa: F401
 from .sampling import get_mask_chedule  # noqa: F401
+
+from .optim import FusedAdamW  # noqa: F401,E402

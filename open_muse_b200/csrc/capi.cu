@@ -30,6 +30,7 @@ int gemm_tcgen05(const void*, const void*, void*, const float*, int, int, int, i
 long long gemm_splitk_workspace_bytes(int, int, int, int*);
 int gemm_mma(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int pack_bf16(const void*, int, long long, cudaStream_t);
+int adamw_ema_step(const void*, int, long long, float*, long long*, const float*, float, float, float, float, float, int, float, float, int, int, int, float, float, cudaStream_t);
 int cast_bf16(const float*, void*, long long, cudaStream_t);
 int embed_fwd(const long long*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
 int embed_bwd(const long long*, const float*, float*, float*, int, int, int, int, cudaStream_t);
@@ -118,6 +119,14 @@ int muse_pack_bf16(const void* table_dev, int n_entries, long long total_blocks,
   return pack_bf16(table_dev, n_entries, total_blocks, ST(stream));
 }
 int muse_cast_bf16(const float* src, void* dst, long long n, void* stream) { return cast_bf16(src, dst, n, ST(stream)); }
+int muse_adamw_ema_step(const void* table_dev, int n_entries, long long total_blocks, float* scal_dev, long long* step_dev,
+                        const float* lr_dev, float lr_host, float beta1, float beta2, float eps, float weight_decay,
+                        int ema_enabled, float ema_decay, float ema_min_decay, int ema_update_after_step,
+                        int ema_update_every, int ema_use_warmup, float ema_inv_gamma, float ema_power, void* stream) {
+  return adamw_ema_step(table_dev, n_entries, total_blocks, scal_dev, step_dev, lr_dev, lr_host, beta1, beta2, eps,
+                        weight_decay, ema_enabled, ema_decay, ema_min_decay, ema_update_after_step, ema_update_every,
+                        ema_use_warmup, ema_inv_gamma, ema_power, ST(stream));
+}
 
 int muse_embed_fwd(const long long* ids, const float* word, const float* pos, float* out, int B, int S, int H, int vocab, void* stream) {
   return embed_fwd(ids, word, pos, out, B, S, H, vocab, ST(stream));
