@@ -415,6 +415,10 @@ def main():
                     help="skip decode steps/s, the tokenizer round trip, torch-eager-on-this-GPU and the per-kernel rooflines")
     ap.add_argument("--no-cuda-graph", action="store_true",
                     help="launch the kernels of each step one by one instead of replaying the captured step (N=1 default: graph)")
+    ap.add_argument("--ddp-graph", type=int, default=int(os.environ.get("MUSE_B200_DDP_GRAPH", "0")),
+                    help="N>1: capture the whole DDP step (NCCL bucket all-reduces included) in one CUDA graph")
+    ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
+                    help="torch.optim.AdamW(fused=True) or open_muse_b200.FusedAdamW (AdamW + bf16 operand packing in one pass)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu (the reference arm) or cuda (same eager ops under bf16 autocast, informational)")
     args = ap.parse_args()
@@ -430,7 +434,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    ddp_graph = world > 1 and bool(args.ddp_graph) and not args.no_cuda_graph
     if world > 1:
+        if ddp_graph:  # graph capture of NCCL collectives: the watchdog must not poll events while the stream is capturing
+            os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(3, args.warmup)
     B = args.batch
@@ -439,9 +446,21 @@ def main():
     model = MaskGitTransformer(**BASE_CFG).to(dev).train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
-    use_graph = world == 1 and not args.no_cuda_graph
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True, capturable=use_graph)
+        if ddp_graph:  # DDP constructed on a side stream (torch's recipe for capturing a DDP step)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    use_graph = (world == 1 or ddp_graph) and not args.no_cuda_graph
+    if args.optimizer == "fused":
+        from open_muse_b200 import FusedAdamW
+
+        opt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=0.01, model=model)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True, capturable=use_graph)
     gen = None if use_graph else torch.Generator(device=dev).manual_seed(100 + rank)  # graph capture: default generator
     torch.cuda.manual_seed(100 + rank)
     n_buf = 4
@@ -488,7 +507,9 @@ def main():
         from open_muse_b200.graphs import GraphedStep
 
         try:
-            run = GraphedStep(step, (dev_tok[0], dev_cls[0]), warmup=2)
+            # DDP: >= 11 eager warm-up iterations before capture (torch's documented requirement), thread-local capture mode
+            run = GraphedStep(step, (dev_tok[0], dev_cls[0]), warmup=12 if world > 1 else 2,
+                              capture_error_mode="thread_local" if world > 1 else "global")
             for i in range(2):
                 run(dev_tok[i % n_buf], dev_cls[i % n_buf])
         except Exception as e:  # same kernels launched one by one (reported in config.cuda_graph)
@@ -600,7 +621,7 @@ def main():
                        "global_batch": gb, "per_gpu_batch": B, "seq_len": 257,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "no explicit flush: per-step working set (~15 GB activations + 0.5 GB weights/grads/optimizer) >> 126 MB L2",
-                       "cuda_graph": bool(use_graph)},
+                       "cuda_graph": bool(use_graph), "optimizer": args.optimizer},
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4},
             "gpu_launches": launches,

@@ -21,7 +21,7 @@ extern "C" {
 #define MUSE_ERR_CUDA 2
 #define MUSE_ERR_UNSUPPORTED 3
 
-#define MUSE_B200_ABI_VERSION 2
+#define MUSE_B200_ABI_VERSION 3
 
 /* library / device plumbing */
 int muse_abi_version(void);
@@ -35,8 +35,6 @@ int muse_device_info(int* sm_major, int* sm_minor, int* num_sms);
 #define MUSE_EPI_ATOMIC_F32 2  /* C fp32 += acc (split-K; weight gradients)      */
 #define MUSE_EPI_RESADD_F32 3  /* C fp32 = res fp32 + bf16(acc) (residual add)   */
 #define MUSE_EPI_SPLITK_F32 4  /* C fp32 = acc, deterministic split-K (muse_gemm_bf16_splitk only) */
-#define MUSE_GEMM_TCGEN05 0
-#define MUSE_GEMM_MMA_SYNC 1   /* legacy tensor-core cross-check kernel, not the product path */
 
 /* C[M,N] = opA(A) * opB(B)^T, bf16 inputs, fp32 accumulation.
  *   a_mn == 0: A is row-major [M,K] (pitch lda); a_mn == 1: A is row-major [K,M].
@@ -44,7 +42,7 @@ int muse_device_info(int* sm_major, int* sm_minor, int* num_sms);
  * Replaces every nn.Linear forward (muse/modeling_transformer.py:198-200,218,789-798,980,984) and,
  * through the a_mn/b_mn views, their autograd dgrad / wgrad matmuls. */
 int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
-                   int ldc, int a_mn, int b_mn, int epilogue, int backend, void* stream);
+                   int ldc, int a_mn, int b_mn, int epilogue, void* stream);
 
 /* Weight-gradient GEMM with a run-to-run reproducible result: C fp32 [M,N] = opA(A) * opB(B)^T split over K (= tokens) so
  * that the few output tiles fill the SMs; every split stores its partial tile into `ws`, the CTA finishing a tile last

@@ -22,7 +22,7 @@ SIGNATURES = {
     "muse_last_error": (c_char_p, []),
     "muse_set_device": (c_int, [_I]),
     "muse_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
-    "muse_gemm_bf16": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "muse_gemm_bf16": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "muse_gemm_splitk_workspace_bytes": (c_longlong, [_I, _I, _I, POINTER(c_int)]),
     "muse_gemm_bf16_splitk": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P]),
     "muse_pack_bf16": (c_int, [_P, _I, _L, _P]),
@@ -69,7 +69,7 @@ SIGNATURES = {
     "muse_transpose_batched": (c_int, [_P, _P, _I, _I, _I, _P]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class MuseB200Error(RuntimeError):

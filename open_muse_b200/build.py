@@ -68,6 +68,40 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     return LIB_PATH
 
 
+XCHECK_DIR = PKG_DIR.parent / "tests" / "xcheck"
+XCHECK_LIB = XCHECK_DIR / "libmuse_b200_xcheck.so"
+
+
+def build_xcheck(verbose: bool = False, force: bool = False) -> Path:
+    """TEST-ONLY cross-check library (tests/xcheck): the first-generation mma.sync GEMM / attention kernels the GPU tests
+    compare the tcgen05 product kernels against.  Never linked into libmuse_b200.so."""
+    nvcc = _nvcc()
+    src_dir = XCHECK_DIR / "csrc"
+    out_dir = src_dir / "build"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    sources = sorted(src_dir.glob("*.cu"))
+    headers = [CSRC / "common.cuh"]
+    objs, jobs = [], []
+    for src in sources:
+        obj = out_dir / (src.stem + ".o")
+        objs.append(obj)
+        if force or _newer(src, obj, headers):
+            jobs.append([nvcc, *NVCC_FLAGS, "-I", str(CSRC), "-c", str(src), "-o", str(obj)])
+    for cmd in jobs:
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    if jobs or force or not XCHECK_LIB.exists():
+        r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(XCHECK_LIB), *map(str, objs)],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc link failed:\n{r.stdout}\n{r.stderr}")
+    return XCHECK_LIB
+
+
 if __name__ == "__main__":
     p = build(verbose=True, force="--force" in sys.argv)
     print(p)
+    print(build_xcheck(verbose=True, force="--force" in sys.argv))

@@ -28,7 +28,6 @@ int check_launch(const char* what) {
 // kernels (defined in the other translation units)
 int gemm_tcgen05(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t, void*, long long, int*);
 long long gemm_splitk_workspace_bytes(int, int, int, int*);
-int gemm_mma(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int pack_bf16(const void*, int, long long, cudaStream_t);
 int adamw_ema_step(const void*, int, long long, float*, long long*, const float*, float, float, float, float, float, int, float, float, int, int, int, float, float, cudaStream_t);
 int cast_bf16(const float*, void*, long long, cudaStream_t);
@@ -99,9 +98,8 @@ int muse_device_info(int* sm_major, int* sm_minor, int* num_sms) {
 }
 
 int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
-                   int ldc, int a_mn, int b_mn, int epilogue, int backend, void* stream) {
+                   int ldc, int a_mn, int b_mn, int epilogue, void* stream) {
   if (epilogue == MUSE_EPI_RESADD_F32 && res == nullptr) { set_last_error("gemm: RESADD epilogue needs res"); return MUSE_ERR_INVALID; }
-  if (backend == MUSE_GEMM_MMA_SYNC) return gemm_mma(A, B, C, res, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, ST(stream));
   if (epilogue == MUSE_EPI_SPLITK_F32) { set_last_error("gemm: the deterministic split-K epilogue goes through muse_gemm_bf16_splitk"); return MUSE_ERR_INVALID; }
   return gemm_tcgen05(A, B, C, res, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, ST(stream), nullptr, 0, nullptr);
 }

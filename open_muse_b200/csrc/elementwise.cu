@@ -208,7 +208,7 @@ __device__ __forceinline__ void ordered_rows_sum(RowFn row, int n, int H, float*
   __syncthreads();
 }
 
-__global__ void embed_seg_chunk_kernel(const long long* __restrict__ order, const long long* __restrict__ bounds,
+__global__ void __launch_bounds__(512) embed_seg_chunk_kernel(const long long* __restrict__ order, const long long* __restrict__ bounds,
                                        const int* __restrict__ chunk_off, const float* __restrict__ dx,
                                        float* __restrict__ dword, float* __restrict__ ws, int H, int vocab) {
   extern __shared__ __align__(16) float s_q[];  // [4][H]
@@ -228,7 +228,7 @@ __global__ void embed_seg_chunk_kernel(const long long* __restrict__ order, cons
   ordered_rows_sum([&](int i) { return dx + static_cast<size_t>(order[p0 + i]) * H; }, n, H, s_q, out);
 }
 
-__global__ void embed_seg_final_kernel(const int* __restrict__ chunk_off, const float* __restrict__ ws,
+__global__ void __launch_bounds__(512) embed_seg_final_kernel(const int* __restrict__ chunk_off, const float* __restrict__ ws,
                                        float* __restrict__ dword, int H, int vocab) {
   extern __shared__ __align__(16) float s_q[];
   const int v = blockIdx.x;
@@ -340,7 +340,7 @@ int embed_bwd_sorted(const long long* order, const long long* bounds, const floa
   float* partial = reinterpret_cast<float*>(ws);
   int* chunk_off = reinterpret_cast<int*>(partial + static_cast<size_t>(max_chunks) * H);
   int ncol = H / 4;
-  if (ncol > 256) ncol = 256;
+  if (ncol > 128) ncol = 128;  // 4 groups x ncol threads <= 512 (the kernels' launch bound)
   const size_t smem = static_cast<size_t>(4) * H * sizeof(float);
   if (smem > 48 * 1024) { set_last_error("embed_bwd_sorted: H=%d too wide", H); return MUSE_ERR_UNSUPPORTED; }
   embed_seg_plan_kernel<<<1, 1024, 0, s>>>(bounds, chunk_off, vocab);

@@ -12,7 +12,9 @@ replayed: the ~330 launches of a base-256 train step then cost one graph launch 
     loss = graphed(tokens, class_ids)        # copies the inputs into the static buffers and replays
 
 Rules (the usual ones of ``torch.cuda.graph``): fixed shapes, no host synchronisation inside ``fn``, random numbers from the
-default CUDA generator (graph-safe), optimizer created with ``capturable=True``.  Not for DDP steps (use the eager path).
+default CUDA generator (graph-safe), optimizer created with ``capturable=True``.  DDP steps: construct DDP on a side stream,
+set TORCH_NCCL_ASYNC_ERROR_HANDLING=0 before init_process_group, warm up >= 11 iterations and capture with
+``capture_error_mode="thread_local"`` (bench.py --ddp-graph 1 does exactly that; the NCCL bucket all-reduces become graph nodes).
 """
 from __future__ import annotations
 
@@ -22,7 +24,8 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, fn: Callable, example_inputs: Sequence[torch.Tensor], warmup: int = 3):
+    def __init__(self, fn: Callable, example_inputs: Sequence[torch.Tensor], warmup: int = 3,
+                 capture_error_mode: str = "global"):
         self.static_inputs = [t.clone() for t in example_inputs]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -31,7 +34,7 @@ class GraphedStep:
                 fn(*self.static_inputs)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.static_output = fn(*self.static_inputs)
 
     def __call__(self, *inputs):

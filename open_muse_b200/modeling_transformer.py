@@ -237,6 +237,7 @@ class _LayerSpec:
         self.eps, self.rms, self.normformer, self.cross = eps, rms, normformer, cross
         self.Skv, self.E = Skv, E
         self.enc_op = enc_op  # bf16 copy of the (projected, fp32) encoder states used as the K/V GEMM operand
+        self.train = torch.is_grad_enabled()  # Function.forward always runs with grad mode off: record the caller's mode
         self.w = w  # dict of packed bf16 weights for this layer
         self.scale = 1.0 / math.sqrt(H // nh)
 
@@ -271,7 +272,7 @@ class _LayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, enc, spec, *params):
         s = spec
-        grad = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward)
+        grad = s.train and any(ctx.needs_input_grad)  # nothing is saved (no statistics written) under no_grad
         it = iter(params)
         w_attn_ln, _, _, _, _ = next(it), next(it), next(it), next(it), next(it)
         w_post = next(it) if s.normformer else None
@@ -416,6 +417,7 @@ class _HeadSpec:
         # inference only: compute just the first n_cols logit columns (generate2 reads the codebook_size columns of a
         # vocab_size-wide head, reference :1417 -- the other half of that GEMM would be thrown away)
         self.n_cols = n_cols
+        self.train = torch.is_grad_enabled()
 
 
 class _HeadFn(torch.autograd.Function):
@@ -424,7 +426,7 @@ class _HeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, labels, spec, *params):
         s = spec
-        grad = any(ctx.needs_input_grad)  # (grad mode is always off inside Function.forward)
+        grad = s.train and any(ctx.needs_input_grad)  # nothing is saved (no statistics written) under no_grad
         it = iter(params)
         w_enc = next(it) if s.use_enc_ln else None
         if s.use_mlm:

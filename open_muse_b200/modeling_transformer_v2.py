@@ -413,11 +413,9 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
             # training: one autograd Function for the whole network (uvit_v2_train.py)
             if self.training and (c.hidden_dropout > 0.0 or c.attention_dropout > 0.0):
                 raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: dropout > 0 in training mode is not implemented")
-            import os
-
             from . import uvit_v2_train as T
 
-            if os.environ.get("MUSE_B200_UVIT_TRAIN", "blocks") == "mono":  # one Function for the whole network (cross-check)
+            if getattr(self, "_single_train_function", False):  # private test hook: one Function for the whole network
                 padded, loss = T.UViTTrainFn.apply(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels,
                                                    label_smoothing, loss_weight, *self.parameters())
             else:  # default: one Function per block, so parameter gradients appear during backward (DDP overlap)

@@ -18,10 +18,6 @@ EPI_BF16, EPI_F32, EPI_ATOMIC_F32, EPI_RESADD_F32 = 0, 1, 2, 3
 _state = {"device": None, "launches": 0}
 
 
-def gemm_backend() -> int:
-    return 1 if os.environ.get("MUSE_B200_GEMM", "tcgen05") == "mma" else 0
-
-
 def launches() -> int:
     """Number of libmuse_b200 kernel-launching calls made so far (bench.py's gpu_launches)."""
     return _state["launches"]
@@ -83,7 +79,7 @@ def gemm(a, b, c, M, N, K, lda, ldb, ldc, a_mn=0, b_mn=0, epi=EPI_BF16, res=None
     if _prof["on"]:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _call("muse_gemm_bf16", _p(a), _p(b), _p(c), _p(res), M, N, K, lda, ldb, ldc, a_mn, b_mn, epi, gemm_backend(), st)
+    _call("muse_gemm_bf16", _p(a), _p(b), _p(c), _p(res), M, N, K, lda, ldb, ldc, a_mn, b_mn, epi, st)
     if _prof["on"]:
         e1.record()
         _prof["events"].append((e0, e1, 2.0 * M * N * K))

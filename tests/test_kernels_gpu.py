@@ -30,11 +30,9 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("backend", ["tcgen05", "mma"])
 @pytest.mark.parametrize("majors", [(0, 0), (0, 1), (1, 1), (1, 0)])
 @pytest.mark.parametrize("shape", GEMM_SHAPES)
-def test_gemm_bf16_out(monkeypatch, backend, majors, shape):
-    monkeypatch.setenv("MUSE_B200_GEMM", backend)
+def test_gemm_bf16_out(majors, shape):
     M, N, K = shape
     a_mn, b_mn = majors
     A = _rand((K, M) if a_mn else (M, K), 1)
@@ -47,11 +45,15 @@ def test_gemm_bf16_out(monkeypatch, backend, majors, shape):
     assert _rel(C[:, :N], ref) < 6e-3  # bf16 output rounding (2^-9 relative per element)
     if ldc > N:
         assert bool((C[:, N:] == 7.0).all())  # pad columns untouched
+    # independent on-device cross-check: the first-generation mma.sync kernel (tests/xcheck, not in the product library)
+    from tests import xcheck
+
+    C2 = torch.full((M, ldc), 7.0, dtype=torch.bfloat16, device=DEV)
+    xcheck.gemm(A, B, C2, M, N, K, A.stride(0), B.stride(0), ldc, a_mn, b_mn, ops.EPI_BF16)
+    assert _rel(C[:, :N], C2[:, :N]) < 3e-3  # same fp32 products, different accumulation order, bf16 output rounding
 
 
-@pytest.mark.parametrize("backend", ["tcgen05", "mma"])
-def test_gemm_epilogues(monkeypatch, backend):
-    monkeypatch.setenv("MUSE_B200_GEMM", backend)
+def test_gemm_epilogues():
     M, N, K = 384, 320, 192
     A, B = _rand((M, K), 3), _rand((N, K), 4)
     ref = A.float() @ B.float().t()
@@ -192,6 +194,14 @@ def test_attention_fwd_bwd(B, nh, Sq, Skv):
     assert _rel(dq.reshape(B, Sq, nh, 64).transpose(1, 2), qr.grad) < 1.5e-2
     assert _rel(dk.reshape(B, Skv, nh, 64).transpose(1, 2), kr.grad) < 1.5e-2
     assert _rel(dv.reshape(B, Skv, nh, 64).transpose(1, 2), vr.grad) < 1.5e-2
+    # independent on-device cross-check: the first-generation mma.sync attention kernels (tests/xcheck)
+    from tests import xcheck
+
+    o2, lse2 = xcheck.attn_fwd(q, k, v, B, nh, Sq, Skv, scale)
+    assert _rel(o, o2) < 8e-3 and _rel(lse, lse2) < 1e-4
+    dq2, dk2, dv2 = torch.empty_like(dq), torch.empty_like(dk.contiguous()), torch.empty_like(dv.contiguous())
+    xcheck.attn_bwd(q, k, v, o2, do, lse2, dq2, dk2, dv2, B, nh, Sq, Skv, scale)
+    assert _rel(dq, dq2) < 2e-2 and _rel(dk, dk2) < 2e-2 and _rel(dv, dv2) < 2e-2
 
 
 @pytest.mark.parametrize("n,ncodes,D", [(512, 1024, 256), (300, 128, 64), (1, 64, 16), (4096, 1024, 256)])

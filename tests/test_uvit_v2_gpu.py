@@ -358,16 +358,16 @@ def test_micro_uvit_v2_loss_weight_training(golden):
 
 def test_uvit_v2_block_functions_match_whole_network_function(golden, monkeypatch):
     """The per-block autograd Functions (default: gradients appear during backward, DDP overlap) and the single
-    whole-network Function (MUSE_B200_UVIT_TRAIN=mono) run the same kernels: loss identical, gradients equal up to the
+    whole-network Function (private ``_single_train_function`` test hook) run the same kernels: loss identical, gradients equal up to the
     summation order of the shared accumulators."""
     g = golden("micro_uvit_v2.pt")
     args = [g[k].to(DEV) for k in ("input_ids", "encoder_hidden_states", "cond_embeds", "micro_conds")]
     grads, losses = {}, {}
     for mode in ("blocks", "mono"):
-        monkeypatch.setenv("MUSE_B200_UVIT_TRAIN", mode)
         m = MaskGiTUViT_v2(**g["config"])
         m.load_state_dict(g["state_dict"])
         m.to(DEV).train()
+        m._single_train_function = mode == "mono"
         with torch.autocast("cuda", dtype=torch.bfloat16):
             _, loss = m(*args, labels=g["labels"].to(DEV), label_smoothing=0.1)
         loss.backward()

@@ -7,8 +7,9 @@
 // [tokens, 3H] QKV projection (strided per head) and writes [tokens, H] context directly.
 // Used for self-attention (kv_len = S = 257/256/1024) and cross-attention (kv_len = 77, :886-899).
 //
-// Round-1 implementation uses mma.sync.m16n8k16 bf16 tensor-core tiles (attention core is ~5.7 % of
-// the step FLOPs at the base config); the tcgen05/TMEM version is the planned upgrade.
+// TEST-ONLY: the first-generation mma.sync.m16n8k16 implementation, kept as an independent on-device cross-check of the
+// product's tcgen05 kernels (open_muse_b200/csrc/attention_tc.cu).  Built into tests/xcheck/libmuse_b200_xcheck.so,
+// never into libmuse_b200.so.
 #include <stdlib.h>
 #include <string.h>
 
@@ -522,47 +523,13 @@ int check_strides(const char* who, int hd, int a, int b, int c) {
 
 }  // namespace
 
-// tcgen05 kernels (attention_tc.cu)
-int attn_fwd_tc(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, float,
-                cudaStream_t, int*);
-int attn_bwd_dq_tc(const void*, const void*, const void*, const void*, const float*, float*, void*, int, int, int, int,
-                   int, int, int, int, int, float, cudaStream_t, int*);
-int attn_bwd_dkdv_tc(const void*, const void*, const void*, const void*, const float*, const float*, void*, void*, int,
-                     int, int, int, int, int, int, int, int, int, float, cudaStream_t, int*);
-
-// CUDA-core kernels for a few ragged rows (attention_rows.cu)
-bool attn_rows_ok(int nrows);
-int attn_fwd_rows(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, float,
-                  int, int, cudaStream_t);
-int attn_bwd_dq_rows(const void*, const void*, const void*, const void*, const float*, float*, void*, int, int, int,
-                     int, int, int, int, int, int, float, int, int, cudaStream_t);
-int attn_bwd_dkdv_rows(const void*, const void*, const void*, const void*, const float*, const float*, void*, void*,
-                       int, int, int, int, int, int, int, int, int, int, float, int, int, cudaStream_t);
-
-static bool use_tc_attention() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MUSE_B200_ATTN");
-    v = (e && strcmp(e, "legacy") == 0) ? 0 : 1;
-  }
-  return v == 1;
-}
-
-// Full 128-row tiles of the owned dimension run on the tcgen05 kernels; the ragged remainder (and everything when
-// MUSE_B200_ATTN=legacy) runs on the mma.sync kernels above.
-int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv, int hd,
+// TEST-ONLY cross-check library (tests/xcheck): the mma.sync kernels above behind the product's attention contract.
+int attn_fwd_legacy(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv, int hd,
              int q_rs, int k_rs, int v_rs, int o_rs, float scale, cudaStream_t s) {
   if (B <= 0 || Sq <= 0 || Skv <= 0) return MUSE_OK;
   int rc = check_strides("attn_fwd", hd, q_rs | o_rs, k_rs, v_rs);
   if (rc) return rc;
-  int done = 0;
-  if (use_tc_attention()) {
-    rc = attn_fwd_tc(q, k, v, o, lse, B, nh, Sq, Skv, q_rs, k_rs, v_rs, o_rs, scale, s, &done);
-    if (rc) return rc;
-  }
-  if (done >= Sq) return MUSE_OK;
-  if (done > 0 && attn_rows_ok(Sq - done))
-    return attn_fwd_rows(q, k, v, o, lse, B, nh, Sq, Skv, q_rs, k_rs, v_rs, o_rs, scale, done, Sq - done, s);
+  const int done = 0;
   AttnPtrs P;
   P.q = reinterpret_cast<const bf16*>(q); P.k = reinterpret_cast<const bf16*>(k); P.v = reinterpret_cast<const bf16*>(v);
   P.q_rs = q_rs; P.k_rs = k_rs; P.v_rs = v_rs;
@@ -573,7 +540,7 @@ int attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, i
   return check_launch("attn_fwd");
 }
 
-int attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+int attn_bwd_legacy(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
              float* dvec, void* dq, void* dk, void* dv, int B, int nh, int Sq, int Skv, int hd, int q_rs, int k_rs,
              int v_rs, int o_rs, int do_rs, int dq_rs, int dk_rs, int dv_rs, float scale, cudaStream_t s) {
   if (B <= 0 || Sq <= 0 || Skv <= 0) return MUSE_OK;
@@ -584,17 +551,8 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   P.q = reinterpret_cast<const bf16*>(q); P.k = reinterpret_cast<const bf16*>(k); P.v = reinterpret_cast<const bf16*>(v);
   P.q_rs = q_rs; P.k_rs = k_rs; P.v_rs = v_rs;
   P.q_bs = static_cast<long long>(Sq) * q_rs; P.k_bs = static_cast<long long>(Skv) * k_rs; P.v_bs = static_cast<long long>(Skv) * v_rs;
-  const bool tc = use_tc_attention();
-  int done_q = 0, done_kv = 0;
-  if (tc) {
-    rc = attn_bwd_dq_tc(q, k, v, d_o, lse, dvec, dq, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dq_rs, scale, s, &done_q);
-    if (rc) return rc;
-  }
-  if (done_q > 0 && attn_rows_ok(Sq - done_q)) {
-    rc = attn_bwd_dq_rows(q, k, v, d_o, lse, dvec, dq, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dq_rs, scale, done_q,
-                          Sq - done_q, s);
-    if (rc) return rc;
-  } else if (done_q < Sq) {
+  const int done_q = 0, done_kv = 0;
+  {
     const int blk0 = done_q / BQ;
     attn_bwd_dq_kernel<<<dim3(ceil_div(Sq, BQ) - blk0, nh, B), 128, 0, s>>>(
         P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,
@@ -602,16 +560,7 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
     rc = check_launch("attn_bwd_dq");
     if (rc) return rc;
   }
-  if (tc) {
-    rc = attn_bwd_dkdv_tc(q, k, v, d_o, lse, dvec, dk, dv, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dk_rs, dv_rs, scale,
-                          s, &done_kv);
-    if (rc) return rc;
-  }
-  if (done_kv > 0 && attn_rows_ok(Skv - done_kv)) {
-    rc = attn_bwd_dkdv_rows(q, k, v, d_o, lse, dvec, dk, dv, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dk_rs, dv_rs,
-                            scale, done_kv, Skv - done_kv, s);
-    if (rc) return rc;
-  } else if (done_kv < Skv) {
+  {
     const int blk0 = done_kv / BKV;
     attn_bwd_dkdv_kernel<<<dim3(ceil_div(Skv, BKV) - blk0, nh, B), 128, 0, s>>>(
         P, reinterpret_cast<const bf16*>(d_o), static_cast<long long>(Sq) * do_rs, do_rs, lse, dvec,

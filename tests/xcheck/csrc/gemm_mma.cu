@@ -1,6 +1,6 @@
 // Legacy-tensor-core (mma.sync m16n8k16) bf16 GEMM with the same contract as gemm_tcgen05().
-// It exists only as an on-device cross-check for the tcgen05 kernel (tests compare the two,
-// MUSE_B200_GEMM=mma selects it for bring-up); it is not the product path.
+// TEST-ONLY: an independent on-device cross-check for the product's tcgen05 kernel (tests compare the two).  Built into
+// tests/xcheck/libmuse_b200_xcheck.so, never into libmuse_b200.so.
 #include "common.cuh"
 
 namespace muse {
