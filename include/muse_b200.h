@@ -251,6 +251,10 @@ int muse_split_bf16_nhwc(const float* x, void* hi, void* lo, int B, int H, int W
 int muse_im2col_split_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int Cin, int ksize, void* stream);
 /* F.avg_pool2d(2,2) (:112): x [B,2Ho,2Wo,C] -> y [B,Ho,Wo,C]. */
 int muse_avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, void* stream);
+/* Decoder output (fp32, any layout; the caller passes the NHWC tensor) -> display bytes with the reference's recipe
+ * (muse/pipeline_muse.py:245-252): byte = (uint8)(255 * ((clip(2x - 1, -1, 1) + 1) / 2)), same fp32 operation order. */
+int muse_image_to_uint8(const float* x, unsigned char* y, long long n, void* stream);
+
 /* [B, rows, cols] -> [B, cols, rows] (NCHW <-> NHWC at the model boundary). */
 int muse_transpose_batched(const float* in, float* out, int B, int rows, int cols, void* stream);
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "muse_im2col_split_nhwc": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "muse_split_bf16_nhwc": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "muse_avgpool2_nhwc": (c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "muse_image_to_uint8": (c_int, [_P, _P, _L, _P]),
     "muse_transpose_batched": (c_int, [_P, _P, _I, _I, _I, _P]),
 }
 

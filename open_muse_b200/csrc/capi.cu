@@ -69,6 +69,7 @@ int split_bf16_nhwc(const float*, void*, void*, int, int, int, int, int, cudaStr
 int im2col_split_nhwc(const float*, void*, void*, int, int, int, int, int, cudaStream_t);
 long long gn_workspace_floats(int, int, int);
 int avgpool2_nhwc(const float*, float*, int, int, int, int, cudaStream_t);
+int image_to_uint8(const float*, unsigned char*, long long, cudaStream_t);
 int transpose_batched(const float*, float*, int, int, int, cudaStream_t);
 
 }  // namespace muse
@@ -276,6 +277,7 @@ int muse_im2col_split_nhwc(const float* x, void* hi, void* lo, int B, int H, int
 int muse_avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, void* stream) {
   return avgpool2_nhwc(x, y, B, Ho, Wo, C, ST(stream));
 }
+int muse_image_to_uint8(const float* x, unsigned char* y, long long n, void* stream) { return image_to_uint8(x, y, n, ST(stream)); }
 int muse_transpose_batched(const float* in, float* out, int B, int rows, int cols, void* stream) {
   return transpose_batched(in, out, B, rows, cols, ST(stream));
 }

@@ -380,6 +380,35 @@ int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, f
   return check_launch("gn_apply_silu");
 }
 
+// Decoder output -> display bytes with the reference's recipe (muse/pipeline_muse.py:245-252, quirk Q10), same fp32 operation
+// order so the bytes are identical: t = 2x - 1; t = clip(t, -1, 1); t = (t + 1) / 2; byte = (uint8)(255 * t)  (truncation).
+// Input is the decoder's native NHWC tensor, output HWC uint8 per image: the NCHW round trip of the reference
+// (decode -> permute(1, 2, 0) -> numpy) and the 4x larger fp32 device->host copy disappear.
+__global__ void __launch_bounds__(256)
+image_to_uint8_kernel(const float* __restrict__ x, unsigned char* __restrict__ y, long long n4) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  uchar4 o;
+  unsigned char* ob = reinterpret_cast<unsigned char*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float t = __fsub_rn(__fmul_rn(2.0f, f[k]), 1.0f);
+    t = fminf(fmaxf(t, -1.0f), 1.0f);
+    t = __fdiv_rn(__fadd_rn(t, 1.0f), 2.0f);
+    ob[k] = static_cast<unsigned char>(static_cast<int>(__fmul_rn(255.0f, t)));  // truncation toward zero, values in [0, 255]
+  }
+  *reinterpret_cast<uchar4*>(y + i * 4) = o;
+}
+
+int image_to_uint8(const float* x, unsigned char* y, long long n, cudaStream_t s) {
+  if (n <= 0) return MUSE_OK;
+  if (n % 4 != 0) { set_last_error("image_to_uint8: element count must be a multiple of 4"); return MUSE_ERR_INVALID; }
+  image_to_uint8_kernel<<<static_cast<unsigned>(ceil_div_ll(n / 4, 256)), 256, 0, s>>>(x, y, n / 4);
+  return check_launch("image_to_uint8");
+}
+
 int avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, cudaStream_t s) {
   if (C % 4 != 0) { set_last_error("avgpool: C must be a multiple of 4"); return MUSE_ERR_UNSUPPORTED; }
   const long long total = static_cast<long long>(B) * Ho * Wo * (C / 4);

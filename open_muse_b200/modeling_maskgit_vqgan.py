@@ -251,6 +251,15 @@ class MaskGitVQGAN(ModelMixin, ConfigMixin):
         return self.decode(self.quantize.get_codebook_entry(codebook_indices))
 
     @torch.no_grad()
+    def decode_code_uint8(self, codebook_indices):
+        """ids -> display bytes uint8 [B, H, W, 3] (HWC per image, what PIL wants): the decoder's native NHWC output goes
+        straight through the reference's clamp / truncation recipe on the device (pipeline_muse.py:245-252) -- no NCHW
+        round trip, a 4x smaller device->host copy.  Extension used by PipelineMuse for output_type="pil"."""
+        z_q = self.quantize.get_codebook_entry(codebook_indices)
+        with ops.conv_precision(self.conv_precision):
+            return ops.image_to_uint8(self.decoder.run(ops.to_nhwc(z_q.float().contiguous())))
+
+    @torch.no_grad()
     def get_soft_code(self, pixel_values, temp=1.0, stochastic=False):
         return self.quantize.get_soft_code_nhwc(self._encode_nhwc(pixel_values), temp, stochastic)
 

@@ -813,3 +813,12 @@ def to_nchw(x_nhwc):
     y = torch.empty(B, C, H, W, dtype=torch.float32, device=x_nhwc.device)
     _call("muse_transpose_batched", _p(x_nhwc), _p(y), B, H * W, C, st)
     return y
+
+
+def image_to_uint8(x):
+    """fp32 image tensor (any layout) -> uint8 with the reference's to_pil_image recipe, on the device."""
+    st = _prep(x)
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    _call("muse_image_to_uint8", _p(x), _p(y), x.numel(), st)
+    return y

@@ -118,10 +118,18 @@ class PipelineMuse:
         with torch.autocast("cuda", dtype=torch.bfloat16):
             tokens = self.transformer.generate2(timesteps=timesteps, temperature=temperature, generator=generator,
                                                 noise_schedule=get_mask_chedule(noise_schedule), **kwargs)
-        images = self.vae.decode_code(tokens)
+        return self._decode(tokens, output_type)
+
+    def _decode(self, tokens, output_type):
+        """ids -> PIL images (or the fp32 tensor for output_type="pt").  Tokenizers with a fused uint8 path hand back display
+        bytes from the device; others go through to_pil_image on the host like the reference."""
         if output_type == "pt":
-            return images
-        return [self.to_pil_image(img) for img in images]
+            return self.vae.decode_code(tokens)
+        if hasattr(self.vae, "decode_code_uint8"):
+            from PIL import Image
+
+            return [Image.fromarray(a).convert("RGB") for a in self.vae.decode_code_uint8(tokens).cpu().numpy()]
+        return [self.to_pil_image(img) for img in self.vae.decode_code(tokens)]
 
     def _call_uvit_v2(self, prompt_embeds, pooled_embeds, negative_prompt_embeds, negative_pooled_embeds, timesteps,
                       noise_schedule, guidance_scale, guidance_schedule, temperature, num_images_per_prompt, generator,
@@ -298,7 +306,4 @@ class PipelineMuseInpainting(PipelineMuse):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             tokens = self.transformer.generate2(input_ids=image_tokens, timesteps=timesteps, temperature=temperature,
                                                 generator=generator, **kwargs)
-        images = self.vae.decode_code(tokens)
-        if output_type == "pt":
-            return images
-        return [self.to_pil_image(img) for img in images]
+        return self._decode(tokens, output_type)

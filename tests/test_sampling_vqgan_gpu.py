@@ -337,6 +337,26 @@ def test_pipeline_class_conditional_end_to_end():
     assert pt.shape == (1, 3, 32, 32)
 
 
+def test_decode_code_uint8_matches_reference_pil_recipe(golden):
+    """Device-side display bytes == the reference's host recipe (pipeline_muse.py:245-252) applied to the decoded tensor,
+    byte for byte, including out-of-range decoder values (the recipe clamps) and the truncation."""
+    from open_muse_b200 import MaskGitVQGAN, PipelineMuse
+
+    g = golden("micro_vqgan.pt")
+    m = MaskGitVQGAN(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    with torch.no_grad():
+        m.decoder.conv_out.bias.add_(torch.tensor([0.6, -0.4, 0.1]))  # push part of the output outside [0, 1]
+    m.to(DEV).eval()
+    ids = g["ids"].to(DEV)
+    got = m.decode_code_uint8(ids).cpu().numpy()
+    rec = m.decode_code(ids)
+    assert float(rec.max()) > 1.0 and float(rec.min()) < 0.0
+    pipe = PipelineMuse(vae=m, transformer=None, is_class_conditioned=True)
+    for i in range(rec.shape[0]):
+        assert np.array_equal(got[i], np.asarray(pipe.to_pil_image(rec[i])))
+
+
 def test_pipeline_inpainting_keeps_known_tokens():
     from open_muse_b200 import MaskGitTransformer, MaskGitVQGAN, PipelineMuseInpainting
 
