@@ -45,14 +45,12 @@ int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int 
                    int ldc, int a_mn, int b_mn, int epilogue, void* stream);
 
 /* Weight-gradient GEMM with a run-to-run reproducible result: C fp32 [M,N] = opA(A) * opB(B)^T split over K (= tokens) so
- * that the few output tiles fill the SMs; every split stores its partial tile into `ws`, the CTA finishing a tile last
- * sums the partials in split order and stores C (no zero fill of C needed, no atomics on C).  `counters` is an int array of
- * at least *n_counters entries that is zero before the first call; the kernel leaves it zero.  One (ws, counters) pair per
- * stream.  Replaces the autograd weight-gradient matmuls of every nn.Linear (muse/modeling_transformer.py:198-200,218,
+ * that the few output tiles fill the SMs; every split stores its partial tile into `ws` and a second kernel sums the
+ * partials in split order and stores C (no zero fill of C needed, no atomics on C).  One ws per stream.  Replaces the autograd weight-gradient matmuls of every nn.Linear (muse/modeling_transformer.py:198-200,218,
  * 789-798,980,984), which the reference's bf16 step computes reproducibly. */
-long long muse_gemm_splitk_workspace_bytes(int M, int N, int K, int* n_counters);
+long long muse_gemm_splitk_workspace_bytes(int M, int N, int K);
 int muse_gemm_bf16_splitk(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
-                          int a_mn, int b_mn, void* ws, long long ws_bytes, int* counters, void* stream);
+                          int a_mn, int b_mn, void* ws, long long ws_bytes, void* stream);
 
 /* fp32 -> bf16 weight packing: table_dev is a device array of n_entries
  * {const float* src; bf16* dst; int64 numel; int64 first_block} with 1024 elements per block.
@@ -63,11 +61,12 @@ int muse_cast_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 /* One pass over all parameters: AdamW (training/train_maskgit_imagenet.py:242-261,438 -- torch.optim.AdamW / apex FusedAdam,
  * decoupled weight decay, bias-corrected) + EMAModel.step of the UPDATED weights (muse/modeling_ema.py:89-126, same decay
  * schedule incl. warm-up / update_after_step / update_every) + the bf16 copy into the packed GEMM operand cache.
- * table_dev: device array of n_entries {float* p; const float* g; float* m; float* v; float* ema (nullable);
- * bf16* packed (nullable); int64 numel (multiple of 4); int64 first_block} with 1024 elements per block.
+ * entries_host: HOST array of n_entries {float* p; const float* g; float* m; float* v; float* ema (nullable);
+ * bf16* packed (nullable); int64 numel (multiple of 4); int64 reserved}: the table is passed to the kernels as launch
+ * arguments in chunks of 48 tensors (no device copy of it exists, so the call can be captured even when buffers moved).
  * step_dev (int64, steps taken so far) is incremented on the device and scal_dev (8 floats) receives the per-step scalars, so
  * the call is CUDA-graph capturable; lr_dev (nullable device float) overrides lr_host. */
-int muse_adamw_ema_step(const void* table_dev, int n_entries, long long total_blocks, float* scal_dev, long long* step_dev,
+int muse_adamw_ema_step(const void* entries_host, int n_entries, float* scal_dev, long long* step_dev,
                         const float* lr_dev, float lr_host, float beta1, float beta2, float eps, float weight_decay,
                         int ema_enabled, float ema_decay, float ema_min_decay, int ema_update_after_step,
                         int ema_update_every, int ema_use_warmup, float ema_inv_gamma, float ema_power, void* stream);

@@ -23,10 +23,10 @@ SIGNATURES = {
     "muse_set_device": (c_int, [_I]),
     "muse_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "muse_gemm_bf16": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "muse_gemm_splitk_workspace_bytes": (c_longlong, [_I, _I, _I, POINTER(c_int)]),
-    "muse_gemm_bf16_splitk": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P, _P]),
+    "muse_gemm_splitk_workspace_bytes": (c_longlong, [_I, _I, _I]),
+    "muse_gemm_bf16_splitk": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     "muse_pack_bf16": (c_int, [_P, _I, _L, _P]),
-    "muse_adamw_ema_step": (c_int, [_P, _I, _L, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _F, _I, _I, _I, _F, _F, _P]),
+    "muse_adamw_ema_step": (c_int, [_P, _I, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _F, _I, _I, _I, _F, _F, _P]),
     "muse_cast_bf16": (c_int, [_P, _P, _L, _P]),
     "muse_embed_fwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_embed_bwd": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -26,10 +26,10 @@ int check_launch(const char* what) {
 }
 
 // kernels (defined in the other translation units)
-int gemm_tcgen05(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t, void*, long long, int*);
-long long gemm_splitk_workspace_bytes(int, int, int, int*);
+int gemm_tcgen05(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t, void*, long long);
+long long gemm_splitk_workspace_bytes(int, int, int);
 int pack_bf16(const void*, int, long long, cudaStream_t);
-int adamw_ema_step(const void*, int, long long, float*, long long*, const float*, float, float, float, float, float, int, float, float, int, int, int, float, float, cudaStream_t);
+int adamw_ema_step(const void*, int, float*, long long*, const float*, float, float, float, float, float, int, float, float, int, int, int, float, float, cudaStream_t);
 int cast_bf16(const float*, void*, long long, cudaStream_t);
 int embed_fwd(const long long*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
 int embed_bwd(const long long*, const float*, float*, float*, int, int, int, int, cudaStream_t);
@@ -102,27 +102,24 @@ int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int 
                    int ldc, int a_mn, int b_mn, int epilogue, void* stream) {
   if (epilogue == MUSE_EPI_RESADD_F32 && res == nullptr) { set_last_error("gemm: RESADD epilogue needs res"); return MUSE_ERR_INVALID; }
   if (epilogue == MUSE_EPI_SPLITK_F32) { set_last_error("gemm: the deterministic split-K epilogue goes through muse_gemm_bf16_splitk"); return MUSE_ERR_INVALID; }
-  return gemm_tcgen05(A, B, C, res, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, ST(stream), nullptr, 0, nullptr);
+  return gemm_tcgen05(A, B, C, res, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, ST(stream), nullptr, 0);
 }
 
-long long muse_gemm_splitk_workspace_bytes(int M, int N, int K, int* n_counters) {
-  return gemm_splitk_workspace_bytes(M, N, K, n_counters);
-}
+long long muse_gemm_splitk_workspace_bytes(int M, int N, int K) { return gemm_splitk_workspace_bytes(M, N, K); }
 int muse_gemm_bf16_splitk(const void* A, const void* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
-                          int a_mn, int b_mn, void* ws, long long ws_bytes, int* counters, void* stream) {
-  return gemm_tcgen05(A, B, C, nullptr, M, N, K, lda, ldb, ldc, a_mn, b_mn, MUSE_EPI_SPLITK_F32, ST(stream), ws, ws_bytes,
-                      counters);
+                          int a_mn, int b_mn, void* ws, long long ws_bytes, void* stream) {
+  return gemm_tcgen05(A, B, C, nullptr, M, N, K, lda, ldb, ldc, a_mn, b_mn, MUSE_EPI_SPLITK_F32, ST(stream), ws, ws_bytes);
 }
 
 int muse_pack_bf16(const void* table_dev, int n_entries, long long total_blocks, void* stream) {
   return pack_bf16(table_dev, n_entries, total_blocks, ST(stream));
 }
 int muse_cast_bf16(const float* src, void* dst, long long n, void* stream) { return cast_bf16(src, dst, n, ST(stream)); }
-int muse_adamw_ema_step(const void* table_dev, int n_entries, long long total_blocks, float* scal_dev, long long* step_dev,
+int muse_adamw_ema_step(const void* entries_host, int n_entries, float* scal_dev, long long* step_dev,
                         const float* lr_dev, float lr_host, float beta1, float beta2, float eps, float weight_decay,
                         int ema_enabled, float ema_decay, float ema_min_decay, int ema_update_after_step,
                         int ema_update_every, int ema_use_warmup, float ema_inv_gamma, float ema_power, void* stream) {
-  return adamw_ema_step(table_dev, n_entries, total_blocks, scal_dev, step_dev, lr_dev, lr_host, beta1, beta2, eps,
+  return adamw_ema_step(entries_host, n_entries, scal_dev, step_dev, lr_dev, lr_host, beta1, beta2, eps,
                         weight_decay, ema_enabled, ema_decay, ema_min_decay, ema_update_after_step, ema_update_every,
                         ema_use_warmup, ema_inv_gamma, ema_power, ST(stream));
 }

@@ -27,9 +27,10 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 
-// EPI_SPLITK_F32: deterministic split-K.  Every split stores its fp32 partial tile into a workspace; the CTA that
-// finishes a tile last (ticket counter) sums the partials in split order and STORES the result, so the output needs no
-// zero fill and is bit-identical from run to run (the atomic variant is order-dependent).
+// EPI_SPLITK_F32: deterministic split-K.  Every split stores its fp32 partial tile into a workspace and a second, fully
+// parallel kernel sums the partials in split order and STORES the result, so the output needs no zero fill and is
+// bit-identical from run to run (the atomic variant is order-dependent).  (A first version let the CTA finishing a tile
+// last do the reduction: ~400 dependent L2 loads per thread at the tail of a 60 us GEMM made it 2x slower.)
 enum Epi { EPI_BF16 = 0, EPI_F32 = 1, EPI_ATOMIC_F32 = 2, EPI_RESADD_F32 = 3, EPI_SPLITK_F32 = 4 };
 
 template <int BN>
@@ -52,7 +53,6 @@ struct GemmParams {
   int ldc;
   int num_m, num_n, num_kb, kb_per_split, splits;
   float* ws;      // EPI_SPLITK_F32: [splits][num_m * num_n][BM * BN] fp32 partial tiles
-  int* counters;  // EPI_SPLITK_F32: [num_m * num_n] tickets, zero on entry, zero again on exit
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -70,7 +70,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full = bars + 2 * C_::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  int* ticket_sh = reinterpret_cast<int*>(tmem_holder) + 2;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -301,40 +300,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-      if (EPI == EPI_SPLITK_F32 && partial) {
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 128) *ticket_sh = atomicAdd(&p.counters[tile_mn], 1);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const bool last = (*ticket_sh == p.splits - 1);
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone has read the ticket before the next tile rewrites it
-        if (last) {
-          __threadfence();
-          if (threadIdx.x == 128) p.counters[tile_mn] = 0;
-          const float* ws0 = p.ws + static_cast<size_t>(tile_mn) * (BM * BN);
-          const size_t split_stride = static_cast<size_t>(tiles_mn) * (BM * BN);
-#pragma unroll 1
-          for (int c = 0; c < BN; c += 32) {
-            if (n0 + c >= p.N) break;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = (lane >> 3) + 4 * it, ch = lane & 7;
-              const int grow = row_base + rr, gcol = n0 + c + ch * 4;
-              if (grow < p.M && gcol < p.N) {
-                const float* src = ws0 + static_cast<size_t>(ew * 32 + rr) * BN + c + ch * 4;
-                float4 a = __ldcg(reinterpret_cast<const float4*>(src));
-                for (int sp = 1; sp < p.splits; ++sp) {
-                  const float4 b = __ldcg(reinterpret_cast<const float4*>(src + sp * split_stride));
-                  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-                }
-                float* dst = reinterpret_cast<float*>(p.C) + static_cast<size_t>(grow) * p.ldc + gcol;
-                if (gcol + 4 <= p.N) *reinterpret_cast<float4*>(dst) = a;
-                else { const float f[4] = {a.x, a.y, a.z, a.w}; for (int k = 0; k < 4; ++k) if (gcol + k < p.N) dst[k] = f[k]; }
-              }
-            }
-          }
-        }
-      }
     }
   }
 
@@ -344,6 +309,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C_::kTmemCols);
   }
+}
+
+// C[r][c..c+3] = sum over splits (ascending) of the partial tiles; one thread per float4 of the output
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc, int num_n, int tiles_mn,
+                     int bn, int splits) {
+  const int n4 = (N + 3) >> 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= static_cast<long long>(M) * n4) return;
+  const int r = static_cast<int>(idx / n4), c = static_cast<int>(idx % n4) * 4;
+  const int tile = (r / BM) * num_n + c / bn;
+  const float* src = ws + static_cast<size_t>(tile) * (BM * bn) + static_cast<size_t>(r % BM) * bn + (c % bn);
+  const size_t stride = static_cast<size_t>(tiles_mn) * (BM * bn);
+  float4 a = *reinterpret_cast<const float4*>(src);
+  for (int sp = 1; sp < splits; ++sp) {
+    const float4 b = *reinterpret_cast<const float4*>(src + sp * stride);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  float* dst = C + static_cast<size_t>(r) * ldc + c;
+  if (c + 4 <= N) *reinterpret_cast<float4*>(dst) = a;
+  else { const float f[4] = {a.x, a.y, a.z, a.w}; for (int k = 0; k < 4 && c + k < N; ++k) dst[k] = f[k]; }
 }
 
 // ------------------------------------------------------------------ host side
@@ -512,16 +498,15 @@ static void split_plan(int M, int N, int K, int* num_m, int* num_n, int* num_kb,
   *splits = ceil_div(*num_kb, *kb_per_split);
 }
 
-long long gemm_splitk_workspace_bytes(int M, int N, int K, int* n_counters) {
+long long gemm_splitk_workspace_bytes(int M, int N, int K) {
   int num_m, num_n, num_kb, kbs, splits, bn;
   split_plan(M, N, K, &num_m, &num_n, &num_kb, &kbs, &splits, &bn);
-  if (n_counters) *n_counters = num_m * num_n;
   if (splits <= 1) return 0;
   return static_cast<long long>(splits) * num_m * num_n * BM * bn * 4;
 }
 
 int gemm_tcgen05(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
-                 int ldc, int a_mn, int b_mn, int epi, cudaStream_t stream, void* ws, long long ws_bytes, int* counters) {
+                 int ldc, int a_mn, int b_mn, int epi, cudaStream_t stream, void* ws, long long ws_bytes) {
   if (M <= 0 || N <= 0 || K <= 0) return MUSE_OK;
   if (epi == EPI_BF16 ? (ldc % 8 != 0) : (ldc % 4 != 0)) {
     set_last_error("gemm: ldc=%d must be a multiple of %d", ldc, epi == EPI_BF16 ? 8 : 4);
@@ -549,21 +534,23 @@ int gemm_tcgen05(const void* A, const void* B, void* C, const float* res, int M,
   p.splits = 1;
   p.kb_per_split = p.num_kb;
   p.ws = reinterpret_cast<float*>(ws);
-  p.counters = counters;
   if (epi == EPI_ATOMIC_F32 || epi == EPI_SPLITK_F32) {
     int num_m, num_n, num_kb, bn;
     split_plan(M, N, K, &num_m, &num_n, &num_kb, &p.kb_per_split, &p.splits, &bn);
     if (epi == EPI_SPLITK_F32 && p.splits > 1) {
       const long long need = static_cast<long long>(p.splits) * p.num_m * p.num_n * BM * BN * 4;
-      if (ws == nullptr || counters == nullptr || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) {
-        set_last_error("gemm: deterministic split-K needs a 16B-aligned workspace of %lld bytes (got %lld) and a counter array",
-                       need, ws_bytes);
+      if (ws == nullptr || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) {
+        set_last_error("gemm: deterministic split-K needs a 16B-aligned workspace of %lld bytes (got %lld)", need, ws_bytes);
         return MUSE_ERR_INVALID;
       }
     }
   }
-  if (BN == 256) return launch_major<256>(a_mn, b_mn, epi, ta, tb, p, stream);
-  return launch_major<128>(a_mn, b_mn, epi, ta, tb, p, stream);
+  rc = (BN == 256) ? launch_major<256>(a_mn, b_mn, epi, ta, tb, p, stream) : launch_major<128>(a_mn, b_mn, epi, ta, tb, p, stream);
+  if (rc || epi != EPI_SPLITK_F32 || p.splits <= 1) return rc;
+  const long long n_out4 = static_cast<long long>(M) * ((N + 3) / 4);
+  splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div_ll(n_out4, 256)), 256, 0, stream>>>(
+      p.ws, reinterpret_cast<float*>(C), M, N, ldc, p.num_n, p.num_m * p.num_n, BN, p.splits);
+  return check_launch("gemm splitk reduce");
 }
 
 }  // namespace muse

@@ -59,15 +59,24 @@ __global__ void adamw_prepare_kernel(float* scal, long long* step, const float* 
   scal[5] = static_cast<float>(decay);
 }
 
+// The parameter table travels in the kernel ARGUMENTS (like ATen's multi_tensor_apply), not in device memory: no
+// host->device copy exists, so the step can be captured in a CUDA graph even when the gradient buffers move between the
+// eager warm-up and the capture (the graph bakes the arguments of that launch).
+constexpr int kOptChunk = 48;  // 48 x 64 B of entries + hyper-parameters stay under the 4 KB kernel-parameter limit
+struct OptChunk {
+  OptEntry e[kOptChunk];
+  int n;
+};
+
 __global__ void __launch_bounds__(256)
-adamw_ema_pack_kernel(const OptEntry* __restrict__ table, int n_entries, const float* __restrict__ scal, OptHyper h) {
+adamw_ema_pack_kernel(const __grid_constant__ OptChunk chunk, const float* __restrict__ scal, const OptHyper h) {
   const long long blk = blockIdx.x;
-  int lo = 0, hi = n_entries - 1;
+  int lo = 0, hi = chunk.n - 1;
   while (lo < hi) {  // last entry with first_block <= blk
     const int mid = (lo + hi + 1) >> 1;
-    if (table[mid].first_block <= blk) lo = mid; else hi = mid - 1;
+    if (chunk.e[mid].first_block <= blk) lo = mid; else hi = mid - 1;
   }
-  const OptEntry e = table[lo];
+  const OptEntry& e = chunk.e[lo];
   const long long i = ((blk - e.first_block) * 256 + threadIdx.x) * 4;
   if (i >= e.numel) return;
   const float inv_bc1 = scal[1], inv_sqrt_bc2 = scal[2], lr = scal[3], omd = scal[4];
@@ -106,14 +115,14 @@ adamw_ema_pack_kernel(const OptEntry* __restrict__ table, int n_entries, const f
 
 }  // namespace
 
-// table_dev: device array of n_entries {p, g, m, v, ema, packed, numel, first_block} (1024 elements per block);
-// hyper: 12 floats/ints as OptHyper; scal_dev: 8 floats; step_dev: one int64 (number of optimizer steps taken so far);
-// lr_dev: nullable device float (graph-capturable learning-rate schedule) else lr_host is used.
-int adamw_ema_step(const void* table_dev, int n_entries, long long total_blocks, float* scal_dev, long long* step_dev,
+// entries_host: HOST array of n_entries {p, g, m, v, ema, packed, numel, unused} (8 x int64 each; device pointers inside);
+// scal_dev: 8 floats; step_dev: one int64 (number of optimizer steps taken so far); lr_dev: nullable device float
+// (graph-capturable learning-rate schedule) else lr_host is used.
+int adamw_ema_step(const void* entries_host, int n_entries, float* scal_dev, long long* step_dev,
                    const float* lr_dev, float lr_host, float beta1, float beta2, float eps, float weight_decay,
                    int ema_enabled, float ema_decay, float ema_min_decay, int ema_update_after_step, int ema_update_every,
                    int ema_use_warmup, float ema_inv_gamma, float ema_power, cudaStream_t s) {
-  if (n_entries <= 0 || total_blocks <= 0) return MUSE_OK;
+  if (n_entries <= 0) return MUSE_OK;
   OptHyper h;
   h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
   h.ema_enabled = ema_enabled; h.ema_decay = ema_decay; h.ema_min_decay = ema_min_decay;
@@ -122,9 +131,22 @@ int adamw_ema_step(const void* table_dev, int n_entries, long long total_blocks,
   adamw_prepare_kernel<<<1, 32, 0, s>>>(scal_dev, step_dev, lr_dev, lr_host, h);
   int rc = check_launch("adamw_prepare");
   if (rc) return rc;
-  adamw_ema_pack_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, s>>>(reinterpret_cast<const OptEntry*>(table_dev),
-                                                                           n_entries, scal_dev, h);
-  return check_launch("adamw_ema_pack");
+  const OptEntry* all = reinterpret_cast<const OptEntry*>(entries_host);
+  for (int base = 0; base < n_entries; base += kOptChunk) {
+    OptChunk chunk;
+    chunk.n = n_entries - base < kOptChunk ? n_entries - base : kOptChunk;
+    long long blocks = 0;
+    for (int i = 0; i < chunk.n; ++i) {
+      chunk.e[i] = all[base + i];
+      if (chunk.e[i].numel % 4 != 0 || chunk.e[i].numel <= 0) { set_last_error("adamw: numel must be a positive multiple of 4"); return MUSE_ERR_INVALID; }
+      chunk.e[i].first_block = blocks;
+      blocks += (chunk.e[i].numel + 1023) / 1024;
+    }
+    adamw_ema_pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(chunk, scal_dev, h);
+    rc = check_launch("adamw_ema_pack");
+    if (rc) return rc;
+  }
+  return MUSE_OK;
 }
 
 }  // namespace muse

@@ -197,6 +197,7 @@ class _PackedWeights:
                         self.slow.append((p, dst))
                     r += p.shape[0]
             self.n_entries, self.n_blocks = len(entries), block
+            self.dst_of = {e[0]: e[1] for e in entries}  # parameter pointer -> bf16 copy (used by FusedAdamW)
             self.table = torch.tensor(entries, dtype=torch.int64).to(dev) if entries else None
             self.layout_key = layout_key
         if self.table is not None:

@@ -47,7 +47,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-_KERNELS_PER_CALL = {"muse_adamw_ema_step": 2, "muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_embed_bwd_sorted": 4, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
+_KERNELS_PER_CALL = {"muse_gemm_bf16_splitk": 2, "muse_adamw_ema_step": 4, "muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_embed_bwd_sorted": 4, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
                      "muse_groupnorm_silu_nhwc": 3, "muse_grn_fwd": 3, "muse_grn_bwd": 3,
                      "muse_dwconv3x3_norm_bwd": 2}
 _prof = {"on": False, "events": []}
@@ -120,31 +120,21 @@ def linear_wgrad(dy, x, dw):
     return gemm(dy, x, dw, N, K, T, dy.stride(0), x.stride(0), dw.stride(0), 1, 1, EPI_ATOMIC_F32)
 
 
-_splitk_counters = {}
-
-
 def linear_wgrad_det(dy, x, out=None):
-    """dw[N,K] = dy[T,N]^T @ x[T,K], run-to-run bit-identical: split-K partial tiles go to a workspace and the CTA that
-    finishes a tile last sums them in split order and stores dw (no zero fill, no atomics on dw)."""
-    import ctypes
-
+    """dw[N,K] = dy[T,N]^T @ x[T,K], run-to-run bit-identical: split-K partial tiles go to a workspace and an ordered
+    reduction kernel sums them in split order and stores dw (no zero fill, no atomics on dw)."""
     st = _prep(dy)
     T, N = dy.shape
     K = x.shape[1]
     dev = dy.device
     dw = out if out is not None else torch.empty(N, K, dtype=torch.float32, device=dev)
-    ncnt = ctypes.c_int(0)
-    need = _lib.load().muse_gemm_splitk_workspace_bytes(N, K, T, ctypes.byref(ncnt))
-    cnt = _splitk_counters.get(dev.index)
-    if cnt is None or cnt.numel() < ncnt.value:
-        cnt = torch.zeros(max(4096, ncnt.value), dtype=torch.int32, device=dev)
-        _splitk_counters[dev.index] = cnt
+    need = _lib.load().muse_gemm_splitk_workspace_bytes(N, K, T)
     ws = torch.empty(max(need, 16) // 4, dtype=torch.float32, device=dev)
     if _prof["on"]:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _call("muse_gemm_bf16_splitk", _p(dy), _p(x), _p(dw), N, K, T, dy.stride(0), x.stride(0), dw.stride(0), 1, 1, _p(ws),
-          need, _p(cnt), st)
+          need, st)
     if _prof["on"]:
         e1.record()
         _prof["events"].append((e0, e1, 2.0 * N * K * T))

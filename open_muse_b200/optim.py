@@ -33,16 +33,13 @@ class FusedAdamW(torch.optim.Optimizer):
 
     # ---- per-group launch plan (device table), rebuilt when pointers change (new grads storage, .to(device), ...)
     def _packed_dst(self):
+        """parameter data_ptr -> address of its bf16 copy in the model's packed operand cache (host-side bookkeeping kept
+        by the cache itself: no device read, so this is legal during graph capture)."""
         m = self.model
         if m is None or not hasattr(m, "_packed"):
             return {}
         pk = m._packed.refresh()
-        out = {}
-        if getattr(pk, "table", None) is None:
-            return out
-        for src, dst, numel, _ in pk.table.cpu().tolist():
-            out[src] = dst
-        return out
+        return dict(getattr(pk, "dst_of", {}) or {})
 
     def _plan(self, gi, group, shadow_of, packed_dst):
         params = [p for p in group["params"] if p.grad is not None]
@@ -50,7 +47,7 @@ class FusedAdamW(torch.optim.Optimizer):
         plan = self._plans.get(gi)
         if plan is not None and plan["key"] == key:
             return plan
-        entries, block = [], 0
+        entries = []
         dev = params[0].device
         for p in params:
             if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous() \
@@ -62,8 +59,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             sh = shadow_of.get(id(p))
             entries.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                            0 if sh is None else sh.data_ptr(), packed_dst.get(p.data_ptr(), 0), p.numel(), block))
-            block += (p.numel() + 1023) // 1024
+                            0 if sh is None else sh.data_ptr(), packed_dst.get(p.data_ptr(), 0), p.numel(), 0))
         plan = self._plans.get(gi) or {}
         if "step" not in plan:
             # one device-resident step counter per group, shared by the group's parameters' state entries so that
@@ -75,7 +71,10 @@ class FusedAdamW(torch.optim.Optimizer):
                 self.state[p]["step"] = step
             plan["step"] = step
             plan["scal"] = torch.zeros(8, dtype=torch.float32, device=dev)
-        plan.update(key=key, table=torch.tensor(entries, dtype=torch.int64).to(dev), n=len(entries), blocks=block, params=params)
+        # host-side table (passed to the kernels as launch arguments by the library): numpy keeps the buffer alive
+        import numpy as np
+
+        plan.update(key=key, table=np.ascontiguousarray(np.array(entries, dtype=np.int64)), n=len(entries), params=params)
         self._plans[gi] = plan
         return plan
 
@@ -97,9 +96,9 @@ class FusedAdamW(torch.optim.Optimizer):
             plan = self._plan(gi, group, shadow_of, packed_dst)
             lr = group["lr"]
             lr_dev = lr if torch.is_tensor(lr) else None
-            st = ops._prep(plan["table"])
+            st = ops._prep(plan["scal"])
             b1, b2 = group["betas"]
-            ops._call("muse_adamw_ema_step", plan["table"].data_ptr(), plan["n"], plan["blocks"], plan["scal"].data_ptr(),
+            ops._call("muse_adamw_ema_step", plan["table"].ctypes.data, plan["n"], plan["scal"].data_ptr(),
                       plan["step"].data_ptr(), None if lr_dev is None else lr_dev.data_ptr(),
                       0.0 if lr_dev is not None else float(lr), float(b1), float(b2), float(group["eps"]),
                       float(group["weight_decay"]), 1 if ema is not None else 0,
@@ -107,7 +106,8 @@ class FusedAdamW(torch.optim.Optimizer):
                       int(ema.update_after_step) if ema is not None else 0, int(ema.update_every) if ema is not None else 1,
                       1 if (ema is not None and ema.use_ema_warmup) else 0, float(ema.inv_gamma) if ema is not None else 1.0,
                       float(ema.power) if ema is not None else 1.0, st)
-        if ema is not None:
-            ema.optimization_step += 1  # host mirror of the device counter (state_dict / logging)
-            ema.cur_decay_value = ema.get_decay(ema.optimization_step)
+        if ema is not None:  # host mirror of the device-side schedule (state_dict / logging), same rule as EMAModel.step
+            ema.optimization_step += 1
+            if (ema.optimization_step - 1) % ema.update_every == 0:
+                ema.cur_decay_value = ema.get_decay(ema.optimization_step)
         return loss

@@ -297,8 +297,6 @@ def test_wgrad_deterministic_splitk(T, N, K):
     torch.cuda.synchronize()
     assert _rel(outs[0], ref) < 1e-5
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
-    cnt = ops._splitk_counters[torch.cuda.current_device()]
-    assert int(cnt.abs().sum()) == 0  # the tickets are left at zero for the next launch
 
 
 @pytest.mark.parametrize("H,act,xdt", [(512, 0, torch.float32), (1024, 1, torch.bfloat16), (2048, 0, torch.bfloat16), (2048, 2, torch.bfloat16)])

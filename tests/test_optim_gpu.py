@@ -48,7 +48,9 @@ def test_fused_adamw_ema_matches_torch_adamw_and_emamodel(golden, warmup):
         for i, (sa, sb) in enumerate(zip(ref_ema.shadow_params, ema.shadow_params)):
             torch.testing.assert_close(sb, sa, rtol=2e-6, atol=1e-8, msg=lambda m_: f"step {step} shadow {i}: {m_}")
             sb.copy_(sa)
-        assert ema.optimization_step == ref_ema.optimization_step and abs(ema.cur_decay_value - ref_ema.cur_decay_value) < 1e-12
+        assert ema.optimization_step == ref_ema.optimization_step
+        assert (ema.cur_decay_value is None) == (ref_ema.cur_decay_value is None)
+        assert ema.cur_decay_value is None or abs(ema.cur_decay_value - ref_ema.cur_decay_value) < 1e-12
 
 
 def test_fused_step_fills_the_packed_operands_and_replays_in_a_graph(golden):

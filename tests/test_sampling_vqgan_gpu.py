@@ -371,8 +371,8 @@ def test_pipeline_inpainting_keeps_known_tokens():
     mask = torch.zeros(256, dtype=torch.bool)
     mask[64:192] = True
     seen = {}
-    decode = vae.decode_code
-    vae.decode_code = lambda ids: (seen.__setitem__("ids", ids.clone()), decode(ids))[1]
+    decode = vae.decode_code_uint8  # the pipeline's PIL path goes ids -> display bytes on the device
+    vae.decode_code_uint8 = lambda ids: (seen.__setitem__("ids", ids.clone()), decode(ids))[1]
     out = pipe(image, mask, class_ids=[2], timesteps=4, num_images_per_prompt=3,
                generator=torch.Generator(device=DEV).manual_seed(1))
     assert len(out) == 3 and out[0].size == (32, 32)
