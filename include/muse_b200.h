@@ -189,11 +189,13 @@ int muse_vq_soft_code(const float* z, const float* codebook, float* enorm_ws, fl
 int muse_vq_lookup_nchw(const long long* ids, const float* codebook, float* out, int B, int P, int D, int ncodes,
                         void* stream);
 
-/* One generate2 decoding step fused into one kernel (muse/modeling_transformer.py:1424-1454 + muse/sampling.py:9-35):
+/* One generate2 decoding step (muse/modeling_transformer.py:1424-1454 + muse/sampling.py:9-35) as a token-parallel pass over
+ * the logits and noise plus a per-row re-mask:
  * categorical sample (argmax softmax/q_exp == torch.multinomial(p,1) given the same Exp(1) draws), confidence
  * = log p_sel + temperature * gumbel(u), per-row (k+1)-th smallest cut-off, re-mask.  logits bf16 with
  * row_stride / batch_stride in elements (first K columns used); logits_unc (nullable) + guidance fuse CFG (:1410-1414).
- * input_ids/sampled/next_ids int64 [B,L]; q_exp fp32 [B,L,K]; u fp32 [B,L]; conf_out (nullable) fp32 [B,L]. */
+ * input_ids/sampled/next_ids int64 [B,L]; q_exp fp32 [B,L,K]; u fp32 [B,L]; conf_out fp32 [B,L] (required: it carries the
+ * confidences from the first kernel to the second). */
 int muse_sample_step(const void* logits, const void* logits_unc, long long row_stride, long long batch_stride,
                      float guidance, const long long* input_ids, const float* q_exp, const float* u,
                      long long* sampled, long long* next_ids, float* conf_out, int B, int L, int K,

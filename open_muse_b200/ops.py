@@ -47,7 +47,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-_KERNELS_PER_CALL = {"muse_gemm_bf16_splitk": 2, "muse_adamw_ema_step": 4, "muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_embed_bwd_sorted": 4, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
+_KERNELS_PER_CALL = {"muse_sample_step": 2, "muse_gemm_bf16_splitk": 2, "muse_adamw_ema_step": 4, "muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_embed_bwd_sorted": 4, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
                      "muse_groupnorm_silu_nhwc": 3, "muse_grn_fwd": 3, "muse_grn_bwd": 3,
                      "muse_dwconv3x3_norm_bwd": 2}
 _prof = {"on": False, "events": []}
@@ -183,11 +183,15 @@ def embed_bwd_det(ids, dx, vocab, n_pos):
     H = dx.shape[1]
     dev = dx.device
     flat = ids.reshape(-1)
-    sorted_ids, order = torch.sort(flat, stable=True)
-    key = (vocab, dev)
+    # ids outside [0, vocab) are clamped to the sentinel `vocab`: they sort behind every real id and are ignored, like the
+    # forward kernel ignores them.  16-bit keys when they fit (vocab < 32767): the radix sort then needs 2 passes, not 8.
+    kdt = torch.int16 if vocab < 32767 else torch.int32
+    keys = torch.where((flat < 0) | (flat >= vocab), vocab, flat).to(kdt)
+    sorted_ids, order = torch.sort(keys, stable=True)
+    key = (vocab, dev, kdt)
     probe = _arange_cache.get(key)
     if probe is None:
-        probe = _arange_cache[key] = torch.arange(vocab + 1, device=dev, dtype=torch.int64)
+        probe = _arange_cache[key] = torch.arange(vocab + 1, device=dev, dtype=kdt)
     bounds = torch.searchsorted(sorted_ids, probe)
     dword = torch.empty(vocab, H, dtype=torch.float32, device=dev)
     dpos = None
@@ -440,7 +444,7 @@ def sample_step(logits, input_ids, q_exp, u, K, mask_id, mask_len, temperature, 
     lu = logits_unc[:, off:] if logits_unc is not None else None
     sampled = torch.empty(B, L, dtype=torch.int64, device=logits.device)
     nxt = torch.empty(B, L, dtype=torch.int64, device=logits.device)
-    conf = torch.empty(B, L, dtype=torch.float32, device=logits.device) if return_conf else None
+    conf = torch.empty(B, L, dtype=torch.float32, device=logits.device)
     _call("muse_sample_step", _p(lg), _p(lu), lg.stride(1), lg.stride(0), float(guidance), _p(input_ids), _p(q_exp),
           _p(u), _p(sampled), _p(nxt), _p(conf), B, L, K, int(mask_id), int(mask_len), float(temperature), st)
     return (sampled, nxt, conf) if return_conf else (sampled, nxt)

@@ -24,7 +24,9 @@ def _fwd_bwd(m, g):
     with torch.autocast("cuda", dtype=torch.bfloat16):
         _, loss = m(g["batch"]["input_ids"].to(DEV), labels=g["batch"]["labels"].to(DEV))
     loss.backward()
-    return loss
+    # detached: a live loss keeps the autograd graph -- and its AccumulateGrad nodes, bound to the stream they were created
+    # on -- alive, which breaks a later CUDA-graph capture of the same model on another stream
+    return loss.detach()
 
 
 @pytest.mark.parametrize("warmup", [False, True])
