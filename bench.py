@@ -417,9 +417,6 @@ def main():
                     help="launch the kernels of each step one by one instead of replaying the captured step (N=1 default: graph)")
     ap.add_argument("--ddp-graph", type=int, default=int(os.environ.get("MUSE_B200_DDP_GRAPH", "0")),
                     help="N>1: capture the whole DDP step (NCCL bucket all-reduces included) in one CUDA graph")
-    ap.add_argument("--no-wgrad-overlap", action="store_true",
-                    help="A/B: keep the weight-gradient GEMMs on the main stream instead of co-running them with the backward's "
-                         "HBM-bound kernels on a side stream")
     ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
                     help="torch.optim.AdamW(fused=True) or open_muse_b200.FusedAdamW (AdamW + bf16 operand packing in one pass)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -429,12 +426,9 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from open_muse_b200 import modeling_transformer as _mt
     from open_muse_b200 import ops
     from open_muse_b200.modeling_transformer import MaskGitTransformer
 
-    if args.no_wgrad_overlap:
-        _mt._WGRAD_OVERLAP = False
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -627,8 +621,7 @@ def main():
                        "global_batch": gb, "per_gpu_batch": B, "seq_len": 257,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "no explicit flush: per-step working set (~15 GB activations + 0.5 GB weights/grads/optimizer) >> 126 MB L2",
-                       "cuda_graph": bool(use_graph), "optimizer": args.optimizer,
-                       "wgrad_side_stream": not args.no_wgrad_overlap},
+                       "cuda_graph": bool(use_graph), "optimizer": args.optimizer},
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4},
             "gpu_launches": launches,

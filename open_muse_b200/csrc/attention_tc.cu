@@ -51,6 +51,13 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 // 16-column TMEM load (used for ragged 16-wide tails)
@@ -285,6 +292,240 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward, short kv
+// Fast path for kv lengths up to 256 (+ a few extra keys): the image-token grids of every reference config (256 tokens,
+// 257 with the class token) and the 77 text states of cross-attention.  The WHOLE score row block S = Q K^T [128 x n16]
+// lives in TMEM at once (<= 256 columns), so there is no kv loop, no online-softmax rescaling and no per-tile
+// MMA -> softmax -> MMA serialisation: 4 score MMAs (N up to 256) back to back, an exact two-pass softmax per row straight out
+// of TMEM (max, then exp2 / sum / bf16 pack into a K-major P operand in shared memory), then 16 accumulate MMAs back to
+// back.  O reuses the first 64 TMEM columns of S (dead once every thread has packed its P row); P reuses the shared memory
+// of Q and K (dead once the score MMAs have completed).  256 TMEM columns and 96 KB of shared memory per CTA -> two CTAs
+// per SM overlap each other's MMA and softmax phases.
+// Keys beyond the 256 the tensor core handles (the class token makes Skv = 257) are folded in on the CUDA cores: one
+// 64-long dot product per row for the score and one 64-long axpy on the output row for P V -- the same fp32 softmax
+// statistics cover them, so the result is the exact softmax over all Skv keys.
+constexpr int FULL_MAX_EXTRA = 8;
+constexpr int FULL_SMEM = 65536 /*P | (Q, K)*/ + 32768 /*V*/ + FULL_MAX_EXTRA * 256 /*extra k, v rows*/ + 64;
+
+__global__ void __launch_bounds__(128)
+attn_fwd_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const TcParams p, const bf16* __restrict__ kptr,
+                     const bf16* __restrict__ vptr, long long k_rs, long long v_rs) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sP = smem;                 // 4 atoms x 16 KB (written after the score MMAs)
+  uint8_t* sQ = smem;                 // 16 KB
+  uint8_t* sK = smem + 16384;         // up to 4 x 8 KB (64 keys each), consecutive = one 256-row K-major operand
+  uint8_t* sV = smem + 65536;         // up to 4 x 8 KB
+  bf16* sKe = reinterpret_cast<bf16*>(smem + 65536 + 32768);                    // [extra][64]
+  bf16* sVe = sKe + FULL_MAX_EXTRA * 64;                                        // [extra][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536 + 32768 + FULL_MAX_EXTRA * 256);
+  uint64_t* bar_k = bars;       // Q + K landed
+  uint64_t* bar_v = bars + 1;   // V landed
+  uint64_t* bar_s = bars + 2;   // score MMAs done
+  uint64_t* bar_o = bars + 3;   // accumulate MMAs done
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * p.tile_rows, h = blockIdx.y, b = blockIdx.z;
+  const int rows_here = min(p.tile_rows, p.Sq - q0);
+  const bool warp_active = warp * 32 < rows_here;
+  const int skv_mma = min(p.Skv, 256);
+  const int n16 = (skv_mma + 15) & ~15;
+  const int nkb = (n16 + 63) >> 6;          // 64-key TMA boxes
+  const int nextra = p.Skv - skv_mma;       // 0 .. FULL_MAX_EXTRA keys handled on the CUDA cores
+  if (tid == 0) {
+    ptx::mbar_init(bar_k, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 256);
+    ptx::tmem_relinquish();
+  }
+  // extra key / value rows (plain loads: a few hundred bytes)
+  for (int i = tid; i < nextra * 8; i += 128) {
+    const int e = i >> 3, c8 = (i & 7) * 8;
+    const long long row = static_cast<long long>(b) * p.Skv + 256 + e;
+    *reinterpret_cast<uint4*>(sKe + e * 64 + c8) = *reinterpret_cast<const uint4*>(kptr + row * k_rs + h * HD + c8);
+    *reinterpret_cast<uint4*>(sVe + e * 64 + c8) = *reinterpret_cast<const uint4*>(vptr + row * v_rs + h * HD + c8);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  if (tid == 0) {
+    ptx::mbar_expect_tx(bar_k, 16384 + nkb * 8192);
+    tma_load_3d(sQ, &tmQ, bar_k, h * HD, q0, b);
+    for (int i = 0; i < nkb; ++i) tma_load_3d(sK + i * 8192, &tmK, bar_k, h * HD, i * 64, b);
+    ptx::mbar_expect_tx(bar_v, nkb * 8192);
+    for (int i = 0; i < nkb; ++i) tma_load_3d(sV + i * 8192, &tmV, bar_v, h * HD, i * 64, b);
+    ptx::mbar_wait(bar_k, 0);
+    ptx::tc_fence_after();
+    const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc, ks > 0);
+    ptx::umma_commit(bar_s);
+  }
+  const float sl2 = p.scale * kLog2e;
+  // scores against the extra keys (CUDA cores), from this thread's own q row -- read before P overwrites Q
+  float s_extra[FULL_MAX_EXTRA];
+#pragma unroll
+  for (int e = 0; e < FULL_MAX_EXTRA; ++e) s_extra[e] = -INFINITY;
+  if (nextra > 0) {
+    ptx::mbar_wait(bar_k, 0);  // Q landed (every thread observes the TMA completion itself)
+    if (warp_active) {
+      float qv[64];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(sQ + tid * 128 + ((c8 ^ (tid & 7)) << 4));
+        const float2 a = unpack_bf16(u.x), bq = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        qv[c8 * 8 + 0] = a.x; qv[c8 * 8 + 1] = a.y; qv[c8 * 8 + 2] = bq.x; qv[c8 * 8 + 3] = bq.y;
+        qv[c8 * 8 + 4] = c.x; qv[c8 * 8 + 5] = c.y; qv[c8 * 8 + 6] = d.x; qv[c8 * 8 + 7] = d.y;
+      }
+      for (int e = 0; e < nextra; ++e) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d2 = 0; d2 < 32; ++d2) {
+          const float2 kk = unpack_bf16(reinterpret_cast<const uint32_t*>(sKe + e * 64)[d2]);
+          acc = fmaf(qv[2 * d2], kk.x, acc);
+          acc = fmaf(qv[2 * d2 + 1], kk.y, acc);
+        }
+#pragma unroll
+        for (int e2 = 0; e2 < FULL_MAX_EXTRA; ++e2) if (e2 == e) s_extra[e2] = acc;
+      }
+    }
+  }
+  ptx::mbar_wait(bar_s, 0);
+  ptx::tc_fence_after();
+  float m2 = -INFINITY, l = 0.f;
+  float p_extra[FULL_MAX_EXTRA];
+  if (warp_active) {
+    // ---- pass 1: exact row maximum over all keys
+    float raw = -INFINITY;
+    for (int c = 0; c < n16; c += 32) {
+      if (c + 32 <= n16) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        ptx::tmem_ld_wait();
+        if (c + 32 <= skv_mma) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw = fmaxf(raw, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw = fmaxf(raw, (c + i < skv_mma) ? __uint_as_float(r[i]) : -INFINITY);
+        }
+      } else {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_row + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) raw = fmaxf(raw, (c + i < skv_mma) ? __uint_as_float(r[i]) : -INFINITY);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < FULL_MAX_EXTRA; ++e) raw = fmaxf(raw, s_extra[e]);
+    m2 = raw * sl2;
+    // ---- pass 2: p = exp2(s * scale * log2e - m), row sum, bf16 P row into the K-major operand (over the dead Q / K)
+    for (int c = 0; c < n16; c += 32) {
+      const int w = (c + 32 <= n16) ? 32 : 16;
+      uint32_t r[32];
+      if (w == 32) {
+        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+      } else {
+        uint32_t r16[16];
+        tmem_ld_32x32b_x16(t_row + c, r16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = r16[i];
+      }
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i8 = 0; i8 < 32; i8 += 8) {
+        if (i8 < w) {
+          float pr[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            pr[i] = ex2(fmaf(__uint_as_float(r[i8 + i]), sl2, -m2));
+            if (c + 32 > skv_mma) pr[i] = (c + i8 + i < skv_mma) ? pr[i] : 0.f;
+            l += pr[i];
+          }
+          uint4 u;
+          u.x = pack_bf16(pr[0], pr[1]); u.y = pack_bf16(pr[2], pr[3]);
+          u.z = pack_bf16(pr[4], pr[5]); u.w = pack_bf16(pr[6], pr[7]);
+          st_operand_chunk(sP, tid, c + i8, u);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < FULL_MAX_EXTRA; ++e) {
+      p_extra[e] = (e < nextra) ? ex2(fmaf(s_extra[e], sl2, -m2)) : 0.f;
+      l += p_extra[e];
+      p_extra[e] = bf16_round(p_extra[e]);  // the tensor-core keys enter P V as bf16 too
+    }
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();  // every P row is in shared memory and every thread is done reading S: O may overwrite S[0,64)
+  if (tid == 0) {
+    ptx::mbar_wait(bar_v, 0);
+    ptx::tc_fence_after();
+    const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
+    const int ksteps = n16 >> 4;
+    for (int ks = 0; ks < ksteps; ++ks)
+      ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sP) + (ks >> 2) * 16384, ks & 3),
+                    ptx::make_smem_desc_sw128(ptx::smem_u32(sV) + ks * 2048, 8192, 1024), idesc, ks > 0 ? 1u : 0u);
+    ptx::umma_commit(bar_o);
+  }
+  ptx::mbar_wait(bar_o, 0);
+  ptx::tc_fence_after();
+  const int row = q0 + tid;
+  const bool row_ok = tid < rows_here;
+  const float inv = 1.f / l;
+  bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD;
+#pragma unroll
+  for (int c = 0; c < HD; c += 32) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32b_x32(t_row + c, r);
+    ptx::tmem_ld_wait();
+    if (row_ok) {
+      float o[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
+      for (int e = 0; e < nextra; ++e) {
+        float pe = 0.f;
+#pragma unroll
+        for (int e2 = 0; e2 < FULL_MAX_EXTRA; ++e2) if (e2 == e) pe = p_extra[e2];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 vv = unpack_bf16(reinterpret_cast<const uint32_t*>(sVe + e * 64 + c)[i >> 1]);
+          o[i] = fmaf(pe, vv.x, o[i]);
+          o[i + 1] = fmaf(pe, vv.y, o[i + 1]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16(o[i] * inv, o[i + 1] * inv); u.y = pack_bf16(o[i + 2] * inv, o[i + 3] * inv);
+        u.z = pack_bf16(o[i + 4] * inv, o[i + 5] * inv); u.w = pack_bf16(o[i + 6] * inv, o[i + 7] * inv);
+        *reinterpret_cast<uint4*>(orow + c + i) = u;
+      }
+    }
+  }
+  if (row_ok) p.lse[(static_cast<long long>(b) * p.nh + h) * p.Sq + row] = (m2 + log2f(l)) * kLn2;
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ backward: dQ
 // 256 threads: warps w and w+4 share TMEM lanes (rows) 32*(w%4).. and split the 64 score columns in two halves.
 // Software pipeline inside the CTA: as soon as every thread has pulled its S / dP columns out of TMEM into registers
@@ -511,6 +752,303 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dQ, short kv
+// Same idea as attn_fwd_full_kernel for the dQ half of the backward pass: with kv <= 256 (+ a few extra keys) the whole row
+// blocks S = Q K^T and dP = dO V^T [128 x n16] fit in the 512 TMEM columns together, so ONE pair of score MMAs replaces
+// the two sweeps of attn_bwd_dq_tc_kernel: pass 1 turns S into P in place (tcgen05.st back into the S columns, one
+// exp2 per element instead of two) while accumulating D = sum P * dP; pass 2 reads P and dP back and writes
+// dS = P * (dP - D) * scale as the bf16 K-major operand (over the dead Q / dO / V tiles); 16 accumulate MMAs then form
+// dQ = dS K in the first 64 TMEM columns.  The kernel is persistent (one CTA per SM, 512 TMEM columns) with a two-stage
+// shared-memory ring: the control warp streams the operands of the next (tile, head, batch) item in while the eight
+// math warps work on the current one.
+constexpr int DQF_STAGE = 65536 /*Q 16K | dO 16K | V 32K  (dS after the score MMAs)*/ + 32768 /*K*/;
+constexpr int DQF_SMEM = 2 * DQF_STAGE + 2 * FULL_MAX_EXTRA * 256 /*extra k, v rows per stage*/ + 1024 /*D halves*/ +
+                         FULL_MAX_EXTRA * 512 /*extra-key dS per row*/ + 128;
+
+__global__ void __launch_bounds__(288, 1)
+attn_bwd_dq_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const TcParams p,
+                        const bf16* __restrict__ kptr, const bf16* __restrict__ vptr, long long k_rs, long long v_rs,
+                        int ntile, int nbatch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  bf16* sExtra = reinterpret_cast<bf16*>(smem + 2 * DQF_STAGE);               // [stage][k rows | v rows][extra][64]
+  float* sDp = reinterpret_cast<float*>(smem + 2 * DQF_STAGE + 2 * FULL_MAX_EXTRA * 256);  // [2][128]
+  float* sDse = sDp + 256;                                                      // [extra][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * DQF_STAGE + 2 * FULL_MAX_EXTRA * 256 + 1024 + FULL_MAX_EXTRA * 512);
+  uint64_t* bar_full = bars;        // [2] operands of the stage landed
+  uint64_t* bar_s = bars + 2;       //     score MMAs done
+  uint64_t* bar_ds = bars + 3;      //     dS operand written (count 256)
+  uint64_t* bar_o = bars + 4;       //     dQ MMAs done
+  uint64_t* bar_tfree = bars + 5;   //     dQ read out of TMEM by every math thread (count 256)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = (warp >> 2) & 1;
+  const int r = (warp & 3) * 32 + lane;
+  if (tid == 0) {
+    ptx::mbar_init(&bar_full[0], 1);
+    ptx::mbar_init(&bar_full[1], 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_ds, 256);
+    ptx::mbar_init(bar_o, 1);
+    ptx::mbar_init(bar_tfree, 256);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_holder, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const int skv_mma = min(p.Skv, 256);
+  const int n16 = (skv_mma + 15) & ~15;
+  const int nkb = (n16 + 63) >> 6;
+  const int nextra = p.Skv - skv_mma;
+  const int nch = (n16 + 31) >> 5;             // 32-column chunks; half 0 takes the first ceil(nch / 2)
+  const int ch0 = half == 0 ? 0 : (nch + 1) >> 1;
+  const int ch1 = half == 0 ? (nch + 1) >> 1 : nch;
+  const int items = ntile * p.nh * nbatch;
+  const float sl2 = p.scale * kLog2e;
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------- control thread: TMA + MMA issue
+    if (lane == 0) {
+      auto load = [&](int it, int st) {
+        const int tile = it % ntile, h = (it / ntile) % p.nh, b = it / (ntile * p.nh);
+        uint8_t* base = smem + st * DQF_STAGE;
+        ptx::mbar_expect_tx(&bar_full[st], 32768 + 2 * nkb * 8192);
+        tma_load_3d(base, &tmQ, &bar_full[st], h * HD, tile * p.tile_rows, b);
+        tma_load_3d(base + 16384, &tmdO, &bar_full[st], h * HD, tile * p.tile_rows, b);
+        for (int i = 0; i < nkb; ++i) tma_load_3d(base + 32768 + i * 8192, &tmV, &bar_full[st], h * HD, i * 64, b);
+        for (int i = 0; i < nkb; ++i) tma_load_3d(base + 65536 + i * 8192, &tmK, &bar_full[st], h * HD, i * 64, b);
+      };
+      int n = 0;
+      if (static_cast<int>(blockIdx.x) < items) load(blockIdx.x, 0);
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const int st = n & 1;
+        const int nxt = it + gridDim.x;
+        // stage st^1 was last read by the dQ MMAs of item n-1 (dS and K): waited for at the end of the previous iteration
+        if (nxt < items) load(nxt, st ^ 1);
+        ptx::mbar_wait(&bar_full[st], (n >> 1) & 1);
+        if (n > 0) ptx::mbar_wait(bar_tfree, (n - 1) & 1);  // dQ of the previous item has left TMEM columns [0, 64)
+        ptx::tc_fence_after();
+        uint8_t* base = smem + st * DQF_STAGE;
+        const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(base), ks), desc_kmajor(ptx::smem_u32(base + 65536), ks), idesc, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          ptx::umma_f16(tmem + 256, desc_kmajor(ptx::smem_u32(base + 16384), ks), desc_kmajor(ptx::smem_u32(base + 32768), ks), idesc, ks > 0);
+        ptx::umma_commit(bar_s);
+        ptx::mbar_wait(bar_ds, n & 1);
+        ptx::tc_fence_after();
+        const uint32_t idq = ptx::make_idesc_bf16(128, HD, 0, 1);
+        const int ksteps = n16 >> 4;
+        for (int ks = 0; ks < ksteps; ++ks)  // dQ = dS K  (K consumed as an MN-major operand)
+          ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(base) + (ks >> 2) * 16384, ks & 3),
+                        ptx::make_smem_desc_sw128(ptx::smem_u32(base + 65536) + ks * 2048, 8192, 1024), idq, ks > 0 ? 1u : 0u);
+        ptx::umma_commit(bar_o);
+        ptx::mbar_wait(bar_o, n & 1);  // the stage (dS, K) is free for the load issued at the top of the next iteration
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- math threads: two per row, each half of the columns
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int st = n & 1;
+      const int tile = it % ntile, h = (it / ntile) % p.nh, b = it / (ntile * p.nh);
+      const int q0 = tile * p.tile_rows;
+      const int rows_here = min(p.tile_rows, p.Sq - q0);
+      const bool warp_active = (warp & 3) * 32 < rows_here;
+      const bool row_ok = r < rows_here;
+      const int row = q0 + r;
+      uint8_t* base = smem + st * DQF_STAGE;
+      bf16* sKe = sExtra + st * (2 * FULL_MAX_EXTRA * 64);
+      bf16* sVe = sKe + FULL_MAX_EXTRA * 64;
+      const long long stat_idx = (static_cast<long long>(b) * p.nh + h) * p.Sq + row;
+      const float lse2 = row_ok ? p.lse[stat_idx] * kLog2e : 0.f;
+      // extra key / value rows of this (b, h): plain loads into the stage's side buffer
+      for (int i = tid; i < nextra * 8; i += 256) {
+        const int e = i >> 3, c8 = (i & 7) * 8;
+        const long long krow = static_cast<long long>(b) * p.Skv + 256 + e;
+        *reinterpret_cast<uint4*>(sKe + e * 64 + c8) = *reinterpret_cast<const uint4*>(kptr + krow * k_rs + h * HD + c8);
+        *reinterpret_cast<uint4*>(sVe + e * 64 + c8) = *reinterpret_cast<const uint4*>(vptr + krow * v_rs + h * HD + c8);
+      }
+      float s_e[FULL_MAX_EXTRA], dp_e[FULL_MAX_EXTRA], p_e[FULL_MAX_EXTRA];
+#pragma unroll
+      for (int e = 0; e < FULL_MAX_EXTRA; ++e) { s_e[e] = 0.f; dp_e[e] = 0.f; p_e[e] = 0.f; }
+      if (nextra > 0) {
+        math_sync();                                   // side buffer visible
+        ptx::mbar_wait(&bar_full[st], (n >> 1) & 1);   // Q / dO rows landed
+        if (warp_active && half == 0) {
+          float qv[64], dov[64];
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint4 u = *reinterpret_cast<const uint4*>(base + r * 128 + ((c8 ^ (r & 7)) << 4));
+            const uint4 w = *reinterpret_cast<const uint4*>(base + 16384 + r * 128 + ((c8 ^ (r & 7)) << 4));
+            const uint32_t uu[4] = {u.x, u.y, u.z, u.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_bf16(uu[j]), d = unpack_bf16(ww[j]);
+              qv[c8 * 8 + 2 * j] = a.x; qv[c8 * 8 + 2 * j + 1] = a.y;
+              dov[c8 * 8 + 2 * j] = d.x; dov[c8 * 8 + 2 * j + 1] = d.y;
+            }
+          }
+          for (int e = 0; e < nextra; ++e) {
+            float a = 0.f, d = 0.f;
+#pragma unroll
+            for (int d2 = 0; d2 < 32; ++d2) {
+              const float2 kk = unpack_bf16(reinterpret_cast<const uint32_t*>(sKe + e * 64)[d2]);
+              const float2 vv = unpack_bf16(reinterpret_cast<const uint32_t*>(sVe + e * 64)[d2]);
+              a = fmaf(qv[2 * d2], kk.x, a); a = fmaf(qv[2 * d2 + 1], kk.y, a);
+              d = fmaf(dov[2 * d2], vv.x, d); d = fmaf(dov[2 * d2 + 1], vv.y, d);
+            }
+#pragma unroll
+            for (int e2 = 0; e2 < FULL_MAX_EXTRA; ++e2) if (e2 == e) { s_e[e2] = a; dp_e[e2] = d; }
+          }
+        }
+      }
+      ptx::mbar_wait(bar_s, n & 1);
+      ptx::tc_fence_after();
+      // ---- pass 1: P in place of S (TMEM), D partial
+      float dsum = 0.f;
+      if (warp_active) {
+        for (int ch = ch0; ch < ch1; ++ch) {
+          const int c = ch * 32;
+          const bool wide = c + 32 <= n16;
+          uint32_t sr[32], dr[32];
+          if (wide) {
+            ptx::tmem_ld_32x32b_x32(t_row + c, sr);
+            ptx::tmem_ld_32x32b_x32(t_row + 256 + c, dr);
+          } else {
+            uint32_t a16[16], b16[16];
+            tmem_ld_32x32b_x16(t_row + c, a16);
+            tmem_ld_32x32b_x16(t_row + 256 + c, b16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { sr[i] = a16[i]; dr[i] = b16[i]; sr[16 + i] = 0u; dr[16 + i] = 0u; }
+          }
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float pv = ex2(fmaf(__uint_as_float(sr[i]), sl2, -lse2));
+            if (c + 32 > skv_mma) pv = (c + i < skv_mma) ? pv : 0.f;
+            dsum = fmaf(pv, __uint_as_float(dr[i]), dsum);
+            sr[i] = __float_as_uint(pv);
+          }
+          if (wide) {
+            tmem_st_32x32b_x32(t_row + c, sr);
+          } else {
+            uint32_t a16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a16[i] = sr[i];
+            tmem_st_32x32b_x16(t_row + c, a16);
+          }
+        }
+        tmem_st_wait();
+        if (half == 0) {
+#pragma unroll
+          for (int e = 0; e < FULL_MAX_EXTRA; ++e) {
+            p_e[e] = (e < nextra) ? ex2(fmaf(s_e[e], sl2, -lse2)) : 0.f;
+            dsum = fmaf(p_e[e], dp_e[e], dsum);
+          }
+        }
+      }
+      sDp[half * 128 + r] = dsum;
+      math_sync();
+      const float dfull = sDp[r] + sDp[128 + r];
+      if (half == 0 && row_ok) p.dvec[stat_idx] = dfull;
+      const float neg_d_scaled = -dfull * p.scale;
+      if (nextra > 0) {  // dS against the extra keys: computed by the half-0 thread, needed by both halves in the epilogue
+        if (half == 0) {
+#pragma unroll
+          for (int e = 0; e < FULL_MAX_EXTRA; ++e)
+            if (e < nextra) sDse[e * 128 + r] = p_e[e] * fmaf(dp_e[e], p.scale, neg_d_scaled);
+        }
+        math_sync();
+      }
+      // ---- pass 2: dS = P * (dP - D) * scale -> bf16 K-major operand over the dead Q / dO / V tiles
+      if (warp_active) {
+        for (int ch = ch0; ch < ch1; ++ch) {
+          const int c = ch * 32;
+          const bool wide = c + 32 <= n16;
+          uint32_t pr[32], dr[32];
+          if (wide) {
+            ptx::tmem_ld_32x32b_x32(t_row + c, pr);
+            ptx::tmem_ld_32x32b_x32(t_row + 256 + c, dr);
+          } else {
+            uint32_t a16[16], b16[16];
+            tmem_ld_32x32b_x16(t_row + c, a16);
+            tmem_ld_32x32b_x16(t_row + 256 + c, b16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { pr[i] = a16[i]; dr[i] = b16[i]; pr[16 + i] = 0u; dr[16 + i] = 0u; }
+          }
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i8 = 0; i8 < 32; i8 += 8) {
+            if (c + i8 < n16) {
+              float ds[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                ds[i] = __uint_as_float(pr[i8 + i]) * fmaf(__uint_as_float(dr[i8 + i]), p.scale, neg_d_scaled);
+              uint4 v;
+              v.x = pack_bf16(ds[0], ds[1]); v.y = pack_bf16(ds[2], ds[3]);
+              v.z = pack_bf16(ds[4], ds[5]); v.w = pack_bf16(ds[6], ds[7]);
+              st_operand_chunk(base, r, c + i8, v);
+            }
+          }
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_ds);
+      ptx::mbar_wait(bar_o, n & 1);
+      ptx::tc_fence_after();
+      // ---- epilogue: dQ row (each thread 32 of the 64 columns) + the extra keys' contribution
+      {
+        uint32_t rr[32];
+        ptx::tmem_ld_32x32b_x32(t_row + half * 32, rr);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(bar_tfree);
+        if (row_ok) {
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(rr[i]);
+          for (int e = 0; e < nextra; ++e) {  // dQ += dS_e * k_e  (CUDA cores; k_e from the stage's side buffer)
+            const float dse = sDse[e * 128 + r];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float2 kk = unpack_bf16(reinterpret_cast<const uint32_t*>(sKe + e * 64 + half * 32)[i >> 1]);
+              o[i] = fmaf(dse, kk.x, o[i]);
+              o[i + 1] = fmaf(dse, kk.y, o[i + 1]);
+            }
+          }
+          bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD + half * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 v;
+            v.x = pack_bf16(o[i], o[i + 1]); v.y = pack_bf16(o[i + 2], o[i + 3]);
+            v.z = pack_bf16(o[i + 4], o[i + 5]); v.w = pack_bf16(o[i + 6], o[i + 7]);
+            *reinterpret_cast<uint4*>(orow + i) = v;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
   }
 }
 
@@ -758,13 +1296,20 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
   if ((rc = make_tmap3(&tq, q, nh * HD, Sq, B, q_rs, 128))) return rc;
   if ((rc = make_tmap3(&tk, k, nh * HD, Skv, B, k_rs, FWD_BN))) return rc;
   if ((rc = make_tmap3(&tv, v, nh * HD, Skv, B, v_rs, FWD_BN))) return rc;
-  static bool attr = false;
-  if ((rc = set_smem(attn_fwd_tc_kernel, FWD_SMEM, &attr))) return rc;
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale; p.tile_rows = tile_rows;
   p.out0 = reinterpret_cast<bf16*>(o); p.out0_rs = o_rs; p.lse = lse;
-  attn_fwd_tc_kernel<<<dim3(ntile, nh, B), 128, FWD_SMEM, s>>>(tq, tk, tv, p);
   *rows_done = Sq;
+  if (Skv <= 256 + FULL_MAX_EXTRA) {  // whole score rows fit in TMEM: no kv loop (every reference config lands here)
+    static bool attr_full = false;
+    if ((rc = set_smem(attn_fwd_full_kernel, FULL_SMEM, &attr_full))) return rc;
+    attn_fwd_full_kernel<<<dim3(ntile, nh, B), 128, FULL_SMEM, s>>>(tq, tk, tv, p, reinterpret_cast<const bf16*>(k),
+                                                                    reinterpret_cast<const bf16*>(v), k_rs, v_rs);
+    return check_launch("attn_fwd_full");
+  }
+  static bool attr = false;
+  if ((rc = set_smem(attn_fwd_tc_kernel, FWD_SMEM, &attr))) return rc;
+  attn_fwd_tc_kernel<<<dim3(ntile, nh, B), 128, FWD_SMEM, s>>>(tq, tk, tv, p);
   return check_launch("attn_fwd_tc");
 }
 
@@ -780,14 +1325,26 @@ int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o,
   if ((rc = make_tmap3(&tdo, d_o, nh * HD, Sq, B, do_rs, 128))) return rc;
   if ((rc = make_tmap3(&tk, k, nh * HD, Skv, B, k_rs, BWD_BN))) return rc;
   if ((rc = make_tmap3(&tv, v, nh * HD, Skv, B, v_rs, BWD_BN))) return rc;
-  static bool attr = false;
-  if ((rc = set_smem(attn_bwd_dq_tc_kernel, DQ_SMEM, &attr))) return rc;
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dq); p.out0_rs = dq_rs; p.lse = const_cast<float*>(lse); p.dvec = dvec;
   p.tile_rows = tile_rows;
-  attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 288, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
   *rows_done = Sq;
+  if (Skv <= 256 + FULL_MAX_EXTRA) {  // whole S / dP row blocks in TMEM: persistent single-sweep kernel
+    static bool attr_full = false;
+    if ((rc = set_smem(attn_bwd_dq_full_kernel, DQF_SMEM, &attr_full))) return rc;
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int items = ntile * nh * B;
+    const int grid = items < sms ? items : sms;
+    attn_bwd_dq_full_kernel<<<grid, 288, DQF_SMEM, s>>>(tq, tdo, tk, tv, p, reinterpret_cast<const bf16*>(k),
+                                                       reinterpret_cast<const bf16*>(v), k_rs, v_rs, ntile, B);
+    return check_launch("attn_bwd_dq_full");
+  }
+  static bool attr = false;
+  if ((rc = set_smem(attn_bwd_dq_tc_kernel, DQ_SMEM, &attr))) return rc;
+  attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 288, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
   return check_launch("attn_bwd_dq_tc");
 }
 

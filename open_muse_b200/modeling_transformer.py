@@ -215,37 +215,6 @@ def _f32(p):
     return p if p.dtype == torch.float32 else p.float()
 
 
-# Weight-gradient GEMMs are off the critical path of a layer's backward: nothing downstream in the layer reads them.  They
-# are tensor-core-bound while the kernels that follow on the critical path (norm / GLU backward, attention backward) are
-# HBM- or issue-bound, so they are enqueued on a side stream and co-run with those kernels; the layer's backward joins the
-# side stream before it returns its gradients.  (Module-level flag so that bench.py can A/B the schedule.)
-_WGRAD_OVERLAP = True
-_side_streams = {}
-
-
-class _WgradStream:
-    def __init__(self, device):
-        self.on = _WGRAD_OVERLAP and device.type == "cuda"
-        if self.on:
-            self.main = torch.cuda.current_stream(device)
-            self.side = _side_streams.get(device.index)
-            if self.side is None:
-                self.side = _side_streams[device.index] = torch.cuda.Stream(device)
-
-    def wgrad(self, dy, x):
-        if not self.on:
-            return ops.linear_wgrad_det(dy, x)
-        out = torch.empty(dy.shape[1], x.shape[1], dtype=torch.float32, device=dy.device)  # owned by the main stream
-        self.side.wait_stream(self.main)  # dy / x were produced on the main stream
-        with torch.cuda.stream(self.side):
-            ops.linear_wgrad_det(dy, x, out=out)
-        return out
-
-    def join(self):
-        if self.on:
-            self.main.wait_stream(self.side)
-
-
 class _EmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ids, word, pos):
@@ -379,10 +348,9 @@ class _LayerFn(torch.autograd.Function):
         # ---- FFN
         # every weight gradient below is STORED by a fixed-order reduction (deterministic split-K / ordered column sums):
         # no zero-filled buffers, no atomics, bit-identical from run to run
-        wg = _WgradStream(dev)
         dy = ops.cast_bf16(dx3)
-        d_ml = ops.linear_dgrad(dy, s.w["wo"])  # (critical path first; the sibling wgrad then co-runs with what follows)
-        g_wo = wg.wgrad(dy, sv["ml"])
+        d_ml = ops.linear_dgrad(dy, s.w["wo"])
+        g_wo = ops.linear_wgrad_det(dy, sv["ml"])
         if s.normformer:  # LN backward + GLU backward fused: reads d_ml and [a|b], writes d[a|b]
             d_ab, g_mid = ops.norm_bwd(d_ml, sv["ab"], _f32(w_mid), sv["st4"], torch.bfloat16, act=2, rms=s.rms,
                                        y_fwd=sv["ml"], want_dw=True)
@@ -390,7 +358,7 @@ class _LayerFn(torch.autograd.Function):
             g_mid = None
             d_ab = ops.glu_bwd(sv["ab"], d_ml)
         d_h2 = ops.linear_dgrad(d_ab, s.w["wi"])
-        g_wi = wg.wgrad(d_ab, sv["h2"])
+        g_wi = ops.linear_wgrad_det(d_ab, sv["h2"])
         x_mid = sv["x2b"] if s.cross else sv["x2"]
         dx2, g_pre = ops.norm_bwd(d_h2, x_mid, _f32(w_pre), sv["st3"], torch.float32, dres=dx3, rms=0, want_dw=True)
         # ---- cross attention
@@ -402,17 +370,17 @@ class _LayerFn(torch.autograd.Function):
             else:
                 g_cpost, d_cao = None, ops.cast_bf16(dx2)
             d_cctx = ops.linear_dgrad(d_cao, s.w["co"])
-            g_co = wg.wgrad(d_cao, sv["cctx"])
+            g_co = ops.linear_wgrad_det(d_cao, sv["cctx"])
             d_qc = torch.empty_like(sv["qc"])
             d_kvc = torch.empty_like(sv["kvc"])
             kvc = sv["kvc"]
             ops.attn_bwd(sv["qc"], kvc[:, :H], kvc[:, H:], sv["cctx"], d_cctx, sv["clse"], d_qc, d_kvc[:, :H],
                          d_kvc[:, H:], B, nh, S, s.Skv, s.scale)
-            g_ckv = wg.wgrad(d_kvc, sv["enc"])
+            g_ckv = ops.linear_wgrad_det(d_kvc, sv["enc"])
             if ctx.needs_input_grad[1]:  # projected encoder states: d enc = d[k|v] @ [Wk;Wv], fp32, summed over layers by autograd
                 d_enc = ops.linear_dgrad(d_kvc, s.w["ckv"], out_dtype=torch.float32)
             d_hc = ops.linear_dgrad(d_qc, s.w["cq"])
-            g_cq = wg.wgrad(d_qc, sv["hc"])
+            g_cq = ops.linear_wgrad_det(d_qc, sv["hc"])
             dx2, g_cln = ops.norm_bwd(d_hc, sv["x2"], _f32(w_cln), sv["stc"], torch.float32, dres=dx2, rms=s.rms,
                                       want_dw=True)
             cross_grads = [g_cln, g_cq, g_ckv[:H], g_ckv[H:], g_co] + ([g_cpost] if s.normformer else [])
@@ -422,13 +390,13 @@ class _LayerFn(torch.autograd.Function):
         else:
             g_post, d_ao = None, ops.cast_bf16(dx2)
         d_ctx = ops.linear_dgrad(d_ao, s.w["ao"])
-        g_ao = wg.wgrad(d_ao, sv["ctxt"])
+        g_ao = ops.linear_wgrad_det(d_ao, sv["ctxt"])
         qkv = sv["qkv"]
         d_qkv = torch.empty_like(qkv)
         ops.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["ctxt"], d_ctx, sv["lse"], d_qkv[:, :H],
                      d_qkv[:, H:2 * H], d_qkv[:, 2 * H:], B, nh, S, S, s.scale)
         d_h1 = ops.linear_dgrad(d_qkv, s.w["qkv"])
-        g_qkv = wg.wgrad(d_qkv, sv["h1"])
+        g_qkv = ops.linear_wgrad_det(d_qkv, sv["h1"])
         dx1, g_attn_ln = ops.norm_bwd(d_h1, sv["x"], _f32(w_attn_ln), sv["st1"], torch.float32, dres=dx2, rms=s.rms,
                                       want_dw=True)
         grads = [g_attn_ln, g_qkv[:H], g_qkv[H:2 * H], g_qkv[2 * H:], g_ao]
@@ -439,7 +407,6 @@ class _LayerFn(torch.autograd.Function):
             grads.append(g_mid)
         grads.append(g_wo)
         grads += cross_grads
-        wg.join()  # the gradients handed back to autograd (DDP buckets, optimizer) are complete on the main stream
         ctx.sv = None
         return (dx1, d_enc, None, *grads)
 
@@ -518,15 +485,14 @@ class _HeadFn(torch.autograd.Function):
             dl = extra if dl is None else dl + extra
         if dl is None:
             raise RuntimeError("MaskGitTransformer head: backward called without any gradient")
-        wg = _WgradStream(dev)
         d_e = ops.linear_dgrad(dl, s.w["logits"])
-        g_logits = wg.wgrad(dl, sv["e"])
+        g_logits = ops.linear_wgrad_det(dl, sv["e"])
         grads = []
         if s.use_mlm:
             d_d, g_mlm_ln = ops.norm_bwd(d_e, sv["d"], _f32(w_mlm_ln), sv["st1"], torch.bfloat16, act=1, rms=s.rms,
                                          want_dw=True)
             d_hN = ops.linear_dgrad(d_d, s.w["dense"])
-            g_dense = wg.wgrad(d_d, sv["hN"])
+            g_dense = ops.linear_wgrad_det(d_d, sv["hN"])
             grads = [g_dense, g_mlm_ln]
         else:
             d_hN = d_e
@@ -536,7 +502,6 @@ class _HeadFn(torch.autograd.Function):
         else:
             dx = d_hN.float()
         grads.append(g_logits[: s.V])
-        wg.join()
         ctx.sv = None
         return (dx, None, None, *grads)
 
