@@ -305,9 +305,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // 64-long dot product per row for the score and one 64-long axpy on the output row for P V -- the same fp32 softmax
 // statistics cover them, so the result is the exact softmax over all Skv keys.
 constexpr int FULL_MAX_EXTRA = 8;
-constexpr int FULL_SMEM = 65536 /*P | (Q, K)*/ + 32768 /*V*/ + FULL_MAX_EXTRA * 256 /*extra k, v rows*/ + 64;
+constexpr int FULL_SMEM = 65536 /*P | (Q, K)*/ + 32768 /*V*/ + FULL_MAX_EXTRA * 256 /*extra k, v rows*/ + 2048 /*row max / sum halves*/ +
+                          FULL_MAX_EXTRA * 512 /*extra-key P per row*/ + 64;
 
-__global__ void __launch_bounds__(128)
+// 256 threads: warps w and w+4 share the TMEM lanes (rows) 32*(w%4).. and split the score columns in two halves, so that
+// sixteen warps per SM (two CTAs) hide each other's TMEM / MUFU latencies; row max and row sum are exchanged through
+// shared memory.
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const TcParams p, const bf16* __restrict__ kptr,
                      const bf16* __restrict__ vptr, long long k_rs, long long v_rs) {
@@ -320,21 +324,29 @@ attn_fwd_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sV = smem + 65536;         // up to 4 x 8 KB
   bf16* sKe = reinterpret_cast<bf16*>(smem + 65536 + 32768);                    // [extra][64]
   bf16* sVe = sKe + FULL_MAX_EXTRA * 64;                                        // [extra][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536 + 32768 + FULL_MAX_EXTRA * 256);
+  float* sMax = reinterpret_cast<float*>(smem + 65536 + 32768 + FULL_MAX_EXTRA * 256);  // [2][128]
+  float* sSum = sMax + 256;                                                     // [2][128]
+  float* sPe = sSum + 256;                                                      // [extra][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536 + 32768 + FULL_MAX_EXTRA * 256 + 2048 + FULL_MAX_EXTRA * 512);
   uint64_t* bar_k = bars;       // Q + K landed
   uint64_t* bar_v = bars + 1;   // V landed
   uint64_t* bar_s = bars + 2;   // score MMAs done
   uint64_t* bar_o = bars + 3;   // accumulate MMAs done
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
+  const int r = (warp & 3) * 32 + lane;
   const int q0 = blockIdx.x * p.tile_rows, h = blockIdx.y, b = blockIdx.z;
   const int rows_here = min(p.tile_rows, p.Sq - q0);
-  const bool warp_active = warp * 32 < rows_here;
+  const bool warp_active = (warp & 3) * 32 < rows_here;
   const int skv_mma = min(p.Skv, 256);
   const int n16 = (skv_mma + 15) & ~15;
   const int nkb = (n16 + 63) >> 6;          // 64-key TMA boxes
   const int nextra = p.Skv - skv_mma;       // 0 .. FULL_MAX_EXTRA keys handled on the CUDA cores
+  const int nch = (n16 + 31) >> 5;          // 32-column chunks: half 0 takes the first ceil(nch / 2)
+  const int ch0 = half == 0 ? 0 : (nch + 1) >> 1;
+  const int ch1 = half == 0 ? (nch + 1) >> 1 : nch;
   if (tid == 0) {
     ptx::mbar_init(bar_k, 1);
     ptx::mbar_init(bar_v, 1);
@@ -346,8 +358,7 @@ attn_fwd_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     ptx::tmem_alloc(tmem_holder, 256);
     ptx::tmem_relinquish();
   }
-  // extra key / value rows (plain loads: a few hundred bytes)
-  for (int i = tid; i < nextra * 8; i += 128) {
+  for (int i = tid; i < nextra * 8; i += 256) {  // extra key / value rows (plain loads: a few hundred bytes)
     const int e = i >> 3, c8 = (i & 7) * 8;
     const long long row = static_cast<long long>(b) * p.Skv + 256 + e;
     *reinterpret_cast<uint4*>(sKe + e * 64 + c8) = *reinterpret_cast<const uint4*>(kptr + row * k_rs + h * HD + c8);
@@ -357,7 +368,7 @@ attn_fwd_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 
   if (tid == 0) {
     ptx::mbar_expect_tx(bar_k, 16384 + nkb * 8192);
@@ -374,75 +385,79 @@ attn_fwd_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     ptx::umma_commit(bar_s);
   }
   const float sl2 = p.scale * kLog2e;
-  // scores against the extra keys (CUDA cores), from this thread's own q row -- read before P overwrites Q
+  // scores against the extra keys (CUDA cores, half-0 thread of the row), from the q row -- read before P overwrites Q
   float s_extra[FULL_MAX_EXTRA];
 #pragma unroll
   for (int e = 0; e < FULL_MAX_EXTRA; ++e) s_extra[e] = -INFINITY;
   if (nextra > 0) {
     ptx::mbar_wait(bar_k, 0);  // Q landed (every thread observes the TMA completion itself)
-    if (warp_active) {
+    if (warp_active && half == 0) {
       float qv[64];
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(sQ + tid * 128 + ((c8 ^ (tid & 7)) << 4));
+        const uint4 u = *reinterpret_cast<const uint4*>(sQ + r * 128 + ((c8 ^ (r & 7)) << 4));
         const float2 a = unpack_bf16(u.x), bq = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
         qv[c8 * 8 + 0] = a.x; qv[c8 * 8 + 1] = a.y; qv[c8 * 8 + 2] = bq.x; qv[c8 * 8 + 3] = bq.y;
         qv[c8 * 8 + 4] = c.x; qv[c8 * 8 + 5] = c.y; qv[c8 * 8 + 6] = d.x; qv[c8 * 8 + 7] = d.y;
       }
       for (int e = 0; e < nextra; ++e) {
-        float acc = 0.f;
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int d2 = 0; d2 < 32; ++d2) {
           const float2 kk = unpack_bf16(reinterpret_cast<const uint32_t*>(sKe + e * 64)[d2]);
-          acc = fmaf(qv[2 * d2], kk.x, acc);
-          acc = fmaf(qv[2 * d2 + 1], kk.y, acc);
+          a0 = fmaf(qv[2 * d2], kk.x, a0);
+          a1 = fmaf(qv[2 * d2 + 1], kk.y, a1);
         }
 #pragma unroll
-        for (int e2 = 0; e2 < FULL_MAX_EXTRA; ++e2) if (e2 == e) s_extra[e2] = acc;
+        for (int e2 = 0; e2 < FULL_MAX_EXTRA; ++e2) if (e2 == e) s_extra[e2] = a0 + a1;
       }
     }
   }
   ptx::mbar_wait(bar_s, 0);
   ptx::tc_fence_after();
-  float m2 = -INFINITY, l = 0.f;
-  float p_extra[FULL_MAX_EXTRA];
+  // ---- pass 1: row maximum over this thread's column half (four independent chains), then exchanged between the halves
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   if (warp_active) {
-    // ---- pass 1: exact row maximum over all keys
-    float raw = -INFINITY;
-    for (int c = 0; c < n16; c += 32) {
+    for (int ch = ch0; ch < ch1; ++ch) {
+      const int c = ch * 32;
+      uint32_t rr[32];
       if (c + 32 <= n16) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_row + c, r);
-        ptx::tmem_ld_wait();
-        if (c + 32 <= skv_mma) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) raw = fmaxf(raw, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) raw = fmaxf(raw, (c + i < skv_mma) ? __uint_as_float(r[i]) : -INFINITY);
-        }
-      } else {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_row + c, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) raw = fmaxf(raw, (c + i < skv_mma) ? __uint_as_float(r[i]) : -INFINITY);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < FULL_MAX_EXTRA; ++e) raw = fmaxf(raw, s_extra[e]);
-    m2 = raw * sl2;
-    // ---- pass 2: p = exp2(s * scale * log2e - m), row sum, bf16 P row into the K-major operand (over the dead Q / K)
-    for (int c = 0; c < n16; c += 32) {
-      const int w = (c + 32 <= n16) ? 32 : 16;
-      uint32_t r[32];
-      if (w == 32) {
-        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        ptx::tmem_ld_32x32b_x32(t_row + c, rr);
       } else {
         uint32_t r16[16];
         tmem_ld_32x32b_x16(t_row + c, r16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = r16[i];
+        for (int i = 0; i < 16; ++i) { rr[i] = r16[i]; rr[16 + i] = 0xff800000u; }
+      }
+      ptx::tmem_ld_wait();
+      if (c + 32 <= skv_mma) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rr[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], (c + i < skv_mma) ? __uint_as_float(rr[i]) : -INFINITY);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < FULL_MAX_EXTRA; ++e) mx[e & 3] = fmaxf(mx[e & 3], s_extra[e]);
+  }
+  sMax[half * 128 + r] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+  __syncthreads();
+  const float m2 = fmaxf(sMax[r], sMax[128 + r]) * sl2;
+  // ---- pass 2: p = exp2(s * scale * log2e - m), partial row sums, bf16 P into the K-major operand (over the dead Q / K)
+  float ls[4] = {0.f, 0.f, 0.f, 0.f};
+  if (warp_active) {
+    for (int ch = ch0; ch < ch1; ++ch) {
+      const int c = ch * 32;
+      const int w = (c + 32 <= n16) ? 32 : 16;
+      uint32_t rr[32];
+      if (w == 32) {
+        ptx::tmem_ld_32x32b_x32(t_row + c, rr);
+      } else {
+        uint32_t r16[16];
+        tmem_ld_32x32b_x16(t_row + c, r16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rr[i] = r16[i];
       }
       ptx::tmem_ld_wait();
 #pragma unroll
@@ -451,24 +466,29 @@ attn_fwd_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           float pr[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            pr[i] = ex2(fmaf(__uint_as_float(r[i8 + i]), sl2, -m2));
+            pr[i] = ex2(fmaf(__uint_as_float(rr[i8 + i]), sl2, -m2));
             if (c + 32 > skv_mma) pr[i] = (c + i8 + i < skv_mma) ? pr[i] : 0.f;
-            l += pr[i];
+            ls[i & 3] += pr[i];
           }
           uint4 u;
           u.x = pack_bf16(pr[0], pr[1]); u.y = pack_bf16(pr[2], pr[3]);
           u.z = pack_bf16(pr[4], pr[5]); u.w = pack_bf16(pr[6], pr[7]);
-          st_operand_chunk(sP, tid, c + i8, u);
+          st_operand_chunk(sP, r, c + i8, u);
         }
       }
     }
+    if (half == 0) {
 #pragma unroll
-    for (int e = 0; e < FULL_MAX_EXTRA; ++e) {
-      p_extra[e] = (e < nextra) ? ex2(fmaf(s_extra[e], sl2, -m2)) : 0.f;
-      l += p_extra[e];
-      p_extra[e] = bf16_round(p_extra[e]);  // the tensor-core keys enter P V as bf16 too
+      for (int e = 0; e < FULL_MAX_EXTRA; ++e) {
+        if (e < nextra) {
+          const float pe = ex2(fmaf(s_extra[e], sl2, -m2));
+          ls[e & 3] += pe;
+          sPe[e * 128 + r] = bf16_round(pe);  // the tensor-core keys enter P V as bf16 too
+        }
+      }
     }
   }
+  sSum[half * 128 + r] = (ls[0] + ls[1]) + (ls[2] + ls[3]);
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();  // every P row is in shared memory and every thread is done reading S: O may overwrite S[0,64)
@@ -484,26 +504,24 @@ attn_fwd_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   ptx::mbar_wait(bar_o, 0);
   ptx::tc_fence_after();
-  const int row = q0 + tid;
-  const bool row_ok = tid < rows_here;
+  const int row = q0 + r;
+  const bool row_ok = r < rows_here;
+  const float l = sSum[r] + sSum[128 + r];
   const float inv = 1.f / l;
-  bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD;
-#pragma unroll
-  for (int c = 0; c < HD; c += 32) {
-    uint32_t r[32];
-    ptx::tmem_ld_32x32b_x32(t_row + c, r);
+  bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD + half * 32;
+  {
+    uint32_t rr[32];
+    ptx::tmem_ld_32x32b_x32(t_row + half * 32, rr);
     ptx::tmem_ld_wait();
     if (row_ok) {
       float o[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]);
+      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(rr[i]);
       for (int e = 0; e < nextra; ++e) {
-        float pe = 0.f;
-#pragma unroll
-        for (int e2 = 0; e2 < FULL_MAX_EXTRA; ++e2) if (e2 == e) pe = p_extra[e2];
+        const float pe = sPe[e * 128 + r];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float2 vv = unpack_bf16(reinterpret_cast<const uint32_t*>(sVe + e * 64 + c)[i >> 1]);
+          const float2 vv = unpack_bf16(reinterpret_cast<const uint32_t*>(sVe + e * 64 + half * 32)[i >> 1]);
           o[i] = fmaf(pe, vv.x, o[i]);
           o[i + 1] = fmaf(pe, vv.y, o[i + 1]);
         }
@@ -513,11 +531,11 @@ attn_fwd_full_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint4 u;
         u.x = pack_bf16(o[i] * inv, o[i + 1] * inv); u.y = pack_bf16(o[i + 2] * inv, o[i + 3] * inv);
         u.z = pack_bf16(o[i + 4] * inv, o[i + 5] * inv); u.w = pack_bf16(o[i + 6] * inv, o[i + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + c + i) = u;
+        *reinterpret_cast<uint4*>(orow + i) = u;
       }
     }
   }
-  if (row_ok) p.lse[(static_cast<long long>(b) * p.nh + h) * p.Sq + row] = (m2 + log2f(l)) * kLn2;
+  if (row_ok && half == 0) p.lse[(static_cast<long long>(b) * p.nh + h) * p.Sq + row] = (m2 + log2f(l)) * kLn2;
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -1303,7 +1321,7 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
   if (Skv <= 256 + FULL_MAX_EXTRA) {  // whole score rows fit in TMEM: no kv loop (every reference config lands here)
     static bool attr_full = false;
     if ((rc = set_smem(attn_fwd_full_kernel, FULL_SMEM, &attr_full))) return rc;
-    attn_fwd_full_kernel<<<dim3(ntile, nh, B), 128, FULL_SMEM, s>>>(tq, tk, tv, p, reinterpret_cast<const bf16*>(k),
+    attn_fwd_full_kernel<<<dim3(ntile, nh, B), 256, FULL_SMEM, s>>>(tq, tk, tv, p, reinterpret_cast<const bf16*>(k),
                                                                     reinterpret_cast<const bf16*>(v), k_rs, v_rs);
     return check_launch("attn_fwd_full");
   }
