@@ -201,16 +201,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float raw = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 64; ++i) raw = fmaxf(raw, sc[i]);
-    const float mx = fmaxf(m, raw * sl2);
-    const float alpha = ex2(m - mx);  // 0 on the first tile (m = -inf)
+    // Lazy running maximum: the reference point m only moves when the tile's maximum exceeds it by more than 8 (log2
+    // units), i.e. P entries stay below 2^8 -- harmless in bf16 / fp32 -- and the final 1 / l normalisation and the LSE
+    // (m + log2 l) are exact for any reference point.  Most tiles then leave m alone, alpha is exactly 1 for the whole warp
+    // and the TMEM round trip that rescales the running output is skipped (warp-uniform vote below).
+    const float cand = raw * sl2;
+    const float mx = (cand > m + 8.0f) ? cand : m;
+    const float alpha = ex2(m - mx);  // 0 on the first tile (m = -inf), 1 when the reference point stays
     m = mx;
-    float ladd = 0.f;
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains instead of one 64-long dependent add chain
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
       sc[i] = ex2(fmaf(sc[i], sl2, -m));
-      ladd += sc[i];
+      l4[i & 3] += sc[i];
     }
-    l = fmaf(l, alpha, ladd);
+    l = fmaf(l, alpha, (l4[0] + l4[1]) + (l4[2] + l4[3]));
 #pragma unroll
     for (int i = 0; i < 64; i += 8) {
       if (i < n16) {
@@ -221,7 +226,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     // rescale the running output (the previous accumulate MMA finished: bar_o was waited at the end of iteration j-1)
-    if (j > 0) {
+    if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) {
 #pragma unroll
       for (int c = 0; c < HD; c += 32) {
         uint32_t r[32];
