@@ -417,6 +417,8 @@ def main():
                     help="launch the kernels of each step one by one instead of replaying the captured step (N=1 default: graph)")
     ap.add_argument("--ddp-graph", type=int, default=int(os.environ.get("MUSE_B200_DDP_GRAPH", "0")),
                     help="N>1: capture the whole DDP step (NCCL bucket all-reduces included) in one CUDA graph")
+    ap.add_argument("--nccl-sms", type=int, default=int(os.environ.get("MUSE_B200_NCCL_SMS", "4")),
+                    help="N>1: SMs left to NCCL (NCCL_MAX_NCHANNELS is capped to the same number); 0 = full GEMM grids, NCCL default")
     ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
                     help="torch.optim.AdamW(fused=True) or open_muse_b200.FusedAdamW (AdamW + bf16 operand packing in one pass)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -438,6 +440,12 @@ def main():
     if world > 1:
         if ddp_graph:  # graph capture of NCCL collectives: the watchdog must not poll events while the stream is capturing
             os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
+        if args.nccl_sms > 0:
+            # the gradient all-reduce needs ~11 GB/s here (144 MB per 13 ms of backward): a few NCCL channels (= CTAs = SMs)
+            # are plenty on NVLink 5, and the persistent GEMMs give exactly those SMs up instead of stalling behind them
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_sms))
+            os.environ.setdefault("NCCL_MIN_NCHANNELS", str(min(2, args.nccl_sms)))
+            ops.reserve_sms(args.nccl_sms)
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(3, args.warmup)
     B = args.batch
@@ -621,7 +629,8 @@ def main():
                        "global_batch": gb, "per_gpu_batch": B, "seq_len": 257,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "no explicit flush: per-step working set (~15 GB activations + 0.5 GB weights/grads/optimizer) >> 126 MB L2",
-                       "cuda_graph": bool(use_graph), "optimizer": args.optimizer},
+                       "cuda_graph": bool(use_graph), "optimizer": args.optimizer,
+                       "nccl_sms_reserved": args.nccl_sms if world > 1 else 0},
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4},
             "gpu_launches": launches,
@@ -632,6 +641,9 @@ def main():
             out.update(secondary)
         print(json.dumps(out))
     if world > 1:
+        run = None  # drop the captured graph (its NCCL nodes) before the process group goes away
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -29,6 +29,13 @@ const char* muse_last_error(void);
 int muse_set_device(int device);            /* cudaSetDevice for this library's runtime instance */
 int muse_device_info(int* sm_major, int* sm_minor, int* num_sms);
 
+/* Data-parallel training: leave `n` SMs free for the collective (NCCL) kernels that run concurrently with backward.  The
+ * persistent GEMM kernels then launch (SM count - n) CTAs, so a CTA never has to wait for an SM an all-reduce CTA is
+ * holding (with a static tile assignment such a late CTA would delay the whole GEMM by its full duration).  n = 0 restores
+ * the full grid.  Process-wide, set once after init (the reference reaches this path through accelerate / DDP,
+ * training/train_maskgit_imagenet.py:305). */
+int muse_reserve_sms(int n);
+
 /* GEMM epilogues */
 #define MUSE_EPI_BF16 0        /* C bf16 = acc                                   */
 #define MUSE_EPI_F32 1         /* C fp32 = acc                                   */
@@ -94,14 +101,16 @@ int muse_embed_bwd_sorted(const long long* order, const long long* bounds, const
 int muse_norm_fwd(const void* x, int x_dtype, const float* w, const float* res, void* y, int y_dtype, float* mean,
                   float* rstd, int rows, int H, float eps, int act, int rms, void* stream);
 /* dx = norm_bwd(dy) (* gelu'(x) if act 1) (+ dres if given).  Weight gradient dw[H] = sum_rows dy * xhat (nullable):
+ *   dx_bf16_copy (nullable; fp32 dx, H <= 1024, no GLU): a bf16 copy of dx written in the same pass (the residual-stream
+ *   gradient is the next GEMM operand).
  *   dw_ws given (muse_norm_bwd_workspace_floats(rows, H, act) floats): dw is STORED, reduced in a fixed order -> run-to-run
  *   bit-identical, no zero fill needed; dw_ws null: dw += ... with atomics (caller zero-fills; order-dependent).
  * act 2: dx is [rows, 2H] = d[a | b] (LayerNorm backward and GLU backward in one pass; v is recomputed from x).
  * y_fwd (nullable, act 2 with bf16 tensors only): the forward output bf16 [rows, H]; when given, the row reductions of
  * the first pass come from (dy, y_fwd) alone instead of re-evaluating the GELU over [a | b]. */
 int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
-                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, float* dw,
-                  float* dw_ws, int rows, int H, int act, int rms, void* stream);
+                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, void* dx_bf16_copy,
+                  float* dw, float* dw_ws, int rows, int H, int act, int rms, void* stream);
 long long muse_norm_bwd_workspace_floats(int rows, int H, int act);
 
 /* GLU of FeedForward (:789-792): ab bf16 [rows, 2I] = [wi_0(x) | wi_1(x)], out bf16 [rows, I] = gelu(a) * b. */

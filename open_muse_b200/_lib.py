@@ -22,6 +22,7 @@ SIGNATURES = {
     "muse_last_error": (c_char_p, []),
     "muse_set_device": (c_int, [_I]),
     "muse_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "muse_reserve_sms": (c_int, [_I]),
     "muse_gemm_bf16": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "muse_gemm_splitk_workspace_bytes": (c_longlong, [_I, _I, _I]),
     "muse_gemm_bf16_splitk": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
@@ -33,7 +34,7 @@ SIGNATURES = {
     "muse_embed_bwd_sorted_workspace_bytes": (c_longlong, [_I, _I, _I]),
     "muse_embed_bwd_sorted": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_norm_fwd": (c_int, [_P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P]),
-    "muse_norm_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "muse_norm_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_norm_bwd_workspace_floats": (c_longlong, [_I, _I, _I]),
     "muse_glu_fwd": (c_int, [_P, _P, _L, _I, _P]),
     "muse_glu_bwd": (c_int, [_P, _P, _P, _L, _I, _P]),

@@ -28,6 +28,7 @@ int check_launch(const char* what) {
 // kernels (defined in the other translation units)
 int gemm_tcgen05(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, cudaStream_t, void*, long long);
 long long gemm_splitk_workspace_bytes(int, int, int);
+void set_reserved_sms(int);
 int pack_bf16(const void*, int, long long, cudaStream_t);
 int adamw_ema_step(const void*, int, float*, long long*, const float*, float, float, float, float, float, int, float, float, int, int, int, float, float, cudaStream_t);
 int cast_bf16(const float*, void*, long long, cudaStream_t);
@@ -36,7 +37,7 @@ int embed_bwd(const long long*, const float*, float*, float*, int, int, int, int
 int embed_bwd_sorted(const long long*, const long long*, const float*, float*, float*, void*, int, int, int, int, cudaStream_t);
 long long embed_bwd_sorted_workspace_bytes(int, int, int);
 int norm_fwd(const void*, int, const float*, const float*, void*, int, float*, float*, int, int, float, int, int, cudaStream_t);
-int norm_bwd(const void*, int, const void*, int, const float*, const float*, const float*, const float*, const void*, void*, int, float*, float*, int, int, int, int, cudaStream_t);
+int norm_bwd(const void*, int, const void*, int, const float*, const float*, const float*, const float*, const void*, void*, int, void*, float*, float*, int, int, int, int, cudaStream_t);
 long long norm_bwd_workspace_floats(int, int, int);
 int glu_fwd(const void*, void*, long long, int, cudaStream_t);
 int glu_bwd(const void*, const void*, void*, long long, int, cudaStream_t);
@@ -98,6 +99,11 @@ int muse_device_info(int* sm_major, int* sm_minor, int* num_sms) {
   return MUSE_OK;
 }
 
+int muse_reserve_sms(int n) {
+  set_reserved_sms(n);
+  return MUSE_OK;
+}
+
 int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
                    int ldc, int a_mn, int b_mn, int epilogue, void* stream) {
   if (epilogue == MUSE_EPI_RESADD_F32 && res == nullptr) { set_last_error("gemm: RESADD epilogue needs res"); return MUSE_ERR_INVALID; }
@@ -142,9 +148,10 @@ int muse_norm_fwd(const void* x, int x_dtype, const float* w, const float* res, 
   return norm_fwd(x, x_dtype, w, res, y, y_dtype, mean, rstd, rows, H, eps, act, rms, ST(stream));
 }
 int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
-                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, float* dw,
-                  float* dw_ws, int rows, int H, int act, int rms, void* stream) {
-  return norm_bwd(dy, dy_dtype, x, x_dtype, w, mean, rstd, dres, y_fwd, dx, dx_dtype, dw, dw_ws, rows, H, act, rms, ST(stream));
+                  const float* rstd, const float* dres, const void* y_fwd, void* dx, int dx_dtype, void* dx_bf16_copy,
+                  float* dw, float* dw_ws, int rows, int H, int act, int rms, void* stream) {
+  return norm_bwd(dy, dy_dtype, x, x_dtype, w, mean, rstd, dres, y_fwd, dx, dx_dtype, dx_bf16_copy, dw, dw_ws, rows, H, act, rms,
+                  ST(stream));
 }
 long long muse_norm_bwd_workspace_floats(int rows, int H, int act) { return norm_bwd_workspace_floats(rows, H, act); }
 

@@ -428,6 +428,7 @@ int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const unsigned lo
 namespace {
 
 int g_num_sms = 0;
+int g_reserved_sms = 0;  // SMs left free for concurrently running collective kernels (set_reserved_sms)
 int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
@@ -435,7 +436,8 @@ int num_sms() {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  return g_num_sms;
+  const int n = g_num_sms - g_reserved_sms;
+  return n > 16 ? n : 16;
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -479,6 +481,11 @@ int launch_major(int a_mn, int b_mn, int epi, const CUtensorMap& ta, const CUten
 }
 
 }  // namespace
+
+// The persistent GEMM owns one CTA per SM with a static tile assignment, so a CTA that cannot start (its SM is held by an
+// NCCL all-reduce CTA during data-parallel training) delays the whole kernel by its full duration.  Under DDP the host
+// reserves as many SMs as NCCL has channels: the GEMM grid shrinks by that many CTAs and both kernels fit side by side.
+void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
 
 // C[M,N] (ldc) = op(A) * op(B)^T with op selected by a_mn / b_mn:
 //   a_mn == 0: A points at a row-major [M, K] matrix (pitch lda);  a_mn == 1: at a row-major [K, M] matrix.

@@ -129,7 +129,7 @@ template <typename TDY, typename TX, typename TDX, int CH>
 __global__ void __launch_bounds__(kBwdWarps * 32)
 norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw,
+                const float* __restrict__ dres, TDX* __restrict__ dx, bf16* __restrict__ dx_copy, float* __restrict__ dw,
                 float* __restrict__ dw_ws, int rows, int H, int act, int rms) {
   extern __shared__ float s_dw[];  // [kBwdWarps][H] private rows
   const int lane = threadIdx.x & 31;
@@ -190,6 +190,9 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
           for (int j = 0; j < 8; ++j) o[j] += rs[c][j];
         }
         store8(dxr + col, o);
+        // bf16 copy of the residual-stream gradient: the GEMM operand of the previous layer's wo dgrad / wgrad (saves the
+        // separate fp32 -> bf16 cast pass over the same tensor)
+        if (dx_copy) store8(dx_copy + static_cast<size_t>(row) * H + col, o);
       }
     }
   }
@@ -619,7 +622,7 @@ int reduce_dw(const float* dw_ws, float* dw, int grid, int H, cudaStream_t s) {
 
 template <typename TDY, typename TX, typename TDX>
 int bwd_dispatch(const void* dy, const void* x, const float* w, const float* mean, const float* rstd,
-                 const float* dres, void* dx, float* dw, float* dw_ws, int rows, int H, int act, int rms,
+                 const float* dres, void* dx, void* dx_copy, float* dw, float* dw_ws, int rows, int H, int act, int rms,
                  cudaStream_t s) {
   const int grid = bwd_grid(rows, H, act);
   if (H <= 1024 && act != ACT_GLU) {
@@ -628,12 +631,13 @@ int bwd_dispatch(const void* dy, const void* x, const float* w, const float* mea
 #define MUSE_NB(CH)                                                                                          \
   norm_bwd_warp_kernel<TDY, TX, TDX, CH><<<grid, kBwdWarps * 32, smem, s>>>(                                 \
       reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd, dres,                 \
-      reinterpret_cast<TDX*>(dx), dw, dw_ws, rows, H, act, rms)
+      reinterpret_cast<TDX*>(dx), reinterpret_cast<bf16*>(dx_copy), dw, dw_ws, rows, H, act, rms)
     if (ch <= 1) MUSE_NB(1);
     else if (ch <= 2) MUSE_NB(2);
     else MUSE_NB(4);
 #undef MUSE_NB
   } else {
+    if (dx_copy) { set_last_error("norm_bwd: the bf16 copy of dx is only produced for H <= 1024 without GLU"); return MUSE_ERR_UNSUPPORTED; }
     const size_t smem = dw ? static_cast<size_t>(kWideWarps) * H * sizeof(float) : 0;
     auto kern = norm_bwd_wide_kernel<TDY, TX, TDX>;
     static bool attr = false;
@@ -690,11 +694,12 @@ long long norm_bwd_workspace_floats(int rows, int H, int act) {
 }
 
 int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w, const float* mean, const float* rstd,
-             const float* dres, const void* y_fwd, void* dx, int dx_dt, float* dw, float* dw_ws, int rows, int H, int act,
-             int rms, cudaStream_t s) {
+             const float* dres, const void* y_fwd, void* dx, int dx_dt, void* dx_copy, float* dw, float* dw_ws, int rows,
+             int H, int act, int rms, cudaStream_t s) {
   if (rows <= 0) return MUSE_OK;
   int rc = check_args("norm_bwd", H, act, dres);
   if (rc) return rc;
+  if (dx_copy && (dx_dt != 0 || act == ACT_GLU)) { set_last_error("norm_bwd: dx_copy needs an fp32 dx and no GLU"); return MUSE_ERR_INVALID; }
   if (act == ACT_GLU && dy_dt == 1 && x_dt == 1 && dx_dt == 1 && H <= 4096) {
     const int grid = bwd_grid(rows, H, act);
     const size_t smem = dw ? static_cast<size_t>(kGluWarps) * H * sizeof(float) : 0;
@@ -718,14 +723,14 @@ int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w,
   }
   const int key = dy_dt * 4 + x_dt * 2 + dx_dt;
   switch (key) {
-    case 0: return bwd_dispatch<float, float, float>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
-    case 1: return bwd_dispatch<float, float, bf16>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
-    case 2: return bwd_dispatch<float, bf16, float>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
-    case 3: return bwd_dispatch<float, bf16, bf16>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
-    case 4: return bwd_dispatch<bf16, float, float>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
-    case 5: return bwd_dispatch<bf16, float, bf16>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
-    case 6: return bwd_dispatch<bf16, bf16, float>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
-    case 7: return bwd_dispatch<bf16, bf16, bf16>(dy, x, w, mean, rstd, dres, dx, dw, dw_ws, rows, H, act, rms, s);
+    case 0: return bwd_dispatch<float, float, float>(dy, x, w, mean, rstd, dres, dx, dx_copy, dw, dw_ws, rows, H, act, rms, s);
+    case 1: return bwd_dispatch<float, float, bf16>(dy, x, w, mean, rstd, dres, dx, dx_copy, dw, dw_ws, rows, H, act, rms, s);
+    case 2: return bwd_dispatch<float, bf16, float>(dy, x, w, mean, rstd, dres, dx, dx_copy, dw, dw_ws, rows, H, act, rms, s);
+    case 3: return bwd_dispatch<float, bf16, bf16>(dy, x, w, mean, rstd, dres, dx, dx_copy, dw, dw_ws, rows, H, act, rms, s);
+    case 4: return bwd_dispatch<bf16, float, float>(dy, x, w, mean, rstd, dres, dx, dx_copy, dw, dw_ws, rows, H, act, rms, s);
+    case 5: return bwd_dispatch<bf16, float, bf16>(dy, x, w, mean, rstd, dres, dx, dx_copy, dw, dw_ws, rows, H, act, rms, s);
+    case 6: return bwd_dispatch<bf16, bf16, float>(dy, x, w, mean, rstd, dres, dx, dx_copy, dw, dw_ws, rows, H, act, rms, s);
+    case 7: return bwd_dispatch<bf16, bf16, bf16>(dy, x, w, mean, rstd, dres, dx, dx_copy, dw, dw_ws, rows, H, act, rms, s);
   }
   set_last_error("norm_bwd: bad dtype codes");
   return MUSE_ERR_INVALID;

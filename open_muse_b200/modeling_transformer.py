@@ -348,7 +348,9 @@ class _LayerFn(torch.autograd.Function):
         # ---- FFN
         # every weight gradient below is STORED by a fixed-order reduction (deterministic split-K / ordered column sums):
         # no zero-filled buffers, no atomics, bit-identical from run to run
-        dy = ops.cast_bf16(dx3)
+        dy = ops.take_bf16_copy(dx3)  # written by the norm backward that produced dx3 (the next layer's, or the head's)
+        if dy is None:
+            dy = ops.cast_bf16(dx3)
         d_ml = ops.linear_dgrad(dy, s.w["wo"])
         g_wo = ops.linear_wgrad_det(dy, sv["ml"])
         if s.normformer:  # LN backward + GLU backward fused: reads d_ml and [a|b], writes d[a|b]
@@ -398,7 +400,7 @@ class _LayerFn(torch.autograd.Function):
         d_h1 = ops.linear_dgrad(d_qkv, s.w["qkv"])
         g_qkv = ops.linear_wgrad_det(d_qkv, sv["h1"])
         dx1, g_attn_ln = ops.norm_bwd(d_h1, sv["x"], _f32(w_attn_ln), sv["st1"], torch.float32, dres=dx2, rms=s.rms,
-                                      want_dw=True)
+                                      want_dw=True, bf16_copy=True)  # dx1 is the previous layer's dx3
         grads = [g_attn_ln, g_qkv[:H], g_qkv[H:2 * H], g_qkv[2 * H:], g_ao]
         if s.normformer:
             grads.append(g_post)
@@ -497,7 +499,8 @@ class _HeadFn(torch.autograd.Function):
         else:
             d_hN = d_e
         if s.use_enc_ln:
-            dx, g_enc = ops.norm_bwd(d_hN, sv["x"], _f32(w_enc), sv["st0"], torch.float32, rms=s.rms, want_dw=True)
+            dx, g_enc = ops.norm_bwd(d_hN, sv["x"], _f32(w_enc), sv["st0"], torch.float32, rms=s.rms, want_dw=True,
+                                     bf16_copy=True)  # dx is the last layer's dx3
             grads = [g_enc] + grads
         else:
             dx = d_hN.float()

@@ -18,6 +18,12 @@ EPI_BF16, EPI_F32, EPI_ATOMIC_F32, EPI_RESADD_F32 = 0, 1, 2, 3
 _state = {"device": None, "launches": 0}
 
 
+def reserve_sms(n: int):
+    """Data-parallel training: leave n SMs to the NCCL all-reduce kernels that overlap backward (the persistent GEMMs then
+    launch SM-count - n CTAs).  Pair it with NCCL_MAX_NCHANNELS=n (set before init_process_group)."""
+    _lib.check(_lib.load().muse_reserve_sms(int(n)), "muse_reserve_sms")
+
+
 def launches() -> int:
     """Number of libmuse_b200 kernel-launching calls made so far (bench.py's gpu_launches)."""
     return _state["launches"]
@@ -220,7 +226,18 @@ def norm_fwd(x, w, eps, out_dtype, res=None, act=0, rms=0, save_stats=True):
     return y, stats
 
 
-def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None, want_dw=False):
+_bf16_copies = {}
+
+
+def take_bf16_copy(t):
+    """The bf16 copy norm_bwd(..., bf16_copy=True) produced alongside the fp32 tensor `t` (or None): consumed once."""
+    hit = _bf16_copies.pop(t.data_ptr(), None)
+    if hit is not None and hit[0] == (t._version, tuple(t.shape)):
+        return hit[1]
+    return None
+
+
+def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None, want_dw=False, bf16_copy=False):
     """y_fwd: the saved forward output (act=2, bf16 only) -- lets the kernel skip one GELU pass over [a | b].
     dw: fp32 [H] buffer the weight gradient is ADDED to (atomics; caller zero-fills).  want_dw=True instead returns
     (dx, dw) with a freshly stored dw reduced in a fixed order (run-to-run bit-identical)."""
@@ -230,13 +247,19 @@ def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=
     dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
     if y_fwd is not None and not (act == 2 and y_fwd.dtype == torch.bfloat16 and y_fwd.is_contiguous()):
         y_fwd = None
+    copy = None
+    if bf16_copy and dx_dtype == torch.float32 and act != 2 and H <= 1024:
+        copy = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        if len(_bf16_copies) > 8:
+            _bf16_copies.clear()
+        _bf16_copies[dx.data_ptr()] = ((dx._version, tuple(dx.shape)), copy)
     ws = None
     if want_dw:
         dw = torch.empty(H, dtype=torch.float32, device=x.device)
         ws = torch.empty(max(1, _lib.load().muse_norm_bwd_workspace_floats(rows, H, act)), dtype=torch.float32, device=x.device)
         _state["launches"] += 1  # the ordered column sum
     _call("muse_norm_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(w), _p(stats[0]), _p(stats[1]), _p(dres), _p(y_fwd), _p(dx),
-          _dt(dx), _p(dw), _p(ws), rows, H, act, rms, st)
+          _dt(dx), _p(copy), _p(dw), _p(ws), rows, H, act, rms, st)
     return (dx, dw) if want_dw else dx
 
 

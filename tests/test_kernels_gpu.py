@@ -328,3 +328,16 @@ def test_embed_bwd_deterministic(B, S, H, V):
     assert _rel(dword, rw) < 1e-6 and bool((dword[V - 10:V - 1] == 0).all())
     assert _rel(dpos[:S], dx.view(B, S, H).sum(0)) < 1e-6 and bool((dpos[S:] == 0).all())
     assert torch.equal(dword, outs[1][0]) and torch.equal(dpos, outs[1][1])
+
+
+def test_norm_bwd_emits_bf16_copy_of_dx():
+    rows, H = 1031, 512
+    x = _rand((rows, H), 1, dtype=torch.float32)
+    w = (1 + 0.1 * torch.randn(H, generator=torch.Generator().manual_seed(2))).to(DEV)
+    _, stats = ops.norm_fwd(x, w, 1e-5, torch.bfloat16)
+    dy, dres = _rand((rows, H), 3), torch.randn(rows, H, device=DEV)
+    dx, dw = ops.norm_bwd(dy, x, w, stats, torch.float32, dres=dres, want_dw=True, bf16_copy=True)
+    ref, _ = ops.norm_bwd(dy, x, w, stats, torch.float32, dres=dres, want_dw=True)
+    copy = ops.take_bf16_copy(dx)
+    assert torch.equal(dx, ref) and copy is not None and torch.equal(copy, dx.to(torch.bfloat16))
+    assert ops.take_bf16_copy(dx) is None  # consumed once

@@ -31,7 +31,7 @@ def _fake_ops(mp):
         assert w is None or w.shape == (H,)
         return torch.zeros(x.shape[0], H, dtype=out_dtype), (torch.zeros(2, x.shape[0]) if save_stats else None)
 
-    def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None, want_dw=False):
+    def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None, want_dw=False, bf16_copy=False):
         H = x.shape[1] // 2 if act == 2 else x.shape[1]
         assert dy.shape == (x.shape[0], H) and stats is not None
         if dres is not None:
@@ -48,7 +48,7 @@ def _fake_ops(mp):
 
     fakes = dict(
         gemm=gemm, linear_fwd=lin_fwd, linear_dgrad=lambda dy, w, out_dtype=BF: torch.zeros(dy.shape[0], w.shape[1], dtype=out_dtype),
-        linear_wgrad_det=wgrad, cast_bf16=lambda x: x.to(BF), pack_bf16=lambda table, n, blocks: None,
+        linear_wgrad_det=wgrad, cast_bf16=lambda x: x.to(BF), take_bf16_copy=lambda t: None, pack_bf16=lambda table, n, blocks: None,
         embed_fwd=lambda ids, w, pos: torch.zeros(ids.numel(), w.shape[1]), embed_bwd_det=embed_bwd,
         norm_fwd=norm_fwd, norm_bwd=norm_bwd, glu_fwd=lambda ab: torch.zeros(ab.shape[0], ab.shape[1] // 2, dtype=BF),
         glu_bwd=lambda ab, d: torch.zeros_like(ab),
