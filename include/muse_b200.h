@@ -113,6 +113,17 @@ int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
                   float* dw, float* dw_ws, int rows, int H, int act, int rms, void* stream);
 long long muse_norm_bwd_workspace_floats(int rows, int H, int act);
 
+/* Two chained norms of a normformer layer in one pass (muse/modeling_transformer.py:882-884 then :787):
+ *   x2 fp32 = res fp32 + norm1(a bf16) * w1   (post_attn_layer_norm + residual add)
+ *   h2 bf16 = norm2(x2) * w2                  (FeedForward.pre_mlp_layer_norm, always LayerNorm: rms2 = 0)
+ * and their joint backward: dx2 = norm2_bwd(d_h2) + dres, d_a = norm1_bwd(dx2); dw2 / dw1 are STORED (fixed-order
+ * reduction; ws = 2 * muse_norm_bwd_workspace_floats(rows, H, 0) floats).  H % 8 == 0, H <= 1024. */
+int muse_norm2_fwd(const void* a, const float* res, const float* w1, const float* w2, float* x2, void* h2, float* mean1,
+                   float* rstd1, float* mean2, float* rstd2, int rows, int H, float eps, int rms1, int rms2, void* stream);
+int muse_norm2_bwd(const void* d_h2, const float* x2, const float* w2, const float* mean2, const float* rstd2,
+                   const float* dres, const void* a, const float* w1, const float* mean1, const float* rstd1, float* dx2,
+                   void* d_a, float* dw2, float* dw1, float* ws, int rows, int H, int rms1, int rms2, void* stream);
+
 /* GLU of FeedForward (:789-792): ab bf16 [rows, 2I] = [wi_0(x) | wi_1(x)], out bf16 [rows, I] = gelu(a) * b. */
 int muse_glu_fwd(const void* ab, void* out, long long rows, int I, void* stream);
 int muse_glu_bwd(const void* ab, const void* dout, void* dab, long long rows, int I, void* stream);

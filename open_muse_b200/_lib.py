@@ -36,6 +36,8 @@ SIGNATURES = {
     "muse_norm_fwd": (c_int, [_P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _F, _I, _I, _P]),
     "muse_norm_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "muse_norm_bwd_workspace_floats": (c_longlong, [_I, _I, _I]),
+    "muse_norm2_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P]),
+    "muse_norm2_bwd": (c_int, [_P] * 15 + [_I, _I, _I, _I, _P]),
     "muse_glu_fwd": (c_int, [_P, _P, _L, _I, _P]),
     "muse_glu_bwd": (c_int, [_P, _P, _P, _L, _I, _P]),
     "muse_attn_fwd": (c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P]),

@@ -39,6 +39,8 @@ long long embed_bwd_sorted_workspace_bytes(int, int, int);
 int norm_fwd(const void*, int, const float*, const float*, void*, int, float*, float*, int, int, float, int, int, cudaStream_t);
 int norm_bwd(const void*, int, const void*, int, const float*, const float*, const float*, const float*, const void*, void*, int, void*, float*, float*, int, int, int, int, cudaStream_t);
 long long norm_bwd_workspace_floats(int, int, int);
+int norm2_fwd(const void*, const float*, const float*, const float*, float*, void*, float*, float*, float*, float*, int, int, float, int, int, cudaStream_t);
+int norm2_bwd(const void*, const float*, const float*, const float*, const float*, const float*, const void*, const float*, const float*, const float*, float*, void*, float*, float*, float*, int, int, int, int, cudaStream_t);
 int glu_fwd(const void*, void*, long long, int, cudaStream_t);
 int glu_bwd(const void*, const void*, void*, long long, int, cudaStream_t);
 int attn_fwd(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, float, cudaStream_t);
@@ -154,6 +156,15 @@ int muse_norm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, cons
                   ST(stream));
 }
 long long muse_norm_bwd_workspace_floats(int rows, int H, int act) { return norm_bwd_workspace_floats(rows, H, act); }
+int muse_norm2_fwd(const void* a, const float* res, const float* w1, const float* w2, float* x2, void* h2, float* mean1,
+                   float* rstd1, float* mean2, float* rstd2, int rows, int H, float eps, int rms1, int rms2, void* stream) {
+  return norm2_fwd(a, res, w1, w2, x2, h2, mean1, rstd1, mean2, rstd2, rows, H, eps, rms1, rms2, ST(stream));
+}
+int muse_norm2_bwd(const void* d_h2, const float* x2, const float* w2, const float* mean2, const float* rstd2,
+                   const float* dres, const void* a, const float* w1, const float* mean1, const float* rstd1, float* dx2,
+                   void* d_a, float* dw2, float* dw1, float* ws, int rows, int H, int rms1, int rms2, void* stream) {
+  return norm2_bwd(d_h2, x2, w2, mean2, rstd2, dres, a, w1, mean1, rstd1, dx2, d_a, dw2, dw1, ws, rows, H, rms1, rms2, ST(stream));
+}
 
 int muse_glu_fwd(const void* ab, void* out, long long rows, int I, void* stream) { return glu_fwd(ab, out, rows, I, ST(stream)); }
 int muse_glu_bwd(const void* ab, const void* dout, void* dab, long long rows, int I, void* stream) {

@@ -208,6 +208,184 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
 }
 
 
+// ---- two chained norms in one pass (normformer layer, H <= 1024): the post-attention norm with its residual add
+// (reference :882-884: x2 = x + post_attn_layer_norm(attention_output)) immediately followed by the FeedForward's
+// pre_mlp_layer_norm (:787, always LayerNorm).  Separately these are two HBM round trips of the residual stream (x2 is
+// written by the first and read back by the second); fused, the row stays in registers: 12 instead of 16 bytes per element
+// forward, 18 instead of 22 backward.
+template <int CH>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+norm2_fwd_warp_kernel(const bf16* __restrict__ a, const float* __restrict__ res, const float* __restrict__ w1,
+                      const float* __restrict__ w2, float* __restrict__ x2, bf16* __restrict__ h2,
+                      float* __restrict__ mean1_out, float* __restrict__ rstd1_out, float* __restrict__ mean2_out,
+                      float* __restrict__ rstd2_out, int rows, int H, float eps, int rms1, int rms2) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float inv_h = 1.0f / static_cast<float>(H);
+  float v[CH][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < H) {
+      load8(a + static_cast<size_t>(row) * H + col, v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[c][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
+    }
+  }
+  const float mean1 = rms1 ? 0.f : warp_sum(sum) * inv_h;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    if ((c * 32 + lane) * 8 < H) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean1; sq += d * d; }
+    }
+  const float rstd1 = rsqrtf(warp_sum(sq) * inv_h + eps);
+  // x2 = res + norm1(a) * w1  (kept in v), second statistics over x2
+  float sum2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < H) {
+      float wv[8], r8[8];
+      load8(w1 + col, wv);
+      load8(res + static_cast<size_t>(row) * H + col, r8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[c][j] = r8[j] + (v[c][j] - mean1) * rstd1 * wv[j];
+        sum2 += v[c][j];
+      }
+      store8(x2 + static_cast<size_t>(row) * H + col, v[c]);
+    }
+  }
+  const float mean2 = rms2 ? 0.f : warp_sum(sum2) * inv_h;
+  float sq2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+    if ((c * 32 + lane) * 8 < H) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean2; sq2 += d * d; }
+    }
+  const float rstd2 = rsqrtf(warp_sum(sq2) * inv_h + eps);
+  if (lane == 0) {
+    if (mean1_out) { mean1_out[row] = mean1; rstd1_out[row] = rstd1; mean2_out[row] = mean2; rstd2_out[row] = rstd2; }
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < H) {
+      float wv[8], o[8];
+      load8(w2 + col, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean2) * rstd2 * wv[j];
+      store8(h2 + static_cast<size_t>(row) * H + col, o);
+    }
+  }
+}
+
+// backward of the pair: dx2 = LN2_bwd(d_h2; x2) + dres ; d_a = LN1_bwd(dx2; a) ; dw2 += d_h2 * x2hat ; dw1 += dx2 * ahat
+template <int CH>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+norm2_bwd_warp_kernel(const bf16* __restrict__ d_h2, const float* __restrict__ x2, const float* __restrict__ w2,
+                      const float* __restrict__ mean2_in, const float* __restrict__ rstd2_in, const float* __restrict__ dres,
+                      const bf16* __restrict__ a, const float* __restrict__ w1, const float* __restrict__ mean1_in,
+                      const float* __restrict__ rstd1_in, float* __restrict__ dx2, bf16* __restrict__ d_a,
+                      float* __restrict__ dw2_ws, float* __restrict__ dw1_ws, int rows, int H, int rms1, int rms2) {
+  extern __shared__ float s_dw[];  // [2][kBwdWarps][H] private rows (dw2 then dw1)
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float acc2[CH][8], acc1[CH][8];
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc2[c][j] = 0.f; acc1[c][j] = 0.f; }
+  const float inv_h = 1.0f / static_cast<float>(H);
+  for (int row = blockIdx.x * kBwdWarps + warp; row < rows; row += gridDim.x * kBwdWarps) {
+    const size_t off = static_cast<size_t>(row) * H;
+    const float mean2 = rms2 ? 0.f : mean2_in[row], rstd2 = rstd2_in[row];
+    const float mean1 = rms1 ? 0.f : mean1_in[row], rstd1 = rstd1_in[row];
+    float xh[CH][8], g[CH][8], rs[CH][8], av[CH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < H) {
+        float xv[8], dv[8], wv[8];
+        load8(x2 + off + col, xv);
+        load8(d_h2 + off + col, dv);
+        load8(dres + off + col, rs[c]);
+        load8(a + off + col, av[c]);   // all four streams are requested before the first reduction
+        load8(w2 + col, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[c][j] = (xv[j] - mean2) * rstd2;
+          acc2[c][j] += dv[j] * xh[c][j];
+          g[c][j] = dv[j] * wv[j];
+          s1 += g[c][j];
+          s2 += g[c][j] * xh[c][j];
+        }
+      }
+    }
+    s1 = rms2 ? 0.f : warp_sum(s1) * inv_h;
+    s2 = warp_sum(s2) * inv_h;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < H) {
+        float wv[8];
+        load8(w1 + col, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d2 = rstd2 * (g[c][j] - s1 - xh[c][j] * s2) + rs[c][j];  // dx2
+          rs[c][j] = d2;
+          const float ah = (av[c][j] - mean1) * rstd1;
+          av[c][j] = ah;
+          acc1[c][j] += d2 * ah;
+          g[c][j] = d2 * wv[j];
+          t1 += g[c][j];
+          t2 += g[c][j] * ah;
+        }
+        store8(dx2 + off + col, rs[c]);
+      }
+    }
+    t1 = rms1 ? 0.f : warp_sum(t1) * inv_h;
+    t2 = warp_sum(t2) * inv_h;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < H) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd1 * (g[c][j] - t1 - av[c][j] * t2);
+        store8(d_a + off + col, o);
+      }
+    }
+  }
+  float* my2 = s_dw + static_cast<size_t>(warp) * H;
+  float* my1 = s_dw + static_cast<size_t>(kBwdWarps + warp) * H;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < H) { store8(my2 + col, acc2[c]); store8(my1 + col, acc1[c]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float u2 = 0.f, u1 = 0.f;
+    for (int k = 0; k < kBwdWarps; ++k) {
+      u2 += s_dw[static_cast<size_t>(k) * H + i];
+      u1 += s_dw[static_cast<size_t>(kBwdWarps + k) * H + i];
+    }
+    dw2_ws[static_cast<size_t>(blockIdx.x) * H + i] = u2;
+    dw1_ws[static_cast<size_t>(blockIdx.x) * H + i] = u1;
+  }
+}
+
 // ---- wide rows (H > 1024) and GLU mode: warp-per-row STREAMING kernels.  Nothing row-sized lives in registers:
 // pass 1 streams the row for the statistics, pass 2 streams it again (L1/L2 hits) to produce the output.  Few
 // registers -> many resident warps -> enough bytes in flight to approach HBM bandwidth without any block barrier.
@@ -685,6 +863,46 @@ int norm_fwd(const void* x, int x_dt, const float* w, const float* res, void* y,
   if (x_dt == 0 && y_dt == 0) return fwd_dispatch<float, float>(x, w, res, y, mean, rstd, rows, H, eps, act, rms, s);
   set_last_error("norm_fwd: bad dtype codes %d %d", x_dt, y_dt);
   return MUSE_ERR_INVALID;
+}
+
+// x2 = res + norm1(a) * w1 ; h2 = norm2(x2) * w2  (a bf16 [rows,H], res / x2 fp32, h2 bf16; H % 8 == 0, H <= 1024)
+int norm2_fwd(const void* a, const float* res, const float* w1, const float* w2, float* x2, void* h2, float* mean1,
+              float* rstd1, float* mean2, float* rstd2, int rows, int H, float eps, int rms1, int rms2, cudaStream_t s) {
+  if (rows <= 0) return MUSE_OK;
+  if (H % 8 != 0 || H > 1024 || H < 8) { set_last_error("norm2_fwd: H=%d must be a multiple of 8 in [8, 1024]", H); return MUSE_ERR_UNSUPPORTED; }
+  const int grid = ceil_div(rows, kWarpsPerBlock);
+  const int ch = ceil_div(H, 256);
+#define MUSE_N2F(CH) norm2_fwd_warp_kernel<CH><<<grid, kWarpsPerBlock * 32, 0, s>>>(reinterpret_cast<const bf16*>(a), res, w1, w2, x2, reinterpret_cast<bf16*>(h2), mean1, rstd1, mean2, rstd2, rows, H, eps, rms1, rms2)
+  if (ch <= 1) MUSE_N2F(1); else if (ch <= 2) MUSE_N2F(2); else MUSE_N2F(4);
+#undef MUSE_N2F
+  return check_launch("norm2_fwd");
+}
+
+// ws: 2 * norm_bwd_workspace_floats(rows, H, 0) floats (dw2 partial rows, then dw1 partial rows); dw2 / dw1 are STORED.
+int norm2_bwd(const void* d_h2, const float* x2, const float* w2, const float* mean2, const float* rstd2, const float* dres,
+              const void* a, const float* w1, const float* mean1, const float* rstd1, float* dx2, void* d_a, float* dw2,
+              float* dw1, float* ws, int rows, int H, int rms1, int rms2, cudaStream_t s) {
+  if (rows <= 0) return MUSE_OK;
+  if (H % 8 != 0 || H > 1024 || H < 8) { set_last_error("norm2_bwd: H=%d must be a multiple of 8 in [8, 1024]", H); return MUSE_ERR_UNSUPPORTED; }
+  const int grid = bwd_grid(rows, H, 0);
+  const int ch = ceil_div(H, 256);
+  float* ws2 = ws;
+  float* ws1 = ws + static_cast<size_t>(grid) * H;
+  const size_t smem = static_cast<size_t>(2) * kBwdWarps * H * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(norm2_bwd_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBwdWarps * 1024 * 4);
+    cudaFuncSetAttribute(norm2_bwd_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBwdWarps * 1024 * 4);
+    cudaFuncSetAttribute(norm2_bwd_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBwdWarps * 1024 * 4);
+    attr = true;
+  }
+#define MUSE_N2B(CH) norm2_bwd_warp_kernel<CH><<<grid, kBwdWarps * 32, smem, s>>>(reinterpret_cast<const bf16*>(d_h2), x2, w2, mean2, rstd2, dres, reinterpret_cast<const bf16*>(a), w1, mean1, rstd1, dx2, reinterpret_cast<bf16*>(d_a), ws2, ws1, rows, H, rms1, rms2)
+  if (ch <= 1) MUSE_N2B(1); else if (ch <= 2) MUSE_N2B(2); else MUSE_N2B(4);
+#undef MUSE_N2B
+  int rc = check_launch("norm2_bwd");
+  if (rc) return rc;
+  if ((rc = reduce_dw(ws2, dw2, grid, H, s))) return rc;
+  return reduce_dw(ws1, dw1, grid, H, s);
 }
 
 // floats of workspace a deterministic (dw_ws != nullptr) backward needs: one partial row of H per CTA

@@ -290,7 +290,12 @@ class _LayerFn(torch.autograd.Function):
         h1, st1 = ops.norm_fwd(x, _f32(w_attn_ln), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
         qkv = ops.linear_fwd(h1, s.w["qkv"])
         ctxt, lse = ops.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, nh, S, S, s.scale)
-        if s.normformer:
+        fused_norms = s.normformer and not s.cross and H <= 1024  # post-attention norm + FFN pre-norm in one pass
+        h2 = st3 = None
+        if fused_norms:
+            ao = ops.linear_fwd(ctxt, s.w["ao"])
+            x2, h2, st2 = ops.norm2_fwd(ao, x, _f32(w_post), _f32(w_pre), s.eps, rms1=s.rms, rms2=0, save_stats=grad)
+        elif s.normformer:
             ao = ops.linear_fwd(ctxt, s.w["ao"])
             x2, st2 = ops.norm_fwd(ao, _f32(w_post), s.eps, torch.float32, res=x, rms=s.rms, save_stats=grad)
         else:
@@ -317,7 +322,8 @@ class _LayerFn(torch.autograd.Function):
             if grad:
                 sv["x2b"] = x2b
         # ---- GLU feed-forward (:785-799)
-        h2, st3 = ops.norm_fwd(x2, _f32(w_pre), s.eps, torch.bfloat16, rms=0, save_stats=grad)
+        if h2 is None:
+            h2, st3 = ops.norm_fwd(x2, _f32(w_pre), s.eps, torch.bfloat16, rms=0, save_stats=grad)
         ab = ops.linear_fwd(h2, s.w["wi"])
         if s.normformer:  # GLU product + mid_mlp_layer_norm in one pass; gelu(a)*b is never written to HBM
             ml, st4 = ops.norm_fwd(ab, _f32(w_mid), s.eps, torch.bfloat16, act=2, rms=s.rms, save_stats=grad)
@@ -325,7 +331,7 @@ class _LayerFn(torch.autograd.Function):
             ml, st4 = ops.glu_fwd(ab), None
         x3 = ops.linear_fwd(ml, s.w["wo"], res=x2)
         if grad:
-            sv.update(h2=h2, st3=st3, ab=ab, ml=ml, st4=st4)
+            sv.update(h2=h2, st3=st3, ab=ab, ml=ml, st4=st4, fused_norms=fused_norms)
             ctx.sv, ctx.spec, ctx.params = sv, s, params
         return x3
 
@@ -362,7 +368,11 @@ class _LayerFn(torch.autograd.Function):
         d_h2 = ops.linear_dgrad(d_ab, s.w["wi"])
         g_wi = ops.linear_wgrad_det(d_ab, sv["h2"])
         x_mid = sv["x2b"] if s.cross else sv["x2"]
-        dx2, g_pre = ops.norm_bwd(d_h2, x_mid, _f32(w_pre), sv["st3"], torch.float32, dres=dx3, rms=0, want_dw=True)
+        if sv["fused_norms"]:  # FFN pre-norm backward + post-attention norm backward in one pass
+            dx2, d_ao, g_post, g_pre = ops.norm2_bwd(d_h2, x_mid, _f32(w_pre), dx3, sv["ao"], _f32(w_post), sv["st2"],
+                                                     rms1=s.rms, rms2=0)
+        else:
+            dx2, g_pre = ops.norm_bwd(d_h2, x_mid, _f32(w_pre), sv["st3"], torch.float32, dres=dx3, rms=0, want_dw=True)
         # ---- cross attention
         cross_grads = []
         if s.cross:
@@ -387,7 +397,9 @@ class _LayerFn(torch.autograd.Function):
                                       want_dw=True)
             cross_grads = [g_cln, g_cq, g_ckv[:H], g_ckv[H:], g_co] + ([g_cpost] if s.normformer else [])
         # ---- self attention
-        if s.normformer:
+        if sv["fused_norms"]:
+            pass  # d_ao / g_post came out of the fused norm backward above
+        elif s.normformer:
             d_ao, g_post = ops.norm_bwd(dx2, sv["ao"], _f32(w_post), sv["st2"], torch.bfloat16, rms=s.rms, want_dw=True)
         else:
             g_post, d_ao = None, ops.cast_bf16(dx2)

@@ -53,7 +53,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-_KERNELS_PER_CALL = {"muse_sample_step": 2, "muse_gemm_bf16_splitk": 2, "muse_adamw_ema_step": 4, "muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_embed_bwd_sorted": 4, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
+_KERNELS_PER_CALL = {"muse_norm2_bwd": 3, "muse_sample_step": 2, "muse_gemm_bf16_splitk": 2, "muse_adamw_ema_step": 4, "muse_ce_fwd": 2, "muse_attn_bwd": 2, "muse_embed_bwd": 2, "muse_embed_bwd_sorted": 4, "muse_vq_argmin": 2, "muse_vq_soft_code": 3,
                      "muse_groupnorm_silu_nhwc": 3, "muse_grn_fwd": 3, "muse_grn_bwd": 3,
                      "muse_dwconv3x3_norm_bwd": 2}
 _prof = {"on": False, "events": []}
@@ -261,6 +261,34 @@ def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=
     _call("muse_norm_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(w), _p(stats[0]), _p(stats[1]), _p(dres), _p(y_fwd), _p(dx),
           _dt(dx), _p(copy), _p(dw), _p(ws), rows, H, act, rms, st)
     return (dx, dw) if want_dw else dx
+
+
+def norm2_fwd(a, res, w1, w2, eps, rms1=0, rms2=0, save_stats=True):
+    """x2 = res + norm1(a) * w1 (fp32), h2 = norm2(x2) * w2 (bf16) in one pass; stats = [mean1, rstd1, mean2, rstd2]."""
+    st = _prep(a)
+    rows, H = a.shape
+    x2 = torch.empty(rows, H, dtype=torch.float32, device=a.device)
+    h2 = torch.empty(rows, H, dtype=torch.bfloat16, device=a.device)
+    stats = torch.empty(4, rows, dtype=torch.float32, device=a.device) if save_stats else None
+    sp = [None] * 4 if stats is None else [stats[i] for i in range(4)]
+    _call("muse_norm2_fwd", _p(a), _p(res), _p(w1), _p(w2), _p(x2), _p(h2), _p(sp[0]), _p(sp[1]), _p(sp[2]), _p(sp[3]), rows, H,
+          float(eps), int(rms1), int(rms2), st)
+    return x2, h2, stats
+
+
+def norm2_bwd(d_h2, x2, w2, dres, a, w1, stats, rms1=0, rms2=0):
+    """joint backward of norm2_fwd: returns (dx2 fp32, d_a bf16, dw1, dw2), weight gradients stored in a fixed order."""
+    st = _prep(a)
+    rows, H = a.shape
+    dev = a.device
+    dx2 = torch.empty(rows, H, dtype=torch.float32, device=dev)
+    d_a = torch.empty(rows, H, dtype=torch.bfloat16, device=dev)
+    dw1 = torch.empty(H, dtype=torch.float32, device=dev)
+    dw2 = torch.empty(H, dtype=torch.float32, device=dev)
+    ws = torch.empty(2 * max(1, _lib.load().muse_norm_bwd_workspace_floats(rows, H, 0)), dtype=torch.float32, device=dev)
+    _call("muse_norm2_bwd", _p(d_h2), _p(x2), _p(w2), _p(stats[2]), _p(stats[3]), _p(dres), _p(a), _p(w1), _p(stats[0]),
+          _p(stats[1]), _p(dx2), _p(d_a), _p(dw2), _p(dw1), _p(ws), rows, H, int(rms1), int(rms2), st)
+    return dx2, d_a, dw1, dw2
 
 
 # ------------------------------------------------------------------------------------------ GLU

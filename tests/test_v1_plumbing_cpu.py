@@ -39,6 +39,15 @@ def _fake_ops(mp):
         assert dw is None and want_dw  # the v1 model only uses the reproducible (stored) weight-gradient form
         return torch.zeros(x.shape, dtype=dx_dtype), torch.zeros(H, dtype=F32)
 
+    def norm2_fwd(a, res, w1, w2, eps, rms1=0, rms2=0, save_stats=True):
+        assert a.dtype == BF and res.dtype == F32 and a.shape == res.shape and w1.shape == w2.shape == (a.shape[1],)
+        return torch.zeros(a.shape, dtype=F32), torch.zeros(a.shape, dtype=BF), (torch.zeros(4, a.shape[0]) if save_stats else None)
+
+    def norm2_bwd(d_h2, x2, w2, dres, a, w1, stats, rms1=0, rms2=0):
+        assert d_h2.dtype == BF and x2.dtype == F32 and dres.dtype == F32 and a.dtype == BF and stats.shape[0] == 4
+        H = a.shape[1]
+        return torch.zeros(a.shape, dtype=F32), torch.zeros(a.shape, dtype=BF), torch.zeros(H), torch.zeros(H)
+
     def attb(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, sc):
         assert do.dtype == BF and do.shape == o.shape and dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape
 
@@ -50,7 +59,7 @@ def _fake_ops(mp):
         gemm=gemm, linear_fwd=lin_fwd, linear_dgrad=lambda dy, w, out_dtype=BF: torch.zeros(dy.shape[0], w.shape[1], dtype=out_dtype),
         linear_wgrad_det=wgrad, cast_bf16=lambda x: x.to(BF), take_bf16_copy=lambda t: None, pack_bf16=lambda table, n, blocks: None,
         embed_fwd=lambda ids, w, pos: torch.zeros(ids.numel(), w.shape[1]), embed_bwd_det=embed_bwd,
-        norm_fwd=norm_fwd, norm_bwd=norm_bwd, glu_fwd=lambda ab: torch.zeros(ab.shape[0], ab.shape[1] // 2, dtype=BF),
+        norm_fwd=norm_fwd, norm_bwd=norm_bwd, norm2_fwd=norm2_fwd, norm2_bwd=norm2_bwd, glu_fwd=lambda ab: torch.zeros(ab.shape[0], ab.shape[1] // 2, dtype=BF),
         glu_bwd=lambda ab, d: torch.zeros_like(ab),
         attn_fwd=lambda q, k, v, B, nh, Sq, Skv, sc: (torch.zeros(q.shape[0], nh * 64, dtype=BF), torch.zeros(B, nh, Sq)),
         attn_bwd=attb, ce_fwd=lambda lg, lab, V, ls: (torch.zeros(2), torch.zeros(2, lg.shape[0])),
