@@ -346,7 +346,7 @@ def test_norm_bwd_emits_bf16_copy_of_dx():
 @pytest.mark.parametrize("H,rms1", [(512, 0), (128, 1), (1024, 0), (768, 1)])
 def test_fused_double_norm_matches_the_two_single_kernels(H, rms1):
     """post-attention norm + residual followed by the FFN pre-norm, forward and backward, fused vs the two single-norm
-    kernels (same arithmetic order: outputs and statistics identical, weight gradients identical)."""
+    kernels (same formulas; the compiler contracts multiply-adds differently, so fp32 values agree to rounding)."""
     rows, eps = 2051, 1e-6
     a = _rand((rows, H), 1)
     x = _rand((rows, H), 2, dtype=torch.float32)
@@ -356,8 +356,8 @@ def test_fused_double_norm_matches_the_two_single_kernels(H, rms1):
     x2_ref, st1 = ops.norm_fwd(a, w1, eps, torch.float32, res=x, rms=rms1)
     h2_ref, st2 = ops.norm_fwd(x2_ref, w2, eps, torch.bfloat16, rms=0)
     x2, h2, st = ops.norm2_fwd(a, x, w1, w2, eps, rms1=rms1, rms2=0)
-    assert torch.equal(x2, x2_ref) and torch.equal(h2, h2_ref)
-    assert torch.equal(st[1], st1[1]) and torch.equal(st[2], st2[0]) and torch.equal(st[3], st2[1])
+    assert _rel(x2, x2_ref) < 1e-6 and _rel(h2, h2_ref) < 4e-3  # h2 is bf16: rounding flips on fp32 last-bit differences
+    assert _rel(st[1], st1[1]) < 1e-6 and _rel(st[2] + 1.0, st2[0] + 1.0) < 1e-6 and _rel(st[3], st2[1]) < 1e-6
     d_h2, dres = _rand((rows, H), 4), torch.randn(rows, H, device=DEV)
     dx2_ref, dw2_ref = ops.norm_bwd(d_h2, x2_ref, w2, st2, torch.float32, dres=dres, rms=0, want_dw=True)
     da_ref, dw1_ref = ops.norm_bwd(dx2_ref, a, w1, st1, torch.bfloat16, rms=rms1, want_dw=True)
