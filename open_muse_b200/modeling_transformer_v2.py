@@ -124,20 +124,28 @@ class AttentionBlock2D(nn.Module):
         self.crossattention = Attention(hidden_size, hidden_size, cfg["block_num_heads"], cfg)
 
 
-class _SampleBlock(nn.Module):
+class DownsampleBlock(nn.Module):
+    """(:505-523) optional Norm2D + Conv2d(k=2, s=2) in front of the res/attention blocks; module order == reference."""
+
     def __init__(self, channels, cfg):
         super().__init__()
+        self.downsample = (nn.Sequential(Norm2D(channels, cfg), nn.Conv2d(channels, channels, kernel_size=2, stride=2, bias=False))
+                           if cfg["force_down_up_sample"] else None)
         self.res_blocks = nn.ModuleList([ResBlock(channels, cfg) for _ in range(cfg["num_res_blocks"])])
         self.attention_blocks = nn.ModuleList([AttentionBlock2D(channels, cfg) for _ in range(cfg["num_res_blocks"])])
         self.gradient_checkpointing = False
 
 
-class DownsampleBlock(_SampleBlock):
-    pass
+class UpsampleBlock(nn.Module):
+    """(:543-565) res/attention blocks followed by an optional Norm2D + ConvTranspose2d(k=2, s=2)."""
 
-
-class UpsampleBlock(_SampleBlock):
-    pass
+    def __init__(self, channels, cfg):
+        super().__init__()
+        self.res_blocks = nn.ModuleList([ResBlock(channels, cfg) for _ in range(cfg["num_res_blocks"])])
+        self.attention_blocks = nn.ModuleList([AttentionBlock2D(channels, cfg) for _ in range(cfg["num_res_blocks"])])
+        self.upsample = (nn.Sequential(Norm2D(channels, cfg), nn.ConvTranspose2d(channels, channels, kernel_size=2, stride=2, bias=False))
+                         if cfg["force_down_up_sample"] else None)
+        self.gradient_checkpointing = False
 
 
 class GLUFeedForward(nn.Module):
@@ -195,7 +203,7 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
         self.register_to_config(**cfg)
         self.register_to_config(mask_token_id=cfg["vocab_size"] - 1)
         assert len(cfg["block_out_channels"]) == 1
-        for flag in ("use_bias", "force_down_up_sample", "use_fused_mlp"):
+        for flag in ("use_bias", "use_fused_mlp"):
             if cfg[flag]:
                 raise NotImplementedError(f"open_muse_b200.MaskGiTUViT_v2: {flag}=True is not supported")
         self.output_size = cfg["codebook_size"]
@@ -300,6 +308,12 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
                     "ln2": f32(ab.crossattn_layer_norm.weight), "a2": attn(ab.crossattention, False)})
             return out
 
+        if c_down := self.down_blocks[0].downsample:  # [co, ci, dy, dx] -> [co, (dy, dx, ci)]: a GEMM over 2x2 patches
+            W["ds_norm"] = f32(c_down[0].norm.weight)
+            W["ds"] = bf(c_down[1].weight.detach().permute(0, 2, 3, 1))
+            c_up = self.up_blocks[0].upsample  # ConvTranspose2d weight [ci, co, dy, dx] -> [(dy, dx, co), ci]
+            W["us_norm"] = f32(c_up[0].norm.weight)
+            W["us"] = bf(c_up[1].weight.detach().permute(2, 3, 1, 0).reshape(-1, c_up[1].weight.shape[0]))
         W["down"] = block(self.down_blocks[0])
         W["layers"] = []
         for l in self.transformer_layers:
@@ -378,6 +392,16 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
         dbg = self._debug_stages
         if dbg is not None:
             dbg.update(enc=enc.float().view(B, Skv, -1), cond=cond.float(), embed=h.view(B, S, -1).clone())
+        if "ds" in W:  # force_down_up_sample (:509-513): Norm2D, then the k2s2 conv as one GEMM over [B*S/4, (dy, dx, ci)] patches
+            if hw % 2:
+                raise ValueError(f"force_down_up_sample needs an even token grid, got {hw}x{hw}")
+            C = h.shape[1]
+            _, y = ops.add_norm_mod(h, W["ds_norm"], eps, rms, want_residual=False)
+            y = y.view(B, hw // 2, 2, hw // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * S // 4, 4 * C)
+            h = ops.linear_fwd(y, W["ds"], out_dtype=torch.float32)
+            hw, S = hw // 2, S // 4
+            if dbg is not None:
+                dbg["downsample"] = h.view(B, hw, hw, C).permute(0, 3, 1, 2).clone()
         for w in W["down"]:
             h = self._res_block(h, w, mod_all, B, hw)
             h = self._attention_block(h, enc, w, B, S, Skv)
@@ -400,6 +424,14 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
             h = self._attention_block(h, enc, w, B, S, Skv)
         if dbg is not None:
             dbg["up"] = h.view(B, S, -1).clone()
+        if "us" in W:  # (:555-559): Norm2D, then ConvTranspose2d(2, 2) as one GEMM to [B*S, (dy, dx, co)] + depth-to-space
+            C = h.shape[1]
+            _, y = ops.add_norm_mod(h, W["us_norm"], eps, rms, want_residual=False)
+            t = ops.linear_fwd(y, W["us"], out_dtype=torch.float32)
+            h = t.view(B, hw, hw, 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * S * 4, C)
+            hw, S = hw * 2, S * 4
+            if dbg is not None:
+                dbg["upsample"] = h.view(B, hw, hw, C).permute(0, 3, 1, 2).clone()
         # ConvMlmLayer: 1x1 conv -> Norm2D -> 1x1 conv
         y1 = ops.linear_fwd(ops.cast_bf16(h), W["mlm1"])
         _, y2 = ops.add_norm_mod(y1, W["mlm_norm"], eps, rms, want_residual=False)
@@ -413,6 +445,9 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
             # training: one autograd Function for the whole network (uvit_v2_train.py)
             if self.training and (c.hidden_dropout > 0.0 or c.attention_dropout > 0.0):
                 raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: dropout > 0 in training mode is not implemented")
+            if c.force_down_up_sample:
+                raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: force_down_up_sample=True is inference-only "
+                                          "(forward under torch.no_grad() / generate2); its backward is not implemented")
             from . import uvit_v2_train as T
 
             if getattr(self, "_single_train_function", False):  # private test hook: one Function for the whole network

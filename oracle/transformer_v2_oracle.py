@@ -114,10 +114,11 @@ def forward(p: Dict[str, torch.Tensor], cfg: dict, input_ids, encoder_hidden_sta
             labels=None, label_smoothing: float = 0.0, loss_weight=None, stages: Optional[dict] = None):
     """MaskGiTUViT_v2.forward (:242-319).  Returns logits [B, S, codebook_size] or (logits, loss)."""
     c = full_config(cfg)
-    if c["use_bias"] or c["force_down_up_sample"] or c["use_fused_mlp"]:
-        raise NotImplementedError("oracle restates the default wiring only (no bias, no down/up-sampling, GLU MLP)")
+    if c["use_bias"] or c["use_fused_mlp"]:
+        raise NotImplementedError("oracle restates the bias-free GLU wiring only")
     B, S = input_ids.shape
     hw = int(S ** 0.5)
+    C = c["block_out_channels"][0]
     st = stages if stages is not None else {}
     enc, _ = _norm(encoder_hidden_states @ p["encoder_proj.weight"].t(), p.get("encoder_proj_layer_norm.weight"), c)
     mc = sinusoidal_encode(micro_conds.flatten(), c["micro_cond_encode_dim"]).reshape(B, -1)
@@ -128,6 +129,12 @@ def forward(p: Dict[str, torch.Tensor], cfg: dict, input_ids, encoder_hidden_sta
     e, _ = _norm(F.embedding(input_ids, p["embed.embeddings.weight"]), p.get("embed.layer_norm.weight"), c)
     x = e @ p["embed.conv.weight"][:, :, 0, 0].t()
     st["embed"] = x
+    if c["force_down_up_sample"]:  # DownsampleBlock.downsample (:509-513): Norm2D -> Conv2d(k=2, s=2), tokens hw^2 -> (hw/2)^2
+        x, _ = _norm(x, p.get("down_blocks.0.downsample.0.norm.weight"), c)
+        x = F.conv2d(x.view(B, hw, hw, C).permute(0, 3, 1, 2), p["down_blocks.0.downsample.1.weight"], stride=2)
+        st["downsample"] = x
+        hw //= 2
+        x = x.permute(0, 2, 3, 1).reshape(B, hw * hw, C)
     for i in range(c["num_res_blocks"]):
         x = _res_block(x, cond, p, f"down_blocks.0.res_blocks.{i}.", c, hw)
         x = _attention_block(x, enc, p, f"down_blocks.0.attention_blocks.{i}.", c)
@@ -147,6 +154,12 @@ def forward(p: Dict[str, torch.Tensor], cfg: dict, input_ids, encoder_hidden_sta
         x = _res_block(x, cond, p, f"up_blocks.0.res_blocks.{i}.", c, hw)
         x = _attention_block(x, enc, p, f"up_blocks.0.attention_blocks.{i}.", c)
     st["up"] = x
+    if c["force_down_up_sample"]:  # UpsampleBlock.upsample (:555-559): Norm2D -> ConvTranspose2d(k=2, s=2)
+        x, _ = _norm(x, p.get("up_blocks.0.upsample.0.norm.weight"), c)
+        x = F.conv_transpose2d(x.view(B, hw, hw, C).permute(0, 3, 1, 2), p["up_blocks.0.upsample.1.weight"], stride=2)
+        st["upsample"] = x
+        hw *= 2
+        x = x.permute(0, 2, 3, 1).reshape(B, hw * hw, C)
     # ConvMlmLayer (:1002-1022): 1x1 conv -> Norm2D -> 1x1 conv
     y = x @ p["mlm_layer.conv1.weight"][:, :, 0, 0].t()
     y, _ = _norm(y, p.get("mlm_layer.layer_norm.norm.weight"), c)

@@ -154,6 +154,52 @@ def make_signatures(muse):
     print("signatures:", ", ".join(f"{k} ({len(v)})" for k, v in table.items()))
 
 
+def make_uvit_downup(muse):
+    """MaskGiTUViT_v2 with force_down_up_sample=True (modeling_transformer_v2.py:505-583): Norm2D + k2s2 conv before the down
+    block, Norm2D + ConvTranspose2d(2, 2) after the up block.  8x8 tokens -> 4x4 inside the network.  Same re-draw of the
+    zero-initialised tensors as fixture (6)."""
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+
+    cfg = dict(MICRO_V2, force_down_up_sample=True)
+    torch.manual_seed(60)
+    v2 = MaskGiTUViT_v2(**cfg)
+    init_sig = {k: (float(x.double().sum()), float(x.double().norm())) for k, x in v2.state_dict().items()}
+    g = torch.Generator().manual_seed(61)
+    with torch.no_grad():
+        for k, x in v2.state_dict().items():
+            if "adaLN_modulation.mapper" in k or k.endswith("gamma") or k.endswith("beta") or k == "mlm_layer.conv1.weight":
+                x.copy_(torch.randn(x.shape, generator=g) * 0.05)
+            elif k.endswith("norm.weight"):
+                x.copy_(1.0 + 0.1 * torch.randn(x.shape, generator=g))
+    v2.eval()
+    B, S = 2, 64
+    ids = torch.randint(0, 64, (B, S), generator=g)
+    mask = torch.rand(B, S, generator=g) < 0.6
+    inp = torch.where(mask, 71, ids)
+    lab = torch.where(mask, ids, -100)
+    enc = torch.randn(B, 5, 32, generator=g)
+    ce = torch.randn(B, 16, generator=g)
+    mc = torch.tensor([[256.0, 256.0, 0.0, 0.0, 6.0], [512.0, 384.0, 10.0, 20.0, 5.5]])
+    stages = {}
+    hooks = [v2.down_blocks[0].downsample.register_forward_hook(lambda m, i, o: stages.__setitem__("downsample", o.detach().clone())),
+             v2.up_blocks[0].upsample.register_forward_hook(lambda m, i, o: stages.__setitem__("upsample", o.detach().clone()))]
+    with torch.no_grad():
+        logits, loss = v2(inp, enc, ce, mc, labels=lab, label_smoothing=0.1)
+    for h in hooks:
+        h.remove()
+    empty_e, empty_c = torch.randn(1, 5, 32, generator=g), torch.randn(1, 16, generator=g)
+    with torch.no_grad():
+        gen_ids = v2.generate2(enc, ce, mc, empty_e, empty_c, temperature=(2.0, 0.0), timesteps=4,
+                               guidance_scale=3.0, seq_len=S, generator=torch.Generator().manual_seed(62))
+    torch.save(dict(config=cfg, seed=60, init_signature=init_sig, empty_embeds=empty_e, empty_cond_embeds=empty_c,
+                    state_dict={k: x.clone() for k, x in v2.state_dict().items()}, input_ids=inp, labels=lab,
+                    encoder_hidden_states=enc, cond_embeds=ce, micro_conds=mc, logits=logits.detach(), loss=loss.detach(),
+                    stages=stages, gen_seed=62, gen_ids=gen_ids.clone()),
+               os.path.join(HERE, "micro_uvit_v2_downup.pt"))
+    print("micro uvit v2 down/up: loss", float(loss), "logits std", float(logits.std()),
+          "downsample", tuple(stages["downsample"].shape), "upsample", tuple(stages["upsample"].shape))
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -164,6 +210,8 @@ def main():
             make_f16_256(muse)
         if "signatures" in only[0]:
             make_signatures(muse)
+        if "uvit_downup" in only[0]:
+            make_uvit_downup(muse)
         return
 
     # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
@@ -378,6 +426,7 @@ def main():
 
     make_f16_256(muse)
     make_signatures(muse)
+    make_uvit_downup(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

@@ -72,7 +72,7 @@ def test_argument_errors():
     with pytest.raises(ValueError):  # quirk Q14: 1024 is not divisible by the default 12 block heads
         MaskGiTUViT_v2(hidden_size=1024, block_out_channels=(1024,), num_hidden_layers=1, num_res_blocks=1)
     with pytest.raises(NotImplementedError):
-        MaskGiTUViT_v2(num_hidden_layers=1, num_res_blocks=1, force_down_up_sample=True)
+        MaskGiTUViT_v2(num_hidden_layers=1, num_res_blocks=1, use_bias=True)
 
 
 def test_compat_muse_package_and_pipeline_surface(tmp_path):
@@ -135,14 +135,21 @@ def test_uvit_v2_seeded_construction_matches_reference():
 
     from open_muse_b200 import MaskGiTUViT_v2
 
+    for name in ("micro_uvit_v2.pt", "micro_uvit_v2_downup.pt"):  # the second one has force_down_up_sample=True
+        g = torch.load(os.path.join(os.path.dirname(__file__), "golden", name), weights_only=False)
+        torch.manual_seed(g["seed"])
+        m = MaskGiTUViT_v2(**g["config"], some_unknown_legacy_key=3)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(g["state_dict"].keys())
+        for k, (s, n) in g["init_signature"].items():
+            assert abs(float(sd[k].double().sum()) - s) <= 1e-9 * max(1.0, abs(s)), k
+            assert abs(float(sd[k].double().norm()) - n) <= 1e-9 * max(1.0, n), k
+    m.train()
+    with pytest.raises(NotImplementedError):  # down/up-sampling is inference-only here
+        m(g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"])
     g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "micro_uvit_v2.pt"), weights_only=False)
     torch.manual_seed(g["seed"])
     m = MaskGiTUViT_v2(**g["config"], some_unknown_legacy_key=3)
-    sd = m.state_dict()
-    assert list(sd.keys()) == list(g["state_dict"].keys())
-    for k, (s, n) in g["init_signature"].items():
-        assert abs(float(sd[k].double().sum()) - s) <= 1e-9 * max(1.0, abs(s)), k
-        assert abs(float(sd[k].double().norm()) - n) <= 1e-9 * max(1.0, n), k
     assert m.config.mask_token_id == 71 and m.output_size == 64 and "some_unknown_legacy_key" not in m.config
     m.eval()
     with pytest.raises(RuntimeError), torch.no_grad():

@@ -66,6 +66,27 @@ def test_micro_uvit_v2_forward_loss_and_generate2(golden):
     assert torch.equal(ids, g["gen_ids"])
 
 
+def test_micro_uvit_v2_force_down_up_sample(golden):
+    """force_down_up_sample=True (Norm2D + k2s2 conv / Norm2D + ConvTranspose2d, modeling_transformer_v2.py:505-583) against
+    the unmodified reference: the two resampling outputs, logits, loss and the generate2 id trace."""
+    from oracle import transformer_v2_oracle as V2
+
+    g = golden("micro_uvit_v2_downup.pt")
+    p, cfg = g["state_dict"], g["config"]
+    with torch.no_grad():
+        st = {}
+        logits, loss = V2.forward(p, cfg, g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"],
+                                  labels=g["labels"], label_smoothing=0.1, stages=st)
+        _close(st["downsample"], g["stages"]["downsample"], 1e-4, 1e-5)
+        _close(st["upsample"], g["stages"]["upsample"], 1e-4, 2e-5)
+        _close(logits, g["logits"], 1e-4, 2e-5)
+        _close(loss, g["loss"], 1e-5, 0)
+        ids = V2.generate2(p, cfg, g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"], g["empty_embeds"],
+                           g["empty_cond_embeds"], timesteps=4, temperature=(2.0, 0.0), guidance_scale=3.0,
+                           generator=torch.Generator().manual_seed(g["gen_seed"]), seq_len=64)
+    assert torch.equal(ids, g["gen_ids"])
+
+
 def test_micro_taming_vqgan(golden):
     """taming VQGANModel restatement (strided Downsample with (0,1,0,1) padding, AttnBlocks, input-side shortcuts)."""
     from oracle import taming_vqgan_oracle as TG

@@ -112,6 +112,33 @@ def test_micro_uvit_v2_vs_reference_fixture(golden):
     assert out.dtype == torch.float32 and _rel(out, g["logits"]) < 2e-2
 
 
+def test_micro_uvit_v2_force_down_up_sample_vs_reference_fixture(golden):
+    """force_down_up_sample=True (reference :505-583): the k2s2 conv and the ConvTranspose2d run as patch GEMMs; stages,
+    logits, loss and the generate2 trace against the fixture made by the unmodified reference (8x8 tokens, 4x4 inside)."""
+    g = golden("micro_uvit_v2_downup.pt")
+    m = MaskGiTUViT_v2(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.to(DEV).eval()
+    m._debug_stages = {}
+    args = [g[k].to(DEV) for k in ("input_ids", "encoder_hidden_states", "cond_embeds", "micro_conds")]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, loss = m(*args, labels=g["labels"].to(DEV), label_smoothing=0.1)
+    st = m._debug_stages
+    m._debug_stages = None
+    print("stages:", " ".join(f"{k}={_rel(st[k], g['stages'][k]):.2e}" for k in ("downsample", "upsample")))
+    assert st["downsample"].shape == g["stages"]["downsample"].shape and st["upsample"].shape == g["stages"]["upsample"].shape
+    assert _rel(st["downsample"], g["stages"]["downsample"]) < 1e-2
+    assert _rel(st["upsample"], g["stages"]["upsample"]) < 2e-2
+    assert logits.shape == g["logits"].shape and _rel(logits, g["logits"]) < 2e-2, _rel(logits, g["logits"])
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 2e-3
+    ids = m.generate2(*args[1:], g["empty_embeds"].to(DEV), g["empty_cond_embeds"].to(DEV), temperature=(2.0, 0.0),
+                      timesteps=4, guidance_scale=3.0, seq_len=64, generator=torch.Generator(DEV).manual_seed(g["gen_seed"]))
+    assert ids.shape == g["gen_ids"].shape and int(ids.min()) >= 0 and int(ids.max()) < 64
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(*args, labels=g["labels"].to(DEV))
+
+
 def test_uvit_v2_default_widths_vs_oracle():
     """U-ViT widths of the cc12m configs (hidden 1024 / 16 heads, blocks 768 / 12 heads, kv_mapper, 256 tokens, 77 text
     states) with a shortened stack, random re-draw of the zero-initialised tensors; fp32 oracle on the CPU."""
