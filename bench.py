@@ -339,6 +339,46 @@ def kernel_rooflines(dev, peak_tf, peak_hbm):
     return out
 
 
+def t2i_pipeline_latency(dev):
+    """benchmark/muse_perf.py:241-293 on this box: PipelineMuse(default-config MaskGiTUViT_v2, ~603 M parameters, taming f16
+    VQGANModel) with 12 steps and classifier-free guidance, 256 px (256 tokens) and 512 px (1024 tokens, force_down_up_sample
+    as the reference's 512-px model), batch 1 and 8, PIL output.  Random weights, bf16; the CLIP text encoder is third party
+    and not in the timed region (precomputed states go in, as `prompt_embeds=`).  BASELINE.md section 2 holds the A100 / RTX 4090
+    figures of the reference harness (fp16, text encoder included) -- context, different hardware."""
+    from open_muse_b200 import MaskGiTUViT_v2, PipelineMuse
+    from open_muse_b200.modeling_taming_vqgan import VQGANModel
+
+    torch.manual_seed(2)
+    vae = VQGANModel(num_embeddings=8192).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(3)
+    emb = lambda *s: torch.randn(*s, device=dev, generator=g)
+    kw = dict(prompt_embeds=emb(1, 77, 768), pooled_embeds=emb(1, 768), negative_prompt_embeds=emb(1, 77, 768),
+              negative_pooled_embeds=emb(1, 768), timesteps=12)
+    rows = {}
+    for res in (256, 512):
+        torch.manual_seed(4)
+        tr = MaskGiTUViT_v2(force_down_up_sample=(res == 512))
+        with torch.no_grad():  # the zero-initialised output conv would make every logit equal: draw it like the other weights
+            torch.nn.init.trunc_normal_(tr.mlm_layer.conv1.weight, std=0.02)
+        tr = tr.to(dev).eval()
+        pipe = PipelineMuse(vae=vae, transformer=tr, is_class_conditioned=False).to(dev)
+        for bs in (1, 8):
+            run = lambda: pipe(**kw, num_images_per_prompt=bs, transformer_seq_len=(res // 16) ** 2, generator=g)
+            imgs = run()
+            assert len(imgs) == bs and imgs[0].size == (res, res), (len(imgs), imgs[0].size)
+            ms = _timeit(run, n=3, warm=1)
+            rows[f"{res}px_bs{bs}"] = {"latency_ms": ms, "images_per_s": bs / (ms * 1e-3)}
+        del tr, pipe
+        torch.cuda.empty_cache()
+    return {"unit": "ms", "rows": rows,
+            "config": "PipelineMuse text-to-image, MaskGiTUViT_v2 class defaults (22 layers x 1024, 3+3 res/attention blocks x 768, "
+                      "codebook 8192) + taming VQGANModel decode + PIL, 12 steps, CFG (2x batch inside), bf16, random weights, "
+                      "text encoder excluded; 512 px = force_down_up_sample (reference benchmark/muse_perf.py:241-293)",
+            "reference_published_ms": {"A100 256px_bs1": 474.0, "A100 512px_bs1": 538.5, "A100 256px_bs8": 601.8,
+                                       "A100 512px_bs8": 1004.5, "RTX4090 256px_bs8": 454.1, "RTX4090 512px_bs8": 763.3,
+                                       "source": "benchmark/artifacts/all.csv (fp16, xformers + fused norm, text encoder included)"}}
+
+
 def secondary_metrics(dev, base_model, peak_tf, peak_hbm):
     """The rest of BASELINE.json's metric and configs on the same box: decode steps/sec (config 5), the tokenizer round
     trip (config 3), the reference recipe in torch eager on this same GPU (the real bar), per-kernel rooflines."""
@@ -397,6 +437,11 @@ def secondary_metrics(dev, base_model, peak_tf, peak_hbm):
         del rstep
     except Exception as e:  # informational leg: never sinks the bench line
         out["torch_eager_same_gpu"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    try:  # informational leg (the reference's own published benchmark harness), never sinks the bench line
+        out["t2i_pipeline_latency"] = t2i_pipeline_latency(dev)
+    except Exception as e:
+        out["t2i_pipeline_latency"] = {"error": f"{type(e).__name__}: {e}"}
     torch.cuda.empty_cache()
     out["roofline_kernels"] = kernel_rooflines(dev, peak_tf, peak_hbm)
     return out

@@ -318,6 +318,16 @@ class VQGANModel(ModelMixin, ConfigMixin):
         return self.decode(self.quantize.get_codebook_entry(codebook_indices))
 
     @torch.no_grad()
+    def decode_code_uint8(self, codebook_indices):
+        """ids -> display bytes uint8 [B, H, W, 3]: the decoder's NHWC output through the reference's clamp / truncation recipe
+        on the device (pipeline_muse.py:245-252).  Extension used by PipelineMuse for output_type="pil"."""
+        z_q = self.quantize.get_codebook_entry(codebook_indices)
+        with ops.conv_precision(self.conv_precision):
+            z = ops.to_nhwc(z_q.float().contiguous())
+            h = ops.conv2d(z, self.post_quant_conv.weight, bias=self.post_quant_conv.bias)
+            return ops.image_to_uint8(self.decoder.run(h))
+
+    @torch.no_grad()
     def get_code(self, pixel_values):
         return self.quantize.get_code_nhwc(self._encode_nhwc(pixel_values))
 

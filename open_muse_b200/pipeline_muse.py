@@ -159,9 +159,7 @@ class PipelineMuse:
                 noise_schedule=get_mask_chedule(noise_schedule), generator=generator,
                 return_intermediate=return_intermediate, seq_len=seq_len)
         tokens, intermediate = out if return_intermediate else (out, None)
-        images = self.vae.decode_code(tokens)
-        if output_type != "pt":
-            images = [self.to_pil_image(img) for img in images]
+        images = self._decode(tokens, output_type)
         if return_intermediate:
             inter = [self.vae.decode_code(t) for t in intermediate]
             if output_type != "pt":

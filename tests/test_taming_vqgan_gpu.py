@@ -72,6 +72,10 @@ def test_micro_taming_vqgan_vs_reference(golden):
     out = m(img)
     assert len(out) == 3 and out[0].shape == g["recon"].shape
     assert torch.equal(m.get_code(img), ids)
+    # display bytes on the device == the reference's host recipe (pipeline_muse.py:245-252) on the decoded tensor
+    x = rec.permute(0, 2, 3, 1).float().cpu().numpy()
+    want = (255 * ((np.clip(2.0 * x - 1.0, -1.0, 1.0) + 1.0) / 2.0)).astype(np.uint8)
+    assert np.array_equal(m.decode_code_uint8(g["ids"].to(DEV)).cpu().numpy(), want)
 
 
 def test_taming_f16_tensor_core_route_matches_fp32_simt_route(monkeypatch):
