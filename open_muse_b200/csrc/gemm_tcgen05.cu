@@ -185,8 +185,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m_idx = (tile / p.num_n) % p.num_m;
       const int n0 = n_idx * BN;
       // residual epilogue: the residual slab is fetched in the coalesced (row = lane/8 + 4*it, chunk = lane%8) pattern
-      // one slab ahead, starting before the accumulator is even ready, so its HBM latency hides under the mainloop.
-      float4 res_next[8];
+      // kResAhead slabs ahead (a register ring, 16 KB per slab and CTA), starting before the accumulator is even ready.
+      // One slab ahead kept only ~16 KB of reads in flight per SM, which by Little's law caps the K = 512 residual GEMMs
+      // near 3 TB/s; three slabs cover the HBM latency at the SM's fair share of the bandwidth.
+      constexpr int kResAhead = 3;
+      float4 res_ring[kResAhead][8];
       auto fetch_res = [&](int c, float4 (&dst)[8]) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -197,7 +200,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             dst[it] = *reinterpret_cast<const float4*>(p.res + static_cast<size_t>(grow) * p.ldc + gcol);
         }
       };
-      if (EPI == EPI_RESADD_F32) fetch_res(0, res_next);
+      if (EPI == EPI_RESADD_F32) {
+#pragma unroll
+        for (int sl = 0; sl < kResAhead; ++sl) fetch_res(sl * 32, res_ring[sl]);
+      }
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
@@ -215,15 +221,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float* ws_tile = nullptr;
       if (EPI == EPI_SPLITK_F32 && partial)
         ws_tile = p.ws + (static_cast<size_t>(tile / tiles_mn) * tiles_mn + tile_mn) * (BM * BN);
-#pragma unroll 1
+      // (the residual variant is fully unrolled so that the ring slots are compile-time register names)
+#pragma unroll(EPI == EPI_RESADD_F32 ? BN / kColsPerSlab : 1)
       for (int c = 0; c < BN; c += kColsPerSlab) {
         if (n0 + c >= p.N) break;  // warp-uniform
-        float4 res_cur[8];
-        if (EPI == EPI_RESADD_F32) {
-#pragma unroll
-          for (int it = 0; it < 8; ++it) res_cur[it] = res_next[it];
-          fetch_res(c + kColsPerSlab, res_next);
-        }
         uint4* my_row = reinterpret_cast<uint4*>(stg + lane * C_::kStagingRowBytes);
         if (EPI == EPI_BF16) {
           uint32_t r0[32], r1[32];
@@ -284,7 +285,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               } else {  // EPI_RESADD_F32: out = residual + bf16(acc)  (Linear output is bf16 under autocast)
                 const float* rs = p.res + off;
                 if (full) {
-                  const float4 q4 = res_cur[it];
+                  const float4 q4 = res_ring[(c / kColsPerSlab) % kResAhead][it];
                   *reinterpret_cast<float4*>(dst) = make_float4(q4.x + bf16_round(f[0]), q4.y + bf16_round(f[1]),
                                                                 q4.z + bf16_round(f[2]), q4.w + bf16_round(f[3]));
                 } else {
@@ -294,6 +295,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+        if (EPI == EPI_RESADD_F32) fetch_res(c + kResAhead * kColsPerSlab, res_ring[(c / kColsPerSlab) % kResAhead]);
         __syncwarp();
       }
       ptx::tc_fence_before();

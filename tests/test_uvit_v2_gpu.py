@@ -121,7 +121,7 @@ def test_micro_uvit_v2_force_down_up_sample_vs_reference_fixture(golden):
     m.to(DEV).eval()
     m._debug_stages = {}
     args = [g[k].to(DEV) for k in ("input_ids", "encoder_hidden_states", "cond_embeds", "micro_conds")]
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         logits, loss = m(*args, labels=g["labels"].to(DEV), label_smoothing=0.1)
     st = m._debug_stages
     m._debug_stages = None
