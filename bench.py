@@ -464,6 +464,11 @@ def main():
                     help="N>1: capture the whole DDP step (NCCL bucket all-reduces included) in one CUDA graph")
     ap.add_argument("--nccl-sms", type=int, default=int(os.environ.get("MUSE_B200_NCCL_SMS", "0")),
                     help="N>1: SMs left to NCCL (NCCL_MAX_NCHANNELS is capped to the same number); 0 = full GEMM grids, NCCL default")
+    ap.add_argument("--nccl-channels", type=int, default=0,
+                    help="N>1 diagnostic: cap NCCL_MAX_NCHANNELS without shrinking the GEMM grids (0 = NCCL default)")
+    ap.add_argument("--ddp-no-sync", action="store_true",
+                    help="N>1 DIAGNOSTIC ONLY (invalid as a result): DDP wrapper with the gradient all-reduce skipped, to "
+                         "separate launch overhead from NCCL contention")
     ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
                     help="torch.optim.AdamW(fused=True) or open_muse_b200.FusedAdamW (AdamW + bf16 operand packing in one pass)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -491,6 +496,9 @@ def main():
             os.environ.setdefault("NCCL_MAX_NCHANNELS", str(args.nccl_sms))
             os.environ.setdefault("NCCL_MIN_NCHANNELS", str(min(2, args.nccl_sms)))
             ops.reserve_sms(args.nccl_sms)
+        elif args.nccl_channels > 0:
+            os.environ["NCCL_MAX_NCHANNELS"] = str(args.nccl_channels)
+            os.environ["NCCL_MIN_NCHANNELS"] = str(min(2, args.nccl_channels))
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(3, args.warmup)
     B = args.batch
@@ -522,11 +530,16 @@ def main():
     dev_tok = [t.to(dev) for t in host_tok]
     dev_cls = [t.to(dev) for t in host_cls]
 
+    import contextlib
+
+    no_sync = net.no_sync if (world > 1 and args.ddp_no_sync) else contextlib.nullcontext
+
     def step(tokens, cls):
         inp, lab = mask_batch(tokens, cls, 2024, 1024, gen=gen)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            _, loss = net(inp, labels=lab)
-        loss.backward()
+        with no_sync():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                _, loss = net(inp, labels=lab)
+            loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -675,7 +688,9 @@ def main():
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "no explicit flush: per-step working set (~15 GB activations + 0.5 GB weights/grads/optimizer) >> 126 MB L2",
                        "cuda_graph": bool(use_graph), "optimizer": args.optimizer,
-                       "nccl_sms_reserved": args.nccl_sms if world > 1 else 0},
+                       "nccl_sms_reserved": args.nccl_sms if world > 1 else 0,
+                       **({"nccl_max_channels": args.nccl_channels} if world > 1 and args.nccl_channels else {}),
+                       **({"DIAGNOSTIC_no_allreduce": True} if world > 1 and args.ddp_no_sync else {})},
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4},
             "gpu_launches": launches,

@@ -8,8 +8,8 @@ namespace muse {
 
 int attn_fwd_tc(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, float,
                 cudaStream_t, int*);
-int attn_bwd_dq_tc(const void*, const void*, const void*, const void*, const void*, const float*, float*, void*, int, int,
-                   int, int, int, int, int, int, int, int, float, cudaStream_t, int*);
+int attn_bwd_dq_tc(const void*, const void*, const void*, const void*, const float*, float*, void*, int, int, int, int,
+                   int, int, int, int, int, float, cudaStream_t, int*);
 int attn_bwd_dkdv_tc(const void*, const void*, const void*, const void*, const float*, const float*, void*, void*, int,
                      int, int, int, int, int, int, int, int, int, float, cudaStream_t, int*);
 
@@ -36,10 +36,9 @@ int attn_bwd(const void* q, const void* k, const void* v, const void* o, const v
   if (B <= 0 || Sq <= 0 || Skv <= 0) return MUSE_OK;
   int rc = check_strides("attn_bwd", hd, q_rs | o_rs | do_rs | dq_rs, k_rs | dk_rs, v_rs | dv_rs);
   if (rc) return rc;
-  if (o == nullptr) { set_last_error("attn_bwd: the forward output o is required (D = rowsum(dO * O))"); return MUSE_ERR_INVALID; }
+  (void)o; (void)o_rs;  // D is recomputed from (P, dP) inside the dQ kernel; O is not needed by backward
   int done = 0;
-  rc = attn_bwd_dq_tc(q, k, v, o, d_o, lse, dvec, dq, B, nh, Sq, Skv, q_rs, k_rs, v_rs, o_rs, do_rs, dq_rs, scale, s,
-                      &done);
+  rc = attn_bwd_dq_tc(q, k, v, d_o, lse, dvec, dq, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dq_rs, scale, s, &done);
   if (rc) return rc;
   return attn_bwd_dkdv_tc(q, k, v, d_o, lse, dvec, dk, dv, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dk_rs, dv_rs, scale, s,
                           &done);

@@ -7,7 +7,7 @@
 // (each <= 256 TMEM columns and <= ~112 KB smem), so tensor core, TMA and the softmax lanes of different CTAs overlap.
 //
 //   forward  : owned = q rows.   S = Q K_j^T -> online softmax (fp32) -> P (bf16, smem) -> O += P V_j      (TMEM: S 128 + O 64)
-//   dQ       : owned = q rows.   D = rowsum(dO * O); S, dP = dO V_j^T -> dS = P (dP - D) -> dQ += dS K_j  (TMEM: 64+64+64)
+//   dQ       : owned = q rows.   S, dP = dO V_j^T -> sweep 1: D = sum P*dP ; sweep 2: dS -> dQ += dS K_j  (TMEM: 64+64+64)
 //   dK/dV    : owned = kv rows.  S^T = K Q_i^T, dP^T = V dO_i^T -> P^T, dS^T -> dV += P^T dO_i, dK += dS^T Q_i
 //                                                                                       (TMEM: 64+64+64+64)
 // Operands are read straight from the strided [tokens, 3H] QKV projection through 3-D TMA tensor maps
@@ -99,8 +99,6 @@ struct TcParams {
   bf16* out1;  long long out1_rs;   // dkdv: dV
   float* lse;                        // [B, nh, Sq]
   float* dvec;                       // [B, nh, Sq]
-  const bf16* o_in;  long long o_in_rs;    // dq: the forward output O and dO as plain rows (D = rowsum(dO * O))
-  const bf16* do_in; long long do_in_rs;
 };
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -298,9 +296,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // (barrier A), thread 0 issues the score MMAs of the NEXT step, so the tensor core works while the exp2 / FMA math of
 // the current step runs; the dQ MMA of a step is never waited for by the step that issued it (dS is double-buffered,
 // K/V tiles sit in a 3-stage TMA ring with prefetch distance 2).
-// The softmax-backward row term D_i = sum_j P_ij dP_ij equals sum_d dO_id O_id (O = P V), so it comes from one 128-byte
-// read of the saved forward output and of dO per row before the loop -- ONE sweep over the kv tiles (3 MMA products per
-// tile) instead of a statistics sweep followed by a dS sweep (5 products and twice the exp2 work).
 // TMEM columns: S [0,64)  dP [64,128)  dQ [128,192).
 // smem: Q 16K | dO 16K | 3 x {K_j 8K, V_j 8K} | 2 x dS 16K (the partial-D exchange buffer aliases dS[0])
 constexpr int BWD_BN = 64;
@@ -317,7 +312,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint8_t* sdO = smem + 16384;
   uint8_t* sKV = smem + 32768;             // 3 stages x {K 8 KB, V 8 KB}
   uint8_t* sdS = smem + 32768 + 49152;     // 2 buffers x 16 KB
-  float* sDp = reinterpret_cast<float*>(sdS);  // [2][128] partial D (only used before the loop)
+  float* sDp = reinterpret_cast<float*>(sdS);  // [2][128] partial D (only used between the two sweeps)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768 + 49152 + 32768);
   uint64_t* bar_kv = bars;       // [3] TMA landed
   uint64_t* bar_s = bars + 3;    //     score MMAs done
@@ -353,13 +348,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t tmem = *tmem_holder;
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const int ntiles = ceil_div(p.Skv, BWD_BN);
-  const int nsteps = ntiles;
+  const int nsteps = 2 * ntiles;
   const int row = q0 + r;
   const long long stat_idx = (static_cast<long long>(b) * p.nh + h) * p.Sq + row;
   const float lse2 = row_ok ? p.lse[stat_idx] * kLog2e : 0.f;
   const float sl2 = p.scale * kLog2e;
 
-  auto n16_of = [&](int step) { return (min(BWD_BN, p.Skv - step * BWD_BN) + 15) & ~15; };
+  auto n16_of = [&](int step) { return (min(BWD_BN, p.Skv - (step % ntiles) * BWD_BN) + 15) & ~15; };
   auto issue_scores = [&](int step) {  // thread 0: S = Q K^T and dP = dO V^T of `step` into TMEM [0,128)
     uint8_t* sK = sKV + (step % 3) * 16384;
     const uint32_t idesc = ptx::make_idesc_bf16(128, n16_of(step), 0, 0);
@@ -373,8 +368,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   };
   auto load_kv = [&](int step) {       // thread 0: TMA of the K/V tile of `step` into its ring stage
     uint8_t* sK = sKV + (step % 3) * 16384;
-    tma_load_3d(sK, &tmK, &bar_kv[step % 3], h * HD, step * BWD_BN, b);
-    tma_load_3d(sK + 8192, &tmV, &bar_kv[step % 3], h * HD, step * BWD_BN, b);
+    const int jn = step % ntiles;
+    tma_load_3d(sK, &tmK, &bar_kv[step % 3], h * HD, jn * BWD_BN, b);
+    tma_load_3d(sK + 8192, &tmV, &bar_kv[step % 3], h * HD, jn * BWD_BN, b);
   };
 
   // ---- warp 8: control thread (TMA + MMA issue), never touches the softmax math -----------------------------------
@@ -392,12 +388,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::tc_fence_after();
       issue_scores(0);
       for (int st = 0; st < nsteps; ++st) {
+        const int u = st - ntiles;
         ptx::mbar_wait(bar_free, st & 1);  // scores of step st are in registers: TMEM [0,128) may be overwritten
         ptx::tc_fence_after();
         if (st + 1 < nsteps) {
           if (st + 2 < nsteps) {
             // ring stage (st+2)%3 was last read by the dQ MMA of step st-1
-            if (st >= 1) ptx::mbar_wait(&bar_o[(st - 1) & 1], ((st - 1) >> 1) & 1);
+            if (st - 1 >= ntiles) ptx::mbar_wait(&bar_o[(u - 1) & 1], ((u - 1) >> 1) & 1);
             ptx::mbar_expect_tx(&bar_kv[(st + 2) % 3], 8192 * 2);
             load_kv(st + 2);
           }
@@ -405,46 +402,27 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           ptx::tc_fence_after();
           issue_scores(st + 1);
         }
-        ptx::mbar_wait(&bar_ds[st & 1], (st >> 1) & 1);  // dS of this step is in shared memory
-        const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
-        uint8_t* sK = sKV + (st % 3) * 16384;
-        uint8_t* dS = sdS + (st & 1) * 16384;
-        const int ksteps = n16_of(st) >> 4;
-        for (int ks = 0; ks < ksteps; ++ks)  // dQ += dS K_j   (K_j consumed as an MN-major operand)
-          ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(dS), ks), desc_mnmajor(ptx::smem_u32(sK), ks), idesc,
-                        (st > 0 || ks > 0) ? 1u : 0u);
-        ptx::umma_commit(&bar_o[st & 1]);
+        if (u >= 0) {
+          ptx::mbar_wait(&bar_ds[u & 1], (u >> 1) & 1);  // dS of this step is in shared memory
+          const uint32_t idesc = ptx::make_idesc_bf16(128, HD, 0, 1);
+          uint8_t* sK = sKV + (st % 3) * 16384;
+          uint8_t* dS = sdS + (u & 1) * 16384;
+          const int ksteps = n16_of(st) >> 4;
+          for (int ks = 0; ks < ksteps; ++ks)  // dQ += dS K_j   (K_j consumed as an MN-major operand)
+            ptx::umma_f16(tmem + 128, desc_kmajor(ptx::smem_u32(dS), ks), desc_mnmajor(ptx::smem_u32(sK), ks), idesc,
+                          (u > 0 || ks > 0) ? 1u : 0u);
+          ptx::umma_commit(&bar_o[u & 1]);
+        }
       }
     }
   } else {
   // ---- warps 0-7: math threads ------------------------------------------------------------------------------------
-  // D = rowsum(dO * O): each thread dots its 32-column half of the row, the halves meet through shared memory
   float dsum = 0.f;
-  if (row_ok) {
-    const long long grow = static_cast<long long>(b) * p.Sq + row;
-    const uint4* po = reinterpret_cast<const uint4*>(p.o_in + grow * p.o_in_rs + h * HD + half * 32);
-    const uint4* pd = reinterpret_cast<const uint4*>(p.do_in + grow * p.do_in_rs + h * HD + half * 32);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 a = po[i], d = pd[i];
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 fa = unpack_bf16(aw[k]), fd = unpack_bf16(dw[k]);
-        dsum = fmaf(fa.x, fd.x, dsum);
-        dsum = fmaf(fa.y, fd.y, dsum);
-      }
-    }
-  }
-  sDp[half * 128 + r] = dsum;
-  math_sync();
-  dsum = sDp[r] + sDp[128 + r];
-  if (half == 0 && row_ok) p.dvec[stat_idx] = dsum;  // for the dK/dV kernel
-  math_sync();  // sDp aliases dS[0]: everyone has read it before the loop writes dS
-  const float neg_d_scaled = -dsum * p.scale;
   for (int st = 0; st < nsteps; ++st) {
-    const int u = st;
-    const int nvalid = min(BWD_BN, p.Skv - st * BWD_BN);
+    const int j = st % ntiles;
+    const bool sweep2 = st >= ntiles;
+    const int u = st - ntiles;  // index among the sweep-2 steps
+    const int nvalid = min(BWD_BN, p.Skv - j * BWD_BN);
     const int n16 = (nvalid + 15) & ~15;
     ptx::mbar_wait(bar_s, st & 1);
     ptx::tc_fence_after();
@@ -466,7 +444,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ptx::tc_fence_before();
     ptx::mbar_arrive(bar_free);  // (A) this thread holds its scores in registers
     uint8_t* dS = sdS + (u & 1) * 16384;
-    if (u >= 2) ptx::mbar_wait(&bar_o[u & 1], ((u >> 1) - 1) & 1);  // dQ MMA of step st-2 read this buffer
+    if (sweep2 && u >= 2) ptx::mbar_wait(&bar_o[u & 1], ((u >> 1) - 1) & 1);  // dQ MMA of step st-2 read this buffer
+    const float neg_d_scaled = -dsum * p.scale;
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       const int c = half * 32 + cc;
@@ -480,17 +459,31 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 8; ++i) pr[i] = (c + i8 + i < nvalid) ? pr[i] : 0.f;
           }
+          if (!sweep2) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pr[i] *= fmaf(__uint_as_float(d_reg[cc + i8 + i]), p.scale, neg_d_scaled);
-          uint4 v;
-          v.x = pack_bf16(pr[0], pr[1]); v.y = pack_bf16(pr[2], pr[3]);
-          v.z = pack_bf16(pr[4], pr[5]); v.w = pack_bf16(pr[6], pr[7]);
-          st_operand_chunk(dS, r, c + i8, v);
+            for (int i = 0; i < 8; ++i) dsum = fmaf(pr[i], __uint_as_float(d_reg[cc + i8 + i]), dsum);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pr[i] *= fmaf(__uint_as_float(d_reg[cc + i8 + i]), p.scale, neg_d_scaled);
+            uint4 v;
+            v.x = pack_bf16(pr[0], pr[1]); v.y = pack_bf16(pr[2], pr[3]);
+            v.z = pack_bf16(pr[4], pr[5]); v.w = pack_bf16(pr[6], pr[7]);
+            st_operand_chunk(dS, r, c + i8, v);
+          }
         }
       }
     }
-    ptx::fence_proxy_async();
-    ptx::mbar_arrive(&bar_ds[u & 1]);  // (B) this thread's part of dS is visible to the tensor core
+    if (sweep2) {
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&bar_ds[u & 1]);  // (B) this thread's part of dS is visible to the tensor core
+    }
+    if (st == ntiles - 1) {  // D = sum over both column halves, identical in both threads of the row
+      sDp[half * 128 + r] = dsum;
+      math_sync();
+      dsum = sDp[r] + sDp[128 + r];
+      if (half == 0 && row_ok) p.dvec[stat_idx] = dsum;  // for the dK/dV kernels
+      math_sync();  // sDp aliases dS[0]: everyone has read it before sweep 2 writes dS
+    }
   }
   }  // math threads
   // all dQ MMAs must have landed: last use of each completion barrier
@@ -780,9 +773,9 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
   return check_launch("attn_fwd_tc");
 }
 
-int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
-                   float* dvec, void* dq, int B, int nh, int Sq, int Skv, int q_rs, int k_rs, int v_rs, int o_rs, int do_rs,
-                   int dq_rs, float scale, cudaStream_t s, int* rows_done) {
+int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o, const float* lse, float* dvec,
+                   void* dq, int B, int nh, int Sq, int Skv, int q_rs, int k_rs, int v_rs, int do_rs, int dq_rs,
+                   float scale, cudaStream_t s, int* rows_done) {
   *rows_done = 0;
   int ntile, tile_rows;
   balanced_tiles(Sq, &ntile, &tile_rows);
@@ -797,8 +790,6 @@ int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* o, c
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dq); p.out0_rs = dq_rs; p.lse = const_cast<float*>(lse); p.dvec = dvec;
-  p.o_in = reinterpret_cast<const bf16*>(o); p.o_in_rs = o_rs;
-  p.do_in = reinterpret_cast<const bf16*>(d_o); p.do_in_rs = do_rs;
   p.tile_rows = tile_rows;
   attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 288, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
   *rows_done = Sq;
