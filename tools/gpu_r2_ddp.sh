@@ -4,7 +4,7 @@ N=${NGPU:-2}
 mkdir -p gpurun_out
 exec > >(tee gpurun_out/r2_ddp_n${N}.log) 2>&1
 python -c "import __graft_entry__ as g; g.build(); print('build ok')"
-run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) "$@" > gpurun_out/ddp_tmp.log 2>&1; echo "exit code $?"; grep -E '^\{' gpurun_out/ddp_tmp.log | python -c "
+run() { timeout ${RUN_TIMEOUT:-400} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) "$@" > gpurun_out/ddp_tmp.log 2>&1; echo "exit code $?"; grep -E '^\{' gpurun_out/ddp_tmp.log | python -c "
 import sys, json
 for l in sys.stdin:
     d = json.loads(l)
