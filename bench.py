@@ -460,7 +460,7 @@ def main():
                     help="skip decode steps/s, the tokenizer round trip, torch-eager-on-this-GPU and the per-kernel rooflines")
     ap.add_argument("--no-cuda-graph", action="store_true",
                     help="launch the kernels of each step one by one instead of replaying the captured step (N=1 default: graph)")
-    ap.add_argument("--ddp-graph", type=int, default=int(os.environ.get("MUSE_B200_DDP_GRAPH", "0")),
+    ap.add_argument("--ddp-graph", type=int, default=int(os.environ.get("MUSE_B200_DDP_GRAPH", "1")),
                     help="N>1: capture the whole DDP step (NCCL bucket all-reduces included) in one CUDA graph")
     ap.add_argument("--nccl-sms", type=int, default=int(os.environ.get("MUSE_B200_NCCL_SMS", "0")),
                     help="N>1: SMs left to NCCL (NCCL_MAX_NCHANNELS is capped to the same number); 0 = full GEMM grids, NCCL default")

@@ -160,7 +160,7 @@ def _attn_ref(q, k, v, scale):
     return s.softmax(-1) @ v
 
 
-@pytest.mark.parametrize("B,nh,Sq,Skv", [(2, 2, 257, 257), (1, 1, 64, 64), (3, 2, 16, 77), (2, 8, 256, 256), (1, 2, 130, 5), (4, 8, 257, 257), (2, 16, 256, 77), (3, 4, 385, 385)])
+@pytest.mark.parametrize("B,nh,Sq,Skv", [(2, 2, 257, 257), (1, 1, 64, 64), (3, 2, 16, 77), (2, 8, 256, 256), (1, 2, 130, 5), (4, 8, 257, 257), (2, 16, 256, 77), (3, 4, 385, 385), (2, 2, 66, 194), (1, 3, 193, 129)])
 def test_attention_fwd_bwd(B, nh, Sq, Skv):
     H = nh * 64
     cross = Sq != Skv
