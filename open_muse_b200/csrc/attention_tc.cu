@@ -99,53 +99,7 @@ struct TcParams {
   bf16* out1;  long long out1_rs;   // dkdv: dV
   float* lse;                        // [B, nh, Sq]
   float* dvec;                       // [B, nh, Sq]
-  // plain row pointers of the operands (rows addressed as b*S + s, head h at column h*64) for the CUDA-core tail below
-  const bf16* q_in;  long long q_in_rs;
-  const bf16* k_in;  long long k_in_rs;
-  const bf16* v_in;  long long v_in_rs;
-  const bf16* do_in; long long do_in_rs;
 };
-
-// Tail of the LOOPED dimension on the CUDA cores.  S = 257 (256 image tokens + the class token) leaves ONE row for a fifth
-// 64-wide tile, and a pipeline step costs nearly the same for 1 column as for 64 (TMA, two MMA round trips, barriers, and in
-// the forward the full 64-wide exp2 sweep).  When S % 64 <= kMaxTail the MMA loop runs over the full tiles only and the
-// remaining rows are folded in by fp32 dot products in the epilogue (64 FMAs per row and tail element; exact products like the
-// tensor core's, and P / dS are not rounded to bf16 on this path).
-constexpr int kMaxTail = 2;
-__host__ __device__ __forceinline__ int tail_rows(int S) {
-  const int t = S & 63;
-  return (S > 64 && t > 0 && t <= kMaxTail) ? t : 0;
-}
-// dot product of two 64-element bf16 rows (16-byte aligned), fp32 accumulation
-__device__ __forceinline__ float dot64(const bf16* a, const bf16* b) {
-  float acc = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 x = reinterpret_cast<const uint4*>(a)[c], y = reinterpret_cast<const uint4*>(b)[c];
-    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 fx = unpack_bf16(xw[k]), fy = unpack_bf16(yw[k]);
-      acc = fmaf(fx.x, fy.x, acc);
-      acc = fmaf(fx.y, fy.y, acc);
-    }
-  }
-  return acc;
-}
-// acc[0..32) += w * row[0..32)   (row: 32 bf16, 16-byte aligned)
-__device__ __forceinline__ void axpy32(uint32_t (&acc)[32], float w, const bf16* row) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint4 x = reinterpret_cast<const uint4*>(row)[c];
-    const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = unpack_bf16(xw[k]);
-      acc[8 * c + 2 * k] = __float_as_uint(fmaf(w, f.x, __uint_as_float(acc[8 * c + 2 * k])));
-      acc[8 * c + 2 * k + 1] = __float_as_uint(fmaf(w, f.y, __uint_as_float(acc[8 * c + 2 * k + 1])));
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ forward
 // TMEM columns: S [0,64)  O [64,128) -> 128 columns per CTA; smem 48 KB -> FOUR co-resident CTAs per SM overlap each
@@ -191,9 +145,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem = *tmem_holder;
   const uint32_t t_s = tmem + (static_cast<uint32_t>(warp * 32) << 16);        // S: columns [0,64)
   const uint32_t t_o = t_s + 64;                                                // O: columns [64,128)
-  const int ntail = tail_rows(p.Skv);
-  const int skv_main = p.Skv - ntail;  // keys covered by the MMA loop
-  const int ntiles = ceil_div(skv_main, FWD_BN);
+  const int ntiles = ceil_div(p.Skv, FWD_BN);
 
   if (tid == 0) {
     ptx::mbar_expect_tx(bar_kv, 16384 + 8192);
@@ -207,7 +159,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   for (int j = 0; j < ntiles; ++j) {
     const uint32_t par = j & 1;
-    const int nvalid = min(FWD_BN, skv_main - j * FWD_BN);
+    const int nvalid = min(FWD_BN, p.Skv - j * FWD_BN);
     const int n16 = (nvalid + 15) & ~15;
     if (tid == 0) {
       ptx::mbar_wait(bar_kv, par);
@@ -307,35 +259,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_3d(sV, &tmV, bar_v, h * HD, (j + 1) * FWD_BN, b);
     }
   }
-  // epilogue: (tail keys on the CUDA cores,) O / l -> bf16 rows, LSE
+  // epilogue: O / l -> bf16 rows, LSE
   const int row = q0 + tid;
   const bool row_ok = tid < rows_here;
-  float alpha_t = 1.f, pt[kMaxTail] = {0.f, 0.f};
-  const bf16* vt[kMaxTail] = {nullptr, nullptr};
-  if (ntail > 0 && row_ok) {
-    const bf16* qrow = p.q_in + (static_cast<long long>(b) * p.Sq + row) * p.q_in_rs + h * HD;
-    float cand[kMaxTail] = {-INFINITY, -INFINITY};
-    float mx = m;
-#pragma unroll
-    for (int t = 0; t < kMaxTail; ++t) {
-      if (t < ntail) {
-        const long long krow_i = static_cast<long long>(b) * p.Skv + skv_main + t;
-        cand[t] = dot64(qrow, p.k_in + krow_i * p.k_in_rs + h * HD) * sl2;
-        vt[t] = p.v_in + krow_i * p.v_in_rs + h * HD;
-        mx = fmaxf(mx, cand[t]);
-      }
-    }
-    alpha_t = ex2(m - mx);
-    l *= alpha_t;
-#pragma unroll
-    for (int t = 0; t < kMaxTail; ++t) {
-      if (t < ntail) {
-        pt[t] = ex2(cand[t] - mx);
-        l += pt[t];
-      }
-    }
-    m = mx;
-  }
   const float inv = 1.f / l;
   bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD;
 #pragma unroll
@@ -343,13 +269,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t r[32];
     ptx::tmem_ld_32x32b_x32(t_o + c, r);
     ptx::tmem_ld_wait();
-    if (ntail > 0 && row_ok) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha_t);
-#pragma unroll
-      for (int t = 0; t < kMaxTail; ++t)
-        if (t < ntail) axpy32(r, pt[t], vt[t] + c);
-    }
     if (row_ok) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
@@ -428,16 +347,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const int ntail = tail_rows(p.Skv);
-  const int skv_main = p.Skv - ntail;  // keys covered by the MMA loop
-  const int ntiles = ceil_div(skv_main, BWD_BN);
+  const int ntiles = ceil_div(p.Skv, BWD_BN);
   const int nsteps = 2 * ntiles;
   const int row = q0 + r;
   const long long stat_idx = (static_cast<long long>(b) * p.nh + h) * p.Sq + row;
   const float lse2 = row_ok ? p.lse[stat_idx] * kLog2e : 0.f;
   const float sl2 = p.scale * kLog2e;
 
-  auto n16_of = [&](int step) { return (min(BWD_BN, skv_main - (step % ntiles) * BWD_BN) + 15) & ~15; };
+  auto n16_of = [&](int step) { return (min(BWD_BN, p.Skv - (step % ntiles) * BWD_BN) + 15) & ~15; };
   auto issue_scores = [&](int step) {  // thread 0: S = Q K^T and dP = dO V^T of `step` into TMEM [0,128)
     uint8_t* sK = sKV + (step % 3) * 16384;
     const uint32_t idesc = ptx::make_idesc_bf16(128, n16_of(step), 0, 0);
@@ -455,9 +372,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tma_load_3d(sK, &tmK, &bar_kv[step % 3], h * HD, jn * BWD_BN, b);
     tma_load_3d(sK + 8192, &tmV, &bar_kv[step % 3], h * HD, jn * BWD_BN, b);
   };
-
-  // tail keys (CUDA cores): P and dP of this row against each of them, and the row's D for the epilogue
-  float p_t[kMaxTail] = {0.f, 0.f}, dp_t[kMaxTail] = {0.f, 0.f}, dsum_row = 0.f;
 
   // ---- warp 8: control thread (TMA + MMA issue), never touches the softmax math -----------------------------------
   if (warp == 8) {
@@ -504,26 +418,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   } else {
   // ---- warps 0-7: math threads ------------------------------------------------------------------------------------
   float dsum = 0.f;
-  // both threads of a row compute the same tail values; only the half-0 thread adds them to the row sum D
-  if (ntail > 0 && row_ok) {
-    const long long grow = static_cast<long long>(b) * p.Sq + row;
-    const bf16* qrow = p.q_in + grow * p.q_in_rs + h * HD;
-    const bf16* dorow = p.do_in + grow * p.do_in_rs + h * HD;
-#pragma unroll
-    for (int t = 0; t < kMaxTail; ++t) {
-      if (t < ntail) {
-        const long long krow_i = static_cast<long long>(b) * p.Skv + skv_main + t;
-        p_t[t] = ex2(fmaf(dot64(qrow, p.k_in + krow_i * p.k_in_rs + h * HD), sl2, -lse2));
-        dp_t[t] = dot64(dorow, p.v_in + krow_i * p.v_in_rs + h * HD);
-        if (half == 0) dsum = fmaf(p_t[t], dp_t[t], dsum);
-      }
-    }
-  }
   for (int st = 0; st < nsteps; ++st) {
     const int j = st % ntiles;
     const bool sweep2 = st >= ntiles;
     const int u = st - ntiles;  // index among the sweep-2 steps
-    const int nvalid = min(BWD_BN, skv_main - j * BWD_BN);
+    const int nvalid = min(BWD_BN, p.Skv - j * BWD_BN);
     const int n16 = (nvalid + 15) & ~15;
     ptx::mbar_wait(bar_s, st & 1);
     ptx::tc_fence_after();
@@ -582,7 +481,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       sDp[half * 128 + r] = dsum;
       math_sync();
       dsum = sDp[r] + sDp[128 + r];
-      dsum_row = dsum;
       if (half == 0 && row_ok) p.dvec[stat_idx] = dsum;  // for the dK/dV kernels
       math_sync();  // sDp aliases dS[0]: everyone has read it before sweep 2 writes dS
     }
@@ -601,15 +499,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint32_t rr[32];
     ptx::tmem_ld_32x32b_x32(t_row + 128 + half * 32, rr);
     ptx::tmem_ld_wait();
-    if (ntail > 0 && row_ok) {  // dQ += dS_tail K_tail with dS = P (dP - D) * scale in fp32
-#pragma unroll
-      for (int t = 0; t < kMaxTail; ++t) {
-        if (t < ntail) {
-          const long long krow_i = static_cast<long long>(b) * p.Skv + skv_main + t;
-          axpy32(rr, p_t[t] * (dp_t[t] - dsum_row) * p.scale, p.k_in + krow_i * p.k_in_rs + h * HD + half * 32);
-        }
-      }
-    }
     if (row_ok) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
@@ -680,15 +569,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const int ntail = tail_rows(p.Sq);
-  const int sq_main = p.Sq - ntail;  // q rows covered by the MMA loop
-  const int ntiles = ceil_div(sq_main, BWD_BN);
+  const int ntiles = ceil_div(p.Sq, BWD_BN);
   const int kvrow = kv0 + r;
   const bool kv_ok = r < rows_here;  // rows past the tile's share belong to the next CTA (or lie past the sequence)
   const float sl2 = p.scale * kLog2e;
   const long long stat_base = (static_cast<long long>(b) * p.nh + h) * p.Sq;
 
-  auto n16_of = [&](int i) { return (min(BWD_BN, sq_main - i * BWD_BN) + 15) & ~15; };
+  auto n16_of = [&](int i) { return (min(BWD_BN, p.Sq - i * BWD_BN) + 15) & ~15; };
   auto issue_scores = [&](int i) {  // thread 0: S^T = K Q_i^T, dP^T = V dO_i^T
     uint8_t* sQ = sQO + (i % 3) * 16384;
     const uint32_t idesc = ptx::make_idesc_bf16(128, n16_of(i), 0, 0);
@@ -750,14 +637,14 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   // ---- warps 0-7: math threads ------------------------------------------------------------------------------------
   for (int i = 0; i < ntiles; ++i) {
     const int q0 = i * BWD_BN;
-    const int nvalid = min(BWD_BN, sq_main - q0);
+    const int nvalid = min(BWD_BN, p.Sq - q0);
     const int n16 = (nvalid + 15) & ~15;
     float* sL = sLD;  // (the trailing math_sync of the previous step fenced its readers)
     float* sD = sL + 64;
     if (tid < BWD_BN) {
       const int qr = q0 + tid;
-      sL[tid] = (qr < sq_main) ? p.lse[stat_base + qr] * kLog2e : 0.f;
-      sD[tid] = (qr < sq_main) ? p.dvec[stat_base + qr] * p.scale : 0.f;  // pre-scaled: dS = P (dP*scale - D*scale)
+      sL[tid] = (qr < p.Sq) ? p.lse[stat_base + qr] * kLog2e : 0.f;
+      sD[tid] = (qr < p.Sq) ? p.dvec[stat_base + qr] * p.scale : 0.f;  // pre-scaled: dS = P (dP*scale - D*scale)
     }
     ptx::mbar_wait(bar_s, i & 1);
     ptx::tc_fence_after();
@@ -820,39 +707,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   ptx::tc_fence_after();
   bf16* krow = p.out0 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out0_rs + h * HD + half * 32;
   bf16* vrow = p.out1 + (static_cast<long long>(b) * p.Skv + kvrow) * p.out1_rs + h * HD + half * 32;
-  // tail q rows (CUDA cores): P^T and dS^T of this kv row against each of them
-  float pq[kMaxTail] = {0.f, 0.f}, dsq[kMaxTail] = {0.f, 0.f};
-  if (ntail > 0 && kv_ok) {
-    const long long gkv = static_cast<long long>(b) * p.Skv + kvrow;
-    const bf16* kself = p.k_in + gkv * p.k_in_rs + h * HD;
-    const bf16* vself = p.v_in + gkv * p.v_in_rs + h * HD;
-#pragma unroll
-    for (int t = 0; t < kMaxTail; ++t) {
-      if (t < ntail) {
-        const int qi = sq_main + t;
-        const long long gq = static_cast<long long>(b) * p.Sq + qi;
-        const float s_t = dot64(kself, p.q_in + gq * p.q_in_rs + h * HD);
-        const float dp = dot64(vself, p.do_in + gq * p.do_in_rs + h * HD);
-        pq[t] = ex2(fmaf(s_t, sl2, -p.lse[stat_base + qi] * kLog2e));
-        dsq[t] = pq[t] * (dp - p.dvec[stat_base + qi]) * p.scale;
-      }
-    }
-  }
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
     uint32_t rr[32];
     ptx::tmem_ld_32x32b_x32(t_row + 128 + which * 64 + half * 32, rr);
     ptx::tmem_ld_wait();
-    if (ntail > 0 && kv_ok) {  // dK += dS^T_tail Q_tail ; dV += P^T_tail dO_tail
-#pragma unroll
-      for (int t = 0; t < kMaxTail; ++t) {
-        if (t < ntail) {
-          const long long gq = static_cast<long long>(b) * p.Sq + sq_main + t;
-          if (which == 0) axpy32(rr, dsq[t], p.q_in + gq * p.q_in_rs + h * HD + half * 32);
-          else axpy32(rr, pq[t], p.do_in + gq * p.do_in_rs + h * HD + half * 32);
-        }
-      }
-    }
     if (kv_ok) {
       bf16* dst = which == 0 ? krow : vrow;
 #pragma unroll
@@ -909,9 +768,6 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale; p.tile_rows = tile_rows;
   p.out0 = reinterpret_cast<bf16*>(o); p.out0_rs = o_rs; p.lse = lse;
-  p.q_in = reinterpret_cast<const bf16*>(q); p.q_in_rs = q_rs;
-  p.k_in = reinterpret_cast<const bf16*>(k); p.k_in_rs = k_rs;
-  p.v_in = reinterpret_cast<const bf16*>(v); p.v_in_rs = v_rs;
   attn_fwd_tc_kernel<<<dim3(ntile, nh, B), 128, FWD_SMEM, s>>>(tq, tk, tv, p);
   *rows_done = Sq;
   return check_launch("attn_fwd_tc");
@@ -934,10 +790,6 @@ int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o,
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dq); p.out0_rs = dq_rs; p.lse = const_cast<float*>(lse); p.dvec = dvec;
-  p.q_in = reinterpret_cast<const bf16*>(q); p.q_in_rs = q_rs;
-  p.k_in = reinterpret_cast<const bf16*>(k); p.k_in_rs = k_rs;
-  p.v_in = reinterpret_cast<const bf16*>(v); p.v_in_rs = v_rs;
-  p.do_in = reinterpret_cast<const bf16*>(d_o); p.do_in_rs = do_rs;
   p.tile_rows = tile_rows;
   attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 288, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
   *rows_done = Sq;
@@ -962,10 +814,6 @@ int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dk); p.out0_rs = dk_rs; p.out1 = reinterpret_cast<bf16*>(dv); p.out1_rs = dv_rs;
   p.lse = const_cast<float*>(lse); p.dvec = const_cast<float*>(dvec);
-  p.q_in = reinterpret_cast<const bf16*>(q); p.q_in_rs = q_rs;
-  p.k_in = reinterpret_cast<const bf16*>(k); p.k_in_rs = k_rs;
-  p.v_in = reinterpret_cast<const bf16*>(v); p.v_in_rs = v_rs;
-  p.do_in = reinterpret_cast<const bf16*>(d_o); p.do_in_rs = do_rs;
   p.tile_rows = tile_rows;
   attn_bwd_dkdv_tc_kernel<<<dim3(ntile, nh, B), 288, DKDV_SMEM, s>>>(tk, tv, tq, tdo, p);
   *rows_done = Skv;
