@@ -101,18 +101,20 @@ class ClockSampler:
 
 
 def gemm_traffic_from_profile():
-    """Average DRAM bytes per tcgen05-GEMM launch from the committed `ncu --set full` capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_gemm.txt")
+    """Average DRAM bytes (read + write) per tcgen05-GEMM launch from the committed `ncu --set full` capture of the step's
+    GEMMs (profiles/r02_ncu_kernels.txt: one line per captured launch, sizes in GB / MB), or None."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_kernels.txt")
     if not os.path.exists(path):
         return None
     tot, n = 0.0, 0
     for line in open(path):
-        if "gemm_tcgen05_kernel" not in line:
+        if not line.startswith("gemm_tcgen05_kernel"):
             continue
         try:
-            rd = float(line.split("dram_read=")[1].split("MB")[0])
-            wr = float(line.split("dram_write=")[1].split("MB")[0])
-            tot += (rd + wr) * 1e6
+            rd = line.split("dram_read=")[1].split()[0]
+            wr = line.split("dram_write=")[1].split()[0]
+            unit = lambda v: float(v[:-2]) * {"GB": 1e9, "MB": 1e6, "KB": 1e3}[v[-2:]]
+            tot += unit(rd) + unit(wr)
             n += 1
         except Exception:
             pass
@@ -588,12 +590,30 @@ def main():
     ms_dev = timed(lambda i: run(dev_tok[i % n_buf], dev_cls[i % n_buf]), args.steps)
     launches = launches_per_step * args.steps
 
+    # e2e: every step copies its inputs from pinned host memory and copies its loss back to pinned host memory; the host
+    # consumes the loss of step i-1 while step i runs (lagged logging, the usual training-loop practice), so the device
+    # never idles behind a host round trip.  The last losses are consumed before the closing barrier.
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event() for _ in range(2)]
+    seen = []
+
     def e2e_step(i):
         tok = host_tok[i % n_buf].to(dev, non_blocking=True)
         cls = host_cls[i % n_buf].to(dev, non_blocking=True)
-        return float(run(tok, cls))  # .item(): device->host read of the loss
+        loss = run(tok, cls)
+        slot = i & 1
+        if i >= 2:  # the slot's previous occupant (step i-2) has certainly landed: consume it on the host
+            loss_evt[slot].synchronize()
+            seen.append(float(loss_host[slot]))
+        loss_host[slot].copy_(loss.detach(), non_blocking=True)  # device->host read of this step's loss
+        loss_evt[slot].record()
+        if i == args.steps - 1:  # drain: every step's loss has been read by the host inside the timed region
+            for k in ((i - 1) & 1, slot) if i >= 1 else (slot,):
+                loss_evt[k].synchronize()
+                seen.append(float(loss_host[k]))
 
     ms_e2e = timed(e2e_step, args.steps)
+    assert len(seen) == args.steps and all(math.isfinite(v) for v in seen), seen
     clocks = sampler.stop() if rank == 0 else None
     model._packed.key = None  # graph replays update the parameters without bumping their version counters: re-pack for eager use
 
@@ -692,7 +712,9 @@ def main():
                        **({"nccl_max_channels": args.nccl_channels} if world > 1 and args.nccl_channels else {}),
                        **({"DIAGNOSTIC_no_allreduce": True} if world > 1 and args.ddp_no_sync else {})},
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4},
+                    "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4,
+                    "api": "MaskGitTransformer.forward / loss.backward / optimizer.step (the captured step) fed from pinned "
+                           "host tokens; loss copied to pinned host memory every step and read by the host one step later"},
             "gpu_launches": launches,
             "tflops_per_gpu_model": 3 * FWD_GFLOP_PER_IMG * B / ms_dev,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "full_step_incl_vq_encode": full,
