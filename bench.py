@@ -157,7 +157,7 @@ def reference_module_step_fn(batch, device="cpu"):
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
@@ -185,7 +185,7 @@ def cpu_reference_step_fn(batch, device="cpu"):
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
