@@ -575,13 +575,6 @@ __device__ __forceinline__ uint4 ld_nc16(const void* p) {
   return v;
 }
 
-// 8 fp32 weights through ordered (volatile) loads, so the compiler keeps them next to their use instead of hoisting all
-// of a row's weight loads above the math (register pressure)
-__device__ __forceinline__ void ld_w8(const float* p, float (&v)[8]) {
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p + 4));
-}
-
 __device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {  // bf16 * bf16 -> bf16 (rn), two lanes
   __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
@@ -591,7 +584,8 @@ __device__ __forceinline__ uint32_t bf16x2_mul(uint32_t a, uint32_t b) {  // bf1
 // stays in registers between the statistics and the normalise pass.
 // The row's 2 * CH 16-byte loads are all issued before any math (CH <= 8: 64 registers of loads in flight per lane, two CTAs
 // per SM): with the loads interleaved chunk by chunk only ~24 KB per SM were in flight, which by Little's law capped the
-// kernel at ~3.7 TB/s whatever the instruction count.
+// kernel at ~3.7 TB/s whatever the instruction count (same-box A/B: 219 -> 193 us at [65 792, 2 x 2048]).  The backward
+// got nothing from the same treatment (362 -> 360 us): it is bound by instruction issue, and keeps three CTAs per SM.
 template <int CH>
 __global__ void __launch_bounds__(kGluWarps * 32, (CH <= 8) ? 2 : 1)
 glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf16* __restrict__ y,
@@ -602,9 +596,10 @@ glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf
   const bf16* xr = ab + static_cast<size_t>(row) * 2 * H;
   uint32_t vp[CH][4];
   float sum = 0.f;
-  constexpr int PF = (CH <= 8) ? CH : 1;  // chunks whose loads are in flight together
+  constexpr bool kPf = CH <= 8;
+  constexpr int PF = kPf ? CH : 1;  // chunks whose loads are in flight together
   uint4 aq[PF], bq[PF];
-  if (CH <= 8) {
+  if (kPf) {
 #pragma unroll
     for (int c = 0; c < PF; ++c) {
       const int col = (c * 32 + lane) * 8;
@@ -618,8 +613,8 @@ glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf
   for (int c = 0; c < CH; ++c) {
     const int col = (c * 32 + lane) * 8;
     if (col < H) {
-      const uint4 au = (CH <= 8) ? aq[c % PF] : *reinterpret_cast<const uint4*>(xr + col);
-      const uint4 bu = (CH <= 8) ? bq[c % PF] : *reinterpret_cast<const uint4*>(xr + H + col);
+      const uint4 au = kPf ? aq[c % PF] : *reinterpret_cast<const uint4*>(xr + col);
+      const uint4 bu = kPf ? bq[c % PF] : *reinterpret_cast<const uint4*>(xr + H + col);
       const uint32_t aw[4] = {au.x, au.y, au.z, au.w}, bw[4] = {bu.x, bu.y, bu.z, bu.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -796,131 +791,6 @@ glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, co
   if (dw) flush_cta_dw(s_dw, kGluWarps, H, dw, dw_ws);
 }
 
-// Same math as glu_norm_bwd_kernel<true> (saved forward output available), restructured for memory-level parallelism:
-// H <= CH * 256 so a lane's share of the row is CH 16-byte chunks per tensor, and every pass issues all of its loads before
-// it computes, half a row at a time -- pass 1 the dy and y chunks, pass 2 the [a | b] (and, from L2, dy) chunks.  Two CTAs per SM (register budget 128): ~100 KB of reads in flight per SM instead of ~37 KB, which is
-// what the chunk-by-chunk loop's 4.3 TB/s came from (Little's law), not the instruction count.
-template <int CH>
-__global__ void __launch_bounds__(kGluWarps * 32, 2)
-glu_norm_bwd_pf_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, const float* __restrict__ w,
-                       const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dab,
-                       float* __restrict__ dw, float* __restrict__ dw_ws, const bf16* __restrict__ yf, int rows, int H,
-                       int rms) {
-  extern __shared__ __align__(16) float s_dw[];  // [kGluWarps][H] private rows
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  float* my_dw = s_dw + static_cast<size_t>(warp) * H;
-  if (dw) {
-    for (int i = lane * 4; i < H; i += 128) *reinterpret_cast<float4*>(my_dw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
-  }
-  const float inv_h = 1.0f / static_cast<float>(H);
-  constexpr int HC = (CH + 1) / 2;
-  for (int row = blockIdx.x * kGluWarps + warp; row < rows; row += gridDim.x * kGluWarps) {
-    const bf16* xr = ab + static_cast<size_t>(row) * 2 * H;
-    const bf16* dyr = dy + static_cast<size_t>(row) * H;
-    const bf16* yr = yf + static_cast<size_t>(row) * H;
-    const float mean = rms ? 0.f : mean_in[row];
-    const float rstd = rstd_in[row];
-    // ---- pass 1: s1 = mean(dy * w), s2 = mean(dy * y), half a row of loads in flight at a time
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-    for (int hf = 0; hf < 2; ++hf) {
-      uint4 dq[HC], yq[HC];
-#pragma unroll
-      for (int k = 0; k < HC; ++k) {
-        const int c = hf * HC + k;
-        const int col = (c * 32 + lane) * 8;
-        if (c < CH && col < H) {
-          dq[k] = ld_nc16(dyr + col);
-          yq[k] = ld_nc16(yr + col);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < HC; ++k) {
-        const int c = hf * HC + k;
-        const int col = (c * 32 + lane) * 8;
-        if (c < CH && col < H) {
-          float wv[8];
-          if (w) ld_w8(w + col, wv);
-          const uint32_t dd[4] = {dq[k].x, dq[k].y, dq[k].z, dq[k].w}, yy[4] = {yq[k].x, yq[k].y, yq[k].z, yq[k].w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 d2 = unpack_bf16(dd[j]), y2 = unpack_bf16(yy[j]);
-            s1 += w ? d2.x * wv[2 * j] : d2.x;
-            s1 += w ? d2.y * wv[2 * j + 1] : d2.y;
-            s2 = fmaf(d2.x, y2.x, s2);
-            s2 = fmaf(d2.y, y2.y, s2);
-          }
-        }
-      }
-    }
-    s1 = rms ? 0.f : warp_sum(s1) * inv_h;
-    s2 = warp_sum(s2) * inv_h;
-    // ---- pass 2: dab and the weight gradient, [a | b] fetched half a row at a time
-    bf16* dr = dab + static_cast<size_t>(row) * 2 * H;
-#pragma unroll 1
-    for (int hf = 0; hf < 2; ++hf) {
-      uint4 aq[HC], bq[HC], dq2[HC];  // dy is re-read (an L2 hit) rather than carried: 32 registers cheaper
-#pragma unroll
-      for (int k = 0; k < HC; ++k) {
-        const int c = hf * HC + k;
-        const int col = (c * 32 + lane) * 8;
-        if (c < CH && col < H) {
-          aq[k] = ld_nc16(xr + col);
-          bq[k] = ld_nc16(xr + H + col);
-          dq2[k] = ld_nc16(dyr + col);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < HC; ++k) {
-        const int c = hf * HC + k;
-        const int col = (c * 32 + lane) * 8;
-        if (c < CH && col < H) {
-          const uint32_t aw[4] = {aq[k].x, aq[k].y, aq[k].z, aq[k].w}, bw[4] = {bq[k].x, bq[k].y, bq[k].z, bq[k].w};
-          const uint32_t dd[4] = {dq2[k].x, dq2[k].y, dq2[k].z, dq2[k].w};
-          float wv[8];
-          if (w) ld_w8(w + col, wv);
-          uint4 oa, ob;
-          float pr2[8];
-          uint32_t* pa = reinterpret_cast<uint32_t*>(&oa);
-          uint32_t* pb = reinterpret_cast<uint32_t*>(&ob);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 a2 = unpack_bf16(aw[j]);
-            float g0, g1, t0, t1;
-            gelu_eval(a2.x, g0, t0);
-            gelu_eval(a2.y, g1, t1);
-            const uint32_t gp = pack_bf16(g0, g1);
-            const float2 gr = unpack_bf16(gp);  // bf16(gelu(a))
-            const float2 v2 = unpack_bf16(bf16x2_mul(gp, bw[j]));
-            const float2 b2 = unpack_bf16(bw[j]);
-            const float2 d2 = unpack_bf16(dd[j]);
-            const float xh0 = (v2.x - mean) * rstd, xh1 = (v2.y - mean) * rstd;
-            const float q0 = w ? d2.x * wv[2 * j] : d2.x, q1 = w ? d2.y * wv[2 * j + 1] : d2.y;
-            const float o0 = rstd * (q0 - s1 - xh0 * s2), o1 = rstd * (q1 - s1 - xh1 * s2);
-            pa[j] = pack_bf16(o0 * b2.x * t0, o1 * b2.y * t1);
-            pb[j] = pack_bf16(o0 * gr.x, o1 * gr.y);
-            pr2[2 * j] = d2.x * xh0;
-            pr2[2 * j + 1] = d2.y * xh1;
-          }
-          if (dw) {
-            float4 e0 = *reinterpret_cast<float4*>(my_dw + col);
-            float4 e1 = *reinterpret_cast<float4*>(my_dw + col + 4);
-            e0.x += pr2[0]; e0.y += pr2[1]; e0.z += pr2[2]; e0.w += pr2[3];
-            e1.x += pr2[4]; e1.y += pr2[5]; e1.z += pr2[6]; e1.w += pr2[7];
-            *reinterpret_cast<float4*>(my_dw + col) = e0;
-            *reinterpret_cast<float4*>(my_dw + col + 4) = e1;
-          }
-          *reinterpret_cast<uint4*>(dr + col) = oa;
-          *reinterpret_cast<uint4*>(dr + H + col) = ob;
-        }
-      }
-    }
-  }
-  if (dw) flush_cta_dw(s_dw, kGluWarps, H, dw, dw_ws);
-}
-
 template <typename TX, typename TY>
 int fwd_dispatch(const void* x, const float* w, const float* res, void* y, float* mean, float* rstd, int rows, int H,
                  float eps, int act, int rms, cudaStream_t s) {
@@ -1082,21 +952,6 @@ int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w,
       cudaFuncSetAttribute(glu_norm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 4096 * 4);
       cudaFuncSetAttribute(glu_norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 4096 * 4);
       attr = true;
-    }
-    if (y_fwd != nullptr && H <= 2048) {  // all-loads-first variant, two CTAs per SM (its grid never exceeds bwd_grid's)
-      const int g2 = grid > 148 * 2 ? 148 * 2 : grid;
-      static bool attr_pf = false;
-      if (!attr_pf) {
-        cudaFuncSetAttribute(glu_norm_bwd_pf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 2048 * 4);
-        cudaFuncSetAttribute(glu_norm_bwd_pf_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGluWarps * 2048 * 4);
-        attr_pf = true;
-      }
-#define MUSE_GB(CH) glu_norm_bwd_pf_kernel<CH><<<g2, kGluWarps * 32, smem, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw, dw_ws, reinterpret_cast<const bf16*>(y_fwd), rows, H, rms)
-      if (H <= 1024) MUSE_GB(4); else MUSE_GB(8);
-#undef MUSE_GB
-      rc = check_launch("glu_norm_bwd");
-      if (rc || !dw || !dw_ws) return rc;
-      return reduce_dw(dw_ws, dw, g2, H, s);
     }
     if (y_fwd != nullptr)
       glu_norm_bwd_kernel<true><<<grid, kGluWarps * 32, smem, s>>>(
