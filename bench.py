@@ -597,10 +597,30 @@ def main():
     loss_evt = [torch.cuda.Event() for _ in range(2)]
     seen = []
 
+    # inputs: step i+1's tokens are copied host -> device on a copy stream (two staging slots) while step i computes
+    copy_stream = torch.cuda.Stream()
+    stage = [(torch.empty_like(dev_tok[0]), torch.empty_like(dev_cls[0])) for _ in range(2)]
+    staged, consumed = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+    for ev in consumed:
+        ev.record()
+
+    def prefetch(i):
+        k = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k])  # the slot's previous occupant (step i-2) has been read by its step
+            stage[k][0].copy_(host_tok[i % n_buf], non_blocking=True)
+            stage[k][1].copy_(host_cls[i % n_buf], non_blocking=True)
+            staged[k].record(copy_stream)
+
     def e2e_step(i):
-        tok = host_tok[i % n_buf].to(dev, non_blocking=True)
-        cls = host_cls[i % n_buf].to(dev, non_blocking=True)
-        loss = run(tok, cls)
+        if i == 0:
+            prefetch(0)
+        k = i & 1
+        torch.cuda.current_stream().wait_event(staged[k])
+        loss = run(stage[k][0], stage[k][1])
+        consumed[k].record()
+        if i + 1 < args.steps:
+            prefetch(i + 1)
         slot = i & 1
         if i >= 2:  # the slot's previous occupant (step i-2) has certainly landed: consume it on the host
             loss_evt[slot].synchronize()
@@ -713,8 +733,9 @@ def main():
                        **({"DIAGNOSTIC_no_allreduce": True} if world > 1 and args.ddp_no_sync else {})},
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": world * (B * 256 * 8 + B * 8), "d2h_bytes_per_step": world * 4,
-                    "api": "MaskGitTransformer.forward / loss.backward / optimizer.step (the captured step) fed from pinned "
-                           "host tokens; loss copied to pinned host memory every step and read by the host one step later"},
+                    "api": "MaskGitTransformer.forward / loss.backward / optimizer.step (the captured step); every step's tokens "
+                           "are copied from pinned host memory on a copy stream while the previous step computes (double "
+                           "buffered), its loss is copied to pinned host memory and read by the host one step later"},
             "gpu_launches": launches,
             "tflops_per_gpu_model": 3 * FWD_GFLOP_PER_IMG * B / ms_dev,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "full_step_incl_vq_encode": full,

@@ -107,7 +107,7 @@ struct TcParams {
 constexpr int FWD_BN = 64;
 constexpr int FWD_SMEM = 16384 /*Q*/ + 8192 /*K*/ + 8192 /*V*/ + 16384 /*P*/ + 64;  // 5 mbarriers + the TMEM holder
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzled tiles need 1024 B alignment
@@ -157,24 +157,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const float sl2 = p.scale * kLog2e;
   float m = -INFINITY, l = 0.f;
 
+  // The score MMA of tile j+1 is issued right behind the accumulate MMA of tile j (the scores of tile j are in registers by
+  // then), so one tcgen05.commit covers both and the CTA waits for ONE tensor-core round trip per tile instead of two:
+  // bar_s(j+1) completing means P V_j has landed as well (MMAs of a CTA complete in issue order), which is what frees the
+  // P buffer, the V tile and the running output for iteration j+1.
+  if (tid == 0) {
+    ptx::mbar_wait(bar_kv, 0);
+    ptx::tc_fence_after();
+    const uint32_t idesc0 = ptx::make_idesc_bf16(128, (min(FWD_BN, p.Skv) + 15) & ~15, 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc0, ks > 0);
+    ptx::umma_commit(bar_s);
+  }
   for (int j = 0; j < ntiles; ++j) {
     const uint32_t par = j & 1;
     const int nvalid = min(FWD_BN, p.Skv - j * FWD_BN);
     const int n16 = (nvalid + 15) & ~15;
-    if (tid == 0) {
-      ptx::mbar_wait(bar_kv, par);
-      ptx::tc_fence_after();
-      const uint32_t idesc = ptx::make_idesc_bf16(128, n16, 0, 0);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc, ks > 0);
-      ptx::umma_commit(bar_s);
-    }
-    ptx::mbar_wait(bar_s, par);
+    ptx::mbar_wait(bar_s, par);  // S_j is complete -- and so is P V_{j-1}
     ptx::tc_fence_after();
-    if (tid == 0 && j + 1 < ntiles) {  // the score MMA has consumed K_j: fetch K_{j+1} under the softmax math
-      ptx::mbar_expect_tx(bar_kv, 8192);
-      tma_load_3d(sK, &tmK, bar_kv, h * HD, (j + 1) * FWD_BN, b);
+    if (tid == 0) {
+      if (j + 1 < ntiles) {  // the score MMA has consumed K_j: fetch K_{j+1} under the softmax math
+        ptx::mbar_expect_tx(bar_kv, 8192);
+        tma_load_3d(sK, &tmK, bar_kv, h * HD, (j + 1) * FWD_BN, b);
+      }
+      if (j > 0) {  // the accumulate MMA of tile j-1 has consumed V_{j-1}
+        ptx::mbar_expect_tx(bar_v, 8192);
+        tma_load_3d(sV, &tmV, bar_v, h * HD, j * FWD_BN, b);
+      }
     }
     if (warp_active) {
     // the whole score row (<= 64 columns) fits in registers: one TMEM read, max, exp2, pack.  The instruction count
@@ -225,7 +235,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         st_operand_chunk(sP, tid, i, u);
       }
     }
-    // rescale the running output (the previous accumulate MMA finished: bar_o was waited at the end of iteration j-1)
+    // rescale the running output (P V_{j-1} has finished: see the bar_s wait above)
     if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) {
 #pragma unroll
       for (int c = 0; c < HD; c += 32) {
@@ -241,7 +251,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }  // warp_active
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // every thread holds its scores in registers and has written its part of P
     if (tid == 0) {
       ptx::mbar_wait(bar_v, par);
       ptx::tc_fence_after();
@@ -250,15 +260,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int ks = 0; ks < ksteps; ++ks)
         ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sP), ks), desc_mnmajor(ptx::smem_u32(sV), ks), idesc,
                       (j > 0 || ks > 0) ? 1u : 0u);
-      ptx::umma_commit(bar_o);
-    }
-    ptx::mbar_wait(bar_o, par);
-    ptx::tc_fence_after();
-    if (tid == 0 && j + 1 < ntiles) {  // the accumulate MMA has consumed V_j
-      ptx::mbar_expect_tx(bar_v, 8192);
-      tma_load_3d(sV, &tmV, bar_v, h * HD, (j + 1) * FWD_BN, b);
+      if (j + 1 < ntiles) {
+        ptx::mbar_wait(bar_kv, par ^ 1);  // K_{j+1} landed (requested at the top of this iteration)
+        ptx::tc_fence_after();
+        const int nn16 = (min(FWD_BN, p.Skv - (j + 1) * FWD_BN) + 15) & ~15;
+        const uint32_t idesc_s = ptx::make_idesc_bf16(128, nn16, 0, 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc_s, ks > 0);
+        ptx::umma_commit(bar_s);
+      } else {
+        ptx::umma_commit(bar_o);
+      }
     }
   }
+  ptx::mbar_wait(bar_o, 0);  // the last accumulate MMA
+  ptx::tc_fence_after();
   // epilogue: O / l -> bf16 rows, LSE
   const int row = q0 + tid;
   const bool row_ok = tid < rows_here;
