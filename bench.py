@@ -473,6 +473,8 @@ def main():
                          "separate launch overhead from NCCL contention")
     ap.add_argument("--optimizer", default="torch", choices=["torch", "fused"],
                     help="torch.optim.AdamW(fused=True) or open_muse_b200.FusedAdamW (AdamW + bf16 operand packing in one pass)")
+    ap.add_argument("--pdl", type=int, default=None, choices=[0, 1],
+                    help="programmatic dependent launch for the library's kernels (default: the library's own default / MUSE_B200_PDL)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu (the reference arm) or cuda (same eager ops under bf16 autocast, informational)")
     args = ap.parse_args()
@@ -488,6 +490,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.pdl is not None:
+        ops.set_pdl(bool(args.pdl))
     ddp_graph = world > 1 and bool(args.ddp_graph) and not args.no_cuda_graph
     if world > 1:
         if ddp_graph:  # graph capture of NCCL collectives: the watchdog must not poll events while the stream is capturing
@@ -727,7 +731,7 @@ def main():
                        "global_batch": gb, "per_gpu_batch": B, "seq_len": 257,
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "no explicit flush: per-step working set (~15 GB activations + 0.5 GB weights/grads/optimizer) >> 126 MB L2",
-                       "cuda_graph": bool(use_graph), "optimizer": args.optimizer,
+                       "cuda_graph": bool(use_graph), "pdl": ops.get_pdl(), "optimizer": args.optimizer,
                        "nccl_sms_reserved": args.nccl_sms if world > 1 else 0,
                        **({"nccl_max_channels": args.nccl_channels} if world > 1 and args.nccl_channels else {}),
                        **({"DIAGNOSTIC_no_allreduce": True} if world > 1 and args.ddp_no_sync else {})},

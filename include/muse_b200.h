@@ -36,6 +36,18 @@ int muse_device_info(int* sm_major, int* sm_minor, int* num_sms);
  * training/train_maskgit_imagenet.py:305). */
 int muse_reserve_sms(int n);
 
+/* Programmatic dependent launch.  The reference's step is a chain of several hundred short torch kernels on one stream
+ * (muse/modeling_transformer.py:875-904 per layer, :1397-1454 per decode step); here every kernel of the library opens
+ * with griddepcontrol.launch_dependents / griddepcontrol.wait, and with this switch on each launch carries
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs are scheduled and run their prologue while the
+ * tail of the previous grid drains (memory effects stay in stream order: the wait precedes every global access).
+ * Applies to eager launches and, through stream capture, to the CUDA graphs of the train step and the decode loop.
+ * Process-wide; set it before capturing graphs.  Initial value: environment variable MUSE_B200_PDL if set, else the
+ * build default MUSE_B200_PDL_DEFAULT. */
+#define MUSE_B200_PDL_DEFAULT 0
+int muse_set_pdl(int enabled);
+int muse_get_pdl(void);
+
 /* GEMM epilogues */
 #define MUSE_EPI_BF16 0        /* C bf16 = acc                                   */
 #define MUSE_EPI_F32 1         /* C fp32 = acc                                   */

@@ -23,6 +23,8 @@ SIGNATURES = {
     "muse_set_device": (c_int, [_I]),
     "muse_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "muse_reserve_sms": (c_int, [_I]),
+    "muse_set_pdl": (c_int, [_I]),
+    "muse_get_pdl": (c_int, []),
     "muse_gemm_bf16": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "muse_gemm_splitk_workspace_bytes": (c_longlong, [_I, _I, _I]),
     "muse_gemm_bf16_splitk": (c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),

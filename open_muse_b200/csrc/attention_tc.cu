@@ -110,6 +110,7 @@ constexpr int FWD_SMEM = 16384 /*Q*/ + 8192 /*K*/ + 8192 /*V*/ + 16384 /*P*/ + 6
 __global__ void __launch_bounds__(128, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const TcParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // 128B-swizzled tiles need 1024 B alignment
   uint8_t* smem = smem_raw;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -142,6 +143,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();  // everything above touches only shared memory / TMEM / kernel parameters
   const uint32_t tmem = *tmem_holder;
   const uint32_t t_s = tmem + (static_cast<uint32_t>(warp * 32) << 16);        // S: columns [0,64)
   const uint32_t t_o = t_s + 64;                                                // O: columns [64,128)
@@ -322,6 +324,7 @@ __global__ void __launch_bounds__(288, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const TcParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -362,6 +365,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();  // everything above touches only shared memory / TMEM / kernel parameters
   const uint32_t tmem = *tmem_holder;
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const int ntiles = ceil_div(p.Skv, BWD_BN);
@@ -546,6 +550,7 @@ __global__ void __launch_bounds__(288, 2)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                         const TcParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -584,6 +589,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();  // everything above touches only shared memory / TMEM / kernel parameters
   const uint32_t tmem = *tmem_holder;
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const int ntiles = ceil_div(p.Sq, BWD_BN);
@@ -785,7 +791,7 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale; p.tile_rows = tile_rows;
   p.out0 = reinterpret_cast<bf16*>(o); p.out0_rs = o_rs; p.lse = lse;
-  attn_fwd_tc_kernel<<<dim3(ntile, nh, B), 128, FWD_SMEM, s>>>(tq, tk, tv, p);
+  pdl_launch(dim3(ntile, nh, B), 128, FWD_SMEM, s)(attn_fwd_tc_kernel, tq, tk, tv, p);
   *rows_done = Sq;
   return check_launch("attn_fwd_tc");
 }
@@ -808,7 +814,7 @@ int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o,
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dq); p.out0_rs = dq_rs; p.lse = const_cast<float*>(lse); p.dvec = dvec;
   p.tile_rows = tile_rows;
-  attn_bwd_dq_tc_kernel<<<dim3(ntile, nh, B), 288, DQ_SMEM, s>>>(tq, tdo, tk, tv, p);
+  pdl_launch(dim3(ntile, nh, B), 288, DQ_SMEM, s)(attn_bwd_dq_tc_kernel, tq, tdo, tk, tv, p);
   *rows_done = Sq;
   return check_launch("attn_bwd_dq_tc");
 }
@@ -832,7 +838,7 @@ int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_
   p.out0 = reinterpret_cast<bf16*>(dk); p.out0_rs = dk_rs; p.out1 = reinterpret_cast<bf16*>(dv); p.out1_rs = dv_rs;
   p.lse = const_cast<float*>(lse); p.dvec = const_cast<float*>(dvec);
   p.tile_rows = tile_rows;
-  attn_bwd_dkdv_tc_kernel<<<dim3(ntile, nh, B), 288, DKDV_SMEM, s>>>(tk, tv, tq, tdo, p);
+  pdl_launch(dim3(ntile, nh, B), 288, DKDV_SMEM, s)(attn_bwd_dkdv_tc_kernel, tk, tv, tq, tdo, p);
   *rows_done = Skv;
   return check_launch("attn_bwd_dkdv_tc");
 }

@@ -1,6 +1,7 @@
 // extern "C" boundary of libmuse_b200.so (declared in include/muse_b200.h).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/muse_b200.h"
 #include "common.cuh"
@@ -15,6 +16,17 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// Programmatic dependent launch switch (common.cuh).  Process-wide; the initial value comes from MUSE_B200_PDL.
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("MUSE_B200_PDL");
+    g_pdl = (e != nullptr) ? (atoi(e) != 0) : MUSE_B200_PDL_DEFAULT;
+  }
+  return g_pdl != 0;
+}
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -105,6 +117,12 @@ int muse_reserve_sms(int n) {
   set_reserved_sms(n);
   return MUSE_OK;
 }
+
+int muse_set_pdl(int enabled) {
+  set_pdl(enabled);
+  return MUSE_OK;
+}
+int muse_get_pdl(void) { return pdl_enabled() ? 1 : 0; }
 
 int muse_gemm_bf16(const void* A, const void* B, void* C, const float* res, int M, int N, int K, int lda, int ldb,
                    int ldc, int a_mn, int b_mn, int epilogue, void* stream) {

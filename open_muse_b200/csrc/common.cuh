@@ -19,6 +19,51 @@ typedef __nv_bfloat16 bf16;
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// ---- Programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The hot paths are chains of 300 - 900 short kernels on one stream (a train step, a captured generate2 loop); a plain
+// stream edge costs a full drain + launch between two kernels.  Every kernel of this library therefore (i) tells the
+// hardware right away that its successor may be scheduled (griddepcontrol.launch_dependents: the successor's CTAs take
+// the SM slots that free up while the tail of this grid drains, and run their prologue -- barrier init, TMEM allocation,
+// tensor-map prefetch), and (ii) blocks in griddepcontrol.wait before its first global-memory access until the
+// predecessor grid has COMPLETED and its writes are visible.  Correctness never depends on the trigger: with wait in
+// front of every global access (reads AND writes, so there is no WAR hazard either) the order of memory effects is the
+// stream order; completion is transitive because a grid cannot complete before its own wait returned.  Both
+// instructions are no-ops in a grid launched without the attribute (ATen kernels in between are ordinary full edges).
+// Host side: pdl_launch(grid, block, smem, stream)(kernel, args...) replaces kernel<<<...>>>(args...) and adds
+// cudaLaunchAttributeProgrammaticStreamSerialization when muse_set_pdl(1) is in effect; stream capture records the edge
+// as a programmatic dependency, so the captured step / decode graphs keep the overlap.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
+
+bool pdl_enabled();  // capi.cu (muse_set_pdl / MUSE_B200_PDL)
+
+struct PdlLaunch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr;
+  template <typename... KArgs, typename... Args>
+  void operator()(void (*kernel)(KArgs...), Args&&... args) {
+    if (pdl_enabled()) {
+      attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr.val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through check_launch()
+  }
+};
+inline PdlLaunch pdl_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+  PdlLaunch l{};
+  l.cfg.gridDim = grid;
+  l.cfg.blockDim = block;
+  l.cfg.dynamicSmemBytes = smem;
+  l.cfg.stream = stream;
+  return l;
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256)
 conv2d_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ bias,
                    const float* __restrict__ res, float* __restrict__ y, int B, int H, int W, int Cin, int Cout,
                    int ksize, int up) {
+  pdl_enter();
   constexpr int BM = 16 * TM, BN = 16 * TN;
   __shared__ __align__(16) float sA[KT][BM];
   __shared__ __align__(16) float sB[KT][BN];
@@ -141,6 +142,7 @@ conv2d_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ wk, co
 // pass 3: y = silu(x * scale + shift)
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x, float* __restrict__ partials, int HW, int C, int rows_per_block) {
+  pdl_enter();
   // deterministic: fixed thread->data mapping, fixed-order in-block reduction, per-block partials (no atomics)
   extern __shared__ float s_part[];  // [rstep][C][2]
   const int b = blockIdx.y;
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float* __restrict__ partials, int nblocks, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ scale_shift, int B, int HW, int C, int groups,
                    float eps) {
+  pdl_enter();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (w >= B * groups) return;
   const int lane = threadIdx.x & 31;
@@ -213,6 +216,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift, float* __restrict__ y,
                      bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, long long total4, int HW, int C, int silu) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total4) return;
   const int c4 = C / 4;
@@ -242,6 +246,7 @@ gn_apply_silu_kernel(const float* __restrict__ x, const float* __restrict__ scal
 __global__ void __launch_bounds__(256)
 gn_apply_silu_split8_kernel(const float* __restrict__ x, const float* __restrict__ scale_shift, bf16* __restrict__ y_hi,
                             bf16* __restrict__ y_lo, long long total8, int HW, int C, int silu) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total8) return;
   const int c8 = C / 8;
@@ -269,6 +274,7 @@ gn_apply_silu_split8_kernel(const float* __restrict__ x, const float* __restrict
 // ---------------------------------------------------------------- pooling / layout
 __global__ void __launch_bounds__(256)
 avgpool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int Ho, int Wo, int C) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   const int c4 = C / 4;
   const long long total = static_cast<long long>(B) * Ho * Wo * c4;
@@ -291,6 +297,7 @@ avgpool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, 
 // out[b, p, c] = in[b, c, p] (to_nhwc) or the inverse; 32x32 smem transpose tiles
 __global__ void __launch_bounds__(256)
 transpose_cp_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  pdl_enter();
   __shared__ float t[32][33];
   const int b = blockIdx.z;
   const float* ip = in + static_cast<long long>(b) * rows * cols;
@@ -320,12 +327,12 @@ int conv2d_nhwc(const float* x, const float* wk, const float* bias, const float*
   const bool vec = (Cin % 8 == 0);
   if (Cout > 16) {
     dim3 grid(static_cast<unsigned>(ceil_div_ll(M, 128)), ceil_div(Cout, 128));
-    if (vec) conv2d_nhwc_kernel<8, 8, true><<<grid, 256, 0, s>>>(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
-    else conv2d_nhwc_kernel<8, 8, false><<<grid, 256, 0, s>>>(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
+    if (vec) pdl_launch(grid, 256, 0, s)(conv2d_nhwc_kernel<8, 8, true>, x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
+    else pdl_launch(grid, 256, 0, s)(conv2d_nhwc_kernel<8, 8, false>, x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
   } else {
     dim3 grid(static_cast<unsigned>(ceil_div_ll(M, 128)), 1);
-    if (vec) conv2d_nhwc_kernel<8, 1, true><<<grid, 256, 0, s>>>(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
-    else conv2d_nhwc_kernel<8, 1, false><<<grid, 256, 0, s>>>(x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
+    if (vec) pdl_launch(grid, 256, 0, s)(conv2d_nhwc_kernel<8, 1, true>, x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
+    else pdl_launch(grid, 256, 0, s)(conv2d_nhwc_kernel<8, 1, false>, x, wk, bias, res, y, B, H, W, Cin, Cout, ksize, upsample2x);
   }
   return check_launch("conv2d_nhwc");
 }
@@ -359,23 +366,23 @@ int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, f
     const int rows_per_block = gn_rows_per_block(C);
     nblocks = ceil_div(HW, rows_per_block);
     const int rstep = 256 / (C / 4);
-    gn_stats_kernel<<<dim3(nblocks, B), 256, rstep * C * 2 * sizeof(float), s>>>(x, partials_ws, HW, C, rows_per_block);
+    pdl_launch(dim3(nblocks, B), 256, rstep * C * 2 * sizeof(float), s)(gn_stats_kernel, x, partials_ws, HW, C, rows_per_block);
     rc = check_launch("gn_stats");
     if (rc) return rc;
   }
-  gn_finalize_kernel<<<ceil_div(B * groups, 8), 256, 0, s>>>(partials_ws, nblocks, gamma, beta, scale_shift_ws, B, HW, C,
+  pdl_launch(ceil_div(B * groups, 8), 256, 0, s)(gn_finalize_kernel, partials_ws, nblocks, gamma, beta, scale_shift_ws, B, HW, C,
                                                              groups, eps);
   rc = check_launch("gn_finalize");
   if (rc) return rc;
   const long long total4 = static_cast<long long>(B) * HW * (C / 4);
   const unsigned blocks = static_cast<unsigned>(ceil_div_ll(total4, 256));
   if (y != nullptr)
-    gn_apply_silu_kernel<false><<<blocks, 256, 0, s>>>(x, scale_shift_ws, y, nullptr, nullptr, total4, HW, C, apply_silu);
+    pdl_launch(blocks, 256, 0, s)(gn_apply_silu_kernel<false>, x, scale_shift_ws, y, nullptr, nullptr, total4, HW, C, apply_silu);
   else if (C % 8 == 0)
-    gn_apply_silu_split8_kernel<<<static_cast<unsigned>(ceil_div_ll(total4 / 2, 256)), 256, 0, s>>>(
+    pdl_launch(static_cast<unsigned>(ceil_div_ll(total4 / 2, 256)), 256, 0, s)(gn_apply_silu_split8_kernel,
         x, scale_shift_ws, reinterpret_cast<bf16*>(y_hi), reinterpret_cast<bf16*>(y_lo), total4 / 2, HW, C, apply_silu);
   else
-    gn_apply_silu_kernel<true><<<blocks, 256, 0, s>>>(x, scale_shift_ws, nullptr, reinterpret_cast<bf16*>(y_hi),
+    pdl_launch(blocks, 256, 0, s)(gn_apply_silu_kernel<true>, x, scale_shift_ws, nullptr, reinterpret_cast<bf16*>(y_hi),
                                                       reinterpret_cast<bf16*>(y_lo), total4, HW, C, apply_silu);
   return check_launch("gn_apply_silu");
 }
@@ -386,6 +393,7 @@ int groupnorm_silu_nhwc(const float* x, const float* gamma, const float* beta, f
 // (decode -> permute(1, 2, 0) -> numpy) and the 4x larger fp32 device->host copy disappear.
 __global__ void __launch_bounds__(256)
 image_to_uint8_kernel(const float* __restrict__ x, unsigned char* __restrict__ y, long long n4) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n4) return;
   const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
@@ -405,7 +413,7 @@ image_to_uint8_kernel(const float* __restrict__ x, unsigned char* __restrict__ y
 int image_to_uint8(const float* x, unsigned char* y, long long n, cudaStream_t s) {
   if (n <= 0) return MUSE_OK;
   if (n % 4 != 0) { set_last_error("image_to_uint8: element count must be a multiple of 4"); return MUSE_ERR_INVALID; }
-  image_to_uint8_kernel<<<static_cast<unsigned>(ceil_div_ll(n / 4, 256)), 256, 0, s>>>(x, y, n / 4);
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(n / 4, 256)), 256, 0, s)(image_to_uint8_kernel, x, y, n / 4);
   return check_launch("image_to_uint8");
 }
 
@@ -413,14 +421,14 @@ int avgpool2_nhwc(const float* x, float* y, int B, int Ho, int Wo, int C, cudaSt
   if (C % 4 != 0) { set_last_error("avgpool: C must be a multiple of 4"); return MUSE_ERR_UNSUPPORTED; }
   const long long total = static_cast<long long>(B) * Ho * Wo * (C / 4);
   if (total <= 0) return MUSE_OK;
-  avgpool2_nhwc_kernel<<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, s>>>(x, y, B, Ho, Wo, C);
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, s)(avgpool2_nhwc_kernel, x, y, B, Ho, Wo, C);
   return check_launch("avgpool2_nhwc");
 }
 
 // in: [B, rows, cols] -> out: [B, cols, rows]
 int transpose_batched(const float* in, float* out, int B, int rows, int cols, cudaStream_t s) {
   if (B <= 0 || rows <= 0 || cols <= 0) return MUSE_OK;
-  transpose_cp_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32), B), 256, 0, s>>>(in, out, rows, cols);
+  pdl_launch(dim3(ceil_div(cols, 32), ceil_div(rows, 32), B), 256, 0, s)(transpose_cp_kernel, in, out, rows, cols);
   return check_launch("transpose_batched");
 }
 

@@ -100,6 +100,7 @@ template <int BN, bool SWAP>
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const ConvParams p) {
+  pdl_trigger();
   using C_ = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -139,6 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();  // everything above touches only shared memory / TMEM / kernel parameters
   const uint32_t tmem_base = *tmem_holder;
   const int tiles_mn = p.num_m * p.num_n;
   const int total_tiles = tiles_mn * (p.up ? 4 : 1);
@@ -430,6 +432,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long long total8, int H, int W,
                   int C, int up) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total8) return;
   long long src = i;
@@ -458,6 +461,7 @@ split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __re
 __global__ void __launch_bounds__(256)
 im2col_split_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long long pixels, int H, int W,
                     int Cin, int ksize) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= pixels * 8) return;
   const long long pix = i >> 3;
@@ -487,6 +491,7 @@ im2col_split_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __
 __global__ void __launch_bounds__(256)
 split_s2d_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long long total8, int Ho, int Wo,
                  int C) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total8) return;
   const int c8 = C / 8;
@@ -512,6 +517,7 @@ split_s2d_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __res
 __global__ void __launch_bounds__(256)
 softmax_split_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, float* __restrict__ out,
                      long long rows, int n, float scale) {
+  pdl_enter();
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -554,7 +560,7 @@ int launch_conv(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap&
   }
   const int total = p.num_m * p.num_n;
   const int grid = total < sm_count() ? total : sm_count();
-  kern<<<grid, 256, Cfg<BN>::kSmemBytes, s>>>(ah, al, bh, bl, p);
+  pdl_launch(grid, 256, Cfg<BN>::kSmemBytes, s)(kern, ah, al, bh, bl, p);
   return check_launch("conv_tc");
 }
 
@@ -667,7 +673,7 @@ int im2col_split_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, i
   }
   const long long pixels = static_cast<long long>(B) * H * W;
   if (pixels <= 0) return MUSE_OK;
-  im2col_split_kernel<<<static_cast<unsigned>(ceil_div_ll(pixels * 8, 256)), 256, 0, s>>>(
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(pixels * 8, 256)), 256, 0, s)(im2col_split_kernel,
       x, reinterpret_cast<bf16*>(hi), reinterpret_cast<bf16*>(lo), pixels, H, W, Cin, ksize);
   return check_launch("im2col_split");
 }
@@ -677,7 +683,7 @@ int split_s2d_bf16_nhwc(const float* x, void* hi, void* lo, int B, int Ho, int W
   if (C % 8 != 0) { set_last_error("split_s2d: C must be a multiple of 8"); return MUSE_ERR_UNSUPPORTED; }
   const long long total8 = static_cast<long long>(B) * Ho * Wo * 4 * (C / 8);
   if (total8 <= 0) return MUSE_OK;
-  split_s2d_kernel<<<static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s>>>(x, reinterpret_cast<bf16*>(hi),
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s)(split_s2d_kernel, x, reinterpret_cast<bf16*>(hi),
                                                                                    reinterpret_cast<bf16*>(lo), total8, Ho, Wo, C);
   return check_launch("split_s2d");
 }
@@ -686,7 +692,7 @@ int split_s2d_bf16_nhwc(const float* x, void* hi, void* lo, int B, int Ho, int W
 int softmax_split_rows(const float* x, void* hi, void* lo, float* out_f32, long long rows, int n, float scale, cudaStream_t s) {
   if (rows <= 0 || n <= 0) return MUSE_OK;
   if (out_f32 == x) { set_last_error("softmax: in-place output is not supported"); return MUSE_ERR_INVALID; }
-  softmax_split_kernel<<<static_cast<unsigned>(ceil_div_ll(rows, 8)), 256, 0, s>>>(x, reinterpret_cast<bf16*>(hi),
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(rows, 8)), 256, 0, s)(softmax_split_kernel, x, reinterpret_cast<bf16*>(hi),
                                                                                    reinterpret_cast<bf16*>(lo), out_f32, rows, n, scale);
   return check_launch("softmax_split");
 }
@@ -697,7 +703,7 @@ int split_bf16_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int
   if (upsample2x && ((H | W) & 1)) { set_last_error("split_bf16: upsample2x needs even output dims"); return MUSE_ERR_INVALID; }
   const long long total8 = static_cast<long long>(B) * H * W * (C / 8);
   if (total8 <= 0) return MUSE_OK;
-  split_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s>>>(x, reinterpret_cast<bf16*>(hi),
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s)(split_bf16_kernel, x, reinterpret_cast<bf16*>(hi),
                                                                                     reinterpret_cast<bf16*>(lo), total8, H, W, C, upsample2x);
   return check_launch("split_bf16");
 }

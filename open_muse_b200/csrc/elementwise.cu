@@ -18,6 +18,7 @@ struct PackEntry {
 };
 
 __global__ void __launch_bounds__(256) pack_bf16_kernel(const PackEntry* __restrict__ table, int n_entries) {
+  pdl_enter();
   const long long blk = blockIdx.x;
   int lo = 0, hi = n_entries - 1;
   while (lo < hi) {  // last entry with first_block <= blk
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const PackEntry* __restr
 }
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n8) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i < n8) {
     float v[8];
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 __global__ void __launch_bounds__(128)
 embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
                  float* __restrict__ out, int tokens, int S, int H, int vocab) {
+  pdl_enter();
   const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (t >= tokens) return;
   const int lane = threadIdx.x & 31;
@@ -72,6 +75,7 @@ template <int CH>  // CH float4 chunks per lane: H = CH * 128
 __global__ void __launch_bounds__(256)
 embed_bwd_word_kernel(const long long* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ dword,
                       int tokens, int H, int vocab, int hot_id) {
+  pdl_enter();
   __shared__ float s_hot[CH * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < CH * 128; i += 256) s_hot[i] = 0.f;
@@ -122,6 +126,7 @@ embed_bwd_word_kernel(const long long* __restrict__ ids, const float* __restrict
 __global__ void __launch_bounds__(128)
 embed_bwd_word_generic_kernel(const long long* __restrict__ ids, const float* __restrict__ dx, float* __restrict__ dword,
                               int tokens, int H, int vocab) {
+  pdl_enter();
   const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (t >= tokens) return;
   const int lane = threadIdx.x & 31;
@@ -138,6 +143,7 @@ embed_bwd_word_generic_kernel(const long long* __restrict__ ids, const float* __
 // dpos[s] += sum_b dx[b, s]; block (s, column chunk of 128 floats), threads stride over batch
 __global__ void __launch_bounds__(128)
 embed_bwd_pos_kernel(const float* __restrict__ dx, float* __restrict__ dpos, int B, int S, int H) {
+  pdl_enter();
   const int s = blockIdx.x;
   const int c = blockIdx.y * 128 + threadIdx.x;
   if (c >= H) return;
@@ -156,6 +162,7 @@ constexpr int kSegChunk = 256;
 
 __global__ void __launch_bounds__(1024)
 embed_seg_plan_kernel(const long long* __restrict__ bounds, int* __restrict__ chunk_off, int vocab) {
+  pdl_enter();
   __shared__ int s_part[1024];
   const int per = ceil_div(vocab, 1024);
   const int v0 = threadIdx.x * per;
@@ -211,6 +218,7 @@ __device__ __forceinline__ void ordered_rows_sum(RowFn row, int n, int H, float*
 __global__ void __launch_bounds__(512) embed_seg_chunk_kernel(const long long* __restrict__ order, const long long* __restrict__ bounds,
                                        const int* __restrict__ chunk_off, const float* __restrict__ dx,
                                        float* __restrict__ dword, float* __restrict__ ws, int H, int vocab) {
+  pdl_enter();
   extern __shared__ __align__(16) float s_q[];  // [4][H]
   const int g = blockIdx.x;
   if (g >= chunk_off[vocab]) return;
@@ -230,6 +238,7 @@ __global__ void __launch_bounds__(512) embed_seg_chunk_kernel(const long long* _
 
 __global__ void __launch_bounds__(512) embed_seg_final_kernel(const int* __restrict__ chunk_off, const float* __restrict__ ws,
                                        float* __restrict__ dword, int H, int vocab) {
+  pdl_enter();
   extern __shared__ __align__(16) float s_q[];
   const int v = blockIdx.x;
   const int c0 = chunk_off[v], nc = chunk_off[v + 1] - c0;
@@ -247,6 +256,7 @@ __global__ void __launch_bounds__(512) embed_seg_final_kernel(const int* __restr
 // Rounding points follow the reference under bf16 autocast: gelu(a) is rounded to bf16 before the product.
 __global__ void __launch_bounds__(256)
 glu_fwd_kernel(const bf16* __restrict__ ab, bf16* __restrict__ out, long long rows, int I) {
+  pdl_enter();
   const int chunks = I / 8;
   const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (idx >= rows * chunks) return;
@@ -262,6 +272,7 @@ glu_fwd_kernel(const bf16* __restrict__ ab, bf16* __restrict__ out, long long ro
 
 __global__ void __launch_bounds__(256)
 glu_bwd_kernel(const bf16* __restrict__ ab, const bf16* __restrict__ dout, bf16* __restrict__ dab, long long rows, int I) {
+  pdl_enter();
   const int chunks = I / 8;
   const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (idx >= rows * chunks) return;
@@ -286,7 +297,7 @@ glu_bwd_kernel(const bf16* __restrict__ ab, const bf16* __restrict__ dout, bf16*
 
 int pack_bf16(const void* table_dev, int n_entries, long long total_blocks, cudaStream_t s) {
   if (n_entries <= 0 || total_blocks <= 0) return MUSE_OK;
-  pack_bf16_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, s>>>(reinterpret_cast<const PackEntry*>(table_dev), n_entries);
+  pdl_launch(static_cast<unsigned>(total_blocks), 256, 0, s)(pack_bf16_kernel, reinterpret_cast<const PackEntry*>(table_dev), n_entries);
   return check_launch("pack_bf16");
 }
 
@@ -294,7 +305,7 @@ int cast_bf16(const float* src, void* dst, long long n, cudaStream_t s) {
   if (n <= 0) return MUSE_OK;
   if (n % 8 != 0) { set_last_error("cast_bf16: n=%lld must be a multiple of 8", n); return MUSE_ERR_INVALID; }
   const long long n8 = n / 8;
-  cast_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(n8, 256)), 256, 0, s>>>(src, reinterpret_cast<bf16*>(dst), n8);
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(n8, 256)), 256, 0, s)(cast_bf16_kernel, src, reinterpret_cast<bf16*>(dst), n8);
   return check_launch("cast_bf16");
 }
 
@@ -303,7 +314,7 @@ int embed_fwd(const long long* ids, const float* word, const float* pos, float* 
   if (H % 4 != 0) { set_last_error("embed_fwd: H must be a multiple of 4"); return MUSE_ERR_INVALID; }
   const int tokens = B * S;
   if (tokens <= 0) return MUSE_OK;
-  embed_fwd_kernel<<<ceil_div(tokens, 4), 128, 0, s>>>(ids, word, pos, out, tokens, S, H, vocab);
+  pdl_launch(ceil_div(tokens, 4), 128, 0, s)(embed_fwd_kernel, ids, word, pos, out, tokens, S, H, vocab);
   return check_launch("embed_fwd");
 }
 
@@ -314,15 +325,15 @@ int embed_bwd(const long long* ids, const float* dx, float* dword, float* dpos, 
   if (tokens <= 0) return MUSE_OK;
   const int hot = vocab - 1;  // the reference's mask_token_id
   const int grid = ceil_div(tokens, 8 * kEmbTokPerWarp);
-  if (H == 512) embed_bwd_word_kernel<4><<<grid, 256, 0, s>>>(ids, dx, dword, tokens, H, vocab, hot);
-  else if (H == 768) embed_bwd_word_kernel<6><<<grid, 256, 0, s>>>(ids, dx, dword, tokens, H, vocab, hot);
-  else if (H == 1024) embed_bwd_word_kernel<8><<<grid, 256, 0, s>>>(ids, dx, dword, tokens, H, vocab, hot);
-  else if (H == 128) embed_bwd_word_kernel<1><<<grid, 256, 0, s>>>(ids, dx, dword, tokens, H, vocab, hot);
-  else embed_bwd_word_generic_kernel<<<ceil_div(tokens, 4), 128, 0, s>>>(ids, dx, dword, tokens, H, vocab);
+  if (H == 512) pdl_launch(grid, 256, 0, s)(embed_bwd_word_kernel<4>, ids, dx, dword, tokens, H, vocab, hot);
+  else if (H == 768) pdl_launch(grid, 256, 0, s)(embed_bwd_word_kernel<6>, ids, dx, dword, tokens, H, vocab, hot);
+  else if (H == 1024) pdl_launch(grid, 256, 0, s)(embed_bwd_word_kernel<8>, ids, dx, dword, tokens, H, vocab, hot);
+  else if (H == 128) pdl_launch(grid, 256, 0, s)(embed_bwd_word_kernel<1>, ids, dx, dword, tokens, H, vocab, hot);
+  else pdl_launch(ceil_div(tokens, 4), 128, 0, s)(embed_bwd_word_generic_kernel, ids, dx, dword, tokens, H, vocab);
   int rc = check_launch("embed_bwd_word");
   if (rc) return rc;
   if (dpos == nullptr) return MUSE_OK;  // no position table (ConvEmbed of MaskGiTUViT_v2)
-  embed_bwd_pos_kernel<<<dim3(S, ceil_div(H, 128)), 128, 0, s>>>(dx, dpos, B, S, H);
+  pdl_launch(dim3(S, ceil_div(H, 128)), 128, 0, s)(embed_bwd_pos_kernel, dx, dpos, B, S, H);
   return check_launch("embed_bwd_pos");
 }
 
@@ -343,13 +354,13 @@ int embed_bwd_sorted(const long long* order, const long long* bounds, const floa
   if (ncol > 128) ncol = 128;  // 4 groups x ncol threads <= 512 (the kernels' launch bound)
   const size_t smem = static_cast<size_t>(4) * H * sizeof(float);
   if (smem > 48 * 1024) { set_last_error("embed_bwd_sorted: H=%d too wide", H); return MUSE_ERR_UNSUPPORTED; }
-  embed_seg_plan_kernel<<<1, 1024, 0, s>>>(bounds, chunk_off, vocab);
-  embed_seg_chunk_kernel<<<max_chunks, 4 * ncol, smem, s>>>(order, bounds, chunk_off, dx, dword, partial, H, vocab);
-  embed_seg_final_kernel<<<vocab, 4 * ncol, smem, s>>>(chunk_off, partial, dword, H, vocab);
+  pdl_launch(1, 1024, 0, s)(embed_seg_plan_kernel, bounds, chunk_off, vocab);
+  pdl_launch(max_chunks, 4 * ncol, smem, s)(embed_seg_chunk_kernel, order, bounds, chunk_off, dx, dword, partial, H, vocab);
+  pdl_launch(vocab, 4 * ncol, smem, s)(embed_seg_final_kernel, chunk_off, partial, dword, H, vocab);
   int rc = check_launch("embed_bwd_sorted");
   if (rc) return rc;
   if (dpos == nullptr) return MUSE_OK;
-  embed_bwd_pos_kernel<<<dim3(S, ceil_div(H, 128)), 128, 0, s>>>(dx, dpos, B, S, H);
+  pdl_launch(dim3(S, ceil_div(H, 128)), 128, 0, s)(embed_bwd_pos_kernel, dx, dpos, B, S, H);
   return check_launch("embed_bwd_pos");
 }
 
@@ -357,7 +368,7 @@ int glu_fwd(const void* ab, void* out, long long rows, int I, cudaStream_t s) {
   if (I % 8 != 0) { set_last_error("glu_fwd: I must be a multiple of 8"); return MUSE_ERR_INVALID; }
   const long long n = rows * (I / 8);
   if (n <= 0) return MUSE_OK;
-  glu_fwd_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(reinterpret_cast<const bf16*>(ab), reinterpret_cast<bf16*>(out), rows, I);
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s)(glu_fwd_kernel, reinterpret_cast<const bf16*>(ab), reinterpret_cast<bf16*>(out), rows, I);
   return check_launch("glu_fwd");
 }
 
@@ -365,7 +376,7 @@ int glu_bwd(const void* ab, const void* dout, void* dab, long long rows, int I, 
   if (I % 8 != 0) { set_last_error("glu_bwd: I must be a multiple of 8"); return MUSE_ERR_INVALID; }
   const long long n = rows * (I / 8);
   if (n <= 0) return MUSE_OK;
-  glu_bwd_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(reinterpret_cast<const bf16*>(ab), reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dab), rows, I);
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s)(glu_bwd_kernel, reinterpret_cast<const bf16*>(ab), reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dab), rows, I);
   return check_launch("glu_bwd");
 }
 

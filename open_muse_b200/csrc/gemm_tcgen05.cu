@@ -59,6 +59,7 @@ template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(256, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
+  pdl_trigger();
   using C_ = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -96,6 +97,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();  // everything above touches only shared memory / TMEM / kernel parameters
   const uint32_t tmem_base = *tmem_holder;
 
   const int tiles_mn = p.num_m * p.num_n;
@@ -317,6 +319,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int M, int N, int ldc, int num_n, int tiles_mn,
                      int bn, int splits) {
+  pdl_enter();
   const int n4 = (N + 3) >> 2;
   const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (idx >= static_cast<long long>(M) * n4) return;
@@ -456,7 +459,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   }
   const int total = p.num_m * p.num_n * p.splits;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, 256, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, p);
+  pdl_launch(grid, 256, Cfg<BN>::kSmemBytes, stream)(kern, ta, tb, p);
   return check_launch("gemm_tcgen05");
 }
 
@@ -557,7 +560,7 @@ int gemm_tcgen05(const void* A, const void* B, void* C, const float* res, int M,
   rc = (BN == 256) ? launch_major<256>(a_mn, b_mn, epi, ta, tb, p, stream) : launch_major<128>(a_mn, b_mn, epi, ta, tb, p, stream);
   if (rc || epi != EPI_SPLITK_F32 || p.splits <= 1) return rc;
   const long long n_out4 = static_cast<long long>(M) * ((N + 3) / 4);
-  splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div_ll(n_out4, 256)), 256, 0, stream>>>(
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(n_out4, 256)), 256, 0, stream)(splitk_reduce_kernel,
       p.ws, reinterpret_cast<float*>(C), M, N, ldc, p.num_n, p.num_m * p.num_n, BN, p.splits);
   return check_launch("gemm splitk reduce");
 }

@@ -16,6 +16,7 @@ constexpr long long kIgnore = -100;
 __global__ void __launch_bounds__(128)
 ce_fwd_kernel(const bf16* __restrict__ logits, const long long* __restrict__ labels, float* __restrict__ lse_out,
               float* __restrict__ row_loss, int rows, int V, int ld, float ls) {
+  pdl_enter();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -71,6 +72,7 @@ ce_fwd_kernel(const bf16* __restrict__ logits, const long long* __restrict__ lab
 __global__ void __launch_bounds__(1024)
 ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict__ labels, float* __restrict__ out,
                  int rows, int V) {
+  pdl_enter();
   __shared__ float s_sum[1024];
   __shared__ float s_cnt[1024];
   float a = 0.f, c = 0.f;
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(128)
 ce_bwd_kernel(const bf16* __restrict__ logits, const long long* __restrict__ labels, const float* __restrict__ lse_in,
               const float* __restrict__ dloss, const float* __restrict__ loss_cnt, const float* __restrict__ row_scale,
               bf16* __restrict__ dlogits, int rows, int V, int ld, float ls) {
+  pdl_enter();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -134,10 +137,10 @@ int ce_fwd(const void* logits, const long long* labels, float* lse, float* row_l
            int ld, float ls, cudaStream_t s) {
   if (rows <= 0) return MUSE_OK;
   if (ld % 8 != 0 || ld < V) { set_last_error("ce_fwd: ld=%d must be a multiple of 8 and >= V=%d", ld, V); return MUSE_ERR_INVALID; }
-  ce_fwd_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(reinterpret_cast<const bf16*>(logits), labels, lse, row_loss, rows, V, ld, ls);
+  pdl_launch(ceil_div(rows, 4), 128, 0, s)(ce_fwd_kernel, reinterpret_cast<const bf16*>(logits), labels, lse, row_loss, rows, V, ld, ls);
   int rc = check_launch("ce_fwd");
   if (rc) return rc;
-  ce_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, labels, loss_out, rows, V);
+  pdl_launch(1, 1024, 0, s)(ce_reduce_kernel, row_loss, labels, loss_out, rows, V);
   return check_launch("ce_reduce");
 }
 
@@ -145,7 +148,7 @@ int ce_bwd(const void* logits, const long long* labels, const float* lse, const 
            const float* row_scale, void* dlogits, int rows, int V, int ld, float ls, cudaStream_t s) {
   if (rows <= 0) return MUSE_OK;
   if (ld % 8 != 0 || ld < V) { set_last_error("ce_bwd: ld=%d must be a multiple of 8 and >= V=%d", ld, V); return MUSE_ERR_INVALID; }
-  ce_bwd_kernel<<<ceil_div(rows, 4), 128, 0, s>>>(reinterpret_cast<const bf16*>(logits), labels, lse, dloss, loss_cnt, row_scale, reinterpret_cast<bf16*>(dlogits), rows, V, ld, ls);
+  pdl_launch(ceil_div(rows, 4), 128, 0, s)(ce_bwd_kernel, reinterpret_cast<const bf16*>(logits), labels, lse, dloss, loss_cnt, row_scale, reinterpret_cast<bf16*>(dlogits), rows, V, ld, ls);
   return check_launch("ce_bwd");
 }
 

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 norm_fwd_warp_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ res,
                 TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
                 float eps, int act, int rms) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -107,6 +108,7 @@ __device__ __forceinline__ void flush_cta_dw(const float* s_dw, int nwarps, int 
 
 // dw[i] = sum_g ws[g][i] in ascending g (32 x 32 threads: thread (ty, tx) sums rows ty, ty+32, ... of column tx).
 __global__ void __launch_bounds__(1024) colsum_ordered_kernel(const float* __restrict__ ws, float* __restrict__ dw, int G, int H) {
+  pdl_enter();
   __shared__ float s[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
@@ -131,6 +133,7 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                 const float* __restrict__ dres, TDX* __restrict__ dx, bf16* __restrict__ dx_copy, float* __restrict__ dw,
                 float* __restrict__ dw_ws, int rows, int H, int act, int rms) {
+  pdl_enter();
   extern __shared__ float s_dw[];  // [kBwdWarps][H] private rows
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -219,6 +222,7 @@ norm2_fwd_warp_kernel(const bf16* __restrict__ a, const float* __restrict__ res,
                       const float* __restrict__ w2, float* __restrict__ x2, bf16* __restrict__ h2,
                       float* __restrict__ mean1_out, float* __restrict__ rstd1_out, float* __restrict__ mean2_out,
                       float* __restrict__ rstd2_out, int rows, int H, float eps, int rms1, int rms2) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -296,6 +300,7 @@ norm2_bwd_warp_kernel(const bf16* __restrict__ d_h2, const float* __restrict__ x
                       const bf16* __restrict__ a, const float* __restrict__ w1, const float* __restrict__ mean1_in,
                       const float* __restrict__ rstd1_in, float* __restrict__ dx2, bf16* __restrict__ d_a,
                       float* __restrict__ dw2_ws, float* __restrict__ dw1_ws, int rows, int H, int rms1, int rms2) {
+  pdl_enter();
   extern __shared__ float s_dw[];  // [2][kBwdWarps][H] private rows (dw2 then dw1)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -426,6 +431,7 @@ __global__ void __launch_bounds__(kWideWarps * 32)
 norm_fwd_wide_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ res,
                      TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
                      float eps, int act, int rms) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWideWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -481,6 +487,7 @@ norm_bwd_wide_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const float* __restrict__ dres, TDX* __restrict__ dx, float* __restrict__ dw,
                      float* __restrict__ dw_ws, int rows, int H, int act, int rms) {
+  pdl_enter();
   extern __shared__ __align__(16) float s_dw[];  // [kWideWarps][H] private per-warp weight-gradient rows
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -590,6 +597,7 @@ template <int CH>
 __global__ void __launch_bounds__(kGluWarps * 32, (CH <= 8) ? 2 : 1)
 glu_norm_fwd_kernel(const bf16* __restrict__ ab, const float* __restrict__ w, bf16* __restrict__ y,
                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H, float eps, int rms) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kGluWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -682,6 +690,7 @@ glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, co
                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dab,
                     float* __restrict__ dw, float* __restrict__ dw_ws, const bf16* __restrict__ yf, int rows, int H,
                     int rms) {
+  pdl_enter();
   extern __shared__ __align__(16) float s_dw[];  // [kGluWarps][H] private rows
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -798,7 +807,7 @@ int fwd_dispatch(const void* x, const float* w, const float* res, void* y, float
     const int grid = ceil_div(rows, kWarpsPerBlock);
     const int ch = ceil_div(H, 256);
 #define MUSE_NF(CH)                                                                                                \
-  norm_fwd_warp_kernel<TX, TY, CH><<<grid, kWarpsPerBlock * 32, 0, s>>>(reinterpret_cast<const TX*>(x), w, res,    \
+  pdl_launch(grid, kWarpsPerBlock * 32, 0, s)(norm_fwd_warp_kernel<TX, TY, CH>, reinterpret_cast<const TX*>(x), w, res,    \
                                                                          reinterpret_cast<TY*>(y), mean, rstd, rows, \
                                                                          H, eps, act, rms)
     if (ch <= 1) MUSE_NF(1);
@@ -807,7 +816,7 @@ int fwd_dispatch(const void* x, const float* w, const float* res, void* y, float
 #undef MUSE_NF
     return check_launch("norm_fwd");
   }
-  norm_fwd_wide_kernel<TX, TY><<<ceil_div(rows, kWideWarps), kWideWarps * 32, 0, s>>>(
+  pdl_launch(ceil_div(rows, kWideWarps), kWideWarps * 32, 0, s)(norm_fwd_wide_kernel<TX, TY>,
       reinterpret_cast<const TX*>(x), w, res, reinterpret_cast<TY*>(y), mean, rstd, rows, H, eps, act, rms);
   return check_launch("norm_fwd");
 }
@@ -820,7 +829,7 @@ int bwd_grid(int rows, int H, int act) {
 }
 
 int reduce_dw(const float* dw_ws, float* dw, int grid, int H, cudaStream_t s) {
-  colsum_ordered_kernel<<<ceil_div(H, 32), 1024, 0, s>>>(dw_ws, dw, grid, H);
+  pdl_launch(ceil_div(H, 32), 1024, 0, s)(colsum_ordered_kernel, dw_ws, dw, grid, H);
   return check_launch("norm_bwd colsum");
 }
 
@@ -833,7 +842,7 @@ int bwd_dispatch(const void* dy, const void* x, const float* w, const float* mea
     const int ch = ceil_div(H, 256);
     const size_t smem = dw ? static_cast<size_t>(kBwdWarps) * H * sizeof(float) : 0;
 #define MUSE_NB(CH)                                                                                          \
-  norm_bwd_warp_kernel<TDY, TX, TDX, CH><<<grid, kBwdWarps * 32, smem, s>>>(                                 \
+  pdl_launch(grid, kBwdWarps * 32, smem, s)(norm_bwd_warp_kernel<TDY, TX, TDX, CH>,                                  \
       reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd, dres,                 \
       reinterpret_cast<TDX*>(dx), reinterpret_cast<bf16*>(dx_copy), dw, dw_ws, rows, H, act, rms)
     if (ch <= 1) MUSE_NB(1);
@@ -849,7 +858,7 @@ int bwd_dispatch(const void* dy, const void* x, const float* w, const float* mea
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideWarps * 4096 * 4);
       attr = true;
     }
-    kern<<<grid, kWideWarps * 32, smem, s>>>(reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd,
+    pdl_launch(grid, kWideWarps * 32, smem, s)(kern, reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd,
                                              dres, reinterpret_cast<TDX*>(dx), dw, dw_ws, rows, H, act, rms);
   }
   int rc = check_launch("norm_bwd");
@@ -878,7 +887,7 @@ int norm_fwd(const void* x, int x_dt, const float* w, const float* res, void* y,
   if (act == ACT_GLU && x_dt == 1 && y_dt == 1 && H <= 4096) {
     const int grid = ceil_div(rows, kGluWarps);
     const int ch = ceil_div(H, 256);
-#define MUSE_GF(CH) glu_norm_fwd_kernel<CH><<<grid, kGluWarps * 32, 0, s>>>(reinterpret_cast<const bf16*>(x), w, reinterpret_cast<bf16*>(y), mean, rstd, rows, H, eps, rms)
+#define MUSE_GF(CH) pdl_launch(grid, kGluWarps * 32, 0, s)(glu_norm_fwd_kernel<CH>, reinterpret_cast<const bf16*>(x), w, reinterpret_cast<bf16*>(y), mean, rstd, rows, H, eps, rms)
     if (ch <= 1) MUSE_GF(1); else if (ch <= 2) MUSE_GF(2); else if (ch <= 4) MUSE_GF(4); else if (ch <= 8) MUSE_GF(8); else MUSE_GF(16);
 #undef MUSE_GF
     return check_launch("glu_norm_fwd");
@@ -898,7 +907,7 @@ int norm2_fwd(const void* a, const float* res, const float* w1, const float* w2,
   if (H % 8 != 0 || H > 1024 || H < 8) { set_last_error("norm2_fwd: H=%d must be a multiple of 8 in [8, 1024]", H); return MUSE_ERR_UNSUPPORTED; }
   const int grid = ceil_div(rows, kWarpsPerBlock);
   const int ch = ceil_div(H, 256);
-#define MUSE_N2F(CH) norm2_fwd_warp_kernel<CH><<<grid, kWarpsPerBlock * 32, 0, s>>>(reinterpret_cast<const bf16*>(a), res, w1, w2, x2, reinterpret_cast<bf16*>(h2), mean1, rstd1, mean2, rstd2, rows, H, eps, rms1, rms2)
+#define MUSE_N2F(CH) pdl_launch(grid, kWarpsPerBlock * 32, 0, s)(norm2_fwd_warp_kernel<CH>, reinterpret_cast<const bf16*>(a), res, w1, w2, x2, reinterpret_cast<bf16*>(h2), mean1, rstd1, mean2, rstd2, rows, H, eps, rms1, rms2)
   if (ch <= 1) MUSE_N2F(1); else if (ch <= 2) MUSE_N2F(2); else MUSE_N2F(4);
 #undef MUSE_N2F
   return check_launch("norm2_fwd");
@@ -922,7 +931,7 @@ int norm2_bwd(const void* d_h2, const float* x2, const float* w2, const float* m
     cudaFuncSetAttribute(norm2_bwd_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBwdWarps * 1024 * 4);
     attr = true;
   }
-#define MUSE_N2B(CH) norm2_bwd_warp_kernel<CH><<<grid, kBwdWarps * 32, smem, s>>>(reinterpret_cast<const bf16*>(d_h2), x2, w2, mean2, rstd2, dres, reinterpret_cast<const bf16*>(a), w1, mean1, rstd1, dx2, reinterpret_cast<bf16*>(d_a), ws2, ws1, rows, H, rms1, rms2)
+#define MUSE_N2B(CH) pdl_launch(grid, kBwdWarps * 32, smem, s)(norm2_bwd_warp_kernel<CH>, reinterpret_cast<const bf16*>(d_h2), x2, w2, mean2, rstd2, dres, reinterpret_cast<const bf16*>(a), w1, mean1, rstd1, dx2, reinterpret_cast<bf16*>(d_a), ws2, ws1, rows, H, rms1, rms2)
   if (ch <= 1) MUSE_N2B(1); else if (ch <= 2) MUSE_N2B(2); else MUSE_N2B(4);
 #undef MUSE_N2B
   int rc = check_launch("norm2_bwd");
@@ -954,11 +963,11 @@ int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w,
       attr = true;
     }
     if (y_fwd != nullptr)
-      glu_norm_bwd_kernel<true><<<grid, kGluWarps * 32, smem, s>>>(
+      pdl_launch(grid, kGluWarps * 32, smem, s)(glu_norm_bwd_kernel<true>,
           reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw,
           dw_ws, reinterpret_cast<const bf16*>(y_fwd), rows, H, rms);
     else
-      glu_norm_bwd_kernel<false><<<grid, kGluWarps * 32, smem, s>>>(
+      pdl_launch(grid, kGluWarps * 32, smem, s)(glu_norm_bwd_kernel<false>,
           reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw,
           dw_ws, nullptr, rows, H, rms);
     rc = check_launch("glu_norm_bwd");

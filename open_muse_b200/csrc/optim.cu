@@ -34,6 +34,7 @@ struct OptHyper {
 // scal: [0] step (after increment) [1] 1/bias_correction1 [2] 1/sqrt(bias_correction2) [3] lr [4] 1 - ema_decay_now (0: skip)
 //       [5] ema_decay_now
 __global__ void adamw_prepare_kernel(float* scal, long long* step, const float* lr_dev, float lr_host, OptHyper h) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const long long s = *step + 1;
   *step = s;
@@ -70,6 +71,7 @@ struct OptChunk {
 
 __global__ void __launch_bounds__(256)
 adamw_ema_pack_kernel(const __grid_constant__ OptChunk chunk, const float* __restrict__ scal, const OptHyper h) {
+  pdl_enter();
   const long long blk = blockIdx.x;
   int lo = 0, hi = chunk.n - 1;
   while (lo < hi) {  // last entry with first_block <= blk
@@ -128,7 +130,7 @@ int adamw_ema_step(const void* entries_host, int n_entries, float* scal_dev, lon
   h.ema_enabled = ema_enabled; h.ema_decay = ema_decay; h.ema_min_decay = ema_min_decay;
   h.ema_update_after_step = ema_update_after_step; h.ema_update_every = ema_update_every < 1 ? 1 : ema_update_every;
   h.ema_use_warmup = ema_use_warmup; h.ema_inv_gamma = ema_inv_gamma; h.ema_power = ema_power;
-  adamw_prepare_kernel<<<1, 32, 0, s>>>(scal_dev, step_dev, lr_dev, lr_host, h);
+  pdl_launch(1, 32, 0, s)(adamw_prepare_kernel, scal_dev, step_dev, lr_dev, lr_host, h);
   int rc = check_launch("adamw_prepare");
   if (rc) return rc;
   const OptEntry* all = reinterpret_cast<const OptEntry*>(entries_host);
@@ -142,7 +144,7 @@ int adamw_ema_step(const void* entries_host, int n_entries, float* scal_dev, lon
       chunk.e[i].first_block = blocks;
       blocks += (chunk.e[i].numel + 1023) / 1024;
     }
-    adamw_ema_pack_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(chunk, scal_dev, h);
+    pdl_launch(static_cast<unsigned>(blocks), 256, 0, s)(adamw_ema_pack_kernel, chunk, scal_dev, h);
     rc = check_launch("adamw_ema_pack");
     if (rc) return rc;
   }

@@ -29,6 +29,7 @@ sample_tokens_kernel(const bf16* __restrict__ logits, const bf16* __restrict__ l
                      long long batch_stride, float guidance, const long long* __restrict__ input_ids,
                      const float* __restrict__ q_exp, const float* __restrict__ u, long long* __restrict__ sampled_out,
                      float* __restrict__ conf_out, int B, int L, int K, long long mask_id, float temperature) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tok = static_cast<long long>(blockIdx.x) * kTokWarps + warp;
   if (tok >= static_cast<long long>(B) * L) return;
@@ -111,6 +112,7 @@ sample_tokens_kernel(const bf16* __restrict__ logits, const bf16* __restrict__ l
 __global__ void __launch_bounds__(1024)
 sample_remask_kernel(const long long* __restrict__ input_ids, const long long* __restrict__ sampled, const float* __restrict__ conf,
                      long long* __restrict__ next_ids, int L, long long mask_id, int mask_len) {
+  pdl_enter();
   extern __shared__ float s_conf[];  // [L]
   __shared__ int s_unknown;
   const int b = blockIdx.x;
@@ -144,13 +146,13 @@ int sample_step(const void* logits, const void* logits_unc, long long row_stride
   if (L > 4096) { set_last_error("sample_step: L=%d too long (max 4096)", L); return MUSE_ERR_UNSUPPORTED; }
   if (conf_out == nullptr) { set_last_error("sample_step: conf_out (B*L floats) is required"); return MUSE_ERR_INVALID; }
   const long long tokens = static_cast<long long>(B) * L;
-  sample_tokens_kernel<<<static_cast<unsigned>(ceil_div_ll(tokens, kTokWarps)), kTokWarps * 32, 0, s>>>(
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(tokens, kTokWarps)), kTokWarps * 32, 0, s)(sample_tokens_kernel,
       reinterpret_cast<const bf16*>(logits), reinterpret_cast<const bf16*>(logits_unc), row_stride, batch_stride, guidance,
       input_ids, q_exp, u, sampled, conf_out, B, L, K, mask_id, temperature);
   int rc = check_launch("sample_tokens");
   if (rc) return rc;
   const int threads = L >= 1024 ? 1024 : ((L + 31) / 32) * 32;
-  sample_remask_kernel<<<B, threads, L * sizeof(float), s>>>(input_ids, sampled, conf_out, next_ids, L, mask_id, mask_len);
+  pdl_launch(B, threads, L * sizeof(float), s)(sample_remask_kernel, input_ids, sampled, conf_out, next_ids, L, mask_id, mask_len);
   return check_launch("sample_remask");
 }
 

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 add_norm_mod_kernel(const TA* __restrict__ a, const float* __restrict__ r, const float* __restrict__ w,
                     const float* __restrict__ ss, long long ss_stride, int rows_per_sample, float* __restrict__ r_out,
                     TY* __restrict__ y, int rows, int H, float eps, int rms) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -92,6 +93,7 @@ template <int CH>
 __global__ void __launch_bounds__(kWarps * 32)
 dwconv3x3_norm_kernel(const float* __restrict__ x, const float* __restrict__ wk, const float* __restrict__ nw,
                       bf16* __restrict__ y, bf16* __restrict__ conv_out, int B, int hh, int ww, int C, float eps, int rms) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long pix = static_cast<long long>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
   if (pix >= static_cast<long long>(B) * hh * ww) return;
@@ -156,6 +158,7 @@ dwconv3x3_norm_kernel(const float* __restrict__ x, const float* __restrict__ wk,
 // GRN pass 1: sumsq[b, c] = sum over the image's tokens of bf16(gelu(x))^2.  grid (C/256, B), 128 threads x 2 channels.
 __global__ void __launch_bounds__(128)
 grn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ sumsq, int HW, int C) {
+  pdl_enter();
   const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
   if (c >= C) return;
   const int b = blockIdx.y;
@@ -174,6 +177,7 @@ grn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ sumsq, int HW, 
 // GRN pass 2 (one CTA per image): nx[c] = sqrt(sumsq[c]) / (mean_c sqrt(sumsq) + 1e-6)
 __global__ void __launch_bounds__(256)
 grn_finalize_kernel(const float* __restrict__ stat, float* __restrict__ nx_out, int C) {
+  pdl_enter();
   __shared__ float s_part[8];
   const float* p = stat + static_cast<size_t>(blockIdx.x) * C;
   float* o = nx_out + static_cast<size_t>(blockIdx.x) * C;
@@ -193,6 +197,7 @@ grn_finalize_kernel(const float* __restrict__ stat, float* __restrict__ nx_out, 
 __global__ void __launch_bounds__(256)
 grn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ nx, const float* __restrict__ gamma,
                  const float* __restrict__ beta, bf16* __restrict__ out, long long total8, int HW, int C) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total8) return;
   const int c8 = C / 8;
@@ -214,6 +219,7 @@ grn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ nx, const
 __global__ void __launch_bounds__(256)
 adaln_apply_kernel(float* __restrict__ x, const float* __restrict__ ss, long long ss_stride, long long total4,
                    int rows_per_sample, int C) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total4) return;
   const int c4 = C / 4;
@@ -230,6 +236,7 @@ adaln_apply_kernel(float* __restrict__ x, const float* __restrict__ ss, long lon
 
 template <typename TX>
 __global__ void __launch_bounds__(256) silu_kernel(const TX* __restrict__ x, bf16* __restrict__ y, long long n8) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n8) return;
   float v[8];
@@ -245,7 +252,7 @@ int launch_add_norm(const void* a, const float* r, const float* w, const float* 
   const int grid = ceil_div(rows, kWarps);
   const TA* ap = reinterpret_cast<const TA*>(a);
   TY* yp = reinterpret_cast<TY*>(y);
-#define MUSE_AN(CH) add_norm_mod_kernel<TA, TY, CH><<<grid, kWarps * 32, 0, s>>>(ap, r, w, ss, ss_stride, rows_per_sample, r_out, yp, rows, H, eps, rms)
+#define MUSE_AN(CH) pdl_launch(grid, kWarps * 32, 0, s)(add_norm_mod_kernel<TA, TY, CH>, ap, r, w, ss, ss_stride, rows_per_sample, r_out, yp, rows, H, eps, rms)
   if (H <= 256) MUSE_AN(1);
   else if (H <= 512) MUSE_AN(2);
   else if (H <= 768) MUSE_AN(3);
@@ -279,10 +286,10 @@ int dwconv3x3_norm_fwd(const float* x, const float* wk, const float* nw, void* y
   const unsigned grid = static_cast<unsigned>(ceil_div_ll(pixels, kWarps));
   bf16* yp = reinterpret_cast<bf16*>(y);
   bf16* cp = reinterpret_cast<bf16*>(conv_out);
-  if (C <= 256) dwconv3x3_norm_kernel<1><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
-  else if (C <= 512) dwconv3x3_norm_kernel<2><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
-  else if (C <= 768) dwconv3x3_norm_kernel<3><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
-  else dwconv3x3_norm_kernel<4><<<grid, kWarps * 32, 0, s>>>(x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
+  if (C <= 256) pdl_launch(grid, kWarps * 32, 0, s)(dwconv3x3_norm_kernel<1>, x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
+  else if (C <= 512) pdl_launch(grid, kWarps * 32, 0, s)(dwconv3x3_norm_kernel<2>, x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
+  else if (C <= 768) pdl_launch(grid, kWarps * 32, 0, s)(dwconv3x3_norm_kernel<3>, x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
+  else pdl_launch(grid, kWarps * 32, 0, s)(dwconv3x3_norm_kernel<4>, x, wk, nw, yp, cp, B, hh, ww, C, eps, rms);
   return check_launch("dwconv3x3_norm");
 }
 
@@ -292,14 +299,14 @@ int grn_fwd(const void* x, const float* gamma, const float* beta, void* out, flo
   if (B <= 0 || HW <= 0) return MUSE_OK;
   if (C % 8 != 0) { set_last_error("grn: C must be a multiple of 8"); return MUSE_ERR_UNSUPPORTED; }
   const bf16* xp = reinterpret_cast<const bf16*>(x);
-  grn_stats_kernel<<<dim3(ceil_div(C, 256), B), 128, 0, s>>>(xp, stat_ws, HW, C);
+  pdl_launch(dim3(ceil_div(C, 256), B), 128, 0, s)(grn_stats_kernel, xp, stat_ws, HW, C);
   int rc = check_launch("grn_stats");
   if (rc) return rc;
-  grn_finalize_kernel<<<B, 256, 0, s>>>(stat_ws, nx_ws, C);
+  pdl_launch(B, 256, 0, s)(grn_finalize_kernel, stat_ws, nx_ws, C);
   rc = check_launch("grn_finalize");
   if (rc) return rc;
   const long long total8 = static_cast<long long>(B) * HW * (C / 8);
-  grn_apply_kernel<<<static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s>>>(xp, nx_ws, gamma, beta,
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s)(grn_apply_kernel, xp, nx_ws, gamma, beta,
                                                                                    reinterpret_cast<bf16*>(out), total8, HW, C);
   return check_launch("grn_apply");
 }
@@ -308,7 +315,7 @@ int adaln_apply(float* x, const float* ss, long long ss_stride, int B, int rows_
   if (C % 4 != 0 || ss_stride % 4 != 0) { set_last_error("adaln_apply: C and the modulation stride must be multiples of 4"); return MUSE_ERR_UNSUPPORTED; }
   const long long total4 = static_cast<long long>(B) * rows_per_sample * (C / 4);
   if (total4 <= 0) return MUSE_OK;
-  adaln_apply_kernel<<<static_cast<unsigned>(ceil_div_ll(total4, 256)), 256, 0, s>>>(x, ss, ss_stride, total4, rows_per_sample, C);
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(total4, 256)), 256, 0, s)(adaln_apply_kernel, x, ss, ss_stride, total4, rows_per_sample, C);
   return check_launch("adaln_apply");
 }
 
@@ -317,8 +324,8 @@ int silu_bf16(const void* x, int x_dt, void* y, long long n, cudaStream_t s) {
   if (n % 8 != 0) { set_last_error("silu: n must be a multiple of 8"); return MUSE_ERR_INVALID; }
   const long long n8 = n / 8;
   const unsigned grid = static_cast<unsigned>(ceil_div_ll(n8, 256));
-  if (x_dt == 0) silu_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), reinterpret_cast<bf16*>(y), n8);
-  else silu_kernel<bf16><<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), n8);
+  if (x_dt == 0) pdl_launch(grid, 256, 0, s)(silu_kernel<float>, reinterpret_cast<const float*>(x), reinterpret_cast<bf16*>(y), n8);
+  else pdl_launch(grid, 256, 0, s)(silu_kernel<bf16>, reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(y), n8);
   return check_launch("silu");
 }
 

@@ -20,6 +20,7 @@ add_norm_mod_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ dr
                         const float* __restrict__ w, const float* __restrict__ ss, long long ss_stride, int rows_per_sample,
                         TA* __restrict__ da, float* __restrict__ dr, float* __restrict__ dw, float* __restrict__ dss,
                         int rows, int H, float eps, int rms) {
+  pdl_enter();
   extern __shared__ float s_dw[];  // [H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (dw) {
@@ -150,6 +151,7 @@ template <int CH>
 __global__ void __launch_bounds__(kWarps * 32)
 dwnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ cv, const float* __restrict__ nw,
                   float* __restrict__ dc, float* __restrict__ dnw, long long pixels, int C, float eps, int rms) {
+  pdl_enter();
   extern __shared__ float s_dw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (dnw) {
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(256)
 dwconv_bwd_kernel(const float* __restrict__ dc, const float* __restrict__ x, const float* __restrict__ wk,
                   const float* __restrict__ dres, float* __restrict__ dx, float* __restrict__ dwk, int B, int hh, int ww,
                   int C) {
+  pdl_enter();
   const int c4 = C / 4;
   const long long strips_per_row = (ww + kStrip - 1) / kStrip;
   const long long total = static_cast<long long>(B) * hh * strips_per_row * c4;
@@ -299,6 +302,7 @@ dwconv_bwd_kernel(const float* __restrict__ dc, const float* __restrict__ x, con
 __global__ void __launch_bounds__(128)
 grn_bwd_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout, const float* __restrict__ nx,
                      float* __restrict__ s1_out, float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C) {
+  pdl_enter();
   const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
   if (c >= C) return;
   const int b = blockIdx.y;
@@ -324,6 +328,7 @@ grn_bwd_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout, 
 // Gx = sqrt(sumsq), M = mean_c Gx + 1e-6.  coef overwrites s1.
 __global__ void __launch_bounds__(256)
 grn_bwd_finalize_kernel(float* __restrict__ s1, const float* __restrict__ sumsq, const float* __restrict__ gamma, int C) {
+  pdl_enter();
   __shared__ float s_a[8], s_b[8];
   float* s = s1 + static_cast<size_t>(blockIdx.x) * C;
   const float* q = sumsq + static_cast<size_t>(blockIdx.x) * C;
@@ -354,6 +359,7 @@ __global__ void __launch_bounds__(256)
 grn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout, const float* __restrict__ nx,
                      const float* __restrict__ coef, const float* __restrict__ gamma, bf16* __restrict__ dx,
                      long long total8, int HW, int C) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total8) return;
   const int c8 = C / 8;
@@ -379,6 +385,7 @@ grn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout, 
 __global__ void __launch_bounds__(128)
 adaln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ ss, long long ss_stride,
                  float* __restrict__ dx, float* __restrict__ dss, int rows_per_sample, int C) {
+  pdl_enter();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= C) return;
   const int b = blockIdx.y;
@@ -400,6 +407,7 @@ adaln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, cons
 template <typename TX, typename TDX>
 __global__ void __launch_bounds__(256)
 silu_bwd_kernel(const bf16* __restrict__ dy, const TX* __restrict__ x, TDX* __restrict__ dx, long long n8, int accumulate) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n8) return;
   float d[8], v[8], o[8];
@@ -423,7 +431,7 @@ int launch_anm_bwd(const void* dy, const float* dr_out, const float* x, const fl
   const size_t smem = dw ? static_cast<size_t>(H) * sizeof(float) : 0;
   const TDY* dyp = reinterpret_cast<const TDY*>(dy);
   TA* dap = reinterpret_cast<TA*>(da);
-#define MUSE_ANB(CH) add_norm_mod_bwd_kernel<TDY, TA, CH><<<grid, kWarps * 32, smem, s>>>(dyp, dr_out, x, w, ss, ss_stride, rows_per_sample, dap, dr, dw, dss, rows, H, eps, rms)
+#define MUSE_ANB(CH) pdl_launch(grid, kWarps * 32, smem, s)(add_norm_mod_bwd_kernel<TDY, TA, CH>, dyp, dr_out, x, w, ss, ss_stride, rows_per_sample, dap, dr, dw, dss, rows, H, eps, rms)
   if (H <= 256) MUSE_ANB(1);
   else if (H <= 512) MUSE_ANB(2);
   else if (H <= 768) MUSE_ANB(3);
@@ -462,14 +470,14 @@ int dwconv3x3_norm_bwd(const void* dy, const void* conv, const float* x, const f
   const size_t smem = dnw ? static_cast<size_t>(C) * sizeof(float) : 0;
   const bf16* dyp = reinterpret_cast<const bf16*>(dy);
   const bf16* cp = reinterpret_cast<const bf16*>(conv);
-  if (C <= 256) dwnorm_bwd_kernel<1><<<grid, kWarps * 32, smem, s>>>(dyp, cp, nw, dc_ws, dnw, pixels, C, eps, rms);
-  else if (C <= 512) dwnorm_bwd_kernel<2><<<grid, kWarps * 32, smem, s>>>(dyp, cp, nw, dc_ws, dnw, pixels, C, eps, rms);
-  else if (C <= 768) dwnorm_bwd_kernel<3><<<grid, kWarps * 32, smem, s>>>(dyp, cp, nw, dc_ws, dnw, pixels, C, eps, rms);
-  else dwnorm_bwd_kernel<4><<<grid, kWarps * 32, smem, s>>>(dyp, cp, nw, dc_ws, dnw, pixels, C, eps, rms);
+  if (C <= 256) pdl_launch(grid, kWarps * 32, smem, s)(dwnorm_bwd_kernel<1>, dyp, cp, nw, dc_ws, dnw, pixels, C, eps, rms);
+  else if (C <= 512) pdl_launch(grid, kWarps * 32, smem, s)(dwnorm_bwd_kernel<2>, dyp, cp, nw, dc_ws, dnw, pixels, C, eps, rms);
+  else if (C <= 768) pdl_launch(grid, kWarps * 32, smem, s)(dwnorm_bwd_kernel<3>, dyp, cp, nw, dc_ws, dnw, pixels, C, eps, rms);
+  else pdl_launch(grid, kWarps * 32, smem, s)(dwnorm_bwd_kernel<4>, dyp, cp, nw, dc_ws, dnw, pixels, C, eps, rms);
   int rc = check_launch("dwnorm_bwd");
   if (rc) return rc;
   const long long strips = static_cast<long long>(B) * hh * ((ww + kStrip - 1) / kStrip) * (C / 4);
-  dwconv_bwd_kernel<<<static_cast<unsigned>(ceil_div_ll(strips, 256)), 256, 0, s>>>(dc_ws, x, wk, dres, dx, dwk, B, hh, ww, C);
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(strips, 256)), 256, 0, s)(dwconv_bwd_kernel, dc_ws, x, wk, dres, dx, dwk, B, hh, ww, C);
   return check_launch("dwconv_bwd");
 }
 
@@ -481,14 +489,14 @@ int grn_bwd(const void* x, const void* dout, const float* nx, const float* sumsq
   if (C % 8 != 0) { set_last_error("grn_bwd: C must be a multiple of 8"); return MUSE_ERR_UNSUPPORTED; }
   const bf16* xp = reinterpret_cast<const bf16*>(x);
   const bf16* dp = reinterpret_cast<const bf16*>(dout);
-  grn_bwd_stats_kernel<<<dim3(ceil_div(C, 256), B), 128, 0, s>>>(xp, dp, nx, s1_ws, dgamma, dbeta, HW, C);
+  pdl_launch(dim3(ceil_div(C, 256), B), 128, 0, s)(grn_bwd_stats_kernel, xp, dp, nx, s1_ws, dgamma, dbeta, HW, C);
   int rc = check_launch("grn_bwd_stats");
   if (rc) return rc;
-  grn_bwd_finalize_kernel<<<B, 256, 0, s>>>(s1_ws, sumsq, gamma, C);
+  pdl_launch(B, 256, 0, s)(grn_bwd_finalize_kernel, s1_ws, sumsq, gamma, C);
   rc = check_launch("grn_bwd_finalize");
   if (rc) return rc;
   const long long total8 = static_cast<long long>(B) * HW * (C / 8);
-  grn_bwd_apply_kernel<<<static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s>>>(xp, dp, nx, s1_ws, gamma,
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(total8, 256)), 256, 0, s)(grn_bwd_apply_kernel, xp, dp, nx, s1_ws, gamma,
                                                                                        reinterpret_cast<bf16*>(dx), total8, HW, C);
   return check_launch("grn_bwd_apply");
 }
@@ -496,7 +504,7 @@ int grn_bwd(const void* x, const void* dout, const float* nx, const float* sumsq
 int adaln_bwd(const float* dy, const float* x, const float* ss, long long ss_stride, float* dx, float* dss, int B,
               int rows_per_sample, int C, cudaStream_t s) {
   if (B <= 0 || rows_per_sample <= 0) return MUSE_OK;
-  adaln_bwd_kernel<<<dim3(ceil_div(C, 128), B), 128, 0, s>>>(dy, x, ss, ss_stride, dx, dss, rows_per_sample, C);
+  pdl_launch(dim3(ceil_div(C, 128), B), 128, 0, s)(adaln_bwd_kernel, dy, x, ss, ss_stride, dx, dss, rows_per_sample, C);
   return check_launch("adaln_bwd");
 }
 
@@ -506,9 +514,9 @@ int silu_bwd(const void* dy, const void* x, int x_dt, void* dx, int dx_dt, long 
   const long long n8 = n / 8;
   const unsigned grid = static_cast<unsigned>(ceil_div_ll(n8, 256));
   const bf16* dyp = reinterpret_cast<const bf16*>(dy);
-  if (x_dt == 1 && dx_dt == 1) silu_bwd_kernel<bf16, bf16><<<grid, 256, 0, s>>>(dyp, reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(dx), n8, accumulate);
-  else if (x_dt == 1 && dx_dt == 0) silu_bwd_kernel<bf16, float><<<grid, 256, 0, s>>>(dyp, reinterpret_cast<const bf16*>(x), reinterpret_cast<float*>(dx), n8, accumulate);
-  else if (x_dt == 0 && dx_dt == 0) silu_bwd_kernel<float, float><<<grid, 256, 0, s>>>(dyp, reinterpret_cast<const float*>(x), reinterpret_cast<float*>(dx), n8, accumulate);
+  if (x_dt == 1 && dx_dt == 1) pdl_launch(grid, 256, 0, s)(silu_bwd_kernel<bf16, bf16>, dyp, reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(dx), n8, accumulate);
+  else if (x_dt == 1 && dx_dt == 0) pdl_launch(grid, 256, 0, s)(silu_bwd_kernel<bf16, float>, dyp, reinterpret_cast<const bf16*>(x), reinterpret_cast<float*>(dx), n8, accumulate);
+  else if (x_dt == 0 && dx_dt == 0) pdl_launch(grid, 256, 0, s)(silu_bwd_kernel<float, float>, dyp, reinterpret_cast<const float*>(x), reinterpret_cast<float*>(dx), n8, accumulate);
   else { set_last_error("silu_bwd: unsupported dtype combination"); return MUSE_ERR_INVALID; }
   return check_launch("silu_bwd");
 }

@@ -19,6 +19,7 @@ constexpr int TC = 128;  // codes per inner chunk
 constexpr int TKK = 16;  // k per smem stage
 
 __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int D) {
+  pdl_enter();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const float* r = x + static_cast<size_t>(i) * D;
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256)
 vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb, const float* __restrict__ enorm,
                  long long* __restrict__ ids, float* __restrict__ dmin_out, float* __restrict__ dist_out, int n,
                  int ncodes, int D) {
+  pdl_enter();
   __shared__ __align__(16) float sZ[TKK][TR];
   __shared__ __align__(16) float sE[TKK][TC];
   __shared__ float sZn[TR];
@@ -128,6 +130,7 @@ vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb, cons
 __global__ void __launch_bounds__(256)
 vq_soft_kernel(float* __restrict__ dist, const float* __restrict__ expo, long long* __restrict__ ids, float temp, int n,
                int ncodes) {
+  pdl_enter();
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= n) return;
   const int lane = threadIdx.x & 31;
@@ -164,6 +167,7 @@ vq_soft_kernel(float* __restrict__ dist, const float* __restrict__ expo, long lo
 __global__ void __launch_bounds__(256)
 vq_lookup_nchw_kernel(const long long* __restrict__ ids, const float* __restrict__ cb, float* __restrict__ out, int B,
                       int P, int D, int ncodes) {
+  pdl_enter();
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   const long long total = static_cast<long long>(B) * D * P;
   if (i >= total) return;
@@ -181,10 +185,10 @@ int vq_argmin(const float* z, const float* codebook, float* enorm_ws, long long*
               int D, cudaStream_t s) {
   if (n <= 0) return MUSE_OK;
   if (D % TKK != 0) { set_last_error("vq_argmin: D=%d must be a multiple of %d", D, TKK); return MUSE_ERR_UNSUPPORTED; }
-  sqnorm_kernel<<<ceil_div(ncodes, 256), 256, 0, s>>>(codebook, enorm_ws, ncodes, D);
+  pdl_launch(ceil_div(ncodes, 256), 256, 0, s)(sqnorm_kernel, codebook, enorm_ws, ncodes, D);
   int rc = check_launch("vq_sqnorm");
   if (rc) return rc;
-  vq_argmin_kernel<<<ceil_div(n, TR), 256, 0, s>>>(z, codebook, enorm_ws, ids, dmin, nullptr, n, ncodes, D);
+  pdl_launch(ceil_div(n, TR), 256, 0, s)(vq_argmin_kernel, z, codebook, enorm_ws, ids, dmin, nullptr, n, ncodes, D);
   return check_launch("vq_argmin");
 }
 
@@ -193,13 +197,13 @@ int vq_soft_code(const float* z, const float* codebook, float* enorm_ws, float* 
   if (n <= 0) return MUSE_OK;
   if (D % TKK != 0) { set_last_error("vq_soft_code: D=%d must be a multiple of %d", D, TKK); return MUSE_ERR_UNSUPPORTED; }
   if (!(temp > 0.f)) { set_last_error("vq_soft_code: temp must be > 0"); return MUSE_ERR_INVALID; }
-  sqnorm_kernel<<<ceil_div(ncodes, 256), 256, 0, s>>>(codebook, enorm_ws, ncodes, D);
+  pdl_launch(ceil_div(ncodes, 256), 256, 0, s)(sqnorm_kernel, codebook, enorm_ws, ncodes, D);
   int rc = check_launch("vq_sqnorm");
   if (rc) return rc;
-  vq_argmin_kernel<<<ceil_div(n, TR), 256, 0, s>>>(z, codebook, enorm_ws, ids, nullptr, soft, n, ncodes, D);
+  pdl_launch(ceil_div(n, TR), 256, 0, s)(vq_argmin_kernel, z, codebook, enorm_ws, ids, nullptr, soft, n, ncodes, D);
   rc = check_launch("vq_argmin(dist)");
   if (rc) return rc;
-  vq_soft_kernel<<<ceil_div(n, 8), 256, 0, s>>>(soft, expo, ids, temp, n, ncodes);
+  pdl_launch(ceil_div(n, 8), 256, 0, s)(vq_soft_kernel, soft, expo, ids, temp, n, ncodes);
   return check_launch("vq_soft");
 }
 
@@ -207,7 +211,7 @@ int vq_lookup_nchw(const long long* ids, const float* codebook, float* out, int 
                    cudaStream_t s) {
   const long long total = static_cast<long long>(B) * D * P;
   if (total <= 0) return MUSE_OK;
-  vq_lookup_nchw_kernel<<<static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, s>>>(ids, codebook, out, B, P, D, ncodes);
+  pdl_launch(static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, s)(vq_lookup_nchw_kernel, ids, codebook, out, B, P, D, ncodes);
   return check_launch("vq_lookup_nchw");
 }
 

@@ -24,6 +24,16 @@ def reserve_sms(n: int):
     _lib.check(_lib.load().muse_reserve_sms(int(n)), "muse_reserve_sms")
 
 
+def set_pdl(enabled: bool):
+    """Programmatic dependent launch for every kernel of the library (include/muse_b200.h: muse_set_pdl).  Process-wide;
+    call it before capturing CUDA graphs."""
+    _lib.check(_lib.load().muse_set_pdl(1 if enabled else 0), "muse_set_pdl")
+
+
+def get_pdl() -> bool:
+    return bool(_lib.load().muse_get_pdl())
+
+
 def launches() -> int:
     """Number of libmuse_b200 kernel-launching calls made so far (bench.py's gpu_launches)."""
     return _state["launches"]

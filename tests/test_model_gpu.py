@@ -249,6 +249,73 @@ def test_train_step_gradients_are_bit_reproducible():
             assert torch.equal(gr, other[2][n]), n
 
 
+def test_programmatic_dependent_launch_is_bit_identical(golden):
+    """include/muse_b200.h muse_set_pdl: with programmatic dependent launch every kernel may be scheduled while its
+    predecessor drains, but blocks (griddepcontrol.wait) before its first global access.  Memory effects must therefore be
+    exactly those of plain stream order: logits, loss and EVERY gradient of a train step bit-identical with the switch on
+    and off -- launched one by one and replayed from a captured CUDA graph -- and the same generate2 ids."""
+    from open_muse_b200 import ops
+    from open_muse_b200.graphs import GraphedStep
+
+    cfg = dict(vocab_size=2025, max_position_embeddings=257, hidden_size=512, num_hidden_layers=3,
+               num_attention_heads=8, intermediate_size=2048, codebook_size=1024, num_vq_tokens=256, num_classes=1000,
+               hidden_dropout=0.0, attention_dropout=0.0)
+    g = torch.Generator().manual_seed(11)
+    B = 24
+    tokens = torch.randint(0, 1024, (B, 256), generator=g)
+    cls = torch.randint(0, 1000, (B,), generator=g)
+    inp, lab = T.mask_tokens(tokens, cls, torch.rand(B, generator=g), torch.rand(B, 256, generator=g), 1024, 2024)
+    inp, lab = inp.to(DEV), lab.to(DEV)
+    gm = golden("micro_transformer.pt")
+    was = ops.get_pdl()
+    results = {}
+    try:
+        for pdl in (False, True):
+            ops.set_pdl(pdl)
+            assert ops.get_pdl() == pdl
+            torch.manual_seed(0)
+            m = MaskGitTransformer(**cfg).to(DEV).train()
+
+            def fwd_bwd(i, l):
+                m.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    logits, loss = m(i, labels=l)
+                loss.backward()
+                return logits, loss
+
+            logits, loss = fwd_bwd(inp, lab)
+            torch.cuda.synchronize()
+            eager = (logits.clone(), loss.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
+            graphed = GraphedStep(fwd_bwd, (inp, lab))
+            for _ in range(2):
+                logits, loss = graphed(inp, lab)
+            torch.cuda.synchronize()
+            replay = (logits.clone(), loss.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
+            for a, b in ((eager, replay),):
+                assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+                for n in a[2]:
+                    assert torch.equal(a[2][n], b[2][n]), (pdl, n)
+            # the captured decode loop (fresh model instance: its graph cache is keyed without the launch mode)
+            mg = MaskGitTransformer(**gm["config"])
+            mg.load_state_dict(gm["state_dict"])
+            mg.to(DEV).eval()
+            ids = []
+            for use_graph in (False, True):
+                gen = torch.Generator(device=DEV).manual_seed(7)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    ids.append(mg.generate2(class_ids=torch.tensor([1, 5, 0, 3], device=DEV), timesteps=4, generator=gen,
+                                            use_cuda_graph=use_graph))
+            assert torch.equal(ids[0], ids[1])
+            results[pdl] = (eager, ids[0])
+    finally:
+        ops.set_pdl(was)
+    off, on = results[False], results[True]
+    assert torch.equal(off[0][0], on[0][0]) and torch.equal(off[0][1], on[0][1])
+    for n in off[0][2]:
+        assert torch.equal(off[0][2][n], on[0][2][n]), n
+    assert torch.equal(off[1], on[1])
+
+
 def test_soft_target_loss_on_returned_logits(golden):
     """train_maskgit_imagenet.py:101-117: with soft targets the script computes its own loss from the returned logits,
     so the gradient reaches the model through the logits output (not through the fused CE).  Parity vs the oracle's fp32
