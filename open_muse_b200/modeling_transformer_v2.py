@@ -445,12 +445,12 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
             # training: one autograd Function for the whole network (uvit_v2_train.py)
             if self.training and (c.hidden_dropout > 0.0 or c.attention_dropout > 0.0):
                 raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: dropout > 0 in training mode is not implemented")
-            if c.force_down_up_sample:
-                raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: force_down_up_sample=True is inference-only "
-                                          "(forward under torch.no_grad() / generate2); its backward is not implemented")
             from . import uvit_v2_train as T
 
             if getattr(self, "_single_train_function", False):  # private test hook: one Function for the whole network
+                if c.force_down_up_sample:
+                    raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: force_down_up_sample=True trains through the "
+                                              "per-block Functions only (the default path)")
                 padded, loss = T.UViTTrainFn.apply(self, input_ids, encoder_hidden_states, cond_embeds, micro_conds, labels,
                                                    label_smoothing, loss_weight, *self.parameters())
             else:  # default: one Function per block, so parameter gradients appear during backward (DDP overlap)

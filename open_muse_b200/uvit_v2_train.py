@@ -13,6 +13,8 @@ backward pass of this model yet (the v1 model uses one Function per layer for th
 """
 from __future__ import annotations
 
+import copy
+
 import torch
 
 from . import ops
@@ -619,6 +621,54 @@ class ProjFn(torch.autograd.Function):
         return None, None, dx, dr, g_n, g_l
 
 
+class ResampleFn(torch.autograd.Function):
+    """force_down_up_sample (reference :509-513, :555-559): ``ds`` = Norm2D + Conv2d(k=2, s=2) in front of the down stage,
+    ``us`` = Norm2D + ConvTranspose2d(k=2, s=2) behind the up stage.  Both are ONE GEMM on the token-major layout: the
+    strided conv reads 2x2 patches ``[B*S/4, (dy, dx, ci)]``, the transposed conv writes ``[B*S, (dy, dx, co)]`` followed
+    by depth-to-space; the backward is the same GEMM's dgrad / wgrad with the inverse token permutation around it.
+    ``sh`` describes the grid this op READS (hw x hw tokens per sample)."""
+
+    @staticmethod
+    def forward(ctx, sh, key, h, w_norm, w_conv):
+        W, B, hw = sh.W, sh.B, sh.hw
+        C = h.shape[1]
+        if h.dtype != F32 or h.shape[0] != B * hw * hw:
+            raise ValueError(f"ResampleFn: expected fp32 [{B * hw * hw}, C] tokens, got {h.dtype} {tuple(h.shape)}")
+        h = h.contiguous()
+        _, y = ops.add_norm_mod(h, W[key + "_norm"], sh.eps, sh.rms, want_residual=False)
+        if key == "ds":
+            a = y.view(B, hw // 2, 2, hw // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * hw * hw // 4, 4 * C)
+            out = ops.linear_fwd(a, W["ds"], out_dtype=F32)
+        else:
+            a = y
+            t = ops.linear_fwd(y, W["us"], out_dtype=F32)
+            out = t.view(B, hw, hw, 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * hw * hw * 4, C)
+        ctx.sh, ctx.sv, ctx.key = sh, (h, a), key
+        ctx.has_norm, ctx.conv_shape = w_norm is not None, w_conv.shape
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        sh, (h, a), key = ctx.sh, ctx.sv, ctx.key
+        W, B, hw = sh.W, sh.B, sh.hw
+        C = h.shape[1]
+        g_w = _z(W[key])
+        g_n = _z(W[key + "_norm"]) if ctx.has_norm else None
+        d = d_out.contiguous()
+        if key == "ds":  # d: [B*S/4, co] -> patches [B*S/4, (dy, dx, ci)] -> tokens [B*S, ci]
+            dp = _lin_bwd(d if d.dtype == BF16 else ops.cast_bf16(d), a, W["ds"], g_w)
+            dy = dp.view(B, hw // 2, hw // 2, 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * hw * hw, C)
+            g_conv = g_w.view(C, 2, 2, C).permute(0, 3, 1, 2)  # [co, (dy, dx, ci)] -> Conv2d weight [co, ci, dy, dx]
+        else:            # d: [B*S*4, co] -> space-to-depth [B*S, (dy, dx, co)] -> tokens [B*S, ci]
+            dt = d.view(B, hw, 2, hw, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(B * hw * hw, 4 * C)
+            dy = _lin_bwd(dt if dt.dtype == BF16 else ops.cast_bf16(dt), a, W["us"], g_w)
+            g_conv = g_w.view(2, 2, C, C).permute(3, 2, 0, 1)  # [(dy, dx, co), ci] -> ConvTranspose2d weight [ci, co, dy, dx]
+        dh, _ = ops.add_norm_mod_bwd(dy, None, h, W[key + "_norm"], sh.eps, sh.rms, F32, dw=g_n, want_dr=False)
+        ctx.sv = None  # release the activations now, not when the graph dies
+        return None, None, dh, g_n, g_conv.reshape(ctx.conv_shape)
+
+
 class TailFn(torch.autograd.Function):
     """ConvMlmLayer + cross-entropy"""
 
@@ -686,6 +736,13 @@ def train_forward(model, input_ids, encoder_hidden_states, cond_embeds, micro_co
     h = EmbedFn.apply(sh, input_ids.contiguous().to(torch.int64), model.embed.embeddings.weight, model.embed.layer_norm.weight,
                       model.embed.conv.weight)
     down, up = model.down_blocks[0], model.up_blocks[0]
+    sh_full = sh
+    if c.force_down_up_sample:  # the stages and the transformer layers run on the (hw/2)^2 grid (reference :509-513)
+        if sh.hw % 2:
+            raise ValueError(f"force_down_up_sample needs an even token grid, got {sh.hw}x{sh.hw}")
+        h = ResampleFn.apply(sh_full, "ds", h, down.downsample[0].norm.weight, down.downsample[1].weight)
+        sh = copy.copy(sh_full)  # same operand caches (W, enc, sc), coarse grid
+        sh.S, sh.hw = S // 4, sh_full.hw // 2
     for i, (rb, ab) in enumerate(zip(down.res_blocks, down.attention_blocks)):
         h = UBlockFn.apply(sh, model, "down", i, h, enc32, sc32, *_present(block_params(rb, ab)))
     x = ProjFn.apply(sh, "pth", h, None, model.project_to_hidden_norm.weight, model.project_to_hidden.weight)
@@ -695,5 +752,8 @@ def train_forward(model, input_ids, encoder_hidden_states, cond_embeds, micro_co
     h = ProjFn.apply(sh, "pfh", x, r, model.project_from_hidden_norm.weight, model.project_from_hidden.weight)
     for i, (rb, ab) in enumerate(zip(up.res_blocks, up.attention_blocks)):
         h = UBlockFn.apply(sh, model, "up", i, h, enc32, sc32, *_present(block_params(rb, ab)))
+    if c.force_down_up_sample:  # back to the full grid (:555-559); sh still describes the coarse grid this op reads
+        h = ResampleFn.apply(sh, "us", h, up.upsample[0].norm.weight, up.upsample[1].weight)
+        sh = sh_full
     return TailFn.apply(sh, c.codebook_size, h, labels, label_smoothing, loss_weight, model.mlm_layer.conv1.weight,
                         model.mlm_layer.layer_norm.norm.weight, model.mlm_layer.conv2.weight)

@@ -283,18 +283,20 @@ def test_programmatic_dependent_launch_is_bit_identical(golden):
                 loss.backward()
                 return logits, loss
 
-            logits, loss = fwd_bwd(inp, lab)
-            torch.cuda.synchronize()
-            eager = (logits.clone(), loss.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
+            # graph first: the first backward of this model then runs on GraphedStep's side stream (as in bench.py); an eager
+            # backward on the legacy default stream BEFORE the capture would tie the AccumulateGrad nodes to that stream and
+            # the capture would fail with cudaErrorStreamCaptureImplicit, whatever the launch mode
             graphed = GraphedStep(fwd_bwd, (inp, lab))
             for _ in range(2):
                 logits, loss = graphed(inp, lab)
             torch.cuda.synchronize()
             replay = (logits.clone(), loss.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
-            for a, b in ((eager, replay),):
-                assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
-                for n in a[2]:
-                    assert torch.equal(a[2][n], b[2][n]), (pdl, n)
+            logits, loss = fwd_bwd(inp, lab)
+            torch.cuda.synchronize()
+            eager = (logits.clone(), loss.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
+            assert torch.equal(eager[0], replay[0]) and torch.equal(eager[1], replay[1])
+            for n in eager[2]:
+                assert torch.equal(eager[2][n], replay[2][n]), (pdl, n)
             # the captured decode loop (fresh model instance: its graph cache is keyed without the launch mode)
             mg = MaskGitTransformer(**gm["config"])
             mg.load_state_dict(gm["state_dict"])

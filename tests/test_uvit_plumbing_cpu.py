@@ -97,3 +97,104 @@ def test_uvit_v2_training_plumbing(monkeypatch, cfg, mode):
     (loss + 0 * padded.float().sum()).backward()
     for n, p in m.named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == torch.float32, n
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# force_down_up_sample training (uvit_v2_train.ResampleFn): the token permutations around the patch GEMMs and the mapping of
+# the GEMM weight gradients back to the Conv2d / ConvTranspose2d parameter layouts, checked NUMERICALLY on the CPU with exact
+# fp32 stand-ins for the kernels against torch autograd through F.conv2d / F.conv_transpose2d on the NCHW tensor (what the
+# reference computes, muse/modeling_transformer_v2.py:509-513, :555-559).
+def _math_ops(mp):
+    def norm(x, w, eps, rms):
+        x = x.float()
+        y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) if rms else torch.nn.functional.layer_norm(x, x.shape[-1:], eps=eps)
+        return y if w is None else y * w.float()
+
+    def anm(a, w, eps, rms, out_dtype=BF, residual=None, mod=None, rows_per_sample=1, want_residual=True):
+        assert residual is None and mod is None and not want_residual
+        return None, norm(a, w, eps, rms)
+
+    def anm_bwd(dy, dr_out, x, w, eps, rms, da_dtype, mod=None, rows_per_sample=1, dw=None, dmod=None, want_dr=True):
+        assert dr_out is None and not want_dr and x.dtype == F32 and dy.shape == x.shape
+        xx = x.detach().clone().requires_grad_(True)
+        ww = None if w is None else w.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            y = norm(xx, ww, eps, rms)
+        gs = torch.autograd.grad(y, [xx] + ([] if ww is None else [ww]), dy.float())
+        if dw is not None:
+            dw += gs[1]
+        return gs[0].to(da_dtype), None
+
+    def wgrad(dy, x, dw):
+        assert dw.shape == (dy.shape[1], x.shape[1]) and dw.dtype == F32
+        dw += dy.float().t() @ x.float()
+
+    mp.setattr(ops, "add_norm_mod", anm)
+    mp.setattr(ops, "add_norm_mod_bwd", anm_bwd)
+    mp.setattr(ops, "linear_fwd", lambda x, w, out_dtype=BF, res=None, n_valid=None: x.float() @ w.float().t())
+    mp.setattr(ops, "linear_dgrad", lambda dy, w, out_dtype=BF: dy.float() @ w.float())
+    mp.setattr(ops, "linear_wgrad", wgrad)
+    mp.setattr(ops, "cast_bf16", lambda x: x)
+
+
+@pytest.mark.parametrize("norm_type", ["rmsnorm", "layernorm"])
+def test_uvit_v2_resample_functions_match_conv_autograd(monkeypatch, norm_type):
+    import open_muse_b200.uvit_v2_train as T
+
+    _math_ops(monkeypatch)
+    cfg = dict(CFGS[0], force_down_up_sample=True, norm_type=norm_type)
+    torch.manual_seed(1)
+    m = MaskGiTUViT_v2(**cfg).train()
+    down, up = m.down_blocks[0].downsample, m.up_blocks[0].upsample
+    with torch.no_grad():
+        for p in (down[0].norm.weight, up[0].norm.weight):
+            p.copy_(torch.rand_like(p) + 0.5)
+        for p in (down[1].weight, up[1].weight):  # bf16-representable, so the packed bf16 operands are exact
+            p.copy_(torch.randn_like(p).to(BF).float())
+    W = m._weights()
+    B, hw, C = 3, 6, 64
+    rms, eps = int(norm_type == "rmsnorm"), m.config.layer_norm_eps
+
+    def norm2d(x, w):  # NCHW, normalised over the channels (Norm2D)
+        t = x.permute(0, 2, 3, 1)
+        t = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + eps) if rms else torch.nn.functional.layer_norm(t, (C,), eps=eps)
+        return (t * w).permute(0, 3, 1, 2)
+
+    to_nchw = lambda t, n: t.view(B, n, n, C).permute(0, 3, 1, 2)
+    to_tok = lambda x: x.permute(0, 2, 3, 1).reshape(-1, C)
+    for key, seq, n_in, conv in (("ds", down, hw, torch.nn.functional.conv2d), ("us", up, hw // 2, torch.nn.functional.conv_transpose2d)):
+        sh = T._Shared(m, W, B, n_in * n_in, 5)
+        assert sh.hw == n_in
+        h = torch.randn(B * n_in * n_in, C, requires_grad=True)
+        out = T.ResampleFn.apply(sh, key, h, seq[0].norm.weight, seq[1].weight)
+        n_out = n_in // 2 if key == "ds" else n_in * 2
+        assert out.shape == (B * n_out * n_out, C)
+        d_out = torch.randn_like(out)
+        g_h, g_n, g_w = torch.autograd.grad(out, (h, seq[0].norm.weight, seq[1].weight), d_out)
+        h2 = h.detach().clone().requires_grad_(True)
+        ref = to_tok(conv(norm2d(to_nchw(h2, n_in), seq[0].norm.weight), seq[1].weight, stride=2))
+        r_h, r_n, r_w = torch.autograd.grad(ref, (h2, seq[0].norm.weight, seq[1].weight), d_out)
+        for name, a, b in (("out", out, ref), ("dh", g_h, r_h), ("dnorm", g_n, r_n), ("dconv", g_w, r_w)):
+            assert a.shape == b.shape, (key, name, a.shape, b.shape)
+            err = float((a.detach() - b.detach()).norm() / b.detach().norm())
+            assert err < 1e-5, (key, name, err)
+
+
+def test_uvit_v2_training_plumbing_force_down_up_sample(monkeypatch):
+    """whole train_forward with the shape-checking stand-ins: 8x8 tokens outside, 4x4 inside, every parameter (the two
+    resampling convolutions and their norms included) receives a gradient of its own shape"""
+    import open_muse_b200.uvit_v2_train as T
+
+    _fake_ops(monkeypatch)
+    torch.manual_seed(0)
+    m = MaskGiTUViT_v2(**dict(CFGS[0], force_down_up_sample=True)).train()
+    ids, lab = torch.randint(0, 64, (3, 64)), torch.randint(0, 64, (3, 64))
+    enc, ce, mc = torch.randn(3, 5, 32), torch.randn(3, 16), torch.rand(3, 5)
+    padded, loss = T.train_forward(m, ids, enc, ce, mc, lab, 0.1, None)
+    assert padded.shape == (3 * 64, 64)
+    (loss + 0 * padded.float().sum()).backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == torch.float32, n
+    m._single_train_function = True
+    with pytest.raises(NotImplementedError):
+        m(ids, enc, ce, mc, labels=lab)

@@ -134,7 +134,40 @@ def test_micro_uvit_v2_force_down_up_sample_vs_reference_fixture(golden):
     ids = m.generate2(*args[1:], g["empty_embeds"].to(DEV), g["empty_cond_embeds"].to(DEV), temperature=(2.0, 0.0),
                       timesteps=4, guidance_scale=3.0, seq_len=64, generator=torch.Generator(DEV).manual_seed(g["gen_seed"]))
     assert ids.shape == g["gen_ids"].shape and int(ids.min()) >= 0 and int(ids.max()) < 64
-    m.train()
+
+
+def test_micro_uvit_v2_force_down_up_sample_training_gradients_vs_oracle(golden):
+    """Training with force_down_up_sample=True (the 512-px configs, configs/research_run_512_with_downsample*.yaml): the
+    strided conv / transposed conv train as patch GEMMs (uvit_v2_train.ResampleFn).  Loss and EVERY gradient -- incl. the
+    Conv2d [co, ci, 2, 2] and ConvTranspose2d [ci, co, 2, 2] weights and their Norm2D weights -- against the oracle's fp32
+    autograd on the reference fixture weights (the oracle's forward is pinned to the unmodified reference's stages)."""
+    g = golden("micro_uvit_v2_downup.pt")
+    assert g["config"]["force_down_up_sample"]
+    q = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    _, ref_loss = V2.forward(q, g["config"], g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"],
+                             labels=g["labels"], label_smoothing=0.1)
+    ref_loss.backward()
+    m = MaskGiTUViT_v2(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.to(DEV).train()
+    args = [g[k].to(DEV) for k in ("input_ids", "encoder_hidden_states", "cond_embeds", "micro_conds")]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, loss = m(*args, labels=g["labels"].to(DEV), label_smoothing=0.1)
+    loss.backward()
+    assert logits.shape == g["logits"].shape and _rel(logits, g["logits"]) < 2e-2
+    assert abs(float(loss) - float(ref_loss)) / float(ref_loss) < 2e-3
+    errs = {}
+    for n, p in m.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, n
+        errs[n] = _rel(p.grad, q[n].grad)
+    resample = {k: v for k, v in errs.items() if "sample" in k}
+    print("resampling grads rel-L2:", ", ".join(f"{k}={v:.2e}" for k, v in resample.items()))
+    assert len(resample) >= 2 and max(resample.values()) < 6e-2, resample
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:8]
+    print("worst grad rel-L2:", ", ".join(f"{k}={v:.2e}" for k, v in worst))
+    bad = {k: v for k, v in errs.items() if v > 8e-2 and not (".query." in k or ".key." in k)}
+    assert not bad, bad
+    m._single_train_function = True  # the whole-network Function (test hook) does not cover the resampling ops
     with pytest.raises(NotImplementedError):
         m(*args, labels=g["labels"].to(DEV))
 

@@ -29,9 +29,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--model", default="v1", choices=["v1", "uvit"],
+    ap.add_argument("--model", default="v1", choices=["v1", "uvit", "uvit512"],
                     help="v1: MaskGitTransformer with the cc12m dims (BASELINE config 4); uvit: MaskGiTUViT_v2 at the reference "
-                         "defaults (what configs/cc12m_uvit_clip.yaml's architecture: 'uvit' instantiates)")
+                         "defaults (what configs/cc12m_uvit_clip.yaml's architecture: 'uvit' instantiates); uvit512: the same "
+                         "with force_down_up_sample=True on 32x32 = 1024 tokens (configs/research_run_512_with_downsample.yaml)")
     args = ap.parse_args()
     import torch.distributed as dist
 
@@ -43,10 +44,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    if args.model == "uvit":
+    uvit = args.model in ("uvit", "uvit512")
+    n_tok = 1024 if args.model == "uvit512" else 256
+    if uvit:
         from open_muse_b200 import MaskGiTUViT_v2
 
-        model = MaskGiTUViT_v2().to(dev).train()
+        model = MaskGiTUViT_v2(force_down_up_sample=args.model == "uvit512").to(dev).train()
         with torch.no_grad():  # leave the zero-init regime so that every branch carries signal
             for k, x in model.state_dict().items():
                 if "adaLN_modulation.mapper" in k or k.endswith("gamma") or k.endswith("beta") or k == "mlm_layer.conv1.weight":
@@ -65,15 +68,15 @@ def main():
     micro = torch.tensor([[256.0, 256.0, 0.0, 0.0, 6.0]], device=dev).repeat(B, 1)
 
     def step(i):
-        ids = torch.randint(0, 8192, (B, 256), device=dev, generator=g)
+        ids = torch.randint(0, 8192, (B, n_tok), device=dev, generator=g)
         t = torch.rand(B, device=dev, generator=g)
-        n_mask = (256 * torch.cos(t * torch.pi * 0.5)).round().clamp(min=1)  # train_muse.py:149-226 recipe
-        perm = torch.rand(B, 256, device=dev, generator=g).argsort(dim=-1)
+        n_mask = (n_tok * torch.cos(t * torch.pi * 0.5)).round().clamp(min=1)  # train_muse.py:149-226 recipe
+        perm = torch.rand(B, n_tok, device=dev, generator=g).argsort(dim=-1)
         mask = perm < n_mask[:, None]
         inp = torch.where(mask, mask_id, ids)
         lab = torch.where(mask, ids, -100)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            if args.model == "uvit":
+            if uvit:
                 _, loss = net(inp, enc, pooled, micro, labels=lab)
             else:
                 _, loss = net(inp, encoder_hidden_states=enc, labels=lab)
@@ -103,11 +106,13 @@ def main():
     ms = float(ms) / args.steps
     if rank == 0:
         print(json.dumps({
-            "metric": "samples/sec text2image train step: " + ("MaskGiTUViT_v2 (reference defaults)" if args.model == "uvit"
-                                                                 else "MaskGitTransformer (cc12m dims, config 4)"),
+            "metric": "samples/sec text2image train step: " + (
+                {"uvit": "MaskGiTUViT_v2 (reference defaults, 256 tokens)",
+                 "uvit512": "MaskGiTUViT_v2 (force_down_up_sample, 1024 tokens outside / 256 inside)"}[args.model]
+                if uvit else "MaskGitTransformer (cc12m dims, config 4)"),
             "value": B * world / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "ms_per_step": ms, "steps": args.steps,
             "per_gpu_batch": B, "params_m": n_params / 1e6, "loss": float(loss),
-            "tflops_per_gpu_model": (TRAIN_GFLOP_PER_SAMPLE if args.model == "v1" else 3 * 266.0) * B / ms, "gpu_launches_per_step": (ops.launches() - l0) // args.steps,
+            "tflops_per_gpu_model": (TRAIN_GFLOP_PER_SAMPLE if args.model == "v1" else 3 * 266.0) * B / ms if args.model != "uvit512" else None, "gpu_launches_per_step": (ops.launches() - l0) // args.steps,
             "grad_allreduce_gb": n_params * 4 / 1e9, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
     if world > 1:
         dist.destroy_process_group()
