@@ -127,12 +127,28 @@ __global__ void __launch_bounds__(1024) colsum_ordered_kernel(const float* __res
   }
 }
 
+// L2 prefetch (a hint: no register, no scoreboard entry).  The persistent row-streaming backward kernels are bound by
+// exposed load latency, not by issue slots or DRAM bandwidth (ncu, profiles/r02_ncu_glu_bwd.txt: 60 % of the warp samples
+// sit on the first use of a loaded value, DRAM at 51 %, issue slots at 59 %).  A warp walks its rows strictly one after the
+// other, so the lines of the row it will touch NEXT are requested from HBM while the current row is processed and the demand
+// loads become L2 hits.  prefetch_row: the lanes of a warp cover the 128-byte lines of one row of H elements.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <typename T>
+__device__ __forceinline__ void prefetch_row(const T* row, int H, int lane) {
+  const int bytes = H * static_cast<int>(sizeof(T));
+  for (int off = lane * 128; off < bytes; off += 32 * 128) prefetch_l2(reinterpret_cast<const char*>(row) + off);
+}
+// Measured on one box, same call (profiles/r02_ab_row_prefetch.log): LayerNorm backward 87.5 -> 78.0 us and 71.3 -> 62.1 us
+// (next-row prefetch), GLU + LayerNorm backward 384 -> 361 us (two-iterations-ahead prefetch).  The kernels take the switch as
+// an argument so that the A/B needs one binary.
+constexpr int kRowPrefetch = 1;
+
 template <typename TDY, typename TX, typename TDX, int CH>
 __global__ void __launch_bounds__(kBwdWarps * 32)
 norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                 const float* __restrict__ dres, TDX* __restrict__ dx, bf16* __restrict__ dx_copy, float* __restrict__ dw,
-                float* __restrict__ dw_ws, int rows, int H, int act, int rms) {
+                float* __restrict__ dw_ws, int rows, int H, int act, int rms, int pf) {
   pdl_enter();
   extern __shared__ float s_dw[];  // [kBwdWarps][H] private rows
   const int lane = threadIdx.x & 31;
@@ -152,6 +168,12 @@ norm_bwd_warp_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const
     float xh[CH][8], g[CH][8], rs[CH][8];
     float s1 = 0.f, s2 = 0.f;
     const float* drr = dres ? dres + static_cast<size_t>(row) * H : nullptr;
+    const int next = row + gridDim.x * kBwdWarps;
+    if (pf && next < rows) {  // this warp's next row (see prefetch_row)
+      prefetch_row(x + static_cast<size_t>(next) * H, H, lane);
+      prefetch_row(dy + static_cast<size_t>(next) * H, H, lane);
+      if (dres) prefetch_row(dres + static_cast<size_t>(next) * H, H, lane);
+    }
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int col = (c * 32 + lane) * 8;
@@ -299,7 +321,7 @@ norm2_bwd_warp_kernel(const bf16* __restrict__ d_h2, const float* __restrict__ x
                       const float* __restrict__ mean2_in, const float* __restrict__ rstd2_in, const float* __restrict__ dres,
                       const bf16* __restrict__ a, const float* __restrict__ w1, const float* __restrict__ mean1_in,
                       const float* __restrict__ rstd1_in, float* __restrict__ dx2, bf16* __restrict__ d_a,
-                      float* __restrict__ dw2_ws, float* __restrict__ dw1_ws, int rows, int H, int rms1, int rms2) {
+                      float* __restrict__ dw2_ws, float* __restrict__ dw1_ws, int rows, int H, int rms1, int rms2, int pf) {
   pdl_enter();
   extern __shared__ float s_dw[];  // [2][kBwdWarps][H] private rows (dw2 then dw1)
   const int lane = threadIdx.x & 31;
@@ -316,6 +338,14 @@ norm2_bwd_warp_kernel(const bf16* __restrict__ d_h2, const float* __restrict__ x
     const float mean1 = rms1 ? 0.f : mean1_in[row], rstd1 = rstd1_in[row];
     float xh[CH][8], g[CH][8], rs[CH][8], av[CH][8];
     float s1 = 0.f, s2 = 0.f;
+    const int next = row + gridDim.x * kBwdWarps;
+    if (pf && next < rows) {  // this warp's next row (see prefetch_row)
+      const size_t noff = static_cast<size_t>(next) * H;
+      prefetch_row(x2 + noff, H, lane);
+      prefetch_row(d_h2 + noff, H, lane);
+      prefetch_row(dres + noff, H, lane);
+      prefetch_row(a + noff, H, lane);
+    }
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int col = (c * 32 + lane) * 8;
@@ -689,7 +719,7 @@ __global__ void __launch_bounds__(kGluWarps * 32, 3)
 glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, const float* __restrict__ w,
                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dab,
                     float* __restrict__ dw, float* __restrict__ dw_ws, const bf16* __restrict__ yf, int rows, int H,
-                    int rms) {
+                    int rms, int pf) {
   pdl_enter();
   extern __shared__ __align__(16) float s_dw[];  // [kGluWarps][H] private rows
   const int lane = threadIdx.x & 31;
@@ -706,9 +736,19 @@ glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, co
     const float mean = rms ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
     float s1 = 0.f, s2 = 0.f;
+    // Software pipeline of L2 prefetch hints, two loop iterations (2 x 256 columns) ahead of the demand loads: lanes 0-3
+    // request the four 128-byte lines per stream of the iteration after next -- first the rest of this pass, then the first
+    // columns of the next pass / of this warp's next row.  (Prefetching whole rows one row ahead measured SLOWER here, 375 ->
+    // 392 us: 3 552 warps x 16 KB of requested-but-unused lines do not survive in L2; for the H <= 1024 kernels it wins.)
+    const int next = row + gridDim.x * kGluWarps;
     if (HAVE_Y) {
       const bf16* yr = yf + static_cast<size_t>(row) * H;
       for (int col = lane * 8; col < H; col += 256) {
+        if (pf && lane < 4) {
+          const int nb = col - lane * 8 + 512 + lane * 64;
+          if (nb < H) { prefetch_l2(dyr + nb); prefetch_l2(yr + nb); }
+          else if (nb - H < H) { prefetch_l2(xr + (nb - H)); prefetch_l2(xr + H + (nb - H)); }
+        }
         float d[8], yv[8], wv[8];
         load8(dyr + col, d);
         load8(yr + col, yv);
@@ -756,6 +796,14 @@ glu_norm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ ab, co
     s2 = warp_sum(s2) * inv_h;
     bf16* dr = dab + static_cast<size_t>(row) * 2 * H;
     for (int col = lane * 8; col < H; col += 256) {
+      if (pf && HAVE_Y && lane < 4) {
+        const int nb = col - lane * 8 + 512 + lane * 64;
+        if (nb < H) { prefetch_l2(xr + nb); prefetch_l2(xr + H + nb); }
+        else if (next < rows && nb - H < H) {
+          prefetch_l2(dy + static_cast<size_t>(next) * H + (nb - H));
+          prefetch_l2(yf + static_cast<size_t>(next) * H + (nb - H));
+        }
+      }
       const uint4 au = *reinterpret_cast<const uint4*>(xr + col);
       const uint4 bu = *reinterpret_cast<const uint4*>(xr + H + col);
       const uint4 du = *reinterpret_cast<const uint4*>(dyr + col);
@@ -844,7 +892,7 @@ int bwd_dispatch(const void* dy, const void* x, const float* w, const float* mea
 #define MUSE_NB(CH)                                                                                          \
   pdl_launch(grid, kBwdWarps * 32, smem, s)(norm_bwd_warp_kernel<TDY, TX, TDX, CH>,                                  \
       reinterpret_cast<const TDY*>(dy), reinterpret_cast<const TX*>(x), w, mean, rstd, dres,                 \
-      reinterpret_cast<TDX*>(dx), reinterpret_cast<bf16*>(dx_copy), dw, dw_ws, rows, H, act, rms)
+      reinterpret_cast<TDX*>(dx), reinterpret_cast<bf16*>(dx_copy), dw, dw_ws, rows, H, act, rms, kRowPrefetch)
     if (ch <= 1) MUSE_NB(1);
     else if (ch <= 2) MUSE_NB(2);
     else MUSE_NB(4);
@@ -931,7 +979,7 @@ int norm2_bwd(const void* d_h2, const float* x2, const float* w2, const float* m
     cudaFuncSetAttribute(norm2_bwd_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kBwdWarps * 1024 * 4);
     attr = true;
   }
-#define MUSE_N2B(CH) pdl_launch(grid, kBwdWarps * 32, smem, s)(norm2_bwd_warp_kernel<CH>, reinterpret_cast<const bf16*>(d_h2), x2, w2, mean2, rstd2, dres, reinterpret_cast<const bf16*>(a), w1, mean1, rstd1, dx2, reinterpret_cast<bf16*>(d_a), ws2, ws1, rows, H, rms1, rms2)
+#define MUSE_N2B(CH) pdl_launch(grid, kBwdWarps * 32, smem, s)(norm2_bwd_warp_kernel<CH>, reinterpret_cast<const bf16*>(d_h2), x2, w2, mean2, rstd2, dres, reinterpret_cast<const bf16*>(a), w1, mean1, rstd1, dx2, reinterpret_cast<bf16*>(d_a), ws2, ws1, rows, H, rms1, rms2, kRowPrefetch)
   if (ch <= 1) MUSE_N2B(1); else if (ch <= 2) MUSE_N2B(2); else MUSE_N2B(4);
 #undef MUSE_N2B
   int rc = check_launch("norm2_bwd");
@@ -965,11 +1013,11 @@ int norm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const float* w,
     if (y_fwd != nullptr)
       pdl_launch(grid, kGluWarps * 32, smem, s)(glu_norm_bwd_kernel<true>,
           reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw,
-          dw_ws, reinterpret_cast<const bf16*>(y_fwd), rows, H, rms);
+          dw_ws, reinterpret_cast<const bf16*>(y_fwd), rows, H, rms, kRowPrefetch);
     else
       pdl_launch(grid, kGluWarps * 32, smem, s)(glu_norm_bwd_kernel<false>,
           reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), w, mean, rstd, reinterpret_cast<bf16*>(dx), dw,
-          dw_ws, nullptr, rows, H, rms);
+          dw_ws, nullptr, rows, H, rms, 0);
     rc = check_launch("glu_norm_bwd");
     if (rc || !dw || !dw_ws) return rc;
     return reduce_dw(dw_ws, dw, grid, H, s);

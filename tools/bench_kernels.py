@@ -106,3 +106,10 @@ if want("gemm"):
     w = bf(H, I)
     xin = bf(T, I)
     report("gemm wo + residual (fp32 out)", timeit(lambda: ops.linear_fwd(xin, w, res=res)), gflop=2 * T * H * I / 1e9)
+if want("resgemm"):  # the two residual-epilogue GEMMs of a layer (attention out-projection, FFN wo)
+    res = torch.randn(T, H, device=dev)
+    for name, K in [("attn out", H), ("wo", I)]:
+        w = bf(H, K)
+        xin = bf(T, K)
+        report(f"gemm {name} + residual (fp32 out)", timeit(lambda: ops.linear_fwd(xin, w, res=res), n=20), gbytes=(T * K * 2 + 2 * T * H * 4) / 1e6,
+               gflop=2 * T * H * K / 1e9)
