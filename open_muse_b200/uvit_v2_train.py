@@ -1,15 +1,17 @@
 """Training step (forward with saved activations + hand-written backward) of ``MaskGiTUViT_v2`` on libmuse_b200.
 
-One ``torch.autograd.Function`` covers the whole network: its forward is the inference path of
-``modeling_transformer_v2.py`` with the activations each backward kernel needs kept alive, its backward walks the blocks in
-reverse and returns the gradient of every parameter (reference names, fp32).  All arithmetic is in the C-ABI kernels: tcgen05
-GEMMs for every Linear / 1x1 conv (dgrad with an MN-major weight operand, split-K wgrad), tcgen05 attention backward, and
-the U-ViT kernels of csrc/uvit_bwd.cu.  Things that are single tensors consumed by many blocks get ONE accumulator:
-the text states (fp32, atomic-accumulating dgrad) and the stacked adaLN mapper output ``mod_all`` (each op adds into its own
-column slice), so no gradient is summed with eager ops.
+Default path (``train_forward``): one ``torch.autograd.Function`` per block -- conditioning MLP, text-state projection, token
+embedding, optional down-sampling convolution (``ResampleFn``), every ResBlock + AttentionBlock2D pair, the two projections,
+every transformer layer, optional up-sampling transposed convolution, ConvMlmLayer + cross-entropy.  Each forward is the
+inference path of ``modeling_transformer_v2.py`` with the activations its backward kernels need kept alive; each backward
+returns the gradients of that block's parameters (reference names, fp32) as soon as it has run, so DDP's bucket all-reduces
+overlap the rest of the backward pass.  ``UViTTrainFn`` (private test hook ``model._single_train_function``) is the same
+computation as ONE Function for the whole network; the tests pin the two against each other.
 
-Because all parameter gradients appear when this one Function returns, DDP's bucket all-reduces do not overlap the
-backward pass of this model yet (the v1 model uses one Function per layer for that reason) -- see DESIGN.md.
+All arithmetic is in the C-ABI kernels: tcgen05 GEMMs for every Linear / 1x1 / patch convolution (dgrad with an MN-major
+weight operand, deterministic split-K wgrad), tcgen05 attention backward, and the U-ViT kernels of csrc/uvit_bwd.cu.  Things
+that are single tensors consumed by many blocks get ONE accumulator: the text states (fp32, atomic-accumulating dgrad) and
+the stacked adaLN mapper output (each op adds into its own column slice), so no gradient is summed with eager ops.
 """
 from __future__ import annotations
 
