@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / TMA attention for head_dim 64 (sm_100a): forward, dQ and dK/dV kernels.
+// tcgen05 / TMEM / TMA attention for head_dim 64 and 48 (sm_100a): forward, dQ and dK/dV kernels.
 // Replaces the reference's materialised attention (muse/modeling_transformer.py:221-241) and its autograd backward.
 //
 // One CTA = one (batch, head) x one 128-row tile of the "owned" sequence dimension; its 128 threads each own one
@@ -29,7 +29,11 @@ int make_tmap3(CUtensorMap* map, const void* base, long long cols, long long row
 
 namespace {
 
-constexpr int HD = 64;
+// Head dimension HD is a template parameter: 64 (every text-to-image / U-ViT config, BASELINE configs) or 48 (configs/imagenet.yaml:
+// hidden 768, 16 heads -- the configuration training/train_maskgit_imagenet.py is written for).  For HD = 48 the TMA boxes stay
+// 64 columns wide (head h starts at column 48 h; the 16 trailing columns belong to the next head or are zero-filled past the
+// tensor) and simply never enter a product: Q K^T / dO V^T run 3 instead of 4 k-steps, and the accumulate MMAs (P V, dS K,
+// dS^T Q, P^T dO) have N = 48, reading the first 48 columns of their MN-major 128-byte rows.
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -49,6 +53,14 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
@@ -107,6 +119,7 @@ struct TcParams {
 constexpr int FWD_BN = 64;
 constexpr int FWD_SMEM = 16384 /*Q*/ + 8192 /*K*/ + 8192 /*V*/ + 16384 /*P*/ + 64;  // 5 mbarriers + the TMEM holder
 
+template <int HD>
 __global__ void __launch_bounds__(128, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const TcParams p) {
@@ -168,7 +181,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t idesc0 = ptx::make_idesc_bf16(128, (min(FWD_BN, p.Skv) + 15) & ~15, 0, 0);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
+    for (int ks = 0; ks < HD / 16; ++ks)
       ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc0, ks > 0);
     ptx::umma_commit(bar_s);
   }
@@ -240,13 +253,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // rescale the running output (P V_{j-1} has finished: see the bar_s wait above)
     if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) {
 #pragma unroll
-      for (int c = 0; c < HD; c += 32) {
+      for (int c = 0; c + 32 <= HD; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_o + c, r);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
         tmem_st_32x32b_x32(t_o + c, r);
+      }
+      if constexpr (HD % 32 != 0) {  // HD = 48: the last 16 columns
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_o + (HD & ~31), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+        tmem_st_32x32b_x16(t_o + (HD & ~31), r);
       }
       tmem_st_wait();
     }
@@ -268,7 +289,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int nn16 = (min(FWD_BN, p.Skv - (j + 1) * FWD_BN) + 15) & ~15;
         const uint32_t idesc_s = ptx::make_idesc_bf16(128, nn16, 0, 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
+        for (int ks = 0; ks < HD / 16; ++ks)
           ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc_s, ks > 0);
         ptx::umma_commit(bar_s);
       } else {
@@ -284,7 +305,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const float inv = 1.f / l;
   bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD;
 #pragma unroll
-  for (int c = 0; c < HD; c += 32) {
+  for (int c = 0; c + 32 <= HD; c += 32) {
     uint32_t r[32];
     ptx::tmem_ld_32x32b_x32(t_o + c, r);
     ptx::tmem_ld_wait();
@@ -297,6 +318,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         u.z = pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
         u.w = pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
         *reinterpret_cast<uint4*>(orow + c + i) = u;
+      }
+    }
+  }
+  if constexpr (HD % 32 != 0) {  // HD = 48: the last 16 columns
+    uint32_t r[16];
+    tmem_ld_32x32b_x16(t_o + (HD & ~31), r);
+    ptx::tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 8) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+        u.y = pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+        u.z = pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+        u.w = pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + (HD & ~31) + i) = u;
       }
     }
   }
@@ -320,6 +357,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int BWD_BN = 64;
 constexpr int DQ_SMEM = 16384 * 2 + 3 * 16384 + 2 * 16384 + 64;
 
+template <int HD>
 __global__ void __launch_bounds__(288, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -380,10 +418,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint8_t* sK = sKV + (step % 3) * 16384;
     const uint32_t idesc = ptx::make_idesc_bf16(128, n16_of(step), 0, 0);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
+    for (int ks = 0; ks < HD / 16; ++ks)
       ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sQ), ks), desc_kmajor(ptx::smem_u32(sK), ks), idesc, ks > 0);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
+    for (int ks = 0; ks < HD / 16; ++ks)
       ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sdO), ks), desc_kmajor(ptx::smem_u32(sK + 8192), ks), idesc, ks > 0);
     ptx::umma_commit(bar_s);
   };
@@ -516,13 +554,24 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ptx::tc_fence_after();
   }
   if (warp < 8) {
+    // the two threads of a row write columns [0, 32) and [32, HD) of dQ
     bf16* orow = p.out0 + (static_cast<long long>(b) * p.Sq + row) * p.out0_rs + h * HD + half * 32;
     uint32_t rr[32];
-    ptx::tmem_ld_32x32b_x32(t_row + 128 + half * 32, rr);
-    ptx::tmem_ld_wait();
+    if (HD == 64 || half == 0) {
+      ptx::tmem_ld_32x32b_x32(t_row + 128 + half * 32, rr);
+      ptx::tmem_ld_wait();
+    } else {
+      uint32_t r16[16];
+      tmem_ld_32x32b_x16(t_row + 128 + 32, r16);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) rr[i] = r16[i];
+    }
+    const int ncol = (HD == 64 || half == 0) ? 32 : HD - 32;
     if (row_ok) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
+        if (i >= ncol) break;
         uint4 v;
         v.x = pack_bf16(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1]));
         v.y = pack_bf16(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3]));
@@ -546,6 +595,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // smem: K_j 16K | V_j 16K | 3 x {Q_i 8K, dO_i 8K} | P^T 16K | dS^T 16K | lse/D 512 B
 constexpr int DKDV_SMEM = 16384 * 2 + 3 * 16384 + 16384 * 2 + 512 + 128;
 
+template <int HD>
 __global__ void __launch_bounds__(288, 2)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
@@ -603,10 +653,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     uint8_t* sQ = sQO + (i % 3) * 16384;
     const uint32_t idesc = ptx::make_idesc_bf16(128, n16_of(i), 0, 0);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
+    for (int ks = 0; ks < HD / 16; ++ks)
       ptx::umma_f16(tmem, desc_kmajor(ptx::smem_u32(sK), ks), desc_kmajor(ptx::smem_u32(sQ), ks), idesc, ks > 0);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
+    for (int ks = 0; ks < HD / 16; ++ks)
       ptx::umma_f16(tmem + 64, desc_kmajor(ptx::smem_u32(sV), ks), desc_kmajor(ptx::smem_u32(sQ + 8192), ks), idesc, ks > 0);
     ptx::umma_commit(bar_s);
   };
@@ -733,12 +783,22 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
     uint32_t rr[32];
-    ptx::tmem_ld_32x32b_x32(t_row + 128 + which * 64 + half * 32, rr);
-    ptx::tmem_ld_wait();
+    if (HD == 64 || half == 0) {
+      ptx::tmem_ld_32x32b_x32(t_row + 128 + which * 64 + half * 32, rr);
+      ptx::tmem_ld_wait();
+    } else {
+      uint32_t r16[16];
+      tmem_ld_32x32b_x16(t_row + 128 + which * 64 + 32, r16);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) rr[k] = r16[k];
+    }
+    const int ncol = (HD == 64 || half == 0) ? 32 : HD - 32;
     if (kv_ok) {
       bf16* dst = which == 0 ? krow : vrow;
 #pragma unroll
       for (int k = 0; k < 32; k += 8) {
+        if (k >= ncol) break;
         uint4 v;
         v.x = pack_bf16(__uint_as_float(rr[k]), __uint_as_float(rr[k + 1]));
         v.y = pack_bf16(__uint_as_float(rr[k + 2]), __uint_as_float(rr[k + 3]));
@@ -776,8 +836,9 @@ static inline void balanced_tiles(int S, int* ntile, int* rows) {
 }
 
 // Forward pass over all q rows (rows_done = Sq on return).
-int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv,
-                int q_rs, int k_rs, int v_rs, int o_rs, float scale, cudaStream_t s, int* rows_done) {
+template <int HD>
+static int attn_fwd_tc_impl(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv,
+                            int q_rs, int k_rs, int v_rs, int o_rs, float scale, cudaStream_t s, int* rows_done) {
   *rows_done = 0;
   int ntile, tile_rows;
   balanced_tiles(Sq, &ntile, &tile_rows);
@@ -787,18 +848,24 @@ int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse
   if ((rc = make_tmap3(&tk, k, nh * HD, Skv, B, k_rs, FWD_BN))) return rc;
   if ((rc = make_tmap3(&tv, v, nh * HD, Skv, B, v_rs, FWD_BN))) return rc;
   static bool attr = false;
-  if ((rc = set_smem(attn_fwd_tc_kernel, FWD_SMEM, &attr))) return rc;
+  if ((rc = set_smem(attn_fwd_tc_kernel<HD>, FWD_SMEM, &attr))) return rc;
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale; p.tile_rows = tile_rows;
   p.out0 = reinterpret_cast<bf16*>(o); p.out0_rs = o_rs; p.lse = lse;
-  pdl_launch(dim3(ntile, nh, B), 128, FWD_SMEM, s)(attn_fwd_tc_kernel, tq, tk, tv, p);
+  pdl_launch(dim3(ntile, nh, B), 128, FWD_SMEM, s)(attn_fwd_tc_kernel<HD>, tq, tk, tv, p);
   *rows_done = Sq;
   return check_launch("attn_fwd_tc");
 }
+int attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv, int hd,
+                int q_rs, int k_rs, int v_rs, int o_rs, float scale, cudaStream_t s, int* rows_done) {
+  return hd == 64 ? attn_fwd_tc_impl<64>(q, k, v, o, lse, B, nh, Sq, Skv, q_rs, k_rs, v_rs, o_rs, scale, s, rows_done)
+                  : attn_fwd_tc_impl<48>(q, k, v, o, lse, B, nh, Sq, Skv, q_rs, k_rs, v_rs, o_rs, scale, s, rows_done);
+}
 
-int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o, const float* lse, float* dvec,
-                   void* dq, int B, int nh, int Sq, int Skv, int q_rs, int k_rs, int v_rs, int do_rs, int dq_rs,
-                   float scale, cudaStream_t s, int* rows_done) {
+template <int HD>
+static int attn_bwd_dq_tc_impl(const void* q, const void* k, const void* v, const void* d_o, const float* lse, float* dvec,
+                               void* dq, int B, int nh, int Sq, int Skv, int q_rs, int k_rs, int v_rs, int do_rs, int dq_rs,
+                               float scale, cudaStream_t s, int* rows_done) {
   *rows_done = 0;
   int ntile, tile_rows;
   balanced_tiles(Sq, &ntile, &tile_rows);
@@ -809,19 +876,26 @@ int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o,
   if ((rc = make_tmap3(&tk, k, nh * HD, Skv, B, k_rs, BWD_BN))) return rc;
   if ((rc = make_tmap3(&tv, v, nh * HD, Skv, B, v_rs, BWD_BN))) return rc;
   static bool attr = false;
-  if ((rc = set_smem(attn_bwd_dq_tc_kernel, DQ_SMEM, &attr))) return rc;
+  if ((rc = set_smem(attn_bwd_dq_tc_kernel<HD>, DQ_SMEM, &attr))) return rc;
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dq); p.out0_rs = dq_rs; p.lse = const_cast<float*>(lse); p.dvec = dvec;
   p.tile_rows = tile_rows;
-  pdl_launch(dim3(ntile, nh, B), 288, DQ_SMEM, s)(attn_bwd_dq_tc_kernel, tq, tdo, tk, tv, p);
+  pdl_launch(dim3(ntile, nh, B), 288, DQ_SMEM, s)(attn_bwd_dq_tc_kernel<HD>, tq, tdo, tk, tv, p);
   *rows_done = Sq;
   return check_launch("attn_bwd_dq_tc");
 }
+int attn_bwd_dq_tc(const void* q, const void* k, const void* v, const void* d_o, const float* lse, float* dvec,
+                   void* dq, int B, int nh, int Sq, int Skv, int hd, int q_rs, int k_rs, int v_rs, int do_rs, int dq_rs,
+                   float scale, cudaStream_t s, int* rows_done) {
+  return hd == 64 ? attn_bwd_dq_tc_impl<64>(q, k, v, d_o, lse, dvec, dq, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dq_rs, scale, s, rows_done)
+                  : attn_bwd_dq_tc_impl<48>(q, k, v, d_o, lse, dvec, dq, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dq_rs, scale, s, rows_done);
+}
 
-int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_o, const float* lse,
-                     const float* dvec, void* dk, void* dv, int B, int nh, int Sq, int Skv, int q_rs, int k_rs,
-                     int v_rs, int do_rs, int dk_rs, int dv_rs, float scale, cudaStream_t s, int* rows_done) {
+template <int HD>
+static int attn_bwd_dkdv_tc_impl(const void* q, const void* k, const void* v, const void* d_o, const float* lse,
+                                 const float* dvec, void* dk, void* dv, int B, int nh, int Sq, int Skv, int q_rs, int k_rs,
+                                 int v_rs, int do_rs, int dk_rs, int dv_rs, float scale, cudaStream_t s, int* rows_done) {
   *rows_done = 0;
   int ntile, tile_rows;
   balanced_tiles(Skv, &ntile, &tile_rows);
@@ -832,15 +906,21 @@ int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_
   if ((rc = make_tmap3(&tq, q, nh * HD, Sq, B, q_rs, BWD_BN))) return rc;
   if ((rc = make_tmap3(&tdo, d_o, nh * HD, Sq, B, do_rs, BWD_BN))) return rc;
   static bool attr = false;
-  if ((rc = set_smem(attn_bwd_dkdv_tc_kernel, DKDV_SMEM, &attr))) return rc;
+  if ((rc = set_smem(attn_bwd_dkdv_tc_kernel<HD>, DKDV_SMEM, &attr))) return rc;
   TcParams p{};
   p.Sq = Sq; p.Skv = Skv; p.nh = nh; p.scale = scale;
   p.out0 = reinterpret_cast<bf16*>(dk); p.out0_rs = dk_rs; p.out1 = reinterpret_cast<bf16*>(dv); p.out1_rs = dv_rs;
   p.lse = const_cast<float*>(lse); p.dvec = const_cast<float*>(dvec);
   p.tile_rows = tile_rows;
-  pdl_launch(dim3(ntile, nh, B), 288, DKDV_SMEM, s)(attn_bwd_dkdv_tc_kernel, tk, tv, tq, tdo, p);
+  pdl_launch(dim3(ntile, nh, B), 288, DKDV_SMEM, s)(attn_bwd_dkdv_tc_kernel<HD>, tk, tv, tq, tdo, p);
   *rows_done = Skv;
   return check_launch("attn_bwd_dkdv_tc");
+}
+int attn_bwd_dkdv_tc(const void* q, const void* k, const void* v, const void* d_o, const float* lse,
+                     const float* dvec, void* dk, void* dv, int B, int nh, int Sq, int Skv, int hd, int q_rs, int k_rs,
+                     int v_rs, int do_rs, int dk_rs, int dv_rs, float scale, cudaStream_t s, int* rows_done) {
+  return hd == 64 ? attn_bwd_dkdv_tc_impl<64>(q, k, v, d_o, lse, dvec, dk, dv, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dk_rs, dv_rs, scale, s, rows_done)
+                  : attn_bwd_dkdv_tc_impl<48>(q, k, v, d_o, lse, dvec, dk, dv, B, nh, Sq, Skv, q_rs, k_rs, v_rs, do_rs, dk_rs, dv_rs, scale, s, rows_done);
 }
 
 }  // namespace muse

@@ -289,7 +289,7 @@ class _LayerFn(torch.autograd.Function):
         # ---- self attention
         h1, st1 = ops.norm_fwd(x, _f32(w_attn_ln), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
         qkv = ops.linear_fwd(h1, s.w["qkv"])
-        ctxt, lse = ops.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, nh, S, S, s.scale)
+        ctxt, lse = ops.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, nh, S, S, s.scale, head_dim=H // nh)
         fused_norms = s.normformer and not s.cross and H <= 1024  # post-attention norm + FFN pre-norm in one pass
         h2 = st3 = None
         if fused_norms:
@@ -309,7 +309,7 @@ class _LayerFn(torch.autograd.Function):
             qc = ops.linear_fwd(hc, s.w["cq"])
             enc_op = s.enc_op if s.enc_op is not None else enc  # bf16 GEMM operand (enc itself may be the fp32 projection)
             kvc = ops.linear_fwd(enc_op, s.w["ckv"])
-            cctx, clse = ops.attn_fwd(qc, kvc[:, :H], kvc[:, H:], B, nh, S, s.Skv, s.scale)
+            cctx, clse = ops.attn_fwd(qc, kvc[:, :H], kvc[:, H:], B, nh, S, s.Skv, s.scale, head_dim=H // nh)
             if s.normformer:
                 cao = ops.linear_fwd(cctx, s.w["co"])
                 x2b, stcp = ops.norm_fwd(cao, _f32(w_cpost), s.eps, torch.float32, res=x2, rms=s.rms, save_stats=grad)
@@ -387,7 +387,7 @@ class _LayerFn(torch.autograd.Function):
             d_kvc = torch.empty_like(sv["kvc"])
             kvc = sv["kvc"]
             ops.attn_bwd(sv["qc"], kvc[:, :H], kvc[:, H:], sv["cctx"], d_cctx, sv["clse"], d_qc, d_kvc[:, :H],
-                         d_kvc[:, H:], B, nh, S, s.Skv, s.scale)
+                         d_kvc[:, H:], B, nh, S, s.Skv, s.scale, head_dim=H // nh)
             g_ckv = ops.linear_wgrad_det(d_kvc, sv["enc"])
             if ctx.needs_input_grad[1]:  # projected encoder states: d enc = d[k|v] @ [Wk;Wv], fp32, summed over layers by autograd
                 d_enc = ops.linear_dgrad(d_kvc, s.w["ckv"], out_dtype=torch.float32)
@@ -408,7 +408,7 @@ class _LayerFn(torch.autograd.Function):
         qkv = sv["qkv"]
         d_qkv = torch.empty_like(qkv)
         ops.attn_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["ctxt"], d_ctx, sv["lse"], d_qkv[:, :H],
-                     d_qkv[:, H:2 * H], d_qkv[:, 2 * H:], B, nh, S, S, s.scale)
+                     d_qkv[:, H:2 * H], d_qkv[:, 2 * H:], B, nh, S, S, s.scale, head_dim=H // nh)
         d_h1 = ops.linear_dgrad(d_qkv, s.w["qkv"])
         g_qkv = ops.linear_wgrad_det(d_qkv, sv["h1"])
         dx1, g_attn_ln = ops.norm_bwd(d_h1, sv["x"], _f32(w_attn_ln), sv["st1"], torch.float32, dres=dx2, rms=s.rms,
@@ -567,13 +567,14 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
             raise NotImplementedError("open_muse_b200: embedding_size != hidden_size is not supported")
         if use_mlm_layer and not use_mlm_layernorm:
             raise NotImplementedError("open_muse_b200: use_mlm_layer without use_mlm_layernorm is not supported yet")
-        if hidden_size % num_attention_heads or hidden_size // num_attention_heads != 64:
+        if hidden_size % num_attention_heads or hidden_size // num_attention_heads not in (64, 48):
             if hidden_size % num_attention_heads:
                 raise ValueError(
                     f"embed_dim must be divisible by num_heads (got `embed_dim`: {hidden_size} and `num_heads`:"
                     f" {num_attention_heads})."
                 )
-            raise NotImplementedError("open_muse_b200: only head_dim == 64 is supported (every reference config uses 64)")
+            raise NotImplementedError("open_muse_b200: head_dim must be 64 or 48 (the reference configs use 64, and 48 in "
+                                      "configs/imagenet.yaml / imagenet_movq.yaml: hidden 768, 16 heads)")
         self.vocab_size = vocab_size
         self.hidden_size = hidden_size
         self.num_hidden_layers = num_hidden_layers

@@ -319,10 +319,11 @@ def glu_bwd(ab, dout):
 
 
 # ------------------------------------------------------------------------------------------ attention
-def attn_fwd(q, k, v, B, nh, Sq, Skv, scale):
-    """q: [B*Sq, *] view with head h at columns h*64; k, v: [B*Skv, *] views. Returns ctx [B*Sq, nh*64], lse."""
+def attn_fwd(q, k, v, B, nh, Sq, Skv, scale, head_dim=64):
+    """q: [B*Sq, *] view with head h at columns h*head_dim; k, v: [B*Skv, *] views.  Returns ctx [B*Sq, nh*head_dim], lse.
+    head_dim: 64 (default) or 48 (configs/imagenet.yaml: hidden 768 / 16 heads)."""
     st = _prep(q)
-    hd = 64
+    hd = int(head_dim)
     o = torch.empty(B * Sq, nh * hd, dtype=torch.bfloat16, device=q.device)
     lse = torch.empty(B, nh, Sq, dtype=torch.float32, device=q.device)
     _call("muse_attn_fwd", _p(q), _p(k), _p(v), _p(o), _p(lse), B, nh, Sq, Skv, hd, q.stride(0), k.stride(0),
@@ -330,11 +331,11 @@ def attn_fwd(q, k, v, B, nh, Sq, Skv, scale):
     return o, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, scale):
+def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, scale, head_dim=64):
     st = _prep(q)
     dvec = torch.empty(B, nh, Sq, dtype=torch.float32, device=q.device)
     _call("muse_attn_bwd", _p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _p(dvec), _p(dq), _p(dk), _p(dv), B, nh, Sq,
-          Skv, 64, q.stride(0), k.stride(0), v.stride(0), o.stride(0), do.stride(0), dq.stride(0), dk.stride(0),
+          Skv, int(head_dim), q.stride(0), k.stride(0), v.stride(0), o.stride(0), do.stride(0), dq.stride(0), dk.stride(0),
           dv.stride(0), float(scale), st)
 
 

@@ -200,6 +200,33 @@ def make_uvit_downup(muse):
           "downsample", tuple(stages["downsample"].shape), "upsample", tuple(stages["upsample"].shape))
 
 
+HD48 = dict(vocab_size=2048, hidden_size=768, num_hidden_layers=2, num_attention_heads=16, intermediate_size=3072,
+            hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=264, codebook_size=1024, num_vq_tokens=256,
+            num_classes=1000, layer_norm_eps=1e-6, use_encoder_layernorm=True, use_mlm_layer=True, use_mlm_layernorm=True)
+
+
+def make_hd48(muse):
+    """(12) head_dim 48: configs/imagenet.yaml (hidden 768, 16 heads, intermediate 3072 -- the config
+    training/train_maskgit_imagenet.py is written for) at its own widths with 2 of its 24 layers; seed-constructed
+    (weights not stored); logits slice, loss and every gradient's norm / first elements from the unmodified reference."""
+    torch.manual_seed(70)
+    t = muse.MaskGitTransformer(**HD48)
+    t.train()
+    g = torch.Generator().manual_seed(71)
+    batch = masked_batch(g, 2, 256, 1024, 1000, t.config.mask_token_id)
+    logits, loss = t(batch["input_ids"], labels=batch["labels"], label_smoothing=0.1)
+    loss.backward()
+    gr = grads_of(t)
+    torch.save(dict(config=HD48, seed=70, batch=batch, label_smoothing=0.1, loss=loss.detach(),
+                    logits_slice=logits.detach()[:, ::8, ::16].clone(), logits_mean=logits.mean().detach(),
+                    logits_std=logits.std().detach(),
+                    param_norms={k: v.norm().clone() for k, v in t.state_dict().items()},
+                    grad_norms={k: v.norm() for k, v in gr.items()},
+                    grad_heads={k: v.flatten()[:8].clone() for k, v in gr.items()}),
+               os.path.join(HERE, "hd48_transformer.pt"))
+    print("head_dim 48 transformer: loss", float(loss))
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -212,6 +239,8 @@ def main():
             make_signatures(muse)
         if "uvit_downup" in only[0]:
             make_uvit_downup(muse)
+        if "hd48" in only[0]:
+            make_hd48(muse)
         return
 
     # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
@@ -427,6 +456,7 @@ def main():
     make_f16_256(muse)
     make_signatures(muse)
     make_uvit_downup(muse)
+    make_hd48(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

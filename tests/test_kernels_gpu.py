@@ -204,6 +204,48 @@ def test_attention_fwd_bwd(B, nh, Sq, Skv):
     assert _rel(dq, dq2) < 2e-2 and _rel(dk, dk2) < 2e-2 and _rel(dv, dv2) < 2e-2
 
 
+@pytest.mark.parametrize("B,nh,Sq,Skv", [(2, 2, 257, 257), (1, 16, 257, 257), (3, 4, 16, 77), (2, 16, 256, 256), (1, 3, 193, 129)])
+def test_attention_head_dim_48_fwd_bwd(B, nh, Sq, Skv):
+    """head_dim 48 (configs/imagenet.yaml: hidden 768, 16 heads): the TMA boxes stay 64 columns wide (the trailing 16 belong
+    to the next head, or to the neighbouring K block of the fused projection, or are zero-filled past the tensor) and must
+    never enter a product; the accumulate MMAs run with N = 48.  Forward, LSE and all three gradients vs fp32 torch."""
+    hd = 48
+    H = nh * hd
+    cross = Sq != Skv
+    scale = 1.0 / math.sqrt(hd)
+    if cross:
+        qb = _rand((B * Sq, H), 1)
+        kvb = _rand((B * Skv, 2 * H), 2)
+        q, k, v = qb, kvb[:, :H], kvb[:, H:]
+    else:
+        qkv = _rand((B * Sq, 3 * H), 1)
+        q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    o, lse = ops.attn_fwd(q, k, v, B, nh, Sq, Skv, scale, head_dim=hd)
+    assert o.shape == (B * Sq, H)
+    qr = q.float().reshape(B, Sq, nh, hd).transpose(1, 2).clone().requires_grad_(True)
+    kr = k.float().reshape(B, Skv, nh, hd).transpose(1, 2).clone().requires_grad_(True)
+    vr = v.float().reshape(B, Skv, nh, hd).transpose(1, 2).clone().requires_grad_(True)
+    ref = _attn_ref(qr, kr, vr, scale)
+    assert _rel(o.view(B, Sq, nh, hd).transpose(1, 2), ref) < 8e-3
+    lse_ref = torch.logsumexp((qr @ kr.transpose(-1, -2)) * scale, dim=-1)
+    assert _rel(lse, lse_ref) < 1e-4
+    do = _rand((B * Sq, H), 3)
+    if cross:
+        dq = torch.empty_like(q.contiguous())
+        dkv = torch.empty_like(kvb)
+        ops.attn_bwd(q, k, v, o, do, lse, dq, dkv[:, :H], dkv[:, H:], B, nh, Sq, Skv, scale, head_dim=hd)
+        dk, dv = dkv[:, :H], dkv[:, H:]
+    else:
+        dqkv = torch.full_like(qkv, float("nan"))  # every element of the three gradients must be written
+        ops.attn_bwd(q, k, v, o, do, lse, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, nh, Sq, Skv, scale, head_dim=hd)
+        dq, dk, dv = dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:]
+        assert bool(torch.isfinite(dqkv.float()).all())
+    ref.backward(do.float().view(B, Sq, nh, hd).transpose(1, 2))
+    assert _rel(dq.reshape(B, Sq, nh, hd).transpose(1, 2), qr.grad) < 1.5e-2
+    assert _rel(dk.reshape(B, Skv, nh, hd).transpose(1, 2), kr.grad) < 1.5e-2
+    assert _rel(dv.reshape(B, Skv, nh, hd).transpose(1, 2), vr.grad) < 1.5e-2
+
+
 @pytest.mark.parametrize("n,ncodes,D", [(512, 1024, 256), (300, 128, 64), (1, 64, 16), (4096, 1024, 256)])
 def test_vq_argmin_bit_exact_vs_c_oracle(n, ncodes, D):
     from oracle import vq_oracle as VQ

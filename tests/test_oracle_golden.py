@@ -171,6 +171,28 @@ def test_tiny_config1_seeded(golden):
         _close(grads[k].flatten()[:8], g["grad_heads"][k], 1e-3, 1e-8)
 
 
+def test_head_dim_48_seeded(golden):
+    """configs/imagenet.yaml at its own widths (hidden 768, 16 heads -> head_dim 48, intermediate 3072, vocabulary 2048,
+    264 positions, its norm switches) with 2 of its 24 layers: our facade's seeded init == the reference's, oracle(loss, logits, grads) == reference."""
+    from open_muse_b200.modeling_transformer import MaskGitTransformer
+
+    g = golden("hd48_transformer.pt")
+    assert g["config"]["hidden_size"] // g["config"]["num_attention_heads"] == 48
+    torch.manual_seed(g["seed"])
+    m = MaskGitTransformer(**g["config"])
+    sd = m.state_dict()
+    assert set(sd) == set(g["param_norms"])
+    for k, n in g["param_norms"].items():
+        _close(sd[k].norm(), n, 1e-6, 0)
+    logits, loss, grads = T.forward_backward(sd, g["config"], g["batch"]["input_ids"], g["batch"]["labels"],
+                                             label_smoothing=g["label_smoothing"])
+    _close(loss, g["loss"], 1e-6, 0)
+    _close(logits[:, ::8, ::16], g["logits_slice"], 1e-4, 1e-6)
+    for k, n in g["grad_norms"].items():
+        _close(grads[k].norm(), n, 1e-4, 1e-8)
+        _close(grads[k].flatten()[:8], g["grad_heads"][k], 1e-3, 1e-8)
+
+
 def test_vq_oracle_c_matches_reference_ids(golden):
     g = golden("vq_quantizer.pt")
     z = VQ.nchw_to_rows(g["z"].numpy())

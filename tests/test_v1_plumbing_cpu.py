@@ -48,8 +48,8 @@ def _fake_ops(mp):
         H = a.shape[1]
         return torch.zeros(a.shape, dtype=F32), torch.zeros(a.shape, dtype=BF), torch.zeros(H), torch.zeros(H)
 
-    def attb(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, sc):
-        assert do.dtype == BF and do.shape == o.shape and dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape
+    def attb(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, sc, head_dim=64):
+        assert q.shape[1] == nh * head_dim and do.dtype == BF and do.shape == o.shape and dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape
 
     def gemm(a, b, c, M, N, K, lda, ldb, ldc, a_mn=0, b_mn=0, epi=0, res=None):
         assert a.dtype == BF and b.dtype == BF and c.shape[0] == M and ldc >= N
@@ -61,7 +61,7 @@ def _fake_ops(mp):
         embed_fwd=lambda ids, w, pos: torch.zeros(ids.numel(), w.shape[1]), embed_bwd_det=embed_bwd,
         norm_fwd=norm_fwd, norm_bwd=norm_bwd, norm2_fwd=norm2_fwd, norm2_bwd=norm2_bwd, glu_fwd=lambda ab: torch.zeros(ab.shape[0], ab.shape[1] // 2, dtype=BF),
         glu_bwd=lambda ab, d: torch.zeros_like(ab),
-        attn_fwd=lambda q, k, v, B, nh, Sq, Skv, sc: (torch.zeros(q.shape[0], nh * 64, dtype=BF), torch.zeros(B, nh, Sq)),
+        attn_fwd=lambda q, k, v, B, nh, Sq, Skv, sc, head_dim=64: (torch.zeros(q.shape[0], nh * head_dim, dtype=BF), torch.zeros(B, nh, Sq)),
         attn_bwd=attb, ce_fwd=lambda lg, lab, V, ls: (torch.zeros(2), torch.zeros(2, lg.shape[0])),
         ce_bwd=lambda lg, lab, ws, dl, out, V, ls, row_scale=None: torch.zeros_like(lg))
     for k, v in fakes.items():
@@ -73,6 +73,8 @@ BASE = dict(vocab_size=72, hidden_size=128, num_hidden_layers=2, num_attention_h
             hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=17, codebook_size=64, num_vq_tokens=16)
 CFGS = {
     "class-cond-normformer": dict(BASE, num_classes=7),
+    "class-cond-head-dim-48": dict(BASE, num_classes=7, hidden_size=96),  # configs/imagenet.yaml: 768 / 16 heads = 48
+    "t2i-head-dim-48": dict(BASE, hidden_size=96, max_position_embeddings=16, add_cross_attention=True, encoder_hidden_size=32),
     "t2i-rmsnorm-no-normformer": dict(BASE, max_position_embeddings=16, add_cross_attention=True, encoder_hidden_size=32,
                                       norm_type="rmsnorm", use_normformer=False, use_codebook_size_for_output=True),
     "t2i-projected-text-states": dict(BASE, max_position_embeddings=16, add_cross_attention=True, encoder_hidden_size=32,
