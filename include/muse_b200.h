@@ -140,8 +140,9 @@ int muse_norm2_bwd(const void* d_h2, const float* x2, const float* w2, const flo
 int muse_glu_fwd(const void* ab, void* out, long long rows, int I, void* stream);
 int muse_glu_bwd(const void* ab, const void* dout, void* dab, long long rows, int I, void* stream);
 
-/* Attention.attention (:221-241) fused: O = softmax(Q K^T * scale) V per (batch, head), head_dim 64.
- * Q/K/V/O are bf16 with row strides (elements) q_rs/k_rs/v_rs/o_rs, head h at column offset h*64,
+/* Attention.attention (:221-241) fused: O = softmax(Q K^T * scale) V per (batch, head), head_dim 64 or 48
+ * (configs/imagenet.yaml: hidden 768 / 16 heads).  Q/K/V/O are bf16 with row strides (elements) q_rs/k_rs/v_rs/o_rs, head h at
+ * column offset h*head_dim,
  * batch b at row offset b*Sq (Q,O) or b*Skv (K,V).  lse fp32 [B,nh,Sq] is saved for backward. */
 int muse_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int nh, int Sq, int Skv,
                   int head_dim, int q_rs, int k_rs, int v_rs, int o_rs, float scale, void* stream);
