@@ -55,6 +55,38 @@ def test_reference_training_script_runs_unchanged(monkeypatch, tmp_path, soft_ta
     assert cfg_json["_class_name"] == "MaskGitTransformer" and cfg_json["mask_token_id"] == 74
 
 
+# model.transformer of the reference's configs/imagenet.yaml (the config this script is written for): hidden 768 with 16 heads
+# = head_dim 48, vocabulary 2048, 264 positions
+IMAGENET_YAML_TRANSFORMER = dict(
+    vocab_size=2048, max_position_embeddings=264, hidden_size=768, num_hidden_layers=24, num_attention_heads=16,
+    intermediate_size=3072, codebook_size=1024, num_vq_tokens=256, num_classes=1000, initializer_range=0.02,
+    norm_type="layernorm", layer_norm_eps=1e-6, use_normformer=True, use_encoder_layernorm=True, use_mlm_layer=True,
+    use_mlm_layernorm=True, use_bias=False, hidden_dropout=0.0, attention_dropout=0.0)
+
+
+def test_reference_training_script_with_its_own_imagenet_yaml_model(monkeypatch, tmp_path):
+    """The same unmodified script with the transformer section of the reference's configs/imagenet.yaml (depth cut from 24 to 2
+    layers for time): the constructor accepts head_dim 48 and the step loop runs (stand-in kernels; the kernels themselves are
+    checked at these widths by tests/test_model_gpu.py::test_head_dim_48_vs_reference_and_oracle)."""
+    import yaml
+
+    ref_yaml = os.path.join(os.path.dirname(os.path.dirname(SCRIPT)), "configs", "imagenet.yaml")
+    if os.path.exists(ref_yaml):  # the literal above is the reference's, key for key
+        ref_tr = yaml.safe_load(open(ref_yaml))["model"]["transformer"]
+        ref_tr["layer_norm_eps"] = float(ref_tr["layer_norm_eps"])  # PyYAML reads "1e-6" as a string, OmegaConf as a float
+        assert ref_tr == IMAGENET_YAML_TRANSFORMER
+    _fake_ops(monkeypatch)
+    _fake_tokenizer(monkeypatch)
+    monkeypatch.setenv("ACCELERATE_USE_CPU", "1")
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    cfg, out = make_config(str(tmp_path), steps=2, batch=2, mixed_precision="no",
+                           transformer=dict(IMAGENET_YAML_TRANSFORMER, num_hidden_layers=2))
+    acc = run_script(SCRIPT, cfg)
+    assert [s for v, s in acc.logged if "step_loss" in v] == [1, 2]
+    cfg_json = json.load(open(os.path.join(out, "config.json")))
+    assert cfg_json["hidden_size"] == 768 and cfg_json["num_attention_heads"] == 16 and cfg_json["mask_token_id"] == 2047
+
+
 def test_lr_schedulers_match_reference():
     """compat muse.lr_schedulers.get_scheduler against the reference's, every schedule name, 12 steps."""
     import importlib.util

@@ -26,7 +26,7 @@ def find_script(name="train_maskgit_imagenet.py"):
     return None
 
 
-def make_config(tmp, steps, batch, mixed_precision, soft_targets=False, save_every=1000):
+def make_config(tmp, steps, batch, mixed_precision, soft_targets=False, save_every=1000, transformer=None):
     from open_muse_b200 import MaskGitVQGAN
 
     torch.manual_seed(3)
@@ -59,6 +59,8 @@ def make_config(tmp, steps, batch, mixed_precision, soft_targets=False, save_eve
                      "min_masking_rate": 0.0, "label_smoothing": 0.1, "max_grad_norm": 1.0,
                      "use_soft_code_target": soft_targets, "use_stochastic_code": False, "soft_code_temp": 1.0},
     }
+    if transformer is not None:  # e.g. the model section of the reference's own configs/imagenet.yaml
+        cfg["model"]["transformer"] = dict(transformer)
     path = os.path.join(tmp, "config.yaml")
     with open(path, "w") as f:
         yaml.safe_dump(cfg, f)
