@@ -90,7 +90,7 @@ class Attention(nn.Module):
         if hidden_size % num_heads != 0:
             raise ValueError(f"self.hidden_size: {hidden_size} must be divisible by self.num_heads: {num_heads}")
         if hidden_size // num_heads != 64:
-            raise NotImplementedError("open_muse_b200: only head_dim == 64 is supported (every reference config uses 64)")
+            raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: only head_dim == 64 is supported (every U-ViT config of the reference uses 64)")
         self.num_heads = num_heads
         self.query = nn.Linear(hidden_size, hidden_size, bias=False)
         self.key = nn.Linear(context_dim, hidden_size, bias=False)
