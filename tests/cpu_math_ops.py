@@ -1,0 +1,278 @@
+"""NUMERIC CPU stand-ins for the libmuse_b200 entry points the MaskGitTransformer host code calls (test infrastructure; the
+product never imports this).  Each function restates the documented contract of one ``open_muse_b200.ops`` wrapper in plain
+torch, so the host side -- the autograd Functions, the packed-operand table, the order in which gradients are handed back, the
+generate2 loop -- can be run end to end WITHOUT a GPU and compared with what the unmodified reference computed
+(tests/golden/*.pt).  The kernels themselves are checked on the B200 (tests/test_kernels_gpu.py, tests/test_model_gpu.py).
+
+Two modes:
+  exact=True   ``torch.bfloat16`` is aliased to ``torch.float32`` while the stand-ins are installed, so every tensor the host
+               code allocates "in bf16" carries full fp32 values: the host wiring must then reproduce the reference's fp32
+               outputs and gradients to ~1e-5 -- a mis-routed or mis-scaled gradient cannot hide under bf16 noise.
+  exact=False  outputs are rounded to the dtype the kernel writes (bf16 activations, fp32 residual stream / statistics /
+               weight gradients): the precision RECIPE of the hot path, emulated on the CPU.
+
+Backward stand-ins use the saved statistics (mean, rstd) exactly as the kernels do -- norm_bwd / norm2_bwd receive no eps --
+so a wrong statistics row handed over by the host shows up as a wrong gradient.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+F32 = torch.float32
+
+
+def _bf():  # looked up at call time: aliased to float32 in exact mode
+    return torch.bfloat16
+
+
+def _act(x, act):
+    x = x.float()
+    if act == 1:
+        return F.gelu(x)
+    if act == 2:
+        h = x.shape[1] // 2
+        return F.gelu(x[:, :h]) * x[:, h:]
+    return x
+
+
+def _stats(x, eps, rms):
+    if rms:
+        mean = torch.zeros(x.shape[0])
+        rstd = torch.rsqrt(x.pow(2).mean(-1) + eps)
+    else:
+        mean = x.mean(-1)
+        rstd = torch.rsqrt(x.var(-1, unbiased=False) + eps)
+    return mean, rstd
+
+
+def _norm_apply(x, w, mean, rstd):
+    y = (x - mean[:, None]) * rstd[:, None]
+    return y if w is None else y * w.float()
+
+
+def _norm_grad(dy, x, w, mean, rstd, rms):
+    """gradient of y = ((x - mean) * rstd) * w w.r.t. x and w from the SAVED statistics (layer norm: mean / rstd depend on
+    x; RMS norm: mean is 0 and only rstd depends on x)."""
+    dy = dy.float()
+    xhat = (x - mean[:, None]) * rstd[:, None]
+    g = dy if w is None else dy * w.float()
+    c2 = (g * xhat).mean(-1, keepdim=True)
+    dx = rstd[:, None] * (g - xhat * c2 - (0.0 if rms else g.mean(-1, keepdim=True)))
+    return dx, (dy * xhat).sum(0)
+
+
+# ------------------------------------------------------------------------------------------------------------- GEMMs
+def linear_fwd(x, w, out_dtype=None, res=None, n_valid=None):
+    n = w.shape[0] if n_valid is None else n_valid
+    assert x.dtype == _bf() and w.dtype == _bf() and x.shape[1] == w.shape[1], (x.dtype, w.dtype, x.shape, w.shape)
+    y = x.float() @ w[:n].float().t()
+    if res is not None:
+        assert res.dtype == F32 and res.shape == y.shape
+        return y + res
+    return y.to(_bf() if out_dtype is None else out_dtype)
+
+
+def linear_dgrad(dy, w, out_dtype=None):
+    assert dy.dtype == _bf() and w.dtype == _bf() and dy.shape[1] == w.shape[0]
+    return (dy.float() @ w.float()).to(_bf() if out_dtype is None else out_dtype)
+
+
+def linear_wgrad_det(dy, x, out=None):
+    assert dy.dtype == _bf() and x.dtype == _bf() and dy.shape[0] == x.shape[0]
+    dw = dy.float().t() @ x.float()
+    if out is not None:
+        out.copy_(dw)
+        return out
+    return dw
+
+
+def gemm(a, b, c, M, N, K, lda, ldb, ldc, a_mn=0, b_mn=0, epi=0, res=None):
+    """only the K-major x K-major form the head uses: c[:M, :N] = a[:M, :K] @ b[:N, :K]^T"""
+    assert a_mn == 0 and b_mn == 0 and res is None and a.stride(0) == lda and b.stride(0) == ldb and c.stride(0) == ldc
+    c[:M, :N] = (a[:M, :K].float() @ b[:N, :K].float().t()).to(c.dtype)
+    return c
+
+
+def pack_bf16(table, n_entries, total_blocks):
+    """the pointer table of _PackedWeights: rows (src fp32 pointer, dst bf16 pointer, numel, first block)"""
+    two_byte = torch.bfloat16 != torch.float32
+    for src, dst, numel, _ in table[:n_entries].tolist():
+        s = torch.frombuffer((ctypes.c_float * numel).from_address(src), dtype=F32)
+        if two_byte:
+            d = torch.frombuffer((ctypes.c_uint16 * numel).from_address(dst), dtype=torch.bfloat16)
+        else:
+            d = torch.frombuffer((ctypes.c_float * numel).from_address(dst), dtype=F32)
+        d.copy_(s)
+
+
+def cast_bf16(x):
+    return x.to(_bf())
+
+
+def take_bf16_copy(t):
+    return None
+
+
+# --------------------------------------------------------------------------------------------------------- embedding
+def embed_fwd(ids, word, pos):
+    B, S = ids.shape
+    out = word.float()[ids.reshape(-1)]
+    if pos is not None:
+        out = out + pos.float()[:S].repeat(B, 1)
+    return out
+
+
+def embed_bwd_det(ids, dx, vocab, n_pos):
+    B, S = ids.shape
+    assert dx.dtype == F32 and dx.shape[0] == B * S
+    dword = torch.zeros(vocab, dx.shape[1]).index_add_(0, ids.reshape(-1), dx)
+    dpos = None
+    if n_pos:
+        dpos = torch.zeros(n_pos, dx.shape[1])
+        dpos[:S] = dx.view(B, S, -1).sum(0)
+    return dword, dpos
+
+
+# ------------------------------------------------------------------------------------------------------------- norms
+def norm_fwd(x, w, eps, out_dtype, res=None, act=0, rms=0, save_stats=True):
+    xa = _act(x, act)
+    assert w is None or (w.dtype == F32 and w.shape == (xa.shape[1],))
+    mean, rstd = _stats(xa, eps, rms)
+    y = _norm_apply(xa, w, mean, rstd)
+    if res is not None:
+        assert res.dtype == F32 and res.shape == y.shape
+        y = y + res
+    return y.to(out_dtype), (torch.stack([mean, rstd]) if save_stats else None)
+
+
+def norm_bwd(dy, x, w, stats, dx_dtype, dw=None, dres=None, act=0, rms=0, y_fwd=None, want_dw=False, bf16_copy=False):
+    assert stats is not None and stats.shape == (2, x.shape[0])
+    xin = x.detach().float().requires_grad_(act != 0)
+    with torch.enable_grad():
+        xa = _act(xin, act)
+    assert dy.shape == xa.shape
+    dxa, gw = _norm_grad(dy, xa.detach(), w, stats[0], stats[1], rms)
+    dx = torch.autograd.grad(xa, xin, dxa)[0] if act else dxa
+    if dres is not None:
+        assert dres.dtype == F32 and dres.shape == dx.shape
+        dx = dx + dres
+    if dw is not None:
+        dw += gw
+    return (dx.to(dx_dtype), gw) if want_dw else dx.to(dx_dtype)
+
+
+def norm2_fwd(a, res, w1, w2, eps, rms1=0, rms2=0, save_stats=True):
+    assert a.dtype == _bf() and res.dtype == F32 and a.shape == res.shape
+    m1, r1 = _stats(a.float(), eps, rms1)
+    x2 = res + _norm_apply(a.float(), w1, m1, r1)
+    m2, r2 = _stats(x2, eps, rms2)
+    h2 = _norm_apply(x2, w2, m2, r2)
+    return x2, h2.to(_bf()), (torch.stack([m1, r1, m2, r2]) if save_stats else None)
+
+
+def norm2_bwd(d_h2, x2, w2, dres, a, w1, stats, rms1=0, rms2=0):
+    assert stats.shape == (4, a.shape[0]) and x2.dtype == F32 and dres.dtype == F32
+    d2, dw2 = _norm_grad(d_h2, x2, w2, stats[2], stats[3], rms2)
+    dx2 = d2 + dres
+    d_a, dw1 = _norm_grad(dx2, a.float(), w1, stats[0], stats[1], rms1)
+    return dx2, d_a.to(_bf()), dw1, dw2
+
+
+def glu_fwd(ab):
+    return _act(ab, 2).to(_bf())
+
+
+def glu_bwd(ab, dout):
+    x = ab.detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        y = _act(x, 2)
+    return torch.autograd.grad(y, x, dout.float())[0].to(ab.dtype)
+
+
+# --------------------------------------------------------------------------------------------------------- attention
+def _heads(t, B, S, nh, hd):
+    assert t.shape[0] == B * S and t.shape[1] == nh * hd
+    return t.float().reshape(B, S, nh, hd).permute(0, 2, 1, 3)
+
+
+def _attn(q, k, v, B, nh, Sq, Skv, scale, hd):
+    s = (_heads(q, B, Sq, nh, hd) @ _heads(k, B, Skv, nh, hd).transpose(-1, -2)) * scale
+    o = s.softmax(-1) @ _heads(v, B, Skv, nh, hd)
+    return o.permute(0, 2, 1, 3).reshape(B * Sq, nh * hd), torch.logsumexp(s, -1)
+
+
+def attn_fwd(q, k, v, B, nh, Sq, Skv, scale, head_dim=64):
+    o, lse = _attn(q, k, v, B, nh, Sq, Skv, scale, int(head_dim))
+    return o.to(_bf()), lse
+
+
+def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, scale, head_dim=64):
+    assert do.shape == o.shape and dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape
+    qq, kk, vv = (t.detach().float().clone().requires_grad_(True) for t in (q, k, v))
+    with torch.enable_grad():
+        out, lse2 = _attn(qq, kk, vv, B, nh, Sq, Skv, scale, int(head_dim))
+    assert torch.allclose(lse2.detach(), lse, atol=1e-3, rtol=1e-3)  # the host handed over this call's own log-sum-exp
+    gq, gk, gv = torch.autograd.grad(out, (qq, kk, vv), do.float())
+    dq.copy_(gq), dk.copy_(gk), dv.copy_(gv)
+
+
+# -------------------------------------------------------------------------------------------------------------- loss
+def ce_fwd(logits_padded, labels, V, label_smoothing):
+    lg = logits_padded[:, :V].float()
+    loss = F.cross_entropy(lg, labels, ignore_index=-100, label_smoothing=label_smoothing)
+    n = (labels != -100).sum().float()
+    row = F.cross_entropy(lg, labels, ignore_index=-100, label_smoothing=label_smoothing, reduction="none")
+    return torch.stack([loss, n]), torch.stack([torch.logsumexp(lg, -1), row])
+
+
+def ce_bwd(logits_padded, labels, ws, dloss, loss_out, V, label_smoothing, row_scale=None):
+    assert row_scale is None and dloss.shape == (1,)
+    x = logits_padded[:, :V].detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        loss = F.cross_entropy(x, labels, ignore_index=-100, label_smoothing=label_smoothing)
+    dl = torch.zeros(logits_padded.shape, dtype=logits_padded.dtype)
+    dl[:, :V] = (torch.autograd.grad(loss, x)[0] * dloss).to(dl.dtype)
+    return dl
+
+
+# ---------------------------------------------------------------------------------------------------------- sampling
+def sample_step(logits, input_ids, q_exp, u, K, mask_id, mask_len, temperature, logits_unc=None, guidance=0.0,
+                skip_first_token=False, return_conf=False):
+    """csrc/sample.cu's contract (its header comment), written with torch ops"""
+    B, L = input_ids.shape
+    off = 1 if skip_first_token else 0
+    x = logits[:, off:, :K].float()
+    if logits_unc is not None:
+        xu = logits_unc[:, off:, :K].float()
+        x = xu + guidance * (x - xu)
+    e = torch.exp(x - x.max(-1, keepdim=True).values)
+    sampled = (e / q_exp.view(B, L, K)).argmax(-1)
+    unknown = input_ids == mask_id
+    sampled = torch.where(unknown, sampled, input_ids)
+    p_sel = e.gather(-1, sampled.clamp(max=K - 1)[..., None]).squeeze(-1) / e.sum(-1)
+    p_sel = torch.where(unknown, p_sel, torch.finfo(torch.float32).max)
+    gumbel = -torch.log((-torch.log(u.view(B, L).clamp(min=1e-20))).clamp(min=1e-20))
+    conf = torch.log(p_sel.clamp(min=1e-20)) + temperature * gumbel
+    k = torch.clamp(torch.minimum(unknown.sum(-1, keepdim=True) - 1, torch.tensor(int(mask_len))), min=1)
+    cut = conf.sort(-1).values.gather(1, k)
+    nxt = torch.where(conf < cut, mask_id, sampled)
+    return (sampled, nxt, conf) if return_conf else (sampled, nxt)
+
+
+STAND_INS = dict(
+    linear_fwd=linear_fwd, linear_dgrad=linear_dgrad, linear_wgrad_det=linear_wgrad_det, gemm=gemm, pack_bf16=pack_bf16,
+    cast_bf16=cast_bf16, take_bf16_copy=take_bf16_copy, embed_fwd=embed_fwd, embed_bwd_det=embed_bwd_det, norm_fwd=norm_fwd,
+    norm_bwd=norm_bwd, norm2_fwd=norm2_fwd, norm2_bwd=norm2_bwd, glu_fwd=glu_fwd, glu_bwd=glu_bwd, attn_fwd=attn_fwd,
+    attn_bwd=attn_bwd, ce_fwd=ce_fwd, ce_bwd=ce_bwd, sample_step=sample_step)
+
+
+def install(mp, exact=True):
+    """monkeypatch ``open_muse_b200.ops`` with the stand-ins (restored by pytest's monkeypatch at the end of the test)"""
+    from open_muse_b200 import ops
+
+    if exact:
+        mp.setattr(torch, "bfloat16", torch.float32)
+    for name, fn in STAND_INS.items():
+        mp.setattr(ops, name, fn)
+    mp.setattr(torch.Tensor, "is_cuda", property(lambda self: True))  # the model refuses CPU tensors (no fallback)
