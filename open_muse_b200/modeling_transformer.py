@@ -123,6 +123,41 @@ class MlmLayer(nn.Module):
         self.to_logits = nn.Linear(hidden_size, vocab_size, bias=use_bias)
 
 
+class Norm2D(nn.Module):
+    """Per-pixel channel norm container (reference :302-311): parameter name ``norm.weight``."""
+
+    def __init__(self, dim, eps=1e-5, use_bias=False, norm_type="layernorm"):
+        super().__init__()
+        self.norm = _norm(norm_type, dim, eps, use_bias)
+
+
+class ConvEmbed(nn.Module):
+    """``use_conv_in_out`` input side (reference :988-1041): token embedding -> norm -> PixelUnshuffle(patch) -> 1x1 conv
+    -> + position embedding.  ``max_position_embeddings`` is the class default 256 whatever the model config says (the
+    reference does not forward it, :1133-1141)."""
+
+    def __init__(self, vocab_size, embedding_size, hidden_size, patch_size=2, max_position_embeddings=256,
+                 norm_type="layernorm", layer_norm_eps=1e-5, use_bias=False):
+        super().__init__()
+        self.hidden_size, self.patch_size, self.max_position_embeddings = hidden_size, patch_size, max_position_embeddings
+        self.embeddings = nn.Embedding(vocab_size, embedding_size)
+        self.layer_norm = _norm(norm_type, embedding_size, layer_norm_eps, use_bias)
+        self.conv = nn.Conv2d(embedding_size * (patch_size ** 2), hidden_size, kernel_size=1, bias=use_bias)
+        self.position_embeddings = nn.Embedding(max_position_embeddings, hidden_size)
+
+
+class ConvMlmLayer(nn.Module):
+    """``use_conv_in_out`` output side (reference :1043-1080): 1x1 conv -> PixelShuffle(patch) -> Norm2D -> 1x1 conv."""
+
+    def __init__(self, vocab_size, embedding_size, hidden_size, patch_size=2, norm_type="layernorm", layer_norm_eps=1e-5,
+                 use_bias=False):
+        super().__init__()
+        self.vocab_size, self.patch_size = vocab_size, patch_size
+        self.conv1 = nn.Conv2d(hidden_size, embedding_size * (patch_size ** 2), kernel_size=1, bias=use_bias)
+        self.layer_norm = Norm2D(embedding_size, eps=layer_norm_eps, use_bias=use_bias, norm_type=norm_type)
+        self.conv2 = nn.Conv2d(embedding_size, vocab_size, kernel_size=1, bias=use_bias)
+
+
 # --------------------------------------------------------------------------------------------
 # bf16 operand cache: every Linear weight packed (fused per GEMM) in ONE kernel launch per update
 # --------------------------------------------------------------------------------------------
@@ -153,7 +188,12 @@ class _PackedWeights:
                 groups.append((i, "co", [c.out.weight], None))
         if m.config.add_cross_attention and m.config.project_encoder_hidden_states:
             groups.append((-1, "eproj", [m.encoder_proj.weight], None))
-        if m.config.use_mlm_layer:
+        if m.config.use_conv_in_out:  # 1x1 convolutions are GEMMs over the channel dimension: [out, in, 1, 1] packs as [out, in]
+            groups.append((-1, "cin", [m.embed.conv.weight], None))
+        if m.config.use_mlm_layer and m.config.use_conv_in_out:
+            groups.append((-1, "c1", [m.mlm_layer.conv1.weight], None))
+            groups.append((-1, "logits", [m.mlm_layer.conv2.weight], m.padded_output_size))
+        elif m.config.use_mlm_layer:
             groups.append((-1, "dense", [m.mlm_layer.mlm_dense.weight], None))
             groups.append((-1, "logits", [m.mlm_layer.to_logits.weight], m.padded_output_size))
         else:
@@ -228,6 +268,143 @@ class _EmbedFn(torch.autograd.Function):
         wshape, pshape = ctx.shapes
         dword, dpos = ops.embed_bwd_det(ids, dx.contiguous(), wshape[0], pshape[0])
         return None, dword, dpos
+
+
+class _ConvSpec:
+    """Static description of the ``use_conv_in_out`` embedding / head (reference :988-1080): ``n`` x ``n`` tokens outside the
+    transformer, ``n / p`` x ``n / p`` inside."""
+
+    def __init__(self, B, n, p, E, H, eps, rms, w, V=0, Vpad=0, use_enc_ln=True, label_smoothing=0.0, n_cols=None):
+        self.B, self.n, self.p, self.E, self.H, self.eps, self.rms, self.w = B, n, p, E, H, eps, rms, w
+        self.V, self.Vpad, self.use_enc_ln, self.ls, self.n_cols = V, Vpad, use_enc_ln, label_smoothing, n_cols
+        self.train = torch.is_grad_enabled()
+
+
+def _to_patches(t, B, n, p, C):
+    """tokens [B*n*n, C] -> [B*(n/p)^2, C*p*p] with the channel order of nn.PixelUnshuffle (c, dy, dx), i.e. the input
+    channel order of the reference's 1x1 convolution weight"""
+    m = n // p
+    return t.view(B, m, p, m, p, C).permute(0, 1, 3, 5, 2, 4).reshape(B * m * m, C * p * p)
+
+
+def _from_patches(t, B, n, p, C):
+    """inverse of _to_patches = nn.PixelShuffle on the token-major layout: [B*(n/p)^2, C*p*p] -> tokens [B*n*n, C]"""
+    m = n // p
+    return t.view(B, m, m, C, p, p).permute(0, 1, 4, 2, 5, 3).reshape(B * n * n, C)
+
+
+class _ConvEmbedFn(torch.autograd.Function):
+    """ConvEmbed.forward (reference :1023-1041): gather -> norm -> PixelUnshuffle -> 1x1 conv as ONE GEMM over
+    ``[B*S/p^2, (c, dy, dx)]`` patches whose fp32 residual epilogue adds the position rows."""
+
+    @staticmethod
+    def forward(ctx, ids, spec, w_word, w_ln, w_conv, w_pos):
+        s = spec
+        grad = s.train and any(ctx.needs_input_grad)
+        B, n, p, E = s.B, s.n, s.p, s.E
+        e = ops.embed_fwd(ids, _f32(w_word), None)
+        y, st = ops.norm_fwd(e, _f32(w_ln), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
+        a = _to_patches(y, B, n, p, E)
+        pos_ids = torch.arange((n // p) ** 2, device=ids.device, dtype=torch.int64).repeat(B, 1)
+        pos_rows = ops.embed_fwd(pos_ids, _f32(w_pos), None)
+        x = ops.linear_fwd(a, s.w["cin"], res=pos_rows)
+        if grad:
+            ctx.sv = (ids, pos_ids, e, st, a, w_ln)
+            ctx.spec, ctx.shapes = s, (w_word.shape, w_conv.shape, w_pos.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        s = ctx.spec
+        ids, pos_ids, e, st, a, w_ln = ctx.sv
+        wshape, cshape, pshape = ctx.shapes
+        dx = dx.contiguous()
+        dxb = ops.take_bf16_copy(dx)
+        if dxb is None:
+            dxb = ops.cast_bf16(dx)
+        d_a = ops.linear_dgrad(dxb, s.w["cin"])
+        g_conv = ops.linear_wgrad_det(dxb, a).view(cshape)
+        d_y = _from_patches(d_a, s.B, s.n, s.p, s.E)
+        d_e, g_ln = ops.norm_bwd(d_y, e, _f32(w_ln), st, torch.float32, rms=s.rms, want_dw=True)
+        g_word, _ = ops.embed_bwd_det(ids, d_e, wshape[0], 0)
+        g_pos, _ = ops.embed_bwd_det(pos_ids, dx, pshape[0], 0)  # rows beyond the used positions are stored as zeros
+        ctx.sv = None
+        return None, None, g_word, g_ln, g_conv, g_pos
+
+
+class _ConvHeadFn(torch.autograd.Function):
+    """encoder_layer_norm -> ConvMlmLayer (1x1 conv, PixelShuffle, Norm2D, 1x1 conv; reference :1070-1080) -> masked CE."""
+
+    @staticmethod
+    def forward(ctx, x, labels, spec, *params):
+        s = spec
+        grad = s.train and any(ctx.needs_input_grad)
+        it = iter(params)
+        w_enc = next(it) if s.use_enc_ln else None
+        w_c1, w_ln, w_c2 = next(it), next(it), next(it)
+        B, n, p, E = s.B, s.n, s.p, s.E
+        T = B * n * n
+        if s.use_enc_ln:
+            hN, st0 = ops.norm_fwd(x, _f32(w_enc), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
+        else:
+            hN, st0 = ops.cast_bf16(x), None
+        c1 = ops.linear_fwd(hN, s.w["c1"])
+        t = _from_patches(c1, B, n, p, E)
+        e, st1 = ops.norm_fwd(t, _f32(w_ln), s.eps, torch.bfloat16, rms=s.rms, save_stats=grad)
+        if s.n_cols is not None:
+            if grad or labels is not None:
+                raise RuntimeError("column-restricted logits are an inference-only path")
+            ncol = ((s.n_cols + 7) // 8) * 8
+            logits = torch.empty(T, ncol, dtype=torch.bfloat16, device=x.device)
+            ops.gemm(e, s.w["logits"], logits, T, ncol, E, E, E, ncol)
+            return logits[:, : s.n_cols]
+        logits = torch.empty(T, s.Vpad, dtype=torch.bfloat16, device=x.device)
+        ops.gemm(e, s.w["logits"], logits, T, s.Vpad, E, E, E, s.Vpad)
+        loss = None
+        sv = {}
+        ctx.set_materialize_grads(False)
+        if labels is not None:
+            loss_out, ws = ops.ce_fwd(logits, labels, s.V, s.ls)
+            loss = loss_out[0]
+            sv.update(loss_out=loss_out, ws=ws, labels=labels)
+        if grad:
+            sv.update(x=x, hN=hN, st0=st0, t=t, e=e, st1=st1, logits=logits, w_enc=w_enc, w_ln=w_ln)
+            ctx.sv, ctx.spec, ctx.shapes = sv, s, (w_c1.shape, w_c2.shape)
+        out_logits = logits[:, : s.V]
+        if loss is None:
+            return out_logits
+        return out_logits, loss
+
+    @staticmethod
+    def backward(ctx, d_logits, d_loss=None):
+        s, sv = ctx.spec, ctx.sv
+        B, n, p, E = s.B, s.n, s.p, s.E
+        dev = sv["x"].device
+        dl = None
+        if d_loss is not None and "labels" in sv:
+            dl = ops.ce_bwd(sv["logits"], sv["labels"], sv["ws"], d_loss.to(torch.float32).reshape(1).contiguous(),
+                            sv["loss_out"], s.V, s.ls)
+        if d_logits is not None:  # gradient arriving through the returned logits (soft-target losses)
+            extra = torch.zeros(B * n * n, s.Vpad, dtype=torch.bfloat16, device=dev)
+            extra[:, : s.V] = d_logits.to(torch.bfloat16)
+            dl = extra if dl is None else dl + extra
+        if dl is None:
+            raise RuntimeError("MaskGitTransformer head: backward called without any gradient")
+        d_e = ops.linear_dgrad(dl, s.w["logits"])
+        g_c2 = ops.linear_wgrad_det(dl, sv["e"])[: s.V].reshape(ctx.shapes[1])
+        d_t, g_ln = ops.norm_bwd(d_e, sv["t"], _f32(sv["w_ln"]), sv["st1"], torch.bfloat16, rms=s.rms, want_dw=True)
+        d_c1 = _to_patches(d_t, B, n, p, E)
+        d_hN = ops.linear_dgrad(d_c1, s.w["c1"])
+        g_c1 = ops.linear_wgrad_det(d_c1, sv["hN"]).view(ctx.shapes[0])
+        grads = [g_c1, g_ln, g_c2]
+        if s.use_enc_ln:
+            dx, g_enc = ops.norm_bwd(d_hN, sv["x"], _f32(sv["w_enc"]), sv["st0"], torch.float32, rms=s.rms, want_dw=True,
+                                     bf16_copy=True)
+            grads = [g_enc] + grads
+        else:
+            dx = d_hN.float()
+        ctx.sv = None
+        return (dx, None, None, *grads)
 
 
 class _LayerSpec:
@@ -561,11 +738,20 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
         super().__init__()
         if use_bias:
             raise NotImplementedError("open_muse_b200: use_bias=True is not supported (no reference config enables it)")
-        if use_conv_in_out:
-            raise NotImplementedError("open_muse_b200: use_conv_in_out=True (ConvEmbed/ConvMlmLayer) is not supported yet")
-        if (embedding_size or hidden_size) != hidden_size:
-            raise NotImplementedError("open_muse_b200: embedding_size != hidden_size is not supported")
-        if use_mlm_layer and not use_mlm_layernorm:
+        if use_conv_in_out and not isinstance(embedding_size, int):
+            # the reference hands the raw ``embedding_size`` to ConvEmbed (:1133-1135): left unset -- as in the two yaml files
+            # that enable the flag, configs/cc12m_movq.yaml and imagenet_text2image_movq_conv.yaml -- nn.Embedding(vocab, None)
+            # raises this TypeError there too
+            raise TypeError("use_conv_in_out=True needs an explicit integer embedding_size (the reference raises in "
+                            "nn.Embedding(vocab_size, None) when it is left unset)")
+        if use_conv_in_out and (patch_size < 1 or (embedding_size * patch_size ** 2) % 8 or embedding_size % 8):
+            raise NotImplementedError("open_muse_b200: use_conv_in_out needs embedding_size to be a multiple of 8 (16-byte "
+                                      "rows for the TMA operands)")
+        # without use_conv_in_out the reference ignores embedding_size: Embed is built with hidden_size twice (:1143-1146, Q5)
+        if use_conv_in_out and not use_mlm_layer:
+            raise NotImplementedError("open_muse_b200: use_conv_in_out without use_mlm_layer (logits on the patch grid) is "
+                                      "not supported")
+        if use_mlm_layer and not use_mlm_layernorm and not use_conv_in_out:
             raise NotImplementedError("open_muse_b200: use_mlm_layer without use_mlm_layernorm is not supported yet")
         if hidden_size % num_attention_heads or hidden_size // num_attention_heads not in (64, 48):
             if hidden_size % num_attention_heads:
@@ -588,7 +774,11 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
         self.register_to_config(mask_token_id=vocab_size - 1)
 
         # construction order == reference (:1130-1197) so seeded initialisation is identical
-        self.embed = Embed(vocab_size, hidden_size, hidden_dropout, max_position_embeddings)
+        if use_conv_in_out:  # (:1132-1141; ConvEmbed keeps its own max_position_embeddings default of 256)
+            self.embed = ConvEmbed(vocab_size, embedding_size, hidden_size, patch_size=patch_size, norm_type=norm_type,
+                                   layer_norm_eps=layer_norm_eps, use_bias=use_bias)
+        else:
+            self.embed = Embed(vocab_size, hidden_size, hidden_dropout, max_position_embeddings)
         if add_cross_attention is not None and project_encoder_hidden_states:  # (:1154-1157)
             self.encoder_proj = nn.Linear(encoder_hidden_size, hidden_size, bias=use_bias)
             self.encoder_proj_layer_norm = _norm(norm_type, hidden_size, layer_norm_eps, use_bias)
@@ -605,7 +795,10 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
             self.encoder_layer_norm = _norm(norm_type, hidden_size, layer_norm_eps, use_bias)
         self.output_size = codebook_size if use_codebook_size_for_output else vocab_size
         self.padded_output_size = ((self.output_size + 63) // 64) * 64  # TMA-friendly logits pitch
-        if use_mlm_layer:
+        if use_mlm_layer and use_conv_in_out:  # (:1182-1191)
+            self.mlm_layer = ConvMlmLayer(self.output_size, embedding_size, hidden_size, patch_size=patch_size,
+                                          norm_type=norm_type, layer_norm_eps=layer_norm_eps, use_bias=use_bias)
+        elif use_mlm_layer:
             self.mlm_layer = MlmLayer(hidden_size, self.output_size, norm_type, layer_norm_eps, use_mlm_layernorm, use_bias)
         else:
             self.to_logits = nn.Linear(hidden_size, self.output_size, bias=use_bias)
@@ -649,7 +842,9 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
     def _head_params(self):
         c = self.config
         ps = [self.encoder_layer_norm.weight] if c.use_encoder_layernorm else []
-        if c.use_mlm_layer:
+        if c.use_mlm_layer and c.use_conv_in_out:
+            ps += [self.mlm_layer.conv1.weight, self.mlm_layer.layer_norm.norm.weight, self.mlm_layer.conv2.weight]
+        elif c.use_mlm_layer:
             ps += [self.mlm_layer.mlm_dense.weight, self.mlm_layer.mlm_ln.weight, self.mlm_layer.to_logits.weight]
         else:
             ps.append(self.to_logits.weight)
@@ -690,12 +885,26 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
                 bad = (labels != -100) & ((labels < 0) | (labels >= self.output_size))
                 if bool(bad.any()):
                     raise IndexError(f"labels out of range [0, {self.output_size}) (other than -100)")
-        if S > self.max_position_embeddings:
-            raise IndexError(f"sequence length {S} exceeds max_position_embeddings {self.max_position_embeddings}")
         H = self.hidden_size
+        rms = 0 if c.norm_type == "layernorm" else 1
+        S_out, conv = S, None  # use_conv_in_out: S tokens outside the transformer, S / patch^2 inside
+        if c.use_conv_in_out:
+            n, p = math.isqrt(S), c.patch_size
+            if n * n != S or n % p:
+                raise ValueError(f"use_conv_in_out: the {S} tokens must form a square grid divisible by patch_size {p}")
+            S = S // (p * p)
+            if S > self.embed.max_position_embeddings:
+                raise IndexError(f"{S} patches exceed ConvEmbed's {self.embed.max_position_embeddings} positions")
+        elif S > self.max_position_embeddings:
+            raise IndexError(f"sequence length {S} exceeds max_position_embeddings {self.max_position_embeddings}")
         packed = self._packed.refresh()
         ids = input_ids.contiguous().to(torch.int64)
-        x = _EmbedFn.apply(ids, self.embed.word_embeddings.weight, self.embed.position_embeddings.weight)
+        if c.use_conv_in_out:
+            conv = _ConvSpec(B, n, p, self.embedding_size, H, c.layer_norm_eps, rms, packed.head)
+            x = _ConvEmbedFn.apply(ids, conv, self.embed.embeddings.weight, self.embed.layer_norm.weight,
+                                   self.embed.conv.weight, self.embed.position_embeddings.weight)
+        else:
+            x = _EmbedFn.apply(ids, self.embed.word_embeddings.weight, self.embed.position_embeddings.weight)
 
         enc = None
         Skv = E = 0
@@ -708,7 +917,6 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
                 ehs = ehs * keep
             Skv, E = ehs.shape[1], ehs.shape[2]
             enc = ehs.reshape(B * Skv, E).to(torch.bfloat16).contiguous()
-        rms = 0 if c.norm_type == "layernorm" else 1
         enc_op = None
         # (:1239-1241). The reference drops conditioning after this projection; dropping the raw states first is the same
         # function and the same gradients because the projection and the norm have no bias (zero rows stay zero).
@@ -725,14 +933,20 @@ class MaskGitTransformer(ModelMixin, ConfigMixin):
         flat_labels = labels.reshape(-1).contiguous().to(torch.int64) if labels is not None else None
         if _logit_cols is not None and (_logit_cols >= self.output_size or labels is not None or torch.is_grad_enabled()):
             _logit_cols = None
-        hspec = _HeadSpec(B * S, H, self.output_size, self.padded_output_size, c.layer_norm_eps, rms,
-                          c.use_encoder_layernorm, c.use_mlm_layer, packed.head, label_smoothing, n_cols=_logit_cols)
-        out = _HeadFn.apply(x, flat_labels, hspec, *self._head_params())
+        if conv is not None:
+            hspec = _ConvSpec(B, conv.n, conv.p, conv.E, H, c.layer_norm_eps, rms, packed.head, V=self.output_size,
+                              Vpad=self.padded_output_size, use_enc_ln=c.use_encoder_layernorm,
+                              label_smoothing=label_smoothing, n_cols=_logit_cols)
+            out = _ConvHeadFn.apply(x, flat_labels, hspec, *self._head_params())
+        else:
+            hspec = _HeadSpec(B * S, H, self.output_size, self.padded_output_size, c.layer_norm_eps, rms,
+                              c.use_encoder_layernorm, c.use_mlm_layer, packed.head, label_smoothing, n_cols=_logit_cols)
+            out = _HeadFn.apply(x, flat_labels, hspec, *self._head_params())
         if labels is not None:
             logits, loss = out
         else:
             logits, loss = out, None
-        logits = logits.unflatten(0, (B, S))
+        logits = logits.unflatten(0, (B, S_out))
         if _raw_bf16:
             return logits, loss
         if not torch.is_autocast_enabled("cuda"):

@@ -65,7 +65,8 @@ def _layer(x, enc, p, pre, cfg):
 DEFAULTS = dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
                 max_position_embeddings=256, add_cross_attention=False, norm_type="layernorm", layer_norm_eps=1e-5,
                 use_normformer=True, use_encoder_layernorm=True, use_mlm_layer=True, use_mlm_layernorm=True,
-                codebook_size=1024, num_vq_tokens=256, use_codebook_size_for_output=False)
+                codebook_size=1024, num_vq_tokens=256, use_codebook_size_for_output=False, use_conv_in_out=False,
+                patch_size=1)
 
 
 def full_config(cfg: dict) -> dict:
@@ -81,8 +82,18 @@ def forward(p: Dict[str, torch.Tensor], cfg: dict, input_ids, encoder_hidden_sta
     """MaskGitTransformer.forward, muse/modeling_transformer.py:1224-1281.  Returns logits or (logits, loss)."""
     c = full_config(cfg)
     S = input_ids.shape[-1]
-    # Embed.forward :942-957
-    x = F.embedding(input_ids, p["embed.word_embeddings.weight"]) + p["embed.position_embeddings.weight"][:S][None]
+    conv = c["use_conv_in_out"]
+    if conv:  # ConvEmbed.forward :1023-1041 (NCHW, PixelUnshuffle, 1x1 Conv2d, positions added on the patch grid)
+        B, n, ps = input_ids.shape[0], math.isqrt(S), c["patch_size"]
+        e = _norm(F.embedding(input_ids.view(B, n, n), p["embed.embeddings.weight"]), p["embed.layer_norm.weight"],
+                  c["layer_norm_eps"], c["norm_type"]).permute(0, 3, 1, 2)
+        if ps > 1:
+            e = F.pixel_unshuffle(e, ps)
+        e = F.conv2d(e, p["embed.conv.weight"])
+        x = e.permute(0, 2, 3, 1).reshape(B, -1, e.shape[1])
+        x = x + p["embed.position_embeddings.weight"][: x.shape[1]][None]
+    else:  # Embed.forward :942-957
+        x = F.embedding(input_ids, p["embed.word_embeddings.weight"]) + p["embed.position_embeddings.weight"][:S][None]
     enc = encoder_hidden_states if c["add_cross_attention"] else None
     if enc is not None and c.get("project_encoder_hidden_states", False):  # encoder_proj + norm, :1239-1241
         enc = _norm(enc @ p["encoder_proj.weight"].t(), p["encoder_proj_layer_norm.weight"], c["layer_norm_eps"],
@@ -91,7 +102,14 @@ def forward(p: Dict[str, torch.Tensor], cfg: dict, input_ids, encoder_hidden_sta
         x = _layer(x, enc, p, f"transformer_layers.{i}.", c)
     if c["use_encoder_layernorm"]:
         x = _norm(x, p["encoder_layer_norm.weight"], c["layer_norm_eps"], c["norm_type"])
-    if c["use_mlm_layer"]:  # MlmLayer.forward :979-985
+    if c["use_mlm_layer"] and conv:  # ConvMlmLayer.forward :1070-1080
+        m = n // ps
+        h = F.conv2d(x.view(B, m, m, -1).permute(0, 3, 1, 2), p["mlm_layer.conv1.weight"])
+        if ps > 1:
+            h = F.pixel_shuffle(h, ps)
+        h = _norm(h.permute(0, 2, 3, 1), p["mlm_layer.layer_norm.norm.weight"], c["layer_norm_eps"], c["norm_type"])
+        logits = F.conv2d(h.permute(0, 3, 1, 2), p["mlm_layer.conv2.weight"]).permute(0, 2, 3, 1).reshape(B, n * n, -1)
+    elif c["use_mlm_layer"]:  # MlmLayer.forward :979-985
         x = F.gelu(x @ p["mlm_layer.mlm_dense.weight"].t())
         if c["use_mlm_layernorm"]:
             x = _norm(x, p["mlm_layer.mlm_ln.weight"], c["layer_norm_eps"], c["norm_type"])

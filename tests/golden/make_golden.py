@@ -227,6 +227,47 @@ def make_hd48(muse):
     print("head_dim 48 transformer: loss", float(loss))
 
 
+MICRO_CONV = dict(vocab_size=72, hidden_size=64, embedding_size=32, num_hidden_layers=2, num_attention_heads=1,
+                  intermediate_size=128, hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=16,
+                  codebook_size=64, num_vq_tokens=64, add_cross_attention=True, encoder_hidden_size=32, norm_type="rmsnorm",
+                  use_normformer=False, layer_norm_eps=1e-6, use_codebook_size_for_output=True, use_conv_in_out=True,
+                  patch_size=2)
+
+
+def make_conv_in_out(muse):
+    """use_conv_in_out=True (ConvEmbed / ConvMlmLayer, muse/modeling_transformer.py:988-1080), the wiring of
+    configs/imagenet_text2image_movq_conv.yaml and cc12m_movq.yaml at micro widths: 8x8 tokens outside, 4x4 inside.  Those
+    two yaml files leave ``embedding_size`` unset, with which the reference raises a TypeError in nn.Embedding(vocab, None)
+    (recorded below); the flag only constructs with an explicit embedding_size."""
+    try:
+        muse.MaskGitTransformer(**{k: v for k, v in MICRO_CONV.items() if k != "embedding_size"})
+        unset = "constructs"
+    except TypeError as e:
+        unset = "TypeError: " + str(e)[:60]
+    torch.manual_seed(80)
+    m = muse.MaskGitTransformer(**MICRO_CONV)
+    m.train()
+    with torch.no_grad():  # non-trivial norm weights (they are ones at init)
+        for n, p in m.named_parameters():
+            if p.dim() == 1:
+                p.copy_(torch.rand_like(p) + 0.5)
+    g = torch.Generator().manual_seed(81)
+    ids = torch.randint(0, 64, (2, 64), generator=g)
+    mask = torch.rand(2, 64, generator=g) < 0.5
+    input_ids = torch.where(mask, m.config.mask_token_id, ids)
+    labels = torch.where(mask, ids, -100)
+    enc = torch.randn(2, 5, 32, generator=g)
+    logits, loss = m(input_ids, encoder_hidden_states=enc, labels=labels, label_smoothing=0.1)
+    loss.backward()
+    torch.manual_seed(80)
+    init = {k: float(v.double().norm()) for k, v in muse.MaskGitTransformer(**MICRO_CONV).state_dict().items()}
+    torch.save(dict(config=MICRO_CONV, seed=80, init_norms=init, embedding_size_unset=unset,
+                    state_dict={k: v.clone() for k, v in m.state_dict().items()}, input_ids=input_ids, labels=labels,
+                    encoder_hidden_states=enc, label_smoothing=0.1, logits=logits.detach(), loss=loss.detach(),
+                    grads=grads_of(m)), os.path.join(HERE, "micro_conv_transformer.pt"))
+    print("micro conv in/out transformer: loss", float(loss), "| embedding_size unset ->", unset)
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -241,6 +282,8 @@ def main():
             make_uvit_downup(muse)
         if "hd48" in only[0]:
             make_hd48(muse)
+        if "conv_in_out" in only[0]:
+            make_conv_in_out(muse)
         return
 
     # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
@@ -457,6 +500,7 @@ def main():
     make_signatures(muse)
     make_uvit_downup(muse)
     make_hd48(muse)
+    make_conv_in_out(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

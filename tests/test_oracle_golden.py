@@ -45,6 +45,19 @@ def test_micro_t2i_projected_encoder_states_forward_backward(golden):
         _close(grads[k], v, 1e-4, 1e-7)
 
 
+def test_micro_conv_in_out_forward_backward(golden):
+    """use_conv_in_out=True (ConvEmbed / ConvMlmLayer): oracle == unmodified reference, logits / loss / every gradient."""
+    g = golden("micro_conv_transformer.pt")
+    logits, loss, grads = T.forward_backward(g["state_dict"], g["config"], g["input_ids"], g["labels"],
+                                             encoder_hidden_states=g["encoder_hidden_states"],
+                                             label_smoothing=g["label_smoothing"])
+    _close(logits, g["logits"], 1e-5, 1e-6)
+    _close(loss, g["loss"], 1e-6, 0)
+    assert set(grads) == set(g["grads"])
+    for k, v in g["grads"].items():
+        _close(grads[k], v, 1e-4, 1e-7)
+
+
 def test_micro_uvit_v2_forward_loss_and_generate2(golden):
     """MaskGiTUViT_v2 restatement (oracle/transformer_v2_oracle.py) against the unmodified reference: logits, both loss
     forms, and the CFG generate2 id trace through the same torch generator."""
