@@ -260,6 +260,168 @@ def sample_step(logits, input_ids, q_exp, u, K, mask_id, mask_len, temperature, 
     return (sampled, nxt, conf) if return_conf else (sampled, nxt)
 
 
+# ------------------------------------------------------------------------------------------- U-ViT v2 (csrc/uvit*.cu)
+def _mod_rows(mod, rows_per_sample, H):
+    """mod: fp32 [B, 2H] view (scale | shift) of the stacked adaLN mapper output -> per-row scale, shift"""
+    assert mod.dtype == F32 and mod.shape[1] == 2 * H
+    return mod[:, :H].repeat_interleave(rows_per_sample, 0), mod[:, H:].repeat_interleave(rows_per_sample, 0)
+
+
+def _mod_grad(dmod, dy, n, rows_per_sample, H):
+    B = dmod.shape[0]
+    dmod[:, :H] += (dy * n).view(B, rows_per_sample, H).sum(1)
+    dmod[:, H:] += dy.view(B, rows_per_sample, H).sum(1)
+
+
+def add_norm_mod(a, w, eps, rms, out_dtype=None, residual=None, mod=None, rows_per_sample=1, want_residual=True):
+    r = a.float() if residual is None else a.float() + residual
+    assert residual is None or residual.dtype == F32
+    mean, rstd = _stats(r, eps, rms)
+    y = _norm_apply(r, w, mean, rstd)
+    if mod is not None:
+        sc, sh = _mod_rows(mod, rows_per_sample, r.shape[1])
+        y = y * (1 + sc) + sh
+    return (r if want_residual else None), y.to(_bf() if out_dtype is None else out_dtype)
+
+
+def add_norm_mod_bwd(dy, dr_out, x_saved, w, eps, rms, da_dtype, mod=None, rows_per_sample=1, dw=None, dmod=None,
+                     want_dr=True):
+    assert x_saved.dtype == F32 and dy.shape == x_saved.shape and (dr_out is None or dr_out.dtype == F32)
+    x = x_saved
+    mean, rstd = _stats(x, eps, rms)
+    g = dy.float()
+    if mod is not None:
+        sc, _ = _mod_rows(mod, rows_per_sample, x.shape[1])
+        _mod_grad(dmod, g, _norm_apply(x, w, mean, rstd), rows_per_sample, x.shape[1])
+        g = g * (1 + sc)
+    dx, gw = _norm_grad(g, x, w, mean, rstd, rms)
+    if dw is not None:
+        dw += gw
+    tot = dx if dr_out is None else dx + dr_out
+    return tot.to(da_dtype), (tot if want_dr else None)
+
+
+def _dwconv_norm(x, wk, norm_w, B, hh, ww, eps, rms):
+    C = x.shape[1]
+    img = x.float().view(B, hh, ww, C).permute(0, 3, 1, 2)
+    conv = F.conv2d(img, wk.t().reshape(C, 1, 3, 3), padding=1, groups=C).permute(0, 2, 3, 1).reshape(B * hh * ww, C)
+    mean, rstd = _stats(conv, eps, rms)
+    return conv, _norm_apply(conv, norm_w, mean, rstd)
+
+
+def dwconv3x3_norm(x, wk, norm_w, B, hh, ww, eps, rms, save_conv=False):
+    assert x.dtype == F32 and wk.shape == (9, x.shape[1])
+    conv, y = _dwconv_norm(x, wk, norm_w, B, hh, ww, eps, rms)
+    return (y.to(_bf()), conv.to(_bf())) if save_conv else y.to(_bf())
+
+
+def dwconv3x3_norm_bwd(dy, conv, x, wk, norm_w, dres, dwk, dnw, B, hh, ww, eps, rms):
+    xx, kk = x.detach().clone().requires_grad_(True), wk.detach().clone().requires_grad_(True)
+    nn_ = None if norm_w is None else norm_w.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        _, y = _dwconv_norm(xx, kk, nn_, B, hh, ww, eps, rms)
+    gs = torch.autograd.grad(y, [xx, kk] + ([] if nn_ is None else [nn_]), dy.float())
+    dwk += gs[1]
+    if nn_ is not None:
+        dnw += gs[2]
+    return gs[0] + dres
+
+
+def _grn(x, gamma, beta, B, HW):
+    g = F.gelu(x.float()).view(B, HW, -1)
+    sumsq = g.pow(2).sum(1)
+    nx = sumsq.sqrt() / (sumsq.sqrt().mean(-1, keepdim=True) + 1e-6)
+    out = gamma.float() * (g * nx[:, None]) + beta.float() + g
+    return out.reshape(B * HW, -1), sumsq, nx
+
+
+def grn(x, gamma, beta, B, HW, save_stats=False):
+    out, sumsq, nx = _grn(x, gamma, beta, B, HW)
+    return (out.to(x.dtype), torch.stack([sumsq, nx])) if save_stats else out.to(x.dtype)
+
+
+def grn_bwd(x, dout, stats, gamma, dgamma, dbeta, B, HW):
+    xx = x.detach().float().requires_grad_(True)
+    gg, bb = gamma.detach().clone().requires_grad_(True), torch.zeros_like(gamma).requires_grad_(True)  # d out / d beta = 1
+    with torch.enable_grad():
+        out, _, nx = _grn(xx, gg, bb, B, HW)
+    assert torch.allclose(nx.detach(), stats[1], rtol=2e-2, atol=1e-3)  # the host handed over this block's statistics
+    gx, g_g, g_b = torch.autograd.grad(out, (xx, gg, bb), dout.float())
+    dgamma += g_g
+    dbeta += g_b
+    return gx.to(x.dtype)
+
+
+def adaln_apply(x, mod, B, rows_per_sample):
+    sc, sh = _mod_rows(mod, rows_per_sample, x.shape[1])
+    return x * (1 + sc) + sh
+
+
+def adaln_apply_(x, mod, B, rows_per_sample):
+    x.copy_(adaln_apply(x, mod, B, rows_per_sample))
+    return x
+
+
+def adaln_bwd(dy, x, mod, dmod, B, rows_per_sample):
+    assert dy.dtype == F32 and x.dtype == F32
+    sc, _ = _mod_rows(mod, rows_per_sample, x.shape[1])
+    _mod_grad(dmod, dy, x, rows_per_sample, x.shape[1])
+    return dy * (1 + sc)
+
+
+def silu_bf16(x):
+    return F.silu(x.float()).to(_bf())
+
+
+def silu_bwd(dy, x, out=None, out_dtype=None):
+    xf = x.float()
+    sg = torch.sigmoid(xf)
+    d = dy.float() * (sg * (1 + xf * (1 - sg)))
+    if out is not None:
+        out += d.to(out.dtype)
+        return out
+    return d.to(out_dtype or x.dtype)
+
+
+def linear_wgrad(dy, x, dw):
+    assert dw.dtype == F32 and dw.shape == (dy.shape[1], x.shape[1]) and dy.dtype == _bf() and x.dtype == _bf()
+    dw += dy.float().t() @ x.float()
+    return dw
+
+
+def linear_dgrad_acc(dy, w, acc):
+    assert acc.dtype == F32 and acc.shape == (dy.shape[0], w.shape[1])
+    acc += dy.float() @ w.float()
+    return acc
+
+
+def embed_bwd(ids, dx, dword, dpos):
+    B, S = ids.shape
+    dword.index_add_(0, ids.reshape(-1), dx)
+    if dpos is not None:
+        dpos[:S] = dx.view(B, S, -1).sum(0)
+
+
+def ce_bwd_rows(logits_padded, labels, ws, dloss, loss_out, V, label_smoothing, row_scale=None):
+    """ce_bwd with the optional per-row weights of the loss_weight path (loss = sum_r row_scale_r * loss_r)"""
+    if row_scale is None:
+        return ce_bwd(logits_padded, labels, ws, dloss, loss_out, V, label_smoothing)
+    x = logits_padded[:, :V].detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        rows = F.cross_entropy(x, labels, ignore_index=-100, label_smoothing=label_smoothing, reduction="none")
+        loss = (rows * row_scale).sum()
+    dl = torch.zeros(logits_padded.shape, dtype=logits_padded.dtype)
+    dl[:, :V] = (torch.autograd.grad(loss, x)[0] * dloss).to(dl.dtype)
+    return dl
+
+
+V2_STAND_INS = dict(
+    add_norm_mod=add_norm_mod, add_norm_mod_bwd=add_norm_mod_bwd, dwconv3x3_norm=dwconv3x3_norm,
+    dwconv3x3_norm_bwd=dwconv3x3_norm_bwd, grn=grn, grn_bwd=grn_bwd, adaln_apply=adaln_apply, adaln_apply_=adaln_apply_,
+    adaln_bwd=adaln_bwd, silu_bf16=silu_bf16, silu_bwd=silu_bwd, linear_wgrad=linear_wgrad, linear_dgrad_acc=linear_dgrad_acc,
+    embed_bwd=embed_bwd, ce_bwd=ce_bwd_rows)
+
+
 STAND_INS = dict(
     linear_fwd=linear_fwd, linear_dgrad=linear_dgrad, linear_wgrad_det=linear_wgrad_det, gemm=gemm, pack_bf16=pack_bf16,
     cast_bf16=cast_bf16, take_bf16_copy=take_bf16_copy, embed_fwd=embed_fwd, embed_bwd_det=embed_bwd_det, norm_fwd=norm_fwd,
@@ -273,6 +435,6 @@ def install(mp, exact=True):
 
     if exact:
         mp.setattr(torch, "bfloat16", torch.float32)
-    for name, fn in STAND_INS.items():
+    for name, fn in {**STAND_INS, **V2_STAND_INS}.items():
         mp.setattr(ops, name, fn)
     mp.setattr(torch.Tensor, "is_cuda", property(lambda self: True))  # the model refuses CPU tensors (no fallback)
