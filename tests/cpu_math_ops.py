@@ -422,6 +422,93 @@ V2_STAND_INS = dict(
     embed_bwd=embed_bwd, ce_bwd=ce_bwd_rows)
 
 
+# --------------------------------------------------------------------------------- VQGAN ops (csrc/conv*.cu, vq.cu)
+def _nchw(x):
+    return x.permute(0, 3, 1, 2)
+
+
+def _gn_silu(x_nhwc, gamma, beta, groups, eps, silu=1):
+    y = F.group_norm(_nchw(x_nhwc.float()), int(groups), gamma.float(), beta.float(), float(eps))
+    return (F.silu(y) if silu else y).permute(0, 2, 3, 1)
+
+
+def conv2d(x, w, bias=None, residual=None, upsample2x=False, gn=None):
+    """Conv2dSame (odd kernels, stride 1) on fp32 NHWC, optional GroupNorm+SiLU prologue, nearest x2 upsample first, fp32
+    residual added to the output"""
+    assert x.dtype == F32 and x.dim() == 4 and w.shape[1] == x.shape[3] and w.shape[2] % 2 == 1
+    if gn is not None:
+        x = _gn_silu(x, *gn)
+    t = _nchw(x)
+    if upsample2x:
+        t = F.interpolate(t, scale_factor=2.0, mode="nearest")
+    y = F.conv2d(t, w.float(), None if bias is None else bias.float(), padding=w.shape[2] // 2).permute(0, 2, 3, 1)
+    if residual is not None:
+        assert residual.shape == y.shape and residual.dtype == F32
+        y = y + residual
+    return y.contiguous()
+
+
+def groupnorm_silu(x, gamma, beta, groups, eps, silu=1):
+    return _gn_silu(x, gamma, beta, groups, eps, silu).contiguous()
+
+
+def conv2d_down(x, w, bias=None):
+    t = F.pad(_nchw(x), (0, 1, 0, 1))
+    return F.conv2d(t, w.float(), None if bias is None else bias.float(), stride=2).permute(0, 2, 3, 1).contiguous()
+
+
+def attention_single_head(q, k, v, B, hh, ww):
+    C = q.shape[1]
+    qq, kk, vv = (t.float().view(B, hh * ww, C) for t in (q, k, v))
+    p = torch.softmax(qq @ kk.transpose(1, 2) * (float(C) ** -0.5), dim=-1)
+    return (p @ vv).reshape(B * hh * ww, C)
+
+
+def avg_pool2x2(x):
+    return F.avg_pool2d(_nchw(x), 2).permute(0, 2, 3, 1).contiguous()
+
+
+def to_nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def to_nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def image_to_uint8(x):
+    t = (torch.clamp(2.0 * x - 1.0, -1.0, 1.0) + 1.0) / 2.0
+    return (255.0 * t).to(torch.uint8)  # truncation (pipeline_muse.py:245-252)
+
+
+def _vq_dist(z, cb):
+    """muse/modeling_maskgit_vqgan.py:303-312: |z|^2 + |e|^2 - 2 z e^T"""
+    z, cb = z.float(), cb.float()
+    return z.pow(2).sum(1, keepdim=True) + cb.pow(2).sum(1)[None] - 2.0 * z @ cb.t()
+
+
+def vq_argmin(z_flat, codebook, return_dmin=False):
+    d = _vq_dist(z_flat, codebook)
+    ids = d.argmin(1)
+    return (ids, d.min(1).values) if return_dmin else ids
+
+
+def vq_soft_code(z_flat, codebook, temp=1.0, expo_noise=None):
+    soft = torch.softmax(-_vq_dist(z_flat, codebook) / temp, dim=-1)
+    ids = soft.argmax(1) if expo_noise is None else (soft / expo_noise).argmax(1)
+    return soft, ids
+
+
+def vq_lookup_nchw(ids, codebook):
+    return codebook.float()[ids].permute(0, 2, 1).contiguous()  # [B, P, D] -> [B, D, P]
+
+
+VQGAN_STAND_INS = dict(
+    conv2d=conv2d, groupnorm_silu=groupnorm_silu, conv2d_down=conv2d_down, attention_single_head=attention_single_head,
+    avg_pool2x2=avg_pool2x2, to_nhwc=to_nhwc, to_nchw=to_nchw, image_to_uint8=image_to_uint8, vq_argmin=vq_argmin,
+    vq_soft_code=vq_soft_code, vq_lookup_nchw=vq_lookup_nchw)
+
+
 STAND_INS = dict(
     linear_fwd=linear_fwd, linear_dgrad=linear_dgrad, linear_wgrad_det=linear_wgrad_det, gemm=gemm, pack_bf16=pack_bf16,
     cast_bf16=cast_bf16, take_bf16_copy=take_bf16_copy, embed_fwd=embed_fwd, embed_bwd_det=embed_bwd_det, norm_fwd=norm_fwd,
@@ -435,6 +522,6 @@ def install(mp, exact=True):
 
     if exact:
         mp.setattr(torch, "bfloat16", torch.float32)
-    for name, fn in {**STAND_INS, **V2_STAND_INS}.items():
+    for name, fn in {**STAND_INS, **V2_STAND_INS, **VQGAN_STAND_INS}.items():
         mp.setattr(ops, name, fn)
     mp.setattr(torch.Tensor, "is_cuda", property(lambda self: True))  # the model refuses CPU tensors (no fallback)

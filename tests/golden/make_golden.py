@@ -268,6 +268,50 @@ def make_conv_in_out(muse):
     print("micro conv in/out transformer: loss", float(loss), "| embedding_size unset ->", unset)
 
 
+def make_pipeline(muse):
+    """The reference's PipelineMuse end to end (pipeline_muse.py:66-252) on the micro U-ViT + micro taming VQGAN fixtures'
+    weights: precomputed text states / pooled embeddings (the text encoder is out of scope; a stub only supplies ``.dtype``),
+    explicit negative embeddings, classifier-free guidance, 4 steps -> PIL images.  Stores the display bytes and the token
+    ids the same generator seed produces."""
+    import numpy as np
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+    from muse.sampling import cosine_schedule
+
+    gu = torch.load(os.path.join(HERE, "micro_uvit_v2.pt"), weights_only=False)
+    gv = torch.load(os.path.join(HERE, "micro_taming_vqgan.pt"), weights_only=False)
+    tr = MaskGiTUViT_v2(**gu["config"])
+    tr.load_state_dict(gu["state_dict"])
+    vae = muse.VQGANModel(**gv["config"])
+    vae.load_state_dict(gv["state_dict"])
+    tr.eval(), vae.eval()
+
+    class _Enc:
+        dtype = torch.float32
+
+    pipe = muse.PipelineMuse(vae=vae, transformer=tr, text_encoder=_Enc())
+    g = torch.Generator().manual_seed(90)
+    B = 2
+    inputs = dict(prompt_embeds=torch.randn(B, 5, 32, generator=g), pooled_embeds=torch.randn(B, 16, generator=g),
+                  negative_prompt_embeds=torch.randn(B, 5, 32, generator=g), negative_pooled_embeds=torch.randn(B, 16, generator=g))
+    call = dict(timesteps=4, guidance_scale=3.0, temperature=(2, 0), transformer_seq_len=16, orig_size=(256, 256),
+                crop_coords=(0, 0), aesthetic_score=6.0)
+    images = pipe(text=["a", "b"], negative_text=None, generator=torch.Generator().manual_seed(91), use_tqdm=False,
+                  **inputs, **call)
+    micro = torch.tensor([[256, 256, 0, 0, 6.0]])
+    with torch.no_grad():
+        tokens = tr.generate2(encoder_hidden_states=inputs["prompt_embeds"], cond_embeds=inputs["pooled_embeds"],
+                              negative_embeds=inputs["negative_prompt_embeds"],
+                              negative_cond_embeds=inputs["negative_pooled_embeds"], empty_embeds=None, empty_cond_embeds=None,
+                              micro_conds=micro, timesteps=4,
+                              guidance_scale=3.0, temperature=(2, 0), generator=torch.Generator().manual_seed(91),
+                              noise_schedule=cosine_schedule, seq_len=16, use_tqdm=False)
+        decoded = vae.decode_code(tokens)
+    torch.save(dict(inputs=inputs, call=call, seed=91, tokens=tokens, decoded=decoded,
+                    images=torch.from_numpy(np.stack([np.asarray(im) for im in images]))),
+               os.path.join(HERE, "micro_pipeline.pt"))
+    print("micro pipeline:", len(images), "images", images[0].size, "tokens", tokens.tolist()[0][:8])
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -284,6 +328,8 @@ def main():
             make_hd48(muse)
         if "conv_in_out" in only[0]:
             make_conv_in_out(muse)
+        if "pipeline" in only[0]:
+            make_pipeline(muse)
         return
 
     # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
@@ -501,6 +547,7 @@ def main():
     make_uvit_downup(muse)
     make_hd48(muse)
     make_conv_in_out(muse)
+    make_pipeline(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
