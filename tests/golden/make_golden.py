@@ -312,6 +312,61 @@ def make_pipeline(muse):
     print("micro pipeline:", len(images), "images", images[0].size, "tokens", tokens.tolist()[0][:8])
 
 
+def _yaml_numbers(d):
+    """PyYAML reads "1e-6" as a string where OmegaConf (what the training scripts use) reads a float"""
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, str):
+            try:
+                v = float(v)
+            except ValueError:
+                pass
+        out[k] = v
+    return out
+
+
+def make_config_audit(muse):
+    """Every configs/*.yaml of the reference: the model class training/train_muse.py:358 would pick for it
+    (``architecture`` "transformer" -> MaskGitTransformer, anything else -> MaskGiTUViT = MaskGiTUViT_v2) constructed on the
+    meta device with its ``model.transformer`` section, recording either the exception class or the parameter names / shapes
+    (sha1 of the ordered list) and the parameter count -- what a drop-in constructor has to reproduce."""
+    import hashlib
+    import json
+
+    import yaml
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+
+    out = {}
+    cdir = os.path.join(REF, "configs")
+    for f in sorted(os.listdir(cdir)):
+        if not f.endswith(".yaml"):
+            continue
+        y = yaml.safe_load(open(os.path.join(cdir, f)))
+        if not isinstance(y, dict) or "model" not in y:  # e.g. a prompt list
+            continue
+        model = y.get("model", {})
+        tr = _yaml_numbers(dict(model.get("transformer", {})))
+        arch = model.get("architecture", "transformer")
+        entry = dict(architecture=arch, transformer=tr, vq_model=dict(model.get("vq_model", {})).get("type"))
+        for cls_name, cls in (("MaskGitTransformer", muse.MaskGitTransformer), ("MaskGiTUViT_v2", MaskGiTUViT_v2)):
+            try:
+                with torch.device("meta"):
+                    m = cls(**tr)
+                shapes = [(n, list(p.shape)) for n, p in m.named_parameters()]
+                res = dict(ok=True, n_params=sum(p.numel() for p in m.parameters()), n_tensors=len(shapes),
+                           sha1=hashlib.sha1(json.dumps(shapes).encode()).hexdigest())
+            except Exception as e:  # noqa: BLE001
+                res = dict(ok=False, error=type(e).__name__)
+            entry[cls_name] = res
+        entry["script_class"] = "MaskGitTransformer" if arch == "transformer" else "MaskGiTUViT_v2"
+        out[f] = entry
+    with open(os.path.join(HERE, "configs.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    for f, e in out.items():
+        print(f"{f:48s} {e['script_class']:20s} v1 {e['MaskGitTransformer'].get('n_params', e['MaskGitTransformer'].get('error'))}"
+              f"  v2 {e['MaskGiTUViT_v2'].get('n_params', e['MaskGiTUViT_v2'].get('error'))}")
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -330,6 +385,8 @@ def main():
             make_conv_in_out(muse)
         if "pipeline" in only[0]:
             make_pipeline(muse)
+        if "configs" in only[0]:
+            make_config_audit(muse)
         return
 
     # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
@@ -548,6 +605,7 @@ def main():
     make_hd48(muse)
     make_conv_in_out(muse)
     make_pipeline(muse)
+    make_config_audit(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
