@@ -67,14 +67,88 @@ def make_config(tmp, steps, batch, mixed_precision, soft_targets=False, save_eve
     return path, out
 
 
+def make_tiny_clip(path):
+    """A 2-layer, 32-wide CLIP text encoder with a 768-wide projection (training/train_muse.py:336 forces projection_dim=768)
+    and a 54-entry byte-pair vocabulary, saved where ``CLIPTextModelWithProjection / CLIPTokenizer.from_pretrained`` find them:
+    the text encoder is third-party and out of scope, the script just needs one to call."""
+    import json
+
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection, CLIPTokenizer
+
+    os.makedirs(path, exist_ok=True)
+    chars = [chr(c) for c in range(ord("a"), ord("z") + 1)]
+    vocab = {t: i for i, t in enumerate(chars + [c + "</w>" for c in chars] + ["<|startoftext|>", "<|endoftext|>"])}
+    with open(os.path.join(path, "vocab.json"), "w") as f:
+        json.dump(vocab, f)
+    with open(os.path.join(path, "merges.txt"), "w") as f:
+        f.write("#version: 0.2\n")
+    CLIPTokenizer(os.path.join(path, "vocab.json"), os.path.join(path, "merges.txt"), model_max_length=8).save_pretrained(path)
+    cfg = CLIPTextConfig(vocab_size=len(vocab), hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                         num_attention_heads=2, max_position_embeddings=8, projection_dim=768,
+                         bos_token_id=vocab["<|startoftext|>"], eos_token_id=vocab["<|endoftext|>"],
+                         pad_token_id=vocab["<|endoftext|>"])
+    torch.manual_seed(5)
+    CLIPTextModelWithProjection(cfg).save_pretrained(path)
+    return path
+
+
+UVIT_MICRO = dict(hidden_size=128, num_attention_heads=2, in_channels=64, block_out_channels=[64], block_num_heads=1,
+                  num_res_blocks=1, num_hidden_layers=2, intermediate_size=128, vocab_size=72, codebook_size=64,
+                  encoder_hidden_size=32, cond_embed_dim=768, micro_cond_encode_dim=8, micro_cond_embed_dim=40,
+                  norm_type="rmsnorm", add_cond_embeds=True, add_micro_cond_embeds=True, use_empty_embeds_for_uncond=True,
+                  hidden_dropout=0.0, attention_dropout=0.0)
+
+
+def make_muse_config(tmp, steps, batch, mixed_precision, save_every=1000, extra_experiment=None, use_ema=False):
+    """config for the UNMODIFIED training/train_muse.py on the one wiring that runs end to end at this commit (quirk Q12):
+    ``architecture: uvit`` (MaskGiTUViT = MaskGiTUViT_v2) with pooled + micro conditioning, CLIP text encoder with
+    projection, classifier-free-guidance dropout through the encoded empty prompt, taming-style VQGAN tokenizer."""
+    from open_muse_b200 import VQGANModel
+
+    torch.manual_seed(3)
+    vq_dir = os.path.join(tmp, "vq")
+    VQGANModel(resolution=32, num_channels=3, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=1,
+               attn_resolutions=(16,), z_channels=16, num_embeddings=64, quantized_embed_dim=16).save_pretrained(vq_dir)
+    clip_dir = make_tiny_clip(os.path.join(tmp, "clip"))
+    out = os.path.join(tmp, "run")
+    exp = {"project": "muse", "name": "shim-run", "output_dir": out, "max_train_examples": batch * 64,
+           "max_eval_examples": batch * 2, "save_every": save_every, "eval_every": 1000, "generate_every": 1000,
+           "log_every": 1, "log_grad_norm_every": 1, "resume_from_checkpoint": False, "resume_lr_scheduler": True}
+    exp.update(extra_experiment or {})
+    cfg = {
+        "wandb": {"entity": None},
+        "experiment": exp,
+        "model": {"architecture": "uvit", "vq_model": {"type": "vqgan", "pretrained": vq_dir},
+                  "text_encoder": {"type": "clip", "pretrained": clip_dir}, "transformer": dict(UVIT_MICRO),
+                  "gradient_checkpointing": True, "enable_xformers_memory_efficient_attention": True},
+        "dataset": {"type": "text2image",
+                    "params": {"train_shards_path_or_url": "synthetic", "eval_shards_path_or_url": "synthetic",
+                               "batch_size": batch, "shuffle_buffer_size": 10, "num_workers": 0, "resolution": 32,
+                               "pin_memory": False, "persistent_workers": False},
+                    "preprocessing": {"resolution": 32, "center_crop": True, "random_flip": False, "max_seq_length": 8}},
+        "optimizer": {"name": "adamw", "params": {"learning_rate": 1.0e-3, "scale_lr": False, "beta1": 0.9, "beta2": 0.999,
+                                                  "weight_decay": 0.01, "epsilon": 1.0e-8}},
+        "lr_scheduler": {"scheduler": "constant_with_warmup", "params": {"learning_rate": 1.0e-3, "warmup_steps": 1}},
+        "training": {"gradient_accumulation_steps": 1, "batch_size": batch, "mixed_precision": mixed_precision,
+                     "enable_tf32": True, "use_ema": use_ema, "ema_decay": 0.99, "ema_update_after_step": 0,
+                     "ema_update_every": 1, "seed": 42, "max_train_steps": steps, "overfit_one_batch": False,
+                     "cond_dropout_prob": 0.1, "min_masking_rate": 0.0, "label_smoothing": 0.1, "max_grad_norm": 1.0,
+                     "use_soft_code_target": False, "use_stochastic_code": False, "soft_code_temp": 1.0},
+    }
+    path = os.path.join(tmp, "config.yaml")
+    with open(path, "w") as f:
+        yaml.safe_dump(cfg, f)
+    return path, out
+
+
 def run_script(script, config_path, extra_cli=()):
     """Execute the script as __main__ with the shims and the drop-in package importable; returns the shim Accelerator the
     script created (its .logged list holds every accelerator.log call)."""
     saved_path, saved_argv = list(sys.path), list(sys.argv)
-    saved_mods = {k: sys.modules.get(k) for k in ("muse", "accelerate", "omegaconf", "wandb", "data", "optimizer")}
+    shimmed = ("accelerate", "omegaconf", "wandb", "data", "optimizer", "plotly")
+    saved_mods = {k: sys.modules.get(k) for k in ("muse",) + shimmed}
     for k in list(sys.modules):
-        if k == "muse" or k.startswith("muse.") or k in ("accelerate", "omegaconf", "wandb", "data", "optimizer") or \
-                k.startswith("accelerate."):
+        if k == "muse" or k.startswith("muse.") or k in shimmed or k.startswith("accelerate.") or k.startswith("plotly."):
             del sys.modules[k]
     sys.path[:0] = [SHIMS, COMPAT, os.path.dirname(script)]  # shims shadow the script directory's own data.py
     sys.argv = [script, f"config={config_path}", *extra_cli]
@@ -86,8 +160,7 @@ def run_script(script, config_path, extra_cli=()):
     finally:
         sys.path[:], sys.argv[:] = saved_path, saved_argv
         for k in list(sys.modules):
-            if k == "muse" or k.startswith("muse.") or k in ("accelerate", "omegaconf", "wandb", "data", "optimizer") or \
-                    k.startswith("accelerate."):
+            if k == "muse" or k.startswith("muse.") or k in shimmed or k.startswith("accelerate.") or k.startswith("plotly."):
                 del sys.modules[k]
         for k, v in saved_mods.items():
             if v is not None:
