@@ -124,3 +124,26 @@ def test_lr_schedulers_match_reference():
         assert lrs[0] == pytest.approx(lrs[1], rel=1e-12, abs=1e-15), name
     for k in [k for k in sys.modules if k.startswith("_ref_muse")]:
         del sys.modules[k]
+
+
+@pytest.mark.parametrize("soft_targets", [False, True])
+def test_reference_training_script_trains_on_the_numeric_restatements(monkeypatch, tmp_path, soft_targets):
+    """The same unmodified script with NUMERIC torch restatements of the kernels (tests/cpu_math_ops.py, precision-recipe
+    mode) instead of the shape-checking stand-ins, tokenizer included: images -> MaskGitVQGAN ids / soft codes -> masking ->
+    forward + CE -> hand-written backward -> clip -> AdamW.  The loss the script logs is then a real loss: ~log(vocab) at
+    the random init and falling."""
+    import math
+
+    from tests import cpu_math_ops
+
+    cpu_math_ops.install(monkeypatch, exact=False)
+    monkeypatch.setenv("ACCELERATE_USE_CPU", "1")
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    steps = 6
+    cfg, out = make_config(str(tmp_path), steps=steps, batch=4, mixed_precision="no", soft_targets=soft_targets, save_every=3)
+    acc = run_script(SCRIPT, cfg)
+    losses = [v["step_loss"] for v, s in acc.logged if "step_loss" in v]
+    assert len(losses) == steps and all(math.isfinite(x) for x in losses)
+    assert abs(losses[0] - math.log(64 if soft_targets else 75)) < 0.5 and losses[-1] < losses[0], losses
+    ev = [v["eval_loss"] for v, s in acc.logged if "eval_loss" in v]
+    assert ev and math.isfinite(ev[-1])
