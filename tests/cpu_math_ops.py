@@ -518,10 +518,13 @@ STAND_INS = dict(
 
 def install(mp, exact=True):
     """monkeypatch ``open_muse_b200.ops`` with the stand-ins (restored by pytest's monkeypatch at the end of the test)"""
-    from open_muse_b200 import ops
+    from open_muse_b200 import ops, uvit_v2_train
 
     if exact:
         mp.setattr(torch, "bfloat16", torch.float32)
+        # module-level dtype constants / default arguments bound at import time
+        mp.setattr(uvit_v2_train, "BF16", torch.float32)
+        mp.setattr(uvit_v2_train._lin_bwd, "__defaults__", (torch.float32, True))
     for name, fn in {**STAND_INS, **V2_STAND_INS, **VQGAN_STAND_INS}.items():
         mp.setattr(ops, name, fn)
     mp.setattr(torch.Tensor, "is_cuda", property(lambda self: True))  # the model refuses CPU tensors (no fallback)
