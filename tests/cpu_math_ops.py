@@ -516,6 +516,14 @@ STAND_INS = dict(
     attn_bwd=attn_bwd, ce_fwd=ce_fwd, ce_bwd=ce_bwd, sample_step=sample_step)
 
 
+class PlainSetter:
+    """stands in for pytest's monkeypatch in a spawned worker process (nothing to restore: the process ends)"""
+
+    @staticmethod
+    def setattr(obj, name, value, raising=True):
+        setattr(obj, name, value)
+
+
 def install(mp, exact=True):
     """monkeypatch ``open_muse_b200.ops`` with the stand-ins (restored by pytest's monkeypatch at the end of the test)"""
     from open_muse_b200 import ops, uvit_v2_train

@@ -66,6 +66,52 @@ def test_ddp_mean_of_per_rank_means(tmp_path, golden):
     assert n0 != n1
 
 
+def _product_worker(rank, world, port, sd, batches, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from open_muse_b200 import MaskGitTransformer
+    from tests import cpu_math_ops
+
+    real_bf16 = torch.bfloat16
+    cpu_math_ops.install(cpu_math_ops.PlainSetter, exact=True)
+    m = MaskGitTransformer(**dict(CFG, hidden_dropout=0.0, attention_dropout=0.0))
+    m.load_state_dict(sd)
+    m.train()
+    model = torch.nn.parallel.DistributedDataParallel(m)
+    inp, lab = batches[rank]
+    _, loss = model(inp, labels=lab)
+    loss.backward()
+    torch.bfloat16 = real_bf16  # the alias of exact mode confuses torch.save's dtype tables
+    if rank == 0:
+        torch.save(dict(grads={n: p.grad.clone() for n, p in m.named_parameters()}, loss=loss.detach()), out)
+    dist.destroy_process_group()
+
+
+def test_product_model_under_ddp_matches_mean_of_oracle_rank_gradients(tmp_path, golden):
+    """The PRODUCT's MaskGitTransformer (its per-layer autograd Functions hand their parameter gradients back layer by layer, so
+    DDP's bucket hooks fire during the backward) under torch DDP, gloo world 2, kernels replaced by their exact fp32 torch
+    restatements: the all-reduced gradients equal the equal-weight mean of the oracle's per-rank gradients."""
+    from oracle import transformer_oracle as T
+
+    g = golden("micro_transformer.pt")
+    sd = g["state_dict"]
+    gen = torch.Generator().manual_seed(1)
+    batches = []
+    for r in range(2):
+        tokens = torch.randint(0, 64, (2 + r, 16), generator=gen)
+        cls = torch.randint(0, 7, (2 + r,), generator=gen)
+        batches.append(T.mask_tokens(tokens, cls, torch.rand(2 + r, generator=gen), torch.rand(2 + r, 16, generator=gen), 64, 71))
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_product_worker, args=(2, 31500 + os.getpid() % 2000, sd, batches, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    per_rank = [T.forward_backward(sd, CFG, b[0], b[1])[2] for b in batches]
+    for k in sd:
+        expect = 0.5 * (per_rank[0][k] + per_rank[1][k])
+        torch.testing.assert_close(got["grads"][k], expect, rtol=2e-4, atol=1e-7)
+
+
 def test_reference_arm_prints_only_on_rank0():
     env = dict(os.environ, OMP_NUM_THREADS="2")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
