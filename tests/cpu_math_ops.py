@@ -516,6 +516,61 @@ STAND_INS = dict(
     attn_bwd=attn_bwd, ce_fwd=ce_fwd, ce_bwd=ce_bwd, sample_step=sample_step)
 
 
+# ------------------------------------------------------------------------------------------ fused optimizer (optim.cu)
+def _view(ptr, numel, ctype, dtype):
+    return torch.frombuffer((ctype * numel).from_address(ptr), dtype=dtype)
+
+
+def adamw_ema_step(entries_host, n_entries, scal_ptr, step_ptr, lr_dev_ptr, lr_host, beta1, beta2, eps, weight_decay,
+                   ema_enabled, ema_decay, ema_min_decay, ema_update_after_step, ema_update_every, ema_use_warmup,
+                   ema_inv_gamma, ema_power, stream):
+    """csrc/optim.cu restated: the HOST table of {p, g, m, v, ema, packed, numel, -} pointer rows, the device-resident step
+    counter, the per-step scalars (bias corrections in double, EMA decay schedule of muse/modeling_ema.py:89-106), then ONE
+    pass: decoupled weight decay, Adam moments, update, EMA of the updated weight, bf16 copy into the packed operand."""
+    step = _view(step_ptr, 1, ctypes.c_int64, torch.int64)
+    s = int(step[0]) + 1
+    step[0] = s
+    inv_bc1 = float(torch.tensor(1.0 / (1.0 - beta1 ** s), dtype=F32))
+    inv_sqrt_bc2 = float(torch.tensor(1.0 / (1.0 - beta2 ** s) ** 0.5, dtype=F32))
+    lr = float(_view(lr_dev_ptr, 1, ctypes.c_float, F32)[0]) if lr_dev_ptr else lr_host
+    omd = None
+    if ema_enabled:
+        decay, st = 0.0, max(0, s - ema_update_after_step - 1)
+        if st > 0:
+            value = 1.0 - (1.0 + st / ema_inv_gamma) ** (-ema_power) if ema_use_warmup else (1.0 + st) / (10.0 + st)
+            decay = max(min(value, ema_decay), ema_min_decay)
+        if (s - 1) % max(1, ema_update_every) == 0:
+            omd = float(torch.tensor(1.0 - decay, dtype=F32))
+    table = torch.frombuffer((ctypes.c_int64 * (8 * n_entries)).from_address(entries_host), dtype=torch.int64).view(-1, 8)
+    two_byte = torch.bfloat16 != torch.float32
+    for p_, g_, m_, v_, e_, k_, numel, _ in table.tolist():
+        assert numel > 0 and numel % 4 == 0
+        p, g, m, v = (_view(x, numel, ctypes.c_float, F32) for x in (p_, g_, m_, v_))
+        p -= lr * weight_decay * p
+        m += (1.0 - beta1) * (g - m)
+        v.mul_(beta2).add_((1.0 - beta2) * g * g)
+        p -= (lr * inv_bc1) * m / (v.sqrt() * inv_sqrt_bc2 + eps)
+        if e_ and omd is not None:
+            e = _view(e_, numel, ctypes.c_float, F32)
+            e -= omd * (e - p)
+        if k_:
+            dst = _view(k_, numel, ctypes.c_uint16, torch.bfloat16) if two_byte else _view(k_, numel, ctypes.c_float, F32)
+            dst.copy_(p)
+
+
+def install_optimizer(mp):
+    """route ops._call("muse_adamw_ema_step", ...) to the restatement (FusedAdamW calls the C ABI through ops._call)"""
+    from open_muse_b200 import ops
+
+    def call(name, *args):
+        if name != "muse_adamw_ema_step":
+            raise AssertionError(f"unexpected library call on the CPU: {name}")
+        adamw_ema_step(*args)
+
+    mp.setattr(ops, "_call", call)
+    mp.setattr(ops, "_prep", lambda t: 0)
+
+
 class PlainSetter:
     """stands in for pytest's monkeypatch in a spawned worker process (nothing to restore: the process ends)"""
 
