@@ -37,3 +37,68 @@ def test_pipeline_reproduces_the_reference_images(golden, monkeypatch):
     dec = pipe(text=["a", "b"], negative_text=None, generator=torch.Generator().manual_seed(g["seed"]), output_type="pt",
                **g["inputs"], **g["call"])
     assert float((dec - g["decoded"]).norm() / g["decoded"].norm()) < 2e-5
+
+
+def _v1_models(golden, monkeypatch):
+    from open_muse_b200 import MaskGitTransformer, MaskGitVQGAN
+
+    gt, gv = golden("micro_transformer.pt"), golden("micro_vqgan.pt")
+    cpu_math_ops.install(monkeypatch, exact=True)
+    monkeypatch.setattr(MaskGitTransformer, "device", property(lambda self: torch.device("cpu")), raising=False)
+    monkeypatch.setenv("MUSE_B200_GENERATE_GRAPH", "0")
+    tr = MaskGitTransformer(**gt["config"])
+    tr.load_state_dict(gt["state_dict"])
+    vae = MaskGitVQGAN(**gv["config"])
+    vae.load_state_dict(gv["state_dict"])
+    return gt, gv, tr.eval(), vae.eval()
+
+
+def _bytes(decoded):
+    x = decoded.permute(0, 2, 3, 1).float().numpy()
+    return (255 * ((np.clip(2.0 * x - 1.0, -1.0, 1.0) + 1.0) / 2.0)).astype(np.uint8).astype(np.int16)
+
+
+def test_class_conditional_pipeline_matches_the_oracle_composition(golden, monkeypatch):
+    """PipelineMuse(class_ids=...) with a v1 MaskGitTransformer + MaskGitVQGAN (a superset of upstream, whose pipeline
+    reads U-ViT-only config keys, quirk Q15): class ids -> generate2 -> decode_code -> display bytes, against the oracle's
+    generate2 (pinned to the reference's id traces) followed by the oracle decoder."""
+    from oracle import transformer_oracle as T
+    from oracle import vqgan_oracle as G
+
+    gt, gv, tr, vae = _v1_models(golden, monkeypatch)
+    pipe = PipelineMuse(vae=vae, transformer=tr, is_class_conditioned=True)
+    images = pipe(class_ids=[1, 5], timesteps=4, temperature=1.0, num_images_per_prompt=2,
+                  generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        ids = T.generate2(gt["state_dict"], gt["config"], torch.tensor([1, 1, 5, 5]), 4, 1.0, torch.Generator().manual_seed(7))
+        want = _bytes(G.decode_code(gv["state_dict"], gv["config"], ids))
+    got = np.stack([np.asarray(im) for im in images]).astype(np.int16)
+    assert got.shape == want.shape == (4, 8, 8, 3)
+    assert np.abs(got - want).max() <= 1 and (got != want).mean() < 0.02
+
+
+def test_inpainting_pipeline_matches_the_oracle_composition(golden, monkeypatch):
+    """PipelineMuseInpainting (pipeline_muse.py:372-512): tokenise, overwrite the masked positions with the mask id,
+    generate2 from those start tokens (known tokens kept), decode -- against encoder / quantiser / generate2 / decoder of the
+    oracles chained the same way."""
+    from open_muse_b200 import PipelineMuseInpainting
+    from oracle import transformer_oracle as T
+    from oracle import vqgan_oracle as G
+
+    gt, gv, tr, vae = _v1_models(golden, monkeypatch)
+    pipe = PipelineMuseInpainting(vae=vae, transformer=tr, is_class_conditioned=True)
+    image = torch.rand(1, 3, 8, 8, generator=torch.Generator().manual_seed(5))
+    mask = torch.zeros(16, dtype=torch.bool)
+    mask[4:12] = True
+    out = pipe(image, mask, class_ids=[2], timesteps=3, num_images_per_prompt=2, temperature=1.0,
+               generator=torch.Generator().manual_seed(9), output_type="pt")
+    with torch.no_grad():
+        _, ids0 = G.quantize(gv["state_dict"], G.encoder(gv["state_dict"], gv["config"], image))
+        start = ids0.reshape(1, 16).clone()
+        start[:, mask] = gt["config"]["vocab_size"] - 1
+        ids = T.generate2(gt["state_dict"], gt["config"], torch.tensor([2, 2]), 3, 1.0, torch.Generator().manual_seed(9),
+                          input_ids=start.repeat(2, 1))
+        want = G.decode_code(gv["state_dict"], gv["config"], ids)
+    assert torch.equal(ids[:, ~mask], ids0.reshape(1, 16)[:, ~mask].expand(2, -1))  # known tokens are never resampled
+    assert out.shape == want.shape == (2, 3, 8, 8)
+    assert float((out - want).norm() / want.norm()) < 2e-5
