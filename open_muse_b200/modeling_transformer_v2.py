@@ -556,8 +556,17 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
             u = torch.zeros(B, seq_len, dtype=torch.float32, device=lg.device).uniform_(0, 1, generator=generator)
             ratio = 1.0 * (step + 1) / timesteps
             mask_len = int((seq_len * noise_schedule(torch.tensor(ratio))).floor())
+            prev_ids = input_ids
             sampled, input_ids = ops.sample_step(logits, input_ids, q_exp, u, K, mask_id, mask_len, float(temps[step]),
                                                  logits_unc=logits_unc, guidance=float(scales[step]))
             if return_intermediate:
-                intermediate.append(sampled)  # (after the known tokens were re-inserted)
+                # the reference collects the RAW multinomial sample, before the known tokens are re-inserted (:446-449).  The
+                # fused kernel emits the re-inserted ids; at the already-decoded positions the raw draw is recomputed here
+                # from the same logits and the same Exp(1) noise (argmax p / q) -- a debugging output, off the hot path
+                x = logits[..., :K].float()
+                if logits_unc is not None:
+                    xu = logits_unc[..., :K].float()
+                    x = xu + float(scales[step]) * (x - xu)
+                raw = (torch.softmax(x, dim=-1) / q_exp.view(B, seq_len, K)).argmax(dim=-1)
+                intermediate.append(torch.where(prev_ids == mask_id, sampled, raw))
         return (sampled, intermediate) if return_intermediate else sampled

@@ -367,6 +367,27 @@ def make_config_audit(muse):
               f"  v2 {e['MaskGiTUViT_v2'].get('n_params', e['MaskGiTUViT_v2'].get('error'))}")
 
 
+def make_uvit_intermediate(muse):
+    """MaskGiTUViT_v2.generate2(return_intermediate=True) on the micro_uvit_v2.pt weights and inputs, same generator seed as
+    that fixture's ``gen_ids``: the per-step RAW multinomial samples the reference collects before it re-inserts the known
+    tokens (modeling_transformer_v2.py:446-449)."""
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+
+    g = torch.load(os.path.join(HERE, "micro_uvit_v2.pt"), weights_only=False)
+    v2 = MaskGiTUViT_v2(**g["config"])
+    v2.load_state_dict(g["state_dict"])
+    v2.eval()
+    with torch.no_grad():
+        ids, inter = v2.generate2(g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"][:1], g["empty_embeds"],
+                                  g["empty_cond_embeds"], temperature=(2.0, 0.0), timesteps=4, guidance_scale=3.0, seq_len=16,
+                                  generator=torch.Generator().manual_seed(g["gen_seed"]), return_intermediate=True)
+    assert torch.equal(ids, g["gen_ids"])
+    torch.save(dict(intermediate=[t.clone() for t in inter], final=ids.clone()),
+               os.path.join(HERE, "micro_uvit_v2_intermediate.pt"))
+    print("micro uvit v2 intermediates:", len(inter), "steps; differ from the final-path ids at",
+          int(sum((a != b).sum() for a, b in zip(inter[1:], [ids] * 3))), "positions")
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -387,6 +408,8 @@ def main():
             make_pipeline(muse)
         if "configs" in only[0]:
             make_config_audit(muse)
+        if "uvit_intermediate" in only[0]:
+            make_uvit_intermediate(muse)
         return
 
     # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
@@ -606,6 +629,7 @@ def main():
     make_conv_in_out(muse)
     make_pipeline(muse)
     make_config_audit(muse)
+    make_uvit_intermediate(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

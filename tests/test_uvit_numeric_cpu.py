@@ -89,3 +89,21 @@ def test_uvit_training_with_loss_weight_and_down_up_sampling(golden, monkeypatch
     assert abs(float(loss.detach()) - float(g["loss"])) < 1e-5 * float(g["loss"])
     for n, p in m.named_parameters():
         assert p.grad is not None and _rel(p.grad, ref[n]) < 5e-4, (n, _rel(p.grad, ref[n]))
+
+
+def test_uvit_generate2_intermediates_are_the_raw_samples_of_the_reference(golden, monkeypatch):
+    """return_intermediate=True: the reference collects the RAW multinomial sample of every step, before the known tokens are
+    re-inserted (modeling_transformer_v2.py:446-449); the fused kernel emits the re-inserted ids, so the raw draw at the
+    already-decoded positions is recomputed from the same logits and noise"""
+    g, gi = golden("micro_uvit_v2.pt"), golden("micro_uvit_v2_intermediate.pt")
+    m = _model(g, monkeypatch, train=False)
+    with torch.no_grad():
+        ids, inter = m.generate2(encoder_hidden_states=g["encoder_hidden_states"], cond_embeds=g["cond_embeds"],
+                                 micro_conds=g["micro_conds"][:1], empty_embeds=g["empty_embeds"],
+                                 empty_cond_embeds=g["empty_cond_embeds"], timesteps=4, temperature=(2.0, 0.0),
+                                 guidance_scale=3.0, generator=torch.Generator().manual_seed(g["gen_seed"]), seq_len=16,
+                                 use_cuda_graph=False, return_intermediate=True)
+    assert torch.equal(ids, gi["final"]) and len(inter) == len(gi["intermediate"]) == 4
+    for step, (a, b) in enumerate(zip(inter, gi["intermediate"])):
+        assert torch.equal(a, b), step
+    assert any(not torch.equal(a, ids) for a in inter[1:])  # they do differ from the re-inserted ids at decoded positions
