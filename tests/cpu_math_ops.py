@@ -1,8 +1,10 @@
-"""NUMERIC CPU stand-ins for the libmuse_b200 entry points the MaskGitTransformer host code calls (test infrastructure; the
-product never imports this).  Each function restates the documented contract of one ``open_muse_b200.ops`` wrapper in plain
-torch, so the host side -- the autograd Functions, the packed-operand table, the order in which gradients are handed back, the
-generate2 loop -- can be run end to end WITHOUT a GPU and compared with what the unmodified reference computed
-(tests/golden/*.pt).  The kernels themselves are checked on the B200 (tests/test_kernels_gpu.py, tests/test_model_gpu.py).
+"""NUMERIC CPU stand-ins for the libmuse_b200 entry points the host code calls (test infrastructure; the product never
+imports this).  Each function restates the documented contract of one ``open_muse_b200.ops`` wrapper (or, for the fused
+optimizer, of the C entry point itself) in plain torch, so everything ABOVE the C ABI -- the autograd Functions of
+MaskGitTransformer and MaskGiTUViT_v2, the packed-operand pointer table, the order in which gradients are handed back, the
+generate2 loops, the tokenizers' module wiring, PipelineMuse, FusedAdamW's launch table -- can be run end to end WITHOUT a GPU
+and compared with what the unmodified reference computed (tests/golden/*.pt).  The kernels themselves are checked on the
+B200 (tests/test_kernels_gpu.py, tests/test_model_gpu.py, ...).
 
 Two modes:
   exact=True   ``torch.bfloat16`` is aliased to ``torch.float32`` while the stand-ins are installed, so every tensor the host
@@ -12,7 +14,8 @@ Two modes:
                weight gradients): the precision RECIPE of the hot path, emulated on the CPU.
 
 Backward stand-ins use the saved statistics (mean, rstd) exactly as the kernels do -- norm_bwd / norm2_bwd receive no eps --
-so a wrong statistics row handed over by the host shows up as a wrong gradient.
+so a wrong statistics row handed over by the host shows up as a wrong gradient; pointer tables (muse_pack_bf16,
+muse_adamw_ema_step) are dereferenced with ctypes like the library dereferences them.
 """
 import ctypes
 
