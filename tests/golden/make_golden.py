@@ -388,6 +388,31 @@ def make_uvit_intermediate(muse):
           int(sum((a != b).sum() for a, b in zip(inter[1:], [ids] * 3))), "positions")
 
 
+def make_uvit_grads(muse):
+    """Gradient signatures of the UNMODIFIED MaskGiTUViT_v2 on the micro_uvit_v2.pt / micro_uvit_v2_downup.pt weights and
+    batches (label smoothing 0.1; for the first also the loss_weight form): per-parameter norm and the first 8 elements, which
+    pin the oracle's autograd -- and through it the hand-written backward -- to the reference's own gradients."""
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+
+    out = {}
+    for name in ("micro_uvit_v2", "micro_uvit_v2_downup"):
+        g = torch.load(os.path.join(HERE, name + ".pt"), weights_only=False)
+        forms = {"plain": dict(label_smoothing=0.1)}
+        if "loss_weight" in g:
+            forms["loss_weight"] = dict(loss_weight=g["loss_weight"])
+        for form, kw in forms.items():
+            v2 = MaskGiTUViT_v2(**g["config"])
+            v2.load_state_dict(g["state_dict"])
+            v2.train()
+            _, loss = v2(g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"], labels=g["labels"], **kw)
+            loss.backward()
+            gr = grads_of(v2)
+            out[f"{name}/{form}"] = dict(loss=loss.detach().clone(), norms={k: v.norm().clone() for k, v in gr.items()},
+                                         heads={k: v.flatten()[:8].clone() for k, v in gr.items()})
+            print(name, form, "loss", float(loss), "tensors", len(gr))
+    torch.save(out, os.path.join(HERE, "micro_uvit_v2_grads.pt"))
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -410,6 +435,8 @@ def main():
             make_config_audit(muse)
         if "uvit_intermediate" in only[0]:
             make_uvit_intermediate(muse)
+        if "uvit_grads" in only[0]:
+            make_uvit_grads(muse)
         return
 
     # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
@@ -630,6 +657,7 @@ def main():
     make_pipeline(muse)
     make_config_audit(muse)
     make_uvit_intermediate(muse)
+    make_uvit_grads(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

@@ -79,6 +79,28 @@ def test_micro_uvit_v2_forward_loss_and_generate2(golden):
     assert torch.equal(ids, g["gen_ids"])
 
 
+def test_micro_uvit_v2_oracle_gradients_match_the_reference(golden):
+    """the oracle's autograd gradients (what the hand-written U-ViT backward is compared with) against the gradient signatures
+    of the UNMODIFIED MaskGiTUViT_v2: per-parameter norm and leading elements, plain and loss_weight losses, with and
+    without force_down_up_sample"""
+    from oracle import transformer_v2_oracle as V2
+
+    sig = golden("micro_uvit_v2_grads.pt")
+    for key, ref in sig.items():
+        name, form = key.split("/")
+        g = golden(name + ".pt")
+        kw = dict(label_smoothing=0.1) if form == "plain" else dict(loss_weight=g["loss_weight"])
+        q = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+        _, loss = V2.forward(q, g["config"], g["input_ids"], g["encoder_hidden_states"], g["cond_embeds"], g["micro_conds"],
+                             labels=g["labels"], **kw)
+        loss.backward()
+        _close(loss.detach(), ref["loss"], 1e-5, 0)
+        assert set(ref["norms"]) == set(q)
+        for k in q:
+            _close(q[k].grad.norm(), ref["norms"][k], 2e-4, 1e-9)
+            _close(q[k].grad.flatten()[:8], ref["heads"][k], 2e-3, 1e-8)
+
+
 def test_micro_uvit_v2_force_down_up_sample(golden):
     """force_down_up_sample=True (Norm2D + k2s2 conv / Norm2D + ConvTranspose2d, modeling_transformer_v2.py:505-583) against
     the unmodified reference: the two resampling outputs, logits, loss and the generate2 id trace."""
