@@ -1,0 +1,113 @@
+"""Checkpoints cross the boundary in BOTH directions (no GPU): a model saved by this package's ``save_pretrained`` loads into
+the UNMODIFIED reference class with ``from_pretrained`` (every key consumed, none missing), and a model saved by the reference
+loads here -- ``config.json`` keys, ``pytorch_model.bin`` names and shapes are the compatibility contract.  The
+reference runs in a subprocess (its package is also called ``muse``); the forward of the loaded weights is then compared
+numerically: the reference's own CPU forward against this package's host code on the kernels' torch restatements."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import ref_snapshot
+from tests import cpu_math_ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not ref_snapshot.available(), reason="oracle/_ref snapshot of the reference not available")
+
+V1 = dict(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_attention_heads=1, intermediate_size=128, hidden_dropout=0.0,
+          attention_dropout=0.0, max_position_embeddings=17, codebook_size=64, num_vq_tokens=16, num_classes=7)
+V2 = dict(hidden_size=128, num_attention_heads=2, in_channels=64, block_out_channels=[64], block_num_heads=1, num_res_blocks=1,
+          num_hidden_layers=2, intermediate_size=128, vocab_size=72, codebook_size=64, encoder_hidden_size=32, cond_embed_dim=16,
+          micro_cond_encode_dim=8, micro_cond_embed_dim=40, norm_type="rmsnorm", force_down_up_sample=True)
+VQ = dict(resolution=32, num_channels=3, hidden_channels=32, channel_mult=[1, 2], num_res_blocks=1, z_channels=16,
+          num_embeddings=64, quantized_embed_dim=16)
+TVQ = dict(VQ, num_res_blocks=2, attn_resolutions=[16])
+
+REF_SIDE = r'''
+import json, sys, torch
+sys.path.insert(0, sys.argv[1])
+from oracle.ref_snapshot import import_reference
+muse = import_reference()
+from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+cls = {"MaskGitTransformer": muse.MaskGitTransformer, "MaskGiTUViT_v2": MaskGiTUViT_v2, "MaskGitVQGAN": muse.MaskGitVQGAN,
+       "VQGANModel": muse.VQGANModel}[sys.argv[2]]
+dir_a, dir_b = sys.argv[3], sys.argv[4]
+inputs = torch.load(sys.argv[5])
+# (1) what this package saved loads into the unmodified reference class
+m = cls.from_pretrained(dir_a, low_cpu_mem_usage=False)
+saved = torch.load(dir_a + "/pytorch_model.bin")
+sd = m.state_dict()
+assert list(sd) == list(saved), (set(sd) ^ set(saved))
+assert all(torch.equal(sd[k], saved[k]) for k in sd)
+# (2) a differently seeded reference model, saved by the reference, with its own forward output
+torch.manual_seed(1234)
+r = cls(**json.load(open(sys.argv[6])))
+with torch.no_grad():
+    for p in r.parameters():  # every tensor non-trivial (norm weights are ones, adaLN mappers and GRN parameters zeros at init)
+        p.add_((0.1 if p.dim() == 1 else 0.02) * torch.randn_like(p))
+r.eval()
+r.save_pretrained(dir_b)
+with torch.no_grad():
+    if sys.argv[2] == "MaskGitTransformer":
+        out = r(inputs["input_ids"])
+    elif sys.argv[2] == "MaskGiTUViT_v2":
+        out = r(inputs["input_ids"], inputs["enc"], inputs["cond"], inputs["micro"])
+    else:
+        out = r.decode_code(r.get_code(inputs["image"]))
+torch.save(out, dir_b + "/reference_output.pt")
+print("OK")
+'''
+
+
+def _inputs(kind):
+    g = torch.Generator().manual_seed(7)
+    if kind == "MaskGitTransformer":
+        return dict(input_ids=torch.randint(0, 72, (2, 17), generator=g))
+    if kind == "MaskGiTUViT_v2":
+        return dict(input_ids=torch.randint(0, 72, (2, 64), generator=g), enc=torch.randn(2, 5, 32, generator=g),
+                    cond=torch.randn(2, 16, generator=g), micro=torch.tensor([[256.0, 256.0, 0.0, 0.0, 6.0]] * 2))
+    return dict(image=torch.rand(2, 3, 32, 32, generator=g))
+
+
+@pytest.mark.parametrize("kind,cfg", [("MaskGitTransformer", V1), ("MaskGiTUViT_v2", V2), ("MaskGitVQGAN", VQ), ("VQGANModel", TVQ)])
+def test_checkpoints_are_interchangeable_with_the_unmodified_reference(tmp_path, monkeypatch, kind, cfg):
+    import open_muse_b200 as ours
+
+    cls = getattr(ours, kind)
+    torch.manual_seed(99)
+    m = cls(**cfg)
+    dir_a, dir_b = str(tmp_path / "ours"), str(tmp_path / "theirs")
+    m.save_pretrained(dir_a)
+    inp = _inputs(kind)
+    torch.save(inp, str(tmp_path / "inputs.pt"))
+    with open(tmp_path / "cfg.json", "w") as f:
+        json.dump(cfg, f)
+    r = subprocess.run([sys.executable, "-c", REF_SIDE, ROOT, kind, dir_a, dir_b, str(tmp_path / "inputs.pt"),
+                        str(tmp_path / "cfg.json")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stderr[-3000:]
+    # (3) what the reference saved loads here: same keys / shapes / values, same config
+    theirs = torch.load(os.path.join(dir_b, "pytorch_model.bin"))
+    cpu_math_ops.install(monkeypatch, exact=True)
+    monkeypatch.setenv("MUSE_B200_CUDA_GRAPH", "0")
+    loaded = cls.from_pretrained(dir_b).eval()
+    sd = loaded.state_dict()
+    assert list(sd) == list(theirs) and all(torch.equal(sd[k], theirs[k]) for k in sd)
+    ref_cfg = json.load(open(os.path.join(dir_b, "config.json")))
+    for k, v in cfg.items():
+        assert ref_cfg[k] == v and getattr(loaded.config, k) == (tuple(v) if isinstance(v, list) else v) or \
+            list(getattr(loaded.config, k)) == list(v), k
+    # (4) and computes what the reference computed with them
+    want = torch.load(os.path.join(dir_b, "reference_output.pt"))
+    with torch.no_grad():
+        if kind == "MaskGitTransformer":
+            got = loaded(inp["input_ids"])
+        elif kind == "MaskGiTUViT_v2":
+            got = loaded(inp["input_ids"], inp["enc"], inp["cond"], inp["micro"])
+        else:
+            got = loaded.decode_code(loaded.get_code(inp["image"]))
+    assert got.shape == want.shape
+    assert float((got.float() - want).norm() / want.norm()) < (5e-5 if "VQ" not in kind else 1e-3)
