@@ -193,3 +193,19 @@ def test_conv_in_out_precision_recipe_and_inference_paths(golden, monkeypatch):
     assert torch.equal(part.float(), full[..., :40])  # column-restricted logits (generate2) = the same GEMM, fewer columns
     with pytest.raises(ValueError):
         m(g["input_ids"][:, :60], encoder_hidden_states=g["encoder_hidden_states"])  # not a square grid
+
+
+def test_conv_in_out_external_loss_through_the_returned_logits(golden, monkeypatch):
+    """soft-target style training with use_conv_in_out: the caller's loss back-propagates through the returned logits"""
+    g = golden("micro_conv_transformer.pt")
+    cpu_math_ops.install(monkeypatch, exact=True)
+    m = MaskGitTransformer(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.train()
+    logits = m(g["input_ids"], encoder_hidden_states=g["encoder_hidden_states"])
+    assert logits.dtype == torch.float32 and _rel(logits, g["logits"]) < 2e-5
+    loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), g["labels"].reshape(-1), ignore_index=-100,
+                                             label_smoothing=g["label_smoothing"])
+    loss.backward()
+    for n, p in m.named_parameters():
+        assert _rel(p.grad, g["grads"][n]) < 2e-4, n
