@@ -107,3 +107,34 @@ def test_uvit_generate2_intermediates_are_the_raw_samples_of_the_reference(golde
     for step, (a, b) in enumerate(zip(inter, gi["intermediate"])):
         assert torch.equal(a, b), step
     assert any(not torch.equal(a, ids) for a in inter[1:])  # they do differ from the re-inserted ids at decoded positions
+
+
+def test_reference_smoke_script_scenario(monkeypatch):
+    """The reference's only test, /root/reference/test.py:64-95: a 1-layer MaskGiTUViT (hidden 768, 384 block channels, 8192
+    codes, pooled + six micro conditions) in eval mode, output shape (2, 256, 8192).  Same constructor call here with TWO
+    head counts set explicitly -- block_num_heads = 6 and num_attention_heads = 12 instead of the class defaults 12 and 16 --
+    because the defaults give head_dim 384 / 12 = 32 and 768 / 16 = 48 at these widths and the U-ViT attention path is built
+    for head_dim 64, the width of every U-ViT training config: the unmodified script stops at that
+    NotImplementedError.  Beyond the shape, the logits are compared with the oracle on the same seeded weights."""
+    cpu_math_ops.install(monkeypatch, exact=True)
+    from open_muse_b200 import MaskGiTUViT
+
+    kw = dict(vocab_size=8193, hidden_size=768, in_channels=384, block_out_channels=(384,), encoder_hidden_size=768,
+              add_cross_attention=True, num_res_blocks=1, num_hidden_layers=1, codebook_size=8192, num_vq_tokens=256,
+              use_codebook_size_for_output=True, add_micro_cond_embeds=True, micro_cond_encode_dim=256,
+              micro_cond_embed_dim=1536, add_cond_embeds=True, cond_embed_dim=512)
+    with pytest.raises(NotImplementedError):
+        MaskGiTUViT(**kw)  # head_dim 32 in the down / up blocks
+    torch.manual_seed(0)
+    model = MaskGiTUViT(**kw, block_num_heads=6, num_attention_heads=12).eval()
+    g = torch.Generator().manual_seed(1)
+    input_ids = torch.randint(0, 8192, (2, 256), generator=g)
+    enc = torch.randn(2, 4, 768, generator=g)
+    micro = torch.tensor([[1024, 1024, 0, 0, 1024, 1024]]).repeat(2, 1)
+    cond = torch.randn(2, 512, generator=g)
+    with torch.no_grad():
+        out = model(input_ids, encoder_hidden_states=enc, micro_conds=micro, cond_embeds=cond)
+        assert out.shape == (2, 256, 8192)
+        cfg = dict(model.config)
+        want = V2.forward({k: v.float() for k, v in model.state_dict().items()}, cfg, input_ids, enc, cond, micro.float())
+    assert _rel(out, want) < 5e-5
