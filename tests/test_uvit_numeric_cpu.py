@@ -138,3 +138,38 @@ def test_reference_smoke_script_scenario(monkeypatch):
         cfg = dict(model.config)
         want = V2.forward({k: v.float() for k, v in model.state_dict().items()}, cfg, input_ids, enc, cond, micro.float())
     assert _rel(out, want) < 5e-5
+
+
+def test_uvit_operand_cache_follows_weight_updates(golden, monkeypatch):
+    """MaskGiTUViT_v2._weights() (bf16 operands, stacked adaLN mappers, fp32 norm / depthwise views) is rebuilt when any
+    parameter's storage or version changes: EMA copy_to / restore, load_state_dict and an in-place edit are each visible in the
+    next forward -- against a freshly built model with the same weights."""
+    from open_muse_b200 import EMAModel
+
+    g = golden("micro_uvit_v2.pt")
+    m = _model(g, monkeypatch, train=False)
+    args = [g[k] for k in ARGS]
+
+    def fresh(sd):
+        f = MaskGiTUViT_v2(**g["config"])
+        f.load_state_dict(sd)
+        return f.eval()(*args)
+
+    with torch.no_grad():
+        base = m(*args)
+        assert torch.equal(base, fresh(m.state_dict()))
+        ema = EMAModel(m.parameters(), decay=0.5)
+        for s in ema.shadow_params:
+            s.mul_(0.9)
+        ema.store(m.parameters())
+        ema.copy_to(m.parameters())
+        with_ema = m(*args)
+        assert not torch.equal(with_ema, base) and torch.equal(with_ema, fresh(m.state_dict()))
+        ema.restore(m.parameters())
+        assert torch.equal(m(*args), base)
+        m.transformer_layers[0].ffn.wo.weight.mul_(1.5)
+        m.down_blocks[0].res_blocks[0].depthwise.weight.mul_(0.5)
+        edited = m(*args)
+        assert not torch.equal(edited, base) and torch.equal(edited, fresh(m.state_dict()))
+        m.load_state_dict(g["state_dict"])
+        assert torch.equal(m(*args), base)

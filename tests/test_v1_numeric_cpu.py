@@ -209,3 +209,53 @@ def test_conv_in_out_external_loss_through_the_returned_logits(golden, monkeypat
     loss.backward()
     for n, p in m.named_parameters():
         assert _rel(p.grad, g["grads"][n]) < 2e-4, n
+
+
+def test_packed_operand_cache_follows_every_kind_of_weight_update(golden, monkeypatch):
+    """The bf16 operand cache is keyed on (storage, version counter) of every Linear weight: an optimizer step, a
+    load_state_dict, ``EMAModel.copy_to`` / ``restore`` (train_muse.py:857-908 validates with the EMA weights) and a plain
+    in-place edit must each be visible in the very next forward -- checked against a freshly built model holding the same
+    weights (the ADVICE r1 'stale packed operands' bug class, on the CPU)."""
+    from open_muse_b200 import EMAModel
+
+    g = golden("micro_transformer.pt")
+    cpu_math_ops.install(monkeypatch, exact=True)
+    ids = g["batch"]["input_ids"]
+
+    def fresh(sd):
+        f = MaskGitTransformer(**g["config"])
+        f.load_state_dict(sd)
+        return f.eval()(ids)
+
+    m = MaskGitTransformer(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.eval()
+    with torch.no_grad():
+        base = m(ids)
+        assert torch.equal(base, fresh(m.state_dict()))
+        # (1) optimizer step
+        m.train()
+    _, loss = m(ids, labels=g["batch"]["labels"])
+    loss.backward()
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    opt.step()
+    m.eval()
+    with torch.no_grad():
+        after_step = m(ids)
+        assert not torch.equal(after_step, base) and torch.equal(after_step, fresh(m.state_dict()))
+        # (2) EMA copy_to / restore
+        ema = EMAModel(m.parameters(), decay=0.5)
+        for s in ema.shadow_params:
+            s.mul_(0.9)
+        ema.store(m.parameters())
+        ema.copy_to(m.parameters())
+        with_ema = m(ids)
+        assert not torch.equal(with_ema, after_step) and torch.equal(with_ema, fresh(m.state_dict()))
+        ema.restore(m.parameters())
+        assert torch.equal(m(ids), after_step)
+        # (3) load_state_dict and (4) a plain in-place edit of one weight
+        m.load_state_dict(g["state_dict"])
+        assert torch.equal(m(ids), base)
+        m.transformer_layers[1].ffn.wo.weight.mul_(1.5)
+        edited = m(ids)
+        assert not torch.equal(edited, base) and torch.equal(edited, fresh(m.state_dict()))
