@@ -190,7 +190,7 @@ def cpu_reference_step_fn(batch, device="cpu"):
     return step
 
 
-CPU_SAMPLE_BATCH = 32
+CPU_SAMPLE_BATCH = int(os.environ.get("MUSE_B200_CPU_SAMPLE_BATCH", "32"))  # the bounded CPU sample (tests shrink it)
 
 
 def cpu_threads():

@@ -89,8 +89,9 @@ class Attention(nn.Module):
         super().__init__()
         if hidden_size % num_heads != 0:
             raise ValueError(f"self.hidden_size: {hidden_size} must be divisible by self.num_heads: {num_heads}")
-        if hidden_size // num_heads != 64:
-            raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: only head_dim == 64 is supported (every U-ViT config of the reference uses 64)")
+        if hidden_size // num_heads not in (64, 48):
+            raise NotImplementedError("open_muse_b200.MaskGiTUViT_v2: head_dim must be 64 (every U-ViT config of the reference) "
+                                      "or 48; the attention kernels are built for these two widths")
         self.num_heads = num_heads
         self.query = nn.Linear(hidden_size, hidden_size, bias=False)
         self.key = nn.Linear(context_dim, hidden_size, bias=False)
@@ -288,7 +289,9 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
             return o
 
         def attn(a, fuse_q):
-            d = {"kv": bf(a.key.weight, a.value.weight), "o": bf(a.out.weight), "nh": a.num_heads}
+            hd = a.out.weight.shape[0] // a.num_heads  # 64: scale 0.125 exactly; 48 for 768-wide / 16-head layers
+            d = {"kv": bf(a.key.weight, a.value.weight), "o": bf(a.out.weight), "nh": a.num_heads, "hd": hd,
+                 "sc": 1.0 / math.sqrt(hd)}
             if fuse_q:
                 d["qkv"] = bf(a.query.weight, a.key.weight, a.value.weight)
             else:
@@ -342,7 +345,7 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
         Hc = a["o"].shape[0]
         q = ops.linear_fwd(y, a["q"])
         kv = ops.linear_fwd(enc, a["kv"])
-        ctx, _ = ops.attn_fwd(q, kv[:, :Hc], kv[:, Hc:], B, a["nh"], S, Skv, 0.125)
+        ctx, _ = ops.attn_fwd(q, kv[:, :Hc], kv[:, Hc:], B, a["nh"], S, Skv, a["sc"], head_dim=a["hd"])
         return ops.linear_fwd(ctx, a["o"], res=res)
 
     def _attention_block(self, h, enc_h, w, B, S, Skv):
@@ -360,7 +363,8 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
         m = lambda k: mod_all[:, w[k][0]:w[k][0] + w[k][1]]
         r1, y = ops.add_norm_mod(x, w["ln1"], eps, rms, residual=r, mod=m("mod1"), rows_per_sample=S)
         qkv = ops.linear_fwd(y, w["sa"]["qkv"])
-        ctx, _ = ops.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, w["sa"]["nh"], S, S, 0.125)
+        ctx, _ = ops.attn_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, w["sa"]["nh"], S, S, w["sa"]["sc"],
+                              head_dim=w["sa"]["hd"])
         a = ops.linear_fwd(ctx, w["sa"]["o"])
         r2, y = ops.add_norm_mod(a, w["ln2"], eps, rms, residual=r1, mod=m("mod2"), rows_per_sample=S)
         cc = self._cross_attn(y, enc, w["ca"], B, S, Skv)

@@ -73,7 +73,7 @@ def _attn_fwd(y, ctx_in, a, B, S, Skv, fused):
         kv = ops.linear_fwd(ctx_in, a["kv"])
         k, v = kv[:, :Hc], kv[:, Hc:]
         saved = (q, kv)
-    o, lse = ops.attn_fwd(q, k, v, B, a["nh"], S, Skv, 0.125)
+    o, lse = ops.attn_fwd(q, k, v, B, a["nh"], S, Skv, a["sc"], head_dim=a["hd"])
     return o, (saved, o, lse)
 
 
@@ -85,11 +85,12 @@ def _attn_bwd(do, y, ctx_in, a, ga, st, B, S, Skv, fused, d_ctx_acc=None):
         qkv = saved
         dqkv = torch.empty_like(qkv)
         ops.attn_bwd(qkv[:, :Hc], qkv[:, Hc:2 * Hc], qkv[:, 2 * Hc:], o, do, lse, dqkv[:, :Hc], dqkv[:, Hc:2 * Hc],
-                     dqkv[:, 2 * Hc:], B, a["nh"], S, Skv, 0.125)
+                     dqkv[:, 2 * Hc:], B, a["nh"], S, Skv, a["sc"], head_dim=a["hd"])
         return _lin_bwd(dqkv, y, a["qkv"], ga.of("qkv"))
     q, kv = saved
     dq, dkv = torch.empty_like(q), torch.empty_like(kv)
-    ops.attn_bwd(q, kv[:, :Hc], kv[:, Hc:], o, do, lse, dq, dkv[:, :Hc], dkv[:, Hc:], B, a["nh"], S, Skv, 0.125)
+    ops.attn_bwd(q, kv[:, :Hc], kv[:, Hc:], o, do, lse, dq, dkv[:, :Hc], dkv[:, Hc:], B, a["nh"], S, Skv, a["sc"],
+                 head_dim=a["hd"])
     ops.linear_wgrad(dkv, ctx_in, ga.of("kv"))
     ops.linear_dgrad_acc(dkv, a["kv"], d_ctx_acc)
     return _lin_bwd(dq, y, a["q"], ga.of("q"))

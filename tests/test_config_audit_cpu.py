@@ -17,9 +17,8 @@ from open_muse_b200 import MaskGitTransformer, MaskGiTUViT_v2
 HERE = os.path.dirname(os.path.abspath(__file__))
 CONFIGS = json.load(open(os.path.join(HERE, "golden", "configs.json")))
 CLASSES = {"MaskGitTransformer": MaskGitTransformer, "MaskGiTUViT_v2": MaskGiTUViT_v2}
-# the reference constructs these, this package refuses them: a v1 yaml (head_dim 48) handed to the OTHER class, which no
-# script does -- the U-ViT attention path is built for head_dim 64, the width of every U-ViT config
-REFUSED = {("imagenet.yaml", "MaskGiTUViT_v2"), ("imagenet_movq.yaml", "MaskGiTUViT_v2")}
+# combinations the reference constructs and this package refuses: none (head_dim 48 is accepted by both classes)
+REFUSED = set()
 
 
 def _construct(cls, kwargs):

@@ -113,7 +113,7 @@ def test_product_model_under_ddp_matches_mean_of_oracle_rank_gradients(tmp_path,
 
 
 def test_reference_arm_prints_only_on_rank0():
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="2", MUSE_B200_CPU_SAMPLE_BATCH="4")  # the launch contract, not the number
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(29700 + os.getpid() % 200), os.path.join(ROOT, "bench.py"), "--impl",
            "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"]

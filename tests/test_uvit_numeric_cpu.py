@@ -111,11 +111,11 @@ def test_uvit_generate2_intermediates_are_the_raw_samples_of_the_reference(golde
 
 def test_reference_smoke_script_scenario(monkeypatch):
     """The reference's only test, /root/reference/test.py:64-95: a 1-layer MaskGiTUViT (hidden 768, 384 block channels, 8192
-    codes, pooled + six micro conditions) in eval mode, output shape (2, 256, 8192).  Same constructor call here with TWO
-    head counts set explicitly -- block_num_heads = 6 and num_attention_heads = 12 instead of the class defaults 12 and 16 --
-    because the defaults give head_dim 384 / 12 = 32 and 768 / 16 = 48 at these widths and the U-ViT attention path is built
-    for head_dim 64, the width of every U-ViT training config: the unmodified script stops at that
-    NotImplementedError.  Beyond the shape, the logits are compared with the oracle on the same seeded weights."""
+    codes, pooled + six micro conditions) in eval mode, output shape (2, 256, 8192).  Same constructor call here with ONE
+    head count set explicitly -- block_num_heads = 6 instead of the class default 12 -- because the default gives head_dim
+    384 / 12 = 32 in the down / up blocks and the attention kernels are built for head_dim 64 and 48 (the transformer layer
+    runs at its default 768 / 16 = 48): the unmodified script stops at that NotImplementedError.  Beyond the shape, the logits
+    are compared with the oracle on the same seeded weights."""
     cpu_math_ops.install(monkeypatch, exact=True)
     from open_muse_b200 import MaskGiTUViT
 
@@ -126,7 +126,8 @@ def test_reference_smoke_script_scenario(monkeypatch):
     with pytest.raises(NotImplementedError):
         MaskGiTUViT(**kw)  # head_dim 32 in the down / up blocks
     torch.manual_seed(0)
-    model = MaskGiTUViT(**kw, block_num_heads=6, num_attention_heads=12).eval()
+    model = MaskGiTUViT(**kw, block_num_heads=6).eval()
+    assert model.config.num_attention_heads == 16  # class default: head_dim 48
     g = torch.Generator().manual_seed(1)
     input_ids = torch.randint(0, 8192, (2, 256), generator=g)
     enc = torch.randn(2, 4, 768, generator=g)
@@ -173,3 +174,32 @@ def test_uvit_operand_cache_follows_weight_updates(golden, monkeypatch):
         assert not torch.equal(edited, base) and torch.equal(edited, fresh(m.state_dict()))
         m.load_state_dict(g["state_dict"])
         assert torch.equal(m(*args), base)
+
+
+def test_uvit_head_dim_48_training_backward_matches_the_oracle(monkeypatch):
+    """head_dim 48 in the transformer layers and in the block attentions (96 / 2 and 48 / 1): the scale 1 / sqrt(48) and the
+    head width reach every attention call of the inference and training paths"""
+    cfg = dict(hidden_size=96, num_attention_heads=2, in_channels=48, block_out_channels=(48,), block_num_heads=1,
+               num_res_blocks=1, num_hidden_layers=2, intermediate_size=128, vocab_size=72, codebook_size=64,
+               encoder_hidden_size=32, cond_embed_dim=16, micro_cond_encode_dim=8, micro_cond_embed_dim=40, norm_type="rmsnorm")
+    cpu_math_ops.install(monkeypatch, exact=True)
+    torch.manual_seed(3)
+    m = MaskGiTUViT_v2(**cfg)
+    with torch.no_grad():
+        for p in m.parameters():  # adaLN mappers and GRN parameters are zeros at init
+            p.add_((0.1 if p.dim() == 1 else 0.02) * torch.randn_like(p))
+    g = torch.Generator().manual_seed(4)
+    ids, lab = torch.randint(0, 64, (2, 16), generator=g), torch.randint(0, 64, (2, 16), generator=g)
+    enc, ce, mc = torch.randn(2, 5, 32, generator=g), torch.randn(2, 16, generator=g), torch.rand(2, 5, generator=g) * 100
+    q = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    ref_logits, ref_loss = V2.forward(q, dict(m.config), ids, enc, ce, mc, labels=lab, label_smoothing=0.1)
+    ref_loss.backward()
+    m.eval()
+    with torch.no_grad():
+        assert _rel(m(ids, enc, ce, mc), ref_logits) < 5e-5
+    m.train()
+    _, loss = m(ids, enc, ce, mc, labels=lab, label_smoothing=0.1)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref_loss)) < 1e-5 * float(ref_loss)
+    for n, p in m.named_parameters():
+        assert _rel(p.grad, q[n].grad) < 5e-4, (n, _rel(p.grad, q[n].grad))

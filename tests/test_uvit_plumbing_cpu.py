@@ -50,7 +50,7 @@ def _fake_ops(mp):
         assert dy.dtype == F32 and mod.shape == dmod.shape == (B, 2 * x.shape[1])
         return torch.zeros_like(x)
 
-    def attb(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, sc):
+    def attb(q, k, v, o, do, lse, dq, dk, dv, B, nh, Sq, Skv, sc, head_dim=64):
         assert do.dtype == BF and do.shape == o.shape and dq.shape == q.shape and dk.shape == k.shape
 
     fakes = dict(
@@ -61,7 +61,7 @@ def _fake_ops(mp):
         dwconv3x3_norm=lambda x, wk, nw, B, hh, ww, eps, rms, save_conv=False: (torch.zeros(x.shape, dtype=BF), torch.zeros(x.shape, dtype=BF)),
         dwconv3x3_norm_bwd=dwb, grn=lambda x, g, b, B, HW, save_stats=False: (torch.zeros_like(x), torch.zeros(2, B, x.shape[1])),
         grn_bwd=grnb, adaln_apply=lambda x, mod, B, rps: x.clone(), adaln_bwd=adb,
-        attn_fwd=lambda q, k, v, B, nh, Sq, Skv, sc: (torch.zeros(q.shape[0], nh * 64, dtype=BF), torch.zeros(B, nh, Sq)),
+        attn_fwd=lambda q, k, v, B, nh, Sq, Skv, sc, head_dim=64: (torch.zeros(q.shape[0], nh * head_dim, dtype=BF), torch.zeros(B, nh, Sq)),
         attn_bwd=attb, glu_fwd=lambda ab: torch.zeros(ab.shape[0], ab.shape[1] // 2, dtype=BF), glu_bwd=lambda ab, d: torch.zeros_like(ab),
         ce_fwd=lambda lg, lab, V, ls: (torch.zeros(2), torch.zeros(2, lg.shape[0])),
         ce_bwd=lambda lg, lab, ws, dl, out, V, ls, row_scale=None: torch.zeros_like(lg))
