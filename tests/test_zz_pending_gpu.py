@@ -77,3 +77,36 @@ def test_reference_train_muse_script_trains_on_gpu(tmp_path, monkeypatch):
     assert abs(losses[0] - math.log(64)) < 0.6 and losses[-1] < losses[0]
     cks = sorted(d for d in os.listdir(out) if d.startswith("checkpoint"))
     assert len(cks) == 1 and json.load(open(os.path.join(out, cks[0], "metadata.json")))["global_step"] == steps
+
+
+@pytest.mark.xfail(strict=False, reason="MaskGiTUViT_v2 at head_dim 48: first GPU run pending (CPU twin: tests/test_uvit_numeric_cpu.py)")
+def test_uvit_head_dim_48_vs_oracle():
+    """MaskGiTUViT_v2 with head_dim 48 in the transformer layers and the block attentions (96 / 2, 48 / 1) against the oracle's
+    fp32 forward / autograd: the attention kernels are validated at head_dim 48 through MaskGitTransformer, this composition
+    (the U-ViT passing head width and 1 / sqrt(48)) has only run on the CPU restatements."""
+    from open_muse_b200 import MaskGiTUViT_v2
+    from oracle import transformer_v2_oracle as V2
+
+    cfg = dict(hidden_size=96, num_attention_heads=2, in_channels=48, block_out_channels=(48,), block_num_heads=1,
+               num_res_blocks=1, num_hidden_layers=2, intermediate_size=128, vocab_size=72, codebook_size=64,
+               encoder_hidden_size=32, cond_embed_dim=16, micro_cond_encode_dim=8, micro_cond_embed_dim=40, norm_type="rmsnorm")
+    torch.manual_seed(3)
+    m = MaskGiTUViT_v2(**cfg)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_((0.1 if p.dim() == 1 else 0.02) * torch.randn_like(p))
+    g = torch.Generator().manual_seed(4)
+    ids, lab = torch.randint(0, 64, (2, 16), generator=g), torch.randint(0, 64, (2, 16), generator=g)
+    enc, ce, mc = torch.randn(2, 5, 32, generator=g), torch.randn(2, 16, generator=g), torch.rand(2, 5, generator=g) * 100
+    q = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    ref_logits, ref_loss = V2.forward(q, dict(m.config), ids, enc, ce, mc, labels=lab, label_smoothing=0.1)
+    ref_loss.backward()
+    m.to(DEV).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, loss = m(ids.to(DEV), enc.to(DEV), ce.to(DEV), mc.to(DEV), labels=lab.to(DEV), label_smoothing=0.1)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert _rel(logits, ref_logits) < 2e-2 and abs(float(loss) - float(ref_loss)) < 2e-3 * float(ref_loss)
+    bad = {n: _rel(p.grad, q[n].grad) for n, p in m.named_parameters()
+           if _rel(p.grad, q[n].grad) > 8e-2 and not (".query." in n or ".key." in n)}
+    assert not bad, bad
