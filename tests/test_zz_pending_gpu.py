@@ -2,7 +2,8 @@
 
   * ``use_conv_in_out=True`` (ConvEmbed / ConvMlmLayer, reference muse/modeling_transformer.py:988-1080) against the unmodified
     reference's fp32 outputs in tests/golden/micro_conv_transformer.pt;
-  * the UNMODIFIED training/train_muse.py through the real kernels.
+  * the UNMODIFIED training/train_muse.py through the real kernels;
+  * MaskGiTUViT_v2 at head_dim 48 (the attention kernels are validated at that width through MaskGitTransformer).
 
 Their host side is checked numerically on the CPU (tests/test_v1_numeric_cpu.py::test_conv_in_out_*: logits 1e-7, every
 gradient < 2e-4 of the reference; tests/test_train_muse_script_cpu.py: the script trains on the kernels' torch restatements)
