@@ -147,3 +147,50 @@ def test_reference_training_script_trains_on_the_numeric_restatements(monkeypatc
     assert abs(losses[0] - math.log(64 if soft_targets else 75)) < 0.5 and losses[-1] < losses[0], losses
     ev = [v["eval_loss"] for v, s in acc.logged if "eval_loss" in v]
     assert ev and math.isfinite(ev[-1])
+
+
+def test_reference_offline_ema_script_runs_unchanged(monkeypatch, tmp_path):
+    """scripts/compute_offline_ema.py of the reference (load_config / from_pretrained over the checkpoint-N/unwrapped_model
+    directories a training run leaves behind, EMAModel.step / copy_to, save_pretrained), unmodified, against the drop-in
+    package -- on the checkpoints written by the unmodified training script above.  Host-side only (no kernel is involved)."""
+    import runpy
+    import sys
+
+    script = os.path.join(os.path.dirname(os.path.dirname(SCRIPT)), "scripts", "compute_offline_ema.py")
+    if not os.path.exists(script):
+        pytest.skip("reference scripts/ not available (only muse/ and training/ are snapshotted to the GPU box)")
+    _fake_ops(monkeypatch)
+    _fake_tokenizer(monkeypatch)
+    monkeypatch.setenv("ACCELERATE_USE_CPU", "1")
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    cfg, out = make_config(str(tmp_path), steps=4, batch=2, mixed_precision="no", save_every=2)
+    run_script(SCRIPT, cfg)
+    assert {"checkpoint-2", "checkpoint-4"} <= set(os.listdir(out))
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "open_muse_b200", "compat")
+    ema_dir = str(tmp_path / "ema")
+    saved_argv, saved_path = list(sys.argv), list(sys.path)
+    for k in [k for k in sys.modules if k == "muse" or k.startswith("muse.")]:
+        del sys.modules[k]
+    sys.path.insert(0, compat)
+    sys.argv = [script, "--checkpoint_dir_path", out, "--ema_save_path", ema_dir, "--ema_decay", "0.5",
+                "--checkpoint_interval", "2"]
+    try:
+        runpy.run_path(script, run_name="__main__")
+    finally:
+        sys.argv[:], sys.path[:] = saved_argv, saved_path
+        for k in [k for k in sys.modules if k == "muse" or k.startswith("muse.")]:
+            del sys.modules[k]
+    from open_muse_b200 import EMAModel, MaskGitTransformer
+
+    got = MaskGitTransformer.from_pretrained(ema_dir).state_dict()
+    # the same schedule by hand: shadow = checkpoint-2 weights; steps 1..4, an update on every second one, with the model
+    # swapped to checkpoint-2 at step 2 and checkpoint-4 at step 4
+    m = MaskGitTransformer.from_pretrained(os.path.join(out, "checkpoint-2", "unwrapped_model"))
+    ema = EMAModel(parameters=m.parameters(), decay=0.5, update_every=2)
+    for step in range(4):
+        if (step + 1) % 2 == 0:
+            m = MaskGitTransformer.from_pretrained(os.path.join(out, f"checkpoint-{step + 1}", "unwrapped_model"))
+        ema.step(m.parameters())
+    ema.copy_to(m.parameters())
+    for k, v in m.state_dict().items():
+        assert torch.equal(got[k], v), k
