@@ -194,3 +194,30 @@ def test_reference_offline_ema_script_runs_unchanged(monkeypatch, tmp_path):
     ema.copy_to(m.parameters())
     for k, v in m.state_dict().items():
         assert torch.equal(got[k], v), k
+
+
+def test_reference_training_script_resumes_from_its_checkpoint(monkeypatch, tmp_path):
+    """Checkpoint / resume of the unmodified script (train_maskgit_imagenet.py:329-355): a 4-step run that saved at step 2
+    is resumed with ``experiment.resume_from_checkpoint=latest`` for two more steps -- model weights, AdamW moments and the
+    LR schedule come back from checkpoint-2 (the step counter from the directory name), and the run ends with the same
+    checkpoint layout, AdamW's own step counter continuing at 3.  Runs on the numeric kernel restatements."""
+    from tests import cpu_math_ops
+
+    cpu_math_ops.install(monkeypatch, exact=False)
+    monkeypatch.setenv("ACCELERATE_USE_CPU", "1")
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    # run A: 2 steps, checkpoint at 2
+    cfg, out = make_config(str(tmp_path), steps=2, batch=3, mixed_precision="no", save_every=2)
+    acc = run_script(SCRIPT, cfg)
+    assert [s for v, s in acc.logged if "step_loss" in v] == [1, 2]
+    sd2 = torch.load(os.path.join(out, "checkpoint-2", "unwrapped_model", "pytorch_model.bin"))
+    # run B: same config, resume, train to step 4
+    acc = run_script(SCRIPT, cfg, extra_cli=("experiment.resume_from_checkpoint=latest", "training.max_train_steps=4"))
+    steps = [s for v, s in acc.logged if "step_loss" in v]
+    assert steps == [3, 4], steps
+    assert json.load(open(os.path.join(out, "checkpoint-4", "metadata.json"))) == {"global_step": 4}
+    sd4 = torch.load(os.path.join(out, "checkpoint-4", "unwrapped_model", "pytorch_model.bin"))
+    w = "transformer_layers.0.ffn.wi_0.weight"
+    assert not torch.equal(sd2[w], sd4[w])
+    opt = torch.load(os.path.join(out, "checkpoint-4", "optimizer.bin"))
+    assert int(next(iter(opt["state"].values()))["step"]) == 4  # AdamW's own step counter continued from the loaded state
