@@ -38,6 +38,23 @@ class Config(dict):
         for k, v in self.items():
             object.__setattr__(self, k, v)
 
+    # the reference's FrozenDict (:770-801) refuses structural edits; item / attribute assignment stays possible there (its
+    # frozen flag is never seen through the name mangling), and so it does here
+    def _refuse(self, what):
+        raise Exception(f"You cannot use ``{what}`` on a {self.__class__.__name__} instance.")
+
+    def __delitem__(self, *args, **kwargs):
+        self._refuse("__delitem__")
+
+    def setdefault(self, *args, **kwargs):
+        self._refuse("setdefault")
+
+    def pop(self, *args, **kwargs):
+        self._refuse("pop")
+
+    def update(self, *args, **kwargs):
+        self._refuse("update")
+
 
 class ConfigMixin:
     config_name = CONFIG_NAME
@@ -69,6 +86,11 @@ class ConfigMixin:
             return v
 
         return json.dumps({k: enc(v) for k, v in d.items()}, indent=2, sort_keys=True) + "\n"
+
+    def to_json_file(self, json_file_path):
+        """reference :1116-1125"""
+        with open(json_file_path, "w", encoding="utf-8") as writer:
+            writer.write(self.to_json_string())
 
     def save_config(self, save_directory, **kwargs):
         if os.path.isfile(save_directory):
@@ -154,6 +176,9 @@ class ModelMixin(nn.Module):
     def disable_gradient_checkpointing(self):
         if self._supports_gradient_checkpointing:
             self.gradient_checkpointing = False
+
+    def set_use_memory_efficient_attention_xformers(self, valid: bool, attention_op=None) -> None:
+        """No-op (reference :276-291 forwards the switch to every child that exposes it)."""
 
     def enable_xformers_memory_efficient_attention(self, attention_op=None):
         """No-op: attention is always the fused on-chip kernel here (reference :276-329 toggles xformers)."""

@@ -232,3 +232,26 @@ def test_ema_model_matches_reference_bit_for_bit(tmp_path):
     assert back.optimization_step == 3 and back.decay == 0.5
     for a, b in zip(back.shadow_params, ema.shadow_params):
         assert torch.equal(a, b)
+
+
+def test_config_object_behaves_like_the_reference_frozen_dict(tmp_path):
+    """FrozenDict of the reference (muse/modeling_utils.py:770-801): pop / update / setdefault / del raise, attribute and item
+    assignment do not (its frozen flag is never seen through the name mangling); to_json_file and the xformers setters exist."""
+    import json
+
+    from open_muse_b200 import MaskGitTransformer
+
+    with torch.device("meta"):
+        m = MaskGitTransformer(vocab_size=72, hidden_size=64, num_attention_heads=1, num_hidden_layers=1, intermediate_size=128)
+    c = m.config
+    for bad in (lambda: c.pop("vocab_size"), lambda: c.update(a=1), lambda: c.setdefault("a", 1), lambda: c.__delitem__("vocab_size")):
+        with pytest.raises(Exception, match="You cannot use"):
+            bad()
+    c.some_note = 3
+    c["other"] = 4
+    assert c.some_note == 3 and c["other"] == 4 and c.vocab_size == c["vocab_size"] == 72
+    m.to_json_file(tmp_path / "c.json")
+    assert json.load(open(tmp_path / "c.json"))["_class_name"] == "MaskGitTransformer"
+    m.set_use_memory_efficient_attention_xformers(True)
+    m.enable_xformers_memory_efficient_attention()
+    m.disable_xformers_memory_efficient_attention()
