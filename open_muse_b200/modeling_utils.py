@@ -59,6 +59,7 @@ class Config(dict):
 class ConfigMixin:
     config_name = CONFIG_NAME
     ignore_for_config: list = []
+    has_compatibles = False
 
     def register_to_config(self, **kwargs):
         kwargs.pop("kwargs", None)

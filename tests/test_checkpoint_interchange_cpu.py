@@ -111,3 +111,48 @@ def test_checkpoints_are_interchangeable_with_the_unmodified_reference(tmp_path,
             got = loaded.decode_code(loaded.get_code(inp["image"]))
     assert got.shape == want.shape
     assert float((got.float() - want).norm() / want.norm()) < (5e-5 if "VQ" not in kind else 1e-3)
+
+
+SURFACE_SIDE = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+from oracle.ref_snapshot import import_reference
+ref = import_reference()
+from muse.modeling_transformer_v2 import MaskGiTUViT_v2 as RefV2
+import open_muse_b200 as ours
+base = set(dir(torch.nn.Module))
+V1 = dict(vocab_size=72, hidden_size=64, num_hidden_layers=1, num_attention_heads=1, intermediate_size=128, add_cross_attention=True,
+          encoder_hidden_size=32, project_encoder_hidden_states=True)
+V2 = dict(hidden_size=128, num_attention_heads=2, in_channels=64, block_out_channels=(64,), block_num_heads=1, num_res_blocks=1,
+          num_hidden_layers=1, intermediate_size=128, vocab_size=72, codebook_size=64, encoder_hidden_size=32, cond_embed_dim=16,
+          micro_cond_encode_dim=8, micro_cond_embed_dim=40)
+VQ = dict(resolution=32, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=1, z_channels=16, num_embeddings=64,
+          quantized_embed_dim=16)
+bad = []
+for name, r, o, kw in (("MaskGitTransformer", ref.MaskGitTransformer, ours.MaskGitTransformer, V1), ("MaskGiTUViT_v2", RefV2, ours.MaskGiTUViT_v2, V2),
+                       ("MaskGitVQGAN", ref.MaskGitVQGAN, ours.MaskGitVQGAN, VQ), ("VQGANModel", ref.VQGANModel, ours.VQGANModel, VQ),
+                       ("EMAModel", ref.EMAModel, ours.EMAModel, None), ("PipelineMuse", ref.PipelineMuse, ours.PipelineMuse, None),
+                       ("PipelineMuseInpainting", ref.PipelineMuseInpainting, ours.PipelineMuseInpainting, None)):
+    missing = ({a for a in dir(r) if not a.startswith("_")} - base) - {a for a in dir(o) if not a.startswith("_")}
+    if missing:
+        bad.append((name, "class attributes", sorted(missing)))
+    if kw is None:
+        continue
+    with torch.device("meta"):
+        a, b = r(**kw), o(**kw)
+    missing = {k for k in vars(a) if not k.startswith("_")} - {k for k in vars(b) if not k.startswith("_")}
+    if missing:
+        bad.append((name, "instance attributes", sorted(missing)))
+    if list(a.config.keys()) != list(b.config.keys()):
+        bad.append((name, "config keys", sorted(set(a.config.keys()) ^ set(b.config.keys()))))
+    if [n for n, _ in a.named_modules()] != [n for n, _ in b.named_modules()]:
+        bad.append((name, "module tree", "differs"))
+print("BAD", bad) if bad else print("OK")
+'''
+
+
+def test_public_surface_of_every_class_covers_the_reference():
+    """every public class attribute / method, every public instance attribute, the config keys in order and the module tree
+    (names, order) of the reference classes exist on the drop-in classes (reference imported in a subprocess)"""
+    r = subprocess.run([sys.executable, "-c", SURFACE_SIDE, ROOT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-2000:], r.stderr[-2000:])
