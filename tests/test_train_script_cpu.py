@@ -122,6 +122,27 @@ def test_lr_schedulers_match_reference():
                 opt.step(); sch.step(); seq.append(sch.get_last_lr()[0])
             lrs.append(seq)
         assert lrs[0] == pytest.approx(lrs[1], rel=1e-12, abs=1e-15), name
+    import muse.lr_schedulers as mine
+
+    # the named constructors and the enum of the reference module, with non-default arguments
+    cases = [("get_cosine_schedule_with_warmup", dict(num_warmup_steps=2, num_training_steps=10, num_cycles=1.5)),
+             ("get_cosine_schedule_with_warmup", dict(num_warmup_steps=2, num_training_steps=10, num_cycles=1)),
+             ("get_cosine_with_hard_restarts_schedule_with_warmup", dict(num_warmup_steps=2, num_training_steps=10, num_cycles=3)),
+             ("get_polynomial_decay_schedule_with_warmup", dict(num_warmup_steps=2, num_training_steps=10, lr_end=1e-3, power=2.0)),
+             ("get_linear_schedule_with_warmup", dict(num_warmup_steps=2, num_training_steps=10)),
+             ("get_constant_schedule_with_warmup", dict(num_warmup_steps=2)), ("get_constant_schedule", {})]
+    for fn, kw in cases:
+        seqs = []
+        for mod in (ref, mine):
+            opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.5)
+            sch = getattr(mod, fn)(opt, **kw)
+            seq = []
+            for _ in range(12):
+                opt.step(); sch.step(); seq.append(sch.get_last_lr()[0])
+            seqs.append(seq)
+        assert seqs[0] == pytest.approx(seqs[1], rel=1e-12, abs=1e-15), fn
+    assert [e.value for e in mine.SchedulerType] == [e.value for e in ref.SchedulerType]
+    assert set(mine.TYPE_TO_SCHEDULER_FUNCTION) == set(mine.SchedulerType)
     for k in [k for k in sys.modules if k.startswith("_ref_muse")]:
         del sys.modules[k]
 
