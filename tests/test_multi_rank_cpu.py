@@ -112,6 +112,52 @@ def test_product_model_under_ddp_matches_mean_of_oracle_rank_gradients(tmp_path,
         torch.testing.assert_close(got["grads"][k], expect, rtol=2e-4, atol=1e-7)
 
 
+def _uvit_worker(rank, world, port, g, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from open_muse_b200 import MaskGiTUViT_v2
+    from tests import cpu_math_ops
+
+    real_bf16 = torch.bfloat16
+    cpu_math_ops.install(cpu_math_ops.PlainSetter, exact=True)
+    m = MaskGiTUViT_v2(**g["config"])
+    m.load_state_dict(g["state_dict"])
+    m.train()
+    model = torch.nn.parallel.DistributedDataParallel(m)
+    sl = slice(0, 2) if rank == 0 else slice(2, 3)  # uneven per-rank batches
+    _, loss = model(g["input_ids"][sl], g["encoder_hidden_states"][sl], g["cond_embeds"][sl], g["micro_conds"][sl],
+                    labels=g["labels"][sl], label_smoothing=0.1)
+    loss.backward()
+    torch.bfloat16 = real_bf16
+    if rank == 0:
+        torch.save({n: p.grad.clone() for n, p in m.named_parameters()}, out)
+    dist.destroy_process_group()
+
+
+def test_uvit_product_model_under_ddp_matches_mean_of_oracle_rank_gradients(tmp_path, golden):
+    """MaskGiTUViT_v2's per-block autograd Functions (text states and the conditioning vector enter every block as shared
+    inputs whose gradients autograd sums; each block hands its parameter gradients back as soon as it has run) under torch
+    DDP, gloo world 2, uneven per-rank batches: all-reduced gradients == equal-weight mean of the oracle's per-rank ones."""
+    from oracle import transformer_v2_oracle as V2
+
+    g = golden("micro_uvit_v2.pt")
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_uvit_worker, args=(2, 33500 + os.getpid() % 2000, g, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    per_rank = []
+    for sl in (slice(0, 2), slice(2, 3)):
+        q = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+        _, loss = V2.forward(q, g["config"], g["input_ids"][sl], g["encoder_hidden_states"][sl], g["cond_embeds"][sl],
+                             g["micro_conds"][sl], labels=g["labels"][sl], label_smoothing=0.1)
+        loss.backward()
+        per_rank.append({k: v.grad for k, v in q.items()})
+    for k in got:
+        expect = 0.5 * (per_rank[0][k] + per_rank[1][k])
+        assert float((got[k] - expect).norm() / expect.norm().clamp_min(1e-20)) < 1e-4, k
+
+
 def test_reference_arm_prints_only_on_rank0():
     env = dict(os.environ, OMP_NUM_THREADS="2", MUSE_B200_CPU_SAMPLE_BATCH="4")  # the launch contract, not the number
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
