@@ -32,32 +32,34 @@ sys.path.insert(0, sys.argv[1])
 from oracle.ref_snapshot import import_reference
 muse = import_reference()
 from muse.modeling_transformer_v2 import MaskGiTUViT_v2
-cls = {"MaskGitTransformer": muse.MaskGitTransformer, "MaskGiTUViT_v2": MaskGiTUViT_v2, "MaskGitVQGAN": muse.MaskGitVQGAN,
-       "VQGANModel": muse.VQGANModel}[sys.argv[2]]
-dir_a, dir_b = sys.argv[3], sys.argv[4]
-inputs = torch.load(sys.argv[5])
-# (1) what this package saved loads into the unmodified reference class
-m = cls.from_pretrained(dir_a, low_cpu_mem_usage=False)
-saved = torch.load(dir_a + "/pytorch_model.bin")
-sd = m.state_dict()
-assert list(sd) == list(saved), (set(sd) ^ set(saved))
-assert all(torch.equal(sd[k], saved[k]) for k in sd)
-# (2) a differently seeded reference model, saved by the reference, with its own forward output
-torch.manual_seed(1234)
-r = cls(**json.load(open(sys.argv[6])))
-with torch.no_grad():
-    for p in r.parameters():  # every tensor non-trivial (norm weights are ones, adaLN mappers and GRN parameters zeros at init)
-        p.add_((0.1 if p.dim() == 1 else 0.02) * torch.randn_like(p))
-r.eval()
-r.save_pretrained(dir_b)
-with torch.no_grad():
-    if sys.argv[2] == "MaskGitTransformer":
-        out = r(inputs["input_ids"])
-    elif sys.argv[2] == "MaskGiTUViT_v2":
-        out = r(inputs["input_ids"], inputs["enc"], inputs["cond"], inputs["micro"])
-    else:
-        out = r.decode_code(r.get_code(inputs["image"]))
-torch.save(out, dir_b + "/reference_output.pt")
+classes = {"MaskGitTransformer": muse.MaskGitTransformer, "MaskGiTUViT_v2": MaskGiTUViT_v2, "MaskGitVQGAN": muse.MaskGitVQGAN,
+           "VQGANModel": muse.VQGANModel}
+for kind, base in json.load(open(sys.argv[2])):  # one job per model class: <base>/{ours, theirs, inputs.pt, cfg.json}
+    cls = classes[kind]
+    dir_a, dir_b = base + "/ours", base + "/theirs"
+    inputs = torch.load(base + "/inputs.pt")
+    # (1) what this package saved loads into the unmodified reference class
+    m = cls.from_pretrained(dir_a, low_cpu_mem_usage=False)
+    saved = torch.load(dir_a + "/pytorch_model.bin")
+    sd = m.state_dict()
+    assert list(sd) == list(saved), (kind, set(sd) ^ set(saved))
+    assert all(torch.equal(sd[k], saved[k]) for k in sd), kind
+    # (2) a differently seeded reference model, saved by the reference, with its own forward output
+    torch.manual_seed(1234)
+    r = cls(**json.load(open(base + "/cfg.json")))
+    with torch.no_grad():
+        for p in r.parameters():  # every tensor non-trivial (norm weights are ones, adaLN mappers and GRN parameters zeros at init)
+            p.add_((0.1 if p.dim() == 1 else 0.02) * torch.randn_like(p))
+    r.eval()
+    r.save_pretrained(dir_b)
+    with torch.no_grad():
+        if kind == "MaskGitTransformer":
+            out = r(inputs["input_ids"])
+        elif kind == "MaskGiTUViT_v2":
+            out = r(inputs["input_ids"], inputs["enc"], inputs["cond"], inputs["micro"])
+        else:
+            out = r.decode_code(r.get_code(inputs["image"]))
+    torch.save(out, dir_b + "/reference_output.pt")
 print("OK")
 '''
 
@@ -72,23 +74,40 @@ def _inputs(kind):
     return dict(image=torch.rand(2, 3, 32, 32, generator=g))
 
 
-@pytest.mark.parametrize("kind,cfg", [("MaskGitTransformer", V1), ("MaskGiTUViT_v2", V2), ("MaskGitVQGAN", VQ), ("VQGANModel", TVQ)])
-def test_checkpoints_are_interchangeable_with_the_unmodified_reference(tmp_path, monkeypatch, kind, cfg):
+KINDS = [("MaskGitTransformer", V1), ("MaskGiTUViT_v2", V2), ("MaskGitVQGAN", VQ), ("VQGANModel", TVQ)]
+
+
+@pytest.fixture(scope="module")
+def exchanged(tmp_path_factory):
+    """this package saves one model per class, ONE reference subprocess loads them all and saves its own"""
+    import open_muse_b200 as ours
+
+    root = tmp_path_factory.mktemp("interchange")
+    jobs = []
+    for kind, cfg in KINDS:
+        base = str(root / kind)
+        os.makedirs(base)
+        torch.manual_seed(99)
+        getattr(ours, kind)(**cfg).save_pretrained(os.path.join(base, "ours"))
+        torch.save(_inputs(kind), os.path.join(base, "inputs.pt"))
+        with open(os.path.join(base, "cfg.json"), "w") as f:
+            json.dump(cfg, f)
+        jobs.append((kind, base))
+    with open(root / "jobs.json", "w") as f:
+        json.dump(jobs, f)
+    r = subprocess.run([sys.executable, "-c", REF_SIDE, ROOT, str(root / "jobs.json")], capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stderr[-3000:]
+    return dict(jobs)
+
+
+@pytest.mark.parametrize("kind,cfg", KINDS)
+def test_checkpoints_are_interchangeable_with_the_unmodified_reference(exchanged, monkeypatch, kind, cfg):
     import open_muse_b200 as ours
 
     cls = getattr(ours, kind)
-    torch.manual_seed(99)
-    m = cls(**cfg)
-    dir_a, dir_b = str(tmp_path / "ours"), str(tmp_path / "theirs")
-    m.save_pretrained(dir_a)
+    dir_b = os.path.join(exchanged[kind], "theirs")
     inp = _inputs(kind)
-    torch.save(inp, str(tmp_path / "inputs.pt"))
-    with open(tmp_path / "cfg.json", "w") as f:
-        json.dump(cfg, f)
-    r = subprocess.run([sys.executable, "-c", REF_SIDE, ROOT, kind, dir_a, dir_b, str(tmp_path / "inputs.pt"),
-                        str(tmp_path / "cfg.json")], capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, OMP_NUM_THREADS="4"))
-    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stderr[-3000:]
     # (3) what the reference saved loads here: same keys / shapes / values, same config
     theirs = torch.load(os.path.join(dir_b, "pytorch_model.bin"))
     cpu_math_ops.install(monkeypatch, exact=True)
