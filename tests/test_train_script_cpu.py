@@ -242,3 +242,39 @@ def test_reference_training_script_resumes_from_its_checkpoint(monkeypatch, tmp_
     assert not torch.equal(sd2[w], sd4[w])
     opt = torch.load(os.path.join(out, "checkpoint-4", "optimizer.bin"))
     assert int(next(iter(opt["state"].values()))["step"]) == 4  # AdamW's own step counter continued from the loaded state
+
+
+def test_reference_benchmark_models_script_runs_unchanged(monkeypatch, tmp_path, capsys):
+    """scripts/benchmark_models.py of the reference, unmodified (load_config / from_config, text-conditional generate2 in
+    fp32, after ``model.half()`` and after enable_xformers_memory_efficient_attention(), timed with torch.utils.benchmark),
+    against the drop-in package on the numeric kernel restatements: the calls it makes exist and run end to end."""
+    import runpy
+    import sys
+
+    script = os.path.join(os.path.dirname(os.path.dirname(SCRIPT)), "scripts", "benchmark_models.py")
+    if not os.path.exists(script):
+        pytest.skip("reference scripts/ not available")
+    from open_muse_b200 import MaskGitTransformer
+    from tests import cpu_math_ops
+
+    cpu_math_ops.install(monkeypatch, exact=False)
+    monkeypatch.setattr(MaskGitTransformer, "device", property(lambda self: torch.device("cpu")), raising=False)
+    monkeypatch.setenv("MUSE_B200_GENERATE_GRAPH", "0")
+    cfg_dir = str(tmp_path / "cfg")
+    MaskGitTransformer(vocab_size=72, hidden_size=64, num_hidden_layers=1, num_attention_heads=1, intermediate_size=128,
+                       hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=16, codebook_size=64, num_vq_tokens=16,
+                       add_cross_attention=True, encoder_hidden_size=32, use_codebook_size_for_output=True).save_config(cfg_dir)
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "open_muse_b200", "compat")
+    saved_argv, saved_path = list(sys.argv), list(sys.path)
+    for k in [k for k in sys.modules if k == "muse" or k.startswith("muse.")]:
+        del sys.modules[k]
+    sys.path.insert(0, compat)
+    sys.argv = [script, "--config_path", cfg_dir, "--batch_size", "2", "--text_length", "5", "--time_steps", "2", "--device", "cpu"]
+    try:
+        runpy.run_path(script, run_name="__main__")
+    finally:
+        sys.argv[:], sys.path[:] = saved_argv, saved_path
+        for k in [k for k in sys.modules if k == "muse" or k.startswith("muse.")]:
+            del sys.modules[k]
+    out = capsys.readouterr().out
+    assert "Vanilla attention in FP32" in out and "Efficient attention in FP16" in out
