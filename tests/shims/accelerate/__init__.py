@@ -45,6 +45,40 @@ class _AutocastForward(torch.nn.Module):
             return getattr(self.module, name)
 
 
+class _AcceleratedOptimizer:
+    """accelerate's optimizer wrapper: ``step`` / ``zero_grad`` only act on the micro-step that closes an accumulation
+    window (``accelerator.sync_gradients``); everything else is the wrapped optimizer."""
+
+    def __init__(self, optimizer, accelerator):
+        self.__dict__["optimizer"], self.__dict__["_acc"] = optimizer, accelerator
+
+    def step(self, *a, **k):
+        if self._acc.sync_gradients:
+            return self.optimizer.step(*a, **k)
+
+    def zero_grad(self, *a, **k):
+        if self._acc.sync_gradients:
+            return self.optimizer.zero_grad(*a, **k)
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["optimizer"], name)
+
+    def __setattr__(self, name, value):
+        setattr(self.__dict__["optimizer"], name, value)
+
+
+class _AcceleratedScheduler:
+    def __init__(self, scheduler, accelerator):
+        self.__dict__["scheduler"], self.__dict__["_acc"] = scheduler, accelerator
+
+    def step(self, *a, **k):
+        if self._acc.sync_gradients:
+            return self.scheduler.step(*a, **k)
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["scheduler"], name)
+
+
 class Accelerator:
     last = None  # the most recently constructed instance (tests inspect what the script logged)
 
@@ -103,8 +137,10 @@ class Accelerator:
                 self._models.append(o)
             elif isinstance(o, torch.optim.Optimizer):
                 self._optimizers.append(o)
+                o = _AcceleratedOptimizer(o, self)
             elif hasattr(o, "get_last_lr"):
                 self._schedulers.append(o)
+                o = _AcceleratedScheduler(o, self)
             out.append(o)
         return out[0] if len(out) == 1 else tuple(out)
 

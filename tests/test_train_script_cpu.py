@@ -278,3 +278,22 @@ def test_reference_benchmark_models_script_runs_unchanged(monkeypatch, tmp_path,
             del sys.modules[k]
     out = capsys.readouterr().out
     assert "Vanilla attention in FP32" in out and "Efficient attention in FP16" in out
+
+
+def test_reference_training_script_with_gradient_accumulation(monkeypatch, tmp_path):
+    """training.gradient_accumulation_steps = 2: the script's ``accelerator.accumulate(model)`` windows -- gradients of two
+    micro-batches add up in the parameters' .grad (each per-layer Function hands its gradients to autograd's accumulation) and
+    the optimizer / scheduler act once per window."""
+    import math
+
+    from tests import cpu_math_ops
+
+    cpu_math_ops.install(monkeypatch, exact=False)
+    monkeypatch.setenv("ACCELERATE_USE_CPU", "1")
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    cfg, out = make_config(str(tmp_path), steps=3, batch=2, mixed_precision="no", save_every=3)
+    acc = run_script(SCRIPT, cfg, extra_cli=("training.gradient_accumulation_steps=2",))
+    losses = [v["step_loss"] for v, s in acc.logged if "step_loss" in v]
+    assert [s for v, s in acc.logged if "step_loss" in v] == [1, 2, 3] and all(math.isfinite(x) for x in losses)
+    opt = torch.load(os.path.join(out, "checkpoint-3", "optimizer.bin"))
+    assert int(next(iter(opt["state"].values()))["step"]) == 3  # six micro-batches, three optimizer steps
