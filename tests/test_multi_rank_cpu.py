@@ -158,6 +158,36 @@ def test_uvit_product_model_under_ddp_matches_mean_of_oracle_rank_gradients(tmp_
         assert float((got[k] - expect).norm() / expect.norm().clamp_min(1e-20)) < 1e-4, k
 
 
+def test_reference_training_script_under_two_rank_ddp(tmp_path):
+    """The UNMODIFIED training/train_maskgit_imagenet.py on two ranks (gloo): the accelerate stand-in wraps the drop-in model
+    in torch DDP, the script's own multi-process plumbing runs -- loss gather for logging, main-process guards around
+    evaluation / checkpoint writing, wait_for_everyone, state-dict retrieval through the DDP wrapper -- and the ranks end with
+    identical weights (the all-reduced gradients of the product's per-layer Functions)."""
+    from tests.train_script_harness import find_script, make_config
+
+    script = find_script()
+    if script is None:
+        import pytest
+
+        pytest.skip("reference training script not available")
+    cfg, out = make_config(str(tmp_path), steps=3, batch=2, mixed_precision="no", save_every=3)
+    res = str(tmp_path / "res.json")
+    env = dict(os.environ, OMP_NUM_THREADS="2", ACCELERATE_USE_CPU="1", WANDB_MODE="disabled")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29900 + os.getpid() % 90), os.path.join(ROOT, "tests", "ddp_script_launcher.py"), script, cfg, res]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ranks = [json.load(open(f"{res}.rank{i}")) for i in range(2)]
+    assert [x["world"] for x in ranks] == [2, 2] and ranks[0]["is_main"] and not ranks[1]["is_main"]
+    steps0 = [s for v, s in ranks[0]["logged"] if "step_loss" in v]
+    assert steps0 == [1, 2, 3] and any("eval_loss" in v for v, _ in ranks[0]["logged"])
+    # the gathered loss is the same number on both ranks, the checkpoint was written once (by the main process)
+    l0 = [v["step_loss"] for v, s in ranks[0]["logged"] if "step_loss" in v]
+    l1 = [v["step_loss"] for v, s in ranks[1]["logged"] if "step_loss" in v]
+    assert l0 == l1
+    assert os.path.exists(os.path.join(out, "checkpoint-3", "unwrapped_model", "pytorch_model.bin"))
+
+
 def test_reference_arm_prints_only_on_rank0():
     env = dict(os.environ, OMP_NUM_THREADS="2", MUSE_B200_CPU_SAMPLE_BATCH="4")  # the launch contract, not the number
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
