@@ -4,7 +4,8 @@ Host-side Python only: it wires ``MaskGitTransformer.generate2`` (fused decode-s
 ``MaskGitVQGAN.decode_code`` (CUDA detokeniser) and converts to PIL.  Class-conditional generation and text
 conditioning with *precomputed* ``prompt_embeds`` run fully on the B200 path; raw ``text=`` needs a third-party
 text encoder / tokenizer object (CLIP / T5 from ``transformers``), which is outside this repository's scope and is
-used as-is when supplied.
+called as-is when attached -- for ``MaskGiTUViT_v2`` exactly as the reference pipeline calls it (penultimate-layer states,
+projected pooled embedding, encoded negative / empty prompt, ``clip_skip``).
 """
 from __future__ import annotations
 
@@ -49,6 +50,33 @@ class PipelineMuse:
                              max_length=self.tokenizer.model_max_length).input_ids.to(self.device)
         return self.text_encoder(ids).last_hidden_state
 
+    def _encode_text_uvit(self, text, negative_text, negative_prompt_embeds, negative_pooled_embeds, clip_skip=None):
+        """The text side of the reference pipeline for models with pooled conditioning (muse/pipeline_muse.py:113-197): the
+        attached (third-party) CLIP encoder is called as is -- penultimate-layer states (``clip_skip`` picks another layer) and
+        the projected pooled embedding for the prompt, layer -2 for the negative prompt, and the encoded empty prompt when
+        there is no negative one.  Returns (states, pooled, negative states, negative pooled, (empty states, empty pooled))."""
+        if self.text_encoder is None or self.tokenizer is None:
+            raise ValueError("MaskGiTUViT_v2 needs prompt_embeds (text states) and pooled_embeds, or a text_encoder and "
+                             "tokenizer attached to the pipeline to compute them from `text`")
+        if text is None:
+            raise ValueError("Either text or class_ids must be provided.")
+        text = [text] if isinstance(text, str) else text
+        tok = lambda t: self.tokenizer(t, return_tensors="pt", padding="max_length", truncation=True,
+                                       max_length=self.tokenizer.model_max_length).input_ids.to(self.device)
+        out = self.text_encoder(tok(text), return_dict=True, output_hidden_states=True)
+        layer = -(clip_skip + 1) if clip_skip is not None else -2
+        pooled, states = out.text_embeds, out.hidden_states[layer]
+        empty = (None, None)
+        if negative_text is not None:
+            neg = [negative_text] * len(text) if isinstance(negative_text, str) else negative_text
+            nout = self.text_encoder(tok(neg), return_dict=True, output_hidden_states=True)
+            negative_pooled_embeds, negative_prompt_embeds = nout.text_embeds, nout.hidden_states[-2]
+        elif negative_prompt_embeds is None:
+            ids = self.tokenizer("", padding="max_length", return_tensors="pt").input_ids.to(self.device)
+            eout = self.text_encoder(ids, output_hidden_states=True)
+            empty = (eout.hidden_states[-2], eout[0])
+        return states, pooled, negative_prompt_embeds, negative_pooled_embeds, empty
+
     @torch.no_grad()
     def __call__(
         self,
@@ -88,10 +116,14 @@ class PipelineMuse:
         if text is not None and class_ids is not None:
             raise ValueError("Only one of text or class_ids may be provided.")
         if getattr(self.transformer.config, "add_micro_cond_embeds", False):  # MaskGiTUViT_v2 conditioning (:121-214)
+            empty = (None, None)
+            if prompt_embeds is None or pooled_embeds is None:  # run the attached text encoder like the reference (:113-197)
+                (prompt_embeds, pooled_embeds, negative_prompt_embeds, negative_pooled_embeds,
+                 empty) = self._encode_text_uvit(text, negative_text, negative_prompt_embeds, negative_pooled_embeds, clip_skip)
             return self._call_uvit_v2(prompt_embeds, pooled_embeds, negative_prompt_embeds, negative_pooled_embeds, timesteps,
                                       noise_schedule, guidance_scale, guidance_schedule, temperature,
                                       num_images_per_prompt, generator, return_intermediate, output_type, orig_size,
-                                      crop_coords, aesthetic_score, transformer_seq_len)
+                                      crop_coords, aesthetic_score, transformer_seq_len, empty=empty)
         if return_intermediate:
             raise NotImplementedError("return_intermediate is a MaskGiTUViT_v2.generate2 feature")
         if isinstance(temperature, (tuple, list)):
@@ -133,14 +165,15 @@ class PipelineMuse:
 
     def _call_uvit_v2(self, prompt_embeds, pooled_embeds, negative_prompt_embeds, negative_pooled_embeds, timesteps,
                       noise_schedule, guidance_scale, guidance_schedule, temperature, num_images_per_prompt, generator,
-                      return_intermediate, output_type, orig_size, crop_coords, aesthetic_score, seq_len=None):
+                      return_intermediate, output_type, orig_size, crop_coords, aesthetic_score, seq_len=None,
+                      empty=(None, None)):
         """Text-to-image with ``MaskGiTUViT_v2``: penultimate-layer text states + pooled embedding + micro-conditioning
         (reference pipeline_muse.py:121-233).  The text encoder is third-party and out of scope, so the embeddings (and the
         negative / empty ones needed for guidance) are passed in precomputed."""
         if prompt_embeds is None or pooled_embeds is None:
             raise ValueError("MaskGiTUViT_v2 needs prompt_embeds (text states) and pooled_embeds; run the text encoder "
                              "outside or attach one and encode before calling")
-        if guidance_scale > 0 and (negative_prompt_embeds is None or negative_pooled_embeds is None):
+        if guidance_scale > 0 and (negative_prompt_embeds is None or negative_pooled_embeds is None) and empty[0] is None:
             raise ValueError("classifier-free guidance needs negative_prompt_embeds and negative_pooled_embeds (the encoded "
                              "empty prompt)")
         n = num_images_per_prompt
@@ -152,8 +185,10 @@ class PipelineMuse:
             temperature = tuple(temperature)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = self.transformer.generate2(
-                encoder_hidden_states=states, cond_embeds=pooled, micro_conds=micro, empty_embeds=None,
-                empty_cond_embeds=None, negative_embeds=rep(negative_prompt_embeds),
+                encoder_hidden_states=states, cond_embeds=pooled, micro_conds=micro,
+                empty_embeds=None if empty[0] is None else empty[0].to(self.device),
+                empty_cond_embeds=None if empty[1] is None else empty[1].to(self.device),
+                negative_embeds=rep(negative_prompt_embeds),
                 negative_cond_embeds=rep(negative_pooled_embeds), temperature=temperature, timesteps=timesteps,
                 guidance_scale=guidance_scale, guidance_schedule=guidance_schedule,
                 noise_schedule=get_mask_chedule(noise_schedule), generator=generator,

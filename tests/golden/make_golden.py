@@ -413,6 +413,53 @@ def make_uvit_grads(muse):
     torch.save(out, os.path.join(HERE, "micro_uvit_v2_grads.pt"))
 
 
+def make_pipeline_text(muse):
+    """The reference's PipelineMuse with the text encoder run INSIDE the pipeline (pipeline_muse.py:113-197): a tiny random CLIP
+    text encoder with projection + tokenizer (tests/train_script_harness.make_tiny_clip, seeded), the micro U-ViT and taming
+    VQGAN fixtures' weights.  Two calls: default ``negative_text=""`` (negative prompt encoded, layer -2) and
+    ``negative_text=None`` (guidance against the encoded empty prompt).  Stores images, the token ids handed to the
+    detokeniser and a signature of the CLIP weights (the test rebuilds the same encoder from the same seed)."""
+    import tempfile
+
+    import numpy as np
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+    from transformers import CLIPTextModelWithProjection, CLIPTokenizer
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from tests.train_script_harness import make_tiny_clip
+
+    gu = torch.load(os.path.join(HERE, "micro_uvit_v2.pt"), weights_only=False)
+    gv = torch.load(os.path.join(HERE, "micro_taming_vqgan.pt"), weights_only=False)
+    tr = MaskGiTUViT_v2(**gu["config"])
+    tr.load_state_dict(gu["state_dict"])
+    vae = muse.VQGANModel(**gv["config"])
+    vae.load_state_dict(gv["state_dict"])
+    tr.eval(), vae.eval()
+    with tempfile.TemporaryDirectory() as d:
+        make_tiny_clip(d, projection_dim=gu["config"]["cond_embed_dim"], weight_std=0.3)
+        clip = CLIPTextModelWithProjection.from_pretrained(d).eval()
+        tok = CLIPTokenizer.from_pretrained(d)
+    seen, fed = [], []
+    decode, gen2 = vae.decode_code, tr.generate2
+    vae.decode_code = lambda ids: (seen.append(ids.clone()), decode(ids))[1]
+
+    def spy(**kw):  # what the pipeline hands to generate2: the text side of the pipeline, tensor by tensor
+        fed.append({k: v.clone() for k, v in kw.items() if torch.is_tensor(v)})
+        return gen2(**kw)
+
+    tr.generate2 = spy
+    pipe = muse.PipelineMuse(vae=vae, transformer=tr, text_encoder=clip, tokenizer=tok)
+    call = dict(timesteps=4, guidance_scale=3.0, temperature=(2, 0), transformer_seq_len=16, orig_size=(256, 256))
+    text = ["a cat", "dog on a log"]
+    out = {}
+    for name, kw in (("negative_default", {}), ("negative_none", dict(negative_text=None)), ("clip_skip", dict(clip_skip=2))):
+        images = pipe(text=text, generator=torch.Generator().manual_seed(92), use_tqdm=False, **call, **kw)
+        out[name] = dict(images=torch.from_numpy(np.stack([np.asarray(im) for im in images])), tokens=seen[-1], fed=fed[-1])
+    sig = float(sum(v.double().abs().sum() for v in clip.state_dict().values()))
+    torch.save(dict(text=text, call=call, seed=92, clip_signature=sig, runs=out), os.path.join(HERE, "micro_pipeline_text.pt"))
+    print("micro pipeline (text inside):", {k: v["tokens"][0, :6].tolist() for k, v in out.items()})
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -433,6 +480,8 @@ def main():
             make_pipeline(muse)
         if "configs" in only[0]:
             make_config_audit(muse)
+        if "pipeline_text" in only[0]:
+            make_pipeline_text(muse)
         if "uvit_intermediate" in only[0]:
             make_uvit_intermediate(muse)
         if "uvit_grads" in only[0]:
@@ -658,6 +707,7 @@ def main():
     make_config_audit(muse)
     make_uvit_intermediate(muse)
     make_uvit_grads(muse)
+    make_pipeline_text(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

@@ -102,3 +102,50 @@ def test_inpainting_pipeline_matches_the_oracle_composition(golden, monkeypatch)
     assert torch.equal(ids[:, ~mask], ids0.reshape(1, 16)[:, ~mask].expand(2, -1))  # known tokens are never resampled
     assert out.shape == want.shape == (2, 3, 8, 8)
     assert float((out - want).norm() / want.norm()) < 2e-5
+
+
+def test_pipeline_runs_the_text_encoder_like_the_reference(golden, monkeypatch, tmp_path):
+    """``pipe(text=[...])`` with a text encoder and tokenizer ATTACHED (the reference's main entry, pipeline_muse.py:113-197):
+    tokenisation, penultimate-layer states + projected pooled embedding, the encoded negative prompt (default "") or the
+    encoded empty prompt (``negative_text=None``), ``clip_skip``, micro-conditioning -- every tensor the pipeline hands to
+    generate2 equals what the unmodified reference pipeline handed over with the same (tiny, seeded, real ``transformers``)
+    CLIP encoder; token ids equal, images within one LSB."""
+    from transformers import CLIPTextModelWithProjection, CLIPTokenizer
+
+    from tests.train_script_harness import make_tiny_clip
+
+    g, gu, gv = golden("micro_pipeline_text.pt"), golden("micro_uvit_v2.pt"), golden("micro_taming_vqgan.pt")
+    real_bf16 = torch.bfloat16
+    clip_dir = make_tiny_clip(str(tmp_path / "clip"), projection_dim=gu["config"]["cond_embed_dim"], weight_std=0.3)
+    clip = CLIPTextModelWithProjection.from_pretrained(clip_dir).eval()
+    tok = CLIPTokenizer.from_pretrained(clip_dir)
+    assert abs(float(sum(v.double().abs().sum() for v in clip.state_dict().values())) - g["clip_signature"]) < 1e-6 * g["clip_signature"]
+    cpu_math_ops.install(monkeypatch, exact=True)
+    monkeypatch.setenv("MUSE_B200_CUDA_GRAPH", "0")
+    monkeypatch.setattr(MaskGiTUViT_v2, "device", property(lambda self: torch.device("cpu")), raising=False)
+    tr = MaskGiTUViT_v2(**gu["config"])
+    tr.load_state_dict(gu["state_dict"])
+    vae = VQGANModel(**gv["config"])
+    vae.load_state_dict(gv["state_dict"])
+    pipe = PipelineMuse(vae=vae.eval(), transformer=tr.eval(), text_encoder=clip, tokenizer=tok)
+    fed, gen2 = [], tr.generate2
+
+    def spy(**kw):
+        fed.append({k: v for k, v in kw.items() if torch.is_tensor(v)})
+        return gen2(**kw)
+
+    monkeypatch.setattr(tr, "generate2", spy, raising=False)
+    for name, kw in (("negative_default", {}), ("negative_none", dict(negative_text=None)), ("clip_skip", dict(clip_skip=2))):
+        ref = g["runs"][name]
+        images = pipe(text=g["text"], generator=torch.Generator().manual_seed(g["seed"]), use_tqdm=False, **g["call"], **kw)
+        got = fed[-1]
+        assert set(ref["fed"]) <= set(got), (name, set(ref["fed"]) - set(got))
+        for k, v in ref["fed"].items():
+            assert got[k].shape == v.shape, (name, k, got[k].shape, v.shape)
+            torch.testing.assert_close(got[k].float(), v.float(), rtol=1e-5, atol=1e-6, msg=lambda m: f"{name} {k}: {m}")
+        a = np.stack([np.asarray(im) for im in images]).astype(np.int16)
+        b = ref["images"].numpy().astype(np.int16)
+        assert np.abs(a - b).max() <= 1 and (a != b).mean() < 0.02, name
+    assert not torch.equal(g["runs"]["clip_skip"]["fed"]["encoder_hidden_states"],
+                           g["runs"]["negative_default"]["fed"]["encoder_hidden_states"])
+    assert torch.bfloat16 is not real_bf16  # (exact mode was active for the product code above)

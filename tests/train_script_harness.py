@@ -67,7 +67,7 @@ def make_config(tmp, steps, batch, mixed_precision, soft_targets=False, save_eve
     return path, out
 
 
-def make_tiny_clip(path):
+def make_tiny_clip(path, projection_dim=768, weight_std=None):
     """A 2-layer, 32-wide CLIP text encoder with a 768-wide projection (training/train_muse.py:336 forces projection_dim=768)
     and a 54-entry byte-pair vocabulary, saved where ``CLIPTextModelWithProjection / CLIPTokenizer.from_pretrained`` find them:
     the text encoder is third-party and out of scope, the script just needs one to call."""
@@ -84,11 +84,17 @@ def make_tiny_clip(path):
         f.write("#version: 0.2\n")
     CLIPTokenizer(os.path.join(path, "vocab.json"), os.path.join(path, "merges.txt"), model_max_length=8).save_pretrained(path)
     cfg = CLIPTextConfig(vocab_size=len(vocab), hidden_size=32, intermediate_size=64, num_hidden_layers=2,
-                         num_attention_heads=2, max_position_embeddings=8, projection_dim=768,
+                         num_attention_heads=2, max_position_embeddings=8, projection_dim=projection_dim,
                          bos_token_id=vocab["<|startoftext|>"], eos_token_id=vocab["<|endoftext|>"],
                          pad_token_id=vocab["<|endoftext|>"])
     torch.manual_seed(5)
-    CLIPTextModelWithProjection(cfg).save_pretrained(path)
+    clip = CLIPTextModelWithProjection(cfg)
+    if weight_std is not None:  # large random matrices: prompts, layers and the empty prompt give clearly different outputs
+        with torch.no_grad():
+            for p in clip.parameters():
+                if p.dim() > 1:
+                    p.normal_(0.0, weight_std)
+    clip.save_pretrained(path)
     return path
 
 
