@@ -552,12 +552,15 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
                 padded = self._graphed_forward(model_in, encoder_hidden_states, cond_embeds, micro_conds)
             else:
                 padded = self._forward_tokens(model_in, encoder_hidden_states, cond_embeds, micro_conds)
-            lg = padded.view(model_in.shape[0], seq_len, -1)
+            # tensor shapes follow the ids (inpainting passes its own); ``seq_len`` only enters the mask_len schedule below,
+            # as in the reference (:330-479)
+            L = input_ids.shape[1]
+            lg = padded.view(model_in.shape[0], L, -1)
             logits, logits_unc = (lg[:B], lg[B:]) if use_cfg else (lg, None)
             # generator consumed like the reference: multinomial(n=1) draws Exp(1) noise of the probabilities' shape,
             # mask_by_random_topk one uniform per token
-            q_exp = torch.empty(B * seq_len, K, dtype=torch.float32, device=lg.device).exponential_(1, generator=generator)
-            u = torch.zeros(B, seq_len, dtype=torch.float32, device=lg.device).uniform_(0, 1, generator=generator)
+            q_exp = torch.empty(B * L, K, dtype=torch.float32, device=lg.device).exponential_(1, generator=generator)
+            u = torch.zeros(B, L, dtype=torch.float32, device=lg.device).uniform_(0, 1, generator=generator)
             ratio = 1.0 * (step + 1) / timesteps
             mask_len = int((seq_len * noise_schedule(torch.tensor(ratio))).floor())
             prev_ids = input_ids
@@ -571,6 +574,6 @@ class MaskGiTUViT_v2(ModelMixin, ConfigMixin):
                 if logits_unc is not None:
                     xu = logits_unc[..., :K].float()
                     x = xu + float(scales[step]) * (x - xu)
-                raw = (torch.softmax(x, dim=-1) / q_exp.view(B, seq_len, K)).argmax(dim=-1)
+                raw = (torch.softmax(x, dim=-1) / q_exp.view(B, L, K)).argmax(dim=-1)
                 intermediate.append(torch.where(prev_ids == mask_id, sampled, raw))
         return (sampled, intermediate) if return_intermediate else sampled

@@ -267,6 +267,38 @@ class PipelineMuseInpainting(PipelineMuse):
     """Masked-region regeneration (muse/pipeline_muse.py:372-512): tokenise the image, overwrite the masked token
     positions with the mask id and let ``generate2`` fill them in; known tokens are kept by the fused decode step."""
 
+    def _inpaint_uvit_v2(self, image_tokens, text, negative_text, timesteps, guidance_scale, guidance_schedule, temperature,
+                         n, generator, orig_size, crop_coords, aesthetic_score, output_type):
+        """Text-conditioned inpainting with ``MaskGiTUViT_v2`` through the attached text encoder, as the reference wires it
+        (:424-498): penultimate-layer states + pooled embedding for the prompt, the LAST layer for an explicit negative prompt
+        (upstream's choice here, unlike PipelineMuse), the encoded empty prompt always passed along, micro-conditioning; the
+        start tokens keep their own length while ``seq_len`` stays at generate2's default of 256 for the mask schedule."""
+        if self.text_encoder is None or self.tokenizer is None or text is None:
+            raise ValueError("PipelineMuseInpainting with MaskGiTUViT_v2 needs `text` and an attached text_encoder / tokenizer")
+        text = [text] if isinstance(text, str) else text
+        tok = lambda t: self.tokenizer(t, return_tensors="pt", padding="max_length", truncation=True,
+                                       max_length=self.tokenizer.model_max_length).input_ids.to(self.device)
+        pooled = None
+        if getattr(self.transformer.config, "add_cond_embeds", False):
+            out = self.text_encoder(tok(text), return_dict=True, output_hidden_states=True)
+            pooled, states = out.text_embeds, out.hidden_states[-2]
+        else:
+            states = self.text_encoder(tok(text)).last_hidden_state
+        neg = None
+        if negative_text is not None:
+            neg = self.text_encoder(tok([negative_text] if isinstance(negative_text, str) else negative_text)).last_hidden_state
+        rep = lambda t: None if t is None else t.repeat_interleave(n, dim=0)
+        ids = self.tokenizer("", padding="max_length", return_tensors="pt").input_ids.to(self.device)
+        eout = self.text_encoder(ids, output_hidden_states=True)
+        micro = torch.tensor([list(orig_size) + list(crop_coords) + [aesthetic_score]], device=self.device, dtype=states.dtype)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            tokens = self.transformer.generate2(
+                input_ids=image_tokens, encoder_hidden_states=rep(states), negative_embeds=rep(neg),
+                empty_embeds=eout.hidden_states[-2], empty_cond_embeds=eout[0], cond_embeds=rep(pooled), micro_conds=micro,
+                timesteps=timesteps, guidance_scale=guidance_scale, guidance_schedule=guidance_schedule,
+                temperature=temperature, generator=generator)
+        return self._decode(tokens, output_type)
+
     @staticmethod
     def _to_pixel_values(image, image_size):
         """Resize(shorter side, bilinear) -> CenterCrop -> ToTensor of the reference (:404-410), without torchvision."""
@@ -319,6 +351,10 @@ class PipelineMuseInpainting(PipelineMuse):
         _, image_tokens = self.vae.encode(pixel_values)
         image_tokens[mask.to(image_tokens.device).reshape(1, -1).expand_as(image_tokens)] = self.transformer.config.mask_token_id
         image_tokens = image_tokens.repeat(num_images_per_prompt, 1)
+        if getattr(self.transformer.config, "add_micro_cond_embeds", False) and class_ids is None:
+            return self._inpaint_uvit_v2(image_tokens, text, negative_text, timesteps, guidance_scale, guidance_schedule,
+                                         temperature, num_images_per_prompt, generator, orig_size, crop_coords,
+                                         aesthetic_score, output_type)
         kwargs = {}
         if class_ids is not None:
             if isinstance(class_ids, int):

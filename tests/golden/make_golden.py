@@ -460,6 +460,54 @@ def make_pipeline_text(muse):
     print("micro pipeline (text inside):", {k: v["tokens"][0, :6].tolist() for k, v in out.items()})
 
 
+def make_inpainting_text(muse):
+    """The reference's PipelineMuseInpainting (pipeline_muse.py:372-512) with MaskGiTUViT_v2, the taming VQGAN and the tiny
+    seeded CLIP of make_pipeline_text: PIL image -> Resize / CenterCrop / ToTensor -> tokens, masked positions overwritten,
+    text + explicit negative text, generate2 from the start tokens, decode.  Stores the image bytes, the mask, what the
+    pipeline handed to generate2, the generated token ids and the output images."""
+    import tempfile
+
+    import numpy as np
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+    from PIL import Image
+    from transformers import CLIPTextModelWithProjection, CLIPTokenizer
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from tests.train_script_harness import make_tiny_clip
+
+    gu = torch.load(os.path.join(HERE, "micro_uvit_v2.pt"), weights_only=False)
+    gv = torch.load(os.path.join(HERE, "micro_taming_vqgan.pt"), weights_only=False)
+    tr = MaskGiTUViT_v2(**gu["config"])
+    tr.load_state_dict(gu["state_dict"])
+    vae = muse.VQGANModel(**gv["config"])
+    vae.load_state_dict(gv["state_dict"])
+    tr.eval(), vae.eval()
+    with tempfile.TemporaryDirectory() as d:
+        make_tiny_clip(d, projection_dim=gu["config"]["cond_embed_dim"], weight_std=0.3)
+        clip = CLIPTextModelWithProjection.from_pretrained(d).eval()
+        tok = CLIPTokenizer.from_pretrained(d)
+    seen, fed = [], []
+    decode, gen2 = vae.decode_code, tr.generate2
+    vae.decode_code = lambda ids: (seen.append(ids.clone()), decode(ids))[1]
+
+    def spy(**kw):
+        fed.append({k: v.clone() for k, v in kw.items() if torch.is_tensor(v)})
+        return gen2(**kw)
+
+    tr.generate2 = spy
+    pipe = muse.PipelineMuseInpainting(vae=vae, transformer=tr, text_encoder=clip, tokenizer=tok)
+    pixels = (np.random.RandomState(3).rand(10, 12, 3) * 255).astype(np.uint8)  # resized (shorter side 8) and centre-cropped
+    mask = torch.zeros(16, dtype=torch.bool)
+    mask[5:13] = True
+    out = {}
+    for name, kw in (("negative_text", dict(negative_text="dog")), ("no_negative", {})):
+        images = pipe(Image.fromarray(pixels), mask, text="a cat", timesteps=3, guidance_scale=2.0, temperature=1.0,
+                      num_images_per_prompt=1, image_size=8, generator=torch.Generator().manual_seed(93), **kw)
+        out[name] = dict(images=torch.from_numpy(np.stack([np.asarray(im) for im in images])), tokens=seen[-1], fed=fed[-1])
+    torch.save(dict(pixels=torch.from_numpy(pixels), mask=mask, seed=93, runs=out), os.path.join(HERE, "micro_inpainting_text.pt"))
+    print("micro inpainting (text):", {k: v["tokens"][0].tolist() for k, v in out.items()})
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -482,6 +530,8 @@ def main():
             make_config_audit(muse)
         if "pipeline_text" in only[0]:
             make_pipeline_text(muse)
+        if "inpainting_text" in only[0]:
+            make_inpainting_text(muse)
         if "uvit_intermediate" in only[0]:
             make_uvit_intermediate(muse)
         if "uvit_grads" in only[0]:
@@ -708,6 +758,7 @@ def main():
     make_uvit_intermediate(muse)
     make_uvit_grads(muse)
     make_pipeline_text(muse)
+    make_inpainting_text(muse)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

@@ -149,3 +149,48 @@ def test_pipeline_runs_the_text_encoder_like_the_reference(golden, monkeypatch, 
     assert not torch.equal(g["runs"]["clip_skip"]["fed"]["encoder_hidden_states"],
                            g["runs"]["negative_default"]["fed"]["encoder_hidden_states"])
     assert torch.bfloat16 is not real_bf16  # (exact mode was active for the product code above)
+
+
+def test_inpainting_pipeline_with_text_encoder_matches_the_reference(golden, monkeypatch, tmp_path):
+    """PipelineMuseInpainting with MaskGiTUViT_v2, text + attached encoder (pipeline_muse.py:372-512): PIL -> resize / centre
+    crop / ToTensor -> tokens -> masked start ids -> generate2 (start tokens of their own length, default seq_len for the
+    mask schedule) -> decode.  Every tensor handed to generate2 (start ids included), the generated ids and the images against
+    the unmodified reference pipeline (fixture micro_inpainting_text.pt)."""
+    from PIL import Image
+    from transformers import CLIPTextModelWithProjection, CLIPTokenizer
+
+    from open_muse_b200 import PipelineMuseInpainting
+    from tests.train_script_harness import make_tiny_clip
+
+    g, gu, gv = golden("micro_inpainting_text.pt"), golden("micro_uvit_v2.pt"), golden("micro_taming_vqgan.pt")
+    clip_dir = make_tiny_clip(str(tmp_path / "clip"), projection_dim=gu["config"]["cond_embed_dim"], weight_std=0.3)
+    clip = CLIPTextModelWithProjection.from_pretrained(clip_dir).eval()
+    tok = CLIPTokenizer.from_pretrained(clip_dir)
+    cpu_math_ops.install(monkeypatch, exact=True)
+    monkeypatch.setenv("MUSE_B200_CUDA_GRAPH", "0")
+    monkeypatch.setattr(MaskGiTUViT_v2, "device", property(lambda self: torch.device("cpu")), raising=False)
+    tr = MaskGiTUViT_v2(**gu["config"])
+    tr.load_state_dict(gu["state_dict"])
+    vae = VQGANModel(**gv["config"])
+    vae.load_state_dict(gv["state_dict"])
+    pipe = PipelineMuseInpainting(vae=vae.eval(), transformer=tr.eval(), text_encoder=clip, tokenizer=tok)
+    fed, gen2 = [], tr.generate2
+
+    def spy(**kw):
+        fed.append({k: v.clone() for k, v in kw.items() if torch.is_tensor(v)})
+        return gen2(**kw)
+
+    monkeypatch.setattr(tr, "generate2", spy, raising=False)
+    image = Image.fromarray(g["pixels"].numpy())
+    for name, kw in (("negative_text", dict(negative_text="dog")), ("no_negative", {})):
+        ref = g["runs"][name]
+        images = pipe(image, g["mask"], text="a cat", timesteps=3, guidance_scale=2.0, temperature=1.0,
+                      num_images_per_prompt=1, image_size=8, generator=torch.Generator().manual_seed(g["seed"]), **kw)
+        got = fed[-1]
+        assert set(ref["fed"]) <= set(got), (name, set(ref["fed"]) - set(got))
+        assert torch.equal(got["input_ids"], ref["fed"]["input_ids"]), name  # tokenised image with the masked positions
+        for k, v in ref["fed"].items():
+            torch.testing.assert_close(got[k].float(), v.float(), rtol=1e-5, atol=1e-6, msg=lambda m: f"{name} {k}: {m}")
+        a = np.stack([np.asarray(im) for im in images]).astype(np.int16)
+        b = ref["images"].numpy().astype(np.int16)
+        assert a.shape == b.shape and np.abs(a - b).max() <= 1 and (a != b).mean() < 0.02, name
