@@ -251,13 +251,19 @@ class PipelineMuse:
             else:
                 raise ValueError(f"Unknown Transformer class: {name}")
         tokenizer = None
-        if not is_class_conditioned and text_encoder is None:
+        if not is_class_conditioned:  # (reference :298-314: the tokenizer is always loaded, the encoder unless one was passed)
             path, folder = sub(text_encoder_path, "text_encoder")
-            from transformers import AutoTokenizer, CLIPTextModel, T5EncoderModel
+            from transformers import AutoTokenizer, CLIPTextModel, CLIPTextModelWithProjection, T5EncoderModel
 
             full = os.path.join(path, folder) if folder else path
-            enc_cls = CLIPTextModel if "clip" in str(full).lower() else T5EncoderModel
-            text_encoder = enc_cls.from_pretrained(full)
+            if text_encoder is None:
+                if getattr(transformer.config, "add_cond_embeds", False):
+                    # models with pooled conditioning (MaskGiTUViT_v2): upstream loads CLIPTextModelWithProjection
+                    # unconditionally -- the only class whose outputs carry text_embeds
+                    enc_cls = CLIPTextModelWithProjection
+                else:  # v1 transformers read last_hidden_state only (upstream's pipeline cannot drive them, quirk Q15)
+                    enc_cls = CLIPTextModel if "clip" in str(full).lower() else T5EncoderModel
+                text_encoder = enc_cls.from_pretrained(full)
             tokenizer = AutoTokenizer.from_pretrained(full)
         return cls(vae=vae, transformer=transformer, is_class_conditioned=is_class_conditioned,
                    text_encoder=text_encoder, tokenizer=tokenizer)

@@ -2,6 +2,8 @@
 generate2 with classifier-free guidance -> taming VQGAN decode -> display bytes, every kernel replaced by its torch
 restatement, against the PIL images the UNMODIFIED reference pipeline produced from the same weights, inputs and generator
 seed (tests/golden/micro_pipeline.pt, written by make_golden.py::make_pipeline)."""
+import os
+
 import numpy as np
 import torch
 
@@ -148,6 +150,16 @@ def test_pipeline_runs_the_text_encoder_like_the_reference(golden, monkeypatch, 
         assert np.abs(a - b).max() <= 1 and (a != b).mean() < 0.02, name
     assert not torch.equal(g["runs"]["clip_skip"]["fed"]["encoder_hidden_states"],
                            g["runs"]["negative_default"]["fed"]["encoder_hidden_states"])
+    # <dir>/{text_encoder, vae, transformer} round trip: the text encoder comes back as the projection class, the tokenizer
+    # is loaded with it, and the reloaded pipeline computes the same images
+    pipe.save_pretrained(str(tmp_path / "pipe"))
+    assert sorted(os.listdir(tmp_path / "pipe")) == ["text_encoder", "transformer", "vae"]
+    pipe2 = PipelineMuse.from_pretrained(str(tmp_path / "pipe"))
+    assert type(pipe2.text_encoder).__name__ == "CLIPTextModelWithProjection" and pipe2.tokenizer is not None
+    assert isinstance(pipe2.transformer, MaskGiTUViT_v2) and isinstance(pipe2.vae, VQGANModel)
+    pipe2.text_encoder.eval()
+    images2 = pipe2(text=g["text"], generator=torch.Generator().manual_seed(g["seed"]), use_tqdm=False, **g["call"], clip_skip=2)
+    assert all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(images, images2))
     assert torch.bfloat16 is not real_bf16  # (exact mode was active for the product code above)
 
 
