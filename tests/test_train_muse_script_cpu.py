@@ -88,3 +88,45 @@ def test_training_utils_diagnostics_match_reference():
     assert r.equals(m) and len(r) > 0
     for k in [k for k in sys.modules if k == "muse" or k.startswith("muse.")]:
         del sys.modules[k]
+
+
+def test_reference_train_muse_script_generates_and_inpaints_during_training(monkeypatch, tmp_path):
+    """``experiment.generate_every`` of the unmodified train_muse.py: ``generate_images`` (16 validation prompts through the
+    text encoder, classifier-free guidance against the encoded empty prompt, per-sample micro conditions, generate2 -> clamp ->
+    decode_code -> PIL -> wandb) and ``generate_inpainting_images`` (reads ./inpainting_validation/<prompt>/{image, mask},
+    tokenises, masks at latent resolution with its hard-coded /16, generate2 from those start tokens) both run against the
+    drop-in classes in the middle of training, EMA weights swapped in and out around them."""
+    from PIL import Image
+
+    import numpy as np
+
+    cpu_math_ops.install(monkeypatch, exact=False)
+    monkeypatch.setenv("ACCELERATE_USE_CPU", "1")
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    monkeypatch.setenv("MUSE_B200_CUDA_GRAPH", "0")
+    from open_muse_b200 import MaskGiTUViT_v2
+
+    monkeypatch.setattr(MaskGiTUViT_v2, "device", property(lambda self: torch.device("cpu")), raising=False)
+    work = tmp_path / "cwd"
+    rs = np.random.RandomState(0)
+    for prompt in ("a red cube", "two dogs"):
+        d = work / "inpainting_validation" / prompt
+        os.makedirs(d)
+        Image.fromarray((rs.rand(64, 64, 3) * 255).astype(np.uint8)).save(d / "image.png")
+        m = np.zeros((64, 64), dtype=np.uint8)
+        m[16:48, 16:48] = 255
+        Image.fromarray(m).save(d / "mask.png")
+    monkeypatch.chdir(work)
+    cfg, out = make_muse_config(str(tmp_path), steps=2, batch=2, mixed_precision="no", save_every=1000, use_ema=True,
+                                f16_tokenizer=True, extra_experiment={"generate_every": 2})
+    log = tmp_path / "wandb.jsonl"
+    monkeypatch.setenv("MUSE_SHIM_WANDB_LOG", str(log))
+    acc = run_script(SCRIPT, cfg)
+    assert [s for v, s in acc.logged if "step_loss" in v] == [1, 2]
+    rows = [json.loads(l) for l in open(log)]
+    gen = [r for r in rows if "generated_images" in r["keys"]]
+    inp = [r for r in rows if "generated_inpainting_images" in r["keys"]]
+    assert len(gen) == 1 and gen[0]["step"] == 2 and gen[0]["keys"]["generated_images"] == 16
+    assert gen[0]["captions"][0] == "jay" and all(s == [64, 64] for s in gen[0]["sizes"])
+    assert len(inp) == 1 and inp[0]["keys"]["generated_inpainting_images"] == 2
+    assert sorted(inp[0]["captions"]) == ["a red cube", "two dogs"] and all(s == [64, 64] for s in inp[0]["sizes"])

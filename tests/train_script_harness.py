@@ -105,7 +105,8 @@ UVIT_MICRO = dict(hidden_size=128, num_attention_heads=2, in_channels=64, block_
                   hidden_dropout=0.0, attention_dropout=0.0)
 
 
-def make_muse_config(tmp, steps, batch, mixed_precision, save_every=1000, extra_experiment=None, use_ema=False):
+def make_muse_config(tmp, steps, batch, mixed_precision, save_every=1000, extra_experiment=None, use_ema=False,
+                     f16_tokenizer=False):
     """config for the UNMODIFIED training/train_muse.py on the one wiring that runs end to end at this commit (quirk Q12):
     ``architecture: uvit`` (MaskGiTUViT = MaskGiTUViT_v2) with pooled + micro conditioning, CLIP text encoder with
     projection, classifier-free-guidance dropout through the encoded empty prompt, taming-style VQGAN tokenizer."""
@@ -113,7 +114,9 @@ def make_muse_config(tmp, steps, batch, mixed_precision, save_every=1000, extra_
 
     torch.manual_seed(3)
     vq_dir = os.path.join(tmp, "vq")
-    VQGANModel(resolution=32, num_channels=3, hidden_channels=32, channel_mult=(1, 2), num_res_blocks=1,
+    res = 64 if f16_tokenizer else 32  # f16_tokenizer: five levels (x16 reduction, what the script's inpainting-mask helper
+    mult = (1, 1, 1, 1, 1) if f16_tokenizer else (1, 2)  # hard-codes), 64 px -> 4 x 4 = 16 tokens; else x2, 32 px -> 256
+    VQGANModel(resolution=res, num_channels=3, hidden_channels=32, channel_mult=mult, num_res_blocks=1,
                attn_resolutions=(16,), z_channels=16, num_embeddings=64, quantized_embed_dim=16).save_pretrained(vq_dir)
     clip_dir = make_tiny_clip(os.path.join(tmp, "clip"))
     out = os.path.join(tmp, "run")
@@ -125,20 +128,21 @@ def make_muse_config(tmp, steps, batch, mixed_precision, save_every=1000, extra_
         "wandb": {"entity": None},
         "experiment": exp,
         "model": {"architecture": "uvit", "vq_model": {"type": "vqgan", "pretrained": vq_dir},
-                  "text_encoder": {"type": "clip", "pretrained": clip_dir}, "transformer": dict(UVIT_MICRO),
+                  "text_encoder": {"type": "clip", "pretrained": clip_dir},
+                  "transformer": dict(UVIT_MICRO, num_vq_tokens=16 if f16_tokenizer else 256),
                   "gradient_checkpointing": True, "enable_xformers_memory_efficient_attention": True},
         "dataset": {"type": "text2image",
                     "params": {"train_shards_path_or_url": "synthetic", "eval_shards_path_or_url": "synthetic",
-                               "batch_size": batch, "shuffle_buffer_size": 10, "num_workers": 0, "resolution": 32,
-                               "pin_memory": False, "persistent_workers": False},
-                    "preprocessing": {"resolution": 32, "center_crop": True, "random_flip": False, "max_seq_length": 8}},
+                               "batch_size": batch, "shuffle_buffer_size": 10, "num_workers": 0, "resolution": res,
+                               "pin_memory": False, "persistent_workers": False, "validation_prompts_file": None},
+                    "preprocessing": {"resolution": res, "center_crop": True, "random_flip": False, "max_seq_length": 8}},
         "optimizer": {"name": "adamw", "params": {"learning_rate": 1.0e-3, "scale_lr": False, "beta1": 0.9, "beta2": 0.999,
                                                   "weight_decay": 0.01, "epsilon": 1.0e-8}},
         "lr_scheduler": {"scheduler": "constant_with_warmup", "params": {"learning_rate": 1.0e-3, "warmup_steps": 1}},
         "training": {"gradient_accumulation_steps": 1, "batch_size": batch, "mixed_precision": mixed_precision,
                      "enable_tf32": True, "use_ema": use_ema, "ema_decay": 0.99, "ema_update_after_step": 0,
                      "ema_update_every": 1, "seed": 42, "max_train_steps": steps, "overfit_one_batch": False,
-                     "cond_dropout_prob": 0.1, "min_masking_rate": 0.0, "label_smoothing": 0.1, "max_grad_norm": 1.0,
+                     "cond_dropout_prob": 0.1, "guidance_scale": 2.0, "generation_timesteps": 3, "min_masking_rate": 0.0, "label_smoothing": 0.1, "max_grad_norm": 1.0,
                      "use_soft_code_target": False, "use_stochastic_code": False, "soft_code_temp": 1.0},
     }
     path = os.path.join(tmp, "config.yaml")
