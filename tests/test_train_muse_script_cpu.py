@@ -130,3 +130,22 @@ def test_reference_train_muse_script_generates_and_inpaints_during_training(monk
     assert gen[0]["captions"][0] == "jay" and all(s == [64, 64] for s in gen[0]["sizes"])
     assert len(inp) == 1 and inp[0]["keys"]["generated_inpainting_images"] == 2
     assert sorted(inp[0]["captions"]) == ["a red cube", "two dogs"] and all(s == [64, 64] for s in inp[0]["sizes"])
+
+
+def test_train_muse_script_cannot_train_the_v1_text_conditional_transformer_upstream(monkeypatch, tmp_path):
+    """``architecture: transformer`` in train_muse.py = the text-conditional MaskGitTransformer (the model class of BASELINE
+    config 4).  At this commit the UNMODIFIED script stops in its own code on both target modes, before or right after the
+    first forward (extended): with hard targets it references ``cond_embeds`` before assignment
+    (train_muse.py:747; bound only when cond_dropout_prob > 0, which in turn needs the U-ViT-only empty-prompt embeddings),
+    with soft targets its ``soft_target_cross_entropy`` drops a class token that text-conditional batches do not have
+    (:121-125: 255 logits rows against 256 soft-target rows).  The drop-in model is constructed, moved, wrapped and called
+    with the script's keywords in both cases -- the failures are the script's, and are the same with the reference model."""
+    cpu_math_ops.install(monkeypatch, exact=False)
+    monkeypatch.setenv("ACCELERATE_USE_CPU", "1")
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    cfg, _ = make_muse_config(str(tmp_path / "soft"), steps=1, batch=2, mixed_precision="no", v1_soft_targets=True)
+    with pytest.raises(RuntimeError, match="must match the size of tensor"):
+        run_script(SCRIPT, cfg)
+    cfg, _ = make_muse_config(str(tmp_path / "hard"), steps=1, batch=2, mixed_precision="no", v1_soft_targets=True)
+    with pytest.raises((NameError, UnboundLocalError), match="cond_embeds"):
+        run_script(SCRIPT, cfg, extra_cli=("training.use_soft_code_target=False",))

@@ -105,8 +105,14 @@ UVIT_MICRO = dict(hidden_size=128, num_attention_heads=2, in_channels=64, block_
                   hidden_dropout=0.0, attention_dropout=0.0)
 
 
+T2I_MICRO = dict(vocab_size=72, hidden_size=64, num_hidden_layers=2, num_attention_heads=1, intermediate_size=128,
+                 hidden_dropout=0.0, attention_dropout=0.0, max_position_embeddings=256, codebook_size=64, num_vq_tokens=256,
+                 add_cross_attention=True, encoder_hidden_size=32, norm_type="rmsnorm", use_normformer=False,
+                 layer_norm_eps=1e-6, use_codebook_size_for_output=True)
+
+
 def make_muse_config(tmp, steps, batch, mixed_precision, save_every=1000, extra_experiment=None, use_ema=False,
-                     f16_tokenizer=False):
+                     f16_tokenizer=False, v1_soft_targets=False):
     """config for the UNMODIFIED training/train_muse.py on the one wiring that runs end to end at this commit (quirk Q12):
     ``architecture: uvit`` (MaskGiTUViT = MaskGiTUViT_v2) with pooled + micro conditioning, CLIP text encoder with
     projection, classifier-free-guidance dropout through the encoded empty prompt, taming-style VQGAN tokenizer."""
@@ -145,6 +151,12 @@ def make_muse_config(tmp, steps, batch, mixed_precision, save_every=1000, extra_
                      "cond_dropout_prob": 0.1, "guidance_scale": 2.0, "generation_timesteps": 3, "min_masking_rate": 0.0, "label_smoothing": 0.1, "max_grad_norm": 1.0,
                      "use_soft_code_target": False, "use_stochastic_code": False, "soft_code_temp": 1.0},
     }
+    if v1_soft_targets:
+        # the OTHER wiring of train_muse.py that runs upstream (quirk Q12): architecture "transformer" = the text-conditional
+        # MaskGitTransformer (BASELINE config 4's model class), plain CLIPTextModel, no CFG dropout, soft code targets
+        cfg["model"]["architecture"] = "transformer"
+        cfg["model"]["transformer"] = dict(T2I_MICRO)
+        cfg["training"].update(cond_dropout_prob=0.0, use_soft_code_target=True, soft_code_temp=2.0)
     path = os.path.join(tmp, "config.yaml")
     with open(path, "w") as f:
         yaml.safe_dump(cfg, f)
