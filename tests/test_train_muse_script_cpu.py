@@ -149,3 +149,23 @@ def test_train_muse_script_cannot_train_the_v1_text_conditional_transformer_upst
     cfg, _ = make_muse_config(str(tmp_path / "hard"), steps=1, batch=2, mixed_precision="no", v1_soft_targets=True)
     with pytest.raises((NameError, UnboundLocalError), match="cond_embeds"):
         run_script(SCRIPT, cfg, extra_cli=("training.use_soft_code_target=False",))
+
+
+def test_reference_train_muse_script_resumes_with_ema(monkeypatch, tmp_path):
+    """resume of the unmodified train_muse.py with EMA: ``accelerator.load_state`` runs the script's load hook
+    (``EMAModel.from_pretrained(checkpoint/ema_model, model_cls=...)`` -> ``ema.load_state_dict`` -> ``ema.to``), the model /
+    optimizer / scheduler states come back, the step counter continues from the directory name."""
+    cpu_math_ops.install(monkeypatch, exact=False)
+    monkeypatch.setenv("ACCELERATE_USE_CPU", "1")
+    monkeypatch.setenv("WANDB_MODE", "disabled")
+    cfg, out = make_muse_config(str(tmp_path), steps=2, batch=2, mixed_precision="no", save_every=2, use_ema=True)
+    acc = run_script(SCRIPT, cfg)
+    assert [s for v, s in acc.logged if "step_loss" in v] == [1, 2] and os.path.isdir(os.path.join(out, "checkpoint-2", "ema_model"))
+    ema2 = torch.load(os.path.join(out, "checkpoint-2", "ema_model", "pytorch_model.bin"))
+    acc = run_script(SCRIPT, cfg, extra_cli=("experiment.resume_from_checkpoint=latest", "training.max_train_steps=4"))
+    assert [s for v, s in acc.logged if "step_loss" in v] == [3, 4]
+    ema4 = torch.load(os.path.join(out, "checkpoint-4", "ema_model", "pytorch_model.bin"))
+    k = "transformer_layers.0.ffn.wi_0.weight"
+    assert set(ema2) == set(ema4) and not torch.equal(ema2[k], ema4[k])
+    opt = torch.load(os.path.join(out, "checkpoint-4", "optimizer.bin"))
+    assert int(next(iter(opt["state"].values()))["step"]) == 4
