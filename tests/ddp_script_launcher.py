@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
+import transformers  # noqa: E402,F401  (before the accelerate stand-in is on sys.path: its own accelerate probing needs a real version)
 
 from tests import cpu_math_ops  # noqa: E402
 from tests.train_script_harness import run_script  # noqa: E402

@@ -188,6 +188,31 @@ def test_reference_training_script_under_two_rank_ddp(tmp_path):
     assert os.path.exists(os.path.join(out, "checkpoint-3", "unwrapped_model", "pytorch_model.bin"))
 
 
+def test_reference_train_muse_script_under_two_rank_ddp(tmp_path):
+    """The UNMODIFIED training/train_muse.py on two ranks (gloo): MaskGiTUViT_v2's per-block Functions under the DDP the
+    accelerate stand-in builds, text encoder + tokenizer per rank, EMA, main-process checkpointing."""
+    from tests.train_script_harness import find_script, make_muse_config
+
+    script = find_script("train_muse.py")
+    if script is None:
+        import pytest
+
+        pytest.skip("reference training script not available")
+    cfg, out = make_muse_config(str(tmp_path), steps=2, batch=2, mixed_precision="no", save_every=2, use_ema=True)
+    res = str(tmp_path / "res.json")
+    env = dict(os.environ, OMP_NUM_THREADS="2", ACCELERATE_USE_CPU="1", WANDB_MODE="disabled")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(30100 + os.getpid() % 90), os.path.join(ROOT, "tests", "ddp_script_launcher.py"), script, cfg, res]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ranks = [json.load(open(f"{res}.rank{i}")) for i in range(2)]
+    assert [x["world"] for x in ranks] == [2, 2]
+    l0 = [v["step_loss"] for v, s in ranks[0]["logged"] if "step_loss" in v]
+    l1 = [v["step_loss"] for v, s in ranks[1]["logged"] if "step_loss" in v]
+    assert len(l0) == 2 and l0 == l1
+    assert os.path.isdir(os.path.join(out, "checkpoint-2", "ema_model"))
+
+
 def test_reference_arm_prints_only_on_rank0():
     env = dict(os.environ, OMP_NUM_THREADS="2", MUSE_B200_CPU_SAMPLE_BATCH="4")  # the launch contract, not the number
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
