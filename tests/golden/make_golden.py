@@ -508,6 +508,37 @@ def make_inpainting_text(muse):
     print("micro inpainting (text):", {k: v["tokens"][0].tolist() for k, v in out.items()})
 
 
+def make_uvit_schedules(muse):
+    """MaskGiTUViT_v2.generate2 variants on the micro_uvit_v2.pt weights: guidance_schedule "linear" / "cosine", a scalar
+    temperature (annealed to 0.01), explicit negative embeddings, start tokens, guidance off -- the final ids of each."""
+    from muse.modeling_transformer_v2 import MaskGiTUViT_v2
+
+    g = torch.load(os.path.join(HERE, "micro_uvit_v2.pt"), weights_only=False)
+    v2 = MaskGiTUViT_v2(**g["config"])
+    v2.load_state_dict(g["state_dict"])
+    v2.eval()
+    gen = torch.Generator().manual_seed(94)
+    neg_e, neg_c = torch.randn(3, 5, 32, generator=gen), torch.randn(3, 16, generator=gen)
+    start = torch.full((3, 16), 71, dtype=torch.long)
+    start[:, :6] = torch.randint(0, 64, (3, 6), generator=gen)
+    base = dict(encoder_hidden_states=g["encoder_hidden_states"], cond_embeds=g["cond_embeds"], micro_conds=g["micro_conds"],
+                empty_embeds=g["empty_embeds"], empty_cond_embeds=g["empty_cond_embeds"], timesteps=5, seq_len=16)
+    variants = {
+        "linear": dict(guidance_scale=4.0, guidance_schedule="linear", temperature=(2.0, 0.0)),
+        "cosine": dict(guidance_scale=4.0, guidance_schedule="cosine", temperature=(2.0, 0.0)),
+        "scalar_temperature": dict(guidance_scale=2.0, temperature=1.5),
+        "negative": dict(guidance_scale=3.0, temperature=(1.0, 0.5), negative_embeds=neg_e, negative_cond_embeds=neg_c),
+        "start_tokens": dict(guidance_scale=3.0, temperature=(2.0, 0.0), input_ids=start.clone()),
+    }
+    out = {}
+    with torch.no_grad():
+        for name, kw in variants.items():
+            out[name] = v2.generate2(**base, **kw, generator=torch.Generator().manual_seed(95)).clone()
+    torch.save(dict(negative_embeds=neg_e, negative_cond_embeds=neg_c, start=start, ids=out, seed=95),
+               os.path.join(HERE, "micro_uvit_v2_schedules.pt"))
+    print("micro uvit v2 generate2 variants:", {k: v[0, :5].tolist() for k, v in out.items()})
+
+
 def main():
     muse = import_reference()
     torch.set_num_threads(4)
@@ -536,6 +567,8 @@ def main():
             make_uvit_intermediate(muse)
         if "uvit_grads" in only[0]:
             make_uvit_grads(muse)
+        if "uvit_schedules" in only[0]:
+            make_uvit_schedules(muse)
         return
 
     # ---- (1) micro class-conditional transformer: weights + inputs + logits/loss/all grads
@@ -757,6 +790,7 @@ def main():
     make_config_audit(muse)
     make_uvit_intermediate(muse)
     make_uvit_grads(muse)
+    make_uvit_schedules(muse)
     make_pipeline_text(muse)
     make_inpainting_text(muse)
 

@@ -203,3 +203,26 @@ def test_uvit_head_dim_48_training_backward_matches_the_oracle(monkeypatch):
     assert abs(float(loss.detach()) - float(ref_loss)) < 1e-5 * float(ref_loss)
     for n, p in m.named_parameters():
         assert _rel(p.grad, q[n].grad) < 5e-4, (n, _rel(p.grad, q[n].grad))
+
+
+def test_uvit_generate2_variants_reproduce_the_reference(golden, monkeypatch):
+    """guidance_schedule "linear" / "cosine", scalar temperature (annealed to 0.01), explicit negative embeddings, given
+    start tokens: the final ids of each against the unmodified reference (fixture micro_uvit_v2_schedules.pt)"""
+    g, gs = golden("micro_uvit_v2.pt"), golden("micro_uvit_v2_schedules.pt")
+    m = _model(g, monkeypatch, train=False)
+    base = dict(encoder_hidden_states=g["encoder_hidden_states"], cond_embeds=g["cond_embeds"], micro_conds=g["micro_conds"],
+                empty_embeds=g["empty_embeds"], empty_cond_embeds=g["empty_cond_embeds"], timesteps=5, seq_len=16,
+                use_cuda_graph=False)
+    variants = {
+        "linear": dict(guidance_scale=4.0, guidance_schedule="linear", temperature=(2.0, 0.0)),
+        "cosine": dict(guidance_scale=4.0, guidance_schedule="cosine", temperature=(2.0, 0.0)),
+        "scalar_temperature": dict(guidance_scale=2.0, temperature=1.5),
+        "negative": dict(guidance_scale=3.0, temperature=(1.0, 0.5), negative_embeds=gs["negative_embeds"],
+                         negative_cond_embeds=gs["negative_cond_embeds"]),
+        "start_tokens": dict(guidance_scale=3.0, temperature=(2.0, 0.0), input_ids=gs["start"].clone()),
+    }
+    with torch.no_grad():
+        for name, kw in variants.items():
+            ids = m.generate2(**base, **kw, generator=torch.Generator().manual_seed(gs["seed"]))
+            assert torch.equal(ids, gs["ids"][name]), name
+    assert torch.equal(gs["ids"]["start_tokens"][:, :6], gs["start"][:, :6])
